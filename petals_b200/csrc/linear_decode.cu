@@ -1,0 +1,406 @@
+// petals_b200 — decode-shape linear layer (1..8 tokens): a pure HBM weight streamer.
+//
+//   out[m, n] = epilogue( sum_k prologue(x)[m, k] * W[n, k] )          W is the HF nn.Linear layout
+//
+// At decode time tensor cores are idle and the op is bound by reading W exactly once
+// (SURVEY.md §7.3 item 1), so this kernel is built around keeping >= 64 KB of 128-bit
+// non-allocating loads in flight per SM and fusing everything around the GEMV into it:
+//
+//   prologue  : [wait on NVLink peer flag] -> [x = residual + sum of TP partials] ->
+//               [RMSNorm | LayerNorm] -> bf16 x staged once in shared memory
+//   main loop : one warp owns a pair of output columns and streams their two weight rows
+//               (plus the two `up_proj` rows for SwiGLU) with 8 independent 16-byte loads per lane
+//   epilogue  : [+bias] -> [SwiGLU | GELU] -> [+residual] -> store to local HBM and/or straight
+//               into peer GPUs' buffers over NVLink, then a release-increment of the peers' flags.
+//
+// The last two items are the decode-time "stage hop" (pipeline) and the one-shot all-reduce
+// (tensor parallel) fused into the producing GEMV and the consuming GEMV: no NCCL call and no
+// separate communication kernel on the token path (replaces X1/X4/X5 of SURVEY.md §2.5(c),
+// reference: src/petals/client/inference_session.py:153-172, utils/convert_block.py:128).
+#include "common.cuh"
+#include "petals_b200.h"
+
+namespace pb {
+
+constexpr int kMaxPeers = 8;
+
+struct LinearDecodeParams {
+  const __nv_bfloat16* x;         // [M, K] input / residual-in for the reduce prologue
+  const __nv_bfloat16* w;         // [N, K]
+  const __nv_bfloat16* w2;        // [N, K] second weight (SwiGLU up_proj) or null
+  const __nv_bfloat16* bias;      // [N] or null
+  const __nv_bfloat16* bias2;     // [N] or null
+  const __nv_bfloat16* residual;  // [M, N] or null (epilogue residual add)
+  __nv_bfloat16* out;             // [M, N] local output or null (push only)
+  const __nv_bfloat16* norm_w;    // [K] or null
+  const __nv_bfloat16* norm_b;    // [K] or null (LayerNorm)
+  __nv_bfloat16* x_out;           // [M, K] optional: block 0 writes the reduced (pre-norm) x here
+  float eps;
+  int norm_kind;                  // 0 none, 1 RMSNorm, 2 LayerNorm
+  int act;                        // 0 none, 1 SwiGLU(w, w2), 2 GELU(tanh), 3 GELU(erf)
+  int M, N, K;
+  // --- fused communication -------------------------------------------------------------
+  int n_parts;                                  // reduce prologue: x += sum_r parts[r]
+  const __nv_bfloat16* parts[kMaxPeers];        // local buffers written by peers
+  const uint64_t* wait_flag;                    // prologue waits until *wait_flag >= *epoch * wait_per_epoch
+  uint64_t wait_per_epoch;
+  const uint64_t* epoch;                        // device-resident step counter (graph friendly)
+  int n_push;                                   // epilogue also stores to these (peer) buffers
+  __nv_bfloat16* push_out[kMaxPeers];           // [M, N] each
+  uint64_t* push_flag[kMaxPeers];               // incremented (release.sys) once per CTA
+  int* error_flag;                              // set to 1 on watchdog expiry
+};
+
+PB_DEVICE float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  return 0.5f * x * (1.f + tanhf(k0 * (x + k1 * x * x * x)));
+}
+PB_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865475f)); }
+PB_DEVICE float silu(float x) { return x / (1.f + __expf(-x)); }
+
+template <int M>
+PB_DEVICE void fma8(float (&acc)[M], const uint4& w, const uint4 (&xv)[M]) {
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    acc[m] = fmaf(bf16_lo(w.x), bf16_lo(xv[m].x), acc[m]);
+    acc[m] = fmaf(bf16_hi(w.x), bf16_hi(xv[m].x), acc[m]);
+    acc[m] = fmaf(bf16_lo(w.y), bf16_lo(xv[m].y), acc[m]);
+    acc[m] = fmaf(bf16_hi(w.y), bf16_hi(xv[m].y), acc[m]);
+    acc[m] = fmaf(bf16_lo(w.z), bf16_lo(xv[m].z), acc[m]);
+    acc[m] = fmaf(bf16_hi(w.z), bf16_hi(xv[m].z), acc[m]);
+    acc[m] = fmaf(bf16_lo(w.w), bf16_lo(xv[m].w), acc[m]);
+    acc[m] = fmaf(bf16_hi(w.w), bf16_hi(xv[m].w), acc[m]);
+  }
+}
+
+// Block-wide sum of `v` (one value per thread) broadcast to all threads. `red` holds >= 32 floats.
+PB_DEVICE float block_sum(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect `red` from the previous use
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  return warp_sum(t);
+}
+
+// M = tokens, DUAL = SwiGLU (two weight matrices), XSMEM = x staged in shared memory.
+template <int M, bool DUAL, bool XSMEM>
+__global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(const LinearDecodeParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+  __shared__ float red[32];
+  __shared__ float stat[2 * M];
+
+  const int K = p.K, N = p.N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+
+  // ---- prologue ----------------------------------------------------------------------------
+  if (p.wait_flag != nullptr) {
+    if (tid == 0) {
+      const uint64_t target = *p.epoch * p.wait_per_epoch;
+      if (!spin_wait_ge(p.wait_flag, target)) atomicExch(p.error_flag, 1);
+    }
+    __syncthreads();
+  }
+  if (XSMEM) {
+    const int kvec = K >> 3;  // 8 bf16 per 16-byte vector
+    float ssum[M], ssq[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) ssum[m] = ssq[m] = 0.f;
+    for (int v = tid; v < kvec; v += nthr) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const size_t off = static_cast<size_t>(m) * K + (static_cast<size_t>(v) << 3);
+        uint4 xv = __ldcg(reinterpret_cast<const uint4*>(p.x + off));
+        if (p.n_parts > 0) {
+          float f[8] = {bf16_lo(xv.x), bf16_hi(xv.x), bf16_lo(xv.y), bf16_hi(xv.y),
+                        bf16_lo(xv.z), bf16_hi(xv.z), bf16_lo(xv.w), bf16_hi(xv.w)};
+          for (int r = 0; r < p.n_parts; ++r) {
+            uint4 pv = __ldcg(reinterpret_cast<const uint4*>(p.parts[r] + off));
+            f[0] += bf16_lo(pv.x); f[1] += bf16_hi(pv.x); f[2] += bf16_lo(pv.y); f[3] += bf16_hi(pv.y);
+            f[4] += bf16_lo(pv.z); f[5] += bf16_hi(pv.z); f[6] += bf16_lo(pv.w); f[7] += bf16_hi(pv.w);
+          }
+          xv.x = pack_bf16(f[0], f[1]); xv.y = pack_bf16(f[2], f[3]);
+          xv.z = pack_bf16(f[4], f[5]); xv.w = pack_bf16(f[6], f[7]);
+          if (p.x_out != nullptr && blockIdx.x == 0)
+            *reinterpret_cast<uint4*>(p.x_out + off) = xv;
+        }
+        *reinterpret_cast<uint4*>(xs + off) = xv;
+        if (p.norm_kind != 0) {
+          const float f0 = bf16_lo(xv.x), f1 = bf16_hi(xv.x), f2 = bf16_lo(xv.y), f3 = bf16_hi(xv.y);
+          const float f4 = bf16_lo(xv.z), f5 = bf16_hi(xv.z), f6 = bf16_lo(xv.w), f7 = bf16_hi(xv.w);
+          ssum[m] += (f0 + f1) + (f2 + f3) + (f4 + f5) + (f6 + f7);
+          ssq[m] += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + f4 * f4 + f5 * f5 + f6 * f6 + f7 * f7;
+        }
+      }
+    }
+    if (p.norm_kind != 0) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const float s1 = block_sum(ssum[m], red);
+        const float s2 = block_sum(ssq[m], red);
+        if (tid == 0) {
+          if (p.norm_kind == 1) {
+            stat[2 * m] = 0.f;
+            stat[2 * m + 1] = rsqrtf(s2 / K + p.eps);
+          } else {
+            const float mean = s1 / K;
+            const float var = fmaxf(s2 / K - mean * mean, 0.f);
+            stat[2 * m] = mean;
+            stat[2 * m + 1] = rsqrtf(var + p.eps);
+          }
+        }
+      }
+      __syncthreads();
+      for (int v = tid; v < kvec; v += nthr) {
+        const uint4 gv = __ldg(reinterpret_cast<const uint4*>(p.norm_w) + v);
+        uint4 bv = make_uint4(0, 0, 0, 0);
+        if (p.norm_kind == 2 && p.norm_b != nullptr) bv = __ldg(reinterpret_cast<const uint4*>(p.norm_b) + v);
+        const float g[8] = {bf16_lo(gv.x), bf16_hi(gv.x), bf16_lo(gv.y), bf16_hi(gv.y),
+                            bf16_lo(gv.z), bf16_hi(gv.z), bf16_lo(gv.w), bf16_hi(gv.w)};
+        const float b[8] = {bf16_lo(bv.x), bf16_hi(bv.x), bf16_lo(bv.y), bf16_hi(bv.y),
+                            bf16_lo(bv.z), bf16_hi(bv.z), bf16_lo(bv.w), bf16_hi(bv.w)};
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          const float mean = stat[2 * m], rstd = stat[2 * m + 1];
+          uint4* px = reinterpret_cast<uint4*>(xs + static_cast<size_t>(m) * K) + v;
+          const uint4 xv = *px;
+          float f[8] = {bf16_lo(xv.x), bf16_hi(xv.x), bf16_lo(xv.y), bf16_hi(xv.y),
+                        bf16_lo(xv.z), bf16_hi(xv.z), bf16_lo(xv.w), bf16_hi(xv.w)};
+          if (p.norm_kind == 1) {
+            // HF RMSNorm rounding: weight * bf16(x * rstd)
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              f[i] = __bfloat162float(__float2bfloat16_rn(f[i] * rstd)) * g[i];
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = (f[i] - mean) * rstd * g[i] + b[i];
+          }
+          uint4 o;
+          o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]);
+          o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+          *px = o;
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- main loop: each warp owns a pair of output columns ------------------------------------
+  constexpr int U = DUAL ? 2 : 4;  // 16-byte loads per weight row per iteration (8 in flight per lane)
+  const int ntasks = N >> 1;
+  const int total_warps = gridDim.x * nwarps;
+  const int kstep = 256 * U;
+  for (int task = warp * gridDim.x + blockIdx.x; task < ntasks; task += total_warps) {
+    const int n0 = task << 1;
+    const __nv_bfloat16* w0 = p.w + static_cast<size_t>(n0) * K;
+    const __nv_bfloat16* w1 = w0 + K;
+    const __nv_bfloat16* u0 = DUAL ? p.w2 + static_cast<size_t>(n0) * K : nullptr;
+    const __nv_bfloat16* u1 = DUAL ? u0 + K : nullptr;
+    float a0[M], a1[M], b0[M], b1[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) a0[m] = a1[m] = b0[m] = b1[m] = 0.f;
+
+    for (int kb = 0; kb < K; kb += kstep) {
+      uint4 wa[U], wb[U], ua[U], ub[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int k = kb + u * 256 + lane * 8;
+        ok[u] = k < K;
+        if (ok[u]) {
+          wa[u] = ld_stream(w0 + k);
+          wb[u] = ld_stream(w1 + k);
+          if (DUAL) {
+            ua[u] = ld_stream(u0 + k);
+            ub[u] = ld_stream(u1 + k);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (ok[u]) {
+          const int k = kb + u * 256 + lane * 8;
+          uint4 xv[M];
+#pragma unroll
+          for (int m = 0; m < M; ++m) {
+            if (XSMEM) xv[m] = *reinterpret_cast<const uint4*>(xs + static_cast<size_t>(m) * K + k);
+            else xv[m] = ld_cached(p.x + static_cast<size_t>(m) * K + k);
+          }
+          fma8<M>(a0, wa[u], xv);
+          fma8<M>(a1, wb[u], xv);
+          if (DUAL) {
+            fma8<M>(b0, ua[u], xv);
+            fma8<M>(b1, ub[u], xv);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      a0[m] = warp_sum(a0[m]);
+      a1[m] = warp_sum(a1[m]);
+      if (DUAL) {
+        b0[m] = warp_sum(b0[m]);
+        b1[m] = warp_sum(b1[m]);
+      }
+    }
+    // ---- epilogue: lane m handles token m --------------------------------------------------
+    float v0 = 0.f, v1 = 0.f, c0 = 0.f, c1 = 0.f;
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      if (lane == m) {
+        v0 = a0[m]; v1 = a1[m];
+        if (DUAL) { c0 = b0[m]; c1 = b1[m]; }
+      }
+    }
+    if (lane < M) {
+      if (p.bias != nullptr) {
+        v0 += __bfloat162float(p.bias[n0]);
+        v1 += __bfloat162float(p.bias[n0 + 1]);
+      }
+      if (DUAL) {
+        if (p.bias2 != nullptr) {
+          c0 += __bfloat162float(p.bias2[n0]);
+          c1 += __bfloat162float(p.bias2[n0 + 1]);
+        }
+        // HF: act(gate) * up, each projection rounded to bf16 first
+        v0 = __bfloat162float(__float2bfloat16_rn(v0));
+        v1 = __bfloat162float(__float2bfloat16_rn(v1));
+        c0 = __bfloat162float(__float2bfloat16_rn(c0));
+        c1 = __bfloat162float(__float2bfloat16_rn(c1));
+        v0 = __bfloat162float(__float2bfloat16_rn(silu(v0))) * c0;
+        v1 = __bfloat162float(__float2bfloat16_rn(silu(v1))) * c1;
+      } else if (p.act == 2) {
+        v0 = gelu_tanh(v0); v1 = gelu_tanh(v1);
+      } else if (p.act == 3) {
+        v0 = gelu_erf(v0); v1 = gelu_erf(v1);
+      }
+      const size_t o = static_cast<size_t>(lane) * N + n0;
+      if (p.residual != nullptr) {
+        const uint32_t rv = *reinterpret_cast<const uint32_t*>(p.residual + o);
+        // HF: residual + bf16(proj)
+        v0 = __bfloat162float(__float2bfloat16_rn(v0)) + bf16_lo(rv);
+        v1 = __bfloat162float(__float2bfloat16_rn(v1)) + bf16_hi(rv);
+      }
+      const uint32_t packed = pack_bf16(v0, v1);
+      if (p.out != nullptr) *reinterpret_cast<uint32_t*>(p.out + o) = packed;
+      for (int r = 0; r < p.n_push; ++r) *reinterpret_cast<uint32_t*>(p.push_out[r] + o) = packed;
+    }
+  }
+
+  // ---- publish: one release-increment per CTA per peer ---------------------------------------
+  if (p.n_push > 0) {
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence_system();
+      for (int r = 0; r < p.n_push; ++r)
+        if (p.push_flag[r] != nullptr) red_release_sys_add(p.push_flag[r], 1ull);
+    }
+  }
+}
+
+template <int M, bool DUAL, bool XSMEM>
+static cudaError_t launch_one(const LinearDecodeParams& p, int grid, int block, size_t smem,
+                              cudaStream_t stream) {
+  auto kern = linear_decode_kernel<M, DUAL, XSMEM>;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
+  kern<<<grid, block, smem, stream>>>(p);
+  return cudaGetLastError();
+}
+
+template <int M>
+static cudaError_t launch_m(const LinearDecodeParams& p, bool dual, bool xsmem, int grid, int block,
+                            size_t smem, cudaStream_t s) {
+  if (dual) return xsmem ? launch_one<M, true, true>(p, grid, block, smem, s)
+                         : launch_one<M, true, false>(p, grid, block, smem, s);
+  return xsmem ? launch_one<M, false, true>(p, grid, block, smem, s)
+               : launch_one<M, false, false>(p, grid, block, smem, s);
+}
+
+}  // namespace pb
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
+  using namespace pb;
+  if (a->M < 1 || a->M > 8 || (a->N & 1) || (a->K & 7)) return PB_ERR_SHAPE;
+  if (a->n_parts > kMaxPeers || a->n_push > kMaxPeers) return PB_ERR_SHAPE;
+  LinearDecodeParams p{};
+  p.x = static_cast<const __nv_bfloat16*>(a->x);
+  p.w = static_cast<const __nv_bfloat16*>(a->w);
+  p.w2 = static_cast<const __nv_bfloat16*>(a->w2);
+  p.bias = static_cast<const __nv_bfloat16*>(a->bias);
+  p.bias2 = static_cast<const __nv_bfloat16*>(a->bias2);
+  p.residual = static_cast<const __nv_bfloat16*>(a->residual);
+  p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.norm_w = static_cast<const __nv_bfloat16*>(a->norm_w);
+  p.norm_b = static_cast<const __nv_bfloat16*>(a->norm_b);
+  p.x_out = static_cast<__nv_bfloat16*>(a->x_out);
+  p.eps = a->eps;
+  p.norm_kind = a->norm_kind;
+  p.act = a->act;
+  p.M = a->M; p.N = a->N; p.K = a->K;
+  p.n_parts = a->n_parts;
+  for (int i = 0; i < a->n_parts; ++i) p.parts[i] = static_cast<const __nv_bfloat16*>(a->parts[i]);
+  p.wait_flag = static_cast<const uint64_t*>(a->wait_flag);
+  p.wait_per_epoch = a->wait_per_epoch;
+  p.epoch = static_cast<const uint64_t*>(a->epoch);
+  p.n_push = a->n_push;
+  for (int i = 0; i < a->n_push; ++i) {
+    p.push_out[i] = static_cast<__nv_bfloat16*>(a->push_out[i]);
+    p.push_flag[i] = static_cast<uint64_t*>(a->push_flag[i]);
+  }
+  p.error_flag = static_cast<int*>(a->error_flag);
+
+  const bool dual = a->act == 1;
+  if (dual && p.w2 == nullptr) return PB_ERR_SHAPE;
+  const bool need_smem = a->norm_kind != 0 || a->n_parts > 0;
+  const size_t xbytes = static_cast<size_t>(a->M) * a->K * 2;
+  const bool xsmem = need_smem || xbytes <= 160 * 1024;
+  if (need_smem && xbytes > 200 * 1024) return PB_ERR_SHAPE;
+  const size_t smem = xsmem ? xbytes : 0;
+
+  // Pick warps/SM in [12, 24] that minimises the last-wave quantisation loss. If a fixed grid
+  // was requested (flag accounting across ranks needs identical CTA counts) honour it.
+  const int sms = a->num_sms > 0 ? a->num_sms : 148;
+  const int ntasks = a->N / 2;
+  const int max_w = a->M <= 4 ? 24 : 16;
+  int best_w = max_w;
+  double best_eff = -1.0;
+  for (int w = max_w; w >= max_w / 2; --w) {
+    const long tw = static_cast<long>(sms) * w;
+    const long rounds = (ntasks + tw - 1) / tw;
+    const double eff = static_cast<double>(ntasks) / static_cast<double>(rounds * tw);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_w = w; }
+  }
+  int grid = sms;
+  if (ntasks < sms * best_w) {  // small problem: do not launch idle CTAs beyond need
+    grid = (ntasks + best_w - 1) / best_w;
+    if (grid < 1) grid = 1;
+    if (grid > sms) grid = sms;
+  }
+  if (a->fixed_grid > 0) grid = a->fixed_grid;
+  const int block = best_w * 32;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaSuccess;
+  switch (a->M) {
+    case 1: e = launch_m<1>(p, dual, xsmem, grid, block, smem, s); break;
+    case 2: e = launch_m<2>(p, dual, xsmem, grid, block, smem, s); break;
+    case 3: e = launch_m<3>(p, dual, xsmem, grid, block, smem, s); break;
+    case 4: e = launch_m<4>(p, dual, xsmem, grid, block, smem, s); break;
+    case 5: e = launch_m<5>(p, dual, xsmem, grid, block, smem, s); break;
+    case 6: e = launch_m<6>(p, dual, xsmem, grid, block, smem, s); break;
+    case 7: e = launch_m<7>(p, dual, xsmem, grid, block, smem, s); break;
+    case 8: e = launch_m<8>(p, dual, xsmem, grid, block, smem, s); break;
+  }
+  if (e != cudaSuccess) return PB_ERR_CUDA;
+  return a->out_grid ? (*(a->out_grid) = grid, PB_OK) : PB_OK;
+}

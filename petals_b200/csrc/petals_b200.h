@@ -1,0 +1,112 @@
+// petals_b200 — C ABI of the native library (loaded from Python through ctypes).
+// Every launcher takes raw device pointers plus a cudaStream_t (as void*), returns PB_OK or an error
+// code, and never synchronises: the Python layer captures whole pipeline stages into CUDA graphs.
+#pragma once
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { PB_OK = 0, PB_ERR_SHAPE = 1, PB_ERR_CUDA = 2, PB_ERR_UNSUPPORTED = 3, PB_ERR_DRIVER = 4 };
+
+#define PB_MAX_PEERS 8
+
+// ---- decode-shape linear (linear_decode.cu) ------------------------------------------------------
+typedef struct {
+  const void* x; const void* w; const void* w2; const void* bias; const void* bias2;
+  const void* residual; void* out; const void* norm_w; const void* norm_b; void* x_out;
+  float eps; int norm_kind; int act; int M, N, K;
+  int n_parts; const void* parts[PB_MAX_PEERS];
+  const void* wait_flag; uint64_t wait_per_epoch; const void* epoch;
+  int n_push; void* push_out[PB_MAX_PEERS]; void* push_flag[PB_MAX_PEERS];
+  void* error_flag;
+  int num_sms; int fixed_grid; int* out_grid;
+} PbLinearDecodeArgs;
+int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream);
+
+// ---- tcgen05 GEMM (gemm_tcgen05.cu) -----------------------------------------------------------------
+// D[M,N] = epilogue(A[M,K] * B^T) with A K-major [M,K]; B either K-major [N,K] (nn.Linear weight,
+// forward) or MN-major [K,N] (the same weight used transposed: dgrad). bf16 in, fp32 accumulate.
+typedef struct {
+  const void* a; const void* b; const void* b2;  // b2: second weight for fused SwiGLU (gate=b, up=b2)
+  const void* bias; const void* bias2; const void* residual; void* out;
+  int M, N, K;
+  int lda, ldb, ldo, ldres;   // leading dimensions in elements (0 = packed)
+  int b_mn_major;             // 0: B is [N,K]; 1: B is [K,N]
+  int act;                    // 0 none, 1 SwiGLU (needs b2; out has N columns), 2 GELU tanh, 3 GELU erf
+  int out_fp32;               // store fp32 instead of bf16
+  int accumulate;             // out += result (fp32 out only)
+  // fused stage hop / TP push: also store tiles to peer buffers and bump their flags per tile
+  int n_push; void* push_out[PB_MAX_PEERS]; void* push_flag[PB_MAX_PEERS];
+  // consumer side: wait for flag >= *epoch * wait_per_epoch before loading A
+  const void* wait_flag; uint64_t wait_per_epoch; const void* epoch; void* error_flag;
+  int num_sms; int block_n;   // 0 = auto
+} PbGemmArgs;
+int pb_gemm_bf16(const PbGemmArgs* a, void* stream);
+
+// ---- norms / elementwise (elementwise.cu) ---------------------------------------------------------
+// out = norm(x [+ residual]); if sum_out != null also stores (x + residual).
+int pb_norm(const void* x, const void* residual, const void* weight, const void* bias, void* out,
+            void* sum_out, int rows, int cols, float eps, int kind /*1 rms, 2 layernorm*/, void* stream);
+int pb_swiglu(const void* gate, const void* up, void* out, long n, void* stream);
+int pb_add(const void* a, const void* b, void* out, long n, void* stream);
+int pb_embedding(const void* table, const void* ids /*int64*/, void* out, int n_tokens, int hidden,
+                 void* stream);
+// argmax over vocab of logits [rows, vocab] (bf16 or fp32) -> int64 ids
+int pb_argmax(const void* logits, int is_fp32, void* out_ids, int rows, int vocab, void* stream);
+int pb_add_prompts(void* hidden /*[B,T,H]*/, const void* prompts /*[Bp,P,H]*/, int B, int T, int H,
+                   int Bp, int P, const void* pos_ptr, void* stream);
+int pb_bump_epoch(void* epoch, void* stream);
+int pb_advance_pos(void* pos, int delta, void* stream);
+
+// ---- RoPE + paged KV append (rope_kv.cu) ------------------------------------------------------------
+typedef struct {
+  const void* qkv;        // [B*T, (Hq + 2*Hkv) * D]
+  void* q_out;            // [B*T, Hq * D]
+  void* k_pool; void* v_pool;   // this layer's pools: [num_pages, Hkv, PAGE, D]
+  const void* block_table;      // int32 [B, max_pages]
+  const void* pos_ptr;          // int32 device scalar: tokens already in the cache
+  const void* cos; const void* sin;  // fp32 [max_pos, D/2] or null (no rotary: BLOOM/ALiBi)
+  const void* qkv_bias;         // optional [ (Hq+2Hkv)*D ]
+  int B, T, Hq, Hkv, D, page, max_pages, max_pos;
+  int interleaved_qkv;          // 1: Falcon/BLOOM fused layout [Hkv, G+2, D] per token
+  void* error_flag;
+} PbRopeKvArgs;
+int pb_rope_kv(const PbRopeKvArgs* a, void* stream);
+
+// ---- flash attention over the paged KV cache (attention.cu) ---------------------------------------
+typedef struct {
+  const void* q;          // [B*T, Hq*D]
+  const void* k_pool; const void* v_pool;
+  const void* block_table; const void* pos_ptr;
+  void* out;              // [B*T, Hq*D]
+  void* partial_o;        // fp32 [splits, B*T*Hq, D] (splits > 1)
+  void* partial_lse;      // fp32 [splits, B*T*Hq]
+  const void* alibi_slopes;  // fp32 [Hq] or null
+  float scale;
+  int B, T, Hq, Hkv, D, page, max_pages;
+  int window;             // sliding window (0 = none)
+  int splits;             // >= 1
+  int pos_static;         // used when pos_ptr == null
+} PbAttnArgs;
+int pb_attention(const PbAttnArgs* a, void* stream);
+
+// dense causal attention for the no-cache training path (forward + backward)
+typedef struct {
+  const void* q; const void* k; const void* v;   // [B, T, H*, D] token-major
+  void* out; void* lse;                           // lse fp32 [B, Hq, T]
+  const void* alibi_slopes; float scale; int B, T, Hq, Hkv, D, window;
+} PbAttnDenseArgs;
+
+// ---- KV cache utilities -----------------------------------------------------------------------------
+int pb_kv_copy_pages(void* pool, const void* src_pages, const void* dst_pages, int n, long page_elems,
+                     long layer_stride_elems, int n_layer_slabs, void* stream);
+
+// ---- runtime (host) ---------------------------------------------------------------------------------
+int pb_device_sm_count(int device);
+int pb_version(void);
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,317 @@
+"""Python entry points of the sm_100a kernels + their plain-PyTorch fp32 oracles.
+
+Each ``op(...)`` launches the hand-written CUDA kernel on the current stream (CUDA tensors only; raises
+if the native library is unavailable). Each ``op_ref(...)`` is the straightforward PyTorch definition of
+the same math — used on CPU (plumbing tests, BASELINE config #1) and as the numerics oracle in
+``tests/test_kernels_gpu.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+
+from petals_b200.ops import native
+from petals_b200.ops.native import AttnArgs, GemmArgs, LinearDecodeArgs, RopeKvArgs, check, ptr, stream_ptr
+
+PAGE = 64  # tokens per KV-cache page (== attention KV tile)
+
+ACT_NONE, ACT_SWIGLU, ACT_GELU_TANH, ACT_GELU_ERF = 0, 1, 2, 3
+NORM_NONE, NORM_RMS, NORM_LAYER = 0, 1, 2
+
+
+def _bf16c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.bfloat16 or not t.is_cuda:
+        raise TypeError(f"{name}: expected a CUDA bfloat16 tensor, got {t.dtype} on {t.device}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t
+
+
+# ----------------------------------------------------------------------------------------------------
+# decode-shape linear
+# ----------------------------------------------------------------------------------------------------
+def linear_decode(
+    x: torch.Tensor, w: torch.Tensor, *, w2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+    bias2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
+    norm_weight: Optional[torch.Tensor] = None, norm_bias: Optional[torch.Tensor] = None, norm_kind: int = NORM_NONE,
+    eps: float = 1e-6, act: int = ACT_NONE, out: Optional[torch.Tensor] = None, x_out: Optional[torch.Tensor] = None,
+    parts: Sequence[torch.Tensor] = (), wait_flag: Optional[int] = None, wait_per_epoch: int = 0,
+    epoch: Optional[int] = None, push_out: Sequence[int] = (), push_flag: Sequence[int] = (),
+    error_flag: Optional[int] = None, fixed_grid: int = 0, store_local: bool = True,
+) -> torch.Tensor:
+    """``out[M,N] = epilogue(prologue(x)[M,K] @ w[N,K]^T)`` for M <= 8 tokens. See csrc/linear_decode.cu.
+
+    ``push_out`` / ``push_flag`` / ``wait_flag`` / ``epoch`` are raw device addresses (peer-mapped buffers
+    from :mod:`petals_b200.parallel.symmetric`).
+    """
+    x = _bf16c(x, "x"); w = _bf16c(w, "w")
+    M, K = x.reshape(-1, x.shape[-1]).shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"weight shape {tuple(w.shape)} incompatible with K={K}")
+    if out is None and store_local:
+        out = torch.empty(*x.shape[:-1], N, dtype=torch.bfloat16, device=x.device)
+    a = LinearDecodeArgs()
+    a.x, a.w, a.w2 = ptr(x), ptr(w), ptr(_bf16c(w2, "w2"))
+    a.bias, a.bias2 = ptr(_bf16c(bias, "bias")), ptr(_bf16c(bias2, "bias2"))
+    a.residual = ptr(_bf16c(residual, "residual"))
+    a.out = ptr(out) if store_local else None
+    a.norm_w, a.norm_b = ptr(_bf16c(norm_weight, "norm_weight")), ptr(_bf16c(norm_bias, "norm_bias"))
+    a.x_out = ptr(x_out)
+    a.eps, a.norm_kind, a.act = eps, norm_kind, act
+    a.M, a.N, a.K = M, N, K
+    a.n_parts = len(parts)
+    for i, p in enumerate(parts):
+        a.parts[i] = p if isinstance(p, int) else ptr(p)
+    a.wait_flag, a.wait_per_epoch, a.epoch = wait_flag, wait_per_epoch, epoch
+    a.n_push = len(push_out)
+    for i, p in enumerate(push_out):
+        a.push_out[i] = p
+        a.push_flag[i] = push_flag[i] if i < len(push_flag) else None
+    a.error_flag = error_flag
+    a.num_sms = native.sm_count(x.device.index)
+    a.fixed_grid = fixed_grid
+    check(native.lib().pb_linear_decode(C.byref(a), stream_ptr()), "linear_decode")
+    return out
+
+
+def linear_decode_grid(N: int, M: int = 1, device: Optional[int] = None) -> int:
+    """CTA count linear_decode launches for a given N (peers need it to size flag targets)."""
+    sms = native.sm_count(device)
+    ntasks = N // 2
+    max_w = 24 if M <= 4 else 16
+    best_w, best_eff = max_w, -1.0
+    for w in range(max_w, max_w // 2 - 1, -1):
+        tw = sms * w
+        rounds = -(-ntasks // tw)
+        eff = ntasks / (rounds * tw)
+        if eff > best_eff + 1e-9:
+            best_eff, best_w = eff, w
+    if ntasks < sms * best_w:
+        return max(1, min(sms, -(-ntasks // best_w)))
+    return sms
+
+
+def _act_ref(v: torch.Tensor, act: int) -> torch.Tensor:
+    if act == ACT_GELU_TANH:
+        return F.gelu(v, approximate="tanh")
+    if act == ACT_GELU_ERF:
+        return F.gelu(v)
+    return v
+
+
+def norm_ref(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], kind: int, eps: float) -> torch.Tensor:
+    xf = x.float()
+    if kind == NORM_RMS:
+        y = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+        return (y.to(x.dtype).float() * weight.float()).to(x.dtype)
+    y = F.layer_norm(xf, (x.shape[-1],), weight.float(), None if bias is None else bias.float(), eps)
+    return y.to(x.dtype)
+
+
+def linear_ref(
+    x: torch.Tensor, w: torch.Tensor, *, w2=None, bias=None, bias2=None, residual=None, norm_weight=None,
+    norm_bias=None, norm_kind: int = NORM_NONE, eps: float = 1e-6, act: int = ACT_NONE,
+) -> torch.Tensor:
+    """Oracle for both linear_decode and gemm (same math, HF rounding points)."""
+    dt = x.dtype
+    if norm_kind != NORM_NONE:
+        x = norm_ref(x, norm_weight, norm_bias, norm_kind, eps)
+    y = F.linear(x.float(), w.float(), None if bias is None else bias.float())
+    if act == ACT_SWIGLU:
+        u = F.linear(x.float(), w2.float(), None if bias2 is None else bias2.float())
+        y = (F.silu(y.to(dt).float()).to(dt).float() * u.to(dt).float())
+    else:
+        y = _act_ref(y, act)
+    if residual is not None:
+        y = y.to(dt).float() + residual.float()
+    return y.to(dt)
+
+
+# ----------------------------------------------------------------------------------------------------
+# tcgen05 GEMM
+# ----------------------------------------------------------------------------------------------------
+def gemm(
+    a_: torch.Tensor, b: torch.Tensor, *, b2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+    bias2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+    b_mn_major: bool = False, out: Optional[torch.Tensor] = None, out_fp32: bool = False, block_n: int = 0,
+    wait_flag: Optional[int] = None, wait_per_epoch: int = 0, epoch: Optional[int] = None,
+    push_out: Sequence[int] = (), push_flag: Sequence[int] = (), error_flag: Optional[int] = None,
+    store_local: bool = True,
+) -> torch.Tensor:
+    """``out[M,N] = epilogue(a[M,K] @ op(b))`` on the tcgen05 tensor cores. See csrc/gemm_tcgen05.cu.
+
+    ``b`` is ``[N,K]`` (nn.Linear weight) or, with ``b_mn_major=True``, ``[K,N]`` (weight used transposed).
+    """
+    a2 = _bf16c(a_, "a").reshape(-1, a_.shape[-1])
+    b = _bf16c(b, "b")
+    M, K = a2.shape
+    N = b.shape[1] if b_mn_major else b.shape[0]
+    if (b.shape[0] if b_mn_major else b.shape[1]) != K:
+        raise ValueError(f"b shape {tuple(b.shape)} incompatible with K={K}")
+    if out is None and store_local:
+        out = torch.empty(*a_.shape[:-1], N, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=a_.device)
+    g = GemmArgs()
+    g.a, g.b, g.b2 = ptr(a2), ptr(b), ptr(_bf16c(b2, "b2"))
+    g.bias, g.bias2, g.residual = ptr(_bf16c(bias, "bias")), ptr(_bf16c(bias2, "bias2")), ptr(_bf16c(residual, "residual"))
+    g.out = ptr(out) if store_local else None
+    g.M, g.N, g.K = M, N, K
+    g.lda = g.ldb = g.ldo = g.ldres = 0
+    g.b_mn_major, g.act, g.out_fp32, g.accumulate = int(b_mn_major), act, int(out_fp32), 0
+    g.n_push = len(push_out)
+    for i, p in enumerate(push_out):
+        g.push_out[i] = p
+        g.push_flag[i] = push_flag[i] if i < len(push_flag) else None
+    g.wait_flag, g.wait_per_epoch, g.epoch, g.error_flag = wait_flag, wait_per_epoch, epoch, error_flag
+    g.num_sms = native.sm_count(a_.device.index)
+    g.block_n = block_n
+    check(native.lib().pb_gemm_bf16(C.byref(g), stream_ptr()), "gemm_bf16")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------
+# norms / elementwise
+# ----------------------------------------------------------------------------------------------------
+def norm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None, *, kind: int = NORM_RMS,
+         eps: float = 1e-6, residual: Optional[torch.Tensor] = None, sum_out: Optional[torch.Tensor] = None,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    x = _bf16c(x, "x")
+    if out is None:
+        out = torch.empty_like(x)
+    rows, cols = x.numel() // x.shape[-1], x.shape[-1]
+    check(native.lib().pb_norm(ptr(x), ptr(_bf16c(residual, "residual")), ptr(_bf16c(weight, "weight")),
+                               ptr(_bf16c(bias, "bias")), ptr(out), ptr(sum_out), rows, cols, eps, kind, stream_ptr()),
+          "norm")
+    return out
+
+
+def swiglu(gate: torch.Tensor, up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty_like(gate)
+    check(native.lib().pb_swiglu(ptr(_bf16c(gate, "gate")), ptr(_bf16c(up, "up")), ptr(out), gate.numel(), stream_ptr()), "swiglu")
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty_like(a)
+    check(native.lib().pb_add(ptr(_bf16c(a, "a")), ptr(_bf16c(b, "b")), ptr(out), a.numel(), stream_ptr()), "add")
+    return out
+
+
+def embedding(table: torch.Tensor, ids: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    ids = ids.contiguous()
+    if ids.dtype != torch.int64:
+        ids = ids.long()
+    if out is None:
+        out = torch.empty(*ids.shape, table.shape[1], dtype=torch.bfloat16, device=table.device)
+    check(native.lib().pb_embedding(ptr(_bf16c(table, "table")), ptr(ids), ptr(out), ids.numel(), table.shape[1], stream_ptr()), "embedding")
+    return out
+
+
+def argmax(logits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    rows, vocab = logits.numel() // logits.shape[-1], logits.shape[-1]
+    if out is None:
+        out = torch.empty(logits.shape[:-1], dtype=torch.int64, device=logits.device)
+    check(native.lib().pb_argmax(ptr(logits.contiguous()), int(logits.dtype == torch.float32), ptr(out), rows, vocab, stream_ptr()), "argmax")
+    return out
+
+
+def add_prompts(hidden: torch.Tensor, prompts: torch.Tensor, pos_ptr: Optional[int] = None) -> torch.Tensor:
+    """In place: hidden[:, :P] += prompts (deep-prompt injection, reference backend.py:231-233)."""
+    B, T, H = hidden.shape
+    Bp, P, _ = prompts.shape
+    check(native.lib().pb_add_prompts(ptr(_bf16c(hidden, "hidden")), ptr(_bf16c(prompts, "prompts")), B, T, H, Bp, P, pos_ptr, stream_ptr()), "add_prompts")
+    return hidden
+
+
+# ----------------------------------------------------------------------------------------------------
+# RoPE + paged KV, attention
+# ----------------------------------------------------------------------------------------------------
+def rope_tables(head_dim: int, max_pos: int, theta: float = 10000.0, scaling: Optional[dict] = None,
+                device="cpu") -> tuple[torch.Tensor, torch.Tensor]:
+    """fp32 cos/sin tables [max_pos, D/2]; supports the Llama-3 ("llama3") and linear rope_scaling types."""
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    if scaling:
+        kind = scaling.get("rope_type", scaling.get("type"))
+        factor = float(scaling.get("factor", 1.0))
+        if kind == "llama3":
+            lo, hi = float(scaling.get("low_freq_factor", 1.0)), float(scaling.get("high_freq_factor", 4.0))
+            old = float(scaling.get("original_max_position_embeddings", 8192))
+            wavelen = 2 * math.pi / inv
+            smooth = ((old / wavelen) - lo) / (hi - lo)
+            scaled = torch.where(wavelen > old / lo, inv / factor, inv)
+            mid = (wavelen <= old / lo) & (wavelen >= old / hi)
+            inv = torch.where(mid, (1 - smooth) * inv / factor + smooth * inv, scaled)
+        elif kind == "linear":
+            inv = inv / factor
+    ang = torch.arange(max_pos, dtype=torch.float32)[:, None] * inv[None, :]
+    return ang.cos().to(device).contiguous(), ang.sin().to(device).contiguous()
+
+
+def rope_kv_append(qkv: torch.Tensor, q_out: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor,
+                   block_table: torch.Tensor, pos_ptr: int, cos: Optional[torch.Tensor], sin: Optional[torch.Tensor],
+                   *, B: int, T: int, Hq: int, Hkv: int, D: int, qkv_bias: Optional[torch.Tensor] = None,
+                   interleaved: bool = False, error_flag: Optional[int] = None) -> None:
+    a = RopeKvArgs()
+    a.qkv, a.q_out, a.k_pool, a.v_pool = ptr(qkv), ptr(q_out), ptr(k_pool), ptr(v_pool)
+    a.block_table, a.pos_ptr = ptr(block_table), pos_ptr
+    a.cos, a.sin, a.qkv_bias = ptr(cos), ptr(sin), ptr(qkv_bias)
+    a.B, a.T, a.Hq, a.Hkv, a.D, a.page = B, T, Hq, Hkv, D, PAGE
+    a.max_pages = block_table.shape[1]
+    a.max_pos = cos.shape[0] if cos is not None else 0
+    a.interleaved_qkv = int(interleaved)
+    a.error_flag = error_flag
+    check(native.lib().pb_rope_kv(C.byref(a), stream_ptr()), "rope_kv")
+
+
+def paged_attention(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, block_table: torch.Tensor,
+                    pos_ptr: Optional[int], out: torch.Tensor, *, B: int, T: int, Hq: int, Hkv: int, D: int,
+                    scale: float, splits: int = 1, partial_o: Optional[torch.Tensor] = None,
+                    partial_lse: Optional[torch.Tensor] = None, alibi_slopes: Optional[torch.Tensor] = None,
+                    window: int = 0, pos_static: int = 0) -> torch.Tensor:
+    a = AttnArgs()
+    a.q, a.k_pool, a.v_pool, a.block_table, a.pos_ptr = ptr(q), ptr(k_pool), ptr(v_pool), ptr(block_table), pos_ptr
+    a.out, a.partial_o, a.partial_lse, a.alibi_slopes = ptr(out), ptr(partial_o), ptr(partial_lse), ptr(alibi_slopes)
+    a.scale = scale
+    a.B, a.T, a.Hq, a.Hkv, a.D, a.page = B, T, Hq, Hkv, D, PAGE
+    a.max_pages, a.window, a.splits, a.pos_static = block_table.shape[1], window, splits, pos_static
+    check(native.lib().pb_attention(C.byref(a), stream_ptr()), "attention")
+    return out
+
+
+def rope_ref(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor) -> torch.Tensor:
+    """HF rotate_half RoPE with HF's rounding (cos/sin cast to x.dtype). x: [..., T, H, D]; cos/sin: [T, D/2]."""
+    dt = x.dtype
+    c = torch.cat([cos, cos], -1).to(dt)[:, None, :]
+    s = torch.cat([sin, sin], -1).to(dt)[:, None, :]
+    half = x.shape[-1] // 2
+    rot = torch.cat([-x[..., half:], x[..., :half]], -1)
+    return (x * c) + (rot * s)
+
+
+def attention_ref(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, pos0: int, scale: float,
+                  alibi_slopes: Optional[torch.Tensor] = None, window: int = 0) -> torch.Tensor:
+    """fp32 oracle. q: [B,T,Hq,D]; k,v: [B,L,Hkv,D] with L = pos0 + T. Returns [B,T,Hq,D] in q.dtype."""
+    B, T, Hq, D = q.shape
+    L, Hkv = k.shape[1], k.shape[2]
+    G = Hq // Hkv
+    kf = k.float().repeat_interleave(G, dim=2)
+    vf = v.float().repeat_interleave(G, dim=2)
+    s = torch.einsum("bthd,blhd->bhtl", q.float(), kf) * scale
+    qpos = pos0 + torch.arange(T, device=q.device)[:, None]
+    kpos = torch.arange(L, device=q.device)[None, :]
+    if alibi_slopes is not None:
+        s = s + alibi_slopes.float().view(1, Hq, 1, 1) * (kpos - qpos).float()[None, None]
+    ok = kpos <= qpos
+    if window > 0:
+        ok = ok & (kpos > qpos - window)
+    s = s.masked_fill(~ok[None, None], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return torch.einsum("bhtl,blhd->bthd", p, vf).to(q.dtype)

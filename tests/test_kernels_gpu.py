@@ -1,0 +1,237 @@
+"""Numerics of every sm_100a kernel against a plain PyTorch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+
+from petals_b200.ops import functional as Fn
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, scale=1.0, seed=None):
+    if seed is not None:
+        torch.manual_seed(seed)
+    return (torch.randn(*shape, device=DEV, dtype=torch.float32) * scale).to(torch.bfloat16)
+
+
+def _close(got, want, atol, rtol, what=""):
+    got, want = got.float(), want.float()
+    err = (got - want).abs()
+    tol = atol + rtol * want.abs()
+    bad = (err > tol).float().mean().item()
+    assert bad < 1e-3, f"{what}: {bad * 100:.3f}% elements out of tolerance, max err {err.max().item():.4g}"
+
+
+@pytest.mark.parametrize("M", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("N,K", [(1024, 512), (4096, 4096), (2050, 1032)])
+def test_linear_decode_plain(M, N, K):
+    torch.manual_seed(0)
+    x, w = _rand(M, K), _rand(N, K, scale=K ** -0.5)
+    got = Fn.linear_decode(x, w)
+    _close(got, Fn.linear_ref(x, w), 2e-2, 2e-2, "plain")
+
+
+@pytest.mark.parametrize("M", [1, 4])
+def test_linear_decode_rmsnorm_residual(M):
+    torch.manual_seed(1)
+    K, N = 4096, 6144
+    x, w, g, res = _rand(M, K), _rand(N, K, scale=K ** -0.5), _rand(K) * 0.1 + 1, _rand(M, N)
+    got = Fn.linear_decode(x, w, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5, residual=res)
+    want = Fn.linear_ref(x, w, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5, residual=res)
+    _close(got, want, 3e-2, 2e-2, "rmsnorm+residual")
+
+
+def test_linear_decode_layernorm_gelu_bias():
+    torch.manual_seed(2)
+    M, K, N = 2, 1024, 4096
+    x, w = _rand(M, K), _rand(N, K, scale=K ** -0.5)
+    g, b, bias = _rand(K) * 0.1 + 1, _rand(K) * 0.1, _rand(N) * 0.1
+    got = Fn.linear_decode(x, w, norm_weight=g, norm_bias=b, norm_kind=Fn.NORM_LAYER, eps=1e-5, bias=bias, act=Fn.ACT_GELU_TANH)
+    want = Fn.linear_ref(x, w, norm_weight=g, norm_bias=b, norm_kind=Fn.NORM_LAYER, eps=1e-5, bias=bias, act=Fn.ACT_GELU_TANH)
+    _close(got, want, 2e-2, 2e-2, "layernorm+gelu")
+
+
+@pytest.mark.parametrize("M", [1, 3])
+def test_linear_decode_swiglu(M):
+    torch.manual_seed(3)
+    K, N = 2048, 5632
+    x, wg, wu, g = _rand(M, K), _rand(N, K, scale=K ** -0.5), _rand(N, K, scale=K ** -0.5), _rand(K) * 0.1 + 1
+    got = Fn.linear_decode(x, wg, w2=wu, act=Fn.ACT_SWIGLU, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+    want = Fn.linear_ref(x, wg, w2=wu, act=Fn.ACT_SWIGLU, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+    _close(got, want, 2e-2, 3e-2, "swiglu")
+
+
+def test_linear_decode_reduce_parts():
+    """Tensor-parallel prologue: x = residual + sum(parts), written back as the new residual stream."""
+    torch.manual_seed(4)
+    M, K, N = 2, 2048, 2048
+    res, parts = _rand(M, K), [_rand(M, K) for _ in range(4)]
+    w, g = _rand(N, K, scale=K ** -0.5), _rand(K) * 0.1 + 1
+    x_out = torch.zeros(M, K, device=DEV, dtype=torch.bfloat16)
+    got = Fn.linear_decode(res, w, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5, parts=parts, x_out=x_out)
+    xs = (res.float() + sum(p.float() for p in parts)).to(torch.bfloat16)
+    _close(x_out, xs, 1e-2, 1e-2, "reduced x")
+    _close(got, Fn.linear_ref(xs, w, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5), 3e-2, 2e-2, "reduce+norm+gemv")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 512), (256, 512, 1024), (1000, 4096, 4096), (77, 1024, 2048), (4096, 8192, 1024)])
+def test_gemm_plain(M, N, K):
+    torch.manual_seed(5)
+    a, b = _rand(M, K), _rand(N, K, scale=K ** -0.5)
+    got = Fn.gemm(a, b)
+    _close(got, Fn.linear_ref(a, b), 2e-2, 2e-2, f"gemm {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("bn", [64, 128, 256])
+def test_gemm_block_n(bn):
+    torch.manual_seed(6)
+    M, N, K = 384, 1024, 768
+    a, b = _rand(M, K), _rand(N, K, scale=K ** -0.5)
+    _close(Fn.gemm(a, b, block_n=bn), Fn.linear_ref(a, b), 2e-2, 2e-2, f"gemm bn={bn}")
+
+
+def test_gemm_bias_gelu_residual():
+    torch.manual_seed(7)
+    M, N, K = 300, 2048, 1024
+    a, b, bias, res = _rand(M, K), _rand(N, K, scale=K ** -0.5), _rand(N) * 0.1, _rand(M, N)
+    got = Fn.gemm(a, b, bias=bias, act=Fn.ACT_GELU_TANH)
+    _close(got, Fn.linear_ref(a, b, bias=bias, act=Fn.ACT_GELU_TANH), 2e-2, 2e-2, "bias+gelu")
+    got = Fn.gemm(a, b, residual=res)
+    _close(got, Fn.linear_ref(a, b, residual=res), 3e-2, 2e-2, "residual")
+
+
+def test_gemm_swiglu():
+    torch.manual_seed(8)
+    M, N, K = 520, 2816, 1024
+    a, wg, wu = _rand(M, K), _rand(N, K, scale=K ** -0.5), _rand(N, K, scale=K ** -0.5)
+    got = Fn.gemm(a, wg, b2=wu, act=Fn.ACT_SWIGLU)
+    _close(got, Fn.linear_ref(a, wg, w2=wu, act=Fn.ACT_SWIGLU), 2e-2, 3e-2, "gemm swiglu")
+
+
+@pytest.mark.parametrize("bn", [64, 256])
+def test_gemm_b_transposed(bn):
+    """dgrad form: out = a[M,K] @ b[K,N] with b consumed MN-major straight from the nn.Linear weight."""
+    torch.manual_seed(9)
+    M, N, K = 256, 1024, 512
+    a, b = _rand(M, K), _rand(K, N, scale=K ** -0.5)
+    got = Fn.gemm(a, b, b_mn_major=True, block_n=bn)
+    want = (a.float() @ b.float()).to(torch.bfloat16)
+    _close(got, want, 2e-2, 2e-2, "gemm MN-major B")
+
+
+def test_gemm_fp32_out():
+    torch.manual_seed(10)
+    M, N, K = 256, 512, 1024
+    a, b = _rand(M, K), _rand(N, K, scale=K ** -0.5)
+    got = Fn.gemm(a, b, out_fp32=True)
+    assert got.dtype == torch.float32
+    _close(got, a.float() @ b.float().T, 2e-3, 2e-3, "fp32 out")
+
+
+@pytest.mark.parametrize("kind", [Fn.NORM_RMS, Fn.NORM_LAYER])
+def test_norm(kind):
+    torch.manual_seed(11)
+    x, res = _rand(37, 4096), _rand(37, 4096)
+    w, b = _rand(4096) * 0.1 + 1, (_rand(4096) * 0.1 if kind == Fn.NORM_LAYER else None)
+    s = torch.empty_like(x)
+    got = Fn.norm(x, w, b, kind=kind, eps=1e-5, residual=res, sum_out=s)
+    xs = (x.float() + res.float()).to(torch.bfloat16)
+    _close(s, xs, 1e-2, 1e-2, "sum_out")
+    _close(got, Fn.norm_ref(xs, w, b, kind, 1e-5), 2e-2, 2e-2, "norm")
+
+
+def test_elementwise():
+    torch.manual_seed(12)
+    g, u = _rand(16, 1024), _rand(16, 1024)
+    want = (torch.nn.functional.silu(g.float()).to(torch.bfloat16).float() * u.float()).to(torch.bfloat16)
+    _close(Fn.swiglu(g, u), want, 1e-2, 2e-2, "swiglu")
+    _close(Fn.add(g, u), (g.float() + u.float()).to(torch.bfloat16), 1e-2, 1e-2, "add")
+    table = _rand(1000, 512)
+    ids = torch.randint(0, 1000, (3, 7), device=DEV)
+    assert torch.equal(Fn.embedding(table, ids), table[ids])
+    logits = torch.randn(5, 32003, device=DEV)
+    assert torch.equal(Fn.argmax(logits), logits.argmax(-1))
+    lb = logits.to(torch.bfloat16)
+    assert torch.equal(lb.float().max(-1).values, lb.float().gather(-1, Fn.argmax(lb)[:, None])[:, 0])
+    h, pr = _rand(2, 5, 256), _rand(2, 3, 256)
+    want = h.clone()
+    want[:, :3] = (want[:, :3].float() + pr.float()).to(torch.bfloat16)
+    _close(Fn.add_prompts(h.clone(), pr), want, 1e-2, 1e-2, "add_prompts")
+
+
+def _paged_setup(B, L_max, Hkv, D, n_extra_pages=3, seed=0):
+    """A pool with shuffled page ids and per-sequence block tables."""
+    torch.manual_seed(seed)
+    pages_per_seq = (L_max + Fn.PAGE - 1) // Fn.PAGE
+    n_pages = B * pages_per_seq + n_extra_pages
+    perm = torch.randperm(n_pages)[: B * pages_per_seq].to(torch.int32)
+    table = perm.view(B, pages_per_seq).contiguous().to(DEV)
+    k_pool = torch.zeros(n_pages, Hkv, Fn.PAGE, D, device=DEV, dtype=torch.bfloat16)
+    v_pool = torch.zeros_like(k_pool)
+    return k_pool, v_pool, table
+
+
+def _gather_cache(pool, table, L):
+    """[B, L, Hkv, D] view of the paged cache."""
+    B = table.shape[0]
+    out = []
+    for b in range(B):
+        pages = pool[table[b].long()]  # [P, Hkv, PAGE, D]
+        seq = pages.permute(0, 2, 1, 3).reshape(-1, pool.shape[1], pool.shape[3])
+        out.append(seq[:L])
+    return torch.stack(out)
+
+
+@pytest.mark.parametrize("D,Hq,Hkv", [(128, 8, 2), (64, 4, 4)])
+@pytest.mark.parametrize("steps", [[10, 1, 1], [70, 3], [130, 1]])
+def test_rope_kv_and_attention(D, Hq, Hkv, steps):
+    """Multi-step session: append with RoPE, attend; compare with the dense fp32 oracle at every step."""
+    torch.manual_seed(13)
+    B, L_max = 2, sum(steps)
+    k_pool, v_pool, table = _paged_setup(B, L_max, Hkv, D)
+    cos, sin = Fn.rope_tables(D, 512, theta=10000.0, device=DEV)
+    pos = torch.zeros(1, dtype=torch.int32, device=DEV)
+    k_all = torch.zeros(B, 0, Hkv, D, device=DEV, dtype=torch.bfloat16)
+    v_all = torch.zeros_like(k_all)
+    scale = D ** -0.5
+    p0 = 0
+    for T in steps:
+        qkv = _rand(B, T, (Hq + 2 * Hkv) * D)
+        q_out = torch.empty(B, T, Hq, D, device=DEV, dtype=torch.bfloat16)
+        Fn.rope_kv_append(qkv, q_out, k_pool, v_pool, table, pos.data_ptr(), cos, sin, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D)
+        q, k, v = qkv.view(B, T, Hq + 2 * Hkv, D).split([Hq, Hkv, Hkv], dim=2)
+        q_ref = Fn.rope_ref(q, cos[p0:p0 + T], sin[p0:p0 + T])
+        k_ref = Fn.rope_ref(k, cos[p0:p0 + T], sin[p0:p0 + T])
+        k_all, v_all = torch.cat([k_all, k_ref], 1), torch.cat([v_all, v], 1)
+        _close(q_out, q_ref, 1e-2, 1e-2, "rope q")
+        _close(_gather_cache(k_pool, table, p0 + T), k_all, 1e-2, 1e-2, "cache k")
+        _close(_gather_cache(v_pool, table, p0 + T), v_all, 1e-2, 1e-2, "cache v")
+        want = Fn.attention_ref(q_ref, k_all, v_all, pos0=p0, scale=scale)
+        for splits in (1, 3):
+            out = torch.empty(B, T, Hq, D, device=DEV, dtype=torch.bfloat16)
+            po = torch.empty(splits, B * T * Hq, D, device=DEV, dtype=torch.float32)
+            pl = torch.empty(splits, B * T * Hq, device=DEV, dtype=torch.float32)
+            Fn.paged_attention(q_out, k_pool, v_pool, table, pos.data_ptr(), out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D,
+                               scale=scale, splits=splits, partial_o=po, partial_lse=pl)
+            _close(out, want, 2e-2, 2e-2, f"attention T={T} splits={splits}")
+        pos += T
+        p0 += T
+
+
+def test_attention_alibi_window_long():
+    torch.manual_seed(14)
+    B, T, Hq, Hkv, D = 1, 300, 4, 4, 64
+    k_pool, v_pool, table = _paged_setup(B, T, Hkv, D)
+    pos = torch.zeros(1, dtype=torch.int32, device=DEV)
+    qkv = _rand(B, T, (Hq + 2 * Hkv) * D)
+    q_out = torch.empty(B, T, Hq, D, device=DEV, dtype=torch.bfloat16)
+    Fn.rope_kv_append(qkv, q_out, k_pool, v_pool, table, pos.data_ptr(), None, None, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D)
+    q, k, v = qkv.view(B, T, Hq + 2 * Hkv, D).split([Hq, Hkv, Hkv], dim=2)
+    slopes = torch.tensor([2 ** (-8 * (i + 1) / Hq) for i in range(Hq)], device=DEV)
+    out = torch.empty_like(q_out)
+    Fn.paged_attention(q_out, k_pool, v_pool, table, pos.data_ptr(), out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, alibi_slopes=slopes)
+    _close(out, Fn.attention_ref(q, k, v, pos0=0, scale=D ** -0.5, alibi_slopes=slopes), 2e-2, 2e-2, "alibi")
+    Fn.paged_attention(q_out, k_pool, v_pool, table, pos.data_ptr(), out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, window=100)
+    _close(out, Fn.attention_ref(q, k, v, pos0=0, scale=D ** -0.5, window=100), 2e-2, 2e-2, "window")

@@ -1,0 +1,130 @@
+"""Device-timed micro-benchmarks of the hot kernels at Llama-3-70B / 8B shapes.
+
+Timing hygiene (B200_PROFILING.md): CUDA events on the launching stream, >= 3 warm-ups, inputs rotated
+through a pool larger than the 126 MB L2 so every timed launch streams from HBM.
+Writes gpurun_out/kernel_bench.json and prints a table with roofline fractions against MEASURED_PEAKS.json.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from petals_b200.ops import functional as Fn  # noqa: E402
+from petals_b200.utils.peaks import measured_peaks  # noqa: E402
+
+
+def time_fn(fns, iters=20, warmup=3):
+    """fns: list of callables rotated round-robin (distinct buffers => cold L2). Returns ms per call."""
+    for i in range(warmup):
+        fns[i % len(fns)]()
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for i in range(iters):
+        fns[i % len(fns)]()
+    end.record()
+    torch.cuda.synchronize()
+    return start.elapsed_time(end) / iters
+
+
+def bench_gemv(results, peaks):
+    shapes = [
+        ("70b.qkv", 10240, 8192, dict(norm=True)),
+        ("70b.o", 8192, 8192, dict(residual=True)),
+        ("70b.gate_up", 28672, 8192, dict(norm=True, dual=True)),
+        ("70b.down", 8192, 28672, dict(residual=True)),
+        ("8b.qkv", 6144, 4096, dict(norm=True)),
+        ("8b.gate_up", 14336, 4096, dict(norm=True, dual=True)),
+        ("8b.down", 4096, 14336, dict(residual=True)),
+    ]
+    for name, N, K, opt in shapes:
+        for M in (1, 4):
+            nbuf = max(2, int(300e6 // (N * K * 2 * (2 if opt.get("dual") else 1))) + 1)
+            ws = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * K ** -0.5 for _ in range(nbuf)]
+            w2s = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * K ** -0.5 for _ in range(nbuf)] if opt.get("dual") else None
+            x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+            g = torch.ones(K, device="cuda", dtype=torch.bfloat16)
+            res = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+            out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+
+            def mk(i):
+                kw = dict(out=out)
+                if opt.get("norm"):
+                    kw.update(norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+                if opt.get("residual"):
+                    kw.update(residual=res)
+                if opt.get("dual"):
+                    kw.update(w2=w2s[i], act=Fn.ACT_SWIGLU)
+                return lambda: Fn.linear_decode(x, ws[i], **kw)
+
+            ms = time_fn([mk(i) for i in range(nbuf)], iters=40)
+            nbytes = N * K * 2 * (2 if opt.get("dual") else 1)
+            gbs = nbytes / ms / 1e6
+            # cuBLAS baseline for the bare GEMV (no fusion)
+            ref_ms = time_fn([(lambda i=i: torch.nn.functional.linear(x, ws[i])) for i in range(nbuf)], iters=40)
+            row = dict(kernel="linear_decode", shape=name, M=M, N=N, K=K, ms=ms, GBps=gbs, frac_hbm=gbs / peaks["hbm_gbs"],
+                       cublas_ms=ref_ms * (2 if opt.get("dual") else 1))
+            results.append(row)
+            print(f"gemv {name:12s} M={M} {ms * 1e3:8.1f} us  {gbs:7.0f} GB/s  {row['frac_hbm'] * 100:5.1f}% of measured HBM   (cuBLAS {row['cublas_ms'] * 1e3:.1f} us)", flush=True)
+            del ws, w2s
+
+
+def bench_gemm(results, peaks):
+    shapes = [
+        ("70b.qkv", 8192, 10240, 8192, {}),
+        ("70b.o", 8192, 8192, 8192, dict(residual=True)),
+        ("70b.gate_up", 8192, 28672, 8192, dict(dual=True)),
+        ("70b.down", 8192, 8192, 28672, dict(residual=True)),
+        ("8b.qkv", 8192, 6144, 4096, {}),
+        ("sq4096", 4096, 4096, 4096, {}),
+        ("sq8192", 8192, 8192, 8192, {}),
+    ]
+    for name, M, N, K, opt in shapes:
+        nbuf = 3
+        As = [torch.randn(M, K, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
+        Bs = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * K ** -0.5 for _ in range(nbuf)]
+        B2 = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * K ** -0.5 for _ in range(nbuf)] if opt.get("dual") else None
+        res = torch.randn(M, N, device="cuda", dtype=torch.bfloat16) if opt.get("residual") else None
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+
+        def mk(i):
+            kw = dict(out=out)
+            if opt.get("dual"):
+                kw.update(b2=B2[i], act=Fn.ACT_SWIGLU)
+            if res is not None:
+                kw.update(residual=res)
+            return lambda: Fn.gemm(As[i], Bs[i], **kw)
+
+        ms = time_fn([mk(i) for i in range(nbuf)], iters=10)
+        flops = 2.0 * M * N * K * (2 if opt.get("dual") else 1)
+        tf = flops / ms / 1e9
+        ref_ms = time_fn([(lambda i=i: torch.matmul(As[i], Bs[i].T)) for i in range(nbuf)], iters=10) * (2 if opt.get("dual") else 1)
+        row = dict(kernel="gemm_tcgen05", shape=name, M=M, N=N, K=K, ms=ms, TFLOPs=tf, frac_bf16=tf / peaks["bf16_tflops"], cublas_ms=ref_ms,
+                   cublas_TFLOPs=flops / ref_ms / 1e9)
+        results.append(row)
+        print(f"gemm {name:12s} {M}x{N}x{K} {ms:8.3f} ms {tf:7.0f} TFLOP/s {row['frac_bf16'] * 100:5.1f}% of measured cuBLAS peak (cuBLAS here: {row['cublas_TFLOPs']:.0f})", flush=True)
+        del As, Bs, B2
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    peaks = measured_peaks()
+    results = []
+    if args.only in ("", "gemv"):
+        bench_gemv(results, peaks)
+    if args.only in ("", "gemm"):
+        bench_gemm(results, peaks)
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(f"gpurun_out/kernel_bench{('_' + args.only) if args.only else ''}.json", "w") as f:
+        json.dump(dict(peaks=peaks, results=results), f, indent=1)
+
+
+if __name__ == "__main__":
+    main()
