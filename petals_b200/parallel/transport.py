@@ -1,0 +1,234 @@
+"""Control-plane transport between a client and stage workers.
+
+The reference speaks protobuf-over-libp2p through a Go daemon (hivemind P2P). Inside one box
+that collapses to two cases:
+
+* same process  -> the "stub" *is* the handler object; tensors are passed by reference (CUDA tensors stay on
+  the GPU, nothing is serialised);
+* other process -> a Unix-domain-socket RPC with a msgpack header + raw tensor bytes (this is the CPU
+  plumbing path used by ``run_server`` swarms and the multi-process tests; the GPU data plane between
+  stages never uses it — activations move by fused NVLink stores, see parallel/symmetric.py).
+
+Request = ``{"method", "uids", "meta", "tensors": [{"dtype", "shape"}...]}``; response = ``{"ok", "error",
+"meta", "tensors"}``. ``rpc_inference`` keeps its connection open as a bidirectional stream, one request per
+step, exactly one response per request, an empty request closes the session (reference
+src/petals/client/inference_session.py:198-207).
+"""
+from __future__ import annotations
+
+import os
+import socket
+import socketserver
+import struct
+import threading
+import traceback
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import msgpack
+import torch
+
+from petals_b200.utils.logging import get_logger
+
+logger = get_logger(__name__)
+
+_DTYPE_NAMES = {torch.float32: "f32", torch.float16: "f16", torch.bfloat16: "bf16", torch.int64: "i64", torch.int32: "i32",
+                torch.uint8: "u8", torch.bool: "b1", torch.float64: "f64"}
+_DTYPES = {v: k for k, v in _DTYPE_NAMES.items()}
+
+
+def _recv_exact(sock: socket.socket, n: int) -> bytes:
+    chunks, got = [], 0
+    while got < n:
+        c = sock.recv(min(n - got, 1 << 20))
+        if not c:
+            raise ConnectionError("peer closed the connection")
+        chunks.append(c)
+        got += len(c)
+    return b"".join(chunks)
+
+
+def send_message(sock: socket.socket, header: Dict[str, Any], tensors: Sequence[torch.Tensor] = ()) -> None:
+    metas, blobs = [], []
+    for t in tensors:
+        t = t.detach().to("cpu").contiguous()
+        raw = t.view(torch.uint8).numpy().tobytes() if t.numel() else b""
+        metas.append({"dtype": _DTYPE_NAMES[t.dtype], "shape": list(t.shape), "nbytes": len(raw)})
+        blobs.append(raw)
+    header = dict(header, tensors=metas)
+    payload = msgpack.packb(header, use_bin_type=True)
+    sock.sendall(struct.pack("<I", len(payload)) + payload + b"".join(blobs))
+
+
+def recv_message(sock: socket.socket) -> Tuple[Dict[str, Any], List[torch.Tensor]]:
+    (n,) = struct.unpack("<I", _recv_exact(sock, 4))
+    header = msgpack.unpackb(_recv_exact(sock, n), raw=False)
+    tensors = []
+    for m in header.get("tensors", []):
+        raw = _recv_exact(sock, m["nbytes"]) if m["nbytes"] else b""
+        dtype = _DTYPES[m["dtype"]]
+        if raw:
+            t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).view(dtype).reshape(m["shape"])
+        else:
+            t = torch.empty(m["shape"], dtype=dtype)
+        tensors.append(t)
+    return header, tensors
+
+
+class RemoteError(RuntimeError):
+    """An exception raised by the remote handler, re-raised on the caller's side."""
+
+
+# ---------------------------------------------------------------------------------------------------------
+# server side
+# ---------------------------------------------------------------------------------------------------------
+class _Conn(socketserver.BaseRequestHandler):
+    def handle(self) -> None:
+        handler = self.server.rpc_handler  # type: ignore[attr-defined]
+        sock: socket.socket = self.request
+        stream = None
+        try:
+            while True:
+                try:
+                    header, tensors = recv_message(sock)
+                except ConnectionError:
+                    break
+                method = header.get("method")
+                try:
+                    if method == "rpc_inference":
+                        if stream is None:
+                            stream = handler.rpc_inference(header["uids"], header.get("meta", {}))
+                        if header.get("close") or not tensors:
+                            stream.close()
+                            stream = None
+                            send_message(sock, {"ok": True, "closed": True})
+                            continue
+                        out = stream.step(*tensors, metadata=header.get("meta", {}))
+                        send_message(sock, {"ok": True}, [out])
+                    elif method == "rpc_info":
+                        send_message(sock, {"ok": True, "meta": handler.rpc_info(header.get("uids"))})
+                    elif method == "rpc_forward":
+                        out = handler.rpc_forward(header["uids"], *tensors, metadata=header.get("meta", {}))
+                        send_message(sock, {"ok": True}, [out])
+                    elif method == "rpc_backward":
+                        outs = handler.rpc_backward(header["uids"], *tensors, metadata=header.get("meta", {}))
+                        send_message(sock, {"ok": True}, list(outs))
+                    elif method == "rpc_push":
+                        handler.rpc_push(header["uids"], *tensors, metadata=header.get("meta", {}))
+                        send_message(sock, {"ok": True})
+                    elif method == "rpc_ping":
+                        send_message(sock, {"ok": True})
+                    else:
+                        send_message(sock, {"ok": False, "error": f"unknown method {method!r}", "etype": "ValueError"})
+                except Exception as e:  # noqa: BLE001 - report to the caller, keep serving
+                    logger.debug("rpc failed:\n" + traceback.format_exc())
+                    send_message(sock, {"ok": False, "error": str(e), "etype": type(e).__name__})
+        finally:
+            if stream is not None:
+                stream.close()
+
+
+class _ThreadedUnixServer(socketserver.ThreadingMixIn, socketserver.UnixStreamServer):
+    daemon_threads = True
+    allow_reuse_address = True
+
+
+class RpcServer:
+    """Serves a handler on a Unix socket (one thread per connection = one per in-flight request/stream)."""
+
+    def __init__(self, handler, socket_path: str):
+        if os.path.exists(socket_path):
+            os.unlink(socket_path)
+        self.socket_path = socket_path
+        self._server = _ThreadedUnixServer(socket_path, _Conn)
+        self._server.rpc_handler = handler  # type: ignore[attr-defined]
+        self._thread = threading.Thread(target=self._server.serve_forever, kwargs=dict(poll_interval=0.1), daemon=True)
+
+    def start(self) -> None:
+        self._thread.start()
+
+    def shutdown(self) -> None:
+        self._server.shutdown()
+        self._server.server_close()
+        if os.path.exists(self.socket_path):
+            os.unlink(self.socket_path)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# client side
+# ---------------------------------------------------------------------------------------------------------
+_EXC = {"ValueError": ValueError, "KeyError": KeyError, "TimeoutError": TimeoutError, "RuntimeError": RuntimeError}
+
+
+def _raise_remote(header: Dict[str, Any]) -> None:
+    etype = header.get("etype", "RuntimeError")
+    if etype == "AllocationFailed":
+        from petals_b200.server.memory_cache import AllocationFailed
+
+        raise AllocationFailed(header.get("error"))
+    raise _EXC.get(etype, RemoteError)(header.get("error"))
+
+
+class _RemoteStream:
+    def __init__(self, sock: socket.socket, uids: Sequence[str], metadata: dict):
+        self._sock, self._uids, self._open_meta, self._first, self.closed = sock, list(uids), metadata, True, False
+
+    def step(self, *tensors: torch.Tensor, metadata: Optional[dict] = None) -> torch.Tensor:
+        meta = dict(self._open_meta if self._first else {}, **(metadata or {}))
+        self._first = False
+        send_message(self._sock, {"method": "rpc_inference", "uids": self._uids, "meta": meta}, tensors)
+        header, outs = recv_message(self._sock)
+        if not header.get("ok"):
+            _raise_remote(header)
+        return outs[0]
+
+    def close(self) -> None:
+        if self.closed:
+            return
+        self.closed = True
+        try:
+            send_message(self._sock, {"method": "rpc_inference", "uids": self._uids, "close": True})
+            recv_message(self._sock)
+        except (OSError, ConnectionError):
+            pass
+        finally:
+            self._sock.close()
+
+
+class RemoteHandlerProxy:
+    """Client stub for a stage worker living in another process."""
+
+    def __init__(self, socket_path: str, connect_timeout: float = 5.0, request_timeout: float = 180.0):
+        self.socket_path, self.connect_timeout, self.request_timeout = socket_path, connect_timeout, request_timeout
+
+    def _connect(self) -> socket.socket:
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        s.settimeout(self.connect_timeout)
+        s.connect(self.socket_path)
+        s.settimeout(self.request_timeout)
+        return s
+
+    def _call(self, header: Dict[str, Any], tensors: Sequence[torch.Tensor] = ()):
+        with self._connect() as s:
+            send_message(s, header, tensors)
+            reply, outs = recv_message(s)
+        if not reply.get("ok"):
+            _raise_remote(reply)
+        return reply, outs
+
+    def rpc_info(self, uids=None) -> dict:
+        return self._call({"method": "rpc_info", "uids": uids})[0]["meta"]
+
+    def rpc_ping(self) -> None:
+        self._call({"method": "rpc_ping"})
+
+    def rpc_forward(self, uids, *tensors, metadata=None) -> torch.Tensor:
+        return self._call({"method": "rpc_forward", "uids": list(uids), "meta": metadata or {}}, tensors)[1][0]
+
+    def rpc_backward(self, uids, *tensors, metadata=None) -> List[torch.Tensor]:
+        return self._call({"method": "rpc_backward", "uids": list(uids), "meta": metadata or {}}, tensors)[1]
+
+    def rpc_push(self, uids, *tensors, metadata=None) -> None:
+        self._call({"method": "rpc_push", "uids": list(uids), "meta": metadata or {}}, tensors)
+
+    def rpc_inference(self, uids, metadata=None) -> _RemoteStream:
+        return _RemoteStream(self._connect(), uids, metadata or {})

@@ -1,0 +1,228 @@
+"""Serving back-ends: ``Stage`` executes a span of blocks, ``TransformerBackend`` is the per-block facade
+with the reference's name and methods (reference: src/petals/server/backend.py:24-235).
+
+``Stage`` has two executors behind one interface:
+  * CUDA + supported family -> :class:`petals_b200.server.stage_engine.StageEngine` (fused sm_100a kernels,
+    paged KV, CUDA graphs) for inference and forward;
+  * otherwise (CPU plumbing tests, exotic configs) -> the oracle blocks with dense per-session KV tensors.
+Backward (prompt-tuning) recomputes each block once with autograd enabled (activation checkpointing per
+block: 2 forwards per step instead of the reference's 3) and returns the gradient
+w.r.t. the span input and the deep prompts; weights are frozen (reference backend.py:48-51).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from petals_b200.data_structures import make_uid
+from petals_b200.models.block_oracle import GenericBlock
+from petals_b200.server.memory_cache import MemoryCache, SessionCache
+from petals_b200.server.task_pool import PrioritizedTaskPool, Runtime
+from petals_b200.utils.logging import get_logger
+from petals_b200.utils.misc import is_dummy
+
+logger = get_logger(__name__)
+
+
+class Stage:
+    """A contiguous span ``[start_block, end_block)`` of one model living on one device."""
+
+    def __init__(self, config, blocks: Sequence[GenericBlock], start_block: int, *, device, memory_cache: MemoryCache,
+                 torch_dtype: torch.dtype, max_chunk_size_bytes: int = 256 * 1024 * 1024, use_cuda_graphs: bool = True,
+                 force_oracle: bool = False):
+        self.config, self.blocks = config, list(blocks)
+        self.start_block, self.end_block = start_block, start_block + len(blocks)
+        self.device, self.dtype = torch.device(device), torch_dtype
+        self.memory_cache = memory_cache
+        self.spec = config.block_spec()
+        self.max_chunk_size_bytes = max_chunk_size_bytes
+        self.engine = None
+        if memory_cache.paged and not force_oracle:
+            from petals_b200.server.stage_engine import StageEngine
+
+            chunk_tokens = max(256, min(8192, max_chunk_size_bytes // max(1, 2 * self.spec.intermediate_size)))
+            self.engine = StageEngine(self.spec, self.blocks, memory_cache, device=self.device, max_chunk_tokens=chunk_tokens,
+                                      use_cuda_graphs=use_cuda_graphs)
+        self.active_adapter: Optional[str] = None
+
+    def __len__(self) -> int:
+        return len(self.blocks)
+
+    # ---- adapters -------------------------------------------------------------------------------------
+    def use_adapter(self, name: Optional[str]) -> None:
+        """Activate a LoRA adapter for the *next call only* (per request, not process-global: Q10)."""
+        from petals_b200.utils.peft import set_active_adapter
+
+        if name != self.active_adapter:
+            for block in self.blocks:
+                set_active_adapter(block, name)
+            self.active_adapter = name
+
+    # ---- oracle helpers ----------------------------------------------------------------------------------
+    @staticmethod
+    def _add_prompt(hidden: torch.Tensor, prompt: Optional[torch.Tensor]) -> torch.Tensor:
+        if prompt is None or is_dummy(prompt):
+            return hidden
+        P = min(prompt.shape[1], hidden.shape[1])
+        if P == 0:
+            return hidden
+        return torch.cat([hidden[:, :P] + prompt[:, :P].to(hidden.dtype), hidden[:, P:]], dim=1)
+
+    def _oracle_chunk_len(self, batch: int, prefix: int, T: int) -> int:
+        """Chunk length such that attention logits stay below max_chunk_size_bytes (reference backend.py:146-152)."""
+        heads = self.spec.num_heads
+        per_token = max(1, heads * batch * 4 * max(prefix + T, 1))
+        return max(1, self.max_chunk_size_bytes // per_token)
+
+    # ---- public span ops -----------------------------------------------------------------------------------
+    def forward(self, hidden: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
+        hi = len(self.blocks) if hi is None else hi
+        hidden = hidden.to(self.device)
+        prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device) for p in prompts]
+        if self.engine is not None and self._lora_free() and not torch.is_grad_enabled():
+            return self.engine.forward(hidden, prompts, (lo, hi))
+        h = hidden.to(self.dtype)
+        with torch.no_grad():
+            for i in range(lo, hi):
+                h = self._add_prompt(h, prompts[i - lo] if prompts is not None else None)
+                h = self.blocks[i].forward_cached(h, None, None, 0)
+        return h
+
+    def backward(self, hidden: torch.Tensor, grad_out: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None,
+                 lo: int = 0, hi: Optional[int] = None) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
+        """Returns (grad wrt span input, [grad wrt each block's prompt or None])."""
+        hi = len(self.blocks) if hi is None else hi
+        hidden, grad = hidden.to(self.device, self.dtype), grad_out.to(self.device, self.dtype)
+        prompts = [None] * (hi - lo) if prompts is None else [None if is_dummy(p) else p.to(self.device, self.dtype) for p in prompts]
+        # pass 1 (no grad): remember every block's input
+        inputs = []
+        h = hidden
+        with torch.no_grad():
+            for i in range(lo, hi):
+                inputs.append(h)
+                if i + 1 < hi:
+                    h = self.blocks[i].forward_cached(self._add_prompt(h, prompts[i - lo]), None, None, 0)
+        # pass 2: per-block recompute with autograd, last block first
+        grad_prompts: List[Optional[torch.Tensor]] = [None] * (hi - lo)
+        for i in reversed(range(lo, hi)):
+            x = inputs[i - lo].detach().requires_grad_(True)
+            p = prompts[i - lo]
+            p = p.detach().requires_grad_(True) if p is not None else None
+            with torch.enable_grad():
+                y = self.blocks[i].forward_cached(self._add_prompt(x, p), None, None, 0)
+            targets = [x] + ([p] if p is not None else [])
+            grads = torch.autograd.grad(y, targets, grad)
+            grad = grads[0]
+            if p is not None:
+                grad_prompts[i - lo] = grads[1]
+        return grad, grad_prompts
+
+    def inference_step(self, session: SessionCache, hidden: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None,
+                       hypo_ids: Optional[torch.Tensor] = None, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
+        hi = len(self.blocks) if hi is None else hi
+        hidden = hidden.to(self.device)
+        prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device) for p in prompts]
+        if self.engine is not None and self._lora_free():
+            return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi))
+        return self._oracle_inference(session, hidden, prompts, hypo_ids, lo, hi)
+
+    def _lora_free(self) -> bool:
+        return self.active_adapter is None
+
+    @torch.no_grad()
+    def _oracle_inference(self, session: SessionCache, hidden, prompts, hypo_ids, lo: int, hi: int) -> torch.Tensor:
+        B, T, _ = hidden.shape
+        if hypo_ids is not None and not is_dummy(hypo_ids):
+            session.reorder(hypo_ids)
+        if T == 0:
+            return hidden
+        session.prepare_write(T)
+        pos = session.position
+        h = hidden.to(self.dtype)
+        if prompts is not None:
+            # deep prompts are added to the first positions of the step input, per block (backend.py:231-233)
+            pass
+        out = torch.empty_like(h)
+        chunk = self._oracle_chunk_len(B, pos, T)
+        for t0 in range(0, T, chunk):
+            t1 = min(T, t0 + chunk)
+            c = h[:, t0:t1]
+            for i in range(lo, hi):
+                p = prompts[i - lo] if prompts is not None else None
+                if p is not None and t0 < p.shape[1]:
+                    c = self._add_prompt(c, p[:, t0:t1])
+                k, v = session.dense_kv(i, self.spec, self.dtype, self.device)
+                c = self.blocks[i].forward_cached(c, k, v, pos + t0)
+            out[:, t0:t1] = c
+        session.set_position(pos + T)
+        return out
+
+
+class TransformerBackend:
+    """One served block: uid, module, schemas and task pools. Execution is delegated to the owning ``Stage``."""
+
+    def __init__(self, name: str, module: GenericBlock, *, stage: Stage, slot: int, max_batch_size: int, runtime: Optional[Runtime] = None):
+        self.name, self.module, self.stage, self.slot = name, module, stage, slot
+        self.config, self.dtype = stage.config, stage.dtype
+        self.max_batch_size = max_batch_size
+        self.inference_pool = PrioritizedTaskPool(self.inference_step, max_batch_size, f"{name}_inference", runtime)
+        self.forward_pool = PrioritizedTaskPool(self.forward, max_batch_size, f"{name}_forward", runtime)
+        self.backward_pool = PrioritizedTaskPool(self.backward, max_batch_size, f"{name}_backward", runtime)
+        for p in module.parameters():
+            p.requires_grad_(False)
+
+    @property
+    def memory_cache(self) -> MemoryCache:
+        return self.stage.memory_cache
+
+    def forward(self, hidden: torch.Tensor, prompt: Optional[torch.Tensor] = None, active_adapter: Optional[str] = None) -> torch.Tensor:
+        self.stage.use_adapter(active_adapter)
+        return self.stage.forward(hidden, [prompt], self.slot, self.slot + 1)
+
+    def backward(self, hidden: torch.Tensor, grad_out: torch.Tensor, prompt: Optional[torch.Tensor] = None,
+                 active_adapter: Optional[str] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        self.stage.use_adapter(active_adapter)
+        g, gp = self.stage.backward(hidden, grad_out, [prompt], self.slot, self.slot + 1)
+        return g, gp[0]
+
+    def inference_step(self, hidden: torch.Tensor, hypo_ids: Optional[torch.Tensor], session: SessionCache,
+                       prompt: Optional[torch.Tensor] = None, active_adapter: Optional[str] = None) -> torch.Tensor:
+        self.stage.use_adapter(active_adapter)
+        return self.stage.inference_step(session, hidden, [prompt], hypo_ids, self.slot, self.slot + 1)
+
+    def get_inference_cache_descriptors(self, batch_size: int, max_length: int) -> Dict[str, object]:
+        """Shape/size of the KV reservation a session of this block needs (reference backend.py:88-99)."""
+        spec = self.stage.spec
+        return dict(batch_size=batch_size, max_length=max_length, num_kv_heads=spec.num_kv_heads, head_dim=spec.head_dim,
+                    dtype=str(self.dtype), bytes=batch_size * max_length * spec.kv_bytes_per_token(self.dtype))
+
+    def get_pools(self) -> Sequence[PrioritizedTaskPool]:
+        return self.forward_pool, self.backward_pool, self.inference_pool
+
+    def get_info(self) -> Dict[str, object]:
+        return dict(name=self.name, dtype=str(self.dtype), max_batch_size=self.max_batch_size)
+
+    def shutdown(self) -> None:
+        for p in self.module.parameters():
+            p.data = torch.empty(0, dtype=p.dtype)  # release device memory promptly (reference backend.py:190-198)
+
+
+class _MergedInferenceStep:
+    """Runs all requested blocks of a span back to back as ONE task (reference backend.py:201-235)."""
+
+    def __init__(self, stage: Stage):
+        self.stage = stage
+
+    def __call__(self, hidden: torch.Tensor, hypo_ids: Optional[torch.Tensor], session: SessionCache, lo: int, hi: int,
+                 prompts: Optional[Sequence[torch.Tensor]], active_adapter: Optional[str]) -> torch.Tensor:
+        self.stage.use_adapter(active_adapter)
+        return self.stage.inference_step(session, hidden, prompts, hypo_ids, lo, hi)
+
+
+def merge_inference_pools_inplace(backends: Dict[str, TransformerBackend], stage: Stage, runtime: Optional[Runtime], max_batch_size: int) -> PrioritizedTaskPool:
+    """All blocks of a stage share one inference pool whose task executes the whole requested sub-span."""
+    pool = PrioritizedTaskPool(_MergedInferenceStep(stage), max_batch_size, "span_inference", runtime)
+    for backend in backends.values():
+        backend.inference_pool = pool
+    return pool

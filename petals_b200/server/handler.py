@@ -1,0 +1,285 @@
+"""Request front-end of a stage (reference: src/petals/server/handler.py:55-592 and
+src/petals/server/block_functions.py:1-237, which this module + block_functions.py re-implement).
+
+The reference forks ``num_handlers`` processes that deserialise protobufs, talk to the runtime through mp
+queues and keep a cross-process session registry. One B200 worker is a single process, so the handler is an
+ordinary object whose methods *are* the RPCs; ``parallel/transport.py`` exposes the same methods to other
+processes. Contract kept from the reference:
+
+* ``rpc_inference(uids, metadata)`` opens a stream with a server-side KV session (``max_length`` checked
+  against ``inference_max_length``, cache reserved for all requested blocks with ``alloc_timeout``); every
+  ``step(hidden, prompts, hypo_ids, metadata)`` may carry ``start_from_position`` (KV rollback, *validated*
+  here unlike the reference's always-true assert), 0-token steps are legal, exceeding
+  ``max_length`` raises ``ValueError("Maximum length exceeded ...")``;
+* short steps (``B*T <= MAX_SHORT_INFERENCE_TOKENS``) run the whole requested span as ONE runtime task, longer
+  ones are submitted block by block so latency-critical tasks of other sessions can interleave;
+* ``rpc_forward`` / ``rpc_backward`` are stateless; ``rpc_backward`` returns ``grad_inputs`` and, if prompts
+  were given, ``grad_prompts``; ``rpc_push`` lets the previous stage deliver a step's input directly
+  (de-duplicated by ``step_id``); ``rpc_info`` reports version, cache budget and schemas.
+"""
+from __future__ import annotations
+
+import threading
+import time
+import uuid
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+import petals_b200
+from petals_b200.data_structures import CHAIN_DELIMITER, ModuleUID, split_uids
+from petals_b200.server.backend import Stage, TransformerBackend
+from petals_b200.server.block_functions import MAX_SHORT_INFERENCE_TOKENS, run_rpc_backward, run_rpc_forward
+from petals_b200.server.memory_cache import AllocationFailed, SessionCache
+from petals_b200.server.task_pool import PrioritizedTaskPool
+from petals_b200.server.task_prioritizer import DummyTaskPrioritizer, TaskPrioritizerBase
+from petals_b200.utils.logging import get_logger
+from petals_b200.utils.misc import DUMMY, is_dummy
+
+logger = get_logger(__name__)
+
+
+class InferenceStream:
+    """Server side of one ``rpc_inference`` stream: a KV session + step loop state."""
+
+    def __init__(self, handler: "TransformerConnectionHandler", uids: Sequence[ModuleUID], metadata: Dict[str, Any]):
+        self.handler = handler
+        self.uids = list(uids)
+        self.backends = [handler.module_backends[u] for u in self.uids]
+        self.lo, self.hi = self.backends[0].slot, self.backends[-1].slot + 1
+        self.max_length = int(metadata.get("max_length", 0))
+        if self.max_length <= 0:
+            raise ValueError("rpc_inference requires a positive max_length")
+        if self.max_length > handler.inference_max_length:
+            raise ValueError(f"Cannot allocate KV cache for {self.max_length} tokens, max = {handler.inference_max_length}")
+        self.session_id = metadata.get("session_id") or str(uuid.uuid4())
+        self.active_adapter = metadata.get("active_adapter") or None
+        handler.check_adapter(self.active_adapter)
+        self.points = float(metadata.get("points", 0))
+        self.alloc_timeout = float(metadata.get("alloc_timeout", 0.0))
+        self.cache: Optional[SessionCache] = None
+        self.batch_size: Optional[int] = None
+        self.opened_at = self.last_step_at = time.monotonic()
+        self.closed = False
+        self._pushed: Dict[str, Tuple[torch.Tensor, ...]] = {}
+        self._done_steps: set = set()
+        self._lock = threading.Lock()
+        handler._register(self)
+
+    # ---- lifecycle ----------------------------------------------------------------------------------------
+    def _ensure_cache(self, batch_size: int) -> SessionCache:
+        if self.cache is None:
+            self.batch_size = batch_size
+            self.cache = self.handler.stage.memory_cache.open_session(batch_size, self.max_length, self.alloc_timeout)
+        elif batch_size != self.batch_size:
+            raise ValueError(f"batch size changed within a session ({self.batch_size} -> {batch_size})")
+        return self.cache
+
+    def close(self) -> None:
+        with self._lock:
+            if self.closed:
+                return
+            self.closed = True
+            if self.cache is not None:
+                self.cache.close()
+            self.handler._unregister(self)
+
+    @property
+    def position(self) -> int:
+        return 0 if self.cache is None else self.cache.position
+
+    def expired(self, now: float) -> bool:
+        return (now - self.opened_at > self.handler.session_timeout) or (now - self.last_step_at > self.handler.step_timeout)
+
+    # ---- pushed inputs (server-to-server) ---------------------------------------------------------------------
+    def push(self, step_id: str, tensors: Tuple[torch.Tensor, ...]) -> None:
+        with self._lock:
+            if step_id not in self._done_steps:
+                self._pushed[step_id] = tensors
+
+    # ---- one step -------------------------------------------------------------------------------------------
+    def step(self, hidden: torch.Tensor, prompts: Optional[torch.Tensor] = None, hypo_ids: Optional[torch.Tensor] = None,
+             metadata: Optional[Dict[str, Any]] = None) -> torch.Tensor:
+        metadata = metadata or {}
+        if self.closed:
+            raise RuntimeError("inference session is closed")
+        now = time.monotonic()
+        if self.expired(now):
+            self.close()
+            raise TimeoutError("inference session timed out on the server")
+        self.last_step_at = now
+        step_id = metadata.get("step_id")
+        if step_id is not None:
+            with self._lock:
+                pushed = self._pushed.pop(step_id, None)
+                self._done_steps.add(step_id)
+            if pushed is not None:  # the previous stage already delivered this step's input
+                hidden = pushed[0]
+                prompts = pushed[1] if len(pushed) > 1 else prompts
+                hypo_ids = pushed[2] if len(pushed) > 2 else hypo_ids
+        if hidden.dim() != 3:
+            raise ValueError(f"hidden states must be [batch, seq, hidden], got {tuple(hidden.shape)}")
+        B, T, H = hidden.shape
+        cache = self._ensure_cache(B)
+        start = metadata.get("start_from_position")
+        if start is not None:
+            start = int(start)
+            if not 0 <= start <= cache.position:
+                raise ValueError(f"start_from_position={start} must be within the current prefix [0, {cache.position}]")
+            cache.set_position(start)
+        prefix = cache.position
+        if prefix + T > self.max_length:
+            raise ValueError(f"Maximum length exceeded: prefix {prefix} + current {T} exceeds pre-allocated maximum {self.max_length}")
+        n = self.hi - self.lo
+        if prompts is None or is_dummy(prompts):
+            block_prompts = None
+        else:
+            if prompts.dim() != 4 or prompts.shape[0] != n or prompts.shape[1] not in (1, B) or prompts.shape[3] != H:
+                raise ValueError(f"prompts must be [{n}, {B} or 1, pre_seq_len, {H}], got {tuple(prompts.shape)}")
+            block_prompts = list(prompts.unbind(0))
+        if hypo_ids is not None and not is_dummy(hypo_ids):
+            if hypo_ids.dtype != torch.int64 or hypo_ids.shape != (B,):
+                raise ValueError(f"hypo_ids must be int64 [{B}]")
+        else:
+            hypo_ids = None
+        priority = self.handler.prioritizer.prioritize(hidden, hypo_ids, points=self.points / max(n, 1), type="inference")
+        h = self.handler
+        if B * T <= MAX_SHORT_INFERENCE_TOKENS or n == 1:
+            fut = h.inference_pool.submit_task(hidden, hypo_ids, cache, self.lo, self.hi, block_prompts, self.active_adapter,
+                                               priority=priority, size=B * T)
+            out = fut.result(timeout=h.step_timeout)
+        else:
+            out = hidden
+            for i, backend in enumerate(self.backends):
+                cache.set_position(prefix)  # every block sees the same prefix; advanced once at the end
+                p = [block_prompts[i]] if block_prompts is not None else None
+                fut = h.inference_pool.submit_task(out, hypo_ids if i == 0 else None, cache, backend.slot, backend.slot + 1, p,
+                                                   self.active_adapter, priority=priority, size=B * T)
+                out = fut.result(timeout=h.step_timeout)
+            cache.set_position(prefix + T)
+        next_servers = metadata.get("next_servers")
+        if next_servers:
+            h._push_outputs(out, metadata, next_servers)
+        return out
+
+
+class TransformerConnectionHandler:
+    """All RPCs of one stage worker."""
+
+    def __init__(self, swarm, module_backends: Dict[ModuleUID, TransformerBackend], *, stage: Stage, peer_id: str,
+                 inference_pool: PrioritizedTaskPool, forward_pool: PrioritizedTaskPool, backward_pool: PrioritizedTaskPool,
+                 adapters: Sequence[str] = (), inference_max_length: int = 8192, request_timeout: float = 3 * 60,
+                 session_timeout: float = 30 * 60, step_timeout: float = 5 * 60,
+                 task_prioritizer: Optional[TaskPrioritizerBase] = None, quant_type=None):
+        self.swarm, self.module_backends, self.stage, self.peer_id = swarm, module_backends, stage, peer_id
+        self.inference_pool, self.forward_pool, self.backward_pool = inference_pool, forward_pool, backward_pool
+        self.adapters = tuple(adapters)
+        self.inference_max_length = inference_max_length
+        self.request_timeout, self.session_timeout, self.step_timeout = request_timeout, session_timeout, step_timeout
+        self.prioritizer = task_prioritizer or DummyTaskPrioritizer()
+        self.quant_type = quant_type
+        self._sessions: Dict[str, InferenceStream] = {}
+        self._sessions_lock = threading.Lock()
+
+    # ---- validation ------------------------------------------------------------------------------------------
+    def _check_uids(self, uids) -> List[ModuleUID]:
+        if isinstance(uids, str):
+            uids = split_uids(uids)
+        uids = list(uids)
+        if not uids:
+            raise RuntimeError("User must specify at least one block for inference, but got none")
+        for uid in uids:
+            if uid not in self.module_backends:
+                raise RuntimeError(f"Remote peer does not serve {uid}")
+        slots = [self.module_backends[u].slot for u in uids]
+        if slots != list(range(slots[0], slots[0] + len(slots))):
+            raise RuntimeError(f"requested blocks must be consecutive, got {uids}")
+        return uids
+
+    def check_adapter(self, active_adapter: Optional[str]) -> None:
+        if active_adapter and active_adapter not in self.adapters:
+            raise KeyError(f"adapter {active_adapter} not found (this server holds {list(self.adapters)})")
+
+    # ---- session registry --------------------------------------------------------------------------------------
+    def _register(self, stream: InferenceStream) -> None:
+        with self._sessions_lock:
+            self._sessions[stream.session_id] = stream
+
+    def _unregister(self, stream: InferenceStream) -> None:
+        with self._sessions_lock:
+            self._sessions.pop(stream.session_id, None)
+
+    def sweep_sessions(self) -> int:
+        """Close sessions whose session/step timeout expired; returns how many were closed."""
+        now = time.monotonic()
+        with self._sessions_lock:
+            stale = [s for s in self._sessions.values() if s.expired(now)]
+        for s in stale:
+            logger.info(f"closing expired inference session {s.session_id}")
+            s.close()
+        return len(stale)
+
+    # ---- RPCs ----------------------------------------------------------------------------------------------------
+    def rpc_inference(self, uids, metadata: Optional[Dict[str, Any]] = None) -> InferenceStream:
+        return InferenceStream(self, self._check_uids(uids), metadata or {})
+
+    def rpc_forward(self, uids, hidden: torch.Tensor, prompts: Optional[torch.Tensor] = None, metadata: Optional[Dict[str, Any]] = None) -> torch.Tensor:
+        uids = self._check_uids(uids)
+        metadata = metadata or {}
+        self.check_adapter(metadata.get("active_adapter"))
+        backends = [self.module_backends[u] for u in uids]
+        return run_rpc_forward(hidden, prompts, backends=backends, handler=self, active_adapter=metadata.get("active_adapter"),
+                               points=float(metadata.get("points", 0)))
+
+    def rpc_backward(self, uids, inputs: torch.Tensor, grad_outputs: torch.Tensor, prompts: Optional[torch.Tensor] = None,
+                     metadata: Optional[Dict[str, Any]] = None) -> List[torch.Tensor]:
+        uids = self._check_uids(uids)
+        metadata = metadata or {}
+        self.check_adapter(metadata.get("active_adapter"))
+        backends = [self.module_backends[u] for u in uids]
+        return run_rpc_backward(inputs, grad_outputs, prompts, backends=backends, handler=self,
+                                active_adapter=metadata.get("active_adapter"), points=float(metadata.get("points", 0)))
+
+    def rpc_push(self, uids, *tensors: torch.Tensor, metadata: Optional[Dict[str, Any]] = None) -> None:
+        metadata = metadata or {}
+        session_id, step_id = metadata.get("session_id"), metadata.get("step_id")
+        with self._sessions_lock:
+            stream = self._sessions.get(session_id)
+        if stream is None:
+            logger.debug(f"rpc_push for unknown session {session_id} ignored")
+            return
+        stream.push(step_id, tuple(tensors))
+
+    def _push_outputs(self, out: torch.Tensor, metadata: Dict[str, Any], next_servers) -> None:
+        try:
+            next_peer, next_session_id, start, end = next_servers[0]
+            stub = self.swarm.connect(next_peer)
+            prefix = next(iter(self.module_backends)).rsplit(".", 1)[0]
+            next_uids = [f"{prefix}.{i}" for i in range(start, end)]
+            meta = dict(session_id=next_session_id, step_id=metadata.get("step_id"), pushed=True, next_servers=next_servers[1:])
+            stub.rpc_push(next_uids, out, metadata=meta)
+        except Exception as e:  # noqa: BLE001 - pushing is an optimisation; the client resends anyway
+            logger.debug(f"failed to push outputs to {next_servers[0]}: {e!r}")
+
+    def rpc_ping(self) -> None:
+        return None
+
+    def rpc_info(self, uids=None) -> Dict[str, Any]:
+        cache = self.stage.memory_cache
+        spec = self.stage.spec
+        return dict(
+            version=petals_b200.__version__, dht_client_mode=False, peer_id=self.peer_id,
+            cache_tokens_available=cache.tokens_left * len(self.stage), inference_max_length=self.inference_max_length,
+            start_block=self.stage.start_block, end_block=self.stage.end_block, torch_dtype=str(self.stage.dtype).replace("torch.", ""),
+            quant_type=(self.quant_type.name.lower() if self.quant_type is not None else "none"), adapters=list(self.adapters),
+            keyword_names=("prompts", "hypo_ids"),
+            forward_schema=dict(args=("hidden_states", "prompts"), hidden_size=spec.hidden_size),
+            outputs_schema=dict(hidden_size=spec.hidden_size),
+            inference_schema=dict(args=("hidden_states", "prompts", "hypo_ids"), hidden_size=spec.hidden_size),
+            device=str(self.stage.device), engine="sm_100a" if self.stage.engine is not None else "oracle")
+
+    def shutdown(self) -> None:
+        with self._sessions_lock:
+            streams = list(self._sessions.values())
+        for s in streams:
+            s.close()

@@ -1,0 +1,321 @@
+"""Stage engine: executes a contiguous span of transformer blocks on one B200 with the sm_100a kernels.
+
+This is the B200-native counterpart of the reference's per-block ``TransformerBackend`` +
+``_MergedInferenceStep`` (src/petals/server/backend.py:24-235): the *whole span* is the unit of execution.
+
+* decode shapes (B*T <= 8 rows): every block is 7 launches — fused norm+QKV GEMV, RoPE+KV-append, paged
+  split-KV attention (+combine), O-proj GEMV+residual, fused norm+gate/up GEMV+SwiGLU, down GEMV+residual —
+  and the entire span is captured once per (B, T) into a CUDA graph whose only mutable inputs are device
+  buffers (activation, block table, cache position). One graph replay per token per stage replaces the
+  reference's per-block task-pool round trips and its six tiny per-op graphs.
+* prefill / parallel-forward shapes: tcgen05 GEMMs with fused bias/GELU/SwiGLU/residual epilogues, flash
+  attention over the paged cache, chunked by ``max_chunk_tokens`` (the pipelining unit).
+* no-cache forward (rpc_forward / training forward) reuses the same kernels against a one-layer scratch pool.
+* anything without a hand-written kernel yet (MoE experts, backward) runs the oracle math on the same weight
+  tensors, so every family is always servable.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from petals_b200.models.block_oracle import GenericBlock
+from petals_b200.models.spec import BlockSpec, alibi_slopes
+from petals_b200.ops import functional as Fn
+from petals_b200.ops import native
+from petals_b200.ops.functional import PAGE
+from petals_b200.server.memory_cache import MemoryCache, SessionCache
+from petals_b200.utils.logging import get_logger
+from petals_b200.utils.misc import is_dummy
+
+logger = get_logger(__name__)
+MAX_DECODE_ROWS = 8
+
+
+def fast_path_supported(spec: BlockSpec) -> bool:
+    """Can the fused sm_100a kernels run this block family end to end?"""
+    if spec.head_dim not in (64, 128) or spec.post_ln_residual:
+        return False
+    if spec.hidden_size % 8 or spec.intermediate_size % 8 or spec.qkv_dim % 8:
+        return False
+    return spec.mlp in ("swiglu", "gelu", "moe")
+
+
+class StageEngine:
+    def __init__(self, spec: BlockSpec, blocks: Sequence[GenericBlock], cache: MemoryCache, *, device,
+                 max_chunk_tokens: int = 8192, use_cuda_graphs: bool = True):
+        self.spec, self.blocks, self.cache = spec, list(blocks), cache
+        self.device = torch.device(device)
+        self.n_blocks = len(self.blocks)
+        self.max_chunk_tokens = max_chunk_tokens
+        self.use_cuda_graphs = use_cuda_graphs
+        self.dtype = torch.bfloat16
+        s = spec
+        self.norm_kind = Fn.NORM_RMS if s.norm == "rms" else Fn.NORM_LAYER
+        self.act = Fn.ACT_SWIGLU if s.mlp == "swiglu" else (Fn.ACT_GELU_TANH if s.gelu_tanh else Fn.ACT_GELU_ERF)
+        self.cos = self.sin = None
+        if s.rotary:
+            self.cos, self.sin = Fn.rope_tables(s.head_dim, s.max_position, s.rope_theta, s.rope_scaling, device=self.device)
+        self.slopes = alibi_slopes(s.num_heads).to(self.device) if s.alibi else None
+        self.sms = native.sm_count(self.device.index)
+        # device-resident step state shared by all graphs
+        self.max_pages = cache.max_pages_per_seq
+        self.pos_static = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._tables: Dict[int, torch.Tensor] = {}  # batch -> static block table
+        self._graphs: Dict[Tuple[int, int, int, int], dict] = {}
+        self._active: Optional[SessionCache] = None
+        self._dev_pos = -1
+        self._bufs: Dict[Tuple[str, int], torch.Tensor] = {}
+        # scratch one-layer pool for cache-less forward passes
+        n_scratch = max(1, (max_chunk_tokens + PAGE - 1) // PAGE) + 1
+        self._scratch_pool = torch.zeros(2, n_scratch, s.num_kv_heads, PAGE, s.head_dim, dtype=self.dtype, device=self.device)
+        self._scratch_pages = n_scratch
+
+    # ---- buffers ---------------------------------------------------------------------------------------
+    def _buf(self, name: str, rows: int, cols: int, dtype=None) -> torch.Tensor:
+        key = (name, rows)
+        t = self._bufs.get(key)
+        if t is None or t.shape[1] != cols:
+            t = torch.empty(rows, cols, dtype=dtype or self.dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def _table(self, B: int) -> torch.Tensor:
+        if B not in self._tables:
+            self._tables[B] = torch.zeros(B, self.max_pages, dtype=torch.int32, device=self.device)
+        return self._tables[B]
+
+    def _splits(self, B: int, T: int) -> int:
+        G = self.spec.group_size
+        m_tiles = (T * G + 63) // 64
+        ctas = B * self.spec.num_kv_heads * m_tiles
+        return int(min(16, max(1, (2 * self.sms) // max(1, ctas))))
+
+    # ---- one block ---------------------------------------------------------------------------------------
+    def _attention(self, qkv: torch.Tensor, slot: int, B: int, T: int, table: torch.Tensor, pos_ptr: int,
+                   pools: Tuple[torch.Tensor, torch.Tensor], splits: int, tag: str) -> torch.Tensor:
+        s = self.spec
+        M = B * T
+        w = self.blocks[slot]
+        q_buf = self._buf(f"q{tag}", M, s.num_heads * s.head_dim)
+        attn = self._buf(f"attn{tag}", M, s.num_heads * s.head_dim)
+        Fn.rope_kv_append(qkv, q_buf, pools[0], pools[1], table, pos_ptr, self.cos, self.sin, B=B, T=T, Hq=s.num_heads,
+                          Hkv=s.num_kv_heads, D=s.head_dim, qkv_bias=None, interleaved=s.qkv_interleaved,
+                          error_flag=self.err_flag.data_ptr())
+        po = pl = None
+        if splits > 1:
+            po = self._buf(f"po{tag}", splits * M * s.num_heads, s.head_dim, torch.float32)
+            pl = self._buf(f"pl{tag}", splits, M * s.num_heads, torch.float32)
+        Fn.paged_attention(q_buf, pools[0], pools[1], table, pos_ptr, attn, B=B, T=T, Hq=s.num_heads, Hkv=s.num_kv_heads,
+                           D=s.head_dim, scale=s.attn_scale, splits=splits, partial_o=po, partial_lse=pl,
+                           alibi_slopes=self.slopes, window=s.sliding_window)
+        return attn
+
+    def _block_decode(self, x: torch.Tensor, out: torch.Tensor, slot: int, B: int, T: int, table, pos_ptr, pools, splits) -> torch.Tensor:
+        """x, out: [M, H] ping-pong residual buffers. Returns the buffer holding the block output."""
+        s, w = self.spec, self.blocks[slot]
+        M = B * T
+        eps = s.norm_eps
+        qkv = Fn.linear_decode(x, w.wqkv, bias=w._p("bqkv"), norm_weight=w.ln1_w, norm_bias=w._p("ln1_b"), norm_kind=self.norm_kind,
+                               eps=eps, out=self._buf("qkv", M, s.qkv_dim))
+        attn = self._attention(qkv, slot, B, T, table, pos_ptr, pools, splits, "")
+        h1 = Fn.linear_decode(attn, w.wo, bias=w._p("bo"), residual=x, out=out)
+        if s.mlp == "moe":
+            h1.copy_(self._moe(h1.view(B, T, -1), w).view(M, -1))
+            return h1
+        if s.parallel_attn:
+            mlp_in, ln_w, ln_b = x, (w.ln2_w if s.dual_ln else w.ln1_w), (w._p("ln2_b") if s.dual_ln else w._p("ln1_b"))
+        else:
+            mlp_in, ln_w, ln_b = h1, w.ln2_w, w._p("ln2_b")
+        if s.mlp == "swiglu":
+            act = Fn.linear_decode(mlp_in, w.w_gate, w2=w.w_up, act=Fn.ACT_SWIGLU, norm_weight=ln_w, norm_bias=ln_b,
+                                   norm_kind=self.norm_kind, eps=eps, out=self._buf("act", M, s.intermediate_size))
+        else:
+            act = Fn.linear_decode(mlp_in, w.w_up, bias=w._p("b_up"), act=self.act, norm_weight=ln_w, norm_bias=ln_b,
+                                   norm_kind=self.norm_kind, eps=eps, out=self._buf("act", M, s.intermediate_size))
+        # down projection + residual; write into x's buffer (x is dead for sequential blocks, and for
+        # parallel blocks h1 already contains x + attn)
+        return Fn.linear_decode(act, w.w_down, bias=w._p("b_down"), residual=h1, out=x)
+
+    def _block_prefill(self, x: torch.Tensor, slot: int, B: int, T: int, table, pos_ptr, pools) -> torch.Tensor:
+        """x: [M, H] (overwritten with the block output)."""
+        s, w = self.spec, self.blocks[slot]
+        M = B * T
+        eps = s.norm_eps
+        xn = Fn.norm(x, w.ln1_w, w._p("ln1_b"), kind=self.norm_kind, eps=eps, out=self._buf("xn_p", M, s.hidden_size))
+        qkv = Fn.gemm(xn, w.wqkv, bias=w._p("bqkv"), out=self._buf("qkv_p", M, s.qkv_dim))
+        attn = self._attention(qkv, slot, B, T, table, pos_ptr, pools, 1, "_p")
+        h1 = Fn.gemm(attn, w.wo, bias=w._p("bo"), residual=x, out=self._buf("h1_p", M, s.hidden_size))
+        if s.mlp == "moe":
+            x.copy_(self._moe(h1.view(B, T, -1), w).view(M, -1))
+            return x
+        if s.parallel_attn:
+            xn2 = Fn.norm(x, w.ln2_w, w._p("ln2_b"), kind=self.norm_kind, eps=eps, out=xn) if s.dual_ln else xn
+        else:
+            xn2 = Fn.norm(h1, w.ln2_w, w._p("ln2_b"), kind=self.norm_kind, eps=eps, out=xn)
+        act_buf = self._buf("act_p", M, s.intermediate_size)
+        if s.mlp == "swiglu":
+            act = Fn.gemm(xn2, w.w_gate, b2=w.w_up, act=Fn.ACT_SWIGLU, out=act_buf)
+        else:
+            act = Fn.gemm(xn2, w.w_up, bias=w._p("b_up"), act=self.act, out=act_buf)
+        return Fn.gemm(act, w.w_down, bias=w._p("b_down"), residual=h1, out=x)
+
+    def _moe(self, h1: torch.Tensor, w: GenericBlock) -> torch.Tensor:
+        """h1 = residual stream after attention [B,T,H]; returns h1 + MoE(ln2(h1)). Oracle math on the engine's weights."""
+        ln2 = Fn.norm(h1.reshape(-1, h1.shape[-1]), w.ln2_w, None, kind=self.norm_kind, eps=self.spec.norm_eps).view_as(h1)
+        return h1 + w.mlp(ln2)
+
+    # ---- span execution ------------------------------------------------------------------------------------
+    def _sync_session(self, session: SessionCache, B: int) -> torch.Tensor:
+        table = self._table(B)
+        if self._active is not session or session._synced_version != session._version:
+            table.copy_(session.table_dev[:, : self.max_pages], non_blocking=True)
+            session._synced_version = session._version
+            self._active = session
+            self._dev_pos = -1
+        if self._dev_pos != session.position:
+            self.pos_static.fill_(session.position)
+            self._dev_pos = session.position
+        return table
+
+    def _run_span(self, x: torch.Tensor, B: int, T: int, lo: int, hi: int, table, pos_ptr, pools_of, prompts, decode: bool, splits: int) -> torch.Tensor:
+        M = B * T
+        other = self._buf("h_alt", M, self.spec.hidden_size) if decode else None
+        cur = x
+        for slot in range(lo, hi):
+            if prompts is not None and not is_dummy(prompts[slot - lo]):
+                Fn.add_prompts(cur.view(B, T, -1), prompts[slot - lo])
+            if decode:
+                nxt = self._block_decode(cur, other, slot, B, T, table, pos_ptr, pools_of(slot), splits)
+                if nxt is not cur:  # MoE path returned the alternate buffer
+                    cur, other = nxt, cur
+            else:
+                cur = self._block_prefill(cur, slot, B, T, table, pos_ptr, pools_of(slot))
+        return cur
+
+    def inference_step(self, session: SessionCache, hidden: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None,
+                       hypo_ids: Optional[torch.Tensor] = None, block_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """One rpc_inference step through blocks [lo, hi) of this stage (reference: backend.py:111-144)."""
+        lo, hi = block_range or (0, self.n_blocks)
+        B, T, H = hidden.shape
+        if hypo_ids is not None and not is_dummy(hypo_ids):
+            session.reorder(hypo_ids)
+        if T == 0:
+            return hidden
+        if hidden.dtype != self.dtype:
+            hidden = hidden.to(self.dtype)
+        out = torch.empty(B, T, H, dtype=self.dtype, device=self.device)
+        has_prompts = prompts is not None and any(not is_dummy(p) for p in prompts)
+        # chunked prefill: the chunk is also the unit a downstream stage can start on
+        max_t = max(1, self.max_chunk_tokens // B)
+        for t0 in range(0, T, max_t):
+            t1 = min(T, t0 + max_t)
+            chunk = hidden[:, t0:t1]
+            cp = None
+            if has_prompts:
+                cp = [p[:, t0:t1] if (not is_dummy(p) and t0 < p.shape[1]) else None for p in prompts]
+                if all(c is None for c in cp):
+                    cp = None
+            out[:, t0:t1] = self._step_chunk(session, chunk, cp, lo, hi)
+        return out
+
+    def _step_chunk(self, session: SessionCache, hidden: torch.Tensor, prompts, lo: int, hi: int) -> torch.Tensor:
+        B, T, H = hidden.shape
+        M = B * T
+        session.prepare_write(T)
+        table = self._sync_session(session, B)
+        pos_ptr = self.pos_static.data_ptr()
+        pools_of = self.cache.layer_pools
+        decode = M <= MAX_DECODE_ROWS
+        if decode and self.use_cuda_graphs and prompts is None and self.spec.mlp != "moe":
+            key = (B, T, lo, hi)
+            g = self._graphs.get(key)
+            if g is None:
+                g = self._capture(B, T, lo, hi, table)
+            g["x"].copy_(hidden.reshape(M, H))
+            g["graph"].replay()
+            result = g["out"].view(B, T, H).clone()
+        else:
+            x = self._buf("x_in" if decode else "x_in_p", M, H)
+            x.copy_(hidden.reshape(M, H))
+            splits = self._splits(B, T) if decode else 1
+            y = self._run_span(x, B, T, lo, hi, table, pos_ptr, pools_of, prompts, decode, splits)
+            native.check(native.lib().pb_advance_pos(pos_ptr, T, native.stream_ptr()), "advance_pos")
+            result = y.view(B, T, H).clone()
+        session.set_position(session.position + T, sync_device=False)
+        self._dev_pos = session.position
+        return result
+
+    def _capture(self, B: int, T: int, lo: int, hi: int, table: torch.Tensor) -> dict:
+        """Capture the decode step of blocks [lo, hi) for a (B, T) shape into a CUDA graph."""
+        M, H = B * T, self.spec.hidden_size
+        x = torch.zeros(M, H, dtype=self.dtype, device=self.device)
+        pos_ptr = self.pos_static.data_ptr()
+        splits = self._splits(B, T)
+        saved_pos = self.pos_static.clone()
+
+        def run():
+            xin = self._buf("x_in", M, H)
+            xin.copy_(x)
+            y = self._run_span(xin, B, T, lo, hi, table, pos_ptr, self.cache.layer_pools, None, True, splits)
+            native.check(native.lib().pb_advance_pos(pos_ptr, T, native.stream_ptr()), "advance_pos")
+            return y
+
+        # warm-up on a side stream (sets kernel attributes, allocates buffers), then capture
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.pos_static.copy_(saved_pos)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = run()
+        self.pos_static.copy_(saved_pos)  # capture does not execute, but keep the invariant explicit
+        g = dict(graph=graph, x=x, out=out)
+        self._graphs[(B, T, lo, hi)] = g
+        logger.debug(f"captured decode graph B={B} T={T} blocks [{lo},{hi}) splits={splits}")
+        return g
+
+    # ---- cache-less forward (rpc_forward / training forward) ----------------------------------------------------
+    def forward(self, hidden: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None,
+                block_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        lo, hi = block_range or (0, self.n_blocks)
+        B, T, H = hidden.shape
+        if T == 0 or B == 0:
+            return hidden
+        if hidden.dtype != self.dtype:
+            hidden = hidden.to(self.dtype)
+        out = torch.empty_like(hidden)
+        # attention is causal within a sequence, so batch rows are independent: process them in groups that
+        # fit the scratch pool
+        rows_per_group = max(1, ((self._scratch_pages - 1) * PAGE) // max(T, 1))
+        if T > (self._scratch_pages - 1) * PAGE:
+            raise ValueError(f"sequence of {T} tokens exceeds max_chunk_tokens={self.max_chunk_tokens} for a cache-less forward")
+        pages_per_seq = (T + PAGE - 1) // PAGE
+        zero = torch.zeros(1, dtype=torch.int32, device=self.device)
+        for b0 in range(0, B, rows_per_group):
+            b1 = min(B, b0 + rows_per_group)
+            nb = b1 - b0
+            table = torch.arange(nb * pages_per_seq, dtype=torch.int32, device=self.device).view(nb, pages_per_seq).contiguous()
+            x = self._buf("x_fwd", nb * T, H)
+            x.copy_(hidden[b0:b1].reshape(nb * T, H))
+            pr = None
+            if prompts is not None and any(not is_dummy(p) for p in prompts):
+                pr = [p if is_dummy(p) or p.shape[0] == 1 else p[b0:b1] for p in prompts]
+            scratch = lambda slot: (self._scratch_pool[0], self._scratch_pool[1])
+            decode = nb * T <= MAX_DECODE_ROWS and self.spec.mlp != "moe"
+            y = self._run_span(x, nb, T, lo, hi, table, zero.data_ptr(), scratch, pr, decode, 1)
+            out[b0:b1] = y.view(nb, T, H)
+        self._active = None  # the static table/pos were not touched, but be conservative
+        return out
+
+    def check_errors(self) -> None:
+        code = int(self.err_flag.item())
+        if code:
+            self.err_flag.zero_()
+            raise RuntimeError(f"device-side error flag {code} (1 = peer flag watchdog, 2 = KV page table overflow)")
