@@ -1,0 +1,212 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): Llama-3-70B single-stream decode tokens/s (+ prefill tokens/s) on N B200s.
+
+    python bench.py --gpus 1 --steps 32 --warmup 4
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+    python bench.py --impl reference ...   # the unmodified reference, if it could be installed (it cannot: see DESIGN.md)
+
+Method (mirrors the reference's benchmarks/benchmark_inference.py:44-68): one inference session with
+``max_length = seq_len``, then one token per step through the public client API. ``value`` is device-timed over
+exactly K steps (CUDA events, barrier + synchronize on both sides, max over ranks) with tokens staying on the
+device; ``e2e`` repeats the K steps with, per step, the input token copied from pinned host memory and the sampled
+token read back to the host. Weights are random-init bf16 of the named architecture, prompts are synthetic ids.
+L2 hygiene: every decode step streams the full ~141 GB weight set (>> 126 MB L2), so inputs are larger than L2.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+BASELINE_TOKENS_PER_S = 6.0  # README.md:86 of the reference ("up to 6 tokens/s" single-batch, Llama 2 70B)
+
+
+def reference_arm(args) -> None:
+    """Run the unmodified reference from baseline/_ref through its own public API — if it is importable."""
+    ref = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref")
+    why = None
+    if not os.path.isdir(os.path.join(ref, "petals")):
+        why = "reference not installed under baseline/_ref (pip --no-index install fails: hivemind/tensor_parallel/bitsandbytes wheels absent offline)"
+    else:
+        sys.path.insert(0, ref)
+        try:
+            os.environ.setdefault("PETALS_IGNORE_DEPENDENCY_VERSION", "1")
+            import importlib
+
+            importlib.import_module("hivemind")
+            importlib.import_module("petals")
+        except Exception as e:  # noqa: BLE001
+            why = f"reference import fails offline: {type(e).__name__}: {str(e)[:120]}"
+    if why is None:
+        why = "reference imported but its swarm needs hivemind's libp2p daemon (p2pd binary), unavailable without network"
+    if int(os.environ.get("RANK", "0")) == 0:
+        print(json.dumps({"impl": "reference", "unavailable": why}))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int = 0, period: float = 0.2):
+        super().__init__(daemon=True)
+        self.index, self.period, self.samples, self._stop = index, period, [], threading.Event()
+
+    def run(self) -> None:
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(self.period)
+
+    def stop(self) -> dict:
+        self._stop.set()
+        self.join(timeout=3)
+        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama-3-70b")
+    ap.add_argument("--seq-len", type=int, default=2048, help="session max_length (reference benchmark default)")
+    ap.add_argument("--prompt-len", type=int, default=128)
+    ap.add_argument("--parallelism", default="auto", help="auto | ppN | tpN")
+    ap.add_argument("--prefill-seq", type=int, default=4096)
+    ap.add_argument("--prefill-batch", type=int, default=8)
+    ap.add_argument("--prefill-steps", type=int, default=2)
+    ap.add_argument("--skip-prefill", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    if args.warmup < 3:
+        args.warmup = 3
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        from petals_b200.parallel.multi_gpu_bench import run_multi_gpu
+
+        return run_multi_gpu(args)
+    run_single_gpu(args)
+
+
+def run_single_gpu(args) -> None:
+    import torch
+
+    from petals_b200.ops import native
+    from petals_b200.parallel.swarm import Swarm
+    from petals_b200.utils.peaks import measured_peaks
+    from petals_b200.utils.random_model import MODEL_PRESETS, launch_random_stage, random_client_model, write_config_only
+
+    torch.cuda.set_device(0)
+    dev = "cuda:0"
+    native.lib()
+    path = write_config_only(args.model)
+    n_layers = MODEL_PRESETS[args.model]["num_hidden_layers"]
+    swarm = Swarm("bench")
+    t0 = time.time()
+    stage = launch_random_stage(path, range(n_layers), swarm, dev, attn_cache_tokens=max(args.seq_len, args.prefill_seq) + 256,
+                                inference_max_length=max(args.seq_len, args.prefill_seq), max_batch_size=1 << 20)
+    model = random_client_model(path, swarm, dev)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    K, W = args.steps, args.warmup
+    vocab = model.config.vocab_size
+    prompt = torch.randint(0, vocab, (1, args.prompt_len), device=dev)
+    pinned_in = torch.zeros(1, 1, dtype=torch.int64).pin_memory()
+    pinned_out = torch.zeros(1, dtype=torch.int64).pin_memory()
+    result = {}
+    with torch.inference_mode(), model.inference_session(max_length=args.seq_len) as sess:
+        # prompt ingestion (prefill path) is not part of the single-stream metric, like the reference benchmark
+        logits = model(input_ids=prompt).logits
+        tok = logits[:, -1].argmax(-1, keepdim=True)
+        for _ in range(W):
+            tok = model(input_ids=tok).logits[:, -1].argmax(-1, keepdim=True)
+        # ---- device-timed: tokens never leave the GPU ----------------------------------------------------------
+        from petals_b200.ops import functional as Fn
+
+        sampler = ClockSampler(0)
+        sampler.start()
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = native.launch_count
+        start.record()
+        for _ in range(K):
+            tok = Fn.argmax(model(input_ids=tok).logits[:, -1])[:, None]
+        end.record()
+        torch.cuda.synchronize()
+        launches = native.launch_count - launches0
+        ms = start.elapsed_time(end)
+        clocks = sampler.stop()
+        # ---- end to end: pinned-host token in, sampled token out, every step --------------------------------------
+        pinned_in.copy_(tok.cpu())
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(K):
+            ids = pinned_in.to(dev, non_blocking=True)  # H2D of this step's input
+            nxt = Fn.argmax(model(input_ids=ids).logits[:, -1])
+            pinned_out.copy_(nxt, non_blocking=True)  # D2H of this step's result
+            torch.cuda.synchronize()
+            pinned_in[0, 0] = pinned_out[0]
+        e2e_s = time.perf_counter() - t1
+    value = K / (ms / 1e3)
+    peaks = measured_peaks()
+    spec = model.config.block_spec()
+    weight_bytes = (spec.num_params() * n_layers + vocab * spec.hidden_size) * 2
+    result = {
+        "metric": "Llama-3-70B single-stream decode tokens/s (device-timed); prefill tokens/s in `prefill`",
+        "value": round(value, 3), "unit": "tokens/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",
+        "data": "synthetic token ids; random-init weights of the named architecture",
+        "config": {"model": args.model, "global_batch": 1, "seq_len": args.seq_len, "parallelism": "pp1 (1 stage x 80 blocks)",
+                   "l2": "each step streams the full weight set (>> 126 MB L2): inputs larger than L2", "build_s": round(build_s, 1)},
+        "clocks": clocks,
+        "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8},
+        "gpu_launches": launches,
+        "roofline": {"weight_bytes_per_token": weight_bytes, "achieved_GBps": round(weight_bytes * value / 1e9, 1),
+                     "frac_of_measured_hbm": round(weight_bytes * value / 1e9 / peaks["hbm_gbs"], 3), "peaks": peaks["source"]},
+    }
+    if not args.skip_prefill:
+        result["prefill"] = bench_prefill(model, args, peaks, spec, n_layers)
+    stage.shutdown()
+    print(json.dumps(result))
+
+
+def bench_prefill(model, args, peaks, spec, n_layers) -> dict:
+    """Parallel forward (benchmark_forward.py analogue): tokens/s = B*T / step time, no LM head."""
+    import torch
+
+    dev = "cuda:0"
+    B, T = args.prefill_batch, args.prefill_seq
+    ids = torch.randint(0, model.config.vocab_size, (B, T), device=dev)
+    with torch.inference_mode():
+        for _ in range(1):
+            model.model(input_ids=ids)
+        torch.cuda.synchronize()
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(args.prefill_steps):
+            model.model(input_ids=ids)
+        end.record()
+        torch.cuda.synchronize()
+    ms = start.elapsed_time(end) / args.prefill_steps
+    flops = 2.0 * spec.num_params() * n_layers * B * T + 4.0 * n_layers * B * T * T * spec.num_heads * spec.head_dim / 2
+    return {"tokens_per_s": round(B * T / (ms / 1e3), 1), "ms_per_step": round(ms, 2), "batch": B, "seq_len": T,
+            "TFLOPs": round(flops / ms / 1e9, 1), "frac_of_measured_bf16_sustained": round(flops / ms / 1e9 / peaks["bf16_tflops_sustained"], 3)}
+
+
+if __name__ == "__main__":
+    main()

@@ -21,27 +21,12 @@ from petals_b200.client.lm_head import LMHeadConfig
 from petals_b200.client.ptune import PTuneConfig
 from petals_b200.constants import DTYPE_MAP
 from petals_b200.models.spec import BlockSpec
+from petals_b200.utils.paths import resolve_model_path  # noqa: F401  (re-exported)
 
 _EXTRA_DEFAULTS: Dict[str, Any] = {}
 for _cls in (ClientConfig, PTuneConfig, LMHeadConfig):
     for _f in dataclasses.fields(_cls):
         _EXTRA_DEFAULTS[_f.name] = _f.default
-
-
-def resolve_model_path(name_or_path: str) -> str:
-    """Local directory for a checkpoint: a path, or an already-cached HF hub snapshot (offline box)."""
-    if os.path.isdir(name_or_path):
-        return name_or_path
-    roots = [os.environ.get("PETALS_CACHE"), os.environ.get("HF_HOME") and os.path.join(os.environ["HF_HOME"], "hub"),
-             os.path.expanduser("~/.cache/huggingface/hub"), os.path.expanduser("~/.cache/petals")]
-    folder = "models--" + name_or_path.replace("/", "--")
-    for root in filter(None, roots):
-        snaps = sorted(glob.glob(os.path.join(root, folder, "snapshots", "*")))
-        if snaps:
-            return snaps[-1]
-    raise FileNotFoundError(
-        f"{name_or_path!r} is neither a local checkpoint directory nor a cached hub snapshot "
-        "(this build runs offline; use petals_b200.utils.checkpoints.make_random_checkpoint to synthesise one)")
 
 
 class DistributedConfig:

@@ -28,7 +28,8 @@ from petals_b200.client.lm_head import LMHead
 from petals_b200.client.ptune import PTuneMixin
 from petals_b200.client.remote_generation import RemoteGenerationMixin, RemotePastKeyValues
 from petals_b200.client.remote_sequential import RemoteSequential
-from petals_b200.models.base import DistributedConfig, resolve_model_path
+from petals_b200.models.base import DistributedConfig
+from petals_b200.utils.paths import resolve_model_path
 from petals_b200.utils.logging import get_logger
 from petals_b200.utils.misc import DUMMY, is_dummy
 from petals_b200.utils.safetensors_io import SafetensorsFile

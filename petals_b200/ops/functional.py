@@ -282,7 +282,7 @@ def paged_attention(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor,
     a.scale = scale
     a.B, a.T, a.Hq, a.Hkv, a.D, a.page = B, T, Hq, Hkv, D, PAGE
     a.max_pages, a.window, a.splits, a.pos_static = block_table.shape[1], window, splits, pos_static
-    check(native.lib().pb_attention(C.byref(a), stream_ptr()), "attention")
+    check(native.lib().pb_attention(C.byref(a), stream_ptr()), "attention", 2 if splits > 1 else 1)
     return out
 
 

@@ -171,9 +171,19 @@ def available() -> bool:
     return True
 
 
-def check(code: int, what: str) -> None:
+launch_count = 0  # kernels of this library launched (directly) by this process; graph replays add their captured count
+
+
+def check(code: int, what: str, launches: int = 1) -> None:
+    global launch_count
     if code != 0:
         raise NativeError(f"{what} failed: {_ERRORS.get(code, code)}")
+    launch_count += launches
+
+
+def add_launches(n: int) -> None:
+    global launch_count
+    launch_count += n
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:

@@ -80,7 +80,7 @@ class Stage:
         hi = len(self.blocks) if hi is None else hi
         hidden = hidden.to(self.device)
         prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device) for p in prompts]
-        if self.engine is not None and self._lora_free() and not torch.is_grad_enabled():
+        if self.engine is not None and self._lora_free():  # stages are stateless: forward never records autograd state
             return self.engine.forward(hidden, prompts, (lo, hi))
         h = hidden.to(self.dtype)
         with torch.no_grad():

@@ -14,7 +14,7 @@ from typing import Dict, Optional, Union
 
 import torch
 
-from petals_b200.models.base import resolve_model_path
+from petals_b200.utils.paths import resolve_model_path
 from petals_b200.server.block_utils import get_model_block, resolve_block_dtype
 from petals_b200.utils.auto_config import AutoDistributedConfig
 from petals_b200.utils.logging import get_logger

@@ -237,6 +237,7 @@ class StageEngine:
                 g = self._capture(B, T, lo, hi, table)
             g["x"].copy_(hidden.reshape(M, H))
             g["graph"].replay()
+            native.add_launches(g["launches"])
             result = g["out"].view(B, T, H).clone()
         else:
             x = self._buf("x_in" if decode else "x_in_p", M, H)
@@ -273,10 +274,13 @@ class StageEngine:
         torch.cuda.synchronize(self.device)
         self.pos_static.copy_(saved_pos)
         graph = torch.cuda.CUDAGraph()
+        before = native.launch_count
         with torch.cuda.graph(graph):
             out = run()
+        launches = native.launch_count - before
+        native.add_launches(-launches)  # captured, not executed
         self.pos_static.copy_(saved_pos)  # capture does not execute, but keep the invariant explicit
-        g = dict(graph=graph, x=x, out=out)
+        g = dict(graph=graph, x=x, out=out, launches=launches)
         self._graphs[(B, T, lo, hi)] = g
         logger.debug(f"captured decode graph B={B} T={T} blocks [{lo},{hi}) splits={splits}")
         return g

@@ -5,7 +5,7 @@ import json
 import os
 from typing import Dict, Optional, Type
 
-from petals_b200.models.base import resolve_model_path
+from petals_b200.utils.paths import resolve_model_path
 
 _REGISTRY: Dict[str, Dict[str, type]] = {}
 

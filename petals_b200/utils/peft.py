@@ -17,7 +17,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-from petals_b200.models.base import resolve_model_path
+from petals_b200.utils.paths import resolve_model_path
 from petals_b200.utils.logging import get_logger
 from petals_b200.utils.safetensors_io import SafetensorsFile
 
