@@ -25,7 +25,6 @@ _ALIASES = [
     "utils", "utils.auto_config", "utils.convert_block", "utils.cuda_graphs", "utils.peft", "utils.packaging", "utils.misc",
     "utils.disk_cache", "utils.dht", "utils.ping", "utils.logging", "utils.version", "utils.hf_auth", "utils.random", "utils.asyncio",
     "models", "models.llama", "models.bloom", "models.falcon", "models.mixtral",
-    "cli", "cli.run_server", "cli.run_dht",
 ]
 for _name in _ALIASES:
     try:

@@ -50,6 +50,8 @@ def _recv_exact(sock: socket.socket, n: int) -> bytes:
 def send_message(sock: socket.socket, header: Dict[str, Any], tensors: Sequence[torch.Tensor] = ()) -> None:
     metas, blobs = [], []
     for t in tensors:
+        if t is None:
+            t = torch.empty(0)  # an empty tensor means "argument absent" (utils/misc.py DUMMY convention)
         t = t.detach().to("cpu").contiguous()
         raw = t.view(torch.uint8).numpy().tobytes() if t.numel() else b""
         metas.append({"dtype": _DTYPE_NAMES[t.dtype], "shape": list(t.shape), "nbytes": len(raw)})

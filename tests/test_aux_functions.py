@@ -1,0 +1,105 @@
+"""Unit tests of auxiliary pieces (reference tests/test_aux_functions.py, test_dtype.py): packaging round trip, compute
+throughput measurement, dtype resolution, block size accounting, data structures, safetensors reader, block selection."""
+import os
+
+import pytest
+import torch
+
+from petals_b200.data_structures import ServerInfo, ServerState, RemoteModuleInfo, make_uid, parse_uid
+from petals_b200.server.block_utils import get_block_size, resolve_block_dtype
+from petals_b200.server.from_pretrained import load_pretrained_block
+from petals_b200.server.throughput import measure_compute_rps
+from petals_b200.utils.auto_config import AutoDistributedConfig
+from petals_b200.utils.convert_block import QuantType
+from petals_b200.utils.misc import DUMMY, is_dummy
+from petals_b200.utils.packaging import pack_args_kwargs, unpack_args_kwargs
+from tests.utils import checkpoint
+
+
+def test_pack_unpack_roundtrip():
+    x, y = torch.randn(3), torch.randn(2, 2)
+    args = (x, [y, {"k": x, "n": 3}], "s", None)
+    kwargs = dict(a=y, b=[1, 2, (x,)], c=DUMMY)
+    flat, structure = pack_args_kwargs(*args, **kwargs)
+    assert len(flat) == 6 and all(isinstance(t, torch.Tensor) for t in flat)
+    import msgpack
+
+    structure = msgpack.unpackb(msgpack.packb(structure), raw=False)  # survives the control channel encoding
+    rargs, rkwargs = unpack_args_kwargs(flat, structure)
+    assert torch.equal(rargs[0], x) and torch.equal(rargs[1][0], y) and rargs[1][1]["n"] == 3 and rargs[2] == "s" and rargs[3] is None
+    assert torch.equal(rkwargs["a"], y) and torch.equal(rkwargs["b"][2][0], x) and is_dummy(rkwargs["c"])
+
+
+def test_uids_and_server_info():
+    assert parse_uid(make_uid("llama-hf", 17)) == ("llama-hf", 17)
+    with pytest.raises(ValueError):
+        parse_uid("a.1 a.2")
+    info = ServerInfo(state=ServerState.ONLINE, throughput=12.5, start_block=1, end_block=4, adapters=("x",), next_pings={"p": 0.1})
+    assert ServerInfo.from_tuple(info.to_tuple()) == info
+    fwd = ServerInfo.from_tuple((2, 1.0, {"unknown_future_field": 1, "version": "9"}))  # forward compatible
+    assert fwd.version == "9" and fwd.state == ServerState.ONLINE
+
+
+@pytest.mark.parametrize("inference", [True, False])
+def test_measure_compute_rps(inference):
+    config = AutoDistributedConfig.from_pretrained(checkpoint("llama"))
+    rps = measure_compute_rps(config, torch.device("cpu"), torch.float32, n_tokens=2, n_steps=2, inference=inference)
+    assert isinstance(rps, float) and rps > 0
+
+
+def test_dtype_resolution_and_block_loading():
+    path = checkpoint("llama")
+    config = AutoDistributedConfig.from_pretrained(path)
+    assert resolve_block_dtype(config, torch.float16) == torch.float16
+    assert resolve_block_dtype(config, "auto") == torch.bfloat16  # fp32 checkpoints are served in bf16 by default
+    for dtype in (torch.float32, torch.bfloat16):
+        block = load_pretrained_block(path, 0, torch_dtype=dtype)
+        assert all(p.dtype == dtype for p in block.parameters())
+        assert all(not p.requires_grad for p in block.parameters())
+    with pytest.raises(KeyError):
+        load_pretrained_block(path, 99, torch_dtype=torch.float32)
+    n = config.block_spec().num_params()
+    assert abs(get_block_size(config, "memory", dtype=torch.bfloat16) - 2 * n * 1.01) < 8
+    assert get_block_size(config, "memory", quant_type=QuantType.FP8) < get_block_size(config, "memory", dtype=torch.bfloat16) * 0.6
+
+
+def test_native_safetensors_reader_matches_python_package(tmp_path):
+    from petals_b200.utils.safetensors_io import SafetensorsFile, save_file
+
+    tensors = {"a.weight": torch.randn(5, 7), "b": torch.arange(10, dtype=torch.int64), "c.bf16": torch.randn(3, 3).to(torch.bfloat16),
+               "empty": torch.zeros(0, 4)}
+    p = str(tmp_path / "t.safetensors")
+    save_file(tensors, p, metadata={"format": "pt"})
+    with SafetensorsFile(p) as f:
+        assert sorted(f.keys()) == sorted(tensors)
+        for k, t in tensors.items():
+            assert f.info(k) == (t.dtype, tuple(t.shape))
+            assert torch.equal(f.get_tensor(k), t)
+    st = pytest.importorskip("safetensors.torch")
+    theirs = st.load_file(p)  # files we write are readable by the reference's loader ...
+    assert all(torch.equal(theirs[k], tensors[k]) for k in tensors)
+    p2 = str(tmp_path / "t2.safetensors")
+    st.save_file({k: v for k, v in tensors.items()}, p2)  # ... and vice versa
+    with SafetensorsFile(p2) as f:
+        assert all(torch.equal(f.get_tensor(k), tensors[k]) for k in tensors)
+    with pytest.raises(IOError):
+        SafetensorsFile(str(tmp_path / "missing.safetensors"))
+
+
+def test_block_selection_policy():
+    from petals_b200.server.block_selection import choose_best_blocks, should_choose_other_blocks
+
+    def infos(assign):  # assign: {peer: (start, end, throughput)}
+        out = []
+        for i in range(8):
+            servers = {p: ServerInfo(state=ServerState.ONLINE, throughput=t, start_block=s, end_block=e) for p, (s, e, t) in assign.items() if s <= i < e}
+            out.append(RemoteModuleInfo(uid=f"m.{i}", servers=servers))
+        return out
+
+    # blocks 4..7 are unserved -> a new 4-block server should take them
+    assert choose_best_blocks(4, infos({"a": (0, 4, 1.0)})) == [4, 5, 6, 7]
+    # two servers on the same half, nobody on the other: the swarm is badly balanced -> move
+    assert should_choose_other_blocks("b", infos({"a": (0, 4, 1.0), "b": (0, 4, 1.0), "c": (4, 8, 0.1)}), balance_quality=0.75)
+    # evenly covered -> stay
+    assert not should_choose_other_blocks("b", infos({"a": (0, 4, 1.0), "b": (4, 8, 1.0)}), balance_quality=0.75)
+    assert should_choose_other_blocks("b", infos({"a": (0, 4, 1.0), "b": (4, 8, 1.0)}), balance_quality=1.5)  # forced

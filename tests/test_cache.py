@@ -1,0 +1,75 @@
+"""MemoryCache admission control (reference tests/test_cache.py:24-184): budgets, timeouts, fail-fast, FIFO queueing,
+release on close; plus paged-table behaviours the reference does not have (rollback, beam reorder bookkeeping)."""
+import threading
+import time
+
+import pytest
+import torch
+
+from petals_b200.ops.functional import PAGE
+from petals_b200.server.memory_cache import AllocationFailed, MemoryCache
+
+
+def test_budget_and_release():
+    cache = MemoryCache(max_size_tokens=8 * PAGE, max_alloc_timeout=0.5, device="cpu")
+    assert cache.tokens_left == 8 * PAGE
+    with cache.allocate_cache(1, 2 * PAGE, timeout=0) as a:  # 2 pages + 1 slack
+        assert cache.tokens_left == 5 * PAGE
+        with cache.allocate_cache(2, PAGE, timeout=0):  # 2 * (1 + 1) pages
+            assert cache.tokens_left == PAGE
+            with pytest.raises(AllocationFailed):
+                cache.open_session(1, 2 * PAGE, timeout=0)  # fail fast, like the reference's alloc_timeout=0
+        assert cache.tokens_left == 5 * PAGE
+    assert cache.tokens_left == 8 * PAGE
+    with pytest.raises(AllocationFailed):
+        cache.open_session(1, 100 * PAGE, timeout=0)  # can never fit
+
+
+def test_timeout_and_queueing():
+    cache = MemoryCache(max_size_tokens=4 * PAGE, max_alloc_timeout=5.0, device="cpu")
+    big = cache.open_session(1, 3 * PAGE, timeout=0)  # takes all 4 pages
+    t0 = time.perf_counter()
+    with pytest.raises(AllocationFailed):
+        cache.open_session(1, PAGE, timeout=0.3)
+    assert 0.25 < time.perf_counter() - t0 < 2.0
+    order = []
+
+    def waiter(name, delay):
+        time.sleep(delay)
+        s = cache.open_session(1, PAGE, timeout=4.0)
+        order.append(name)
+        time.sleep(0.05)
+        s.close()
+
+    threads = [threading.Thread(target=waiter, args=("first", 0.0)), threading.Thread(target=waiter, args=("second", 0.15))]
+    for t in threads:
+        t.start()
+    time.sleep(0.4)
+    assert order == []  # both are queued behind the big session
+    big.close()
+    for t in threads:
+        t.join(timeout=5)
+    assert order == ["first", "second"]  # FIFO among waiters
+    assert cache.tokens_left == 4 * PAGE
+
+
+def test_dense_session_semantics():
+    from petals_b200.models.spec import BlockSpec
+
+    spec = BlockSpec(family="llama", hidden_size=32, num_heads=4, num_kv_heads=2, head_dim=8, intermediate_size=64)
+    cache = MemoryCache(max_size_tokens=16 * PAGE, device="cpu", spec=spec, dtype=torch.float32)
+    with cache.allocate_cache(3, 10, timeout=0) as sess:
+        k, v = sess.dense_kv(0, spec, torch.float32, "cpu")
+        assert k.shape == (3, 10, 2, 8)
+        k[:] = torch.arange(3.0).view(3, 1, 1, 1)
+        sess.prepare_write(4)
+        sess.set_position(4)
+        with pytest.raises(ValueError, match="Maximum length exceeded"):
+            sess.prepare_write(7)
+        sess.reorder(torch.tensor([2, 0, 0]))
+        k2, _ = sess.dense_kv(0, spec, torch.float32, "cpu")
+        assert k2[:, 0, 0, 0].tolist() == [2.0, 0.0, 0.0]
+        sess.set_position(2)  # rollback
+        assert sess.position == 2
+        with pytest.raises(ValueError):
+            sess.set_position(11)

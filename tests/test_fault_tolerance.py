@@ -1,0 +1,66 @@
+"""Fault injection — what the reference's suite lacks: kill a stage in the middle of a session / of a
+training step and check that the client fails over to a replica, replays its input history and continues exactly."""
+import pytest
+import torch
+
+from petals_b200.client.remote_sequential import RemoteSequential
+from petals_b200.utils.auto_config import AutoDistributedConfig, AutoDistributedModelForCausalLM
+from tests.utils import checkpoint, local_blocks, swarm_of
+
+
+def test_inference_failover_replays_history():
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:2", "2:4"]) as (swarm, primary):
+        config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm, min_backoff=0.01, max_backoff=0.05, max_retries=5)
+        seq = RemoteSequential(config, dht=swarm)
+        blocks = local_blocks(path, config.num_hidden_layers)
+        x = torch.randn(1, 10, config.hidden_size)
+        with torch.inference_mode():
+            h = x
+            for b in blocks:
+                h = b(h)[0]
+            with seq.inference_session(max_length=10) as sess:
+                outs = [sess.step(x[:, :4]), sess.step(x[:, 4:5])]
+                # a replica of the second half joins, then the original second-half stage dies mid-session
+                with swarm_of(path, ["2:4"], swarm=swarm) as (_, replica):
+                    seq.sequence_manager.update(wait=True)
+                    primary[1].shutdown()
+                    outs.append(sess.step(x[:, 5:7]))  # fails over: history [0,5) is replayed into the replica
+                    outs.append(sess.step(x[:, 7:]))
+                    assert sess._server_sessions[-1].span.peer_id == replica[0].peer_id
+            got = torch.cat(outs, dim=1)
+        assert torch.allclose(got, h, atol=1e-4), (got - h).abs().max()
+
+
+def test_training_failover_between_forward_and_backward():
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:4"]) as (swarm, primary):
+        config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm, min_backoff=0.01, max_backoff=0.05, max_retries=5)
+        seq = RemoteSequential(config, dht=swarm)
+        blocks = local_blocks(path, config.num_hidden_layers)
+        x = torch.randn(2, 5, config.hidden_size, requires_grad=True)
+        out = seq(x)
+        with swarm_of(path, ["0:2", "2:4"], swarm=swarm):
+            seq.sequence_manager.update(wait=True)
+            primary[0].shutdown()  # the stage that ran the forward is gone before backward
+            out.pow(2).sum().backward()  # recomputes the forward on the replacement route, then backpropagates
+        g = x.grad.clone()
+        x.grad = None
+        h = x
+        for b in blocks:
+            h = b(h)[0]
+        h.pow(2).sum().backward()
+        assert torch.allclose(g, x.grad, atol=1e-3)
+
+
+def test_all_retries_exhausted_raises():
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:4"]) as (swarm, servers):
+        config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm, min_backoff=0.01, max_backoff=0.02, max_retries=2)
+        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=swarm, min_backoff=0.01, max_backoff=0.02, max_retries=2)
+        ids = torch.randint(0, 500, (1, 4))
+        with model.inference_session(max_length=8):
+            model(ids[:, :2])
+            servers[0].shutdown()
+            with pytest.raises(Exception):
+                model(ids[:, 2:])

@@ -1,0 +1,67 @@
+"""A real multi-process local swarm on CPU (BASELINE config #1, the reference CI's harness .github/workflows/run-tests.yaml:52-91):
+`run_dht` rendezvous + two `run_server` OS processes + a client in this process, talking over the Unix-socket transport."""
+import os
+import signal
+import subprocess
+import sys
+import time
+
+import pytest
+import torch
+
+from petals_b200.utils.auto_config import AutoDistributedConfig, AutoDistributedModelForCausalLM
+from tests.utils import checkpoint, local_blocks
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _spawn(args, log):
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""), PETALS_LOGLEVEL="INFO")
+    return subprocess.Popen([sys.executable, "-m", *args], stdout=log, stderr=subprocess.STDOUT, env=env, cwd=ROOT)
+
+
+@pytest.mark.parametrize("family", ["bloom"])
+def test_two_server_processes(family, tmp_path):
+    path = checkpoint(family)
+    rendezvous = str(tmp_path / "swarm")
+    subprocess.run([sys.executable, "-m", "petals.cli.run_dht", "--rendezvous", rendezvous, "--once"], check=True, cwd=ROOT,
+                   env=dict(os.environ, PYTHONPATH=ROOT))
+    logs = [open(tmp_path / f"server{i}.log", "w") for i in range(2)]
+    common = ["--initial_peers", rendezvous, "--torch_dtype", "float32", "--device", "cpu", "--throughput", "1", "--update_period", "1"]
+    procs = [_spawn(["petals.cli.run_server", path, "--block_indices", "0:2", "--peer_id", "stage0", *common], logs[0]),
+             _spawn(["petals.cli.run_server", path, "--block_indices", "2:4", "--peer_id", "stage1", "--attn_cache_tokens", "2048",
+                     "--max_chunk_size_bytes", "1024", *common], logs[1])]  # tiny chunk size => chunked prefill is exercised
+    try:
+        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[rendezvous], max_retries=40, min_backoff=0.5, max_backoff=1.0)
+        config = AutoDistributedConfig.from_pretrained(path)
+        ids = torch.randint(0, config.vocab_size, (1, 7), generator=torch.Generator().manual_seed(0))
+        with torch.inference_mode():
+            parallel = model(ids).logits  # waits (with retries) until both server processes are ONLINE
+            assert all(p.poll() is None for p in procs), "a server process died"
+            h = model.model.embed(ids)
+            for b in local_blocks(path, config.num_hidden_layers):
+                h = b(h)[0]
+            local = model.lm_head(model.model.final_norm(h))
+            embs = model.model.embed(ids)
+            with model.model.layers.inference_session(max_length=8) as sess:
+                outs = [sess.step(embs[:, :5])] + [sess.step(embs[:, t: t + 1]) for t in range(5, 7)]
+                peers = [s.span.peer_id for s in sess._server_sessions]
+            step = model.lm_head(model.model.final_norm(torch.cat(outs, 1)))
+        assert peers == ["stage0", "stage1"]
+        assert torch.allclose(parallel, local, atol=1e-3) and torch.allclose(step, local, atol=1e-3)
+        # gradients flow through other processes too
+        x = torch.randn(2, 3, config.hidden_size, requires_grad=True)
+        model.model.layers(x).sum().backward()
+        assert x.grad is not None and torch.isfinite(x.grad).all()
+        out = model.generate(ids, max_new_tokens=3)
+        assert out.shape == (1, 10)
+    finally:
+        for p in procs:
+            p.send_signal(signal.SIGTERM)
+        for p in procs:
+            try:
+                p.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                p.kill()
+        for f in logs:
+            f.close()
