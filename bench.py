@@ -53,21 +53,21 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index: int = 0, period: float = 0.2):
         super().__init__(daemon=True)
-        self.index, self.period, self.samples, self._stop = index, period, [], threading.Event()
+        self.index, self.period, self.samples, self._halt = index, period, [], threading.Event()
 
     def run(self) -> None:
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 self.samples.append([x.strip() for x in out.split(",")])
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(self.period)
+            self._halt.wait(self.period)
 
     def stop(self) -> dict:
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=3)
         sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
         mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]

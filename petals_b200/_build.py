@@ -93,6 +93,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     # Host-only runtime (scheduler, KV page allocator, safetensors reader): no CUDA dependency, so it
     # also loads — and is unit-tested — on the CPU-only build box.
     _run(["g++", "-shared", "-o", str(RT_LIB_PATH), *map(str, cpp_objs), "-pthread"])
+    import ctypes
+
+    ctypes.CDLL(str(LIB_PATH))  # unresolved symbols must fail the build here, not on the GPU box
+    ctypes.CDLL(str(RT_LIB_PATH))
     STAMP.write_text(source_hash())
     if verbose:
         print(f"built {LIB_PATH} and {RT_LIB_PATH}", file=sys.stderr)

@@ -124,9 +124,13 @@ def _gather_forward(input_batches, prompt_batches, sequence_manager):
 
 
 def _gather_backward(grad_output_batches, intermediate_input_batches, prompt_batches, forward_sequences, sequence_manager):
-    futures = [_executor.submit(sequential_backward, (g,), inp, p, spans, sequence_manager)
-               for g, inp, p, spans in zip(grad_output_batches, intermediate_input_batches, prompt_batches, forward_sequences)]
-    return [f.result() for f in futures]
+    """Backward of every micro-batch, in the calling thread.
+
+    This runs inside ``torch.autograd``'s backward pass — for CUDA tensors that is the device's autograd worker
+    thread. An in-process stage computes its own backward with a (re-entrant) autograd call, which must therefore be
+    issued from this very thread: handing it to another thread would queue it behind the worker we are blocking."""
+    return [sequential_backward((g,), inp, p, spans, sequence_manager)
+            for g, inp, p, spans in zip(grad_output_batches, intermediate_input_batches, prompt_batches, forward_sequences)]
 
 
 class _RemoteSequentialAutogradFunction(torch.autograd.Function):

@@ -316,11 +316,11 @@ static int launch_attn(const PbAttnArgs* a, cudaStream_t s) {
     return PB_ERR_CUDA;
   dim3 grid(m_tiles, a->B * a->Hkv, p.splits);
   kern<<<grid, 128, smem, s>>>(p);
-  if (cudaGetLastError() != cudaSuccess) return PB_ERR_CUDA;
+  if (pb_check_launch("attention") != PB_OK) return PB_ERR_CUDA;
   if (p.splits > 1) {
     const size_t R = static_cast<size_t>(a->B) * a->T * a->Hq;
     attn_combine_kernel<<<static_cast<unsigned>(R), D, 0, s>>>(p.partial_o, p.partial_lse, p.out, p.splits, R, D);
-    if (cudaGetLastError() != cudaSuccess) return PB_ERR_CUDA;
+    if (pb_check_launch("attention") != PB_OK) return PB_ERR_CUDA;
   }
   return PB_OK;
 }

@@ -186,7 +186,7 @@ extern "C" int pb_norm(const void* x, const void* residual, const void* weight, 
   const size_t smem = static_cast<size_t>(cols) * 2;
   auto k1 = norm_kernel<1>;
   auto k2 = norm_kernel<2>;
-  if (smem > 48 * 1024) {
+  if (smem > 32 * 1024) {
     cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   }
@@ -198,7 +198,7 @@ extern "C" int pb_norm(const void* x, const void* residual, const void* weight, 
   auto S = static_cast<__nv_bfloat16*>(sum_out);
   if (kind == 1) k1<<<rows, 256, smem, s>>>(X, R, W, Bv, O, S, cols, eps);
   else k2<<<rows, 256, smem, s>>>(X, R, W, Bv, O, S, cols, eps);
-  return cudaGetLastError() == cudaSuccess ? PB_OK : PB_ERR_CUDA;
+  return pb_check_launch("elementwise");
 }
 
 static int grid_for(long nvec) {
@@ -213,7 +213,7 @@ extern "C" int pb_swiglu(const void* gate, const void* up, void* out, long n, vo
   if (n == 0) return PB_OK;
   swiglu_kernel<<<grid_for(n >> 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(gate), static_cast<const uint4*>(up), static_cast<uint4*>(out), n >> 3);
-  return cudaGetLastError() == cudaSuccess ? PB_OK : PB_ERR_CUDA;
+  return pb_check_launch("elementwise");
 }
 
 extern "C" int pb_add(const void* a, const void* b, void* out, long n, void* stream) {
@@ -221,7 +221,7 @@ extern "C" int pb_add(const void* a, const void* b, void* out, long n, void* str
   if (n == 0) return PB_OK;
   add_kernel<<<grid_for(n >> 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), n >> 3);
-  return cudaGetLastError() == cudaSuccess ? PB_OK : PB_ERR_CUDA;
+  return pb_check_launch("elementwise");
 }
 
 extern "C" int pb_embedding(const void* table, const void* ids, void* out, int n_tokens, int hidden, void* stream) {
@@ -230,7 +230,7 @@ extern "C" int pb_embedding(const void* table, const void* ids, void* out, int n
   embedding_kernel<<<n_tokens, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(table), static_cast<const long long*>(ids),
       static_cast<__nv_bfloat16*>(out), hidden);
-  return cudaGetLastError() == cudaSuccess ? PB_OK : PB_ERR_CUDA;
+  return pb_check_launch("elementwise");
 }
 
 extern "C" int pb_argmax(const void* logits, int is_fp32, void* out_ids, int rows, int vocab, void* stream) {
@@ -238,7 +238,7 @@ extern "C" int pb_argmax(const void* logits, int is_fp32, void* out_ids, int row
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (is_fp32) argmax_kernel<float><<<rows, 1024, 0, s>>>(static_cast<const float*>(logits), static_cast<long long*>(out_ids), vocab);
   else argmax_kernel<__nv_bfloat16><<<rows, 1024, 0, s>>>(static_cast<const __nv_bfloat16*>(logits), static_cast<long long*>(out_ids), vocab);
-  return cudaGetLastError() == cudaSuccess ? PB_OK : PB_ERR_CUDA;
+  return pb_check_launch("elementwise");
 }
 
 extern "C" int pb_add_prompts(void* hidden, const void* prompts, int B, int T, int H, int Bp, int P,
@@ -248,16 +248,16 @@ extern "C" int pb_add_prompts(void* hidden, const void* prompts, int B, int T, i
   add_prompts_kernel<<<dim3(T, B), 128, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<__nv_bfloat16*>(hidden), static_cast<const __nv_bfloat16*>(prompts), T, H, Bp, P,
       static_cast<const int*>(pos_ptr));
-  return cudaGetLastError() == cudaSuccess ? PB_OK : PB_ERR_CUDA;
+  return pb_check_launch("elementwise");
 }
 
 extern "C" int pb_bump_epoch(void* epoch, void* stream) {
   bump_epoch_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<unsigned long long*>(epoch));
-  return cudaGetLastError() == cudaSuccess ? PB_OK : PB_ERR_CUDA;
+  return pb_check_launch("elementwise");
 }
 extern "C" int pb_advance_pos(void* pos, int delta, void* stream) {
   advance_pos_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<int*>(pos), delta);
-  return cudaGetLastError() == cudaSuccess ? PB_OK : PB_ERR_CUDA;
+  return pb_check_launch("elementwise");
 }
 
 extern "C" int pb_device_sm_count(int device) {
@@ -265,4 +265,13 @@ extern "C" int pb_device_sm_count(int device) {
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
   return n;
 }
+static thread_local char g_last_error[512] = "";
+extern "C" const char* pb_last_error(void) { return g_last_error; }
+extern "C" int pb_check_launch(const char* what) {
+  const cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) return PB_OK;
+  snprintf(g_last_error, sizeof(g_last_error), "%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return PB_ERR_CUDA;
+}
+extern "C" int pb_set_error(const char* msg) { snprintf(g_last_error, sizeof(g_last_error), "%s", msg); return 0; }
 extern "C" int pb_version(void) { return 1; }

@@ -410,7 +410,7 @@ static int launch_gemm(const PbGemmArgs* a, cudaStream_t stream) {
   const int tiles = m_blocks * n_blocks;
   const int grid = tiles < sms ? tiles : sms;
   kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tb2, p);
-  return cudaGetLastError() == cudaSuccess ? PB_OK : PB_ERR_CUDA;
+  return pb_check_launch("gemm_tcgen05");
 }
 
 }  // namespace pb

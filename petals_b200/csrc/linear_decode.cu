@@ -20,6 +20,8 @@
 #include "common.cuh"
 #include "petals_b200.h"
 
+extern "C" int pb_set_error(const char* msg);
+
 namespace pb {
 
 constexpr int kMaxPeers = 8;
@@ -47,7 +49,8 @@ struct LinearDecodeParams {
   const uint64_t* epoch;                        // device-resident step counter (graph friendly)
   int n_push;                                   // epilogue also stores to these (peer) buffers
   __nv_bfloat16* push_out[kMaxPeers];           // [M, N] each
-  uint64_t* push_flag[kMaxPeers];               // incremented (release.sys) once per CTA
+  uint64_t* push_flag[kMaxPeers];               // incremented (release.sys) ONCE per launch, by the last CTA to finish
+  unsigned int* done_counter;                   // local device counter used to elect that last CTA (self-resetting)
   int* error_flag;                              // set to 1 on watchdog expiry
 };
 
@@ -291,13 +294,19 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
     }
   }
 
-  // ---- publish: one release-increment per CTA per peer ---------------------------------------
+  // ---- publish: every CTA fences its peer stores and checks in on a local counter; the last one to arrive
+  // performs ONE release-increment per peer (so a consumer waits for `n_sources` per step, independent of grids).
   if (p.n_push > 0) {
     __syncthreads();
     if (tid == 0) {
       __threadfence_system();
-      for (int r = 0; r < p.n_push; ++r)
-        if (p.push_flag[r] != nullptr) red_release_sys_add(p.push_flag[r], 1ull);
+      const unsigned int prev = atomicAdd(p.done_counter, 1u);
+      if (prev == gridDim.x - 1) {
+        __threadfence_system();
+        *p.done_counter = 0u;
+        for (int r = 0; r < p.n_push; ++r)
+          if (p.push_flag[r] != nullptr) red_release_sys_add(p.push_flag[r], 1ull);
+      }
     }
   }
 }
@@ -306,7 +315,7 @@ template <int M, bool DUAL, bool XSMEM>
 static cudaError_t launch_one(const LinearDecodeParams& p, int grid, int block, size_t smem,
                               cudaStream_t stream) {
   auto kern = linear_decode_kernel<M, DUAL, XSMEM>;
-  if (smem > 48 * 1024) {
+  if (smem > 32 * 1024) {  // static shared memory counts against the 48 KB default too
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
@@ -359,6 +368,8 @@ extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
     p.push_flag[i] = static_cast<uint64_t*>(a->push_flag[i]);
   }
   p.error_flag = static_cast<int*>(a->error_flag);
+  p.done_counter = static_cast<unsigned int*>(a->done_counter);
+  if (a->n_push > 0 && p.done_counter == nullptr) return PB_ERR_SHAPE;
 
   const bool dual = a->act == 1;
   if (dual && p.w2 == nullptr) return PB_ERR_SHAPE;
@@ -370,7 +381,7 @@ extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
 
   // Pick warps/SM in [12, 24] that minimises the last-wave quantisation loss. If a fixed grid
   // was requested (flag accounting across ranks needs identical CTA counts) honour it.
-  const int sms = a->num_sms > 0 ? a->num_sms : 148;
+  const int sms = a->fixed_grid > 0 ? a->fixed_grid : (a->num_sms > 0 ? a->num_sms : 148);
   const int ntasks = a->N / 2;
   const int max_w = a->M <= 4 ? 24 : 16;
   int best_w = max_w;
@@ -401,6 +412,12 @@ extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
     case 7: e = launch_m<7>(p, dual, xsmem, grid, block, smem, s); break;
     case 8: e = launch_m<8>(p, dual, xsmem, grid, block, smem, s); break;
   }
-  if (e != cudaSuccess) return PB_ERR_CUDA;
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    char what[160];
+    snprintf(what, sizeof(what), "linear_decode M=%d N=%d K=%d grid=%d block=%d smem=%zu: %s", a->M, a->N, a->K, grid, block, smem, cudaGetErrorString(e));
+    pb_set_error(what);
+    return PB_ERR_CUDA;
+  }
   return a->out_grid ? (*(a->out_grid) = grid, PB_OK) : PB_OK;
 }

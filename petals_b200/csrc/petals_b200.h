@@ -22,6 +22,7 @@ typedef struct {
   int n_push; void* push_out[PB_MAX_PEERS]; void* push_flag[PB_MAX_PEERS];
   void* error_flag;
   int num_sms; int fixed_grid; int* out_grid;
+  void* done_counter;
 } PbLinearDecodeArgs;
 int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream);
 
@@ -105,6 +106,8 @@ int pb_kv_copy_pages(void* pool, const void* src_pages, const void* dst_pages, i
 
 // ---- runtime (host) ---------------------------------------------------------------------------------
 int pb_device_sm_count(int device);
+const char* pb_last_error(void);
+int pb_check_launch(const char* what);  // cudaGetLastError -> PB_OK / PB_ERR_CUDA, remembers the message
 int pb_version(void);
 
 #ifdef __cplusplus

@@ -121,7 +121,7 @@ extern "C" int pb_rope_kv(const PbRopeKvArgs* a, void* stream) {
   p.error_flag = static_cast<int*>(a->error_flag);
   dim3 grid(a->B * a->T, a->Hq + 2 * a->Hkv);
   rope_kv_kernel<<<grid, a->D / 2, 0, static_cast<cudaStream_t>(stream)>>>(p);
-  return cudaGetLastError() == cudaSuccess ? PB_OK : PB_ERR_CUDA;
+  return pb_check_launch("rope_kv");
 }
 
 extern "C" int pb_kv_copy_pages(void* pool, const void* src_pages, const void* dst_pages, int n, long page_elems,
@@ -133,5 +133,5 @@ extern "C" int pb_kv_copy_pages(void* pool, const void* src_pages, const void* d
   kv_copy_pages_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<uint4*>(pool), static_cast<const int*>(src_pages), static_cast<const int*>(dst_pages),
       page_elems >> 3, slab_stride_elems >> 3);
-  return cudaGetLastError() == cudaSuccess ? PB_OK : PB_ERR_CUDA;
+  return pb_check_launch("rope_kv");
 }

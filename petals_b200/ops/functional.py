@@ -43,7 +43,7 @@ def linear_decode(
     eps: float = 1e-6, act: int = ACT_NONE, out: Optional[torch.Tensor] = None, x_out: Optional[torch.Tensor] = None,
     parts: Sequence[torch.Tensor] = (), wait_flag: Optional[int] = None, wait_per_epoch: int = 0,
     epoch: Optional[int] = None, push_out: Sequence[int] = (), push_flag: Sequence[int] = (),
-    error_flag: Optional[int] = None, fixed_grid: int = 0, store_local: bool = True,
+    error_flag: Optional[int] = None, fixed_grid: int = 0, store_local: bool = True, done_counter: Optional[int] = None,
 ) -> torch.Tensor:
     """``out[M,N] = epilogue(prologue(x)[M,K] @ w[N,K]^T)`` for M <= 8 tokens. See csrc/linear_decode.cu.
 
@@ -77,6 +77,7 @@ def linear_decode(
     a.error_flag = error_flag
     a.num_sms = native.sm_count(x.device.index)
     a.fixed_grid = fixed_grid
+    a.done_counter = done_counter
     check(native.lib().pb_linear_decode(C.byref(a), stream_ptr()), "linear_decode")
     return out
 

@@ -39,6 +39,7 @@ class LinearDecodeArgs(C.Structure):
         ("n_push", C.c_int), ("push_out", C.c_void_p * PB_MAX_PEERS), ("push_flag", C.c_void_p * PB_MAX_PEERS),
         ("error_flag", C.c_void_p),
         ("num_sms", C.c_int), ("fixed_grid", C.c_int), ("out_grid", C.POINTER(C.c_int)),
+        ("done_counter", C.c_void_p),
     ]
 
 
@@ -93,6 +94,26 @@ def _declare(lib: C.CDLL) -> None:
     lib.pb_attention.argtypes = [C.POINTER(AttnArgs), vp]
     lib.pb_kv_copy_pages.argtypes = [vp, vp, vp, ci, cl, cl, ci, vp]
     lib.pb_device_sm_count.argtypes = [ci]
+    vpp = C.POINTER(C.c_void_p)
+    u64 = C.c_uint64
+    lib.pb_ipc_malloc.argtypes = [vpp, cl]
+    lib.pb_ipc_free.argtypes = [vp]
+    lib.pb_ipc_get_handle.argtypes = [vp, C.c_char_p]
+    lib.pb_ipc_open_handle.argtypes = [C.c_char_p, vpp]
+    lib.pb_ipc_close_handle.argtypes = [vp]
+    lib.pb_ipc_handle_size.argtypes = []
+    lib.pb_push_rows.argtypes = [vp, vpp, vpp, ci, cl, vp]
+    lib.pb_wait_flag.argtypes = [vp, vp, u64, u64, vp, vp]
+    lib.pb_argmax_val.argtypes = [vp, vp, vp, ci, ci, vp]
+    lib.pb_argmax_exchange.argtypes = [vp, vp, cl, ci, ci, ci, vpp, vpp, ci, vp, vp, vp, vp, vp, vp]
+    lib.pb_reduce_parts.argtypes = [vp, vpp, ci, vp, u64, vp, vp, cl, vp, vp]
+    lib.pb_peer_copy.argtypes = [vp, vp, cl, ci, vp]
+    lib.pb_pingpong.argtypes = [vp, vp, ci, ci, vp, vp, vp]
+    for name in ("pb_ipc_malloc", "pb_ipc_free", "pb_ipc_get_handle", "pb_ipc_open_handle", "pb_ipc_close_handle", "pb_ipc_handle_size",
+                 "pb_push_rows", "pb_wait_flag", "pb_argmax_val", "pb_argmax_exchange", "pb_reduce_parts", "pb_peer_copy", "pb_pingpong"):
+        getattr(lib, name).restype = ci
+    lib.pb_last_error.argtypes = []
+    lib.pb_last_error.restype = C.c_char_p
     for name in ("pb_linear_decode", "pb_gemm_bf16", "pb_gemm_tiles", "pb_norm", "pb_swiglu", "pb_add", "pb_embedding",
                  "pb_argmax", "pb_add_prompts", "pb_bump_epoch", "pb_advance_pos", "pb_rope_kv", "pb_attention",
                  "pb_kv_copy_pages", "pb_device_sm_count", "pb_version"):
@@ -177,7 +198,12 @@ launch_count = 0  # kernels of this library launched (directly) by this process;
 def check(code: int, what: str, launches: int = 1) -> None:
     global launch_count
     if code != 0:
-        raise NativeError(f"{what} failed: {_ERRORS.get(code, code)}")
+        detail = ""
+        try:
+            detail = lib().pb_last_error().decode()
+        except Exception:  # noqa: BLE001
+            pass
+        raise NativeError(f"{what} failed: {_ERRORS.get(code, code)}" + (f" [{detail}]" if detail else ""))
     launch_count += launches
 
 

@@ -1,0 +1,181 @@
+"""bench.py back-end for N > 1 GPUs (one process per GPU, launched by torch.distributed.run).
+
+Single-stream decode is bound by streaming the weights once per token, so the configuration that scales it is tensor
+parallelism over NVLink: every GPU streams 1/N of every block and the two all-reduces per block are fused into the
+GEMV epilogues/prologues (parallel/tensor_parallel.py). Rank 0 hosts the client model shell and the TP leader; the
+timed loops go through the same public client API as the 1-GPU run (``model(input_ids=...)`` inside an inference
+session). Device time is measured on every rank with CUDA events around the same K steps; the reported time is the
+maximum over ranks."""
+from __future__ import annotations
+
+import json
+import os
+import time
+
+import torch
+import torch.distributed as dist
+
+BASELINE_TOKENS_PER_S = 6.0
+
+
+def run_multi_gpu(args) -> None:
+    from petals_b200.data_structures import ModelInfo, ServerInfo, ServerState
+    from petals_b200.ops import functional as Fn
+    from petals_b200.ops import native
+    from petals_b200.parallel.swarm import Swarm
+    from petals_b200.parallel.symmetric import measure_hop_latency, measure_peer_bandwidth
+    from petals_b200.parallel.tp_worker import TPLeaderEngine, build_tp_engine, follower_loop, make_ring
+    from petals_b200.server.backend import Stage
+    from petals_b200.server.server import ModuleContainer
+    from petals_b200.utils.auto_config import AutoDistributedConfig
+    from petals_b200.utils.peaks import NVLINK_PEER_GBS, measured_peaks
+    from petals_b200.utils.random_model import MODEL_PRESETS, random_client_model, write_config_only
+    import petals_b200
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=dev)
+    native.lib()
+    path = write_config_only(args.model)
+    config = AutoDistributedConfig.from_pretrained(path)
+    n_layers = MODEL_PRESETS[args.model]["num_hidden_layers"]
+    t0 = time.time()
+    engine, cache, heap = build_tp_engine(config, n_layers, attn_cache_tokens=args.seq_len + 256, inference_max_length=args.seq_len)
+    ring = make_ring()
+    build_s = time.time() - t0
+    # ---- NVLink probes (stage-hop denominators) -------------------------------------------------------------------
+    probe_flag = heap.alloc(8)
+    peer_gbs = measure_peer_bandwidth(heap, 0, 1, nbytes=min(256 << 20, heap.nbytes // 2))
+    hop_us = measure_hop_latency(heap, probe_flag, 0, 1)
+    K, W = args.steps, max(args.warmup, 3)
+
+    if rank != 0:
+        marks = follower_loop_with_marks(engine, cache, ring, rank - 1)
+        ms = marks["start"].elapsed_time(marks["end"]) if "start" in marks and "end" in marks else 0.0
+        gathered = [None] * world
+        dist.all_gather_object(gathered, ms)
+        dist.barrier()
+        heap.close()
+        dist.destroy_process_group()
+        return
+
+    # ---- rank 0: leader + client ----------------------------------------------------------------------------------------
+    swarm = Swarm("bench")
+    leader = TPLeaderEngine(engine, ring)
+    stage = Stage(config, [torch.nn.Identity() for _ in range(n_layers)], 0, device=dev, memory_cache=cache, torch_dtype=torch.bfloat16, engine=leader)
+    info = ServerInfo(state=ServerState.JOINING, throughput=1.0, version=petals_b200.__version__, torch_dtype="bfloat16", quant_type="none", using_relay=False)
+    container = ModuleContainer.from_stage(dht=swarm, dht_prefix=config.dht_prefix, block_config=config, stage=stage, server_info=info,
+                                           model_info=ModelInfo(num_blocks=n_layers, repository=path), peer_id=f"tp{world}-leader",
+                                           inference_max_length=args.seq_len)
+    model = random_client_model(path, swarm, dev)
+    vocab = model.config.vocab_size
+    prompt = torch.randint(0, vocab, (1, args.prompt_len), device=dev)
+    pinned_in = torch.zeros(1, 1, dtype=torch.int64).pin_memory()
+    pinned_out = torch.zeros(1, dtype=torch.int64).pin_memory()
+    from bench import ClockSampler  # noqa: E402  (bench.py is the entry script)
+
+    with torch.inference_mode(), model.inference_session(max_length=args.seq_len) as sess:
+        logits = model(input_ids=prompt).logits
+        tok = logits[:, -1].argmax(-1, keepdim=True)
+        for _ in range(W):
+            tok = model(input_ids=tok).logits[:, -1].argmax(-1, keepdim=True)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        torch.cuda.synchronize()
+        ring.send({"op": "mark", "name": "start"})
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = native.launch_count
+        start.record()
+        for _ in range(K):
+            tok = Fn.argmax(model(input_ids=tok).logits[:, -1])[:, None]
+        end.record()
+        torch.cuda.synchronize()
+        ring.send({"op": "mark", "name": "end"})
+        launches = native.launch_count - launches0
+        ms0 = start.elapsed_time(end)
+        clocks = sampler.stop()
+        pinned_in.copy_(tok.cpu())
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        for _ in range(K):
+            ids = pinned_in.to(dev, non_blocking=True)
+            nxt = Fn.argmax(model(input_ids=ids).logits[:, -1])
+            pinned_out.copy_(nxt, non_blocking=True)
+            torch.cuda.synchronize()
+            pinned_in[0, 0] = pinned_out[0]
+        e2e_s = time.perf_counter() - t1
+    engine.check_errors()
+    leader.shutdown()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, ms0)
+    ms = max(float(x) for x in gathered)
+    value = K / (ms / 1e3)
+    peaks = measured_peaks()
+    spec = config.block_spec()
+    weight_bytes_rank = (spec.num_params() * n_layers) * 2 / world + vocab * spec.hidden_size * 2  # LM head is replicated on rank 0
+    hop_bytes = spec.hidden_size * 2
+    result = {
+        "metric": "Llama-3-70B single-stream decode tokens/s (device-timed, max over ranks)",
+        "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",
+        "data": "synthetic token ids; random-init weights of the named architecture",
+        "config": {"model": args.model, "global_batch": 1, "seq_len": args.seq_len, "parallelism": f"tp{world} (1 stage x {n_layers} blocks, fused GEMV+NVLink all-reduce)",
+                   "l2": "each step streams every rank's full weight shard (>> 126 MB L2): inputs larger than L2", "build_s": round(build_s, 1),
+                   "per_rank_ms": [round(float(x), 3) for x in gathered]},
+        "clocks": clocks,
+        "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8},
+        "gpu_launches": launches,
+        "roofline": {"weight_bytes_per_token_per_rank": int(weight_bytes_rank), "achieved_GBps_per_rank": round(weight_bytes_rank * value / 1e9, 1),
+                     "frac_of_measured_hbm": round(weight_bytes_rank * value / 1e9 / peaks["hbm_gbs"], 3), "peaks": peaks["source"]},
+        "stage_hop": {"peer_store_GBps": None if peer_gbs is None else round(peer_gbs, 1), "frac_of_measured_peer_copy": None if peer_gbs is None else round(peer_gbs / NVLINK_PEER_GBS, 3),
+                      "flag_latency_us": None if hop_us is None else round(hop_us, 2), "allreduce_payload_bytes": hop_bytes,
+                      "fused_allreduces_per_token": 2 * n_layers},
+    }
+    container.shutdown()
+    dist.barrier()
+    heap.close()
+    print(json.dumps(result))
+    dist.destroy_process_group()
+
+
+def follower_loop_with_marks(engine, cache, ring, consumer: int) -> dict:
+    """follower_loop + CUDA-event marks so that every rank times the same K steps on its own device."""
+    from petals_b200.server.memory_cache import SessionCache
+
+    sessions = {}
+    marks = {}
+    while True:
+        cmd = ring.recv(consumer, timeout=None)
+        op = cmd["op"]
+        if op == "step":
+            s = sessions[cmd["sid"]]
+            if cmd["pos"] != s.position:
+                s.set_position(cmd["pos"])
+            if "hypo" in cmd:
+                s.reorder(torch.tensor(cmd["hypo"], dtype=torch.int64))
+            engine.run_step(s, cmd["B"], cmd["T"])
+        elif op == "open":
+            sessions[cmd["sid"]] = cache.open_session(cmd["B"], cmd["max_length"], timeout=None)
+        elif op == "close":
+            s = sessions.pop(cmd["sid"], None)
+            if s is not None:
+                s.close()
+        elif op == "mark":
+            if cmd["name"] == "end":
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                torch.cuda.synchronize()
+            else:
+                torch.cuda.synchronize()
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+            marks[cmd["name"]] = ev
+        elif op == "stop":
+            break
+    for s in sessions.values():
+        s.close()
+    torch.cuda.synchronize()
+    engine.check_errors()
+    return marks

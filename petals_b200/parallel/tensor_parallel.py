@@ -1,0 +1,305 @@
+"""Tensor parallelism inside a stage: one process per GPU, fused compute + NVLink collectives.
+
+The reference delegates intra-server TP to the ``tensor_parallel`` package: one Python thread per device and an
+NCCL/``torch.cuda.comm`` all-reduce after every row-parallel linear (src/petals/utils/convert_block.py:118-135,
+SURVEY.md §2.4 X5). Here a TP group is N worker *processes* (rank = GPU) sharing a symmetric heap:
+
+* column-parallel projections (QKV, gate/up) need no communication;
+* every row-parallel projection (attention out, MLP down) is a weight-streaming GEMV whose **epilogue stores its
+  partial result straight into all peers' HBM over NVLink** and publishes one flag per peer; the *next* kernel
+  (fused norm + column-parallel GEMV) **waits on the flag, sums the N partials + residual in its prologue** and goes
+  on. That is a one-shot all-reduce with zero extra launches, zero NCCL calls and no host involvement — per layer
+  the critical path sees two flag waits (~NVLink latency) instead of two all-reduce kernels;
+* KV caches, attention heads and FFN columns are sharded; norms and the residual stream are replicated.
+
+Control plane: the leader (rank 0 of the group, the process that owns the swarm endpoint) broadcasts tiny step
+commands through a shared-memory ring (``parallel/control.py``); followers replay the same CUDA graph. Every rank
+bumps a device-resident epoch per step; flag targets are ``epoch * n_sources`` so nothing is ever reset.
+"""
+from __future__ import annotations
+
+import dataclasses
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from petals_b200.models.block_oracle import GenericBlock
+from petals_b200.models.spec import BlockSpec
+from petals_b200.ops import functional as Fn
+from petals_b200.ops import native
+from petals_b200.parallel.symmetric import SymmetricHeap, ptr_array
+from petals_b200.server.memory_cache import MemoryCache, SessionCache
+from petals_b200.utils.logging import get_logger
+
+logger = get_logger(__name__)
+MAX_ROWS = 8
+
+
+def tp_supported(spec: BlockSpec, world: int) -> bool:
+    return (spec.mlp in ("swiglu", "gelu") and not spec.parallel_attn and not spec.qkv_interleaved and not spec.post_ln_residual
+            and spec.num_kv_heads % world == 0 and spec.num_heads % world == 0 and spec.intermediate_size % (2 * world) == 0
+            and spec.head_dim in (64, 128))
+
+
+def local_spec(spec: BlockSpec, world: int) -> BlockSpec:
+    """The shard's view: 1/world of the heads and FFN columns, full hidden size."""
+    return dataclasses.replace(spec, num_heads=spec.num_heads // world, num_kv_heads=spec.num_kv_heads // world,
+                               intermediate_size=spec.intermediate_size // world)
+
+
+def shard_block(block: GenericBlock, spec: BlockSpec, rank: int, world: int, device) -> Dict[str, torch.Tensor]:
+    """Megatron-style split of one block's canonical tensors (column-parallel rows / row-parallel columns)."""
+    D = spec.head_dim
+    hq, hkv, I = spec.num_heads // world, spec.num_kv_heads // world, spec.intermediate_size // world
+    q0, k0, v0 = 0, spec.num_heads * D, (spec.num_heads + spec.num_kv_heads) * D
+    w = block.wqkv
+    out = {
+        "wqkv": torch.cat([w[q0 + rank * hq * D: q0 + (rank + 1) * hq * D], w[k0 + rank * hkv * D: k0 + (rank + 1) * hkv * D],
+                           w[v0 + rank * hkv * D: v0 + (rank + 1) * hkv * D]], 0),
+        "wo": block.wo[:, rank * hq * D: (rank + 1) * hq * D],
+        "w_down": block.w_down[:, rank * I: (rank + 1) * I],
+        "w_up": block.w_up[rank * I: (rank + 1) * I],
+        "ln1_w": block.ln1_w, "ln2_w": block.ln2_w,
+    }
+    if spec.mlp == "swiglu":
+        out["w_gate"] = block.w_gate[rank * I: (rank + 1) * I]
+    for name in ("ln1_b", "ln2_b"):
+        if getattr(block, name, None) is not None:
+            out[name] = getattr(block, name)
+    return {k: v.detach().to(device).contiguous() for k, v in out.items()}
+
+
+def random_shard(spec: BlockSpec, rank: int, world: int, layer: int, device, seed: int = 0, std: float = 0.02) -> Dict[str, torch.Tensor]:
+    """A random shard generated in place (benchmarks: the full 140 GB model never exists anywhere)."""
+    ls = local_spec(spec, world)
+    g = torch.Generator(device=device).manual_seed(seed * 1000003 + layer * 64 + rank)
+    H = spec.hidden_size
+
+    def rnd(*shape):
+        return (torch.randn(*shape, device=device, dtype=torch.float32, generator=g) * std).to(torch.bfloat16)
+
+    out = {"wqkv": rnd(ls.qkv_dim, H), "wo": rnd(H, ls.num_heads * ls.head_dim), "w_up": rnd(ls.intermediate_size, H),
+           "w_down": rnd(H, ls.intermediate_size), "ln1_w": torch.ones(H, device=device, dtype=torch.bfloat16),
+           "ln2_w": torch.ones(H, device=device, dtype=torch.bfloat16)}
+    if spec.mlp == "swiglu":
+        out["w_gate"] = rnd(ls.intermediate_size, H)
+    if spec.norm == "layer":
+        out["ln1_b"] = torch.zeros(H, device=device, dtype=torch.bfloat16)
+        out["ln2_b"] = torch.zeros(H, device=device, dtype=torch.bfloat16)
+    return out
+
+
+class TPDecodeEngine:
+    """Executes a span of blocks sharded over a TP group for decode-shaped steps (B*T <= 8 rows)."""
+
+    def __init__(self, spec: BlockSpec, shards: Sequence[Dict[str, torch.Tensor]], heap: SymmetricHeap, cache: MemoryCache, *,
+                 use_cuda_graphs: bool = True):
+        self.spec, self.shards, self.heap, self.cache = spec, list(shards), heap, cache
+        self.rank, self.world = heap.rank, heap.world
+        self.ls = local_spec(spec, self.world)
+        self.device = heap.device
+        self.n_blocks = len(self.shards)
+        self.use_cuda_graphs = use_cuda_graphs
+        H = spec.hidden_size
+        self.norm_kind = Fn.NORM_RMS if spec.norm == "rms" else Fn.NORM_LAYER
+        self.act = Fn.ACT_SWIGLU if spec.mlp == "swiglu" else (Fn.ACT_GELU_TANH if spec.gelu_tanh else Fn.ACT_GELU_ERF)
+        self.cos = self.sin = None
+        if spec.rotary:
+            self.cos, self.sin = Fn.rope_tables(spec.head_dim, spec.max_position, spec.rope_theta, spec.rope_scaling, device=self.device)
+        self.sms = native.sm_count(self.device.index)
+        # ---- symmetric allocations (identical order on every rank) ----------------------------------------------
+        R, L = self.world, self.n_blocks
+        self.slot_bytes = MAX_ROWS * H * 2
+        self.off_x_in = heap.alloc(self.slot_bytes)
+        self.off_parts_attn = heap.alloc(R * self.slot_bytes)
+        self.off_parts_mlp = heap.alloc(R * self.slot_bytes)
+        self.off_flags = heap.alloc((2 * L + 2) * 8)
+        self.x_in = heap.tensor(self.off_x_in, (MAX_ROWS, H), torch.bfloat16)
+        # ---- local state ----------------------------------------------------------------------------------------------
+        dev = self.device
+        self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.done_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.pos_static = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.max_pages = cache.max_pages_per_seq
+        self._tables: Dict[int, torch.Tensor] = {}
+        self._graphs: Dict[Tuple[int, int], dict] = {}
+        self._bufs: Dict[Tuple[str, int], torch.Tensor] = {}
+        self._active: Optional[SessionCache] = None
+        self._dev_pos = -1
+        self.out = torch.zeros(MAX_ROWS, H, dtype=torch.bfloat16, device=dev)
+
+    # ---- addresses -------------------------------------------------------------------------------------------------
+    def flag(self, rank: int, index: int) -> int:
+        return self.heap.addr(rank, self.off_flags + 8 * index)
+
+    def flag_attn(self, rank: int, layer: int) -> int:
+        return self.flag(rank, 2 + 2 * layer)
+
+    def flag_mlp(self, rank: int, layer: int) -> int:
+        return self.flag(rank, 3 + 2 * layer)
+
+    def parts(self, off: int, owner: int, src: int) -> int:
+        return self.heap.addr(owner, off + src * self.slot_bytes)
+
+    def _buf(self, name: str, rows: int, cols: int, dtype=torch.bfloat16) -> torch.Tensor:
+        key = (name, rows)
+        t = self._bufs.get(key)
+        if t is None or t.shape[1] != cols:
+            t = torch.empty(rows, cols, dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def _table(self, B: int) -> torch.Tensor:
+        if B not in self._tables:
+            self._tables[B] = torch.zeros(B, self.max_pages, dtype=torch.int32, device=self.device)
+        return self._tables[B]
+
+    # ---- one decode step of the whole span (launch sequence; captured into a graph) ------------------------------------
+    def _launch_span(self, B: int, T: int, table: torch.Tensor, final_reduce: bool) -> torch.Tensor:
+        s, ls, R, me = self.spec, self.ls, self.world, self.rank
+        M, H = B * T, s.hidden_size
+        eps = s.norm_eps
+        ep, err, ctr = self.epoch.data_ptr(), self.err.data_ptr(), self.done_counter.data_ptr()
+        pos_ptr = self.pos_static.data_ptr()
+        native.check(native.lib().pb_bump_epoch(ep, native.stream_ptr()), "bump_epoch")
+        h = [self._buf("h_a", M, H), self._buf("h_b", M, H)]
+        cur = self.x_in[:M]  # residual stream entering layer 0 (pushed by the leader)
+        nxt = 0
+        qkv_buf = self._buf("qkv", M, ls.qkv_dim)
+        q_buf = self._buf("q", M, ls.num_heads * ls.head_dim)
+        attn = self._buf("attn", M, ls.num_heads * ls.head_dim)
+        act = self._buf("act", M, ls.intermediate_size)
+        splits = int(min(16, max(1, (2 * self.sms) // max(1, B * ls.num_kv_heads))))
+        po = self._buf("po", splits * M * ls.num_heads, ls.head_dim, torch.float32) if splits > 1 else None
+        pl = self._buf("pl", splits, M * ls.num_heads, torch.float32) if splits > 1 else None
+        attn_parts = [self.parts(self.off_parts_attn, me, r) for r in range(R)]
+        mlp_parts = [self.parts(self.off_parts_mlp, me, r) for r in range(R)]
+        for l, w in enumerate(self.shards):
+            pools = self.cache.layer_pools(l)
+            # K1: [all-reduce tail of previous MLP] + norm + column-parallel QKV
+            if l == 0:
+                Fn.linear_decode(cur, w["wqkv"], norm_weight=w["ln1_w"], norm_bias=w.get("ln1_b"), norm_kind=self.norm_kind, eps=eps,
+                                 out=qkv_buf, wait_flag=self.flag(me, 0), wait_per_epoch=1, epoch=ep, error_flag=err)
+            else:
+                Fn.linear_decode(cur, w["wqkv"], norm_weight=w["ln1_w"], norm_bias=w.get("ln1_b"), norm_kind=self.norm_kind, eps=eps,
+                                 out=qkv_buf, parts=mlp_parts, wait_flag=self.flag_mlp(me, l - 1), wait_per_epoch=R, epoch=ep,
+                                 x_out=h[nxt], error_flag=err)
+                cur, nxt = h[nxt], nxt ^ 1
+            Fn.rope_kv_append(qkv_buf, q_buf, pools[0], pools[1], table, pos_ptr, self.cos, self.sin, B=B, T=T, Hq=ls.num_heads,
+                              Hkv=ls.num_kv_heads, D=ls.head_dim, error_flag=err)
+            Fn.paged_attention(q_buf, pools[0], pools[1], table, pos_ptr, attn, B=B, T=T, Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim,
+                               scale=s.attn_scale, splits=splits, partial_o=po, partial_lse=pl, window=s.sliding_window)
+            # K2: row-parallel O-projection; epilogue pushes the partial into every rank's slot [me]
+            Fn.linear_decode(attn, w["wo"], store_local=False, push_out=[self.parts(self.off_parts_attn, r, me) for r in range(R)],
+                             push_flag=[self.flag_attn(r, l) for r in range(R)], done_counter=ctr, error_flag=err)
+            # K3: [all-reduce tail of attention] + norm + column-parallel gate/up (+SwiGLU)
+            kw = dict(norm_weight=w["ln2_w"], norm_bias=w.get("ln2_b"), norm_kind=self.norm_kind, eps=eps, out=act, parts=attn_parts,
+                      wait_flag=self.flag_attn(me, l), wait_per_epoch=R, epoch=ep, x_out=h[nxt], error_flag=err)
+            if s.mlp == "swiglu":
+                Fn.linear_decode(cur, w["w_gate"], w2=w["w_up"], act=Fn.ACT_SWIGLU, **kw)
+            else:
+                Fn.linear_decode(cur, w["w_up"], act=self.act, **kw)
+            cur, nxt = h[nxt], nxt ^ 1
+            # K4: row-parallel down projection, pushed like K2
+            Fn.linear_decode(act, w["w_down"], store_local=False, push_out=[self.parts(self.off_parts_mlp, r, me) for r in range(R)],
+                             push_flag=[self.flag_mlp(r, l) for r in range(R)], done_counter=ctr, error_flag=err)
+        if final_reduce:
+            parts = ptr_array(mlp_parts)
+            native.check(native.lib().pb_reduce_parts(cur.data_ptr(), parts, R, self.flag_mlp(me, self.n_blocks - 1), R, ep, self.out.data_ptr(),
+                                                      M * H * 2, err, native.stream_ptr()), "reduce_parts")
+        native.check(native.lib().pb_advance_pos(pos_ptr, T, native.stream_ptr()), "advance_pos")
+        self._last_residual, self._last_parts = cur, mlp_parts
+        return self.out[:M]
+
+    def _graph(self, B: int, T: int, table: torch.Tensor) -> dict:
+        key = (B, T)
+        g = self._graphs.get(key)
+        if g is not None:
+            return g
+        # No warm-up replay here: a warm-up would consume flag epochs on this rank only. Kernel attributes were set by
+        # `warm_kernels()` (communication-free launches) before any peer traffic.
+        graph = torch.cuda.CUDAGraph()
+        before = native.launch_count
+        with torch.cuda.graph(graph):
+            self._launch_span(B, T, table, final_reduce=True)
+        launches = native.launch_count - before
+        native.add_launches(-launches)
+        g = dict(graph=graph, launches=launches)
+        self._graphs[key] = g
+        return g
+
+    def warm_kernels(self, B: int, T: int) -> None:
+        """Launch every kernel variant of a (B, T) step once WITHOUT communication so that lazy module loading,
+        cudaFuncSetAttribute and buffer allocation happen before graph capture (which must not allocate)."""
+        s, ls = self.spec, self.ls
+        M, H = B * T, s.hidden_size
+        w = self.shards[0]
+        x = self._buf("h_a", M, H)
+        self._buf("h_b", M, H)
+        x.zero_()
+        table = self._table(B)
+        qkv = Fn.linear_decode(x, w["wqkv"], norm_weight=w["ln1_w"], norm_bias=w.get("ln1_b"), norm_kind=self.norm_kind, eps=s.norm_eps,
+                               out=self._buf("qkv", M, ls.qkv_dim))
+        q_buf, attn = self._buf("q", M, ls.num_heads * ls.head_dim), self._buf("attn", M, ls.num_heads * ls.head_dim)
+        attn.zero_()
+        act = self._buf("act", M, ls.intermediate_size)
+        splits = int(min(16, max(1, (2 * self.sms) // max(1, B * ls.num_kv_heads))))
+        if splits > 1:
+            self._buf("po", splits * M * ls.num_heads, ls.head_dim, torch.float32), self._buf("pl", splits, M * ls.num_heads, torch.float32)
+        scratch = torch.zeros(M, H, dtype=torch.bfloat16, device=self.device)
+        Fn.linear_decode(attn, w["wo"], out=scratch)
+        if s.mlp == "swiglu":
+            Fn.linear_decode(x, w["w_gate"], w2=w["w_up"], act=Fn.ACT_SWIGLU, norm_weight=w["ln2_w"], norm_kind=self.norm_kind, eps=s.norm_eps,
+                             out=act, parts=[scratch], x_out=self._buf("h_b", M, H))
+        else:
+            Fn.linear_decode(x, w["w_up"], act=self.act, norm_weight=w["ln2_w"], norm_bias=w.get("ln2_b"), norm_kind=self.norm_kind,
+                             eps=s.norm_eps, out=act, parts=[scratch], x_out=self._buf("h_b", M, H))
+        Fn.linear_decode(act, w["w_down"], out=scratch)
+        torch.cuda.synchronize(self.device)
+
+    # ---- session bookkeeping (identical on every rank) ---------------------------------------------------------------------
+    def _sync_session(self, session: SessionCache, B: int) -> torch.Tensor:
+        table = self._table(B)
+        if self._active is not session or session._synced_version != session._version:
+            table.copy_(session.table_dev[:, : self.max_pages], non_blocking=True)
+            session._synced_version = session._version
+            self._active = session
+            self._dev_pos = -1
+        if self._dev_pos != session.position:
+            self.pos_static.fill_(session.position)
+            self._dev_pos = session.position
+        return table
+
+    def run_step(self, session: SessionCache, B: int, T: int) -> torch.Tensor:
+        """Every rank calls this once per step command (the leader after pushing the inputs)."""
+        assert B * T <= MAX_ROWS
+        session.prepare_write(T)
+        table = self._sync_session(session, B)
+        if (B, T) not in self._graphs:
+            self.warm_kernels(B, T)
+        if self.use_cuda_graphs:
+            g = self._graph(B, T, table)
+            g["graph"].replay()
+            native.add_launches(g["launches"])
+        else:
+            self._launch_span(B, T, table, final_reduce=True)
+        session.set_position(session.position + T)
+        self._dev_pos = session.position
+        return self.out[: B * T]
+
+    def push_inputs(self, hidden: torch.Tensor) -> None:
+        """Leader: broadcast the step's input rows into every rank's ``x_in`` (+ one flag each) over NVLink."""
+        M = hidden.shape[0]
+        src = self._buf("x_stage", MAX_ROWS, self.spec.hidden_size)
+        src[:M].copy_(hidden)
+        R = self.world
+        dsts = ptr_array([self.heap.addr(r, self.off_x_in) for r in range(R)])
+        flags = ptr_array([self.flag(r, 0) for r in range(R)])
+        native.check(native.lib().pb_push_rows(src.data_ptr(), dsts, flags, R, M * self.spec.hidden_size * 2, native.stream_ptr()), "push_rows")
+
+    def check_errors(self) -> None:
+        code = int(self.err.item())
+        if code:
+            self.err.zero_()
+            raise RuntimeError(f"rank {self.rank}: device-side error flag {code} (1 = peer flag watchdog expired, 2 = KV page table overflow)")

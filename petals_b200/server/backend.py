@@ -30,15 +30,15 @@ class Stage:
 
     def __init__(self, config, blocks: Sequence[GenericBlock], start_block: int, *, device, memory_cache: MemoryCache,
                  torch_dtype: torch.dtype, max_chunk_size_bytes: int = 256 * 1024 * 1024, use_cuda_graphs: bool = True,
-                 force_oracle: bool = False):
+                 force_oracle: bool = False, engine=None):
         self.config, self.blocks = config, list(blocks)
         self.start_block, self.end_block = start_block, start_block + len(blocks)
         self.device, self.dtype = torch.device(device), torch_dtype
         self.memory_cache = memory_cache
         self.spec = config.block_spec()
         self.max_chunk_size_bytes = max_chunk_size_bytes
-        self.engine = None
-        if memory_cache.paged and not force_oracle:
+        self.engine = engine  # e.g. a tensor-parallel leader engine (parallel/tp_worker.py)
+        if engine is None and memory_cache.paged and not force_oracle:
             from petals_b200.server.stage_engine import StageEngine
 
             chunk_tokens = max(256, min(8192, max_chunk_size_bytes // max(1, 2 * self.spec.intermediate_size)))
@@ -168,7 +168,7 @@ class TransformerBackend:
         self.max_batch_size = max_batch_size
         self.inference_pool = PrioritizedTaskPool(self.inference_step, max_batch_size, f"{name}_inference", runtime)
         self.forward_pool = PrioritizedTaskPool(self.forward, max_batch_size, f"{name}_forward", runtime)
-        self.backward_pool = PrioritizedTaskPool(self.backward, max_batch_size, f"{name}_backward", runtime)
+        self.backward_pool = PrioritizedTaskPool(self.backward, max_batch_size, f"{name}_backward", runtime, in_caller_thread=True)
         for p in module.parameters():
             p.requires_grad_(False)
 

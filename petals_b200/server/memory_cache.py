@@ -40,6 +40,7 @@ class SessionCache:
         self.reserved_pages = reserved_pages
         self.position = 0
         self.closed = False
+        self.on_close = []  # callbacks(session): e.g. a TP leader tells its followers to drop their mirror session
         self.pages_per_seq = (max_length + PAGE - 1) // PAGE
         if owner.paged:
             self.tables: List[List[int]] = [[] for _ in range(batch_size)]
@@ -135,6 +136,11 @@ class SessionCache:
         if self.closed:
             return
         self.closed = True
+        for cb in self.on_close:
+            try:
+                cb(self)
+            except Exception:  # noqa: BLE001
+                pass
         if self.owner.paged:
             for t in self.tables:
                 self._free(t)

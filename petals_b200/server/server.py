@@ -279,26 +279,52 @@ class ModuleContainer:
                                        paged=paged, max_length=inference_max_length)
             stage = Stage(block_config, blocks, block_indices[0], device=device, memory_cache=memory_cache, torch_dtype=torch_dtype,
                           max_chunk_size_bytes=max_chunk_size_bytes, use_cuda_graphs=use_cuda_graphs, force_oracle=force_oracle)
-            runtime = Runtime(name=f"runtime-{peer_id}", stats_report_interval=stats_report_interval, device=device)
-            backends: Dict[str, TransformerBackend] = {}
-            for slot, (uid, block) in enumerate(zip(module_uids, blocks)):
-                backends[uid] = TransformerBackend(uid, block, stage=stage, slot=slot, max_batch_size=max_batch_size, runtime=runtime)
-            inference_pool = merge_inference_pools_inplace(backends, stage, runtime, max_batch_size)
-
-            def span_forward(hidden, prompts, lo, hi, active_adapter):
-                stage.use_adapter(active_adapter)
-                return stage.forward(hidden, prompts, lo, hi)
-
-            def span_backward(hidden, grad, prompts, lo, hi, active_adapter):
-                stage.use_adapter(active_adapter)
-                return stage.backward(hidden, grad, prompts, lo, hi)
-
-            forward_pool = PrioritizedTaskPool(span_forward, max_batch_size, "span_forward", runtime)
-            backward_pool = PrioritizedTaskPool(span_backward, max_batch_size, "span_backward", runtime)
+            container_parts = cls._build_pools(stage, module_uids, blocks, max_batch_size, stats_report_interval, peer_id, device)
         except BaseException:
             announcer.announce(ServerState.OFFLINE)
             announcer.stop.set()
             raise
+        backends, runtime, inference_pool, forward_pool, backward_pool = container_parts
+        return cls(dht, dht_prefix, backends, stage=stage, runtime=runtime, inference_pool=inference_pool, forward_pool=forward_pool,
+                   backward_pool=backward_pool, announcer=announcer, peer_id=peer_id, adapters=adapters,
+                   inference_max_length=inference_max_length, request_timeout=request_timeout, session_timeout=session_timeout,
+                   step_timeout=step_timeout, quant_type=quant_type)
+
+    @staticmethod
+    def _build_pools(stage: Stage, module_uids: List[str], blocks, max_batch_size: int, stats_report_interval, peer_id: str, device):
+        runtime = Runtime(name=f"runtime-{peer_id}", stats_report_interval=stats_report_interval, device=device)
+        backends: Dict[str, TransformerBackend] = {}
+        for slot, (uid, block) in enumerate(zip(module_uids, blocks)):
+            backends[uid] = TransformerBackend(uid, block, stage=stage, slot=slot, max_batch_size=max_batch_size, runtime=runtime)
+        inference_pool = merge_inference_pools_inplace(backends, stage, runtime, max_batch_size)
+
+        def span_forward(hidden, prompts, lo, hi, active_adapter):
+            stage.use_adapter(active_adapter)
+            return stage.forward(hidden, prompts, lo, hi)
+
+        def span_backward(hidden, grad, prompts, lo, hi, active_adapter):
+            stage.use_adapter(active_adapter)
+            return stage.backward(hidden, grad, prompts, lo, hi)
+
+        forward_pool = PrioritizedTaskPool(span_forward, max_batch_size, "span_forward", runtime)
+        backward_pool = PrioritizedTaskPool(span_backward, max_batch_size, "span_backward", runtime, in_caller_thread=True)
+        return backends, runtime, inference_pool, forward_pool, backward_pool
+
+    @classmethod
+    def from_stage(cls, *, dht: Swarm, dht_prefix: str, block_config, stage: Stage, server_info: ServerInfo, model_info: ModelInfo,
+                   peer_id: str, max_batch_size: int = 1 << 20, inference_max_length: int = 8192, update_period: float = 30,
+                   expiration: float = 3600, request_timeout: float = 180, session_timeout: float = 1800, step_timeout: float = 300,
+                   adapters: Sequence[str] = (), quant_type: QuantType = QuantType.NONE) -> "ModuleContainer":
+        """Serve an already constructed stage (e.g. the leader of a tensor-parallel worker group)."""
+        block_indices = list(range(stage.start_block, stage.end_block))
+        module_uids = [make_uid(dht_prefix, i) for i in block_indices]
+        server_info.start_block, server_info.end_block = block_indices[0], block_indices[-1] + 1
+        announcer = ModuleAnnouncerThread(module_uids, dht, server_info, model_info, peer_id=peer_id, block_config=block_config,
+                                          update_period=update_period, expiration=expiration, daemon=True)
+        announcer.announce(ServerState.JOINING)
+        announcer.start()
+        parts = cls._build_pools(stage, module_uids, stage.blocks, max_batch_size, None, peer_id, stage.device)
+        backends, runtime, inference_pool, forward_pool, backward_pool = parts
         return cls(dht, dht_prefix, backends, stage=stage, runtime=runtime, inference_pool=inference_pool, forward_pool=forward_pool,
                    backward_pool=backward_pool, announcer=announcer, peer_id=peer_id, adapters=adapters,
                    inference_max_length=inference_max_length, request_timeout=request_timeout, session_timeout=session_timeout,

@@ -42,10 +42,16 @@ class Runtime(threading.Thread):
         self.allow_inline = True
 
     # -- submission ------------------------------------------------------------------------------------
-    def submit(self, pool: "PrioritizedTaskPool", priority: float, args: Sequence[Any]) -> Future:
+    def submit(self, pool: "PrioritizedTaskPool", priority: float, args: Sequence[Any], in_caller_thread: bool = False) -> Future:
         fut: Future = Future()
         if self._shutdown.is_set():
             fut.set_exception(RuntimeError("runtime is shut down"))
+            return fut
+        if in_caller_thread:
+            # Tasks that use torch.autograd (span backward) must run in the submitting thread: when that thread is
+            # a CUDA autograd worker, the nested autograd call is re-entrant only from the same thread.
+            with self._exec_lock:
+                self._execute(pool, args, fut)
             return fut
         if self.allow_inline and self._rt.pb_tq_size(self._queue) == 0 and self._exec_lock.acquire(blocking=False):
             try:
@@ -119,7 +125,8 @@ class PrioritizedTaskPool:
     """A named entry point (inference / forward / backward of a block or span) into the runtime."""
 
     def __init__(self, process_func: Callable[..., Any], max_batch_size: int, name: str, runtime: Optional[Runtime] = None,
-                 min_batch_size: int = 1, device=None):
+                 min_batch_size: int = 1, device=None, in_caller_thread: bool = False):
+        self.in_caller_thread = in_caller_thread
         if min_batch_size != 1:
             raise ValueError("batching across requests is not supported (min_batch_size must be 1)")
         self.process_func, self.max_batch_size, self.name = process_func, max_batch_size, name
@@ -145,4 +152,4 @@ class PrioritizedTaskPool:
             return fut
         if self.runtime is None:
             raise RuntimeError(f"pool {self.name} is not attached to a runtime")
-        return self.runtime.submit(self, priority, args)
+        return self.runtime.submit(self, priority, args, in_caller_thread=self.in_caller_thread)

@@ -12,7 +12,7 @@ DEV = "cuda:0"
 def _oracle_logits(model, stage, ids):
     """Run the same weights through the oracle blocks in fp32-accumulating PyTorch (bf16 weights)."""
     blocks = stage.stage.blocks
-    h = model.model.embed_tokens(ids)
+    h = model.model.embed(ids)  # includes BLOOM's embedding LayerNorm
     for b in blocks:
         h = b.forward_cached(h, None, None, 0)
     return model.lm_head(model.model.final_norm(h))

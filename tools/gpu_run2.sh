@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_engine_gpu.py -q -x -m gpu > gpurun_out/test_engine.log 2>&1; echo "engine tests exit=$?" | tee gpurun_out/summary2.txt
+timeout 600 python -m pytest tests/test_engine_gpu.py -q -m gpu > gpurun_out/test_engine.log 2>&1; echo "engine tests exit=$?" | tee gpurun_out/summary2.txt
 tail -25 gpurun_out/test_engine.log
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke.log 2>&1; echo "smoke exit=$?" | tee -a gpurun_out/summary2.txt
 tail -5 gpurun_out/smoke.log
