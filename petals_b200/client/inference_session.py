@@ -43,6 +43,8 @@ class _ServerInferenceSession:
         self._position = 0
         self.history: Optional[torch.Tensor] = None  # every input this stage has seen (for fail-over replay)
         self.next_session: Optional["_ServerInferenceSession"] = None
+        self.fabric_rank: Optional[int] = None  # rank of the stage in the NVLink fabric (None: tensors travel with the RPC)
+        self.no_history = False  # inputs arrived over the fabric: the client never saw them
 
     @classmethod
     def create(cls, config, sequence_manager: RemoteSequenceManager, span: RemoteSpanInfo, uids: Sequence[ModuleUID], *,
@@ -51,7 +53,15 @@ class _ServerInferenceSession:
         session_id = str(uuid.uuid4())
         meta = dict(max_length=max_length, session_id=session_id, alloc_timeout=float(metadata.pop("alloc_timeout", 0.0)), **metadata)
         stream = stub.rpc_inference(list(uids), meta)
-        return cls(config, span, uids, stream, max_length=max_length, session_id=session_id)
+        session = cls(config, span, uids, stream, max_length=max_length, session_id=session_id)
+        from petals_b200.parallel.fabric import get_fabric
+
+        if get_fabric() is not None and config.use_server_to_server:
+            try:
+                session.fabric_rank = stub.rpc_info().get("fabric_rank")
+            except Exception:  # noqa: BLE001 - a stage without fabric info simply uses the tensor path
+                session.fabric_rank = None
+        return session
 
     @property
     def position(self) -> int:
@@ -64,8 +74,27 @@ class _ServerInferenceSession:
         if self.history is not None and self.history.shape[1] >= start_from_position:
             self.history = self.history[:, :start_from_position] if start_from_position > 0 else None
 
+    def step_pushed(self, shape: tuple, src_rank: int, prompts: torch.Tensor, hypo_ids: torch.Tensor, *, step_id: str, n_new: int,
+                    fabric_out: Optional[dict]) -> torch.Tensor:
+        """A step whose input already sits in the stage's landing zone (pushed by ``src_rank`` over NVLink)."""
+        if self.closed:
+            raise Exception("Session is closed, cannot perform step")
+        B, L, H = shape
+        if not self.stepped and L != self._position + n_new:
+            raise RuntimeError("a fresh server session needs the full input history, but only the new tokens were pushed")
+        self.history, self.no_history = None, True
+        metadata = dict(step_id=step_id, fabric_in=dict(src_rank=src_rank, B=B, T=L))
+        if self.stepped:
+            metadata["start_from_position"] = self._position
+        if fabric_out is not None:
+            metadata["fabric_out"] = fabric_out
+        outputs = self.stream.step(torch.empty(0), prompts, hypo_ids, metadata=metadata)
+        self.stepped = True
+        self._position += n_new
+        return outputs
+
     def step(self, inputs: torch.Tensor, prompts: torch.Tensor, hypo_ids: torch.Tensor, *, step_id: str,
-             n_new: Optional[int] = None) -> torch.Tensor:
+             n_new: Optional[int] = None, fabric_out: Optional[dict] = None) -> torch.Tensor:
         """Send the new tokens (or, on a fresh stream after fail-over, the whole history) to the stage.
 
         ``inputs`` may be longer than ``n_new``: a predecessor that is itself replaying hands over its full-length
@@ -91,8 +120,13 @@ class _ServerInferenceSession:
             metadata["start_from_position"] = self._position  # cheap no-op unless a rollback happened
         if self.config.use_server_to_server and self.next_session is not None:
             metadata["next_servers"] = self._collect_next_servers()
+        if fabric_out is not None:
+            metadata["fabric_out"] = fabric_out
         outputs = self.stream.step(to_send, prompts, hypo_ids, metadata=metadata)
-        assert outputs.shape == to_send.shape, f"output activation shape is different from input shape: {outputs.shape} != {to_send.shape}"
+        if fabric_out is None:
+            assert outputs.shape == to_send.shape, f"output activation shape is different from input shape: {outputs.shape} != {to_send.shape}"
+        else:
+            outputs = (to_send.shape[0], to_send.shape[1], to_send.shape[2])  # lives in the next landing zone: only its shape is known here
         self.stepped = True
         self._position += n_new
         return outputs
@@ -205,20 +239,41 @@ class InferenceSession:
         if self._position + n_input_tokens > self._max_length:
             raise ValueError(f"Maximum length exceeded: prefix {self._position} + current {n_input_tokens} exceeds pre-allocated maximum {self._max_length}")
 
+        from petals_b200.parallel.fabric import get_fabric
+
+        fabric = get_fabric() if self._sequence_manager.config.use_server_to_server else None
         server_idx = 0
         block_idx = 0
         inputs = inputs.detach()
+        step_inputs = inputs
+        pushed = None  # (src_rank, (B, L, H)): the current activations live in the next stage's landing zone, not here
         while block_idx < self.num_blocks:
             for attempt_no in itertools.count():
                 logger.debug(f"Inference: block {block_idx}, attempt {attempt_no}")
                 server_session = None
                 try:
                     if not self._server_sessions or attempt_no >= 1:
+                        if attempt_no >= 1 and (pushed is not None or any(s.no_history for s in self._server_sessions)):
+                            # activations that travelled over the fabric were never seen by the client: rebuild the whole
+                            # chain and replay the first stage's input history through it
+                            inputs = self._full_history(step_inputs, n_input_tokens)
+                            self._exit_server_sessions(self._server_sessions)
+                            self._server_sessions, server_idx, block_idx, pushed = [], 0, 0, None
                         self._update_sequence(server_idx, block_idx, attempt_no)
                     server_session = self._server_sessions[server_idx]
                     assert server_session.position == self._position, f"Position mismatch: {server_session.position} and {self._position}"
                     span_prompts = prompts[server_session.span.start: server_session.span.end] if not is_dummy(prompts) else DUMMY
-                    inputs = server_session.step(inputs, span_prompts, hypo_ids, step_id=step_id, n_new=n_input_tokens)
+                    fabric_out = self._fabric_target(fabric, server_idx, inputs if pushed is None else pushed[1])
+                    if pushed is not None:
+                        result = server_session.step_pushed(pushed[1], pushed[0], span_prompts, hypo_ids, step_id=step_id, n_new=n_input_tokens,
+                                                            fabric_out=fabric_out)
+                    else:
+                        result = server_session.step(inputs, span_prompts, hypo_ids, step_id=step_id, n_new=n_input_tokens, fabric_out=fabric_out)
+                    if fabric_out is not None:
+                        shape = result if isinstance(result, tuple) else pushed[1]
+                        pushed = (server_session.fabric_rank, tuple(shape))
+                    else:
+                        inputs, pushed = result, None
                     server_idx += 1
                     block_idx = server_session.span.end
                     self._sequence_manager.on_request_success(server_session.span.peer_id)
@@ -234,9 +289,42 @@ class InferenceSession:
                                    f"(retry in {delay:.0f} sec): {e!r}")
                     maybe_log_traceback(e)
                     time.sleep(delay)
+        if pushed is not None:  # the last stage stored the result into this process's landing zone
+            B, L, H = pushed[1]
+            inputs = fabric.recv(B * L, "y_ret", pushed[0]).view(B, L, H)
         self._position += n_input_tokens
         outputs = inputs[:, -n_input_tokens:]
         return outputs.to(device=inputs_device, dtype=inputs_dtype)
+
+    def _fabric_target(self, fabric, server_idx: int, like) -> Optional[dict]:
+        """Where should server ``server_idx`` store its output? None = return it with the RPC (no fabric on that hop)."""
+        if fabric is None:
+            return None
+        cur = self._server_sessions[server_idx]
+        shape = tuple(like) if isinstance(like, tuple) else tuple(like.shape)
+        rows = shape[0] * shape[1]
+        if cur.fabric_rank is None or rows == 0 or rows > min(fabric.max_tokens, 4096) or shape[2] != fabric.hidden_size:
+            return None
+        if server_idx + 1 < len(self._server_sessions):
+            nxt = self._server_sessions[server_idx + 1]
+            if nxt.fabric_rank is None or nxt.fabric_rank == cur.fabric_rank:
+                return None
+            return dict(kind="x_in", rank=nxt.fabric_rank)
+        if cur.span.end == self.num_blocks and cur.fabric_rank != fabric.rank:
+            return dict(kind="y_ret", rank=fabric.rank)
+        return None
+
+    def _full_history(self, step_inputs: torch.Tensor, n_new: int) -> torch.Tensor:
+        """Everything the first stage has ever received in this session, ending with the current step's inputs."""
+        first = self._server_sessions[0] if self._server_sessions else None
+        hist = first.history if first is not None else None
+        if hist is None or self._position == 0:
+            if self._position > 0:
+                raise RuntimeError("cannot rebuild remote attention caches: the input history of the first stage is gone")
+            return step_inputs[:, step_inputs.shape[1] - n_new:]
+        if hist.shape[1] == self._position + n_new:
+            return hist
+        return torch.cat([hist[:, : self._position], step_inputs[:, step_inputs.shape[1] - n_new:].to(hist.device)], dim=1)
 
     def _update_sequence(self, server_idx: int, block_idx: int, attempt_no: int) -> int:
         """Replace the chain from ``server_idx`` on with a fresh route covering the failed span (reference :364-391).
@@ -257,7 +345,7 @@ class InferenceSession:
             new_session._position = self._position
             if i == 0 and old and old[0].history is not None:
                 new_session.history = old[0].history[:, : self._position] if self._position > 0 else None
-        if self._position > 0 and updated_sessions and updated_sessions[0].history is None:
+        if self._position > 0 and updated_sessions and updated_sessions[0].history is None and not (server_idx == 0 and block_idx == 0):
             raise RuntimeError("cannot rebuild a remote attention cache: no input history for the failed span")
         self._server_sessions[server_idx: server_idx + 1] = updated_sessions
         for a, b in zip(self._server_sessions[:-1], self._server_sessions[1:]):

@@ -43,7 +43,9 @@ struct GemmParams {
   int act, out_fp32;
   int n_push;
   void* push_out[PB_MAX_PEERS];
-  uint64_t* push_flag[PB_MAX_PEERS];
+  uint64_t* push_flag[PB_MAX_PEERS];       // per-tile release-increment (lets a consumer start on finished row blocks)
+  uint64_t* push_done_flag[PB_MAX_PEERS];  // ONE release-increment per launch, by the last CTA to finish all its tiles
+  unsigned int* done_counter;              // local self-resetting counter electing that last CTA
   const uint64_t* wait_flag;
   uint64_t wait_per_epoch;
   const uint64_t* epoch;
@@ -316,6 +318,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
+  if (p.n_push > 0 && p.done_counter != nullptr && threadIdx.x == 64) {
+    // every peer store of this CTA happened before the __syncthreads above; publish completion of the whole GEMM once
+    __threadfence_system();
+    const unsigned int prev = atomicAdd(p.done_counter, 1u);
+    if (prev == gridDim.x - 1) {
+      __threadfence_system();
+      *p.done_counter = 0u;
+      for (int rnk = 0; rnk < p.n_push; ++rnk)
+        if (p.push_done_flag[rnk] != nullptr) red_release_sys_add(p.push_done_flag[rnk], 1ull);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -392,7 +405,9 @@ static int launch_gemm(const PbGemmArgs* a, cudaStream_t stream) {
   for (int i = 0; i < a->n_push; ++i) {
     p.push_out[i] = a->push_out[i];
     p.push_flag[i] = static_cast<uint64_t*>(a->push_flag[i]);
+    p.push_done_flag[i] = static_cast<uint64_t*>(a->push_done_flag[i]);
   }
+  p.done_counter = static_cast<unsigned int*>(a->done_counter);
   p.wait_flag = static_cast<const uint64_t*>(a->wait_flag);
   p.wait_per_epoch = a->wait_per_epoch;
   p.epoch = static_cast<const uint64_t*>(a->epoch);

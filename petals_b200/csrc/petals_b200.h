@@ -43,6 +43,7 @@ typedef struct {
   // consumer side: wait for flag >= *epoch * wait_per_epoch before loading A
   const void* wait_flag; uint64_t wait_per_epoch; const void* epoch; void* error_flag;
   int num_sms; int block_n;   // 0 = auto
+  void* push_done_flag[PB_MAX_PEERS]; void* done_counter;  // once-per-launch completion flag (last CTA)
 } PbGemmArgs;
 int pb_gemm_bf16(const PbGemmArgs* a, void* stream);
 

@@ -144,7 +144,7 @@ def gemm(
     b_mn_major: bool = False, out: Optional[torch.Tensor] = None, out_fp32: bool = False, block_n: int = 0,
     wait_flag: Optional[int] = None, wait_per_epoch: int = 0, epoch: Optional[int] = None,
     push_out: Sequence[int] = (), push_flag: Sequence[int] = (), error_flag: Optional[int] = None,
-    store_local: bool = True,
+    store_local: bool = True, push_done_flag: Sequence[int] = (), done_counter: Optional[int] = None,
 ) -> torch.Tensor:
     """``out[M,N] = epilogue(a[M,K] @ op(b))`` on the tcgen05 tensor cores. See csrc/gemm_tcgen05.cu.
 
@@ -169,6 +169,8 @@ def gemm(
     for i, p in enumerate(push_out):
         g.push_out[i] = p
         g.push_flag[i] = push_flag[i] if i < len(push_flag) else None
+        g.push_done_flag[i] = push_done_flag[i] if i < len(push_done_flag) else None
+    g.done_counter = done_counter
     g.wait_flag, g.wait_per_epoch, g.epoch, g.error_flag = wait_flag, wait_per_epoch, epoch, error_flag
     g.num_sms = native.sm_count(a_.device.index)
     g.block_n = block_n

@@ -53,6 +53,7 @@ class GemmArgs(C.Structure):
         ("n_push", C.c_int), ("push_out", C.c_void_p * PB_MAX_PEERS), ("push_flag", C.c_void_p * PB_MAX_PEERS),
         ("wait_flag", C.c_void_p), ("wait_per_epoch", C.c_uint64), ("epoch", C.c_void_p), ("error_flag", C.c_void_p),
         ("num_sms", C.c_int), ("block_n", C.c_int),
+        ("push_done_flag", C.c_void_p * PB_MAX_PEERS), ("done_counter", C.c_void_p),
     ]
 
 

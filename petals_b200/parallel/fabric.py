@@ -1,0 +1,145 @@
+"""The NVLink activation fabric between pipeline stages (one process per GPU).
+
+In the reference every hop between servers is an RPC that drags the activation through host memory, protobuf and the
+libp2p daemon, and the router budgets 18 ms for it (src/petals/client/routing/sequence_manager.py:223).
+Here each worker process owns a *landing zone* in a CUDA-IPC symmetric heap:
+
+* ``x_in``  — where the previous stage's **last kernel** (down-projection GEMV or tcgen05 GEMM + residual) stores its
+  output tiles directly over NVLink (``push_out`` epilogue), followed by one release-increment of ``in_flag``;
+* ``y_ret`` — the same for the last stage returning the final hidden states to the client's GPU.
+
+The consuming stage's **first kernel** waits on the flag (``ld.acquire.sys``) — so the hop costs one NVLink store stream
+overlapped with the producer's math plus a flag latency, and the control RPC between processes carries *no tensor
+bytes* (only "your input is in your landing zone"). Flags are monotonic; every consumer keeps a device-resident count
+of consumed transfers (the "epoch" passed to the kernels), so nothing is ever reset and CUDA graphs stay valid.
+
+Created once per process by :func:`init_fabric` after ``torch.distributed`` is initialised; absent (``get_fabric()`` is
+None) in single-process / CPU runs, where stages exchange tensors by reference or over the Unix-socket transport."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from petals_b200.ops import native
+from petals_b200.parallel.symmetric import SymmetricHeap, ptr_array, tensor_from_ptr
+from petals_b200.utils.logging import get_logger
+
+logger = get_logger(__name__)
+_fabric: Optional["Fabric"] = None
+
+
+class Fabric:
+    def __init__(self, hidden_size: int, max_tokens: int = 8192, group=None, extra_bytes: int = 1 << 20):
+        self.hidden_size, self.max_tokens = hidden_size, max_tokens
+        zone = max_tokens * hidden_size * 2
+        self.heap = SymmetricHeap(2 * zone + extra_bytes, group=group)
+        self.rank, self.world, self.device = self.heap.rank, self.heap.world, self.heap.device
+        self.off_x_in = self.heap.alloc(zone)
+        self.off_y_ret = self.heap.alloc(zone)
+        self.off_flags = self.heap.alloc(64)
+        self.x_in = self.heap.tensor(self.off_x_in, (max_tokens, hidden_size), torch.bfloat16)
+        self.y_ret = self.heap.tensor(self.off_y_ret, (max_tokens, hidden_size), torch.bfloat16)
+        # device-resident counts of consumed transfers (one per landing zone) + producer-side election counter
+        self.in_epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.ret_epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.done_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._flag_src = torch.zeros(16, dtype=torch.uint8, device=self.device)
+        self._scratch_off = self.heap.alloc(64)
+        # back-pressure: a producer may not overwrite a landing zone before the consumer copied the previous transfer out.
+        # Every consumer acknowledges to the producer's ack flag; the pushing kernel's prologue waits for
+        # ack >= number of pushes issued so far (the flag starts at 1, so the first push never waits).
+        self.push_epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.heap.tensor(self.off_flags + 16, (1,), torch.int64).fill_(1)
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)
+
+    # ---- addresses ---------------------------------------------------------------------------------------------
+    def x_in_addr(self, rank: int) -> int:
+        return self.heap.addr(rank, self.off_x_in)
+
+    def y_ret_addr(self, rank: int) -> int:
+        return self.heap.addr(rank, self.off_y_ret)
+
+    def in_flag_addr(self, rank: int) -> int:
+        return self.heap.addr(rank, self.off_flags)
+
+    def ret_flag_addr(self, rank: int) -> int:
+        return self.heap.addr(rank, self.off_flags + 8)
+
+    def ack_flag_addr(self, rank: int) -> int:
+        return self.heap.addr(rank, self.off_flags + 16)
+
+    def begin_push(self) -> dict:
+        """Call right before launching a kernel whose epilogue pushes into a peer's landing zone: returns the prologue
+        wait arguments that implement the back-pressure described above."""
+        native.check(native.lib().pb_bump_epoch(self.push_epoch.data_ptr(), native.stream_ptr()), "bump_epoch")
+        return dict(wait_flag=self.ack_flag_addr(self.rank), wait_per_epoch=1, epoch=self.push_epoch.data_ptr(), error_flag=self.err.data_ptr())
+
+    def take(self, M: int, kind: str, src_rank: int, out: torch.Tensor) -> torch.Tensor:
+        """Consume the next transfer into this rank's ``kind`` zone: wait, copy the rows out, acknowledge to ``src_rank``."""
+        self.wait(kind)
+        buf = self.y_ret if kind == "y_ret" else self.x_in
+        out.copy_(buf[:M])
+        self._signal(self.ack_flag_addr(src_rank), src_rank)
+        return out
+
+    def _signal(self, flag_addr: int, rank: int) -> None:
+        scratch = ptr_array([self.heap.addr(rank, self._scratch_off)])
+        native.check(native.lib().pb_push_rows(self._flag_src.data_ptr(), scratch, ptr_array([flag_addr]), 1, 16, native.stream_ptr()), "fabric signal")
+
+    def zone(self, kind: str, rank: int):
+        """(data address, flag address) of a landing zone on ``rank``."""
+        if kind == "x_in":
+            return self.x_in_addr(rank), self.in_flag_addr(rank)
+        if kind == "y_ret":
+            return self.y_ret_addr(rank), self.ret_flag_addr(rank)
+        raise ValueError(kind)
+
+    # ---- host-issued transfers (client -> first stage; anything not produced by a fused epilogue) ---------------------
+    def send(self, rows: torch.Tensor, rank: int, kind: str = "x_in") -> None:
+        """Copy ``rows`` [M, H] into a landing zone of ``rank`` and publish it (stream ordered)."""
+        M = rows.shape[0]
+        if M > self.max_tokens:
+            raise ValueError(f"{M} rows exceed the fabric landing zone ({self.max_tokens})")
+        data, flag = self.zone(kind, rank)
+        dst = tensor_from_ptr(data, (M, self.hidden_size), torch.bfloat16, self.device)
+        kw = self.begin_push()  # honour back-pressure like the fused pushes do
+        native.check(native.lib().pb_wait_flag(kw["wait_flag"], kw["epoch"], 1, 0, kw["error_flag"], native.stream_ptr()), "wait_flag")
+        dst.copy_(rows.reshape(M, self.hidden_size))  # P2P memcpy over NVLink
+        self._signal(flag, rank)
+
+    def wait(self, kind: str = "y_ret") -> None:
+        """Enqueue a wait for the next transfer into this rank's zone (advances the zone's epoch)."""
+        epoch = self.ret_epoch if kind == "y_ret" else self.in_epoch
+        _, flag = self.zone(kind, self.rank)
+        lib = native.lib()
+        native.check(lib.pb_bump_epoch(epoch.data_ptr(), native.stream_ptr()), "bump_epoch")
+        native.check(lib.pb_wait_flag(flag, epoch.data_ptr(), 1, 0, self.err.data_ptr(), native.stream_ptr()), "wait_flag")
+
+    def recv(self, M: int, kind: str, src_rank: int) -> torch.Tensor:
+        out = torch.empty(M, self.hidden_size, dtype=torch.bfloat16, device=self.device)
+        return self.take(M, kind, src_rank, out)
+
+    def check_errors(self) -> None:
+        if int(self.err.item()):
+            self.err.zero_()
+            raise RuntimeError(f"rank {self.rank}: a fabric flag wait timed out (a peer stage is gone or stalled)")
+
+    def close(self) -> None:
+        self.heap.close()
+
+
+def init_fabric(hidden_size: int, max_tokens: int = 8192, group=None) -> Optional[Fabric]:
+    """Collective over ``group``. Returns None when there is nothing to connect (single process or no CUDA)."""
+    global _fabric
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2 or not torch.cuda.is_available():
+        return None
+    _fabric = Fabric(hidden_size, max_tokens, group)
+    return _fabric
+
+
+def get_fabric() -> Optional[Fabric]:
+    return _fabric

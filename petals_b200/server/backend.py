@@ -119,13 +119,23 @@ class Stage:
         return grad, grad_prompts
 
     def inference_step(self, session: SessionCache, hidden: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None,
-                       hypo_ids: Optional[torch.Tensor] = None, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
+                       hypo_ids: Optional[torch.Tensor] = None, lo: int = 0, hi: Optional[int] = None,
+                       take_from: Optional[tuple] = None, push_to: Optional[tuple] = None) -> torch.Tensor:
         hi = len(self.blocks) if hi is None else hi
         hidden = hidden.to(self.device)
         prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device) for p in prompts]
         if self.engine is not None and self._lora_free():
+            if take_from is not None or push_to is not None:
+                return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi), take_from=take_from, push_to=push_to)
             return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi))
-        return self._oracle_inference(session, hidden, prompts, hypo_ids, lo, hi)
+        if take_from is not None:  # executors without fused hops still honour the fabric protocol (host-issued copies)
+            fabric, src_rank, B, T = take_from
+            hidden = fabric.recv(B * T, "x_in", src_rank).view(B, T, -1)
+        out = self._oracle_inference(session, hidden, prompts, hypo_ids, lo, hi)
+        if push_to is not None:
+            push_to[0].send(out.reshape(-1, out.shape[-1]).to(torch.bfloat16), push_to[2], push_to[1])
+            return out[:, :0]
+        return out
 
     def _lora_free(self) -> bool:
         return self.active_adapter is None
@@ -215,9 +225,10 @@ class _MergedInferenceStep:
         self.stage = stage
 
     def __call__(self, hidden: torch.Tensor, hypo_ids: Optional[torch.Tensor], session: SessionCache, lo: int, hi: int,
-                 prompts: Optional[Sequence[torch.Tensor]], active_adapter: Optional[str]) -> torch.Tensor:
+                 prompts: Optional[Sequence[torch.Tensor]], active_adapter: Optional[str], take_from: Optional[tuple] = None,
+                 push_to: Optional[tuple] = None) -> torch.Tensor:
         self.stage.use_adapter(active_adapter)
-        return self.stage.inference_step(session, hidden, prompts, hypo_ids, lo, hi)
+        return self.stage.inference_step(session, hidden, prompts, hypo_ids, lo, hi, take_from=take_from, push_to=push_to)
 
 
 def merge_inference_pools_inplace(backends: Dict[str, TransformerBackend], stage: Stage, runtime: Optional[Runtime], max_batch_size: int) -> PrioritizedTaskPool:

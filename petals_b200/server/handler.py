@@ -117,6 +117,23 @@ class InferenceStream:
                 hidden = pushed[0]
                 prompts = pushed[1] if len(pushed) > 1 else prompts
                 hypo_ids = pushed[2] if len(pushed) > 2 else hypo_ids
+        # NVLink fabric (parallel/fabric.py): the input may already sit in this rank's landing zone, and/or the output
+        # may have to be stored straight into the next stage's (or the client's) landing zone by the span's last kernel
+        from petals_b200.parallel.fabric import get_fabric
+
+        fabric = get_fabric()
+        fin, fout = metadata.get("fabric_in"), metadata.get("fabric_out")
+        take_from = push_to = None
+        if fin is not None:
+            if fabric is None:
+                raise RuntimeError("this stage has no NVLink fabric but the request says its input was pushed")
+            take_from = (fabric, int(fin["src_rank"]), int(fin["B"]), int(fin["T"]))
+            hidden = torch.empty(int(fin["B"]), int(fin["T"]), self.handler.stage.spec.hidden_size, dtype=self.handler.stage.dtype,
+                                 device=self.handler.stage.device)  # shape carrier only
+        if fout is not None:
+            if fabric is None:
+                raise RuntimeError("this stage has no NVLink fabric but the request asks to push its output")
+            push_to = (fabric, str(fout["kind"]), int(fout["rank"]))
         if hidden.dim() != 3:
             raise ValueError(f"hidden states must be [batch, seq, hidden], got {tuple(hidden.shape)}")
         B, T, H = hidden.shape
@@ -144,8 +161,8 @@ class InferenceStream:
             hypo_ids = None
         priority = self.handler.prioritizer.prioritize(hidden, hypo_ids, points=self.points / max(n, 1), type="inference")
         h = self.handler
-        if B * T <= MAX_SHORT_INFERENCE_TOKENS or n == 1:
-            fut = h.inference_pool.submit_task(hidden, hypo_ids, cache, self.lo, self.hi, block_prompts, self.active_adapter,
+        if B * T <= MAX_SHORT_INFERENCE_TOKENS or n == 1 or take_from is not None or push_to is not None:
+            fut = h.inference_pool.submit_task(hidden, hypo_ids, cache, self.lo, self.hi, block_prompts, self.active_adapter, take_from, push_to,
                                                priority=priority, size=B * T)
             out = fut.result(timeout=h.step_timeout)
         else:
@@ -276,7 +293,15 @@ class TransformerConnectionHandler:
             forward_schema=dict(args=("hidden_states", "prompts"), hidden_size=spec.hidden_size),
             outputs_schema=dict(hidden_size=spec.hidden_size),
             inference_schema=dict(args=("hidden_states", "prompts", "hypo_ids"), hidden_size=spec.hidden_size),
-            device=str(self.stage.device), engine="sm_100a" if self.stage.engine is not None else "oracle")
+            device=str(self.stage.device), engine="sm_100a" if self.stage.engine is not None else "oracle",
+            fabric_rank=self._fabric_rank())
+
+    @staticmethod
+    def _fabric_rank() -> Optional[int]:
+        from petals_b200.parallel.fabric import get_fabric
+
+        fabric = get_fabric()
+        return None if fabric is None else fabric.rank
 
     def shutdown(self) -> None:
         with self._sessions_lock:

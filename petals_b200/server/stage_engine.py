@@ -114,7 +114,22 @@ class StageEngine:
                            alibi_slopes=self.slopes, window=s.sliding_window)
         return attn
 
-    def _block_decode(self, x: torch.Tensor, out: torch.Tensor, slot: int, B: int, T: int, table, pos_ptr, pools, splits) -> torch.Tensor:
+    def _push_kwargs(self, hop: Optional[tuple], gemm: bool = False) -> dict:
+        """Epilogue/prologue arguments that turn the span's last kernel into the fused stage hop (see parallel/fabric.py)."""
+        if hop is None:
+            return {}
+        fabric, kind, rank = hop
+        data, flag = fabric.zone(kind, rank)
+        kw = fabric.begin_push()
+        kw.update(push_out=[data], done_counter=fabric.done_counter.data_ptr())
+        if gemm:
+            kw["push_done_flag"] = [flag]
+        else:
+            kw["push_flag"] = [flag]
+        return kw
+
+    def _block_decode(self, x: torch.Tensor, out: torch.Tensor, slot: int, B: int, T: int, table, pos_ptr, pools, splits,
+                      hop: Optional[tuple] = None) -> torch.Tensor:
         """x, out: [M, H] ping-pong residual buffers. Returns the buffer holding the block output."""
         s, w = self.spec, self.blocks[slot]
         M = B * T
@@ -137,10 +152,11 @@ class StageEngine:
             act = Fn.linear_decode(mlp_in, w.w_up, bias=w._p("b_up"), act=self.act, norm_weight=ln_w, norm_bias=ln_b,
                                    norm_kind=self.norm_kind, eps=eps, out=self._buf("act", M, s.intermediate_size))
         # down projection + residual; write into x's buffer (x is dead for sequential blocks, and for
-        # parallel blocks h1 already contains x + attn)
-        return Fn.linear_decode(act, w.w_down, bias=w._p("b_down"), residual=h1, out=x)
+        # parallel blocks h1 already contains x + attn). With `hop`, the same epilogue also stores the rows into the
+        # next stage's landing zone over NVLink and publishes its flag: the stage hop costs no extra kernel.
+        return Fn.linear_decode(act, w.w_down, bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop))
 
-    def _block_prefill(self, x: torch.Tensor, slot: int, B: int, T: int, table, pos_ptr, pools) -> torch.Tensor:
+    def _block_prefill(self, x: torch.Tensor, slot: int, B: int, T: int, table, pos_ptr, pools, hop: Optional[tuple] = None) -> torch.Tensor:
         """x: [M, H] (overwritten with the block output)."""
         s, w = self.spec, self.blocks[slot]
         M = B * T
@@ -161,7 +177,7 @@ class StageEngine:
             act = Fn.gemm(xn2, w.w_gate, b2=w.w_up, act=Fn.ACT_SWIGLU, out=act_buf)
         else:
             act = Fn.gemm(xn2, w.w_up, bias=w._p("b_up"), act=self.act, out=act_buf)
-        return Fn.gemm(act, w.w_down, bias=w._p("b_down"), residual=h1, out=x)
+        return Fn.gemm(act, w.w_down, bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop, gemm=True))
 
     def _moe(self, h1: torch.Tensor, w: GenericBlock) -> torch.Tensor:
         """h1 = residual stream after attention [B,T,H]; returns h1 + MoE(ln2(h1)). Oracle math on the engine's weights."""
@@ -181,25 +197,40 @@ class StageEngine:
             self._dev_pos = session.position
         return table
 
-    def _run_span(self, x: torch.Tensor, B: int, T: int, lo: int, hi: int, table, pos_ptr, pools_of, prompts, decode: bool, splits: int) -> torch.Tensor:
+    def _run_span(self, x: torch.Tensor, B: int, T: int, lo: int, hi: int, table, pos_ptr, pools_of, prompts, decode: bool, splits: int,
+                  hop: Optional[tuple] = None) -> torch.Tensor:
         M = B * T
         other = self._buf("h_alt", M, self.spec.hidden_size) if decode else None
         cur = x
         for slot in range(lo, hi):
             if prompts is not None and not is_dummy(prompts[slot - lo]):
                 Fn.add_prompts(cur.view(B, T, -1), prompts[slot - lo])
+            fused_hop = hop if (slot == hi - 1 and self.spec.mlp != "moe") else None
             if decode:
-                nxt = self._block_decode(cur, other, slot, B, T, table, pos_ptr, pools_of(slot), splits)
+                nxt = self._block_decode(cur, other, slot, B, T, table, pos_ptr, pools_of(slot), splits, fused_hop)
                 if nxt is not cur:  # MoE path returned the alternate buffer
                     cur, other = nxt, cur
             else:
-                cur = self._block_prefill(cur, slot, B, T, table, pos_ptr, pools_of(slot))
+                cur = self._block_prefill(cur, slot, B, T, table, pos_ptr, pools_of(slot), fused_hop)
+        if hop is not None and self.spec.mlp == "moe":  # no fused epilogue for this family yet: host-issued NVLink copy
+            hop[0].send(cur, hop[2], hop[1])
         return cur
 
     def inference_step(self, session: SessionCache, hidden: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None,
-                       hypo_ids: Optional[torch.Tensor] = None, block_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
-        """One rpc_inference step through blocks [lo, hi) of this stage (reference: backend.py:111-144)."""
+                       hypo_ids: Optional[torch.Tensor] = None, block_range: Optional[Tuple[int, int]] = None,
+                       take_from: Optional[tuple] = None, push_to: Optional[tuple] = None) -> torch.Tensor:
+        """One rpc_inference step through blocks [lo, hi) of this stage (reference: backend.py:111-144).
+
+        ``take_from = (fabric, src_rank, B, T)``: the input was pushed into this rank's landing zone by ``src_rank``'s last
+        kernel (``hidden`` is then only a shape carrier). ``push_to = (fabric, kind, rank)``: the span's last kernel stores
+        its output into that rank's landing zone; the returned tensor is then empty."""
         lo, hi = block_range or (0, self.n_blocks)
+        if take_from is not None:
+            fabric, src_rank, B, T = take_from
+            H = self.spec.hidden_size
+            staged = self._buf("x_taken", B * T, H)
+            fabric.take(B * T, "x_in", src_rank, staged)
+            hidden = staged.view(B, T, H)
         B, T, H = hidden.shape
         if hypo_ids is not None and not is_dummy(hypo_ids):
             session.reorder(hypo_ids)
@@ -211,6 +242,12 @@ class StageEngine:
         has_prompts = prompts is not None and any(not is_dummy(p) for p in prompts)
         # chunked prefill: the chunk is also the unit a downstream stage can start on
         max_t = max(1, self.max_chunk_tokens // B)
+        if push_to is not None:
+            if T > max_t or B * T > push_to[0].max_tokens:
+                raise ValueError("a fused stage hop needs the whole step in one chunk; split the input on the client")
+            self._step_chunk(session, hidden, [p[:, :T] if (p is not None and not is_dummy(p)) else None for p in prompts] if has_prompts else None,
+                             lo, hi, push_to)
+            return hidden[:, :0]
         for t0 in range(0, T, max_t):
             t1 = min(T, t0 + max_t)
             chunk = hidden[:, t0:t1]
@@ -222,7 +259,7 @@ class StageEngine:
             out[:, t0:t1] = self._step_chunk(session, chunk, cp, lo, hi)
         return out
 
-    def _step_chunk(self, session: SessionCache, hidden: torch.Tensor, prompts, lo: int, hi: int) -> torch.Tensor:
+    def _step_chunk(self, session: SessionCache, hidden: torch.Tensor, prompts, lo: int, hi: int, hop: Optional[tuple] = None) -> torch.Tensor:
         B, T, H = hidden.shape
         M = B * T
         session.prepare_write(T)
@@ -231,10 +268,10 @@ class StageEngine:
         pools_of = self.cache.layer_pools
         decode = M <= MAX_DECODE_ROWS
         if decode and self.use_cuda_graphs and prompts is None and self.spec.mlp != "moe":
-            key = (B, T, lo, hi)
+            key = (B, T, lo, hi) if hop is None else (B, T, lo, hi, hop[1], hop[2])
             g = self._graphs.get(key)
             if g is None:
-                g = self._capture(B, T, lo, hi, table)
+                g = self._capture(B, T, lo, hi, table, hop)
             g["x"].copy_(hidden.reshape(M, H))
             g["graph"].replay()
             native.add_launches(g["launches"])
@@ -243,14 +280,14 @@ class StageEngine:
             x = self._buf("x_in" if decode else "x_in_p", M, H)
             x.copy_(hidden.reshape(M, H))
             splits = self._splits(B, T) if decode else 1
-            y = self._run_span(x, B, T, lo, hi, table, pos_ptr, pools_of, prompts, decode, splits)
+            y = self._run_span(x, B, T, lo, hi, table, pos_ptr, pools_of, prompts, decode, splits, hop)
             native.check(native.lib().pb_advance_pos(pos_ptr, T, native.stream_ptr()), "advance_pos")
             result = y.view(B, T, H).clone()
         session.set_position(session.position + T, sync_device=False)
         self._dev_pos = session.position
         return result
 
-    def _capture(self, B: int, T: int, lo: int, hi: int, table: torch.Tensor) -> dict:
+    def _capture(self, B: int, T: int, lo: int, hi: int, table: torch.Tensor, hop: Optional[tuple] = None) -> dict:
         """Capture the decode step of blocks [lo, hi) for a (B, T) shape into a CUDA graph."""
         M, H = B * T, self.spec.hidden_size
         x = torch.zeros(M, H, dtype=self.dtype, device=self.device)
@@ -261,15 +298,18 @@ class StageEngine:
         def run():
             xin = self._buf("x_in", M, H)
             xin.copy_(x)
-            y = self._run_span(xin, B, T, lo, hi, table, pos_ptr, self.cache.layer_pools, None, True, splits)
+            y = self._run_span(xin, B, T, lo, hi, table, pos_ptr, self.cache.layer_pools, None, True, splits, cap_hop[0])
             native.check(native.lib().pb_advance_pos(pos_ptr, T, native.stream_ptr()), "advance_pos")
             return y
 
-        # warm-up on a side stream (sets kernel attributes, allocates buffers), then capture
+        # warm-up on a side stream (sets kernel attributes, allocates buffers), then capture. The warm-up runs WITHOUT the
+        # hop: a push would consume a transfer slot on the peer.
+        cap_hop = [None]
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             run()
+        cap_hop[0] = hop
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.pos_static.copy_(saved_pos)
@@ -281,7 +321,7 @@ class StageEngine:
         native.add_launches(-launches)  # captured, not executed
         self.pos_static.copy_(saved_pos)  # capture does not execute, but keep the invariant explicit
         g = dict(graph=graph, x=x, out=out, launches=launches)
-        self._graphs[(B, T, lo, hi)] = g
+        self._graphs[(B, T, lo, hi) if hop is None else (B, T, lo, hi, hop[1], hop[2])] = g
         logger.debug(f"captured decode graph B={B} T={T} blocks [{lo},{hi}) splits={splits}")
         return g
 

@@ -1,0 +1,40 @@
+"""Launch one hot kernel a few times at a Llama-3-70B shape (for `ncu -k regex:... -s N -c 1`)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from petals_b200.ops import functional as Fn  # noqa: E402
+
+which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+torch.manual_seed(0)
+if which == "gemm":  # gate/up projection with fused SwiGLU, 8192 tokens
+    a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    wg = torch.randn(28672, 8192, device="cuda", dtype=torch.bfloat16) * 0.01
+    wu = torch.randn(28672, 8192, device="cuda", dtype=torch.bfloat16) * 0.01
+    for _ in range(4):
+        Fn.gemm(a, wg, b2=wu, act=Fn.ACT_SWIGLU)
+elif which == "gemm_plain":
+    a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    w = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16) * 0.01
+    for _ in range(4):
+        Fn.gemm(a, w)
+elif which == "gemv":  # decode gate/up with fused RMSNorm + SwiGLU, 1 token
+    x = torch.randn(1, 8192, device="cuda", dtype=torch.bfloat16)
+    g = torch.ones(8192, device="cuda", dtype=torch.bfloat16)
+    ws = [(torch.randn(28672, 8192, device="cuda", dtype=torch.bfloat16) * 0.01, torch.randn(28672, 8192, device="cuda", dtype=torch.bfloat16) * 0.01) for _ in range(2)]
+    for i in range(4):
+        Fn.linear_decode(x, ws[i % 2][0], w2=ws[i % 2][1], act=Fn.ACT_SWIGLU, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+elif which == "attn":  # prefill attention, 4096 tokens, GQA 64/8
+    B, T, Hq, Hkv, D = 1, 4096, 64, 8, 128
+    pages = T // Fn.PAGE
+    k_pool = torch.randn(pages, Hkv, Fn.PAGE, D, device="cuda", dtype=torch.bfloat16)
+    v_pool = torch.randn_like(k_pool)
+    table = torch.arange(pages, dtype=torch.int32, device="cuda").view(1, pages)
+    q = torch.randn(B * T, Hq * D, device="cuda", dtype=torch.bfloat16)
+    out = torch.empty_like(q)
+    for _ in range(3):
+        Fn.paged_attention(q, k_pool, v_pool, table, None, out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, pos_static=0)
+torch.cuda.synchronize()
+print("done", which)
