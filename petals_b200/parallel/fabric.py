@@ -108,7 +108,7 @@ class Fabric:
         dst = tensor_from_ptr(data, (M, self.hidden_size), torch.bfloat16, self.device)
         kw = self.begin_push()  # honour back-pressure like the fused pushes do
         native.check(native.lib().pb_wait_flag(kw["wait_flag"], kw["epoch"], 1, 0, kw["error_flag"], native.stream_ptr()), "wait_flag")
-        dst.copy_(rows.reshape(M, self.hidden_size))  # P2P memcpy over NVLink
+        dst.copy_(rows.reshape(M, self.hidden_size).to(torch.bfloat16))  # P2P memcpy over NVLink
         self._signal(flag, rank)
 
     def wait(self, kind: str = "y_ret") -> None:
@@ -132,12 +132,95 @@ class Fabric:
         self.heap.close()
 
 
-def init_fabric(hidden_size: int, max_tokens: int = 8192, group=None) -> Optional[Fabric]:
-    """Collective over ``group``. Returns None when there is nothing to connect (single process or no CUDA)."""
+class HostFabric:
+    """The same protocol over POSIX shared memory, for CPU processes (gloo): lets the multi-process plumbing tests exercise
+    the fabric code paths of the client and the handlers (landing zones, flags, acknowledgements) without GPUs."""
+
+    def __init__(self, hidden_size: int, max_tokens: int = 1024, group=None, dtype: torch.dtype = torch.float32):
+        import time
+        from multiprocessing import shared_memory
+
+        import numpy as np
+
+        self.hidden_size, self.max_tokens, self.dtype = hidden_size, max_tokens, dtype
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device("cpu")
+        self._time, self._np = time, np
+        itemsize = torch.empty(0, dtype=dtype).element_size()
+        self._zone_bytes = max_tokens * hidden_size * itemsize
+        per_rank = 2 * self._zone_bytes + 64
+        names = [None]
+        if self.rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=per_rank * self.world)
+            self._shm.buf[: per_rank * self.world] = b"\x00" * (per_rank * self.world)
+            names[0] = self._shm.name
+        dist.broadcast_object_list(names, src=0, group=group)
+        if self.rank != 0:
+            self._shm = shared_memory.SharedMemory(name=names[0], create=False)
+        self._per_rank = per_rank
+        self._consumed = {"x_in": 0, "y_ret": 0}
+        self._pushes = 0
+        for r in range(self.world):
+            self._flags(r)[2] = 1  # ack flags start at 1 (first push never waits)
+        dist.barrier(group=group)
+
+    def _flags(self, rank: int):
+        off = rank * self._per_rank + 2 * self._zone_bytes
+        return self._np.ndarray((8,), dtype=self._np.uint64, buffer=self._shm.buf, offset=off)
+
+    def _zone(self, kind: str, rank: int, rows: int) -> torch.Tensor:
+        off = rank * self._per_rank + (0 if kind == "x_in" else self._zone_bytes)
+        itemsize = torch.empty(0, dtype=self.dtype).element_size()
+        flat = torch.frombuffer(self._shm.buf, dtype=self.dtype, count=rows * self.hidden_size, offset=off)
+        return flat.view(rows, self.hidden_size)
+
+    def _spin(self, rank: int, idx: int, target: int, what: str, timeout: float = 30.0) -> None:
+        deadline = self._time.monotonic() + timeout
+        while int(self._flags(rank)[idx]) < target:
+            if self._time.monotonic() > deadline:
+                raise TimeoutError(f"rank {self.rank}: timed out waiting for {what}")
+            self._time.sleep(0)
+
+    def send(self, rows: torch.Tensor, rank: int, kind: str = "x_in") -> None:
+        M = rows.shape[0]
+        if M > self.max_tokens:
+            raise ValueError(f"{M} rows exceed the fabric landing zone ({self.max_tokens})")
+        self._pushes += 1
+        self._spin(self.rank, 2, self._pushes, "the consumer's acknowledgement")
+        self._zone(kind, rank, M).copy_(rows.reshape(M, self.hidden_size).to(self.dtype))
+        self._flags(rank)[0 if kind == "x_in" else 1] += 1
+
+    def take(self, M: int, kind: str, src_rank: int, out: torch.Tensor) -> torch.Tensor:
+        self._consumed[kind] += 1
+        self._spin(self.rank, 0 if kind == "x_in" else 1, self._consumed[kind], f"a transfer into {kind}")
+        out.copy_(self._zone(kind, self.rank, M))
+        self._flags(src_rank)[2] += 1
+        return out
+
+    def recv(self, M: int, kind: str, src_rank: int) -> torch.Tensor:
+        return self.take(M, kind, src_rank, torch.empty(M, self.hidden_size, dtype=self.dtype))
+
+    def check_errors(self) -> None:
+        pass
+
+    def close(self) -> None:
+        try:
+            self._shm.close()
+            if self.rank == 0:
+                self._shm.unlink()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+def init_fabric(hidden_size: int, max_tokens: int = 8192, group=None, host_dtype: torch.dtype = torch.float32):
+    """Collective over ``group``. Returns None when there is nothing to connect (single process)."""
     global _fabric
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2 or not torch.cuda.is_available():
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
         return None
-    _fabric = Fabric(hidden_size, max_tokens, group)
+    if torch.cuda.is_available():
+        _fabric = Fabric(hidden_size, max_tokens, group)
+    else:
+        _fabric = HostFabric(hidden_size, min(max_tokens, 1024), group, host_dtype)
     return _fabric
 
 

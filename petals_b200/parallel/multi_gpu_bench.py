@@ -19,6 +19,8 @@ BASELINE_TOKENS_PER_S = 6.0
 
 
 def run_multi_gpu(args) -> None:
+    if str(args.parallelism).startswith("pp"):
+        return run_pipeline(args)
     from petals_b200.data_structures import ModelInfo, ServerInfo, ServerState
     from petals_b200.ops import functional as Fn
     from petals_b200.ops import native
@@ -179,3 +181,103 @@ def follower_loop_with_marks(engine, cache, ring, consumer: int) -> dict:
     torch.cuda.synchronize()
     engine.check_errors()
     return marks
+
+
+def run_pipeline(args) -> None:
+    """N pipeline stages (one per GPU) joined by the fused NVLink stage hop; single stream through the public client API."""
+    import tempfile
+
+    from petals_b200.ops import functional as Fn
+    from petals_b200.ops import native
+    from petals_b200.parallel.fabric import init_fabric
+    from petals_b200.parallel.swarm import FileSwarm
+    from petals_b200.parallel.symmetric import measure_hop_latency, measure_peer_bandwidth
+    from petals_b200.utils.auto_config import AutoDistributedConfig
+    from petals_b200.utils.peaks import NVLINK_PEER_GBS, measured_peaks
+    from petals_b200.utils.random_model import MODEL_PRESETS, launch_random_stage, random_client_model, write_config_only
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=dev)
+    native.lib()
+    path = write_config_only(args.model)
+    config = AutoDistributedConfig.from_pretrained(path)
+    n_layers = MODEL_PRESETS[args.model]["num_hidden_layers"]
+    fabric = init_fabric(config.hidden_size, max_tokens=4096)
+    probe = fabric.heap.alloc(8)
+    peer_gbs = measure_peer_bandwidth(fabric.heap, 0, 1, nbytes=fabric.heap.nbytes // 2)
+    hop_us = measure_hop_latency(fabric.heap, probe, 0, 1)
+    dirs = [tempfile.mkdtemp(prefix="pb200-bench-") if rank == 0 else None]
+    dist.broadcast_object_list(dirs, src=0)
+    swarm = FileSwarm(dirs[0])
+    bounds = [round(i * n_layers / world) for i in range(world + 1)]
+    t0 = time.time()
+    stage = launch_random_stage(path, range(bounds[rank], bounds[rank + 1]), swarm, dev, peer_id=f"stage{rank}", attn_cache_tokens=args.seq_len + 256,
+                                inference_max_length=args.seq_len, max_batch_size=1 << 20)
+    torch.cuda.synchronize()
+    dist.barrier()
+    build_s = time.time() - t0
+    K, W = args.steps, max(args.warmup, 3)
+    if rank == 0:
+        from bench import ClockSampler
+
+        model = random_client_model(path, swarm, dev)
+        vocab = model.config.vocab_size
+        prompt = torch.randint(0, vocab, (1, args.prompt_len), device=dev)
+        pinned_in = torch.zeros(1, 1, dtype=torch.int64).pin_memory()
+        pinned_out = torch.zeros(1, dtype=torch.int64).pin_memory()
+        with torch.inference_mode(), model.inference_session(max_length=args.seq_len) as sess:
+            tok = model(input_ids=prompt).logits[:, -1].argmax(-1, keepdim=True)
+            for _ in range(W):
+                tok = model(input_ids=tok).logits[:, -1].argmax(-1, keepdim=True)
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            torch.cuda.synchronize()
+            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            launches0 = native.launch_count
+            start.record()
+            for _ in range(K):
+                tok = Fn.argmax(model(input_ids=tok).logits[:, -1])[:, None]
+            end.record()
+            torch.cuda.synchronize()
+            launches = native.launch_count - launches0
+            ms = start.elapsed_time(end)  # rank 0 waits for the last stage's result every step: this IS the max over ranks
+            clocks = sampler.stop()
+            pinned_in.copy_(tok.cpu())
+            t1 = time.perf_counter()
+            for _ in range(K):
+                ids = pinned_in.to(dev, non_blocking=True)
+                nxt = Fn.argmax(model(input_ids=ids).logits[:, -1])
+                pinned_out.copy_(nxt, non_blocking=True)
+                torch.cuda.synchronize()
+                pinned_in[0, 0] = pinned_out[0]
+            e2e_s = time.perf_counter() - t1
+            over_fabric = [s.no_history for s in sess._server_sessions]
+        fabric.check_errors()
+        value = K / (ms / 1e3)
+        peaks = measured_peaks()
+        spec = config.block_spec()
+        result = {
+            "metric": "Llama-3-70B single-stream decode tokens/s (device-timed, max over ranks)",
+            "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",
+            "data": "synthetic token ids; random-init weights of the named architecture",
+            "config": {"model": args.model, "global_batch": 1, "seq_len": args.seq_len,
+                       "parallelism": f"pp{world} ({world} stages x {n_layers // world} blocks, fused GEMV-epilogue NVLink stage hop)",
+                       "l2": "each step streams every stage's full weight span (>> 126 MB L2): inputs larger than L2", "build_s": round(build_s, 1),
+                       "inputs_over_fabric": over_fabric},
+            "clocks": clocks, "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8},
+            "gpu_launches": launches,
+            "stage_hop": {"peer_store_GBps": None if peer_gbs is None else round(peer_gbs, 1),
+                          "frac_of_measured_peer_copy": None if peer_gbs is None else round(peer_gbs / NVLINK_PEER_GBS, 3),
+                          "flag_latency_us": None if hop_us is None else round(hop_us, 2), "hop_payload_bytes": spec.hidden_size * 2,
+                          "hops_per_token": world, "reference_hop_model_ms": 18.0},
+        }
+        print(json.dumps(result))
+    dist.barrier()
+    stage.shutdown()
+    dist.barrier()
+    fabric.close()
+    dist.destroy_process_group()

@@ -133,7 +133,7 @@ class Stage:
             hidden = fabric.recv(B * T, "x_in", src_rank).view(B, T, -1)
         out = self._oracle_inference(session, hidden, prompts, hypo_ids, lo, hi)
         if push_to is not None:
-            push_to[0].send(out.reshape(-1, out.shape[-1]).to(torch.bfloat16), push_to[2], push_to[1])
+            push_to[0].send(out.reshape(-1, out.shape[-1]), push_to[2], push_to[1])
             return out[:, :0]
         return out
 

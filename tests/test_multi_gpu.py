@@ -1,4 +1,5 @@
-"""Tensor-parallel engine numerics on >= 2 GPUs (spawns torch.distributed.run; skipped on single-GPU boxes)."""
+"""Multi-GPU numerics: tensor-parallel engine and the fused pipeline stage hop (spawn torch.distributed.run; skipped on
+single-GPU boxes)."""
 import json
 import os
 import subprocess
@@ -19,3 +20,13 @@ def test_tp2_matches_oracle():
     lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
     assert proc.returncode == 0 and lines, proc.stdout[-2000:] + proc.stderr[-2000:]
     assert json.loads(lines[-1])["tp_selftest"] == "ok"
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_pp2_fused_stage_hop_matches_oracle():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29732",
+           os.path.join(ROOT, "tools", "pp_selftest.py")]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
+    assert proc.returncode == 0 and lines, proc.stdout[-2000:] + proc.stderr[-2000:]
+    assert json.loads(lines[-1])["pp_selftest"] == "ok"

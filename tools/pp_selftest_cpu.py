@@ -1,0 +1,69 @@
+"""CPU twin of tools/pp_selftest.py (gloo + HostFabric): checks the fabric *protocol* end to end — landing zones, flags,
+acknowledgements, tensor-less control RPCs, full-chain replay — with oracle executors. Launched by tests/test_fabric_cpu.py."""
+import json
+import os
+import sys
+import tempfile
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    from petals_b200.parallel.fabric import init_fabric
+    from petals_b200.parallel.swarm import FileSwarm
+    from petals_b200.server.from_pretrained import load_pretrained_block
+    from petals_b200.server.server import Server
+    from petals_b200.utils.auto_config import AutoDistributedConfig, AutoDistributedModelForCausalLM
+
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    dist.init_process_group(backend="gloo")
+    path = sys.argv[1]
+    config = AutoDistributedConfig.from_pretrained(path)
+    n = config.num_hidden_layers
+    fabric = init_fabric(config.hidden_size, max_tokens=256)
+    dirs = [tempfile.mkdtemp(prefix="pb200-ppcpu-") if rank == 0 else None]
+    dist.broadcast_object_list(dirs, src=0)
+    per = n // world
+    server = Server(initial_peers=dirs[0], converted_model_name_or_path=path, block_indices=f"{rank * per}:{(rank + 1) * per}", torch_dtype="float32",
+                    device="cpu", throughput=1.0, update_period=0.5, peer_id=f"stage{rank}")
+    server.run_in_background(timeout=120)
+    dist.barrier()
+    ok, report = True, {}
+    if rank == 0:
+        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[dirs[0]], max_retries=20, min_backoff=0.2, max_backoff=0.5)
+        torch.manual_seed(0)
+        ids = torch.randint(0, config.vocab_size, (2, 12))
+        with torch.inference_mode():
+            h = model.model.embed(ids)
+            for i in range(n):
+                h = load_pretrained_block(path, i, torch_dtype=torch.float32)(h)[0]
+            ref = model.lm_head(model.model.final_norm(h))
+            with model.inference_session(max_length=16) as sess:
+                a = model(ids[:, :7]).logits
+                b_ = model(ids[:, 7:8]).logits
+                junk = model(ids[:, :2]).logits
+                sess.position = 8  # rollback travels as start_from_position next to the fabric metadata
+                c = model(ids[:, 8:]).logits
+                used = [s.no_history for s in sess._server_sessions]
+                peers = [s.span.peer_id for s in sess._server_sessions]
+            got = torch.cat([a, b_, c], 1)
+        err = (got - ref).abs().max().item()
+        parts = [(a - ref[:, :7]).abs().max().item(), (b_ - ref[:, 7:8]).abs().max().item(), (c - ref[:, 8:]).abs().max().item()]
+        ok = err < 1e-3 and all(used[1:]) and len(peers) == world
+        report = {"pp_selftest_cpu": "ok" if ok else "FAILED", "max_err": err, "stages": peers, "inputs_over_fabric": used, "part_errs": parts}
+    dist.barrier()
+    server.shutdown()
+    dist.barrier()
+    if rank == 0:
+        print(json.dumps(report))
+    fabric.close()
+    dist.destroy_process_group()
+    if not ok:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()
