@@ -26,6 +26,15 @@ typedef struct {
 } PbLinearDecodeArgs;
 int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream);
 
+// ---- decode-shape linear over block-scaled FP8 weights (linear_decode_fp8.cu) ---------------------------
+typedef struct {
+  const void* x; const void* w; const void* w_scale; const void* w2; const void* w2_scale;
+  const void* bias; const void* bias2; const void* residual; void* out; const void* norm_w; const void* norm_b;
+  float eps; int norm_kind; int act; int M, N, K; int num_sms;
+} PbLinearFp8Args;
+int pb_linear_decode_fp8(const PbLinearFp8Args* a, void* stream);
+int pb_dequant_mxfp8(const void* q, const void* e, void* out_bf16, long n_elems, void* stream);
+
 // ---- tcgen05 GEMM (gemm_tcgen05.cu) -----------------------------------------------------------------
 // D[M,N] = epilogue(A[M,K] * B^T) with A K-major [M,K]; B either K-major [N,K] (nn.Linear weight,
 // forward) or MN-major [K,N] (the same weight used transposed: dgrad). bf16 in, fp32 accumulate.

@@ -82,6 +82,36 @@ def linear_decode(
     return out
 
 
+def linear_decode_fp8(x: torch.Tensor, w_q: torch.Tensor, w_scale: torch.Tensor, *, w2_q: Optional[torch.Tensor] = None,
+                      w2_scale: Optional[torch.Tensor] = None, bias=None, bias2=None, residual=None, norm_weight=None, norm_bias=None,
+                      norm_kind: int = NORM_NONE, eps: float = 1e-6, act: int = ACT_NONE, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decode linear over MXFP8 weights (``ops.quant.quantize_mxfp8``): payload [N,K] float8_e4m3fn, scales [N,K/32] uint8."""
+    from petals_b200.ops.native import LinearFp8Args
+
+    x = _bf16c(x, "x")
+    M, K = x.reshape(-1, x.shape[-1]).shape
+    N = w_q.shape[0]
+    if out is None:
+        out = torch.empty(*x.shape[:-1], N, dtype=torch.bfloat16, device=x.device)
+    a = LinearFp8Args()
+    a.x, a.w, a.w_scale = ptr(x), ptr(w_q.contiguous()), ptr(w_scale.contiguous())
+    a.w2, a.w2_scale = ptr(w2_q), ptr(w2_scale)
+    a.bias, a.bias2, a.residual = ptr(_bf16c(bias, "bias")), ptr(_bf16c(bias2, "bias2")), ptr(_bf16c(residual, "residual"))
+    a.out, a.norm_w, a.norm_b = ptr(out), ptr(_bf16c(norm_weight, "norm_weight")), ptr(_bf16c(norm_bias, "norm_bias"))
+    a.eps, a.norm_kind, a.act, a.M, a.N, a.K = eps, norm_kind, act, M, N, K
+    a.num_sms = native.sm_count(x.device.index)
+    check(native.lib().pb_linear_decode_fp8(C.byref(a), stream_ptr()), "linear_decode_fp8")
+    return out
+
+
+def dequant_mxfp8(w_q: torch.Tensor, w_scale: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """MXFP8 -> bf16 on the device (feeds the tcgen05 GEMM at prefill time)."""
+    if out is None:
+        out = torch.empty(w_q.shape, dtype=torch.bfloat16, device=w_q.device)
+    check(native.lib().pb_dequant_mxfp8(ptr(w_q), ptr(w_scale), ptr(out), w_q.numel(), stream_ptr()), "dequant_mxfp8")
+    return out
+
+
 def linear_decode_grid(N: int, M: int = 1, device: Optional[int] = None) -> int:
     """CTA count linear_decode launches for a given N (peers need it to size flag targets)."""
     sms = native.sm_count(device)

@@ -43,6 +43,15 @@ class LinearDecodeArgs(C.Structure):
     ]
 
 
+class LinearFp8Args(C.Structure):
+    _fields_ = [
+        ("x", C.c_void_p), ("w", C.c_void_p), ("w_scale", C.c_void_p), ("w2", C.c_void_p), ("w2_scale", C.c_void_p),
+        ("bias", C.c_void_p), ("bias2", C.c_void_p), ("residual", C.c_void_p), ("out", C.c_void_p), ("norm_w", C.c_void_p),
+        ("norm_b", C.c_void_p), ("eps", C.c_float), ("norm_kind", C.c_int), ("act", C.c_int), ("M", C.c_int), ("N", C.c_int),
+        ("K", C.c_int), ("num_sms", C.c_int),
+    ]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("b", C.c_void_p), ("b2", C.c_void_p),
@@ -82,6 +91,10 @@ def _declare(lib: C.CDLL) -> None:
     vp, ci, cl, cf = C.c_void_p, C.c_int, C.c_long, C.c_float
     lib.pb_linear_decode.argtypes = [C.POINTER(LinearDecodeArgs), vp]
     lib.pb_gemm_bf16.argtypes = [C.POINTER(GemmArgs), vp]
+    lib.pb_linear_decode_fp8.argtypes = [C.POINTER(LinearFp8Args), vp]
+    lib.pb_linear_decode_fp8.restype = ci
+    lib.pb_dequant_mxfp8.argtypes = [vp, vp, vp, cl, vp]
+    lib.pb_dequant_mxfp8.restype = ci
     lib.pb_gemm_tiles.argtypes = [ci, ci, ci, ci]
     lib.pb_norm.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, cf, ci, vp]
     lib.pb_swiglu.argtypes = [vp, vp, vp, cl, vp]

@@ -79,7 +79,7 @@ class Stage:
     def forward(self, hidden: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
         hi = len(self.blocks) if hi is None else hi
         hidden = hidden.to(self.device)
-        prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device) for p in prompts]
+        prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device).contiguous() for p in prompts]
         if self.engine is not None and self._lora_free():  # stages are stateless: forward never records autograd state
             return self.engine.forward(hidden, prompts, (lo, hi))
         h = hidden.to(self.dtype)
@@ -94,7 +94,7 @@ class Stage:
         """Returns (grad wrt span input, [grad wrt each block's prompt or None])."""
         hi = len(self.blocks) if hi is None else hi
         hidden, grad = hidden.to(self.device, self.dtype), grad_out.to(self.device, self.dtype)
-        prompts = [None] * (hi - lo) if prompts is None else [None if is_dummy(p) else p.to(self.device, self.dtype) for p in prompts]
+        prompts = [None] * (hi - lo) if prompts is None else [None if is_dummy(p) else p.to(self.device, self.dtype).contiguous() for p in prompts]
         # pass 1 (no grad): remember every block's input
         inputs = []
         h = hidden
@@ -123,7 +123,7 @@ class Stage:
                        take_from: Optional[tuple] = None, push_to: Optional[tuple] = None) -> torch.Tensor:
         hi = len(self.blocks) if hi is None else hi
         hidden = hidden.to(self.device)
-        prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device) for p in prompts]
+        prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device).contiguous() for p in prompts]
         if self.engine is not None and self._lora_free():
             if take_from is not None or push_to is not None:
                 return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi), take_from=take_from, push_to=push_to)

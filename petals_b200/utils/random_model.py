@@ -80,6 +80,7 @@ def random_client_model(model_path: str, swarm: Swarm, device, *, dtype=torch.bf
     from petals_b200.utils.auto_config import detect_model_type, get_model_classes
 
     classes = get_model_classes(detect_model_type(model_path))
+    kwargs.setdefault("max_retries", 3)  # synthetic-model runs should fail fast instead of retrying forever
     config = classes["config"].from_pretrained(model_path, initial_peers=[swarm.address], **kwargs)
     torch.manual_seed(seed)
     with torch.device(device):

@@ -235,3 +235,32 @@ def test_attention_alibi_window_long():
     _close(out, Fn.attention_ref(q, k, v, pos0=0, scale=D ** -0.5, alibi_slopes=slopes), 2e-2, 2e-2, "alibi")
     Fn.paged_attention(q_out, k_pool, v_pool, table, pos.data_ptr(), out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, window=100)
     _close(out, Fn.attention_ref(q, k, v, pos0=0, scale=D ** -0.5, window=100), 2e-2, 2e-2, "window")
+
+
+@pytest.mark.parametrize("M", [1, 3])
+def test_linear_decode_fp8(M):
+    """Block-scaled FP8 weights: exact vs the dequantised-weight oracle (same weights), close to the bf16 original."""
+    from petals_b200.ops.quant import dequantize_mxfp8, quantize_mxfp8
+
+    torch.manual_seed(20)
+    K, N = 4096, 3072
+    x, g = _rand(M, K), _rand(K) * 0.1 + 1
+    w, wu, res = _rand(N, K, scale=K ** -0.5), _rand(N, K, scale=K ** -0.5), _rand(M, N)
+    q, e = quantize_mxfp8(w)
+    qu, eu = quantize_mxfp8(wu)
+    wd, wud = dequantize_mxfp8(q, e), dequantize_mxfp8(qu, eu)
+    got = Fn.linear_decode_fp8(x, q, e, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5, residual=res)
+    _close(got, Fn.linear_ref(x, wd, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5, residual=res), 3e-2, 2e-2, "fp8 plain")
+    rel = (got.float() - Fn.linear_ref(x, w, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5, residual=res).float()).abs().mean() / got.float().abs().mean()
+    assert rel < 0.06, f"fp8 quantisation error too large: {rel}"
+    got = Fn.linear_decode_fp8(x, q, e, w2_q=qu, w2_scale=eu, act=Fn.ACT_SWIGLU, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+    _close(got, Fn.linear_ref(x, wd, w2=wud, act=Fn.ACT_SWIGLU, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5), 2e-2, 3e-2, "fp8 swiglu")
+
+
+def test_dequant_mxfp8():
+    from petals_b200.ops.quant import dequantize_mxfp8, quantize_mxfp8
+
+    torch.manual_seed(21)
+    w = _rand(512, 1024, scale=0.05)
+    q, e = quantize_mxfp8(w)
+    assert torch.equal(Fn.dequant_mxfp8(q, e), dequantize_mxfp8(q, e))
