@@ -61,18 +61,19 @@ PB_DEVICE float gelu_tanh(float x) {
 PB_DEVICE float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.7071067811865475f)); }
 PB_DEVICE float silu(float x) { return x / (1.f + __expf(-x)); }
 
+// 8 bf16 weights (one uint4) times 8 pre-converted fp32 activations per token. Activations are converted ONCE per load
+// slot and reused for every weight row of the slot (2 rows, or 4 with SwiGLU): at M >= 2 the bf16->fp32 unpacking of x would
+// otherwise saturate the integer pipe before HBM saturates.
 template <int M>
-PB_DEVICE void fma8(float (&acc)[M], const uint4& w, const uint4 (&xv)[M]) {
+PB_DEVICE void fma8(float (&acc)[M], const uint4& w, const float (&xf)[M][8]) {
+  const float w0 = bf16_lo(w.x), w1 = bf16_hi(w.x), w2 = bf16_lo(w.y), w3 = bf16_hi(w.y);
+  const float w4 = bf16_lo(w.z), w5 = bf16_hi(w.z), w6 = bf16_lo(w.w), w7 = bf16_hi(w.w);
 #pragma unroll
   for (int m = 0; m < M; ++m) {
-    acc[m] = fmaf(bf16_lo(w.x), bf16_lo(xv[m].x), acc[m]);
-    acc[m] = fmaf(bf16_hi(w.x), bf16_hi(xv[m].x), acc[m]);
-    acc[m] = fmaf(bf16_lo(w.y), bf16_lo(xv[m].y), acc[m]);
-    acc[m] = fmaf(bf16_hi(w.y), bf16_hi(xv[m].y), acc[m]);
-    acc[m] = fmaf(bf16_lo(w.z), bf16_lo(xv[m].z), acc[m]);
-    acc[m] = fmaf(bf16_hi(w.z), bf16_hi(xv[m].z), acc[m]);
-    acc[m] = fmaf(bf16_lo(w.w), bf16_lo(xv[m].w), acc[m]);
-    acc[m] = fmaf(bf16_hi(w.w), bf16_hi(xv[m].w), acc[m]);
+    float a = acc[m];
+    a = fmaf(w0, xf[m][0], a); a = fmaf(w1, xf[m][1], a); a = fmaf(w2, xf[m][2], a); a = fmaf(w3, xf[m][3], a);
+    a = fmaf(w4, xf[m][4], a); a = fmaf(w5, xf[m][5], a); a = fmaf(w6, xf[m][6], a); a = fmaf(w7, xf[m][7], a);
+    acc[m] = a;
   }
 }
 
@@ -226,17 +227,20 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
       for (int u = 0; u < U; ++u) {
         if (ok[u]) {
           const int k = kb + u * 256 + lane * 8;
-          uint4 xv[M];
+          float xf[M][8];
 #pragma unroll
           for (int m = 0; m < M; ++m) {
-            if (XSMEM) xv[m] = *reinterpret_cast<const uint4*>(xs + static_cast<size_t>(m) * K + k);
-            else xv[m] = ld_cached(p.x + static_cast<size_t>(m) * K + k);
+            uint4 xv;
+            if (XSMEM) xv = *reinterpret_cast<const uint4*>(xs + static_cast<size_t>(m) * K + k);
+            else xv = ld_cached(p.x + static_cast<size_t>(m) * K + k);
+            xf[m][0] = bf16_lo(xv.x); xf[m][1] = bf16_hi(xv.x); xf[m][2] = bf16_lo(xv.y); xf[m][3] = bf16_hi(xv.y);
+            xf[m][4] = bf16_lo(xv.z); xf[m][5] = bf16_hi(xv.z); xf[m][6] = bf16_lo(xv.w); xf[m][7] = bf16_hi(xv.w);
           }
-          fma8<M>(a0, wa[u], xv);
-          fma8<M>(a1, wb[u], xv);
+          fma8<M>(a0, wa[u], xf);
+          fma8<M>(a1, wb[u], xf);
           if (DUAL) {
-            fma8<M>(b0, ua[u], xv);
-            fma8<M>(b1, ub[u], xv);
+            fma8<M>(b0, ua[u], xf);
+            fma8<M>(b1, ub[u], xf);
           }
         }
       }

@@ -30,7 +30,7 @@ class Stage:
 
     def __init__(self, config, blocks: Sequence[GenericBlock], start_block: int, *, device, memory_cache: MemoryCache,
                  torch_dtype: torch.dtype, max_chunk_size_bytes: int = 256 * 1024 * 1024, use_cuda_graphs: bool = True,
-                 force_oracle: bool = False, engine=None):
+                 force_oracle: bool = False, engine=None, fp8: bool = False):
         self.config, self.blocks = config, list(blocks)
         self.start_block, self.end_block = start_block, start_block + len(blocks)
         self.device, self.dtype = torch.device(device), torch_dtype
@@ -43,7 +43,8 @@ class Stage:
 
             chunk_tokens = max(256, min(8192, max_chunk_size_bytes // max(1, 2 * self.spec.intermediate_size)))
             self.engine = StageEngine(self.spec, self.blocks, memory_cache, device=self.device, max_chunk_tokens=chunk_tokens,
-                                      use_cuda_graphs=use_cuda_graphs)
+                                      use_cuda_graphs=use_cuda_graphs, fp8=fp8)
+        self.fp8 = fp8 and self.engine is not None
         self.active_adapter: Optional[str] = None
 
     def __len__(self) -> int:
@@ -89,6 +90,23 @@ class Stage:
                 h = self.blocks[i].forward_cached(h, None, None, 0)
         return h
 
+    def _materialize(self, slot: int) -> None:
+        """FP8 stages keep no bf16 projections; the oracle paths (backward) get them dequantised block by block."""
+        if not getattr(self, "fp8", False):
+            return
+        from petals_b200.ops import functional as Fn
+
+        for name, (q, e) in self.engine.fp8[slot].items():
+            p = getattr(self.blocks[slot], name)
+            if p.numel() == 0:
+                p.data = Fn.dequant_mxfp8(q, e)
+
+    def _dematerialize(self, slot: int) -> None:
+        if getattr(self, "fp8", False):
+            for name in self.engine.fp8[slot]:
+                p = getattr(self.blocks[slot], name)
+                p.data = torch.empty(0, dtype=p.dtype, device=p.device)
+
     def backward(self, hidden: torch.Tensor, grad_out: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None,
                  lo: int = 0, hi: Optional[int] = None) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
         """Returns (grad wrt span input, [grad wrt each block's prompt or None])."""
@@ -102,17 +120,21 @@ class Stage:
             for i in range(lo, hi):
                 inputs.append(h)
                 if i + 1 < hi:
+                    self._materialize(i)
                     h = self.blocks[i].forward_cached(self._add_prompt(h, prompts[i - lo]), None, None, 0)
+                    self._dematerialize(i)
         # pass 2: per-block recompute with autograd, last block first
         grad_prompts: List[Optional[torch.Tensor]] = [None] * (hi - lo)
         for i in reversed(range(lo, hi)):
             x = inputs[i - lo].detach().requires_grad_(True)
             p = prompts[i - lo]
             p = p.detach().requires_grad_(True) if p is not None else None
+            self._materialize(i)
             with torch.enable_grad():
                 y = self.blocks[i].forward_cached(self._add_prompt(x, p), None, None, 0)
             targets = [x] + ([p] if p is not None else [])
             grads = torch.autograd.grad(y, targets, grad)
+            self._dematerialize(i)
             grad = grads[0]
             if p is not None:
                 grad_prompts[i - lo] = grads[1]

@@ -274,11 +274,12 @@ class ModuleContainer:
             from petals_b200.server.stage_engine import fast_path_supported
 
             paged = (device.type == "cuda" and torch_dtype == torch.bfloat16 and fast_path_supported(spec) and not force_oracle
-                     and quant_type == QuantType.NONE)
+                     and quant_type in (QuantType.NONE, QuantType.FP8) and not (quant_type == QuantType.FP8 and adapters))
             memory_cache = MemoryCache(attn_cache_tokens, max_alloc_timeout, n_blocks=len(blocks), spec=spec, dtype=torch_dtype, device=device,
                                        paged=paged, max_length=inference_max_length)
             stage = Stage(block_config, blocks, block_indices[0], device=device, memory_cache=memory_cache, torch_dtype=torch_dtype,
-                          max_chunk_size_bytes=max_chunk_size_bytes, use_cuda_graphs=use_cuda_graphs, force_oracle=force_oracle)
+                          max_chunk_size_bytes=max_chunk_size_bytes, use_cuda_graphs=use_cuda_graphs, force_oracle=force_oracle,
+                          fp8=(quant_type == QuantType.FP8 and paged))
             container_parts = cls._build_pools(stage, module_uids, blocks, max_batch_size, stats_report_interval, peer_id, device)
         except BaseException:
             announcer.announce(ServerState.OFFLINE)

@@ -44,9 +44,31 @@ def fast_path_supported(spec: BlockSpec) -> bool:
 
 
 class StageEngine:
+    FP8_NAMES = ("wqkv", "wo", "w_gate", "w_up", "w_down")
+
     def __init__(self, spec: BlockSpec, blocks: Sequence[GenericBlock], cache: MemoryCache, *, device,
-                 max_chunk_tokens: int = 8192, use_cuda_graphs: bool = True):
+                 max_chunk_tokens: int = 8192, use_cuda_graphs: bool = True, fp8: bool = False, free_bf16: bool = True):
         self.spec, self.blocks, self.cache = spec, list(blocks), cache
+        # Block-scaled FP8 serving (--quant_type fp8): projections are kept as E4M3 payload + UE8M0 scales (ops/quant.py).
+        # Decode streams the 1-byte weights directly (csrc/linear_decode_fp8.cu); prefill dequantises one projection at a
+        # time into a bf16 scratch and runs the tcgen05 GEMM on it.
+        self.fp8: Optional[List[Dict[str, Tuple[torch.Tensor, torch.Tensor]]]] = None
+        self.max_decode_rows = MAX_DECODE_ROWS
+        if fp8:
+            from petals_b200.ops.quant import quantize_mxfp8
+
+            self.fp8 = []
+            self.max_decode_rows = 4
+            for block in self.blocks:
+                entry = {}
+                for name in self.FP8_NAMES:
+                    p = getattr(block, name, None)
+                    if p is None or p.dim() != 2 or p.shape[1] % 32:
+                        continue
+                    entry[name] = quantize_mxfp8(p.data)
+                    if free_bf16:
+                        p.data = torch.empty(0, dtype=p.dtype, device=p.device)
+                self.fp8.append(entry)
         self.device = torch.device(device)
         self.n_blocks = len(self.blocks)
         self.max_chunk_tokens = max_chunk_tokens
@@ -75,6 +97,25 @@ class StageEngine:
         self._scratch_pages = n_scratch
 
     # ---- buffers ---------------------------------------------------------------------------------------
+    def _w(self, slot: int, name: str) -> Optional[torch.Tensor]:
+        """bf16 view of a projection weight: the block's tensor, or (FP8 serving) a scratch dequantised on the fly."""
+        p = getattr(self.blocks[slot], name, None)
+        if self.fp8 is None or name not in self.fp8[slot]:
+            return p
+        if p is not None and p.numel() > 0:
+            return p
+        q, e = self.fp8[slot][name]
+        return Fn.dequant_mxfp8(q, e, out=self._buf("dq_" + name, q.shape[0], q.shape[1]))
+
+    def _lin_decode(self, slot: int, name: str, x: torch.Tensor, name2: Optional[str] = None, **kw) -> torch.Tensor:
+        """One decode-shape projection: bf16 weight streamer, or its FP8 twin when this stage serves quantised weights."""
+        w = self.blocks[slot]
+        if self.fp8 is not None and name in self.fp8[slot]:
+            q, e = self.fp8[slot][name]
+            q2, e2 = self.fp8[slot][name2] if name2 else (None, None)
+            return Fn.linear_decode_fp8(x, q, e, w2_q=q2, w2_scale=e2, **kw)
+        return Fn.linear_decode(x, getattr(w, name), w2=getattr(w, name2) if name2 else None, **kw)
+
     def _buf(self, name: str, rows: int, cols: int, dtype=None) -> torch.Tensor:
         key = (name, rows)
         t = self._bufs.get(key)
@@ -134,10 +175,10 @@ class StageEngine:
         s, w = self.spec, self.blocks[slot]
         M = B * T
         eps = s.norm_eps
-        qkv = Fn.linear_decode(x, w.wqkv, bias=w._p("bqkv"), norm_weight=w.ln1_w, norm_bias=w._p("ln1_b"), norm_kind=self.norm_kind,
+        qkv = self._lin_decode(slot, "wqkv", x, bias=w._p("bqkv"), norm_weight=w.ln1_w, norm_bias=w._p("ln1_b"), norm_kind=self.norm_kind,
                                eps=eps, out=self._buf("qkv", M, s.qkv_dim))
         attn = self._attention(qkv, slot, B, T, table, pos_ptr, pools, splits, "")
-        h1 = Fn.linear_decode(attn, w.wo, bias=w._p("bo"), residual=x, out=out)
+        h1 = self._lin_decode(slot, "wo", attn, bias=w._p("bo"), residual=x, out=out)
         if s.mlp == "moe":
             h1.copy_(self._moe(h1.view(B, T, -1), w).view(M, -1))
             return h1
@@ -146,15 +187,15 @@ class StageEngine:
         else:
             mlp_in, ln_w, ln_b = h1, w.ln2_w, w._p("ln2_b")
         if s.mlp == "swiglu":
-            act = Fn.linear_decode(mlp_in, w.w_gate, w2=w.w_up, act=Fn.ACT_SWIGLU, norm_weight=ln_w, norm_bias=ln_b,
+            act = self._lin_decode(slot, "w_gate", mlp_in, "w_up", act=Fn.ACT_SWIGLU, norm_weight=ln_w, norm_bias=ln_b,
                                    norm_kind=self.norm_kind, eps=eps, out=self._buf("act", M, s.intermediate_size))
         else:
-            act = Fn.linear_decode(mlp_in, w.w_up, bias=w._p("b_up"), act=self.act, norm_weight=ln_w, norm_bias=ln_b,
+            act = self._lin_decode(slot, "w_up", mlp_in, bias=w._p("b_up"), act=self.act, norm_weight=ln_w, norm_bias=ln_b,
                                    norm_kind=self.norm_kind, eps=eps, out=self._buf("act", M, s.intermediate_size))
         # down projection + residual; write into x's buffer (x is dead for sequential blocks, and for
         # parallel blocks h1 already contains x + attn). With `hop`, the same epilogue also stores the rows into the
         # next stage's landing zone over NVLink and publishes its flag: the stage hop costs no extra kernel.
-        return Fn.linear_decode(act, w.w_down, bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop))
+        return self._lin_decode(slot, "w_down", act, bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop))
 
     def _block_prefill(self, x: torch.Tensor, slot: int, B: int, T: int, table, pos_ptr, pools, hop: Optional[tuple] = None) -> torch.Tensor:
         """x: [M, H] (overwritten with the block output)."""
@@ -162,9 +203,9 @@ class StageEngine:
         M = B * T
         eps = s.norm_eps
         xn = Fn.norm(x, w.ln1_w, w._p("ln1_b"), kind=self.norm_kind, eps=eps, out=self._buf("xn_p", M, s.hidden_size))
-        qkv = Fn.gemm(xn, w.wqkv, bias=w._p("bqkv"), out=self._buf("qkv_p", M, s.qkv_dim))
+        qkv = Fn.gemm(xn, self._w(slot, "wqkv"), bias=w._p("bqkv"), out=self._buf("qkv_p", M, s.qkv_dim))
         attn = self._attention(qkv, slot, B, T, table, pos_ptr, pools, 1, "_p")
-        h1 = Fn.gemm(attn, w.wo, bias=w._p("bo"), residual=x, out=self._buf("h1_p", M, s.hidden_size))
+        h1 = Fn.gemm(attn, self._w(slot, "wo"), bias=w._p("bo"), residual=x, out=self._buf("h1_p", M, s.hidden_size))
         if s.mlp == "moe":
             x.copy_(self._moe(h1.view(B, T, -1), w).view(M, -1))
             return x
@@ -174,10 +215,10 @@ class StageEngine:
             xn2 = Fn.norm(h1, w.ln2_w, w._p("ln2_b"), kind=self.norm_kind, eps=eps, out=xn)
         act_buf = self._buf("act_p", M, s.intermediate_size)
         if s.mlp == "swiglu":
-            act = Fn.gemm(xn2, w.w_gate, b2=w.w_up, act=Fn.ACT_SWIGLU, out=act_buf)
+            act = Fn.gemm(xn2, self._w(slot, "w_gate"), b2=self._w(slot, "w_up"), act=Fn.ACT_SWIGLU, out=act_buf)
         else:
-            act = Fn.gemm(xn2, w.w_up, bias=w._p("b_up"), act=self.act, out=act_buf)
-        return Fn.gemm(act, w.w_down, bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop, gemm=True))
+            act = Fn.gemm(xn2, self._w(slot, "w_up"), bias=w._p("b_up"), act=self.act, out=act_buf)
+        return Fn.gemm(act, self._w(slot, "w_down"), bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop, gemm=True))
 
     def _moe(self, h1: torch.Tensor, w: GenericBlock) -> torch.Tensor:
         """h1 = residual stream after attention [B,T,H]; returns h1 + MoE(ln2(h1)). Oracle math on the engine's weights."""
@@ -205,14 +246,14 @@ class StageEngine:
         for slot in range(lo, hi):
             if prompts is not None and not is_dummy(prompts[slot - lo]):
                 Fn.add_prompts(cur.view(B, T, -1), prompts[slot - lo])
-            fused_hop = hop if (slot == hi - 1 and self.spec.mlp != "moe") else None
+            fused_hop = hop if (slot == hi - 1 and self.spec.mlp != "moe" and not (decode and self.fp8 is not None)) else None
             if decode:
                 nxt = self._block_decode(cur, other, slot, B, T, table, pos_ptr, pools_of(slot), splits, fused_hop)
                 if nxt is not cur:  # MoE path returned the alternate buffer
                     cur, other = nxt, cur
             else:
                 cur = self._block_prefill(cur, slot, B, T, table, pos_ptr, pools_of(slot), fused_hop)
-        if hop is not None and self.spec.mlp == "moe":  # no fused epilogue for this family yet: host-issued NVLink copy
+        if hop is not None and (self.spec.mlp == "moe" or (decode and self.fp8 is not None)):  # no fused epilogue here yet: host-issued NVLink copy
             hop[0].send(cur, hop[2], hop[1])
         return cur
 
@@ -266,7 +307,7 @@ class StageEngine:
         table = self._sync_session(session, B)
         pos_ptr = self.pos_static.data_ptr()
         pools_of = self.cache.layer_pools
-        decode = M <= MAX_DECODE_ROWS
+        decode = M <= self.max_decode_rows
         if decode and self.use_cuda_graphs and prompts is None and self.spec.mlp != "moe":
             key = (B, T, lo, hi) if hop is None else (B, T, lo, hi, hop[1], hop[2])
             g = self._graphs.get(key)
@@ -352,7 +393,7 @@ class StageEngine:
             if prompts is not None and any(not is_dummy(p) for p in prompts):
                 pr = [p if is_dummy(p) or p.shape[0] == 1 else p[b0:b1] for p in prompts]
             scratch = lambda slot: (self._scratch_pool[0], self._scratch_pool[1])
-            decode = nb * T <= MAX_DECODE_ROWS and self.spec.mlp != "moe"
+            decode = nb * T <= self.max_decode_rows and self.spec.mlp != "moe"
             y = self._run_span(x, nb, T, lo, hi, table, zero.data_ptr(), scratch, pr, decode, 1)
             out[b0:b1] = y.view(nb, T, H)
         self._active = None  # the static table/pos were not touched, but be conservative

@@ -54,7 +54,8 @@ def random_blocks(config, block_indices: Sequence[int], device, dtype=torch.bflo
 
 def launch_random_stage(model_path: str, block_indices: Sequence[int], swarm: Swarm, device, *, dtype=torch.bfloat16, seed: int = 0,
                         attn_cache_tokens: int = 4096, inference_max_length: int = 4096, max_batch_size: int = 65536, peer_id: Optional[str] = None,
-                        use_cuda_graphs: bool = True, force_oracle: bool = False, max_chunk_size_bytes: int = 256 * 1024 * 1024):
+                        use_cuda_graphs: bool = True, force_oracle: bool = False, max_chunk_size_bytes: int = 256 * 1024 * 1024,
+                        quant_type: QuantType = QuantType.NONE):
     """Start serving ``block_indices`` with random weights; returns the ModuleContainer (call ``.shutdown()``)."""
     from petals_b200.server.server import ModuleContainer
     from petals_b200.utils.auto_config import AutoDistributedConfig
@@ -64,12 +65,12 @@ def launch_random_stage(model_path: str, block_indices: Sequence[int], swarm: Sw
     device = torch.device(device)
     blocks = random_blocks(config, block_indices, device, dtype, seed)
     info = ServerInfo(state=ServerState.JOINING, throughput=1.0, version=petals_b200.__version__, torch_dtype=str(dtype).replace("torch.", ""),
-                      quant_type="none", using_relay=False)
+                      quant_type=quant_type.name.lower(), using_relay=False)
     return ModuleContainer.create(
         dht=swarm, dht_prefix=config.dht_prefix, converted_model_name_or_path=model_path, block_config=config,
         attn_cache_tokens=attn_cache_tokens, server_info=info, model_info=ModelInfo(num_blocks=config.num_hidden_layers, repository=model_path),
         block_indices=list(block_indices), min_batch_size=1, max_batch_size=max_batch_size, max_chunk_size_bytes=max_chunk_size_bytes,
-        max_alloc_timeout=600, inference_max_length=inference_max_length, torch_dtype=dtype, device=device, quant_type=QuantType.NONE,
+        max_alloc_timeout=600, inference_max_length=inference_max_length, torch_dtype=dtype, device=device, quant_type=quant_type,
         tensor_parallel_devices=(device,), adapters=(), update_period=30, expiration=3600, request_timeout=180, session_timeout=1800,
         step_timeout=300, stats_report_interval=None, peer_id=peer_id or f"{device.type}{device.index or 0}-stage{block_indices[0]}",
         use_cuda_graphs=use_cuda_graphs, force_oracle=force_oracle, prebuilt_blocks=blocks)
