@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const T* __restrict__ logi
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    if (lane == 0) out[blockIdx.x] = bi;
+    if (lane == 0) out[blockIdx.x] = bi == 0x7fffffff ? 0 : bi;  // all-NaN row: never emit an out-of-range token id
   }
 }
 

@@ -82,7 +82,7 @@ __global__ void argmax_reduce_kernel(const float* cand, int n_peers, int rows, i
       const int i = __float_as_int(__ldcg(slot + 1));
       if (v > best || (v == best && i < bi)) { best = v; bi = i; }
     }
-    out_ids[t] = bi;
+    out_ids[t] = bi == 0x7fffffff ? 0 : bi;
   }
 }
 
@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(1024) argmax_val_kernel(const __nv_bfloat16* _
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    if (lane == 0) { out_val[blockIdx.x] = best; out_idx[blockIdx.x] = bi; }
+    if (lane == 0) { out_val[blockIdx.x] = best; out_idx[blockIdx.x] = bi == 0x7fffffff ? 0 : bi; }
   }
 }
 

@@ -110,6 +110,13 @@ typedef struct {
   const void* alibi_slopes; float scale; int B, T, Hq, Hkv, D, window;
 } PbAttnDenseArgs;
 
+// ---- sparse MoE decode (moe.cu) ------------------------------------------------------------------------------
+int pb_moe_router(const void* h, const void* norm_w, const void* router, void* xn_out, void* topi, void* topw, int M, int H, int E,
+                  int topk, float eps, void* stream);
+int pb_moe_gemv(const void* x, const void* w_all, const void* w2_all, const void* topi, void* out, int pairs, int N, int K,
+                long expert_stride, int x_row_div, int num_sms, void* stream);
+int pb_moe_combine(const void* y, const void* topw, const void* residual, void* out, int M, int H, int topk, void* stream);
+
 // ---- KV cache utilities -----------------------------------------------------------------------------
 int pb_kv_copy_pages(void* pool, const void* src_pages, const void* dst_pages, int n, long page_elems,
                      long layer_stride_elems, int n_layer_slabs, void* stream);

@@ -348,3 +348,34 @@ def attention_ref(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, pos0: in
     s = s.masked_fill(~ok[None, None], float("-inf"))
     p = torch.softmax(s, dim=-1)
     return torch.einsum("bhtl,blhd->bthd", p, vf).to(q.dtype)
+
+
+# ----------------------------------------------------------------------------------------------------
+# sparse MoE (decode)
+# ----------------------------------------------------------------------------------------------------
+def moe_decode(h: torch.Tensor, norm_w: torch.Tensor, router: torch.Tensor, we_gate: torch.Tensor, we_up: torch.Tensor, we_down: torch.Tensor,
+               *, top_k: int, eps: float, out: torch.Tensor, bufs: Optional[dict] = None) -> torch.Tensor:
+    """out = h + MoE(RMSNorm(h)) for M <= 8 rows without any host synchronisation (csrc/moe.cu)."""
+    M, H = h.shape
+    E, I, _ = we_gate.shape
+    bufs = bufs if bufs is not None else {}
+
+    def buf(name, shape, dtype):
+        t = bufs.get(name)
+        if t is None or tuple(t.shape) != tuple(shape):
+            t = torch.empty(shape, dtype=dtype, device=h.device)
+            bufs[name] = t
+        return t
+
+    xn = buf("moe_xn", (M, H), torch.bfloat16)
+    topi = buf("moe_topi", (M * top_k,), torch.int32)
+    topw = buf("moe_topw", (M * top_k,), torch.float32)
+    act = buf("moe_act", (M * top_k, I), torch.bfloat16)
+    y = buf("moe_y", (M * top_k, H), torch.bfloat16)
+    lib, st = native.lib(), stream_ptr()
+    sms = native.sm_count(h.device.index)
+    check(lib.pb_moe_router(ptr(h), ptr(norm_w), ptr(router), ptr(xn), ptr(topi), ptr(topw), M, H, E, top_k, eps, st), "moe_router")
+    check(lib.pb_moe_gemv(ptr(xn), ptr(we_gate), ptr(we_up), ptr(topi), ptr(act), M * top_k, I, H, I * H, top_k, sms, st), "moe_gemv(gate/up)")
+    check(lib.pb_moe_gemv(ptr(act), ptr(we_down), None, ptr(topi), ptr(y), M * top_k, H, I, H * I, 1, sms, st), "moe_gemv(down)")
+    check(lib.pb_moe_combine(ptr(y), ptr(topw), ptr(h), ptr(out), M, H, top_k, st), "moe_combine")
+    return out

@@ -126,6 +126,11 @@ def _declare(lib: C.CDLL) -> None:
     for name in ("pb_ipc_malloc", "pb_ipc_free", "pb_ipc_get_handle", "pb_ipc_open_handle", "pb_ipc_close_handle", "pb_ipc_handle_size",
                  "pb_push_rows", "pb_wait_flag", "pb_argmax_val", "pb_argmax_exchange", "pb_reduce_parts", "pb_peer_copy", "pb_pingpong"):
         getattr(lib, name).restype = ci
+    lib.pb_moe_router.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, cf, vp]
+    lib.pb_moe_gemv.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, cl, ci, ci, vp]
+    lib.pb_moe_combine.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
+    for name in ("pb_moe_router", "pb_moe_gemv", "pb_moe_combine"):
+        getattr(lib, name).restype = ci
     lib.pb_last_error.argtypes = []
     lib.pb_last_error.restype = C.c_char_p
     for name in ("pb_linear_decode", "pb_gemm_bf16", "pb_gemm_tiles", "pb_norm", "pb_swiglu", "pb_add", "pb_embedding",

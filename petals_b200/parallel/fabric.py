@@ -31,7 +31,7 @@ _fabric: Optional["Fabric"] = None
 
 
 class Fabric:
-    def __init__(self, hidden_size: int, max_tokens: int = 8192, group=None, extra_bytes: int = 1 << 20):
+    def __init__(self, hidden_size: int, max_tokens: int = 8192, group=None, extra_bytes: int = (256 << 20) + (1 << 20)):
         self.hidden_size, self.max_tokens = hidden_size, max_tokens
         zone = max_tokens * hidden_size * 2
         self.heap = SymmetricHeap(2 * zone + extra_bytes, group=group)

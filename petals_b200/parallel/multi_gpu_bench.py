@@ -49,7 +49,7 @@ def run_multi_gpu(args) -> None:
     build_s = time.time() - t0
     # ---- NVLink probes (stage-hop denominators) -------------------------------------------------------------------
     probe_flag = heap.alloc(8)
-    peer_gbs = measure_peer_bandwidth(heap, 0, 1, nbytes=min(256 << 20, heap.nbytes // 2))
+    peer_gbs = measure_peer_bandwidth(heap, 0, 1)
     hop_us = measure_hop_latency(heap, probe_flag, 0, 1)
     K, W = args.steps, max(args.warmup, 3)
 
@@ -207,7 +207,7 @@ def run_pipeline(args) -> None:
     n_layers = MODEL_PRESETS[args.model]["num_hidden_layers"]
     fabric = init_fabric(config.hidden_size, max_tokens=4096)
     probe = fabric.heap.alloc(8)
-    peer_gbs = measure_peer_bandwidth(fabric.heap, 0, 1, nbytes=fabric.heap.nbytes // 2)
+    peer_gbs = measure_peer_bandwidth(fabric.heap, 0, 1)
     hop_us = measure_hop_latency(fabric.heap, probe, 0, 1)
     dirs = [tempfile.mkdtemp(prefix="pb200-bench-") if rank == 0 else None]
     dist.broadcast_object_list(dirs, src=0)

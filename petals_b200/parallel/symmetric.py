@@ -110,19 +110,25 @@ def ptr_array(ptrs: Sequence[Optional[int]]):
 
 # ---- probes: hop latency and peer bandwidth (roofline denominators for the fused paths) -------------------------------
 def measure_peer_bandwidth(heap: SymmetricHeap, src_rank: int = 0, dst_rank: int = 1, nbytes: int = 256 << 20, iters: int = 10) -> Optional[float]:
-    """GB/s of SM-issued stores from ``src_rank`` into ``dst_rank``'s heap (what a fused epilogue push can reach)."""
-    nbytes = min(nbytes, heap.nbytes // 2) // 16 * 16
+    """GB/s of SM-issued stores from ``src_rank`` into ``dst_rank``'s heap (what a fused epilogue push can reach).
+
+    Collective: allocates its own scratch region in the symmetric heap (never touches live buffers or flags)."""
+    nbytes = min(nbytes, (heap.nbytes - heap._top - 4096)) // 4096 * 4096
+    if nbytes < (1 << 20):
+        dist.barrier(group=heap.group)
+        return None
+    region = heap.alloc(nbytes, align=4096)
     result = None
     if heap.rank == src_rank:
         src = torch.empty(nbytes, dtype=torch.uint8, device=heap.device)
         lib = native.lib()
         for _ in range(3):
-            lib.pb_peer_copy(src.data_ptr(), heap.addr(dst_rank, 0), nbytes, 0, native.stream_ptr())
+            lib.pb_peer_copy(src.data_ptr(), heap.addr(dst_rank, region), nbytes, 0, native.stream_ptr())
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(iters):
-            lib.pb_peer_copy(src.data_ptr(), heap.addr(dst_rank, 0), nbytes, 0, native.stream_ptr())
+            lib.pb_peer_copy(src.data_ptr(), heap.addr(dst_rank, region), nbytes, 0, native.stream_ptr())
         e.record()
         torch.cuda.synchronize()
         result = nbytes * iters / (s.elapsed_time(e) * 1e-3) / 1e9

@@ -91,6 +91,7 @@ class StageEngine:
         self._active: Optional[SessionCache] = None
         self._dev_pos = -1
         self._bufs: Dict[Tuple[str, int], torch.Tensor] = {}
+        self._moe_bufs: Dict[str, torch.Tensor] = {}
         # scratch one-layer pool for cache-less forward passes
         n_scratch = max(1, (max_chunk_tokens + PAGE - 1) // PAGE) + 1
         self._scratch_pool = torch.zeros(2, n_scratch, s.num_kv_heads, PAGE, s.head_dim, dtype=self.dtype, device=self.device)
@@ -180,8 +181,8 @@ class StageEngine:
         attn = self._attention(qkv, slot, B, T, table, pos_ptr, pools, splits, "")
         h1 = self._lin_decode(slot, "wo", attn, bias=w._p("bo"), residual=x, out=out)
         if s.mlp == "moe":
-            h1.copy_(self._moe(h1.view(B, T, -1), w).view(M, -1))
-            return h1
+            # router + the k chosen experts' GEMVs + combine: sync-free, so the whole block stays graph-capturable
+            return Fn.moe_decode(h1, w.ln2_w, w.router, w.we_gate, w.we_up, w.we_down, top_k=s.top_k, eps=eps, out=x, bufs=self._moe_bufs)
         if s.parallel_attn:
             mlp_in, ln_w, ln_b = x, (w.ln2_w if s.dual_ln else w.ln1_w), (w._p("ln2_b") if s.dual_ln else w._p("ln1_b"))
         else:
@@ -207,8 +208,7 @@ class StageEngine:
         attn = self._attention(qkv, slot, B, T, table, pos_ptr, pools, 1, "_p")
         h1 = Fn.gemm(attn, self._w(slot, "wo"), bias=w._p("bo"), residual=x, out=self._buf("h1_p", M, s.hidden_size))
         if s.mlp == "moe":
-            x.copy_(self._moe(h1.view(B, T, -1), w).view(M, -1))
-            return x
+            return self._moe_prefill(h1, w, x)
         if s.parallel_attn:
             xn2 = Fn.norm(x, w.ln2_w, w._p("ln2_b"), kind=self.norm_kind, eps=eps, out=xn) if s.dual_ln else xn
         else:
@@ -220,10 +220,35 @@ class StageEngine:
             act = Fn.gemm(xn2, self._w(slot, "w_up"), bias=w._p("b_up"), act=self.act, out=act_buf)
         return Fn.gemm(act, self._w(slot, "w_down"), bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop, gemm=True))
 
-    def _moe(self, h1: torch.Tensor, w: GenericBlock) -> torch.Tensor:
-        """h1 = residual stream after attention [B,T,H]; returns h1 + MoE(ln2(h1)). Oracle math on the engine's weights."""
-        ln2 = Fn.norm(h1.reshape(-1, h1.shape[-1]), w.ln2_w, None, kind=self.norm_kind, eps=self.spec.norm_eps).view_as(h1)
-        return h1 + w.mlp(ln2)
+    def _moe_prefill(self, h1: torch.Tensor, w: GenericBlock, out: torch.Tensor) -> torch.Tensor:
+        """out = h1 + MoE(RMSNorm(h1)) for many tokens: tokens are grouped by expert (one host sync for the group sizes) and every
+        expert runs two tcgen05 GEMMs (gate/up fused with SwiGLU, then down) on its own tokens only."""
+        s = self.spec
+        M, H = h1.shape
+        xn = Fn.norm(h1, w.ln2_w, None, kind=self.norm_kind, eps=s.norm_eps, out=self._buf("xn_p", M, H))
+        logits = torch.nn.functional.linear(xn, w.router)  # [M, E]: tiny
+        probs = torch.softmax(logits.float(), dim=-1)
+        topw, topi = torch.topk(probs, s.top_k, dim=-1)
+        topw = (topw / topw.sum(-1, keepdim=True)).to(torch.bfloat16)
+        flat_e = topi.reshape(-1)
+        order = torch.argsort(flat_e, stable=True)
+        counts = torch.bincount(flat_e, minlength=s.num_experts).tolist()  # the only host sync of the block
+        tok_of = (order // s.top_k)
+        gathered = xn.index_select(0, tok_of)  # [M*k, H] grouped by expert
+        y = torch.empty(M * s.top_k, H, dtype=torch.bfloat16, device=h1.device)
+        start = 0
+        for e, n in enumerate(counts):
+            if n == 0:
+                continue
+            xe = gathered[start:start + n]
+            he = Fn.gemm(xe, w.we_gate[e], b2=w.we_up[e], act=Fn.ACT_SWIGLU)
+            Fn.gemm(he, w.we_down[e], out=y[start:start + n])
+            start += n
+        wsorted = topw.reshape(-1).index_select(0, order)
+        acc = torch.zeros(M, H, dtype=torch.bfloat16, device=h1.device)
+        acc.index_add_(0, tok_of, y * wsorted[:, None])
+        torch.add(h1, acc, out=out)
+        return out
 
     # ---- span execution ------------------------------------------------------------------------------------
     def _sync_session(self, session: SessionCache, B: int) -> torch.Tensor:
@@ -308,7 +333,7 @@ class StageEngine:
         pos_ptr = self.pos_static.data_ptr()
         pools_of = self.cache.layer_pools
         decode = M <= self.max_decode_rows
-        if decode and self.use_cuda_graphs and prompts is None and self.spec.mlp != "moe":
+        if decode and self.use_cuda_graphs and prompts is None:
             key = (B, T, lo, hi) if hop is None else (B, T, lo, hi, hop[1], hop[2])
             g = self._graphs.get(key)
             if g is None:
@@ -393,7 +418,7 @@ class StageEngine:
             if prompts is not None and any(not is_dummy(p) for p in prompts):
                 pr = [p if is_dummy(p) or p.shape[0] == 1 else p[b0:b1] for p in prompts]
             scratch = lambda slot: (self._scratch_pool[0], self._scratch_pool[1])
-            decode = nb * T <= self.max_decode_rows and self.spec.mlp != "moe"
+            decode = nb * T <= self.max_decode_rows
             y = self._run_span(x, nb, T, lo, hi, table, zero.data_ptr(), scratch, pr, decode, 1)
             out[b0:b1] = y.view(nb, T, H)
         self._active = None  # the static table/pos were not touched, but be conservative

@@ -24,6 +24,9 @@ MODEL_PRESETS = {
                        num_attention_heads=32, num_key_value_heads=8, max_position_embeddings=8192, rms_norm_eps=1e-5, rope_theta=500000.0),
     "llama-tiny": dict(model_type="llama", vocab_size=4096, hidden_size=1024, intermediate_size=2816, num_hidden_layers=4,
                        num_attention_heads=8, num_key_value_heads=2, max_position_embeddings=2048, rms_norm_eps=1e-5, rope_theta=10000.0),
+    "mixtral-tiny": dict(model_type="mixtral", vocab_size=4096, hidden_size=1024, intermediate_size=1408, num_hidden_layers=3,
+                         num_attention_heads=8, num_key_value_heads=2, num_local_experts=8, num_experts_per_tok=2, rms_norm_eps=1e-5,
+                         rope_theta=1e6, max_position_embeddings=2048, sliding_window=None),
     "mixtral-8x7b": dict(model_type="mixtral", vocab_size=32000, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
                          num_attention_heads=32, num_key_value_heads=8, num_local_experts=8, num_experts_per_tok=2, rms_norm_eps=1e-5,
                          rope_theta=1e6, max_position_embeddings=32768),
@@ -36,10 +39,17 @@ def write_config_only(name: str, overrides: Optional[dict] = None, path: Optiona
     cfg = dict(MODEL_PRESETS[name])
     cfg.update(overrides or {})
     cfg.setdefault("torch_dtype", "bfloat16")
-    path = path or os.path.join(tempfile.gettempdir(), f"petals_b200_{name}_{os.getpid()}")
+    if path is None:
+        # deterministic across processes: every rank of a job must derive the same dht_prefix from the directory name
+        import hashlib
+
+        tag = hashlib.sha1(json.dumps(cfg, sort_keys=True).encode()).hexdigest()[:8]
+        path = os.path.join(tempfile.gettempdir(), f"petals_b200_{name}_{tag}")
     os.makedirs(path, exist_ok=True)
-    with open(os.path.join(path, "config.json"), "w") as f:
+    tmp = os.path.join(path, f"config.json.{os.getpid()}")
+    with open(tmp, "w") as f:
         json.dump(cfg, f)
+    os.replace(tmp, os.path.join(path, "config.json"))
     return path
 
 

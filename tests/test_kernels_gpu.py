@@ -264,3 +264,20 @@ def test_dequant_mxfp8():
     w = _rand(512, 1024, scale=0.05)
     q, e = quantize_mxfp8(w)
     assert torch.equal(Fn.dequant_mxfp8(q, e), dequantize_mxfp8(q, e))
+
+
+@pytest.mark.parametrize("M", [1, 3])
+def test_moe_decode(M):
+    from petals_b200.models.block_oracle import GenericBlock
+    from petals_b200.models.spec import BlockSpec
+
+    torch.manual_seed(22)
+    spec = BlockSpec(family="mixtral", hidden_size=1024, num_heads=8, num_kv_heads=2, head_dim=128, intermediate_size=1408, mlp="moe",
+                     num_experts=8, top_k=2, norm_eps=1e-5)
+    blk = GenericBlock(spec, dtype=torch.bfloat16, device=DEV, init_std=0.03)
+    blk.ln2_w.data = (1 + 0.1 * torch.randn(1024, device=DEV)).to(torch.bfloat16)
+    h = _rand(M, 1024)
+    out = torch.empty_like(h)
+    Fn.moe_decode(h, blk.ln2_w, blk.router, blk.we_gate, blk.we_up, blk.we_down, top_k=2, eps=1e-5, out=out)
+    want = h + blk.mlp(Fn.norm_ref(h, blk.ln2_w, None, Fn.NORM_RMS, 1e-5).view(1, M, 1024)).view(M, 1024)
+    _close(out, want, 3e-2, 3e-2, "moe decode")

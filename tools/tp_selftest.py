@@ -36,7 +36,7 @@ def main():
     engine, cache, heap = build_tp_engine(config, n, blocks=blocks, attn_cache_tokens=512, inference_max_length=256)
     ring = make_ring()
     probe = heap.alloc(8)
-    bw = measure_peer_bandwidth(heap, 0, 1, nbytes=heap.nbytes // 2)
+    bw = measure_peer_bandwidth(heap, 0, 1)
     lat = measure_hop_latency(heap, probe, 0, 1)
     if rank != 0:
         follower_loop(engine, cache, ring, rank - 1)
