@@ -90,6 +90,7 @@ def main() -> None:
     ap.add_argument("--prefill-batch", type=int, default=8)
     ap.add_argument("--prefill-steps", type=int, default=2)
     ap.add_argument("--skip-prefill", action="store_true")
+    ap.add_argument("--tp-prefill-rows", type=int, default=8192, help="rows per sequence-parallel prefill chunk (N > 1, tensor parallel)")
     ap.add_argument("--skip-fp8", action="store_true", help="do not append the block-scaled FP8 decode measurement")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -69,6 +69,8 @@ PB_DEVICE uint32_t swz(int r, int c) {
 
 template <int D>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
+  pdl_trigger();
+  pdl_wait();  // q / KV pages come from the RoPE+append kernel launched just before
   constexpr int BM = 64, BN = 64, CH = D / 8, KS = D / 16;
   constexpr int TILE_BYTES = BN * D * 2;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -279,6 +281,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 // merge split-KV partials: one CTA per (token, head) row, D threads
 __global__ void attn_combine_kernel(const float* __restrict__ po, const float* __restrict__ plse,
                                     __nv_bfloat16* __restrict__ out, int splits, size_t R, int D) {
+  pdl_trigger();
+  pdl_wait();
   const size_t row = blockIdx.x;
   const int d = threadIdx.x;
   float mx = -INFINITY;
@@ -315,11 +319,11 @@ static int launch_attn(const PbAttnArgs* a, cudaStream_t s) {
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
     return PB_ERR_CUDA;
   dim3 grid(m_tiles, a->B * a->Hkv, p.splits);
-  kern<<<grid, 128, smem, s>>>(p);
+  launch_pdl(kern, grid, dim3(128), smem, s, p);
   if (pb_check_launch("attention") != PB_OK) return PB_ERR_CUDA;
   if (p.splits > 1) {
     const size_t R = static_cast<size_t>(a->B) * a->T * a->Hq;
-    attn_combine_kernel<<<static_cast<unsigned>(R), D, 0, s>>>(p.partial_o, p.partial_lse, p.out, p.splits, R, D);
+    launch_pdl(attn_combine_kernel, dim3(static_cast<unsigned>(R)), dim3(D), 0, s, p.partial_o, p.partial_lse, p.out, p.splits, R, D);
     if (pb_check_launch("attention") != PB_OK) return PB_ERR_CUDA;
   }
   return PB_OK;

@@ -15,6 +15,7 @@
 #define PB_DEVICE __device__ __forceinline__
 
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace pb {
 
@@ -69,6 +70,17 @@ PB_DEVICE uint4 ld_stream(const void* p) {
                : "l"(p));
   return r;
 }
+PB_DEVICE void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// ---- programmatic dependent launch (PDL) -------------------------------------------------------------------------
+// A kernel launched with the programmatic-stream-serialization attribute may start while its predecessor in the stream
+// is still draining. Everything before pdl_wait() must touch only memory no earlier kernel writes (weights: L2
+// prefetch); pdl_wait() returns once the predecessor has completed and its writes are visible. pdl_trigger() lets the
+// *next* kernel's CTAs be scheduled as soon as this grid's CTAs have all started (they then park in their pdl_wait()).
+// Both are no-ops when the kernel was launched without the attribute.
+PB_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+PB_DEVICE void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 PB_DEVICE uint4 ld_cached(const void* p) {
   uint4 r;
   asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];"
@@ -304,6 +316,32 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t M, uint32_t N, u
 // kind::f8f6f4 with e4m3 A/B, fp32 accumulate (K-major only).
 __host__ __device__ constexpr uint32_t umma_idesc_e4m3(uint32_t M, uint32_t N) {
   return (1u << 4) | (0u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// ---- host: launch with (optional) programmatic dependent launch ------------------------------------------------------
+// pb_pdl_enabled() reads PETALS_B200_PDL once (default on). Kernels launched through launch_pdl() MUST call pdl_wait()
+// before reading anything an earlier kernel of the stream produced.
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("PETALS_B200_PDL");
+    return e == nullptr || e[0] != '0';
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 }  // namespace pb

@@ -46,6 +46,8 @@ struct GemmParams {
   uint64_t* push_flag[PB_MAX_PEERS];       // per-tile release-increment (lets a consumer start on finished row blocks)
   uint64_t* push_done_flag[PB_MAX_PEERS];  // ONE release-increment per launch, by the last CTA to finish all its tiles
   unsigned int* done_counter;              // local self-resetting counter electing that last CTA
+  int push_rows_per_owner;                 // 0: every tile goes to all n_push peers (broadcast / stage hop);
+                                           // >0: reduce-scatter routing — row r goes ONLY to peer r / rows_per_owner, at local row r % rows_per_owner
   const uint64_t* wait_flag;
   uint64_t wait_per_epoch;
   const uint64_t* epoch;
@@ -280,17 +282,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                 for (int q = 0; q < 4; ++q) op[q] = pk[q];
               }
-              for (int rnk = 0; rnk < p.n_push; ++rnk) {
-                uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.push_out[rnk]) + off);
+              if (p.push_rows_per_owner > 0) {
+                const int owner = row / p.push_rows_per_owner;
+                const size_t roff = static_cast<size_t>(row - owner * p.push_rows_per_owner) * p.ldo + col0;
+                uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.push_out[owner]) + roff);
 #pragma unroll
                 for (int q = 0; q < 4; ++q) op[q] = pk[q];
+              } else {
+                for (int rnk = 0; rnk < p.n_push; ++rnk) {
+                  uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.push_out[rnk]) + off);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) op[q] = pk[q];
+                }
               }
             } else {
               for (int i = 0; i < 32 && col0 + i < p.N; ++i) {
                 const __nv_bfloat16 bv = __float2bfloat16_rn(v[i]);
                 if (p.out != nullptr) static_cast<__nv_bfloat16*>(p.out)[off + i] = bv;
-                for (int rnk = 0; rnk < p.n_push; ++rnk)
-                  static_cast<__nv_bfloat16*>(p.push_out[rnk])[off + i] = bv;
+                if (p.push_rows_per_owner > 0) {
+                  const int owner = row / p.push_rows_per_owner;
+                  static_cast<__nv_bfloat16*>(p.push_out[owner])[static_cast<size_t>(row - owner * p.push_rows_per_owner) * p.ldo + col0 + i] = bv;
+                } else {
+                  for (int rnk = 0; rnk < p.n_push; ++rnk)
+                    static_cast<__nv_bfloat16*>(p.push_out[rnk])[off + i] = bv;
+                }
               }
             }
           }
@@ -408,6 +423,7 @@ static int launch_gemm(const PbGemmArgs* a, cudaStream_t stream) {
     p.push_done_flag[i] = static_cast<uint64_t*>(a->push_done_flag[i]);
   }
   p.done_counter = static_cast<unsigned int*>(a->done_counter);
+  p.push_rows_per_owner = a->push_rows_per_owner;
   p.wait_flag = static_cast<const uint64_t*>(a->wait_flag);
   p.wait_per_epoch = a->wait_per_epoch;
   p.epoch = static_cast<const uint64_t*>(a->epoch);

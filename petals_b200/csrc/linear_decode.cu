@@ -100,6 +100,27 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int tid = threadIdx.x, nthr = blockDim.x;
 
+  // ---- PDL pre-section --------------------------------------------------------------------------
+  // Weights are never written by a kernel, so while the predecessor kernel drains (and while this kernel then waits for
+  // a peer flag and normalises x) every warp pulls the head of its first weight rows into L2: the main loop's first
+  // iterations hit L2 and HBM keeps streaming through what used to be a bubble between two GEMVs.
+  pdl_trigger();
+  {
+    const int task0 = warp * gridDim.x + blockIdx.x;
+    if (task0 < (N >> 1)) {
+      constexpr int kRows = DUAL ? 4 : 2;
+      constexpr int kPfLines = 64;  // 128-byte lines per warp = 8 KB
+      constexpr int kLinesPerRow = kPfLines / kRows;
+      const int n0 = task0 << 1;
+#pragma unroll
+      for (int i = lane; i < kPfLines; i += 32) {
+        const int row = i / kLinesPerRow, k = (i % kLinesPerRow) * 64;
+        if (k < K) prefetch_l2((row < 2 ? p.w : p.w2) + static_cast<size_t>(n0 + (row & 1)) * K + k);
+      }
+    }
+  }
+  pdl_wait();
+
   // ---- prologue ----------------------------------------------------------------------------
   if (p.wait_flag != nullptr) {
     if (tid == 0) {
@@ -324,8 +345,7 @@ static cudaError_t launch_one(const LinearDecodeParams& p, int grid, int block, 
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
-  kern<<<grid, block, smem, stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(grid), dim3(block), smem, stream, p);
 }
 
 template <int M>

@@ -53,6 +53,7 @@ typedef struct {
   const void* wait_flag; uint64_t wait_per_epoch; const void* epoch; void* error_flag;
   int num_sms; int block_n;   // 0 = auto
   void* push_done_flag[PB_MAX_PEERS]; void* done_counter;  // once-per-launch completion flag (last CTA)
+  int push_rows_per_owner;    // > 0: reduce-scatter routing of output rows to their owner rank (see gemm_tcgen05.cu)
 } PbGemmArgs;
 int pb_gemm_bf16(const PbGemmArgs* a, void* stream);
 
@@ -85,6 +86,18 @@ typedef struct {
   void* error_flag;
 } PbRopeKvArgs;
 int pb_rope_kv(const PbRopeKvArgs* a, void* stream);
+
+// ---- owner-side reduce-scatter tail + norm + all-gather for sequence-parallel TP prefill (seq_parallel.cu) ----
+typedef struct {
+  const void* x_res_in; void* x_res_out;            // [rows, H] bf16 owned residual rows (in may be NULL = zero; out may be NULL)
+  int n_parts; const void* parts[PB_MAX_PEERS];     // partial rows written by the peers' GEMM epilogues
+  const void* norm_w; const void* norm_b; float eps; int norm_kind;   // 0: gather the raw sum
+  int n_gather; void* gather_out[PB_MAX_PEERS]; void* gather_flag[PB_MAX_PEERS];
+  const void* wait_flag; uint64_t wait_per_epoch; const void* epoch;
+  void* done_counter; void* error_flag;
+  int rows, H, num_sms;
+} PbNormReduceGatherArgs;
+int pb_norm_reduce_gather(const PbNormReduceGatherArgs* a, void* stream);
 
 // ---- flash attention over the paged KV cache (attention.cu) ---------------------------------------
 typedef struct {

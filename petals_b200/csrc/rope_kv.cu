@@ -36,6 +36,8 @@ PB_DEVICE float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); 
 
 // grid: (B*T, Hq + 2*Hkv); block: D/2 threads — thread i owns the rotary pair (i, i + D/2).
 __global__ void rope_kv_kernel(const RopeKvParams p) {
+  pdl_trigger();  // let the attention kernel's CTAs get scheduled behind ours
+  pdl_wait();     // the fused QKV projection (previous kernel) must be complete and visible
   const int tok = blockIdx.x;            // b * T + t
   const int head = blockIdx.y;           // [0,Hq): q, [Hq,Hq+Hkv): k, rest: v
   const int b = tok / p.T, t = tok - b * p.T;
@@ -120,7 +122,7 @@ extern "C" int pb_rope_kv(const PbRopeKvArgs* a, void* stream) {
   p.max_pages = a->max_pages; p.max_pos = a->max_pos; p.interleaved = a->interleaved_qkv;
   p.error_flag = static_cast<int*>(a->error_flag);
   dim3 grid(a->B * a->T, a->Hq + 2 * a->Hkv);
-  rope_kv_kernel<<<grid, a->D / 2, 0, static_cast<cudaStream_t>(stream)>>>(p);
+  launch_pdl(rope_kv_kernel, grid, dim3(a->D / 2), 0, static_cast<cudaStream_t>(stream), p);
   return pb_check_launch("rope_kv");
 }
 

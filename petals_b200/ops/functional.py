@@ -175,6 +175,7 @@ def gemm(
     wait_flag: Optional[int] = None, wait_per_epoch: int = 0, epoch: Optional[int] = None,
     push_out: Sequence[int] = (), push_flag: Sequence[int] = (), error_flag: Optional[int] = None,
     store_local: bool = True, push_done_flag: Sequence[int] = (), done_counter: Optional[int] = None,
+    push_rows_per_owner: int = 0,
 ) -> torch.Tensor:
     """``out[M,N] = epilogue(a[M,K] @ op(b))`` on the tcgen05 tensor cores. See csrc/gemm_tcgen05.cu.
 
@@ -201,6 +202,7 @@ def gemm(
         g.push_flag[i] = push_flag[i] if i < len(push_flag) else None
         g.push_done_flag[i] = push_done_flag[i] if i < len(push_done_flag) else None
     g.done_counter = done_counter
+    g.push_rows_per_owner = push_rows_per_owner
     g.wait_flag, g.wait_per_epoch, g.epoch, g.error_flag = wait_flag, wait_per_epoch, epoch, error_flag
     g.num_sms = native.sm_count(a_.device.index)
     g.block_n = block_n
@@ -222,6 +224,31 @@ def norm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = N
                                ptr(_bf16c(bias, "bias")), ptr(out), ptr(sum_out), rows, cols, eps, kind, stream_ptr()),
           "norm")
     return out
+
+
+def norm_reduce_gather(x_res_in: Optional[torch.Tensor], x_res_out: Optional[torch.Tensor], *, rows: int, H: int, parts: Sequence[int] = (),
+                       norm_weight: Optional[torch.Tensor] = None, norm_bias: Optional[torch.Tensor] = None, norm_kind: int = NORM_NONE,
+                       eps: float = 1e-6, gather_out: Sequence[int] = (), gather_flag: Sequence[int] = (), wait_flag: Optional[int] = None,
+                       wait_per_epoch: int = 0, epoch: Optional[int] = None, done_counter: Optional[int] = None,
+                       error_flag: Optional[int] = None, device_index: Optional[int] = None) -> None:
+    """Owner-side tail of the fused reduce-scatter (sum of the peers' GEMM-epilogue partial rows + residual slice), norm, and
+    all-gather of the normalised rows into every peer's activation buffer. ``parts``/``gather_out``/``gather_flag`` are raw
+    (symmetric-heap) addresses. See csrc/seq_parallel.cu."""
+    a = native.NormReduceGatherArgs()
+    a.x_res_in, a.x_res_out = ptr(x_res_in), ptr(x_res_out)
+    a.n_parts = len(parts)
+    for i, p_ in enumerate(parts):
+        a.parts[i] = p_
+    a.norm_w, a.norm_b, a.eps, a.norm_kind = ptr(_bf16c(norm_weight, "norm_weight")), ptr(_bf16c(norm_bias, "norm_bias")), eps, norm_kind
+    a.n_gather = len(gather_out)
+    for i, p_ in enumerate(gather_out):
+        a.gather_out[i] = p_
+        a.gather_flag[i] = gather_flag[i] if i < len(gather_flag) else None
+    a.wait_flag, a.wait_per_epoch, a.epoch = wait_flag, wait_per_epoch, epoch
+    a.done_counter, a.error_flag = done_counter, error_flag
+    a.rows, a.H = rows, H
+    a.num_sms = native.sm_count(device_index if device_index is not None else torch.cuda.current_device())
+    check(native.lib().pb_norm_reduce_gather(C.byref(a), stream_ptr()), "norm_reduce_gather")
 
 
 def swiglu(gate: torch.Tensor, up: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -360,11 +387,12 @@ def moe_decode(h: torch.Tensor, norm_w: torch.Tensor, router: torch.Tensor, we_g
     E, I, _ = we_gate.shape
     bufs = bufs if bufs is not None else {}
 
-    def buf(name, shape, dtype):
-        t = bufs.get(name)
-        if t is None or tuple(t.shape) != tuple(shape):
+    def buf(name, shape, dtype):  # keyed by shape, never replaced: captured CUDA graphs hold these addresses
+        key = (name, tuple(shape))
+        t = bufs.get(key)
+        if t is None:
             t = torch.empty(shape, dtype=dtype, device=h.device)
-            bufs[name] = t
+            bufs[key] = t
         return t
 
     xn = buf("moe_xn", (M, H), torch.bfloat16)

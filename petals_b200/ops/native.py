@@ -62,7 +62,7 @@ class GemmArgs(C.Structure):
         ("n_push", C.c_int), ("push_out", C.c_void_p * PB_MAX_PEERS), ("push_flag", C.c_void_p * PB_MAX_PEERS),
         ("wait_flag", C.c_void_p), ("wait_per_epoch", C.c_uint64), ("epoch", C.c_void_p), ("error_flag", C.c_void_p),
         ("num_sms", C.c_int), ("block_n", C.c_int),
-        ("push_done_flag", C.c_void_p * PB_MAX_PEERS), ("done_counter", C.c_void_p),
+        ("push_done_flag", C.c_void_p * PB_MAX_PEERS), ("done_counter", C.c_void_p), ("push_rows_per_owner", C.c_int),
     ]
 
 
@@ -74,6 +74,18 @@ class RopeKvArgs(C.Structure):
         ("B", C.c_int), ("T", C.c_int), ("Hq", C.c_int), ("Hkv", C.c_int), ("D", C.c_int), ("page", C.c_int),
         ("max_pages", C.c_int), ("max_pos", C.c_int), ("interleaved_qkv", C.c_int),
         ("error_flag", C.c_void_p),
+    ]
+
+
+class NormReduceGatherArgs(C.Structure):
+    _fields_ = [
+        ("x_res_in", C.c_void_p), ("x_res_out", C.c_void_p),
+        ("n_parts", C.c_int), ("parts", C.c_void_p * PB_MAX_PEERS),
+        ("norm_w", C.c_void_p), ("norm_b", C.c_void_p), ("eps", C.c_float), ("norm_kind", C.c_int),
+        ("n_gather", C.c_int), ("gather_out", C.c_void_p * PB_MAX_PEERS), ("gather_flag", C.c_void_p * PB_MAX_PEERS),
+        ("wait_flag", C.c_void_p), ("wait_per_epoch", C.c_uint64), ("epoch", C.c_void_p),
+        ("done_counter", C.c_void_p), ("error_flag", C.c_void_p),
+        ("rows", C.c_int), ("H", C.c_int), ("num_sms", C.c_int),
     ]
 
 
@@ -106,6 +118,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.pb_advance_pos.argtypes = [vp, ci, vp]
     lib.pb_rope_kv.argtypes = [C.POINTER(RopeKvArgs), vp]
     lib.pb_attention.argtypes = [C.POINTER(AttnArgs), vp]
+    lib.pb_norm_reduce_gather.argtypes = [C.POINTER(NormReduceGatherArgs), vp]
+    lib.pb_norm_reduce_gather.restype = ci
     lib.pb_kv_copy_pages.argtypes = [vp, vp, vp, ci, cl, cl, ci, vp]
     lib.pb_device_sm_count.argtypes = [ci]
     vpp = C.POINTER(C.c_void_p)

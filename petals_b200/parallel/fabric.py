@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from petals_b200.ops import native
-from petals_b200.parallel.symmetric import SymmetricHeap, ptr_array, tensor_from_ptr
+from petals_b200.parallel.symmetric import SymmetricHeap, host_barrier, ptr_array, tensor_from_ptr
 from petals_b200.utils.logging import get_logger
 
 logger = get_logger(__name__)
@@ -54,7 +54,7 @@ class Fabric:
         self.push_epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
         self.heap.tensor(self.off_flags + 16, (1,), torch.int64).fill_(1)
         torch.cuda.synchronize(self.device)
-        dist.barrier(group=group)
+        host_barrier(group)
 
     # ---- addresses ---------------------------------------------------------------------------------------------
     def x_in_addr(self, rank: int) -> int:
@@ -162,7 +162,7 @@ class HostFabric:
         self._pushes = 0
         for r in range(self.world):
             self._flags(r)[2] = 1  # ack flags start at 1 (first push never waits)
-        dist.barrier(group=group)
+        host_barrier(group)
 
     def _flags(self, rank: int):
         off = rank * self._per_rank + 2 * self._zone_bytes

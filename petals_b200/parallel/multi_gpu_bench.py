@@ -15,6 +15,8 @@ import time
 import torch
 import torch.distributed as dist
 
+from petals_b200.parallel.symmetric import host_barrier
+
 BASELINE_TOKENS_PER_S = 6.0
 
 
@@ -44,7 +46,11 @@ def run_multi_gpu(args) -> None:
     config = AutoDistributedConfig.from_pretrained(path)
     n_layers = MODEL_PRESETS[args.model]["num_hidden_layers"]
     t0 = time.time()
-    engine, cache, heap = build_tp_engine(config, n_layers, attn_cache_tokens=args.seq_len + 256, inference_max_length=args.seq_len)
+    do_prefill = not args.skip_prefill
+    PB, PT = args.prefill_batch, args.prefill_seq
+    max_len = max(args.seq_len, PT) if do_prefill else args.seq_len
+    engine, cache, heap = build_tp_engine(config, n_layers, attn_cache_tokens=(max(args.seq_len, PB * PT) if do_prefill else args.seq_len) + 512,
+                                          inference_max_length=max_len, max_prefill_rows=args.tp_prefill_rows)
     ring = make_ring()
     build_s = time.time() - t0
     # ---- NVLink probes (stage-hop denominators) -------------------------------------------------------------------
@@ -56,9 +62,10 @@ def run_multi_gpu(args) -> None:
     if rank != 0:
         marks = follower_loop_with_marks(engine, cache, ring, rank - 1)
         ms = marks["start"].elapsed_time(marks["end"]) if "start" in marks and "end" in marks else 0.0
+        pms = marks["p_start"].elapsed_time(marks["p_end"]) if "p_start" in marks and "p_end" in marks else 0.0
         gathered = [None] * world
-        dist.all_gather_object(gathered, ms)
-        dist.barrier()
+        dist.all_gather_object(gathered, (ms, pms))
+        host_barrier()
         heap.close()
         dist.destroy_process_group()
         return
@@ -70,7 +77,7 @@ def run_multi_gpu(args) -> None:
     info = ServerInfo(state=ServerState.JOINING, throughput=1.0, version=petals_b200.__version__, torch_dtype="bfloat16", quant_type="none", using_relay=False)
     container = ModuleContainer.from_stage(dht=swarm, dht_prefix=config.dht_prefix, block_config=config, stage=stage, server_info=info,
                                            model_info=ModelInfo(num_blocks=n_layers, repository=path), peer_id=f"tp{world}-leader",
-                                           inference_max_length=args.seq_len)
+                                           inference_max_length=max_len)
     model = random_client_model(path, swarm, dev)
     vocab = model.config.vocab_size
     prompt = torch.randint(0, vocab, (1, args.prompt_len), device=dev)
@@ -109,9 +116,39 @@ def run_multi_gpu(args) -> None:
             pinned_in[0, 0] = pinned_out[0]
         e2e_s = time.perf_counter() - t1
     engine.check_errors()
+    # ---- prompt ingestion: parallel forward of [PB, PT] tokens through the public client API (rpc_forward) ------------------
+    pms0, prefill = 0.0, None
+    if do_prefill:
+        try:
+            ids = torch.randint(0, vocab, (PB, PT), device=dev)
+            with torch.inference_mode():
+                model.model(input_ids=ids)
+                torch.cuda.synchronize()
+                ring.send({"op": "mark", "name": "p_start"})
+                ps, pe = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ps.record()
+                for _ in range(args.prefill_steps):
+                    model.model(input_ids=ids)
+                pe.record()
+                torch.cuda.synchronize()
+                ring.send({"op": "mark", "name": "p_end"})
+            pms0 = ps.elapsed_time(pe)
+            engine.check_errors()
+        except Exception as e:  # the decode number stands on its own
+            prefill = {"error": repr(e)[:300]}
     leader.shutdown()
     gathered = [None] * world
-    dist.all_gather_object(gathered, ms0)
+    dist.all_gather_object(gathered, (ms0, pms0))
+    if do_prefill and prefill is None:
+        pms = max(float(x[1]) for x in gathered) / args.prefill_steps
+        spec_ = config.block_spec()
+        flops = 2.0 * spec_.num_params() * n_layers * PB * PT + 4.0 * n_layers * PB * PT * PT * spec_.num_heads * spec_.head_dim / 2
+        pk = measured_peaks()
+        prefill = {"tokens_per_s": round(PB * PT / (pms / 1e3), 1), "ms_per_step": round(pms, 2), "batch": PB, "seq_len": PT,
+                   "TFLOPs_total": round(flops / pms / 1e9, 1), "frac_of_measured_bf16_sustained_per_gpu": round(flops / pms / 1e9 / world / pk["bf16_tflops_sustained"], 3),
+                   "path": f"sequence-parallel tcgen05 GEMMs, reduce-scatter in the GEMM epilogue + all-gather in the norm kernel over NVLink, chunks of {engine.max_prefill_rows} rows",
+                   "launches_per_chunk_per_rank": getattr(engine, "prefill_launches", None)}
+    gathered = [x[0] for x in gathered]
     ms = max(float(x) for x in gathered)
     value = K / (ms / 1e3)
     peaks = measured_peaks()
@@ -129,6 +166,7 @@ def run_multi_gpu(args) -> None:
         "clocks": clocks,
         "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8},
         "gpu_launches": launches,
+        "prefill": prefill,
         "roofline": {"weight_bytes_per_token_per_rank": int(weight_bytes_rank), "achieved_GBps_per_rank": round(weight_bytes_rank * value / 1e9, 1),
                      "frac_of_measured_hbm": round(weight_bytes_rank * value / 1e9 / peaks["hbm_gbs"], 3), "peaks": peaks["source"]},
         "stage_hop": {"peer_store_GBps": None if peer_gbs is None else round(peer_gbs, 1), "frac_of_measured_peer_copy": None if peer_gbs is None else round(peer_gbs / NVLINK_PEER_GBS, 3),
@@ -136,7 +174,7 @@ def run_multi_gpu(args) -> None:
                       "fused_allreduces_per_token": 2 * n_layers},
     }
     container.shutdown()
-    dist.barrier()
+    host_barrier()
     heap.close()
     print(json.dumps(result))
     dist.destroy_process_group()
@@ -151,13 +189,13 @@ def follower_loop_with_marks(engine, cache, ring, consumer: int) -> dict:
     while True:
         cmd = ring.recv(consumer, timeout=None)
         op = cmd["op"]
-        if op == "step":
+        if op in ("step", "prefill"):
             s = sessions[cmd["sid"]]
             if cmd["pos"] != s.position:
                 s.set_position(cmd["pos"])
             if "hypo" in cmd:
                 s.reorder(torch.tensor(cmd["hypo"], dtype=torch.int64))
-            engine.run_step(s, cmd["B"], cmd["T"])
+            (engine.run_step if op == "step" else engine.run_prefill)(s, cmd["B"], cmd["T"])
         elif op == "open":
             sessions[cmd["sid"]] = cache.open_session(cmd["B"], cmd["max_length"], timeout=None)
         elif op == "close":
@@ -165,7 +203,7 @@ def follower_loop_with_marks(engine, cache, ring, consumer: int) -> dict:
             if s is not None:
                 s.close()
         elif op == "mark":
-            if cmd["name"] == "end":
+            if cmd["name"].endswith("end"):
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record()
                 torch.cuda.synchronize()
@@ -217,7 +255,7 @@ def run_pipeline(args) -> None:
     stage = launch_random_stage(path, range(bounds[rank], bounds[rank + 1]), swarm, dev, peer_id=f"stage{rank}", attn_cache_tokens=args.seq_len + 256,
                                 inference_max_length=args.seq_len, max_batch_size=1 << 20)
     torch.cuda.synchronize()
-    dist.barrier()
+    host_barrier()
     build_s = time.time() - t0
     K, W = args.steps, max(args.warmup, 3)
     if rank == 0:
@@ -276,8 +314,8 @@ def run_pipeline(args) -> None:
                           "hops_per_token": world, "reference_hop_model_ms": 18.0},
         }
         print(json.dumps(result))
-    dist.barrier()
+    host_barrier()
     stage.shutdown()
-    dist.barrier()
+    host_barrier()
     fabric.close()
     dist.destroy_process_group()

@@ -21,6 +21,20 @@ from petals_b200.utils.logging import get_logger
 logger = get_logger(__name__)
 
 
+def host_barrier(group=None) -> None:
+    """A barrier that never touches the GPU: an all-reduce of one CPU scalar (gloo).
+
+    ``dist.barrier()`` on a NCCL-backed group parks a spinning kernel on every waiting rank's GPU. A stage that keeps serving
+    from background threads while its main thread sits in such a barrier dead-locks on its first device-wide
+    synchronisation (CUDA-graph capture, ``cudaFree``): the sync waits for the barrier kernel, the barrier waits for the
+    client, the client waits for the stage. Host barriers order *processes*; callers synchronise their own device first
+    where GPU work must be finished."""
+    try:
+        dist.all_reduce(torch.zeros(1), group=group)
+    except RuntimeError:  # group without a CPU backend
+        dist.barrier(group=group)
+
+
 class _RawCudaBuffer:
     """Adapter exposing a raw device pointer through __cuda_array_interface__ (uint8)."""
 
@@ -63,7 +77,7 @@ class SymmetricHeap:
                 native.check(self._lib.pb_ipc_open_handle(h, C.byref(out)), f"ipc_open_handle(rank {r})", 0)
                 self.ptrs.append(int(out.value))
         self._top = 0
-        dist.barrier(group=group)
+        host_barrier(group)
         logger.info(f"rank {self.rank}: symmetric heap of {self.nbytes >> 20} MiB mapped on {self.world} ranks")
 
     # ---- allocation (must be called in the same order on every rank) ---------------------------------------------
@@ -90,7 +104,7 @@ class SymmetricHeap:
     def zero_(self) -> None:
         self.tensor(0, (self.nbytes,), torch.uint8).zero_()
         torch.cuda.synchronize(self.device)
-        dist.barrier(group=self.group)
+        host_barrier(self.group)
 
     def close(self) -> None:
         for r, p in enumerate(self.ptrs):
@@ -115,7 +129,7 @@ def measure_peer_bandwidth(heap: SymmetricHeap, src_rank: int = 0, dst_rank: int
     Collective: allocates its own scratch region in the symmetric heap (never touches live buffers or flags)."""
     nbytes = min(nbytes, (heap.nbytes - heap._top - 4096)) // 4096 * 4096
     if nbytes < (1 << 20):
-        dist.barrier(group=heap.group)
+        host_barrier(heap.group)
         return None
     region = heap.alloc(nbytes, align=4096)
     result = None
@@ -132,7 +146,7 @@ def measure_peer_bandwidth(heap: SymmetricHeap, src_rank: int = 0, dst_rank: int
         e.record()
         torch.cuda.synchronize()
         result = nbytes * iters / (s.elapsed_time(e) * 1e-3) / 1e9
-    dist.barrier(group=heap.group)
+    host_barrier(heap.group)
     return result
 
 
@@ -141,7 +155,7 @@ def measure_hop_latency(heap: SymmetricHeap, flag_off: int, a: int = 0, b: int =
     lib = native.lib()
     heap.tensor(flag_off, (1,), torch.int64).zero_()
     torch.cuda.synchronize()
-    dist.barrier(group=heap.group)
+    host_barrier(heap.group)
     result = None
     if heap.rank in (a, b):
         peer = b if heap.rank == a else a
@@ -154,5 +168,5 @@ def measure_hop_latency(heap: SymmetricHeap, flag_off: int, a: int = 0, b: int =
             raise RuntimeError("ping-pong watchdog expired")
         if heap.rank == a:
             result = float(rtt[iters // 10:].float().median().item()) / 2e3
-    dist.barrier(group=heap.group)
+    host_barrier(heap.group)
     return result

@@ -89,11 +89,24 @@ def random_shard(spec: BlockSpec, rank: int, world: int, layer: int, device, see
     return out
 
 
+def prefill_heap_bytes(hidden_size: int, world: int, n_blocks: int, max_prefill_rows: int) -> int:
+    """Symmetric-heap bytes the sequence-parallel prefill path needs (landing zone, partial slots, activations, output, flags)."""
+    if max_prefill_rows <= 0:
+        return 0
+    mo = (max_prefill_rows + world - 1) // world
+    row = hidden_size * 2
+    return (mo + world * mo + 2 * max_prefill_rows) * row + (4 * n_blocks + 4) * 8 + 8 * 4096
+
+
 class TPDecodeEngine:
-    """Executes a span of blocks sharded over a TP group for decode-shaped steps (B*T <= 8 rows)."""
+    """Executes a span of blocks sharded over a TP group.
+
+    * decode-shaped steps (B*T <= 8 rows): weight-streaming GEMVs with the all-reduce fused into epilogue + next prologue;
+    * prefill-shaped steps (up to ``max_prefill_rows`` rows): sequence-parallel tcgen05 GEMMs whose epilogue performs the
+      reduce-scatter over NVLink and whose successor norm kernel performs the all-gather (csrc/seq_parallel.cu)."""
 
     def __init__(self, spec: BlockSpec, shards: Sequence[Dict[str, torch.Tensor]], heap: SymmetricHeap, cache: MemoryCache, *,
-                 use_cuda_graphs: bool = True):
+                 use_cuda_graphs: bool = True, max_prefill_rows: int = 4096):
         self.spec, self.shards, self.heap, self.cache = spec, list(shards), heap, cache
         self.rank, self.world = heap.rank, heap.world
         self.ls = local_spec(spec, self.world)
@@ -115,16 +128,30 @@ class TPDecodeEngine:
         self.off_parts_mlp = heap.alloc(R * self.slot_bytes)
         self.off_flags = heap.alloc((2 * L + 2) * 8)
         self.x_in = heap.tensor(self.off_x_in, (MAX_ROWS, H), torch.bfloat16)
+        # sequence-parallel prefill: rows are owned in contiguous slices of `mo` rows per rank
+        self.max_prefill_rows = P = max(0, max_prefill_rows)
+        if P:
+            self.p_mo_max = (P + R - 1) // R
+            self.p_slot_bytes = self.p_mo_max * H * 2
+            self.off_p_x_in = heap.alloc(self.p_slot_bytes, align=4096)        # my residual rows, scattered by the leader
+            self.off_p_parts = heap.alloc(R * self.p_slot_bytes, align=4096)    # [src rank][my rows, H] GEMM-epilogue partials
+            self.off_p_xn = heap.alloc(P * H * 2, align=4096)                   # all rows, normalised (all-gathered)
+            self.off_p_out = heap.alloc(P * H * 2, align=4096)                  # span output, gathered on the leader
+            self.off_p_flags = heap.alloc((4 * L + 4) * 8)
+            self.p_xn = heap.tensor(self.off_p_xn, (P, H), torch.bfloat16)
+            self.p_out = heap.tensor(self.off_p_out, (P, H), torch.bfloat16)
+            self.p_x_in = heap.tensor(self.off_p_x_in, (self.p_mo_max, H), torch.bfloat16)
         # ---- local state ----------------------------------------------------------------------------------------------
         dev = self.device
         self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.epoch_p = torch.zeros(1, dtype=torch.int64, device=dev)  # prefill steps count their own epochs (own flag set)
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.done_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.pos_static = torch.zeros(1, dtype=torch.int32, device=dev)
         self.max_pages = cache.max_pages_per_seq
         self._tables: Dict[int, torch.Tensor] = {}
         self._graphs: Dict[Tuple[int, int], dict] = {}
-        self._bufs: Dict[Tuple[str, int], torch.Tensor] = {}
+        self._bufs: Dict[tuple, torch.Tensor] = {}
         self._active: Optional[SessionCache] = None
         self._dev_pos = -1
         self.out = torch.zeros(MAX_ROWS, H, dtype=torch.bfloat16, device=dev)
@@ -143,9 +170,10 @@ class TPDecodeEngine:
         return self.heap.addr(owner, off + src * self.slot_bytes)
 
     def _buf(self, name: str, rows: int, cols: int, dtype=torch.bfloat16) -> torch.Tensor:
-        key = (name, rows)
+        # keyed by the full shape and never replaced: captured CUDA graphs keep the raw addresses of these buffers
+        key = (name, rows, cols, dtype)
         t = self._bufs.get(key)
-        if t is None or t.shape[1] != cols:
+        if t is None:
             t = torch.empty(rows, cols, dtype=dtype, device=self.device)
             self._bufs[key] = t
         return t
@@ -211,6 +239,103 @@ class TPDecodeEngine:
         native.check(native.lib().pb_advance_pos(pos_ptr, T, native.stream_ptr()), "advance_pos")
         self._last_residual, self._last_parts = cur, mlp_parts
         return self.out[:M]
+
+    # ---- sequence-parallel prefill ---------------------------------------------------------------------------------------
+    def p_flag(self, rank: int, index: int) -> int:
+        return self.heap.addr(rank, self.off_p_flags + 8 * index)
+
+    def _p_layer_flag(self, rank: int, layer: int, which: int) -> int:
+        """which: 0 = xn ready (input of QKV), 1 = attention partials landed, 2 = xn2 ready (input of gate/up), 3 = MLP partials landed."""
+        return self.p_flag(rank, 4 + 4 * layer + which)
+
+    def _launch_prefill(self, B: int, T: int, table: torch.Tensor) -> torch.Tensor:
+        """One prompt chunk of M = B*T rows through the whole span. Per layer and rank: 4 tcgen05 GEMMs, RoPE+KV append, flash
+        attention and 2 norm_reduce_gather kernels; the two reduce-scatters ride in GEMM epilogues, the two all-gathers in the norm
+        kernels; every wait is a flag spin in the consumer's prologue."""
+        s, ls, R, me = self.spec, self.ls, self.world, self.rank
+        M, H = B * T, s.hidden_size
+        if M > self.max_prefill_rows:
+            raise ValueError(f"{M} rows exceed max_prefill_rows={self.max_prefill_rows}")
+        mo = (M + R - 1) // R
+        my_rows = max(0, min(mo, M - me * mo))
+        eps, L = s.norm_eps, self.n_blocks
+        ep, err, ctr = self.epoch_p.data_ptr(), self.err.data_ptr(), self.done_counter.data_ptr()
+        pos_ptr = self.pos_static.data_ptr()
+        native.check(native.lib().pb_bump_epoch(ep, native.stream_ptr()), "bump_epoch")
+        x_res = self._buf("p_res", self.p_mo_max, H)
+        xn = self.p_xn[:M]
+        qkv_buf = self._buf("p_qkv", M, ls.qkv_dim)
+        q_buf = self._buf("p_q", M, ls.num_heads * ls.head_dim)
+        attn = self._buf("p_attn", M, ls.num_heads * ls.head_dim)
+        act = self._buf("p_act", M, ls.intermediate_size)
+        row_b = H * 2
+        my_parts = [self.heap.addr(me, self.off_p_parts + r * self.p_slot_bytes) for r in range(R)]
+        push_parts = [self.heap.addr(r, self.off_p_parts + me * self.p_slot_bytes) for r in range(R)]  # my slot in every owner's buffer
+        gather_xn = [self.heap.addr(r, self.off_p_xn + me * mo * row_b) for r in range(R)]
+        dev = self.device.index
+        common = dict(rows=my_rows, H=H, eps=eps, epoch=ep, done_counter=ctr, error_flag=err, device_index=dev)
+        w0 = self.shards[0]
+        # layer-0 prologue: my slice of the chunk (scattered by the leader) becomes the residual; its norm is all-gathered
+        Fn.norm_reduce_gather(self.p_x_in, x_res, norm_weight=w0["ln1_w"], norm_bias=w0.get("ln1_b"), norm_kind=self.norm_kind,
+                              gather_out=gather_xn, gather_flag=[self._p_layer_flag(r, 0, 0) for r in range(R)],
+                              wait_flag=self.p_flag(me, 0), wait_per_epoch=1, **common)
+        for l, w in enumerate(self.shards):
+            pools = self.cache.layer_pools(l)
+            Fn.gemm(xn, w["wqkv"], out=qkv_buf, wait_flag=self._p_layer_flag(me, l, 0), wait_per_epoch=R, epoch=ep, error_flag=err)
+            Fn.rope_kv_append(qkv_buf, q_buf, pools[0], pools[1], table, pos_ptr, self.cos, self.sin, B=B, T=T, Hq=ls.num_heads,
+                              Hkv=ls.num_kv_heads, D=ls.head_dim, error_flag=err)
+            Fn.paged_attention(q_buf, pools[0], pools[1], table, pos_ptr, attn, B=B, T=T, Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim,
+                               scale=s.attn_scale, splits=1, window=s.sliding_window)
+            # row-parallel O-projection; the epilogue IS the reduce-scatter (row r -> owner r // mo, slot [me])
+            Fn.gemm(attn, w["wo"], store_local=False, push_out=push_parts, push_rows_per_owner=mo,
+                    push_done_flag=[self._p_layer_flag(r, l, 1) for r in range(R)], done_counter=ctr, error_flag=err)
+            Fn.norm_reduce_gather(x_res, x_res, parts=my_parts, norm_weight=w["ln2_w"], norm_bias=w.get("ln2_b"), norm_kind=self.norm_kind,
+                                  gather_out=gather_xn, gather_flag=[self._p_layer_flag(r, l, 2) for r in range(R)],
+                                  wait_flag=self._p_layer_flag(me, l, 1), wait_per_epoch=R, **common)
+            kw = dict(out=act, wait_flag=self._p_layer_flag(me, l, 2), wait_per_epoch=R, epoch=ep, error_flag=err)
+            if s.mlp == "swiglu":
+                Fn.gemm(xn, w["w_gate"], b2=w["w_up"], act=Fn.ACT_SWIGLU, **kw)
+            else:
+                Fn.gemm(xn, w["w_up"], act=self.act, **kw)
+            Fn.gemm(act, w["w_down"], store_local=False, push_out=push_parts, push_rows_per_owner=mo,
+                    push_done_flag=[self._p_layer_flag(r, l, 3) for r in range(R)], done_counter=ctr, error_flag=err)
+            if l + 1 < L:
+                wn = self.shards[l + 1]
+                Fn.norm_reduce_gather(x_res, x_res, parts=my_parts, norm_weight=wn["ln1_w"], norm_bias=wn.get("ln1_b"), norm_kind=self.norm_kind,
+                                      gather_out=gather_xn, gather_flag=[self._p_layer_flag(r, l + 1, 0) for r in range(R)],
+                                      wait_flag=self._p_layer_flag(me, l, 3), wait_per_epoch=R, **common)
+            else:  # span output: raw sum, gathered on the leader only
+                Fn.norm_reduce_gather(x_res, None, parts=my_parts, norm_kind=Fn.NORM_NONE,
+                                      gather_out=[self.heap.addr(0, self.off_p_out + me * mo * row_b)], gather_flag=[self.p_flag(0, 1)],
+                                      wait_flag=self._p_layer_flag(me, l, 3), wait_per_epoch=R, **common)
+        if me == 0:
+            native.check(native.lib().pb_wait_flag(self.p_flag(0, 1), ep, R, 0, err, native.stream_ptr()), "wait_flag")
+        native.check(native.lib().pb_advance_pos(pos_ptr, T, native.stream_ptr()), "advance_pos")
+        return self.p_out[:M]
+
+    def push_prefill_inputs(self, hidden: torch.Tensor) -> None:
+        """Leader: scatter the chunk's rows to their owners' landing zones over NVLink (one multi-CTA copy + flag per owner)."""
+        M, H = hidden.shape
+        R = self.world
+        mo = (M + R - 1) // R
+        src = self._buf("p_stage", self.max_prefill_rows, H)
+        src[:M].copy_(hidden)
+        for r in range(R):
+            rows = max(0, min(mo, M - r * mo))
+            Fn.norm_reduce_gather(src[r * mo: r * mo + rows] if rows else src[:0], None, rows=rows, H=H, norm_kind=Fn.NORM_NONE,
+                                  gather_out=[self.heap.addr(r, self.off_p_x_in)], gather_flag=[self.p_flag(r, 0)],
+                                  done_counter=self.done_counter.data_ptr(), error_flag=self.err.data_ptr(), device_index=self.device.index)
+
+    def run_prefill(self, session: SessionCache, B: int, T: int) -> torch.Tensor:
+        """Every rank calls this once per prefill command (the leader after scattering the inputs)."""
+        session.prepare_write(T)
+        table = self._sync_session(session, B)
+        before = native.launch_count
+        out = self._launch_prefill(B, T, table)
+        self.prefill_launches = native.launch_count - before
+        session.set_position(session.position + T)
+        self._dev_pos = session.position
+        return out
 
     def _graph(self, B: int, T: int, table: torch.Tensor) -> dict:
         key = (B, T)

@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import itertools
 import os
+import threading
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -17,7 +18,7 @@ import torch.distributed as dist
 
 from petals_b200.ops.functional import PAGE
 from petals_b200.parallel.control import CommandRing
-from petals_b200.parallel.symmetric import SymmetricHeap
+from petals_b200.parallel.symmetric import SymmetricHeap, host_barrier
 from petals_b200.parallel.tensor_parallel import MAX_ROWS, TPDecodeEngine, local_spec
 from petals_b200.server.memory_cache import MemoryCache, SessionCache
 from petals_b200.utils.logging import get_logger
@@ -34,6 +35,7 @@ class TPLeaderEngine:
         self.n_blocks = engine.n_blocks
         self._sids: Dict[int, int] = {}
         self._next_sid = itertools.count(1)
+        self._lock = threading.RLock()  # one command stream: ring order must equal launch order on the leader
 
     def _sid(self, session: SessionCache) -> int:
         key = id(session)
@@ -51,6 +53,10 @@ class TPLeaderEngine:
 
     def inference_step(self, session: SessionCache, hidden: torch.Tensor, prompts=None, hypo_ids: Optional[torch.Tensor] = None,
                        block_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        with self._lock:
+            return self._inference_step(session, hidden, prompts, hypo_ids, block_range)
+
+    def _inference_step(self, session, hidden, prompts, hypo_ids, block_range) -> torch.Tensor:
         lo, hi = block_range or (0, self.n_blocks)
         if (lo, hi) != (0, self.n_blocks):
             raise NotImplementedError("a tensor-parallel stage serves its whole span per request")
@@ -63,25 +69,41 @@ class TPLeaderEngine:
             session.reorder(hypo_ids)
         if T == 0:
             return hidden
-        if B > MAX_ROWS:
-            raise ValueError(f"batch of {B} sequences exceeds the tensor-parallel decode engine's {MAX_ROWS} rows")
         hidden = hidden.to(torch.bfloat16)
         out = torch.empty(B, T, H, dtype=torch.bfloat16, device=hidden.device)
-        step_t = max(1, MAX_ROWS // B)  # longer inputs (prompt ingestion) go through in row-limited micro-steps
+        P = self.engine.max_prefill_rows
+        prefill = B * T > MAX_ROWS and P >= B
+        if not prefill and B > MAX_ROWS:
+            raise ValueError(f"batch of {B} sequences exceeds the tensor-parallel decode engine's {MAX_ROWS} rows")
+        # decode-shaped steps replay the GEMV graph; prompt ingestion goes through sequence-parallel GEMM chunks
+        step_t = max(1, (P if prefill else MAX_ROWS) // B)
         for t0 in range(0, T, step_t):
             t1 = min(T, t0 + step_t)
-            cmd = {"op": "step", "sid": sid, "B": B, "T": t1 - t0, "pos": session.position}
+            chunk_prefill = prefill and B * (t1 - t0) > MAX_ROWS
+            cmd = {"op": "prefill" if chunk_prefill else "step", "sid": sid, "B": B, "T": t1 - t0, "pos": session.position}
             if hypo is not None and t0 == 0:
                 cmd["hypo"] = hypo
             self.ring.send(cmd)
-            self.engine.push_inputs(hidden[:, t0:t1].reshape(B * (t1 - t0), H))
-            y = self.engine.run_step(session, B, t1 - t0)
+            rows = hidden[:, t0:t1].reshape(B * (t1 - t0), H)
+            if chunk_prefill:
+                self.engine.push_prefill_inputs(rows)
+                y = self.engine.run_prefill(session, B, t1 - t0)
+            else:
+                self.engine.push_inputs(rows)
+                y = self.engine.run_step(session, B, t1 - t0)
             out[:, t0:t1] = y.view(B, t1 - t0, H)
         return out
 
-    def forward(self, hidden, prompts=None, block_range=None):
-        raise NotImplementedError("cache-less forward/backward through a tensor-parallel stage is not implemented yet; "
-                                  "serve training traffic from pipeline stages")
+    def forward(self, hidden: torch.Tensor, prompts=None, block_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+        """Cache-less parallel forward (rpc_forward): the prompt chunks run through the sequence-parallel prefill path against a
+        scratch KV session that is dropped afterwards (every rank mirrors it)."""
+        B, T, _ = hidden.shape
+        with self._lock:
+            session = self.engine.cache.open_session(B, T, timeout=None)
+            try:
+                return self._inference_step(session, hidden, prompts, None, block_range).clone()
+            finally:
+                session.close()
 
     def check_errors(self) -> None:
         self.engine.check_errors()
@@ -96,13 +118,13 @@ def follower_loop(engine: TPDecodeEngine, cache: MemoryCache, ring: CommandRing,
     while True:
         cmd = ring.recv(consumer, timeout=idle_timeout)
         op = cmd["op"]
-        if op == "step":
+        if op in ("step", "prefill"):
             s = sessions[cmd["sid"]]
             if cmd["pos"] != s.position:
                 s.set_position(cmd["pos"])  # rollback (speculative decoding) decided on the leader
             if "hypo" in cmd:
                 s.reorder(torch.tensor(cmd["hypo"], dtype=torch.int64))
-            engine.run_step(s, cmd["B"], cmd["T"])
+            (engine.run_step if op == "step" else engine.run_prefill)(s, cmd["B"], cmd["T"])
         elif op == "open":
             sessions[cmd["sid"]] = cache.open_session(cmd["B"], cmd["max_length"], timeout=None)
         elif op == "close":
@@ -120,10 +142,10 @@ def follower_loop(engine: TPDecodeEngine, cache: MemoryCache, ring: CommandRing,
 
 
 def build_tp_engine(config, n_blocks: int, *, group=None, attn_cache_tokens: int = 4096, inference_max_length: int = 4096, blocks=None,
-                    seed: int = 0, heap_bytes: Optional[int] = None, use_cuda_graphs: bool = True):
+                    seed: int = 0, heap_bytes: Optional[int] = None, use_cuda_graphs: bool = True, max_prefill_rows: int = 4096):
     """Collective: every rank of ``group`` builds its shard of an ``n_blocks`` span. ``blocks`` (full GenericBlocks, same on
     all ranks) are sharded if given, otherwise shards are random-initialised in place. Returns (engine, cache, heap)."""
-    from petals_b200.parallel.tensor_parallel import random_shard, shard_block, tp_supported
+    from petals_b200.parallel.tensor_parallel import prefill_heap_bytes, random_shard, shard_block, tp_supported
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     device = torch.device("cuda", torch.cuda.current_device())
@@ -131,6 +153,7 @@ def build_tp_engine(config, n_blocks: int, *, group=None, attn_cache_tokens: int
     if not tp_supported(spec, world):
         raise ValueError(f"{spec.family} blocks cannot be tensor-parallelised over {world} ranks by this engine")
     need = (1 + 2 * world) * MAX_ROWS * spec.hidden_size * 2 + (2 * n_blocks + 2) * 8 + (1 << 20)
+    need += prefill_heap_bytes(spec.hidden_size, world, n_blocks, max_prefill_rows)
     heap = SymmetricHeap(heap_bytes or (max(need, 8 << 20) + (256 << 20)), group=group, device=device)  # + room for the bandwidth probe
     if blocks is not None:
         shards = [shard_block(b, spec, rank, world, device) for b in blocks]
@@ -139,9 +162,9 @@ def build_tp_engine(config, n_blocks: int, *, group=None, attn_cache_tokens: int
     ls = local_spec(spec, world)
     cache = MemoryCache(attn_cache_tokens, None, n_blocks=n_blocks, spec=ls, dtype=torch.bfloat16, device=device, paged=True,
                         max_length=inference_max_length)
-    engine = TPDecodeEngine(spec, shards, heap, cache, use_cuda_graphs=use_cuda_graphs)
+    engine = TPDecodeEngine(spec, shards, heap, cache, use_cuda_graphs=use_cuda_graphs, max_prefill_rows=max_prefill_rows)
     torch.cuda.synchronize(device)
-    dist.barrier(group=group)
+    host_barrier(group)
     return engine, cache, heap
 
 
@@ -156,5 +179,5 @@ def make_ring(group=None, n_followers: Optional[int] = None) -> CommandRing:
     dist.broadcast_object_list(names, src=0, group=group)
     if rank != 0:
         ring = CommandRing(names[0], create=False)
-    dist.barrier(group=group)
+    host_barrier(group)
     return ring

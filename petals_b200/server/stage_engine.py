@@ -118,9 +118,10 @@ class StageEngine:
         return Fn.linear_decode(x, getattr(w, name), w2=getattr(w, name2) if name2 else None, **kw)
 
     def _buf(self, name: str, rows: int, cols: int, dtype=None) -> torch.Tensor:
-        key = (name, rows)
+        # keyed by the full shape and never replaced: captured CUDA graphs keep the raw addresses of these buffers
+        key = (name, rows, cols, dtype)
         t = self._bufs.get(key)
-        if t is None or t.shape[1] != cols:
+        if t is None:
             t = torch.empty(rows, cols, dtype=dtype or self.dtype, device=self.device)
             self._bufs[key] = t
         return t

@@ -281,3 +281,54 @@ def test_moe_decode(M):
     Fn.moe_decode(h, blk.ln2_w, blk.router, blk.we_gate, blk.we_up, blk.we_down, top_k=2, eps=1e-5, out=out)
     want = h + blk.mlp(Fn.norm_ref(h, blk.ln2_w, None, Fn.NORM_RMS, 1e-5).view(1, M, 1024)).view(M, 1024)
     _close(out, want, 3e-2, 3e-2, "moe decode")
+
+
+# ---- sequence-parallel prefill primitives, in loopback: the "peers" are local buffers (same kernels, same flag protocol) ----
+def test_gemm_reduce_scatter_routing_loopback():
+    """Row-parallel GEMM whose epilogue routes row r only to owner r // rows_per_owner (at local row r % rows_per_owner) and
+    publishes one completion flag per owner (last CTA)."""
+    torch.manual_seed(11)
+    M, N, K, R = 300, 512, 256, 4  # ragged: 75 rows per owner, tiles straddle owners
+    mo = (M + R - 1) // R
+    a, b = _rand(M, K), _rand(N, K, scale=K ** -0.5)
+    owners = [torch.zeros(mo, N, device=DEV, dtype=torch.bfloat16) for _ in range(R)]
+    flags = torch.zeros(R, device=DEV, dtype=torch.int64)
+    ctr = torch.zeros(1, device=DEV, dtype=torch.int32)
+    err = torch.zeros(1, device=DEV, dtype=torch.int32)
+    Fn.gemm(a, b, store_local=False, push_out=[o.data_ptr() for o in owners], push_rows_per_owner=mo,
+            push_done_flag=[flags[i:].data_ptr() for i in range(R)], done_counter=ctr.data_ptr(), error_flag=err.data_ptr())
+    torch.cuda.synchronize()
+    want = Fn.linear_ref(a, b)
+    for r in range(R):
+        rows = max(0, min(mo, M - r * mo))
+        _close(owners[r][:rows], want[r * mo: r * mo + rows], 2e-2, 2e-2, f"owner {r}")
+    assert flags.tolist() == [1] * R and int(ctr.item()) == 0 and int(err.item()) == 0
+
+
+@pytest.mark.parametrize("kind", [Fn.NORM_RMS, Fn.NORM_LAYER, Fn.NORM_NONE])
+def test_norm_reduce_gather_loopback(kind):
+    """Owner-side reduce (residual + R partials) -> norm -> gather into R destination buffers, gated on an epoch flag."""
+    torch.manual_seed(12)
+    rows, H, R = 37, 2048, 3
+    res = _rand(rows, H)
+    parts = [_rand(rows, H) for _ in range(R)]
+    w, b = _rand(H) * 0.1 + 1, _rand(H) * 0.1
+    res_out = torch.zeros_like(res)
+    dsts = [torch.zeros(rows, H, device=DEV, dtype=torch.bfloat16) for _ in range(R)]
+    flags = torch.zeros(R + 1, device=DEV, dtype=torch.int64)
+    flags[R] = 2 * R  # the wait flag already holds epoch(2) * per_epoch(R)
+    epoch = torch.full((1,), 2, device=DEV, dtype=torch.int64)
+    ctr = torch.zeros(1, device=DEV, dtype=torch.int32)
+    err = torch.zeros(1, device=DEV, dtype=torch.int32)
+    Fn.norm_reduce_gather(res, res_out, rows=rows, H=H, parts=[p.data_ptr() for p in parts], norm_weight=None if kind == Fn.NORM_NONE else w,
+                          norm_bias=b if kind == Fn.NORM_LAYER else None, norm_kind=kind, eps=1e-5,
+                          gather_out=[d.data_ptr() for d in dsts], gather_flag=[flags[i:].data_ptr() for i in range(R)],
+                          wait_flag=flags[R:].data_ptr(), wait_per_epoch=R, epoch=epoch.data_ptr(), done_counter=ctr.data_ptr(),
+                          error_flag=err.data_ptr())
+    torch.cuda.synchronize()
+    xs = (res.float() + sum(p.float() for p in parts)).to(torch.bfloat16)
+    _close(res_out, xs, 1e-2, 1e-2, "residual")
+    want = xs if kind == Fn.NORM_NONE else Fn.norm_ref(xs, w, b if kind == Fn.NORM_LAYER else None, kind=kind, eps=1e-5)
+    for d in dsts:
+        _close(d, want, 2e-2, 2e-2, "gathered rows")
+    assert flags[:R].tolist() == [1] * R and int(err.item()) == 0 and int(ctr.item()) == 0

@@ -16,6 +16,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def main():
+    from petals_b200.parallel.symmetric import host_barrier
     from petals_b200.parallel.fabric import init_fabric
     from petals_b200.parallel.swarm import FileSwarm
     from petals_b200.utils.auto_config import AutoDistributedConfig
@@ -36,7 +37,7 @@ def main():
     per = n_layers // world
     stage = launch_random_stage(path, range(rank * per, (rank + 1) * per), swarm, dev, seed=5, peer_id=f"stage{rank}", attn_cache_tokens=1024,
                                 inference_max_length=512)
-    dist.barrier()
+    host_barrier()
     ok, report = True, {}
     if rank == 0:
         model = random_client_model(path, swarm, dev)
@@ -63,10 +64,10 @@ def main():
         ok = err < 0.05 and agree > 0.9 and all(used_fabric[1:]) and len(peers) == world
         report = {"pp_selftest": "ok" if ok else "FAILED", "world": world, "rel_err": round(err, 5), "argmax_agreement": round(agree, 4),
                   "stages": peers, "inputs_over_fabric": used_fabric, "generated": out[0, 8:].tolist()}
-    dist.barrier()
+    host_barrier()
     stage.shutdown()
     fabric.check_errors()
-    dist.barrier()
+    host_barrier()
     if rank == 0:
         print(json.dumps(report))
     fabric.close()

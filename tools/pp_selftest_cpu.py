@@ -12,6 +12,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def main():
+    from petals_b200.parallel.symmetric import host_barrier
     from petals_b200.parallel.fabric import init_fabric
     from petals_b200.parallel.swarm import FileSwarm
     from petals_b200.server.from_pretrained import load_pretrained_block
@@ -30,7 +31,7 @@ def main():
     server = Server(initial_peers=dirs[0], converted_model_name_or_path=path, block_indices=f"{rank * per}:{(rank + 1) * per}", torch_dtype="float32",
                     device="cpu", throughput=1.0, update_period=0.5, peer_id=f"stage{rank}")
     server.run_in_background(timeout=120)
-    dist.barrier()
+    host_barrier()
     ok, report = True, {}
     if rank == 0:
         model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[dirs[0]], max_retries=20, min_backoff=0.2, max_backoff=0.5)
@@ -54,9 +55,9 @@ def main():
         parts = [(a - ref[:, :7]).abs().max().item(), (b_ - ref[:, 7:8]).abs().max().item(), (c - ref[:, 8:]).abs().max().item()]
         ok = err < 1e-3 and all(used[1:]) and len(peers) == world
         report = {"pp_selftest_cpu": "ok" if ok else "FAILED", "max_err": err, "stages": peers, "inputs_over_fabric": used, "part_errs": parts}
-    dist.barrier()
+    host_barrier()
     server.shutdown()
-    dist.barrier()
+    host_barrier()
     if rank == 0:
         print(json.dumps(report))
     fabric.close()

@@ -14,6 +14,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
 def main():
+    from petals_b200.parallel.symmetric import host_barrier
     from petals_b200.data_structures import ModelInfo, ServerInfo, ServerState
     from petals_b200.parallel.swarm import Swarm
     from petals_b200.parallel.symmetric import measure_hop_latency, measure_peer_bandwidth
@@ -40,7 +41,7 @@ def main():
     lat = measure_hop_latency(heap, probe, 0, 1)
     if rank != 0:
         follower_loop(engine, cache, ring, rank - 1)
-        dist.barrier()
+        host_barrier()
         heap.close()
         dist.destroy_process_group()
         return
@@ -59,7 +60,7 @@ def main():
             h = b.forward_cached(h, None, None, 0)
         ref = model.lm_head(model.model.final_norm(h)).float()
         with model.inference_session(max_length=64) as sess:
-            a = model(ids[:, :13]).logits  # 13 tokens -> two micro-steps (8 + 5 rows)
+            a = model(ids[:, :13]).logits  # 13 rows -> one sequence-parallel prefill chunk with a ragged row split
             b_ = model(ids[:, 13:14]).logits
             junk = model(torch.randint(0, 4000, (1, 3), device=dev)).logits  # will be rolled back
             sess.position = 14
@@ -67,15 +68,26 @@ def main():
             d = model(ids[:, 15:]).logits
         got = torch.cat([a, b_, c, d], 1).float()
         out = model.generate(ids[:, :8], max_new_tokens=6)
+        # long prompt: 150 rows span two 128-row GEMM tiles and several KV pages; then two more chunks on top of the cache
+        ids2 = torch.randint(0, 4000, (1, 200), device=dev)
+        h = model.model.embed(ids2)
+        for b in blocks:
+            h = b.forward_cached(h, None, None, 0)
+        ref2 = model.lm_head(model.model.final_norm(h)).float()
+        with model.inference_session(max_length=256):
+            got2 = torch.cat([model(ids2[:, :150]).logits, model(ids2[:, 150:199]).logits, model(ids2[:, 199:]).logits], 1).float()
     engine.check_errors()
     err = (got - ref).abs().mean().item() / (ref.abs().mean().item() + 1e-9)
+    err2 = (got2 - ref2).abs().mean().item() / (ref2.abs().mean().item() + 1e-9)
     agree = (got.argmax(-1) == ref.argmax(-1)).float().mean().item()
+    agree2 = (got2.argmax(-1) == ref2.argmax(-1)).float().mean().item()
     leader.shutdown()
     container.shutdown()
-    dist.barrier()
+    host_barrier()
     heap.close()
-    ok = err < 0.05 and agree > 0.9
+    ok = err < 0.05 and agree > 0.9 and err2 < 0.05 and agree2 > 0.9
     print(json.dumps({"tp_selftest": "ok" if ok else "FAILED", "world": world, "rel_err": round(err, 5), "argmax_agreement": round(agree, 4),
+                      "prefill_rel_err": round(err2, 5), "prefill_argmax_agreement": round(agree2, 4),
                       "generated": out[0, 8:].tolist(), "peer_store_GBps": bw, "flag_latency_us": lat}))
     dist.destroy_process_group()
     if not ok:
