@@ -52,6 +52,8 @@ struct LinearDecodeParams {
   uint64_t* push_flag[kMaxPeers];               // incremented (release.sys) ONCE per launch, by the last CTA to finish
   unsigned int* done_counter;                   // local device counter used to elect that last CTA (self-resetting)
   int* error_flag;                              // set to 1 on watchdog expiry
+  int pf_lines;                                 // 128-byte weight lines each warp prefetches into L2 before the prologue
+  int late_trigger;                             // 1: release the dependent kernel after the main loop instead of at entry
 };
 
 PB_DEVICE float gelu_tanh(float x) {
@@ -104,18 +106,16 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
   // Weights are never written by a kernel, so while the predecessor kernel drains (and while this kernel then waits for
   // a peer flag and normalises x) every warp pulls the head of its first weight rows into L2: the main loop's first
   // iterations hit L2 and HBM keeps streaming through what used to be a bubble between two GEMVs.
-  pdl_trigger();
+  if (!p.late_trigger) pdl_trigger();
   {
     const int task0 = warp * gridDim.x + blockIdx.x;
-    if (task0 < (N >> 1)) {
+    if (task0 < (N >> 1) && p.pf_lines > 0) {
       constexpr int kRows = DUAL ? 4 : 2;
-      constexpr int kPfLines = 64;  // 128-byte lines per warp = 8 KB
-      constexpr int kLinesPerRow = kPfLines / kRows;
+      const int lines_per_row = p.pf_lines / kRows;
       const int n0 = task0 << 1;
-#pragma unroll
-      for (int i = lane; i < kPfLines; i += 32) {
-        const int row = i / kLinesPerRow, k = (i % kLinesPerRow) * 64;
-        if (k < K) prefetch_l2((row < 2 ? p.w : p.w2) + static_cast<size_t>(n0 + (row & 1)) * K + k);
+      for (int i = lane; i < p.pf_lines; i += 32) {
+        const int row = i / lines_per_row, k = (i - row * lines_per_row) * 64;
+        if (row < kRows && k < K) prefetch_l2((row < 2 ? p.w : p.w2) + static_cast<size_t>(n0 + (row & 1)) * K + k);
       }
     }
   }
@@ -319,6 +319,7 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
     }
   }
 
+  if (p.late_trigger) pdl_trigger();
   // ---- publish: every CTA fences its peer stores and checks in on a local counter; the last one to arrive
   // performs ONE release-increment per peer (so a consumer waits for `n_sources` per step, independent of grids).
   if (p.n_push > 0) {
@@ -392,6 +393,15 @@ extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
     p.push_flag[i] = static_cast<uint64_t*>(a->push_flag[i]);
   }
   p.error_flag = static_cast<int*>(a->error_flag);
+  {
+    static const int env_pf = [] { const char* e = getenv("PETALS_B200_PF_LINES"); return e ? atoi(e) : -1; }();
+    static const int env_pf_wait = [] { const char* e = getenv("PETALS_B200_PF_LINES_WAIT"); return e ? atoi(e) : -1; }();
+    static const int env_late = [] { const char* e = getenv("PETALS_B200_PDL_LATE"); return e ? atoi(e) : 0; }();
+    // a kernel that will spin on a peer flag can hide a deep prefetch behind the wait; one that starts right away cannot
+    p.pf_lines = a->wait_flag != nullptr ? (env_pf_wait >= 0 ? env_pf_wait : 64) : (env_pf >= 0 ? env_pf : 16);
+    if (p.pf_lines > 0 && p.pf_lines < 4) p.pf_lines = 4;
+    p.late_trigger = env_late;
+  }
   p.done_counter = static_cast<unsigned int*>(a->done_counter);
   if (a->n_push > 0 && p.done_counter == nullptr) return PB_ERR_SHAPE;
 

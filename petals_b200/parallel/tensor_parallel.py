@@ -428,3 +428,28 @@ class TPDecodeEngine:
         if code:
             self.err.zero_()
             raise RuntimeError(f"rank {self.rank}: device-side error flag {code} (1 = peer flag watchdog expired, 2 = KV page table overflow)")
+
+
+# ---- CPU oracle of the sharded math (tests; reference: tests/test_tensor_parallel.py) ----------------------------------------
+def shard_oracle_blocks(block: GenericBlock, spec: BlockSpec, world: int) -> List[GenericBlock]:
+    """One plain-PyTorch block per rank holding exactly the tensors :func:`shard_block` gives that rank."""
+    ls = local_spec(spec, world)
+    out = []
+    for rank in range(world):
+        b = GenericBlock(ls, dtype=block.wqkv.dtype, device=block.wqkv.device)
+        with torch.no_grad():
+            for name, t in shard_block(block, spec, rank, world, block.wqkv.device).items():
+                getattr(b, name).copy_(t)
+        out.append(b)
+    return out
+
+
+def tp_oracle_forward(shards: Sequence[GenericBlock], hidden: torch.Tensor, caches: Optional[Sequence[Tuple[torch.Tensor, torch.Tensor]]] = None,
+                      pos: int = 0) -> torch.Tensor:
+    """What the TP engine computes, written with autograd-friendly tensor ops: norms and the residual stream are replicated,
+    every rank contributes a partial attention / MLP output and the partials are summed where the engine all-reduces."""
+    first = shards[0]
+    ln1 = first._norm(hidden, "ln1")
+    h = hidden + sum(b.attention(ln1, *(caches[r] if caches is not None else (None, None)), pos) for r, b in enumerate(shards))
+    ln2 = first._norm(h, "ln2")
+    return h + sum(b.mlp(ln2) for b in shards)

@@ -36,6 +36,8 @@ from petals_b200.server.task_prioritizer import DummyTaskPrioritizer, TaskPriori
 from petals_b200.utils.logging import get_logger
 from petals_b200.utils.misc import DUMMY, is_dummy
 
+CACHE_TOKENS_AVAILABLE = "cache_tokens_available"  # rpc_info key (reference: handler.py:52)
+
 logger = get_logger(__name__)
 
 
@@ -286,7 +288,7 @@ class TransformerConnectionHandler:
         spec = self.stage.spec
         return dict(
             version=petals_b200.__version__, dht_client_mode=False, peer_id=self.peer_id,
-            cache_tokens_available=cache.tokens_left * len(self.stage), inference_max_length=self.inference_max_length,
+            **{CACHE_TOKENS_AVAILABLE: cache.tokens_left * len(self.stage)}, inference_max_length=self.inference_max_length,
             start_block=self.stage.start_block, end_block=self.stage.end_block, torch_dtype=str(self.stage.dtype).replace("torch.", ""),
             quant_type=(self.quant_type.name.lower() if self.quant_type is not None else "none"), adapters=list(self.adapters),
             keyword_names=("prompts", "hypo_ids"),
