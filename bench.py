@@ -91,6 +91,8 @@ def main() -> None:
     ap.add_argument("--prefill-steps", type=int, default=2)
     ap.add_argument("--skip-prefill", action="store_true")
     ap.add_argument("--tp-prefill-rows", type=int, default=8192, help="rows per sequence-parallel prefill chunk (N > 1, tensor parallel)")
+    ap.add_argument("--tp-emulate", type=int, default=0, help="DIAGNOSTIC (not a benchmark result): run the compute of ONE rank of a "
+                    "tensor-parallel group of this size on one GPU (heads, KV heads and FFN columns divided), to measure the fixed per-layer costs")
     ap.add_argument("--skip-fp8", action="store_true", help="do not append the block-scaled FP8 decode measurement")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -116,7 +118,12 @@ def run_single_gpu(args) -> None:
     torch.cuda.set_device(0)
     dev = "cuda:0"
     native.lib()
-    path = write_config_only(args.model)
+    overrides = None
+    if args.tp_emulate > 1:
+        pre, R = MODEL_PRESETS[args.model], args.tp_emulate
+        overrides = dict(num_attention_heads=pre["num_attention_heads"] // R, num_key_value_heads=max(1, pre["num_key_value_heads"] // R),
+                         intermediate_size=pre["intermediate_size"] // R, head_dim=pre["hidden_size"] // pre["num_attention_heads"])
+    path = write_config_only(args.model, overrides)
     n_layers = MODEL_PRESETS[args.model]["num_hidden_layers"]
     swarm = Swarm("bench")
     t0 = time.time()
@@ -169,7 +176,8 @@ def run_single_gpu(args) -> None:
     spec = model.config.block_spec()
     weight_bytes = (spec.num_params() * n_layers + vocab * spec.hidden_size) * 2
     result = {
-        "metric": "Llama-3-70B single-stream decode tokens/s (device-timed); prefill tokens/s in `prefill`",
+        "metric": ("Llama-3-70B single-stream decode tokens/s (device-timed); prefill tokens/s in `prefill`" if args.tp_emulate <= 1 else
+                   f"DIAGNOSTIC: one rank's share of a tp{args.tp_emulate} decode step on one GPU, no communication (NOT a benchmark result)"),
         "value": round(value, 3), "unit": "tokens/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",
         "data": "synthetic token ids; random-init weights of the named architecture",

@@ -319,11 +319,11 @@ static int launch_attn(const PbAttnArgs* a, cudaStream_t s) {
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
     return PB_ERR_CUDA;
   dim3 grid(m_tiles, a->B * a->Hkv, p.splits);
-  launch_pdl(kern, grid, dim3(128), smem, s, p);
+  launch_pdl(kPdlAttn, kern, grid, dim3(128), smem, s, p);
   if (pb_check_launch("attention") != PB_OK) return PB_ERR_CUDA;
   if (p.splits > 1) {
     const size_t R = static_cast<size_t>(a->B) * a->T * a->Hq;
-    launch_pdl(attn_combine_kernel, dim3(static_cast<unsigned>(R)), dim3(D), 0, s, p.partial_o, p.partial_lse, p.out, p.splits, R, D);
+    launch_pdl(kPdlCombine, attn_combine_kernel, dim3(static_cast<unsigned>(R)), dim3(D), 0, s, p.partial_o, p.partial_lse, p.out, p.splits, R, D);
     if (pb_check_launch("attention") != PB_OK) return PB_ERR_CUDA;
   }
   return PB_OK;

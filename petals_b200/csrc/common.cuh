@@ -321,16 +321,19 @@ __host__ __device__ constexpr uint32_t umma_idesc_e4m3(uint32_t M, uint32_t N) {
 // ---- host: launch with (optional) programmatic dependent launch ------------------------------------------------------
 // pb_pdl_enabled() reads PETALS_B200_PDL once (default on). Kernels launched through launch_pdl() MUST call pdl_wait()
 // before reading anything an earlier kernel of the stream produced.
-inline bool pdl_enabled() {
-  static const bool on = [] {
+enum PdlKind : int { kPdlGemv = 1, kPdlRope = 2, kPdlAttn = 4, kPdlCombine = 8, kPdlGemvBigSmem = 16 };
+inline int pdl_mask() {
+  static const int mask = [] {
     const char* e = getenv("PETALS_B200_PDL");
-    return e == nullptr || e[0] != '0';
+    if (e != nullptr && e[0] == '0') return 0;
+    const char* m = getenv("PETALS_B200_PDL_MASK");
+    return m != nullptr ? atoi(m) : (kPdlRope | kPdlAttn | kPdlCombine);  // measured on B200: PDL on the weight-streaming GEMVs costs ~4 % (profiles/r1_pdl_sweep.txt)
   }();
-  return on;
+  return mask;
 }
 
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_pdl(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -340,7 +343,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = (pdl_mask() & kind) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

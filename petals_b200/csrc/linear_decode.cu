@@ -54,6 +54,7 @@ struct LinearDecodeParams {
   int* error_flag;                              // set to 1 on watchdog expiry
   int pf_lines;                                 // 128-byte weight lines each warp prefetches into L2 before the prologue
   int late_trigger;                             // 1: release the dependent kernel after the main loop instead of at entry
+  int wait_all_warps;                           // 1: every warp executes griddepcontrol.wait (default: warp 0 + barrier)
 };
 
 PB_DEVICE float gelu_tanh(float x) {
@@ -106,7 +107,7 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
   // Weights are never written by a kernel, so while the predecessor kernel drains (and while this kernel then waits for
   // a peer flag and normalises x) every warp pulls the head of its first weight rows into L2: the main loop's first
   // iterations hit L2 and HBM keeps streaming through what used to be a bubble between two GEMVs.
-  if (!p.late_trigger) pdl_trigger();
+  if (!p.late_trigger && tid == 0) pdl_trigger();
   {
     const int task0 = warp * gridDim.x + blockIdx.x;
     if (task0 < (N >> 1) && p.pf_lines > 0) {
@@ -119,7 +120,10 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
       }
     }
   }
-  pdl_wait();
+  // one warp parks on the grid dependency, the rest of the CTA parks on the barrier behind it (3552 warps hammering
+  // ACQBULK measurably slowed the kernel down); completion + visibility of the predecessor are grid-wide facts
+  if (p.wait_all_warps || warp == 0) pdl_wait();
+  __syncthreads();
 
   // ---- prologue ----------------------------------------------------------------------------
   if (p.wait_flag != nullptr) {
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
     }
   }
 
-  if (p.late_trigger) pdl_trigger();
+  if (p.late_trigger && tid == 0) pdl_trigger();
   // ---- publish: every CTA fences its peer stores and checks in on a local counter; the last one to arrive
   // performs ONE release-increment per peer (so a consumer waits for `n_sources` per step, independent of grids).
   if (p.n_push > 0) {
@@ -346,7 +350,7 @@ static cudaError_t launch_one(const LinearDecodeParams& p, int grid, int block, 
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
-  return launch_pdl(kern, dim3(grid), dim3(block), smem, stream, p);
+  return launch_pdl(smem > 32 * 1024 ? kPdlGemvBigSmem : kPdlGemv, kern, dim3(grid), dim3(block), smem, stream, p);
 }
 
 template <int M>
@@ -401,6 +405,8 @@ extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
     p.pf_lines = a->wait_flag != nullptr ? (env_pf_wait >= 0 ? env_pf_wait : 64) : (env_pf >= 0 ? env_pf : 16);
     if (p.pf_lines > 0 && p.pf_lines < 4) p.pf_lines = 4;
     p.late_trigger = env_late;
+    static const int env_allw = [] { const char* e = getenv("PETALS_B200_PDL_WAIT_ALL"); return e ? atoi(e) : 0; }();
+    p.wait_all_warps = env_allw;
   }
   p.done_counter = static_cast<unsigned int*>(a->done_counter);
   if (a->n_push > 0 && p.done_counter == nullptr) return PB_ERR_SHAPE;

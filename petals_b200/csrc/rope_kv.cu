@@ -122,7 +122,7 @@ extern "C" int pb_rope_kv(const PbRopeKvArgs* a, void* stream) {
   p.max_pages = a->max_pages; p.max_pos = a->max_pos; p.interleaved = a->interleaved_qkv;
   p.error_flag = static_cast<int*>(a->error_flag);
   dim3 grid(a->B * a->T, a->Hq + 2 * a->Hkv);
-  launch_pdl(rope_kv_kernel, grid, dim3(a->D / 2), 0, static_cast<cudaStream_t>(stream), p);
+  launch_pdl(kPdlRope, rope_kv_kernel, grid, dim3(a->D / 2), 0, static_cast<cudaStream_t>(stream), p);
   return pb_check_launch("rope_kv");
 }
 
