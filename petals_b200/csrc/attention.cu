@@ -331,12 +331,22 @@ static int launch_attn(const PbAttnArgs* a, cudaStream_t s) {
 
 }  // namespace pb
 
+namespace pb { int attention_tc_dispatch(const PbAttnArgs* a, cudaStream_t s); }
+
 extern "C" int pb_attention(const PbAttnArgs* a, void* stream) {
   using namespace pb;
   if (a->page != 64 || a->Hq % a->Hkv) return PB_ERR_SHAPE;
   if (a->B * a->T == 0) return PB_OK;
   if (a->splits > 1 && (a->partial_o == nullptr || a->partial_lse == nullptr)) return PB_ERR_SHAPE;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  {
+    // prefill-sized work (at least one full 128-row tile of packed query rows per kv head) runs on the tcgen05 kernel
+    static const int env_tc = [] { const char* e = getenv("PETALS_B200_ATTN_TC"); return e ? atoi(e) : 1; }();
+    const int G = a->Hq / a->Hkv;
+    const bool tc_ok = a->splits <= 1 && a->num_pages > 0 && (a->D == 128 || a->D == 64);
+    if (tc_ok && (a->impl == 2 || (a->impl == 0 && env_tc && a->T * G >= 128))) return attention_tc_dispatch(a, s);
+    if (a->impl == 2) return PB_ERR_UNSUPPORTED;
+  }
   if (a->D == 128) return launch_attn<128>(a, s);
   if (a->D == 64) return launch_attn<64>(a, s);
   return PB_ERR_UNSUPPORTED;

@@ -382,6 +382,11 @@ static bool make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64
   return r == CUDA_SUCCESS;
 }
 
+// exported to the other translation units that build TMA descriptors (attention_tc.cu)
+bool make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  return make_tmap_2d(m, base, rows, cols, ld, box_rows, box_cols);
+}
+
 template <int BN, bool B_MN, bool DUAL>
 static int launch_gemm(const PbGemmArgs* a, cudaStream_t stream) {
   constexpr int STAGE_BYTES = (BM + BN) * BK * 2;

@@ -113,6 +113,8 @@ typedef struct {
   int window;             // sliding window (0 = none)
   int splits;             // >= 1
   int pos_static;         // used when pos_ptr == null
+  int num_pages;          // pages in k_pool / v_pool (bounds the TMA tensor map of the tcgen05 path)
+  int impl;               // 0 auto, 1 mma.sync kernel, 2 tcgen05 kernel
 } PbAttnArgs;
 int pb_attention(const PbAttnArgs* a, void* stream);
 

@@ -174,13 +174,15 @@ class TPDecodeEngine:
         key = (name, rows, cols, dtype)
         t = self._bufs.get(key)
         if t is None:
-            t = torch.empty(rows, cols, dtype=dtype, device=self.device)
+            with torch.inference_mode(False):  # persistent: must stay writable from threads outside inference mode
+                t = torch.empty(rows, cols, dtype=dtype, device=self.device)
             self._bufs[key] = t
         return t
 
     def _table(self, B: int) -> torch.Tensor:
         if B not in self._tables:
-            self._tables[B] = torch.zeros(B, self.max_pages, dtype=torch.int32, device=self.device)
+            with torch.inference_mode(False):
+                self._tables[B] = torch.zeros(B, self.max_pages, dtype=torch.int32, device=self.device)
         return self._tables[B]
 
     # ---- one decode step of the whole span (launch sequence; captured into a graph) ------------------------------------

@@ -28,7 +28,9 @@ logger = get_logger(__name__)
 
 
 class TPLeaderEngine:
-    """Drop-in for ``StageEngine`` on the leader rank (inference sessions only)."""
+    """Drop-in for ``StageEngine`` on the leader rank."""
+
+    whole_span_only = True  # the handler must not split a step into per-block tasks
 
     def __init__(self, engine: TPDecodeEngine, ring: CommandRing):
         self.engine, self.ring = engine, ring

@@ -163,7 +163,8 @@ class InferenceStream:
             hypo_ids = None
         priority = self.handler.prioritizer.prioritize(hidden, hypo_ids, points=self.points / max(n, 1), type="inference")
         h = self.handler
-        if B * T <= MAX_SHORT_INFERENCE_TOKENS or n == 1 or take_from is not None or push_to is not None:
+        whole_span = getattr(h.stage.engine, "whole_span_only", False)  # tensor-parallel groups step their span as one unit
+        if B * T <= MAX_SHORT_INFERENCE_TOKENS or n == 1 or take_from is not None or push_to is not None or whole_span:
             fut = h.inference_pool.submit_task(hidden, hypo_ids, cache, self.lo, self.hi, block_prompts, self.active_adapter, take_from, push_to,
                                                priority=priority, size=B * T)
             out = fut.result(timeout=h.step_timeout)

@@ -45,7 +45,8 @@ class SessionCache:
         if owner.paged:
             self.tables: List[List[int]] = [[] for _ in range(batch_size)]
             dev = owner.device
-            self.table_dev = torch.zeros(batch_size, owner.max_pages_per_seq, dtype=torch.int32, device=dev)
+            with torch.inference_mode(False):  # sessions are opened and stepped from different threads
+                self.table_dev = torch.zeros(batch_size, owner.max_pages_per_seq, dtype=torch.int32, device=dev)
             self._table_dirty = False
             self._version, self._synced_version = 0, -1
         else:
@@ -129,7 +130,8 @@ class SessionCache:
     def dense_kv(self, slot: int, spec, dtype: torch.dtype, device) -> tuple:
         if slot not in self.dense:
             shape = (self.batch_size, self.max_length, spec.num_kv_heads, spec.head_dim)
-            self.dense[slot] = (torch.zeros(shape, dtype=dtype, device=device), torch.zeros(shape, dtype=dtype, device=device))
+            with torch.inference_mode(False):
+                self.dense[slot] = (torch.zeros(shape, dtype=dtype, device=device), torch.zeros(shape, dtype=dtype, device=device))
         return self.dense[slot]
 
     def close(self) -> None:

@@ -122,13 +122,15 @@ class StageEngine:
         key = (name, rows, cols, dtype)
         t = self._bufs.get(key)
         if t is None:
-            t = torch.empty(rows, cols, dtype=dtype or self.dtype, device=self.device)
+            with torch.inference_mode(False):  # persistent: must stay writable from threads outside inference mode
+                t = torch.empty(rows, cols, dtype=dtype or self.dtype, device=self.device)
             self._bufs[key] = t
         return t
 
     def _table(self, B: int) -> torch.Tensor:
         if B not in self._tables:
-            self._tables[B] = torch.zeros(B, self.max_pages, dtype=torch.int32, device=self.device)
+            with torch.inference_mode(False):
+                self._tables[B] = torch.zeros(B, self.max_pages, dtype=torch.int32, device=self.device)
         return self._tables[B]
 
     def _splits(self, B: int, T: int) -> int:
@@ -357,7 +359,8 @@ class StageEngine:
     def _capture(self, B: int, T: int, lo: int, hi: int, table: torch.Tensor, hop: Optional[tuple] = None) -> dict:
         """Capture the decode step of blocks [lo, hi) for a (B, T) shape into a CUDA graph."""
         M, H = B * T, self.spec.hidden_size
-        x = torch.zeros(M, H, dtype=self.dtype, device=self.device)
+        with torch.inference_mode(False):
+            x = torch.zeros(M, H, dtype=self.dtype, device=self.device)
         pos_ptr = self.pos_static.data_ptr()
         splits = self._splits(B, T)
         saved_pos = self.pos_static.clone()

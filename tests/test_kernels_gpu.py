@@ -332,3 +332,52 @@ def test_norm_reduce_gather_loopback(kind):
     for d in dsts:
         _close(d, want, 2e-2, 2e-2, "gathered rows")
     assert flags[:R].tolist() == [1] * R and int(err.item()) == 0 and int(ctr.item()) == 0
+
+
+@pytest.mark.parametrize("D,Hq,Hkv", [(128, 8, 1), (128, 4, 2), (64, 4, 2), (64, 3, 3)])
+@pytest.mark.parametrize("chunks", [[256, 200], [130, 300, 77]])
+def test_attention_tcgen05_prefill(D, Hq, Hkv, chunks):
+    """The tcgen05/TMEM prefill kernel (impl=2) against the fp32 oracle and the mma.sync kernel (impl=1): chunked prefill over a
+    shuffled paged cache, ragged last tiles, GQA packing with group sizes 1/2/3/8."""
+    torch.manual_seed(21)
+    B, L_max = 2, sum(chunks)
+    k_pool, v_pool, table = _paged_setup(B, L_max, Hkv, D, seed=3)
+    cos, sin = Fn.rope_tables(D, 1024, theta=10000.0, device=DEV)
+    pos = torch.zeros(1, dtype=torch.int32, device=DEV)
+    k_all = torch.zeros(B, 0, Hkv, D, device=DEV, dtype=torch.bfloat16)
+    v_all = torch.zeros_like(k_all)
+    scale, p0 = D ** -0.5, 0
+    for T in chunks:
+        qkv = _rand(B, T, (Hq + 2 * Hkv) * D)
+        q_out = torch.empty(B, T, Hq, D, device=DEV, dtype=torch.bfloat16)
+        Fn.rope_kv_append(qkv, q_out, k_pool, v_pool, table, pos.data_ptr(), cos, sin, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D)
+        q, k, v = qkv.view(B, T, Hq + 2 * Hkv, D).split([Hq, Hkv, Hkv], dim=2)
+        q_ref = Fn.rope_ref(q, cos[p0:p0 + T], sin[p0:p0 + T])
+        k_all, v_all = torch.cat([k_all, Fn.rope_ref(k, cos[p0:p0 + T], sin[p0:p0 + T])], 1), torch.cat([v_all, v], 1)
+        want = Fn.attention_ref(q_ref, k_all, v_all, pos0=p0, scale=scale)
+        outs = {}
+        for impl in (1, 2):
+            out = torch.full((B, T, Hq, D), float("nan"), device=DEV, dtype=torch.bfloat16)
+            Fn.paged_attention(q_out, k_pool, v_pool, table, pos.data_ptr(), out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=scale, impl=impl)
+            outs[impl] = out
+            _close(out, want, 2e-2, 2e-2, f"impl={impl} T={T} pos0={p0}")
+        _close(outs[2], outs[1], 2e-2, 2e-2, "tcgen05 vs mma.sync")
+        pos += T
+        p0 += T
+
+
+def test_attention_tcgen05_alibi_window():
+    torch.manual_seed(22)
+    B, T, Hq, Hkv, D = 1, 400, 4, 2, 64
+    k_pool, v_pool, table = _paged_setup(B, T, Hkv, D)
+    pos = torch.zeros(1, dtype=torch.int32, device=DEV)
+    qkv = _rand(B, T, (Hq + 2 * Hkv) * D)
+    q_out = torch.empty(B, T, Hq, D, device=DEV, dtype=torch.bfloat16)
+    Fn.rope_kv_append(qkv, q_out, k_pool, v_pool, table, pos.data_ptr(), None, None, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D)
+    q, k, v = qkv.view(B, T, Hq + 2 * Hkv, D).split([Hq, Hkv, Hkv], dim=2)
+    slopes = torch.tensor([2 ** (-8 * (i + 1) / Hq) for i in range(Hq)], device=DEV)
+    out = torch.empty_like(q_out)
+    Fn.paged_attention(q_out, k_pool, v_pool, table, pos.data_ptr(), out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, alibi_slopes=slopes, impl=2)
+    _close(out, Fn.attention_ref(q, k, v, pos0=0, scale=D ** -0.5, alibi_slopes=slopes), 2e-2, 2e-2, "tcgen05 alibi")
+    Fn.paged_attention(q_out, k_pool, v_pool, table, pos.data_ptr(), out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, window=150, impl=2)
+    _close(out, Fn.attention_ref(q, k, v, pos0=0, scale=D ** -0.5, window=150), 2e-2, 2e-2, "tcgen05 window")

@@ -34,7 +34,36 @@ elif which == "attn":  # prefill attention, 4096 tokens, GQA 64/8
     table = torch.arange(pages, dtype=torch.int32, device="cuda").view(1, pages)
     q = torch.randn(B * T, Hq * D, device="cuda", dtype=torch.bfloat16)
     out = torch.empty_like(q)
+    impl = int(os.environ.get("ATTN_IMPL", "0"))
     for _ in range(3):
-        Fn.paged_attention(q, k_pool, v_pool, table, None, out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, pos_static=0)
+        Fn.paged_attention(q, k_pool, v_pool, table, None, out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, pos_static=0, impl=impl)
+elif which == "attn_time":  # CUDA-event timing of both attention kernels at the 70B prefill shape
+    import json
+
+    B, T, Hq, Hkv, D = 1, 4096, 64, 8, 128
+    pages = T // Fn.PAGE
+    k_pool = torch.randn(pages, Hkv, Fn.PAGE, D, device="cuda", dtype=torch.bfloat16)
+    v_pool = torch.randn_like(k_pool)
+    table = torch.arange(pages, dtype=torch.int32, device="cuda").view(1, pages)
+    q = torch.randn(B * T, Hq * D, device="cuda", dtype=torch.bfloat16)
+    flops = 4.0 * T * T * Hq * D / 2
+    res = {}
+    outs = {}
+    for impl in (1, 2):
+        out = torch.empty_like(q)
+        for _ in range(3):
+            Fn.paged_attention(q, k_pool, v_pool, table, None, out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, pos_static=0, impl=impl)
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(10):
+            Fn.paged_attention(q, k_pool, v_pool, table, None, out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, pos_static=0, impl=impl)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / 10
+        res["mma_sync" if impl == 1 else "tcgen05"] = {"ms": round(ms, 4), "TFLOPs": round(flops / ms / 1e9, 1)}
+        outs[impl] = out.float()
+    res["max_abs_diff"] = round((outs[1] - outs[2]).abs().max().item(), 5)
+    print(json.dumps({"attention_prefill_4096x64h_d128_causal": res}))
 torch.cuda.synchronize()
 print("done", which)
