@@ -36,6 +36,7 @@ struct AttnParams {
   const float* alibi;
   float scale_log2;
   int B, T, Hq, Hkv, page, max_pages, window, splits, pos_static;
+  int* split_counter;   // [m_tiles * B * Hkv] zero-initialised; non-null fuses the split-KV combine into this kernel
 };
 
 PB_DEVICE void cp_async16(uint32_t dst, const void* src, bool valid) {
@@ -247,8 +248,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
   }
   cp_async_wait<0>();
 
-  if (!warp_active) return;
   // ---- finalize ---------------------------------------------------------------------------------
+  if (warp_active) {
 #pragma unroll
   for (int hr = 0; hr < 2; ++hr) {
     l_i[hr] += __shfl_xor_sync(0xffffffffu, l_i[hr], 1);
@@ -274,6 +275,49 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
         *reinterpret_cast<float2*>(dst + dn * 8) = make_float2(o[dn][hr * 2] * inv, o[dn][hr * 2 + 1] * inv);
       if ((lane & 3) == 0)
         p.partial_lse[static_cast<size_t>(split) * R + rowid] = l_i[hr] > 0.f ? m_i[hr] + log2f(l_i[hr]) : -INFINITY;
+    }
+  }
+  }  // warp_active
+
+  // ---- fused split-KV combine: the last split CTA of this (m tile, sequence, kv head) to finish merges the partials, so the
+  // decode step needs no separate combine launch (one kernel boundary less per block and token)
+  if (p.splits > 1 && p.split_counter != nullptr) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      int* ctr = p.split_counter + (bh * gridDim.x + mt);
+      const int prev = atomicAdd(ctr, 1);
+      s_last = prev == p.splits - 1;
+      if (s_last) *ctr = 0;  // self-resetting: ready for the next launch / graph replay
+    }
+    __syncthreads();
+    if (s_last) {
+      __threadfence();
+      const size_t R = static_cast<size_t>(p.B) * p.T * p.Hq;
+      const int rows_here = min(BM, rows_total - m0);
+      for (int idx = tid; idx < rows_here * (D / 4); idx += 128) {
+        const int rr = idx / (D / 4), c4 = idx - rr * (D / 4);
+        const int row = m0 + rr;
+        const int t = row / G, g = row - t * G;
+        const size_t rowid = (static_cast<size_t>(b) * p.T + t) * p.Hq + kvh * G + g;
+        float mx = -INFINITY;
+        for (int sp = 0; sp < p.splits; ++sp) mx = fmaxf(mx, __ldcg(p.partial_lse + sp * R + rowid));
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float wsum = 0.f;
+        for (int sp = 0; sp < p.splits; ++sp) {
+          const float l = __ldcg(p.partial_lse + sp * R + rowid);
+          const float w = l == -INFINITY ? 0.f : exp2f(l - mx);
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(p.partial_o + (sp * R + rowid) * D) + c4);
+          wsum += w;
+          acc.x += w * v.x; acc.y += w * v.y; acc.z += w * v.z; acc.w += w * v.w;
+        }
+        const float inv = wsum > 0.f ? 1.f / wsum : 0.f;
+        uint2 o2;
+        o2.x = pack_bf16(acc.x * inv, acc.y * inv);
+        o2.y = pack_bf16(acc.z * inv, acc.w * inv);
+        *reinterpret_cast<uint2*>(p.out + rowid * D + c4 * 4) = o2;
+      }
     }
   }
 }
@@ -309,6 +353,7 @@ static int launch_attn(const PbAttnArgs* a, cudaStream_t s) {
   p.partial_o = static_cast<float*>(a->partial_o);
   p.partial_lse = static_cast<float*>(a->partial_lse);
   p.alibi = static_cast<const float*>(a->alibi_slopes);
+  p.split_counter = static_cast<int*>(a->split_counter);
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.B = a->B; p.T = a->T; p.Hq = a->Hq; p.Hkv = a->Hkv; p.page = a->page; p.max_pages = a->max_pages;
   p.window = a->window; p.splits = a->splits < 1 ? 1 : a->splits; p.pos_static = a->pos_static;
@@ -321,7 +366,7 @@ static int launch_attn(const PbAttnArgs* a, cudaStream_t s) {
   dim3 grid(m_tiles, a->B * a->Hkv, p.splits);
   launch_pdl(kPdlAttn, kern, grid, dim3(128), smem, s, p);
   if (pb_check_launch("attention") != PB_OK) return PB_ERR_CUDA;
-  if (p.splits > 1) {
+  if (p.splits > 1 && p.split_counter == nullptr) {
     const size_t R = static_cast<size_t>(a->B) * a->T * a->Hq;
     launch_pdl(kPdlCombine, attn_combine_kernel, dim3(static_cast<unsigned>(R)), dim3(D), 0, s, p.partial_o, p.partial_lse, p.out, p.splits, R, D);
     if (pb_check_launch("attention") != PB_OK) return PB_ERR_CUDA;

@@ -10,9 +10,10 @@
 //   warp 0    TMA producer: per KV tile, 2 pages x D/64 boxes of [64 keys x 64 d] for K and for V (128B swizzle), 2 stages
 //   warp 1    MMA issuer (one thread):  S = Q K^T   (M128 x N128 x K16 tcgen05.mma, D/16 steps, fp32 in TMEM, double buffered)
 //                                       O' = P V    (M128 x N=D x K16, 8 steps; A = P from shared memory, B = V MN-major)
-//   warps 2-5 softmax + accumulate (thread = query row): tcgen05.ld S -> mask/scale -> online softmax in the exp2 domain ->
-//             P (bf16) into 128B-swizzled shared memory -> after the PV MMA, tcgen05.ld O' and O = O * alpha + O' in registers
-//             (no TMEM read-modify-write of the accumulator) -> normalise, store bf16.
+//   warps 2-9 softmax + accumulate: thread (row r, half h) pulls its 64 logits out of TMEM once (the S buffer is released
+//             immediately), online softmax in the exp2 domain with the row maximum exchanged between the two halves through
+//             shared memory, P (bf16) into 128B-swizzled shared memory; after the PV MMA, tcgen05.ld O' and
+//             O = O * alpha + O' in registers (D/2 columns per thread; no TMEM read-modify-write) -> normalise, store bf16.
 //
 // Pipelining: S(j+1) is issued before P(j)V(j), so the tensor core computes the next logits tile while the softmax
 // warps work on the current one; K/V stages are released by tcgen05.commit.
@@ -33,8 +34,14 @@ struct AttnTcParams {
   int B, T, Hq, Hkv, max_pages, num_pages, window, pos_static;
 };
 
-constexpr int kAtcThreads = 192;
+constexpr int kAtcThreads = 320;  // TMA warp + MMA warp + 8 softmax warps
 constexpr int kAtcBM = 128, kAtcBN = 128;
+
+PB_DEVICE float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 template <int D>
 __global__ void __launch_bounds__(kAtcThreads, 1)
@@ -62,9 +69,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
   uint64_t* o_empty = bars + 10;       // [1]       softmax (4 warps) -> MMA
   uint64_t* q_full = bars + 11;        // [1]       softmax (4 warps) -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  float* sMax = reinterpret_cast<float*>(bars + 16);  // [2 parities][2 halves][128 rows] row-max exchange + [2][128] row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int mt = blockIdx.x, bh = blockIdx.y;
+  // causal work grows with the tile index: schedule the long tiles first so the last wave is made of short ones
+  const int lin = blockIdx.y * gridDim.x + blockIdx.x;  // dispatch order
+  const int mt = gridDim.x - 1 - lin / static_cast<int>(gridDim.y), bh = lin % static_cast<int>(gridDim.y);
   const int b = bh / p.Hkv, kvh = bh - b * p.Hkv;
   const int G = p.Hq / p.Hkv;
 
@@ -72,11 +82,11 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     prefetch_tmap(&tmap_k);
     prefetch_tmap(&tmap_v);
     for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 4); }
-    mbar_init(p_full, 4);
+    for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8); }
+    mbar_init(p_full, 8);
     mbar_init(o_full, 1);
-    mbar_init(o_empty, 4);
-    mbar_init(q_full, 4);
+    mbar_init(o_empty, 8);
+    mbar_init(q_full, 8);
     mbar_fence_init();
   }
   if (warp == 1) {
@@ -170,20 +180,26 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     }
   } else {
     // =============================== softmax / accumulate ========================
+    // 8 warps: thread (row r, half h) owns keys [64h, 64h+64) of the logits tile and columns [h*D/2, (h+1)*D/2) of O.
     const int quarter = warp & 3;
+    const int h = (warp - 2) >> 2;
     const int r = quarter * 32 + lane;           // tile row == TMEM lane
     const int row = m0 + r;
     const bool row_ok = row < rows_total;
     const int t = row_ok ? row / G : 0, g = row_ok ? row - (row / G) * G : 0;
     const int head = kvh * G + g;
     const int qpos = pos0 + t;
-    const float slope2 = p.alibi != nullptr ? p.alibi[head] * 1.4426950408889634f : 0.f;
+    const bool has_alibi = p.alibi != nullptr;
+    const float slope2 = has_alibi ? p.alibi[head] * 1.4426950408889634f : 0.f;
+    const float inv_scale = 1.f / p.scale_log2;
+    constexpr int DH = D / 2;                    // O columns per thread
 
-    // ---- Q: global -> swizzled shared (each thread its own row) ----
+    // ---- Q: global -> swizzled shared (thread (r, h) copies half of row r) ----
     {
       const uint4* src = reinterpret_cast<const uint4*>(p.q + ((static_cast<size_t>(b) * p.T + t) * p.Hq + head) * D);
 #pragma unroll
-      for (int c = 0; c < D / 8; ++c) {
+      for (int cc = 0; cc < D / 16; ++cc) {
+        const int c = h * (D / 16) + cc;         // 16-byte chunk index within the row
         const uint4 v = row_ok ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(sQ + (c >> 3) * 16384 + r * 128 + (((c & 7) ^ (r & 7)) << 4)) = v;
       }
@@ -192,112 +208,121 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
       if (lane == 0) mbar_arrive(q_full);
     }
 
-    float o[D];
+    float o[DH];
 #pragma unroll
-    for (int i = 0; i < D; ++i) o[i] = 0.f;
+    for (int i = 0; i < DH; ++i) o[i] = 0.f;
     float m_i = -INFINITY, l_i = 0.f;
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
 
-    for (int j = 0; j < nt; ++j) {
-      const int sb = j & 1;
-      const int k0 = (tile_lo + j) * kAtcBN;
-      mbar_wait(&s_full[sb], (j >> 1) & 1);
-      tc_fence_after();
-      // pass 1: row maximum of the masked, scaled logits (exp2 domain)
-      float m_new = m_i;
-      const bool need_mask = (k0 + kAtcBN - 1 > qpos) || (p.window > 0 && k0 < qpos - p.window + 1) || !row_ok;
-#pragma unroll 1
-      for (int c = 0; c < kAtcBN; c += 32) {
+    auto fold_o = [&]() {
+#pragma unroll
+      for (int c = 0; c < DH; c += 32) {
         uint32_t rr[32];
-        tmem_ld_32x32(lane_addr + sb * 128 + c, rr);
+        tmem_ld_32x32(lane_addr + 256 + h * DH + c, rr);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int kpos = k0 + c + i;
-          float s = __uint_as_float(rr[i]) * p.scale_log2 + slope2 * static_cast<float>(kpos - qpos);
-          const bool ok = !need_mask || (kpos <= qpos && (p.window <= 0 || kpos > qpos - p.window));
-          s = ok ? s : -INFINITY;
-          m_new = fmaxf(m_new, s);
+        for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(rr[i]);
+      }
+    };
+
+    for (int j = 0; j < nt; ++j) {
+      const int sb = j & 1;
+      const int k0 = (tile_lo + j) * kAtcBN + h * 64;   // first key of this thread's half
+      mbar_wait(&s_full[sb], (j >> 1) & 1);
+      tc_fence_after();
+      float sv[64];
+#pragma unroll
+      for (int c = 0; c < 64; c += 32) {
+        uint32_t rr[32];
+        tmem_ld_32x32(lane_addr + sb * 128 + h * 64 + c, rr);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) sv[c + i] = __uint_as_float(rr[i]);
+      }
+      // the logits now live in registers: hand the TMEM buffer back so S(j+2) can be issued
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[sb]);
+
+      // scaled logits (exp2 domain) with position biases / masks; the common case (full tile, no ALiBi) is one FMUL
+      const bool need_mask = (k0 + 63 > qpos) || (p.window > 0 && k0 < qpos - p.window + 1) || !row_ok;
+      float m_loc = -INFINITY;
+      if (!need_mask && !has_alibi) {
+        // raw maximum with four independent chains; the scale is folded into the exponent FMA below
+        float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+          mx[0] = fmaxf(mx[0], sv[i]); mx[1] = fmaxf(mx[1], sv[i + 1]);
+          mx[2] = fmaxf(mx[2], sv[i + 2]); mx[3] = fmaxf(mx[3], sv[i + 3]);
+        }
+        m_loc = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * p.scale_log2;  // scale > 0
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const int kpos = k0 + i;
+          // stored back UNscaled-equivalent: (v / scale) so that the exponent FMA below is the same in both paths
+          float v = sv[i] + (has_alibi ? slope2 * static_cast<float>(kpos - qpos) * inv_scale : 0.f);
+          const bool ok = row_ok && kpos <= qpos && (p.window <= 0 || kpos > qpos - p.window);
+          v = ok ? v : -INFINITY;
+          sv[i] = v;
+          m_loc = fmaxf(m_loc, v * p.scale_log2);
         }
       }
+      // row maximum across the two halves
+      sMax[((j & 1) * 2 + h) * 128 + r] = m_loc;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      const float m_new = fmaxf(m_i, fmaxf(m_loc, sMax[((j & 1) * 2 + (h ^ 1)) * 128 + r]));
       const float m_safe = m_new == -INFINITY ? 0.f : m_new;
-      const float alpha = exp2f(m_i - m_safe);  // m_i = -inf -> 0
-      // P(j-1) must have been consumed before sP is overwritten: o_full of the previous tile says so
+      const float alpha = fast_exp2(m_i - m_safe);  // m_i = -inf -> 0
+
       if (j > 0) {
+        // O'(j-1) = P(j-1) V(j-1) was formed at the scale m_i; o_full also says P(j-1) has been consumed (sP reusable)
         mbar_wait(o_full, (j - 1) & 1);
         tc_fence_after();
-        // fold O'(j-1) into the running accumulator with the scale that was current when P(j-1) was formed
-#pragma unroll
-        for (int c = 0; c < D; c += 32) {
-          uint32_t rr[32];
-          tmem_ld_32x32(lane_addr + 256 + c, rr);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(rr[i]);
-        }
+        fold_o();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(o_empty);
       }
+      if (__any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll
-      for (int i = 0; i < D; ++i) o[i] *= alpha;
-      // pass 2: probabilities -> bf16 -> swizzled shared memory, row sum
-      float l_new = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < kAtcBN; c += 32) {
-        uint32_t rr[32];
-        tmem_ld_32x32(lane_addr + sb * 128 + c, rr);
-        tmem_ld_wait();
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float pv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int kpos = k0 + c + i + e;
-            float s = __uint_as_float(rr[i + e]) * p.scale_log2 + slope2 * static_cast<float>(kpos - qpos);
-            const bool ok = !need_mask || (kpos <= qpos && (p.window <= 0 || kpos > qpos - p.window));
-            pv[e] = ok ? exp2f(s - m_safe) : 0.f;
-          }
-          const uint32_t packed = pack_bf16(pv[0], pv[1]);
-          pk[i >> 1] = packed;
-          l_new += bf16_lo(packed) + bf16_hi(packed);  // sum what the tensor core will actually multiply
-        }
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (c >> 3) + q4;  // 16-byte chunk index within the 128-key row (0..15)
-          *reinterpret_cast<uint4*>(sP + (chunk >> 3) * 16384 + r * 128 + (((chunk & 7) ^ (r & 7)) << 4)) =
-              make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
-        }
+        for (int i = 0; i < DH; ++i) o[i] *= alpha;
       }
-      l_i = l_i * alpha + l_new;
+      // probabilities -> bf16 -> row r of key block h of sP (128B swizzle), partial row sum
+      float ls[4] = {0.f, 0.f, 0.f, 0.f};
+      const float neg_m = -m_safe;
+#pragma unroll
+      for (int c8 = 0; c8 < 8; ++c8) {
+        uint32_t pk[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p0 = fast_exp2(fmaf(sv[c8 * 8 + 2 * e], p.scale_log2, neg_m));      // exp2(-inf) = 0 for masked keys
+          const float p1 = fast_exp2(fmaf(sv[c8 * 8 + 2 * e + 1], p.scale_log2, neg_m));
+          pk[e] = pack_bf16(p0, p1);
+          ls[e] += p0 + p1;
+        }
+        *reinterpret_cast<uint4*>(sP + h * 16384 + r * 128 + ((c8 ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+      }
+      l_i = l_i * alpha + ((ls[0] + ls[1]) + (ls[2] + ls[3]));
       m_i = m_new;
-      // S buffer free, P ready
-      tc_fence_before();
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&s_empty[sb]);
-        mbar_arrive(p_full);
-      }
+      if (lane == 0) mbar_arrive(p_full);
     }
     // last O'
     mbar_wait(o_full, (nt - 1) & 1);
     tc_fence_after();
-#pragma unroll
-    for (int c = 0; c < D; c += 32) {
-      uint32_t rr[32];
-      tmem_ld_32x32(lane_addr + 256 + c, rr);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(rr[i]);
-    }
+    fold_o();
     tc_fence_before();
+    // total row sum = both halves
+    sMax[(4 + h) * 128 + r] = l_i;  // dedicated slots: the partner may still be reading the last row-max exchange
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float l_tot = l_i + sMax[(4 + (h ^ 1)) * 128 + r];
     if (row_ok) {
-      const float inv = l_i > 0.f ? 1.f / l_i : 0.f;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + ((static_cast<size_t>(b) * p.T + t) * p.Hq + head) * D);
+      const float inv = l_tot > 0.f ? 1.f / l_tot : 0.f;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + ((static_cast<size_t>(b) * p.T + t) * p.Hq + head) * D + h * DH);
 #pragma unroll
-      for (int c = 0; c < D / 8; ++c) {
+      for (int c = 0; c < DH / 8; ++c) {
         uint4 v;
         v.x = pack_bf16(o[8 * c] * inv, o[8 * c + 1] * inv);
         v.y = pack_bf16(o[8 * c + 2] * inv, o[8 * c + 3] * inv);
@@ -318,7 +343,7 @@ bool make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t
 template <int D>
 static int launch_attn_tc(const PbAttnArgs* a, cudaStream_t s) {
   constexpr int NB = D / 64;
-  const size_t smem = static_cast<size_t>(NB * 128 * 128 + 2 * 128 * 128 + 2 * 2 * (2 * NB * 8192)) + 1024 + 256;
+  const size_t smem = static_cast<size_t>(NB * 128 * 128 + 2 * 128 * 128 + 2 * 2 * (2 * NB * 8192)) + 1024 + 128 + 6 * 128 * 4 + 64;
   const uint64_t rows = static_cast<uint64_t>(a->num_pages) * a->Hkv * 64;
   CUtensorMap tk, tv;
   if (!make_tmap_2d_bf16(&tk, a->k_pool, rows, D, D, 64, 64)) return PB_ERR_DRIVER;

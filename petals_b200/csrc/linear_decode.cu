@@ -350,7 +350,13 @@ static cudaError_t launch_one(const LinearDecodeParams& p, int grid, int block, 
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return e;
   }
-  return launch_pdl(smem > 32 * 1024 ? kPdlGemvBigSmem : kPdlGemv, kern, dim3(grid), dim3(block), smem, stream, p);
+  // Programmatic dependent launch pays for small weight matrices (kernel-boundary latency is a visible fraction of a short
+  // kernel: 8B-class shapes, tensor-parallel shards) and costs ~4 % on long streaming kernels (70B on one GPU); measured in
+  // profiles/r1_pdl_sweep.txt. The cut-over is a byte threshold on the streamed weights.
+  static const long max_mb = [] { const char* e = getenv("PETALS_B200_PDL_GEMV_MAX_MB"); return e ? atol(e) : 128L; }();
+  const long wbytes = static_cast<long>(p.N) * p.K * 2 * (DUAL ? 2 : 1);
+  const int kind = wbytes <= (max_mb << 20) ? (kPdlGemv | kPdlGemvBigSmem | kPdlGemvAuto) : (smem > 32 * 1024 ? kPdlGemvBigSmem : kPdlGemv);
+  return launch_pdl(kind, kern, dim3(grid), dim3(block), smem, stream, p);
 }
 
 template <int M>

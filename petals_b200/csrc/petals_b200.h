@@ -115,6 +115,7 @@ typedef struct {
   int pos_static;         // used when pos_ptr == null
   int num_pages;          // pages in k_pool / v_pool (bounds the TMA tensor map of the tcgen05 path)
   int impl;               // 0 auto, 1 mma.sync kernel, 2 tcgen05 kernel
+  void* split_counter;    // int32 [m_tiles * B * Hkv], zeroed once: fuses the split-KV combine into the attention kernel
 } PbAttnArgs;
 int pb_attention(const PbAttnArgs* a, void* stream);
 

@@ -335,7 +335,7 @@ def paged_attention(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor,
                     pos_ptr: Optional[int], out: torch.Tensor, *, B: int, T: int, Hq: int, Hkv: int, D: int,
                     scale: float, splits: int = 1, partial_o: Optional[torch.Tensor] = None,
                     partial_lse: Optional[torch.Tensor] = None, alibi_slopes: Optional[torch.Tensor] = None,
-                    window: int = 0, pos_static: int = 0, impl: int = 0) -> torch.Tensor:
+                    window: int = 0, pos_static: int = 0, impl: int = 0, split_counter: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Flash attention over the paged cache. ``impl``: 0 = auto (tcgen05 kernel for prefill-sized tiles, split-KV mma.sync kernel for
     decode), 1 / 2 force the mma.sync / tcgen05 kernel."""
     a = AttnArgs()
@@ -344,8 +344,8 @@ def paged_attention(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor,
     a.scale = scale
     a.B, a.T, a.Hq, a.Hkv, a.D, a.page = B, T, Hq, Hkv, D, PAGE
     a.max_pages, a.window, a.splits, a.pos_static = block_table.shape[1], window, splits, pos_static
-    a.num_pages, a.impl = k_pool.shape[0], impl
-    check(native.lib().pb_attention(C.byref(a), stream_ptr()), "attention", 2 if splits > 1 else 1)
+    a.num_pages, a.impl, a.split_counter = k_pool.shape[0], impl, ptr(split_counter)
+    check(native.lib().pb_attention(C.byref(a), stream_ptr()), "attention", 2 if (splits > 1 and split_counter is None) else 1)
     return out
 
 

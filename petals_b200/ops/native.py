@@ -95,7 +95,7 @@ class AttnArgs(C.Structure):
         ("pos_ptr", C.c_void_p), ("out", C.c_void_p), ("partial_o", C.c_void_p), ("partial_lse", C.c_void_p),
         ("alibi_slopes", C.c_void_p), ("scale", C.c_float),
         ("B", C.c_int), ("T", C.c_int), ("Hq", C.c_int), ("Hkv", C.c_int), ("D", C.c_int), ("page", C.c_int),
-        ("max_pages", C.c_int), ("window", C.c_int), ("splits", C.c_int), ("pos_static", C.c_int), ("num_pages", C.c_int), ("impl", C.c_int),
+        ("max_pages", C.c_int), ("window", C.c_int), ("splits", C.c_int), ("pos_static", C.c_int), ("num_pages", C.c_int), ("impl", C.c_int), ("split_counter", C.c_void_p),
     ]
 
 

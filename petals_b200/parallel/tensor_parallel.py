@@ -147,6 +147,7 @@ class TPDecodeEngine:
         self.epoch_p = torch.zeros(1, dtype=torch.int64, device=dev)  # prefill steps count their own epochs (own flag set)
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.done_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._split_ctr = torch.zeros(1024, dtype=torch.int32, device=dev)  # split-KV arrival counters (self-resetting)
         self.pos_static = torch.zeros(1, dtype=torch.int32, device=dev)
         self.max_pages = cache.max_pages_per_seq
         self._tables: Dict[int, torch.Tensor] = {}
@@ -219,7 +220,8 @@ class TPDecodeEngine:
             Fn.rope_kv_append(qkv_buf, q_buf, pools[0], pools[1], table, pos_ptr, self.cos, self.sin, B=B, T=T, Hq=ls.num_heads,
                               Hkv=ls.num_kv_heads, D=ls.head_dim, error_flag=err)
             Fn.paged_attention(q_buf, pools[0], pools[1], table, pos_ptr, attn, B=B, T=T, Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim,
-                               scale=s.attn_scale, splits=splits, partial_o=po, partial_lse=pl, window=s.sliding_window)
+                               scale=s.attn_scale, splits=splits, partial_o=po, partial_lse=pl, window=s.sliding_window,
+                               split_counter=self._split_ctr if splits > 1 and B * ls.num_kv_heads <= 1024 else None)
             # K2: row-parallel O-projection; epilogue pushes the partial into every rank's slot [me]
             Fn.linear_decode(attn, w["wo"], store_local=False, push_out=[self.parts(self.off_parts_attn, r, me) for r in range(R)],
                              push_flag=[self.flag_attn(r, l) for r in range(R)], done_counter=ctr, error_flag=err)

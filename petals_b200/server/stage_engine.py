@@ -86,6 +86,7 @@ class StageEngine:
         self.max_pages = cache.max_pages_per_seq
         self.pos_static = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._split_ctr = torch.zeros(8192, dtype=torch.int32, device=self.device)  # split-KV arrival counters (self-resetting)
         self._tables: Dict[int, torch.Tensor] = {}  # batch -> static block table
         self._graphs: Dict[Tuple[int, int, int, int], dict] = {}
         self._active: Optional[SessionCache] = None
@@ -139,6 +140,13 @@ class StageEngine:
         ctas = B * self.spec.num_kv_heads * m_tiles
         return int(min(16, max(1, (2 * self.sms) // max(1, ctas))))
 
+    def _split_counter(self, B: int, T: int, splits: int) -> Optional[torch.Tensor]:
+        """Arrival counters that let the last split CTA merge the split-KV partials inside the attention kernel."""
+        if splits <= 1:
+            return None
+        m_tiles = (T * self.spec.group_size + 63) // 64
+        return self._split_ctr if m_tiles * B * self.spec.num_kv_heads <= self._split_ctr.numel() else None
+
     # ---- one block ---------------------------------------------------------------------------------------
     def _attention(self, qkv: torch.Tensor, slot: int, B: int, T: int, table: torch.Tensor, pos_ptr: int,
                    pools: Tuple[torch.Tensor, torch.Tensor], splits: int, tag: str) -> torch.Tensor:
@@ -156,7 +164,7 @@ class StageEngine:
             pl = self._buf(f"pl{tag}", splits, M * s.num_heads, torch.float32)
         Fn.paged_attention(q_buf, pools[0], pools[1], table, pos_ptr, attn, B=B, T=T, Hq=s.num_heads, Hkv=s.num_kv_heads,
                            D=s.head_dim, scale=s.attn_scale, splits=splits, partial_o=po, partial_lse=pl,
-                           alibi_slopes=self.slopes, window=s.sliding_window)
+                           alibi_slopes=self.slopes, window=s.sliding_window, split_counter=self._split_counter(B, T, splits))
         return attn
 
     def _push_kwargs(self, hop: Optional[tuple], gemm: bool = False) -> dict:

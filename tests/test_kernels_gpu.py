@@ -216,6 +216,14 @@ def test_rope_kv_and_attention(D, Hq, Hkv, steps):
             Fn.paged_attention(q_out, k_pool, v_pool, table, pos.data_ptr(), out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D,
                                scale=scale, splits=splits, partial_o=po, partial_lse=pl)
             _close(out, want, 2e-2, 2e-2, f"attention T={T} splits={splits}")
+            if splits > 1:  # combine fused into the attention kernel (last split CTA merges), twice: the counters self-reset
+                ctr = torch.zeros(256, device=DEV, dtype=torch.int32)
+                for _ in range(2):
+                    out2 = torch.full_like(out, float("nan"))
+                    Fn.paged_attention(q_out, k_pool, v_pool, table, pos.data_ptr(), out2, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D,
+                                       scale=scale, splits=splits, partial_o=po, partial_lse=pl, split_counter=ctr, impl=1)
+                    _close(out2, want, 2e-2, 2e-2, f"attention T={T} splits={splits} fused combine")
+                assert int(ctr.abs().sum().item()) == 0
         pos += T
         p0 += T
 
