@@ -44,7 +44,7 @@ PB_DEVICE float fast_exp2(float x) {
 }
 
 template <int D>
-__global__ void __launch_bounds__(kAtcThreads, 1)
+__global__ void __maxnreg__(192)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
   constexpr int NB = D / 64;                       // 64-element (128-byte) swizzle blocks along d
   constexpr int Q_BYTES = NB * kAtcBM * 128;       // [NB][128 rows][128 B]
@@ -60,16 +60,18 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
   uint8_t* sP = sQ + Q_BYTES;
   uint8_t* sKV = sP + P_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + STAGES * STAGE_BYTES);
-  uint64_t* kv_full = bars;            // [STAGES]  TMA -> MMA
-  uint64_t* kv_empty = bars + 2;       // [STAGES]  MMA (commit after PV) -> TMA
-  uint64_t* s_full = bars + 4;         // [2]       MMA -> softmax
-  uint64_t* s_empty = bars + 6;        // [2]       softmax (4 warps) -> MMA
-  uint64_t* p_full = bars + 8;         // [1]       softmax (4 warps) -> MMA
-  uint64_t* o_full = bars + 9;         // [1]       MMA (commit after PV) -> softmax ; also means "P consumed"
-  uint64_t* o_empty = bars + 10;       // [1]       softmax (4 warps) -> MMA
-  uint64_t* q_full = bars + 11;        // [1]       softmax (4 warps) -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  float* sMax = reinterpret_cast<float*>(bars + 16);  // [2 parities][2 halves][128 rows] row-max exchange + [2][128] row sums
+  uint64_t* k_full = bars;             // [2]  TMA -> MMA
+  uint64_t* k_empty = bars + 2;        // [2]  MMA (commit after S) -> TMA: the K stage is free as soon as the logits MMAs retire
+  uint64_t* v_full = bars + 4;         // [2]  TMA -> MMA
+  uint64_t* v_empty = bars + 6;        // [2]  MMA (commit after PV) -> TMA
+  uint64_t* s_full = bars + 8;         // [2]  MMA -> softmax
+  uint64_t* s_empty = bars + 10;       // [2]  softmax (8 warps) -> MMA
+  uint64_t* p_full = bars + 12;        // [1]  softmax (8 warps) -> MMA
+  uint64_t* o_full = bars + 13;        // [1]  MMA (commit after PV) -> softmax ; also means "P consumed"
+  uint64_t* o_empty = bars + 14;       // [1]  softmax (8 warps) -> MMA
+  uint64_t* q_full = bars + 15;        // [1]  softmax (8 warps) -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* sMax = reinterpret_cast<float*>(bars + 24);  // [2 parities][2 halves][128 rows] row-max exchange + [2][128] row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // causal work grows with the tile index: schedule the long tiles first so the last wave is made of short ones
@@ -81,7 +83,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmap_k);
     prefetch_tmap(&tmap_v);
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1); mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], 8); }
     mbar_init(p_full, 8);
     mbar_init(o_full, 1);
@@ -115,25 +117,36 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
     // =============================== TMA producer ===============================
     if (lane == 0) {
       const int* table = p.block_table + static_cast<size_t>(b) * p.max_pages;
+      auto page_row = [&](int tile, int pg) {
+        const int pidx = tile * 2 + pg;
+        // the second page of the last tile may lie past the sequence's pages: fetch any valid page (its keys are masked)
+        int page = pidx < p.max_pages ? table[pidx] : 0;
+        if (page < 0 || page >= p.num_pages || pidx * 64 >= kv_hi) page = table[tile * 2];
+        return (page * p.Hkv + kvh) * 64;
+      };
       for (int j = 0; j < nt; ++j) {
         const int stage = j & 1;
-        mbar_wait(&kv_empty[stage], ((j >> 1) & 1) ^ 1);
+        const uint32_t par = ((j >> 1) & 1) ^ 1;
         uint8_t* sk = sKV + stage * STAGE_BYTES;
         uint8_t* sv = sk + KV_BYTES;
-        mbar_expect_tx(&kv_full[stage], STAGE_BYTES);
         const int tile = tile_lo + j;
+        mbar_wait(&k_empty[stage], par);
+        mbar_expect_tx(&k_full[stage], KV_BYTES);
 #pragma unroll
         for (int pg = 0; pg < 2; ++pg) {
-          int pidx = tile * 2 + pg;
-          // the second page of the last tile may lie past the sequence's pages: fetch any valid page (its keys are masked)
-          int page = pidx < p.max_pages ? table[pidx] : 0;
-          if (page < 0 || page >= p.num_pages || pidx * 64 >= kv_hi) page = table[tile * 2];
-          const int row = (page * p.Hkv + kvh) * 64;
+          const int row = page_row(tile, pg);
 #pragma unroll
-          for (int db = 0; db < NB; ++db) {
-            tma_load_2d(sk + db * 16384 + pg * 8192, &tmap_k, &kv_full[stage], db * 64, row);  // K: [d block][128 keys][128 B]
-            tma_load_2d(sv + (pg * NB + db) * 8192, &tmap_v, &kv_full[stage], db * 64, row);
-          }
+          for (int db = 0; db < NB; ++db)
+            tma_load_2d(sk + db * 16384 + pg * 8192, &tmap_k, &k_full[stage], db * 64, row);  // K: [d block][128 keys][128 B]
+        }
+        mbar_wait(&v_empty[stage], par);
+        mbar_expect_tx(&v_full[stage], KV_BYTES);
+#pragma unroll
+        for (int pg = 0; pg < 2; ++pg) {
+          const int row = page_row(tile, pg);
+#pragma unroll
+          for (int db = 0; db < NB; ++db)
+            tma_load_2d(sv + (pg * NB + db) * 8192, &tmap_v, &v_full[stage], db * 64, row);     // V: [page][d block][64 keys][128 B]
         }
       }
     }
@@ -146,7 +159,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
       const uint32_t tmem_o = tmem_base + 256;
       auto issue_s = [&](int j) {
         const int stage = j & 1, sb = j & 1;
-        mbar_wait(&kv_full[stage], (j >> 1) & 1);
+        mbar_wait(&k_full[stage], (j >> 1) & 1);
         mbar_wait(&s_empty[sb], ((j >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sKV + stage * STAGE_BYTES);
@@ -157,6 +170,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
           tc_mma_f16(tmem_base + sb * 128, adesc, bdesc, idesc_s, kk != 0 ? 1u : 0u);
         }
         tc_commit(&s_full[sb]);
+        tc_commit(&k_empty[stage]);
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -164,6 +178,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
       for (int j = 0; j < nt; ++j) {
         if (j + 1 < nt) issue_s(j + 1);  // next logits tile runs under this tile's softmax
         const int stage = j & 1;
+        mbar_wait(&v_full[stage], (j >> 1) & 1);
         mbar_wait(p_full, j & 1);
         mbar_wait(o_empty, (j & 1) ^ 1);
         tc_fence_after();
@@ -174,7 +189,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
           const uint64_t bdesc = umma_desc_mn_sw128(v_addr + (kk >> 2) * NB * 8192 + (kk & 3) * 2048, 8192);
           tc_mma_f16(tmem_o, adesc, bdesc, idesc_o, kk != 0 ? 1u : 0u);
         }
-        tc_commit(&kv_empty[stage]);  // K and V of this stage are no longer needed once these MMAs retire
+        tc_commit(&v_empty[stage]);
         tc_commit(o_full);
       }
     }
@@ -216,12 +231,12 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_cons
 
     auto fold_o = [&]() {
 #pragma unroll
-      for (int c = 0; c < DH; c += 32) {
-        uint32_t rr[32];
-        tmem_ld_32x32(lane_addr + 256 + h * DH + c, rr);
+      for (int c = 0; c < DH; c += 16) {
+        uint32_t rr[16];
+        tmem_ld_32x16(lane_addr + 256 + h * DH + c, rr);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(rr[i]);
+        for (int i = 0; i < 16; ++i) o[c + i] += __uint_as_float(rr[i]);
       }
     };
 
@@ -343,7 +358,7 @@ bool make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t
 template <int D>
 static int launch_attn_tc(const PbAttnArgs* a, cudaStream_t s) {
   constexpr int NB = D / 64;
-  const size_t smem = static_cast<size_t>(NB * 128 * 128 + 2 * 128 * 128 + 2 * 2 * (2 * NB * 8192)) + 1024 + 128 + 6 * 128 * 4 + 64;
+  const size_t smem = static_cast<size_t>(NB * 128 * 128 + 2 * 128 * 128 + 2 * 2 * (2 * NB * 8192)) + 1024 + 192 + 6 * 128 * 4 + 64;
   const uint64_t rows = static_cast<uint64_t>(a->num_pages) * a->Hkv * 64;
   CUtensorMap tk, tv;
   if (!make_tmap_2d_bf16(&tk, a->k_pool, rows, D, D, 64, 64)) return PB_ERR_DRIVER;

@@ -52,6 +52,26 @@ struct LinearDecodeParams {
   uint64_t* push_flag[kMaxPeers];               // incremented (release.sys) ONCE per launch, by the last CTA to finish
   unsigned int* done_counter;                   // local device counter used to elect that last CTA (self-resetting)
   int* error_flag;                              // set to 1 on watchdog expiry
+  // ---- LL ("low latency") one-shot all-reduce: every partial is sent as 8-byte {2 x bf16, 32-bit tag} stores, so data and
+  // validity arrive in one NVLink transaction and the consumer polls the payload itself. No fence, no last-CTA election, no
+  // flag round trip (the flag protocol above costs a release fence + atomic + flag hop per all-reduce). tag = epoch * mul + add
+  // identifies (step, layer); buffers are never cleared.
+  const uint2* ll_parts[kMaxPeers];             // prologue: local buffers [M, K/2] written by the peers' epilogues
+  int n_ll_parts;
+  uint2* ll_push[kMaxPeers];                    // epilogue: peers' buffers [M, N/2] (this rank's slot)
+  int n_ll_push;
+  uint32_t ll_tag_mul, ll_tag_add;
+  // ---- fused RoPE + paged KV append (QKV projection of Llama-style blocks): the epilogue rotates q/k with HF's bf16
+  // rounding, stores q token-major for the attention kernel and writes k/v straight into the session's cache pages, so the
+  // decode step needs no separate RoPE/append launch. Output columns are then processed as rotary pairs (i, i + D/2).
+  __nv_bfloat16* rope_q_out;                    // [M, Hq*D]; non-null enables the fusion (template flag ROPE)
+  __nv_bfloat16* rope_k_pool;
+  __nv_bfloat16* rope_v_pool;
+  const int* rope_block_table;                  // [B, max_pages]
+  const int* rope_pos_ptr;                      // device-resident position of the first new token
+  const float* rope_cos;                        // [max_pos, D/2] fp32 (null: no rotation, append only)
+  const float* rope_sin;
+  int rope_T, rope_Hq, rope_Hkv, rope_D, rope_max_pages, rope_max_pos;
   int pf_lines;                                 // 128-byte weight lines each warp prefetches into L2 before the prologue
   int late_trigger;                             // 1: release the dependent kernel after the main loop instead of at entry
   int wait_all_warps;                           // 1: every warp executes griddepcontrol.wait (default: warp 0 + barrier)
@@ -91,8 +111,10 @@ PB_DEVICE float block_sum(float v, float* red) {
   return warp_sum(t);
 }
 
-// M = tokens, DUAL = SwiGLU (two weight matrices), XSMEM = x staged in shared memory.
-template <int M, bool DUAL, bool XSMEM>
+PB_DEVICE float rbf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// M = tokens, DUAL = SwiGLU (two weight matrices), XSMEM = x staged in shared memory, ROPE = fused RoPE + KV append epilogue.
+template <int M, bool DUAL, bool XSMEM, bool ROPE = false>
 __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(const LinearDecodeParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
@@ -113,10 +135,11 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
     if (task0 < (N >> 1) && p.pf_lines > 0) {
       constexpr int kRows = DUAL ? 4 : 2;
       const int lines_per_row = p.pf_lines / kRows;
-      const int n0 = task0 << 1;
+      const int half_d = ROPE ? (p.rope_D >> 1) : 1;
+      const int n0 = ROPE ? (task0 / half_d) * p.rope_D + task0 % half_d : task0 << 1;
       for (int i = lane; i < p.pf_lines; i += 32) {
         const int row = i / lines_per_row, k = (i - row * lines_per_row) * 64;
-        if (row < kRows && k < K) prefetch_l2((row < 2 ? p.w : p.w2) + static_cast<size_t>(n0 + (row & 1)) * K + k);
+        if (row < kRows && k < K) prefetch_l2((row < 2 ? p.w : p.w2) + static_cast<size_t>(n0 + (row & 1) * half_d) * K + k);
       }
     }
   }
@@ -133,6 +156,7 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
     }
     __syncthreads();
   }
+  const uint32_t ll_tag = (p.n_ll_parts > 0 || p.n_ll_push > 0) ? static_cast<uint32_t>(*p.epoch) * p.ll_tag_mul + p.ll_tag_add : 0u;
   if (XSMEM) {
     const int kvec = K >> 3;  // 8 bf16 per 16-byte vector
     float ssum[M], ssq[M];
@@ -143,9 +167,27 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
       for (int m = 0; m < M; ++m) {
         const size_t off = static_cast<size_t>(m) * K + (static_cast<size_t>(v) << 3);
         uint4 xv = __ldcg(reinterpret_cast<const uint4*>(p.x + off));
-        if (p.n_parts > 0) {
+        if (p.n_parts > 0 || p.n_ll_parts > 0) {
           float f[8] = {bf16_lo(xv.x), bf16_hi(xv.x), bf16_lo(xv.y), bf16_hi(xv.y),
                         bf16_lo(xv.z), bf16_hi(xv.z), bf16_lo(xv.w), bf16_hi(xv.w)};
+          for (int r = 0; r < p.n_ll_parts; ++r) {
+            // 8 values = 4 LL units = 32 bytes; spin until all four carry this step's tag
+            const uint4* src = reinterpret_cast<const uint4*>(p.ll_parts[r] + (off >> 1));
+            uint4 a, b;
+            unsigned long long t0 = 0;
+            for (unsigned spins = 0;; ++spins) {
+              a = ld_relaxed_sys_v4(src);
+              b = ld_relaxed_sys_v4(src + 1);
+              if (a.y == ll_tag && a.w == ll_tag && b.y == ll_tag && b.w == ll_tag) break;
+              if ((spins & 1023u) == 1023u) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > PB_FLAG_TIMEOUT_NS) { if (p.error_flag != nullptr) atomicExch(p.error_flag, 1); break; }
+              }
+            }
+            f[0] += bf16_lo(a.x); f[1] += bf16_hi(a.x); f[2] += bf16_lo(a.z); f[3] += bf16_hi(a.z);
+            f[4] += bf16_lo(b.x); f[5] += bf16_hi(b.x); f[6] += bf16_lo(b.z); f[7] += bf16_hi(b.z);
+          }
           for (int r = 0; r < p.n_parts; ++r) {
             uint4 pv = __ldcg(reinterpret_cast<const uint4*>(p.parts[r] + off));
             f[0] += bf16_lo(pv.x); f[1] += bf16_hi(pv.x); f[2] += bf16_lo(pv.y); f[3] += bf16_hi(pv.y);
@@ -223,9 +265,11 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
   const int total_warps = gridDim.x * nwarps;
   const int kstep = 256 * U;
   for (int task = warp * gridDim.x + blockIdx.x; task < ntasks; task += total_warps) {
-    const int n0 = task << 1;
+    // plain: adjacent output columns (n0, n0+1); ROPE: the rotary pair (i, i + D/2) of one head
+    const int half_d = ROPE ? (p.rope_D >> 1) : 1;
+    const int n0 = ROPE ? (task / half_d) * p.rope_D + task % half_d : task << 1;
     const __nv_bfloat16* w0 = p.w + static_cast<size_t>(n0) * K;
-    const __nv_bfloat16* w1 = w0 + K;
+    const __nv_bfloat16* w1 = w0 + static_cast<size_t>(half_d) * K;
     const __nv_bfloat16* u0 = DUAL ? p.w2 + static_cast<size_t>(n0) * K : nullptr;
     const __nv_bfloat16* u1 = DUAL ? u0 + K : nullptr;
     float a0[M], a1[M], b0[M], b1[M];
@@ -288,7 +332,41 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
         if (DUAL) { c0 = b0[m]; c1 = b1[m]; }
       }
     }
-    if (lane < M) {
+    if (ROPE) {
+      if (lane < M) {
+        const int D = p.rope_D, head = n0 / D, i = n0 - head * D;
+        const int b = lane / p.rope_T, t = lane - b * p.rope_T;
+        const int pos = *p.rope_pos_ptr + t;
+        float x0 = rbf16(v0), x1 = rbf16(v1);  // the projection output is a bf16 tensor in the unfused pipeline
+        const bool is_v = head >= p.rope_Hq + p.rope_Hkv;
+        if (!is_v && p.rope_cos != nullptr) {
+          const int pp = pos < p.rope_max_pos ? pos : p.rope_max_pos - 1;
+          const float c = rbf16(p.rope_cos[static_cast<size_t>(pp) * half_d + i]);
+          const float sn = rbf16(p.rope_sin[static_cast<size_t>(pp) * half_d + i]);
+          const float y0 = rbf16(rbf16(x0 * c) + rbf16(-x1 * sn));   // HF rotate_half with bf16 rounding of every product
+          const float y1 = rbf16(rbf16(x1 * c) + rbf16(x0 * sn));
+          x0 = y0; x1 = y1;
+        }
+        __nv_bfloat16* dst;
+        if (head < p.rope_Hq) {
+          dst = p.rope_q_out + (static_cast<size_t>(lane) * p.rope_Hq + head) * D;
+        } else {
+          const int kvh = is_v ? head - p.rope_Hq - p.rope_Hkv : head - p.rope_Hq;
+          const int pg_idx = pos >> 6;  // 64-token pages
+          if (pg_idx >= p.rope_max_pages) {
+            if (p.error_flag != nullptr) atomicExch(p.error_flag, 2);
+            dst = nullptr;
+          } else {
+            const int pg = p.rope_block_table[static_cast<size_t>(b) * p.rope_max_pages + pg_idx];
+            dst = (is_v ? p.rope_v_pool : p.rope_k_pool) + ((static_cast<size_t>(pg) * p.rope_Hkv + kvh) * 64 + (pos & 63)) * D;
+          }
+        }
+        if (dst != nullptr) {
+          dst[i] = __float2bfloat16_rn(x0);
+          dst[i + half_d] = __float2bfloat16_rn(x1);
+        }
+      }
+    } else if (lane < M) {
       if (p.bias != nullptr) {
         v0 += __bfloat162float(p.bias[n0]);
         v1 += __bfloat162float(p.bias[n0 + 1]);
@@ -320,6 +398,7 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
       const uint32_t packed = pack_bf16(v0, v1);
       if (p.out != nullptr) *reinterpret_cast<uint32_t*>(p.out + o) = packed;
       for (int r = 0; r < p.n_push; ++r) *reinterpret_cast<uint32_t*>(p.push_out[r] + o) = packed;
+      for (int r = 0; r < p.n_ll_push; ++r) st_relaxed_sys_v2(p.ll_push[r] + (o >> 1), packed, ll_tag);
     }
   }
 
@@ -341,10 +420,10 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
   }
 }
 
-template <int M, bool DUAL, bool XSMEM>
+template <int M, bool DUAL, bool XSMEM, bool ROPE = false>
 static cudaError_t launch_one(const LinearDecodeParams& p, int grid, int block, size_t smem,
                               cudaStream_t stream) {
-  auto kern = linear_decode_kernel<M, DUAL, XSMEM>;
+  auto kern = linear_decode_kernel<M, DUAL, XSMEM, ROPE>;
   if (smem > 32 * 1024) {  // static shared memory counts against the 48 KB default too
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
@@ -362,6 +441,7 @@ static cudaError_t launch_one(const LinearDecodeParams& p, int grid, int block, 
 template <int M>
 static cudaError_t launch_m(const LinearDecodeParams& p, bool dual, bool xsmem, int grid, int block,
                             size_t smem, cudaStream_t s) {
+  if (p.rope_q_out != nullptr) return launch_one<M, false, true, true>(p, grid, block, smem, s);  // validated: !dual && xsmem
   if (dual) return xsmem ? launch_one<M, true, true>(p, grid, block, smem, s)
                          : launch_one<M, true, false>(p, grid, block, smem, s);
   return xsmem ? launch_one<M, false, true>(p, grid, block, smem, s)
@@ -403,12 +483,35 @@ extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
     p.push_flag[i] = static_cast<uint64_t*>(a->push_flag[i]);
   }
   p.error_flag = static_cast<int*>(a->error_flag);
+  if (a->n_ll_parts < 0 || a->n_ll_parts > kMaxPeers || a->n_ll_push < 0 || a->n_ll_push > kMaxPeers) return PB_ERR_SHAPE;
+  if ((a->n_ll_parts > 0 || a->n_ll_push > 0) && a->epoch == nullptr) return PB_ERR_SHAPE;
+  if (a->n_ll_push > 0 && a->act == 1) return PB_ERR_SHAPE;  // LL pushes come from the row-parallel projections
+  p.n_ll_parts = a->n_ll_parts; p.n_ll_push = a->n_ll_push;
+  for (int i = 0; i < a->n_ll_parts; ++i) p.ll_parts[i] = static_cast<const uint2*>(a->ll_parts[i]);
+  for (int i = 0; i < a->n_ll_push; ++i) p.ll_push[i] = static_cast<uint2*>(a->ll_push[i]);
+  p.ll_tag_mul = a->ll_tag_mul; p.ll_tag_add = a->ll_tag_add;
+  if (a->rope_q_out != nullptr) {
+    const int D = a->rope_D, heads = a->rope_Hq + 2 * a->rope_Hkv;
+    if (a->act != 0 || a->bias != nullptr || a->residual != nullptr || a->n_push > 0 || D < 2 || (D & 1) || a->N != heads * D || a->rope_T < 1 ||
+        a->M % a->rope_T != 0 || a->rope_k_pool == nullptr || a->rope_v_pool == nullptr || a->rope_block_table == nullptr ||
+        a->rope_pos_ptr == nullptr || (a->rope_cos != nullptr && a->rope_sin == nullptr))
+      return PB_ERR_SHAPE;
+    p.rope_q_out = static_cast<__nv_bfloat16*>(a->rope_q_out);
+    p.rope_k_pool = static_cast<__nv_bfloat16*>(a->rope_k_pool);
+    p.rope_v_pool = static_cast<__nv_bfloat16*>(a->rope_v_pool);
+    p.rope_block_table = static_cast<const int*>(a->rope_block_table);
+    p.rope_pos_ptr = static_cast<const int*>(a->rope_pos_ptr);
+    p.rope_cos = static_cast<const float*>(a->rope_cos);
+    p.rope_sin = static_cast<const float*>(a->rope_sin);
+    p.rope_T = a->rope_T; p.rope_Hq = a->rope_Hq; p.rope_Hkv = a->rope_Hkv; p.rope_D = D;
+    p.rope_max_pages = a->rope_max_pages; p.rope_max_pos = a->rope_max_pos;
+  }
   {
     static const int env_pf = [] { const char* e = getenv("PETALS_B200_PF_LINES"); return e ? atoi(e) : -1; }();
     static const int env_pf_wait = [] { const char* e = getenv("PETALS_B200_PF_LINES_WAIT"); return e ? atoi(e) : -1; }();
     static const int env_late = [] { const char* e = getenv("PETALS_B200_PDL_LATE"); return e ? atoi(e) : 0; }();
     // a kernel that will spin on a peer flag can hide a deep prefetch behind the wait; one that starts right away cannot
-    p.pf_lines = a->wait_flag != nullptr ? (env_pf_wait >= 0 ? env_pf_wait : 64) : (env_pf >= 0 ? env_pf : 16);
+    p.pf_lines = (a->wait_flag != nullptr || a->n_ll_parts > 0) ? (env_pf_wait >= 0 ? env_pf_wait : 64) : (env_pf >= 0 ? env_pf : 16);
     if (p.pf_lines > 0 && p.pf_lines < 4) p.pf_lines = 4;
     p.late_trigger = env_late;
     static const int env_allw = [] { const char* e = getenv("PETALS_B200_PDL_WAIT_ALL"); return e ? atoi(e) : 0; }();
@@ -419,7 +522,7 @@ extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
 
   const bool dual = a->act == 1;
   if (dual && p.w2 == nullptr) return PB_ERR_SHAPE;
-  const bool need_smem = a->norm_kind != 0 || a->n_parts > 0;
+  const bool need_smem = a->norm_kind != 0 || a->n_parts > 0 || a->n_ll_parts > 0;
   const size_t xbytes = static_cast<size_t>(a->M) * a->K * 2;
   const bool xsmem = need_smem || xbytes <= 160 * 1024;
   if (need_smem && xbytes > 200 * 1024) return PB_ERR_SHAPE;

@@ -23,6 +23,14 @@ typedef struct {
   void* error_flag;
   int num_sms; int fixed_grid; int* out_grid;
   void* done_counter;
+  // fused RoPE + paged KV append epilogue for the QKV projection (rope_q_out != NULL enables it; see linear_decode.cu)
+  void* rope_q_out; void* rope_k_pool; void* rope_v_pool; const void* rope_block_table; const void* rope_pos_ptr;
+  const void* rope_cos; const void* rope_sin;
+  int rope_T, rope_Hq, rope_Hkv, rope_D, rope_max_pages, rope_max_pos;
+  // LL one-shot all-reduce (8-byte {payload, tag} units; see linear_decode.cu): tag = (uint32)*epoch * ll_tag_mul + ll_tag_add
+  int n_ll_parts; const void* ll_parts[PB_MAX_PEERS];
+  int n_ll_push; void* ll_push[PB_MAX_PEERS];
+  uint32_t ll_tag_mul, ll_tag_add;
 } PbLinearDecodeArgs;
 int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream);
 

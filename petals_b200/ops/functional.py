@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
-from typing import Optional, Sequence
+from typing import Optional, Sequence, Tuple
 
 import torch
 import torch.nn.functional as F
@@ -44,8 +44,13 @@ def linear_decode(
     parts: Sequence[torch.Tensor] = (), wait_flag: Optional[int] = None, wait_per_epoch: int = 0,
     epoch: Optional[int] = None, push_out: Sequence[int] = (), push_flag: Sequence[int] = (),
     error_flag: Optional[int] = None, fixed_grid: int = 0, store_local: bool = True, done_counter: Optional[int] = None,
+    rope: Optional[dict] = None, ll_parts: Sequence[int] = (), ll_push: Sequence[int] = (), ll_tag: Tuple[int, int] = (1, 0),
 ) -> torch.Tensor:
     """``out[M,N] = epilogue(prologue(x)[M,K] @ w[N,K]^T)`` for M <= 8 tokens. See csrc/linear_decode.cu.
+
+    ``rope`` (QKV projection of Llama-style blocks) fuses RoPE + the paged KV append into the epilogue: a dict with ``q_out``
+    [M, Hq*D], ``k_pool``/``v_pool`` (this block's page pools), ``block_table`` [B, max_pages] int32, ``pos_ptr`` (device address),
+    ``cos``/``sin`` (fp32 tables or None), ``T``, ``Hq``, ``Hkv``, ``D``. Nothing is stored to ``out`` then; ``q_out`` is returned.
 
     ``push_out`` / ``push_flag`` / ``wait_flag`` / ``epoch`` are raw device addresses (peer-mapped buffers
     from :mod:`petals_b200.parallel.symmetric`).
@@ -55,6 +60,8 @@ def linear_decode(
     N = w.shape[0]
     if w.shape[1] != K:
         raise ValueError(f"weight shape {tuple(w.shape)} incompatible with K={K}")
+    if rope is not None:
+        store_local = False
     if out is None and store_local:
         out = torch.empty(*x.shape[:-1], N, dtype=torch.bfloat16, device=x.device)
     a = LinearDecodeArgs()
@@ -78,8 +85,21 @@ def linear_decode(
     a.num_sms = native.sm_count(x.device.index)
     a.fixed_grid = fixed_grid
     a.done_counter = done_counter
+    a.n_ll_parts, a.n_ll_push = len(ll_parts), len(ll_push)
+    for i, p in enumerate(ll_parts):
+        a.ll_parts[i] = p
+    for i, p in enumerate(ll_push):
+        a.ll_push[i] = p
+    a.ll_tag_mul, a.ll_tag_add = ll_tag
+    if rope is not None:
+        cos, sin, table = rope.get("cos"), rope.get("sin"), rope["block_table"]
+        a.rope_q_out, a.rope_k_pool, a.rope_v_pool = ptr(rope["q_out"]), ptr(rope["k_pool"]), ptr(rope["v_pool"])
+        a.rope_block_table, a.rope_pos_ptr = ptr(table), rope["pos_ptr"]
+        a.rope_cos, a.rope_sin = ptr(cos), ptr(sin)
+        a.rope_T, a.rope_Hq, a.rope_Hkv, a.rope_D = rope["T"], rope["Hq"], rope["Hkv"], rope["D"]
+        a.rope_max_pages, a.rope_max_pos = table.shape[1], (cos.shape[0] if cos is not None else 0)
     check(native.lib().pb_linear_decode(C.byref(a), stream_ptr()), "linear_decode")
-    return out
+    return rope["q_out"] if rope is not None else out
 
 
 def linear_decode_fp8(x: torch.Tensor, w_q: torch.Tensor, w_scale: torch.Tensor, *, w2_q: Optional[torch.Tensor] = None,

@@ -40,6 +40,11 @@ class LinearDecodeArgs(C.Structure):
         ("error_flag", C.c_void_p),
         ("num_sms", C.c_int), ("fixed_grid", C.c_int), ("out_grid", C.POINTER(C.c_int)),
         ("done_counter", C.c_void_p),
+        ("rope_q_out", C.c_void_p), ("rope_k_pool", C.c_void_p), ("rope_v_pool", C.c_void_p), ("rope_block_table", C.c_void_p),
+        ("rope_pos_ptr", C.c_void_p), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
+        ("rope_T", C.c_int), ("rope_Hq", C.c_int), ("rope_Hkv", C.c_int), ("rope_D", C.c_int), ("rope_max_pages", C.c_int), ("rope_max_pos", C.c_int),
+        ("n_ll_parts", C.c_int), ("ll_parts", C.c_void_p * PB_MAX_PEERS), ("n_ll_push", C.c_int), ("ll_push", C.c_void_p * PB_MAX_PEERS),
+        ("ll_tag_mul", C.c_uint32), ("ll_tag_add", C.c_uint32),
     ]
 
 

@@ -19,6 +19,7 @@ bumps a device-resident epoch per step; flag targets are ``epoch * n_sources`` s
 from __future__ import annotations
 
 import dataclasses
+import os
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -127,6 +128,11 @@ class TPDecodeEngine:
         self.off_parts_attn = heap.alloc(R * self.slot_bytes)
         self.off_parts_mlp = heap.alloc(R * self.slot_bytes)
         self.off_flags = heap.alloc((2 * L + 2) * 8)
+        # LL all-reduce buffers: [source rank][MAX_ROWS, H/2] x 8-byte {2 x bf16, tag} units (twice the payload bytes)
+        self.use_ll = os.environ.get("PETALS_B200_TP_LL", "1") != "0"
+        self.ll_slot_bytes = MAX_ROWS * H * 4
+        self.off_ll_attn = heap.alloc(R * self.ll_slot_bytes, align=4096)
+        self.off_ll_mlp = heap.alloc(R * self.ll_slot_bytes, align=4096)
         self.x_in = heap.tensor(self.off_x_in, (MAX_ROWS, H), torch.bfloat16)
         # sequence-parallel prefill: rows are owned in contiguous slices of `mo` rows per rank
         self.max_prefill_rows = P = max(0, max_prefill_rows)
@@ -147,6 +153,7 @@ class TPDecodeEngine:
         self.epoch_p = torch.zeros(1, dtype=torch.int64, device=dev)  # prefill steps count their own epochs (own flag set)
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.done_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.fuse_rope = os.environ.get("PETALS_B200_FUSE_ROPE", "1") != "0"
         self._split_ctr = torch.zeros(1024, dtype=torch.int32, device=dev)  # split-KV arrival counters (self-resetting)
         self.pos_static = torch.zeros(1, dtype=torch.int32, device=dev)
         self.max_pages = cache.max_pages_per_seq
@@ -206,36 +213,56 @@ class TPDecodeEngine:
         pl = self._buf("pl", splits, M * ls.num_heads, torch.float32) if splits > 1 else None
         attn_parts = [self.parts(self.off_parts_attn, me, r) for r in range(R)]
         mlp_parts = [self.parts(self.off_parts_mlp, me, r) for r in range(R)]
+        # LL protocol (default): partials travel as {payload, tag} units, consumers poll the payload; the flag protocol stays for
+        # the step input and for the last layer's MLP (its consumer is the final reduce kernel)
+        L, ll = self.n_blocks, self.use_ll
+        ll_attn_in = [self.heap.addr(me, self.off_ll_attn + r * self.ll_slot_bytes) for r in range(R)]
+        ll_mlp_in = [self.heap.addr(me, self.off_ll_mlp + r * self.ll_slot_bytes) for r in range(R)]
+        ll_attn_out = [self.heap.addr(r, self.off_ll_attn + me * self.ll_slot_bytes) for r in range(R)]
+        ll_mlp_out = [self.heap.addr(r, self.off_ll_mlp + me * self.ll_slot_bytes) for r in range(R)]
         for l, w in enumerate(self.shards):
             pools = self.cache.layer_pools(l)
             # K1: [all-reduce tail of previous MLP] + norm + column-parallel QKV
+            # the QKV epilogue rotates q/k and appends k/v to this rank's cache pages (no RoPE launch)
+            rope = dict(q_out=q_buf, k_pool=pools[0], v_pool=pools[1], block_table=table, pos_ptr=pos_ptr, cos=self.cos, sin=self.sin, T=T,
+                        Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim) if self.fuse_rope else None
+            out_kw = dict(rope=rope) if rope is not None else dict(out=qkv_buf)
             if l == 0:
                 Fn.linear_decode(cur, w["wqkv"], norm_weight=w["ln1_w"], norm_bias=w.get("ln1_b"), norm_kind=self.norm_kind, eps=eps,
-                                 out=qkv_buf, wait_flag=self.flag(me, 0), wait_per_epoch=1, epoch=ep, error_flag=err)
+                                 wait_flag=self.flag(me, 0), wait_per_epoch=1, epoch=ep, error_flag=err, **out_kw)
             else:
+                red = (dict(ll_parts=ll_mlp_in, ll_tag=(L, l - 1)) if ll else
+                       dict(parts=mlp_parts, wait_flag=self.flag_mlp(me, l - 1), wait_per_epoch=R))
                 Fn.linear_decode(cur, w["wqkv"], norm_weight=w["ln1_w"], norm_bias=w.get("ln1_b"), norm_kind=self.norm_kind, eps=eps,
-                                 out=qkv_buf, parts=mlp_parts, wait_flag=self.flag_mlp(me, l - 1), wait_per_epoch=R, epoch=ep,
-                                 x_out=h[nxt], error_flag=err)
+                                 epoch=ep, x_out=h[nxt], error_flag=err, **red, **out_kw)
                 cur, nxt = h[nxt], nxt ^ 1
-            Fn.rope_kv_append(qkv_buf, q_buf, pools[0], pools[1], table, pos_ptr, self.cos, self.sin, B=B, T=T, Hq=ls.num_heads,
-                              Hkv=ls.num_kv_heads, D=ls.head_dim, error_flag=err)
+            if rope is None:
+                Fn.rope_kv_append(qkv_buf, q_buf, pools[0], pools[1], table, pos_ptr, self.cos, self.sin, B=B, T=T, Hq=ls.num_heads,
+                                  Hkv=ls.num_kv_heads, D=ls.head_dim, error_flag=err)
             Fn.paged_attention(q_buf, pools[0], pools[1], table, pos_ptr, attn, B=B, T=T, Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim,
                                scale=s.attn_scale, splits=splits, partial_o=po, partial_lse=pl, window=s.sliding_window,
                                split_counter=self._split_ctr if splits > 1 and B * ls.num_kv_heads <= 1024 else None)
             # K2: row-parallel O-projection; epilogue pushes the partial into every rank's slot [me]
-            Fn.linear_decode(attn, w["wo"], store_local=False, push_out=[self.parts(self.off_parts_attn, r, me) for r in range(R)],
-                             push_flag=[self.flag_attn(r, l) for r in range(R)], done_counter=ctr, error_flag=err)
+            if ll:
+                Fn.linear_decode(attn, w["wo"], store_local=False, ll_push=ll_attn_out, ll_tag=(L, l), epoch=ep, error_flag=err)
+            else:
+                Fn.linear_decode(attn, w["wo"], store_local=False, push_out=[self.parts(self.off_parts_attn, r, me) for r in range(R)],
+                                 push_flag=[self.flag_attn(r, l) for r in range(R)], done_counter=ctr, error_flag=err)
             # K3: [all-reduce tail of attention] + norm + column-parallel gate/up (+SwiGLU)
-            kw = dict(norm_weight=w["ln2_w"], norm_bias=w.get("ln2_b"), norm_kind=self.norm_kind, eps=eps, out=act, parts=attn_parts,
-                      wait_flag=self.flag_attn(me, l), wait_per_epoch=R, epoch=ep, x_out=h[nxt], error_flag=err)
+            kw = dict(norm_weight=w["ln2_w"], norm_bias=w.get("ln2_b"), norm_kind=self.norm_kind, eps=eps, out=act, epoch=ep, x_out=h[nxt],
+                      error_flag=err)
+            kw.update(dict(ll_parts=ll_attn_in, ll_tag=(L, l)) if ll else dict(parts=attn_parts, wait_flag=self.flag_attn(me, l), wait_per_epoch=R))
             if s.mlp == "swiglu":
                 Fn.linear_decode(cur, w["w_gate"], w2=w["w_up"], act=Fn.ACT_SWIGLU, **kw)
             else:
                 Fn.linear_decode(cur, w["w_up"], act=self.act, **kw)
             cur, nxt = h[nxt], nxt ^ 1
             # K4: row-parallel down projection, pushed like K2
-            Fn.linear_decode(act, w["w_down"], store_local=False, push_out=[self.parts(self.off_parts_mlp, r, me) for r in range(R)],
-                             push_flag=[self.flag_mlp(r, l) for r in range(R)], done_counter=ctr, error_flag=err)
+            if ll and l + 1 < L:
+                Fn.linear_decode(act, w["w_down"], store_local=False, ll_push=ll_mlp_out, ll_tag=(L, l), epoch=ep, error_flag=err)
+            else:
+                Fn.linear_decode(act, w["w_down"], store_local=False, push_out=[self.parts(self.off_parts_mlp, r, me) for r in range(R)],
+                                 push_flag=[self.flag_mlp(r, l) for r in range(R)], done_counter=ctr, error_flag=err)
         if final_reduce:
             parts = ptr_array(mlp_parts)
             native.check(native.lib().pb_reduce_parts(cur.data_ptr(), parts, R, self.flag_mlp(me, self.n_blocks - 1), R, ep, self.out.data_ptr(),
@@ -371,6 +398,13 @@ class TPDecodeEngine:
         qkv = Fn.linear_decode(x, w["wqkv"], norm_weight=w["ln1_w"], norm_bias=w.get("ln1_b"), norm_kind=self.norm_kind, eps=s.norm_eps,
                                out=self._buf("qkv", M, ls.qkv_dim))
         q_buf, attn = self._buf("q", M, ls.num_heads * ls.head_dim), self._buf("attn", M, ls.num_heads * ls.head_dim)
+        if self.fuse_rope:
+            # the RoPE-fused QKV variant too; it writes k/v of layer 0 at the positions the real step overwrites right after
+            pools = self.cache.layer_pools(0)
+            Fn.linear_decode(x, w["wqkv"], norm_weight=w["ln1_w"], norm_bias=w.get("ln1_b"), norm_kind=self.norm_kind, eps=s.norm_eps,
+                             error_flag=self.err.data_ptr(),
+                             rope=dict(q_out=q_buf, k_pool=pools[0], v_pool=pools[1], block_table=table, pos_ptr=self.pos_static.data_ptr(),
+                                       cos=self.cos, sin=self.sin, T=T, Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim))
         attn.zero_()
         act = self._buf("act", M, ls.intermediate_size)
         splits = int(min(16, max(1, (2 * self.sms) // max(1, B * ls.num_kv_heads))))

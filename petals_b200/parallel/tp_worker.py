@@ -155,6 +155,7 @@ def build_tp_engine(config, n_blocks: int, *, group=None, attn_cache_tokens: int
     if not tp_supported(spec, world):
         raise ValueError(f"{spec.family} blocks cannot be tensor-parallelised over {world} ranks by this engine")
     need = (1 + 2 * world) * MAX_ROWS * spec.hidden_size * 2 + (2 * n_blocks + 2) * 8 + (1 << 20)
+    need += 2 * world * MAX_ROWS * spec.hidden_size * 4 + (1 << 16)  # LL all-reduce buffers
     need += prefill_heap_bytes(spec.hidden_size, world, n_blocks, max_prefill_rows)
     heap = SymmetricHeap(heap_bytes or (max(need, 8 << 20) + (256 << 20)), group=group, device=device)  # + room for the bandwidth probe
     if blocks is not None:

@@ -16,6 +16,8 @@ This is the B200-native counterpart of the reference's per-block ``TransformerBa
 """
 from __future__ import annotations
 
+import os
+
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -86,6 +88,7 @@ class StageEngine:
         self.max_pages = cache.max_pages_per_seq
         self.pos_static = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.fuse_rope = os.environ.get("PETALS_B200_FUSE_ROPE", "1") != "0"
         self._split_ctr = torch.zeros(8192, dtype=torch.int32, device=self.device)  # split-KV arrival counters (self-resetting)
         self._tables: Dict[int, torch.Tensor] = {}  # batch -> static block table
         self._graphs: Dict[Tuple[int, int, int, int], dict] = {}
@@ -155,9 +158,10 @@ class StageEngine:
         w = self.blocks[slot]
         q_buf = self._buf(f"q{tag}", M, s.num_heads * s.head_dim)
         attn = self._buf(f"attn{tag}", M, s.num_heads * s.head_dim)
-        Fn.rope_kv_append(qkv, q_buf, pools[0], pools[1], table, pos_ptr, self.cos, self.sin, B=B, T=T, Hq=s.num_heads,
-                          Hkv=s.num_kv_heads, D=s.head_dim, qkv_bias=None, interleaved=s.qkv_interleaved,
-                          error_flag=self.err_flag.data_ptr())
+        if qkv is not None:  # None: RoPE + KV append already happened in the QKV projection's epilogue
+            Fn.rope_kv_append(qkv, q_buf, pools[0], pools[1], table, pos_ptr, self.cos, self.sin, B=B, T=T, Hq=s.num_heads,
+                              Hkv=s.num_kv_heads, D=s.head_dim, qkv_bias=None, interleaved=s.qkv_interleaved,
+                              error_flag=self.err_flag.data_ptr())
         po = pl = None
         if splits > 1:
             po = self._buf(f"po{tag}", splits * M * s.num_heads, s.head_dim, torch.float32)
@@ -187,8 +191,16 @@ class StageEngine:
         s, w = self.spec, self.blocks[slot]
         M = B * T
         eps = s.norm_eps
-        qkv = self._lin_decode(slot, "wqkv", x, bias=w._p("bqkv"), norm_weight=w.ln1_w, norm_bias=w._p("ln1_b"), norm_kind=self.norm_kind,
-                               eps=eps, out=self._buf("qkv", M, s.qkv_dim))
+        if self.fuse_rope and self.fp8 is None and w._p("bqkv") is None and not s.qkv_interleaved:
+            # QKV projection whose epilogue rotates q/k and appends k/v to the cache pages: no RoPE launch, no qkv round trip
+            Fn.linear_decode(x, w.wqkv, norm_weight=w.ln1_w, norm_bias=w._p("ln1_b"), norm_kind=self.norm_kind, eps=eps,
+                             error_flag=self.err_flag.data_ptr(),
+                             rope=dict(q_out=self._buf("q", M, s.num_heads * s.head_dim), k_pool=pools[0], v_pool=pools[1], block_table=table,
+                                       pos_ptr=pos_ptr, cos=self.cos, sin=self.sin, T=T, Hq=s.num_heads, Hkv=s.num_kv_heads, D=s.head_dim))
+            qkv = None
+        else:
+            qkv = self._lin_decode(slot, "wqkv", x, bias=w._p("bqkv"), norm_weight=w.ln1_w, norm_bias=w._p("ln1_b"), norm_kind=self.norm_kind,
+                                   eps=eps, out=self._buf("qkv", M, s.qkv_dim))
         attn = self._attention(qkv, slot, B, T, table, pos_ptr, pools, splits, "")
         h1 = self._lin_decode(slot, "wo", attn, bias=w._p("bo"), residual=x, out=out)
         if s.mlp == "moe":

@@ -389,3 +389,32 @@ def test_attention_tcgen05_alibi_window():
     _close(out, Fn.attention_ref(q, k, v, pos0=0, scale=D ** -0.5, alibi_slopes=slopes), 2e-2, 2e-2, "tcgen05 alibi")
     Fn.paged_attention(q_out, k_pool, v_pool, table, pos.data_ptr(), out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=D ** -0.5, window=150, impl=2)
     _close(out, Fn.attention_ref(q, k, v, pos0=0, scale=D ** -0.5, window=150), 2e-2, 2e-2, "tcgen05 window")
+
+
+@pytest.mark.parametrize("D,Hq,Hkv", [(128, 8, 2), (64, 4, 4)])
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 3), (1, 8)])
+def test_linear_decode_fused_rope_append(D, Hq, Hkv, B, T):
+    """QKV projection with the RoPE + paged-KV-append epilogue == (projection -> rope_kv_append kernel), bit for bit."""
+    torch.manual_seed(31)
+    K, M = 1024, B * T
+    N = (Hq + 2 * Hkv) * D
+    x, w, g = _rand(M, K), _rand(N, K, scale=K ** -0.5), _rand(K) * 0.1 + 1
+    cos, sin = Fn.rope_tables(D, 512, theta=10000.0, device=DEV)
+    pos = torch.full((1,), 70, dtype=torch.int32, device=DEV)  # mid-page, second page of each sequence
+    kp1, vp1, table = _paged_setup(B, 200, Hkv, D, seed=5)
+    kp2, vp2 = kp1.clone(), vp1.clone()
+    # unfused reference pipeline
+    qkv = Fn.linear_decode(x, w, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+    q1 = torch.empty(M, Hq * D, device=DEV, dtype=torch.bfloat16)
+    Fn.rope_kv_append(qkv, q1, kp1, vp1, table, pos.data_ptr(), cos, sin, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D)
+    # fused
+    q2 = torch.full_like(q1, float("nan"))
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    Fn.linear_decode(x, w, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5, error_flag=err.data_ptr(),
+                     rope=dict(q_out=q2, k_pool=kp2, v_pool=vp2, block_table=table, pos_ptr=pos.data_ptr(), cos=cos, sin=sin, T=T, Hq=Hq, Hkv=Hkv, D=D))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    _close(q2, q1, 1e-2, 1e-2, "q")
+    _close(kp2, kp1, 1e-2, 1e-2, "k pages")
+    _close(vp2, vp1, 1e-2, 1e-2, "v pages")
+    assert (kp2 != 0).any() and (vp2 != 0).any()
