@@ -44,7 +44,7 @@ PB_DEVICE float fast_exp2(float x) {
 }
 
 template <int D>
-__global__ void __maxnreg__(192)
+__global__ void __launch_bounds__(kAtcThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v, const AttnTcParams p) {
   constexpr int NB = D / 64;                       // 64-element (128-byte) swizzle blocks along d
   constexpr int Q_BYTES = NB * kAtcBM * 128;       // [NB][128 rows][128 B]

@@ -8,7 +8,9 @@
 // bytes, so 1-byte weights halve the time per token. Same structure as linear_decode.cu (warp per output-column
 // pair, 8 x 16-byte non-allocating loads in flight per lane, fused norm prologue and bias / SwiGLU / GELU / residual
 // epilogue); the 16 FP8 values of a load share one scale, so the inner product of a load is accumulated
-// unscaled in fp32 and scaled once. x is staged in shared memory as fp32 (no per-use conversion).
+// unscaled and scaled once. x is staged in shared memory as fp16, pre-scaled per token by a power of two so that |x| <= 8:
+// the 16 products of a load are then accumulated with packed HFMA2 (e4m3 -> f16x2 is one cvt; |sum| <= 8*448*8 < 65504 cannot
+// overflow) and only the per-load partial goes to fp32 - half the instructions and half the shared-memory traffic of an fp32 path.
 #include "common.cuh"
 #include "petals_b200.h"
 
@@ -45,34 +47,38 @@ PB_DEVICE float gelu_tanh8(float x) {
 }
 PB_DEVICE float rb(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// x lives in shared memory as fp32; a lane reads 4 consecutive float4 chunks per load (64-byte lane stride), which would be
-// a 4-way bank conflict. Chunk c of a row is therefore stored at c ^ ((c >> 3) & 7): conflict-free for this access pattern.
-PB_DEVICE int swz_chunk(int c) { return c ^ ((c >> 3) & 7); }
+// x lives in shared memory as fp16; a lane reads two consecutive 16-byte chunks per load (32-byte lane stride), which would be a
+// 2-way bank conflict. Chunk c of a row is therefore stored at c ^ ((c >> 3) & 1): conflict-free for this access pattern.
+PB_DEVICE int swz_chunk(int c) { return c ^ ((c >> 3) & 1); }
 
-// 16 e4m3 values (one uint4) times 16 fp32 activations per token
+PB_DEVICE __half2 e4m3x2_to_half2(uint16_t v) {
+  uint32_t h2;
+  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(h2) : "h"(v));
+  return *reinterpret_cast<__half2*>(&h2);
+}
+PB_DEVICE __half2 as_half2(uint32_t v) { return *reinterpret_cast<__half2*>(&v); }
+
+// 16 e4m3 values (one uint4) times 16 fp16 activations per token: 8 cvt + 8 HFMA2 per token
 template <int M>
-PB_DEVICE void dot16(float (&acc)[M], const uint4& w, float scale, const float* xs, int K, int k) {
+PB_DEVICE void dot16(float (&acc)[M], const uint4& w, float scale, const __half* xs, int K, int k) {
   const uint32_t words[4] = {w.x, w.y, w.z, w.w};
-  float wf[16];
+  __half2 wh[8];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 a = e4m3x2_to_float2(static_cast<uint16_t>(words[i] & 0xffffu));
-    const float2 b = e4m3x2_to_float2(static_cast<uint16_t>(words[i] >> 16));
-    wf[4 * i] = a.x; wf[4 * i + 1] = a.y; wf[4 * i + 2] = b.x; wf[4 * i + 3] = b.y;
+    wh[2 * i] = e4m3x2_to_half2(static_cast<uint16_t>(words[i] & 0xffffu));
+    wh[2 * i + 1] = e4m3x2_to_half2(static_cast<uint16_t>(words[i] >> 16));
   }
+  const int c = k >> 3;  // 16-byte chunk (8 halves) index within the row; k is a multiple of 16
 #pragma unroll
   for (int m = 0; m < M; ++m) {
-    const float4* xrow = reinterpret_cast<const float4*>(xs + static_cast<size_t>(m) * K);
-    float part = 0.f;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 xv = xrow[swz_chunk((k >> 2) + q)];
-      part = fmaf(wf[4 * q], xv.x, part);
-      part = fmaf(wf[4 * q + 1], xv.y, part);
-      part = fmaf(wf[4 * q + 2], xv.z, part);
-      part = fmaf(wf[4 * q + 3], xv.w, part);
-    }
-    acc[m] = fmaf(part, scale, acc[m]);
+    const uint4* xrow = reinterpret_cast<const uint4*>(xs + static_cast<size_t>(m) * K);
+    const uint4 xa = xrow[swz_chunk(c)], xb = xrow[swz_chunk(c + 1)];
+    __half2 s0 = __hmul2(wh[0], as_half2(xa.x)), s1 = __hmul2(wh[4], as_half2(xb.x));
+    s0 = __hfma2(wh[1], as_half2(xa.y), s0); s1 = __hfma2(wh[5], as_half2(xb.y), s1);
+    s0 = __hfma2(wh[2], as_half2(xa.z), s0); s1 = __hfma2(wh[6], as_half2(xb.z), s1);
+    s0 = __hfma2(wh[3], as_half2(xa.w), s0); s1 = __hfma2(wh[7], as_half2(xb.w), s1);
+    const float2 f = __half22float2(__hadd2(s0, s1));
+    acc[m] = fmaf(f.x + f.y, scale, acc[m]);
   }
 }
 
@@ -86,29 +92,39 @@ PB_DEVICE float block_sum8(float v, float* red) {
   return warp_sum(t);
 }
 
+PB_DEVICE float block_max8(float v, float* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.f;
+  return warp_max(t);
+}
+
 template <int M, bool DUAL>
 __global__ void __launch_bounds__(768, 1) linear_decode_fp8_kernel(const LinearFp8Params p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  float* xs = reinterpret_cast<float*>(smem_raw);  // [M, K] fp32
+  __half* xs = reinterpret_cast<__half*>(smem_raw);  // [M, K] fp16, row m scaled by 2^-xexp[m]
   __shared__ float red[32];
   __shared__ float stat[2 * M];
+  __shared__ float xinv[M];  // 2^xexp[m]: undoes the activation scaling in the epilogue
   const int K = p.K, N = p.N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5, tid = threadIdx.x, nthr = blockDim.x;
 
-  // ---- prologue: x (+ norm) -> fp32 in shared memory -------------------------------------------------------
+  // ---- prologue: x (+ norm) -> scaled fp16 in shared memory ----------------------------------------------------
   {
-    float ssum[M], ssq[M];
-#pragma unroll
-    for (int m = 0; m < M; ++m) ssum[m] = ssq[m] = 0.f;
-    for (int k = tid; k < M * K; k += nthr) {
-      const float f = __bfloat162float(p.x[k]);
-      const int m = k / K, kk0 = k - m * K;
-      xs[static_cast<size_t>(m) * K + swz_chunk(kk0 >> 2) * 4 + (kk0 & 3)] = f;
-#pragma unroll
-      for (int mm = 0; mm < M; ++mm)
-        if (mm == m) { ssum[mm] += f; ssq[mm] += f * f; }
-    }
     if (p.norm_kind != 0) {
+      float ssum[M], ssq[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) ssum[m] = ssq[m] = 0.f;
+      for (int k = tid; k < M * K; k += nthr) {
+        const float f = __bfloat162float(p.x[k]);
+        const int m = k / K;
+#pragma unroll
+        for (int mm = 0; mm < M; ++mm)
+          if (mm == m) { ssum[mm] += f; ssq[mm] += f * f; }
+      }
 #pragma unroll
       for (int m = 0; m < M; ++m) {
         const float s1 = block_sum8(ssum[m], red), s2 = block_sum8(ssq[m], red);
@@ -122,14 +138,41 @@ __global__ void __launch_bounds__(768, 1) linear_decode_fp8_kernel(const LinearF
         }
       }
       __syncthreads();
-      for (int k = tid; k < M * K; k += nthr) {
-        const int m = k / K, kk = k - m * K;
-        const size_t idx = static_cast<size_t>(m) * K + swz_chunk(kk >> 2) * 4 + (kk & 3);
-        const float g = __bfloat162float(p.norm_w[kk]);
-        float v = xs[idx];
-        if (p.norm_kind == 1) v = rb(rb(v * stat[2 * m + 1]) * g);
-        else v = rb((v - stat[2 * m]) * stat[2 * m + 1] * g + (p.norm_b != nullptr ? __bfloat162float(p.norm_b[kk]) : 0.f));
-        xs[idx] = v;
+    }
+    // normalised activations (bf16-rounded like the dense path) -> fp16 in smem, and the per-token maximum
+    float amax[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) amax[m] = 0.f;
+    for (int k = tid; k < M * K; k += nthr) {
+      const int m = k / K, kk = k - m * K;
+      float v = __bfloat162float(p.x[k]);  // second read hits L2
+      if (p.norm_kind == 1) v = rb(rb(v * stat[2 * m + 1]) * __bfloat162float(p.norm_w[kk]));
+      else if (p.norm_kind == 2)
+        v = rb((v - stat[2 * m]) * stat[2 * m + 1] * __bfloat162float(p.norm_w[kk]) + (p.norm_b != nullptr ? __bfloat162float(p.norm_b[kk]) : 0.f));
+      v = fminf(fmaxf(v, -60000.f), 60000.f);  // fp16 storage range
+      xs[static_cast<size_t>(m) * K + swz_chunk(kk >> 3) * 8 + (kk & 7)] = __float2half_rn(v);
+#pragma unroll
+      for (int mm = 0; mm < M; ++mm)
+        if (mm == m) amax[mm] = fmaxf(amax[mm], fabsf(v));
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      const float mx = block_max8(amax[m], red);
+      if (tid == 0) {
+        // power of two that brings the row maximum into (4, 8]; exact in fp16 for everything that matters
+        int e = 0;
+        if (mx > 0.f) { frexpf(mx, &e); e -= 3; }   // mx = f * 2^e', f in [0.5, 1): mx * 2^-(e'-3) in [4, 8)
+        stat[2 * m] = ldexpf(1.f, -e);              // reuse: multiplier applied to the staged row
+        xinv[m] = ldexpf(1.f, e);
+      }
+    }
+    __syncthreads();
+    for (int k2 = tid; k2 < (M * K) >> 1; k2 += nthr) {
+      const int m = (k2 << 1) / K;
+      const float sc = stat[2 * m];
+      if (sc != 1.f) {
+        __half2* px = reinterpret_cast<__half2*>(xs) + k2;
+        *px = __hmul2(*px, __float2half2_rn(sc));
       }
     }
     __syncthreads();
@@ -198,6 +241,8 @@ __global__ void __launch_bounds__(768, 1) linear_decode_fp8_kernel(const LinearF
     for (int m = 0; m < M; ++m)
       if (lane == m) { v0 = a0[m]; v1 = a1[m]; if (DUAL) { c0 = b0[m]; c1 = b1[m]; } }
     if (lane < M) {
+      const float xi = xinv[lane];  // undo the fp16 activation scaling
+      v0 *= xi; v1 *= xi; c0 *= xi; c1 *= xi;
       if (p.bias != nullptr) { v0 += __bfloat162float(p.bias[n0]); v1 += __bfloat162float(p.bias[n0 + 1]); }
       if (DUAL) {
         if (p.bias2 != nullptr) { c0 += __bfloat162float(p.bias2[n0]); c1 += __bfloat162float(p.bias2[n0 + 1]); }
@@ -259,7 +304,7 @@ static int launch_fp8(const LinearFp8Params& p, bool dual, int grid, int block, 
 extern "C" int pb_linear_decode_fp8(const PbLinearFp8Args* a, void* stream) {
   using namespace pb;
   if (a->M < 1 || a->M > 4 || (a->N & 1) || (a->K & 31)) return PB_ERR_SHAPE;
-  const size_t smem = static_cast<size_t>(a->M) * a->K * 4;
+  const size_t smem = static_cast<size_t>(a->M) * a->K * 2;  // fp16 staging
   if (smem > 200 * 1024) return PB_ERR_SHAPE;
   LinearFp8Params p{};
   p.x = static_cast<const __nv_bfloat16*>(a->x);

@@ -418,3 +418,25 @@ def test_linear_decode_fused_rope_append(D, Hq, Hkv, B, T):
     _close(kp2, kp1, 1e-2, 1e-2, "k pages")
     _close(vp2, vp1, 1e-2, 1e-2, "v pages")
     assert (kp2 != 0).any() and (vp2 != 0).any()
+
+
+def test_linear_decode_fp8_activation_outliers():
+    """The fp16 staging of x is scaled per token by a power of two: huge and tiny rows (no norm, e.g. the down projection's
+    input) must neither overflow the packed-half accumulation nor lose the small row."""
+    from petals_b200.ops.quant import dequantize_mxfp8, quantize_mxfp8
+
+    torch.manual_seed(23)
+    K, N, M = 2048, 1024, 3
+    x = _rand(M, K)
+    x[0] *= 300.0          # massive activations
+    x[0, 7] = 20000.0      # one outlier
+    x[1] *= 1e-3           # tiny row
+    w = _rand(N, K, scale=K ** -0.5)
+    q, e = quantize_mxfp8(w)
+    wd = dequantize_mxfp8(q, e)
+    got = Fn.linear_decode_fp8(x, q, e)
+    want = Fn.linear_ref(x, wd)
+    assert torch.isfinite(got.float()).all()
+    for m in range(M):
+        err = (got[m].float() - want[m].float()).abs().max() / want[m].float().abs().max()
+        assert err < 2e-2, f"row {m}: {err}"
