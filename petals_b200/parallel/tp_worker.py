@@ -184,3 +184,99 @@ def make_ring(group=None, n_followers: Optional[int] = None) -> CommandRing:
         ring = CommandRing(names[0], create=False)
     host_barrier(group)
     return ring
+
+
+# ---- a TP group started from ONE server process (`run_server --tensor_parallel_devices cuda:0 cuda:1 ...`) -------------------
+class TPGroup:
+    """Owns the follower processes of a tensor-parallel stage. The calling (server) process becomes rank 0 / the leader: it
+    initialises ``torch.distributed`` for the group, loads + shards its blocks, builds the engine and the command ring;
+    every other device gets a spawned worker running :func:`_follower_main` on the same checkpoint."""
+
+    def __init__(self, config, converted_model_name_or_path: str, block_indices: Sequence[int], devices: Sequence[torch.device], *,
+                 torch_dtype: torch.dtype, attn_cache_tokens: int, inference_max_length: int, use_cuda_graphs: bool = True,
+                 max_prefill_rows: int = 4096, start_timeout: float = 600.0):
+        import socket
+
+        import torch.multiprocessing as mp
+
+        from petals_b200.parallel.tensor_parallel import tp_supported
+
+        if torch_dtype != torch.bfloat16:
+            raise ValueError("tensor-parallel stages run in bfloat16")
+        spec = config.block_spec()
+        world = len(devices)
+        if not tp_supported(spec, world):
+            raise ValueError(f"{spec.family} blocks cannot be tensor-parallelised over {world} devices by this engine "
+                             f"(needs kv heads, heads and FFN columns divisible by {world}, sequential attention/MLP, no fused-interleaved QKV)")
+        if dist.is_available() and dist.is_initialized():
+            raise RuntimeError("this process already belongs to a torch.distributed job; start tensor-parallel stages from a fresh server process")
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        self.world, self.devices = world, [torch.device(d) for d in devices]
+        ctx = mp.get_context("spawn")
+        self.procs = []
+        common = dict(world=world, port=port, path=converted_model_name_or_path, block_indices=list(block_indices),
+                      attn_cache_tokens=attn_cache_tokens, inference_max_length=inference_max_length, use_cuda_graphs=use_cuda_graphs,
+                      max_prefill_rows=max_prefill_rows)
+        for rank in range(1, world):
+            p = ctx.Process(target=_follower_main, kwargs=dict(rank=rank, device=str(self.devices[rank]), **common), daemon=True,
+                            name=f"tp-follower-{rank}")
+            p.start()
+            self.procs.append(p)
+        self.engine, self.cache, self.heap, self.ring = _join_group(rank=0, device=self.devices[0], config=config, **common)
+        self.leader = TPLeaderEngine(self.engine, self.ring)
+
+    def shutdown(self, timeout: float = 30.0) -> None:
+        try:
+            self.leader.shutdown()
+        finally:
+            for p in self.procs:
+                p.join(timeout)
+                if p.is_alive():
+                    p.terminate()
+            try:
+                self.heap.close()
+                dist.destroy_process_group()
+            except Exception:  # noqa: BLE001 - best effort on the way out
+                pass
+
+
+def _join_group(*, rank: int, device, world: int, port: int, path: str, block_indices, attn_cache_tokens: int, inference_max_length: int,
+                use_cuda_graphs: bool, max_prefill_rows: int, config=None):
+    """Collective over the TP group: initialise the process group, load + shard this rank's blocks, build engine and ring."""
+    from petals_b200.parallel.tensor_parallel import TPDecodeEngine, local_spec, prefill_heap_bytes, shard_block
+    from petals_b200.server.from_pretrained import load_pretrained_block
+    from petals_b200.utils.auto_config import AutoDistributedConfig
+
+    device = torch.device(device)
+    torch.cuda.set_device(device)
+    dist.init_process_group(backend="cpu:gloo,cuda:nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world, device_id=device)
+    config = config or AutoDistributedConfig.from_pretrained(path)
+    spec = config.block_spec()
+    n_blocks = len(block_indices)
+    need = (1 + 2 * world) * MAX_ROWS * spec.hidden_size * 2 + (2 * n_blocks + 2) * 8 + (1 << 20)
+    need += 2 * world * MAX_ROWS * spec.hidden_size * 4 + (1 << 16)
+    need += prefill_heap_bytes(spec.hidden_size, world, n_blocks, max_prefill_rows)
+    heap = SymmetricHeap(max(need, 8 << 20) + (64 << 20), device=device)
+    shards = []
+    for block_index in block_indices:  # one block at a time: the dense block never lives on the GPU
+        block = load_pretrained_block(path, block_index, config=config, torch_dtype=torch.bfloat16)
+        shards.append(shard_block(block, spec, rank, world, device))
+        del block
+    cache = MemoryCache(attn_cache_tokens, None, n_blocks=n_blocks, spec=local_spec(spec, world), dtype=torch.bfloat16, device=device, paged=True,
+                        max_length=inference_max_length)
+    engine = TPDecodeEngine(spec, shards, heap, cache, use_cuda_graphs=use_cuda_graphs, max_prefill_rows=max_prefill_rows)
+    torch.cuda.synchronize(device)
+    host_barrier()
+    ring = make_ring()
+    return engine, cache, heap, ring
+
+
+def _follower_main(*, rank: int, device: str, **kwargs) -> None:
+    engine, cache, heap, ring = _join_group(rank=rank, device=device, **kwargs)
+    try:
+        follower_loop(engine, cache, ring, rank - 1)
+    finally:
+        heap.close()
+        dist.destroy_process_group()

@@ -261,35 +261,51 @@ class ModuleContainer:
         announcer.announce(ServerState.JOINING)
         announcer.start()
         logger.info(f"Announced that blocks {block_indices[0]}:{block_indices[-1] + 1} are joining")
+        tp_group = None
         try:
-            blocks = []
-            for i, block_index in enumerate(block_indices):
-                if prebuilt_blocks is not None:
-                    block = prebuilt_blocks[i]
-                else:
-                    block = load_pretrained_block(converted_model_name_or_path, block_index, config=block_config, torch_dtype=torch_dtype)
-                block = convert_block(block, block_index, block_config, tensor_parallel_devices, device, quant_type, freeze=True, adapters=adapters)
-                blocks.append(block)
-            spec = block_config.block_spec()
-            from petals_b200.server.stage_engine import fast_path_supported
+            if len(tensor_parallel_devices) > 1 and device.type == "cuda":
+                # one stage = a tensor-parallel group of worker processes (reference: --tensor_parallel_devices, run_server.py:154-157):
+                # this process leads, every other device gets a worker; the weights live in the group's shards
+                from petals_b200.parallel.tp_worker import TPGroup
 
-            paged = (device.type == "cuda" and torch_dtype == torch.bfloat16 and fast_path_supported(spec) and not force_oracle
-                     and quant_type in (QuantType.NONE, QuantType.FP8) and not (quant_type == QuantType.FP8 and adapters))
-            memory_cache = MemoryCache(attn_cache_tokens, max_alloc_timeout, n_blocks=len(blocks), spec=spec, dtype=torch_dtype, device=device,
-                                       paged=paged, max_length=inference_max_length)
-            stage = Stage(block_config, blocks, block_indices[0], device=device, memory_cache=memory_cache, torch_dtype=torch_dtype,
-                          max_chunk_size_bytes=max_chunk_size_bytes, use_cuda_graphs=use_cuda_graphs, force_oracle=force_oracle,
-                          fp8=(quant_type == QuantType.FP8 and paged))
+                if quant_type != QuantType.NONE or adapters or prebuilt_blocks is not None:
+                    raise ValueError("tensor-parallel stages serve bf16 checkpoints without adapters; use pipeline stages for quantised / LoRA serving")
+                tp_group = TPGroup(block_config, converted_model_name_or_path, block_indices, tensor_parallel_devices, torch_dtype=torch_dtype,
+                                   attn_cache_tokens=attn_cache_tokens, inference_max_length=inference_max_length, use_cuda_graphs=use_cuda_graphs)
+                blocks = [torch.nn.Identity() for _ in block_indices]
+                stage = Stage(block_config, blocks, block_indices[0], device=device, memory_cache=tp_group.cache, torch_dtype=torch_dtype,
+                              engine=tp_group.leader)
+            else:
+                blocks = []
+                for i, block_index in enumerate(block_indices):
+                    if prebuilt_blocks is not None:
+                        block = prebuilt_blocks[i]
+                    else:
+                        block = load_pretrained_block(converted_model_name_or_path, block_index, config=block_config, torch_dtype=torch_dtype)
+                    block = convert_block(block, block_index, block_config, tensor_parallel_devices, device, quant_type, freeze=True, adapters=adapters)
+                    blocks.append(block)
+                spec = block_config.block_spec()
+                from petals_b200.server.stage_engine import fast_path_supported
+
+                paged = (device.type == "cuda" and torch_dtype == torch.bfloat16 and fast_path_supported(spec) and not force_oracle
+                         and quant_type in (QuantType.NONE, QuantType.FP8) and not (quant_type == QuantType.FP8 and adapters))
+                memory_cache = MemoryCache(attn_cache_tokens, max_alloc_timeout, n_blocks=len(blocks), spec=spec, dtype=torch_dtype, device=device,
+                                           paged=paged, max_length=inference_max_length)
+                stage = Stage(block_config, blocks, block_indices[0], device=device, memory_cache=memory_cache, torch_dtype=torch_dtype,
+                              max_chunk_size_bytes=max_chunk_size_bytes, use_cuda_graphs=use_cuda_graphs, force_oracle=force_oracle,
+                              fp8=(quant_type == QuantType.FP8 and paged))
             container_parts = cls._build_pools(stage, module_uids, blocks, max_batch_size, stats_report_interval, peer_id, device)
         except BaseException:
             announcer.announce(ServerState.OFFLINE)
             announcer.stop.set()
+            if tp_group is not None:
+                tp_group.shutdown()
             raise
         backends, runtime, inference_pool, forward_pool, backward_pool = container_parts
         return cls(dht, dht_prefix, backends, stage=stage, runtime=runtime, inference_pool=inference_pool, forward_pool=forward_pool,
                    backward_pool=backward_pool, announcer=announcer, peer_id=peer_id, adapters=adapters,
                    inference_max_length=inference_max_length, request_timeout=request_timeout, session_timeout=session_timeout,
-                   step_timeout=step_timeout, quant_type=quant_type)
+                   step_timeout=step_timeout, quant_type=quant_type, tp_group=tp_group)
 
     @staticmethod
     def _build_pools(stage: Stage, module_uids: List[str], blocks, max_batch_size: int, stats_report_interval, peer_id: str, device):
@@ -333,8 +349,9 @@ class ModuleContainer:
 
     def __init__(self, dht: Swarm, dht_prefix: str, module_backends: Dict[str, TransformerBackend], *, stage: Stage, runtime: Runtime,
                  inference_pool, forward_pool, backward_pool, announcer: "ModuleAnnouncerThread", peer_id: str, adapters,
-                 inference_max_length: int, request_timeout: float, session_timeout: float, step_timeout: float, quant_type):
+                 inference_max_length: int, request_timeout: float, session_timeout: float, step_timeout: float, quant_type, tp_group=None):
         self.dht, self.dht_prefix, self.module_backends, self.stage, self.runtime = dht, dht_prefix, module_backends, stage, runtime
+        self.tp_group = tp_group
         self.announcer, self.peer_id = announcer, peer_id
         self.handler = TransformerConnectionHandler(
             dht, module_backends, stage=stage, peer_id=peer_id, inference_pool=inference_pool, forward_pool=forward_pool,
@@ -362,6 +379,9 @@ class ModuleContainer:
         self.runtime.shutdown()
         for backend in self.module_backends.values():
             backend.shutdown()
+        if self.tp_group is not None:
+            self.tp_group.shutdown()
+            self.tp_group = None
         logger.info(f"Stage {self.peer_id} shut down")
 
 

@@ -30,3 +30,12 @@ def test_pp2_fused_stage_hop_matches_oracle():
     lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
     assert proc.returncode == 0 and lines, proc.stdout[-2000:] + proc.stderr[-2000:]
     assert json.loads(lines[-1])["pp_selftest"] == "ok"
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_server_tensor_parallel_devices():
+    """`run_server --tensor_parallel_devices cuda:0 cuda:1`: one server process leads a spawned worker group."""
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tp_server_selftest.py")], capture_output=True, text=True, timeout=900, cwd=ROOT)
+    lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
+    assert proc.returncode == 0 and lines, proc.stdout[-2000:] + proc.stderr[-2000:]
+    assert json.loads(lines[-1])["tp_server_selftest"] == "ok"
