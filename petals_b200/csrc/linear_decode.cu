@@ -113,40 +113,36 @@ PB_DEVICE float block_sum(float v, float* red) {
 
 PB_DEVICE float rbf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-// M = tokens, DUAL = SwiGLU (two weight matrices), XSMEM = x staged in shared memory, ROPE = fused RoPE + KV append epilogue.
-template <int M, bool DUAL, bool XSMEM, bool ROPE = false>
-__global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(const LinearDecodeParams p) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+// Warm L2 with the head of the first weight rows every warp will stream (weights are never written by a kernel, so this may
+// run before the producer of x has finished: behind a programmatic dependency, a peer-flag wait or a grid barrier).
+template <bool DUAL, bool ROPE>
+PB_DEVICE void gemv_prefetch(const LinearDecodeParams& p, int grid, int bid, int nwarps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int task0 = warp * grid + bid;
+  if (warp < nwarps && task0 < (p.N >> 1) && p.pf_lines > 0) {
+    constexpr int kRows = DUAL ? 4 : 2;
+    const int lines_per_row = p.pf_lines / kRows;
+    const int half_d = ROPE ? (p.rope_D >> 1) : 1;
+    const int n0 = ROPE ? (task0 / half_d) * p.rope_D + task0 % half_d : task0 << 1;
+    for (int i = lane; i < p.pf_lines; i += 32) {
+      const int row = i / lines_per_row, k = (i - row * lines_per_row) * 64;
+      if (row < kRows && k < p.K) prefetch_l2((row < 2 ? p.w : p.w2) + static_cast<size_t>(n0 + (row & 1) * half_d) * p.K + k);
+    }
+  }
+}
+
+// One decode-shape linear layer executed by the whole CTA: `grid` CTAs cooperate, this one is number `bid`; warps >= nwarps
+// only take part in the prologue. M = tokens, DUAL = SwiGLU (two weight matrices), XSMEM = x staged in shared memory,
+// ROPE = fused RoPE + KV append epilogue. Called once by linear_decode_kernel and back to back by gemv_chain_kernel.
+template <int M, bool DUAL, bool XSMEM, bool ROPE>
+PB_DEVICE void gemv_body(const LinearDecodeParams& p, uint8_t* smem_raw, int grid, int bid, int nwarps) {
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __shared__ float red[32];
   __shared__ float stat[2 * M];
 
   const int K = p.K, N = p.N;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tid = threadIdx.x, nthr = blockDim.x;
-
-  // ---- PDL pre-section --------------------------------------------------------------------------
-  // Weights are never written by a kernel, so while the predecessor kernel drains (and while this kernel then waits for
-  // a peer flag and normalises x) every warp pulls the head of its first weight rows into L2: the main loop's first
-  // iterations hit L2 and HBM keeps streaming through what used to be a bubble between two GEMVs.
-  if (!p.late_trigger && tid == 0) pdl_trigger();
-  {
-    const int task0 = warp * gridDim.x + blockIdx.x;
-    if (task0 < (N >> 1) && p.pf_lines > 0) {
-      constexpr int kRows = DUAL ? 4 : 2;
-      const int lines_per_row = p.pf_lines / kRows;
-      const int half_d = ROPE ? (p.rope_D >> 1) : 1;
-      const int n0 = ROPE ? (task0 / half_d) * p.rope_D + task0 % half_d : task0 << 1;
-      for (int i = lane; i < p.pf_lines; i += 32) {
-        const int row = i / lines_per_row, k = (i - row * lines_per_row) * 64;
-        if (row < kRows && k < K) prefetch_l2((row < 2 ? p.w : p.w2) + static_cast<size_t>(n0 + (row & 1) * half_d) * K + k);
-      }
-    }
-  }
-  // one warp parks on the grid dependency, the rest of the CTA parks on the barrier behind it (3552 warps hammering
-  // ACQBULK measurably slowed the kernel down); completion + visibility of the predecessor are grid-wide facts
-  if (p.wait_all_warps || warp == 0) pdl_wait();
-  __syncthreads();
 
   // ---- prologue ----------------------------------------------------------------------------
   if (p.wait_flag != nullptr) {
@@ -195,7 +191,7 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
           }
           xv.x = pack_bf16(f[0], f[1]); xv.y = pack_bf16(f[2], f[3]);
           xv.z = pack_bf16(f[4], f[5]); xv.w = pack_bf16(f[6], f[7]);
-          if (p.x_out != nullptr && blockIdx.x == 0)
+          if (p.x_out != nullptr && bid == 0)
             *reinterpret_cast<uint4*>(p.x_out + off) = xv;
         }
         *reinterpret_cast<uint4*>(xs + off) = xv;
@@ -262,9 +258,9 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
   // ---- main loop: each warp owns a pair of output columns ------------------------------------
   constexpr int U = DUAL ? 2 : 4;  // 16-byte loads per weight row per iteration (8 in flight per lane)
   const int ntasks = N >> 1;
-  const int total_warps = gridDim.x * nwarps;
+  const int total_warps = grid * nwarps;
   const int kstep = 256 * U;
-  for (int task = warp * gridDim.x + blockIdx.x; task < ntasks; task += total_warps) {
+  for (int task = warp < nwarps ? warp * grid + bid : ntasks; task < ntasks; task += total_warps) {
     // plain: adjacent output columns (n0, n0+1); ROPE: the rotary pair (i, i + D/2) of one head
     const int half_d = ROPE ? (p.rope_D >> 1) : 1;
     const int n0 = ROPE ? (task / half_d) * p.rope_D + task % half_d : task << 1;
@@ -410,11 +406,99 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
     if (tid == 0) {
       __threadfence_system();
       const unsigned int prev = atomicAdd(p.done_counter, 1u);
-      if (prev == gridDim.x - 1) {
+      if (prev == static_cast<unsigned int>(grid) - 1) {
         __threadfence_system();
         *p.done_counter = 0u;
         for (int r = 0; r < p.n_push; ++r)
           if (p.push_flag[r] != nullptr) red_release_sys_add(p.push_flag[r], 1ull);
+      }
+    }
+  }
+}
+
+template <int M, bool DUAL, bool XSMEM, bool ROPE = false>
+__global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(const LinearDecodeParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  // ---- PDL pre-section: while the predecessor kernel drains (and while this kernel then waits for a peer flag and normalises x)
+  // every warp pulls the head of its first weight rows into L2, so HBM keeps streaming through the bubble between two GEMVs
+  if (!p.late_trigger && threadIdx.x == 0) pdl_trigger();
+  gemv_prefetch<DUAL, ROPE>(p, gridDim.x, blockIdx.x, blockDim.x >> 5);
+  // one warp parks on the grid dependency, the rest of the CTA parks on the barrier behind it
+  if (p.wait_all_warps || (threadIdx.x >> 5) == 0) pdl_wait();
+  __syncthreads();
+  gemv_body<M, DUAL, XSMEM, ROPE>(p, smem_raw, gridDim.x, blockIdx.x, blockDim.x >> 5);
+}
+
+// ---- a chain of dependent decode linears in ONE persistent launch ------------------------------------------------------------
+// O-projection -> gate/up (+SwiGLU) -> down [-> next block's QKV with RoPE/KV append]: four kernel boundaries per block become
+// grid barriers (or nothing at all where the consumer polls LL all-reduce payloads from every rank, itself included). At
+// tensor-parallel shard sizes a boundary costs about as much as streaming the weights; while a CTA waits at a barrier its warps
+// have already prefetched the next phase's first weight rows into L2.
+constexpr int kMaxChain = 4;
+struct GemvChainParams {
+  LinearDecodeParams ph[kMaxChain];
+  int n_phases;
+  int nwarps[kMaxChain];          // active warps per phase (tail-quantisation heuristic of the standalone launch)
+  int dual[kMaxChain], rope[kMaxChain];
+  int barrier_after[kMaxChain];   // 1: grid barrier between phase i and i+1; 0: data-flow synchronised (LL polling)
+  unsigned int* bar;              // {arrival count, generation} of THIS launch site, zero-initialised once
+  int n_barriers;
+};
+
+// Sense-reversing grid barrier on {arrival count, generation}: the last CTA to arrive resets the count and bumps the generation,
+// everyone else spins on the generation it read BEFORE arriving (it cannot change until this CTA has arrived too). Self-contained:
+// no step counter, any launch of the site works as long as all its CTAs are co-resident (grid <= #SMs, one CTA per SM).
+PB_DEVICE void grid_barrier(unsigned int* bar, int grid, int* error_flag) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(bar + 1);
+    __threadfence();
+    const unsigned int prev = atomicAdd(bar, 1u);
+    if (prev == static_cast<unsigned int>(grid) - 1u) {
+      *reinterpret_cast<volatile unsigned int*>(bar) = 0u;
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      const uint64_t t0 = globaltimer_ns();
+      unsigned spins = 0;
+      while (*reinterpret_cast<volatile unsigned int*>(bar + 1) == gen) {
+        if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > PB_FLAG_TIMEOUT_NS) {
+          if (error_flag != nullptr) atomicExch(error_flag, 1);
+          break;
+        }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int M>
+PB_DEVICE void chain_phase(const GemvChainParams& c, int i, uint8_t* smem_raw) {
+  const LinearDecodeParams& p = c.ph[i];
+  if (c.rope[i]) gemv_body<M, false, true, true>(p, smem_raw, gridDim.x, blockIdx.x, c.nwarps[i]);
+  else if (c.dual[i]) gemv_body<M, true, true, false>(p, smem_raw, gridDim.x, blockIdx.x, c.nwarps[i]);
+  else gemv_body<M, false, true, false>(p, smem_raw, gridDim.x, blockIdx.x, c.nwarps[i]);
+}
+
+template <int M>
+__global__ void __launch_bounds__(768, 1) gemv_chain_kernel(const __grid_constant__ GemvChainParams c) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  if (threadIdx.x == 0) pdl_trigger();
+  gemv_prefetch<false, false>(c.ph[0], gridDim.x, blockIdx.x, c.nwarps[0]);
+  if ((threadIdx.x >> 5) == 0) pdl_wait();
+  __syncthreads();
+  for (int i = 0; i < c.n_phases; ++i) {
+    chain_phase<M>(c, i, smem_raw);
+    if (i + 1 < c.n_phases) {
+      // next phase's first weight rows -> L2 while we wait for the other CTAs (or for the peers' partial sums)
+      if (c.rope[i + 1]) gemv_prefetch<false, true>(c.ph[i + 1], gridDim.x, blockIdx.x, c.nwarps[i + 1]);
+      else if (c.dual[i + 1]) gemv_prefetch<true, false>(c.ph[i + 1], gridDim.x, blockIdx.x, c.nwarps[i + 1]);
+      else gemv_prefetch<false, false>(c.ph[i + 1], gridDim.x, blockIdx.x, c.nwarps[i + 1]);
+      if (c.barrier_after[i]) {
+        grid_barrier(c.bar, gridDim.x, c.ph[i].error_flag);
+      } else {
+        __syncthreads();  // shared memory (x staging, reduction scratch) is reused by the next phase
       }
     }
   }
@@ -453,11 +537,15 @@ static cudaError_t launch_m(const LinearDecodeParams& p, bool dual, bool xsmem, 
 // ------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------
-extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
-  using namespace pb;
+namespace pb {
+
+struct GemvGeom { bool dual, xsmem; size_t smem; int grid, best_w; };
+
+// Validate one linear's arguments, translate them into kernel parameters and pick its launch geometry.
+static int gemv_fill(const PbLinearDecodeArgs* a, LinearDecodeParams& p, GemvGeom& g) {
   if (a->M < 1 || a->M > 8 || (a->N & 1) || (a->K & 7)) return PB_ERR_SHAPE;
   if (a->n_parts > kMaxPeers || a->n_push > kMaxPeers) return PB_ERR_SHAPE;
-  LinearDecodeParams p{};
+  p = LinearDecodeParams{};
   p.x = static_cast<const __nv_bfloat16*>(a->x);
   p.w = static_cast<const __nv_bfloat16*>(a->w);
   p.w2 = static_cast<const __nv_bfloat16*>(a->w2);
@@ -548,6 +636,21 @@ extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
     if (grid > sms) grid = sms;
   }
   if (a->fixed_grid > 0) grid = a->fixed_grid;
+  g.dual = dual; g.xsmem = xsmem; g.smem = smem; g.grid = grid; g.best_w = best_w;
+  return PB_OK;
+}
+
+}  // namespace pb
+
+extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
+  using namespace pb;
+  LinearDecodeParams p;
+  GemvGeom g;
+  const int rc = gemv_fill(a, p, g);
+  if (rc != PB_OK) return rc;
+  const bool dual = g.dual, xsmem = g.xsmem;
+  const size_t smem = g.smem;
+  const int grid = g.grid, best_w = g.best_w;
   const int block = best_w * 32;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
@@ -569,4 +672,62 @@ extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
     return PB_ERR_CUDA;
   }
   return a->out_grid ? (*(a->out_grid) = grid, PB_OK) : PB_OK;
+}
+
+// A chain of dependent decode linears in one persistent launch (see gemv_chain_kernel). `phases[i]` are ordinary linear_decode
+// argument blocks; `barrier_after[i]` says whether phase i+1 may only start once EVERY CTA finished phase i (a grid barrier) or
+// is synchronised by data flow (it polls LL all-reduce payloads). `bar` points at two zero-initialised 32-bit words
+// {arrival count, generation} owned by this launch site.
+extern "C" int pb_gemv_chain(const PbLinearDecodeArgs* const* phases, int n_phases, const int* barrier_after, void* bar, void* stream) {
+  using namespace pb;
+  if (n_phases < 1 || n_phases > kMaxChain) return PB_ERR_SHAPE;
+  GemvChainParams c{};
+  c.n_phases = n_phases;
+  const int M = phases[0]->M;
+  if (M < 1 || M > 4) return PB_ERR_SHAPE;  // 768-thread CTAs: the register budget of the M <= 4 variants
+  const int sms = phases[0]->num_sms > 0 ? phases[0]->num_sms : 148;
+  size_t smem = 0;
+  for (int i = 0; i < n_phases; ++i) {
+    GemvGeom g;
+    const int rc = gemv_fill(phases[i], c.ph[i], g);
+    if (rc != PB_OK) return rc;
+    if (phases[i]->M != M || !g.xsmem || phases[i]->fixed_grid > 0) return PB_ERR_SHAPE;
+    c.dual[i] = g.dual ? 1 : 0;
+    c.rope[i] = c.ph[i].rope_q_out != nullptr ? 1 : 0;
+    // all phases share the full grid; a phase with few output columns keeps its tasks spread over all SMs with fewer warps
+    const int ntasks = phases[i]->N / 2;
+    c.nwarps[i] = ntasks < sms * g.best_w ? (ntasks + sms - 1) / sms : g.best_w;
+    if (c.nwarps[i] < 1) c.nwarps[i] = 1;
+    if (c.nwarps[i] > 24) c.nwarps[i] = 24;
+    if (g.smem > smem) smem = g.smem;
+    c.barrier_after[i] = (i + 1 < n_phases && barrier_after != nullptr && barrier_after[i]) ? 1 : 0;
+    c.n_barriers += c.barrier_after[i];
+    // inside the chain a phase never waits on a programmatic dependency of its own; deep prefetch is issued by the chain kernel
+    c.ph[i].pf_lines = i == 0 ? c.ph[i].pf_lines : 64;
+  }
+  if (c.n_barriers > 0 && bar == nullptr) return PB_ERR_SHAPE;
+  c.bar = static_cast<unsigned int*>(bar);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e = cudaSuccess;
+  auto launch = [&](auto kern) {
+    if (smem > 32 * 1024) {
+      const cudaError_t ea = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+      if (ea != cudaSuccess) return ea;
+    }
+    return launch_pdl(kPdlGemvChain, kern, dim3(sms), dim3(768), smem, s, c);
+  };
+  switch (M) {
+    case 1: e = launch(gemv_chain_kernel<1>); break;
+    case 2: e = launch(gemv_chain_kernel<2>); break;
+    case 3: e = launch(gemv_chain_kernel<3>); break;
+    case 4: e = launch(gemv_chain_kernel<4>); break;
+  }
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    char what[160];
+    snprintf(what, sizeof(what), "gemv_chain M=%d phases=%d smem=%zu: %s", M, n_phases, smem, cudaGetErrorString(e));
+    pb_set_error(what);
+    return PB_ERR_CUDA;
+  }
+  return PB_OK;
 }

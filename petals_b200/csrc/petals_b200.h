@@ -33,6 +33,8 @@ typedef struct {
   uint32_t ll_tag_mul, ll_tag_add;
 } PbLinearDecodeArgs;
 int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream);
+// up to 4 dependent decode linears in one persistent launch (grid barriers or LL data-flow between phases; linear_decode.cu)
+int pb_gemv_chain(const PbLinearDecodeArgs* const* phases, int n_phases, const int* barrier_after, void* bar, void* stream);
 
 // ---- decode-shape linear over block-scaled FP8 weights (linear_decode_fp8.cu) ---------------------------
 typedef struct {

@@ -36,7 +36,7 @@ def _bf16c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
 # ----------------------------------------------------------------------------------------------------
 # decode-shape linear
 # ----------------------------------------------------------------------------------------------------
-def linear_decode(
+def _linear_decode_args(
     x: torch.Tensor, w: torch.Tensor, *, w2: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
     bias2: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None,
     norm_weight: Optional[torch.Tensor] = None, norm_bias: Optional[torch.Tensor] = None, norm_kind: int = NORM_NONE,
@@ -45,16 +45,8 @@ def linear_decode(
     epoch: Optional[int] = None, push_out: Sequence[int] = (), push_flag: Sequence[int] = (),
     error_flag: Optional[int] = None, fixed_grid: int = 0, store_local: bool = True, done_counter: Optional[int] = None,
     rope: Optional[dict] = None, ll_parts: Sequence[int] = (), ll_push: Sequence[int] = (), ll_tag: Tuple[int, int] = (1, 0),
-) -> torch.Tensor:
-    """``out[M,N] = epilogue(prologue(x)[M,K] @ w[N,K]^T)`` for M <= 8 tokens. See csrc/linear_decode.cu.
-
-    ``rope`` (QKV projection of Llama-style blocks) fuses RoPE + the paged KV append into the epilogue: a dict with ``q_out``
-    [M, Hq*D], ``k_pool``/``v_pool`` (this block's page pools), ``block_table`` [B, max_pages] int32, ``pos_ptr`` (device address),
-    ``cos``/``sin`` (fp32 tables or None), ``T``, ``Hq``, ``Hkv``, ``D``. Nothing is stored to ``out`` then; ``q_out`` is returned.
-
-    ``push_out`` / ``push_flag`` / ``wait_flag`` / ``epoch`` are raw device addresses (peer-mapped buffers
-    from :mod:`petals_b200.parallel.symmetric`).
-    """
+):
+    """Build the C argument block of one decode linear. Returns (args, result tensor, tensors that must outlive the launch)."""
     x = _bf16c(x, "x"); w = _bf16c(w, "w")
     M, K = x.reshape(-1, x.shape[-1]).shape
     N = w.shape[0]
@@ -64,12 +56,14 @@ def linear_decode(
         store_local = False
     if out is None and store_local:
         out = torch.empty(*x.shape[:-1], N, dtype=torch.bfloat16, device=x.device)
+    keep = [x, w, _bf16c(w2, "w2"), _bf16c(bias, "bias"), _bf16c(bias2, "bias2"), _bf16c(residual, "residual"), _bf16c(norm_weight, "norm_weight"),
+            _bf16c(norm_bias, "norm_bias")]
     a = LinearDecodeArgs()
-    a.x, a.w, a.w2 = ptr(x), ptr(w), ptr(_bf16c(w2, "w2"))
-    a.bias, a.bias2 = ptr(_bf16c(bias, "bias")), ptr(_bf16c(bias2, "bias2"))
-    a.residual = ptr(_bf16c(residual, "residual"))
+    a.x, a.w, a.w2 = ptr(x), ptr(w), ptr(keep[2])
+    a.bias, a.bias2 = ptr(keep[3]), ptr(keep[4])
+    a.residual = ptr(keep[5])
     a.out = ptr(out) if store_local else None
-    a.norm_w, a.norm_b = ptr(_bf16c(norm_weight, "norm_weight")), ptr(_bf16c(norm_bias, "norm_bias"))
+    a.norm_w, a.norm_b = ptr(keep[6]), ptr(keep[7])
     a.x_out = ptr(x_out)
     a.eps, a.norm_kind, a.act = eps, norm_kind, act
     a.M, a.N, a.K = M, N, K
@@ -98,8 +92,46 @@ def linear_decode(
         a.rope_cos, a.rope_sin = ptr(cos), ptr(sin)
         a.rope_T, a.rope_Hq, a.rope_Hkv, a.rope_D = rope["T"], rope["Hq"], rope["Hkv"], rope["D"]
         a.rope_max_pages, a.rope_max_pos = table.shape[1], (cos.shape[0] if cos is not None else 0)
+    return a, (rope["q_out"] if rope is not None else out), keep
+
+
+def linear_decode(x: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
+    """``out[M,N] = epilogue(prologue(x)[M,K] @ w[N,K]^T)`` for M <= 8 tokens. See csrc/linear_decode.cu.
+
+    Keyword arguments: ``w2`` (SwiGLU up projection, with ``act=ACT_SWIGLU``), ``bias``/``bias2``, ``residual``, ``norm_weight`` /
+    ``norm_bias`` / ``norm_kind`` / ``eps`` (fused norm prologue), ``act``, ``out``, ``x_out``, ``parts`` (+ ``wait_flag`` /
+    ``wait_per_epoch`` / ``epoch``: flag-protocol all-reduce tail), ``push_out`` / ``push_flag`` / ``done_counter`` (peer pushes),
+    ``ll_parts`` / ``ll_push`` / ``ll_tag`` (LL-protocol all-reduce), ``error_flag``, ``fixed_grid``, ``store_local``.
+    ``push_out`` / ``push_flag`` / ``wait_flag`` / ``epoch`` / ``ll_*`` are raw device addresses (peer-mapped buffers from
+    :mod:`petals_b200.parallel.symmetric`).
+
+    ``rope`` (QKV projection of Llama-style blocks) fuses RoPE + the paged KV append into the epilogue: a dict with ``q_out``
+    [M, Hq*D], ``k_pool``/``v_pool`` (this block's page pools), ``block_table`` [B, max_pages] int32, ``pos_ptr`` (device address),
+    ``cos``/``sin`` (fp32 tables or None), ``T``, ``Hq``, ``Hkv``, ``D``. Nothing is stored to ``out`` then; ``q_out`` is returned.
+    """
+    a, result, _keep = _linear_decode_args(x, w, **kw)
     check(native.lib().pb_linear_decode(C.byref(a), stream_ptr()), "linear_decode")
-    return rope["q_out"] if rope is not None else out
+    return result
+
+
+def gemv_chain(phases: Sequence[dict], barrier_after: Sequence[bool], bar: Optional[torch.Tensor]) -> list:
+    """Run up to four dependent decode linears (O-projection -> gate/up -> down -> next block's QKV) as ONE persistent kernel.
+
+    ``phases`` are keyword dicts of :func:`linear_decode` (with ``x`` and ``w``); ``barrier_after[i]`` puts a grid barrier between
+    phase i and i+1 (omit it where phase i+1 polls LL all-reduce payloads instead). ``bar``: two zero-initialised int32 words
+    {arrival count, generation} owned by this launch site. Returns the phases' result tensors."""
+    n = len(phases)
+    arg_blocks, results, keep = [], [], []
+    for ph in phases:
+        kw = dict(ph)
+        a, r, k = _linear_decode_args(kw.pop("x"), kw.pop("w"), **kw)
+        arg_blocks.append(a)
+        results.append(r)
+        keep.append(k)
+    arr = (C.POINTER(LinearDecodeArgs) * n)(*[C.pointer(a) for a in arg_blocks])
+    bars = (C.c_int * n)(*[int(bool(b)) for b in list(barrier_after) + [False] * (n - len(barrier_after))])
+    check(native.lib().pb_gemv_chain(arr, n, bars, ptr(bar), stream_ptr()), "gemv_chain")
+    return results
 
 
 def linear_decode_fp8(x: torch.Tensor, w_q: torch.Tensor, w_scale: torch.Tensor, *, w2_q: Optional[torch.Tensor] = None,

@@ -154,6 +154,8 @@ class TPDecodeEngine:
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.done_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.fuse_rope = os.environ.get("PETALS_B200_FUSE_ROPE", "1") != "0"
+        self.use_chain = os.environ.get("PETALS_B200_CHAIN", "1") != "0"
+        self._chain_bar = torch.zeros(max(1, len(self.shards)), 2, dtype=torch.int32, device=dev)  # grid-barrier words per block
         self._split_ctr = torch.zeros(1024, dtype=torch.int32, device=dev)  # split-KV arrival counters (self-resetting)
         self.pos_static = torch.zeros(1, dtype=torch.int32, device=dev)
         self.max_pages = cache.max_pages_per_seq
@@ -220,49 +222,68 @@ class TPDecodeEngine:
         ll_mlp_in = [self.heap.addr(me, self.off_ll_mlp + r * self.ll_slot_bytes) for r in range(R)]
         ll_attn_out = [self.heap.addr(r, self.off_ll_attn + me * self.ll_slot_bytes) for r in range(R)]
         ll_mlp_out = [self.heap.addr(r, self.off_ll_mlp + me * self.ll_slot_bytes) for r in range(R)]
+        chain = self.use_chain and ll and self.fuse_rope and M <= 4
+        split_ctr = self._split_ctr if splits > 1 and B * ls.num_kv_heads <= 1024 else None
+
+        def k1_kwargs(l: int, cur, nxt):
+            """[all-reduce tail of the previous MLP] + norm + column-parallel QKV; the epilogue rotates q/k and appends k/v to this
+            rank's cache pages. Returns (kwargs, residual buffer after the call, next ping-pong index)."""
+            w, pools = self.shards[l], self.cache.layer_pools(l)
+            kw = dict(x=cur, w=w["wqkv"], norm_weight=w["ln1_w"], norm_bias=w.get("ln1_b"), norm_kind=self.norm_kind, eps=eps, epoch=ep, error_flag=err)
+            if self.fuse_rope:
+                kw["rope"] = dict(q_out=q_buf, k_pool=pools[0], v_pool=pools[1], block_table=table, pos_ptr=pos_ptr, cos=self.cos, sin=self.sin, T=T,
+                                  Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim)
+            else:
+                kw["out"] = qkv_buf
+            if l == 0:
+                kw.update(wait_flag=self.flag(me, 0), wait_per_epoch=1)
+                return kw, cur, nxt
+            kw.update(dict(ll_parts=ll_mlp_in, ll_tag=(L, l - 1)) if ll else dict(parts=mlp_parts, wait_flag=self.flag_mlp(me, l - 1), wait_per_epoch=R))
+            kw["x_out"] = h[nxt]
+            return kw, h[nxt], nxt ^ 1
+
+        def launch(kw: dict):
+            kw = dict(kw)
+            return Fn.linear_decode(kw.pop("x"), kw.pop("w"), **kw)
+
+        kw1, cur, nxt = k1_kwargs(0, cur, nxt)
+        launch(kw1)
         for l, w in enumerate(self.shards):
             pools = self.cache.layer_pools(l)
-            # K1: [all-reduce tail of previous MLP] + norm + column-parallel QKV
-            # the QKV epilogue rotates q/k and appends k/v to this rank's cache pages (no RoPE launch)
-            rope = dict(q_out=q_buf, k_pool=pools[0], v_pool=pools[1], block_table=table, pos_ptr=pos_ptr, cos=self.cos, sin=self.sin, T=T,
-                        Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim) if self.fuse_rope else None
-            out_kw = dict(rope=rope) if rope is not None else dict(out=qkv_buf)
-            if l == 0:
-                Fn.linear_decode(cur, w["wqkv"], norm_weight=w["ln1_w"], norm_bias=w.get("ln1_b"), norm_kind=self.norm_kind, eps=eps,
-                                 wait_flag=self.flag(me, 0), wait_per_epoch=1, epoch=ep, error_flag=err, **out_kw)
-            else:
-                red = (dict(ll_parts=ll_mlp_in, ll_tag=(L, l - 1)) if ll else
-                       dict(parts=mlp_parts, wait_flag=self.flag_mlp(me, l - 1), wait_per_epoch=R))
-                Fn.linear_decode(cur, w["wqkv"], norm_weight=w["ln1_w"], norm_bias=w.get("ln1_b"), norm_kind=self.norm_kind, eps=eps,
-                                 epoch=ep, x_out=h[nxt], error_flag=err, **red, **out_kw)
-                cur, nxt = h[nxt], nxt ^ 1
-            if rope is None:
+            if not self.fuse_rope:
                 Fn.rope_kv_append(qkv_buf, q_buf, pools[0], pools[1], table, pos_ptr, self.cos, self.sin, B=B, T=T, Hq=ls.num_heads,
                                   Hkv=ls.num_kv_heads, D=ls.head_dim, error_flag=err)
             Fn.paged_attention(q_buf, pools[0], pools[1], table, pos_ptr, attn, B=B, T=T, Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim,
-                               scale=s.attn_scale, splits=splits, partial_o=po, partial_lse=pl, window=s.sliding_window,
-                               split_counter=self._split_ctr if splits > 1 and B * ls.num_kv_heads <= 1024 else None)
-            # K2: row-parallel O-projection; epilogue pushes the partial into every rank's slot [me]
+                               scale=s.attn_scale, splits=splits, partial_o=po, partial_lse=pl, window=s.sliding_window, split_counter=split_ctr)
+            # K2: row-parallel O-projection; the epilogue sends this rank's partial to every rank's slot [me]
             if ll:
-                Fn.linear_decode(attn, w["wo"], store_local=False, ll_push=ll_attn_out, ll_tag=(L, l), epoch=ep, error_flag=err)
+                k2 = dict(x=attn, w=w["wo"], store_local=False, ll_push=ll_attn_out, ll_tag=(L, l), epoch=ep, error_flag=err)
             else:
-                Fn.linear_decode(attn, w["wo"], store_local=False, push_out=[self.parts(self.off_parts_attn, r, me) for r in range(R)],
-                                 push_flag=[self.flag_attn(r, l) for r in range(R)], done_counter=ctr, error_flag=err)
+                k2 = dict(x=attn, w=w["wo"], store_local=False, push_out=[self.parts(self.off_parts_attn, r, me) for r in range(R)],
+                          push_flag=[self.flag_attn(r, l) for r in range(R)], done_counter=ctr, error_flag=err)
             # K3: [all-reduce tail of attention] + norm + column-parallel gate/up (+SwiGLU)
-            kw = dict(norm_weight=w["ln2_w"], norm_bias=w.get("ln2_b"), norm_kind=self.norm_kind, eps=eps, out=act, epoch=ep, x_out=h[nxt],
+            k3 = dict(x=cur, norm_weight=w["ln2_w"], norm_bias=w.get("ln2_b"), norm_kind=self.norm_kind, eps=eps, out=act, epoch=ep, x_out=h[nxt],
                       error_flag=err)
-            kw.update(dict(ll_parts=ll_attn_in, ll_tag=(L, l)) if ll else dict(parts=attn_parts, wait_flag=self.flag_attn(me, l), wait_per_epoch=R))
-            if s.mlp == "swiglu":
-                Fn.linear_decode(cur, w["w_gate"], w2=w["w_up"], act=Fn.ACT_SWIGLU, **kw)
-            else:
-                Fn.linear_decode(cur, w["w_up"], act=self.act, **kw)
+            k3.update(dict(ll_parts=ll_attn_in, ll_tag=(L, l)) if ll else dict(parts=attn_parts, wait_flag=self.flag_attn(me, l), wait_per_epoch=R))
+            k3.update(dict(w=w["w_gate"], w2=w["w_up"], act=Fn.ACT_SWIGLU) if s.mlp == "swiglu" else dict(w=w["w_up"], act=self.act))
             cur, nxt = h[nxt], nxt ^ 1
-            # K4: row-parallel down projection, pushed like K2
+            # K4: row-parallel down projection, sent like K2 (the last block uses the flag protocol: its consumer is the final reduce)
             if ll and l + 1 < L:
-                Fn.linear_decode(act, w["w_down"], store_local=False, ll_push=ll_mlp_out, ll_tag=(L, l), epoch=ep, error_flag=err)
+                k4 = dict(x=act, w=w["w_down"], store_local=False, ll_push=ll_mlp_out, ll_tag=(L, l), epoch=ep, error_flag=err)
             else:
-                Fn.linear_decode(act, w["w_down"], store_local=False, push_out=[self.parts(self.off_parts_mlp, r, me) for r in range(R)],
-                                 push_flag=[self.flag_mlp(r, l) for r in range(R)], done_counter=ctr, error_flag=err)
+                k4 = dict(x=act, w=w["w_down"], store_local=False, push_out=[self.parts(self.off_parts_mlp, r, me) for r in range(R)],
+                          push_flag=[self.flag_mlp(r, l) for r in range(R)], done_counter=ctr, error_flag=err)
+            phases = [k2, k3, k4]
+            if l + 1 < L:
+                kw1, cur, nxt = k1_kwargs(l + 1, cur, nxt)
+                phases.append(kw1)
+            if chain:
+                # ONE persistent launch: K2 -> K3 are synchronised by the LL payloads K3 polls (from every rank, this one included),
+                # K3 -> K4 by a grid barrier (every CTA needs the whole activation vector), K4 -> next K1 by LL polling again
+                Fn.gemv_chain(phases, [False, True, False][: len(phases) - 1], self._chain_bar[l])
+            else:
+                for kw in phases:
+                    launch(kw)
         if final_reduce:
             parts = ptr_array(mlp_parts)
             native.check(native.lib().pb_reduce_parts(cur.data_ptr(), parts, R, self.flag_mlp(me, self.n_blocks - 1), R, ep, self.out.data_ptr(),
@@ -419,6 +440,19 @@ class TPDecodeEngine:
             Fn.linear_decode(x, w["w_up"], act=self.act, norm_weight=w["ln2_w"], norm_bias=w.get("ln2_b"), norm_kind=self.norm_kind,
                              eps=s.norm_eps, out=act, parts=[scratch], x_out=self._buf("h_b", M, H))
         Fn.linear_decode(act, w["w_down"], out=scratch)
+        if self.use_chain and self.use_ll and self.fuse_rope and M <= 4:
+            # the persistent chain kernel (same four phases, local buffers only)
+            pools = self.cache.layer_pools(0)
+            mlp = (dict(w=w["w_gate"], w2=w["w_up"], act=Fn.ACT_SWIGLU) if s.mlp == "swiglu" else dict(w=w["w_up"], act=self.act))
+            Fn.gemv_chain([
+                dict(x=attn, w=w["wo"], out=scratch),
+                dict(x=x, norm_weight=w["ln2_w"], norm_bias=w.get("ln2_b"), norm_kind=self.norm_kind, eps=s.norm_eps, out=act, **mlp),
+                dict(x=act, w=w["w_down"], out=scratch),
+                dict(x=x, w=w["wqkv"], norm_weight=w["ln1_w"], norm_bias=w.get("ln1_b"), norm_kind=self.norm_kind, eps=s.norm_eps,
+                     error_flag=self.err.data_ptr(),
+                     rope=dict(q_out=q_buf, k_pool=pools[0], v_pool=pools[1], block_table=table, pos_ptr=self.pos_static.data_ptr(), cos=self.cos,
+                               sin=self.sin, T=T, Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim)),
+            ], [True, True, True], self._chain_bar[0])
         torch.cuda.synchronize(self.device)
 
     # ---- session bookkeeping (identical on every rank) ---------------------------------------------------------------------

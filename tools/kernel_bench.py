@@ -111,12 +111,51 @@ def bench_gemm(results, peaks):
         del As, Bs, B2
 
 
+def bench_gemv_fp8(results, peaks):
+    """Decode linears over MXFP8 weights (1 byte/weight + 1 scale byte per 32)."""
+    from petals_b200.ops.quant import quantize_mxfp8
+
+    shapes = [("70b.qkv", 10240, 8192, dict(norm=True)), ("70b.o", 8192, 8192, dict(residual=True)),
+              ("70b.gate_up", 28672, 8192, dict(norm=True, dual=True)), ("70b.down", 8192, 28672, dict(residual=True))]
+    for name, N, K, opt in shapes:
+        for M in (1, 4):
+            nbuf = max(2, int(300e6 // (N * K * (2 if opt.get("dual") else 1))) + 1)
+            qs = [quantize_mxfp8(torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * K ** -0.5) for _ in range(nbuf)]
+            q2s = [quantize_mxfp8(torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * K ** -0.5) for _ in range(nbuf)] if opt.get("dual") else None
+            x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+            g = torch.ones(K, device="cuda", dtype=torch.bfloat16)
+            res = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+            out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+
+            def mk(i):
+                kw = dict(out=out)
+                if opt.get("norm"):
+                    kw.update(norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+                if opt.get("residual"):
+                    kw.update(residual=res)
+                if opt.get("dual"):
+                    kw.update(w2_q=q2s[i][0], w2_scale=q2s[i][1], act=Fn.ACT_SWIGLU)
+                return lambda: Fn.linear_decode_fp8(x, qs[i][0], qs[i][1], **kw)
+
+            ms = time_fn([mk(i) for i in range(nbuf)], iters=40)
+            nbytes = N * K * (1 + 1 / 32) * (2 if opt.get("dual") else 1)
+            gbs = nbytes / ms / 1e6
+            row = dict(kernel="linear_decode_fp8", shape=name, M=M, N=N, K=K, ms=ms, GBps=gbs, frac_hbm=gbs / peaks["hbm_gbs"])
+            results.append(row)
+            print(f"gemv.fp8 {name:12s} M={M} {ms * 1e3:8.1f} us  {gbs:7.0f} GB/s  {row['frac_hbm'] * 100:5.1f}% of measured HBM", flush=True)
+            del qs, q2s
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
+    ap.add_argument("--fp8", action="store_true", help="only the MXFP8 decode linears")
     args = ap.parse_args()
     peaks = measured_peaks()
     results = []
+    if args.fp8:
+        args.only = "fp8"
+        bench_gemv_fp8(results, peaks)
     if args.only in ("", "gemv"):
         bench_gemv(results, peaks)
     if args.only in ("", "gemm"):
