@@ -31,6 +31,7 @@ namespace pb {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kGemmThreads = 192;
+constexpr bool kPushTransposed = true;  // peer-push epilogue through a shared-memory transpose (full-sector NVLink stores)
 constexpr int kGroupM = 8;
 
 struct GemmParams {
@@ -93,6 +94,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  // per-epilogue-warp transpose buffer for peer pushes: 32 rows x (64 B payload + 16 B pad)
+  uint8_t* push_stage = reinterpret_cast<uint8_t*>(tmem_slot) + 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_blocks = (p.M + BM - 1) / BM;
@@ -282,17 +285,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
                 for (int q = 0; q < 4; ++q) op[q] = pk[q];
               }
-              if (p.push_rows_per_owner > 0) {
-                const int owner = row / p.push_rows_per_owner;
-                const size_t roff = static_cast<size_t>(row - owner * p.push_rows_per_owner) * p.ldo + col0;
-                uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.push_out[owner]) + roff);
+              if (p.n_push > 0 && kPushTransposed) {
+                uint4* st = reinterpret_cast<uint4*>(push_stage + (warp - 2) * (32 * 80) + lane * 80);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) op[q] = pk[q];
-              } else {
-                for (int rnk = 0; rnk < p.n_push; ++rnk) {
-                  uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.push_out[rnk]) + off);
+                for (int q = 0; q < 4; ++q) st[q] = pk[q];
+              }
+              if (p.n_push > 0 && !kPushTransposed) {
+                if (p.push_rows_per_owner > 0) {
+                  const int owner = row / p.push_rows_per_owner;
+                  const size_t roff = static_cast<size_t>(row - owner * p.push_rows_per_owner) * p.ldo + col0;
+                  uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.push_out[owner]) + roff);
 #pragma unroll
                   for (int q = 0; q < 4; ++q) op[q] = pk[q];
+                } else {
+                  for (int rnk = 0; rnk < p.n_push; ++rnk) {
+                    uint4* op = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.push_out[rnk]) + off);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) op[q] = pk[q];
+                  }
                 }
               }
             } else {
@@ -309,6 +319,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
               }
             }
           }
+        }
+        if (kPushTransposed && p.n_push > 0 && !p.out_fp32 && col0 + 32 <= p.N) {
+          // Peer stores, transposed through shared memory: instead of 32 lanes writing 16 bytes to 32 different rows (partial
+          // sectors on NVLink), 4 consecutive lanes write one row's 64 contiguous bytes -> 8 rows x 2 full sectors per instruction.
+          __syncwarp();
+          const uint8_t* sbase = push_stage + (warp - 2) * (32 * 80);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = 8 * i + (lane >> 2), piece = lane & 3;
+            const int grow = m_blk * BM + quarter * 32 + rr;
+            if (grow < p.M) {
+              const uint4 val = *reinterpret_cast<const uint4*>(sbase + rr * 80 + piece * 16);
+              if (p.push_rows_per_owner > 0) {
+                const int owner = grow / p.push_rows_per_owner;
+                const size_t roff = static_cast<size_t>(grow - owner * p.push_rows_per_owner) * p.ldo + col0 + piece * 8;
+                *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.push_out[owner]) + roff) = val;
+              } else {
+                const size_t goff = static_cast<size_t>(grow) * p.ldo + col0 + piece * 8;
+                for (int rnk = 0; rnk < p.n_push; ++rnk)
+                  *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.push_out[rnk]) + goff) = val;
+              }
+            }
+          }
+          __syncwarp();  // the staging rows are rewritten by the next 32-column chunk
         }
       }
       // accumulator fully read: hand the TMEM stage back to the MMA warp
@@ -392,7 +426,7 @@ static int launch_gemm(const PbGemmArgs* a, cudaStream_t stream) {
   constexpr int STAGE_BYTES = (BM + BN) * BK * 2;
   constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
   constexpr int OUT_BN = DUAL ? BN / 2 : BN;
-  const size_t smem = static_cast<size_t>(STAGES) * STAGE_BYTES + 1024 + 256;
+  const size_t smem = static_cast<size_t>(STAGES) * STAGE_BYTES + 1024 + 256 + 4 * 32 * 80;  // + per-warp push transpose buffers
 
   const int lda = a->lda > 0 ? a->lda : a->K;
   CUtensorMap ta, tb, tb2;

@@ -448,20 +448,24 @@ struct GemvChainParams {
 // Sense-reversing grid barrier on {arrival count, generation}: the last CTA to arrive resets the count and bumps the generation,
 // everyone else spins on the generation it read BEFORE arriving (it cannot change until this CTA has arrived too). Self-contained:
 // no step counter, any launch of the site works as long as all its CTAs are co-resident (grid <= #SMs, one CTA per SM).
+// `bar` points at 64 zero-initialised 32-bit words (two 128-byte lines).
 PB_DEVICE void grid_barrier(unsigned int* bar, int grid, int* error_flag) {
+  // bar[0] = arrival count, bar[32] = generation (separate 128-byte lines: pollers must not queue in front of the arrivals' atomics)
   __syncthreads();
   if (threadIdx.x == 0) {
-    const unsigned int gen = *reinterpret_cast<volatile unsigned int*>(bar + 1);
+    volatile unsigned int* gen_p = reinterpret_cast<volatile unsigned int*>(bar + 32);
+    const unsigned int gen = *gen_p;
     __threadfence();
     const unsigned int prev = atomicAdd(bar, 1u);
     if (prev == static_cast<unsigned int>(grid) - 1u) {
       *reinterpret_cast<volatile unsigned int*>(bar) = 0u;
       __threadfence();
-      atomicAdd(bar + 1, 1u);
+      atomicAdd(bar + 32, 1u);
     } else {
       const uint64_t t0 = globaltimer_ns();
       unsigned spins = 0;
-      while (*reinterpret_cast<volatile unsigned int*>(bar + 1) == gen) {
+      while (*gen_p == gen) {
+        __nanosleep(40);
         if ((++spins & 0x3ffu) == 0 && globaltimer_ns() - t0 > PB_FLAG_TIMEOUT_NS) {
           if (error_flag != nullptr) atomicExch(error_flag, 1);
           break;
@@ -473,34 +477,42 @@ PB_DEVICE void grid_barrier(unsigned int* bar, int grid, int* error_flag) {
   __syncthreads();
 }
 
-template <int M>
-PB_DEVICE void chain_phase(const GemvChainParams& c, int i, uint8_t* smem_raw) {
-  const LinearDecodeParams& p = c.ph[i];
-  if (c.rope[i]) gemv_body<M, false, true, true>(p, smem_raw, gridDim.x, blockIdx.x, c.nwarps[i]);
-  else if (c.dual[i]) gemv_body<M, true, true, false>(p, smem_raw, gridDim.x, blockIdx.x, c.nwarps[i]);
-  else gemv_body<M, false, true, false>(p, smem_raw, gridDim.x, blockIdx.x, c.nwarps[i]);
-}
-
+// The phases have FIXED roles by position (0: O-projection, 1: MLP input projection, 2: down projection, 3: next block's QKV with
+// RoPE/KV append), so every gemv_body below reads its parameters from a compile-time offset of the kernel's constant bank, exactly
+// like the standalone kernels do. (Indexing c.ph[] at run time — or passing the block by pointer to a non-inlined function — turns
+// those operands into register-held loads and made ptxas spill the weight buffers of the main loop: 25 % slower.)
 template <int M>
 __global__ void __launch_bounds__(768, 1) gemv_chain_kernel(const __grid_constant__ GemvChainParams c) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int grid = gridDim.x, bid = blockIdx.x;
   if (threadIdx.x == 0) pdl_trigger();
-  gemv_prefetch<false, false>(c.ph[0], gridDim.x, blockIdx.x, c.nwarps[0]);
+  gemv_prefetch<false, false>(c.ph[0], grid, bid, c.nwarps[0]);
   if ((threadIdx.x >> 5) == 0) pdl_wait();
   __syncthreads();
-  for (int i = 0; i < c.n_phases; ++i) {
-    chain_phase<M>(c, i, smem_raw);
-    if (i + 1 < c.n_phases) {
-      // next phase's first weight rows -> L2 while we wait for the other CTAs (or for the peers' partial sums)
-      if (c.rope[i + 1]) gemv_prefetch<false, true>(c.ph[i + 1], gridDim.x, blockIdx.x, c.nwarps[i + 1]);
-      else if (c.dual[i + 1]) gemv_prefetch<true, false>(c.ph[i + 1], gridDim.x, blockIdx.x, c.nwarps[i + 1]);
-      else gemv_prefetch<false, false>(c.ph[i + 1], gridDim.x, blockIdx.x, c.nwarps[i + 1]);
-      if (c.barrier_after[i]) {
-        grid_barrier(c.bar, gridDim.x, c.ph[i].error_flag);
-      } else {
-        __syncthreads();  // shared memory (x staging, reduction scratch) is reused by the next phase
-      }
-    }
+
+  // ---- phase 0: O-projection (+ residual / + LL push of the partial) ----
+  gemv_body<M, false, true, false>(c.ph[0], smem_raw, grid, bid, c.nwarps[0]);
+  // next phase's first weight rows -> L2 while we wait for the other CTAs (or for the peers' partial sums)
+  if (c.dual[1]) gemv_prefetch<true, false>(c.ph[1], grid, bid, c.nwarps[1]);
+  else gemv_prefetch<false, false>(c.ph[1], grid, bid, c.nwarps[1]);
+  if (c.barrier_after[0]) grid_barrier(c.bar, grid, c.ph[0].error_flag);
+  else __syncthreads();  // shared memory (x staging, reduction scratch) is reused by the next phase
+
+  // ---- phase 1: norm + gate/up (+SwiGLU) or up (+GELU) ----
+  if (c.dual[1]) gemv_body<M, true, true, false>(c.ph[1], smem_raw, grid, bid, c.nwarps[1]);
+  else gemv_body<M, false, true, false>(c.ph[1], smem_raw, grid, bid, c.nwarps[1]);
+  gemv_prefetch<false, false>(c.ph[2], grid, bid, c.nwarps[2]);
+  if (c.barrier_after[1]) grid_barrier(c.bar, grid, c.ph[1].error_flag);
+  else __syncthreads();
+
+  // ---- phase 2: down projection (+ residual / + LL push / + stage-hop push) ----
+  gemv_body<M, false, true, false>(c.ph[2], smem_raw, grid, bid, c.nwarps[2]);
+  if (c.n_phases > 3) {
+    gemv_prefetch<false, true>(c.ph[3], grid, bid, c.nwarps[3]);
+    if (c.barrier_after[2]) grid_barrier(c.bar, grid, c.ph[2].error_flag);
+    else __syncthreads();
+    // ---- phase 3: the next block's norm + QKV projection with RoPE + KV append ----
+    gemv_body<M, false, true, true>(c.ph[3], smem_raw, grid, bid, c.nwarps[3]);
   }
 }
 
@@ -680,7 +692,7 @@ extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
 // {arrival count, generation} owned by this launch site.
 extern "C" int pb_gemv_chain(const PbLinearDecodeArgs* const* phases, int n_phases, const int* barrier_after, void* bar, void* stream) {
   using namespace pb;
-  if (n_phases < 1 || n_phases > kMaxChain) return PB_ERR_SHAPE;
+  if (n_phases < 3 || n_phases > kMaxChain) return PB_ERR_SHAPE;  // O-proj, MLP-in, down [, next QKV]
   GemvChainParams c{};
   c.n_phases = n_phases;
   const int M = phases[0]->M;
@@ -694,6 +706,7 @@ extern "C" int pb_gemv_chain(const PbLinearDecodeArgs* const* phases, int n_phas
     if (phases[i]->M != M || !g.xsmem || phases[i]->fixed_grid > 0) return PB_ERR_SHAPE;
     c.dual[i] = g.dual ? 1 : 0;
     c.rope[i] = c.ph[i].rope_q_out != nullptr ? 1 : 0;
+    if ((i != 1 && c.dual[i]) || c.rope[i] != (i == 3 ? 1 : 0)) return PB_ERR_SHAPE;  // fixed roles by position
     // all phases share the full grid; a phase with few output columns keeps its tasks spread over all SMs with fewer warps
     const int ntasks = phases[i]->N / 2;
     c.nwarps[i] = ntasks < sms * g.best_w ? (ntasks + sms - 1) / sms : g.best_w;
@@ -703,7 +716,8 @@ extern "C" int pb_gemv_chain(const PbLinearDecodeArgs* const* phases, int n_phas
     c.barrier_after[i] = (i + 1 < n_phases && barrier_after != nullptr && barrier_after[i]) ? 1 : 0;
     c.n_barriers += c.barrier_after[i];
     // inside the chain a phase never waits on a programmatic dependency of its own; deep prefetch is issued by the chain kernel
-    c.ph[i].pf_lines = i == 0 ? c.ph[i].pf_lines : 64;
+    static const int chain_pf = [] { const char* e = getenv("PETALS_B200_CHAIN_PF"); return e ? atoi(e) : 16; }();
+    c.ph[i].pf_lines = i == 0 ? c.ph[i].pf_lines : (chain_pf > 0 && chain_pf < 4 ? 4 : chain_pf);
   }
   if (c.n_barriers > 0 && bar == nullptr) return PB_ERR_SHAPE;
   c.bar = static_cast<unsigned int*>(bar);

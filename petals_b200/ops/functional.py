@@ -118,8 +118,8 @@ def gemv_chain(phases: Sequence[dict], barrier_after: Sequence[bool], bar: Optio
     """Run up to four dependent decode linears (O-projection -> gate/up -> down -> next block's QKV) as ONE persistent kernel.
 
     ``phases`` are keyword dicts of :func:`linear_decode` (with ``x`` and ``w``); ``barrier_after[i]`` puts a grid barrier between
-    phase i and i+1 (omit it where phase i+1 polls LL all-reduce payloads instead). ``bar``: two zero-initialised int32 words
-    {arrival count, generation} owned by this launch site. Returns the phases' result tensors."""
+    phase i and i+1 (omit it where phase i+1 polls LL all-reduce payloads instead). ``bar``: 64 zero-initialised int32 words
+    (arrival count and generation on separate 128-byte lines) owned by this launch site. Returns the phases' result tensors."""
     n = len(phases)
     arg_blocks, results, keep = [], [], []
     for ph in phases:

@@ -154,8 +154,8 @@ class TPDecodeEngine:
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.done_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.fuse_rope = os.environ.get("PETALS_B200_FUSE_ROPE", "1") != "0"
-        self.use_chain = os.environ.get("PETALS_B200_CHAIN", "1") != "0"
-        self._chain_bar = torch.zeros(max(1, len(self.shards)), 2, dtype=torch.int32, device=dev)  # grid-barrier words per block
+        self.use_chain = os.environ.get("PETALS_B200_CHAIN", "0") != "0"
+        self._chain_bar = torch.zeros(max(1, len(self.shards)), 64, dtype=torch.int32, device=dev)  # grid-barrier words per block
         self._split_ctr = torch.zeros(1024, dtype=torch.int32, device=dev)  # split-KV arrival counters (self-resetting)
         self.pos_static = torch.zeros(1, dtype=torch.int32, device=dev)
         self.max_pages = cache.max_pages_per_seq

@@ -90,8 +90,8 @@ class StageEngine:
         self.err_flag = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.fuse_rope = os.environ.get("PETALS_B200_FUSE_ROPE", "1") != "0"
         # O-proj -> gate/up -> down -> next block's QKV as one persistent launch per block (grid barriers instead of kernel boundaries)
-        self.use_chain = os.environ.get("PETALS_B200_CHAIN", "1") != "0"
-        self._chain_bar = torch.zeros(max(1, len(self.blocks)), 2, dtype=torch.int32, device=self.device)  # {count, generation} per block
+        self.use_chain = os.environ.get("PETALS_B200_CHAIN", "0") != "0"
+        self._chain_bar = torch.zeros(max(1, len(self.blocks)), 64, dtype=torch.int32, device=self.device)  # {count, generation} per block
         self._split_ctr = torch.zeros(8192, dtype=torch.int32, device=self.device)  # split-KV arrival counters (self-resetting)
         self._tables: Dict[int, torch.Tensor] = {}  # batch -> static block table
         self._graphs: Dict[Tuple[int, int, int, int], dict] = {}

@@ -477,11 +477,11 @@ def test_gemv_chain_matches_separate_launches(M):
         torch.cuda.synchronize()
         return x, h1, act, q
 
-    bar = torch.zeros(2, dtype=torch.int32, device=DEV)
+    bar = torch.zeros(64, dtype=torch.int32, device=DEV)
     want = run(False, kp_a, vp_a)
     for _ in range(2):
         got = run(True, kp_b, vp_b)
         for g, w_, name in zip(got, want, ["x", "h1", "act", "q"]):
             assert torch.equal(g, w_), f"{name} differs: max {((g.float() - w_.float()).abs().max().item())}"
         assert torch.equal(kp_b, kp_a) and torch.equal(vp_b, vp_a)
-    assert int(bar[0].item()) == 0 and int(bar[1].item()) == 6  # 3 barriers x 2 launches
+    assert int(bar[0].item()) == 0 and int(bar[32].item()) == 6  # {count, generation}: 3 barriers x 2 launches

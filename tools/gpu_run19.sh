@@ -16,5 +16,6 @@ run nochain llama-3-8b "" PETALS_B200_CHAIN=0
 run chain_tp8emu llama-3-70b "--tp-emulate 8" PETALS_B200_CHAIN=1
 run nochain_tp8emu llama-3-70b "--tp-emulate 8" PETALS_B200_CHAIN=0
 run chain2 llama-3-70b "" PETALS_B200_CHAIN=1
+timeout 300 python bench.py --steps 32 --warmup 4 --skip-prefill > gpurun_out/b19_fp8_70b.log 2>&1; echo "fp8 appendix: $(grep -E '^\{' gpurun_out/b19_fp8_70b.log | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['fp8_weights'])")" | tee -a $S
 python tools/kernel_bench.py --fp8 > gpurun_out/kbench_fp8.log 2>&1; echo "kernel_bench fp8 exit=$?" | tee -a $S
 tail -12 gpurun_out/kbench_fp8.log | cut -c1-200 | tee -a $S

@@ -26,6 +26,20 @@ elif which == "gemv":  # decode gate/up with fused RMSNorm + SwiGLU, 1 token
     ws = [(torch.randn(28672, 8192, device="cuda", dtype=torch.bfloat16) * 0.01, torch.randn(28672, 8192, device="cuda", dtype=torch.bfloat16) * 0.01) for _ in range(2)]
     for i in range(4):
         Fn.linear_decode(x, ws[i % 2][0], w2=ws[i % 2][1], act=Fn.ACT_SWIGLU, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+elif which == "gemv_fp8":  # decode O-projection over MXFP8 weights, 1 token
+    from petals_b200.ops.quant import quantize_mxfp8
+
+    x = torch.randn(1, 8192, device="cuda", dtype=torch.bfloat16)
+    res = torch.randn(1, 8192, device="cuda", dtype=torch.bfloat16)
+    qs = [quantize_mxfp8(torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16) * 0.01) for _ in range(4)]
+    for i in range(6):
+        Fn.linear_decode_fp8(x, qs[i % 4][0], qs[i % 4][1], residual=res)
+elif which == "gemv_o":  # bf16 twin of gemv_fp8 (same shape)
+    x = torch.randn(1, 8192, device="cuda", dtype=torch.bfloat16)
+    res = torch.randn(1, 8192, device="cuda", dtype=torch.bfloat16)
+    ws = [torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16) * 0.01 for _ in range(4)]
+    for i in range(6):
+        Fn.linear_decode(x, ws[i % 4], residual=res)
 elif which == "attn":  # prefill attention, 4096 tokens, GQA 64/8
     B, T, Hq, Hkv, D = 1, 4096, 64, 8, 128
     pages = T // Fn.PAGE
