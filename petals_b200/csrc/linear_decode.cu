@@ -134,7 +134,7 @@ PB_DEVICE void gemv_prefetch(const LinearDecodeParams& p, int grid, int bid, int
 // One decode-shape linear layer executed by the whole CTA: `grid` CTAs cooperate, this one is number `bid`; warps >= nwarps
 // only take part in the prologue. M = tokens, DUAL = SwiGLU (two weight matrices), XSMEM = x staged in shared memory,
 // ROPE = fused RoPE + KV append epilogue. Called once by linear_decode_kernel and back to back by gemv_chain_kernel.
-template <int M, bool DUAL, bool XSMEM, bool ROPE>
+template <int M, bool DUAL, bool XSMEM, bool ROPE, bool PIPE = false>
 PB_DEVICE void gemv_body(const LinearDecodeParams& p, uint8_t* smem_raw, int grid, int bid, int nwarps) {
   __nv_bfloat16* xs = reinterpret_cast<__nv_bfloat16*>(smem_raw);
   __shared__ float red[32];
@@ -256,60 +256,69 @@ PB_DEVICE void gemv_body(const LinearDecodeParams& p, uint8_t* smem_raw, int gri
   }
 
   // ---- main loop: each warp owns a pair of output columns ------------------------------------
-  constexpr int U = DUAL ? 2 : 4;  // 16-byte loads per weight row per iteration (8 in flight per lane)
+  // A warp's work is the sequence of "slots" (task, it): U 16-byte loads per weight row of row pair `task` at K offset it*kstep.
+  //   !PIPE: load slot, multiply, next slot — 24 warps/SM hide the latency by interleaving.
+  //    PIPE: two slot buffers (512-thread CTAs, 128 registers): the next slot's loads — also across a task boundary — are issued
+  //          before the current slot is multiplied, so a warp always has loads in flight; short rows (tensor-parallel shards:
+  //          1-4 slots per task) no longer pay one exposed memory latency per task.
+  constexpr int U = DUAL ? 2 : 4;  // 16-byte loads per weight row per slot (8 in flight per lane)
   const int ntasks = N >> 1;
   const int total_warps = grid * nwarps;
   const int kstep = 256 * U;
-  for (int task = warp < nwarps ? warp * grid + bid : ntasks; task < ntasks; task += total_warps) {
-    // plain: adjacent output columns (n0, n0+1); ROPE: the rotary pair (i, i + D/2) of one head
-    const int half_d = ROPE ? (p.rope_D >> 1) : 1;
-    const int n0 = ROPE ? (task / half_d) * p.rope_D + task % half_d : task << 1;
+  const int nit = (K + kstep - 1) / kstep;
+  const int half_d = ROPE ? (p.rope_D >> 1) : 1;
+  struct Slot { uint4 wa[U], wb[U], ua[U], ub[U]; };
+  float a0[M], a1[M], b0[M], b1[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) a0[m] = a1[m] = b0[m] = b1[m] = 0.f;
+
+  // plain: adjacent output columns (n0, n0+1); ROPE: the rotary pair (i, i + D/2) of one head
+  auto first_col = [&](int task) { return ROPE ? (task / half_d) * p.rope_D + task % half_d : task << 1; };
+  auto load_slot = [&](Slot& s, int task, int it) {
+    const int n0 = first_col(task);
     const __nv_bfloat16* w0 = p.w + static_cast<size_t>(n0) * K;
     const __nv_bfloat16* w1 = w0 + static_cast<size_t>(half_d) * K;
     const __nv_bfloat16* u0 = DUAL ? p.w2 + static_cast<size_t>(n0) * K : nullptr;
     const __nv_bfloat16* u1 = DUAL ? u0 + K : nullptr;
-    float a0[M], a1[M], b0[M], b1[M];
 #pragma unroll
-    for (int m = 0; m < M; ++m) a0[m] = a1[m] = b0[m] = b1[m] = 0.f;
-
-    for (int kb = 0; kb < K; kb += kstep) {
-      uint4 wa[U], wb[U], ua[U], ub[U];
-      bool ok[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int k = kb + u * 256 + lane * 8;
-        ok[u] = k < K;
-        if (ok[u]) {
-          wa[u] = ld_stream(w0 + k);
-          wb[u] = ld_stream(w1 + k);
-          if (DUAL) {
-            ua[u] = ld_stream(u0 + k);
-            ub[u] = ld_stream(u1 + k);
-          }
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (ok[u]) {
-          const int k = kb + u * 256 + lane * 8;
-          float xf[M][8];
-#pragma unroll
-          for (int m = 0; m < M; ++m) {
-            uint4 xv;
-            if (XSMEM) xv = *reinterpret_cast<const uint4*>(xs + static_cast<size_t>(m) * K + k);
-            else xv = ld_cached(p.x + static_cast<size_t>(m) * K + k);
-            xf[m][0] = bf16_lo(xv.x); xf[m][1] = bf16_hi(xv.x); xf[m][2] = bf16_lo(xv.y); xf[m][3] = bf16_hi(xv.y);
-            xf[m][4] = bf16_lo(xv.z); xf[m][5] = bf16_hi(xv.z); xf[m][6] = bf16_lo(xv.w); xf[m][7] = bf16_hi(xv.w);
-          }
-          fma8<M>(a0, wa[u], xf);
-          fma8<M>(a1, wb[u], xf);
-          if (DUAL) {
-            fma8<M>(b0, ua[u], xf);
-            fma8<M>(b1, ub[u], xf);
-          }
+    for (int u = 0; u < U; ++u) {
+      const int k = it * kstep + u * 256 + lane * 8;
+      if (k < K) {
+        s.wa[u] = ld_stream(w0 + k);
+        s.wb[u] = ld_stream(w1 + k);
+        if (DUAL) {
+          s.ua[u] = ld_stream(u0 + k);
+          s.ub[u] = ld_stream(u1 + k);
         }
       }
     }
+  };
+  auto compute_slot = [&](const Slot& s, int it) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int k = it * kstep + u * 256 + lane * 8;
+      if (k < K) {
+        float xf[M][8];
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          uint4 xv;
+          if (XSMEM) xv = *reinterpret_cast<const uint4*>(xs + static_cast<size_t>(m) * K + k);
+          else xv = ld_cached(p.x + static_cast<size_t>(m) * K + k);
+          xf[m][0] = bf16_lo(xv.x); xf[m][1] = bf16_hi(xv.x); xf[m][2] = bf16_lo(xv.y); xf[m][3] = bf16_hi(xv.y);
+          xf[m][4] = bf16_lo(xv.z); xf[m][5] = bf16_hi(xv.z); xf[m][6] = bf16_lo(xv.w); xf[m][7] = bf16_hi(xv.w);
+        }
+        fma8<M>(a0, s.wa[u], xf);
+        fma8<M>(a1, s.wb[u], xf);
+        if (DUAL) {
+          fma8<M>(b0, s.ua[u], xf);
+          fma8<M>(b1, s.ub[u], xf);
+        }
+      }
+    }
+  };
+  // reduce the row pair over the warp, run the epilogue, reset the accumulators
+  auto finish_task = [&](int task) {
+    const int n0 = first_col(task);
 #pragma unroll
     for (int m = 0; m < M; ++m) {
       a0[m] = warp_sum(a0[m]);
@@ -396,6 +405,39 @@ PB_DEVICE void gemv_body(const LinearDecodeParams& p, uint8_t* smem_raw, int gri
       for (int r = 0; r < p.n_push; ++r) *reinterpret_cast<uint32_t*>(p.push_out[r] + o) = packed;
       for (int r = 0; r < p.n_ll_push; ++r) st_relaxed_sys_v2(p.ll_push[r] + (o >> 1), packed, ll_tag);
     }
+#pragma unroll
+    for (int m = 0; m < M; ++m) a0[m] = a1[m] = b0[m] = b1[m] = 0.f;
+  };
+
+  int task = warp < nwarps ? warp * grid + bid : ntasks;
+  if (!PIPE) {
+    Slot s;
+    for (; task < ntasks; task += total_warps) {
+      for (int it = 0; it < nit; ++it) {
+        load_slot(s, task, it);
+        compute_slot(s, it);
+      }
+      finish_task(task);
+    }
+  } else {
+    Slot sa, sb;
+    int it = 0;
+    if (task < ntasks) load_slot(sa, task, 0);
+    while (task < ntasks) {
+      int t1 = task, i1 = it + 1;
+      if (i1 == nit) { i1 = 0; t1 += total_warps; }
+      if (t1 < ntasks) load_slot(sb, t1, i1);
+      compute_slot(sa, it);
+      if (it == nit - 1) finish_task(task);
+      task = t1; it = i1;
+      if (task >= ntasks) break;
+      int t2 = task, i2 = it + 1;
+      if (i2 == nit) { i2 = 0; t2 += total_warps; }
+      if (t2 < ntasks) load_slot(sa, t2, i2);
+      compute_slot(sb, it);
+      if (it == nit - 1) finish_task(task);
+      task = t2; it = i2;
+    }
   }
 
   if (p.late_trigger && tid == 0) pdl_trigger();
@@ -416,8 +458,8 @@ PB_DEVICE void gemv_body(const LinearDecodeParams& p, uint8_t* smem_raw, int gri
   }
 }
 
-template <int M, bool DUAL, bool XSMEM, bool ROPE = false>
-__global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(const LinearDecodeParams p) {
+template <int M, bool DUAL, bool XSMEM, bool ROPE = false, bool PIPE = false>
+__global__ void __launch_bounds__((M <= 4 && !PIPE ? 768 : 512), 1) linear_decode_kernel(const LinearDecodeParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   // ---- PDL pre-section: while the predecessor kernel drains (and while this kernel then waits for a peer flag and normalises x)
   // every warp pulls the head of its first weight rows into L2, so HBM keeps streaming through the bubble between two GEMVs
@@ -426,7 +468,7 @@ __global__ void __launch_bounds__((M <= 4 ? 768 : 512), 1) linear_decode_kernel(
   // one warp parks on the grid dependency, the rest of the CTA parks on the barrier behind it
   if (p.wait_all_warps || (threadIdx.x >> 5) == 0) pdl_wait();
   __syncthreads();
-  gemv_body<M, DUAL, XSMEM, ROPE>(p, smem_raw, gridDim.x, blockIdx.x, blockDim.x >> 5);
+  gemv_body<M, DUAL, XSMEM, ROPE, PIPE>(p, smem_raw, gridDim.x, blockIdx.x, blockDim.x >> 5);
 }
 
 // ---- a chain of dependent decode linears in ONE persistent launch ------------------------------------------------------------
@@ -516,10 +558,10 @@ __global__ void __launch_bounds__(768, 1) gemv_chain_kernel(const __grid_constan
   }
 }
 
-template <int M, bool DUAL, bool XSMEM, bool ROPE = false>
+template <int M, bool DUAL, bool XSMEM, bool ROPE = false, bool PIPE = false>
 static cudaError_t launch_one(const LinearDecodeParams& p, int grid, int block, size_t smem,
                               cudaStream_t stream) {
-  auto kern = linear_decode_kernel<M, DUAL, XSMEM, ROPE>;
+  auto kern = linear_decode_kernel<M, DUAL, XSMEM, ROPE, PIPE>;
   if (smem > 32 * 1024) {  // static shared memory counts against the 48 KB default too
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
@@ -536,7 +578,13 @@ static cudaError_t launch_one(const LinearDecodeParams& p, int grid, int block, 
 
 template <int M>
 static cudaError_t launch_m(const LinearDecodeParams& p, bool dual, bool xsmem, int grid, int block,
-                            size_t smem, cudaStream_t s) {
+                            size_t smem, cudaStream_t s, bool pipe = false) {
+  if constexpr (M <= 2) {
+    if (pipe && xsmem) {  // software-pipelined main loop (512-thread CTAs)
+      if (p.rope_q_out != nullptr) return launch_one<M, false, true, true, true>(p, grid, block, smem, s);
+      return dual ? launch_one<M, true, true, false, true>(p, grid, block, smem, s) : launch_one<M, false, true, false, true>(p, grid, block, smem, s);
+    }
+  }
   if (p.rope_q_out != nullptr) return launch_one<M, false, true, true>(p, grid, block, smem, s);  // validated: !dual && xsmem
   if (dual) return xsmem ? launch_one<M, true, true>(p, grid, block, smem, s)
                          : launch_one<M, true, false>(p, grid, block, smem, s);
@@ -551,7 +599,14 @@ static cudaError_t launch_m(const LinearDecodeParams& p, bool dual, bool xsmem, 
 // ------------------------------------------------------------------------------------------------
 namespace pb {
 
-struct GemvGeom { bool dual, xsmem; size_t smem; int grid, best_w; };
+// software-pipelined main loop for M <= 2 (PETALS_B200_GEMV_PIPE, or pb_set_gemv_pipe at run time)
+static int g_gemv_pipe = -1;
+static int gemv_pipe_mode() {
+  if (g_gemv_pipe < 0) { const char* e = getenv("PETALS_B200_GEMV_PIPE"); g_gemv_pipe = e ? atoi(e) : 0; }
+  return g_gemv_pipe;
+}
+
+struct GemvGeom { bool dual, xsmem, pipe; size_t smem; int grid, best_w; };
 
 // Validate one linear's arguments, translate them into kernel parameters and pick its launch geometry.
 static int gemv_fill(const PbLinearDecodeArgs* a, LinearDecodeParams& p, GemvGeom& g) {
@@ -632,7 +687,8 @@ static int gemv_fill(const PbLinearDecodeArgs* a, LinearDecodeParams& p, GemvGeo
   // was requested (flag accounting across ranks needs identical CTA counts) honour it.
   const int sms = a->fixed_grid > 0 ? a->fixed_grid : (a->num_sms > 0 ? a->num_sms : 148);
   const int ntasks = a->N / 2;
-  const int max_w = a->M <= 4 ? 24 : 16;
+  const bool pipe = gemv_pipe_mode() != 0 && a->M <= 2 && xsmem;
+  const int max_w = (a->M <= 4 && !pipe) ? 24 : 16;
   int best_w = max_w;
   double best_eff = -1.0;
   for (int w = max_w; w >= max_w / 2; --w) {
@@ -648,11 +704,13 @@ static int gemv_fill(const PbLinearDecodeArgs* a, LinearDecodeParams& p, GemvGeo
     if (grid > sms) grid = sms;
   }
   if (a->fixed_grid > 0) grid = a->fixed_grid;
-  g.dual = dual; g.xsmem = xsmem; g.smem = smem; g.grid = grid; g.best_w = best_w;
+  g.dual = dual; g.xsmem = xsmem; g.pipe = pipe; g.smem = smem; g.grid = grid; g.best_w = best_w;
   return PB_OK;
 }
 
 }  // namespace pb
+
+extern "C" int pb_set_gemv_pipe(int on) { pb::g_gemv_pipe = on ? 1 : 0; return PB_OK; }
 
 extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
   using namespace pb;
@@ -667,14 +725,14 @@ extern "C" int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e = cudaSuccess;
   switch (a->M) {
-    case 1: e = launch_m<1>(p, dual, xsmem, grid, block, smem, s); break;
-    case 2: e = launch_m<2>(p, dual, xsmem, grid, block, smem, s); break;
-    case 3: e = launch_m<3>(p, dual, xsmem, grid, block, smem, s); break;
-    case 4: e = launch_m<4>(p, dual, xsmem, grid, block, smem, s); break;
-    case 5: e = launch_m<5>(p, dual, xsmem, grid, block, smem, s); break;
-    case 6: e = launch_m<6>(p, dual, xsmem, grid, block, smem, s); break;
-    case 7: e = launch_m<7>(p, dual, xsmem, grid, block, smem, s); break;
-    case 8: e = launch_m<8>(p, dual, xsmem, grid, block, smem, s); break;
+    case 1: e = launch_m<1>(p, dual, xsmem, grid, block, smem, s, g.pipe); break;
+    case 2: e = launch_m<2>(p, dual, xsmem, grid, block, smem, s, g.pipe); break;
+    case 3: e = launch_m<3>(p, dual, xsmem, grid, block, smem, s, g.pipe); break;
+    case 4: e = launch_m<4>(p, dual, xsmem, grid, block, smem, s, g.pipe); break;
+    case 5: e = launch_m<5>(p, dual, xsmem, grid, block, smem, s, g.pipe); break;
+    case 6: e = launch_m<6>(p, dual, xsmem, grid, block, smem, s, g.pipe); break;
+    case 7: e = launch_m<7>(p, dual, xsmem, grid, block, smem, s, g.pipe); break;
+    case 8: e = launch_m<8>(p, dual, xsmem, grid, block, smem, s, g.pipe); break;
   }
   if (e != cudaSuccess) {
     cudaGetLastError();

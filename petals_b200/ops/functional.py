@@ -114,6 +114,11 @@ def linear_decode(x: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
     return result
 
 
+def set_gemv_pipe(on: bool) -> None:
+    """Select the software-pipelined decode-linear main loop (M <= 2). Default: env ``PETALS_B200_GEMV_PIPE`` (off)."""
+    native.lib().pb_set_gemv_pipe(int(bool(on)))
+
+
 def gemv_chain(phases: Sequence[dict], barrier_after: Sequence[bool], bar: Optional[torch.Tensor]) -> list:
     """Run up to four dependent decode linears (O-projection -> gate/up -> down -> next block's QKV) as ONE persistent kernel.
 

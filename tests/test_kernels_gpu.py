@@ -485,3 +485,27 @@ def test_gemv_chain_matches_separate_launches(M):
             assert torch.equal(g, w_), f"{name} differs: max {((g.float() - w_.float()).abs().max().item())}"
         assert torch.equal(kp_b, kp_a) and torch.equal(vp_b, vp_a)
     assert int(bar[0].item()) == 0 and int(bar[32].item()) == 6  # {count, generation}: 3 barriers x 2 launches
+
+
+@pytest.mark.parametrize("M", [1, 2])
+def test_linear_decode_pipelined_main_loop_is_bit_identical(M):
+    """The software-pipelined main loop (two slot buffers, loads issued across task boundaries) keeps the accumulation order."""
+    torch.manual_seed(51)
+    cases = [(1280, 8192, {}), (8192, 1024, dict(residual=True)), (3584, 8192, dict(dual=True, norm=True)), (2050, 1032, {})]
+    for N, K, opt in cases:
+        x, w, w2 = _rand(M, K), _rand(N, K, scale=K ** -0.5), _rand(N, K, scale=K ** -0.5)
+        kw = {}
+        if opt.get("residual"):
+            kw["residual"] = _rand(M, N)
+        if opt.get("norm"):
+            kw.update(norm_weight=_rand(K) * 0.1 + 1, norm_kind=Fn.NORM_RMS, eps=1e-5)
+        if opt.get("dual"):
+            kw.update(w2=w2, act=Fn.ACT_SWIGLU)
+        try:
+            Fn.set_gemv_pipe(False)
+            want = Fn.linear_decode(x, w, **kw)
+            Fn.set_gemv_pipe(True)
+            got = Fn.linear_decode(x, w, **kw)
+        finally:
+            Fn.set_gemv_pipe(False)
+        assert torch.equal(got, want), f"N={N} K={K} {opt}: max diff {(got.float() - want.float()).abs().max().item()}"
