@@ -60,18 +60,22 @@ __global__ void __launch_bounds__(kNrgThreads) norm_reduce_gather_kernel(const N
     for (int j = 0; j < kNrgMaxVec; ++j) {
       const int v = tid + j * kNrgThreads;
       if (v < nvec) {
-        if (p.x_res_in != nullptr) {
-          const uint4 x = __ldcg(p.x_res_in + base + v);
-          f[j][0] = bf16_lo(x.x); f[j][1] = bf16_hi(x.x); f[j][2] = bf16_lo(x.y); f[j][3] = bf16_hi(x.y);
-          f[j][4] = bf16_lo(x.z); f[j][5] = bf16_hi(x.z); f[j][6] = bf16_lo(x.w); f[j][7] = bf16_hi(x.w);
-        } else {
+        // issue every load of this slot first (residual + all partials), then add: an in-order warp that consumed each load right
+        // after issuing it paid (1 + n_parts) serial memory latencies per slot
+        uint4 ld[kMaxPeers + 1];
+        ld[0] = p.x_res_in != nullptr ? __ldcg(p.x_res_in + base + v) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) f[j][i] = 0.f;
-        }
-        for (int r = 0; r < p.n_parts; ++r) {
-          const uint4 y = __ldcg(p.parts[r] + base + v);
-          f[j][0] += bf16_lo(y.x); f[j][1] += bf16_hi(y.x); f[j][2] += bf16_lo(y.y); f[j][3] += bf16_hi(y.y);
-          f[j][4] += bf16_lo(y.z); f[j][5] += bf16_hi(y.z); f[j][6] += bf16_lo(y.w); f[j][7] += bf16_hi(y.w);
+        for (int r = 0; r < kMaxPeers; ++r)
+          if (r < p.n_parts) ld[r + 1] = __ldcg(p.parts[r] + base + v);
+        f[j][0] = bf16_lo(ld[0].x); f[j][1] = bf16_hi(ld[0].x); f[j][2] = bf16_lo(ld[0].y); f[j][3] = bf16_hi(ld[0].y);
+        f[j][4] = bf16_lo(ld[0].z); f[j][5] = bf16_hi(ld[0].z); f[j][6] = bf16_lo(ld[0].w); f[j][7] = bf16_hi(ld[0].w);
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r) {
+          if (r < p.n_parts) {
+            const uint4 y = ld[r + 1];
+            f[j][0] += bf16_lo(y.x); f[j][1] += bf16_hi(y.x); f[j][2] += bf16_lo(y.y); f[j][3] += bf16_hi(y.y);
+            f[j][4] += bf16_lo(y.z); f[j][5] += bf16_hi(y.z); f[j][6] += bf16_lo(y.w); f[j][7] += bf16_hi(y.w);
+          }
         }
         // the residual stream is carried in bf16 (as the dense model does): round first, normalise the rounded value
         uint4 o;

@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
 S=gpurun_out/summary24.txt; : > $S
-timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "pipelined or linear_decode_plain or chain" > gpurun_out/t24_k.log 2>&1; echo "pipe tests exit=$?" | tee -a $S
+timeout 300 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x -k "pipelined or linear_decode_plain or chain or loopback" > gpurun_out/t24_k.log 2>&1; echo "pipe tests exit=$?" | tee -a $S
 tail -3 gpurun_out/t24_k.log | cut -c1-400 | tee -a $S
 run() { name=$1; shift; model=$1; shift; extra=$1; shift
   env "$@" timeout 300 python bench.py --model $model --steps 64 --warmup 4 --skip-prefill --skip-fp8 $extra > gpurun_out/b24_${name}_${model}.log 2>&1
