@@ -76,6 +76,10 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
 
 
+def _model_label(name: str) -> str:
+    return {"llama-3-70b": "Llama-3-70B", "llama-3-8b": "Llama-3-8B", "mixtral-8x7b": "Mixtral-8x7B"}.get(name, name)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,7 +180,7 @@ def run_single_gpu(args) -> None:
     spec = model.config.block_spec()
     weight_bytes = (spec.num_params() * n_layers + vocab * spec.hidden_size) * 2
     result = {
-        "metric": ("Llama-3-70B single-stream decode tokens/s (device-timed); prefill tokens/s in `prefill`" if args.tp_emulate <= 1 else
+        "metric": (f"{_model_label(args.model)} single-stream decode tokens/s (device-timed); prefill tokens/s in `prefill`" if args.tp_emulate <= 1 else
                    f"DIAGNOSTIC: one rank's share of a tp{args.tp_emulate} decode step on one GPU, no communication (NOT a benchmark result)"),
         "value": round(value, 3), "unit": "tokens/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",

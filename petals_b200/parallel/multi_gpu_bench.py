@@ -20,6 +20,10 @@ from petals_b200.parallel.symmetric import host_barrier
 BASELINE_TOKENS_PER_S = 6.0
 
 
+def _model_label(name: str) -> str:
+    return {"llama-3-70b": "Llama-3-70B", "llama-3-8b": "Llama-3-8B", "mixtral-8x7b": "Mixtral-8x7B"}.get(name, name)
+
+
 def run_multi_gpu(args) -> None:
     if str(args.parallelism).startswith("pp"):
         return run_pipeline(args)
@@ -156,7 +160,7 @@ def run_multi_gpu(args) -> None:
     weight_bytes_rank = (spec.num_params() * n_layers) * 2 / world + vocab * spec.hidden_size * 2  # LM head is replicated on rank 0
     hop_bytes = spec.hidden_size * 2
     result = {
-        "metric": "Llama-3-70B single-stream decode tokens/s (device-timed, max over ranks)",
+        "metric": f"{_model_label(args.model)} single-stream decode tokens/s (device-timed, max over ranks)",
         "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",
         "data": "synthetic token ids; random-init weights of the named architecture",
@@ -298,7 +302,7 @@ def run_pipeline(args) -> None:
         peaks = measured_peaks()
         spec = config.block_spec()
         result = {
-            "metric": "Llama-3-70B single-stream decode tokens/s (device-timed, max over ranks)",
+            "metric": f"{_model_label(args.model)} single-stream decode tokens/s (device-timed, max over ranks)",
             "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",
             "data": "synthetic token ids; random-init weights of the named architecture",

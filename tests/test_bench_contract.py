@@ -1,0 +1,30 @@
+"""The driver-facing contract of bench.py that can be checked without a GPU: the reference arm answers with one JSON line and
+exit code 0, and the argument defaults respect the timing rules (>= 3 warm-up steps, N = 1 by default)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_reports_unavailable_or_a_result():
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2", "--warmup", "3"],
+                          capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, proc.stdout[-2000:]
+    out = json.loads(lines[0])
+    assert out["impl"] == "reference"
+    assert "unavailable" in out or {"metric", "value", "unit", "n_gpus"} <= set(out)
+
+
+def test_defaults_follow_the_timing_rules():
+    sys.path.insert(0, ROOT)
+    import importlib
+
+    bench = importlib.import_module("bench")
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert 'add_argument("--gpus", type=int, default=1)' in src
+    assert 'add_argument("--warmup", type=int, default=4)' in src and "args.warmup < 3" in src
+    assert callable(bench.main) and callable(bench.reference_arm)
