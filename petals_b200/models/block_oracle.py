@@ -11,6 +11,8 @@ reference forces on every model.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Optional, Tuple
 
 import torch
@@ -19,6 +21,20 @@ import torch.nn.functional as F
 
 from petals_b200.models.spec import BlockSpec, alibi_slopes
 from petals_b200.ops.functional import rope_tables
+
+
+def _tc_ok(x, w, b) -> bool:
+    if not x.is_cuda:
+        return False
+    from petals_b200.ops.autograd import tc_linear_supported
+
+    return tc_linear_supported(x, w, b)
+
+
+def _tc_linear(x, w, b):
+    from petals_b200.ops.autograd import tc_linear
+
+    return tc_linear(x, w, b)
 
 
 def _rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float) -> torch.Tensor:
@@ -46,6 +62,8 @@ class GenericBlock(nn.Module):
             self.register_parameter(name, nn.Parameter(t, requires_grad=False))
         self._rope: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
         self._slopes: Optional[torch.Tensor] = None
+        # frozen bf16 blocks on CUDA run their linears (forward + dgrad) on the tcgen05 GEMM when autograd is recording
+        self.tc_backward = os.environ.get("PETALS_B200_TC_BACKWARD", "1") != "0"
         self.lora: dict = {}  # target param name -> list[(A [r,in], B [out,r], scale)] for the active adapter
 
     # ---- helpers -----------------------------------------------------------------------------------
@@ -64,7 +82,10 @@ class GenericBlock(nn.Module):
         if rows is not None:
             w = w[rows]
             b = b[rows] if b is not None else None
-        y = F.linear(x, w, b)
+        if self.tc_backward and torch.is_grad_enabled() and x.requires_grad and _tc_ok(x, w, b):
+            y = _tc_linear(x, w, b)  # training path of a frozen stage: forward and dgrad on the tcgen05 GEMM (ops/autograd.py)
+        else:
+            y = F.linear(x, w, b)
         for (A, Bm, scale, target_rows) in self.lora.get(wname, ()):  # LoRA: y += scale * (x A^T) B^T
             delta = F.linear(F.linear(x, A.to(x.dtype)), Bm.to(x.dtype)) * scale
             if target_rows is None:

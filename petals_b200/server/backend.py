@@ -119,13 +119,17 @@ class Stage:
         # pass 1 (no grad): remember every block's input
         inputs = []
         h = hidden
+        use_engine = self.engine is not None and self._lora_free()  # pass 1 is a plain forward: run it on the kernels
         with torch.no_grad():
             for i in range(lo, hi):
                 inputs.append(h)
                 if i + 1 < hi:
-                    self._materialize(i)
-                    h = self.blocks[i].forward_cached(self._add_prompt(h, prompts[i - lo]), None, None, 0)
-                    self._dematerialize(i)
+                    if use_engine:
+                        h = self.engine.forward(h, [prompts[i - lo]] if prompts[i - lo] is not None else None, (i, i + 1))
+                    else:
+                        self._materialize(i)
+                        h = self.blocks[i].forward_cached(self._add_prompt(h, prompts[i - lo]), None, None, 0)
+                        self._dematerialize(i)
         # pass 2: per-block recompute with autograd, last block first
         grad_prompts: List[Optional[torch.Tensor]] = [None] * (hi - lo)
         for i in reversed(range(lo, hi)):

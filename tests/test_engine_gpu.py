@@ -93,3 +93,30 @@ def test_backward_through_engine_stage(tmp_path):
         assert g2 is not None and torch.isfinite(g2).all() and g2.abs().sum() > 0
     finally:
         stage.shutdown()
+
+
+def test_tc_backward_matches_pytorch_autograd(tmp_path):
+    """Frozen blocks under autograd: linears on the tcgen05 GEMM (forward + dgrad with the weight as MN-major operand) give the
+    same activation gradients as the plain PyTorch path."""
+    from petals_b200.utils.auto_config import AutoDistributedConfig
+    from petals_b200.utils.random_model import random_blocks
+
+    path = write_config_only("llama-tiny", {}, str(tmp_path / "m"))
+    config = AutoDistributedConfig.from_pretrained(path)
+    blocks = random_blocks(config, range(2), DEV, seed=9)
+    for b in blocks:
+        b.requires_grad_(False)
+    torch.manual_seed(0)
+    x0 = (torch.randn(2, 40, config.hidden_size, device=DEV) * 0.5).to(torch.bfloat16)
+    grads, outs = {}, {}
+    for tc in (False, True):
+        x = x0.clone().requires_grad_(True)
+        h = x
+        for b in blocks:
+            b.tc_backward = tc
+            h = b.forward_cached(h, None, None, 0)
+        (g,) = torch.autograd.grad(h.float().pow(2).sum(), x)
+        grads[tc], outs[tc] = g.float(), h.float()
+    rel_o = (outs[True] - outs[False]).abs().mean() / outs[False].abs().mean()
+    rel_g = (grads[True] - grads[False]).abs().mean() / grads[False].abs().mean()
+    assert rel_o < 2e-2 and rel_g < 3e-2, (rel_o.item(), rel_g.item())
