@@ -17,8 +17,8 @@
 //    a tiny combine kernel merges the slices. The cache length is read from device memory so the
 //    launch is CUDA-graph replayable while the sequence grows.
 //
-// TODO(perf): the S/PV products use the legacy mma.sync path (HMMA in SASS); a tcgen05/TMEM variant is
-// the next step for long-prompt prefill, where attention is ~5-15 % of the FLOPs at 4k tokens.
+// Prefill-sized tiles (>= 128 packed query rows per kv head) are dispatched to the tcgen05/TMEM kernel in attention_tc.cu; this
+// mma.sync kernel serves decode and short verify steps, where one 16-row MMA tile per kv head is KV-bandwidth bound.
 #include "common.cuh"
 #include "petals_b200.h"
 
