@@ -20,6 +20,7 @@ from petals_b200.models.block_oracle import GenericBlock
 from petals_b200.server.memory_cache import MemoryCache, SessionCache
 from petals_b200.server.task_pool import PrioritizedTaskPool, Runtime
 from petals_b200.utils.logging import get_logger
+from petals_b200.utils.tracing import nvtx_range
 from petals_b200.utils.misc import is_dummy
 
 logger = get_logger(__name__)
@@ -82,7 +83,8 @@ class Stage:
         hidden = hidden.to(self.device)
         prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device).contiguous() for p in prompts]
         if self.engine is not None and self._lora_free():  # stages are stateless: forward never records autograd state
-            return self.engine.forward(hidden, prompts, (lo, hi))
+            with nvtx_range(f"stage[{self.start_block + lo}:{self.start_block + hi}].forward"):
+                return self.engine.forward(hidden, prompts, (lo, hi))
         h = hidden.to(self.dtype)
         with torch.no_grad():
             for i in range(lo, hi):
@@ -154,9 +156,10 @@ class Stage:
         hidden = hidden.to(self.device)
         prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device).contiguous() for p in prompts]
         if self.engine is not None and self._lora_free():
-            if take_from is not None or push_to is not None:
-                return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi), take_from=take_from, push_to=push_to)
-            return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi))
+            with nvtx_range(f"stage[{self.start_block + lo}:{self.start_block + hi}].inference_step"):
+                if take_from is not None or push_to is not None:
+                    return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi), take_from=take_from, push_to=push_to)
+                return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi))
         if take_from is not None:  # executors without fused hops still honour the fabric protocol (host-issued copies)
             fabric, src_rank, B, T = take_from
             hidden = fabric.recv(B * T, "x_in", src_rank).view(B, T, -1)

@@ -34,7 +34,9 @@ from petals_b200.server.memory_cache import AllocationFailed, SessionCache
 from petals_b200.server.task_pool import PrioritizedTaskPool
 from petals_b200.server.task_prioritizer import DummyTaskPrioritizer, TaskPrioritizerBase
 from petals_b200.utils.logging import get_logger
+from petals_b200.utils.fault_injection import maybe_fail
 from petals_b200.utils.misc import DUMMY, is_dummy
+from petals_b200.utils.tracing import nvtx_range
 
 CACHE_TOKENS_AVAILABLE = "cache_tokens_available"  # rpc_info key (reference: handler.py:52)
 
@@ -103,6 +105,7 @@ class InferenceStream:
     def step(self, hidden: torch.Tensor, prompts: Optional[torch.Tensor] = None, hypo_ids: Optional[torch.Tensor] = None,
              metadata: Optional[Dict[str, Any]] = None) -> torch.Tensor:
         metadata = metadata or {}
+        maybe_fail("rpc_inference", self.handler.peer_id)
         if self.closed:
             raise RuntimeError("inference session is closed")
         now = time.monotonic()
@@ -244,6 +247,7 @@ class TransformerConnectionHandler:
         return InferenceStream(self, self._check_uids(uids), metadata or {})
 
     def rpc_forward(self, uids, hidden: torch.Tensor, prompts: Optional[torch.Tensor] = None, metadata: Optional[Dict[str, Any]] = None) -> torch.Tensor:
+        maybe_fail("rpc_forward", self.peer_id)
         uids = self._check_uids(uids)
         metadata = metadata or {}
         self.check_adapter(metadata.get("active_adapter"))
@@ -253,6 +257,7 @@ class TransformerConnectionHandler:
 
     def rpc_backward(self, uids, inputs: torch.Tensor, grad_outputs: torch.Tensor, prompts: Optional[torch.Tensor] = None,
                      metadata: Optional[Dict[str, Any]] = None) -> List[torch.Tensor]:
+        maybe_fail("rpc_backward", self.peer_id)
         uids = self._check_uids(uids)
         metadata = metadata or {}
         self.check_adapter(metadata.get("active_adapter"))

@@ -64,3 +64,33 @@ def test_all_retries_exhausted_raises():
             servers[0].shutdown()
             with pytest.raises(Exception):
                 model(ids[:, 2:])
+
+
+def test_env_style_fault_plan_triggers_failover():
+    """The fault injector (utils/fault_injection.py, also driven by PETALS_B200_FAULTS) makes one stage fail its 3rd inference step;
+    the session fails over to the redundant stage by replaying its history and the output stays exact."""
+    from petals_b200.utils import fault_injection
+
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:4", "0:4"]) as (swarm, servers):
+        config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm)
+        seq = RemoteSequential(config, dht=swarm)
+        blocks = local_blocks(path, config.num_hidden_layers)
+        torch.manual_seed(0)
+        x = torch.randn(1, 6, config.hidden_size)
+        try:
+            with torch.inference_mode(), seq.inference_session(max_length=8) as sess:
+                outs = [sess.step(x[:, :2])]
+                victim = sess._server_sessions[0].span.peer_id
+                fault_injection.set_fault_plan(f"rpc=rpc_inference,peer={victim},after=0,times=100")
+                for t in range(2, 6):
+                    outs.append(sess.step(x[:, t: t + 1]))
+                assert sess._server_sessions[0].span.peer_id != victim
+            assert fault_injection.fired_count() >= 1
+        finally:
+            fault_injection.set_fault_plan(None)
+        h = x
+        with torch.no_grad():
+            for b in blocks:
+                h = b(h)[0]
+        assert torch.allclose(torch.cat(outs, dim=1), h, atol=1e-4)
