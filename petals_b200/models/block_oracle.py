@@ -62,8 +62,9 @@ class GenericBlock(nn.Module):
             self.register_parameter(name, nn.Parameter(t, requires_grad=False))
         self._rope: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
         self._slopes: Optional[torch.Tensor] = None
-        # frozen bf16 blocks on CUDA run their linears (forward + dgrad) on the tcgen05 GEMM when autograd is recording
-        self.tc_backward = os.environ.get("PETALS_B200_TC_BACKWARD", "1") != "0"
+        # opt-in (PETALS_B200_TC_BACKWARD=1): frozen bf16 blocks on CUDA run their linears (forward + dgrad) on the tcgen05 GEMM when autograd
+        # is recording. Measured on Llama-3-8B prompt tuning: 6.7k vs 7.8k backward tokens/s for cuBLAS at these small-M shapes, so off by default
+        self.tc_backward = os.environ.get("PETALS_B200_TC_BACKWARD", "0") != "0"
         self.lora: dict = {}  # target param name -> list[(A [r,in], B [out,r], scale)] for the active adapter
 
     # ---- helpers -----------------------------------------------------------------------------------
