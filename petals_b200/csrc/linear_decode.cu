@@ -72,6 +72,7 @@ struct LinearDecodeParams {
   const float* rope_cos;                        // [max_pos, D/2] fp32 (null: no rotation, append only)
   const float* rope_sin;
   int rope_T, rope_Hq, rope_Hkv, rope_D, rope_max_pages, rope_max_pos;
+  int split_k;                                  // > 1: that many warps share one row pair, each streaming 1/split_k of K
   int pf_lines;                                 // 128-byte weight lines each warp prefetches into L2 before the prologue
   int late_trigger;                             // 1: release the dependent kernel after the main loop instead of at entry
   int wait_all_warps;                           // 1: every warp executes griddepcontrol.wait (default: warp 0 + barrier)
@@ -317,15 +318,17 @@ PB_DEVICE void gemv_body(const LinearDecodeParams& p, uint8_t* smem_raw, int gri
     }
   };
   // reduce the row pair over the warp, run the epilogue, reset the accumulators
-  auto finish_task = [&](int task) {
+  auto finish_task = [&](int task, bool reduced = false) {
     const int n0 = first_col(task);
+    if (!reduced) {  // split-K callers pass sums that are already warp-uniform
 #pragma unroll
-    for (int m = 0; m < M; ++m) {
-      a0[m] = warp_sum(a0[m]);
-      a1[m] = warp_sum(a1[m]);
-      if (DUAL) {
-        b0[m] = warp_sum(b0[m]);
-        b1[m] = warp_sum(b1[m]);
+      for (int m = 0; m < M; ++m) {
+        a0[m] = warp_sum(a0[m]);
+        a1[m] = warp_sum(a1[m]);
+        if (DUAL) {
+          b0[m] = warp_sum(b0[m]);
+          b1[m] = warp_sum(b1[m]);
+        }
       }
     }
     // ---- epilogue: lane m handles token m --------------------------------------------------
@@ -410,7 +413,49 @@ PB_DEVICE void gemv_body(const LinearDecodeParams& p, uint8_t* smem_raw, int gri
   };
 
   int task = warp < nwarps ? warp * grid + bid : ntasks;
-  if (!PIPE) {
+  if (p.split_k > 1) {
+    // Split-K inside the CTA for projections with few output columns (tensor-parallel QKV shards): S consecutive warps share one
+    // row pair, each streams 1/S of K, partial sums meet in shared memory. Without it such a launch has one warp per row pair
+    // in total (e.g. 640 warps for a 21 MB matrix) and is bound by the bytes it can keep in flight, not by HBM.
+    __shared__ float sk_part[24][M][4];
+    const int S = p.split_k;
+    const int groups = nwarps / S;
+    const int g = warp / S, sidx = warp - g * S;
+    const int spw = (nit + S - 1) / S;  // slots per warp
+    for (int tb = bid * groups; tb < ntasks; tb += grid * groups) {  // trip count is CTA-uniform (barriers inside)
+      const int t = tb + g;
+      const bool active = warp < groups * S && t < ntasks;
+      if (active) {
+        Slot sl;
+        const int it1 = min(nit, (sidx + 1) * spw);
+        for (int it = sidx * spw; it < it1; ++it) {
+          load_slot(sl, t, it);
+          compute_slot(sl, it);
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const float r0 = warp_sum(a0[m]), r1 = warp_sum(a1[m]);
+        const float r2 = DUAL ? warp_sum(b0[m]) : 0.f, r3 = DUAL ? warp_sum(b1[m]) : 0.f;
+        if (lane == 0) { sk_part[warp][m][0] = r0; sk_part[warp][m][1] = r1; sk_part[warp][m][2] = r2; sk_part[warp][m][3] = r3; }
+      }
+      __syncthreads();
+      if (active && sidx == 0) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) {
+          a0[m] = a1[m] = b0[m] = b1[m] = 0.f;
+          for (int q = 0; q < S; ++q) {
+            a0[m] += sk_part[warp + q][m][0]; a1[m] += sk_part[warp + q][m][1];
+            if (DUAL) { b0[m] += sk_part[warp + q][m][2]; b1[m] += sk_part[warp + q][m][3]; }
+          }
+        }
+        finish_task(t, true);
+      }
+#pragma unroll
+      for (int m = 0; m < M; ++m) a0[m] = a1[m] = b0[m] = b1[m] = 0.f;
+      __syncthreads();
+    }
+  } else if (!PIPE) {
     Slot s;
     for (; task < ntasks; task += total_warps) {
       for (int it = 0; it < nit; ++it) {
@@ -697,6 +742,18 @@ static int gemv_fill(const PbLinearDecodeArgs* a, LinearDecodeParams& p, GemvGeo
     const double eff = static_cast<double>(ntasks) / static_cast<double>(rounds * tw);
     if (eff > best_eff + 1e-9) { best_eff = eff; best_w = w; }
   }
+  p.split_k = 1;
+  static const int env_splitk = [] { const char* e = getenv("PETALS_B200_GEMV_SPLITK"); return e ? atoi(e) : 1; }();
+  if (env_splitk && !pipe && xsmem && a->M <= 4 && a->fixed_grid <= 0 && ntasks < sms * 12 && a->K >= 2048) {
+    // few output columns: spread the row pairs over ALL SMs and let 4 (or 2) warps share each pair along K
+    const int groups = (ntasks + sms - 1) / sms;
+    const int S = groups * 4 <= 24 ? 4 : (groups * 2 <= 24 ? 2 : 1);
+    if (S > 1) {
+      p.split_k = S;
+      g.dual = a->act == 1; g.xsmem = xsmem; g.pipe = false; g.smem = smem; g.grid = sms; g.best_w = groups * S;
+      return PB_OK;
+    }
+  }
   int grid = sms;
   if (ntasks < sms * best_w) {  // small problem: do not launch idle CTAs beyond need
     grid = (ntasks + best_w - 1) / best_w;
@@ -762,12 +819,13 @@ extern "C" int pb_gemv_chain(const PbLinearDecodeArgs* const* phases, int n_phas
     const int rc = gemv_fill(phases[i], c.ph[i], g);
     if (rc != PB_OK) return rc;
     if (phases[i]->M != M || !g.xsmem || phases[i]->fixed_grid > 0) return PB_ERR_SHAPE;
+    c.ph[i].split_k = 1;  // the chain distributes row pairs itself (nwarps below)
     c.dual[i] = g.dual ? 1 : 0;
     c.rope[i] = c.ph[i].rope_q_out != nullptr ? 1 : 0;
     if ((i != 1 && c.dual[i]) || c.rope[i] != (i == 3 ? 1 : 0)) return PB_ERR_SHAPE;  // fixed roles by position
     // all phases share the full grid; a phase with few output columns keeps its tasks spread over all SMs with fewer warps
     const int ntasks = phases[i]->N / 2;
-    c.nwarps[i] = ntasks < sms * g.best_w ? (ntasks + sms - 1) / sms : g.best_w;
+    c.nwarps[i] = (ntasks < sms * g.best_w || g.grid != sms) ? (ntasks + sms - 1) / sms : g.best_w;
     if (c.nwarps[i] < 1) c.nwarps[i] = 1;
     if (c.nwarps[i] > 24) c.nwarps[i] = 24;
     if (g.smem > smem) smem = g.smem;

@@ -169,23 +169,6 @@ def dequant_mxfp8(w_q: torch.Tensor, w_scale: torch.Tensor, out: Optional[torch.
     return out
 
 
-def linear_decode_grid(N: int, M: int = 1, device: Optional[int] = None) -> int:
-    """CTA count linear_decode launches for a given N (peers need it to size flag targets)."""
-    sms = native.sm_count(device)
-    ntasks = N // 2
-    max_w = 24 if M <= 4 else 16
-    best_w, best_eff = max_w, -1.0
-    for w in range(max_w, max_w // 2 - 1, -1):
-        tw = sms * w
-        rounds = -(-ntasks // tw)
-        eff = ntasks / (rounds * tw)
-        if eff > best_eff + 1e-9:
-            best_eff, best_w = eff, w
-    if ntasks < sms * best_w:
-        return max(1, min(sms, -(-ntasks // best_w)))
-    return sms
-
-
 def _act_ref(v: torch.Tensor, act: int) -> torch.Tensor:
     if act == ACT_GELU_TANH:
         return F.gelu(v, approximate="tanh")

@@ -509,3 +509,35 @@ def test_linear_decode_pipelined_main_loop_is_bit_identical(M):
         finally:
             Fn.set_gemv_pipe(False)
         assert torch.equal(got, want), f"N={N} K={K} {opt}: max diff {(got.float() - want.float()).abs().max().item()}"
+
+
+@pytest.mark.parametrize("M", [1, 4])
+def test_linear_decode_split_k_small_n(M):
+    """Projections with few output columns (tensor-parallel QKV shards) run split-K inside the CTA: 4 warps share a row pair."""
+    torch.manual_seed(61)
+    # plain + norm, and SwiGLU, at shapes that take the split-K path (N/2 < 12 * SMs, K >= 2048)
+    K = 8192
+    x, g = _rand(M, K), _rand(K) * 0.1 + 1
+    w = _rand(1280, K, scale=K ** -0.5)
+    got = Fn.linear_decode(x, w, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+    _close(got, Fn.linear_ref(x, w, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5), 3e-2, 2e-2, "split-k plain")
+    wg, wu = _rand(896, K, scale=K ** -0.5), _rand(896, K, scale=K ** -0.5)
+    got = Fn.linear_decode(x, wg, w2=wu, act=Fn.ACT_SWIGLU, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+    _close(got, Fn.linear_ref(x, wg, w2=wu, act=Fn.ACT_SWIGLU, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5), 2e-2, 3e-2, "split-k swiglu")
+    # fused RoPE + KV append epilogue on a one-kv-head shard (8 q heads + 1 k + 1 v, d=128): equals projection -> rope kernel
+    if M == 1:
+        D, Hq, Hkv = 128, 8, 1
+        wq = _rand((Hq + 2 * Hkv) * D, K, scale=K ** -0.5)
+        cos, sin = Fn.rope_tables(D, 512, theta=10000.0, device=DEV)
+        pos = torch.full((1,), 5, dtype=torch.int32, device=DEV)
+        kp1, vp1, table = _paged_setup(1, 64, Hkv, D, seed=9)
+        kp2, vp2 = kp1.clone(), vp1.clone()
+        qkv = Fn.linear_decode(x, wq, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+        q1 = torch.empty(1, Hq * D, device=DEV, dtype=torch.bfloat16)
+        Fn.rope_kv_append(qkv, q1, kp1, vp1, table, pos.data_ptr(), cos, sin, B=1, T=1, Hq=Hq, Hkv=Hkv, D=D)
+        q2 = torch.empty_like(q1)
+        Fn.linear_decode(x, wq, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5,
+                         rope=dict(q_out=q2, k_pool=kp2, v_pool=vp2, block_table=table, pos_ptr=pos.data_ptr(), cos=cos, sin=sin, T=1, Hq=Hq, Hkv=Hkv, D=D))
+        _close(q2, q1, 2e-2, 2e-2, "split-k rope q")
+        _close(kp2, kp1, 2e-2, 2e-2, "split-k rope k")
+        _close(vp2, vp1, 2e-2, 2e-2, "split-k v")
