@@ -491,7 +491,8 @@ def test_gemv_chain_matches_separate_launches(M):
 def test_linear_decode_pipelined_main_loop_is_bit_identical(M):
     """The software-pipelined main loop (two slot buffers, loads issued across task boundaries) keeps the accumulation order."""
     torch.manual_seed(51)
-    cases = [(1280, 8192, {}), (8192, 1024, dict(residual=True)), (3584, 8192, dict(dual=True, norm=True)), (2050, 1032, {})]
+    # (shapes outside the split-K regime: that path sums in a different order)
+    cases = [(4096, 8192, {}), (8192, 1024, dict(residual=True)), (3584, 8192, dict(dual=True, norm=True)), (2050, 1032, {})]
     for N, K, opt in cases:
         x, w, w2 = _rand(M, K), _rand(N, K, scale=K ** -0.5), _rand(N, K, scale=K ** -0.5)
         kw = {}
