@@ -30,7 +30,11 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=dev)
-    path = write_config_only("llama-tiny", dict(num_attention_heads=8, num_key_value_heads=max(2, world), num_hidden_layers=3))
+    overrides = dict(num_attention_heads=8, num_key_value_heads=max(2, world), num_hidden_layers=3)
+    if os.environ.get("TP_SELFTEST_HIDDEN"):  # e.g. 2048: wide enough for the split-K decode path of small QKV shards
+        h = int(os.environ["TP_SELFTEST_HIDDEN"])
+        overrides.update(hidden_size=h, intermediate_size=2 * h, head_dim=128 if h >= 1024 else 64)
+    path = write_config_only("llama-tiny", overrides)
     config = AutoDistributedConfig.from_pretrained(path)
     n = config.num_hidden_layers
     blocks = random_blocks(config, range(n), dev, seed=3)  # identical on every rank (seeded)
