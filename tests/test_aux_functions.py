@@ -103,3 +103,36 @@ def test_block_selection_policy():
     # evenly covered -> stay
     assert not should_choose_other_blocks("b", infos({"a": (0, 4, 1.0), "b": (4, 8, 1.0)}), balance_quality=0.75)
     assert should_choose_other_blocks("b", infos({"a": (0, 4, 1.0), "b": (4, 8, 1.0)}), balance_quality=1.5)  # forced
+
+
+def test_fault_plan_parsing_and_counters():
+    from petals_b200.utils import fault_injection as fi
+
+    try:
+        fi.set_fault_plan("rpc=rpc_forward,peer=a,after=1,times=2,error=boom; rpc=rpc_info")
+        fi.maybe_fail("rpc_forward", "b")          # other peer: rule does not apply
+        fi.maybe_fail("rpc_forward", "a")          # call 1 <= after
+        for _ in range(2):                         # calls 2 and 3 fire
+            with pytest.raises(fi.InjectedFault, match="boom"):
+                fi.maybe_fail("rpc_forward", "a")
+        fi.maybe_fail("rpc_forward", "a")          # exhausted
+        with pytest.raises(fi.InjectedFault):
+            fi.maybe_fail("rpc_info", "whoever")   # peer-less rule matches any peer
+        assert fi.fired_count() == 3
+        with pytest.raises(ValueError):
+            fi.set_fault_plan("peer=a,after=1")
+    finally:
+        fi.set_fault_plan(None)
+    fi.maybe_fail("rpc_forward", "a")              # no plan: no-op
+
+
+def test_step_timer_and_nvtx_noop():
+    from petals_b200.utils.tracing import StepTimer, nvtx_range
+
+    t = StepTimer()
+    with t.measure("x"), nvtx_range("cpu-range-is-a-no-op"):
+        pass
+    with t.measure("x"):
+        pass
+    snap = t.snapshot()
+    assert snap["x"]["count"] == 2 and snap["x"]["seconds"] >= 0 and t.snapshot() == {}
