@@ -26,6 +26,10 @@ class DistributedLlamaModel(DistributedModelBase):
     def ln_f(self):
         return self.final_norm
 
+    @property
+    def norm(self):  # Hugging Face's name of the final RMSNorm
+        return self.final_norm
+
 
 class DistributedLlamaForCausalLM(DistributedModelForCausalLM):
     config_class = DistributedLlamaConfig

@@ -19,6 +19,10 @@ class DistributedMixtralModel(DistributedModelBase):
     def ln_f(self):
         return self.final_norm
 
+    @property
+    def norm(self):  # Hugging Face's name of the final RMSNorm
+        return self.final_norm
+
 
 class DistributedMixtralForCausalLM(DistributedModelForCausalLM):
     config_class = DistributedMixtralConfig

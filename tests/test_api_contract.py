@@ -1,0 +1,96 @@
+"""The client-facing behavioural contract of the reference, checked in one place on a CPU swarm:
+compat properties, RemoteSequential container protocol, session attributes and rollback rules, generate() argument rules,
+rejected HF options, deep-prompt broadcasting."""
+import pytest
+import torch
+
+from petals_b200.client.remote_sequential import RemoteSequential
+from petals_b200.utils.auto_config import (AutoDistributedConfig, AutoDistributedModel, AutoDistributedModelForCausalLM,
+                                           AutoDistributedModelForSequenceClassification)
+from tests.utils import checkpoint, swarm_of
+
+
+@pytest.fixture(scope="module")
+def llama():
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:4"]) as (swarm, _):
+        yield path, swarm
+
+
+def test_auto_classes_and_compat_properties(llama):
+    path, swarm = llama
+    lm = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=swarm)
+    base = AutoDistributedModel.from_pretrained(path, initial_peers=swarm)
+    cls = AutoDistributedModelForSequenceClassification.from_pretrained(path, initial_peers=swarm, num_labels=3)
+    assert isinstance(lm.model.layers, RemoteSequential) and isinstance(base.layers, RemoteSequential)
+    assert lm.transformer is lm.model and lm.model.h is lm.model.layers and lm.model.word_embeddings is lm.model.embed_tokens
+    assert lm.model.ln_f == lm.model.norm and callable(lm.model.ln_f)  # the final norm (a bound method of the client shell)
+    ids = torch.randint(0, lm.config.vocab_size, (2, 5))
+    assert cls(ids).logits.shape == (2, 3) and base(ids).last_hidden_state.shape == (2, 5, lm.config.hidden_size)
+    bloom_path = checkpoint("bloom")
+    with swarm_of(bloom_path, ["0:4"]) as (bswarm, _):
+        bloom = AutoDistributedModelForCausalLM.from_pretrained(bloom_path, initial_peers=bswarm)
+        assert isinstance(bloom.transformer.h, RemoteSequential) and bloom.transformer.word_embeddings_layernorm is not None
+
+
+def test_remote_sequential_container_protocol_and_sessions(llama):
+    path, swarm = llama
+    config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm)
+    seq = RemoteSequential(config, dht=swarm)
+    assert len(seq) == config.num_hidden_layers and len(seq[1:3]) == 2 and len(seq[2]) == 1 and len(list(seq)) == len(seq)
+    assert seq.active_session is None
+    x = torch.randn(1, 3, config.hidden_size)
+    with seq.inference_session(max_length=8) as sess:
+        assert seq.active_session is sess and sess.num_blocks == len(seq) and sess.position == 0
+        y = seq(x)                       # forward inside a session = a step
+        assert y.shape == x.shape and y.dtype == x.dtype and sess.position == 3 and seq.position == 3
+        with pytest.raises(AssertionError):
+            with seq.inference_session(max_length=8):
+                pass                     # no nested sessions
+        sess.position = 1                # rollback
+        assert sess.position == 1
+        with pytest.raises(ValueError):
+            sess.position = 5            # cannot move forward by assignment
+        with pytest.raises(ValueError, match="Maximum length exceeded"):
+            sess.step(torch.randn(1, 8, config.hidden_size))
+        with pytest.raises(RuntimeError):
+            sess.last_token_id = torch.zeros(1, 1, dtype=torch.long)   # nothing generated yet
+    assert seq.active_session is None
+    other = seq.inference_session(max_length=4)
+    with other, seq.use_session(other):
+        assert seq.active_session is other
+
+
+def test_generate_argument_rules_and_rejected_options(llama):
+    path, swarm = llama
+    model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=swarm)
+    ids = torch.randint(0, model.config.vocab_size, (1, 4))
+    with pytest.raises(ValueError):
+        model.generate(ids)                                      # neither max_length nor max_new_tokens
+    with pytest.raises(ValueError):
+        model.generate(ids, max_length=8, max_new_tokens=2)      # both
+    out = model.generate(ids, max_new_tokens=3, do_sample=0)    # int do_sample accepted (compat)
+    assert out.shape == (1, 7) and torch.equal(out[:, :4], ids)
+    with model.inference_session(max_length=16) as sess:         # multi-call continuation on one session
+        a = model.generate(ids, max_new_tokens=2, session=sess)
+        b = model.generate(None, max_new_tokens=2, session=sess)
+        assert b.shape[1] == a.shape[1] + 2 and sess.position >= 7 and sess.output_ids is not None
+        assert torch.equal(sess.last_token_id, sess.output_ids[:, -1:])
+    for bad in (dict(attention_mask=torch.tensor([[1, 0, 1, 1]])), dict(position_ids=torch.tensor([[0, 2, 3, 4]])),
+                dict(output_attentions=True), dict(output_hidden_states=True)):
+        with pytest.raises((ValueError, NotImplementedError)):
+            model(ids, **bad)
+    model(ids, attention_mask=torch.ones_like(ids))              # all-ones mask is fine
+
+
+def test_deep_prompts_broadcast_over_the_batch(llama):
+    path, swarm = llama
+    config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm)
+    seq = RemoteSequential(config, dht=swarm)
+    x = torch.randn(3, 5, config.hidden_size)
+    p1 = torch.randn(len(seq), 1, 2, config.hidden_size) * 0.1
+    with torch.no_grad():
+        assert torch.allclose(seq(x, prompts=p1), seq(x, prompts=p1.expand(-1, 3, -1, -1).contiguous()), atol=1e-5)
+        with seq.inference_session(max_length=8) as sess:
+            stepped = sess.step(x, prompts=p1)
+        assert torch.allclose(stepped, seq(x, prompts=p1), atol=1e-4)
