@@ -7,6 +7,8 @@ the same math — used on CPU (plumbing tests, BASELINE config #1) and as the nu
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import math
 from typing import Optional, Sequence, Tuple
@@ -110,8 +112,48 @@ def linear_decode(x: torch.Tensor, w: torch.Tensor, **kw) -> torch.Tensor:
     ``cos``/``sin`` (fp32 tables or None), ``T``, ``Hq``, ``Hkv``, ``D``. Nothing is stored to ``out`` then; ``q_out`` is returned.
     """
     a, result, _keep = _linear_decode_args(x, w, **kw)
+    if _SKINNY["on"] and _skinny_ok(a):
+        scratch, counters = _skinny_buffers(x.device, a.N)
+        check(native.lib().pb_linear_decode_mma(C.byref(a), ptr(scratch), ptr(counters), stream_ptr()), "linear_decode_mma")
+        return result
     check(native.lib().pb_linear_decode(C.byref(a), stream_ptr()), "linear_decode")
     return result
+
+
+# ---- 4..8 rows on the tensor cores (csrc/linear_decode_mma.cu) -------------------------------------------------------------------
+# Measured on B200 at Llama-3-70B shapes (profiles/r1_kernel_bench_skinny.txt): the mma.sync kernel wins for every shape at
+# M >= 5 (the FMA kernel drops to 34-52 % of HBM there) and for the large MLP matrices at M = 4 (86 vs 52 %); the FMA kernel
+# keeps M <= 3 and the small matrices at M = 4 (its prologue is cheaper). PETALS_B200_SKINNY=0 disables the routing,
+# =2 forces the tensor-core kernel wherever it is applicable.
+_SKINNY = {"on": os.environ.get("PETALS_B200_SKINNY", "1") not in ("", "0"), "force": os.environ.get("PETALS_B200_SKINNY", "1") == "2", "bufs": {}}
+
+
+def set_skinny_gemm(on: bool, force: bool = True) -> None:
+    """Route plain decode linears with 2..8 rows (no peer traffic, no RoPE epilogue) to the mma.sync skinny-GEMM kernel.
+    ``force`` bypasses the size heuristic (tests, benchmarks)."""
+    _SKINNY["on"], _SKINNY["force"] = bool(on), bool(on and force)
+
+
+def _skinny_ok(a) -> bool:
+    if not _SKINNY["force"]:
+        big = a.N * a.K * (2 if a.act == ACT_SWIGLU else 1) >= (128 << 20)
+        if a.M < 4 or (a.M == 4 and not big):
+            return False
+    return (2 <= a.M <= 8 and a.N % 16 == 0 and a.K % 128 == 0 and a.n_parts == 0 and a.n_push == 0 and a.n_ll_parts == 0 and a.n_ll_push == 0
+            and not a.wait_flag and not a.rope_q_out and not a.x_out and a.out and (a.norm_kind == 0 or 8 * (a.K * 2 + 8) <= 160 * 1024))
+
+
+def _skinny_buffers(device: torch.device, N: int):
+    """Zero-initialised reduction scratch [2, N, 8] fp32 and per-row-block arrival counters; every launch leaves them zero."""
+    key = (device.type, device.index)
+    have = _SKINNY["bufs"].get(key)
+    if have is None or have[2] < N:
+        cap = max(N, 32768)
+        with torch.inference_mode(False):
+            have = (torch.zeros(2 * cap * 8, dtype=torch.float32, device=device), torch.zeros(cap // 16, dtype=torch.int32, device=device), cap)
+        _SKINNY.setdefault("keep", []).append(have)  # captured CUDA graphs may still hold the previous (smaller) buffers
+        _SKINNY["bufs"][key] = have
+    return have[0], have[1]
 
 
 def set_gemv_pipe(on: bool) -> None:

@@ -542,3 +542,34 @@ def test_linear_decode_split_k_small_n(M):
         _close(q2, q1, 2e-2, 2e-2, "split-k rope q")
         _close(kp2, kp1, 2e-2, 2e-2, "split-k rope k")
         _close(vp2, vp1, 2e-2, 2e-2, "split-k v")
+
+
+@pytest.mark.parametrize("M", [2, 4, 8])
+def test_linear_decode_skinny_tensor_core_path(M):
+    """2..8 rows on mma.sync (tokens as the N dimension, k-permuted fragments, K-sliced row blocks reduced through global scratch)
+    against the fp32 oracle and the FMA kernel; the scratch / counters must be left zero by every launch."""
+    torch.manual_seed(71)
+    try:
+        Fn.set_skinny_gemm(True)
+        # plain + residual
+        x, w, res = _rand(M, 4096), _rand(4096, 4096, scale=4096 ** -0.5), _rand(M, 4096)
+        got = Fn.linear_decode(x, w, residual=res)
+        _close(got, Fn.linear_ref(x, w, residual=res), 3e-2, 2e-2, "skinny plain+residual")
+        # RMSNorm + SwiGLU
+        x, g = _rand(M, 1024), _rand(1024) * 0.1 + 1
+        wg, wu = _rand(2816, 1024, scale=1024 ** -0.5), _rand(2816, 1024, scale=1024 ** -0.5)
+        got = Fn.linear_decode(x, wg, w2=wu, act=Fn.ACT_SWIGLU, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+        _close(got, Fn.linear_ref(x, wg, w2=wu, act=Fn.ACT_SWIGLU, norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5), 2e-2, 3e-2, "skinny swiglu")
+        # LayerNorm + bias + GELU
+        x, g, b = _rand(M, 2048), _rand(2048) * 0.1 + 1, _rand(2048) * 0.1
+        w, bias = _rand(1024, 2048, scale=2048 ** -0.5), _rand(1024) * 0.1
+        got = Fn.linear_decode(x, w, bias=bias, act=Fn.ACT_GELU_TANH, norm_weight=g, norm_bias=b, norm_kind=Fn.NORM_LAYER, eps=1e-5)
+        _close(got, Fn.linear_ref(x, w, bias=bias, act=Fn.ACT_GELU_TANH, norm_weight=g, norm_bias=b, norm_kind=Fn.NORM_LAYER, eps=1e-5), 3e-2, 3e-2, "skinny ln+gelu")
+        # very wide K (down projection): x read from global memory, no staging
+        x, w, res = _rand(M, 28672, scale=0.3), _rand(1024, 28672, scale=28672 ** -0.5), _rand(M, 1024)
+        got = Fn.linear_decode(x, w, residual=res)
+        _close(got, Fn.linear_ref(x, w, residual=res), 3e-2, 2e-2, "skinny wide-K")
+        for scratch, counters, _cap in Fn._SKINNY["keep"]:
+            assert float(scratch.abs().sum().item()) == 0.0 and int(counters.abs().sum().item()) == 0
+    finally:
+        Fn.set_skinny_gemm(False)

@@ -111,6 +111,49 @@ def bench_gemm(results, peaks):
         del As, Bs, B2
 
 
+def bench_skinny(results, peaks):
+    """M = 2 / 4 / 8 rows: FMA kernel vs the mma.sync skinny-GEMM kernel on the same shapes."""
+    shapes = [("70b.qkv", 10240, 8192, dict(norm=True)), ("70b.o", 8192, 8192, dict(residual=True)),
+              ("70b.gate_up", 28672, 8192, dict(norm=True, dual=True)), ("70b.down", 8192, 28672, dict(residual=True))]
+    for name, N, K, opt in shapes:
+        nbuf = max(2, int(300e6 // (N * K * 2 * (2 if opt.get("dual") else 1))) + 1)
+        ws = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * K ** -0.5 for _ in range(nbuf)]
+        w2s = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * K ** -0.5 for _ in range(nbuf)] if opt.get("dual") else None
+        g = torch.ones(K, device="cuda", dtype=torch.bfloat16)
+        for M in (2, 4, 8):
+            x = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+            res = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+            out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+
+            def mk(i):
+                kw = dict(out=out)
+                if opt.get("norm"):
+                    kw.update(norm_weight=g, norm_kind=Fn.NORM_RMS, eps=1e-5)
+                if opt.get("residual"):
+                    kw.update(residual=res)
+                if opt.get("dual"):
+                    kw.update(w2=w2s[i], act=Fn.ACT_SWIGLU)
+                return lambda: Fn.linear_decode(x, ws[i], **kw)
+
+            row = dict(kernel="linear_decode vs linear_decode_mma", shape=name, M=M, N=N, K=K)
+            nbytes = N * K * 2 * (2 if opt.get("dual") else 1)
+            for label, on in (("fma", False), ("mma", True)):
+                Fn.set_skinny_gemm(on)
+                try:
+                    ms = time_fn([mk(i) for i in range(nbuf)], iters=30)
+                    row[label + "_ms"], row[label + "_frac_hbm"] = ms, nbytes / ms / 1e6 / peaks["hbm_gbs"]
+                except Exception as e:  # noqa: BLE001 - e.g. the FMA kernel cannot stage M*K activations
+                    row[label + "_ms"], row[label + "_frac_hbm"] = None, None
+                    print(f"  {label} {name} M={M}: {e!r}"[:200])
+                finally:
+                    Fn.set_skinny_gemm(False)
+            results.append(row)
+            f = lambda v: "   n/a" if v is None else f"{v * 100:5.1f}%"
+            t = lambda v: "    n/a" if v is None else f"{v * 1e3:7.1f}"
+            print(f"gemv.skinny {name:12s} M={M}  fma {t(row['fma_ms'])} us {f(row['fma_frac_hbm'])}   mma {t(row['mma_ms'])} us {f(row['mma_frac_hbm'])} of measured HBM", flush=True)
+        del ws, w2s
+
+
 def bench_gemv_fp8(results, peaks):
     """Decode linears over MXFP8 weights (1 byte/weight + 1 scale byte per 32)."""
     from petals_b200.ops.quant import quantize_mxfp8
@@ -158,6 +201,8 @@ def main():
     if args.fp8:
         args.only = "fp8"
         bench_gemv_fp8(results, peaks)
+    if args.only == "skinny":
+        bench_skinny(results, peaks)
     if args.only in ("", "gemv"):
         bench_gemv(results, peaks)
     if args.only in ("", "gemm"):
