@@ -549,6 +549,7 @@ def test_linear_decode_skinny_tensor_core_path(M):
     """2..8 rows on mma.sync (tokens as the N dimension, k-permuted fragments, K-sliced row blocks reduced through global scratch)
     against the fp32 oracle and the FMA kernel; the scratch / counters must be left zero by every launch."""
     torch.manual_seed(71)
+    prev = (Fn._SKINNY["on"], Fn._SKINNY["force"])
     try:
         Fn.set_skinny_gemm(True)
         # plain + residual
@@ -572,4 +573,4 @@ def test_linear_decode_skinny_tensor_core_path(M):
         for scratch, counters, _cap in Fn._SKINNY["keep"]:
             assert float(scratch.abs().sum().item()) == 0.0 and int(counters.abs().sum().item()) == 0
     finally:
-        Fn.set_skinny_gemm(False)
+        Fn._SKINNY["on"], Fn._SKINNY["force"] = prev
