@@ -20,7 +20,8 @@ def make_inference_graphed_callable(callable_: Callable, sample_args: Sequence[t
         raise RuntimeError("make_inference_graphed_callable does not support autocast caching; disable it")
     static_args = tuple(a.clone() if isinstance(a, torch.Tensor) else a for a in sample_args)
     flat = [a for a in static_args if isinstance(a, torch.Tensor)]
-    assert flat and all(a.is_cuda for a in flat), "sample_args must contain CUDA tensors"
+    if not flat or not all(a.is_cuda for a in flat):
+        return callable_  # nothing to capture off the GPU: the plain callable has the same semantics
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side), torch.no_grad():

@@ -48,6 +48,7 @@ def free_disk_space_for(size: int, *, cache_dir: Optional[str], max_disk_space: 
     cache_dir = Path(cache_dir or DEFAULT_CACHE_DIR)
     os.makedirs(cache_dir, exist_ok=True)
     entries = [p for p in cache_dir.iterdir() if p.is_dir()]
+    last_used = {p: p.stat().st_atime for p in entries}  # before walking the directories: reading them refreshes atime
     sizes = {p: _dir_size(p) for p in entries}
     occupied = sum(sizes.values())
     available = shutil.disk_usage(cache_dir).free - os_quota
@@ -56,7 +57,7 @@ def free_disk_space_for(size: int, *, cache_dir: Optional[str], max_disk_space: 
     if size <= available:
         return
     needed = size - available
-    for p in sorted(entries, key=lambda q: q.stat().st_atime):  # LRU first
+    for p in sorted(entries, key=lambda q: last_used[q]):  # LRU first
         logger.info(f"Evicting {p} ({sizes[p] / 2**30:.2f} GiB) from the checkpoint cache")
         shutil.rmtree(p, ignore_errors=True)
         needed -= sizes[p]

@@ -1,0 +1,79 @@
+"""Small utility modules of the reference's inventory that no other test touches by name: disk cache housekeeping, asyncio
+shielding, reachability, spending policy, deprecated aliases, auth plumbing, dtype map."""
+import asyncio
+import os
+import time
+import warnings
+
+import pytest
+import torch
+
+
+def test_disk_cache_lru_eviction_and_locks(tmp_path):
+    from petals_b200.utils.disk_cache import allow_cache_reads, allow_cache_writes, free_disk_space_for
+
+    cache = tmp_path / "cache"
+    for i, name in enumerate(["old-model", "mid-model", "new-model"]):
+        d = cache / name
+        d.mkdir(parents=True)
+        (d / "weights.bin").write_bytes(b"x" * 1000)
+        t = time.time() - 1000 + 100 * i
+        os.utime(d, (t, t))
+    with allow_cache_reads(str(cache)), allow_cache_reads(str(cache)):  # shared locks stack
+        pass
+    with allow_cache_writes(str(cache)):
+        free_disk_space_for(1500, cache_dir=str(cache), max_disk_space=3500, os_quota=0)  # 3000 used: evict just the LRU entry
+    assert not (cache / "old-model").exists() and (cache / "mid-model").exists() and (cache / "new-model").exists()
+    free_disk_space_for(10, cache_dir=str(cache), max_disk_space=10**9, os_quota=0)      # fits: nothing evicted
+    assert (cache / "mid-model").exists()
+
+
+def test_shield_and_wait_finishes_the_task_before_propagating_cancellation():
+    from petals_b200.utils.asyncio import shield_and_wait
+
+    async def scenario():
+        done = []
+
+        async def critical():
+            await asyncio.sleep(0.05)
+            done.append(True)
+            return 7
+
+        assert await shield_and_wait(critical()) == 7
+        waiter = asyncio.create_task(shield_and_wait(critical()))
+        await asyncio.sleep(0.01)
+        waiter.cancel()
+        with pytest.raises(asyncio.CancelledError):
+            await waiter
+        return done
+
+    assert asyncio.run(scenario()) == [True, True]  # the shielded task ran to completion despite the cancellation
+
+
+def test_reachability_spending_policy_aliases_and_constants():
+    from petals_b200.client.routing.spending_policy import NoSpendingPolicy, SpendingPolicyBase
+    from petals_b200.constants import DTYPE_MAP
+    from petals_b200.server.reachability import check_direct_reachability, check_p2p_access
+    from petals_b200.utils.hf_auth import always_needs_auth, resolve_token
+
+    assert check_direct_reachability() is True
+    assert isinstance(check_p2p_access(), dict)
+    assert isinstance(NoSpendingPolicy(), SpendingPolicyBase) and NoSpendingPolicy().get_points("rpc_inference", 1, 2) == 0
+    assert DTYPE_MAP["bfloat16"] is torch.bfloat16 and DTYPE_MAP["float16"] is torch.float16 and DTYPE_MAP["auto"] == "auto"
+    assert not always_needs_auth("any/model") and resolve_token("hf_x") == "hf_x" and resolve_token(True) is None
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        import importlib
+
+        import petals_b200.dht_utils as alias
+
+        importlib.reload(alias)
+        assert any(issubclass(x.category, DeprecationWarning) for x in w)
+        assert hasattr(alias, "declare_active_modules") and hasattr(alias, "get_remote_module_infos")
+
+
+def test_graphed_callable_falls_back_on_cpu():
+    from petals_b200.utils.cuda_graphs import make_inference_graphed_callable
+
+    fn = make_inference_graphed_callable(lambda a, b: a * 2 + b, (torch.ones(3), torch.zeros(3)))
+    assert torch.equal(fn(torch.full((3,), 2.0), torch.ones(3)), torch.full((3,), 5.0))
