@@ -15,6 +15,7 @@ import yaml
 
 from petals_b200.constants import DTYPE_MAP
 from petals_b200.server.server import Server
+from petals_b200.utils.compression import parse_compression
 from petals_b200.utils.convert_block import QuantType
 from petals_b200.utils.logging import get_logger
 from petals_b200.utils.version import validate_version
@@ -51,7 +52,9 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--public_ip", type=str, default=None, help="(ignored)")
     p.add_argument("--no_auto_relay", action="store_false", dest="use_auto_relay")
     p.add_argument("--daemon_startup_timeout", type=float, default=60)
-    p.add_argument("--compression", type=str, default="NONE", help="activation compression for the control transport (NONE only; the data plane is NVLink)")
+    p.add_argument("--compression", type=str, default="NONE", help="wire codec for the hidden states this server returns over the socket transport: NONE, FLOAT16, MEANSTD_16BIT, "
+                        "QUANTILE_8BIT, UNIFORM_8BIT or BLOCKWISE_8BIT (clients can override per request with output_compression; "
+                        "NVLink stage hops are never compressed)")
     p.add_argument("--num_handlers", type=int, default=8)
     p.add_argument("--prefetch_batches", type=int, default=1)
     p.add_argument("--sender_threads", type=int, default=1)
@@ -106,9 +109,7 @@ def main(argv=None) -> None:
         args["initial_peers"] = []
     max_disk_space = args.pop("max_disk_space")
     args["max_disk_space"] = parse_size(max_disk_space) if max_disk_space is not None else None
-    if args["compression"] not in (None, "NONE"):
-        logger.warning("activation compression is not used: hidden states move over NVLink in bf16")
-    args["compression"] = None
+    args["compression"] = parse_compression(args["compression"])
     if args["quant_type"] is not None:
         args["quant_type"] = QuantType[args["quant_type"].upper()]
     if args["tensor_parallel_devices"]:

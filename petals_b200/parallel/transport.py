@@ -27,6 +27,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import msgpack
 import torch
 
+from petals_b200.utils.compression import decode as decode_tensor, encode as encode_tensor, normalize_output_compression
 from petals_b200.utils.logging import get_logger
 
 logger = get_logger(__name__)
@@ -47,15 +48,18 @@ def _recv_exact(sock: socket.socket, n: int) -> bytes:
     return b"".join(chunks)
 
 
-def send_message(sock: socket.socket, header: Dict[str, Any], tensors: Sequence[torch.Tensor] = ()) -> None:
+def send_message(sock: socket.socket, header: Dict[str, Any], tensors: Sequence[torch.Tensor] = (), compression=None) -> None:
+    """``compression``: one codec for every tensor or a list with one entry per tensor (utils/compression.py);
+    integer/bool tensors and empty tensors always travel raw."""
     metas, blobs = [], []
-    for t in tensors:
+    per_tensor = list(compression) if isinstance(compression, (list, tuple)) else [compression] * len(tensors)
+    for t, codec in zip(tensors, per_tensor):
         if t is None:
             t = torch.empty(0)  # an empty tensor means "argument absent" (utils/misc.py DUMMY convention)
-        t = t.detach().to("cpu").contiguous()
-        raw = t.view(torch.uint8).numpy().tobytes() if t.numel() else b""
-        metas.append({"dtype": _DTYPE_NAMES[t.dtype], "shape": list(t.shape), "nbytes": len(raw)})
-        blobs.append(raw)
+        cmeta, parts = encode_tensor(t, codec)
+        metas.append({"dtype": _DTYPE_NAMES[t.dtype], "shape": list(t.shape), "nbytes": sum(len(b) for b in parts),
+                      "parts": [len(b) for b in parts], "c": cmeta})
+        blobs.extend(parts)
     header = dict(header, tensors=metas)
     payload = msgpack.packb(header, use_bin_type=True)
     sock.sendall(struct.pack("<I", len(payload)) + payload + b"".join(blobs))
@@ -66,13 +70,8 @@ def recv_message(sock: socket.socket) -> Tuple[Dict[str, Any], List[torch.Tensor
     header = msgpack.unpackb(_recv_exact(sock, n), raw=False)
     tensors = []
     for m in header.get("tensors", []):
-        raw = _recv_exact(sock, m["nbytes"]) if m["nbytes"] else b""
-        dtype = _DTYPES[m["dtype"]]
-        if raw:
-            t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).view(dtype).reshape(m["shape"])
-        else:
-            t = torch.empty(m["shape"], dtype=dtype)
-        tensors.append(t)
+        parts = [_recv_exact(sock, k) if k else b"" for k in m.get("parts", [m["nbytes"]])]
+        tensors.append(decode_tensor(m.get("c", {"codec": "NONE"}), parts, _DTYPES[m["dtype"]], m["shape"]))
     return header, tensors
 
 
@@ -87,7 +86,7 @@ class _Conn(socketserver.BaseRequestHandler):
     def handle(self) -> None:
         handler = self.server.rpc_handler  # type: ignore[attr-defined]
         sock: socket.socket = self.request
-        stream = None
+        stream, stream_codec = None, None
         try:
             while True:
                 try:
@@ -96,24 +95,29 @@ class _Conn(socketserver.BaseRequestHandler):
                     break
                 method = header.get("method")
                 try:
+                    meta = header.get("meta") or {}
+                    default_codec = getattr(handler, "compression", None)
                     if method == "rpc_inference":
                         if stream is None:
                             stream = handler.rpc_inference(header["uids"], header.get("meta", {}))
+                            stream_codec = meta.get("output_compression")  # sticky for the whole session
                         if header.get("close") or not tensors:
                             stream.close()
                             stream = None
                             send_message(sock, {"ok": True, "closed": True})
                             continue
                         out = stream.step(*tensors, metadata=header.get("meta", {}))
-                        send_message(sock, {"ok": True}, [out])
+                        send_message(sock, {"ok": True}, [out],
+                                     normalize_output_compression(meta.get("output_compression", stream_codec), 1, default_codec))
                     elif method == "rpc_info":
                         send_message(sock, {"ok": True, "meta": handler.rpc_info(header.get("uids"))})
                     elif method == "rpc_forward":
+                        codecs = normalize_output_compression(meta.get("output_compression"), 1, default_codec)
                         out = handler.rpc_forward(header["uids"], *tensors, metadata=header.get("meta", {}))
-                        send_message(sock, {"ok": True}, [out])
+                        send_message(sock, {"ok": True}, [out], codecs)
                     elif method == "rpc_backward":
-                        outs = handler.rpc_backward(header["uids"], *tensors, metadata=header.get("meta", {}))
-                        send_message(sock, {"ok": True}, list(outs))
+                        outs = list(handler.rpc_backward(header["uids"], *tensors, metadata=header.get("meta", {})))
+                        send_message(sock, {"ok": True}, outs, normalize_output_compression(meta.get("output_compression"), len(outs), default_codec))
                     elif method == "rpc_push":
                         handler.rpc_push(header["uids"], *tensors, metadata=header.get("meta", {}))
                         send_message(sock, {"ok": True})
@@ -171,13 +175,16 @@ def _raise_remote(header: Dict[str, Any]) -> None:
 
 
 class _RemoteStream:
-    def __init__(self, sock: socket.socket, uids: Sequence[str], metadata: dict):
+    def __init__(self, sock: socket.socket, uids: Sequence[str], metadata: dict, compression=None):
         self._sock, self._uids, self._open_meta, self._first, self.closed = sock, list(uids), metadata, True, False
+        self._compression = compression
 
     def step(self, *tensors: torch.Tensor, metadata: Optional[dict] = None) -> torch.Tensor:
         meta = dict(self._open_meta if self._first else {}, **(metadata or {}))
         self._first = False
-        send_message(self._sock, {"method": "rpc_inference", "uids": self._uids, "meta": meta}, tensors)
+        # only the hidden states (first tensor) are compressed; prompts / hypo_ids travel raw
+        codecs = [self._compression] + [None] * (len(tensors) - 1)
+        send_message(self._sock, {"method": "rpc_inference", "uids": self._uids, "meta": meta}, tensors, codecs)
         header, outs = recv_message(self._sock)
         if not header.get("ok"):
             _raise_remote(header)
@@ -199,8 +206,9 @@ class _RemoteStream:
 class RemoteHandlerProxy:
     """Client stub for a stage worker living in another process."""
 
-    def __init__(self, socket_path: str, connect_timeout: float = 5.0, request_timeout: float = 180.0):
+    def __init__(self, socket_path: str, connect_timeout: float = 5.0, request_timeout: float = 180.0, compression=None):
         self.socket_path, self.connect_timeout, self.request_timeout = socket_path, connect_timeout, request_timeout
+        self.compression = compression  # codec for the activations this client sends (utils/compression.py)
 
     def _connect(self) -> socket.socket:
         s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
@@ -211,7 +219,7 @@ class RemoteHandlerProxy:
 
     def _call(self, header: Dict[str, Any], tensors: Sequence[torch.Tensor] = ()):
         with self._connect() as s:
-            send_message(s, header, tensors)
+            send_message(s, header, tensors, self.compression if header.get("method") in ("rpc_forward", "rpc_backward", "rpc_push") else None)
             reply, outs = recv_message(s)
         if not reply.get("ok"):
             _raise_remote(reply)
@@ -233,4 +241,4 @@ class RemoteHandlerProxy:
         self._call({"method": "rpc_push", "uids": list(uids), "meta": metadata or {}}, tensors)
 
     def rpc_inference(self, uids, metadata=None) -> _RemoteStream:
-        return _RemoteStream(self._connect(), uids, metadata or {})
+        return _RemoteStream(self._connect(), uids, metadata or {}, self.compression)

@@ -201,6 +201,7 @@ class TransformerConnectionHandler:
         self.request_timeout, self.session_timeout, self.step_timeout = request_timeout, session_timeout, step_timeout
         self.prioritizer = task_prioritizer or DummyTaskPrioritizer()
         self.quant_type = quant_type
+        self.compression = None  # default wire codec of the responses on the socket transport (utils/compression.py)
         self._sessions: Dict[str, InferenceStream] = {}
         self._sessions_lock = threading.Lock()
 

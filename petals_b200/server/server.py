@@ -183,6 +183,7 @@ class Server:
                 expiration=self.expiration, request_timeout=self.request_timeout, session_timeout=self.session_timeout,
                 step_timeout=self.step_timeout, stats_report_interval=self.stats_report_interval, peer_id=self.peer_id,
                 use_cuda_graphs=self.use_cuda_graphs, force_oracle=self.force_oracle)
+            self.module_container.handler.compression = self.compression
             try:
                 self.module_container.ready.wait()
                 while not self.stop.is_set():

@@ -20,14 +20,16 @@ def _spawn(args, log):
     return subprocess.Popen([sys.executable, "-m", *args], stdout=log, stderr=subprocess.STDOUT, env=env, cwd=ROOT)
 
 
-@pytest.mark.parametrize("family", ["bloom"])
-def test_two_server_processes(family, tmp_path):
+@pytest.mark.parametrize("family,compression,atol", [("bloom", None, 1e-3), ("llama", "FLOAT16", 3e-2)])
+def test_two_server_processes(family, compression, atol, tmp_path):
     path = checkpoint(family)
     rendezvous = str(tmp_path / "swarm")
     subprocess.run([sys.executable, "-m", "petals.cli.run_dht", "--rendezvous", rendezvous, "--once"], check=True, cwd=ROOT,
                    env=dict(os.environ, PYTHONPATH=ROOT))
     logs = [open(tmp_path / f"server{i}.log", "w") for i in range(2)]
     common = ["--initial_peers", rendezvous, "--torch_dtype", "float32", "--device", "cpu", "--throughput", "1", "--update_period", "1"]
+    if compression:  # the servers answer over the socket transport in this wire codec (utils/compression.py)
+        common += ["--compression", compression]
     procs = [_spawn(["petals.cli.run_server", path, "--block_indices", "0:2", "--peer_id", "stage0", *common], logs[0]),
              _spawn(["petals.cli.run_server", path, "--block_indices", "2:4", "--peer_id", "stage1", "--attn_cache_tokens", "2048",
                      "--max_chunk_size_bytes", "1024", *common], logs[1])]  # tiny chunk size => chunked prefill is exercised
@@ -48,7 +50,8 @@ def test_two_server_processes(family, tmp_path):
                 peers = [s.span.peer_id for s in sess._server_sessions]
             step = model.lm_head(model.model.final_norm(torch.cat(outs, 1)))
         assert peers == ["stage0", "stage1"]
-        assert torch.allclose(parallel, local, atol=1e-3) and torch.allclose(step, local, atol=1e-3)
+        assert torch.allclose(parallel, local, atol=atol) and torch.allclose(step, local, atol=atol)
+        assert (compression is None) or not torch.equal(parallel, local)
         # gradients flow through other processes too
         x = torch.randn(2, 3, config.hidden_size, requires_grad=True)
         model.model.layers(x).sum().backward()
