@@ -71,19 +71,60 @@ def load_client_tensors(model_name_or_path: str, names: Dict[str, str]) -> Dict[
     return out
 
 
+# Trainable client-side state that a fine-tuning run adds on top of the checkpoint's own tensors: canonical key ->
+# name in the saved file (the reference stores them as ordinary parameters of the HF module, src/petals/client/ptune.py:24-39,
+# models/llama/model.py:157-174; they "may be missing at load", ptune.py:22).
+TRAINABLE_STATE_NAMES = {"prompts": "prompt_embeddings.weight", "deep_prompts": "intermediate_prompt_embeddings.weight",
+                         "score": "score.weight"}
+
+
+def client_state_names(config) -> Dict[str, str]:
+    """Checkpoint names of everything the client owns: the family's embeddings / final norm / head plus the trainable
+    prompt-tuning and classifier tensors (stored under the backbone's own prefix, e.g. ``model.prompt_embeddings.weight``)."""
+    names = dict(type(config).client_weight_names)
+    embed = names.get("embed", "")
+    prefix = embed.split(".")[0] + "." if embed.count(".") >= 2 else ""
+    names["prompts"] = prefix + TRAINABLE_STATE_NAMES["prompts"]
+    names["deep_prompts"] = prefix + TRAINABLE_STATE_NAMES["deep_prompts"]
+    names["score"] = TRAINABLE_STATE_NAMES["score"]
+    return names
+
+
+def _load_trainable(param: torch.Tensor, t: Dict[str, torch.Tensor], key: str) -> None:
+    if key in t:
+        if tuple(t[key].shape) != tuple(param.shape):
+            raise ValueError(f"checkpoint tensor {key!r} has shape {tuple(t[key].shape)}, the model expects {tuple(param.shape)} "
+                             f"(was it saved with another pre_seq_len / tuning_mode / num_labels?)")
+        with torch.no_grad():
+            param.copy_(t[key].to(param.dtype))
+
+
 class FromPretrainedMixin:
+    def save_pretrained(self, path: str) -> None:
+        """Write ``config.json`` + ``model.safetensors`` with the *client* tensors only (embeddings, final norm, head,
+        trained prompts / classifier); ``from_pretrained(path)`` resumes from it while the blocks stay remote
+        (trainable state is ordinary client parameters saved with save_pretrained)."""
+        from petals_b200.utils.safetensors_io import save_file
+
+        os.makedirs(path, exist_ok=True)
+        self.config.save_pretrained(path)
+        names = client_state_names(self.config)
+        state = {names[k]: v.detach().to("cpu").contiguous() for k, v in self.client_state().items()}
+        save_file(state, os.path.join(path, "model.safetensors"), metadata={"format": "pt"})
+
     @classmethod
     def from_pretrained(cls, model_name_or_path, *args, torch_dtype=None, dht=None, device=None, **kwargs):
         config = cls.config_class.from_pretrained(model_name_or_path, **kwargs)
         if torch_dtype is None or torch_dtype == "auto":
             torch_dtype = config.torch_dtype if isinstance(getattr(config, "torch_dtype", None), torch.dtype) else torch.float32
         model = cls(config, dht=dht)
-        tensors = load_client_tensors(model_name_or_path, type(config).client_weight_names)
+        tensors = load_client_tensors(model_name_or_path, client_state_names(config))
         missing = model.load_client_state(tensors)
         if missing:
             logger.info(f"Client parameters initialised randomly (not in checkpoint): {sorted(missing)}")
         model = model.to(torch_dtype)
         model.float_trainable_()
+        model.load_trainable_state(tensors)  # again, now in fp32: the cast to the model dtype above must not round them
         if device is not None:
             model = model.to(device)
         model.eval()
@@ -136,7 +177,27 @@ class DistributedModelBase(nn.Module, PTuneMixin, FromPretrainedMixin):
                     self.embed_layernorm.requires_grad_(False)
                 else:
                     missing.add("embed_ln")
+        self.load_trainable_state(t)
         return missing
+
+    def load_trainable_state(self, t: Dict[str, torch.Tensor]) -> None:
+        if hasattr(self, "prompt_embeddings"):
+            _load_trainable(self.prompt_embeddings.weight, t, "prompts")
+        if hasattr(self, "intermediate_prompt_embeddings"):
+            _load_trainable(self.intermediate_prompt_embeddings.weight, t, "deep_prompts")
+
+    def client_state(self) -> Dict[str, torch.Tensor]:
+        out = {"embed": self.embed_tokens.weight, "norm_w": self.norm_weight}
+        if self.norm_bias is not None:
+            out["norm_b"] = self.norm_bias
+        if self.has_embedding_layernorm:
+            out["embed_ln_w"], out["embed_ln_b"] = self.embed_layernorm.weight, self.embed_layernorm.bias
+        if hasattr(self, "prompt_embeddings"):
+            out["prompts"] = self.prompt_embeddings.weight
+        if hasattr(self, "intermediate_prompt_embeddings"):
+            out["deep_prompts"] = self.intermediate_prompt_embeddings.weight
+        names = type(self.config).client_weight_names
+        return {k: v for k, v in out.items() if k in names or k in TRAINABLE_STATE_NAMES}
 
     def float_trainable_(self) -> None:
         """Prompt-tuning parameters stay fp32 regardless of the model dtype (reference ptune.py:24-39)."""
@@ -241,6 +302,15 @@ class DistributedModelForCausalLM(nn.Module, RemoteGenerationMixin, FromPretrain
             self.lm_head.weight.data = t["head"].clone()
         return missing
 
+    def load_trainable_state(self, t: Dict[str, torch.Tensor]) -> None:
+        self.model.load_trainable_state(t)
+
+    def client_state(self) -> Dict[str, torch.Tensor]:
+        out = self.model.client_state()
+        if not getattr(self.config, "tie_word_embeddings", False) and "head" in type(self.config).client_weight_names:
+            out["head"] = self.lm_head.weight
+        return out
+
     def float_trainable_(self) -> None:
         self.model.float_trainable_()
 
@@ -313,7 +383,16 @@ class DistributedModelForSequenceClassification(nn.Module, FromPretrainedMixin):
         self.score = nn.Linear(config.hidden_size, self.num_labels, bias=False)
 
     def load_client_state(self, t):
-        return self.model.load_client_state(t)
+        missing = self.model.load_client_state(t)
+        _load_trainable(self.score.weight, t, "score")
+        return missing
+
+    def load_trainable_state(self, t: Dict[str, torch.Tensor]) -> None:
+        self.model.load_trainable_state(t)
+        _load_trainable(self.score.weight, t, "score")
+
+    def client_state(self) -> Dict[str, torch.Tensor]:
+        return dict(self.model.client_state(), score=self.score.weight)
 
     def float_trainable_(self) -> None:
         self.model.float_trainable_()
