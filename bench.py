@@ -185,7 +185,7 @@ def run_single_gpu(args) -> None:
         "value": round(value, 3), "unit": "tokens/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",
         "data": "synthetic token ids; random-init weights of the named architecture",
-        "config": {"model": args.model, "global_batch": 1, "seq_len": args.seq_len, "parallelism": "pp1 (1 stage x 80 blocks)",
+        "config": {"model": args.model, "global_batch": 1, "seq_len": args.seq_len, "parallelism": f"pp1 (1 stage x {n_layers} blocks)",
                    "l2": "each step streams the full weight set (>> 126 MB L2): inputs larger than L2", "build_s": round(build_s, 1)},
         "clocks": clocks,
         "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8},

@@ -17,13 +17,13 @@ from petals_b200.utils.auto_config import (AutoDistributedConfig, AutoDistribute
 _ALIASES = [
     "constants", "data_structures", "dht_utils",
     "client", "client.config", "client.inference_session", "client.remote_sequential", "client.sequential_autograd",
-    "client.remote_forward_backward", "client.remote_generation", "client.lm_head", "client.ptune", "client.routing",
+    "client.remote_forward_backward", "client.remote_generation", "client.lm_head", "client.ptune", "client.from_pretrained", "client.routing",
     "client.routing.sequence_manager", "client.routing.sequence_info", "client.routing.spending_policy",
     "server", "server.server", "server.backend", "server.handler", "server.block_functions", "server.task_pool",
     "server.task_prioritizer", "server.memory_cache", "server.block_selection", "server.throughput", "server.block_utils",
     "server.from_pretrained", "server.reachability",
     "utils", "utils.auto_config", "utils.convert_block", "utils.cuda_graphs", "utils.peft", "utils.packaging", "utils.misc",
-    "utils.disk_cache", "utils.dht", "utils.ping", "utils.logging", "utils.version", "utils.hf_auth", "utils.random", "utils.asyncio",
+    "utils.disk_cache", "utils.compression", "utils.dht", "utils.ping", "utils.logging", "utils.version", "utils.hf_auth", "utils.random", "utils.asyncio",
     "models", "models.llama", "models.bloom", "models.falcon", "models.mixtral",
 ]
 for _name in _ALIASES:
