@@ -39,6 +39,11 @@ const void* pb_st_data(void* h);                             // base of the tens
 int pb_st_read(void* h, int idx, void* dst, int64_t cap, int threads);
 const char* pb_st_error(void);
 
+// ---- framed socket I/O of the control transport (scatter-gather send, receive into place; no GIL) ---------------
+// timeout_s < 0 blocks forever. Return 0 ok, -ETIMEDOUT, other -errno; recv: -1 = peer closed the connection.
+int pb_sock_send_frames(int fd, const void* const* bufs, const int64_t* lens, int n, double timeout_s);
+int pb_sock_recv_exact(int fd, void* dst, int64_t n, double timeout_s);
+
 #ifdef __cplusplus
 }
 #endif

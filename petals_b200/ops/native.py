@@ -193,6 +193,8 @@ def _declare_rt(rt: C.CDLL) -> None:
     rt.pb_st_data.argtypes = [vp]; rt.pb_st_data.restype = vp
     rt.pb_st_read.argtypes = [vp, ci, vp, C.c_int64, ci]; rt.pb_st_read.restype = ci
     rt.pb_st_error.argtypes = []; rt.pb_st_error.restype = C.c_char_p
+    rt.pb_sock_send_frames.argtypes = [ci, C.POINTER(vp), C.POINTER(C.c_int64), ci, cd]; rt.pb_sock_send_frames.restype = ci
+    rt.pb_sock_recv_exact.argtypes = [ci, vp, C.c_int64, cd]; rt.pb_sock_recv_exact.restype = ci
 
 
 def _ensure_built() -> None:

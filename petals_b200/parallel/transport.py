@@ -16,6 +16,8 @@ src/petals/client/inference_session.py:198-207).
 """
 from __future__ import annotations
 
+import ctypes as C
+import errno
 import os
 import socket
 import socketserver
@@ -37,6 +39,33 @@ _DTYPE_NAMES = {torch.float32: "f32", torch.float16: "f16", torch.bfloat16: "bf1
 _DTYPES = {v: k for k, v in _DTYPE_NAMES.items()}
 
 
+def _native_io():
+    """The C++ socket loops (csrc/runtime/socket_io.cpp); ``PETALS_B200_PY_TRANSPORT=1`` forces the pure-Python path."""
+    if os.environ.get("PETALS_B200_PY_TRANSPORT", "0") == "1":
+        return None
+    try:
+        from petals_b200.ops import native
+
+        return native.rt()
+    except Exception:  # noqa: BLE001 - no compiler on this host: the Python loops below do the same job
+        return None
+
+
+def _raise_io(rc: int, what: str) -> None:
+    if rc == -1:
+        raise ConnectionError("peer closed the connection")
+    if rc == -errno.ETIMEDOUT:
+        raise socket.timeout(f"{what} timed out")
+    if rc in (-errno.EPIPE, -errno.ECONNRESET, -errno.EBADF, -errno.ENOTCONN):
+        raise ConnectionError(f"{what}: {os.strerror(-rc)}")
+    raise OSError(-rc, f"{what}: {os.strerror(-rc)}")
+
+
+def _timeout_of(sock: socket.socket) -> float:
+    t = sock.gettimeout()
+    return -1.0 if t is None else float(t)
+
+
 def _recv_exact(sock: socket.socket, n: int) -> bytes:
     chunks, got = [], 0
     while got < n:
@@ -48,6 +77,24 @@ def _recv_exact(sock: socket.socket, n: int) -> bytes:
     return b"".join(chunks)
 
 
+def _recv_into(sock: socket.socket, n: int) -> torch.Tensor:
+    """n payload bytes -> a fresh flat uint8 tensor, received in place (no intermediate bytes objects)."""
+    buf = torch.empty(n, dtype=torch.uint8)
+    io = _native_io()
+    if io is not None:
+        rc = io.pb_sock_recv_exact(sock.fileno(), buf.data_ptr(), n, _timeout_of(sock))
+        if rc != 0:
+            _raise_io(rc, "recv")
+        return buf
+    view, got = memoryview(buf.numpy()), 0
+    while got < n:
+        k = sock.recv_into(view[got:], n - got)
+        if k == 0:
+            raise ConnectionError("peer closed the connection")
+        got += k
+    return buf
+
+
 def send_message(sock: socket.socket, header: Dict[str, Any], tensors: Sequence[torch.Tensor] = (), compression=None) -> None:
     """``compression``: one codec for every tensor or a list with one entry per tensor (utils/compression.py);
     integer/bool tensors and empty tensors always travel raw."""
@@ -57,12 +104,23 @@ def send_message(sock: socket.socket, header: Dict[str, Any], tensors: Sequence[
         if t is None:
             t = torch.empty(0)  # an empty tensor means "argument absent" (utils/misc.py DUMMY convention)
         cmeta, parts = encode_tensor(t, codec)
-        metas.append({"dtype": _DTYPE_NAMES[t.dtype], "shape": list(t.shape), "nbytes": sum(len(b) for b in parts),
-                      "parts": [len(b) for b in parts], "c": cmeta})
+        metas.append({"dtype": _DTYPE_NAMES[t.dtype], "shape": list(t.shape), "nbytes": sum(b.numel() for b in parts),
+                      "parts": [b.numel() for b in parts], "c": cmeta})
         blobs.extend(parts)
     header = dict(header, tensors=metas)
     payload = msgpack.packb(header, use_bin_type=True)
-    sock.sendall(struct.pack("<I", len(payload)) + payload + b"".join(blobs))
+    head = struct.pack("<I", len(payload)) + payload
+    io = _native_io()
+    if io is None:
+        sock.sendall(head + b"".join(b.numpy().tobytes() for b in blobs if b.numel()))
+        return
+    blobs = [b for b in blobs if b.numel()]  # the tensors stay referenced (alive) until sendmsg has consumed them
+    n = 1 + len(blobs)
+    ptrs = (C.c_void_p * n)(C.cast(C.c_char_p(head), C.c_void_p), *[b.data_ptr() for b in blobs])
+    lens = (C.c_int64 * n)(len(head), *[b.numel() for b in blobs])
+    rc = io.pb_sock_send_frames(sock.fileno(), ptrs, lens, n, _timeout_of(sock))
+    if rc != 0:
+        _raise_io(rc, "send")
 
 
 def recv_message(sock: socket.socket) -> Tuple[Dict[str, Any], List[torch.Tensor]]:
@@ -70,7 +128,7 @@ def recv_message(sock: socket.socket) -> Tuple[Dict[str, Any], List[torch.Tensor
     header = msgpack.unpackb(_recv_exact(sock, n), raw=False)
     tensors = []
     for m in header.get("tensors", []):
-        parts = [_recv_exact(sock, k) if k else b"" for k in m.get("parts", [m["nbytes"]])]
+        parts = [_recv_into(sock, k) for k in m.get("parts", [m["nbytes"]])]
         tensors.append(decode_tensor(m.get("c", {"codec": "NONE"}), parts, _DTYPES[m["dtype"]], m["shape"]))
     return header, tensors
 

@@ -17,7 +17,7 @@ from the definitions, with torch ops only:
 * ``BLOCKWISE_8BIT`` – blocks of 4096 values scaled by their absmax, signed 8-bit code on a quadratic grid
                         (dense near zero, where hidden states live).
 
-``encode`` returns ``(meta, [byte blobs])`` and ``decode`` inverts it; both are exact inverses for ``NONE`` and
+``encode`` returns ``(meta, [flat uint8 tensors])`` and ``decode`` inverts it; both are exact inverses for ``NONE`` and
 lossy within the bounds tested in tests/test_compression.py otherwise.
 """
 from __future__ import annotations
@@ -62,15 +62,23 @@ def parse_compression(spec: CodecSpec) -> CompressionType:
         raise ValueError(f"unknown compression {spec!r}; choose from {[c.name for c in CompressionType]}") from None
 
 
-def _raw(t: torch.Tensor) -> bytes:
-    t = t.detach().to("cpu").contiguous()
-    return t.view(torch.uint8).numpy().tobytes() if t.numel() else b""
+_EMPTY = torch.empty(0, dtype=torch.uint8)
 
 
-def _from_raw(raw: bytes, dtype: torch.dtype, shape: Sequence[int]) -> torch.Tensor:
-    if not raw:
+def _raw(t: torch.Tensor) -> torch.Tensor:
+    """The tensor's bytes as a flat uint8 CPU view (no copy for contiguous CPU tensors): the transport hands the storage
+    pointer to a scatter-gather ``sendmsg`` instead of building a ``bytes`` object."""
+    if t.numel() == 0:
+        return _EMPTY
+    return t.detach().to("cpu").contiguous().reshape(-1).view(torch.uint8)
+
+
+def _from_raw(raw, dtype: torch.dtype, shape: Sequence[int]) -> torch.Tensor:
+    if isinstance(raw, (bytes, bytearray, memoryview)):
+        raw = torch.frombuffer(bytearray(raw), dtype=torch.uint8) if len(raw) else _EMPTY
+    if raw.numel() == 0:
         return torch.empty(list(shape), dtype=dtype)
-    return torch.frombuffer(bytearray(raw), dtype=torch.uint8).view(dtype).reshape(list(shape))
+    return raw.view(dtype).reshape(list(shape))
 
 
 def _codebook_from_buckets(x: torch.Tensor, idx: torch.Tensor, fallback: torch.Tensor) -> torch.Tensor:
@@ -100,8 +108,8 @@ def _block_grid() -> torch.Tensor:
     return _BLOCK_GRID
 
 
-def encode(t: torch.Tensor, compression: CodecSpec = None) -> Tuple[Dict[str, Any], List[bytes]]:
-    """-> (meta, blobs). Non-float and empty tensors always travel as ``NONE``."""
+def encode(t: torch.Tensor, compression: CodecSpec = None) -> Tuple[Dict[str, Any], List[torch.Tensor]]:
+    """-> (meta, blobs); every blob is a flat uint8 CPU tensor. Non-float and empty tensors always travel as ``NONE``."""
     codec = parse_compression(compression)
     t = t.detach()
     if codec != CompressionType.NONE and (t.dtype not in _DTYPE_NAMES or t.numel() == 0):
@@ -153,7 +161,7 @@ def encode(t: torch.Tensor, compression: CodecSpec = None) -> Tuple[Dict[str, An
     raise AssertionError(codec)
 
 
-def decode(meta: Dict[str, Any], blobs: Sequence[bytes], dtype: torch.dtype, shape: Sequence[int]) -> torch.Tensor:
+def decode(meta: Dict[str, Any], blobs: Sequence[torch.Tensor], dtype: torch.dtype, shape: Sequence[int]) -> torch.Tensor:
     codec = parse_compression(meta.get("codec", "NONE"))
     if codec == CompressionType.NONE:
         return _from_raw(blobs[0], dtype, shape)
@@ -193,7 +201,7 @@ def roundtrip(t: torch.Tensor, compression: CodecSpec) -> torch.Tensor:
 
 
 def compressed_nbytes(t: torch.Tensor, compression: CodecSpec) -> int:
-    return sum(len(b) for b in encode(t, compression)[1])
+    return sum(b.numel() for b in encode(t, compression)[1])
 
 
 def normalize_output_compression(spec: Any, n_outputs: int, default: CodecSpec = None) -> List[CompressionType]:
