@@ -46,10 +46,12 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--num_blocks", type=int, default=None, help="number of transformer blocks to serve")
     p.add_argument("--block_indices", type=str, default=None, help="specific block indices to serve, e.g. 0:40")
     p.add_argument("--dht_prefix", type=str, default=None)
-    p.add_argument("--port", type=int, default=None, help="(ignored)")
-    for name in ("--host_maddrs", "--announce_maddrs"):
-        p.add_argument(name, nargs="+", default=None, help="(ignored)")
-    p.add_argument("--public_ip", type=str, default=None, help="(ignored)")
+    p.add_argument("--port", type=int, default=None, help="(ignored: RPC ports are picked by the OS and announced through the registry)")
+    p.add_argument("--host_maddrs", nargs="+", default=None,
+                   help="multi-box swarms (tcp:// or /ip4/ initial peers): interface to serve RPCs on, e.g. /ip4/0.0.0.0/tcp/0 (default)")
+    p.add_argument("--announce_maddrs", nargs="+", default=None,
+                   help="multi-box swarms: address other peers should use to reach this server, e.g. /ip4/10.0.0.5/tcp/0")
+    p.add_argument("--public_ip", type=str, default=None, help="multi-box swarms: shorthand for --announce_maddrs /ip4/<ip>/tcp/0")
     p.add_argument("--no_auto_relay", action="store_false", dest="use_auto_relay")
     p.add_argument("--daemon_startup_timeout", type=float, default=60)
     p.add_argument("--compression", type=str, default="NONE", help="wire codec for the hidden states this server returns over the socket transport: NONE, FLOAT16, MEANSTD_16BIT, "
@@ -103,7 +105,7 @@ def main(argv=None) -> None:
     args["converted_model_name_or_path"] = args.pop("model") or args["converted_model_name_or_path"]
     if not args["converted_model_name_or_path"]:
         parser.error("a model name or path is required")
-    for ignored in ("port", "host_maddrs", "announce_maddrs", "public_ip", "increase_file_limit", "identity_path", "daemon_startup_timeout"):
+    for ignored in ("port", "increase_file_limit", "identity_path", "daemon_startup_timeout"):
         args.pop(ignored, None)
     if args.pop("new_swarm"):
         args["initial_peers"] = []

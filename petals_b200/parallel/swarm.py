@@ -6,7 +6,9 @@ model — key = block uid, subkey = peer id, value = ``ServerInfo.to_tuple()``, 
 
 * ``Swarm``      — in-process (default for single-process serving, benchmarks and most tests);
 * ``FileSwarm``  — a rendezvous directory shared by several OS processes (``run_server`` + clients); peers
-  are reached through Unix-socket RPC (parallel/transport.py).
+  are reached through Unix-socket RPC (parallel/transport.py);
+* ``TcpSwarm``   — (parallel/registry.py) a registry process on the network + TCP endpoints, for swarms that span
+  several boxes, addressed like the reference's bootstrap peers (``/ip4/<host>/tcp/<port>`` or ``tcp://host:port``).
 
 ``resolve_swarm(initial_peers)`` maps the reference's ``initial_peers`` argument onto these.
 """
@@ -195,6 +197,17 @@ def resolve_swarm(initial_peers: Union[None, str, Swarm, Sequence[Union[str, Swa
         return first
     if first.startswith(INPROC_SCHEME):
         return Swarm.named(first[len(INPROC_SCHEME):])
+    from petals_b200.parallel.transport import format_address, is_network_address, parse_address
+
+    if is_network_address(first):  # tcp://host:port or /ip4/<host>/tcp/<port>[/p2p/..]: a registry on the network
+        from petals_b200.parallel.registry import TcpSwarm
+
+        _, host, port = parse_address(first)
+        key = "tcp:" + format_address(host, port)
+        with _named_lock:
+            if key in _named:
+                return _named[key]
+        return TcpSwarm(first)
     key = "file:" + os.path.abspath(first)
     with _named_lock:
         if key in _named:

@@ -34,6 +34,49 @@ from petals_b200.utils.logging import get_logger
 
 logger = get_logger(__name__)
 
+def parse_address(address: str) -> Tuple[str, ...]:
+    """``/path/to.sock`` -> ("unix", path); ``tcp://host:port`` or a libp2p-style multiaddr
+    (``/ip4/10.0.0.1/tcp/31337[/p2p/<id>]``, ``/dns/name/tcp/31337``; the form the reference prints and accepts as
+    ``--initial_peers``) -> ("tcp", host, port)."""
+    if address.startswith("tcp://"):
+        host, _, port = address[len("tcp://"):].rpartition(":")
+        return ("tcp", host.strip("[]") or "127.0.0.1", int(port))
+    parts = address.strip("/").split("/")
+    if len(parts) >= 4 and parts[0] in ("ip4", "ip6", "dns", "dns4", "dns6") and parts[2] == "tcp":
+        return ("tcp", parts[1], int(parts[3]))
+    return ("unix", address)
+
+
+def is_network_address(address: str) -> bool:
+    return isinstance(address, str) and parse_address(address)[0] == "tcp"
+
+
+def format_address(host: str, port: int) -> str:
+    return f"tcp://{host}:{port}"
+
+
+def to_multiaddr(address: str) -> str:
+    kind, *rest = parse_address(address)
+    if kind != "tcp":
+        return address
+    host, port = rest
+    proto = "ip4" if host.replace(".", "").isdigit() else ("ip6" if ":" in host else "dns")
+    return f"/{proto}/{host}/tcp/{port}"
+
+
+def open_connection(address: str, connect_timeout: float, request_timeout: Optional[float]) -> socket.socket:
+    kind, *rest = parse_address(address)
+    if kind == "tcp":
+        s = socket.create_connection((rest[0], rest[1]), timeout=connect_timeout)
+        s.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)  # one decode step = one small frame each way
+    else:
+        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        s.settimeout(connect_timeout)
+        s.connect(rest[0])
+    s.settimeout(request_timeout)
+    return s
+
+
 _DTYPE_NAMES = {torch.float32: "f32", torch.float16: "f16", torch.bfloat16: "bf16", torch.int64: "i64", torch.int32: "i32",
                 torch.uint8: "u8", torch.bool: "b1", torch.float64: "f64"}
 _DTYPES = {v: k for k, v in _DTYPE_NAMES.items()}
@@ -140,7 +183,24 @@ class RemoteError(RuntimeError):
 # ---------------------------------------------------------------------------------------------------------
 # server side
 # ---------------------------------------------------------------------------------------------------------
-class _Conn(socketserver.BaseRequestHandler):
+class TrackedConn(socketserver.BaseRequestHandler):
+    """Registers the connection with its server so that ``RpcServer.shutdown`` can drop established connections too
+    (a stopped stage must not keep answering on old streams; clients then fail over like after a crash)."""
+
+    def setup(self) -> None:
+        conns = getattr(self.server, "open_conns", None)
+        if conns is not None:
+            with self.server.open_conns_lock:  # type: ignore[attr-defined]
+                conns.add(self.request)
+
+    def finish(self) -> None:
+        conns = getattr(self.server, "open_conns", None)
+        if conns is not None:
+            with self.server.open_conns_lock:  # type: ignore[attr-defined]
+                conns.discard(self.request)
+
+
+class _Conn(TrackedConn):
     def handle(self) -> None:
         handler = self.server.rpc_handler  # type: ignore[attr-defined]
         sock: socket.socket = self.request
@@ -181,6 +241,8 @@ class _Conn(socketserver.BaseRequestHandler):
                         send_message(sock, {"ok": True})
                     elif method == "rpc_ping":
                         send_message(sock, {"ok": True})
+                    elif method == "rpc_check":
+                        send_message(sock, {"ok": True, "meta": bool(handler.rpc_check(meta["check_peer"], float(meta.get("wait_timeout", 5.0))))})
                     else:
                         send_message(sock, {"ok": False, "error": f"unknown method {method!r}", "etype": "ValueError"})
                 except Exception as e:  # noqa: BLE001 - report to the caller, keep serving
@@ -196,15 +258,38 @@ class _ThreadedUnixServer(socketserver.ThreadingMixIn, socketserver.UnixStreamSe
     allow_reuse_address = True
 
 
-class RpcServer:
-    """Serves a handler on a Unix socket (one thread per connection = one per in-flight request/stream)."""
+class _ThreadedTcpServer(socketserver.ThreadingMixIn, socketserver.TCPServer):
+    daemon_threads = True
+    allow_reuse_address = True
+    request_queue_size = 128
 
-    def __init__(self, handler, socket_path: str):
-        if os.path.exists(socket_path):
-            os.unlink(socket_path)
-        self.socket_path = socket_path
-        self._server = _ThreadedUnixServer(socket_path, _Conn)
+    def get_request(self):
+        conn, addr = super().get_request()
+        conn.setsockopt(socket.IPPROTO_TCP, socket.TCP_NODELAY, 1)
+        return conn, addr
+
+
+class RpcServer:
+    """Serves a handler on a Unix socket or on TCP (one thread per connection = one per in-flight request/stream).
+
+    ``address``: a filesystem path, or ``tcp://host:port`` (port 0 = pick a free one; ``self.address`` is the bound one).
+    ``conn_class`` lets other services (the swarm registry) reuse the framing with their own dispatcher."""
+
+    def __init__(self, handler, address: str, conn_class=None):
+        kind, *rest = parse_address(address)
+        self.socket_path = None
+        if kind == "tcp":
+            self._server = _ThreadedTcpServer((rest[0], rest[1]), conn_class or _Conn)
+            host, port = self._server.server_address[:2]
+            self.address = format_address(rest[0] if rest[0] not in ("", "0.0.0.0", "::") else host, port)
+            self.port = port
+        else:
+            if os.path.exists(address):
+                os.unlink(address)
+            self.socket_path = self.address = address
+            self._server = _ThreadedUnixServer(address, conn_class or _Conn)
         self._server.rpc_handler = handler  # type: ignore[attr-defined]
+        self._server.open_conns, self._server.open_conns_lock = set(), threading.Lock()  # type: ignore[attr-defined]
         self._thread = threading.Thread(target=self._server.serve_forever, kwargs=dict(poll_interval=0.1), daemon=True)
 
     def start(self) -> None:
@@ -213,7 +298,14 @@ class RpcServer:
     def shutdown(self) -> None:
         self._server.shutdown()
         self._server.server_close()
-        if os.path.exists(self.socket_path):
+        with self._server.open_conns_lock:  # type: ignore[attr-defined]
+            conns = list(self._server.open_conns)  # type: ignore[attr-defined]
+        for c in conns:
+            try:
+                c.shutdown(socket.SHUT_RDWR)
+            except OSError:
+                pass
+        if self.socket_path is not None and os.path.exists(self.socket_path):
             os.unlink(self.socket_path)
 
 
@@ -262,18 +354,14 @@ class _RemoteStream:
 
 
 class RemoteHandlerProxy:
-    """Client stub for a stage worker living in another process."""
+    """Client stub for a stage worker living in another process (``socket_path``: unix path or ``tcp://host:port``)."""
 
     def __init__(self, socket_path: str, connect_timeout: float = 5.0, request_timeout: float = 180.0, compression=None):
         self.socket_path, self.connect_timeout, self.request_timeout = socket_path, connect_timeout, request_timeout
         self.compression = compression  # codec for the activations this client sends (utils/compression.py)
 
     def _connect(self) -> socket.socket:
-        s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        s.settimeout(self.connect_timeout)
-        s.connect(self.socket_path)
-        s.settimeout(self.request_timeout)
-        return s
+        return open_connection(self.socket_path, self.connect_timeout, self.request_timeout)
 
     def _call(self, header: Dict[str, Any], tensors: Sequence[torch.Tensor] = ()):
         with self._connect() as s:
@@ -288,6 +376,9 @@ class RemoteHandlerProxy:
 
     def rpc_ping(self) -> None:
         self._call({"method": "rpc_ping"})
+
+    def rpc_check(self, check_peer: str, wait_timeout: float = 5.0) -> bool:
+        return bool(self._call({"method": "rpc_check", "meta": {"check_peer": check_peer, "wait_timeout": wait_timeout}})[0]["meta"])
 
     def rpc_forward(self, uids, *tensors, metadata=None) -> torch.Tensor:
         return self._call({"method": "rpc_forward", "uids": list(uids), "meta": metadata or {}}, tensors)[1][0]

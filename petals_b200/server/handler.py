@@ -287,6 +287,15 @@ class TransformerConnectionHandler:
         except Exception as e:  # noqa: BLE001 - pushing is an optimisation; the client resends anyway
             logger.debug(f"failed to push outputs to {next_servers[0]}: {e!r}")
 
+    def rpc_check(self, check_peer: str, wait_timeout: float = 5.0) -> bool:
+        """Peer-assisted reachability (reference src/petals/server/reachability.py:55-164 ``ReachabilityProtocol.rpc_check``):
+        can *this* process dial ``check_peer``'s announced endpoint?  The address is looked up afresh in the registry."""
+        from petals_b200.utils.ping import ping
+
+        if hasattr(self.swarm, "forget"):
+            self.swarm.forget(check_peer)
+        return ping(check_peer, self.swarm, wait_timeout=wait_timeout) != float("inf")
+
     def rpc_ping(self) -> None:
         return None
 

@@ -31,6 +31,7 @@ from petals_b200.server.from_pretrained import load_pretrained_block
 from petals_b200.server.handler import TransformerConnectionHandler
 from petals_b200.server.memory_cache import MemoryCache
 from petals_b200.server.task_pool import PrioritizedTaskPool, Runtime
+from petals_b200.server.reachability import validate_direct_reachability
 from petals_b200.server.throughput import get_server_throughput
 from petals_b200.utils.auto_config import AutoDistributedConfig
 from petals_b200.utils.convert_block import QuantType, check_device_balance, convert_block, resolve_quant_type
@@ -65,11 +66,13 @@ class Server:
                  quant_type: Optional[QuantType] = None, tensor_parallel_devices: Optional[Sequence[torch.device]] = None,
                  skip_reachability_check: bool = False, reachable_via_relay: Optional[bool] = None, use_relay: bool = True,
                  use_auto_relay: bool = True, adapters: Sequence[str] = (), peer_id: Optional[str] = None,
-                 use_cuda_graphs: bool = True, force_oracle: bool = False, **kwargs):
+                 use_cuda_graphs: bool = True, force_oracle: bool = False, host_maddrs: Optional[Sequence[str]] = None,
+                 announce_maddrs: Optional[Sequence[str]] = None, public_ip: Optional[str] = None, **kwargs):
         if kwargs:
             logger.debug(f"ignoring networking options that have no meaning on one box: {sorted(kwargs)}")
         self.converted_model_name_or_path = converted_model_name_or_path
         self.num_handlers, self.compression = num_handlers, compression
+        self.skip_reachability_check = skip_reachability_check
         self.stats_report_interval, self.update_period = stats_report_interval, update_period
         self.prefetch_batches, self.sender_threads = prefetch_batches, sender_threads
         self.revision, self.token, self.adapters = revision, token, tuple(adapters)
@@ -86,6 +89,15 @@ class Server:
         self.module_uids = [make_uid(self.dht_prefix, i) for i in range(self.block_config.num_hidden_layers)]
 
         self.dht: Swarm = resolve_swarm(initial_peers)
+        if hasattr(self.dht, "bind_host"):  # a network registry (parallel/registry.py): where to listen, what to announce
+            from petals_b200.parallel.transport import parse_address
+
+            if host_maddrs:
+                self.dht.bind_host = parse_address(host_maddrs[0])[1]
+            if announce_maddrs:
+                self.dht.announce_host = parse_address(announce_maddrs[0])[1]
+            elif public_ip:
+                self.dht.announce_host = public_ip
         if device is None:
             device = "cuda" if torch.cuda.is_available() else "cpu"
         device = torch.device(device)
@@ -186,6 +198,8 @@ class Server:
             self.module_container.handler.compression = self.compression
             try:
                 self.module_container.ready.wait()
+                if not self.skip_reachability_check:
+                    validate_direct_reachability(self.dht, self.peer_id)
                 while not self.stop.is_set():
                     timeout = random.random() * 2 * self.mean_balance_check_period
                     if self.stop.wait(timeout):
@@ -408,12 +422,17 @@ class ModuleAnnouncerThread(threading.Thread):
         while True:
             start = time.perf_counter()
             self.server_info.cache_tokens_left = (self.memory_cache.tokens_left * self.n_blocks) if self.memory_cache is not None else None
-            if self.server_info.state != ServerState.OFFLINE:
-                self._ping_next_servers()
-                self.server_info.next_pings = {p: r for p, r in self.ping_aggregator.to_dict().items()}
-            else:
-                self.server_info.next_pings = None
-            self._publish()
+            try:
+                if self.server_info.state != ServerState.OFFLINE:
+                    self._ping_next_servers()
+                    self.server_info.next_pings = {p: r for p, r in self.ping_aggregator.to_dict().items()}
+                else:
+                    self.server_info.next_pings = None
+                self._publish()
+                if self.server_info.state != ServerState.OFFLINE and hasattr(self.dht, "refresh_endpoint"):
+                    self.dht.refresh_endpoint(self.peer_id)  # a restarted network registry learns our address again
+            except ConnectionError as e:  # the registry of a multi-box swarm is away: keep serving, announce again later
+                logger.warning(f"could not announce to the swarm registry: {e}")
             if self.server_info.state == ServerState.OFFLINE:
                 break
             delay = self.update_period - (time.perf_counter() - start)

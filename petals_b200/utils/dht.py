@@ -25,9 +25,11 @@ def get_remote_module_infos(dht: Swarm, uids: Sequence[ModuleUID], expiration_ti
     """For every uid: the servers currently announcing it (optionally only those holding ``active_adapter``)."""
     now = get_dht_time() if expiration_time is None else expiration_time
     infos = []
+    # a network registry answers for all uids in one round trip (parallel/registry.py); local ones are dict lookups
+    records = dht.get_many(uids) if hasattr(dht, "get_many") else None
     for uid in uids:
         servers: Dict[PeerID, ServerInfo] = {}
-        for peer_id, (value, exp) in dht.get(uid).items():
+        for peer_id, (value, exp) in (records.get(uid, {}) if records is not None else dht.get(uid)).items():
             if exp < now:
                 continue
             try:
