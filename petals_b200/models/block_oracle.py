@@ -142,7 +142,8 @@ class GenericBlock(nn.Module):
         kpos = torch.arange(L, device=x.device)[None, :]
         if s.alibi:
             if self._slopes is None or self._slopes.device != x.device:
-                self._slopes = alibi_slopes(s.num_heads).to(x.device)
+                first = s.alibi_head_offset
+                self._slopes = alibi_slopes(s.alibi_total_heads or s.num_heads)[first: first + s.num_heads].to(x.device)
             scores = scores + self._slopes.view(1, -1, 1, 1) * (kpos - qpos).float()[None, None]
         ok = kpos <= qpos
         if s.sliding_window:

@@ -45,6 +45,9 @@ class BlockSpec:
     top_k: int = 0
     sliding_window: int = 0
     block_prefix: str = "model.layers"
+    # a tensor-parallel shard holds a slice of the heads: ALiBi slopes are those of the *global* head indices
+    alibi_total_heads: int = 0  # 0 = num_heads (not sharded)
+    alibi_head_offset: int = 0
 
     @property
     def group_size(self) -> int:

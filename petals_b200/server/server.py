@@ -278,7 +278,13 @@ class ModuleContainer:
         logger.info(f"Announced that blocks {block_indices[0]}:{block_indices[-1] + 1} are joining")
         tp_group = None
         try:
-            if len(tensor_parallel_devices) > 1 and device.type == "cuda":
+            tp_world = len(tensor_parallel_devices)
+            use_tp_engine = False
+            if tp_world > 1 and device.type == "cuda" and torch_dtype == torch.bfloat16 and all(d.type == "cuda" for d in tensor_parallel_devices):
+                from petals_b200.parallel.tensor_parallel import tp_supported
+
+                use_tp_engine = tp_supported(block_config.block_spec(), tp_world)
+            if use_tp_engine:
                 # one stage = a tensor-parallel group of worker processes (reference: --tensor_parallel_devices, run_server.py:154-157):
                 # this process leads, every other device gets a worker; the weights live in the group's shards
                 from petals_b200.parallel.tp_worker import TPGroup
@@ -302,7 +308,10 @@ class ModuleContainer:
                 spec = block_config.block_spec()
                 from petals_b200.server.stage_engine import fast_path_supported
 
-                paged = (device.type == "cuda" and torch_dtype == torch.bfloat16 and fast_path_supported(spec) and not force_oracle
+                if tp_world > 1:
+                    logger.info(f"Blocks are split over {[str(d) for d in tensor_parallel_devices]} by the generic tensor-parallel path "
+                                f"(parallel/tp_generic.py); the NVLink engine shards bf16 Llama-style blocks on CUDA devices")
+                paged = (device.type == "cuda" and torch_dtype == torch.bfloat16 and fast_path_supported(spec) and not force_oracle and tp_world == 1
                          and quant_type in (QuantType.NONE, QuantType.FP8) and not (quant_type == QuantType.FP8 and adapters))
                 memory_cache = MemoryCache(attn_cache_tokens, max_alloc_timeout, n_blocks=len(blocks), spec=spec, dtype=torch_dtype, device=device,
                                            paged=paged, max_length=inference_max_length)

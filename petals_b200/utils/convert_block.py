@@ -58,8 +58,19 @@ def convert_block(block: nn.Module, block_index: int, config, tensor_parallel_de
     """Prepare a freshly loaded block for serving. Returns the same module (moved / quantised / with adapters)."""
     if freeze:
         block.requires_grad_(False)
+    devices = tuple(torch.device(d) for d in tensor_parallel_devices)
+    if len(devices) > 1:
+        # same order as the reference (freeze -> make_tensor_parallel -> quantize -> adapters, convert_block.py:25-73); the generic
+        # split runs on the oracle blocks, so it is combined with neither weight quantisation nor LoRA
+        if quant_type != QuantType.NONE or adapters:
+            raise ValueError("tensor-parallel blocks serve unquantised checkpoints without adapters; use pipeline stages for quantised / LoRA serving")
+        from petals_b200.parallel.tp_generic import make_tensor_parallel
+
+        block = make_tensor_parallel(block, config.block_spec(), devices)
+        block.tensor_parallel_devices = devices
+        return block
     block = quantize_module(block, quant_type=quant_type)
-    block.tensor_parallel_devices = tuple(tensor_parallel_devices)
+    block.tensor_parallel_devices = devices
     block = block.to(output_device)
     if adapters:
         from petals_b200.utils.peft import add_adapter_to_block, create_lora_adapter, load_peft
