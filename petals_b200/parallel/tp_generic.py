@@ -199,3 +199,141 @@ def make_tensor_parallel(block: GenericBlock, spec: BlockSpec, devices: Sequence
     if len(devices) <= 1:
         return block
     return TensorParallelBlock(block, spec, devices)
+
+
+# =====================================================================================================================
+# One shard per process: the same split with collectives (what the ranks of a tensor-parallel worker group execute for
+# the paths that have no fused kernels — training forward/backward through a TP stage).
+# =====================================================================================================================
+import torch.distributed as dist  # noqa: E402
+
+
+class _CopyToTP(torch.autograd.Function):
+    """Megatron's ``f``: identity going in, all-reduce of the gradient coming back (the replicated activation feeds
+    every rank's sharded sub-layer, so its gradient is the sum of the ranks' contributions)."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous().clone()
+        dist.all_reduce(g, group=ctx.group)
+        return g, None
+
+
+class _ReduceFromTP(torch.autograd.Function):
+    """Megatron's ``g``: all-reduce of the partial outputs going out, identity for the gradient."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        y = x.contiguous().clone()
+        dist.all_reduce(y, group=group)
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class ShardedBlock(nn.Module):
+    """This rank's shard of a block + the process group it all-reduces over; call surface of :class:`GenericBlock`.
+
+    Every rank must make the same calls with the same (replicated) inputs.  The KV caches passed in hold this rank's kv
+    heads only (``shard.spec.num_kv_heads``)."""
+
+    def __init__(self, shard: GenericBlock, spec: BlockSpec, group=None):
+        super().__init__()
+        self.shard, self.spec, self.group = shard, spec, group
+        self.lora: dict = {}
+
+    @classmethod
+    def from_block(cls, block: GenericBlock, spec: BlockSpec, group=None, device=None) -> "ShardedBlock":
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        shard = GenericBlock(shard_spec(spec, rank, world), dtype=block.wqkv.dtype, device=device or block.wqkv.device)
+        with torch.no_grad():
+            for name, t in shard_tensors(block, spec, rank, world).items():
+                getattr(shard, name).copy_(t)
+        shard.requires_grad_(False)
+        return cls(shard, spec, group)
+
+    @classmethod
+    def from_tensors(cls, tensors: Dict[str, torch.Tensor], spec: BlockSpec, rank: int, world: int, group=None) -> "ShardedBlock":
+        """Wrap shard tensors that already live on this rank's device (no copy: the parameters alias them)."""
+        ls = shard_spec(spec, rank, world)
+        any_t = next(iter(tensors.values()))
+        shard = GenericBlock(ls, dtype=any_t.dtype, device="meta")
+        for name in ls.param_shapes():
+            t = tensors.get(name)
+            if t is None:
+                if name in ("bo", "b_down"):
+                    raise KeyError(name)
+                raise KeyError(f"shard tensor {name!r} is missing")
+            setattr(shard, name, nn.Parameter(t, requires_grad=False))
+        return cls(shard, spec, group)
+
+    def _sub(self, fn, x: torch.Tensor, *args) -> torch.Tensor:
+        return _ReduceFromTP.apply(fn(_CopyToTP.apply(x, self.group), *args), self.group)
+
+    def forward_cached(self, hidden: torch.Tensor, k_cache: Optional[torch.Tensor], v_cache: Optional[torch.Tensor], pos: int = 0) -> torch.Tensor:
+        s, b = self.spec, self.shard
+        if s.parallel_attn:
+            a_in = b._norm(hidden, "ln1")
+            m_in = b._norm(hidden, "ln2") if s.dual_ln else a_in
+            return hidden + self._sub(b.attention, a_in, k_cache, v_cache, pos) + self._sub(b.mlp, m_in)
+        ln1 = b._norm(hidden, "ln1")
+        res = ln1 if s.post_ln_residual else hidden
+        h = res + self._sub(b.attention, ln1, k_cache, v_cache, pos)
+        ln2 = b._norm(h, "ln2")
+        res = ln2 if s.post_ln_residual else h
+        return res + self._sub(b.mlp, ln2)
+
+    def forward(self, hidden_states: torch.Tensor, **_):
+        return (self.forward_cached(hidden_states, None, None, 0),)
+
+
+def add_deep_prompt(hidden: torch.Tensor, prompt: Optional[torch.Tensor]) -> torch.Tensor:
+    """``hidden[:, :pre] += prompt`` out of place (a batch-1 prompt broadcasts), the per-block deep-prompt rule."""
+    if prompt is None or prompt.numel() == 0:
+        return hidden
+    pre = prompt.shape[1]
+    return torch.cat([hidden[:, :pre] + prompt, hidden[:, pre:]], dim=1)
+
+
+def span_forward(blocks: Sequence[nn.Module], hidden: torch.Tensor, prompts: Optional[Sequence[Optional[torch.Tensor]]] = None) -> torch.Tensor:
+    h = hidden
+    with torch.no_grad():
+        for i, block in enumerate(blocks):
+            h = block.forward_cached(add_deep_prompt(h, prompts[i] if prompts is not None else None), None, None, 0)
+    return h
+
+
+def span_backward(blocks: Sequence[nn.Module], hidden: torch.Tensor, grad_out: torch.Tensor,
+                  prompts: Optional[Sequence[Optional[torch.Tensor]]] = None):
+    """Gradient of a span of frozen blocks wrt its input and its deep prompts: one no-grad forward that keeps every block's
+    input, then per-block recompute under autograd from the last block to the first (2 forwards per step in total).
+    With :class:`ShardedBlock` s this is a collective: every rank of the group calls it with the same arguments and gets
+    the same result."""
+    n = len(blocks)
+    prompts = list(prompts) if prompts is not None else [None] * n
+    inputs, h = [], hidden
+    with torch.no_grad():
+        for i, block in enumerate(blocks):
+            inputs.append(h)
+            if i + 1 < n:
+                h = block.forward_cached(add_deep_prompt(h, prompts[i]), None, None, 0)
+    grad = grad_out
+    grad_prompts: List[Optional[torch.Tensor]] = [None] * n
+    for i in reversed(range(n)):
+        x = inputs[i].detach().requires_grad_(True)
+        p = prompts[i]
+        p = p.detach().requires_grad_(True) if p is not None and p.numel() else None
+        with torch.enable_grad():
+            y = blocks[i].forward_cached(add_deep_prompt(x, p), None, None, 0)
+        grads = torch.autograd.grad(y, [x] + ([p] if p is not None else []), grad)
+        grad = grads[0]
+        if p is not None:
+            grad_prompts[i] = grads[1]
+    return grad, grad_prompts

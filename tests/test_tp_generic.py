@@ -158,3 +158,50 @@ def test_tensor_parallel_refuses_quantisation_and_adapters():
         convert_block(block, 0, config, ["cpu", "cpu"], torch.device("cpu"), QuantType.FP8)
     tp = convert_block(block, 0, config, ["cpu", "cpu"], torch.device("cpu"), QuantType.NONE)
     assert isinstance(tp, TensorParallelBlock) and tp.tensor_parallel_devices == (torch.device("cpu"), torch.device("cpu"))
+
+
+def _dist_worker(rank, world, port, name, results):
+    import os
+
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from petals_b200.parallel.tp_generic import ShardedBlock, span_backward, span_forward
+
+        spec, block = _load(name)
+        sharded = ShardedBlock.from_block(block, spec)
+        assert sharded.shard.spec.num_heads * world == spec.num_heads
+        torch.manual_seed(0)
+        x, g = torch.randn(2, 5, spec.hidden_size), torch.randn(2, 5, spec.hidden_size)
+        prompts = [torch.randn(1, 2, spec.hidden_size), None]  # a broadcast deep prompt on the first block only
+        y = span_forward([sharded, sharded], x, prompts)
+        gi, gp = span_backward([sharded, sharded], x, g, prompts)
+        y_ref = span_forward([block, block], x, prompts)
+        gi_ref, gp_ref = span_backward([block, block], x, g, prompts)
+        ok = (torch.allclose(y, y_ref, atol=1e-4, rtol=1e-4) and torch.allclose(gi, gi_ref, atol=1e-4, rtol=1e-4)
+              and torch.allclose(gp[0], gp_ref[0], atol=1e-4, rtol=1e-4) and gp[1] is None and gp[0].shape == prompts[0].shape)
+        # incremental decoding against this rank's own kv heads
+        ls = sharded.shard.spec
+        kc = torch.zeros(2, 8, ls.num_kv_heads, ls.head_dim)
+        vc = torch.zeros_like(kc)
+        with torch.no_grad():
+            steps = torch.cat([sharded.forward_cached(x[:, :3], kc, vc, 0), sharded.forward_cached(x[:, 3:], kc, vc, 3)], 1)
+            ok = ok and torch.allclose(steps, block.forward_cached(x, None, None, 0), atol=1e-4, rtol=1e-4)
+        results[rank] = bool(ok)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["llama", "bloom", "falcon-7b-style", "mixtral"])
+def test_one_shard_per_process_forward_backward(name):
+    """The collective form (Megatron f/g autograd functions over a gloo group of 2 processes): the same numbers as the dense
+    block on every rank — forward, input gradients, deep-prompt gradients, cached decoding."""
+    import torch.multiprocessing as mp
+
+    port = 29700 + sorted(FAMILIES).index(name)
+    with mp.Manager() as manager:
+        results = manager.dict()
+        mp.spawn(_dist_worker, args=(2, port, name, results), nprocs=2, join=True)
+        assert dict(results) == {0: True, 1: True}
