@@ -268,8 +268,6 @@ class ShardedBlock(nn.Module):
         for name in ls.param_shapes():
             t = tensors.get(name)
             if t is None:
-                if name in ("bo", "b_down"):
-                    raise KeyError(name)
                 raise KeyError(f"shard tensor {name!r} is missing")
             setattr(shard, name, nn.Parameter(t, requires_grad=False))
         return cls(shard, spec, group)

@@ -107,11 +107,60 @@ class TPLeaderEngine:
             finally:
                 session.close()
 
+    def backward(self, hidden: torch.Tensor, grad_out: torch.Tensor, prompts=None, block_range: Optional[Tuple[int, int]] = None):
+        """Gradient of the span wrt its input and deep prompts (rpc_backward). No fused kernels here: every rank runs the
+        autograd recompute on its shard and the two all-reduces per block go through NCCL (parallel/tp_generic.py)."""
+        lo, hi = block_range or (0, self.n_blocks)
+        B, T, H = hidden.shape
+        n = hi - lo
+        plist = [None] * n if prompts is None else [None if (p is None or is_dummy(p)) else p for p in prompts]
+        if len(plist) != n or grad_out.shape != hidden.shape:
+            raise ValueError("backward: mismatched prompts / gradient shapes")
+        shapes = [None if p is None else [int(p.shape[0]), int(p.shape[1])] for p in plist]
+        with self._lock:
+            self.ring.send({"op": "backward", "B": B, "T": T, "lo": lo, "hi": hi, "prompts": shapes})
+            return tp_collective_backward(self.engine, hidden, grad_out, plist, lo, hi, shapes)
+
     def check_errors(self) -> None:
         self.engine.check_errors()
 
     def shutdown(self) -> None:
         self.ring.send({"op": "stop"})
+
+
+def _sharded_blocks(engine: TPDecodeEngine):
+    """ShardedBlock views of the engine's weight shards (built once; the parameters alias the shard tensors)."""
+    blocks = getattr(engine, "_sharded_blocks", None)
+    if blocks is None:
+        from petals_b200.parallel.tp_generic import ShardedBlock
+
+        blocks = [ShardedBlock.from_tensors(t, engine.spec, engine.rank, engine.world, getattr(engine.heap, "group", None)) for t in engine.shards]
+        engine._sharded_blocks = blocks
+    return blocks
+
+
+def tp_collective_backward(engine: TPDecodeEngine, hidden, grad_out, prompts, lo: int, hi: int, prompt_shapes):
+    """Collective over the TP group. The leader passes the real tensors; followers pass ``None`` and receive them by broadcast."""
+    from petals_b200.parallel.tp_generic import span_backward
+
+    dev, H = engine.device, engine.spec.hidden_size
+    group = getattr(engine.heap, "group", None)
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+
+    def bcast(t, shape):
+        buf = t.to(dev, torch.bfloat16).contiguous() if t is not None else torch.empty(shape, dtype=torch.bfloat16, device=dev)
+        dist.broadcast(buf, src=src, group=group)
+        return buf
+
+    B, T = (hidden.shape[0], hidden.shape[1]) if hidden is not None else prompt_shapes["BT"]
+    shapes = prompt_shapes["prompts"] if isinstance(prompt_shapes, dict) else prompt_shapes
+    x = bcast(hidden, (B, T, H))
+    g = bcast(grad_out, (B, T, H))
+    ps = [None if sh is None else bcast(prompts[i] if prompts is not None else None, (sh[0], sh[1], H)) for i, sh in enumerate(shapes)]
+    grad, grad_prompts = span_backward(_sharded_blocks(engine)[lo:hi], x, g, ps)
+    if dev.type == "cuda":
+        torch.cuda.synchronize(dev)
+    return grad, grad_prompts
 
 
 def follower_loop(engine: TPDecodeEngine, cache: MemoryCache, ring: CommandRing, consumer: int, idle_timeout: Optional[float] = None) -> None:
@@ -127,6 +176,8 @@ def follower_loop(engine: TPDecodeEngine, cache: MemoryCache, ring: CommandRing,
             if "hypo" in cmd:
                 s.reorder(torch.tensor(cmd["hypo"], dtype=torch.int64))
             (engine.run_step if op == "step" else engine.run_prefill)(s, cmd["B"], cmd["T"])
+        elif op == "backward":
+            tp_collective_backward(engine, None, None, None, cmd["lo"], cmd["hi"], {"BT": (cmd["B"], cmd["T"]), "prompts": cmd["prompts"]})
         elif op == "open":
             sessions[cmd["sid"]] = cache.open_session(cmd["B"], cmd["max_length"], timeout=None)
         elif op == "close":

@@ -112,10 +112,13 @@ class Stage:
     def backward(self, hidden: torch.Tensor, grad_out: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None,
                  lo: int = 0, hi: Optional[int] = None) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
         """Returns (grad wrt span input, [grad wrt each block's prompt or None])."""
-        if getattr(self.engine, "whole_span_only", False):
-            raise NotImplementedError("backward through a tensor-parallel stage is not implemented: its weights exist only as per-rank shards; "
-                                      "serve prompt-tuning traffic from pipeline stages")
         hi = len(self.blocks) if hi is None else hi
+        if getattr(self.engine, "whole_span_only", False):
+            # a tensor-parallel stage: the weights exist only as per-rank shards, so the whole worker group runs the recompute
+            if not hasattr(self.engine, "backward"):
+                raise NotImplementedError("backward through this tensor-parallel stage is not implemented; serve prompt-tuning from pipeline stages")
+            ps = None if prompts is None else [None if is_dummy(p) else p.to(self.device, self.dtype).contiguous() for p in prompts]
+            return self.engine.backward(hidden.to(self.device, self.dtype), grad_out.to(self.device, self.dtype), ps, (lo, hi))
         hidden, grad = hidden.to(self.device, self.dtype), grad_out.to(self.device, self.dtype)
         prompts = [None] * (hi - lo) if prompts is None else [None if is_dummy(p) else p.to(self.device, self.dtype).contiguous() for p in prompts]
         # pass 1 (no grad): remember every block's input

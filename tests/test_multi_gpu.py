@@ -39,3 +39,18 @@ def test_server_tensor_parallel_devices():
     lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
     assert proc.returncode == 0 and lines, proc.stdout[-2000:] + proc.stderr[-2000:]
     assert json.loads(lines[-1])["tp_server_selftest"] == "ok"
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.skipif(os.environ.get("PETALS_B200_RUN_UNVALIDATED", "0") != "1",
+                    reason="rpc_backward through a TP worker group is validated with gloo on CPU (tests/test_tp_leader_logic.py); its first NCCL run on "
+                           "hardware is pending - opt in with PETALS_B200_RUN_UNVALIDATED=1")
+def test_server_tensor_parallel_backward():
+    """Prompt-tuning gradients through `--tensor_parallel_devices`: every rank recomputes on its shard, partials are all-reduced."""
+    env = dict(os.environ, TP_SELFTEST_BACKWARD="1")
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "tp_server_selftest.py")], capture_output=True, text=True, timeout=420, cwd=ROOT,
+                          env=env)
+    lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
+    assert proc.returncode == 0 and lines, proc.stdout[-2000:] + proc.stderr[-2000:]
+    report = json.loads(lines[-1])
+    assert report["tp_server_selftest"] == "ok" and report["backward_rel_err"] < 0.08

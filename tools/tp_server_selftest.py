@@ -43,12 +43,25 @@ def main():
                 got = torch.cat([model(ids[:, :150]).logits, model(ids[:, 150:151]).logits, model(ids[:, 151:]).logits], 1).float()
             fwd = model(ids).logits.float()  # cache-less parallel forward (rpc_forward) through the TP group
             out = model.generate(ids[:, :8], max_new_tokens=5)
+        bwd = {}
+        if os.environ.get("TP_SELFTEST_BACKWARD", "0") == "1":
+            # rpc_backward through the worker group (parallel/tp_worker.py: tp_collective_backward) vs autograd through the dense blocks
+            x = (torch.randn(2, 24, config.hidden_size, device="cuda:0") * 0.5).to(torch.bfloat16).requires_grad_(True)
+            model.model.layers(x).float().pow(2).sum().backward()
+            g_tp = x.grad.float().clone()
+            x.grad = None
+            hh = x
+            for i in range(config.num_hidden_layers):
+                hh = load_pretrained_block(path, i, torch_dtype=torch.bfloat16).to("cuda:0").forward_cached(hh, None, None, 0)
+            hh.float().pow(2).sum().backward()
+            bwd = {"backward_rel_err": round(((g_tp - x.grad.float()).abs().mean() / (x.grad.float().abs().mean() + 1e-9)).item(), 5)}
         err = (got - ref).abs().mean().item() / (ref.abs().mean().item() + 1e-9)
         err_f = (fwd - ref).abs().mean().item() / (ref.abs().mean().item() + 1e-9)
         agree = (got.argmax(-1) == ref.argmax(-1)).float().mean().item()
         ok = err < 0.05 and err_f < 0.05 and agree > 0.9 and all(0 <= t < config.vocab_size for t in out[0].tolist())
+        ok = ok and bwd.get("backward_rel_err", 0.0) < 0.08
         report = {"tp_server_selftest": "ok" if ok else "FAILED", "world": world, "rel_err": round(err, 5), "forward_rel_err": round(err_f, 5),
-                  "argmax_agreement": round(agree, 4), "generated": out[0, 8:].tolist()}
+                  "argmax_agreement": round(agree, 4), "generated": out[0, 8:].tolist(), **bwd}
     finally:
         server.shutdown()
     print(json.dumps(report))
