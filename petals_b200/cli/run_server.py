@@ -89,6 +89,8 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--quant_type", type=str, default=None, choices=[c.name.lower() for c in QuantType])
     p.add_argument("--tensor_parallel_devices", nargs="+", default=None)
     p.add_argument("--skip_reachability_check", action="store_true")
+    p.add_argument("--metrics_port", type=int, default=None, help="serve Prometheus metrics (requests, tokens, latency histograms, sessions, "
+                   "KV tokens left) on this port; 0 picks a free one")
     p.add_argument("--adapters", nargs="*", default=())
     p.add_argument("--peer_id", type=str, default=None, help="name of this stage in the swarm (default: derived from the device)")
     return p

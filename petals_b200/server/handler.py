@@ -34,6 +34,7 @@ from petals_b200.server.memory_cache import AllocationFailed, SessionCache
 from petals_b200.server.task_pool import PrioritizedTaskPool
 from petals_b200.server.task_prioritizer import DummyTaskPrioritizer, TaskPrioritizerBase
 from petals_b200.utils.logging import get_logger
+from petals_b200.utils.metrics import ServerMetrics
 from petals_b200.utils.fault_injection import maybe_fail
 from petals_b200.utils.misc import DUMMY, is_dummy
 from petals_b200.utils.tracing import nvtx_range
@@ -66,6 +67,7 @@ class InferenceStream:
         self.opened_at = self.last_step_at = time.monotonic()
         self.closed = False
         self._pushed: Dict[str, Tuple[torch.Tensor, ...]] = {}
+        self._last_tokens = 0
         self._done_steps: set = set()
         self._lock = threading.Lock()
         handler._register(self)
@@ -104,6 +106,17 @@ class InferenceStream:
     # ---- one step -------------------------------------------------------------------------------------------
     def step(self, hidden: torch.Tensor, prompts: Optional[torch.Tensor] = None, hypo_ids: Optional[torch.Tensor] = None,
              metadata: Optional[Dict[str, Any]] = None) -> torch.Tensor:
+        t0 = time.perf_counter()
+        try:
+            out = self._step(hidden, prompts, hypo_ids, metadata)
+        except Exception:
+            self.handler.metrics.error("inference")
+            raise
+        self.handler.metrics.observe("inference", self._last_tokens, time.perf_counter() - t0)
+        return out
+
+    def _step(self, hidden: torch.Tensor, prompts: Optional[torch.Tensor] = None, hypo_ids: Optional[torch.Tensor] = None,
+              metadata: Optional[Dict[str, Any]] = None) -> torch.Tensor:
         metadata = metadata or {}
         maybe_fail("rpc_inference", self.handler.peer_id)
         if self.closed:
@@ -142,6 +155,7 @@ class InferenceStream:
         if hidden.dim() != 3:
             raise ValueError(f"hidden states must be [batch, seq, hidden], got {tuple(hidden.shape)}")
         B, T, H = hidden.shape
+        self._last_tokens = B * T  # for the metrics: a fused stage hop returns an empty tensor
         cache = self._ensure_cache(B)
         start = metadata.get("start_from_position")
         if start is not None:
@@ -201,6 +215,9 @@ class TransformerConnectionHandler:
         self.request_timeout, self.session_timeout, self.step_timeout = request_timeout, session_timeout, step_timeout
         self.prioritizer = task_prioritizer or DummyTaskPrioritizer()
         self.quant_type = quant_type
+        self.metrics = ServerMetrics(peer_id)
+        self.metrics.gauge("cache_tokens_left", lambda: stage.memory_cache.tokens_left * len(stage))
+        self.metrics.gauge("queue_size", lambda: inference_pool.runtime.queue_size() if getattr(inference_pool, "runtime", None) is not None else None)
         self.compression = None  # default wire codec of the responses on the socket transport (utils/compression.py)
         self._sessions: Dict[str, InferenceStream] = {}
         self._sessions_lock = threading.Lock()
@@ -228,10 +245,13 @@ class TransformerConnectionHandler:
     def _register(self, stream: InferenceStream) -> None:
         with self._sessions_lock:
             self._sessions[stream.session_id] = stream
+        self.metrics.session_opened()
 
     def _unregister(self, stream: InferenceStream) -> None:
         with self._sessions_lock:
-            self._sessions.pop(stream.session_id, None)
+            known = self._sessions.pop(stream.session_id, None)
+        if known is not None:
+            self.metrics.session_closed()
 
     def sweep_sessions(self) -> int:
         """Close sessions whose session/step timeout expired; returns how many were closed."""
@@ -248,6 +268,16 @@ class TransformerConnectionHandler:
         return InferenceStream(self, self._check_uids(uids), metadata or {})
 
     def rpc_forward(self, uids, hidden: torch.Tensor, prompts: Optional[torch.Tensor] = None, metadata: Optional[Dict[str, Any]] = None) -> torch.Tensor:
+        t0 = time.perf_counter()
+        try:
+            out = self._rpc_forward(uids, hidden, prompts, metadata)
+        except Exception:
+            self.metrics.error("forward")
+            raise
+        self.metrics.observe("forward", hidden.shape[0] * hidden.shape[1] if hidden.dim() == 3 else 0, time.perf_counter() - t0)
+        return out
+
+    def _rpc_forward(self, uids, hidden: torch.Tensor, prompts: Optional[torch.Tensor] = None, metadata: Optional[Dict[str, Any]] = None) -> torch.Tensor:
         maybe_fail("rpc_forward", self.peer_id)
         uids = self._check_uids(uids)
         metadata = metadata or {}
@@ -258,6 +288,17 @@ class TransformerConnectionHandler:
 
     def rpc_backward(self, uids, inputs: torch.Tensor, grad_outputs: torch.Tensor, prompts: Optional[torch.Tensor] = None,
                      metadata: Optional[Dict[str, Any]] = None) -> List[torch.Tensor]:
+        t0 = time.perf_counter()
+        try:
+            out = self._rpc_backward(uids, inputs, grad_outputs, prompts, metadata)
+        except Exception:
+            self.metrics.error("backward")
+            raise
+        self.metrics.observe("backward", inputs.shape[0] * inputs.shape[1] if inputs.dim() == 3 else 0, time.perf_counter() - t0)
+        return out
+
+    def _rpc_backward(self, uids, inputs: torch.Tensor, grad_outputs: torch.Tensor, prompts: Optional[torch.Tensor] = None,
+                      metadata: Optional[Dict[str, Any]] = None) -> List[torch.Tensor]:
         maybe_fail("rpc_backward", self.peer_id)
         uids = self._check_uids(uids)
         metadata = metadata or {}
@@ -311,7 +352,7 @@ class TransformerConnectionHandler:
             forward_schema=dict(args=("hidden_states", "prompts"), hidden_size=spec.hidden_size),
             outputs_schema=dict(hidden_size=spec.hidden_size),
             inference_schema=dict(args=("hidden_states", "prompts", "hypo_ids"), hidden_size=spec.hidden_size),
-            device=str(self.stage.device), engine="sm_100a" if self.stage.engine is not None else "oracle",
+            device=str(self.stage.device), engine="sm_100a" if self.stage.engine is not None else "oracle", metrics=self.metrics.snapshot(),
             fabric_rank=self._fabric_rank())
 
     @staticmethod

@@ -67,12 +67,21 @@ class Server:
                  skip_reachability_check: bool = False, reachable_via_relay: Optional[bool] = None, use_relay: bool = True,
                  use_auto_relay: bool = True, adapters: Sequence[str] = (), peer_id: Optional[str] = None,
                  use_cuda_graphs: bool = True, force_oracle: bool = False, host_maddrs: Optional[Sequence[str]] = None,
-                 announce_maddrs: Optional[Sequence[str]] = None, public_ip: Optional[str] = None, **kwargs):
+                 announce_maddrs: Optional[Sequence[str]] = None, public_ip: Optional[str] = None, metrics_port: Optional[int] = None,
+                 **kwargs):
         if kwargs:
             logger.debug(f"ignoring networking options that have no meaning on one box: {sorted(kwargs)}")
         self.converted_model_name_or_path = converted_model_name_or_path
         self.num_handlers, self.compression = num_handlers, compression
         self.skip_reachability_check = skip_reachability_check
+        # Prometheus endpoint (utils/metrics.py): survives re-balancing because it reads whichever container is live
+        self.metrics_server = None
+        if metrics_port is not None:
+            from petals_b200.utils.metrics import MetricsServer
+
+            self.metrics_server = MetricsServer(lambda: (lambda c: c.handler.metrics if c is not None else None)(getattr(self, "module_container", None)),
+                                                metrics_port).start()
+            logger.info(f"Serving metrics on http://0.0.0.0:{self.metrics_server.port}/metrics")
         self.stats_report_interval, self.update_period = stats_report_interval, update_period
         self.prefetch_batches, self.sender_threads = prefetch_batches, sender_threads
         self.revision, self.token, self.adapters = revision, token, tuple(adapters)
@@ -251,6 +260,9 @@ class Server:
 
     def shutdown(self, timeout: Optional[float] = 5) -> None:
         self.stop.set()
+        if self.metrics_server is not None:
+            self.metrics_server.shutdown()
+            self.metrics_server = None
         if self._thread is not None and self._thread.is_alive() and threading.current_thread() is not self._thread:
             self._thread.join(timeout)
         if self.module_container is not None:
