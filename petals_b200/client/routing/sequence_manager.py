@@ -20,6 +20,7 @@ import logging
 import random
 import threading
 import time
+import weakref
 from typing import Any, Dict, List, Optional, Sequence, Set, Tuple, Union
 
 import numpy as np
@@ -113,24 +114,24 @@ class RemoteSequenceManager:
     # ---- background refresh (reference :493-519) ---------------------------------------------------------------
     def _ensure_thread(self) -> None:
         if self._thread is None or not self._thread.is_alive():
-            self._thread = threading.Thread(target=self._update_loop, name="sequence-manager", daemon=True)
+            # the thread only holds a weak reference: a manager (and the model that owns it) that nobody uses any more is
+            # collected and its refresh loop ends, instead of polling the registry for the rest of the process's life
+            self._thread = threading.Thread(target=_update_loop, args=(weakref.ref(self), self._stop, self._need_update),
+                                            name="sequence-manager", daemon=True)
             self._thread.start()
 
-    def _update_loop(self) -> None:
-        while not self._stop.is_set():
-            try:
-                self._update()
-            except Exception as e:  # noqa: BLE001 - keep refreshing
-                logger.debug(f"sequence info update failed: {e!r}")
-            self._need_update.wait(self.config.update_period)
-            self._need_update.clear()
+    def __del__(self):
+        stop = getattr(self, "_stop", None)
+        if stop is not None:
+            stop.set()
+            self._need_update.set()
 
     def update(self, *, wait: bool = True) -> None:
         """Refresh the block -> servers map now."""
         self._update()
         self._ensure_thread()
 
-    def _update(self) -> None:
+    def _update(self, background: bool = False) -> None:
         for attempt_no in itertools.count():
             try:
                 self._update_once()
@@ -140,8 +141,8 @@ class RemoteSequenceManager:
                 self.ready.set()
                 return
             except MissingBlocksError as e:
-                if self.config.max_retries is not None and attempt_no >= self.config.max_retries:
-                    raise
+                if background or (self.config.max_retries is not None and attempt_no >= self.config.max_retries):
+                    raise  # the refresh loop retries on its own schedule; callers that wait for a route retry here
                 delay = self.get_retry_delay(attempt_no)
                 logger.warning(f"Could not find route through the model: {e!r} (retry in {delay:.0f} sec)")
                 if self._stop.wait(delay):
@@ -351,6 +352,25 @@ class RemoteSequenceManager:
         self._need_update.set()
         if self._thread is not None and self._thread.is_alive():
             self._thread.join(timeout=2)
+
+
+def _update_loop(manager_ref, stop: threading.Event, need_update: threading.Event) -> None:
+    """Background refresh (reference sequence_manager.py:493-519). Holds the manager only while refreshing."""
+    failures = 0
+    while not stop.is_set():
+        manager = manager_ref()
+        if manager is None:
+            return
+        try:
+            manager._update(background=True)
+            failures, delay = 0, manager.config.update_period
+        except Exception as e:  # noqa: BLE001 - keep refreshing
+            delay = min(manager.config.update_period, manager.get_retry_delay(failures))
+            failures += 1
+            logger.debug(f"sequence info update failed: {e!r} (next attempt in {delay:.0f} sec)")
+        del manager
+        need_update.wait(delay)
+        need_update.clear()
 
 
 def _dijkstra(graph: Dict[Any, Dict[Any, float]], src: Any, dst: Any) -> Optional[List[Any]]:

@@ -82,3 +82,28 @@ def test_server_stats_cache_accounting(served):
         during = handler.rpc_info()["cache_tokens_available"]
         assert during <= before - 128 * config.num_hidden_layers  # max_length tokens x n_blocks are reserved up front
     assert handler.rpc_info()["cache_tokens_available"] == before  # and released when the session closes
+
+
+def test_refresh_thread_ends_with_its_manager():
+    """The background refresh only holds a weak reference: dropping the model/manager ends the thread (the reference's
+    managers poll the DHT until the process exits unless shutdown() is called, src/petals/client/routing/sequence_manager.py:493-519)."""
+    import gc
+    import threading
+    import time
+
+    from petals_b200.client.config import ClientConfig
+    from petals_b200.client.routing.sequence_manager import RemoteSequenceManager
+    from petals_b200.parallel.swarm import Swarm
+
+    swarm = Swarm("empty-swarm-for-thread-test")
+    config = ClientConfig(initial_peers=[swarm.address], dht_prefix="nobody", update_period=0.05, max_retries=0)
+    manager = RemoteSequenceManager(config, ["nobody.0", "nobody.1"], dht=swarm)
+    manager._ensure_thread()  # no server holds these blocks: the loop keeps failing quietly and retrying
+    thread = manager._thread
+    time.sleep(0.3)
+    assert thread.is_alive() and not manager.ready.is_set()
+    del manager
+    gc.collect()
+    thread.join(timeout=5)
+    assert not thread.is_alive()
+    assert not any(t.name == "sequence-manager" and t is thread for t in threading.enumerate())
