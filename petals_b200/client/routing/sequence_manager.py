@@ -295,6 +295,8 @@ class RemoteSequenceManager:
         if peer_id is not None:
             logger.debug(f"Peer {peer_id} did not respond, banning it temporarily")
             self.state.banned_peers.register_failure(peer_id)
+            if hasattr(self.dht, "forget"):  # network swarms cache peer addresses: a restarted server announces a new port
+                self.dht.forget(peer_id)
         with self.lock_changes:
             should_update = False
             for info in self.state.sequence_info.block_infos:
