@@ -65,6 +65,10 @@ class GenericBlock(nn.Module):
         # opt-in (PETALS_B200_TC_BACKWARD=1): frozen bf16 blocks on CUDA run their linears (forward + dgrad) on the tcgen05 GEMM when autograd
         # is recording. Measured on Llama-3-8B prompt tuning: 6.7k vs 7.8k backward tokens/s for cuBLAS at these small-M shapes, so off by default
         self.tc_backward = os.environ.get("PETALS_B200_TC_BACKWARD", "0") != "0"
+        # opt-in (PETALS_B200_SDPA_BACKWARD=1): the cache-less recompute pass of rpc_backward runs its attention through the fused
+        # scaled_dot_product_attention (one flash kernel each way instead of ~20 eager ones over a [B, H, T, T] fp32 logits tensor).
+        # A library call, so only a stop-gap until the flash-attention backward kernel exists; unmeasured, hence off.
+        self.sdpa_backward = os.environ.get("PETALS_B200_SDPA_BACKWARD", "0") != "0"
         self.lora: dict = {}  # target param name -> list[(A [r,in], B [out,r], scale)] for the active adapter
 
     # ---- helpers -----------------------------------------------------------------------------------
@@ -135,6 +139,10 @@ class GenericBlock(nn.Module):
             k, v = k_cache[:, :pos + T], v_cache[:, :pos + T]
         L = k.shape[1]
         G = s.group_size
+        if (self.sdpa_backward and k_cache is None and not s.alibi and not s.sliding_window and torch.is_grad_enabled() and x.requires_grad):
+            ctx = F.scaled_dot_product_attention(q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2), is_causal=True, scale=s.attn_scale,
+                                                 enable_gqa=G > 1)
+            return self._linear(ctx.transpose(1, 2).reshape(B, T, s.num_heads * s.head_dim), "wo", "bo")
         kf = k.repeat_interleave(G, dim=2) if G > 1 else k
         vf = v.repeat_interleave(G, dim=2) if G > 1 else v
         scores = torch.einsum("bthd,blhd->bhtl", q, kf).float() * s.attn_scale

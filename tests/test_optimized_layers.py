@@ -46,3 +46,34 @@ def test_blocks_match_hf_layers(family, atol=2e-4):
                 steps.append(blocks[i].forward_cached(x[:, t: t + 1], kc, vc, t))
             inc = torch.cat(steps, dim=1)
             assert torch.allclose(inc, want, atol=atol), f"{family} layer {i} (cached): {(inc - want).abs().max().item():.3g}"
+
+
+def test_sdpa_recompute_path_matches_eager_attention(monkeypatch):
+    """PETALS_B200_SDPA_BACKWARD=1 swaps the eager attention of the training recompute pass for the fused SDPA: same
+    outputs and input gradients (GQA, causal), and it is only taken when autograd is recording and no KV cache is involved."""
+    import torch
+
+    from petals_b200.server.from_pretrained import load_pretrained_block
+    from tests.utils import checkpoint
+
+    path = checkpoint("llama", num_attention_heads=8, num_key_value_heads=2)
+    eager = load_pretrained_block(path, 0, torch_dtype=torch.float32)
+    fused = load_pretrained_block(path, 0, torch_dtype=torch.float32)
+    fused.sdpa_backward = True
+    torch.manual_seed(0)
+    x1 = torch.randn(2, 9, eager.spec.hidden_size, requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    g = torch.randn_like(x1)
+    y1, y2 = eager.forward_cached(x1, None, None, 0), fused.forward_cached(x2, None, None, 0)
+    y1.backward(g), y2.backward(g)
+    assert torch.allclose(y1, y2, atol=1e-5) and torch.allclose(x1.grad, x2.grad, atol=1e-4)
+    calls = []
+    real = torch.nn.functional.scaled_dot_product_attention
+    monkeypatch.setattr(torch.nn.functional, "scaled_dot_product_attention", lambda *a, **k: (calls.append(1), real(*a, **k))[1])
+    with torch.no_grad():
+        fused.forward_cached(x2.detach(), None, None, 0)  # inference / pass 1: the oracle's own attention
+    kc = torch.zeros(2, 16, 2, eager.spec.head_dim)
+    fused.forward_cached(x2, kc, torch.zeros_like(kc), 0)  # cached decoding keeps the explicit path too
+    assert not calls
+    fused.forward_cached(x2, None, None, 0)
+    assert calls
