@@ -21,3 +21,6 @@ run default PETALS_B200_L2_PREFETCH=0
 run l2pf_a1_c8 PETALS_B200_L2_PREFETCH=1 PETALS_B200_L2_PREFETCH_AHEAD=1 PETALS_B200_L2_PREFETCH_CTAS=8
 run l2pf_a2_c8 PETALS_B200_L2_PREFETCH=1 PETALS_B200_L2_PREFETCH_AHEAD=2 PETALS_B200_L2_PREFETCH_CTAS=8
 run l2pf_a1_c16 PETALS_B200_L2_PREFETCH=1 PETALS_B200_L2_PREFETCH_AHEAD=1 PETALS_B200_L2_PREFETCH_CTAS=16
+# kernels are 3-19 us at tp8: programmatic dependent launch on the GEMVs (slower at 1 GPU, profiles/r1_pdl_sweep.txt) may pay here
+run pdl15 PETALS_B200_PDL_MASK=15
+run pdl15_l2pf PETALS_B200_PDL_MASK=15 PETALS_B200_L2_PREFETCH=1
