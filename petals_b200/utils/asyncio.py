@@ -1,19 +1,23 @@
-"""Cancellation-safe waiting (reference: src/petals/utils/asyncio.py:4-21). The engine is thread-based, but the
-helper is kept for user code that drives the client from asyncio."""
+"""Cancellation-safe waiting for user code that drives the client from asyncio (reference: src/petals/utils/asyncio.py:4-21,
+used there so that a cancelled handler does not leak the KV allocation lock).  The engine itself is thread-based."""
 import asyncio
+from typing import Any, Awaitable
 
 
-async def shield_and_wait(task):
-    """Await ``task`` to completion even if the awaiting coroutine is cancelled; re-raise the cancellation after."""
-    if not isinstance(task, asyncio.Task):
-        task = asyncio.create_task(task)
-    cancel_exc = None
-    while True:
+async def shield_and_wait(task: Awaitable[Any]) -> Any:
+    """Run ``task`` to completion no matter how often the caller is cancelled meanwhile; then deliver the cancellation
+    (if there was one) or the task's result / exception."""
+    inner = asyncio.ensure_future(task)
+    loop = asyncio.get_running_loop()
+    was_cancelled = False
+    while not inner.done():
+        wake = loop.create_future()
+        inner.add_done_callback(lambda _done, wake=wake: wake.cancelled() or wake.done() or wake.set_result(None))
         try:
-            result = await asyncio.shield(task)
-            break
-        except asyncio.CancelledError as e:
-            cancel_exc = e
-    if cancel_exc is not None:
-        raise cancel_exc
-    return result
+            await wake
+        except asyncio.CancelledError:
+            was_cancelled = True  # remember it; the critical section is not finished yet
+    if was_cancelled:
+        inner.exception() if not inner.cancelled() else None  # mark a possible exception as retrieved
+        raise asyncio.CancelledError()
+    return inner.result()
