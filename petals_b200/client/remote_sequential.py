@@ -1,10 +1,16 @@
-"""``RemoteSequential``: an ``nn.Module`` whose layers are transformer blocks served by stage workers
-(reference: src/petals/client/remote_sequential.py:20-111)."""
+"""``RemoteSequential``: the transformer blocks of a model, as an ``nn.Module`` whose layers live on stage workers.
+
+Call surface of the reference (src/petals/client/remote_sequential.py:20-111): differentiable ``forward`` outside a session,
+a KV-cached step inside ``with seq.inference_session(max_length=...)``, ``seq[i]`` / ``seq[a:b]`` views, ``use_session``,
+``active_session``, ``position``.  The implementation is organised around one small object, :class:`_SessionScope`, that owns
+the "which session is active in this context" state, so nested / concurrent contexts (threads, asyncio tasks) each see
+their own session.
+"""
 from __future__ import annotations
 
-from contextlib import contextmanager
-from contextvars import ContextVar
-from typing import Optional, Union
+import contextlib
+import contextvars
+from typing import Iterator, Optional, Union
 
 import torch
 from torch import nn
@@ -13,7 +19,7 @@ from petals_b200.client.config import ClientConfig
 from petals_b200.client.inference_session import InferenceSession
 from petals_b200.client.routing import RemoteSequenceManager
 from petals_b200.client.sequential_autograd import _RemoteSequentialAutogradFunction
-from petals_b200.data_structures import UID_DELIMITER, make_uid
+from petals_b200.data_structures import make_uid
 from petals_b200.parallel.swarm import Swarm
 from petals_b200.utils.logging import get_logger
 from petals_b200.utils.misc import DUMMY
@@ -21,74 +27,93 @@ from petals_b200.utils.misc import DUMMY
 logger = get_logger(__name__)
 
 
-class RemoteSequential(nn.Module):
-    """A sequence of transformer blocks hosted by the swarm of stages.
+class _SessionScope:
+    """Context-local pointer to the inference session that ``forward`` should step."""
 
-    Outside of an inference session, ``forward`` is differentiable (w.r.t. inputs and deep prompts) and pipelines
-    micro-batches through the stages; inside ``with seq.inference_session(max_length=...)`` it is a step of a
-    fault-tolerant server-side-KV session. ``seq[a:b]`` / ``seq[i]`` are views that share routing state."""
+    def __init__(self):
+        self._var: contextvars.ContextVar = contextvars.ContextVar("petals_b200_active_session", default=None)
+
+    @property
+    def current(self) -> Optional[InferenceSession]:
+        return self._var.get()
+
+    @contextlib.contextmanager
+    def bound_to(self, session: Optional[InferenceSession]) -> Iterator[Optional[InferenceSession]]:
+        token = self._var.set(session)
+        try:
+            yield session
+        finally:
+            self._var.reset(token)
+
+
+def _span_uids(config: ClientConfig, start_block: Optional[int], end_block: Optional[int]) -> tuple:
+    first = 0 if start_block is None else start_block
+    last = config.num_hidden_layers if end_block is None else end_block
+    return tuple(make_uid(config.dht_prefix, index) for index in range(first, last))
+
+
+class RemoteSequential(nn.Module):
+    """A span of blocks served by the swarm.
+
+    * no session active: ``forward(inputs[, prompts])`` pipelines micro-batches through the stages and is differentiable
+      with respect to ``inputs`` and the deep ``prompts`` (``[n_blocks, batch, pre_seq_len, hidden]``);
+    * inside ``inference_session`` / ``use_session``: ``forward`` is one step of a fault-tolerant session whose KV caches
+      live on the stages."""
 
     def __init__(self, config: ClientConfig, *, sequence_manager: Optional[RemoteSequenceManager] = None, dht: Optional[Swarm] = None,
                  start_block: Optional[int] = None, end_block: Optional[int] = None, **kwargs):
         super().__init__()
         self.config = config
-        assert sequence_manager is None or (dht is None and start_block is None and end_block is None), \
-            "`dht`, `start_block`, and `end_block` have no effect when you provide a custom `sequence_manager`"
-        if sequence_manager is None:
-            if start_block is None:
-                start_block = 0
-            if end_block is None:
-                end_block = self.config.num_hidden_layers
-            block_uids = tuple(make_uid(config.dht_prefix, i) for i in range(start_block, end_block))
-            sequence_manager = RemoteSequenceManager(config, block_uids, dht=dht, **kwargs)
-        self.sequence_manager = sequence_manager
-        self._active_session: ContextVar = ContextVar("active_session", default=None)
+        if sequence_manager is not None:
+            assert dht is None and start_block is None and end_block is None, \
+                "`dht`, `start_block`, and `end_block` have no effect when you provide a custom `sequence_manager`"
+            self.sequence_manager = sequence_manager
+        else:
+            self.sequence_manager = RemoteSequenceManager(config, _span_uids(config, start_block, end_block), dht=dht, **kwargs)
+        self._scope = _SessionScope()
 
+    # ---- execution ---------------------------------------------------------------------------------------------------------
     def forward(self, inputs: torch.Tensor, prompts: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
         assert inputs.ndim == 3, "inputs must be a tensor of shape [batch_size, seq_length, hidden_size]"
-        if self.active_session is None:
-            assert all(v is None for v in kwargs.values()), f"Extra kwargs are not supported in forward: {kwargs}"
-            return _RemoteSequentialAutogradFunction.apply(inputs, prompts if prompts is not None else DUMMY, self.sequence_manager)
-        return self.active_session.step(inputs, prompts, **kwargs)
+        session = self._scope.current
+        if session is not None:
+            return session.step(inputs, prompts, **kwargs)
+        unsupported = {name: value for name, value in kwargs.items() if value is not None}
+        assert not unsupported, f"Extra kwargs are not supported in forward: {unsupported}"
+        return _RemoteSequentialAutogradFunction.apply(inputs, DUMMY if prompts is None else prompts, self.sequence_manager)
 
+    # ---- sessions ------------------------------------------------------------------------------------------------------------
     @property
     def active_session(self) -> Optional[InferenceSession]:
-        """The session used by ``forward`` (set by ``inference_session`` / ``use_session``), per context."""
-        return self._active_session.get()
+        """The session ``forward`` steps in the current context (thread / task), if any."""
+        return self._scope.current
 
     @property
     def position(self) -> int:
-        return self.active_session.position
+        return self._scope.current.position
 
-    @contextmanager
-    def use_session(self, session: Optional[InferenceSession]) -> InferenceSession:
-        """Run ``forward`` calls through an existing session (or, with ``None``, outside of any session)."""
-        token = self._active_session.set(session)
-        try:
+    def use_session(self, session: Optional[InferenceSession]):
+        """``with seq.use_session(sess):`` routes ``forward`` through an existing session (``None``: outside of any)."""
+        return self._scope.bound_to(session)
+
+    @contextlib.contextmanager
+    def inference_session(self, **kwargs) -> Iterator[InferenceSession]:
+        """``with seq.inference_session(max_length=N) as sess:`` opens a session, makes it active, closes it on exit."""
+        assert self._scope.current is None, "Already in an inference session"
+        with InferenceSession(self.sequence_manager, **kwargs) as session, self._scope.bound_to(session):
             yield session
-        finally:
-            self._active_session.reset(token)
 
-    @contextmanager
-    def inference_session(self, **kwargs) -> InferenceSession:
-        """``with seq.inference_session(max_length=N) as sess:`` — creates a session and makes it active."""
-        assert self.active_session is None, "Already in an inference session"
-        with InferenceSession(self.sequence_manager, **kwargs) as session:
-            token = self._active_session.set(session)
-            try:
-                yield session
-            finally:
-                self._active_session.reset(token)
-
-    def __getitem__(self, ix: Union[int, slice]) -> "RemoteSequential":
-        return RemoteSequential(self.config, sequence_manager=self.sequence_manager[ix])
-
-    def __iter__(self):
-        for block_index in range(len(self)):
-            yield self[block_index]
-
+    # ---- container protocol -----------------------------------------------------------------------------------------------------
     def __len__(self) -> int:
         return len(self.sequence_manager)
 
+    def __getitem__(self, ix: Union[int, slice]) -> "RemoteSequential":
+        """A view over a sub-span; it shares the routing state (known servers, bans, pings) with its parent."""
+        return type(self)(self.config, sequence_manager=self.sequence_manager[ix])
+
+    def __iter__(self) -> Iterator["RemoteSequential"]:
+        return (self[index] for index in range(len(self)))
+
     def extra_repr(self) -> str:
-        return f"modules={self.sequence_manager.block_uids[0]}..{self.sequence_manager.block_uids[-1]}"
+        uids = self.sequence_manager.block_uids
+        return f"modules={uids[0]}..{uids[-1]}"

@@ -77,3 +77,22 @@ def test_graphed_callable_falls_back_on_cpu():
 
     fn = make_inference_graphed_callable(lambda a, b: a * 2 + b, (torch.ones(3), torch.zeros(3)))
     assert torch.equal(fn(torch.full((3,), 2.0), torch.ones(3)), torch.full((3,), 5.0))
+
+
+def test_task_prioritizers_and_spending_policies():
+    from petals_b200.client.routing.spending_policy import ConstantSpendingPolicy, NoSpendingPolicy, SpendingPolicyBase
+    from petals_b200.server.task_prioritizer import DummyTaskPrioritizer, PointsTaskPrioritizer, TaskPrioritizerBase
+
+    dummy = DummyTaskPrioritizer()
+    assert dummy.prioritize(points=0.0, type="inference") == 1.0 < dummy.prioritize(points=5.0, type="forward") == 2.0
+    assert dummy.prioritize(points=0.0, type="backward") == 2.0
+    paid = PointsTaskPrioritizer()
+    assert paid.prioritize(points=0, type="inference") == 1.0 and paid.prioritize(points=3, type="inference") < 1.0
+    assert 1.0 < paid.prioritize(points=1e9, type="forward") < paid.prioritize(points=1, type="forward") < 2.0  # never overtakes inference
+    with pytest.raises(NotImplementedError):
+        TaskPrioritizerBase().prioritize(points=0.0)
+    assert NoSpendingPolicy().get_points("rpc_inference") == 0.0 and ConstantSpendingPolicy(2).get_points("rpc_forward", 1, x=2) == 2.0
+    with pytest.raises(ValueError):
+        ConstantSpendingPolicy(-1)
+    with pytest.raises(NotImplementedError):
+        SpendingPolicyBase().get_points("rpc_forward")
