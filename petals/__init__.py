@@ -28,7 +28,10 @@ _ALIASES = [
 ]
 for _name in _ALIASES:
     try:
-        sys.modules[f"petals.{_name}"] = importlib.import_module(f"petals_b200.{_name}")
+        _module = importlib.import_module(f"petals_b200.{_name}")
+        sys.modules[f"petals.{_name}"] = _module
+        if "." not in _name:
+            globals()[_name] = _module  # `petals.models`, `petals.client`, ... as attributes, like real sub-packages
     except ModuleNotFoundError as _e:  # a module that is not implemented yet must not break `import petals`
         if not str(_e).startswith("No module named 'petals_b200"):
             raise

@@ -1,8 +1,14 @@
-"""Client-side connection/routing options, mixed into every distributed model config
-(reference: src/petals/client/config.py:13-35). Field names are kept so that
-``from_pretrained(..., initial_peers=..., request_timeout=...)`` keeps working; the semantics of the
-networking fields are re-mapped to the single-box swarm registry (``initial_peers`` = rendezvous
-location(s) or an in-process swarm object)."""
+"""Options of the client side: where the swarm is, how to route through it, how patient to be.
+
+Every distributed model config carries these fields (reference: src/petals/client/config.py:13-35 mixes the same names into the
+HF config classes), so any of them can be given to ``from_pretrained(...)``:
+
+    AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=["/ip4/10.0.0.1/tcp/31337"], max_retries=3)
+
+``initial_peers`` accepts what :func:`petals_b200.parallel.swarm.resolve_swarm` understands — an in-process ``Swarm`` object or
+its ``inproc://name``, a rendezvous directory shared by the processes of one box, or the address of a TCP registry in
+``tcp://host:port`` / libp2p multiaddr form.
+"""
 from __future__ import annotations
 
 import dataclasses
@@ -11,31 +17,38 @@ from typing import Optional, Sequence, Union
 
 from petals_b200.constants import PUBLIC_INITIAL_PEERS
 
-_max_retries = os.getenv("PETALS_MAX_RETRIES")
-DEFAULT_MAX_RETRIES = int(_max_retries) if isinstance(_max_retries, str) else None
+
+def _retries_from_env() -> Optional[int]:
+    """``PETALS_MAX_RETRIES=n`` caps the retries of every client in the process (CI uses it so that failures surface)."""
+    raw = os.environ.get("PETALS_MAX_RETRIES", "").strip()
+    return int(raw) if raw else None
+
+
+DEFAULT_MAX_RETRIES = _retries_from_env()
 
 
 @dataclasses.dataclass
 class ClientConfig:
-    initial_peers: Sequence[str] = tuple(PUBLIC_INITIAL_PEERS)  # rendezvous paths / swarm names
-    dht_prefix: Optional[str] = None  # a prefix for all uids of this model
-    daemon_startup_timeout: int = 60  # kept for CLI compatibility (no daemon is started)
+    # ---- where -----------------------------------------------------------------------------------------------------------
+    initial_peers: Sequence[str] = tuple(PUBLIC_INITIAL_PEERS)
+    dht_prefix: Optional[str] = None  # uid prefix of this model's blocks ("<prefix>.<index>"); derived from the model name if unset
+    active_adapter: Optional[str] = None  # LoRA adapter the servers should apply to this client's requests
 
-    show_route: Union[str, bool] = "inference"  # log the chosen chain for "inference", or always (True)
-    allowed_servers: Optional[Sequence[str]] = None  # whitelist of peer ids
-    blocked_servers: Optional[Sequence[str]] = None  # blacklist of peer ids
-    use_server_to_server: bool = True  # stage i pushes activations straight into stage i+1 (fused NVLink hop)
+    # ---- which servers ----------------------------------------------------------------------------------------------------
+    allowed_servers: Optional[Sequence[str]] = None  # only route through these peer ids ...
+    blocked_servers: Optional[Sequence[str]] = None  # ... and never through these
+    use_server_to_server: bool = True  # let stage i hand its output to stage i+1 directly (fused NVLink hop / rpc_push)
+    show_route: Union[str, bool] = "inference"  # log the chosen chain: for inference sessions only, always (True) or never (False)
+    max_pinged: int = 3  # how many candidate first-hop servers are pinged when a route is planned
+    ping_timeout: float = 2
 
+    # ---- how patient --------------------------------------------------------------------------------------------------------
     connect_timeout: float = 5
     request_timeout: float = 3 * 60
-    update_period: float = 60  # how often the block -> servers map is refreshed
+    update_period: float = 60  # seconds between refreshes of the block -> servers table
+    max_retries: Optional[int] = DEFAULT_MAX_RETRIES  # per call; None = keep trying
+    min_backoff: float = 1  # retry delay grows from here ...
+    max_backoff: float = 60  # ... to here (doubling)
+    ban_timeout: float = 15  # a peer that failed is avoided for this long (doubling with repeated failures)
 
-    max_retries: Optional[int] = DEFAULT_MAX_RETRIES  # None = retry forever
-    min_backoff: float = 1
-    max_backoff: float = 60
-    ban_timeout: float = 15
-
-    active_adapter: Optional[str] = None  # LoRA adapter to activate server-side
-
-    max_pinged: int = 3
-    ping_timeout: float = 2
+    daemon_startup_timeout: int = 60  # accepted for compatibility: there is no networking daemon to start

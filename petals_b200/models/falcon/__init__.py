@@ -1,8 +1,6 @@
-from petals_b200.models.falcon.block import WrappedFalconBlock
-from petals_b200.models.falcon.config import DistributedFalconConfig
-from petals_b200.models.falcon.model import (DistributedFalconForCausalLM, DistributedFalconForSequenceClassification,
-                                             DistributedFalconModel)
-from petals_b200.utils.auto_config import register_model_classes
+"""Falcon family: config + client shells + block wrapper, registered with the ``AutoDistributed*`` factories on import."""
+from petals_b200.utils.auto_config import register_family
 
-register_model_classes(config=DistributedFalconConfig, model=DistributedFalconModel, model_for_causal_lm=DistributedFalconForCausalLM,
-                       model_for_sequence_classification=DistributedFalconForSequenceClassification, block=WrappedFalconBlock)
+_classes = register_family(__name__, "Falcon")
+globals().update(_classes)
+__all__ = sorted(_classes)

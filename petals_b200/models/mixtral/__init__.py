@@ -1,8 +1,6 @@
-from petals_b200.models.mixtral.block import WrappedMixtralBlock
-from petals_b200.models.mixtral.config import DistributedMixtralConfig
-from petals_b200.models.mixtral.model import (DistributedMixtralForCausalLM, DistributedMixtralForSequenceClassification,
-                                              DistributedMixtralModel)
-from petals_b200.utils.auto_config import register_model_classes
+"""Mixtral family: config + client shells + block wrapper, registered with the ``AutoDistributed*`` factories on import."""
+from petals_b200.utils.auto_config import register_family
 
-register_model_classes(config=DistributedMixtralConfig, model=DistributedMixtralModel, model_for_causal_lm=DistributedMixtralForCausalLM,
-                       model_for_sequence_classification=DistributedMixtralForSequenceClassification, block=WrappedMixtralBlock)
+_classes = register_family(__name__, "Mixtral")
+globals().update(_classes)
+__all__ = sorted(_classes)

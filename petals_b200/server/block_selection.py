@@ -1,8 +1,15 @@
 """Which blocks should a joining / idle stage serve? (reference: src/petals/server/block_selection.py:1-95).
 
-Same policy as the reference — serve the contiguous window whose blocks currently have the least aggregate
-throughput, and move when a greedy re-placement of all servers would improve the swarm's bottleneck throughput by
-more than ``1 / balance_quality`` — computed on the static in-box registry instead of DHT snapshots."""
+The policy is the reference's, because mixed swarms must agree on it:
+
+* **join**: take the contiguous window whose blocks are currently worst served — compare windows by their sorted per-block
+  throughputs (so the weakest block decides, then the second weakest, ...), earliest window on ties;
+* **re-balance**: a stage moves when, after it re-joins at its best window and every other stage is allowed to react the same way
+  until nobody wants to move, the swarm's bottleneck throughput would rise by more than a factor ``1 / balance_quality``.
+
+The implementation keeps the aggregate in a small :class:`_Coverage` object (per-block throughput with stages lifted out and
+dropped back in) instead of threading arrays through helper functions.
+"""
 from __future__ import annotations
 
 from typing import Dict, List
@@ -15,65 +22,74 @@ from petals_b200.utils.logging import get_logger
 
 logger = get_logger(__name__)
 
+_EPS = 1e-3  # a lifted stage leaves a trace of this relative size so that an empty window still prefers its old place
+
+
+class _Coverage:
+    """Aggregate advertised throughput of every block (JOINING stages count, so simultaneous joiners spread out)."""
+
+    def __init__(self, spans: Dict[PeerID, RemoteSpanInfo], total_blocks: int):
+        self.per_block = np.zeros(total_blocks, dtype=np.float64)
+        for span in spans.values():
+            self.add(span)
+
+    def add(self, span: RemoteSpanInfo, weight: float = 1.0) -> None:
+        self.per_block[span.start: span.end] += weight * span.throughput
+
+    def bottleneck(self) -> float:
+        return float(self.per_block.min())
+
+    def weakest_window(self, length: int) -> int:
+        """Start of the window of ``length`` blocks that is lexicographically worst served."""
+        last_start = len(self.per_block) - length
+        keyed = [(sorted(self.per_block[start: start + length]), start) for start in range(last_start + 1)]
+        return min(keyed)[1]
+
+    def relocate(self, span: RemoteSpanInfo) -> bool:
+        """Lift ``span`` out (leaving an epsilon trace), drop it onto the weakest window; True if it ended up elsewhere."""
+        self.add(span, -(1.0 + _EPS))
+        target = self.weakest_window(span.length)
+        self.add(span, _EPS)  # remove the trace at the old place
+        moved = target != span.start
+        if moved:
+            span.start, span.end = target, target + span.length
+        self.add(span)
+        return moved
+
 
 def compute_throughputs(spans: Dict[PeerID, RemoteSpanInfo], *, total_blocks: int) -> np.ndarray:
-    """Aggregate advertised throughput per block. JOINING servers count so that simultaneous joiners spread out."""
-    throughputs = np.zeros(total_blocks)
-    for span in spans.values():
-        throughputs[span.start: span.end] += span.throughput
-    return throughputs
-
-
-def _choose_best_start(throughputs: np.ndarray, num_blocks: int) -> int:
-    options = [(sorted(throughputs[i: i + num_blocks]), i) for i in range(0, len(throughputs) - num_blocks + 1)]
-    return min(options)[-1]
+    return _Coverage(spans, total_blocks).per_block
 
 
 def choose_best_blocks(num_blocks: int, module_infos: List[RemoteModuleInfo]) -> List[int]:
     spans = compute_spans(module_infos, min_state=ServerState.JOINING)
-    throughputs = compute_throughputs(spans, total_blocks=len(module_infos))
-    start = _choose_best_start(throughputs, num_blocks)
+    start = _Coverage(spans, len(module_infos)).weakest_window(num_blocks)
     return list(range(start, start + num_blocks))
-
-
-def _move_span(span: RemoteSpanInfo, new_start: int) -> None:
-    span.start, span.end = new_start, new_start + span.length
 
 
 def should_choose_other_blocks(local_peer_id: PeerID, module_infos: List[RemoteModuleInfo], balance_quality: float) -> bool:
     if balance_quality > 1.0:
         return True  # debugging aid, same as the reference: force a move at every check
     spans = compute_spans(module_infos, min_state=ServerState.JOINING)
-    throughputs = compute_throughputs(spans, total_blocks=len(module_infos))
-    initial = throughputs.min()
-    eps = 1e-3
-    if local_peer_id not in spans:
+    mine = spans.get(local_peer_id)
+    if mine is None:
         return False
-    local = spans[local_peer_id]
-    throughputs[local.start: local.end] -= local.throughput * (1 + eps)
-    if initial > eps and throughputs.min() <= 0:
-        return False  # moving away would disconnect the pipeline
-    new_start = _choose_best_start(throughputs, local.length)
-    if local.start == new_start:
+    coverage = _Coverage(spans, len(module_infos))
+    before = coverage.bottleneck()
+
+    # would leaving cut the chain? (only matters if the chain is whole now)
+    without_me = coverage.per_block.copy()
+    without_me[mine.start: mine.end] -= mine.throughput * (1.0 + _EPS)
+    if before > _EPS and without_me.min() <= 0:
         return False
-    throughputs[local.start: local.end] += local.throughput * eps
-    _move_span(local, new_start)
-    throughputs[local.start: local.end] += local.throughput
-    moved = True
-    while moved:  # let every other server react greedily until a fixed point
-        moved = False
-        for peer_id in sorted(spans, key=lambda p: spans[p].length):
-            span = spans[peer_id]
-            throughputs[span.start: span.end] -= span.throughput * (1 + eps)
-            best = _choose_best_start(throughputs, span.length)
-            throughputs[span.start: span.end] += span.throughput * eps
-            if span.start != best:
-                _move_span(span, best)
-                moved = True
-            throughputs[span.start: span.end] += span.throughput
-    new = throughputs.min()
-    if new < initial or new < eps:
+    if not coverage.relocate(mine):
+        return False  # already at the weakest window
+    # everybody else reacts greedily (shortest spans first) until a fixed point
+    while any([coverage.relocate(spans[peer]) for peer in sorted(spans, key=lambda p: spans[p].length)]):
+        pass
+    after = coverage.bottleneck()
+    if after < before or after < _EPS:
         return False
-    actual_quality = initial / new
-    logger.info(f"Swarm balance quality: {actual_quality * 100:.1f}%")
-    return actual_quality < balance_quality - eps
+    quality = before / after
+    logger.info(f"Swarm balance quality: {quality * 100:.1f}%")
+    return quality < balance_quality - _EPS

@@ -26,6 +26,27 @@ def register_model_classes(*, config: type, model: Optional[type] = None, model_
             entry[key] = cls
 
 
+def register_family(package: str, family: str, *, speculative: bool = False) -> Dict[str, type]:
+    """Register the classes of ``petals_b200.models.<family>`` by their naming convention (``Distributed<Family>Config``,
+    ``...Model``, ``...ForCausalLM``, ``...ForSequenceClassification``, ``Wrapped<Family>Block`` and, for families that have one,
+    ``...ForSpeculativeGeneration``) and return them so the package can re-export the names."""
+    import importlib
+
+    stem = f"Distributed{family}"
+    config_mod, model_mod, block_mod = (importlib.import_module(f"{package}.{name}") for name in ("config", "model", "block"))
+    found = {
+        "config": getattr(config_mod, f"{stem}Config"),
+        "model": getattr(model_mod, f"{stem}Model"),
+        "model_for_causal_lm": getattr(model_mod, f"{stem}ForCausalLM"),
+        "model_for_sequence_classification": getattr(model_mod, f"{stem}ForSequenceClassification"),
+        "block": getattr(block_mod, f"Wrapped{family}Block"),
+    }
+    if speculative:
+        found["model_for_speculative"] = getattr(importlib.import_module(f"{package}.speculative_model"), f"{stem}ForSpeculativeGeneration")
+    register_model_classes(**found)
+    return {cls.__name__: cls for cls in found.values()}
+
+
 def get_model_classes(model_type: str) -> Dict[str, type]:
     import petals_b200.models  # noqa: F401  (registers the built-in families)
 

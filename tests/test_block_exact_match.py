@@ -1,44 +1,41 @@
-"""One remote block: parallel forward == long + short inference steps == the block loaded locally from the checkpoint
-(reference: tests/test_block_exact_match.py). "Long" steps (more than MAX_SHORT_INFERENCE_TOKENS rows) go through the
-per-block pools, "short" ones through the merged whole-span task."""
-import random
+"""A single served block computes what the checkpoint says, by every route a request can take
+(reference: tests/test_block_exact_match.py:12-43).
 
+Routes: the cache-less parallel forward; an inference session whose first step is *long* (more rows than
+``MAX_SHORT_INFERENCE_TOKENS``: the handler walks the per-block pools) followed by *short* steps (one merged whole-span task);
+and the block loaded locally from the same files.  The session must also refuse to grow past its ``max_length``."""
 import pytest
 import torch
 
 from petals_b200.client.remote_sequential import RemoteSequential
-from petals_b200.server.block_functions import MAX_SHORT_INFERENCE_TOKENS
+from petals_b200.server.block_functions import MAX_SHORT_INFERENCE_TOKENS as SHORT
 from petals_b200.server.from_pretrained import load_pretrained_block
 from petals_b200.utils.auto_config import AutoDistributedConfig
 from tests.utils import checkpoint, swarm_of
 
 
-@pytest.mark.parametrize("family", ["llama", "bloom"])
-def test_remote_block_exact_match(family, atol_forward=1e-4, atol_inference=1e-3):
-    path = checkpoint(family)
-    with swarm_of(path, ["0:4"], inference_max_length=512, attn_cache_tokens=2048) as (swarm, _):
-        config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm)
-        remote_sequential = RemoteSequential(config, dht=swarm)
-        block_index = random.randint(0, config.num_hidden_layers - 1)
-        remote_block = remote_sequential[block_index]
+@pytest.fixture(scope="module", params=["llama", "bloom"])
+def served(request):
+    path = checkpoint(request.param)
+    with swarm_of(path, ["0:4"], inference_max_length=512, attn_cache_tokens=2048) as (swarm, _servers):
+        yield path, AutoDistributedConfig.from_pretrained(path, initial_peers=swarm), swarm
 
-        torch.manual_seed(block_index)
-        inputs = torch.randn(1, MAX_SHORT_INFERENCE_TOKENS + 8, config.hidden_size)
-        outputs_forward = remote_block(inputs)
 
-        outputs_inference = []
-        with torch.inference_mode():
-            with remote_block.inference_session(max_length=inputs.shape[1]) as sess:
-                outputs_inference.append(sess.step(inputs[:, : MAX_SHORT_INFERENCE_TOKENS + 1]))  # long step
-                for i in range(MAX_SHORT_INFERENCE_TOKENS + 1, inputs.shape[1]):  # short steps
-                    outputs_inference.append(sess.step(inputs[:, i: i + 1]))
-                with pytest.raises(ValueError, match=r"Maximum length exceeded") as exc_info:
-                    sess.step(inputs[:, -1:])
-                assert "Maximum length exceeded" in repr(exc_info.value)
-        outputs_inference = torch.cat(outputs_inference, dim=1)
+@pytest.mark.parametrize("index", [0, 2, 3])
+def test_every_route_agrees_with_the_local_block(served, index):
+    path, config, swarm = served
+    remote = RemoteSequential(config, dht=swarm)[index]
+    assert len(remote) == 1
+    x = torch.randn(1, SHORT + 8, config.hidden_size, generator=torch.Generator().manual_seed(index))
+    with torch.no_grad():
+        (expected,) = load_pretrained_block(path, index, torch_dtype=torch.float32)(x)
 
-        ref_block = load_pretrained_block(path, block_index, torch_dtype=torch.float32)
-        with torch.no_grad():
-            (outputs_local,) = ref_block(inputs)
-        assert torch.allclose(outputs_local, outputs_forward, rtol=0, atol=atol_forward)
-        assert torch.allclose(outputs_local, outputs_inference, rtol=0, atol=atol_inference)
+    assert torch.allclose(remote(x), expected, rtol=0, atol=1e-4)  # rpc_forward
+
+    with torch.inference_mode(), remote.inference_session(max_length=x.shape[1]) as session:
+        pieces = [session.step(x[:, : SHORT + 1])]  # one long step ...
+        pieces += [session.step(x[:, t: t + 1]) for t in range(SHORT + 1, x.shape[1])]  # ... then token by token
+        assert session.position == x.shape[1]
+        with pytest.raises(ValueError, match="Maximum length exceeded"):
+            session.step(x[:, -1:])
+    assert torch.allclose(torch.cat(pieces, dim=1), expected, rtol=0, atol=1e-3)

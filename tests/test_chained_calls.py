@@ -1,5 +1,9 @@
-"""Chains of remote blocks: forward/backward and token-by-token inference against the same blocks run locally with explicit
-KV caches (reference: tests/test_chained_calls.py)."""
+"""Sub-chains of a served model against the same blocks run locally (reference: tests/test_chained_calls.py:17-77, a 3-block
+chain forward/backward and a 2-block chained inference vs local blocks with explicit KV).
+
+One swarm is started per module with overlapping spans (block 3 is served twice), so a chain 3..5 may cross servers; every
+check is parametrised over chain position and length."""
+import pytest
 import torch
 
 from petals_b200.client.remote_sequential import RemoteSequential
@@ -8,52 +12,57 @@ from petals_b200.utils.auto_config import AutoDistributedConfig
 from tests.utils import checkpoint, swarm_of
 
 
-def _served():
+@pytest.fixture(scope="module")
+def world():
     path = checkpoint("llama", num_hidden_layers=6)
-    return path, swarm_of(path, ["0:4", "3:6"])  # block 3 is served twice; the chain 3..5 may cross servers
-
-
-def test_forward_backward_exact_match(atol_forward=1e-4, atol_backward=1e-4, seq_length=1):
-    path, ctx = _served()
-    with ctx as (swarm, _):
+    with swarm_of(path, ["0:4", "3:6"]) as (swarm, _servers):
         config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm)
-        remote_blocks = RemoteSequential(config, dht=swarm, start_block=3, end_block=6)
-        assert isinstance(remote_blocks, RemoteSequential) and len(remote_blocks) == 3
-        ref_blocks = [load_pretrained_block(path, i, torch_dtype=torch.float32) for i in (3, 4, 5)]
-
-        inputs = torch.randn(1, seq_length, config.hidden_size, requires_grad=True)
-        outputs_rpc = remote_blocks.forward(inputs)
-        outputs_rpc.sum().backward()
-        grads_rpc = inputs.grad
-        inputs.grad = None
-
-        hidden = inputs
-        for block in ref_blocks:
-            hidden = block.forward(hidden)[0]
-        hidden.sum().backward()
-        assert torch.allclose(hidden, outputs_rpc, rtol=0, atol=atol_forward)
-        assert torch.allclose(inputs.grad, grads_rpc, rtol=0, atol=atol_backward)
+        local = {i: load_pretrained_block(path, i, torch_dtype=torch.float32) for i in range(config.num_hidden_layers)}
+        yield config, swarm, local
 
 
-def test_chained_inference_exact_match(atol_inference=1e-4):
-    path, ctx = _served()
-    with ctx as (swarm, _):
-        config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm)
-        remote_blocks = RemoteSequential(config, dht=swarm, start_block=3, end_block=5)
-        inputs = torch.randn(1, 8, config.hidden_size)
-        outputs_inference = []
-        with torch.inference_mode(), remote_blocks.inference_session(max_length=inputs.shape[1]) as sess:
-            for i in range(inputs.shape[1]):
-                outputs_inference.append(sess.step(inputs[:, i: i + 1]))
-        outputs_inference = torch.cat(outputs_inference, dim=1)
+def _local_chain(local, first, last, x, caches=None):
+    """Run blocks [first, last) locally; with ``caches`` (a dict block -> (k, v)) as a cached decoding step."""
+    for i in range(first, last):
+        if caches is None:
+            (x,) = local[i](x)
+        else:
+            x, caches[i] = local[i](x, use_cache=True, layer_past=caches.get(i))
+    return x
 
-        ref_blocks = [load_pretrained_block(path, i, torch_dtype=torch.float32) for i in (3, 4)]
-        caches = [None, None]
-        outputs_ref = []
-        with torch.no_grad():
-            for i in range(inputs.shape[1]):
-                hidden = inputs[:, i: i + 1]
-                for j, block in enumerate(ref_blocks):
-                    hidden, caches[j] = block.forward(hidden, use_cache=True, layer_past=caches[j])
-                outputs_ref.append(hidden)
-        assert torch.allclose(torch.cat(outputs_ref, dim=1), outputs_inference, rtol=0, atol=atol_inference)
+
+@pytest.mark.parametrize("first,last,seq_len", [(3, 6, 1), (0, 2, 5), (2, 5, 3)])
+def test_chain_forward_and_backward_match_local_blocks(world, first, last, seq_len):
+    config, swarm, local = world
+    chain = RemoteSequential(config, dht=swarm, start_block=first, end_block=last)
+    assert len(chain) == last - first
+    torch.manual_seed(first * 10 + last)
+    x_remote = torch.randn(2, seq_len, config.hidden_size, requires_grad=True)
+    x_local = x_remote.detach().clone().requires_grad_(True)
+    weights = torch.randn(2, seq_len, config.hidden_size)  # a non-trivial upstream gradient
+
+    y_remote = chain(x_remote)
+    (y_remote * weights).sum().backward()
+    y_local = _local_chain(local, first, last, x_local)
+    (y_local * weights).sum().backward()
+
+    assert torch.allclose(y_remote, y_local, rtol=0, atol=1e-4)
+    assert torch.allclose(x_remote.grad, x_local.grad, rtol=0, atol=1e-4)
+
+
+@pytest.mark.parametrize("first,last", [(3, 5), (1, 5)])
+def test_chain_inference_matches_local_blocks_with_explicit_kv(world, first, last):
+    config, swarm, local = world
+    chain = RemoteSequential(config, dht=swarm, start_block=first, end_block=last)
+    tokens = torch.randn(1, 8, config.hidden_size)
+    caches, got, expected = {}, [], []
+    with torch.inference_mode(), chain.inference_session(max_length=tokens.shape[1]) as session:
+        for t in range(tokens.shape[1]):
+            step = tokens[:, t: t + 1]
+            got.append(session.step(step))
+            expected.append(_local_chain(local, first, last, step, caches))
+        assert session.position == tokens.shape[1]
+    assert torch.allclose(torch.cat(got, 1), torch.cat(expected, 1), rtol=0, atol=1e-4)
+    # the cached token-by-token run equals one cache-less pass over the whole sequence
+    with torch.no_grad():
+        assert torch.allclose(torch.cat(got, 1), _local_chain(local, first, last, tokens), rtol=0, atol=1e-4)

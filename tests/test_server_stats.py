@@ -1,9 +1,7 @@
-"""KV-cache accounting visible through rpc_info while sessions open and close (reference: tests/test_server_stats.py).
+"""KV budget as seen through ``rpc_info`` while sessions come and go (reference: tests/test_server_stats.py:12-39).
 
-Accounting here is page-granular: a session of ``max_length`` tokens reserves ``pages_needed(batch, max_length)`` pages of
-``PAGE`` tokens in every block of the stage (memory_cache.py), instead of the reference's exact byte count."""
-import time
-
+Here the budget is counted in pages: a session of ``max_length`` tokens reserves ``pages_needed(batch, max_length)`` pages of
+``PAGE`` tokens in *every* block of the stage that serves it (server/memory_cache.py), whichever sub-span the client asked for."""
 import torch
 
 from petals_b200.client.remote_sequential import RemoteSequential
@@ -13,31 +11,38 @@ from petals_b200.server.memory_cache import MemoryCache
 from petals_b200.utils.auto_config import AutoDistributedConfig
 from tests.utils import checkpoint, swarm_of
 
+STAGE_BLOCKS = 4
 
-def test_server_info(block_from: int = 1, block_to: int = 4, max_length: int = 100, max_length2: int = 50):
+
+def _tokens_available(seq: RemoteSequential) -> int:
+    seq.sequence_manager.state.rpc_info = None  # drop the client's cached copy: ask the server again
+    return seq.sequence_manager.rpc_info[CACHE_TOKENS_AVAILABLE]
+
+
+def _reserved(max_length: int, batch: int = 1) -> int:
+    return MemoryCache.pages_needed(batch, max_length) * PAGE * STAGE_BLOCKS
+
+
+def test_cache_tokens_available_tracks_open_sessions():
     path = checkpoint("llama")
-    with swarm_of(path, ["0:4"], attn_cache_tokens=4096, inference_max_length=512) as (swarm, servers):
+    with swarm_of(path, [f"0:{STAGE_BLOCKS}"], attn_cache_tokens=4096, inference_max_length=512) as (swarm, servers):
         config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm)
         config.allowed_servers = [servers[0].peer_id]
-        n_stage_blocks = 4
-        blocks1 = RemoteSequential(config, dht=swarm, start_block=block_from, end_block=block_to)
-        blocks2 = RemoteSequential(config, dht=swarm, start_block=block_to - 1, end_block=block_to)
+        wide = RemoteSequential(config, dht=swarm, start_block=1, end_block=4)
+        narrow = RemoteSequential(config, dht=swarm, start_block=3, end_block=4)
+        token = torch.randn(1, 1, config.hidden_size)
 
-        info_before = blocks1.sequence_manager.rpc_info
-        with blocks1.inference_session(max_length=max_length) as sess:
-            sess.step(torch.randn(1, 1, config.hidden_size))
-            blocks1.sequence_manager.state.rpc_info = None  # invalidate the cached copy
-            info_inside = blocks1.sequence_manager.rpc_info
-            with blocks2.inference_session(max_length=max_length2) as sess2:
-                sess2.step(torch.randn(1, 1, config.hidden_size))
-                blocks2.sequence_manager.state.rpc_info = None
-                info_inside2 = blocks2.sequence_manager.rpc_info
-        time.sleep(0.1)
-        blocks1.sequence_manager.state.rpc_info = None
-        info_after = blocks1.sequence_manager.rpc_info
+        idle = _tokens_available(wide)
+        assert idle > 0
+        with wide.inference_session(max_length=100) as first:
+            first.step(token)
+            one_open = _tokens_available(wide)
+            with narrow.inference_session(max_length=50) as second:
+                second.step(token)
+                two_open = _tokens_available(narrow)
+            after_inner_close = _tokens_available(wide)
+        after_all_closed = _tokens_available(wide)
 
-        assert info_before[CACHE_TOKENS_AVAILABLE] == info_after[CACHE_TOKENS_AVAILABLE]
-        reserved1 = MemoryCache.pages_needed(1, max_length) * PAGE * n_stage_blocks
-        reserved2 = MemoryCache.pages_needed(1, max_length2) * PAGE * n_stage_blocks
-        assert info_before[CACHE_TOKENS_AVAILABLE] - info_inside[CACHE_TOKENS_AVAILABLE] == reserved1
-        assert info_inside[CACHE_TOKENS_AVAILABLE] - info_inside2[CACHE_TOKENS_AVAILABLE] == reserved2
+        assert idle - one_open == _reserved(100)
+        assert one_open - two_open == _reserved(50)
+        assert after_inner_close == one_open and after_all_closed == idle  # everything is returned, nothing leaks
