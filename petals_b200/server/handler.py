@@ -217,7 +217,7 @@ class TransformerConnectionHandler:
         self.quant_type = quant_type
         self.metrics = ServerMetrics(peer_id)
         self.metrics.gauge("cache_tokens_left", lambda: stage.memory_cache.tokens_left * len(stage))
-        self.metrics.gauge("queue_size", lambda: inference_pool.runtime.queue_size() if getattr(inference_pool, "runtime", None) is not None else None)
+        self.metrics.gauge("queue_size", lambda: inference_pool.runtime.queue_size if getattr(inference_pool, "runtime", None) is not None else None)
         self.compression = None  # default wire codec of the responses on the socket transport (utils/compression.py)
         self._sessions: Dict[str, InferenceStream] = {}
         self._sessions_lock = threading.Lock()

@@ -58,7 +58,7 @@ def test_server_records_and_serves_metrics():
         assert snap["requests"] == {"inference": 2, "forward": 1, "backward": 1}
         assert snap["tokens"] == {"inference": 8, "forward": 10, "backward": 10}
         assert snap["errors"]["inference"] == 1 and snap["sessions_active"] == 0 and snap["sessions_opened"] == 1
-        assert snap["cache_tokens_left"] > 0 and snap["mean_latency_ms"]["inference"] > 0
+        assert snap["cache_tokens_left"] > 0 and snap["mean_latency_ms"]["inference"] > 0 and snap["queue_size"] == 0
         port = server.metrics_server.port
         text = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=5).read().decode()
         assert 'rpc="inference"} 2' in text and "petals_sessions_active" in text and "petals_cache_tokens_left" in text
