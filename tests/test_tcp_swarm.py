@@ -176,3 +176,56 @@ def test_run_dht_registry_and_two_server_processes_over_tcp(tmp_path):
                 p.kill()
         for f in logs:
             f.close()
+
+
+def test_failover_when_a_server_process_is_killed_mid_session(tmp_path):
+    """Blocks 2:4 are served by two processes; the one an inference session is using is SIGKILLed between two steps. The client
+    must notice the dead TCP stream, ban the peer, re-route through the replica and rebuild its KV cache by replaying the
+    history — the outputs stay exact (reference fault model: client/inference_session.py:364-391; its CI never kills a server)."""
+    path = checkpoint("llama")
+    registry = RegistryServer("tcp://127.0.0.1:0").start()
+    maddr = to_multiaddr(registry.address)
+    common = ["--initial_peers", maddr, "--torch_dtype", "float32", "--device", "cpu", "--throughput", "1", "--update_period", "1",
+              "--host_maddrs", "/ip4/127.0.0.1/tcp/0", "--skip_reachability_check"]
+    spans = {"head": "0:2", "tail-a": "2:4", "tail-b": "2:4"}
+    procs, logs = {}, []
+    try:
+        for name, span in spans.items():
+            logs.append(open(tmp_path / f"{name}.log", "w"))
+            procs[name] = _spawn(["petals.cli.run_server", path, "--block_indices", span, "--peer_id", name, *common], logs[-1])
+        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[maddr], max_retries=40, min_backoff=0.3, max_backoff=1.0,
+                                                                update_period=1.0)
+        config = AutoDistributedConfig.from_pretrained(path)
+        manager = model.model.layers.sequence_manager
+        deadline = time.monotonic() + 90
+        while sorted(manager.dht.peers()) != sorted(spans):  # all three have announced their endpoints
+            assert time.monotonic() < deadline and all(p.poll() is None for p in procs.values())
+            time.sleep(0.2)
+        manager.update()
+        x = torch.randn(1, 6, config.hidden_size, generator=torch.Generator().manual_seed(0))
+        with torch.inference_mode():
+            expected = x
+            for b in local_blocks(path, config.num_hidden_layers):
+                expected = b(expected)[0]
+            with model.model.layers.inference_session(max_length=8) as session:
+                first = session.step(x[:, :4])
+                used = [s.span.peer_id for s in session._server_sessions]
+                assert used[0] == "head" and used[1] in ("tail-a", "tail-b")
+                procs[used[1]].kill()  # no goodbye: the stream just dies
+                procs[used[1]].wait(timeout=10)
+                rest = torch.cat([session.step(x[:, 4:5]), session.step(x[:, 5:6])], dim=1)
+                survivor = [s.span.peer_id for s in session._server_sessions][1]
+        assert survivor != used[1] and survivor in ("tail-a", "tail-b")
+        assert torch.allclose(torch.cat([first, rest], dim=1), expected, atol=1e-4)
+    finally:
+        for p in procs.values():
+            if p.poll() is None:
+                p.send_signal(signal.SIGTERM)
+        for p in procs.values():
+            try:
+                p.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                p.kill()
+        for f in logs:
+            f.close()
+        registry.shutdown()
