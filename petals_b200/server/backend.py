@@ -59,6 +59,8 @@ class Stage:
         if name != self.active_adapter:
             for block in self.blocks:
                 set_active_adapter(block, name)
+            if getattr(self.engine, "lora_on_engine", False):
+                self.engine.use_adapter(name)  # merged-weight views + per-adapter graphs (server/stage_engine.py)
             self.active_adapter = name
 
     # ---- oracle helpers ----------------------------------------------------------------------------------
@@ -173,7 +175,8 @@ class Stage:
         return out
 
     def _lora_free(self) -> bool:
-        return self.active_adapter is None
+        """May this call run on the engine? Yes without an adapter, or when the engine serves adapters from merged weights."""
+        return self.active_adapter is None or getattr(self.engine, "lora_on_engine", False)
 
     @torch.no_grad()
     def _oracle_inference(self, session: SessionCache, hidden, prompts, hypo_ids, lo: int, hi: int) -> torch.Tensor:

@@ -99,10 +99,35 @@ class StageEngine:
         self._dev_pos = -1
         self._bufs: Dict[Tuple[str, int], torch.Tensor] = {}
         self._moe_bufs: Dict[str, torch.Tensor] = {}
+        # opt-in (PETALS_B200_LORA_ENGINE=1): requests with an active LoRA adapter run on the kernels against per-adapter merged copies
+        # of the targeted projections (utils/peft.py:MergedAdapterBlock) instead of falling back to the PyTorch executor. Each adapter
+        # has its own weight views and its own captured graphs; activation buffers are shared. Not combined with FP8 weights.
+        self.lora_on_engine = os.environ.get("PETALS_B200_LORA_ENGINE", "0") != "0" and not fp8
+        self._adapter: Optional[str] = None
+        self._adapter_state: Dict[Optional[str], tuple] = {}
         # scratch one-layer pool for cache-less forward passes
         n_scratch = max(1, (max_chunk_tokens + PAGE - 1) // PAGE) + 1
         self._scratch_pool = torch.zeros(2, n_scratch, s.num_kv_heads, PAGE, s.head_dim, dtype=self.dtype, device=self.device)
         self._scratch_pages = n_scratch
+
+    # ---- adapters ------------------------------------------------------------------------------------------
+    def use_adapter(self, name: Optional[str]) -> None:
+        """Switch the weight views and the graph cache to those of ``name`` (``None`` = the base weights)."""
+        if name == self._adapter:
+            return
+        if not self.lora_on_engine and name is not None:
+            raise RuntimeError("this engine does not serve adapters (PETALS_B200_LORA_ENGINE=1 enables merged-weight serving)")
+        self._adapter_state[self._adapter] = (self.blocks, self._graphs)
+        if name not in self._adapter_state:
+            from petals_b200.utils.peft import MergedAdapterBlock
+
+            base = self._adapter_state[None][0] if None in self._adapter_state else self.blocks
+            with torch.inference_mode(False):
+                views = [MergedAdapterBlock(b, name) for b in base]
+            logger.info(f"adapter {name}: merged copies of the targeted projections take {sum(v.merged_bytes for v in views) / 2**20:.0f} MiB")
+            self._adapter_state[name] = (views, {})
+        self.blocks, self._graphs = self._adapter_state[name]
+        self._adapter = name
 
     # ---- buffers ---------------------------------------------------------------------------------------
     def _w(self, slot: int, name: str) -> Optional[torch.Tensor]:

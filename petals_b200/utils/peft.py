@@ -106,6 +106,51 @@ def add_adapter_to_block(block, block_index: int, adapter_name: str, peft_config
     logger.debug(f"block {block_index}: loaded adapter {adapter_name} ({sum(len(v) for v in entry.values())} LoRA pairs)")
 
 
+def merge_lora(weight: torch.Tensor, entries) -> torch.Tensor:
+    """``W + sum(scale * B @ A)`` as a new tensor of ``weight``'s dtype. ``entries`` is one value of a block's adapter table:
+    ``[(A [r, in], B [rows, r], scale, rows-or-None)]`` where ``rows`` selects the output rows of a fused projection the pair applies to
+    (e.g. the q rows of ``wqkv``).  Accumulated in fp32 so that several pairs on one matrix round once."""
+    merged = weight.detach().float().clone()
+    for A, Bm, scale, rows in entries:
+        delta = (Bm.float() @ A.float()) * float(scale)
+        if rows is None:
+            merged += delta
+        else:
+            merged[rows] += delta
+    return merged.to(weight.dtype)
+
+
+class MergedAdapterBlock:
+    """A read-only view of a block in which the projections an adapter targets are replaced by merged copies ``W + scale * B A``;
+    every other attribute (norms, untouched projections, spec, helpers) is the base block's.  The kernels then serve a LoRA request at
+    full speed, at the price of one extra copy of the targeted matrices per adapter."""
+
+    def __init__(self, base, adapter_name: str):
+        create_lora_adapter(base)
+        if adapter_name not in base.lora_adapters:
+            raise KeyError(f"Adapter {adapter_name!r} is not loaded on this server (available: {sorted(base.lora_adapters)})")
+        object.__setattr__(self, "_base", base)
+        object.__setattr__(self, "_merged", {name: merge_lora(getattr(base, name), entries)
+                                             for name, entries in base.lora_adapters[adapter_name].items()})
+        object.__setattr__(self, "lora", {})  # already folded into the weights
+
+    def __getattr__(self, name: str):
+        merged = object.__getattribute__(self, "_merged")
+        if name in merged:
+            return merged[name]
+        return getattr(object.__getattribute__(self, "_base"), name)
+
+    def __setattr__(self, name, value):
+        raise AttributeError("MergedAdapterBlock is read-only")
+
+    def _p(self, name: str):
+        return getattr(self, name, None)
+
+    @property
+    def merged_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in object.__getattribute__(self, "_merged").values())
+
+
 def set_active_adapter(block, adapter_name: Optional[str]) -> None:
     create_lora_adapter(block)
     if adapter_name in (None, ""):

@@ -81,3 +81,88 @@ def test_lora_served_per_request(tmp_path):
         with pytest.raises(Exception):
             missing = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=swarm, active_adapter="nope", max_retries=1)
             missing(ids)
+
+
+def test_merged_adapter_views_equal_the_lora_forward(tmp_path):
+    """utils/peft.py:MergedAdapterBlock folds an adapter into copies of the targeted projections (what the kernels serve with
+    PETALS_B200_LORA_ENGINE=1): a plain block holding those weights computes exactly what the LoRA branch computes."""
+    from petals_b200.models.block_oracle import GenericBlock
+    from petals_b200.server.from_pretrained import load_pretrained_block
+    from petals_b200.utils.peft import MergedAdapterBlock, add_adapter_to_block, merge_lora, set_active_adapter
+
+    path = checkpoint("llama")
+    config = AutoDistributedConfig.from_pretrained(path)
+    adapter = make_adapter(str(tmp_path / "adapter"), config)
+    block = load_pretrained_block(path, 1, torch_dtype=torch.float32)
+    cfg, state = load_peft(adapter, block_idx=1)
+    add_adapter_to_block(block, 1, "a", cfg, state)
+    view = MergedAdapterBlock(block, "a")
+    spec = block.spec
+    # q and v pairs land on their rows of the fused projection, the k rows and untargeted matrices are the base tensors themselves
+    D, nq, nkv = spec.head_dim, spec.num_heads, spec.num_kv_heads
+    assert not torch.equal(view.wqkv[: nq * D], block.wqkv[: nq * D]) and torch.equal(view.wqkv[nq * D: (nq + nkv) * D], block.wqkv[nq * D: (nq + nkv) * D])
+    assert not torch.equal(view.wqkv[(nq + nkv) * D:], block.wqkv[(nq + nkv) * D:]) and not torch.equal(view.w_down, block.w_down)
+    assert view.w_up is block.w_up and view.ln1_w is block.ln1_w and view.spec is spec and view._p("bqkv") is None
+    assert view.merged_bytes == (block.wqkv.numel() + block.w_down.numel()) * 4
+    with pytest.raises(AttributeError):
+        view.wqkv = None
+    with pytest.raises(KeyError):
+        MergedAdapterBlock(block, "unknown")
+
+    merged = GenericBlock(spec, dtype=torch.float32)
+    with torch.no_grad():
+        for name in spec.param_shapes():
+            getattr(merged, name).copy_(getattr(view, name))
+    x = torch.randn(2, 5, spec.hidden_size)
+    set_active_adapter(block, "a")
+    with torch.no_grad():
+        with_lora = block.forward_cached(x, None, None, 0)
+        set_active_adapter(block, None)
+        without = block.forward_cached(x, None, None, 0)
+        folded = merged.forward_cached(x, None, None, 0)
+    assert torch.allclose(folded, with_lora, atol=1e-5) and not torch.allclose(with_lora, without, atol=1e-3)
+    # several pairs on one matrix accumulate; fp32 accumulation rounds once
+    w = torch.randn(6, 4).to(torch.bfloat16)
+    pairs = [(torch.randn(2, 4), torch.randn(6, 2), 0.5, None), (torch.randn(2, 4), torch.randn(3, 2), 2.0, slice(3, 6))]
+    ref = w.float() + 0.5 * pairs[0][1] @ pairs[0][0]
+    ref[3:6] += 2.0 * pairs[1][1] @ pairs[1][0]
+    assert torch.equal(merge_lora(w, pairs), ref.to(torch.bfloat16))
+
+
+def test_engine_adapter_switching_keeps_separate_graph_caches():
+    """server/stage_engine.py:StageEngine.use_adapter swaps (weight views, captured graphs) as a pair."""
+    import types
+
+    from petals_b200.server.stage_engine import StageEngine
+
+    base_blocks, base_graphs = [object(), object()], {("g", 0): "base-graph"}
+    eng = types.SimpleNamespace(lora_on_engine=True, _adapter=None, _adapter_state={}, blocks=base_blocks, _graphs=base_graphs)
+    made = []
+
+    class FakeView:
+        merged_bytes = 0
+
+        def __init__(self, base, name):
+            made.append((base, name))
+
+    import petals_b200.utils.peft as peft
+
+    real = peft.MergedAdapterBlock
+    peft.MergedAdapterBlock = FakeView
+    try:
+        StageEngine.use_adapter(eng, None)  # no-op
+        assert eng.blocks is base_blocks and not made
+        StageEngine.use_adapter(eng, "a")
+        assert [m[1] for m in made] == ["a", "a"] and [m[0] for m in made] == base_blocks and eng._graphs == {} and eng._adapter == "a"
+        eng._graphs[("g", 0)] = "a-graph"
+        StageEngine.use_adapter(eng, "b")
+        assert [m[0] for m in made[2:]] == base_blocks  # built from the base blocks, not from adapter a's views
+        StageEngine.use_adapter(eng, None)
+        assert eng.blocks is base_blocks and eng._graphs is base_graphs
+        StageEngine.use_adapter(eng, "a")
+        assert eng._graphs == {("g", 0): "a-graph"} and len(made) == 4  # cached views and graphs come back
+        eng.lora_on_engine = False
+        with pytest.raises(RuntimeError):
+            StageEngine.use_adapter(eng, "b")
+    finally:
+        peft.MergedAdapterBlock = real

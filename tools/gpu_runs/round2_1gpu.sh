@@ -8,6 +8,9 @@ tail -3 gpurun_out/r2_gpu_tests.log | cut -c1-300 | tee -a $S
 PETALS_B200_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_l2_prefetch_gpu.py -q -x > gpurun_out/r2_l2pf_tests.log 2>&1; echo "l2 prefetch tests exit=$?" | tee -a $S
 tail -3 gpurun_out/r2_l2pf_tests.log | cut -c1-300 | tee -a $S
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; echo "smoke exit=$?" | tee -a $S
+# LoRA on the kernels (merged-weight views): the LoRA engine tests with the opt-in switched on
+PETALS_B200_LORA_ENGINE=1 timeout 400 python -m pytest tests/test_engine_gpu.py -q -x -k "lora or adapter" > gpurun_out/r2_lora_engine.log 2>&1; echo "lora-on-engine tests exit=$?" | tee -a $S
+tail -3 gpurun_out/r2_lora_engine.log | cut -c1-300 | tee -a $S
 cd benchmarks
 for sdpa in 0 1; do
   PETALS_B200_SDPA_BACKWARD=$sdpa timeout 400 python benchmark_training.py --model llama-3-8b --n_steps 8 --warmup_steps 3 --batch_size 8 --seq_len 128 \
