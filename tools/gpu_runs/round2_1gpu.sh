@@ -9,7 +9,7 @@ PETALS_B200_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_l2_prefetc
 tail -3 gpurun_out/r2_l2pf_tests.log | cut -c1-300 | tee -a $S
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; echo "smoke exit=$?" | tee -a $S
 # LoRA on the kernels (merged-weight views): the LoRA engine tests with the opt-in switched on
-PETALS_B200_LORA_ENGINE=1 timeout 400 python -m pytest tests/test_engine_gpu.py -q -x -k "lora or adapter" > gpurun_out/r2_lora_engine.log 2>&1; echo "lora-on-engine tests exit=$?" | tee -a $S
+PETALS_B200_RUN_UNVALIDATED=1 timeout 400 python -m pytest tests/test_lora_engine_gpu.py -q -x > gpurun_out/r2_lora_engine.log 2>&1; echo "lora-on-engine tests exit=$?" | tee -a $S
 tail -3 gpurun_out/r2_lora_engine.log | cut -c1-300 | tee -a $S
 cd benchmarks
 for sdpa in 0 1; do
