@@ -37,7 +37,10 @@ MAX_ROWS = 8
 
 
 def tp_supported(spec: BlockSpec, world: int) -> bool:
+    """Layouts the NVLink engine shards itself. Everything else (biases on the projections, ALiBi, fused interleaved QKV, parallel
+    attention, MoE) is split by the generic path (parallel/tp_generic.py) — `shard_block` below carries no bias tensors."""
     return (spec.mlp in ("swiglu", "gelu") and not spec.parallel_attn and not spec.qkv_interleaved and not spec.post_ln_residual
+            and not (spec.qkv_bias or spec.out_bias or spec.mlp_bias) and not spec.alibi
             and spec.num_kv_heads % world == 0 and spec.num_heads % world == 0 and spec.intermediate_size % (2 * world) == 0
             and spec.head_dim in (64, 128))
 

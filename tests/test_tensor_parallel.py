@@ -59,3 +59,20 @@ def test_tp_support_matrix():
     assert tp_supported(llama, 2) and tp_supported(llama, 4) and not tp_supported(llama, 8) and not tp_supported(llama, 3)
     falcon = AutoDistributedConfig.from_pretrained(checkpoint("falcon")).block_spec()
     assert not tp_supported(falcon, 2)  # fused interleaved QKV + parallel attention: served by pipeline stages instead
+
+
+def test_engine_refuses_layouts_whose_tensors_it_does_not_shard():
+    """`shard_block` carries no projection biases and no ALiBi slopes: such blocks must go to the generic path instead of
+    silently losing them (e.g. Llama-style checkpoints with `attention_bias=true`)."""
+    import dataclasses
+
+    from petals_b200.parallel.tp_generic import tp_shardable
+
+    llama = AutoDistributedConfig.from_pretrained(checkpoint("llama", hidden_size=512, intermediate_size=1024, num_attention_heads=8, num_key_value_heads=4)).block_spec()
+    assert tp_supported(llama, 2)
+    for field in ("qkv_bias", "out_bias", "mlp_bias", "alibi"):
+        odd = dataclasses.replace(llama, **{field: True})
+        assert not tp_supported(odd, 2) and tp_shardable(odd, 2), field
+    biased = AutoDistributedConfig.from_pretrained(checkpoint("llama", hidden_size=512, intermediate_size=1024, num_attention_heads=8, num_key_value_heads=4,
+                                                              attention_bias=True)).block_spec()
+    assert biased.qkv_bias and not tp_supported(biased, 2)

@@ -15,6 +15,7 @@ from tests.utils import checkpoint
 
 FAMILIES = {
     "llama": ("llama", dict(num_attention_heads=8, num_key_value_heads=4)),
+    "llama-attention-bias": ("llama", dict(num_attention_heads=8, num_key_value_heads=4, attention_bias=True)),
     "mixtral": ("mixtral", dict(num_attention_heads=8, num_key_value_heads=4)),
     "bloom": ("bloom", dict(n_head=8)),
     "falcon-40b-style": ("falcon", dict(num_attention_heads=8, num_kv_heads=4)),
