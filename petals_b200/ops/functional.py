@@ -378,12 +378,40 @@ def add_prompts(hidden: torch.Tensor, prompts: torch.Tensor, pos_ptr: Optional[i
 # ----------------------------------------------------------------------------------------------------
 def rope_tables(head_dim: int, max_pos: int, theta: float = 10000.0, scaling: Optional[dict] = None,
                 device="cpu") -> tuple[torch.Tensor, torch.Tensor]:
-    """fp32 cos/sin tables [max_pos, D/2]; supports the Llama-3 ("llama3") and linear rope_scaling types."""
+    """fp32 cos/sin tables [max_pos, D/2] for the position-independent ``rope_scaling`` types: ``linear``, ``llama3`` and ``yarn``
+    (YaRN, arXiv:2309.00071: per-frequency blend of interpolation and extrapolation + an attention temperature folded into the
+    tables). Types that change with the running sequence length (``dynamic``, ``longrope``) are rejected instead of ignored."""
     inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    amplitude = 1.0
     if scaling:
         kind = scaling.get("rope_type", scaling.get("type"))
         factor = float(scaling.get("factor", 1.0))
-        if kind == "llama3":
+        if kind in (None, "default"):
+            pass
+        elif kind == "yarn":
+            orig = float(scaling.get("original_max_position_embeddings") or max(1, round(max_pos / factor)))
+            beta_fast, beta_slow = float(scaling.get("beta_fast") or 32.0), float(scaling.get("beta_slow") or 1.0)
+
+            def temperature(scale: float, m: float = 1.0) -> float:
+                return 1.0 if scale <= 1 else 0.1 * m * math.log(scale) + 1.0
+
+            amplitude = scaling.get("attention_factor")
+            if amplitude is None:
+                m, m_all = scaling.get("mscale"), scaling.get("mscale_all_dim")
+                amplitude = temperature(factor, m) / temperature(factor, m_all) if m and m_all else temperature(factor)
+
+            def dim_of_rotations(n_rot: float) -> float:  # the dimension whose wavelength makes n_rot turns over the original context
+                return head_dim * math.log(orig / (n_rot * 2 * math.pi)) / (2 * math.log(theta))
+
+            low, high = dim_of_rotations(beta_fast), dim_of_rotations(beta_slow)
+            if scaling.get("truncate", True):
+                low, high = math.floor(low), math.ceil(high)
+            low, high = max(low, 0), min(high, head_dim - 1)
+            if low == high:
+                high += 0.001
+            ramp = ((torch.arange(head_dim // 2, dtype=torch.float32) - low) / (high - low)).clamp_(0, 1)
+            inv = (inv / factor) * ramp + inv * (1 - ramp)  # high frequencies extrapolate, low frequencies interpolate
+        elif kind == "llama3":
             lo, hi = float(scaling.get("low_freq_factor", 1.0)), float(scaling.get("high_freq_factor", 4.0))
             old = float(scaling.get("original_max_position_embeddings", 8192))
             wavelen = 2 * math.pi / inv
@@ -393,8 +421,10 @@ def rope_tables(head_dim: int, max_pos: int, theta: float = 10000.0, scaling: Op
             inv = torch.where(mid, (1 - smooth) * inv / factor + smooth * inv, scaled)
         elif kind == "linear":
             inv = inv / factor
+        else:
+            raise NotImplementedError(f"rope_scaling type {kind!r} is not supported (supported: default, linear, llama3, yarn)")
     ang = torch.arange(max_pos, dtype=torch.float32)[:, None] * inv[None, :]
-    return ang.cos().to(device).contiguous(), ang.sin().to(device).contiguous()
+    return (ang.cos() * float(amplitude)).to(device).contiguous(), (ang.sin() * float(amplitude)).to(device).contiguous()
 
 
 def rope_kv_append(qkv: torch.Tensor, q_out: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor,

@@ -96,3 +96,38 @@ def test_task_prioritizers_and_spending_policies():
         ConstantSpendingPolicy(-1)
     with pytest.raises(NotImplementedError):
         SpendingPolicyBase().get_points("rpc_forward")
+
+
+@pytest.mark.parametrize("scaling", [
+    dict(rope_type="linear", factor=4.0),
+    dict(rope_type="llama3", factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0, original_max_position_embeddings=512),
+    dict(rope_type="yarn", factor=4.0, original_max_position_embeddings=512),
+    dict(rope_type="yarn", factor=16.0, original_max_position_embeddings=256, beta_fast=16, beta_slow=2, mscale=1.0, mscale_all_dim=0.5),
+    dict(rope_type="yarn", factor=2.0, original_max_position_embeddings=1024, attention_factor=1.25, truncate=False),
+])
+def test_rope_tables_match_the_library_definitions(scaling):
+    """cos/sin tables of every supported rope_scaling type against transformers' own initialisers (used as an oracle only)."""
+    from transformers import LlamaConfig
+    from transformers.modeling_rope_utils import ROPE_INIT_FUNCTIONS
+
+    from petals_b200.ops.functional import rope_tables
+
+    head_dim, theta, max_pos = 64, 10000.0, 2048
+    cfg = LlamaConfig(hidden_size=head_dim * 4, num_attention_heads=4, max_position_embeddings=max_pos,
+                      rope_parameters=dict(scaling, rope_theta=theta))
+    inv_freq, attention_factor = ROPE_INIT_FUNCTIONS[scaling["rope_type"]](cfg, "cpu")
+    ang = torch.arange(max_pos, dtype=torch.float32)[:, None] * inv_freq[None, :].float()
+    cos, sin = rope_tables(head_dim, max_pos, theta, scaling)
+    assert cos.shape == (max_pos, head_dim // 2)
+    assert torch.allclose(cos, ang.cos() * attention_factor, atol=2e-4) and torch.allclose(sin, ang.sin() * attention_factor, atol=2e-4)
+
+
+def test_rope_tables_reject_length_dependent_scaling():
+    from petals_b200.ops.functional import rope_tables
+
+    for kind in ("dynamic", "longrope", "made-up"):
+        with pytest.raises(NotImplementedError, match="rope_scaling"):
+            rope_tables(64, 128, 10000.0, {"rope_type": kind, "factor": 2.0})
+    plain = rope_tables(64, 128, 10000.0, None)
+    same = rope_tables(64, 128, 10000.0, {"rope_type": "default"})
+    assert torch.equal(plain[0], same[0]) and torch.equal(plain[1], same[1])
