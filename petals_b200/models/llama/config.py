@@ -19,6 +19,11 @@ class DistributedLlamaConfig(DistributedConfig):
     client_weight_names = {"embed": "model.embed_tokens.weight", "norm_w": "model.norm.weight", "head": "lm_head.weight"}
 
     def block_spec(self) -> BlockSpec:
+        # options of the Hugging Face Llama family that would change the math must not be dropped silently
+        if getattr(self, "mlp_bias", False):
+            raise NotImplementedError("Llama checkpoints with mlp_bias=true are not supported (the SwiGLU path has no bias tensors)")
+        if getattr(self, "hidden_act", "silu") not in ("silu", "swish"):
+            raise NotImplementedError(f"hidden_act={self.hidden_act!r} is not supported for Llama blocks (SwiGLU uses SiLU)")
         kv = self.num_key_value_heads or self.num_attention_heads
         rope = getattr(self, "rope_parameters", None) or {}
         theta = rope.get("rope_theta", self.rope_theta) if isinstance(rope, dict) else self.rope_theta

@@ -20,6 +20,8 @@ class DistributedMixtralConfig(DistributedConfig):
     client_weight_names = {"embed": "model.embed_tokens.weight", "norm_w": "model.norm.weight", "head": "lm_head.weight"}
 
     def block_spec(self) -> BlockSpec:
+        if getattr(self, "hidden_act", "silu") not in ("silu", "swish"):
+            raise NotImplementedError(f"hidden_act={self.hidden_act!r} is not supported for Mixtral experts (SwiGLU uses SiLU)")
         return BlockSpec(
             family="mixtral", hidden_size=self.hidden_size, num_heads=self.num_attention_heads,
             num_kv_heads=self.num_key_value_heads or self.num_attention_heads,

@@ -94,3 +94,25 @@ def test_deep_prompts_broadcast_over_the_batch(llama):
         with seq.inference_session(max_length=8) as sess:
             stepped = sess.step(x, prompts=p1)
         assert torch.allclose(stepped, seq(x, prompts=p1), atol=1e-4)
+
+
+def test_config_options_that_change_the_math_are_not_dropped():
+    """A checkpoint option this engine does not implement must be an error at load time, never a silently different model."""
+    import pytest
+
+    from petals_b200.models.llama.config import DistributedLlamaConfig
+    from petals_b200.models.mixtral.config import DistributedMixtralConfig
+
+    ok = DistributedLlamaConfig(hidden_size=256, num_attention_heads=4, intermediate_size=512)
+    assert ok.block_spec().mlp == "swiglu"
+    with pytest.raises(NotImplementedError, match="mlp_bias"):
+        DistributedLlamaConfig(hidden_size=256, num_attention_heads=4, intermediate_size=512, mlp_bias=True).block_spec()
+    with pytest.raises(NotImplementedError, match="hidden_act"):
+        DistributedLlamaConfig(hidden_size=256, num_attention_heads=4, intermediate_size=512, hidden_act="gelu").block_spec()
+    with pytest.raises(NotImplementedError, match="hidden_act"):
+        DistributedMixtralConfig(hidden_size=256, num_attention_heads=4, intermediate_size=512, hidden_act="relu").block_spec()
+    with pytest.raises(NotImplementedError, match="rope_scaling"):
+        from petals_b200.models.block_oracle import GenericBlock
+
+        spec = DistributedLlamaConfig(hidden_size=256, num_attention_heads=4, intermediate_size=512, rope_scaling={"rope_type": "dynamic", "factor": 2.0}).block_spec()
+        GenericBlock(spec, init_std=0.02).rope_cache("cpu")
