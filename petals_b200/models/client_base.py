@@ -121,7 +121,7 @@ class FromPretrainedMixin:
         tensors = load_client_tensors(model_name_or_path, client_state_names(config))
         missing = model.load_client_state(tensors)
         if missing:
-            logger.info(f"Client parameters initialised randomly (not in checkpoint): {sorted(missing)}")
+            logger.warning(f"Client parameters initialised randomly (not in checkpoint): {sorted(missing)}")
         model = model.to(torch_dtype)
         model.float_trainable_()
         model.load_trainable_state(tensors)  # again, now in fp32: the cast to the model dtype above must not round them

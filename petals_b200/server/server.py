@@ -133,6 +133,11 @@ class Server:
             max_batch_size = 8192 if is_multiquery_attn else 2048
         if inference_max_length is None:
             inference_max_length = 8192 if is_multiquery_attn else 2048
+        if spec.rotary and inference_max_length > spec.max_position:
+            # positions beyond the rotary table would be rotated like its last row: cap the session length the server accepts instead
+            logger.warning(f"inference_max_length={inference_max_length} exceeds the {spec.max_position} positions of this model's rotary embedding "
+                           f"(max_position_embeddings); serving sessions of up to {spec.max_position} tokens")
+            inference_max_length = spec.max_position
         self.min_batch_size, self.max_batch_size, self.inference_max_length = min_batch_size, max_batch_size, inference_max_length
         self.max_chunk_size_bytes, self.max_alloc_timeout = max_chunk_size_bytes, max_alloc_timeout
         if attn_cache_tokens is None:

@@ -116,3 +116,16 @@ def test_config_options_that_change_the_math_are_not_dropped():
 
         spec = DistributedLlamaConfig(hidden_size=256, num_attention_heads=4, intermediate_size=512, rope_scaling={"rope_type": "dynamic", "factor": 2.0}).block_spec()
         GenericBlock(spec, init_std=0.02).rope_cache("cpu")
+
+
+def test_server_caps_sessions_at_the_rotary_table():
+    from petals_b200.parallel.swarm import Swarm
+    from petals_b200.server.server import Server
+    from tests.utils import checkpoint
+
+    path = checkpoint("llama")  # max_position_embeddings 512 -> tables cover max(512, 2048) positions
+    common = dict(initial_peers=Swarm("rotary-limit"), converted_model_name_or_path=path, block_indices="0:1", torch_dtype="float32", device="cpu",
+                  throughput=1.0)
+    assert Server(inference_max_length=4096, **common).inference_max_length == 2048  # positions past the table would be rotated wrongly
+    assert Server(inference_max_length=1024, **common).inference_max_length == 1024
+    assert Server(**common).inference_max_length == 2048  # the GQA default of 8192, capped
