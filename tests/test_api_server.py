@@ -1,0 +1,109 @@
+"""HTTP completions front-end (client/api_server.py): plain and streamed completions, multi-turn sessions that keep their
+KV caches on the stages, validation errors — against the tokens the Python API generates for the same prompts."""
+import json
+import urllib.error
+import urllib.request
+
+import pytest
+import torch
+
+from petals_b200.client.api_server import ApiServer, GenerationService
+from petals_b200.utils.auto_config import AutoDistributedModelForCausalLM
+from tests.utils import checkpoint, swarm_of
+
+
+@pytest.fixture(scope="module")
+def api():
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:2", "2:4"]) as (swarm, servers):
+        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=swarm)
+        service = GenerationService(model, None, model_name="tiny-llama", max_session_length=64, session_ttl=0.5)
+        server = ApiServer(service, port=0, host="127.0.0.1").start()
+        try:
+            yield f"http://127.0.0.1:{server.port}", model, service, servers
+        finally:
+            server.shutdown()
+
+
+def _post(base, path, body):
+    req = urllib.request.Request(base + path, data=json.dumps(body).encode(), headers={"Content-Type": "application/json"})
+    with urllib.request.urlopen(req, timeout=60) as resp:
+        return resp.status, resp.read().decode()
+
+
+def _get(base, path):
+    with urllib.request.urlopen(base + path, timeout=10) as resp:
+        return json.loads(resp.read())
+
+
+def test_completion_matches_the_python_api(api):
+    base, model, service, _ = api
+    prompt = [5, 17, 200, 3]
+    with torch.inference_mode():
+        expected = model.generate(torch.tensor([prompt]), max_new_tokens=6)[0, len(prompt):].tolist()
+    status, body = _post(base, "/v1/completions", {"prompt": prompt, "max_tokens": 6})
+    out = json.loads(body)
+    assert status == 200 and out["object"] == "text_completion" and out["model"] == "tiny-llama"
+    choice = out["choices"][0]
+    assert choice["token_ids"] == expected and choice["finish_reason"] == "length" and choice["text"] is None  # no tokenizer offline
+    assert out["usage"] == {"prompt_tokens": 4, "completion_tokens": 6, "total_tokens": 10}
+    # a stop token ends the completion early
+    status, body = _post(base, "/v1/completions", {"prompt": prompt, "max_tokens": 6, "stop_token_ids": [expected[2]]})
+    choice = json.loads(body)["choices"][0]
+    assert choice["finish_reason"] == "stop" and choice["token_ids"] == expected[: expected.index(expected[2]) + 1]
+    # seeded sampling is reproducible and differs from greedy at a high temperature
+    sample = {"prompt": prompt, "max_tokens": 6, "temperature": 5.0, "top_k": 50, "seed": 7}
+    a, b = (json.loads(_post(base, "/v1/completions", sample)[1])["choices"][0]["token_ids"] for _ in range(2))
+    assert a == b and a != expected
+    assert _get(base, "/health") == {"status": "ok", "open_sessions": 0} and _get(base, "/v1/models")["data"][0]["id"] == "tiny-llama"
+
+
+def test_streaming_emits_one_event_per_token(api):
+    base, model, _, _ = api
+    prompt = [9, 8, 7]
+    with torch.inference_mode():
+        expected = model.generate(torch.tensor([prompt]), max_new_tokens=5)[0, 3:].tolist()
+    status, body = _post(base, "/v1/completions", {"prompt": prompt, "max_tokens": 5, "stream": True})
+    events = [line[len("data: "):] for line in body.split("\n") if line.startswith("data: ")]
+    assert status == 200 and events[-1] == "[DONE]"
+    chunks = [json.loads(e) for e in events[:-1]]
+    assert [c["choices"][0]["token_id"] for c in chunks[:-1]] == expected and all(c["object"] == "text_completion.chunk" for c in chunks[:-1])
+    assert chunks[-1]["object"] == "text_completion" and chunks[-1]["choices"][0]["token_ids"] == expected
+
+
+def test_conversations_keep_their_kv_caches_between_requests(api):
+    base, model, service, servers = api
+    first, second = [11, 12, 13], [40, 41]
+    with torch.inference_mode():  # the same conversation through the Python API, in one session
+        with model.inference_session(max_length=32) as sess:
+            turn1 = model.generate(torch.tensor([first]), max_new_tokens=3, session=sess)[0, len(first):].tolist()
+            turn2 = model.generate(torch.tensor([second]), max_new_tokens=3, session=sess)[0, -3:].tolist()
+    r1 = json.loads(_post(base, "/v1/completions", {"prompt": first, "max_tokens": 3, "session_id": "chat-1"})[1])
+    assert r1["choices"][0]["token_ids"] == turn1 and r1["session_id"] == "chat-1" and _get(base, "/health")["open_sessions"] == 1
+    tokens_before = sum(s.module_container.handler.metrics.snapshot()["tokens"]["inference"] for s in servers)
+    r2 = json.loads(_post(base, "/v1/completions", {"prompt": second, "max_tokens": 3, "session_id": "chat-1"})[1])
+    assert r2["choices"][0]["token_ids"] == turn2
+    # the second turn only sent its own tokens to the stages (2 prompt + 3 decode steps' worth per stage), not the history again
+    tokens_after = sum(s.module_container.handler.metrics.snapshot()["tokens"]["inference"] for s in servers)
+    assert tokens_after - tokens_before <= 2 * (len(second) + 3)
+    # explicit close, and the idle sweep for forgotten ones
+    assert json.loads(_post(base, "/v1/sessions/close", {"session_id": "chat-1"})[1]) == {"closed": True}
+    _post(base, "/v1/completions", {"prompt": first, "max_tokens": 1, "session_id": "chat-2"})
+    assert service.open_sessions == 1
+    import time
+
+    time.sleep(0.7)
+    assert service.sweep() == 1 and service.open_sessions == 0
+
+
+def test_bad_requests_are_reported_not_crashed(api):
+    base, *_ = api
+    for body in ({"prompt": "text needs a tokenizer"}, {"prompt": [1, 2], "max_tokens": 0}, {"prompt": [10 ** 9]}, {"prompt": []},
+                 {"prompt": [1] * 60, "max_tokens": 30}, {"prompt": {"not": "valid"}}):
+        with pytest.raises(urllib.error.HTTPError) as err:
+            _post(base, "/v1/completions", body)
+        assert err.value.code == 400 and "message" in json.loads(err.value.read())["error"]
+    with pytest.raises(urllib.error.HTTPError) as err:
+        _post(base, "/v1/unknown", {})
+    assert err.value.code == 404
+    assert json.loads(_post(base, "/v1/completions", {"prompt": [1, 2, 3], "max_tokens": 2})[1])["usage"]["completion_tokens"] == 2  # still serving
