@@ -107,3 +107,21 @@ def test_bad_requests_are_reported_not_crashed(api):
         _post(base, "/v1/unknown", {})
     assert err.value.code == 404
     assert json.loads(_post(base, "/v1/completions", {"prompt": [1, 2, 3], "max_tokens": 2})[1])["usage"]["completion_tokens"] == 2  # still serving
+
+
+def test_concurrent_requests_do_not_interfere(api):
+    """Eight clients at once, each with its own prompt: every answer equals the one computed alone (sessions are bound per call)."""
+    import concurrent.futures
+
+    base, model, _, _ = api
+    prompts = [[3 + i, 50 + 2 * i, 7, 300 + i] for i in range(8)]
+    with torch.inference_mode():
+        alone = [model.generate(torch.tensor([p]), max_new_tokens=4)[0, len(p):].tolist() for p in prompts]
+    with concurrent.futures.ThreadPoolExecutor(8) as pool:
+        bodies = list(pool.map(lambda p: _post(base, "/v1/completions", {"prompt": p, "max_tokens": 4, "stream": bool(p[0] % 2)})[1], prompts))
+    for body, expected in zip(bodies, alone):
+        if body.startswith("data:"):
+            final = json.loads([l for l in body.split("\n") if l.startswith("data: ") and l != "data: [DONE]"][-1][len("data: "):])
+        else:
+            final = json.loads(body)
+        assert final["choices"][0]["token_ids"] == expected
