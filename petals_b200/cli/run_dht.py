@@ -26,6 +26,10 @@ def main(argv=None) -> None:
                         help="listen address of a network registry for swarms that span several boxes, e.g. /ip4/0.0.0.0/tcp/31337 or "
                              "tcp://0.0.0.0:31337 (a plain path here is taken as --rendezvous)")
     parser.add_argument("--announce_maddrs", nargs="+", default=None, help="address to print for peers when listening on 0.0.0.0")
+    parser.add_argument("--initial_peers", nargs="*", default=None,
+                        help="accepted for compatibility: a registry is a single process, it does not join other bootstrap peers")
+    for flag in ("--no_relay", "--use_auto_relay", "--use_ipfs"):
+        parser.add_argument(flag, action="store_true", help="accepted for compatibility (no NAT traversal / IPFS bootstrap on a private network)")
     parser.add_argument("--identity_path", default=None, help="accepted for compatibility (peers are named by their GPU rank)")
     parser.add_argument("--refresh_period", type=float, default=30.0, help="how often to report swarm membership")
     parser.add_argument("--once", action="store_true", help="create the rendezvous and exit (for scripts)")
