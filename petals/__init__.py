@@ -11,6 +11,7 @@ from petals_b200 import __version__  # noqa: F401
 from petals_b200.client import *  # noqa: F401,F403
 from petals_b200.client import ClientConfig, InferenceSession, RemoteSequenceManager, RemoteSequential  # noqa: F401
 from petals_b200.models import *  # noqa: F401,F403
+from petals_b200.utils import *  # noqa: F401,F403
 from petals_b200.utils.auto_config import (AutoDistributedConfig, AutoDistributedModel, AutoDistributedModelForCausalLM,  # noqa: F401
                                            AutoDistributedModelForSequenceClassification, AutoDistributedSpeculativeModel)
 

@@ -129,3 +129,25 @@ def test_server_caps_sessions_at_the_rotary_table():
     assert Server(inference_max_length=4096, **common).inference_max_length == 2048  # positions past the table would be rotated wrongly
     assert Server(inference_max_length=1024, **common).inference_max_length == 1024
     assert Server(**common).inference_max_length == 2048  # the GQA default of 8192, capped
+
+
+def test_every_entry_module_imports_first_in_a_fresh_interpreter():
+    """Circular imports only show when a particular module happens to be imported first; scripts and tools do import deep modules
+    directly. Each of these must load on its own."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    modules = ["petals", "petals_b200.parallel.swarm", "petals_b200.parallel.transport", "petals_b200.parallel.registry",
+               "petals_b200.parallel.tensor_parallel", "petals_b200.server.server", "petals_b200.server.stage_engine", "petals_b200.client",
+               "petals_b200.utils.dht", "petals_b200.utils.logging", "petals_b200.ops.native", "petals_b200.cli.run_server", "bench", "__graft_entry__"]
+    failures = []
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    procs = [(m, subprocess.Popen([sys.executable, "-c", f"import {m}"], cwd=root, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+             for m in modules]
+    for m, p in procs:
+        _, err = p.communicate(timeout=300)
+        if p.returncode != 0:
+            failures.append((m, err.strip().splitlines()[-1] if err.strip() else "?"))
+    assert not failures, failures
