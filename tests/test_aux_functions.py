@@ -136,3 +136,20 @@ def test_step_timer_and_nvtx_noop():
         pass
     snap = t.snapshot()
     assert snap["x"]["count"] == 2 and snap["x"]["seconds"] >= 0 and t.snapshot() == {}
+
+
+def test_importing_the_package_pulls_in_no_heavy_optional_dependency():
+    """reference tests/test_aux_functions.py:16-29 checks that bitsandbytes is not imported by `import petals` (slow, noisy, optional).
+    The equivalents here: Hugging Face transformers (only the tokenizer of the HTTP front-end and test oracles use it), triton and the
+    library kernels in the image (flash_attn / flashinfer / vllm), pydantic — none is needed to serve or to run a client."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, petals, petals.client, petals.server.server, petals.utils.peft\n"
+            "heavy = [m for m in ('transformers', 'triton', 'flash_attn', 'flashinfer', 'vllm', 'pydantic', 'scipy', 'pandas') if m in sys.modules]\n"
+            "print(','.join(heavy))")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, PYTHONPATH=root), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert out.stdout.strip() == "", f"imported on `import petals`: {out.stdout.strip()}"
