@@ -161,8 +161,11 @@ class _ServerInferenceSession:
 class InferenceSession:
     """Multi-step inference over a chain of stages with fail-over (reference :220-414)."""
 
-    def __init__(self, sequence_manager: RemoteSequenceManager, max_length: int):
+    def __init__(self, sequence_manager: RemoteSequenceManager, max_length: int, *, alloc_timeout: float = 0.0):
+        """``alloc_timeout``: how long a server may keep this session waiting for KV-cache room before refusing it (the reference's
+        ``alloc_timeout`` request field, handler.py:148-154; 0 = fail fast so that routing can try another server)."""
         self._sequence_manager = sequence_manager
+        self._alloc_timeout = float(alloc_timeout)
         self._closed = False
         self._server_sessions: List[_ServerInferenceSession] = []
         self._position = 0
@@ -197,6 +200,8 @@ class InferenceSession:
             for span in chosen_spans:
                 uids = self._sequence_manager.block_uids[span.start: span.end]
                 metadata = self._sequence_manager.get_request_metadata("rpc_inference", None, *uids)
+                if self._alloc_timeout > 0:
+                    metadata = dict(metadata, alloc_timeout=self._alloc_timeout)
                 session = _ServerInferenceSession.create(self._sequence_manager.config, self._sequence_manager, span, uids,
                                                          max_length=self._max_length, **{k: v for k, v in metadata.items() if k != "args_structure"})
                 server_sessions.append(session)
@@ -355,7 +360,7 @@ class InferenceSession:
         return len(self._server_sessions) - n_prev_spans
 
     def close(self, *exc_details) -> None:
-        if not self._closed:
+        if not getattr(self, "_closed", True):  # also safe when __init__ did not finish (called from __del__)
             self._exit_server_sessions(self._server_sessions)
             self._server_sessions.clear()
             self._closed = True
