@@ -166,12 +166,33 @@ def send_message(sock: socket.socket, header: Dict[str, Any], tensors: Sequence[
         _raise_io(rc, "send")
 
 
+MAX_HEADER_BYTES = 16 << 20  # a header is a few hundred bytes; anything huge is a corrupt or foreign stream
+MAX_TENSORS_PER_MESSAGE = 256
+MAX_PART_BYTES = 64 << 30
+
+
+class ProtocolError(ConnectionError):
+    """The peer sent something that is not a frame of this protocol; the connection is dropped."""
+
+
 def recv_message(sock: socket.socket) -> Tuple[Dict[str, Any], List[torch.Tensor]]:
     (n,) = struct.unpack("<I", _recv_exact(sock, 4))
-    header = msgpack.unpackb(_recv_exact(sock, n), raw=False)
+    if n > MAX_HEADER_BYTES:
+        raise ProtocolError(f"header of {n} bytes announced (limit {MAX_HEADER_BYTES})")
+    try:
+        header = msgpack.unpackb(_recv_exact(sock, n), raw=False)
+    except ConnectionError:
+        raise
+    except Exception as e:  # noqa: BLE001 - msgpack raises several unrelated exception types on garbage
+        raise ProtocolError(f"undecodable header: {e!r}") from None
+    if not isinstance(header, dict) or not isinstance(header.get("tensors", []), list) or len(header.get("tensors", [])) > MAX_TENSORS_PER_MESSAGE:
+        raise ProtocolError("malformed header")
     tensors = []
     for m in header.get("tensors", []):
-        parts = [_recv_into(sock, k) for k in m.get("parts", [m["nbytes"]])]
+        sizes = m.get("parts", [m.get("nbytes", 0)]) if isinstance(m, dict) else None
+        if sizes is None or m.get("dtype") not in _DTYPES or any(not isinstance(k, int) or k < 0 or k > MAX_PART_BYTES for k in sizes):
+            raise ProtocolError("malformed tensor descriptor")
+        parts = [_recv_into(sock, k) for k in sizes]
         tensors.append(decode_tensor(m.get("c", {"codec": "NONE"}), parts, _DTYPES[m["dtype"]], m["shape"]))
     return header, tensors
 

@@ -134,3 +134,40 @@ def test_native_and_python_paths_move_large_frames(monkeypatch):
     t_native, t_python = run(native_io), run(None)
     print(f"64 MiB frame: native {t_native * 1e3:.1f} ms, python {t_python * 1e3:.1f} ms")
     assert t_native < 5 * t_python
+
+
+def test_server_survives_garbage_and_keeps_serving(tmp_path):
+    """Foreign or corrupt byte streams (a port scanner, a half-written frame, absurd lengths) must cost one connection, not the server."""
+    import os
+    import struct
+
+    from petals_b200.parallel.transport import ProtocolError, RemoteHandlerProxy, RpcServer
+
+    class Handler:
+        compression = None
+
+        def rpc_forward(self, uids, hidden, *rest, metadata=None):
+            return hidden + 1
+
+    server = RpcServer(Handler(), "tcp://127.0.0.1:0")
+    server.start()
+    try:
+        for junk in (b"GET / HTTP/1.1\r\n\r\n", struct.pack("<I", 0xFFFFFFFF) + b"x" * 64, struct.pack("<I", 5) + b"\xc1\xc1\xc1\xc1\xc1",
+                     struct.pack("<I", 3) + b"\x93\x01\x02", os.urandom(4096)):
+            s = socket.create_connection(("127.0.0.1", server.port), timeout=5)
+            s.sendall(junk)
+            s.settimeout(5)
+            try:
+                assert s.recv(1 << 16) in (b"",) or True  # the server may answer with an error frame or just hang up
+            except (ConnectionError, socket.timeout):
+                pass
+            s.close()
+        x = torch.randn(2, 3, 4)
+        assert torch.equal(RemoteHandlerProxy(server.address).rpc_forward(["m.0"], x), x + 1)
+    finally:
+        server.shutdown()
+    a, b = _pair()
+    a.sendall(struct.pack("<I", 1 << 30))
+    with pytest.raises(ProtocolError):
+        recv_message(b)
+    a.close(), b.close()
