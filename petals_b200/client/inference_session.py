@@ -164,8 +164,11 @@ class InferenceSession:
     def __init__(self, sequence_manager: RemoteSequenceManager, max_length: int, *, alloc_timeout: float = 0.0):
         """``alloc_timeout``: how long a server may keep this session waiting for KV-cache room before refusing it (the reference's
         ``alloc_timeout`` request field, handler.py:148-154; 0 = fail fast so that routing can try another server)."""
+        if isinstance(max_length, bool) or not isinstance(max_length, int) or max_length < 1:
+            raise ValueError(f"max_length must be a positive number of tokens to reserve KV caches for, got {max_length!r}")
         self._sequence_manager = sequence_manager
         self._alloc_timeout = float(alloc_timeout)
+        self._batch_size: Optional[int] = None  # fixed by the first step
         self._closed = False
         self._server_sessions: List[_ServerInferenceSession] = []
         self._position = 0
@@ -225,6 +228,21 @@ class InferenceSession:
         assert not self._closed
         if torch.is_grad_enabled():
             logger.warning("Running inference session with grad enabled. Gradients will *not* be propagated correctly.")
+        # mistakes of the caller are reported here, once: a server would reject them too, and a rejection is indistinguishable from a
+        # failing server for the retry loop below (it would re-route and retry for as long as max_retries allows)
+        hidden_size = getattr(self._sequence_manager.config, "hidden_size", None)
+        if not isinstance(inputs, torch.Tensor) or inputs.ndim != 3 or not inputs.is_floating_point():
+            raise ValueError("inputs must be a floating-point tensor [batch_size, seq_length, hidden_size]")
+        if hidden_size is not None and inputs.shape[2] != hidden_size:
+            raise ValueError(f"inputs have hidden size {inputs.shape[2]}, the model's is {hidden_size}")
+        if self._batch_size is None:
+            if inputs.shape[0] < 1:
+                raise ValueError("inputs must contain at least one sequence")
+        elif inputs.shape[0] != self._batch_size:
+            raise ValueError(f"batch size changed within a session ({self._batch_size} -> {inputs.shape[0]})")
+        if hypo_ids is not None and not is_dummy(hypo_ids) and (hypo_ids.ndim != 1 or hypo_ids.shape[0] != inputs.shape[0] or hypo_ids.dtype != torch.int64
+                                                               or bool(((hypo_ids < 0) | (hypo_ids >= inputs.shape[0])).any())):
+            raise ValueError(f"hypo_ids must be an int64 vector of {inputs.shape[0]} indices into the batch")
         if prompts is None or is_dummy(prompts):
             prompts = DUMMY
         else:
@@ -298,6 +316,7 @@ class InferenceSession:
             B, L, H = pushed[1]
             inputs = fabric.recv(B * L, "y_ret", pushed[0]).view(B, L, H)
         self._position += n_input_tokens
+        self._batch_size = inputs.shape[0]
         outputs = inputs[:, -n_input_tokens:]
         return outputs.to(device=inputs_device, dtype=inputs_dtype)
 

@@ -80,6 +80,15 @@ class RemoteSequential(nn.Module):
             return session.step(inputs, prompts, **kwargs)
         unsupported = {name: value for name, value in kwargs.items() if value is not None}
         assert not unsupported, f"Extra kwargs are not supported in forward: {unsupported}"
+        # caller mistakes are reported here: a server's rejection would look like a failing server to the retry logic
+        hidden_size = getattr(self.config, "hidden_size", None)
+        if not inputs.is_floating_point() or (hidden_size is not None and inputs.shape[-1] != hidden_size):
+            raise ValueError(f"inputs must be floating-point hidden states of size {hidden_size}, got {inputs.dtype} {tuple(inputs.shape)}")
+        if inputs.shape[0] == 0 or inputs.shape[1] == 0:
+            raise ValueError(f"inputs must contain at least one token, got shape {tuple(inputs.shape)}")
+        if prompts is not None and prompts.numel() and (prompts.ndim != 4 or prompts.shape[0] != len(self) or prompts.shape[1] not in (1, inputs.shape[0])
+                                                         or prompts.shape[2] > inputs.shape[1] or prompts.shape[3] != inputs.shape[2]):
+            raise ValueError(f"deep prompts must be [{len(self)}, {inputs.shape[0]} or 1, <= {inputs.shape[1]}, {inputs.shape[2]}], got {tuple(prompts.shape)}")
         return _RemoteSequentialAutogradFunction.apply(inputs, DUMMY if prompts is None else prompts, self.sequence_manager)
 
     # ---- sessions ------------------------------------------------------------------------------------------------------------

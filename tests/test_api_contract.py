@@ -151,3 +151,44 @@ def test_every_entry_module_imports_first_in_a_fresh_interpreter():
         if p.returncode != 0:
             failures.append((m, err.strip().splitlines()[-1] if err.strip() else "?"))
     assert not failures, failures
+
+
+def test_caller_mistakes_fail_fast_instead_of_being_retried():
+    """A request that every server would reject is the caller's mistake: it must raise at once. (If it reached a server, the rejection
+    would look like a failing server to the retry loop, which re-routes and retries for as long as ``max_retries`` allows — forever by
+    default, as in the reference.)"""
+    import time
+
+    import pytest
+    import torch
+
+    from petals_b200.client.remote_sequential import RemoteSequential
+    from petals_b200.utils.auto_config import AutoDistributedConfig
+    from tests.utils import checkpoint, swarm_of
+
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:4"]) as (swarm, _):
+        config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm)  # max_retries=None: a retried mistake would hang this test
+        seq, H = RemoteSequential(config, dht=swarm), config.hidden_size
+        t0 = time.monotonic()
+        for bad in (torch.randn(1, 2, H + 1), torch.zeros(1, 2, H, dtype=torch.int64), torch.randn(0, 2, H), torch.randn(1, 0, H)):
+            with pytest.raises(ValueError):
+                seq(bad)
+        with pytest.raises(ValueError, match="deep prompts"):
+            seq(torch.randn(1, 2, H), prompts=torch.randn(3, 1, 1, H))
+        for bad_length in (0, -3, 2.5, True):
+            with pytest.raises(ValueError, match="max_length"):
+                seq.inference_session(max_length=bad_length).__enter__()
+        with torch.inference_mode(), seq.inference_session(max_length=16) as sess:
+            assert sess.step(torch.randn(1, 0, H)).shape == (1, 0, H)  # a zero-token step is legal (reference test_full_model.py)
+            sess.step(torch.randn(1, 3, H))
+            for bad in (torch.randn(2, 1, H), torch.randn(1, 1, H - 1), torch.randn(1, H), torch.zeros(1, 1, H, dtype=torch.int32)):
+                with pytest.raises(ValueError):
+                    sess.step(bad)
+            for bad_hypo in (torch.tensor([0, 0]), torch.tensor([1]), torch.tensor([-1])):
+                with pytest.raises(ValueError, match="hypo_ids"):
+                    sess.step(torch.randn(1, 1, H), hypo_ids=bad_hypo)
+            with pytest.raises(ValueError, match="position"):
+                sess.position = 99
+            assert sess.position == 3 and sess.step(torch.randn(1, 1, H)).shape == (1, 1, H)  # the session survived all of it
+        assert time.monotonic() - t0 < 20
