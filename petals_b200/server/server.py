@@ -117,7 +117,10 @@ class Server:
         self.public_name = public_name
 
         if isinstance(torch_dtype, str):
-            torch_dtype = petals_b200.DTYPE_MAP[torch_dtype.replace("torch.", "")]
+            key = torch_dtype.replace("torch.", "")
+            if key not in petals_b200.DTYPE_MAP:
+                raise ValueError(f"torch_dtype must be one of {sorted(petals_b200.DTYPE_MAP)}, got {torch_dtype!r}")
+            torch_dtype = petals_b200.DTYPE_MAP[key]
         torch_dtype = resolve_block_dtype(self.block_config, torch_dtype)
         if device.type == "cpu" and torch_dtype == torch.float16:
             raise ValueError("float16 is not supported on CPU; use float32 or bfloat16")
@@ -142,6 +145,8 @@ class Server:
         self.max_chunk_size_bytes, self.max_alloc_timeout = max_chunk_size_bytes, max_alloc_timeout
         if attn_cache_tokens is None:
             attn_cache_tokens = 16384 if is_multiquery_attn else 4096
+        if attn_cache_tokens < 1:
+            raise ValueError(f"attn_cache_tokens must be positive, got {attn_cache_tokens}")
         self.attn_cache_tokens = attn_cache_tokens
         self.cache_bytes_per_block = attn_cache_tokens * spec.kv_bytes_per_token(torch_dtype)
 
@@ -157,8 +162,8 @@ class Server:
             num_blocks = len(block_indices)
         self.strict_block_indices = block_indices
         self.num_blocks = num_blocks if num_blocks is not None else self._choose_num_blocks()
-        if self.num_blocks > self.block_config.num_hidden_layers:
-            raise ValueError(f"num_blocks={self.num_blocks} exceeds the model's {self.block_config.num_hidden_layers} blocks")
+        if not 1 <= self.num_blocks <= self.block_config.num_hidden_layers:
+            raise ValueError(f"num_blocks={self.num_blocks} must be between 1 and the model's {self.block_config.num_hidden_layers} blocks")
 
         if throughput in ("auto", "eval", "dry_run"):
             info = get_server_throughput(converted_model_name_or_path, self.block_config, device, torch_dtype, num_blocks=self.num_blocks,

@@ -30,6 +30,8 @@ QUANTIZABLE = ("wqkv", "wo", "w_gate", "w_up", "w_down", "we_gate", "we_up", "we
 
 def resolve_quant_type(quant_type) -> QuantType:
     if isinstance(quant_type, str):
+        if quant_type.upper() not in QuantType.__members__:
+            raise ValueError(f"quant_type must be one of {[q.name.lower() for q in QuantType]}, got {quant_type!r}")
         quant_type = QuantType[quant_type.upper()]
     if quant_type in (QuantType.INT8, QuantType.NF4):
         logger.warning(f"quant_type={quant_type.name.lower()} has no sm_100 kernels (bitsandbytes); using block-scaled FP8 instead")

@@ -192,3 +192,22 @@ def test_caller_mistakes_fail_fast_instead_of_being_retried():
                 sess.position = 99
             assert sess.position == 3 and sess.step(torch.randn(1, 1, H)).shape == (1, 1, H)  # the session survived all of it
         assert time.monotonic() - t0 < 20
+
+
+def test_server_arguments_are_validated_with_readable_errors():
+    import pytest
+
+    from petals_b200.parallel.swarm import Swarm
+    from petals_b200.server.server import Server
+    from tests.utils import checkpoint
+
+    common = dict(initial_peers=Swarm("server-args"), converted_model_name_or_path=checkpoint("llama"), torch_dtype="float32", device="cpu", throughput=1.0)
+    for bad, needle in [(dict(block_indices="3:1"), "block_indices"), (dict(block_indices="2:9"), "block_indices"), (dict(block_indices="a:b"), "start:end"),
+                        (dict(num_blocks=0), "num_blocks"), (dict(num_blocks=99), "num_blocks"), (dict(block_indices="0:1", torch_dtype="int8"), "torch_dtype"),
+                        (dict(block_indices="0:1", quant_type="fp4"), "quant_type"), (dict(block_indices="0:1", attn_cache_tokens=-5), "attn_cache_tokens")]:
+        with pytest.raises(ValueError, match=needle):
+            Server(**dict(common, **bad))
+    with pytest.raises(FileNotFoundError):
+        Server(**dict(common, converted_model_name_or_path="/nonexistent/model", block_indices="0:1"))
+    with pytest.raises(AssertionError, match="not both"):
+        Server(**dict(common, block_indices="0:1", num_blocks=1))
