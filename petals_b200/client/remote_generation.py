@@ -109,7 +109,23 @@ class RemoteGenerationMixin:
             raise ValueError("pass either `inputs` or `input_ids`, not both")
         if inputs is not None and (not isinstance(inputs, torch.Tensor) or inputs.dim() != 2 or inputs.dtype != torch.int64):
             raise ValueError("inputs must be an int64 tensor [batch, seq]")
+        if inputs is not None and inputs.numel():
+            lo, hi = int(inputs.min()), int(inputs.max())  # one host sync per call; an id outside the table would read out of bounds on the GPU
+            if lo < 0 or hi >= self.config.vocab_size:
+                raise ValueError(f"token ids must be within [0, {self.config.vocab_size}), got values in [{lo}, {hi}]")
+        if max_length is not None and inputs is not None and session is None and max_length < inputs.shape[1]:
+            raise ValueError(f"max_length={max_length} is shorter than the prompt ({inputs.shape[1]} tokens)")
+        if max_new_tokens is not None and max_new_tokens < 0:
+            raise ValueError("max_new_tokens must be >= 0")
+        if num_beams < 1 or num_return_sequences < 1:
+            raise ValueError("num_beams and num_return_sequences must be >= 1")
         do_sample = bool(do_sample)  # ints were accepted by older Petals releases (reference :157-160)
+        if do_sample and not temperature > 0:
+            raise ValueError("temperature must be positive when sampling (use do_sample=False for greedy decoding)")
+        if top_p is not None and not 0 < top_p <= 1:
+            raise ValueError("top_p must be in (0, 1]")
+        if top_k is not None and top_k < 0:
+            raise ValueError("top_k must be >= 0 (0 disables it)")
         if num_beams > 1 and do_sample:
             raise NotImplementedError("beam search with sampling is not supported")
         if num_return_sequences > num_beams and not do_sample and num_return_sequences > 1:

@@ -211,3 +211,27 @@ def test_server_arguments_are_validated_with_readable_errors():
         Server(**dict(common, converted_model_name_or_path="/nonexistent/model", block_indices="0:1"))
     with pytest.raises(AssertionError, match="not both"):
         Server(**dict(common, block_indices="0:1", num_blocks=1))
+
+
+def test_generate_rejects_arguments_that_cannot_work():
+    import pytest
+    import torch
+
+    from petals_b200.utils.auto_config import AutoDistributedModelForCausalLM
+    from tests.utils import checkpoint, swarm_of
+
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:4"]) as (swarm, _):
+        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=swarm)
+        ids = torch.tensor([[1, 2, 3]])
+        bad_calls = [dict(), dict(max_length=5, max_new_tokens=2), dict(max_length=2), dict(max_new_tokens=-1), dict(max_new_tokens=2, num_beams=0),
+                     dict(max_new_tokens=2, do_sample=True, temperature=0.0), dict(max_new_tokens=2, do_sample=True, top_p=0.0),
+                     dict(max_new_tokens=2, do_sample=True, top_k=-1), dict(max_new_tokens=2, num_beams=2, num_return_sequences=3)]
+        for kwargs in bad_calls:
+            with pytest.raises(ValueError):
+                model.generate(ids, **kwargs)
+        for bad_ids in (ids.float(), torch.tensor([[model.config.vocab_size]]), torch.tensor([[-1]]), torch.tensor([1, 2, 3])):
+            with pytest.raises(ValueError):  # an id outside the embedding table would be an out-of-bounds read on a GPU
+                model.generate(bad_ids, max_new_tokens=2)
+        assert model.generate(ids, max_new_tokens=0).shape == (1, 3)  # nothing to add is fine
+        assert model.generate(ids, max_new_tokens=2, do_sample=True, top_k=0, top_p=1.0).shape == (1, 5)  # 0 / 1.0 disable the filters
