@@ -176,6 +176,8 @@ class InferenceStream:
         if hypo_ids is not None and not is_dummy(hypo_ids):
             if hypo_ids.dtype != torch.int64 or hypo_ids.shape != (B,):
                 raise ValueError(f"hypo_ids must be int64 [{B}]")
+            if bool(((hypo_ids < 0) | (hypo_ids >= B)).any()):  # they index KV pages / cache rows: never trust them unchecked
+                raise ValueError(f"hypo_ids must index the {B} sequences of the batch")
         else:
             hypo_ids = None
         priority = self.handler.prioritizer.prioritize(hidden, hypo_ids, points=self.points / max(n, 1), type="inference")

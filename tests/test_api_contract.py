@@ -235,3 +235,42 @@ def test_generate_rejects_arguments_that_cannot_work():
                 model.generate(bad_ids, max_new_tokens=2)
         assert model.generate(ids, max_new_tokens=0).shape == (1, 3)  # nothing to add is fine
         assert model.generate(ids, max_new_tokens=2, do_sample=True, top_k=0, top_p=1.0).shape == (1, 5)  # 0 / 1.0 disable the filters
+
+
+def test_server_checks_what_a_client_sends():
+    """The server does not rely on clients being well-behaved for anything that indexes device memory."""
+    import pytest
+    import torch
+
+    from petals_b200.utils.auto_config import AutoDistributedConfig
+    from tests.utils import checkpoint, swarm_of
+
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:4"]) as (swarm, servers):
+        config = AutoDistributedConfig.from_pretrained(path)
+        handler = servers[0].module_container.handler
+        uids = [f"{config.dht_prefix}.{i}" for i in range(4)]
+        H = config.hidden_size
+        stream = handler.rpc_inference(uids, {"max_length": 8})
+        try:
+            stream.step(torch.randn(2, 2, H))
+            for bad in (torch.tensor([0, 2]), torch.tensor([-1, 0]), torch.tensor([0]), torch.tensor([0.0, 1.0])):
+                with pytest.raises(ValueError, match="hypo_ids"):
+                    stream.step(torch.randn(2, 1, H), hypo_ids=bad)
+            with pytest.raises(ValueError, match="batch size"):
+                stream.step(torch.randn(3, 1, H))
+            with pytest.raises(ValueError, match="prompts"):
+                stream.step(torch.randn(2, 1, H), prompts=torch.randn(2, 2, 1, H))
+            with pytest.raises(ValueError, match="start_from_position"):
+                stream.step(torch.randn(2, 1, H), metadata={"start_from_position": 7})
+            with pytest.raises(ValueError, match="Maximum length exceeded"):
+                stream.step(torch.randn(2, 7, H))
+            assert stream.step(torch.randn(2, 1, H), hypo_ids=torch.tensor([1, 0])).shape == (2, 1, H) and stream.position == 3
+        finally:
+            stream.close()
+        with pytest.raises(ValueError):
+            handler.rpc_inference(uids, {"max_length": 10 ** 9})
+        with pytest.raises(Exception):
+            handler.rpc_inference([uids[0], uids[2]], {"max_length": 8})  # not a contiguous chain
+        with pytest.raises(Exception):
+            handler.rpc_forward(["other-model.0"], torch.randn(1, 1, H))
