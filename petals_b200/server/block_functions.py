@@ -28,10 +28,20 @@ def _split_prompts(prompts: Optional[torch.Tensor], n_blocks: int, batch: int, h
     return list(prompts.unbind(0))
 
 
+def _check_activations(name: str, t: torch.Tensor, handler) -> None:
+    """Shape / dtype of a tensor that kernels will index by the model's hidden size: never trusted from the wire."""
+    hidden_size = handler.stage.spec.hidden_size
+    if not isinstance(t, torch.Tensor) or t.dim() != 3 or not t.is_floating_point():
+        raise ValueError(f"{name} must be a 3-D floating-point tensor [batch, seq, hidden], got {tuple(getattr(t, 'shape', ()))} {getattr(t, 'dtype', type(t))}")
+    if t.shape[2] != hidden_size:
+        raise ValueError(f"{name} have hidden size {t.shape[2]}, this model's is {hidden_size}")
+    if t.shape[0] < 1 or t.shape[1] < 1:
+        raise ValueError(f"{name} must contain at least one token, got {tuple(t.shape)}")
+
+
 def run_rpc_forward(hidden_states: torch.Tensor, prompts: Optional[torch.Tensor], *, backends: Sequence, handler,
                     active_adapter: Optional[str] = None, points: float = 0.0) -> torch.Tensor:
-    if hidden_states.dim() != 3:
-        raise ValueError(f"hidden_states must be a 3-D tensor [batch, seq, hidden], got {tuple(hidden_states.shape)}")
+    _check_activations("hidden_states", hidden_states, handler)
     B, T, H = hidden_states.shape
     block_prompts = _split_prompts(prompts, len(backends), B, H)
     lo, hi = backends[0].slot, backends[-1].slot + 1
@@ -42,6 +52,8 @@ def run_rpc_forward(hidden_states: torch.Tensor, prompts: Optional[torch.Tensor]
 
 def run_rpc_backward(inputs: torch.Tensor, grad_outputs: torch.Tensor, prompts: Optional[torch.Tensor], *, backends: Sequence,
                      handler, active_adapter: Optional[str] = None, points: float = 0.0) -> List[torch.Tensor]:
+    _check_activations("inputs", inputs, handler)
+    _check_activations("grad_outputs", grad_outputs, handler)
     if inputs.shape != grad_outputs.shape:
         raise ValueError(f"inputs {tuple(inputs.shape)} and grad_outputs {tuple(grad_outputs.shape)} must have the same shape")
     B, T, H = inputs.shape

@@ -152,8 +152,10 @@ class InferenceStream:
             if fabric is None:
                 raise RuntimeError("this stage has no NVLink fabric but the request asks to push its output")
             push_to = (fabric, str(fout["kind"]), int(fout["rank"]))
-        if hidden.dim() != 3:
-            raise ValueError(f"hidden states must be [batch, seq, hidden], got {tuple(hidden.shape)}")
+        if hidden.dim() != 3 or not hidden.is_floating_point():
+            raise ValueError(f"hidden states must be a floating-point tensor [batch, seq, hidden], got {tuple(hidden.shape)} {hidden.dtype}")
+        if hidden.shape[2] != self.handler.stage.spec.hidden_size:  # kernels index by the model's hidden size: never trust the wire
+            raise ValueError(f"hidden states have hidden size {hidden.shape[2]}, this model's is {self.handler.stage.spec.hidden_size}")
         B, T, H = hidden.shape
         self._last_tokens = B * T  # for the metrics: a fused stage hop returns an empty tensor
         cache = self._ensure_cache(B)

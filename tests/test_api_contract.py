@@ -274,3 +274,18 @@ def test_server_checks_what_a_client_sends():
             handler.rpc_inference([uids[0], uids[2]], {"max_length": 8})  # not a contiguous chain
         with pytest.raises(Exception):
             handler.rpc_forward(["other-model.0"], torch.randn(1, 1, H))
+        # tensors whose shape the kernels index by the model's hidden size
+        for bad in (torch.randn(1, 3, H + 2), torch.randn(3, H), torch.zeros(1, 3, H, dtype=torch.int64), torch.randn(0, 3, H)):
+            with pytest.raises(ValueError):
+                handler.rpc_forward(uids, bad)
+            with pytest.raises(ValueError):
+                handler.rpc_backward(uids, bad, bad)
+        with pytest.raises(ValueError, match="same shape"):
+            handler.rpc_backward(uids, torch.randn(1, 3, H), torch.randn(1, 2, H))
+        stream = handler.rpc_inference(uids, {"max_length": 8})
+        try:
+            for bad in (torch.randn(1, 1, H - 2), torch.zeros(1, 1, H, dtype=torch.int32), torch.randn(1, H)):
+                with pytest.raises(ValueError):
+                    stream.step(bad)
+        finally:
+            stream.close()
