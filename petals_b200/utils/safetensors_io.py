@@ -19,6 +19,7 @@ from petals_b200.ops import native
 _DTYPES = {
     "F64": torch.float64, "F32": torch.float32, "F16": torch.float16, "BF16": torch.bfloat16,
     "I64": torch.int64, "I32": torch.int32, "I16": torch.int16, "I8": torch.int8, "U8": torch.uint8, "BOOL": torch.bool,
+    "U16": torch.uint16, "U32": torch.uint32, "U64": torch.uint64,
     "F8_E4M3": torch.float8_e4m3fn, "F8_E5M2": torch.float8_e5m2,
 }
 _NAMES = {v: k for k, v in _DTYPES.items()}
@@ -39,7 +40,23 @@ class SafetensorsFile:
         off, nbytes = C.c_int64(), C.c_int64()
         for i in range(self._rt.pb_st_num_tensors(self._h)):
             nd = self._rt.pb_st_tensor_info(self._h, i, name, 1024, dtype, 32, shape, C.byref(off), C.byref(nbytes))
-            self._index[name.value.decode()] = (i, dtype.value.decode(), tuple(shape[:nd]), off.value, nbytes.value)
+            key, kind, dims = name.value.decode(), dtype.value.decode(), tuple(shape[:max(nd, 0)])
+            # the header is untrusted input: a record whose shape does not account for exactly its byte range would make the copy in
+            # get_tensor() overrun the destination (or leave most of it uninitialised)
+            if nd < 0:
+                self.close()
+                raise IOError(f"cannot read {path}: malformed record for tensor {key!r}")
+            if kind not in _DTYPES:  # some other tool's dtype: the file stays usable, only this tensor is refused when asked for
+                self._index[key] = (i, kind, dims, off.value, nbytes.value)
+                continue
+            numel = 1
+            for d in dims:
+                numel *= d
+            expected = numel * torch.empty((), dtype=_DTYPES[kind]).element_size()
+            if any(d < 0 for d in dims) or expected != nbytes.value:
+                self.close()
+                raise IOError(f"cannot read {path}: tensor {key!r} of shape {dims} ({kind}) needs {expected} bytes but its data range has {nbytes.value}")
+            self._index[key] = (i, kind, dims, off.value, nbytes.value)
         self._base = self._rt.pb_st_data(self._h)
 
     def keys(self) -> List[str]:
@@ -48,14 +65,19 @@ class SafetensorsFile:
     def __contains__(self, name: str) -> bool:
         return name in self._index
 
+    def _dtype_of(self, name: str, kind: str) -> torch.dtype:
+        if kind not in _DTYPES:
+            raise IOError(f"tensor {name!r} in {self.path} has an unsupported dtype {kind!r}")
+        return _DTYPES[kind]
+
     def info(self, name: str) -> Tuple[torch.dtype, Tuple[int, ...]]:
         _, dt, shape, _, _ = self._index[name]
-        return _DTYPES[dt], shape
+        return self._dtype_of(name, dt), shape
 
     def get_tensor(self, name: str, pinned: bool = False, threads: int = 8) -> torch.Tensor:
         """A private copy of the tensor (optionally in pinned memory, filled with a multi-threaded memcpy)."""
         idx, dt, shape, _, nbytes = self._index[name]
-        dtype = _DTYPES[dt]
+        dtype = self._dtype_of(name, dt)
         out = torch.empty(shape, dtype=dtype, pin_memory=pinned and torch.cuda.is_available())
         if nbytes:
             rc = self._rt.pb_st_read(self._h, idx, out.data_ptr(), nbytes, threads)

@@ -131,3 +131,45 @@ def test_rope_tables_reject_length_dependent_scaling():
     plain = rope_tables(64, 128, 10000.0, None)
     same = rope_tables(64, 128, 10000.0, {"rope_type": "default"})
     assert torch.equal(plain[0], same[0]) and torch.equal(plain[1], same[1])
+
+
+def test_safetensors_reader_refuses_inconsistent_files(tmp_path):
+    """The header of a checkpoint file is untrusted input for the C++ reader: truncated / absurd / inconsistent records are errors,
+    never crashes, over-long copies or half-initialised tensors."""
+    import json
+    import struct
+
+    from petals_b200.utils.safetensors_io import SafetensorsFile, save_file
+
+    good = tmp_path / "good.safetensors"
+    save_file({"a": torch.arange(12, dtype=torch.float32).reshape(3, 4), "b": torch.ones(5, dtype=torch.bfloat16)}, str(good))
+    raw = good.read_bytes()
+    (hl,) = struct.unpack("<Q", raw[:8])
+    body = raw[8 + hl:]
+
+    def with_header(h):
+        hb = json.dumps(h).encode()
+        return struct.pack("<Q", len(hb)) + hb + body
+
+    rec = lambda **kw: {"a": dict(dict(dtype="F32", shape=[3, 4], data_offsets=[0, 48]), **kw)}  # noqa: E731
+    broken = {
+        "empty": b"", "short": raw[:5], "truncated_header": raw[:8 + hl // 2], "truncated_body": raw[:-7],
+        "huge_header_len": struct.pack("<Q", 1 << 60) + raw[8:], "garbage_header": struct.pack("<Q", 16) + b"\\xff" * 16 + body,
+        "not_an_object": with_header([1, 2, 3]), "offsets_past_eof": with_header(rec(data_offsets=[0, 10 ** 9])),
+        "negative_offsets": with_header(rec(data_offsets=[-8, 40])), "reversed_offsets": with_header(rec(data_offsets=[48, 0])),
+        "shape_larger_than_data": with_header(rec(shape=[300, 400])), "shape_smaller_than_data": with_header(rec(shape=[2, 2])),
+        "missing_fields": with_header({"a": {"dtype": "F32"}}), "huge_shape": with_header(rec(shape=[2 ** 40, 2 ** 40])),
+        "deep_nesting": struct.pack("<Q", 20000) + b"[" * 20000 + body,
+    }
+    for name, data in broken.items():
+        path = tmp_path / f"{name}.safetensors"
+        path.write_bytes(data)
+        with pytest.raises(IOError):
+            SafetensorsFile(str(path))
+    # a dtype this reader does not know makes only that tensor unavailable
+    odd = tmp_path / "odd.safetensors"
+    odd.write_bytes(with_header({"a": {"dtype": "F32", "shape": [3, 4], "data_offsets": [0, 48]}, "z": {"dtype": "Q7", "shape": [2], "data_offsets": [48, 58]}}))
+    with SafetensorsFile(str(odd)) as f:
+        assert torch.equal(f.get_tensor("a"), torch.arange(12, dtype=torch.float32).reshape(3, 4))
+        with pytest.raises(IOError, match="unsupported dtype"):
+            f.get_tensor("z")
