@@ -24,6 +24,7 @@ struct KvAllocator {
 }  // namespace
 
 extern "C" void* pb_kv_create(int num_pages) {
+  if (num_pages < 0) return nullptr;  // a C ABI must not let std::length_error escape
   auto* a = new KvAllocator();
   a->total = num_pages;
   a->refs.assign(num_pages, 0);
@@ -48,7 +49,11 @@ extern "C" int pb_kv_alloc(void* h, int n, int* out) {
 extern "C" void pb_kv_incref(void* h, const int* pages, int n) {
   auto* a = static_cast<KvAllocator*>(h);
   std::lock_guard<std::mutex> g(a->mu);
-  for (int i = 0; i < n; ++i) a->refs[pages[i]]++;
+  for (int i = 0; i < n; ++i) {
+    const int p = pages[i];
+    if (p < 0 || p >= static_cast<int>(a->refs.size()) || a->refs[p] <= 0) continue;  // only live pages can gain an owner
+    a->refs[p]++;
+  }
 }
 extern "C" void pb_kv_free(void* h, const int* pages, int n) {
   auto* a = static_cast<KvAllocator*>(h);
@@ -67,12 +72,13 @@ extern "C" int pb_kv_num_free(void* h) {
 extern "C" int pb_kv_refcount(void* h, int page) {
   auto* a = static_cast<KvAllocator*>(h);
   std::lock_guard<std::mutex> g(a->mu);
+  if (page < 0 || page >= a->total) return -1;
   return a->refs[page];
 }
 extern "C" int pb_kv_reserve(void* h, long pages, double timeout_s) {
   auto* a = static_cast<KvAllocator*>(h);
   std::unique_lock<std::mutex> lk(a->mu);
-  if (pages > a->total) return -1;
+  if (pages < 0 || pages > a->total) return -1;
   const uint64_t ticket = a->next_ticket++;
   const auto deadline = std::chrono::steady_clock::now() + std::chrono::duration<double>(timeout_s < 0 ? 0 : timeout_s);
   auto ready = [&] { return a->serving == ticket && a->reserved + pages <= a->total; };
@@ -98,7 +104,7 @@ extern "C" void pb_kv_unreserve(void* h, long pages) {
   auto* a = static_cast<KvAllocator*>(h);
   {
     std::lock_guard<std::mutex> g(a->mu);
-    a->reserved -= pages;
+    if (pages > 0) a->reserved -= pages;
     if (a->reserved < 0) a->reserved = 0;
   }
   a->cv.notify_all();

@@ -7,6 +7,7 @@
 
 #include <chrono>
 #include <condition_variable>
+#include <limits>
 #include <mutex>
 #include <queue>
 #include <vector>
@@ -38,6 +39,7 @@ extern "C" void pb_tq_push(void* h, double priority, int64_t id) {
   auto* t = static_cast<TaskQueue*>(h);
   {
     std::lock_guard<std::mutex> g(t->mu);
+    if (priority != priority) priority = std::numeric_limits<double>::infinity();  // NaN would break the heap's ordering: run it last
     t->q.push(Item{priority, t->seq++, id});
   }
   t->cv.notify_one();

@@ -73,3 +73,45 @@ def test_dense_session_semantics():
         assert sess.position == 2
         with pytest.raises(ValueError):
             sess.set_position(11)
+
+
+def test_native_allocator_and_queue_tolerate_misuse():
+    """The C ABI of the host runtime (csrc/runtime) is called through ctypes: nothing a caller passes may corrupt memory or let a C++
+    exception escape (found by fuzzing: out-of-range incref / refcount, negative sizes, NaN priorities)."""
+    import ctypes as C
+
+    from petals_b200.ops import native
+
+    rt = native.rt()
+    assert not rt.pb_kv_create(-3)  # no std::length_error through the ABI
+    h = rt.pb_kv_create(8)
+    pages = (C.c_int * 16)()
+    assert rt.pb_kv_alloc(h, 3, pages) == 0 and rt.pb_kv_num_free(h) == 5
+    assert rt.pb_kv_alloc(h, 100, pages) == -1 and rt.pb_kv_num_free(h) == 5  # all or nothing
+    wild = (C.c_int * 4)(-5, 99, 1 << 30, 7)  # 7 is a valid but free page: it cannot gain an owner either
+    rt.pb_kv_incref(h, wild, 4)
+    rt.pb_kv_free(h, wild, 4)
+    assert rt.pb_kv_num_free(h) == 5 and rt.pb_kv_refcount(h, 7) == 0
+    assert rt.pb_kv_refcount(h, 1000) == -1 and rt.pb_kv_refcount(h, -1) == -1
+    live = (C.c_int * 3)(0, 1, 2)
+    rt.pb_kv_free(h, live, 3)
+    rt.pb_kv_free(h, live, 3)  # double free is ignored, pages are not duplicated in the free list
+    assert rt.pb_kv_num_free(h) == 8
+    assert rt.pb_kv_alloc(h, 8, pages) == 0 and sorted(pages[:8]) == list(range(8))
+    assert rt.pb_kv_reserve(h, -4, 0.01) == -1 and rt.pb_kv_reserve(h, 1000, 0.01) == -1 and rt.pb_kv_reserved(h) == 0
+    rt.pb_kv_unreserve(h, 50)
+    rt.pb_kv_unreserve(h, -50)
+    assert rt.pb_kv_reserved(h) == 0
+    rt.pb_kv_destroy(h)
+
+    q = rt.pb_tq_create()
+    tid, prio = C.c_int64(), C.c_double()
+    for priority, task in ((float("nan"), 1), (1.0, 2), (float("-inf"), 3), (1.0, 4)):
+        rt.pb_tq_push(q, priority, task)
+    order = []
+    while rt.pb_tq_pop(q, 0.0, C.byref(tid), C.byref(prio)) == 0:
+        order.append(tid.value)
+    assert order == [3, 2, 4, 1]  # -inf first, FIFO among equals, the NaN task last instead of scrambling the heap
+    rt.pb_tq_close(q)
+    assert rt.pb_tq_pop(q, 0.0, C.byref(tid), C.byref(prio)) == -2
+    rt.pb_tq_destroy(q)
