@@ -159,6 +159,10 @@ class DistributedModelBase(nn.Module, PTuneMixin, FromPretrainedMixin):
 
     def load_client_state(self, t: Dict[str, torch.Tensor]) -> set:
         missing = set()
+        H, V = self.config.hidden_size, self.config.vocab_size
+        for key, want in (("embed", (V, H)), ("norm_w", (H,)), ("norm_b", (H,)), ("embed_ln_w", (H,)), ("embed_ln_b", (H,)), ("head", (V, H))):
+            if key in t and tuple(t[key].shape) != want:  # lookups and GEMMs are sized from the config: refuse a checkpoint that disagrees with it
+                raise ValueError(f"checkpoint tensor {key!r} has shape {tuple(t[key].shape)}, config.json implies {want}")
         with torch.no_grad():
             if "embed" in t:
                 self.embed_tokens.weight.data = t["embed"].clone()

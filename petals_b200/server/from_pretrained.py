@@ -85,6 +85,13 @@ def load_pretrained_block(model_name: str, block_index: int, *, config=None, tor
     missing, unexpected = expected - set(canon), set(canon) - expected
     if missing or unexpected:
         raise RuntimeError(f"block {block_index}: missing {sorted(missing)}, unexpected {sorted(unexpected)}")
+    # the kernels size their launches from the config (BlockSpec): a checkpoint whose tensors disagree with its own config.json must be
+    # refused here, not discovered as an out-of-bounds read on the device
+    wrong = {name: (tuple(tensor.shape), tuple(getattr(block, name).shape)) for name, tensor in canon.items()
+             if tuple(tensor.shape) != tuple(getattr(block, name).shape)}
+    if wrong:
+        details = ", ".join(f"{n}: checkpoint {got} vs config {want}" for n, (got, want) in sorted(wrong.items()))
+        raise RuntimeError(f"block {block_index} of {model_name}: tensor shapes do not match config.json ({details})")
     for name, tensor in canon.items():
         getattr(block, name).data = tensor
     block.requires_grad_(False)

@@ -153,3 +153,35 @@ def test_importing_the_package_pulls_in_no_heavy_optional_dependency():
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ, PYTHONPATH=root), capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert out.stdout.strip() == "", f"imported on `import petals`: {out.stdout.strip()}"
+
+
+def test_checkpoints_that_disagree_with_their_config_are_refused(tmp_path):
+    """Kernel launches are sized from config.json (BlockSpec, vocab, hidden size). A checkpoint whose tensors have other shapes must fail
+    at load time with a readable message — on a GPU it would otherwise be an out-of-bounds access."""
+    import json
+    import os
+    import shutil
+
+    from petals_b200.parallel.swarm import Swarm
+    from petals_b200.server.from_pretrained import load_pretrained_block
+    from petals_b200.utils.auto_config import AutoDistributedModelForCausalLM
+    from tests.utils import checkpoint
+
+    def variant(**overrides):
+        d = str(tmp_path / ("v" + "-".join(overrides)))
+        shutil.copytree(checkpoint("llama"), d)
+        cfg_path = os.path.join(d, "config.json")
+        cfg = json.load(open(cfg_path))
+        cfg.update({k: (cfg[k] * 2 if v == "double" else v) for k, v in overrides.items()})
+        json.dump(cfg, open(cfg_path, "w"))
+        return d
+
+    with pytest.raises(RuntimeError, match="do not match config.json"):
+        load_pretrained_block(variant(intermediate_size="double"), 1, torch_dtype=torch.float32)
+    with pytest.raises(RuntimeError, match="do not match config.json"):
+        load_pretrained_block(variant(num_key_value_heads=4), 0, torch_dtype=torch.float32)
+    with pytest.raises(ValueError, match="config.json implies"):
+        AutoDistributedModelForCausalLM.from_pretrained(variant(vocab_size="double"), initial_peers=Swarm("shape-check"))
+    for index in (99, -1):
+        with pytest.raises(KeyError, match="no tensors for block"):
+            load_pretrained_block(checkpoint("llama"), index, torch_dtype=torch.float32)
