@@ -101,7 +101,13 @@ def add_adapter_to_block(block, block_index: int, adapter_name: str, peft_config
         if "A" not in ab or "B" not in ab:
             raise ValueError(f"adapter {adapter_name}: incomplete LoRA pair for {module} in block {block_index}")
         name, rows = targets[module]
-        entry.setdefault(name, []).append((ab["A"].to(dev, dt), ab["B"].to(dev, dt), scale, rows))
+        weight = getattr(block, name)
+        out_rows = weight.shape[0] if rows is None else len(range(*rows.indices(weight.shape[0])))
+        A, B = ab["A"], ab["B"]
+        if A.dim() != 2 or B.dim() != 2 or A.shape[1] != weight.shape[1] or B.shape[0] != out_rows or A.shape[0] != B.shape[1]:
+            raise ValueError(f"adapter {adapter_name}: LoRA pair for {module} in block {block_index} has shapes A {tuple(A.shape)}, B {tuple(B.shape)}; "
+                             f"the projection maps {weight.shape[1]} -> {out_rows} features (an adapter trained for another model?)")
+        entry.setdefault(name, []).append((A.to(dev, dt), B.to(dev, dt), scale, rows))
     block.lora_adapters[adapter_name] = entry
     logger.debug(f"block {block_index}: loaded adapter {adapter_name} ({sum(len(v) for v in entry.values())} LoRA pairs)")
 

@@ -166,3 +166,21 @@ def test_engine_adapter_switching_keeps_separate_graph_caches():
             StageEngine.use_adapter(eng, "b")
     finally:
         peft.MergedAdapterBlock = real
+
+
+def test_adapter_for_another_model_is_refused_at_load_time(tmp_path):
+    from petals_b200.server.from_pretrained import load_pretrained_block
+    from petals_b200.utils.peft import add_adapter_to_block
+
+    path = checkpoint("llama")
+    config = AutoDistributedConfig.from_pretrained(path)
+    other = AutoDistributedConfig.from_pretrained(checkpoint("llama", hidden_size=256, intermediate_size=512))
+    adapter = make_adapter(str(tmp_path / "wrong"), other)
+    block = load_pretrained_block(path, 0, torch_dtype=torch.float32)
+    cfg, state = load_peft(adapter, block_idx=0)
+    with pytest.raises(ValueError, match="another model"):
+        add_adapter_to_block(block, 0, "wrong", cfg, state)
+    assert "wrong" not in getattr(block, "lora_adapters", {})
+    good_cfg, good_state = load_peft(make_adapter(str(tmp_path / "right"), config), block_idx=0)
+    add_adapter_to_block(block, 0, "right", good_cfg, good_state)
+    assert set(block.lora_adapters["right"]) == {"wqkv", "w_down"}
