@@ -36,7 +36,7 @@ def join_uids(uids: Iterable[ModuleUID]) -> str:
 
 
 def split_uids(chain: str) -> List[ModuleUID]:
-    return chain.split()
+    return [uid for uid in chain.split(CHAIN_DELIMITER) if uid]  # only the delimiter separates: prefixes may contain other whitespace
 
 
 # ---- validation helpers (what pydantic's conint / confloat enforce in the reference) ---------------------------------------

@@ -7,11 +7,16 @@ from typing import Any, Dict, List, Tuple
 
 import torch
 
+import re
+
 _TENSOR_TAG = "__T"
+_PLACEHOLDER = re.compile(rb"^__T(\d+)$")
+_ESCAPE = b"__E"  # user bytes that look like a placeholder (or like an escape) travel with this prefix
 
 
 def _is_placeholder(x: Any) -> bool:
-    return isinstance(x, (bytes, str)) and (x.decode() if isinstance(x, bytes) else x).startswith(_TENSOR_TAG)
+    """Only *bytes* of the exact form ``__T<index>`` stand for a tensor; text arguments are never reinterpreted."""
+    return isinstance(x, bytes) and _PLACEHOLDER.match(x) is not None
 
 
 def _flatten(obj: Any, tensors: List[torch.Tensor]) -> Any:
@@ -22,13 +27,16 @@ def _flatten(obj: Any, tensors: List[torch.Tensor]) -> Any:
         return [_flatten(o, tensors) for o in obj]
     if isinstance(obj, dict):
         return {k: _flatten(v, tensors) for k, v in obj.items()}
+    if isinstance(obj, bytes) and (obj.startswith(_ESCAPE) or _PLACEHOLDER.match(obj)):
+        return _ESCAPE + obj
     return obj
 
 
 def _restore(obj: Any, tensors: List[torch.Tensor]) -> Any:
     if _is_placeholder(obj):
-        text = obj.decode() if isinstance(obj, bytes) else obj
-        return tensors[int(text[len(_TENSOR_TAG):])]
+        return tensors[int(_PLACEHOLDER.match(obj).group(1))]
+    if isinstance(obj, bytes) and obj.startswith(_ESCAPE):
+        return obj[len(_ESCAPE):]
     if isinstance(obj, (list, tuple)):
         return [_restore(o, tensors) for o in obj]
     if isinstance(obj, dict):
