@@ -242,6 +242,9 @@ class MemoryCache:
         self._rt.pb_kv_unreserve(self._alloc, session.reserved_pages)
 
     def copy_pages(self, src: Sequence[int], dst: Sequence[int]) -> None:
+        if self.device.type != "cuda":  # host pools (tests of the page bookkeeping): same semantics with tensor indexing
+            self.pool[:, :, list(dst)] = self.pool[:, :, list(src)]
+            return
         s = torch.tensor(src, dtype=torch.int32, device=self.device)
         d = torch.tensor(dst, dtype=torch.int32, device=self.device)
         page_elems = self.pool.shape[3] * self.pool.shape[4] * self.pool.shape[5]

@@ -115,3 +115,58 @@ def test_native_allocator_and_queue_tolerate_misuse():
     rt.pb_tq_close(q)
     assert rt.pb_tq_pop(q, 0.0, C.byref(tid), C.byref(prio)) == -2
     rt.pb_tq_destroy(q)
+
+
+def test_paged_sessions_survive_random_beam_reorders_and_rollbacks():
+    """The page-table bookkeeping of the GPU path (bind pages, copy-on-write of pages shared between hypotheses, reorder, rollback), run
+    against a host pool: every sequence must always read back exactly the history it is supposed to have. Tokens are written into the
+    pool the way the kernels address it — page = table[pos // PAGE], slot = pos % PAGE."""
+    import random
+
+    from petals_b200.models.spec import BlockSpec
+    from petals_b200.ops.functional import PAGE
+
+    spec = BlockSpec(family="llama", hidden_size=8, num_heads=1, num_kv_heads=1, head_dim=2, intermediate_size=8)
+    rng = random.Random(0)
+    for trial in range(25):
+        cache = MemoryCache(64 * PAGE, None, n_blocks=1, spec=spec, dtype=torch.float32, device="cpu", paged=True, max_length=6 * PAGE)
+        B = rng.choice([1, 2, 3, 4])
+        session = cache.open_session(B, 6 * PAGE, timeout=0)
+        histories = [[] for _ in range(B)]  # what each sequence should contain
+        stamp = 0
+
+        def read(b):
+            table = session.tables[b]
+            return [int(cache.pool[0, 0, table[p // PAGE], 0, p % PAGE, 0]) for p in range(session.position)]
+
+        for _ in range(40):
+            op = rng.choice(["write", "write", "write", "reorder", "rollback"])
+            if op == "write":
+                n = rng.randint(1, PAGE + 5)
+                if session.position + n > session.max_length:
+                    continue
+                session.prepare_write(n)
+                for b in range(B):
+                    for p in range(session.position, session.position + n):
+                        stamp += 1
+                        cache.pool[0, :, session.tables[b][p // PAGE], 0, p % PAGE, :] = stamp
+                        histories[b].append(stamp)
+                session.set_position(session.position + n)
+            elif op == "reorder":
+                ids = [rng.randrange(B) for _ in range(B)]
+                session.reorder(torch.tensor(ids))
+                histories = [list(histories[i]) for i in ids]
+            else:
+                back = rng.randint(0, session.position)
+                session.set_position(back)
+                histories = [h[:back] for h in histories]
+            for b in range(B):
+                assert read(b) == histories[b], (trial, op, b)
+            # no page is referenced by more sequences than its reference count says, none is both free and in use
+            in_use = [p for t in session.tables for p in t]
+            for p in set(in_use):
+                assert cache._rt.pb_kv_refcount(cache._alloc, p) == in_use.count(p)
+        used = len({p for t in session.tables for p in t})
+        assert cache._rt.pb_kv_num_free(cache._alloc) == cache.num_pages - used
+        session.close()
+        assert cache._rt.pb_kv_num_free(cache._alloc) == cache.num_pages and cache.tokens_left == cache.num_pages * PAGE
