@@ -230,12 +230,19 @@ class ApiServer:
                     self.wfile.flush()
 
                 event = first
-                while True:
-                    if "finish_reason" in event:
-                        emit(outer.service._envelope(event, request))
-                        break
-                    emit({"object": "text_completion.chunk", "choices": [{"index": 0, "text": event["text"], "token_id": event["token_id"]}]})
-                    event = next(events)
+                try:
+                    while True:
+                        if "finish_reason" in event:
+                            emit(outer.service._envelope(event, request))
+                            break
+                        emit({"object": "text_completion.chunk", "choices": [{"index": 0, "text": event["text"], "token_id": event["token_id"]}]})
+                        event = next(events)
+                except (BrokenPipeError, ConnectionError):
+                    events.close()  # the client went away: stop generating (the generator's finally releases the session)
+                    return
+                except Exception as e:  # noqa: BLE001 - the headers are out: report in-band, then end the stream
+                    logger.warning(f"stream failed: {e!r}")
+                    emit({"error": {"message": repr(e), "type": "server_error"}})
                 self.wfile.write(b"data: [DONE]\n\n")
                 self.wfile.flush()
 

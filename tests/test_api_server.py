@@ -125,3 +125,33 @@ def test_concurrent_requests_do_not_interfere(api):
         else:
             final = json.loads(body)
         assert final["choices"][0]["token_ids"] == expected
+
+
+def test_stream_reports_a_failure_in_band_and_releases_the_session(api, monkeypatch):
+    """Once the event-stream headers are out a failure cannot become an HTTP status any more: it is sent as an error event, the stream
+    ends properly and the conversation's lock / session are released."""
+    base, model, service, _ = api
+    real = model.generate
+    calls = {"n": 0}
+
+    def flaky(*args, **kwargs):
+        calls["n"] += 1
+        if calls["n"] == 3:
+            raise RuntimeError("stage lost")
+        return real(*args, **kwargs)
+
+    monkeypatch.setattr(model, "generate", flaky)
+    status, body = _post(base, "/v1/completions", {"prompt": [4, 5, 6], "max_tokens": 6, "stream": True})
+    events = [line[len("data: "):] for line in body.split("\n") if line.startswith("data: ")]
+    assert status == 200 and events[-1] == "[DONE]"
+    payloads = [json.loads(e) for e in events[:-1]]
+    assert len(payloads) == 3 and "error" in payloads[-1] and "stage lost" in payloads[-1]["error"]["message"]
+    assert service.open_sessions == 0
+    monkeypatch.setattr(model, "generate", real)
+    assert json.loads(_post(base, "/v1/completions", {"prompt": [4, 5, 6], "max_tokens": 2})[1])["usage"]["completion_tokens"] == 2
+    # the same failure without streaming is an HTTP error
+    calls["n"] = 2
+    monkeypatch.setattr(model, "generate", flaky)
+    with pytest.raises(urllib.error.HTTPError) as err:
+        _post(base, "/v1/completions", {"prompt": [4, 5, 6], "max_tokens": 3})
+    assert err.value.code == 503
