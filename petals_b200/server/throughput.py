@@ -44,7 +44,7 @@ def get_server_throughput(model_name: str, config, device: torch.device, dtype: 
             except Exception:  # noqa: BLE001 - a corrupt cache is simply re-measured
                 logger.warning("throughput cache is unreadable; re-measuring")
         if key not in cache:
-            cache[key] = measure_throughput_info(config, device, dtype, quant_type=quant_type)
+            cache[key] = measure_throughput_info(config, device, dtype, quant_type=quant_type, tensor_parallel_devices=tensor_parallel_devices)
             cache_path.write_text(json.dumps(cache, indent=1))
     info = dict(cache[key])
     # a stage of n blocks spends on average (n + 1) / 2 blocks of compute per routed request (reference :96-106)
@@ -59,12 +59,15 @@ def _device_name(device: torch.device) -> str:
     return torch.cuda.get_device_name(device) if device.type == "cuda" else "cpu"
 
 
-def measure_throughput_info(config, device, dtype, *, quant_type: QuantType) -> Dict[str, float]:
+def measure_throughput_info(config, device, dtype, *, quant_type: QuantType, tensor_parallel_devices: Sequence[torch.device] = ()) -> Dict[str, float]:
+    """The generic (in-process) tensor-parallel split is measured as it will run; a stage served by the NVLink worker group is
+    measured on its leader device alone (a lower bound: the group is faster), since the group does not exist yet at this point."""
     logger.info("Measuring this stage's throughput (a few seconds)")
+    tp = tuple(tensor_parallel_devices) if tensor_parallel_devices and not all(torch.device(d).type == "cuda" for d in tensor_parallel_devices) else ()
     return dict(
-        inference_rps=measure_compute_rps(config, device, dtype, quant_type=quant_type, n_tokens=1, n_steps=50, inference=True),
-        forward_rps=measure_compute_rps(config, device, dtype, quant_type=quant_type, n_tokens=1024 if torch.device(device).type == "cuda" else 64,
-                                        n_steps=5, inference=False),
+        inference_rps=measure_compute_rps(config, device, dtype, quant_type=quant_type, tensor_parallel_devices=tp, n_tokens=1, n_steps=50, inference=True),
+        forward_rps=measure_compute_rps(config, device, dtype, quant_type=quant_type, tensor_parallel_devices=tp,
+                                        n_tokens=1024 if torch.device(device).type == "cuda" else 64, n_steps=5, inference=False),
         network_rps=measure_network_rps(config, dtype),
     )
 

@@ -185,3 +185,30 @@ def test_checkpoints_that_disagree_with_their_config_are_refused(tmp_path):
     for index in (99, -1):
         with pytest.raises(KeyError, match="no tensors for block"):
             load_pretrained_block(checkpoint("llama"), index, torch_dtype=torch.float32)
+
+
+def test_throughput_cache_keys_and_corrupt_cache(tmp_path, monkeypatch):
+    """`--throughput auto`: measured once per (model, device, dtype, quantisation, TP width) and cached on disk; an unreadable cache
+    file is re-measured, not fatal (reference server/throughput.py:56-92)."""
+    from petals_b200.server import throughput as tp_mod
+
+    config = AutoDistributedConfig.from_pretrained(checkpoint("llama"))
+    calls = []
+
+    def fake_measure(cfg, device, dtype, *, quant_type, tensor_parallel_devices=()):
+        calls.append(len(tensor_parallel_devices))
+        return dict(inference_rps=100.0, forward_rps=1000.0, network_rps=1e6)
+
+    monkeypatch.setattr(tp_mod, "measure_throughput_info", fake_measure)
+    kw = dict(num_blocks=3, cache_dir=str(tmp_path))
+    a = tp_mod.get_server_throughput("m", config, torch.device("cpu"), torch.float32, **kw)
+    b = tp_mod.get_server_throughput("m", config, torch.device("cpu"), torch.float32, **kw)  # served from the cache
+    assert a == b and calls == [0] and a["throughput"] == pytest.approx(1000.0 / 2)  # (3 + 1) / 2 blocks of compute per request
+    tp_mod.get_server_throughput("m", config, torch.device("cpu"), torch.float32, tensor_parallel_devices=(torch.device("cpu"),) * 2, **kw)
+    tp_mod.get_server_throughput("m", config, torch.device("cpu"), torch.bfloat16, **kw)
+    assert calls == [0, 2, 0]  # other TP width / dtype = other cache entries
+    (tmp_path / "throughput_v1.json").write_text("{ not json")
+    tp_mod.get_server_throughput("m", config, torch.device("cpu"), torch.float32, **kw)
+    assert calls == [0, 2, 0, 0]
+    tp_mod.get_server_throughput("m", config, torch.device("cpu"), torch.float32, force_eval=True, **kw)
+    assert len(calls) == 5
