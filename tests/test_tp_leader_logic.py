@@ -138,7 +138,7 @@ def test_collective_backward_of_a_tp_worker_group():
 
     with mp.Manager() as manager:
         results = manager.dict()
-        mp.spawn(_backward_worker, args=(2, 29741, results), nprocs=2, join=True)
+        mp.spawn(_backward_worker, args=(2, 29761, results), nprocs=2, join=True)
         out = dict(results)
     assert out[0][0] and out[1][0], out
 
