@@ -64,8 +64,13 @@ class DistributedLlamaForSpeculativeGeneration(DistributedLlamaForCausalLM):
                 # KV is valid for everything fed except rejected draft tokens; the correction token is not fed yet
                 fed = min(cand.shape[1] - (k - n_ok), ids.shape[1] - 1)
                 sess.position = pre + fed
-                if eos and any(int(t) in eos for t in ids[0, -(n_ok + 1):]):
-                    break
+                if eos:
+                    new_from = ids.shape[1] - min(n_ok + 1, ids.shape[1])
+                    hits = [i for i in range(new_from, ids.shape[1]) if int(ids[0, i]) in eos]
+                    if hits:  # stop right after the first end-of-sequence token, like token-by-token decoding would
+                        ids = ids[:, : hits[0] + 1]
+                        sess.position = pre + min(fed, ids.shape[1] - 1)
+                        break
             sess.output_ids = ids
             return ids
 

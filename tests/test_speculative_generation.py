@@ -64,3 +64,30 @@ def test_speculative_generation_equals_greedy(served):
     out = spec.generate(ids, max_new_tokens=40, speculative_chunk=6)
     assert torch.equal(out, greedy)
     assert draft.calls < 40  # several tokens were accepted per remote step
+
+
+def test_speculative_generation_stops_right_after_eos():
+    """An end-of-sequence token accepted in the middle of a verified chunk ends the output there (what greedy decoding would return)."""
+    import torch
+
+    from petals_b200.utils.auto_config import AutoDistributedModelForCausalLM, AutoDistributedSpeculativeModel
+    from tests.utils import checkpoint, swarm_of
+
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:4"]) as (swarm, _):
+        plain = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=swarm)
+        ids = torch.tensor([[7, 8, 9, 10]])
+        with torch.inference_mode():
+            greedy = plain.generate(ids, max_new_tokens=12)[0].tolist()
+        eos = greedy[len(ids[0]) + 4]  # the 5th generated token plays end-of-sequence
+        cut = greedy.index(eos, len(ids[0])) + 1
+
+        class PerfectDraft:  # proposes exactly what the big model will say: whole chunks are accepted, eos lands mid-chunk
+            def generate(self, x, max_new_tokens, do_sample=False):
+                n = x.shape[1]
+                return torch.tensor([greedy[: n + max_new_tokens] + [0] * max(0, n + max_new_tokens - len(greedy))])[:, : n + max_new_tokens]
+
+        spec = AutoDistributedSpeculativeModel.from_pretrained(path, initial_peers=swarm, small_model=PerfectDraft())
+        with torch.inference_mode():
+            out = spec.generate(ids, max_new_tokens=12, speculative_chunk=8, eos_token_id=eos)[0].tolist()
+        assert out == greedy[:cut]
