@@ -145,7 +145,10 @@ class InferenceStream:
         if fin is not None:
             if fabric is None:
                 raise RuntimeError("this stage has no NVLink fabric but the request says its input was pushed")
-            take_from = (fabric, int(fin["src_rank"]), int(fin["B"]), int(fin["T"]))
+            fb, ft, src = int(fin["B"]), int(fin["T"]), int(fin["src_rank"])
+            if fb < 1 or ft < 1 or fb * ft > fabric.max_tokens or not 0 <= src < getattr(fabric, "world", src + 1):
+                raise ValueError(f"fabric_in describes {fb} x {ft} rows from rank {src}: outside this stage's landing zone ({fabric.max_tokens} rows)")
+            take_from = (fabric, src, fb, ft)
             hidden = torch.empty(int(fin["B"]), int(fin["T"]), self.handler.stage.spec.hidden_size, dtype=self.handler.stage.dtype,
                                  device=self.handler.stage.device)  # shape carrier only
         if fout is not None:
