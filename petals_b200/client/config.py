@@ -42,6 +42,10 @@ class ClientConfig:
     max_pinged: int = 3  # how many candidate first-hop servers are pinged when a route is planned
     ping_timeout: float = 2
 
+    # ---- on the wire (socket transports only; NVLink hops and in-process calls never serialise) --------------------------------------
+    wire_compression: Optional[str] = None  # codec for the activations this client sends: NONE, FLOAT16, MEANSTD_16BIT, QUANTILE_8BIT, ...
+    output_compression: Optional[str] = None  # codec servers are asked to answer in (overrides their --compression for this client)
+
     # ---- how patient --------------------------------------------------------------------------------------------------------
     connect_timeout: float = 5
     request_timeout: float = 3 * 60

@@ -343,11 +343,19 @@ class RemoteSequenceManager:
                 time.sleep(delay)
 
     def get_request_metadata(self, protocol: str, args_structure: Any = None, *args, **kwargs) -> Dict[str, Any]:
-        return dict(points=self.policy.get_points(protocol, *args, **kwargs), active_adapter=self.config.active_adapter,
+        meta = dict(points=self.policy.get_points(protocol, *args, **kwargs), active_adapter=self.config.active_adapter,
                     args_structure=args_structure)
+        codec = getattr(self.config, "output_compression", None)
+        if codec and protocol in ("rpc_inference", "rpc_forward"):  # one output tensor each; backward keeps the server's default per gradient
+            meta["output_compression"] = [codec]
+        return meta
 
     def connect(self, peer_id: str):
-        return self.dht.connect(peer_id, connect_timeout=self.config.connect_timeout, request_timeout=self.config.request_timeout)
+        stub = self.dht.connect(peer_id, connect_timeout=self.config.connect_timeout, request_timeout=self.config.request_timeout)
+        codec = getattr(self.config, "wire_compression", None)
+        if codec and hasattr(stub, "socket_path"):  # a socket proxy: compress what this client sends through it
+            stub.compression = codec
+        return stub
 
     def shutdown(self) -> None:
         self._stop.set()

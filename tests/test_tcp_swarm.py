@@ -229,3 +229,38 @@ def test_failover_when_a_server_process_is_killed_mid_session(tmp_path):
         for f in logs:
             f.close()
         registry.shutdown()
+
+
+def test_client_side_wire_codecs_over_tcp():
+    """`wire_compression` / `output_compression` in the client config: lossy but close results through socket peers, exact without."""
+    from petals_b200.client.remote_sequential import RemoteSequential
+    from petals_b200.server.server import Server
+
+    path = checkpoint("llama")
+    registry = RegistryServer("tcp://127.0.0.1:0").start()
+    serving = TcpSwarm(registry.address, bind_host="127.0.0.1")
+    server = Server(initial_peers=serving, converted_model_name_or_path=path, block_indices="0:4", torch_dtype="float32", device="cpu", throughput=1.0,
+                    update_period=0.5, skip_reachability_check=True)
+    server.run_in_background(timeout=120)
+    client_swarm = TcpSwarm(registry.address, bind_host="127.0.0.1")  # a second handle = "another process": forces the socket path
+    try:
+        x = torch.randn(2, 5, AutoDistributedConfig.from_pretrained(path).hidden_size)
+        results = {}
+        for name, kw in (("exact", {}), ("lossy", dict(wire_compression="FLOAT16", output_compression="BLOCKWISE_8BIT"))):
+            config = AutoDistributedConfig.from_pretrained(path, initial_peers=[registry.address], **kw)
+            seq = RemoteSequential(config, dht=client_swarm)
+            with torch.no_grad():
+                fwd = seq(x)
+                with seq.inference_session(max_length=8) as sess:
+                    inf = torch.cat([sess.step(x[:, :3]), sess.step(x[:, 3:])], dim=1)
+            results[name] = (fwd, inf)
+            seq.sequence_manager.shutdown()
+        exact_f, exact_i = results["exact"]
+        lossy_f, lossy_i = results["lossy"]
+        assert torch.allclose(exact_f, exact_i, atol=1e-4)
+        for lossy, exact in ((lossy_f, exact_f), (lossy_i, exact_i)):
+            assert not torch.equal(lossy, exact) and torch.allclose(lossy, exact, atol=0.25, rtol=0.05)
+    finally:
+        server.shutdown()
+        client_swarm.close(), serving.close()
+        registry.shutdown()
