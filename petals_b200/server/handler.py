@@ -131,7 +131,10 @@ class InferenceStream:
             with self._lock:
                 pushed = self._pushed.pop(step_id, None)
                 self._done_steps.add(step_id)
-            if pushed is not None:  # the previous stage already delivered this step's input
+            # the previous stage may already have delivered this step's input (server-to-server push). It is only a latency shortcut for
+            # the tensor the client sends anyway, and the client is the authority on what this stage must see: a predecessor that is
+            # replaying a longer history after a fail-over pushes more positions than this (healthy) session needs — such a push is dropped
+            if pushed is not None and isinstance(hidden, torch.Tensor) and tuple(pushed[0].shape) == tuple(hidden.shape):
                 hidden = pushed[0]
                 prompts = pushed[1] if len(pushed) > 1 else prompts
                 hypo_ids = pushed[2] if len(pushed) > 2 else hypo_ids

@@ -94,3 +94,59 @@ def test_env_style_fault_plan_triggers_failover():
             for b in blocks:
                 h = b(h)[0]
         assert torch.allclose(torch.cat(outs, dim=1), h, atol=1e-4)
+
+
+def test_random_sessions_with_random_faults_always_match_the_local_model():
+    """End-to-end property: whatever mix of steps, roll-backs and injected stage failures a session goes through (overlapping
+    replicas, several faults per session, faults on different stages), its outputs equal the local blocks' and nothing leaks."""
+    import random
+
+    import torch
+
+    from petals_b200.client.remote_sequential import RemoteSequential
+    from petals_b200.server.handler import CACHE_TOKENS_AVAILABLE
+    from petals_b200.utils.auto_config import AutoDistributedConfig
+    from petals_b200.utils.fault_injection import fired_count, set_fault_plan
+    from tests.utils import checkpoint, local_blocks, swarm_of
+
+    path = checkpoint("llama")
+    import os
+
+    rng = random.Random(int(os.environ.get("PETALS_B200_FUZZ_SEED", "1234")))  # other seeds: PETALS_B200_FUZZ_SEED=n pytest -k random_sessions
+    with swarm_of(path, ["0:2", "0:3", "2:4", "1:4"]) as (swarm, servers):  # every block has two holders
+        config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm, min_backoff=0.01, max_backoff=0.05, ban_timeout=0.05)
+        blocks = local_blocks(path, config.num_hidden_layers)
+        idle = [s.module_container.handler.rpc_info()[CACHE_TOKENS_AVAILABLE] for s in servers]
+        peers = [s.peer_id for s in servers]
+        total_fired = 0
+        try:
+            for trial in range(12):
+                seq = RemoteSequential(config, dht=swarm)
+                B, L = rng.choice([1, 2]), rng.randint(6, 14)
+                x = torch.randn(B, L, config.hidden_size, generator=torch.Generator().manual_seed(trial))
+                with torch.no_grad():
+                    expected = x
+                    for b in blocks:
+                        expected = b(expected)[0]
+                # up to three faults at random points of the session, on random stages
+                plan = ";".join(f"rpc=rpc_inference,peer={rng.choice(peers)},after={rng.randint(0, 6)},times={rng.choice([1, 2])}"
+                                for _ in range(rng.randint(0, 3)))
+                set_fault_plan(plan)  # (installing a plan resets the counters)
+                out = torch.empty_like(expected)
+                with torch.inference_mode(), seq.inference_session(max_length=L + 2) as sess:
+                    pos = 0
+                    while pos < L:
+                        if pos > 0 and rng.random() < 0.25:  # roll back and redo some positions (speculative-decoding style)
+                            pos = rng.randint(0, pos)
+                            sess.position = pos
+                        n = rng.randint(1, min(4, L - pos))
+                        out[:, pos: pos + n] = sess.step(x[:, pos: pos + n])
+                        pos += n
+                total_fired += fired_count()
+                set_fault_plan(None)
+                assert torch.allclose(out, expected, atol=1e-4), f"trial {trial} (plan {plan!r})"
+                seq.sequence_manager.shutdown()
+        finally:
+            set_fault_plan(None)
+        assert total_fired >= 3, "the fault plans never triggered: the test did not exercise fail-over"
+        assert [s.module_container.handler.rpc_info()[CACHE_TOKENS_AVAILABLE] for s in servers] == idle
