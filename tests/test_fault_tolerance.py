@@ -129,8 +129,10 @@ def test_random_sessions_with_random_faults_always_match_the_local_model():
                     for b in blocks:
                         expected = b(expected)[0]
                 # up to three faults at random points of the session, on random stages
-                plan = ";".join(f"rpc=rpc_inference,peer={rng.choice(peers)},after={rng.randint(0, 6)},times={rng.choice([1, 2])}"
-                                for _ in range(rng.randint(0, 3)))
+                rules = [f"rpc=rpc_inference,peer={rng.choice(peers)},after={rng.randint(0, 6)},times={rng.choice([1, 2])}" for _ in range(rng.randint(0, 3))]
+                if trial % 2:
+                    rules.append(f"rpc=rpc_inference,after={rng.randint(1, 4)}")  # whichever stage serves that call: guaranteed to fire
+                plan = ";".join(rules)
                 set_fault_plan(plan)  # (installing a plan resets the counters)
                 out = torch.empty_like(expected)
                 with torch.inference_mode(), seq.inference_session(max_length=L + 2) as sess:
@@ -150,3 +152,62 @@ def test_random_sessions_with_random_faults_always_match_the_local_model():
             set_fault_plan(None)
         assert total_fired >= 3, "the fault plans never triggered: the test did not exercise fail-over"
         assert [s.module_container.handler.rpc_info()[CACHE_TOKENS_AVAILABLE] for s in servers] == idle
+
+
+def test_random_forward_backward_with_random_faults_matches_autograd():
+    """The training path under random stage failures (during forward, during backward, several in a row, micro-batched): outputs,
+    input gradients and deep-prompt gradients equal local autograd."""
+    import os
+    import random
+
+    import torch
+
+    from petals_b200.client import sequential_autograd
+    from petals_b200.client.remote_sequential import RemoteSequential
+    from petals_b200.utils.auto_config import AutoDistributedConfig
+    from petals_b200.utils.fault_injection import fired_count, set_fault_plan
+    from tests.utils import checkpoint, local_blocks, swarm_of
+
+    path = checkpoint("llama")
+    rng = random.Random(int(os.environ.get("PETALS_B200_FUZZ_SEED", "99")))
+    with swarm_of(path, ["0:2", "0:3", "2:4", "1:4"]) as (swarm, servers):
+        config = AutoDistributedConfig.from_pretrained(path, initial_peers=swarm, min_backoff=0.01, max_backoff=0.05, ban_timeout=0.05)
+        blocks = local_blocks(path, config.num_hidden_layers)
+        peers = [s.peer_id for s in servers]
+        total_fired = 0
+        saved = sequential_autograd.MAX_TOKENS_IN_BATCH
+        try:
+            for trial in range(8):
+                sequential_autograd.MAX_TOKENS_IN_BATCH = rng.choice([saved, 8])  # sometimes several micro-batches in flight
+                seq = RemoteSequential(config, dht=swarm)
+                B, T, pre = rng.choice([2, 4]), rng.randint(3, 6), rng.choice([0, 2])
+                gen = torch.Generator().manual_seed(trial)
+                x1 = torch.randn(B, T, config.hidden_size, generator=gen, requires_grad=True)
+                x2 = x1.detach().clone().requires_grad_(True)
+                p1 = (torch.randn(len(blocks), 1, pre, config.hidden_size, generator=gen) * 0.1).requires_grad_(True) if pre else None
+                p2 = p1.detach().clone().requires_grad_(True) if pre else None
+                w = torch.randn(B, T, config.hidden_size, generator=gen)
+                rules = [f"rpc={rng.choice(['rpc_forward', 'rpc_backward'])},peer={rng.choice(peers)},after={rng.randint(0, 2)},times={rng.choice([1, 2])}"
+                         for _ in range(rng.randint(0, 2))]
+                rules.append(f"rpc={rng.choice(['rpc_forward', 'rpc_backward'])},after={rng.randint(0, 1)}")  # whichever stage is asked: always fires
+                plan = ";".join(rules)
+                set_fault_plan(plan)
+                y = seq(x1, prompts=p1)
+                (y * w).sum().backward()
+                total_fired += fired_count()
+                set_fault_plan(None)
+                h = x2
+                for i, b in enumerate(blocks):
+                    if pre:
+                        h = torch.cat([h[:, :pre] + p2[i], h[:, pre:]], dim=1)
+                    h = b(h)[0]
+                (h * w).sum().backward()
+                assert torch.allclose(y, h, atol=1e-4), f"trial {trial} forward (plan {plan!r})"
+                assert torch.allclose(x1.grad, x2.grad, atol=1e-3), f"trial {trial} input gradient (plan {plan!r})"
+                if pre:
+                    assert torch.allclose(p1.grad, p2.grad, atol=1e-3), f"trial {trial} prompt gradient (plan {plan!r})"
+                seq.sequence_manager.shutdown()
+        finally:
+            set_fault_plan(None)
+            sequential_autograd.MAX_TOKENS_IN_BATCH = saved
+        assert total_fired >= 2, "the fault plans never triggered"
