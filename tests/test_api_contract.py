@@ -289,3 +289,41 @@ def test_server_checks_what_a_client_sends():
                     stream.step(bad)
         finally:
             stream.close()
+
+
+def test_server_to_server_push_is_used_when_consistent_and_dropped_otherwise():
+    """Stage i pushes its output to stage i+1 (reference handler.py:320-350, dead on the reference's client side: SURVEY.md §7.4 Q1).
+    The successor uses a pushed tensor only if it is exactly what the client sends for that step."""
+    import torch
+
+    from petals_b200.utils.auto_config import AutoDistributedConfig
+    from tests.utils import checkpoint, swarm_of
+
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:4"]) as (swarm, servers):
+        config = AutoDistributedConfig.from_pretrained(path)
+        handler = servers[0].module_container.handler
+        uids = [f"{config.dht_prefix}.{i}" for i in range(4)]
+        H = config.hidden_size
+        x = torch.randn(1, 3, H)
+        other = torch.randn(1, 3, H)
+        ref = handler.rpc_inference(uids, {"max_length": 8, "session_id": "ref"})
+        expected_x, expected_other = ref.step(x, metadata={"step_id": "a"}), None
+        ref.close()
+        ref = handler.rpc_inference(uids, {"max_length": 8, "session_id": "ref2"})
+        expected_other = ref.step(other, metadata={"step_id": "a"})
+        ref.close()
+
+        stream = handler.rpc_inference(uids, {"max_length": 8, "session_id": "s1"})
+        handler.rpc_push(uids, other, metadata={"session_id": "s1", "step_id": "step-1"})  # same shape as what the client sends: used
+        out = stream.step(x, metadata={"step_id": "step-1"})
+        assert torch.allclose(out, expected_other, atol=1e-5) and not torch.allclose(out, expected_x, atol=1e-3)
+        stream.close()
+
+        stream = handler.rpc_inference(uids, {"max_length": 8, "session_id": "s2"})
+        handler.rpc_push(uids, torch.randn(1, 7, H), metadata={"session_id": "s2", "step_id": "step-1"})  # a replaying predecessor: dropped
+        out = stream.step(x, metadata={"step_id": "step-1"})
+        assert out.shape == x.shape and torch.allclose(out, expected_x, atol=1e-5) and stream.position == 3
+        handler.rpc_push(uids, x, metadata={"session_id": "s2", "step_id": "step-1"})  # late push for a finished step: ignored
+        handler.rpc_push(uids, x, metadata={"session_id": "unknown", "step_id": "zzz"})  # unknown session: ignored
+        stream.close()
