@@ -76,14 +76,35 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     obj_dir = OUT_DIR / "obj"
     obj_dir.mkdir(exist_ok=True)
 
+    # incremental: an object is rebuilt when its source, any header, or the flags changed
+    hdr = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + list((CSRC / "runtime").glob("*.h"))):
+        hdr.update(p.name.encode() + p.read_bytes())
+    hdr.update(" ".join(NVCC_FLAGS + CXX_FLAGS).encode())
+
+    def fresh(src: Path, obj: Path) -> bool:
+        key = hashlib.sha256(hdr.digest() + src.read_bytes()).hexdigest()
+        tag = obj.with_suffix(".hash")
+        if not force and obj.exists() and tag.exists() and tag.read_text() == key:
+            return True
+        tag.unlink(missing_ok=True)
+        return False
+
+    def stamp(src: Path, obj: Path) -> None:
+        obj.with_suffix(".hash").write_text(hashlib.sha256(hdr.digest() + src.read_bytes()).hexdigest())
+
     def compile_cu(src: Path) -> Path:
         obj = obj_dir / (src.stem + ".o")
-        _run([nvcc, *NVCC_FLAGS, "-I", str(CSRC), "-c", str(src), "-o", str(obj)])
+        if not fresh(src, obj):
+            _run([nvcc, *NVCC_FLAGS, "-I", str(CSRC), "-c", str(src), "-o", str(obj)])
+            stamp(src, obj)
         return obj
 
     def compile_cpp(src: Path) -> Path:
         obj = obj_dir / ("rt_" + src.stem + ".o")
-        _run(["g++", *CXX_FLAGS, "-I", str(CSRC), "-c", str(src), "-o", str(obj)])
+        if not fresh(src, obj):
+            _run(["g++", *CXX_FLAGS, "-I", str(CSRC), "-c", str(src), "-o", str(obj)])
+            stamp(src, obj)
         return obj
 
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 2)) as ex:

@@ -35,7 +35,7 @@ struct AttnParams {
   float* partial_lse;
   const float* alibi;
   float scale_log2;
-  int B, T, Hq, Hkv, page, max_pages, window, splits, pos_static;
+  int B, T, Hq, Hkv, page, max_pages, window, splits, pos_static, num_pages;
   int* split_counter;   // [m_tiles * B * Hkv] zero-initialised; non-null fuses the split-KV combine into this kernel
 };
 
@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 
   // ---- async loads -------------------------------------------------------------------------
   auto load_kv = [&](int tile, int buf) {
-    const int pg = p.block_table[static_cast<size_t>(b) * p.max_pages + tile];
+    int pg = p.block_table[static_cast<size_t>(b) * p.max_pages + tile];
+    pg = min(max(pg, 0), p.num_pages - 1);  // a corrupt table entry must not read outside the pool
     const size_t base = (static_cast<size_t>(pg) * p.Hkv + kvh) * p.page * D;
     const __nv_bfloat16* ks = p.k_pool + base;
     const __nv_bfloat16* vs = p.v_pool + base;
@@ -356,6 +357,7 @@ static int launch_attn(const PbAttnArgs* a, cudaStream_t s) {
   p.split_counter = static_cast<int*>(a->split_counter);
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.B = a->B; p.T = a->T; p.Hq = a->Hq; p.Hkv = a->Hkv; p.page = a->page; p.max_pages = a->max_pages;
+  p.num_pages = a->num_pages > 0 ? a->num_pages : 0x7fffffff;
   p.window = a->window; p.splits = a->splits < 1 ? 1 : a->splits; p.pos_static = a->pos_static;
   const int G = a->Hq / a->Hkv;
   const int m_tiles = (a->T * G + 63) / 64;

@@ -71,7 +71,7 @@ struct LinearDecodeParams {
   const int* rope_pos_ptr;                      // device-resident position of the first new token
   const float* rope_cos;                        // [max_pos, D/2] fp32 (null: no rotation, append only)
   const float* rope_sin;
-  int rope_T, rope_Hq, rope_Hkv, rope_D, rope_max_pages, rope_max_pos;
+  int rope_T, rope_Hq, rope_Hkv, rope_D, rope_max_pages, rope_max_pos, rope_num_pages;
   int split_k;                                  // > 1: that many warps share one row pair, each streaming 1/split_k of K
   int pf_lines;                                 // 128-byte weight lines each warp prefetches into L2 before the prologue
   int late_trigger;                             // 1: release the dependent kernel after the main loop instead of at entry
@@ -366,7 +366,12 @@ PB_DEVICE void gemv_body(const LinearDecodeParams& p, uint8_t* smem_raw, int gri
             dst = nullptr;
           } else {
             const int pg = p.rope_block_table[static_cast<size_t>(b) * p.rope_max_pages + pg_idx];
-            dst = (is_v ? p.rope_v_pool : p.rope_k_pool) + ((static_cast<size_t>(pg) * p.rope_Hkv + kvh) * 64 + (pos & 63)) * D;
+            if (pg < 0 || pg >= p.rope_num_pages) {  // never write outside the pool
+              if (p.error_flag != nullptr) atomicExch(p.error_flag, 2);
+              dst = nullptr;
+            } else {
+              dst = (is_v ? p.rope_v_pool : p.rope_k_pool) + ((static_cast<size_t>(pg) * p.rope_Hkv + kvh) * 64 + (pos & 63)) * D;
+            }
           }
         }
         if (dst != nullptr) {
@@ -705,6 +710,7 @@ static int gemv_fill(const PbLinearDecodeArgs* a, LinearDecodeParams& p, GemvGeo
     p.rope_sin = static_cast<const float*>(a->rope_sin);
     p.rope_T = a->rope_T; p.rope_Hq = a->rope_Hq; p.rope_Hkv = a->rope_Hkv; p.rope_D = D;
     p.rope_max_pages = a->rope_max_pages; p.rope_max_pos = a->rope_max_pos;
+    p.rope_num_pages = a->rope_num_pages > 0 ? a->rope_num_pages : 0x7fffffff;
   }
   {
     static const int env_pf = [] { const char* e = getenv("PETALS_B200_PF_LINES"); return e ? atoi(e) : -1; }();

@@ -31,6 +31,7 @@ typedef struct {
   int n_ll_parts; const void* ll_parts[PB_MAX_PEERS];
   int n_ll_push; void* ll_push[PB_MAX_PEERS];
   uint32_t ll_tag_mul, ll_tag_add;
+  int rope_num_pages;           // pages in rope_k_pool / rope_v_pool: a table entry outside [0, num_pages) raises error flag 2
 } PbLinearDecodeArgs;
 int pb_linear_decode(const PbLinearDecodeArgs* a, void* stream);
 int pb_set_gemv_pipe(int on);
@@ -97,6 +98,7 @@ typedef struct {
   int B, T, Hq, Hkv, D, page, max_pages, max_pos;
   int interleaved_qkv;          // 1: Falcon/BLOOM fused layout [Hkv, G+2, D] per token
   void* error_flag;
+  int num_pages;                // pages in k_pool / v_pool: a table entry outside [0, num_pages) raises error flag 2
 } PbRopeKvArgs;
 int pb_rope_kv(const PbRopeKvArgs* a, void* stream);
 

@@ -28,7 +28,7 @@ struct RopeKvParams {
   const float* cos;
   const float* sin;
   const __nv_bfloat16* bias;
-  int B, T, Hq, Hkv, D, page, max_pages, max_pos, interleaved;
+  int B, T, Hq, Hkv, D, page, max_pages, max_pos, interleaved, num_pages;
   int* error_flag;
 };
 
@@ -84,6 +84,7 @@ __global__ void rope_kv_kernel(const RopeKvParams p) {
     const int pg_idx = pos / p.page;
     if (pg_idx >= p.max_pages) { if (i == 0) atomicExch(p.error_flag, 2); return; }
     const int pg = p.block_table[static_cast<size_t>(b) * p.max_pages + pg_idx];
+    if (pg < 0 || pg >= p.num_pages) { if (i == 0) atomicExch(p.error_flag, 2); return; }  // never write outside the pool
     __nv_bfloat16* pool = kind == 1 ? p.k_pool : p.v_pool;
     __nv_bfloat16* dst = pool + ((static_cast<size_t>(pg) * p.Hkv + h) * p.page + (pos % p.page)) * p.D;
     dst[i] = __float2bfloat16_rn(x0);
@@ -120,6 +121,7 @@ extern "C" int pb_rope_kv(const PbRopeKvArgs* a, void* stream) {
   p.bias = static_cast<const __nv_bfloat16*>(a->qkv_bias);
   p.B = a->B; p.T = a->T; p.Hq = a->Hq; p.Hkv = a->Hkv; p.D = a->D; p.page = a->page;
   p.max_pages = a->max_pages; p.max_pos = a->max_pos; p.interleaved = a->interleaved_qkv;
+  p.num_pages = a->num_pages > 0 ? a->num_pages : 0x7fffffff;
   p.error_flag = static_cast<int*>(a->error_flag);
   dim3 grid(a->B * a->T, a->Hq + 2 * a->Hkv);
   launch_pdl(kPdlRope, rope_kv_kernel, grid, dim3(a->D / 2), 0, static_cast<cudaStream_t>(stream), p);

@@ -9,6 +9,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
+#include <set>
 #include <vector>
 
 namespace {
@@ -20,6 +21,12 @@ struct KvAllocator {
   long reserved = 0;  // pages promised to sessions (>= pages actually bound)
   long total = 0;
   uint64_t next_ticket = 0, serving = 0;  // FIFO among waiting reservations
+  std::set<uint64_t> abandoned;           // tickets whose owner timed out before their turn: skipped when `serving` reaches them
+  void advance() {                        // retire the ticket being served and every abandoned one right behind it
+    ++serving;
+    for (auto it = abandoned.find(serving); it != abandoned.end(); it = abandoned.find(serving)) { abandoned.erase(it); ++serving; }
+    cv.notify_all();
+  }
 };
 }  // namespace
 
@@ -85,19 +92,14 @@ extern "C" int pb_kv_reserve(void* h, long pages, double timeout_s) {
   bool ok = ready();
   if (!ok && timeout_s > 0) ok = a->cv.wait_until(lk, deadline, ready);
   if (!ok) {
-    // give up: let later tickets proceed
-    if (a->serving == ticket) { a->serving++; a->cv.notify_all(); }
-    else {
-      // wait (bounded) for our turn only to retire the ticket in order
-      a->cv.wait(lk, [&] { return a->serving == ticket; });
-      a->serving++;
-      a->cv.notify_all();
-    }
+    // give up WITHOUT waiting for our turn (a fail-fast caller with timeout 0 must return at once even when another
+    // reservation is queued ahead): the ticket retires out of order and is skipped when the queue reaches it
+    if (a->serving == ticket) a->advance();
+    else a->abandoned.insert(ticket);
     return -1;
   }
   a->reserved += pages;
-  a->serving++;
-  a->cv.notify_all();
+  a->advance();
   return 0;
 }
 extern "C" void pb_kv_unreserve(void* h, long pages) {

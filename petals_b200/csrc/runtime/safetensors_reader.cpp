@@ -153,7 +153,7 @@ extern "C" void* pb_st_open(const char* path) {
   f->map = static_cast<uint8_t*>(m);
   uint64_t hlen = 0;
   memcpy(&hlen, f->map, 8);
-  if (8 + hlen > f->size) { g_err = "header length exceeds file"; pb_st_close(f); return nullptr; }
+  if (f->size < 8 || hlen > f->size - 8) { g_err = "header length exceeds file"; pb_st_close(f); return nullptr; }
   f->data_off = 8 + hlen;
   if (!parse_header(f, reinterpret_cast<const char*>(f->map + 8), hlen)) {
     g_err = "malformed safetensors header";

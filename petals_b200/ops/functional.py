@@ -94,6 +94,7 @@ def _linear_decode_args(
         a.rope_cos, a.rope_sin = ptr(cos), ptr(sin)
         a.rope_T, a.rope_Hq, a.rope_Hkv, a.rope_D = rope["T"], rope["Hq"], rope["Hkv"], rope["D"]
         a.rope_max_pages, a.rope_max_pos = table.shape[1], (cos.shape[0] if cos is not None else 0)
+        a.rope_num_pages = rope["k_pool"].shape[0]
     return a, (rope["q_out"] if rope is not None else out), keep
 
 
@@ -436,7 +437,7 @@ def rope_kv_append(qkv: torch.Tensor, q_out: torch.Tensor, k_pool: torch.Tensor,
     a.block_table, a.pos_ptr = ptr(block_table), pos_ptr
     a.cos, a.sin, a.qkv_bias = ptr(cos), ptr(sin), ptr(qkv_bias)
     a.B, a.T, a.Hq, a.Hkv, a.D, a.page = B, T, Hq, Hkv, D, PAGE
-    a.max_pages = block_table.shape[1]
+    a.max_pages, a.num_pages = block_table.shape[1], k_pool.shape[0]
     a.max_pos = cos.shape[0] if cos is not None else 0
     a.interleaved_qkv = int(interleaved)
     a.error_flag = error_flag

@@ -44,7 +44,7 @@ class LinearDecodeArgs(C.Structure):
         ("rope_pos_ptr", C.c_void_p), ("rope_cos", C.c_void_p), ("rope_sin", C.c_void_p),
         ("rope_T", C.c_int), ("rope_Hq", C.c_int), ("rope_Hkv", C.c_int), ("rope_D", C.c_int), ("rope_max_pages", C.c_int), ("rope_max_pos", C.c_int),
         ("n_ll_parts", C.c_int), ("ll_parts", C.c_void_p * PB_MAX_PEERS), ("n_ll_push", C.c_int), ("ll_push", C.c_void_p * PB_MAX_PEERS),
-        ("ll_tag_mul", C.c_uint32), ("ll_tag_add", C.c_uint32),
+        ("ll_tag_mul", C.c_uint32), ("ll_tag_add", C.c_uint32), ("rope_num_pages", C.c_int),
     ]
 
 
@@ -78,7 +78,7 @@ class RopeKvArgs(C.Structure):
         ("qkv_bias", C.c_void_p),
         ("B", C.c_int), ("T", C.c_int), ("Hq", C.c_int), ("Hkv", C.c_int), ("D", C.c_int), ("page", C.c_int),
         ("max_pages", C.c_int), ("max_pos", C.c_int), ("interleaved_qkv", C.c_int),
-        ("error_flag", C.c_void_p),
+        ("error_flag", C.c_void_p), ("num_pages", C.c_int),
     ]
 
 

@@ -168,7 +168,8 @@ def send_message(sock: socket.socket, header: Dict[str, Any], tensors: Sequence[
 
 MAX_HEADER_BYTES = 16 << 20  # a header is a few hundred bytes; anything huge is a corrupt or foreign stream
 MAX_TENSORS_PER_MESSAGE = 256
-MAX_PART_BYTES = 64 << 30
+MAX_PART_BYTES = 8 << 30       # one part of one tensor
+MAX_MESSAGE_BYTES = 16 << 30   # all payload bytes of one message (a step's activations are max_batch_size * hidden * 2 bytes: MiB, not GiB)
 
 
 class ProtocolError(ConnectionError):
@@ -187,13 +188,22 @@ def recv_message(sock: socket.socket) -> Tuple[Dict[str, Any], List[torch.Tensor
         raise ProtocolError(f"undecodable header: {e!r}") from None
     if not isinstance(header, dict) or not isinstance(header.get("tensors", []), list) or len(header.get("tensors", [])) > MAX_TENSORS_PER_MESSAGE:
         raise ProtocolError("malformed header")
-    tensors = []
+    tensors, total = [], 0
     for m in header.get("tensors", []):
         sizes = m.get("parts", [m.get("nbytes", 0)]) if isinstance(m, dict) else None
         if sizes is None or m.get("dtype") not in _DTYPES or any(not isinstance(k, int) or k < 0 or k > MAX_PART_BYTES for k in sizes):
             raise ProtocolError("malformed tensor descriptor")
+        shape = m.get("shape")
+        if not isinstance(shape, list) or len(shape) > 8 or any(not isinstance(d, int) or d < 0 for d in shape):
+            raise ProtocolError("malformed tensor shape")
+        total += sum(sizes)
+        if total > MAX_MESSAGE_BYTES:
+            raise ProtocolError(f"message announces more than {MAX_MESSAGE_BYTES} payload bytes")
         parts = [_recv_into(sock, k) for k in sizes]
-        tensors.append(decode_tensor(m.get("c", {"codec": "NONE"}), parts, _DTYPES[m["dtype"]], m["shape"]))
+        try:
+            tensors.append(decode_tensor(m.get("c", {"codec": "NONE"}), parts, _DTYPES[m["dtype"]], shape))
+        except (ValueError, KeyError, TypeError, IndexError, RuntimeError) as e:  # descriptor and payload disagree
+            raise ProtocolError(f"tensor descriptor does not match its payload: {e}") from None
     return header, tensors
 
 

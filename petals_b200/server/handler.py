@@ -19,6 +19,8 @@ processes. Contract kept from the reference:
 """
 from __future__ import annotations
 
+import collections
+import concurrent.futures
 import threading
 import time
 import uuid
@@ -47,6 +49,8 @@ logger = get_logger(__name__)
 class InferenceStream:
     """Server side of one ``rpc_inference`` stream: a KV session + step loop state."""
 
+    MAX_TRACKED_STEPS = 64  # step ids remembered for push de-duplication (a push older than that can only be stale)
+
     def __init__(self, handler: "TransformerConnectionHandler", uids: Sequence[ModuleUID], metadata: Dict[str, Any]):
         self.handler = handler
         self.uids = list(uids)
@@ -68,7 +72,7 @@ class InferenceStream:
         self.closed = False
         self._pushed: Dict[str, Tuple[torch.Tensor, ...]] = {}
         self._last_tokens = 0
-        self._done_steps: set = set()
+        self._done_steps: "collections.OrderedDict[str, None]" = collections.OrderedDict()  # most recent step ids only (bounded)
         self._lock = threading.Lock()
         handler._register(self)
 
@@ -102,6 +106,8 @@ class InferenceStream:
         with self._lock:
             if step_id not in self._done_steps:
                 self._pushed[step_id] = tensors
+                while len(self._pushed) > self.MAX_TRACKED_STEPS:  # pushes for steps the client never sent
+                    self._pushed.pop(next(iter(self._pushed)))
 
     # ---- one step -------------------------------------------------------------------------------------------
     def step(self, hidden: torch.Tensor, prompts: Optional[torch.Tensor] = None, hypo_ids: Optional[torch.Tensor] = None,
@@ -130,7 +136,9 @@ class InferenceStream:
         if step_id is not None:
             with self._lock:
                 pushed = self._pushed.pop(step_id, None)
-                self._done_steps.add(step_id)
+                self._done_steps[step_id] = None
+                while len(self._done_steps) > self.MAX_TRACKED_STEPS:
+                    self._done_steps.popitem(last=False)
             # the previous stage may already have delivered this step's input (server-to-server push). It is only a latency shortcut for
             # the tensor the client sends anyway, and the client is the authority on what this stage must see: a predecessor that is
             # replaying a longer history after a fail-over pushes more positions than this (healthy) session needs — such a push is dropped
@@ -206,7 +214,9 @@ class InferenceStream:
             cache.set_position(prefix + T)
         next_servers = metadata.get("next_servers")
         if next_servers:
-            h._push_outputs(out, metadata, next_servers)
+            # asynchronous like the reference (handler.py:337 asyncio.create_task): the response to the client never waits for
+            # the connection + transfer + acknowledgement of the server-to-server push
+            h._push_pool.submit(h._push_outputs, out, metadata, next_servers)
         return out
 
 
@@ -231,6 +241,7 @@ class TransformerConnectionHandler:
         self.compression = None  # default wire codec of the responses on the socket transport (utils/compression.py)
         self._sessions: Dict[str, InferenceStream] = {}
         self._sessions_lock = threading.Lock()
+        self._push_pool = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix=f"push-{peer_id}")
 
     # ---- validation ------------------------------------------------------------------------------------------
     def _check_uids(self, uids) -> List[ModuleUID]:
@@ -377,3 +388,4 @@ class TransformerConnectionHandler:
             streams = list(self._sessions.values())
         for s in streams:
             s.close()
+        self._push_pool.shutdown(wait=False, cancel_futures=True)

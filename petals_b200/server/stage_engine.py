@@ -150,12 +150,24 @@ class StageEngine:
         return Fn.linear_decode(x, getattr(w, name), w2=getattr(w, name2) if name2 else None, **kw)
 
     def _buf(self, name: str, rows: int, cols: int, dtype=None) -> torch.Tensor:
-        # keyed by the full shape and never replaced: captured CUDA graphs keep the raw addresses of these buffers
+        """Persistent activation buffer. Decode-shape buffers are keyed by their full shape and never replaced (captured CUDA
+        graphs keep their raw addresses). Prefill / forward buffers (row count = B*T of whatever a client sends) are ONE grow-only
+        allocation per name, handed out as views: a client sweeping prompt lengths cannot grow the pool without bound."""
+        dtype = dtype or self.dtype
+        growable = rows > MAX_DECODE_ROWS and (name.endswith("_p") or name in ("x_fwd", "x_taken") or name.startswith("dq_") or name.startswith("bw_"))
+        if growable:
+            key, need = (name, dtype), rows * cols
+            flat = self._bufs.get(key)
+            if flat is None or flat.numel() < need:
+                with torch.inference_mode(False):
+                    flat = torch.empty(need, dtype=dtype, device=self.device)  # the old one is released in stream order
+                self._bufs[key] = flat
+            return flat[:need].view(rows, cols)
         key = (name, rows, cols, dtype)
         t = self._bufs.get(key)
         if t is None:
             with torch.inference_mode(False):  # persistent: must stay writable from threads outside inference mode
-                t = torch.empty(rows, cols, dtype=dtype or self.dtype, device=self.device)
+                t = torch.empty(rows, cols, dtype=dtype, device=self.device)
             self._bufs[key] = t
         return t
 
@@ -498,14 +510,16 @@ class StageEngine:
         out = torch.empty_like(hidden)
         # attention is causal within a sequence, so batch rows are independent: process them in groups that
         # fit the scratch pool
-        rows_per_group = max(1, ((self._scratch_pages - 1) * PAGE) // max(T, 1))
-        if T > (self._scratch_pages - 1) * PAGE:
-            raise ValueError(f"sequence of {T} tokens exceeds max_chunk_tokens={self.max_chunk_tokens} for a cache-less forward")
+        # every row owns ceil(T / PAGE) WHOLE pages of the scratch pool, so groups are sized in pages, not tokens
         pages_per_seq = (T + PAGE - 1) // PAGE
+        if pages_per_seq > self._scratch_pages:
+            raise ValueError(f"sequence of {T} tokens exceeds max_chunk_tokens={self.max_chunk_tokens} for a cache-less forward")
+        rows_per_group = max(1, self._scratch_pages // pages_per_seq)
         zero = torch.zeros(1, dtype=torch.int32, device=self.device)
         for b0 in range(0, B, rows_per_group):
             b1 = min(B, b0 + rows_per_group)
             nb = b1 - b0
+            assert nb * pages_per_seq <= self._scratch_pages
             table = torch.arange(nb * pages_per_seq, dtype=torch.int32, device=self.device).view(nb, pages_per_seq).contiguous()
             x = self._buf("x_fwd", nb * T, H)
             x.copy_(hidden[b0:b1].reshape(nb * T, H))

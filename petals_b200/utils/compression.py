@@ -73,12 +73,27 @@ def _raw(t: torch.Tensor) -> torch.Tensor:
     return t.detach().to("cpu").contiguous().reshape(-1).view(torch.uint8)
 
 
+class WireFormatError(ValueError):
+    """A received tensor descriptor does not match its payload (the shape comes from an untrusted header)."""
+
+
 def _from_raw(raw, dtype: torch.dtype, shape: Sequence[int]) -> torch.Tensor:
+    """Reinterpret received bytes as ``dtype[shape]``. The byte count must match the announced shape EXACTLY: a header that
+    announces a shape with no (or too few) bytes must never yield uninitialised memory or a huge allocation."""
     if isinstance(raw, (bytes, bytearray, memoryview)):
         raw = torch.frombuffer(bytearray(raw), dtype=torch.uint8) if len(raw) else _EMPTY
-    if raw.numel() == 0:
-        return torch.empty(list(shape), dtype=dtype)
-    return raw.view(dtype).reshape(list(shape))
+    shape = [int(s) for s in shape]
+    if any(s < 0 for s in shape):
+        raise WireFormatError(f"negative dimension in {shape}")
+    numel = 1
+    for s in shape:
+        numel *= s
+    itemsize = torch.empty(0, dtype=dtype).element_size()
+    if raw.numel() != numel * itemsize:
+        raise WireFormatError(f"payload of {raw.numel()} bytes does not match {dtype} {shape} ({numel * itemsize} bytes)")
+    if numel == 0:
+        return torch.empty(shape, dtype=dtype)
+    return raw.view(dtype).reshape(shape)
 
 
 def _codebook_from_buckets(x: torch.Tensor, idx: torch.Tensor, fallback: torch.Tensor) -> torch.Tensor:
@@ -174,6 +189,8 @@ def decode(meta: Dict[str, Any], blobs: Sequence[torch.Tensor], dtype: torch.dty
 
     if codec == CompressionType.MEANSTD_16BIT:
         rows = int(meta["rows"])
+        if rows <= 0 or numel % rows:
+            raise WireFormatError(f"MEANSTD_16BIT: {rows} rows do not divide {numel} elements")
         payload = _from_raw(blobs[0], torch.float16, [rows, numel // rows]).float()
         mean = _from_raw(blobs[1], torch.float32, [rows, 1])
         std = _from_raw(blobs[2], torch.float32, [rows, 1])
@@ -186,6 +203,8 @@ def decode(meta: Dict[str, Any], blobs: Sequence[torch.Tensor], dtype: torch.dty
 
     if codec == CompressionType.BLOCKWISE_8BIT:
         n = int(meta["n"])
+        if n != numel:
+            raise WireFormatError(f"BLOCKWISE_8BIT: {n} codes announced for {numel} elements")
         code = _from_raw(blobs[0], torch.uint8, [n]).long()
         absmax = _from_raw(blobs[1], torch.float32, [(n + _BLOCK - 1) // _BLOCK])
         vals = _block_grid()[code] * absmax.repeat_interleave(_BLOCK)[:n]

@@ -170,3 +170,36 @@ def test_paged_sessions_survive_random_beam_reorders_and_rollbacks():
         assert cache._rt.pb_kv_num_free(cache._alloc) == cache.num_pages - used
         session.close()
         assert cache._rt.pb_kv_num_free(cache._alloc) == cache.num_pages and cache.tokens_left == cache.num_pages * PAGE
+
+
+def test_fail_fast_reservation_does_not_queue_behind_a_waiter():
+    """A reservation with timeout 0 (the client's default alloc_timeout) returns at once even when another reservation is
+    blocked ahead of it, and the queue keeps moving after out-of-order give-ups (reference: memory_cache.py:103-131)."""
+    import threading
+    import time
+
+    from petals_b200.ops import native
+
+    rt = native.rt()
+    h = rt.pb_kv_create(8)
+    assert rt.pb_kv_reserve(h, 8, 0.0) == 0  # the pool is fully promised
+    results = {}
+
+    def waiter():
+        t0 = time.perf_counter()
+        results["code"] = rt.pb_kv_reserve(h, 4, 1.5)
+        results["waited"] = time.perf_counter() - t0
+
+    th = threading.Thread(target=waiter)
+    th.start()
+    time.sleep(0.2)  # the waiter is now queued at the head
+    t0 = time.perf_counter()
+    assert rt.pb_kv_reserve(h, 1, 0.0) == -1
+    assert rt.pb_kv_reserve(h, 1, 0.05) == -1
+    assert time.perf_counter() - t0 < 0.5, "fail-fast reservations must not wait for the queue head's timeout"
+    rt.pb_kv_unreserve(h, 8)
+    th.join()
+    assert results["code"] == 0 and results["waited"] < 1.4  # the head got its pages as soon as they were released
+    assert rt.pb_kv_reserve(h, 4, 0.0) == 0  # abandoned tickets were skipped: the queue is not stuck
+    assert rt.pb_kv_reserved(h) == 8
+    rt.pb_kv_destroy(h)

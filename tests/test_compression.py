@@ -173,3 +173,46 @@ def test_transport_compressed_requests_and_sticky_stream_codec(echo_server):
             assert torch.allclose(out.float(), x.float() * 2, rtol=2e-2, atol=2e-2)
     finally:
         stream.close()
+
+
+def test_descriptor_must_match_payload():
+    """The shape in a received header is untrusted: a payload that is shorter (or empty) must never turn into uninitialised
+    memory of the announced shape, and meta-driven sizes are checked too."""
+    import pytest
+    import torch
+
+    from petals_b200.utils.compression import WireFormatError, decode
+
+    with pytest.raises(WireFormatError):
+        decode({"codec": "NONE"}, [torch.empty(0, dtype=torch.uint8)], torch.float32, [4, 1024, 8192])
+    with pytest.raises(WireFormatError):
+        decode({"codec": "NONE"}, [torch.zeros(12, dtype=torch.uint8)], torch.float32, [4])
+    with pytest.raises(WireFormatError):
+        decode({"codec": "FLOAT16"}, [torch.zeros(6, dtype=torch.uint8)], torch.float32, [4])
+    with pytest.raises(WireFormatError):
+        decode({"codec": "NONE"}, [torch.zeros(16, dtype=torch.uint8)], torch.float32, [-4, -1])
+    with pytest.raises(WireFormatError):
+        decode({"codec": "MEANSTD_16BIT", "rows": 3}, [torch.zeros(8, dtype=torch.uint8)] * 3, torch.float32, [4])
+    with pytest.raises(WireFormatError):
+        decode({"codec": "BLOCKWISE_8BIT", "n": 1 << 40}, [torch.zeros(8, dtype=torch.uint8)] * 2, torch.float32, [4])
+    assert decode({"codec": "NONE"}, [torch.empty(0, dtype=torch.uint8)], torch.float32, [0, 8]).shape == (0, 8)  # "argument absent"
+
+
+def test_socket_frame_with_shape_but_no_bytes_is_a_protocol_error():
+    import socket
+    import struct
+
+    import msgpack
+    import pytest
+
+    from petals_b200.parallel.transport import ProtocolError, recv_message
+
+    a, b = socket.socketpair()
+    try:
+        header = msgpack.packb({"method": "rpc_forward", "tensors": [{"dtype": "float32", "shape": [2, 64, 8192], "nbytes": 0, "parts": [0], "c": {"codec": "NONE"}}]})
+        a.sendall(struct.pack("<I", len(header)) + header)
+        with pytest.raises(ProtocolError):
+            recv_message(b)
+    finally:
+        a.close()
+        b.close()
