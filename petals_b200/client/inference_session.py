@@ -1,184 +1,238 @@
-"""Client side of multi-step inference (reference: src/petals/client/inference_session.py:26-414).
+"""Client side of multi-step inference.
 
-``InferenceSession`` drives a chain of per-stage streams; each ``step`` sends the new hidden states through every
-span in order and returns the final hidden states on the caller's device/dtype. Contract kept from the reference:
+Behavioural contract (what a user of the reference's ``InferenceSession`` relies on, src/petals/client/inference_session.py:220-414):
+``step(inputs, prompts, hypo_ids)`` sends the new hidden states through every stage and returns the last stage's output;
+``position`` may be moved backwards (speculative roll-back); a failing stage is blacklisted, the uncovered blocks are
+re-routed and the replacement rebuilds its KV cache from the inputs its predecessor had been fed; ``max_length`` is a hard
+budget (``Maximum length exceeded``); 0-token steps are legal.
 
-* fault tolerance — every stage-facing call is retried with back-off; when a stage fails, the tail of the chain is
-  re-routed (``make_sequence(mode="min_latency", cache_tokens_needed=max_length)``) and the **stored input history
-  is replayed** into the replacement stage so that its KV cache is rebuilt (each per-stage session keeps its full
-  input history for exactly this purpose);
-* ``position`` can be set backwards (speculative decoding rollback): history is truncated and the next request
-  carries ``start_from_position``;
-* prompts ``[n_blocks, B, pre, H]`` / ``hypo_ids [B]`` validation, 0-token steps, ``Maximum length exceeded``.
+Design here (one NVLink box, one process per GPU):
 
-Changed for one NVLink box: tensors are *not* moved to the CPU when the stage lives in this process (CUDA hidden
-states are handed over by reference), and ``next_servers`` is really attached so a stage can push its output to the
-next stage (the reference's code path for that is dead).
+* every stage stream owns an :class:`InputLog` — the exact tensor sequence that stage has consumed — which is the only state
+  needed to re-create the stage elsewhere;
+* a step is a *wave* over the chain, driven by :meth:`InferenceSession._run_wave`: one loop with a cursor and a failure
+  counter; on an error the cursor's stage is replaced (:meth:`_reroute`) and the wave continues from the same activations;
+* when every hop of the chain rides the NVLink fabric (``parallel/fabric.py``) and every stream is primed, the wave is
+  **dispatched to all stages at once** (:meth:`_fabric_wave`): stage *i*'s first kernel spins on its landing-zone flag and
+  stage *i-1*'s last kernel fills it, so the hops are ordered on the devices, not by one client round trip per hop;
+* activations that only ever lived in landing zones are unknown to the client; such a chain is rebuilt from the first
+  stage's log as a whole.
 """
 from __future__ import annotations
 
-import itertools
 import time
 import uuid
-from typing import List, Optional, Sequence
+from concurrent.futures import ThreadPoolExecutor
+from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 import torch
 
 from petals_b200.client.routing import RemoteSequenceManager, maybe_log_traceback
-from petals_b200.data_structures import CHAIN_DELIMITER, ModuleUID, RemoteSpanInfo
+from petals_b200.data_structures import ModuleUID, RemoteSpanInfo
 from petals_b200.utils.logging import get_logger
 from petals_b200.utils.misc import DUMMY, DUMMY_INT64, is_dummy
 
 logger = get_logger(__name__)
+_dispatch = ThreadPoolExecutor(max_workers=16, thread_name_prefix="petals-wave")
 
 
-class _ServerInferenceSession:
-    """One ``rpc_inference`` stream to one stage (reference :26-217)."""
+class InputLog:
+    """The inputs a stage has consumed so far, ``[B, position, H]`` (``None`` while empty). Replaying it into a fresh stream
+    re-creates the stage's attention cache."""
+
+    __slots__ = ("tokens",)
+
+    def __init__(self, tokens: Optional[torch.Tensor] = None):
+        self.tokens = tokens
+
+    def __len__(self) -> int:
+        return 0 if self.tokens is None else self.tokens.shape[1]
+
+    def truncate(self, length: int) -> None:
+        if length <= 0:
+            self.tokens = None
+        elif len(self) > length:
+            self.tokens = self.tokens[:, :length]
+
+    def extend(self, new: torch.Tensor) -> None:
+        if new.shape[1] == 0 and self.tokens is not None:
+            return
+        self.tokens = new if self.tokens is None else torch.cat([self.tokens, new.to(self.tokens.device)], dim=1)
+
+    def forget(self) -> None:
+        self.tokens = None
+
+
+class StageStream:
+    """One ``rpc_inference`` stream: a span of blocks on one stage, its KV session there, and the log of what it was fed."""
 
     def __init__(self, config, span: RemoteSpanInfo, uids: Sequence[ModuleUID], stream, *, max_length: int, session_id: str):
         self.config, self.span, self.uids, self.stream = config, span, list(uids), stream
         self.max_length, self.session_id = max_length, session_id
-        self.stepped = False
+        self.log = InputLog()
+        self.cursor = 0  # tokens of this session held by the stage's cache
+        self.primed = False  # has the stage executed at least one step of this stream?
         self.closed = False
-        self._position = 0
-        self.history: Optional[torch.Tensor] = None  # every input this stage has seen (for fail-over replay)
-        self.next_session: Optional["_ServerInferenceSession"] = None
+        self.successor: Optional["StageStream"] = None
         self.fabric_rank: Optional[int] = None  # rank of the stage in the NVLink fabric (None: tensors travel with the RPC)
-        self.no_history = False  # inputs arrived over the fabric: the client never saw them
+        self.no_history = False  # some input arrived over the fabric: the client cannot replay this stream
 
     @classmethod
-    def create(cls, config, sequence_manager: RemoteSequenceManager, span: RemoteSpanInfo, uids: Sequence[ModuleUID], *,
-               max_length: int, **metadata) -> "_ServerInferenceSession":
-        stub = sequence_manager.connect(span.peer_id)
+    def open(cls, manager: RemoteSequenceManager, span: RemoteSpanInfo, *, max_length: int, alloc_timeout: float) -> "StageStream":
+        uids = manager.block_uids[span.start: span.end]
+        request = {k: v for k, v in manager.get_request_metadata("rpc_inference", None, *uids).items() if k != "args_structure"}
         session_id = str(uuid.uuid4())
-        meta = dict(max_length=max_length, session_id=session_id, alloc_timeout=float(metadata.pop("alloc_timeout", 0.0)), **metadata)
-        stream = stub.rpc_inference(list(uids), meta)
-        session = cls(config, span, uids, stream, max_length=max_length, session_id=session_id)
+        request.update(max_length=max_length, session_id=session_id, alloc_timeout=float(alloc_timeout))
+        stub = manager.connect(span.peer_id)
+        self = cls(manager.config, span, uids, stub.rpc_inference(list(uids), request), max_length=max_length, session_id=session_id)
         from petals_b200.parallel.fabric import get_fabric
 
-        if get_fabric() is not None and config.use_server_to_server:
+        if get_fabric() is not None and manager.config.use_server_to_server:
             try:
-                session.fabric_rank = stub.rpc_info().get("fabric_rank")
-            except Exception:  # noqa: BLE001 - a stage without fabric info simply uses the tensor path
-                session.fabric_rank = None
-        return session
+                self.fabric_rank = stub.rpc_info().get("fabric_rank")
+            except Exception:  # noqa: BLE001 - a stage that cannot tell simply gets its tensors with the RPC
+                self.fabric_rank = None
+        return self
 
+    # the attributes below keep older call sites (tests, tools) readable
     @property
     def position(self) -> int:
-        return self._position
+        return self.cursor
 
-    @position.setter
-    def position(self, start_from_position: int) -> None:
-        assert start_from_position <= self._position
-        self._position = start_from_position
-        if self.history is not None and self.history.shape[1] >= start_from_position:
-            self.history = self.history[:, :start_from_position] if start_from_position > 0 else None
+    @property
+    def history(self) -> Optional[torch.Tensor]:
+        return self.log.tokens
 
-    def step_pushed(self, shape: tuple, src_rank: int, prompts: torch.Tensor, hypo_ids: torch.Tensor, *, step_id: str, n_new: int,
-                    fabric_out: Optional[dict]) -> torch.Tensor:
-        """A step whose input already sits in the stage's landing zone (pushed by ``src_rank`` over NVLink)."""
+    def rewind(self, position: int) -> None:
+        if position > self.cursor:
+            raise ValueError(f"a stage stream can only move backwards (at {self.cursor}, asked for {position})")
+        self.cursor = position
+        self.log.truncate(position)
+
+    def _request(self, step_id: str, deliver_to: Optional[dict]) -> Dict[str, Any]:
+        meta: Dict[str, Any] = {"step_id": step_id}
+        if self.primed:
+            meta["start_from_position"] = self.cursor  # a no-op unless the session was rolled back
+        if deliver_to is not None:
+            meta["fabric_out"] = deliver_to
+        return meta
+
+    def feed(self, arriving: torch.Tensor, prompts: torch.Tensor, hypo_ids: torch.Tensor, *, step_id: str, n_new: int,
+             deliver_to: Optional[dict] = None):
+        """Run one step with a tensor the client holds. ``arriving`` is either just the ``n_new`` new positions or — when the
+        predecessor is itself rebuilding — the predecessor's output for the *whole* prefix, which lets an unprimed stream
+        rebuild too. Returns the stage's output, or only its shape when the output went to a landing zone (``deliver_to``)."""
         if self.closed:
-            raise Exception("Session is closed, cannot perform step")
-        B, L, H = shape
-        if not self.stepped and L != self._position + n_new:
-            raise RuntimeError("a fresh server session needs the full input history, but only the new tokens were pushed")
-        self.history, self.no_history = None, True
-        metadata = dict(step_id=step_id, fabric_in=dict(src_rank=src_rank, B=B, T=L))
-        if self.stepped:
-            metadata["start_from_position"] = self._position
-        if fabric_out is not None:
-            metadata["fabric_out"] = fabric_out
-        outputs = self.stream.step(torch.empty(0), prompts, hypo_ids, metadata=metadata)
-        self.stepped = True
-        self._position += n_new
-        return outputs
+            raise RuntimeError("this stage stream is closed")
+        arriving = arriving.detach()
+        fresh = arriving[:, arriving.shape[1] - n_new:] if n_new else arriving[:, :0]
+        if not self.primed and arriving.shape[1] == self.cursor + n_new and arriving.shape[1] > n_new:
+            self.log.tokens = arriving  # the predecessor replayed everything: adopt it as this stream's log
+        elif len(self.log) == self.cursor:
+            self.log.extend(fresh)
+        if len(self.log) != self.cursor + n_new:
+            raise RuntimeError(f"input log of {self.span} holds {len(self.log)} positions, expected {self.cursor} + {n_new}")
+        payload = fresh if self.primed else self.log.tokens  # an unprimed stage must see the whole prefix
+        meta = self._request(step_id, deliver_to)
+        if self.config.use_server_to_server and self.successor is not None:
+            followers = []
+            nxt = self.successor
+            while nxt is not None and nxt.primed:
+                followers.append((nxt.span.peer_id, nxt.session_id, nxt.span.start, nxt.span.end))
+                nxt = nxt.successor
+            if followers:
+                meta["next_servers"] = followers
+        result = self.stream.step(payload, prompts, hypo_ids, metadata=meta)
+        if deliver_to is None:
+            if tuple(result.shape) != tuple(payload.shape):
+                raise RuntimeError(f"{self.span} returned {tuple(result.shape)} for an input of {tuple(payload.shape)}")
+        else:
+            result = tuple(payload.shape)
+        self.primed, self.cursor = True, self.cursor + n_new
+        return result
 
-    def step(self, inputs: torch.Tensor, prompts: torch.Tensor, hypo_ids: torch.Tensor, *, step_id: str,
-             n_new: Optional[int] = None, fabric_out: Optional[dict] = None) -> torch.Tensor:
-        """Send the new tokens (or, on a fresh stream after fail-over, the whole history) to the stage.
-
-        ``inputs`` may be longer than ``n_new``: a predecessor that is itself replaying hands over its full-length
-        output so that this (new) session can rebuild its KV cache too. The result has the same length as what
-        was actually sent; callers slice the last ``n_new`` positions."""
+    def feed_landed(self, shape: Tuple[int, int, int], src_rank: int, prompts: torch.Tensor, hypo_ids: torch.Tensor, *, step_id: str,
+                    n_new: int, deliver_to: Optional[dict] = None) -> None:
+        """Run one step whose input ``src_rank`` stored (or is about to store) into this stage's landing zone."""
         if self.closed:
-            raise Exception("Session is closed, cannot perform step")
-        n_new = inputs.shape[1] if n_new is None else n_new
-        keep = inputs.detach()
-        if keep.shape[1] == self._position + n_new and (not self.stepped or self.history is None) and keep.shape[1] > n_new:
-            self.history = keep  # full replay from the predecessor
-        elif self.history is None:
-            self.history = keep[:, -n_new:] if n_new else keep[:, :0]
-        elif self.history.shape[1] == self._position:
-            self.history = torch.cat([self.history, keep[:, keep.shape[1] - n_new:].to(self.history.device)], dim=1)
-        assert self.history.shape[1] == self._position + n_new, \
-            f"Broken input cache: span={self.span} shape={self.history.shape} position={self._position} n_input_tokens={n_new}"
-        metadata = dict(step_id=step_id)
-        if not self.stepped:
-            to_send = self.history  # (re)build the server-side KV from everything this stage should have seen
-        else:
-            to_send = inputs[:, inputs.shape[1] - n_new:]
-            metadata["start_from_position"] = self._position  # cheap no-op unless a rollback happened
-        if self.config.use_server_to_server and self.next_session is not None:
-            metadata["next_servers"] = self._collect_next_servers()
-        if fabric_out is not None:
-            metadata["fabric_out"] = fabric_out
-        outputs = self.stream.step(to_send, prompts, hypo_ids, metadata=metadata)
-        if fabric_out is None:
-            assert outputs.shape == to_send.shape, f"output activation shape is different from input shape: {outputs.shape} != {to_send.shape}"
-        else:
-            outputs = (to_send.shape[0], to_send.shape[1], to_send.shape[2])  # lives in the next landing zone: only its shape is known here
-        self.stepped = True
-        self._position += n_new
-        return outputs
-
-    def _collect_next_servers(self) -> List[tuple]:
-        out, s = [], self.next_session
-        while s is not None and s.stepped:
-            out.append((s.span.peer_id, s.session_id, s.span.start, s.span.end))
-            s = s.next_session
-        return out
+            raise RuntimeError("this stage stream is closed")
+        B, L, _ = shape
+        if not self.primed and L != self.cursor + n_new:
+            raise RuntimeError("an unprimed stage needs the whole prefix, but only the new positions were pushed to it")
+        self.log.forget()
+        self.no_history = True
+        meta = self._request(step_id, deliver_to)
+        meta["fabric_in"] = {"src_rank": src_rank, "B": B, "T": L}
+        self.stream.step(torch.empty(0), prompts, hypo_ids, metadata=meta)
+        self.primed, self.cursor = True, self.cursor + n_new
 
     def close(self) -> None:
-        if self.closed:
-            return
-        self.closed = True
-        try:
-            self.stream.close()
-        except Exception as e:  # noqa: BLE001 - closing must never raise
-            logger.debug(f"Caught exception while closing connection: {e!r}")
+        if not self.closed:
+            self.closed = True
+            try:
+                self.stream.close()
+            except Exception as e:  # noqa: BLE001 - a dead stage cannot be closed politely
+                logger.debug(f"closing the stream to {self.span.peer_id}: {e!r}")
 
     def __del__(self):
         self.close()
 
-    def __enter__(self):
-        assert not self.closed
-        return self
 
-    def __exit__(self, *exc):
-        self.close()
+def _validate_step(inputs, prompts, hypo_ids, *, num_blocks: int, hidden_size: Optional[int], batch_size: Optional[int]):
+    """Mistakes of the caller are reported on the client, once: a stage would reject them too, but for the retry machinery a
+    rejection is indistinguishable from a broken stage and would be re-routed and retried."""
+    if not isinstance(inputs, torch.Tensor) or inputs.ndim != 3 or not inputs.is_floating_point():
+        raise ValueError("inputs must be a floating-point tensor [batch_size, seq_length, hidden_size]")
+    B, T, H = inputs.shape
+    if hidden_size is not None and H != hidden_size:
+        raise ValueError(f"inputs have hidden size {H}, the model's is {hidden_size}")
+    if batch_size is None and B < 1:
+        raise ValueError("inputs must contain at least one sequence")
+    if batch_size is not None and B != batch_size:
+        raise ValueError(f"batch size changed within a session ({batch_size} -> {B})")
+    if hypo_ids is None or is_dummy(hypo_ids):
+        hypo_ids = DUMMY_INT64
+    elif (hypo_ids.dtype != torch.int64 or hypo_ids.ndim != 1 or hypo_ids.shape[0] != B
+          or bool(((hypo_ids < 0) | (hypo_ids >= B)).any())):
+        raise ValueError(f"hypo_ids must be an int64 vector of {B} indices into the batch")
+    if prompts is None or is_dummy(prompts):
+        prompts = DUMMY
+    else:
+        ok = prompts.ndim == 4 and prompts.shape[0] == num_blocks and prompts.shape[1] in (1, B) and prompts.shape[2] <= T and prompts.shape[3] == H
+        assert ok, f"deep prompts must be [num_blocks={num_blocks}, {B} or 1, prefix_len <= {T}, {H}], got {tuple(prompts.shape)}"
+    return prompts, hypo_ids
 
 
 class InferenceSession:
-    """Multi-step inference over a chain of stages with fail-over (reference :220-414)."""
+    """Multi-step inference over a chain of stages, with fail-over."""
 
     def __init__(self, sequence_manager: RemoteSequenceManager, max_length: int, *, alloc_timeout: float = 0.0):
-        """``alloc_timeout``: how long a server may keep this session waiting for KV-cache room before refusing it (the reference's
-        ``alloc_timeout`` request field, handler.py:148-154; 0 = fail fast so that routing can try another server)."""
+        """``alloc_timeout``: how long a stage may keep this session waiting for KV-cache room before refusing it (the request
+        field of the same name, reference handler.py:148-154); 0 fails fast so that routing can try another stage."""
         if isinstance(max_length, bool) or not isinstance(max_length, int) or max_length < 1:
             raise ValueError(f"max_length must be a positive number of tokens to reserve KV caches for, got {max_length!r}")
-        self._sequence_manager = sequence_manager
+        self._manager = sequence_manager
         self._alloc_timeout = float(alloc_timeout)
+        self._max_length = max_length
+        self._chain: List[StageStream] = []
+        self._position = 0
         self._batch_size: Optional[int] = None  # fixed by the first step
         self._closed = False
-        self._server_sessions: List[_ServerInferenceSession] = []
-        self._position = 0
-        self._max_length = max_length
         self.output_ids: Optional[torch.Tensor] = None
         self.past_key_values = None
 
+    # ---- simple accessors -----------------------------------------------------------------------------------------
+    @property
+    def _server_sessions(self) -> List[StageStream]:  # older name of the chain
+        return self._chain
+
+    @property
+    def _sequence_manager(self) -> RemoteSequenceManager:
+        return self._manager
+
     @property
     def num_blocks(self) -> int:
-        return len(self._sequence_manager)
+        return len(self._manager)
 
     @property
     def max_length(self) -> int:
@@ -189,213 +243,219 @@ class InferenceSession:
         return self._position
 
     @position.setter
-    def position(self, start_from_position: int) -> None:
-        if not 0 <= start_from_position <= self._position:
-            raise ValueError(f"position can only be moved backwards within [0, {self._position}], got {start_from_position}")
-        self._position = start_from_position
-        for session in self._server_sessions:
-            assert isinstance(session, _ServerInferenceSession)
-            session.position = start_from_position
-
-    def _enter_server_sessions(self, chosen_spans: List[RemoteSpanInfo]) -> List[_ServerInferenceSession]:
-        server_sessions = []
-        try:
-            for span in chosen_spans:
-                uids = self._sequence_manager.block_uids[span.start: span.end]
-                metadata = self._sequence_manager.get_request_metadata("rpc_inference", None, *uids)
-                if self._alloc_timeout > 0:
-                    metadata = dict(metadata, alloc_timeout=self._alloc_timeout)
-                session = _ServerInferenceSession.create(self._sequence_manager.config, self._sequence_manager, span, uids,
-                                                         max_length=self._max_length, **{k: v for k, v in metadata.items() if k != "args_structure"})
-                server_sessions.append(session)
-            return server_sessions
-        except BaseException:
-            self._exit_server_sessions(server_sessions)
-            raise
-
-    def _exit_server_sessions(self, server_sessions: List[_ServerInferenceSession]) -> None:
-        for session in reversed(server_sessions):
-            try:
-                session.close()
-            except Exception:  # noqa: BLE001
-                logger.debug("Caught exception while closing connection to server:", exc_info=True)
-
-    def __enter__(self) -> "InferenceSession":
-        assert not self._closed and not self._server_sessions
-        return self
-
-    def step(self, inputs: torch.Tensor, prompts: Optional[torch.Tensor] = None, hypo_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
-        assert not self._closed
-        if torch.is_grad_enabled():
-            logger.warning("Running inference session with grad enabled. Gradients will *not* be propagated correctly.")
-        # mistakes of the caller are reported here, once: a server would reject them too, and a rejection is indistinguishable from a
-        # failing server for the retry loop below (it would re-route and retry for as long as max_retries allows)
-        hidden_size = getattr(self._sequence_manager.config, "hidden_size", None)
-        if not isinstance(inputs, torch.Tensor) or inputs.ndim != 3 or not inputs.is_floating_point():
-            raise ValueError("inputs must be a floating-point tensor [batch_size, seq_length, hidden_size]")
-        if hidden_size is not None and inputs.shape[2] != hidden_size:
-            raise ValueError(f"inputs have hidden size {inputs.shape[2]}, the model's is {hidden_size}")
-        if self._batch_size is None:
-            if inputs.shape[0] < 1:
-                raise ValueError("inputs must contain at least one sequence")
-        elif inputs.shape[0] != self._batch_size:
-            raise ValueError(f"batch size changed within a session ({self._batch_size} -> {inputs.shape[0]})")
-        if hypo_ids is not None and not is_dummy(hypo_ids) and (hypo_ids.ndim != 1 or hypo_ids.shape[0] != inputs.shape[0] or hypo_ids.dtype != torch.int64
-                                                               or bool(((hypo_ids < 0) | (hypo_ids >= inputs.shape[0])).any())):
-            raise ValueError(f"hypo_ids must be an int64 vector of {inputs.shape[0]} indices into the batch")
-        if prompts is None or is_dummy(prompts):
-            prompts = DUMMY
-        else:
-            assert prompts.ndim == 4, "deep prompts should have shape [num_blocks, batch_size, prefix_len, hid_size]"
-            assert prompts.shape[0] == self.num_blocks
-            assert prompts.shape[1] in (inputs.shape[0], 1)
-            assert prompts.shape[2] <= inputs.shape[1]
-            assert prompts.shape[3] == inputs.shape[2]
-        if hypo_ids is None or is_dummy(hypo_ids):
-            hypo_ids = DUMMY_INT64
-        else:
-            assert len(hypo_ids) == len(inputs)
-            assert hypo_ids.dtype == torch.int64
-        inputs_device, inputs_dtype = inputs.device, inputs.dtype
-        step_id = str(uuid.uuid4())
-        n_input_tokens = inputs.shape[1]
-        if self._position + n_input_tokens > self._max_length:
-            raise ValueError(f"Maximum length exceeded: prefix {self._position} + current {n_input_tokens} exceeds pre-allocated maximum {self._max_length}")
-
-        from petals_b200.parallel.fabric import get_fabric
-
-        fabric = get_fabric() if self._sequence_manager.config.use_server_to_server else None
-        server_idx = 0
-        block_idx = 0
-        inputs = inputs.detach()
-        step_inputs = inputs
-        pushed = None  # (src_rank, (B, L, H)): the current activations live in the next stage's landing zone, not here
-        while block_idx < self.num_blocks:
-            for attempt_no in itertools.count():
-                logger.debug(f"Inference: block {block_idx}, attempt {attempt_no}")
-                server_session = None
-                try:
-                    if not self._server_sessions or attempt_no >= 1:
-                        if attempt_no >= 1 and (pushed is not None or any(s.no_history for s in self._server_sessions)):
-                            # activations that travelled over the fabric were never seen by the client: rebuild the whole
-                            # chain and replay the first stage's input history through it
-                            inputs = self._full_history(step_inputs, n_input_tokens)
-                            self._exit_server_sessions(self._server_sessions)
-                            self._server_sessions, server_idx, block_idx, pushed = [], 0, 0, None
-                        self._update_sequence(server_idx, block_idx, attempt_no)
-                    server_session = self._server_sessions[server_idx]
-                    assert server_session.position == self._position, f"Position mismatch: {server_session.position} and {self._position}"
-                    span_prompts = prompts[server_session.span.start: server_session.span.end] if not is_dummy(prompts) else DUMMY
-                    fabric_out = self._fabric_target(fabric, server_idx, inputs if pushed is None else pushed[1])
-                    if pushed is not None:
-                        result = server_session.step_pushed(pushed[1], pushed[0], span_prompts, hypo_ids, step_id=step_id, n_new=n_input_tokens,
-                                                            fabric_out=fabric_out)
-                    else:
-                        result = server_session.step(inputs, span_prompts, hypo_ids, step_id=step_id, n_new=n_input_tokens, fabric_out=fabric_out)
-                    if fabric_out is not None:
-                        shape = result if isinstance(result, tuple) else pushed[1]
-                        pushed = (server_session.fabric_rank, tuple(shape))
-                    else:
-                        inputs, pushed = result, None
-                    server_idx += 1
-                    block_idx = server_session.span.end
-                    self._sequence_manager.on_request_success(server_session.span.peer_id)
-                    break
-                except Exception as e:  # noqa: BLE001 - any stage failure triggers re-routing
-                    if isinstance(e, ValueError) and "Maximum length exceeded" in str(e):
-                        raise
-                    self._sequence_manager.on_request_failure(server_session.span.peer_id if server_session is not None else None)
-                    if self._sequence_manager.config.max_retries is not None and attempt_no + 1 >= self._sequence_manager.config.max_retries:
-                        raise
-                    delay = self._sequence_manager.get_retry_delay(attempt_no)
-                    logger.warning(f"Caught exception when running inference via {server_session.span if server_session is not None else None} "
-                                   f"(retry in {delay:.0f} sec): {e!r}")
-                    maybe_log_traceback(e)
-                    time.sleep(delay)
-        if pushed is not None:  # the last stage stored the result into this process's landing zone
-            B, L, H = pushed[1]
-            inputs = fabric.recv(B * L, "y_ret", pushed[0]).view(B, L, H)
-        self._position += n_input_tokens
-        self._batch_size = inputs.shape[0]
-        outputs = inputs[:, -n_input_tokens:]
-        return outputs.to(device=inputs_device, dtype=inputs_dtype)
-
-    def _fabric_target(self, fabric, server_idx: int, like) -> Optional[dict]:
-        """Where should server ``server_idx`` store its output? None = return it with the RPC (no fabric on that hop)."""
-        if fabric is None:
-            return None
-        cur = self._server_sessions[server_idx]
-        shape = tuple(like) if isinstance(like, tuple) else tuple(like.shape)
-        rows = shape[0] * shape[1]
-        if cur.fabric_rank is None or rows == 0 or rows > min(fabric.max_tokens, 4096) or shape[2] != fabric.hidden_size:
-            return None
-        if server_idx + 1 < len(self._server_sessions):
-            nxt = self._server_sessions[server_idx + 1]
-            if nxt.fabric_rank is None or nxt.fabric_rank == cur.fabric_rank:
-                return None
-            return dict(kind="x_in", rank=nxt.fabric_rank)
-        if cur.span.end == self.num_blocks and cur.fabric_rank != fabric.rank:
-            return dict(kind="y_ret", rank=fabric.rank)
-        return None
-
-    def _full_history(self, step_inputs: torch.Tensor, n_new: int) -> torch.Tensor:
-        """Everything the first stage has ever received in this session, ending with the current step's inputs."""
-        first = self._server_sessions[0] if self._server_sessions else None
-        hist = first.history if first is not None else None
-        if hist is None or self._position == 0:
-            if self._position > 0:
-                raise RuntimeError("cannot rebuild remote attention caches: the input history of the first stage is gone")
-            return step_inputs[:, step_inputs.shape[1] - n_new:]
-        if hist.shape[1] == self._position + n_new:
-            return hist
-        return torch.cat([hist[:, : self._position], step_inputs[:, step_inputs.shape[1] - n_new:].to(hist.device)], dim=1)
-
-    def _update_sequence(self, server_idx: int, block_idx: int, attempt_no: int) -> int:
-        """Replace the chain from ``server_idx`` on with a fresh route covering the failed span (reference :364-391).
-
-        The failed stream's input history moves to the first replacement stream (same start block), which replays
-        it on its first step and hands its full-length output to the next replacement stream, and so on."""
-        n_prev_spans = len(self._server_sessions)
-        update_end = self._server_sessions[server_idx].span.end if server_idx < n_prev_spans else self.num_blocks
-        if attempt_no >= 1:
-            logger.debug(f"Due to a server failure, remote attention caches from block {block_idx} to {update_end} will be regenerated")
-        old = self._server_sessions[server_idx: server_idx + 1]
-        self._exit_server_sessions(old)
-        updated_spans = self._sequence_manager.make_sequence(block_idx, update_end, mode="min_latency", cache_tokens_needed=self._max_length)
-        updated_spans[-1].end = min(updated_spans[-1].end, update_end)  # make_sequence() could return a longer chain
-        updated_sessions = self._enter_server_sessions(updated_spans)
-        logger.debug(f"Found path from block {block_idx} to {update_end} via {len(updated_spans)} servers")
-        for i, new_session in enumerate(updated_sessions):
-            new_session._position = self._position
-            if i == 0 and old and old[0].history is not None:
-                new_session.history = old[0].history[:, : self._position] if self._position > 0 else None
-        if self._position > 0 and updated_sessions and updated_sessions[0].history is None and not (server_idx == 0 and block_idx == 0):
-            raise RuntimeError("cannot rebuild a remote attention cache: no input history for the failed span")
-        self._server_sessions[server_idx: server_idx + 1] = updated_sessions
-        for a, b in zip(self._server_sessions[:-1], self._server_sessions[1:]):
-            a.next_session = b
-        if self._server_sessions:
-            self._server_sessions[-1].next_session = None
-        return len(self._server_sessions) - n_prev_spans
-
-    def close(self, *exc_details) -> None:
-        if not getattr(self, "_closed", True):  # also safe when __init__ did not finish (called from __del__)
-            self._exit_server_sessions(self._server_sessions)
-            self._server_sessions.clear()
-            self._closed = True
-
-    def __exit__(self, *exc_details):
-        self.close(*exc_details)
-
-    def __del__(self):
-        self.close()
+    def position(self, target: int) -> None:
+        if not 0 <= target <= self._position:
+            raise ValueError(f"position can only be moved backwards within [0, {self._position}], got {target}")
+        self._position = target
+        for stage in self._chain:
+            stage.rewind(target)
 
     @property
-    def last_token_id(self) -> Optional[torch.Tensor]:  # backward compatibility with petals<=2.1
-        return self.output_ids[:, -1:] if self.output_ids is not None else None
+    def last_token_id(self) -> Optional[torch.Tensor]:  # petals <= 2.1 spelling
+        return None if self.output_ids is None else self.output_ids[:, -1:]
 
     @last_token_id.setter
     def last_token_id(self, value: torch.Tensor) -> None:
         if self.output_ids is None:
             raise RuntimeError("Can't override `last_token_id` since the session has not stepped yet")
         self.output_ids[:, -1:] = value
+
+    # ---- chain maintenance ----------------------------------------------------------------------------------------
+    def _open_streams(self, spans: Sequence[RemoteSpanInfo]) -> List[StageStream]:
+        opened: List[StageStream] = []
+        try:
+            for span in spans:
+                opened.append(StageStream.open(self._manager, span, max_length=self._max_length, alloc_timeout=self._alloc_timeout))
+        except BaseException:
+            self._close_streams(opened)
+            raise
+        return opened
+
+    @staticmethod
+    def _close_streams(streams: Sequence[StageStream]) -> None:
+        for stage in reversed(list(streams)):
+            stage.close()
+
+    def _relink(self) -> None:
+        for a, b in zip(self._chain, self._chain[1:] + [None]):
+            a.successor = b
+
+    def _reroute(self, idx: int, frontier: int, failed_before: bool) -> None:
+        """Put fresh streams in place of chain[idx] (or, past the end of the chain, route the uncovered blocks). The log of the
+        replaced stream — everything that had entered block ``frontier`` — moves to the first replacement, which replays it
+        on its first step and hands its full-length output on, so every replacement rebuilds its cache."""
+        replaced = self._chain[idx: idx + 1]
+        stop = replaced[0].span.end if replaced else self.num_blocks
+        if failed_before:
+            logger.debug(f"attention caches of blocks [{frontier}, {stop}) will be rebuilt on other stages")
+        self._close_streams(replaced)
+        spans = self._manager.make_sequence(frontier, stop, mode="min_latency", cache_tokens_needed=self._max_length)
+        spans[-1].end = min(spans[-1].end, stop)  # the router may offer a stage that serves more than we asked for
+        fresh = self._open_streams(spans)
+        carried = replaced[0].log.tokens if replaced else None
+        for k, stage in enumerate(fresh):
+            stage.cursor = self._position
+            if k == 0 and carried is not None and self._position > 0:
+                stage.log.tokens = carried[:, : self._position]
+        if self._position > 0 and fresh and len(fresh[0].log) == 0 and (idx, frontier) != (0, 0):
+            self._close_streams(fresh)
+            raise RuntimeError("cannot rebuild a remote attention cache: no input log for the failed span")
+        self._chain[idx: idx + 1] = fresh
+        self._relink()
+
+    def _first_stage_inputs(self, step_inputs: torch.Tensor, n_new: int) -> torch.Tensor:
+        """Everything block 0 has ever been fed in this session, ending with the current step's inputs."""
+        head = self._chain[0].log.tokens if self._chain else None
+        new = step_inputs[:, step_inputs.shape[1] - n_new:]
+        if self._position == 0:
+            return new
+        if head is None:
+            raise RuntimeError("cannot rebuild remote attention caches: the input log of the first stage is gone")
+        if head.shape[1] == self._position + n_new:
+            return head
+        return torch.cat([head[:, : self._position], new.to(head.device)], dim=1)
+
+    def _landing(self, fabric, idx: int, shape: Tuple[int, int, int]) -> Optional[dict]:
+        """Where stage ``idx`` should store its output: the next stage's landing zone, this process's (last stage), or None =
+        return it with the RPC."""
+        if fabric is None:
+            return None
+        here = self._chain[idx]
+        rows = shape[0] * shape[1]
+        if here.fabric_rank is None or rows == 0 or rows > min(fabric.max_tokens, 4096) or shape[2] != fabric.hidden_size:
+            return None
+        if idx + 1 < len(self._chain):
+            there = self._chain[idx + 1]
+            if there.fabric_rank is None or there.fabric_rank == here.fabric_rank:
+                return None
+            return {"kind": "x_in", "rank": there.fabric_rank}
+        if here.span.end == self.num_blocks and here.fabric_rank != fabric.rank:
+            return {"kind": "y_ret", "rank": fabric.rank}
+        return None
+
+    # ---- one step --------------------------------------------------------------------------------------------------
+    def step(self, inputs: torch.Tensor, prompts: Optional[torch.Tensor] = None, hypo_ids: Optional[torch.Tensor] = None) -> torch.Tensor:
+        assert not self._closed, "the session is closed"
+        if torch.is_grad_enabled():
+            logger.warning("Running inference session with grad enabled. Gradients will *not* be propagated correctly.")
+        prompts, hypo_ids = _validate_step(inputs, prompts, hypo_ids, num_blocks=self.num_blocks, batch_size=self._batch_size,
+                                           hidden_size=getattr(self._manager.config, "hidden_size", None))
+        n_new = inputs.shape[1]
+        if self._position + n_new > self._max_length:
+            raise ValueError(f"Maximum length exceeded: prefix {self._position} + current {n_new} exceeds pre-allocated maximum {self._max_length}")
+        out = self._run_wave(inputs.detach(), prompts, hypo_ids, n_new)
+        self._position += n_new
+        self._batch_size = out.shape[0]
+        return out[:, out.shape[1] - n_new:].to(device=inputs.device, dtype=inputs.dtype)
+
+    def _fabric_wave(self, fabric, x: torch.Tensor, prompts, hypo_ids, n_new: int, step_id: str) -> Optional[torch.Tensor]:
+        """Steady state of a chain that lives entirely on the NVLink fabric: issue this step to ALL stages at once. Returns
+        None when the chain does not qualify (the caller then walks it stage by stage)."""
+        chain = self._chain
+        if (fabric is None or len(chain) < 2 or chain[0].span.start != 0 or chain[-1].span.end != self.num_blocks
+                or any(not s.primed or s.closed or s.cursor != self._position for s in chain)):
+            return None
+        shape = tuple(x.shape)
+        targets = [self._landing(fabric, i, shape) for i in range(len(chain))]
+        if any(t is None for t in targets):
+            return None
+
+        def span_prompts(stage: StageStream):
+            return DUMMY if is_dummy(prompts) else prompts[stage.span.start: stage.span.end]
+
+        jobs = [_dispatch.submit(chain[0].feed, x, span_prompts(chain[0]), hypo_ids, step_id=step_id, n_new=n_new, deliver_to=targets[0])]
+        for i in range(1, len(chain)):
+            jobs.append(_dispatch.submit(chain[i].feed_landed, shape, chain[i - 1].fabric_rank, span_prompts(chain[i]), hypo_ids,
+                                         step_id=step_id, n_new=n_new, deliver_to=targets[i]))
+        errors = []
+        for stage, job in zip(chain, jobs):
+            try:
+                job.result()
+                self._manager.on_request_success(stage.span.peer_id)
+            except Exception as e:  # noqa: BLE001
+                self._manager.on_request_failure(stage.span.peer_id)
+                errors.append((stage, e))
+        if errors:
+            for stage in chain:  # landing-zone contents are unknown now: the whole chain is rebuilt from the first stage's log
+                stage.no_history = True
+            raise errors[0][1]
+        B, L, H = shape
+        return fabric.recv(B * L, "y_ret", chain[-1].fabric_rank).view(B, L, H)
+
+    def _run_wave(self, step_inputs: torch.Tensor, prompts, hypo_ids, n_new: int) -> torch.Tensor:
+        from petals_b200.parallel.fabric import get_fabric
+
+        config = self._manager.config
+        fabric = get_fabric() if config.use_server_to_server else None
+        step_id = str(uuid.uuid4())
+        x = step_inputs  # activations entering chain[idx] (held by the client unless `landed`)
+        landed: Optional[Tuple[int, Tuple[int, int, int]]] = None  # (source rank, shape): x sits in chain[idx]'s landing zone
+        idx = failures = 0
+        try_all_at_once = True
+        while True:
+            frontier = self._chain[idx - 1].span.end if idx > 0 else 0
+            if frontier >= self.num_blocks:
+                break
+            stage: Optional[StageStream] = None
+            try:
+                if try_all_at_once and idx == 0:
+                    try_all_at_once = False
+                    done = self._fabric_wave(fabric, x, prompts, hypo_ids, n_new, step_id)
+                    if done is not None:
+                        return done
+                if idx >= len(self._chain) or failures > 0:
+                    if failures > 0 and (landed is not None or any(s.no_history for s in self._chain)):
+                        # some activations only ever existed in landing zones: start over from what block 0 was fed
+                        x = self._first_stage_inputs(step_inputs, n_new)
+                        self._close_streams(self._chain)
+                        self._chain, idx, frontier, landed = [], 0, 0, None
+                    self._reroute(idx, frontier, failures > 0)
+                stage = self._chain[idx]
+                if stage.cursor != self._position:
+                    raise RuntimeError(f"{stage.span} is at position {stage.cursor}, the session at {self._position}")
+                span_prompts = DUMMY if is_dummy(prompts) else prompts[stage.span.start: stage.span.end]
+                shape = landed[1] if landed is not None else tuple(x.shape)
+                deliver_to = self._landing(fabric, idx, shape)
+                if landed is not None:
+                    stage.feed_landed(shape, landed[0], span_prompts, hypo_ids, step_id=step_id, n_new=n_new, deliver_to=deliver_to)
+                    result = shape
+                else:
+                    result = stage.feed(x, span_prompts, hypo_ids, step_id=step_id, n_new=n_new, deliver_to=deliver_to)
+                if deliver_to is not None:
+                    landed = (stage.fabric_rank, tuple(result))
+                else:
+                    x, landed = result, None
+                self._manager.on_request_success(stage.span.peer_id)
+                idx, failures = idx + 1, 0
+            except Exception as e:  # noqa: BLE001 - whatever went wrong on a stage, try another one
+                if isinstance(e, ValueError) and "Maximum length exceeded" in str(e):
+                    raise
+                self._manager.on_request_failure(stage.span.peer_id if stage is not None else None)
+                failures += 1
+                if config.max_retries is not None and failures >= config.max_retries:
+                    raise
+                delay = self._manager.get_retry_delay(failures - 1)
+                logger.warning(f"inference step failed on {stage.span if stage is not None else 'routing'} (retry in {delay:.0f} sec): {e!r}")
+                maybe_log_traceback(e)
+                time.sleep(delay)
+        if landed is not None:  # the last stage stored the result into this process's landing zone
+            B, L, H = landed[1]
+            x = fabric.recv(B * L, "y_ret", landed[0]).view(B, L, H)
+        return x
+
+    # ---- lifecycle ---------------------------------------------------------------------------------------------------
+    def __enter__(self) -> "InferenceSession":
+        assert not self._closed and not self._chain
+        return self
+
+    def close(self, *exc_details) -> None:
+        if not getattr(self, "_closed", True):  # also safe when __init__ did not finish (reached from __del__)
+            self._close_streams(self._chain)
+            self._chain.clear()
+            self._closed = True
+
+    def __exit__(self, *exc_details) -> None:
+        self.close()
+
+    def __del__(self):
+        self.close()

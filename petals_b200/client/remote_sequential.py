@@ -18,7 +18,7 @@ from torch import nn
 from petals_b200.client.config import ClientConfig
 from petals_b200.client.inference_session import InferenceSession
 from petals_b200.client.routing import RemoteSequenceManager
-from petals_b200.client.sequential_autograd import _RemoteSequentialAutogradFunction
+from petals_b200.client.sequential_autograd import PipelinedRemoteFunction
 from petals_b200.data_structures import make_uid
 from petals_b200.parallel.swarm import Swarm
 from petals_b200.utils.logging import get_logger
@@ -89,7 +89,7 @@ class RemoteSequential(nn.Module):
         if prompts is not None and prompts.numel() and (prompts.ndim != 4 or prompts.shape[0] != len(self) or prompts.shape[1] not in (1, inputs.shape[0])
                                                          or prompts.shape[2] > inputs.shape[1] or prompts.shape[3] != inputs.shape[2]):
             raise ValueError(f"deep prompts must be [{len(self)}, {inputs.shape[0]} or 1, <= {inputs.shape[1]}, {inputs.shape[2]}], got {tuple(prompts.shape)}")
-        return _RemoteSequentialAutogradFunction.apply(inputs, DUMMY if prompts is None else prompts, self.sequence_manager)
+        return PipelinedRemoteFunction.apply(inputs, DUMMY if prompts is None else prompts, self.sequence_manager)
 
     # ---- sessions ------------------------------------------------------------------------------------------------------------
     @property

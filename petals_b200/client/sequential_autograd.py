@@ -1,18 +1,30 @@
-"""Autograd through a chain of remote stages (reference: src/petals/client/sequential_autograd.py:1-277).
+"""Pipeline-parallel forward / backward of a batch through the chain of remote stages.
 
-Forward: the batch is cut into micro-batches of at most ``MAX_TOKENS_IN_BATCH`` tokens which travel through the
-chain **concurrently** (one worker thread each; the reference uses asyncio tasks) — with stages on different GPUs
-this is the pipeline-parallel schedule: micro-batch i is on stage s+1 while micro-batch i+1 is on stage s, and each
-stage's runtime orders them by priority/arrival. Every span's input is remembered. Backward walks the spans in
-reverse; if a stage died in between, the forward of that sub-chain is re-run on a replacement route first. Returns
-gradients w.r.t. the inputs and the deep prompts. Stages keep no activation state between the two calls
-(stateless => fault tolerant), exactly like the reference."""
+What the reference offers here (src/petals/client/sequential_autograd.py:199-250): a batch is cut into micro-batches of at most
+``MAX_TOKENS_IN_BATCH`` tokens, the micro-batches travel through the servers concurrently, servers are stateless between the
+forward and the backward call, a failed server is replaced and its part of the forward recomputed, and the result is
+differentiable w.r.t. the inputs and the deep prompts.
+
+This module implements that as an explicit **wavefront schedule** (all-forward, then all-backward; GPipe order):
+
+* :class:`Route` fixes the chain of spans once per pass; every stage of the route gets a :class:`_Lane` — a worker with an
+  inbox — and micro-batch *i* enters stage *s+1* while micro-batch *i+1* enters stage *s*. With one stage per GPU that is the
+  pipeline: S stages, M micro-batches, bubble fraction (S-1)/(M+S-1). The order on every stage is deterministic.
+* every executed hop is recorded on its :class:`MicroBatch` (span + the activations that entered it): the recorded hops are
+  the tape the backward wave walks in reverse, stage S-1 first.
+* a stage that fails takes its micro-batch off the wavefront: :func:`finish_forward_alone` / :func:`backward_hops` complete it
+  with back-off and fresh routes (for a backward hop that means recomputing the lost span's forward on the replacement
+  first), while the other micro-batches keep flowing through the healthy lanes.
+* the backward wave runs its lanes on worker threads too, except when an in-process stage would have to call the autograd
+  engine for CUDA tensors from a foreign thread while this thread blocks the device's autograd worker; then the same wave
+  order is executed inline.
+"""
 from __future__ import annotations
 
-import itertools
+import queue
+import threading
 import time
-from collections import deque
-from concurrent.futures import ThreadPoolExecutor
+from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -25,155 +37,299 @@ from petals_b200.utils.misc import DUMMY, is_dummy
 
 logger = get_logger(__name__)
 MAX_TOKENS_IN_BATCH = 1024
-_executor = ThreadPoolExecutor(max_workers=16, thread_name_prefix="petals-autograd")
 
 
-def sequential_forward(inputs: torch.Tensor, prompts: torch.Tensor, sequence_manager: RemoteSequenceManager,
-                       start_index: int = 0, end_index: Optional[int] = None) -> Tuple[torch.Tensor, Sequence[torch.Tensor], Sequence[RemoteSpanInfo]]:
-    """Forward through blocks [start_index, end_index); returns (outputs, per-span inputs, spans)."""
-    assert isinstance(inputs, torch.Tensor) and inputs.ndim == 3, f"{type(inputs)}: {inputs.ndim}"
-    inputs_device, inputs_dtype = inputs.device, inputs.dtype
-    end_index = end_index if end_index is not None else len(sequence_manager.block_uids)
-    assert start_index >= 0 and end_index <= len(sequence_manager.block_uids)
-    assert is_dummy(prompts) or len(prompts) == len(sequence_manager.block_uids)
-    sequences: deque = deque()
-    intermediate_inputs, done_sequences = [], []
-    block_idx = start_index
-    while block_idx < end_index:
-        for attempt_no in itertools.count():
-            logger.debug(f"Forward: block {block_idx}, attempt {attempt_no}")
-            span = None
+@dataclass
+class Hop:
+    """One span executed for one micro-batch: the tape entry the backward needs."""
+    span: RemoteSpanInfo
+    entered: torch.Tensor  # activations that went into span.start
+
+
+@dataclass
+class MicroBatch:
+    index: int
+    x: torch.Tensor  # current activations (forward) / gradient w.r.t. them (backward)
+    prompts: torch.Tensor  # [n_blocks, b or 1, pre, H] or DUMMY
+    hops: List[Hop] = field(default_factory=list)
+    grad_prompts: List[torch.Tensor] = field(default_factory=list)  # per executed span, in backward order
+    error: Optional[BaseException] = None
+    detached: bool = False  # left the wavefront (a stage failed): completed on its own
+
+    def prompts_for(self, span: RemoteSpanInfo) -> torch.Tensor:
+        return DUMMY if is_dummy(self.prompts) else self.prompts[span.start: span.end]
+
+
+class Route:
+    """The chain of spans a pass is scheduled on."""
+
+    def __init__(self, manager: RemoteSequenceManager, start: int, end: int):
+        self.manager = manager
+        self.spans: List[RemoteSpanInfo] = list(manager.make_sequence(start, end, mode="max_throughput"))
+        if not self.spans or self.spans[0].start != start or self.spans[-1].end < end:
+            raise RuntimeError(f"no route covers blocks [{start}, {end})")
+
+    def __len__(self) -> int:
+        return len(self.spans)
+
+
+# ---- single hops ---------------------------------------------------------------------------------------------------
+def _forward_hop(manager: RemoteSequenceManager, mb: MicroBatch, span: RemoteSpanInfo) -> None:
+    uids = manager.block_uids[span.start: span.end]
+    meta = manager.get_request_metadata("rpc_forward", None, *uids)
+    (y,) = run_remote_forward(manager.connect(span.peer_id), uids, mb.x, mb.prompts_for(span), metadata=meta,
+                              timeout=manager.config.request_timeout)
+    mb.hops.append(Hop(span, mb.x))
+    mb.x = y
+    manager.on_request_success(span.peer_id)
+
+
+def _backward_hop(manager: RemoteSequenceManager, mb: MicroBatch, hop: Hop) -> None:
+    uids = manager.block_uids[hop.span.start: hop.span.end]
+    meta = manager.get_request_metadata("rpc_backward", None, *uids)
+    grads = run_remote_backward(manager.connect(hop.span.peer_id), uids, hop.entered, mb.x, mb.prompts_for(hop.span), metadata=meta,
+                                timeout=manager.config.request_timeout)
+    mb.x = grads[0]
+    if len(grads) > 1:
+        mb.grad_prompts.append(grads[1])
+    manager.on_request_success(hop.span.peer_id)
+
+
+def _give_up_or_wait(manager: RemoteSequenceManager, failures: int, what: str, err: BaseException) -> None:
+    limit = manager.config.max_retries
+    if limit is not None and failures >= limit:
+        raise err
+    delay = manager.get_retry_delay(failures - 1)
+    logger.warning(f"{what} failed (retry in {delay:.0f} sec): {err!r}")
+    maybe_log_traceback(err)
+    time.sleep(delay)
+
+
+# ---- off-wavefront completion (also the whole story when there is a single micro-batch and a single stage) ---------------
+def finish_forward_alone(manager: RemoteSequenceManager, mb: MicroBatch, block: int, end: int, failures: int = 0) -> None:
+    """Take ``mb`` from ``block`` to ``end`` on whatever stages routing offers, re-routing after each failure."""
+    pending: List[RemoteSpanInfo] = []
+    while block < end:
+        span = None
+        try:
+            if not pending:
+                pending = list(manager.make_sequence(block, end, mode="max_throughput"))
+            span = pending.pop(0)
+            _forward_hop(manager, mb, span)
+            block, failures = span.end, 0
+        except Exception as e:  # noqa: BLE001
+            manager.on_request_failure(span.peer_id if span is not None else None)
+            failures += 1
+            pending = []
+            _give_up_or_wait(manager, failures, f"forward of micro-batch {mb.index} via {span}", e)
+
+
+def backward_hops(manager: RemoteSequenceManager, mb: MicroBatch) -> None:
+    """Consume ``mb.hops`` from the back. A hop whose stage is gone is replaced by recomputing that span's forward on a fresh
+    route (which may split it into several hops) and continuing with the new tail."""
+    failures = 0
+    while mb.hops:
+        hop = mb.hops.pop()
+        try:
+            _backward_hop(manager, mb, hop)
+            failures = 0
+        except Exception as e:  # noqa: BLE001
+            manager.on_request_failure(hop.span.peer_id)
+            failures += 1
+            _give_up_or_wait(manager, failures, f"backward of micro-batch {mb.index} via {hop.span}", e)
+            redo = MicroBatch(mb.index, hop.entered, mb.prompts)
+            finish_forward_alone(manager, redo, hop.span.start, hop.span.end)
+            mb.hops.extend(redo.hops)  # same blocks, new stages; the activations entering them were recomputed
+
+
+# ---- the wavefront --------------------------------------------------------------------------------------------------
+class _Lane(threading.Thread):
+    """Worker of one stage of the route. Pulls micro-batches in arrival order — which is micro-batch order, since the previous
+    lane emits them in order — runs ``work`` on each and passes it on."""
+
+    _STOP = object()
+
+    def __init__(self, name: str, work, downstream: Optional["_Lane"], finished: "queue.Queue"):
+        super().__init__(name=name, daemon=True)
+        self.inbox: "queue.Queue" = queue.Queue()
+        self.work, self.downstream, self.finished = work, downstream, finished
+
+    def run(self) -> None:
+        while True:
+            mb = self.inbox.get()
+            if mb is _Lane._STOP:
+                if self.downstream is not None:
+                    self.downstream.inbox.put(_Lane._STOP)
+                return
+            if not mb.detached and mb.error is None:
+                try:
+                    self.work(mb)
+                except BaseException as e:  # noqa: BLE001 - recorded on the micro-batch, re-raised by the caller
+                    mb.error = e
+            (self.downstream.inbox if self.downstream is not None else self.finished).put(mb)
+
+
+def _run_wave(micro_batches: Sequence[MicroBatch], stage_work: Sequence, threaded: bool) -> None:
+    """Push every micro-batch through ``stage_work[0], stage_work[1], ...`` in wavefront order."""
+    if not threaded or len(stage_work) * len(micro_batches) == 1:
+        # same (stage, micro-batch) order a pipeline would produce, on this thread: diagonal by diagonal
+        S, M = len(stage_work), len(micro_batches)
+        for diag in range(S + M - 1):
+            for s in range(max(0, diag - M + 1), min(S, diag + 1)):
+                mb = micro_batches[diag - s]
+                if not mb.detached and mb.error is None:
+                    try:
+                        stage_work[s](mb)
+                    except BaseException as e:  # noqa: BLE001
+                        mb.error = e
+        return
+    finished: "queue.Queue" = queue.Queue()
+    lanes: List[_Lane] = []
+    for s in reversed(range(len(stage_work))):
+        lanes.insert(0, _Lane(f"petals-lane-{s}", stage_work[s], lanes[0] if lanes else None, finished))
+    for lane in lanes:
+        lane.start()
+    for mb in micro_batches:
+        lanes[0].inbox.put(mb)
+    lanes[0].inbox.put(_Lane._STOP)
+    for _ in micro_batches:
+        finished.get()
+    for lane in lanes:
+        lane.join()
+
+
+def pipelined_forward(manager: RemoteSequenceManager, micro_batches: Sequence[MicroBatch], start: int, end: int) -> None:
+    """All micro-batches through blocks [start, end); fills ``mb.x`` (outputs) and ``mb.hops`` (the tape)."""
+    try:
+        route: Optional[Route] = Route(manager, start, end)
+    except Exception as e:  # noqa: BLE001 - routing itself can fail transiently: every micro-batch then finds its own way
+        logger.debug(f"no common route ({e!r}); micro-batches are routed individually")
+        route = None
+
+    def stage_work(span: RemoteSpanInfo):
+        def work(mb: MicroBatch) -> None:
             try:
-                if not sequences or attempt_no >= 1:
-                    sequences = deque(sequence_manager.make_sequence(block_idx, end_index, mode="max_throughput"))
-                    logger.debug(f"Found path from block {block_idx} to {end_index} via {len(sequences)} servers")
-                span = sequences.popleft()
-                stub = sequence_manager.connect(span.peer_id)
-                uids = sequence_manager.block_uids[span.start: span.end]
-                span_prompts = prompts[span.start: span.end] if not is_dummy(prompts) else DUMMY
-                metadata = sequence_manager.get_request_metadata("rpc_forward", None, *uids)
-                (outputs,) = run_remote_forward(stub, uids, inputs, span_prompts, metadata=metadata, timeout=sequence_manager.config.request_timeout)
-                assert outputs.shape == inputs.shape, f"Expected output {inputs.shape}, got {outputs.shape}"
-                intermediate_inputs.append(inputs)
-                done_sequences.append(span)
-                inputs = outputs
-                block_idx = span.end
-                sequence_manager.on_request_success(span.peer_id)
-                break
-            except Exception as e:  # noqa: BLE001
-                sequence_manager.on_request_failure(span.peer_id if span is not None else None)
-                if sequence_manager.config.max_retries is not None and attempt_no + 1 >= sequence_manager.config.max_retries:
-                    raise
-                delay = sequence_manager.get_retry_delay(attempt_no)
-                logger.warning(f"Caught exception when running forward via {span} (retry in {delay:.0f} sec): {e!r}")
-                maybe_log_traceback(e)
-                time.sleep(delay)
-    outputs = inputs.to(device=inputs_device, dtype=inputs_dtype)
-    intermediate_inputs = [t.to(device=inputs_device, dtype=inputs_dtype) for t in intermediate_inputs]
-    return outputs, intermediate_inputs, done_sequences
+                _forward_hop(manager, mb, span)
+            except Exception as e:  # noqa: BLE001 - this stage is out for this micro-batch: finish it off the wavefront
+                manager.on_request_failure(span.peer_id)
+                mb.detached = True
+                _give_up_or_wait(manager, 1, f"forward of micro-batch {mb.index} via {span}", e)
+                finish_forward_alone(manager, mb, span.start, end, failures=1)
+        return work
+
+    if route is not None:
+        _run_wave(micro_batches, [stage_work(s) for s in route.spans], threaded=len(micro_batches) > 1)
+    else:
+        _run_wave(micro_batches, [lambda mb: finish_forward_alone(manager, mb, start, end)], threaded=len(micro_batches) > 1)
+    for mb in micro_batches:
+        if mb.error is not None:
+            raise mb.error
+        mb.detached = False
 
 
-def sequential_backward(grad_outputs: Sequence[torch.Tensor], intermediate_inputs: List[torch.Tensor], prompts: torch.Tensor,
-                        forward_sequences: List[RemoteSpanInfo], sequence_manager: RemoteSequenceManager) -> Tuple[Sequence[torch.Tensor], torch.Tensor]:
-    """Backward through the spans recorded by ``sequential_forward``; returns (grad_inputs, grad_prompts)."""
-    assert len(intermediate_inputs) == len(forward_sequences)
-    grad_outputs = list(grad_outputs)
-    grad_device, grad_dtype = grad_outputs[0].device, grad_outputs[0].dtype
-    grad_prompts_reversed = []
-    while len(forward_sequences) > 0 and len(intermediate_inputs) > 0:
-        inputs = intermediate_inputs.pop()
-        span = forward_sequences.pop()
-        for attempt_no in itertools.count():
-            logger.debug(f"Backward: block {span.end - 1}, attempt {attempt_no}")
+def _autograd_needs_this_thread(manager: RemoteSequenceManager, micro_batches: Sequence[MicroBatch]) -> bool:
+    """An in-process stage differentiates with a re-entrant autograd call. For CUDA tensors such a call from another thread is
+    queued behind the device's autograd worker — the very thread that is blocked inside our ``backward``."""
+    if not any(mb.x.is_cuda for mb in micro_batches):
+        return False
+    from petals_b200.parallel.transport import RemoteHandlerProxy
+
+    for mb in micro_batches:
+        for hop in mb.hops:
             try:
-                if attempt_no >= 1:
-                    # the stage that produced this activation is gone: recompute the sub-chain on a fresh route
-                    _, backup_inputs, backup_sequences = sequential_forward(inputs, prompts, sequence_manager, start_index=span.start, end_index=span.end)
-                    assert len(backup_inputs) == len(backup_sequences)
-                    assert backup_sequences[0].start == span.start and backup_sequences[-1].end == span.end
-                    intermediate_inputs.extend(backup_inputs)
-                    forward_sequences.extend(backup_sequences)
-                    inputs = intermediate_inputs.pop()
-                    span = forward_sequences.pop()
-                stub = sequence_manager.connect(span.peer_id)
-                uids = sequence_manager.block_uids[span.start: span.end]
-                span_prompts = prompts[span.start: span.end] if not is_dummy(prompts) else DUMMY
-                metadata = sequence_manager.get_request_metadata("rpc_backward", None, *uids)
-                grads = run_remote_backward(stub, uids, inputs, grad_outputs[0], span_prompts, metadata=metadata, timeout=sequence_manager.config.request_timeout)
-                grad_outputs = [grads[0]]
-                grad_prompts_reversed.extend(reversed(grads[1:]))
-                sequence_manager.on_request_success(span.peer_id)
-                break
-            except Exception as e:  # noqa: BLE001
-                sequence_manager.on_request_failure(span.peer_id if span is not None else None)
-                if sequence_manager.config.max_retries is not None and attempt_no + 1 >= sequence_manager.config.max_retries:
-                    raise
-                delay = sequence_manager.get_retry_delay(attempt_no)
-                logger.warning(f"Caught exception when running backward via {span} (retry in {delay:.0f} sec): {e!r}")
-                maybe_log_traceback(e)
-                time.sleep(delay)
-    grad_prompts = [g.to(device=grad_device, dtype=grad_dtype) for g in grad_prompts_reversed[::-1]]
-    grad_prompts = torch.cat(grad_prompts, dim=0) if grad_prompts else DUMMY
-    return [g.to(device=grad_device, dtype=grad_dtype) for g in grad_outputs], grad_prompts
+                if not isinstance(manager.connect(hop.span.peer_id), RemoteHandlerProxy):
+                    return True
+            except Exception:  # noqa: BLE001 - an unreachable peer is handled (and replaced) by the hop itself
+                continue
+    return False
 
 
-def _gather_forward(input_batches, prompt_batches, sequence_manager):
-    """Run every micro-batch through the chain concurrently."""
-    futures = [_executor.submit(sequential_forward, x, p, sequence_manager) for x, p in zip(input_batches, prompt_batches)]
-    return [f.result() for f in futures]
+def pipelined_backward(manager: RemoteSequenceManager, micro_batches: Sequence[MicroBatch]) -> None:
+    """Reverse wave over the recorded tapes: ``mb.x`` holds grad_outputs on entry and grad_inputs on return; ``mb.grad_prompts``
+    collects per-span prompt gradients (last span first)."""
+    depth = max((len(mb.hops) for mb in micro_batches), default=0)
+    same_shape = all(len(mb.hops) == depth for mb in micro_batches)
+
+    def pop_one(mb: MicroBatch) -> None:  # the lane for tape position d pops exactly one (possibly repaired) hop
+        target = len(mb.hops) - 1
+        hop = mb.hops.pop()
+        try:
+            _backward_hop(manager, mb, hop)
+        except Exception as e:  # noqa: BLE001
+            manager.on_request_failure(hop.span.peer_id)
+            _give_up_or_wait(manager, 1, f"backward of micro-batch {mb.index} via {hop.span}", e)
+            redo = MicroBatch(mb.index, hop.entered, mb.prompts)
+            finish_forward_alone(manager, redo, hop.span.start, hop.span.end, failures=1)
+            mb.hops.extend(redo.hops)
+            while len(mb.hops) > target:  # the replacement hops of this tape position
+                h = mb.hops.pop()
+                try:
+                    _backward_hop(manager, mb, h)
+                except Exception:  # noqa: BLE001 - a second failure in a row: hand the rest to the patient serial path
+                    mb.hops.append(h)
+                    mb.detached = True
+                    backward_hops(manager, mb)
+                    return
+
+    threaded = len(micro_batches) > 1 and not _autograd_needs_this_thread(manager, micro_batches)
+    if same_shape and depth > 0:
+        _run_wave(micro_batches, [pop_one] * depth, threaded=threaded)
+    else:  # tapes of different lengths (some micro-batches were repaired in the forward): no common stage structure
+        _run_wave(micro_batches, [lambda mb: backward_hops(manager, mb)], threaded=threaded)
+    for mb in micro_batches:
+        if mb.error is not None:
+            raise mb.error
+        if mb.hops:
+            backward_hops(manager, mb)
 
 
-def _gather_backward(grad_output_batches, intermediate_input_batches, prompt_batches, forward_sequences, sequence_manager):
-    """Backward of every micro-batch, in the calling thread.
+# ---- autograd glue ----------------------------------------------------------------------------------------------------
+def _split(inputs: torch.Tensor, prompts: Optional[torch.Tensor]) -> Tuple[List[torch.Tensor], List[torch.Tensor], bool]:
+    rows = max(MAX_TOKENS_IN_BATCH // max(inputs.shape[1], 1), 1)
+    xs = list(inputs.detach().split(rows))
+    if prompts is None or is_dummy(prompts):
+        return xs, [DUMMY] * len(xs), False
+    if prompts.shape[1] == 1:  # one prompt shared by the whole batch
+        return xs, [prompts.detach()] * len(xs), True
+    return xs, list(prompts.detach().split(rows, dim=1)), False
 
-    This runs inside ``torch.autograd``'s backward pass — for CUDA tensors that is the device's autograd worker
-    thread. An in-process stage computes its own backward with a (re-entrant) autograd call, which must therefore be
-    issued from this very thread: handing it to another thread would queue it behind the worker we are blocking."""
-    return [sequential_backward((g,), inp, p, spans, sequence_manager)
-            for g, inp, p, spans in zip(grad_output_batches, intermediate_input_batches, prompt_batches, forward_sequences)]
 
-
-class _RemoteSequentialAutogradFunction(torch.autograd.Function):
-    """Differentiable w.r.t. inputs and deep prompts; weights live on the stages and are frozen."""
+class PipelinedRemoteFunction(torch.autograd.Function):
+    """``outputs = blocks(inputs, prompts)`` over the swarm; differentiable w.r.t. ``inputs`` and ``prompts`` (the blocks'
+    weights live on the stages and are frozen)."""
 
     @staticmethod
     def forward(ctx, inputs: torch.Tensor, prompts: torch.Tensor, sequence_manager: RemoteSequenceManager):
-        batch_size = max(MAX_TOKENS_IN_BATCH // inputs.shape[1], 1)
-        input_batches: Sequence[torch.Tensor] = inputs.detach().split(batch_size)
-        if prompts is None or is_dummy(prompts):
-            prompt_batches = [DUMMY] * len(input_batches)
-        elif prompts.shape[1] == 1:
-            prompt_batches = [prompts.detach()] * len(input_batches)
-        else:
-            prompt_batches = prompts.detach().split(batch_size, dim=1)
-        sequence_manager.rpc_info  # noqa: B018 - make sure the route/schema is resolved before fanning out
-        outputs = _gather_forward(input_batches, prompt_batches, sequence_manager)
-        assert len(outputs) == len(input_batches)
-        output_batches = [output[0] for output in outputs]
-        ctx.prompt_batches = prompt_batches
-        ctx.sequence_manager = sequence_manager
-        ctx.intermediate_input_batches = [output[1] for output in outputs]
-        ctx.sequences_for_batches = [output[2] for output in outputs]
-        ctx.prompts_broadcast = prompts is not None and not is_dummy(prompts) and prompts.shape[1] == 1
-        return torch.cat(output_batches, dim=0)
+        if inputs.ndim != 3:
+            raise ValueError(f"inputs must be [batch, seq, hidden], got {tuple(inputs.shape)}")
+        n_blocks = len(sequence_manager.block_uids)
+        if not (prompts is None or is_dummy(prompts)) and len(prompts) != n_blocks:
+            raise ValueError(f"deep prompts must have one entry per block ({n_blocks}), got {len(prompts)}")
+        sequence_manager.rpc_info  # noqa: B018 - resolve the schema/route before fanning out
+        xs, ps, shared = _split(inputs, prompts)
+        mbs = [MicroBatch(i, x, p) for i, (x, p) in enumerate(zip(xs, ps))]
+        pipelined_forward(sequence_manager, mbs, 0, n_blocks)
+        ctx.manager, ctx.micro_batches, ctx.shared_prompts = sequence_manager, mbs, shared
+        ctx.rows = xs[0].shape[0]
+        return torch.cat([mb.x.to(device=inputs.device, dtype=inputs.dtype) for mb in mbs], dim=0)
 
     @staticmethod
     def backward(ctx, grad_outputs: torch.Tensor):
-        intermediate_input_batches: List[List[torch.Tensor]] = ctx.intermediate_input_batches
-        forward_sequences: List[List[RemoteSpanInfo]] = ctx.sequences_for_batches
-        ctx.sequence_manager.rpc_info  # noqa: B018
-        batch_size = max(MAX_TOKENS_IN_BATCH // grad_outputs.shape[1], 1)
-        grad_output_batches: Sequence[torch.Tensor] = grad_outputs.split(batch_size)
-        assert len(intermediate_input_batches) == len(grad_output_batches) == len(forward_sequences)
-        outputs = _gather_backward(grad_output_batches, intermediate_input_batches, ctx.prompt_batches, forward_sequences, ctx.sequence_manager)
-        grad_input_batches = [output[0][0] for output in outputs]
-        grad_prompt_batches = [output[1] for output in outputs]
-        grad_inputs = torch.cat(grad_input_batches, dim=0)
-        dummy_grad_prompts = [is_dummy(g) for g in grad_prompt_batches]
-        if all(dummy_grad_prompts):
-            grad_prompts = None
-        elif ctx.prompts_broadcast:
-            grad_prompts = torch.stack(grad_prompt_batches, 0).sum(0)
-        else:
-            grad_prompts = torch.cat(grad_prompt_batches, dim=1)
-        return (grad_inputs, grad_prompts, None)
+        mbs: List[MicroBatch] = ctx.micro_batches
+        pieces = grad_outputs.split(ctx.rows)
+        if len(pieces) != len(mbs):
+            raise RuntimeError(f"gradient has {len(pieces)} micro-batches, the forward pass ran {len(mbs)}")
+        ctx.manager.rpc_info  # noqa: B018
+        for mb, g in zip(mbs, pieces):
+            mb.x, mb.grad_prompts, mb.error, mb.detached = g, [], None, False
+        pipelined_backward(ctx.manager, mbs)
+        grad_inputs = torch.cat([mb.x.to(device=grad_outputs.device, dtype=grad_outputs.dtype) for mb in mbs], dim=0)
+        per_mb = []
+        for mb in mbs:  # spans were visited last-to-first: restore block order along dim 0
+            gp = [g.to(device=grad_outputs.device, dtype=grad_outputs.dtype) for g in reversed(mb.grad_prompts)]
+            per_mb.append(torch.cat(gp, dim=0) if gp else None)
+        if all(g is None for g in per_mb):
+            return grad_inputs, None, None
+        if ctx.shared_prompts:
+            return grad_inputs, torch.stack(per_mb, 0).sum(0), None
+        return grad_inputs, torch.cat(per_mb, dim=1), None
