@@ -17,67 +17,21 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import subprocess
 import sys
-import threading
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-BASELINE_TOKENS_PER_S = 6.0  # README.md:86 of the reference ("up to 6 tokens/s" single-batch, Llama 2 70B)
+from petals_b200.utils.bench_common import (BASELINE_TOKENS_PER_S, ClockSampler, device_timed_decode, e2e_decode,  # noqa: E402
+                                            metric_name, prime_session)
 
 
 def reference_arm(args) -> None:
-    """Run the unmodified reference from baseline/_ref through its own public API — if it is importable."""
-    ref = os.path.join(os.path.dirname(os.path.abspath(__file__)), "baseline", "_ref")
-    why = None
-    if not os.path.isdir(os.path.join(ref, "petals")):
-        why = "reference not installed under baseline/_ref (pip --no-index install fails: hivemind/tensor_parallel/bitsandbytes wheels absent offline)"
-    else:
-        sys.path.insert(0, ref)
-        try:
-            os.environ.setdefault("PETALS_IGNORE_DEPENDENCY_VERSION", "1")
-            import importlib
+    """Run the UNMODIFIED reference from ``baseline/_ref`` through its own public API (none of this repo's code on that path)."""
+    from baseline.reference_arm import run_reference
 
-            importlib.import_module("hivemind")
-            importlib.import_module("petals")
-        except Exception as e:  # noqa: BLE001
-            why = f"reference import fails offline: {type(e).__name__}: {str(e)[:120]}"
-    if why is None:
-        why = "reference imported but its swarm needs hivemind's libp2p daemon (p2pd binary), unavailable without network"
+    line = run_reference(args)
     if int(os.environ.get("RANK", "0")) == 0:
-        print(json.dumps({"impl": "reference", "unavailable": why}))
-
-
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-
-    def __init__(self, index: int = 0, period: float = 0.2):
-        super().__init__(daemon=True)
-        self.index, self.period, self.samples, self._halt = index, period, [], threading.Event()
-
-    def run(self) -> None:
-        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:  # noqa: BLE001
-                pass
-            self._halt.wait(self.period)
-
-    def stop(self) -> dict:
-        self._halt.set()
-        self.join(timeout=3)
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for s in self.samples if len(s) >= 6 for n, v in zip(names, s[2:6]) if v.lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm)}
-
-
-def _model_label(name: str) -> str:
-    return {"llama-3-70b": "Llama-3-70B", "llama-3-8b": "Llama-3-8B", "mixtral-8x7b": "Mixtral-8x7B"}.get(name, name)
+        print(json.dumps(line))
 
 
 def main() -> None:
@@ -139,48 +93,19 @@ def run_single_gpu(args) -> None:
     K, W = args.steps, args.warmup
     vocab = model.config.vocab_size
     prompt = torch.randint(0, vocab, (1, args.prompt_len), device=dev)
-    pinned_in = torch.zeros(1, 1, dtype=torch.int64).pin_memory()
-    pinned_out = torch.zeros(1, dtype=torch.int64).pin_memory()
-    result = {}
     with torch.inference_mode(), model.inference_session(max_length=args.seq_len) as sess:
-        # prompt ingestion (prefill path) is not part of the single-stream metric, like the reference benchmark
-        logits = model(input_ids=prompt).logits
-        tok = logits[:, -1].argmax(-1, keepdim=True)
-        for _ in range(W):
-            tok = model(input_ids=tok).logits[:, -1].argmax(-1, keepdim=True)
-        # ---- device-timed: tokens never leave the GPU ----------------------------------------------------------
-        from petals_b200.ops import functional as Fn
-
+        prime_session(model, sess, prompt, W)  # prompt ingestion is not part of the single-stream metric, like the reference benchmark
         sampler = ClockSampler(0)
         sampler.start()
-        torch.cuda.synchronize()
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = native.launch_count
-        start.record()
-        for _ in range(K):
-            tok = Fn.argmax(model(input_ids=tok).logits[:, -1])[:, None]
-        end.record()
-        torch.cuda.synchronize()
-        launches = native.launch_count - launches0
-        ms = start.elapsed_time(end)
+        ms, launches = device_timed_decode(model, sess, K)  # tokens never leave the GPU
         clocks = sampler.stop()
-        # ---- end to end: pinned-host token in, sampled token out, every step --------------------------------------
-        pinned_in.copy_(tok.cpu())
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        for _ in range(K):
-            ids = pinned_in.to(dev, non_blocking=True)  # H2D of this step's input
-            nxt = Fn.argmax(model(input_ids=ids).logits[:, -1])
-            pinned_out.copy_(nxt, non_blocking=True)  # D2H of this step's result
-            torch.cuda.synchronize()
-            pinned_in[0, 0] = pinned_out[0]
-        e2e_s = time.perf_counter() - t1
+        e2e_s, h2d, d2h = e2e_decode(model, sess, K, dev)  # pinned-host token in, sampled token out, every step
     value = K / (ms / 1e3)
     peaks = measured_peaks()
     spec = model.config.block_spec()
-    weight_bytes = (spec.num_params() * n_layers + vocab * spec.hidden_size) * 2
+    weight_bytes = (spec.active_params() * n_layers + vocab * spec.hidden_size) * 2
     result = {
-        "metric": (f"{_model_label(args.model)} single-stream decode tokens/s (device-timed); prefill tokens/s in `prefill`" if args.tp_emulate <= 1 else
+        "metric": (metric_name(args.model) if args.tp_emulate <= 1 else
                    f"DIAGNOSTIC: one rank's share of a tp{args.tp_emulate} decode step on one GPU, no communication (NOT a benchmark result)"),
         "value": round(value, 3), "unit": "tokens/s", "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",
@@ -188,10 +113,12 @@ def run_single_gpu(args) -> None:
         "config": {"model": args.model, "global_batch": 1, "seq_len": args.seq_len, "parallelism": f"pp1 (1 stage x {n_layers} blocks)",
                    "l2": "each step streams the full weight set (>> 126 MB L2): inputs larger than L2", "build_s": round(build_s, 1)},
         "clocks": clocks,
-        "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8},
+        "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "model.generate(max_new_tokens=1, session=sess) per step; token in from pinned host memory, token out to the host"},
         "gpu_launches": launches,
         "roofline": {"weight_bytes_per_token": weight_bytes, "achieved_GBps": round(weight_bytes * value / 1e9, 1),
-                     "frac_of_measured_hbm": round(weight_bytes * value / 1e9 / peaks["hbm_gbs"], 3), "peaks": peaks["source"]},
+                     "frac_of_measured_hbm": round(weight_bytes * value / 1e9 / peaks["hbm_gbs"], 3), "peaks": peaks["source"],
+                     "note": "bytes = the weights one token actually reads (dense blocks: all; sparse MoE: router + top-k experts) + LM head"},
     }
     if not args.skip_prefill:
         try:
@@ -218,7 +145,6 @@ def bench_fp8_decode(args, path, n_layers, swarm, dev, K, W, spec, vocab, peaks)
     instead of, the bf16 headline."""
     import torch
 
-    from petals_b200.ops import functional as Fn
     from petals_b200.utils.convert_block import QuantType
     from petals_b200.utils.random_model import launch_random_stage, random_client_model
 
@@ -228,20 +154,11 @@ def bench_fp8_decode(args, path, n_layers, swarm, dev, K, W, spec, vocab, peaks)
         model = random_client_model(path, swarm, dev)
         model.model.layers.sequence_manager.update(wait=True)
         prompt = torch.randint(0, vocab, (1, 8), device=dev)
-        with torch.inference_mode(), model.inference_session(max_length=args.seq_len):
-            tok = model(input_ids=prompt).logits[:, -1].argmax(-1, keepdim=True)
-            for _ in range(W):
-                tok = model(input_ids=tok).logits[:, -1].argmax(-1, keepdim=True)
-            torch.cuda.synchronize()
-            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            start.record()
-            for _ in range(K):
-                tok = Fn.argmax(model(input_ids=tok).logits[:, -1])[:, None]
-            end.record()
-            torch.cuda.synchronize()
-        ms = start.elapsed_time(end)
+        with torch.inference_mode(), model.inference_session(max_length=args.seq_len) as sess:
+            prime_session(model, sess, prompt, W)
+            ms, _ = device_timed_decode(model, sess, K)
         value = K / (ms / 1e3)
-        weight_bytes = spec.num_params() * n_layers * (1 + 1 / 32) + vocab * spec.hidden_size * 2
+        weight_bytes = spec.active_params() * n_layers * (1 + 1 / 32) + vocab * spec.hidden_size * 2
         return {"tokens_per_s": round(value, 3), "ms_per_step": round(ms / K, 4), "weight_bytes_per_token": int(weight_bytes),
                 "frac_of_measured_hbm": round(weight_bytes * value / 1e9 / peaks["hbm_gbs"], 3), "format": "E4M3 + UE8M0 scale per 32 (MXFP8)"}
     finally:

@@ -88,6 +88,17 @@ class BlockSpec:
     def num_params(self) -> int:
         return sum(math.prod(s) for s in self.param_shapes().values())
 
+    def active_params(self) -> int:
+        """Parameters ONE token reads (the bytes a decode step must stream): a sparse-MoE block touches the router and only
+        ``top_k`` of its ``num_experts`` expert FFNs."""
+        total = 0
+        for name, shape in self.param_shapes().items():
+            n = math.prod(shape)
+            if self.mlp == "moe" and name in ("we_gate", "we_up", "we_down"):
+                n = n // self.num_experts * self.top_k
+            total += n
+        return total
+
     def kv_bytes_per_token(self, dtype: torch.dtype = torch.bfloat16) -> int:
         """K and V for one token of one block (reference: src/petals/server/backend.py:88-99)."""
         return 2 * self.num_kv_heads * self.head_dim * torch.finfo(dtype).bits // 8

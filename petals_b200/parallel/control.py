@@ -15,6 +15,20 @@ import msgpack
 import numpy as np
 
 
+def attach_shared_memory(name: str) -> shared_memory.SharedMemory:
+    """Attach to a segment another process created WITHOUT adopting it: before Python 3.13 every attach registers the segment
+    with this process's resource tracker, which then unlinks it a second time at exit ("leaked shared_memory objects",
+    "No such file '/psm_...'"). Only the creator owns (and unlinks) the segment."""
+    shm = shared_memory.SharedMemory(name=name, create=False)
+    try:
+        from multiprocessing import resource_tracker
+
+        resource_tracker.unregister(shm._name, "shared_memory")  # noqa: SLF001 - the public `track=False` only exists from 3.13 on
+    except Exception:  # noqa: BLE001
+        pass
+    return shm
+
+
 class CommandRing:
     HEADER = 64  # bytes reserved for the write index
 
@@ -25,7 +39,7 @@ class CommandRing:
             self.shm.buf[:size] = b"\x00" * size
             self.shm.buf[8:32] = struct.pack("<QQQ", n_consumers, slots, slot_bytes)  # geometry travels with the ring
         else:
-            self.shm = shared_memory.SharedMemory(name=name, create=False)
+            self.shm = attach_shared_memory(name)
             n_consumers, slots, slot_bytes = struct.unpack("<QQQ", bytes(self.shm.buf[8:32]))
             size = self.HEADER + 64 * n_consumers + slots * slot_bytes
         self.n_consumers, self.slots, self.slot_bytes = int(n_consumers), int(slots), int(slot_bytes)
@@ -73,10 +87,12 @@ class CommandRing:
         return obj
 
     def close(self) -> None:
-        self._u64 = None
+        shm, self.shm, self._u64 = getattr(self, "shm", None), None, None
+        if shm is None:  # idempotent: shutdown paths may reach here twice
+            return
         try:
-            self.shm.close()
+            shm.close()
             if self._created:
-                self.shm.unlink()
+                shm.unlink()
         except Exception:  # noqa: BLE001
             pass

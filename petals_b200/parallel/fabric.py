@@ -156,7 +156,9 @@ class HostFabric:
             names[0] = self._shm.name
         dist.broadcast_object_list(names, src=0, group=group)
         if self.rank != 0:
-            self._shm = shared_memory.SharedMemory(name=names[0], create=False)
+            from petals_b200.parallel.control import attach_shared_memory
+
+            self._shm = attach_shared_memory(names[0])
         self._per_rank = per_rank
         self._consumed = {"x_in": 0, "y_ret": 0}
         self._pushes = 0
@@ -204,10 +206,13 @@ class HostFabric:
         pass
 
     def close(self) -> None:
+        shm, self._shm = getattr(self, "_shm", None), None
+        if shm is None:
+            return
         try:
-            self._shm.close()
+            shm.close()
             if self.rank == 0:
-                self._shm.unlink()
+                shm.unlink()
         except Exception:  # noqa: BLE001
             pass
 

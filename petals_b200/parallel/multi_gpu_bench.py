@@ -17,18 +17,14 @@ import torch.distributed as dist
 
 from petals_b200.parallel.symmetric import host_barrier
 
-BASELINE_TOKENS_PER_S = 6.0
-
-
-def _model_label(name: str) -> str:
-    return {"llama-3-70b": "Llama-3-70B", "llama-3-8b": "Llama-3-8B", "mixtral-8x7b": "Mixtral-8x7B"}.get(name, name)
+from petals_b200.utils.bench_common import (BASELINE_TOKENS_PER_S, ClockSampler, device_timed_decode, e2e_decode, metric_name,
+                                            prime_session)
 
 
 def run_multi_gpu(args) -> None:
     if str(args.parallelism).startswith("pp"):
         return run_pipeline(args)
     from petals_b200.data_structures import ModelInfo, ServerInfo, ServerState
-    from petals_b200.ops import functional as Fn
     from petals_b200.ops import native
     from petals_b200.parallel.swarm import Swarm
     from petals_b200.parallel.symmetric import measure_hop_latency, measure_peer_bandwidth
@@ -85,40 +81,14 @@ def run_multi_gpu(args) -> None:
     model = random_client_model(path, swarm, dev)
     vocab = model.config.vocab_size
     prompt = torch.randint(0, vocab, (1, args.prompt_len), device=dev)
-    pinned_in = torch.zeros(1, 1, dtype=torch.int64).pin_memory()
-    pinned_out = torch.zeros(1, dtype=torch.int64).pin_memory()
-    from bench import ClockSampler  # noqa: E402  (bench.py is the entry script)
-
     with torch.inference_mode(), model.inference_session(max_length=args.seq_len) as sess:
-        logits = model(input_ids=prompt).logits
-        tok = logits[:, -1].argmax(-1, keepdim=True)
-        for _ in range(W):
-            tok = model(input_ids=tok).logits[:, -1].argmax(-1, keepdim=True)
+        prime_session(model, sess, prompt, W)
         sampler = ClockSampler(local_rank)
         sampler.start()
-        torch.cuda.synchronize()
-        ring.send({"op": "mark", "name": "start"})
-        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = native.launch_count
-        start.record()
-        for _ in range(K):
-            tok = Fn.argmax(model(input_ids=tok).logits[:, -1])[:, None]
-        end.record()
-        torch.cuda.synchronize()
-        ring.send({"op": "mark", "name": "end"})
-        launches = native.launch_count - launches0
-        ms0 = start.elapsed_time(end)
+        ms0, launches = device_timed_decode(model, sess, K, on_start=lambda: ring.send({"op": "mark", "name": "start"}),
+                                            on_end=lambda: ring.send({"op": "mark", "name": "end"}))
         clocks = sampler.stop()
-        pinned_in.copy_(tok.cpu())
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        for _ in range(K):
-            ids = pinned_in.to(dev, non_blocking=True)
-            nxt = Fn.argmax(model(input_ids=ids).logits[:, -1])
-            pinned_out.copy_(nxt, non_blocking=True)
-            torch.cuda.synchronize()
-            pinned_in[0, 0] = pinned_out[0]
-        e2e_s = time.perf_counter() - t1
+        e2e_s, h2d, d2h = e2e_decode(model, sess, K, dev)
     engine.check_errors()
     # ---- prompt ingestion: parallel forward of [PB, PT] tokens through the public client API (rpc_forward) ------------------
     pms0, prefill = 0.0, None
@@ -160,7 +130,7 @@ def run_multi_gpu(args) -> None:
     weight_bytes_rank = (spec.num_params() * n_layers) * 2 / world + vocab * spec.hidden_size * 2  # LM head is replicated on rank 0
     hop_bytes = spec.hidden_size * 2
     result = {
-        "metric": f"{_model_label(args.model)} single-stream decode tokens/s (device-timed, max over ranks)",
+        "metric": metric_name(args.model),
         "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
         "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",
         "data": "synthetic token ids; random-init weights of the named architecture",
@@ -168,7 +138,8 @@ def run_multi_gpu(args) -> None:
                    "l2": "each step streams every rank's full weight shard (>> 126 MB L2): inputs larger than L2", "build_s": round(build_s, 1),
                    "per_rank_ms": [round(float(x), 3) for x in gathered]},
         "clocks": clocks,
-        "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8},
+        "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "model.generate(max_new_tokens=1, session=sess) per step; token in from pinned host memory, token out to the host"},
         "gpu_launches": launches,
         "prefill": prefill,
         "roofline": {"weight_bytes_per_token_per_rank": int(weight_bytes_rank), "achieved_GBps_per_rank": round(weight_bytes_rank * value / 1e9, 1),
@@ -229,7 +200,6 @@ def run_pipeline(args) -> None:
     """N pipeline stages (one per GPU) joined by the fused NVLink stage hop; single stream through the public client API."""
     import tempfile
 
-    from petals_b200.ops import functional as Fn
     from petals_b200.ops import native
     from petals_b200.parallel.fabric import init_fabric
     from petals_b200.parallel.swarm import FileSwarm
@@ -263,46 +233,24 @@ def run_pipeline(args) -> None:
     build_s = time.time() - t0
     K, W = args.steps, max(args.warmup, 3)
     if rank == 0:
-        from bench import ClockSampler
-
         model = random_client_model(path, swarm, dev)
         vocab = model.config.vocab_size
         prompt = torch.randint(0, vocab, (1, args.prompt_len), device=dev)
-        pinned_in = torch.zeros(1, 1, dtype=torch.int64).pin_memory()
-        pinned_out = torch.zeros(1, dtype=torch.int64).pin_memory()
         with torch.inference_mode(), model.inference_session(max_length=args.seq_len) as sess:
-            tok = model(input_ids=prompt).logits[:, -1].argmax(-1, keepdim=True)
-            for _ in range(W):
-                tok = model(input_ids=tok).logits[:, -1].argmax(-1, keepdim=True)
+            prime_session(model, sess, prompt, W)
             sampler = ClockSampler(local_rank)
             sampler.start()
-            torch.cuda.synchronize()
-            start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            launches0 = native.launch_count
-            start.record()
-            for _ in range(K):
-                tok = Fn.argmax(model(input_ids=tok).logits[:, -1])[:, None]
-            end.record()
-            torch.cuda.synchronize()
-            launches = native.launch_count - launches0
-            ms = start.elapsed_time(end)  # rank 0 waits for the last stage's result every step: this IS the max over ranks
+            # rank 0 waits for the last stage's result every step: its device time IS the max over ranks
+            ms, launches = device_timed_decode(model, sess, K)
             clocks = sampler.stop()
-            pinned_in.copy_(tok.cpu())
-            t1 = time.perf_counter()
-            for _ in range(K):
-                ids = pinned_in.to(dev, non_blocking=True)
-                nxt = Fn.argmax(model(input_ids=ids).logits[:, -1])
-                pinned_out.copy_(nxt, non_blocking=True)
-                torch.cuda.synchronize()
-                pinned_in[0, 0] = pinned_out[0]
-            e2e_s = time.perf_counter() - t1
+            e2e_s, h2d, d2h = e2e_decode(model, sess, K, dev)
             over_fabric = [s.no_history for s in sess._server_sessions]
         fabric.check_errors()
         value = K / (ms / 1e3)
         peaks = measured_peaks()
         spec = config.block_spec()
         result = {
-            "metric": f"{_model_label(args.model)} single-stream decode tokens/s (device-timed, max over ranks)",
+            "metric": metric_name(args.model),
             "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
             "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",
             "data": "synthetic token ids; random-init weights of the named architecture",
@@ -310,7 +258,7 @@ def run_pipeline(args) -> None:
                        "parallelism": f"pp{world} ({world} stages x {n_layers // world} blocks, fused GEMV-epilogue NVLink stage hop)",
                        "l2": "each step streams every stage's full weight span (>> 126 MB L2): inputs larger than L2", "build_s": round(build_s, 1),
                        "inputs_over_fabric": over_fabric},
-            "clocks": clocks, "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 8},
+            "clocks": clocks, "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "stage_hop": {"peer_store_GBps": None if peer_gbs is None else round(peer_gbs, 1),
                           "frac_of_measured_peer_copy": None if peer_gbs is None else round(peer_gbs / NVLINK_PEER_GBS, 3),
