@@ -86,6 +86,27 @@ int pb_add_prompts(void* hidden /*[B,T,H]*/, const void* prompts /*[Bp,P,H]*/, i
 int pb_bump_epoch(void* epoch, void* stream);
 int pb_advance_pos(void* pos, int delta, void* stream);
 
+// ---- one-token decode of a span of Llama-style blocks as one persistent data-flow kernel (decode_span.cu) -------------
+typedef struct {
+  const void* layers;      // device array of n_layers x 9 pointers: wqkv, wo, wgate, wup, wdown, ln1, ln2, k_pool, v_pool
+  int n_layers;
+  int H, Hq, Hkv, D, I;    // this rank's heads / FFN columns, full hidden size
+  float eps, attn_scale;
+  const void* x_in; void* x_out;                 // [H] bf16
+  const void* in_flag; uint64_t in_per_epoch;    // optional flag wait before x_in is read
+  const void* block_table; int max_pages, num_pages; const void* pos_ptr;
+  const void* cos; const void* sin; int max_pos;
+  void* qkv_ll; void* attp_ll; void* attn_ll; void* x_ll; void* act_ll; int max_chunks;   // local tagged buffers
+  int R, rank;
+  void* oproj_push[PB_MAX_PEERS]; void* mlp_push[PB_MAX_PEERS];   // slot [rank] of every rank's all-reduce buffers
+  const void* oproj_in; const void* mlp_in;                       // local [R][H/2] units
+  const void* epoch; void* error_flag;
+  int num_sms;
+  int prepare_only;        // 1: validate the shapes and set the kernel's shared-memory attribute, launch nothing
+} PbDecodeSpanArgs;
+int pb_decode_span(const PbDecodeSpanArgs* a, void* stream);
+int pb_decode_span_smem(const PbDecodeSpanArgs* a, int* n_stages, int* vin_elems);
+
 // ---- RoPE + paged KV append (rope_kv.cu) ------------------------------------------------------------
 typedef struct {
   const void* qkv;        // [B*T, (Hq + 2*Hkv) * D]

@@ -552,3 +552,79 @@ def l2_prefetch(plan: L2PrefetchPlan, *, progress_ptr: int = 0, epoch_ptr: int =
     native.check(native.lib().pb_l2_prefetch(plan.ranges.data_ptr(), plan.nbytes.data_ptr(), plan.n_layers, plan.per_layer,
                                              progress_ptr or None, epoch_ptr or None, tag_mul, lookahead, ctas, wait_us, native.stream_ptr()),
                  "l2_prefetch")
+
+
+class DecodeSpanPlan:
+    """Everything ``csrc/decode_span.cu`` needs to run one token through a span of Llama-style blocks in ONE persistent launch:
+    the device table of per-block pointers, the tagged data-flow buffers and the step counter.
+
+    ``layers``: per block a dict with ``wqkv wo w_gate w_up w_down ln1_w ln2_w`` (this rank's shards) and ``k_pool v_pool``
+    ([num_pages, Hkv, PAGE, D]). ``R``/``rank`` + ``oproj`` / ``mlp`` = (push addresses per rank, local receive address) place the
+    two all-reduce buffers in a symmetric heap for tensor parallelism; by default (one GPU) they are plain local tensors."""
+
+    def __init__(self, layers: Sequence[dict], *, H: int, Hq: int, Hkv: int, D: int, I: int, eps: float, attn_scale: float, max_chunks: int,
+                 device, R: int = 1, rank: int = 0, oproj: Optional[tuple] = None, mlp: Optional[tuple] = None, epoch: Optional[torch.Tensor] = None,
+                 error_flag: Optional[torch.Tensor] = None):
+        self.device = torch.device(device)
+        self.H, self.Hq, self.Hkv, self.D, self.I, self.eps, self.attn_scale = H, Hq, Hkv, D, I, eps, attn_scale
+        self.R, self.rank, self.max_chunks = R, rank, max_chunks
+        names = ("wqkv", "wo", "w_gate", "w_up", "w_down", "ln1_w", "ln2_w", "k_pool", "v_pool")
+        self._keep = [[_bf16c(l[n], n) for n in names] for l in layers]
+        with torch.inference_mode(False):
+            self.table = torch.tensor([[t.data_ptr() for t in row] for row in self._keep], dtype=torch.int64, device=self.device)
+            z = lambda n: torch.zeros(n, 2, dtype=torch.int32, device=self.device)  # n LL units {payload, tag}; tag 0 is never valid
+            self.qkv_ll, self.attn_ll, self.x_ll, self.act_ll = z((Hq + 2 * Hkv) * D // 2), z(Hq * D // 2), z(H // 2), z(I // 2)
+            self.attp_ll = z(Hq * max_chunks * (D + 2))
+            self.epoch = epoch if epoch is not None else torch.zeros(1, dtype=torch.int64, device=self.device)
+            self.err = error_flag if error_flag is not None else torch.zeros(1, dtype=torch.int32, device=self.device)
+            if oproj is None:
+                self._oproj, self._mlp = z(R * H // 2), z(R * H // 2)
+                oproj = ([self._oproj.data_ptr()], self._oproj.data_ptr())
+                mlp = ([self._mlp.data_ptr()], self._mlp.data_ptr())
+        self.oproj_push, self.oproj_in = oproj
+        self.mlp_push, self.mlp_in = mlp
+        assert len(self.oproj_push) == R and len(self.mlp_push) == R
+        self.num_pages = layers[0]["k_pool"].shape[0]
+        # validate the shapes and set the kernel attribute now (not under a stream capture, not inside a timed step)
+        dummy = torch.zeros(1, H, dtype=torch.bfloat16, device=self.device)
+        table = torch.zeros(1, 1, dtype=torch.int32, device=self.device)
+        a = self.args(dummy, dummy, table, table.data_ptr(), None, None)
+        a.prepare_only = 1
+        check(native.lib().pb_decode_span(C.byref(a), stream_ptr()), "decode_span (prepare)", launches=0)
+
+    def args(self, x_in: torch.Tensor, x_out: torch.Tensor, block_table: torch.Tensor, pos_ptr: int, cos, sin, in_flag: int = 0,
+             in_per_epoch: int = 0, lo: int = 0, hi: Optional[int] = None):
+        from petals_b200.ops.native import DecodeSpanArgs
+
+        hi = self.table.shape[0] if hi is None else hi
+        a = DecodeSpanArgs()
+        a.layers, a.n_layers = self.table[lo:hi].data_ptr(), hi - lo
+        a.H, a.Hq, a.Hkv, a.D, a.I, a.eps, a.attn_scale = self.H, self.Hq, self.Hkv, self.D, self.I, self.eps, self.attn_scale
+        a.x_in, a.x_out, a.in_flag, a.in_per_epoch = x_in.data_ptr(), x_out.data_ptr(), in_flag or None, in_per_epoch
+        a.block_table, a.max_pages, a.num_pages, a.pos_ptr = block_table.data_ptr(), block_table.shape[1], self.num_pages, pos_ptr
+        a.cos, a.sin, a.max_pos = ptr(cos), ptr(sin), (cos.shape[0] if cos is not None else 0)
+        a.qkv_ll, a.attp_ll, a.attn_ll, a.x_ll, a.act_ll = (self.qkv_ll.data_ptr(), self.attp_ll.data_ptr(), self.attn_ll.data_ptr(),
+                                                            self.x_ll.data_ptr(), self.act_ll.data_ptr())
+        a.max_chunks = min(self.max_chunks, block_table.shape[1])
+        a.R, a.rank = self.R, self.rank
+        for r in range(self.R):
+            a.oproj_push[r], a.mlp_push[r] = self.oproj_push[r], self.mlp_push[r]
+        a.oproj_in, a.mlp_in = self.oproj_in, self.mlp_in
+        a.epoch, a.error_flag = self.epoch.data_ptr(), self.err.data_ptr()
+        a.num_sms = native.sm_count(self.device.index)
+        return a
+
+
+def decode_span_supported(*, H: int, Hq: int, Hkv: int, D: int, I: int) -> bool:
+    """Shapes ``csrc/decode_span.cu`` takes (the launcher re-checks and explains)."""
+    return D in (64, 128) and Hkv > 0 and Hq % Hkv == 0 and Hq // Hkv <= 16 and H % 64 == 0 and I % 4 == 0 and (Hq * D) % 64 == 0
+
+
+def decode_span(plan: DecodeSpanPlan, x_in: torch.Tensor, x_out: torch.Tensor, block_table: torch.Tensor, pos_ptr: int, cos, sin, *,
+                in_flag: int = 0, in_per_epoch: int = 0, lo: int = 0, hi: Optional[int] = None, bump_epoch: bool = True) -> torch.Tensor:
+    """One token (``x_in`` [1, H] -> ``x_out`` [1, H]) through blocks [lo, hi) of the plan: one launch (plus the step-counter bump)."""
+    if bump_epoch:
+        check(native.lib().pb_bump_epoch(plan.epoch.data_ptr(), stream_ptr()), "bump_epoch")
+    a = plan.args(x_in, x_out, block_table, pos_ptr, cos, sin, in_flag, in_per_epoch, lo, hi)
+    check(native.lib().pb_decode_span(C.byref(a), stream_ptr()), "decode_span")
+    return x_out

@@ -82,6 +82,23 @@ class RopeKvArgs(C.Structure):
     ]
 
 
+class DecodeSpanArgs(C.Structure):
+    _fields_ = [
+        ("layers", C.c_void_p), ("n_layers", C.c_int),
+        ("H", C.c_int), ("Hq", C.c_int), ("Hkv", C.c_int), ("D", C.c_int), ("I", C.c_int),
+        ("eps", C.c_float), ("attn_scale", C.c_float),
+        ("x_in", C.c_void_p), ("x_out", C.c_void_p), ("in_flag", C.c_void_p), ("in_per_epoch", C.c_uint64),
+        ("block_table", C.c_void_p), ("max_pages", C.c_int), ("num_pages", C.c_int), ("pos_ptr", C.c_void_p),
+        ("cos", C.c_void_p), ("sin", C.c_void_p), ("max_pos", C.c_int),
+        ("qkv_ll", C.c_void_p), ("attp_ll", C.c_void_p), ("attn_ll", C.c_void_p), ("x_ll", C.c_void_p), ("act_ll", C.c_void_p),
+        ("max_chunks", C.c_int),
+        ("R", C.c_int), ("rank", C.c_int),
+        ("oproj_push", C.c_void_p * PB_MAX_PEERS), ("mlp_push", C.c_void_p * PB_MAX_PEERS),
+        ("oproj_in", C.c_void_p), ("mlp_in", C.c_void_p),
+        ("epoch", C.c_void_p), ("error_flag", C.c_void_p), ("num_sms", C.c_int), ("prepare_only", C.c_int),
+    ]
+
+
 class NormReduceGatherArgs(C.Structure):
     _fields_ = [
         ("x_res_in", C.c_void_p), ("x_res_out", C.c_void_p),
@@ -129,6 +146,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.pb_advance_pos.argtypes = [vp, ci, vp]
     lib.pb_rope_kv.argtypes = [C.POINTER(RopeKvArgs), vp]
     lib.pb_attention.argtypes = [C.POINTER(AttnArgs), vp]
+    lib.pb_decode_span.argtypes = [C.POINTER(DecodeSpanArgs), vp]
+    lib.pb_decode_span.restype = ci
+    lib.pb_decode_span_smem.argtypes = [C.POINTER(DecodeSpanArgs), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.pb_decode_span_smem.restype = ci
     lib.pb_norm_reduce_gather.argtypes = [C.POINTER(NormReduceGatherArgs), vp]
     lib.pb_norm_reduce_gather.restype = ci
     lib.pb_kv_copy_pages.argtypes = [vp, vp, vp, ci, cl, cl, ci, vp]

@@ -137,6 +137,16 @@ class TPDecodeEngine:
         self.off_ll_attn = heap.alloc(R * self.ll_slot_bytes, align=4096)
         self.off_ll_mlp = heap.alloc(R * self.ll_slot_bytes, align=4096)
         self.x_in = heap.tensor(self.off_x_in, (MAX_ROWS, H), torch.bfloat16)
+        # single-token steps: the whole span as ONE persistent data-flow kernel per rank (csrc/decode_span.cu). Its two all-reduce
+        # buffers are [source rank][H/2] 8-byte LL units on every rank (allocated unconditionally: symmetric order).
+        self.span_slot_bytes = H * 4
+        self.off_span_attn = heap.alloc(R * self.span_slot_bytes, align=4096)
+        self.off_span_mlp = heap.alloc(R * self.span_slot_bytes, align=4096)
+        ls_ = self.ls
+        self.use_span_kernel = (os.environ.get("PETALS_B200_SPAN_KERNEL", "1") != "0" and spec.norm == "rms" and spec.mlp == "swiglu" and spec.rotary
+                                and not spec.sliding_window
+                                and Fn.decode_span_supported(H=H, Hq=ls_.num_heads, Hkv=ls_.num_kv_heads, D=ls_.head_dim, I=ls_.intermediate_size))
+        self._span_plan: Optional[Fn.DecodeSpanPlan] = None
         # sequence-parallel prefill: rows are owned in contiguous slices of `mo` rows per rank
         self.max_prefill_rows = P = max(0, max_prefill_rows)
         if P:
@@ -213,6 +223,13 @@ class TPDecodeEngine:
         ep, err, ctr = self.epoch.data_ptr(), self.err.data_ptr(), self.done_counter.data_ptr()
         pos_ptr = self.pos_static.data_ptr()
         native.check(native.lib().pb_bump_epoch(ep, native.stream_ptr()), "bump_epoch")
+        if M == 1 and self.use_span_kernel:
+            # one launch for the whole span: waits for the leader's input flag, streams this rank's shards, pushes the partial sums of
+            # both row-parallel projections to every rank and finishes the all-reduces itself (the span output lands in self.out)
+            Fn.decode_span(self._span_kernel_plan(), self.x_in[:1], self.out[:1], table, pos_ptr, self.cos, self.sin,
+                           in_flag=self.flag(me, 0), in_per_epoch=1, bump_epoch=False)
+            native.check(native.lib().pb_advance_pos(pos_ptr, T, native.stream_ptr()), "advance_pos")
+            return self.out[:M]
         h = [self._buf("h_a", M, H), self._buf("h_b", M, H)]
         cur = self.x_in[:M]  # residual stream entering layer 0 (pushed by the leader)
         nxt = 0
@@ -316,6 +333,22 @@ class TPDecodeEngine:
             torch.cuda.current_stream(self.device).wait_stream(self._l2_stream)
         self._last_residual, self._last_parts = cur, mlp_parts
         return self.out[:M]
+
+    def _span_kernel_plan(self) -> "Fn.DecodeSpanPlan":
+        if self._span_plan is None:
+            s, ls, R, me = self.spec, self.ls, self.world, self.rank
+            layers = []
+            for l, w in enumerate(self.shards):
+                k_pool, v_pool = self.cache.layer_pools(l)
+                layers.append(dict(wqkv=w["wqkv"], wo=w["wo"], w_gate=w["w_gate"], w_up=w["w_up"], w_down=w["w_down"], ln1_w=w["ln1_w"],
+                                   ln2_w=w["ln2_w"], k_pool=k_pool, v_pool=v_pool))
+            push = lambda off: [self.heap.addr(r, off + me * self.span_slot_bytes) for r in range(R)]
+            self._span_plan = Fn.DecodeSpanPlan(
+                layers, H=s.hidden_size, Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim, I=ls.intermediate_size, eps=s.norm_eps,
+                attn_scale=s.attn_scale, max_chunks=self.max_pages, device=self.device, R=R, rank=me,
+                oproj=(push(self.off_span_attn), self.heap.addr(me, self.off_span_attn)),
+                mlp=(push(self.off_span_mlp), self.heap.addr(me, self.off_span_mlp)), epoch=self.epoch, error_flag=self.err)
+        return self._span_plan
 
     # ---- sequence-parallel prefill ---------------------------------------------------------------------------------------
     def p_flag(self, rank: int, index: int) -> int:
@@ -436,6 +469,8 @@ class TPDecodeEngine:
         cudaFuncSetAttribute and buffer allocation happen before graph capture (which must not allocate)."""
         s, ls = self.spec, self.ls
         M, H = B * T, s.hidden_size
+        if self.use_span_kernel:
+            self._span_kernel_plan()  # buffers + kernel attribute now: graph capture must not allocate
         w = self.shards[0]
         x = self._buf("h_a", M, H)
         self._buf("h_b", M, H)

@@ -92,6 +92,10 @@ class StageEngine:
         # O-proj -> gate/up -> down -> next block's QKV as one persistent launch per block (grid barriers instead of kernel boundaries)
         self.use_chain = os.environ.get("PETALS_B200_CHAIN", "0") != "0"
         self._chain_bar = torch.zeros(max(1, len(self.blocks)), 64, dtype=torch.int32, device=self.device)  # {count, generation} per block
+        # single-token steps of Llama-style spans as ONE persistent data-flow kernel (csrc/decode_span.cu): weights stream through
+        # a shared-memory ring across what used to be kernel boundaries, phases are ordered by tagged data instead of launches
+        self.use_span_kernel = os.environ.get("PETALS_B200_SPAN_KERNEL", "1") != "0" and self._span_kernel_ok()
+        self._span_plans: Dict[Optional[str], Fn.DecodeSpanPlan] = {}  # per adapter (captured graphs keep the plan's table address)
         self._split_ctr = torch.zeros(8192, dtype=torch.int32, device=self.device)  # split-KV arrival counters (self-resetting)
         self._tables: Dict[int, torch.Tensor] = {}  # batch -> static block table
         self._graphs: Dict[Tuple[int, int, int, int], dict] = {}
@@ -109,6 +113,27 @@ class StageEngine:
         n_scratch = max(1, (max_chunk_tokens + PAGE - 1) // PAGE) + 1
         self._scratch_pool = torch.zeros(2, n_scratch, s.num_kv_heads, PAGE, s.head_dim, dtype=self.dtype, device=self.device)
         self._scratch_pages = n_scratch
+
+    # ---- persistent span kernel ---------------------------------------------------------------------------------------
+    def _span_kernel_ok(self) -> bool:
+        s = self.spec
+        return (self.fp8 is None and s.norm == "rms" and s.mlp == "swiglu" and s.rotary and not s.qkv_interleaved and not s.parallel_attn
+                and not s.post_ln_residual and not s.alibi and not s.sliding_window and not (s.qkv_bias or s.out_bias or s.mlp_bias)
+                and Fn.decode_span_supported(H=s.hidden_size, Hq=s.num_heads, Hkv=s.num_kv_heads, D=s.head_dim, I=s.intermediate_size)
+                and all(b._p("bqkv") is None for b in self.blocks))
+
+    def _span_kernel_plan(self) -> "Fn.DecodeSpanPlan":
+        if self._adapter not in self._span_plans:
+            s = self.spec
+            layers = []
+            for slot, b in enumerate(self.blocks):
+                k_pool, v_pool = self.cache.layer_pools(slot)
+                layers.append(dict(wqkv=b.wqkv, wo=b.wo, w_gate=b.w_gate, w_up=b.w_up, w_down=b.w_down, ln1_w=b.ln1_w, ln2_w=b.ln2_w,
+                                   k_pool=k_pool, v_pool=v_pool))
+            self._span_plans[self._adapter] = Fn.DecodeSpanPlan(layers, H=s.hidden_size, Hq=s.num_heads, Hkv=s.num_kv_heads, D=s.head_dim, I=s.intermediate_size,
+                                                eps=s.norm_eps, attn_scale=s.attn_scale, max_chunks=self.max_pages, device=self.device,
+                                                error_flag=self.err_flag)
+        return self._span_plans[self._adapter]
 
     # ---- adapters ------------------------------------------------------------------------------------------
     def use_adapter(self, name: Optional[str]) -> None:
@@ -370,6 +395,9 @@ class StageEngine:
     def _run_span(self, x: torch.Tensor, B: int, T: int, lo: int, hi: int, table, pos_ptr, pools_of, prompts, decode: bool, splits: int,
                   hop: Optional[tuple] = None) -> torch.Tensor:
         M = B * T
+        if decode and M == 1 and self.use_span_kernel and prompts is None and hop is None and hi > lo and pools_of == self.cache.layer_pools:
+            out = self._buf("h_alt", M, self.spec.hidden_size)
+            return Fn.decode_span(self._span_kernel_plan(), x, out, table, pos_ptr, self.cos, self.sin, lo=lo, hi=hi)
         if decode and self._chain_ok(M, lo, hi, prompts) and (hop is None or self.spec.mlp != "moe"):
             return self._run_span_chain(x, B, T, lo, hi, table, pos_ptr, pools_of, splits, hop)
         other = self._buf("h_alt", M, self.spec.hidden_size) if decode else None
