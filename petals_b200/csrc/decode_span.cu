@@ -116,6 +116,17 @@ PB_DEVICE void bulk_load_hint(void* smem_dst, const void* gsrc, uint32_t bytes, 
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
+// Spin bookkeeping shared by every poll loop: a wall-clock watchdog that raises the error flag instead of hanging the GPU, and a
+// fast exit once ANY thread has raised it (a broken step must drain in milliseconds, not one time-out per unit).
+PB_DEVICE bool give_up(unsigned spins, unsigned long long& t0, int* error_flag) {
+  if ((spins & 1023u) != 0) return false;
+  if (error_flag != nullptr && *reinterpret_cast<volatile int*>(error_flag) != 0) return true;
+  const unsigned long long now = globaltimer_ns();
+  if (t0 == 0) { t0 = now; return false; }
+  if (now - t0 > PB_FLAG_TIMEOUT_NS) { if (error_flag != nullptr) atomicExch(error_flag, 1); return true; }
+  return false;
+}
+
 // Poll one LL unit until it carries `tag`. The watchdog never hangs the GPU: it raises the error flag and returns garbage.
 PB_DEVICE uint32_t poll_ll(const uint2* p, uint32_t tag, int* error_flag) {
   uint2 v = ld_ll(p);
@@ -124,11 +135,7 @@ PB_DEVICE uint32_t poll_ll(const uint2* p, uint32_t tag, int* error_flag) {
   for (unsigned spins = 1;; ++spins) {
     v = ld_ll(p);
     if (v.y == tag) return v.x;
-    if ((spins & 4095u) == 0) {
-      const unsigned long long now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > PB_FLAG_TIMEOUT_NS) { if (error_flag != nullptr) atomicExch(error_flag, 1); return v.x; }
-    }
+    if (give_up(spins, t0, error_flag)) return v.x;
   }
 }
 // Two units with one 16-byte load (p must be 16-byte aligned).
@@ -138,11 +145,7 @@ PB_DEVICE uint2 poll_ll2(const uint2* p, uint32_t tag, int* error_flag) {
   unsigned long long t0 = 0;
   for (unsigned spins = 1; !(v.y == tag && v.w == tag); ++spins) {
     v = ld_relaxed_sys_v4(q);
-    if ((spins & 4095u) == 0) {
-      const unsigned long long now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > PB_FLAG_TIMEOUT_NS) { if (error_flag != nullptr) atomicExch(error_flag, 1); break; }
-    }
+    if (give_up(spins, t0, error_flag)) break;
   }
   return make_uint2(v.x, v.z);
 }
@@ -289,11 +292,7 @@ PB_DEVICE void settle2(uint4& v, const uint4* q, uint32_t tag, int* err) {
   unsigned long long t0 = 0;
   for (unsigned spins = 1; !(v.y == tag && v.w == tag); ++spins) {
     v = ld_relaxed_sys_v4(q);
-    if ((spins & 4095u) == 0) {
-      const unsigned long long now = globaltimer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > PB_FLAG_TIMEOUT_NS) { if (err != nullptr) atomicExch(err, 1); return; }
-    }
+    if (give_up(spins, t0, err)) return;
   }
 }
 

@@ -173,12 +173,6 @@ int pb_moe_combine(const void* y, const void* topw, const void* residual, void* 
 int pb_kv_copy_pages(void* pool, const void* src_pages, const void* dst_pages, int n, long page_elems,
                      long layer_stride_elems, int n_layer_slabs, void* stream);
 
-// ---- layer-ahead weight prefetch into L2 (side stream; timing only, see l2_prefetch.cu) --------------------------------
-// ranges / nbytes: device arrays [n_layers * per_layer]. progress: LL unit whose .y tag = epoch * tag_mul + layer paces the
-// walk (null = unpaced; then epoch must be null too). wait_us bounds every wait.
-int pb_l2_prefetch(const void* ranges, const void* nbytes, int n_layers, int per_layer, const void* progress, const void* epoch,
-                   unsigned int tag_mul, int lookahead, int ctas, long long wait_us, void* stream);
-
 // ---- runtime (host) ---------------------------------------------------------------------------------
 int pb_device_sm_count(int device);
 const char* pb_last_error(void);

@@ -526,34 +526,6 @@ def moe_decode(h: torch.Tensor, norm_w: torch.Tensor, router: torch.Tensor, we_g
     return out
 
 
-class L2PrefetchPlan:
-    """Device-side description of the weights to walk, layer by layer (csrc/l2_prefetch.cu). Built once per engine."""
-
-    def __init__(self, layers: Sequence[Sequence[torch.Tensor]]):
-        per_layer = max(len(ts) for ts in layers)
-        dev = layers[0][0].device
-        ptrs, sizes = [], []
-        for ts in layers:
-            ts = list(ts) + [None] * (per_layer - len(ts))
-            ptrs += [0 if t is None else t.data_ptr() for t in ts]
-            sizes += [0 if t is None else t.numel() * t.element_size() for t in ts]
-        self.tensors = [t for ts in layers for t in ts]  # keep the storages alive as long as the plan
-        self.n_layers, self.per_layer = len(layers), per_layer
-        self.total_bytes = int(sum(sizes))
-        with torch.inference_mode(False):
-            self.ranges = torch.tensor(ptrs, dtype=torch.int64, device=dev)
-            self.nbytes = torch.tensor(sizes, dtype=torch.int64, device=dev)
-
-
-def l2_prefetch(plan: L2PrefetchPlan, *, progress_ptr: int = 0, epoch_ptr: int = 0, tag_mul: int = 0, lookahead: int = 1, ctas: int = 8,
-                wait_us: int = 2000) -> None:
-    """Launch the layer-ahead L2 prefetcher on the *current* stream (callers put it on a side stream). ``progress_ptr`` = address
-    of the LL unit whose tag paces the walk (0 = unpaced)."""
-    native.check(native.lib().pb_l2_prefetch(plan.ranges.data_ptr(), plan.nbytes.data_ptr(), plan.n_layers, plan.per_layer,
-                                             progress_ptr or None, epoch_ptr or None, tag_mul, lookahead, ctas, wait_us, native.stream_ptr()),
-                 "l2_prefetch")
-
-
 class DecodeSpanPlan:
     """Everything ``csrc/decode_span.cu`` needs to run one token through a span of Llama-style blocks in ONE persistent launch:
     the device table of per-block pointers, the tagged data-flow buffers and the step counter.

@@ -177,8 +177,6 @@ def _declare(lib: C.CDLL) -> None:
     lib.pb_moe_combine.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
     for name in ("pb_moe_router", "pb_moe_gemv", "pb_moe_combine"):
         getattr(lib, name).restype = ci
-    lib.pb_l2_prefetch.argtypes = [vp, vp, ci, ci, vp, vp, C.c_uint, ci, ci, C.c_longlong, vp]
-    lib.pb_l2_prefetch.restype = ci
     lib.pb_last_error.argtypes = []
     lib.pb_last_error.restype = C.c_char_p
     for name in ("pb_linear_decode", "pb_gemm_bf16", "pb_gemm_tiles", "pb_norm", "pb_swiglu", "pb_add", "pb_embedding",

@@ -167,13 +167,6 @@ class TPDecodeEngine:
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.done_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.fuse_rope = os.environ.get("PETALS_B200_FUSE_ROPE", "1") != "0"
-        # opt-in experiment (csrc/l2_prefetch.cu): a few CTAs on a side stream walk the next layer's weights into the 126 MB L2 while
-        # the step's kernels run, paced by the LL all-reduce tags. Off until measured on hardware.
-        self.l2_prefetch = os.environ.get("PETALS_B200_L2_PREFETCH", "0") != "0"
-        self.l2_prefetch_ctas = int(os.environ.get("PETALS_B200_L2_PREFETCH_CTAS", "8"))
-        self.l2_prefetch_lookahead = int(os.environ.get("PETALS_B200_L2_PREFETCH_AHEAD", "1"))
-        self._l2_plan = None
-        self._l2_stream = None
         self.use_chain = os.environ.get("PETALS_B200_CHAIN", "0") != "0"
         self._chain_bar = torch.zeros(max(1, len(self.shards)), 64, dtype=torch.int32, device=dev)  # grid-barrier words per block
         self._split_ctr = torch.zeros(1024, dtype=torch.int32, device=dev)  # split-KV arrival counters (self-resetting)
@@ -273,19 +266,6 @@ class TPDecodeEngine:
             kw = dict(kw)
             return Fn.linear_decode(kw.pop("x"), kw.pop("w"), **kw)
 
-        prefetching = self.l2_prefetch and ll and L > 1
-        if prefetching:
-            # fork after the epoch bump (the prefetcher derives the step's tag base from it); joined before the step ends
-            if self._l2_plan is None:
-                order = ("wqkv", "wo", "w_gate", "w_up", "w_down")
-                self._l2_plan = Fn.L2PrefetchPlan([[w[n] for n in order if n in w] for w in self.shards])
-                self._l2_stream = torch.cuda.Stream(device=self.device)
-            main = torch.cuda.current_stream(self.device)
-            self._l2_stream.wait_stream(main)
-            with torch.cuda.stream(self._l2_stream):
-                # progress word: the tag of the first LL unit this rank sends to itself in the attention all-reduce of each layer
-                Fn.l2_prefetch(self._l2_plan, progress_ptr=ll_attn_in[me], epoch_ptr=ep, tag_mul=L, lookahead=self.l2_prefetch_lookahead,
-                               ctas=self.l2_prefetch_ctas)
         kw1, cur, nxt = k1_kwargs(0, cur, nxt)
         launch(kw1)
         for l, w in enumerate(self.shards):
@@ -329,8 +309,6 @@ class TPDecodeEngine:
             native.check(native.lib().pb_reduce_parts(cur.data_ptr(), parts, R, self.flag_mlp(me, self.n_blocks - 1), R, ep, self.out.data_ptr(),
                                                       M * H * 2, err, native.stream_ptr()), "reduce_parts")
         native.check(native.lib().pb_advance_pos(pos_ptr, T, native.stream_ptr()), "advance_pos")
-        if prefetching:
-            torch.cuda.current_stream(self.device).wait_stream(self._l2_stream)
         self._last_residual, self._last_parts = cur, mlp_parts
         return self.out[:M]
 
