@@ -37,6 +37,7 @@ struct AttnParams {
   float scale_log2;
   int B, T, Hq, Hkv, page, max_pages, window, splits, pos_static, num_pages;
   int* split_counter;   // [m_tiles * B * Hkv] zero-initialised; non-null fuses the split-KV combine into this kernel
+  float* lse_out;       // optional [B*T*Hq]: log2-domain log-sum-exp of every query row (saved for the backward pass; splits == 1)
 };
 
 PB_DEVICE void cp_async16(uint32_t dst, const void* src, bool valid) {
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnParams p) {
 #pragma unroll
       for (int dn = 0; dn < D / 8; ++dn)
         *reinterpret_cast<uint32_t*>(dst + dn * 8) = pack_bf16(o[dn][hr * 2] * inv, o[dn][hr * 2 + 1] * inv);
+      if (p.lse_out != nullptr && (lane & 3) == 0) p.lse_out[rowid] = l_i[hr] > 0.f ? m_i[hr] + log2f(l_i[hr]) : -INFINITY;
     } else {
       const size_t R = static_cast<size_t>(p.B) * p.T * p.Hq;
       float* dst = p.partial_o + (static_cast<size_t>(split) * R + rowid) * D + 2 * (lane & 3);
@@ -355,6 +357,7 @@ static int launch_attn(const PbAttnArgs* a, cudaStream_t s) {
   p.partial_lse = static_cast<float*>(a->partial_lse);
   p.alibi = static_cast<const float*>(a->alibi_slopes);
   p.split_counter = static_cast<int*>(a->split_counter);
+  p.lse_out = static_cast<float*>(a->lse_out);
   p.scale_log2 = a->scale * 1.4426950408889634f;
   p.B = a->B; p.T = a->T; p.Hq = a->Hq; p.Hkv = a->Hkv; p.page = a->page; p.max_pages = a->max_pages;
   p.num_pages = a->num_pages > 0 ? a->num_pages : 0x7fffffff;

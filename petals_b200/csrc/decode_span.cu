@@ -97,7 +97,14 @@ struct Params {
   Geom g_qkv, g_o, g_gu, g_down;
   int n_stages;
   int vin_elems;  // bf16 elements of the activation vector buffer
+  unsigned long long* timing;  // optional [n_layers][24] %globaltimer stamps of CTA 0 (consumer slots 0-12, producer slots 16-20)
 };
+
+// Diagnostics (PETALS_B200_SPAN_DEBUG): bit 0 = treat every polled unit as ready, bit 1 = skip the math. Results are garbage; the
+// two switches separate the cost of streaming, of computing and of waiting (tools/span_probe.py).
+__constant__ int c_debug = 0;
+#define SPAN_STAMP(slot) do { if (p.timing != nullptr && bid == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x == 0 || threadIdx.x == kConsumerThreads)) \
+    p.timing[static_cast<size_t>(l) * 24 + (slot)] = globaltimer_ns(); } while (0)
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------
 PB_DEVICE float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -119,6 +126,7 @@ PB_DEVICE void bulk_load_hint(void* smem_dst, const void* gsrc, uint32_t bytes, 
 // Spin bookkeeping shared by every poll loop: a wall-clock watchdog that raises the error flag instead of hanging the GPU, and a
 // fast exit once ANY thread has raised it (a broken step must drain in milliseconds, not one time-out per unit).
 PB_DEVICE bool give_up(unsigned spins, unsigned long long& t0, int* error_flag) {
+  if (c_debug & 1) return true;
   if ((spins & 1023u) != 0) return false;
   if (error_flag != nullptr && *reinterpret_cast<volatile int*>(error_flag) != 0) return true;
   const unsigned long long now = globaltimer_ns();
@@ -231,7 +239,7 @@ PB_DEVICE void consume_proj(const Params& p, const Ring& ring, Cursor& cur, cons
       const __nv_bfloat16* st = reinterpret_cast<const __nv_bfloat16*>(ring.stage(cur.idx));
       for (int ps = 0; ps < passes; ++ps) {
         const int row = ps * rows_per_pass + warp / wpr, seg = warp % wpr;
-        if (row < rows) {
+        if (row < rows && !(c_debug & 2)) {
           const __nv_bfloat16* wrow = st + static_cast<size_t>(row) * g.kc + seg * kseg;
           const __nv_bfloat16* xrow = vin + static_cast<size_t>(c) * g.kc + seg * kseg;
           float acc0 = 0.f, acc1 = 0.f;
@@ -246,6 +254,8 @@ PB_DEVICE void consume_proj(const Params& p, const Ring& ring, Cursor& cur, cons
           }
           const float s = warp_sum(acc0 + acc1);
           if (lane == 0) part[(c * kMaxGroupRows + row) * kConsumerWarps + seg] = s;
+        } else if (row < rows && lane == 0) {
+          part[(c * kMaxGroupRows + row) * kConsumerWarps + seg] = 0.f;
         }
       }
       consumer_sync();  // every warp is done with the stage; partial sums are visible
@@ -441,6 +451,7 @@ PB_DEVICE void consume_attention(const Params& p, const Ring& ring, Cursor& cur,
       consumer_sync();
     }
     // ---- scores: thread -> key = tid % 64, heads g = tid / 64 + 4 j ----
+    if (c_debug & 2) { consumer_sync(); if (tid == 0) mbar_arrive(&ring.empty[cur.idx]); cur.advance(ring.n); continue; }
     const int key = tid & (kPage - 1);
     const int nchunk16 = D >> 3;  // 16-byte chunks per row
     for (int g = tid >> 6; g < G; g += kConsumerThreads / kPage) {
@@ -580,11 +591,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
       const uint64_t pol = policy_evict_first();
       for (int l = 0; l < p.n_layers; ++l) {
         const Layer& L = p.layers[l];
-        produce_proj(p, ring, cur, p.g_qkv, L.wqkv, nullptr, bid, grid, pol);
-        produce_kv(p, ring, cur, L, pos, bid, grid);
-        produce_proj(p, ring, cur, p.g_o, L.wo, nullptr, bid, grid, pol);
-        produce_proj(p, ring, cur, p.g_gu, L.wgate, L.wup, bid, grid, pol);
-        produce_proj(p, ring, cur, p.g_down, L.wdown, nullptr, bid, grid, pol);
+        produce_proj(p, ring, cur, p.g_qkv, L.wqkv, nullptr, bid, grid, pol);   SPAN_STAMP(16);
+        produce_kv(p, ring, cur, L, pos, bid, grid);                             SPAN_STAMP(17);
+        produce_proj(p, ring, cur, p.g_o, L.wo, nullptr, bid, grid, pol);        SPAN_STAMP(18);
+        produce_proj(p, ring, cur, p.g_gu, L.wgate, L.wup, bid, grid, pol);      SPAN_STAMP(19);
+        produce_proj(p, ring, cur, p.g_down, L.wdown, nullptr, bid, grid, pol);  SPAN_STAMP(20);
       }
     }
     return;
@@ -611,26 +622,27 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
     const Layer& L = p.layers[l];
     const uint32_t tg = tag0 + static_cast<uint32_t>(l) * T_PER_LAYER;
     // ---- P1: norm + QKV ----
-    rmsnorm_inplace(vin, L.ln1, p.H, p.eps, red);
-    consume_proj<0>(p, ring, cur, p.g_qkv, vin, part, nullptr, p.qkv_ll, tg + T_QKV, bid, grid);
+    SPAN_STAMP(0);
+    rmsnorm_inplace(vin, L.ln1, p.H, p.eps, red);                                                   SPAN_STAMP(1);
+    consume_proj<0>(p, ring, cur, p.g_qkv, vin, part, nullptr, p.qkv_ll, tg + T_QKV, bid, grid);    SPAN_STAMP(2);
     // ---- P2: attention of the new token ----
-    consume_attention(p, ring, cur, L, pos, vin, scr, tg + T_QKV, tg + T_ATTP, bid, grid);
-    combine_heads(p, pos, tg + T_ATTP, tg + T_ATTN, bid, grid);
+    consume_attention(p, ring, cur, L, pos, vin, scr, tg + T_QKV, tg + T_ATTP, bid, grid);         SPAN_STAMP(3);
+    combine_heads(p, pos, tg + T_ATTP, tg + T_ATTN, bid, grid);                                     SPAN_STAMP(4);
     // ---- P3: O-projection, partials pushed to every rank ----
     consumer_sync();
     gather_ll(p.attn_ll, vin, p.Hq * p.D, tg + T_ATTN, p.error_flag);
-    consumer_sync();
-    consume_proj<1>(p, ring, cur, p.g_o, vin, part, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid);
+    consumer_sync();                                                                                 SPAN_STAMP(5);
+    consume_proj<1>(p, ring, cur, p.g_o, vin, part, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid); SPAN_STAMP(6);
     // ---- all-reduce tail + norm + gate/up ----
-    reduce_slice(p, p.oproj_in, res, p0, p1, tg + T_OPROJ, tg + T_X1, p.x_ll, nullptr);
+    reduce_slice(p, p.oproj_in, res, p0, p1, tg + T_OPROJ, tg + T_X1, p.x_ll, nullptr);            SPAN_STAMP(7);
     gather_ll(p.x_ll, vin, p.H, tg + T_X1, p.error_flag);
     consumer_sync();
-    rmsnorm_inplace(vin, L.ln2, p.H, p.eps, red);
-    consume_proj<2>(p, ring, cur, p.g_gu, vin, part, nullptr, p.act_ll, tg + T_ACT, bid, grid);
+    rmsnorm_inplace(vin, L.ln2, p.H, p.eps, red);                                                   SPAN_STAMP(8);
+    consume_proj<2>(p, ring, cur, p.g_gu, vin, part, nullptr, p.act_ll, tg + T_ACT, bid, grid);    SPAN_STAMP(9);
     // ---- P5: down projection, partials pushed to every rank ----
     gather_ll(p.act_ll, vin, p.I, tg + T_ACT, p.error_flag);
-    consumer_sync();
-    consume_proj<1>(p, ring, cur, p.g_down, vin, part, p.mlp_push, nullptr, tg + T_MLP, bid, grid);
+    consumer_sync();                                                                                 SPAN_STAMP(10);
+    consume_proj<1>(p, ring, cur, p.g_down, vin, part, p.mlp_push, nullptr, tg + T_MLP, bid, grid); SPAN_STAMP(11);
     // ---- all-reduce tail: next block's input, or the span output ----
     const bool last = (l + 1 == p.n_layers);
     reduce_slice(p, p.mlp_in, res, p0, p1, tg + T_MLP, tg + T_X2, p.x_ll, last ? p.x_out : nullptr);
@@ -638,6 +650,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
       gather_ll(p.x_ll, vin, p.H, tg + T_X2, p.error_flag);
       consumer_sync();
     }
+    SPAN_STAMP(12);
   }
 }
 
@@ -719,6 +732,12 @@ extern "C" int pb_decode_span(const PbDecodeSpanArgs* a, void* stream) {
   const int smem = pb_decode_span_smem(a, &ns, &vin);
   if (smem < 0) { pb_set_error("decode_span: activation vector does not fit beside the weight ring"); return PB_ERR_UNSUPPORTED; }
   p.n_stages = ns; p.vin_elems = vin;
+  p.timing = static_cast<unsigned long long*>(a->timing);
+  {
+    static int cur_debug = 0;
+    static const int env_debug = [] { const char* e = getenv("PETALS_B200_SPAN_DEBUG"); return e ? atoi(e) : 0; }();
+    if (env_debug != cur_debug) { cudaMemcpyToSymbol(c_debug, &env_debug, sizeof(int)); cur_debug = env_debug; }
+  }
   if (a->prepare_only) {  // set the kernel attribute outside any stream capture / before the first timed launch
     if (cudaFuncSetAttribute(decode_span_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) return pb_check_launch("decode_span attr");
     return PB_OK;

@@ -103,6 +103,7 @@ typedef struct {
   const void* epoch; void* error_flag;
   int num_sms;
   int prepare_only;        // 1: validate the shapes and set the kernel's shared-memory attribute, launch nothing
+  void* timing;            // optional uint64 [n_layers][24]: %globaltimer stamps of CTA 0 at every phase boundary (diagnostics)
 } PbDecodeSpanArgs;
 int pb_decode_span(const PbDecodeSpanArgs* a, void* stream);
 int pb_decode_span_smem(const PbDecodeSpanArgs* a, int* n_stages, int* vin_elems);
@@ -152,15 +153,34 @@ typedef struct {
   int num_pages;          // pages in k_pool / v_pool (bounds the TMA tensor map of the tcgen05 path)
   int impl;               // 0 auto, 1 mma.sync kernel, 2 tcgen05 kernel
   void* split_counter;    // int32 [m_tiles * B * Hkv], zeroed once: fuses the split-KV combine into the attention kernel
+  void* lse_out;          // optional fp32 [B*T*Hq]: log2-domain log-sum-exp per query row (training forward; mma.sync kernel, splits == 1)
 } PbAttnArgs;
 int pb_attention(const PbAttnArgs* a, void* stream);
 
-// dense causal attention for the no-cache training path (forward + backward)
+// ---- backward of the causal attention (attention_bwd.cu): activations only, frozen weights -------------------------------
 typedef struct {
-  const void* q; const void* k; const void* v;   // [B, T, H*, D] token-major
-  void* out; void* lse;                           // lse fp32 [B, Hq, T]
-  const void* alibi_slopes; float scale; int B, T, Hq, Hkv, D, window;
-} PbAttnDenseArgs;
+  const void* q;            // [B*T, Hq*D] rotated queries (what the forward consumed)
+  const void* k_pool; const void* v_pool; const void* block_table;   // the keys/values the forward attended to (paged, PAGE = 64)
+  const void* out;          // [B*T, Hq*D] forward output
+  const void* d_out;        // [B*T, Hq*D] gradient w.r.t. the output
+  const void* lse;          // fp32 [B*T*Hq] from the forward (log2 domain)
+  void* delta;              // fp32 [B*T*Hq] scratch: rowsum(d_out * out)
+  void* dq;                 // [B*T, Hq*D]
+  void* dk; void* dv;       // [B*T, Hkv*D] token-major dense gradients of the (rotated) keys / values
+  float scale;
+  int B, T, Hq, Hkv, D, max_pages, num_pages;
+} PbAttnBwdArgs;
+int pb_attention_bwd(const PbAttnBwdArgs* a, void* stream);
+
+// ---- element-wise / row-wise pieces of the block backward (train_kernels.cu) ---------------------------------------------
+// dx = [d_res +] rmsnorm_backward(dy, x, w): rows x H, fp32 math. d_res may alias dx_out.
+int pb_rmsnorm_bwd(const void* dy, const void* x, const void* w, const void* d_res, void* dx_out, int rows, int H, float eps, void* stream);
+// SwiGLU backward in place: g <- d_act * u * silu'(g), u <- d_act * silu(g)  (g, u: the bf16 projections saved by the forward)
+int pb_swiglu_bwd(const void* d_act, void* g, void* u, long n, void* stream);
+// dqkv[M, (Hq+2Hkv) D] = [R^T dq | R^T dk | dv]: the gradients of the rotated queries / keys are rotated back (transposed RoPE,
+// position t = row % T) and written next to dv in the fused projection's column layout, ready for the dgrad GEMM.
+int pb_qkv_grad_merge(const void* dq, const void* dk, const void* dv, const void* cos, const void* sin, void* dqkv, int M, int T, int Hq, int Hkv,
+                      int D, int max_pos, void* stream);
 
 // ---- sparse MoE decode (moe.cu) ------------------------------------------------------------------------------
 int pb_moe_router(const void* h, const void* norm_w, const void* router, void* xn_out, void* topi, void* topw, int M, int H, int E,

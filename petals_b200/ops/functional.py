@@ -448,17 +448,70 @@ def paged_attention(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor,
                     pos_ptr: Optional[int], out: torch.Tensor, *, B: int, T: int, Hq: int, Hkv: int, D: int,
                     scale: float, splits: int = 1, partial_o: Optional[torch.Tensor] = None,
                     partial_lse: Optional[torch.Tensor] = None, alibi_slopes: Optional[torch.Tensor] = None,
-                    window: int = 0, pos_static: int = 0, impl: int = 0, split_counter: Optional[torch.Tensor] = None) -> torch.Tensor:
+                    window: int = 0, pos_static: int = 0, impl: int = 0, split_counter: Optional[torch.Tensor] = None,
+                    lse_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Flash attention over the paged cache. ``impl``: 0 = auto (tcgen05 kernel for prefill-sized tiles, split-KV mma.sync kernel for
-    decode), 1 / 2 force the mma.sync / tcgen05 kernel."""
+    decode), 1 / 2 force the mma.sync / tcgen05 kernel. ``lse_out`` (fp32 [B*T*Hq], training forward): the log2-domain
+    log-sum-exp of every query row, written by the mma.sync kernel (forces ``impl = 1``, needs ``splits == 1``)."""
+    if lse_out is not None:
+        if splits != 1:
+            raise ValueError("lse_out needs splits == 1")
+        impl = 1
     a = AttnArgs()
     a.q, a.k_pool, a.v_pool, a.block_table, a.pos_ptr = ptr(q), ptr(k_pool), ptr(v_pool), ptr(block_table), pos_ptr
     a.out, a.partial_o, a.partial_lse, a.alibi_slopes = ptr(out), ptr(partial_o), ptr(partial_lse), ptr(alibi_slopes)
     a.scale = scale
     a.B, a.T, a.Hq, a.Hkv, a.D, a.page = B, T, Hq, Hkv, D, PAGE
     a.max_pages, a.window, a.splits, a.pos_static = block_table.shape[1], window, splits, pos_static
-    a.num_pages, a.impl, a.split_counter = k_pool.shape[0], impl, ptr(split_counter)
+    a.num_pages, a.impl, a.split_counter, a.lse_out = k_pool.shape[0], impl, ptr(split_counter), ptr(lse_out)
     check(native.lib().pb_attention(C.byref(a), stream_ptr()), "attention", 2 if (splits > 1 and split_counter is None) else 1)
+    return out
+
+
+def attention_bwd(q: torch.Tensor, k_pool: torch.Tensor, v_pool: torch.Tensor, block_table: torch.Tensor, out: torch.Tensor, d_out: torch.Tensor,
+                  lse: torch.Tensor, *, B: int, T: int, Hq: int, Hkv: int, D: int, scale: float, dq: Optional[torch.Tensor] = None,
+                  dk: Optional[torch.Tensor] = None, dv: Optional[torch.Tensor] = None, delta: Optional[torch.Tensor] = None):
+    """Backward of the causal attention of a cache-less forward (positions 0..T-1 per sequence): returns (dq [M, Hq*D],
+    dk [M, Hkv*D], dv [M, Hkv*D]) given the rotated queries, the paged keys/values, the forward output and its ``lse_out``."""
+    from petals_b200.ops.native import AttnBwdArgs
+
+    M = B * T
+    dev = q.device
+    dq = torch.empty(M, Hq * D, dtype=torch.bfloat16, device=dev) if dq is None else dq
+    dk = torch.empty(M, Hkv * D, dtype=torch.bfloat16, device=dev) if dk is None else dk
+    dv = torch.empty(M, Hkv * D, dtype=torch.bfloat16, device=dev) if dv is None else dv
+    delta = torch.empty(M * Hq, dtype=torch.float32, device=dev) if delta is None else delta
+    a = AttnBwdArgs()
+    a.q, a.k_pool, a.v_pool, a.block_table = ptr(_bf16c(q, "q")), ptr(k_pool), ptr(v_pool), ptr(block_table)
+    a.out, a.d_out, a.lse, a.delta = ptr(_bf16c(out, "out")), ptr(_bf16c(d_out, "d_out")), ptr(lse), ptr(delta)
+    a.dq, a.dk, a.dv, a.scale = ptr(dq), ptr(dk), ptr(dv), scale
+    a.B, a.T, a.Hq, a.Hkv, a.D, a.max_pages, a.num_pages = B, T, Hq, Hkv, D, block_table.shape[1], k_pool.shape[0]
+    check(native.lib().pb_attention_bwd(C.byref(a), stream_ptr()), "attention_bwd", 3)
+    return dq, dk, dv
+
+
+def rmsnorm_bwd(dy: torch.Tensor, x: torch.Tensor, weight: torch.Tensor, eps: float, d_res: Optional[torch.Tensor] = None,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``d_res + d/dx [rmsnorm(x) * weight] . dy`` for rows [M, H] (``d_res``: gradient arriving over the residual connection)."""
+    M, H = x.shape
+    out = torch.empty_like(x) if out is None else out
+    check(native.lib().pb_rmsnorm_bwd(ptr(_bf16c(dy, "dy")), ptr(_bf16c(x, "x")), ptr(_bf16c(weight, "weight")), ptr(_bf16c(d_res, "d_res")),
+                                      ptr(out), M, H, eps, stream_ptr()), "rmsnorm_bwd")
+    return out
+
+
+def swiglu_bwd_(d_act: torch.Tensor, g: torch.Tensor, u: torch.Tensor) -> None:
+    """In place: ``g <- d(act)/d(g) * d_act``, ``u <- d(act)/d(u) * d_act`` for ``act = silu(g) * u``."""
+    check(native.lib().pb_swiglu_bwd(ptr(_bf16c(d_act, "d_act")), ptr(_bf16c(g, "g")), ptr(_bf16c(u, "u")), g.numel(), stream_ptr()), "swiglu_bwd")
+
+
+def qkv_grad_merge(dq: torch.Tensor, dk: torch.Tensor, dv: torch.Tensor, cos, sin, *, T: int, Hq: int, Hkv: int, D: int,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """[R^T dq | R^T dk | dv] in the fused QKV projection's column layout (the backward of RoPE + the q/k/v split)."""
+    M = dq.shape[0]
+    out = torch.empty(M, (Hq + 2 * Hkv) * D, dtype=torch.bfloat16, device=dq.device) if out is None else out
+    check(native.lib().pb_qkv_grad_merge(ptr(dq), ptr(dk), ptr(dv), ptr(cos), ptr(sin), ptr(out), M, T, Hq, Hkv, D,
+                                         cos.shape[0] if cos is not None else 0, stream_ptr()), "qkv_grad_merge")
     return out
 
 
@@ -584,6 +637,7 @@ class DecodeSpanPlan:
         a.oproj_in, a.mlp_in = self.oproj_in, self.mlp_in
         a.epoch, a.error_flag = self.epoch.data_ptr(), self.err.data_ptr()
         a.num_sms = native.sm_count(self.device.index)
+        a.timing = ptr(getattr(self, "timing", None))
         return a
 
 

@@ -95,7 +95,7 @@ class DecodeSpanArgs(C.Structure):
         ("R", C.c_int), ("rank", C.c_int),
         ("oproj_push", C.c_void_p * PB_MAX_PEERS), ("mlp_push", C.c_void_p * PB_MAX_PEERS),
         ("oproj_in", C.c_void_p), ("mlp_in", C.c_void_p),
-        ("epoch", C.c_void_p), ("error_flag", C.c_void_p), ("num_sms", C.c_int), ("prepare_only", C.c_int),
+        ("epoch", C.c_void_p), ("error_flag", C.c_void_p), ("num_sms", C.c_int), ("prepare_only", C.c_int), ("timing", C.c_void_p),
     ]
 
 
@@ -117,12 +117,27 @@ class AttnArgs(C.Structure):
         ("pos_ptr", C.c_void_p), ("out", C.c_void_p), ("partial_o", C.c_void_p), ("partial_lse", C.c_void_p),
         ("alibi_slopes", C.c_void_p), ("scale", C.c_float),
         ("B", C.c_int), ("T", C.c_int), ("Hq", C.c_int), ("Hkv", C.c_int), ("D", C.c_int), ("page", C.c_int),
-        ("max_pages", C.c_int), ("window", C.c_int), ("splits", C.c_int), ("pos_static", C.c_int), ("num_pages", C.c_int), ("impl", C.c_int), ("split_counter", C.c_void_p),
+        ("max_pages", C.c_int), ("window", C.c_int), ("splits", C.c_int), ("pos_static", C.c_int), ("num_pages", C.c_int), ("impl", C.c_int), ("split_counter", C.c_void_p), ("lse_out", C.c_void_p),
+    ]
+
+
+class AttnBwdArgs(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("k_pool", C.c_void_p), ("v_pool", C.c_void_p), ("block_table", C.c_void_p),
+        ("out", C.c_void_p), ("d_out", C.c_void_p), ("lse", C.c_void_p), ("delta", C.c_void_p),
+        ("dq", C.c_void_p), ("dk", C.c_void_p), ("dv", C.c_void_p), ("scale", C.c_float),
+        ("B", C.c_int), ("T", C.c_int), ("Hq", C.c_int), ("Hkv", C.c_int), ("D", C.c_int), ("max_pages", C.c_int), ("num_pages", C.c_int),
     ]
 
 
 def _declare(lib: C.CDLL) -> None:
     vp, ci, cl, cf = C.c_void_p, C.c_int, C.c_long, C.c_float
+    lib.pb_attention_bwd.argtypes = [C.POINTER(AttnBwdArgs), vp]
+    lib.pb_rmsnorm_bwd.argtypes = [vp, vp, vp, vp, vp, ci, ci, cf, vp]
+    lib.pb_swiglu_bwd.argtypes = [vp, vp, vp, cl, vp]
+    lib.pb_qkv_grad_merge.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, ci, ci, vp]
+    for name in ("pb_attention_bwd", "pb_rmsnorm_bwd", "pb_swiglu_bwd", "pb_qkv_grad_merge"):
+        getattr(lib, name).restype = ci
     lib.pb_linear_decode.argtypes = [C.POINTER(LinearDecodeArgs), vp]
     lib.pb_gemm_bf16.argtypes = [C.POINTER(GemmArgs), vp]
     lib.pb_gemv_chain.argtypes = [C.POINTER(C.POINTER(LinearDecodeArgs)), ci, C.POINTER(C.c_int), vp, vp]

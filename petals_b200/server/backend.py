@@ -11,6 +11,8 @@ w.r.t. the span input and the deep prompts; weights are frozen (reference backen
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -123,6 +125,12 @@ class Stage:
             return self.engine.backward(hidden.to(self.device, self.dtype), grad_out.to(self.device, self.dtype), ps, (lo, hi))
         hidden, grad = hidden.to(self.device, self.dtype), grad_out.to(self.device, self.dtype)
         prompts = [None] * (hi - lo) if prompts is None else [None if is_dummy(p) else p.to(self.device, self.dtype).contiguous() for p in prompts]
+        if (self.engine is not None and self._lora_free() and getattr(self.engine, "backward_supported", lambda: False)()
+                and os.environ.get("PETALS_B200_ENGINE_BACKWARD", "1") != "0"):
+            # the whole backward on the kernels: dgrad GEMMs (tcgen05, untransposed weights), flash-attention backward, norm / SwiGLU /
+            # RoPE backward kernels (server/stage_engine.py:backward)
+            with torch.no_grad():
+                return self.engine.backward(hidden, grad, prompts, (lo, hi))
         # pass 1 (no grad): remember every block's input
         inputs = []
         h = hidden

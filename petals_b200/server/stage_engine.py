@@ -561,6 +561,116 @@ class StageEngine:
         self._active = None  # the static table/pos were not touched, but be conservative
         return out
 
+    # ---- backward (rpc_backward: gradients w.r.t. activations and deep prompts; the blocks are frozen) -----------------------
+    def backward_supported(self) -> bool:
+        """Block layouts whose backward runs on the kernels end to end (Llama-style: RMSNorm, SwiGLU, rotary GQA, no biases).
+        Other families are differentiated by autograd over the oracle block (server/backend.py)."""
+        s = self.spec
+        return (self.fp8 is None and s.norm == "rms" and s.mlp == "swiglu" and s.rotary and not s.qkv_interleaved and not s.parallel_attn
+                and not s.post_ln_residual and not s.alibi and not s.sliding_window and not (s.qkv_bias or s.out_bias or s.mlp_bias)
+                and s.head_dim in (64, 128) and s.hidden_size % 64 == 0 and s.intermediate_size % 64 == 0 and s.qkv_dim % 64 == 0
+                and all(b._p("bqkv") is None for b in self.blocks))
+
+    def _forward_saving(self, x: torch.Tensor, slot: int, nb: int, T: int, table: torch.Tensor, zero_ptr: int) -> Tuple[torch.Tensor, dict]:
+        """One block forward on the kernels that keeps what its backward needs: the block input, the rotated queries, this block's
+        K/V pages, the attention output with its log-sum-exp, the post-attention residual and the two MLP projections."""
+        s, w = self.spec, self.blocks[slot]
+        M, dev, bf = nb * T, self.device, torch.bfloat16
+        pages = table.numel()
+        sv = dict(x=x, q=torch.empty(M, s.num_heads * s.head_dim, dtype=bf, device=dev),
+                  k_pool=torch.empty(pages, s.num_kv_heads, PAGE, s.head_dim, dtype=bf, device=dev),
+                  v_pool=torch.empty(pages, s.num_kv_heads, PAGE, s.head_dim, dtype=bf, device=dev),
+                  attn=torch.empty(M, s.num_heads * s.head_dim, dtype=bf, device=dev), lse=torch.empty(M * s.num_heads, dtype=torch.float32, device=dev))
+        xn = Fn.norm(x, w.ln1_w, None, kind=self.norm_kind, eps=s.norm_eps, out=self._buf("bw_xn_p", M, s.hidden_size))
+        qkv = Fn.gemm(xn, w.wqkv, out=self._buf("bw_qkv_p", M, s.qkv_dim))
+        Fn.rope_kv_append(qkv, sv["q"], sv["k_pool"], sv["v_pool"], table, zero_ptr, self.cos, self.sin, B=nb, T=T, Hq=s.num_heads, Hkv=s.num_kv_heads,
+                          D=s.head_dim, error_flag=self.err_flag.data_ptr())
+        Fn.paged_attention(sv["q"], sv["k_pool"], sv["v_pool"], table, zero_ptr, sv["attn"], B=nb, T=T, Hq=s.num_heads, Hkv=s.num_kv_heads, D=s.head_dim,
+                           scale=s.attn_scale, splits=1, lse_out=sv["lse"])
+        sv["h1"] = Fn.gemm(sv["attn"], w.wo, residual=x)
+        xn2 = Fn.norm(sv["h1"], w.ln2_w, None, kind=self.norm_kind, eps=s.norm_eps, out=xn)
+        sv["g"], sv["u"] = Fn.gemm(xn2, w.w_gate), Fn.gemm(xn2, w.w_up)
+        act = Fn.swiglu(sv["g"], sv["u"], out=self._buf("bw_act_p", M, s.intermediate_size))
+        return Fn.gemm(act, w.w_down, residual=sv["h1"]), sv
+
+    def _backward_block(self, dy: torch.Tensor, sv: dict, slot: int, nb: int, T: int, table: torch.Tensor) -> torch.Tensor:
+        """dL/d(block input) from dL/d(block output): dgrad GEMMs on the untransposed weights (tcgen05, MN-major B), SwiGLU / RMSNorm /
+        RoPE backward kernels, flash-attention backward."""
+        s, w = self.spec, self.blocks[slot]
+        M = nb * T
+        d_act = Fn.gemm(dy, w.w_down, b_mn_major=True, out=self._buf("bw_act_p", M, s.intermediate_size))
+        Fn.swiglu_bwd_(d_act, sv["g"], sv["u"])  # g <- d gate, u <- d up
+        d_xn2 = Fn.gemm(sv["g"], w.w_gate, b_mn_major=True, out=self._buf("bw_xn_p", M, s.hidden_size))
+        d_xn2 = Fn.gemm(sv["u"], w.w_up, b_mn_major=True, residual=d_xn2, out=d_xn2)
+        d_h1 = Fn.rmsnorm_bwd(d_xn2, sv["h1"], w.ln2_w, s.norm_eps, d_res=dy)
+        d_attn = Fn.gemm(d_h1, w.wo, b_mn_major=True)
+        dq, dk, dv = Fn.attention_bwd(sv["q"], sv["k_pool"], sv["v_pool"], table, sv["attn"], d_attn, sv["lse"], B=nb, T=T, Hq=s.num_heads,
+                                      Hkv=s.num_kv_heads, D=s.head_dim, scale=s.attn_scale)
+        d_qkv = Fn.qkv_grad_merge(dq, dk, dv, self.cos, self.sin, T=T, Hq=s.num_heads, Hkv=s.num_kv_heads, D=s.head_dim,
+                                  out=self._buf("bw_qkv_p", M, s.qkv_dim))
+        d_xn1 = Fn.gemm(d_qkv, w.wqkv, b_mn_major=True, out=d_xn2)
+        return Fn.rmsnorm_bwd(d_xn1, sv["x"], w.ln1_w, s.norm_eps, d_res=d_h1)
+
+    def backward(self, hidden: torch.Tensor, grad_out: torch.Tensor, prompts: Optional[Sequence[Optional[torch.Tensor]]] = None,
+                 block_range: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
+        """``rpc_backward`` of blocks [lo, hi) on the kernels (reference: src/petals/server/block_functions.py:84-141). One forward that
+        saves the per-block intermediates, then the blocks' backward in reverse order — or, when the saved tensors of the whole
+        span would not fit the budget, the reference's schedule: remember the block inputs, recompute one block at a time."""
+        lo, hi = block_range or (0, self.n_blocks)
+        B, T, H = hidden.shape
+        grad_prompts: List[Optional[torch.Tensor]] = [None] * (hi - lo)
+        if B == 0 or T == 0:
+            return grad_out, grad_prompts
+        hidden, grad_out = hidden.to(self.dtype), grad_out.to(self.dtype)
+        s = self.spec
+        pages_per_seq = (T + PAGE - 1) // PAGE
+        per_token = 2 * (3 * s.hidden_size + 2 * s.num_heads * s.head_dim + 2 * s.num_kv_heads * s.head_dim + 2 * s.intermediate_size)
+        budget = float(os.environ.get("PETALS_B200_BWD_SAVE_GB", "16")) * 2 ** 30
+        if pages_per_seq > self._scratch_pages:
+            raise ValueError(f"sequence of {T} tokens exceeds max_chunk_tokens={self.max_chunk_tokens} for a backward pass")
+        rows_per_group = max(1, min(B, self._scratch_pages // pages_per_seq))
+        grad_in = torch.empty_like(hidden)
+        zero = torch.zeros(1, dtype=torch.int32, device=self.device)
+        for b0 in range(0, B, rows_per_group):
+            b1 = min(B, b0 + rows_per_group)
+            nb, M = b1 - b0, (b1 - b0) * T
+            table = torch.arange(nb * pages_per_seq, dtype=torch.int32, device=self.device).view(nb, pages_per_seq).contiguous()
+            keep_all = per_token * M * (hi - lo) <= budget
+            pr = [None if (prompts is None or prompts[i] is None or is_dummy(prompts[i])) else (prompts[i] if prompts[i].shape[0] == 1 else prompts[i][b0:b1])
+                  for i in range(hi - lo)]
+            x = hidden[b0:b1].reshape(M, H).clone()
+            saves: List[object] = []
+            for slot in range(lo, hi):
+                if pr[slot - lo] is not None:
+                    Fn.add_prompts(x.view(nb, T, H), pr[slot - lo].to(self.dtype).contiguous())
+                if keep_all:
+                    x, sv = self._forward_saving(x, slot, nb, T, table, zero.data_ptr())
+                    saves.append(sv)
+                else:
+                    saves.append(x)  # the block input (prompt included); everything else is recomputed when its turn comes
+                    if slot + 1 < hi:
+                        x = self._run_span(x.clone(), nb, T, slot, slot + 1, table, zero.data_ptr(),
+                                           lambda _slot: (self._scratch_pool[0], self._scratch_pool[1]), None, False, 1).clone()
+            d = grad_out[b0:b1].reshape(M, H).contiguous()
+            for slot in reversed(range(lo, hi)):
+                sv = saves.pop()
+                if not keep_all:
+                    _, sv = self._forward_saving(sv, slot, nb, T, table, zero.data_ptr())
+                d = self._backward_block(d, sv, slot, nb, T, table)
+                p = pr[slot - lo]
+                if p is not None:
+                    gp = d.view(nb, T, H)[:, : p.shape[1]]
+                    gp = gp.sum(0, keepdim=True) if p.shape[0] == 1 else gp
+                    if p.shape[0] == 1:
+                        grad_prompts[slot - lo] = gp.clone() if grad_prompts[slot - lo] is None else grad_prompts[slot - lo] + gp
+                    else:
+                        if grad_prompts[slot - lo] is None:
+                            grad_prompts[slot - lo] = torch.zeros(B, p.shape[1], H, dtype=self.dtype, device=self.device)
+                        grad_prompts[slot - lo][b0:b1] = gp
+            grad_in[b0:b1] = d.view(nb, T, H)
+        self._active = None
+        return grad_in, grad_prompts
+
     def check_errors(self) -> None:
         code = int(self.err_flag.item())
         if code:

@@ -1,4 +1,6 @@
 """Stage engine (fused sm_100a kernels, paged KV, CUDA graphs) against the oracle blocks on the same weights."""
+import os
+
 import pytest
 import torch
 
@@ -78,19 +80,65 @@ def test_generate_rollback_and_beams(tmp_path):
         stage.shutdown()
 
 
-def test_backward_through_engine_stage(tmp_path):
-    path = write_config_only("llama-tiny", {}, str(tmp_path / "m"))
-    swarm = Swarm("t-bwd")
+def _fp32_reference_grads(stage, hidden, grad_out, prompts):
+    """fp32 PyTorch autograd over fp32 copies of the same (bf16-valued) weights: the oracle for `rpc_backward`."""
+    import copy
+
+    blocks = [copy.deepcopy(b).float() for b in stage.stage.blocks]
+    x = hidden.float().clone().requires_grad_(True)
+    ps = [p.float().clone().requires_grad_(True) for p in prompts]
+    h = x
+    for b, p in zip(blocks, ps):
+        h = torch.cat([h[:, : p.shape[1]] + p, h[:, p.shape[1]:]], dim=1)
+        h = b.forward_cached(h, None, None, 0)
+    grads = torch.autograd.grad(h, [x] + ps, grad_out.float())
+    return h.detach(), grads[0], list(grads[1:])
+
+
+@pytest.mark.parametrize("overrides,B,T", [
+    ({}, 2, 40),                                                        # GQA 8/2, D = 128
+    ({}, 3, 150),                                                       # several KV pages and query tiles, ragged last tile
+    (dict(num_attention_heads=16, num_key_value_heads=16), 2, 70),      # MHA, D = 64
+])
+def test_backward_through_engine_stage(overrides, B, T, tmp_path):
+    """`rpc_backward` on the kernels (flash-attention backward, norm / SwiGLU / RoPE backward, tcgen05 dgrad GEMMs): gradients w.r.t.
+    the inputs AND the deep prompts against fp32 PyTorch autograd over the same weights (reference: block_functions.py:84-141)."""
+    path = write_config_only("llama-tiny", overrides, str(tmp_path / "m"))
+    swarm = Swarm(f"t-bwd-{B}-{T}")
     stage = launch_random_stage(path, range(4), swarm, DEV)
     try:
+        st = stage.stage
+        assert st.engine is not None and st.engine.backward_supported()
+        H = st.spec.hidden_size
+        torch.manual_seed(3)
+        hidden = (torch.randn(B, T, H, device=DEV) * 0.7).to(torch.bfloat16)
+        grad_out = (torch.randn(B, T, H, device=DEV) * 0.1).to(torch.bfloat16)
+        prompts = [(torch.randn(1, 4, H, device=DEV) * 0.3).to(torch.bfloat16) for _ in range(4)]
+        out_ref, gx_ref, gp_ref = _fp32_reference_grads(stage, hidden, grad_out, prompts)
+        for save_gb in ("16", "0"):  # keep every block's intermediates / recompute block by block
+            os.environ["PETALS_B200_BWD_SAVE_GB"] = save_gb
+            gx, gps = st.backward(hidden, grad_out, prompts, 0, 4)
+            torch.cuda.synchronize()
+            st.engine.check_errors()
+            rel = lambda a, b: ((a.float() - b).norm() / b.norm()).item()
+            assert rel(gx, gx_ref) < 2e-2, ("grad_inputs", save_gb, rel(gx, gx_ref))
+            for i, (g, r) in enumerate(zip(gps, gp_ref)):
+                assert g is not None and g.shape == r.shape
+                assert rel(g, r) < 2e-2, ("grad_prompts", i, save_gb, rel(g, r))
+        os.environ.pop("PETALS_B200_BWD_SAVE_GB", None)
+        # end to end through the client: prompt-tuning gradients exist and match the autograd executor
         model = random_client_model(path, swarm, DEV, tuning_mode="deep_ptune", pre_seq_len=4)
         ids = torch.randint(0, 4000, (2, 16), device=DEV)
-        out = model(ids, labels=ids)
-        out.loss.backward()
-        g1 = model.model.prompt_embeddings.weight.grad
-        g2 = model.model.intermediate_prompt_embeddings.weight.grad
-        assert g1 is not None and torch.isfinite(g1).all() and g1.abs().sum() > 0
-        assert g2 is not None and torch.isfinite(g2).all() and g2.abs().sum() > 0
+        got = {}
+        for engine_bwd in ("1", "0"):
+            os.environ["PETALS_B200_ENGINE_BACKWARD"] = engine_bwd
+            model.zero_grad()
+            model(ids, labels=ids).loss.backward()
+            got[engine_bwd] = (model.model.prompt_embeddings.weight.grad.float().clone(), model.model.intermediate_prompt_embeddings.weight.grad.float().clone())
+        os.environ.pop("PETALS_B200_ENGINE_BACKWARD", None)
+        for a, b in zip(got["1"], got["0"]):
+            assert torch.isfinite(a).all() and a.abs().sum() > 0
+            assert ((a - b).norm() / b.norm()).item() < 5e-2
     finally:
         stage.shutdown()
 

@@ -574,3 +574,96 @@ def test_linear_decode_skinny_tensor_core_path(M):
             assert float(scratch.abs().sum().item()) == 0.0 and int(counters.abs().sum().item()) == 0
     finally:
         Fn._SKINNY["on"], Fn._SKINNY["force"] = prev
+
+
+# ---- backward kernels (csrc/attention_bwd.cu, csrc/train_kernels.cu) against fp32 PyTorch autograd ------------------------------------
+def _paged_from_dense(k, v):
+    """[B, T, Hkv, D] -> pools [B * pages, Hkv, 64, D] with block table arange."""
+    B, T, Hkv, D = k.shape
+    pages = (T + 63) // 64
+    kp = torch.zeros(B * pages, Hkv, 64, D, dtype=k.dtype, device=k.device)
+    vp = torch.zeros_like(kp)
+    for b in range(B):
+        for p in range(pages):
+            n = min(64, T - p * 64)
+            kp[b * pages + p, :, :n] = k[b, p * 64: p * 64 + n].transpose(0, 1)
+            vp[b * pages + p, :, :n] = v[b, p * 64: p * 64 + n].transpose(0, 1)
+    table = torch.arange(B * pages, dtype=torch.int32, device=k.device).view(B, pages).contiguous()
+    return kp, vp, table
+
+
+@pytest.mark.parametrize("B,T,Hq,Hkv,D", [(2, 40, 8, 2, 128), (1, 200, 4, 4, 64), (3, 130, 8, 1, 128), (1, 64, 6, 2, 128)])
+def test_attention_backward_matches_autograd(B, T, Hq, Hkv, D):
+    torch.manual_seed(5)
+    q = (torch.randn(B, T, Hq, D, device=DEV) * 0.8).to(torch.bfloat16)
+    k = (torch.randn(B, T, Hkv, D, device=DEV) * 0.8).to(torch.bfloat16)
+    v = (torch.randn(B, T, Hkv, D, device=DEV) * 0.8).to(torch.bfloat16)
+    d_out = (torch.randn(B, T, Hq, D, device=DEV) * 0.3).to(torch.bfloat16)
+    scale = D ** -0.5
+    # fp32 reference
+    qf, kf, vf = (t.float().clone().requires_grad_(True) for t in (q, k, v))
+    G = Hq // Hkv
+    kk = kf.repeat_interleave(G, dim=2)
+    vv = vf.repeat_interleave(G, dim=2)
+    s = torch.einsum("bthd,bshd->bhts", qf, kk) * scale
+    mask = torch.ones(T, T, dtype=torch.bool, device=DEV).tril()
+    s = s.masked_fill(~mask, float("-inf"))
+    o_ref = torch.einsum("bhts,bshd->bthd", s.softmax(-1), vv)
+    gq, gk, gv = torch.autograd.grad(o_ref, [qf, kf, vf], d_out.float())
+    # kernels: forward (saves lse), then backward
+    kp, vp, table = _paged_from_dense(k, v)
+    M = B * T
+    out = torch.empty(M, Hq * D, dtype=torch.bfloat16, device=DEV)
+    lse = torch.empty(M * Hq, dtype=torch.float32, device=DEV)
+    Fn.paged_attention(q.view(M, Hq * D), kp, vp, table, None, out, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=scale, lse_out=lse)
+    _close(out.view(B, T, Hq, D), o_ref.detach(), 2e-2, 2e-2, "attention forward (lse path)")
+    lse_ref = (torch.logsumexp(s.detach(), dim=-1) * 1.4426950408889634).permute(0, 2, 1).reshape(-1)  # [B, T, Hq], log2 domain
+    assert (lse - lse_ref).abs().max().item() < 2e-2
+    dq, dk, dv = Fn.attention_bwd(q.view(M, Hq * D), kp, vp, table, out, d_out.view(M, Hq * D).contiguous(), lse, B=B, T=T, Hq=Hq, Hkv=Hkv, D=D, scale=scale)
+    torch.cuda.synchronize()
+    for name, got, ref in (("dq", dq.view(B, T, Hq, D), gq), ("dk", dk.view(B, T, Hkv, D), gk), ("dv", dv.view(B, T, Hkv, D), gv)):
+        rel = ((got.float() - ref).norm() / ref.norm()).item()
+        assert rel < 2e-2, (name, rel)
+        _close(got, ref, 2e-2 * ref.abs().max().item(), 3e-2, name)
+
+
+@pytest.mark.parametrize("rows,H", [(37, 1024), (5, 4096), (3, 8192)])
+def test_rmsnorm_backward_matches_autograd(rows, H):
+    torch.manual_seed(6)
+    x = torch.randn(rows, H, device=DEV).to(torch.bfloat16)
+    w = (1 + 0.1 * torch.randn(H, device=DEV)).to(torch.bfloat16)
+    dy = torch.randn(rows, H, device=DEV).to(torch.bfloat16)
+    res = torch.randn(rows, H, device=DEV).to(torch.bfloat16)
+    xf = x.float().requires_grad_(True)
+    y = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + 1e-5) * w.float()
+    (g,) = torch.autograd.grad(y, xf, dy.float())
+    got = Fn.rmsnorm_bwd(dy, x, w, 1e-5, d_res=res)
+    _close(got, g + res.float(), 2e-2, 3e-2, "rmsnorm_bwd")
+
+
+def test_swiglu_and_rope_backward_match_autograd():
+    torch.manual_seed(7)
+    g = torch.randn(33, 2816, device=DEV).to(torch.bfloat16)
+    u = torch.randn(33, 2816, device=DEV).to(torch.bfloat16)
+    d = torch.randn(33, 2816, device=DEV).to(torch.bfloat16)
+    gf, uf = g.float().requires_grad_(True), u.float().requires_grad_(True)
+    rg, ru = torch.autograd.grad(torch.nn.functional.silu(gf) * uf, [gf, uf], d.float())
+    g2, u2 = g.clone(), u.clone()
+    Fn.swiglu_bwd_(d, g2, u2)
+    _close(g2, rg, 2e-2, 3e-2, "d gate")
+    _close(u2, ru, 2e-2, 3e-2, "d up")
+    # RoPE backward + merge: <R x, g> == <x, R^T g>
+    B, T, Hq, Hkv, D = 2, 9, 4, 2, 128
+    M = B * T
+    cos, sin = Fn.rope_tables(D, 64, 10000.0, None, device=DEV)
+    dq = torch.randn(M, Hq * D, device=DEV).to(torch.bfloat16)
+    dk = torch.randn(M, Hkv * D, device=DEV).to(torch.bfloat16)
+    dv = torch.randn(M, Hkv * D, device=DEV).to(torch.bfloat16)
+    merged = Fn.qkv_grad_merge(dq, dk, dv, cos, sin, T=T, Hq=Hq, Hkv=Hkv, D=D).float().view(B, T, Hq + 2 * Hkv, D)
+    xq = torch.randn(B, T, Hq, D, device=DEV, requires_grad=True)
+    pos = torch.arange(T, device=DEV)
+    c, s_ = torch.cat([cos[pos], cos[pos]], -1)[None, :, None, :], torch.cat([sin[pos], sin[pos]], -1)[None, :, None, :]
+    rot = lambda x: x * c + torch.cat([-x[..., D // 2:], x[..., : D // 2]], -1) * s_
+    (ref_q,) = torch.autograd.grad(rot(xq), xq, dq.float().view(B, T, Hq, D))
+    _close(merged[:, :, :Hq], ref_q, 2e-2, 3e-2, "rope^T dq")
+    _close(merged[:, :, Hq + Hkv:], dv.float().view(B, T, Hkv, D), 1e-2, 1e-2, "dv passthrough")
