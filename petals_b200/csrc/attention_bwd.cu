@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const Params p) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int hr = e >> 1, kvpos = kv0 + j * 8 + (e & 1);
-          const float pr = kvpos <= qpos[hr] ? exp2f(s[j][e] * p.scale_log2 - lse[hr]) : 0.f;
-          ds[e] = pr * (dp[j][e] - dl[hr]);
+          const bool ok = kvpos <= qpos[hr];  // select, never multiply: a masked key's page row may hold anything (0 * NaN = NaN)
+          ds[e] = ok ? exp2f(s[j][e] * p.scale_log2 - lse[hr]) * (dp[j][e] - dl[hr]) : 0.f;
         }
         dsa[j >> 1][(j & 1) * 2 + 0] = pack_bf16(ds[0], ds[1]);
         dsa[j >> 1][(j & 1) * 2 + 1] = pack_bf16(ds[2], ds[3]);
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkdv_kernel(const Params p) {
         const float l = s_lse[buf * BQ + col];
         const bool ok = kpos[hr] <= s_qpos[buf * BQ + col];
         pr[e] = ok ? exp2f(st[j][e] * p.scale_log2 - l) : 0.f;
-        ds[e] = pr[e] * (dpt[j][e] - s_dl[buf * BQ + col]);
+        ds[e] = ok ? pr[e] * (dpt[j][e] - s_dl[buf * BQ + col]) : 0.f;
       }
       pa[j >> 1][(j & 1) * 2 + 0] = pack_bf16(pr[0], pr[1]);
       pa[j >> 1][(j & 1) * 2 + 1] = pack_bf16(pr[2], pr[3]);

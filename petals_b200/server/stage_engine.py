@@ -578,8 +578,9 @@ class StageEngine:
         M, dev, bf = nb * T, self.device, torch.bfloat16
         pages = table.numel()
         sv = dict(x=x, q=torch.empty(M, s.num_heads * s.head_dim, dtype=bf, device=dev),
-                  k_pool=torch.empty(pages, s.num_kv_heads, PAGE, s.head_dim, dtype=bf, device=dev),
-                  v_pool=torch.empty(pages, s.num_kv_heads, PAGE, s.head_dim, dtype=bf, device=dev),
+                  # zero-filled: the tail of a sequence's last page is multiplied by exactly-zero probabilities in the tensor cores
+                  k_pool=torch.zeros(pages, s.num_kv_heads, PAGE, s.head_dim, dtype=bf, device=dev),
+                  v_pool=torch.zeros(pages, s.num_kv_heads, PAGE, s.head_dim, dtype=bf, device=dev),
                   attn=torch.empty(M, s.num_heads * s.head_dim, dtype=bf, device=dev), lse=torch.empty(M * s.num_heads, dtype=torch.float32, device=dev))
         xn = Fn.norm(x, w.ln1_w, None, kind=self.norm_kind, eps=s.norm_eps, out=self._buf("bw_xn_p", M, s.hidden_size))
         qkv = Fn.gemm(xn, w.wqkv, out=self._buf("bw_qkv_p", M, s.qkv_dim))
