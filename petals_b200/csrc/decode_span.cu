@@ -34,13 +34,13 @@ extern "C" int pb_check_launch(const char* what);
 namespace pb {
 namespace span {
 
-constexpr int kStageBytes = 32 * 1024;
-constexpr int kMaxStages = 6;
+constexpr int kStageBytes = 16 * 1024;   // one ring slot: one weight row (or R short rows, or one K chunk of a long row), or one K / V page
+constexpr int kMaxStages = 12;
 constexpr int kConsumerWarps = 8;
 constexpr int kConsumerThreads = kConsumerWarps * 32;
 constexpr int kThreads = kConsumerThreads + 32;
 constexpr int kMaxRanks = 8;
-constexpr int kMaxGroupRows = 16;
+constexpr int kMaxStageRows = 8;
 constexpr int kPage = 64;
 constexpr uint32_t kTagStride = 1024;  // >= T_PER_LAYER * max blocks per launch (127)
 
@@ -59,12 +59,14 @@ struct Layer {
   __nv_bfloat16* v_pool;
 };
 
-struct Geom {  // how one projection is cut into ring stages
-  int K;        // contraction length
-  int rows;     // weight rows per group (P4: 2 gate + 2 up)
-  int kc;       // K elements per stage
-  int nkc;      // stages per group
-  int ngroups;  // groups in the projection
+struct Geom {   // how one projection is cut into ring stages and warp tasks
+  int K;         // contraction length
+  int R;         // weight rows per stage (1, 2, 4 or 8; R > 1 only when the rows are contiguous and short)
+  int kc, nkc;   // K elements per stage, stages per row (nkc > 1 only with R == 1)
+  int S;         // stages per task
+  int outs;      // outputs per task (always even: outputs are published as bf16 pairs)
+  int ntasks;    // tasks in the projection; task t is dealt to CTA t % grid, and there to warp (t / grid) % 8
+  int dual;      // gate/up: a task streams `outs` gate rows and `outs` up rows
 };
 
 struct Params {
@@ -159,142 +161,155 @@ PB_DEVICE uint2 poll_ll2(const uint2* p, uint32_t tag, int* error_flag) {
 }
 
 struct Ring {
-  uint8_t* base;    // n stages of kStageBytes
-  uint64_t* full;   // [n_stages]
-  uint64_t* empty;  // [n_stages]
+  uint8_t* base;    // n slots of kStageBytes
+  uint64_t* full;   // [n]
+  uint64_t* empty;  // [n]
   int n;
-  PB_DEVICE uint8_t* stage(int i) const { return base + static_cast<size_t>(i) * kStageBytes; }
+  PB_DEVICE uint8_t* slot(uint32_t stage) const { return base + static_cast<size_t>(stage % n) * kStageBytes; }
+  PB_DEVICE uint64_t* full_bar(uint32_t stage) const { return &full[stage % n]; }
+  PB_DEVICE uint64_t* empty_bar(uint32_t stage) const { return &empty[stage % n]; }
+  PB_DEVICE uint32_t parity(uint32_t stage) const { return (stage / n) & 1u; }
 };
+// Stages are numbered 0, 1, 2, ... in the order the producer issues them; stage i lives in slot i % n. Producer and consumers
+// derive the same numbers from the geometry (nothing is communicated): `base` = first stage of the current phase.
 
-// Stage cursor shared (by construction, not by memory) between the producer and the consumers: both walk the same sequence.
-struct Cursor {
-  int idx; uint32_t phase;
-  PB_DEVICE void advance(int n) { if (++idx == n) { idx = 0; phase ^= 1u; } }
-};
-
-// Rows of group `g`, K chunk `kc_idx` of a plain projection W[N, K]: `rows` consecutive rows, kc elements each.
-// P4 (gate/up) groups are 2 gate rows followed by 2 up rows.
+PB_DEVICE int tasks_of_cta(const Geom& g, int bid, int grid) { return g.ntasks > bid ? (g.ntasks - bid + grid - 1) / grid : 0; }
 
 // ---- producer ------------------------------------------------------------------------------------------------------------
-PB_DEVICE void produce_proj(const Params& p, const Ring& ring, Cursor& cur, const Geom& g, const __nv_bfloat16* w, const __nv_bfloat16* w2,
-                            int bid, int grid, uint64_t policy) {
-  const uint32_t row_bytes = static_cast<uint32_t>(g.kc) * 2u;
-  for (int grp = bid; grp < g.ngroups; grp += grid) {
-    for (int c = 0; c < g.nkc; ++c) {
-      mbar_wait(&ring.empty[cur.idx], cur.phase ^ 1u);
-      mbar_expect_tx(&ring.full[cur.idx], row_bytes * g.rows);
-      uint8_t* dst = ring.stage(cur.idx);
-      if (w2 == nullptr) {
-        const __nv_bfloat16* src = w + static_cast<size_t>(grp) * g.rows * g.K + static_cast<size_t>(c) * g.kc;
-        if (g.nkc == 1) {
-          bulk_load_hint(dst, src, row_bytes * g.rows, &ring.full[cur.idx], policy);  // rows are contiguous: one copy
-        } else {
-          for (int r = 0; r < g.rows; ++r) bulk_load_hint(dst + r * row_bytes, src + static_cast<size_t>(r) * g.K, row_bytes, &ring.full[cur.idx], policy);
-        }
+PB_DEVICE void produce_proj(const Ring& ring, uint32_t& base, const Geom& g, const __nv_bfloat16* w, const __nv_bfloat16* w2, int bid, int grid,
+                            uint64_t policy) {
+  const int nt = tasks_of_cta(g, bid, grid);
+  const uint32_t bytes = static_cast<uint32_t>(g.R) * g.kc * 2u;
+  uint32_t st = base;
+  for (int j = 0; j < nt; ++j) {
+    const size_t t = static_cast<size_t>(bid) + static_cast<size_t>(j) * grid;
+    for (int s_ = 0; s_ < g.S; ++s_, ++st) {
+      // which rows / chunk is stage s_ of a task?  R >= 2: [gate rows][up rows], one stage each.  R == 1: row-major over
+      // (row, chunk) with rows ordered g_i, u_i, g_{i+1}, u_{i+1} (dual) or n, n+1 (plain)
+      const __nv_bfloat16* src;
+      if (g.R >= 2) {
+        src = (g.dual && s_ == 1 ? w2 : w) + t * g.outs * g.K;
       } else {
-        const int half = g.rows >> 1;  // gate rows, then up rows
-        const size_t off = static_cast<size_t>(grp) * half * g.K + static_cast<size_t>(c) * g.kc;
-        for (int r = 0; r < half; ++r) {
-          bulk_load_hint(dst + r * row_bytes, w + off + static_cast<size_t>(r) * g.K, row_bytes, &ring.full[cur.idx], policy);
-          bulk_load_hint(dst + (half + r) * row_bytes, w2 + off + static_cast<size_t>(r) * g.K, row_bytes, &ring.full[cur.idx], policy);
-        }
+        const int row = s_ / g.nkc, c = s_ - row * g.nkc;
+        const size_t out = t * g.outs + (g.dual ? row >> 1 : row);
+        src = (g.dual && (row & 1) ? w2 : w) + out * g.K + static_cast<size_t>(c) * g.kc;
       }
-      cur.advance(ring.n);
+      mbar_wait(ring.empty_bar(st), ring.parity(st) ^ 1u);
+      mbar_expect_tx(ring.full_bar(st), bytes);
+      bulk_load_hint(ring.slot(st), src, bytes, ring.full_bar(st), policy);
     }
   }
+  base = st;
 }
 
-PB_DEVICE void produce_kv(const Params& p, const Ring& ring, Cursor& cur, const Layer& L, int pos, int bid, int grid) {
+PB_DEVICE void produce_kv(const Params& p, const Ring& ring, uint32_t& base, const Layer& L, int pos, int bid, int grid) {
   const int nch = pos / kPage + 1;
   const int units = p.Hkv * nch;
   const uint32_t bytes = static_cast<uint32_t>(kPage) * p.D * 2u;
-  for (int u = bid; u < units; u += grid) {
+  uint32_t st = base;
+  for (int u = bid; u < units; u += grid, st += 2) {
     const int hk = u / nch, c = u - hk * nch;
     int pg = c < p.max_pages ? p.block_table[c] : 0;
     pg = min(max(pg, 0), p.num_pages - 1);
-    const size_t base = (static_cast<size_t>(pg) * p.Hkv + hk) * kPage * p.D;
-    mbar_wait(&ring.empty[cur.idx], cur.phase ^ 1u);
-    mbar_expect_tx(&ring.full[cur.idx], 2u * bytes);
-    bulk_load_1d(ring.stage(cur.idx), L.k_pool + base, bytes, &ring.full[cur.idx]);
-    bulk_load_1d(ring.stage(cur.idx) + bytes, L.v_pool + base, bytes, &ring.full[cur.idx]);
-    cur.advance(ring.n);
+    const size_t off = (static_cast<size_t>(pg) * p.Hkv + hk) * kPage * p.D;
+    mbar_wait(ring.empty_bar(st), ring.parity(st) ^ 1u);
+    mbar_expect_tx(ring.full_bar(st), bytes);
+    bulk_load_1d(ring.slot(st), L.k_pool + off, bytes, ring.full_bar(st));
+    mbar_wait(ring.empty_bar(st + 1), ring.parity(st + 1) ^ 1u);
+    mbar_expect_tx(ring.full_bar(st + 1), bytes);
+    bulk_load_1d(ring.slot(st + 1), L.v_pool + off, bytes, ring.full_bar(st + 1));
+  }
+  base = st;
+}
+
+// ---- consumer: projections. Every warp works alone: it owns whole tasks (task j of this CTA -> warp j % 8), waits for its own
+// stages, reduces inside the warp and publishes its outputs. No block-wide barrier inside a projection: eight independent
+// latency chains per SM instead of one.
+template <int R>
+PB_DEVICE void dot_rows(const __nv_bfloat16* st, const __nv_bfloat16* x, int kc, int lane, float (&acc)[R]) {
+  // R rows of kc elements (row-major) against x[0..kc): each lane takes 16-byte pieces 256 elements apart
+#pragma unroll 2
+  for (int k = lane * 8; k < kc; k += 256) {
+    const uint4 xv = *reinterpret_cast<const uint4*>(x + k);
+    const float x0 = bf16_lo(xv.x), x1 = bf16_hi(xv.x), x2 = bf16_lo(xv.y), x3 = bf16_hi(xv.y);
+    const float x4 = bf16_lo(xv.z), x5 = bf16_hi(xv.z), x6 = bf16_lo(xv.w), x7 = bf16_hi(xv.w);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const uint4 wv = *reinterpret_cast<const uint4*>(st + static_cast<size_t>(r) * kc + k);
+      float a = acc[r];
+      a = fmaf(bf16_lo(wv.x), x0, a); a = fmaf(bf16_hi(wv.x), x1, a); a = fmaf(bf16_lo(wv.y), x2, a); a = fmaf(bf16_hi(wv.y), x3, a);
+      a = fmaf(bf16_lo(wv.z), x4, a); a = fmaf(bf16_hi(wv.z), x5, a); a = fmaf(bf16_lo(wv.w), x6, a); a = fmaf(bf16_hi(wv.w), x7, a);
+      acc[r] = a;
+    }
   }
 }
 
-// ---- consumer: generic projection --------------------------------------------------------------------------------------
 // EPI: 0 = QKV (pairs -> qkv_ll), 1 = row-parallel push (pairs -> R peers), 2 = gate/up (SwiGLU -> act_ll)
-template <int EPI>
-PB_DEVICE void consume_proj(const Params& p, const Ring& ring, Cursor& cur, const Geom& g, const __nv_bfloat16* vin, float* part,
-                            uint2* const* push, uint2* local_out, uint32_t tag, int bid, int grid) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int rows = g.rows;
-  const int wpr = rows >= kConsumerWarps ? 1 : kConsumerWarps / rows;   // warps per row
-  const int rows_per_pass = kConsumerWarps / wpr;
-  const int passes = (rows + rows_per_pass - 1) / rows_per_pass;
-  const int kseg = g.kc / wpr;  // elements of one warp's K segment (multiple of 8)
-  for (int grp = bid; grp < g.ngroups; grp += grid) {
-    // part[c][row][seg]
-    for (int c = 0; c < g.nkc; ++c) {
-      mbar_wait(&ring.full[cur.idx], cur.phase);
-      const __nv_bfloat16* st = reinterpret_cast<const __nv_bfloat16*>(ring.stage(cur.idx));
-      for (int ps = 0; ps < passes; ++ps) {
-        const int row = ps * rows_per_pass + warp / wpr, seg = warp % wpr;
-        if (row < rows && !(c_debug & 2)) {
-          const __nv_bfloat16* wrow = st + static_cast<size_t>(row) * g.kc + seg * kseg;
-          const __nv_bfloat16* xrow = vin + static_cast<size_t>(c) * g.kc + seg * kseg;
-          float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll 4
-          for (int k = lane * 8; k < kseg; k += 256) {
-            const uint4 wv = *reinterpret_cast<const uint4*>(wrow + k);
-            const uint4 xv = *reinterpret_cast<const uint4*>(xrow + k);
-            acc0 = fmaf(bf16_lo(wv.x), bf16_lo(xv.x), acc0); acc1 = fmaf(bf16_hi(wv.x), bf16_hi(xv.x), acc1);
-            acc0 = fmaf(bf16_lo(wv.y), bf16_lo(xv.y), acc0); acc1 = fmaf(bf16_hi(wv.y), bf16_hi(xv.y), acc1);
-            acc0 = fmaf(bf16_lo(wv.z), bf16_lo(xv.z), acc0); acc1 = fmaf(bf16_hi(wv.z), bf16_hi(xv.z), acc1);
-            acc0 = fmaf(bf16_lo(wv.w), bf16_lo(xv.w), acc0); acc1 = fmaf(bf16_hi(wv.w), bf16_hi(xv.w), acc1);
-          }
-          const float s = warp_sum(acc0 + acc1);
-          if (lane == 0) part[(c * kMaxGroupRows + row) * kConsumerWarps + seg] = s;
-        } else if (row < rows && lane == 0) {
-          part[(c * kMaxGroupRows + row) * kConsumerWarps + seg] = 0.f;
-        }
-      }
-      consumer_sync();  // every warp is done with the stage; partial sums are visible
-      if (tid == 0) mbar_arrive(&ring.empty[cur.idx]);
-      cur.advance(ring.n);
-    }
-    // ---- finish the group: thread t handles output pair t ----
-    const int npairs = (EPI == 2) ? rows >> 2 : rows >> 1;
-    if (tid < npairs || (EPI == 2 && tid < (rows >> 1))) {
-      auto row_sum = [&](int row) {
-        float s = 0.f;
-        for (int c = 0; c < g.nkc; ++c)
-          for (int sg = 0; sg < wpr; ++sg) s += part[(c * kMaxGroupRows + row) * kConsumerWarps + sg];
-        return s;
-      };
-      if (EPI == 2) {
-        // rows: [gate 0..half) [up 0..half); half = rows/2 outputs; thread t < half/2 packs outputs (2t, 2t+1)
-        const int half = rows >> 1;
-        if (tid < (half >> 1)) {
-          const int o0 = 2 * tid, o1 = o0 + 1;
-          const float g0 = rbf(row_sum(o0)), g1 = rbf(row_sum(o1));
-          const float u0 = rbf(row_sum(half + o0)), u1 = rbf(row_sum(half + o1));
-          const float a0 = rbf(silu_f(g0)) * u0, a1 = rbf(silu_f(g1)) * u1;
-          const int n0 = grp * half + o0;
-          st_ll(local_out + (n0 >> 1), pack_bf16(a0, a1), tag);
-        }
-      } else {
-        const float v0 = row_sum(2 * tid), v1 = row_sum(2 * tid + 1);
-        const int n0 = grp * rows + 2 * tid;
-        const uint32_t packed = pack_bf16(v0, v1);
-        if (EPI == 0) {
-          st_ll(local_out + (n0 >> 1), packed, tag);
+template <int EPI, int R>
+PB_DEVICE void consume_proj_r(const Params& p, const Ring& ring, uint32_t base, const Geom& g, const __nv_bfloat16* vin, uint2* const* push,
+                              uint2* local_out, uint32_t tag, int bid, int grid) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nt = tasks_of_cta(g, bid, grid);
+  constexpr int NACC = (R >= 2) ? R : 2;   // outputs per task
+  for (int j = warp; j < nt; j += kConsumerWarps) {
+    const size_t t = static_cast<size_t>(bid) + static_cast<size_t>(j) * grid;
+    uint32_t st = base + static_cast<uint32_t>(j) * g.S;
+    float v[NACC], u[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) v[i] = u[i] = 0.f;
+    for (int s_ = 0; s_ < g.S; ++s_, ++st) {
+      mbar_wait(ring.full_bar(st), ring.parity(st));
+      const __nv_bfloat16* sm = reinterpret_cast<const __nv_bfloat16*>(ring.slot(st));
+      if (!(c_debug & 2)) {
+        if constexpr (R >= 2) {
+          float acc[R];
+#pragma unroll
+          for (int i = 0; i < R; ++i) acc[i] = 0.f;
+          dot_rows<R>(sm, vin, g.kc, lane, acc);
+#pragma unroll
+          for (int i = 0; i < R; ++i) { if (EPI == 2 && s_ == 1) u[i] = acc[i]; else v[i] = acc[i]; }
         } else {
-          for (int r = 0; r < p.R; ++r) st_ll(push[r] + (n0 >> 1), packed, tag);
+          const int row = s_ / g.nkc, c = s_ - row * g.nkc;
+          float acc[1] = {0.f};
+          dot_rows<1>(sm, vin + static_cast<size_t>(c) * g.kc, g.kc, lane, acc);
+          // rows of a task: plain n, n+1; dual g_i, u_i, g_{i+1}, u_{i+1}
+          if (EPI == 2) { if (row & 1) u[row >> 1] += acc[0]; else v[row >> 1] += acc[0]; }
+          else v[row] += acc[0];
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ring.empty_bar(st));   // this warp was the stage's only reader
     }
-    consumer_sync();  // `part` is free for the next group
+    // ---- finish the task: all lanes get all sums, lane i publishes output pair i ----
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { v[i] = warp_sum(v[i]); if (EPI == 2) u[i] = warp_sum(u[i]); }
+    if (EPI == 2) {
+#pragma unroll
+      for (int i = 0; i < NACC; ++i) v[i] = rbf(silu_f(rbf(v[i]))) * rbf(u[i]);   // HF: bf16(silu(bf16 gate)) * bf16 up
+    }
+    const size_t n0 = t * NACC;
+#pragma unroll
+    for (int i = 0; i < NACC; i += 2) {
+      if (lane == (i >> 1)) {
+        const uint32_t packed = pack_bf16(v[i], v[i + 1]);
+        if (EPI == 1) { for (int r = 0; r < p.R; ++r) st_ll(push[r] + ((n0 + i) >> 1), packed, tag); }
+        else st_ll(local_out + ((n0 + i) >> 1), packed, tag);
+      }
+    }
   }
+}
+
+template <int EPI>
+PB_DEVICE void consume_proj(const Params& p, const Ring& ring, uint32_t& base, const Geom& g, const __nv_bfloat16* vin, uint2* const* push,
+                            uint2* local_out, uint32_t tag, int bid, int grid) {
+  switch (g.R) {
+    case 1: consume_proj_r<EPI, 1>(p, ring, base, g, vin, push, local_out, tag, bid, grid); break;
+    case 2: consume_proj_r<EPI, 2>(p, ring, base, g, vin, push, local_out, tag, bid, grid); break;
+    case 4: consume_proj_r<EPI, 4>(p, ring, base, g, vin, push, local_out, tag, bid, grid); break;
+    default: consume_proj_r<EPI, 8>(p, ring, base, g, vin, push, local_out, tag, bid, grid); break;
+  }
+  base += static_cast<uint32_t>(tasks_of_cta(g, bid, grid)) * g.S;
+  consumer_sync();   // the activation vector (and the next phase's gathers) belong to the whole CTA again
 }
 
 // Wait for 16 bytes (two LL units) to carry `tag`; `v` holds the first attempt.
@@ -390,7 +405,7 @@ PB_DEVICE void reduce_slice(const Params& p, const uint2* parts_in, float* res, 
 
 // ---- consumer: attention units ---------------------------------------------------------------------------------------------
 // Shared scratch: qs[G][D] fp32-free bf16 rotated q, knew[D], vnew[D], S[G][64], m/l.
-PB_DEVICE void consume_attention(const Params& p, const Ring& ring, Cursor& cur, const Layer& L, int pos, __nv_bfloat16* vin, float* scr,
+PB_DEVICE void consume_attention(const Params& p, const Ring& ring, uint32_t& base, const Layer& L, int pos, __nv_bfloat16* vin, float* scr,
                                  uint32_t tag_qkv, uint32_t tag_attp, int bid, int grid) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = p.D, G = p.Hq / p.Hkv, half_d = D >> 1;
@@ -428,9 +443,12 @@ PB_DEVICE void consume_attention(const Params& p, const Ring& ring, Cursor& cur,
       loaded_hk = hk;
       consumer_sync();
     }
-    mbar_wait(&ring.full[cur.idx], cur.phase);
-    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(ring.stage(cur.idx));
-    __nv_bfloat16* Vs = Ks + kPage * D;
+    const uint32_t st = base;   // K page in stage st, V page in stage st + 1; every warp reads both
+    base += 2;
+    mbar_wait(ring.full_bar(st), ring.parity(st));
+    mbar_wait(ring.full_bar(st + 1), ring.parity(st + 1));
+    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(ring.slot(st));
+    __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(ring.slot(st + 1));
     const int key0 = c * kPage;
     const bool has_new = (pos >= key0 && pos < key0 + kPage);
     if (has_new) {
@@ -451,7 +469,7 @@ PB_DEVICE void consume_attention(const Params& p, const Ring& ring, Cursor& cur,
       consumer_sync();
     }
     // ---- scores: thread -> key = tid % 64, heads g = tid / 64 + 4 j ----
-    if (c_debug & 2) { consumer_sync(); if (tid == 0) mbar_arrive(&ring.empty[cur.idx]); cur.advance(ring.n); continue; }
+    if (c_debug & 2) { consumer_sync(); if (tid == 0) { mbar_arrive(ring.empty_bar(st)); mbar_arrive(ring.empty_bar(st + 1)); } continue; }
     const int key = tid & (kPage - 1);
     const int nchunk16 = D >> 3;  // 16-byte chunks per row
     for (int g = tid >> 6; g < G; g += kConsumerThreads / kPage) {
@@ -503,8 +521,7 @@ PB_DEVICE void consume_attention(const Params& p, const Ring& ring, Cursor& cur,
       st_ll(dst + D + (tid & 1), __float_as_uint(ml[tid]), tag_attp);
     }
     consumer_sync();
-    if (tid == 0) mbar_arrive(&ring.empty[cur.idx]);
-    cur.advance(ring.n);
+    if (tid == 0) { mbar_arrive(ring.empty_bar(st)); mbar_arrive(ring.empty_bar(st + 1)); }
   }
 }
 
@@ -558,7 +575,7 @@ PB_DEVICE void combine_heads(const Params& p, int pos, uint32_t tag_attp, uint32
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_constant__ Params p) {
+__global__ void __maxnreg__(224) decode_span_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int bid = blockIdx.x, grid = gridDim.x;
@@ -568,7 +585,6 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
   ring.base = smem;
   uint8_t* q = smem + static_cast<size_t>(p.n_stages) * kStageBytes;
   __nv_bfloat16* vin = reinterpret_cast<__nv_bfloat16*>(q);              q += static_cast<size_t>(p.vin_elems) * 2;
-  float* part = reinterpret_cast<float*>(q);                            q += 4 * kMaxGroupRows * kConsumerWarps * sizeof(float);
   float* scr = reinterpret_cast<float*>(q);                             q += (16 * kPage + 64) * sizeof(float);
   float* res = reinterpret_cast<float*>(q);                             q += 256 * sizeof(float);
   float* red = reinterpret_cast<float*>(q);                             q += 32 * sizeof(float);
@@ -583,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
 
   const int pos = *p.pos_ptr;
   const uint32_t tag0 = static_cast<uint32_t>(*p.epoch) * kTagStride + 1u;  // fixed stride: spans of different lengths may share the buffers
-  Cursor cur{0, 0u};
+  uint32_t base = 0;   // first ring stage of the current phase (same arithmetic in the producer and in every consumer warp)
 
   if (warp == kConsumerWarps) {
     // =============================== PRODUCER ===============================
@@ -591,11 +607,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
       const uint64_t pol = policy_evict_first();
       for (int l = 0; l < p.n_layers; ++l) {
         const Layer& L = p.layers[l];
-        produce_proj(p, ring, cur, p.g_qkv, L.wqkv, nullptr, bid, grid, pol);   SPAN_STAMP(16);
-        produce_kv(p, ring, cur, L, pos, bid, grid);                             SPAN_STAMP(17);
-        produce_proj(p, ring, cur, p.g_o, L.wo, nullptr, bid, grid, pol);        SPAN_STAMP(18);
-        produce_proj(p, ring, cur, p.g_gu, L.wgate, L.wup, bid, grid, pol);      SPAN_STAMP(19);
-        produce_proj(p, ring, cur, p.g_down, L.wdown, nullptr, bid, grid, pol);  SPAN_STAMP(20);
+        produce_proj(ring, base, p.g_qkv, L.wqkv, nullptr, bid, grid, pol);   SPAN_STAMP(16);
+        produce_kv(p, ring, base, L, pos, bid, grid);                          SPAN_STAMP(17);
+        produce_proj(ring, base, p.g_o, L.wo, nullptr, bid, grid, pol);        SPAN_STAMP(18);
+        produce_proj(ring, base, p.g_gu, L.wgate, L.wup, bid, grid, pol);      SPAN_STAMP(19);
+        produce_proj(ring, base, p.g_down, L.wdown, nullptr, bid, grid, pol);  SPAN_STAMP(20);
       }
     }
     return;
@@ -624,25 +640,25 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
     // ---- P1: norm + QKV ----
     SPAN_STAMP(0);
     rmsnorm_inplace(vin, L.ln1, p.H, p.eps, red);                                                   SPAN_STAMP(1);
-    consume_proj<0>(p, ring, cur, p.g_qkv, vin, part, nullptr, p.qkv_ll, tg + T_QKV, bid, grid);    SPAN_STAMP(2);
+    consume_proj<0>(p, ring, base, p.g_qkv, vin, nullptr, p.qkv_ll, tg + T_QKV, bid, grid);    SPAN_STAMP(2);
     // ---- P2: attention of the new token ----
-    consume_attention(p, ring, cur, L, pos, vin, scr, tg + T_QKV, tg + T_ATTP, bid, grid);         SPAN_STAMP(3);
+    consume_attention(p, ring, base, L, pos, vin, scr, tg + T_QKV, tg + T_ATTP, bid, grid);         SPAN_STAMP(3);
     combine_heads(p, pos, tg + T_ATTP, tg + T_ATTN, bid, grid);                                     SPAN_STAMP(4);
     // ---- P3: O-projection, partials pushed to every rank ----
     consumer_sync();
     gather_ll(p.attn_ll, vin, p.Hq * p.D, tg + T_ATTN, p.error_flag);
     consumer_sync();                                                                                 SPAN_STAMP(5);
-    consume_proj<1>(p, ring, cur, p.g_o, vin, part, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid); SPAN_STAMP(6);
+    consume_proj<1>(p, ring, base, p.g_o, vin, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid); SPAN_STAMP(6);
     // ---- all-reduce tail + norm + gate/up ----
     reduce_slice(p, p.oproj_in, res, p0, p1, tg + T_OPROJ, tg + T_X1, p.x_ll, nullptr);            SPAN_STAMP(7);
     gather_ll(p.x_ll, vin, p.H, tg + T_X1, p.error_flag);
     consumer_sync();
     rmsnorm_inplace(vin, L.ln2, p.H, p.eps, red);                                                   SPAN_STAMP(8);
-    consume_proj<2>(p, ring, cur, p.g_gu, vin, part, nullptr, p.act_ll, tg + T_ACT, bid, grid);    SPAN_STAMP(9);
+    consume_proj<2>(p, ring, base, p.g_gu, vin, nullptr, p.act_ll, tg + T_ACT, bid, grid);    SPAN_STAMP(9);
     // ---- P5: down projection, partials pushed to every rank ----
     gather_ll(p.act_ll, vin, p.I, tg + T_ACT, p.error_flag);
     consumer_sync();                                                                                 SPAN_STAMP(10);
-    consume_proj<1>(p, ring, cur, p.g_down, vin, part, p.mlp_push, nullptr, tg + T_MLP, bid, grid); SPAN_STAMP(11);
+    consume_proj<1>(p, ring, base, p.g_down, vin, p.mlp_push, nullptr, tg + T_MLP, bid, grid); SPAN_STAMP(11);
     // ---- all-reduce tail: next block's input, or the span output ----
     const bool last = (l + 1 == p.n_layers);
     reduce_slice(p, p.mlp_in, res, p0, p1, tg + T_MLP, tg + T_X2, p.x_ll, last ? p.x_out : nullptr);
@@ -654,25 +670,23 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
   }
 }
 
-static bool make_geom(Geom& g, int N, int K, int rows_unit, const char* what) {
-  // rows_unit: 2 (plain, outputs are published in pairs) or 4 (gate/up: 2 gate + 2 up rows per output pair)
+static bool make_geom(Geom& g, int N, int K, bool dual, const char* what) {
+  // N = outputs of the projection (gate/up: I outputs, 2 I weight rows)
   if (K % 8 != 0 || N % 2 != 0) { pb_set_error(what); return false; }
   const long row_bytes = static_cast<long>(K) * 2;
-  int rows = rows_unit, nkc = 1;
-  if (row_bytes * rows_unit <= kStageBytes) {
-    while (rows * 2 <= kMaxGroupRows && row_bytes * rows * 2 <= kStageBytes && (N * (rows_unit / 2)) % (rows * 2) == 0) rows *= 2;
-  } else {
-    nkc = static_cast<int>((row_bytes * rows_unit + kStageBytes - 1) / kStageBytes);
-    while (nkc <= 64 && !(K % nkc == 0 && (K / nkc) % 8 == 0 && static_cast<long>(K / nkc) * 2 * rows_unit <= kStageBytes)) ++nkc;
-    if (nkc > 4) { pb_set_error(what); return false; }  // `part` holds 4 K-chunks
+  g.K = K; g.dual = dual ? 1 : 0;
+  if (row_bytes * 2 <= kStageBytes) {          // short rows: R contiguous rows per stage, one stage (two for gate/up) per task
+    int R = 2;
+    while (R * 2 <= kMaxStageRows && row_bytes * R * 2 <= kStageBytes && N % (R * 2) == 0) R *= 2;
+    g.R = R; g.kc = K; g.nkc = 1; g.outs = R; g.S = dual ? 2 : 1;
+  } else {                                      // long rows: one row (or one K chunk of it) per stage, a task = one output pair
+    int nkc = static_cast<int>((row_bytes + kStageBytes - 1) / kStageBytes);
+    while (nkc <= 64 && !(K % nkc == 0 && (K / nkc) % 8 == 0 && static_cast<long>(K / nkc) * 2 <= kStageBytes)) ++nkc;
+    if (nkc > 64) { pb_set_error(what); return false; }
+    g.R = 1; g.nkc = nkc; g.kc = K / nkc; g.outs = 2; g.S = (dual ? 4 : 2) * nkc;
   }
-  g.K = K; g.rows = rows; g.nkc = nkc; g.kc = K / nkc;
-  const int wpr = rows >= kConsumerWarps ? 1 : kConsumerWarps / rows;
-  if (g.kc % (8 * wpr) != 0) { pb_set_error(what); return false; }
-  const int total_rows = N * (rows_unit / 2);   // gate/up: I outputs = 2 I weight rows
-  g.ngroups = total_rows / rows;
-  if (g.ngroups * rows != total_rows) { pb_set_error(what); return false; }
-  return true;
+  g.ntasks = N / g.outs;
+  return g.ntasks * g.outs == N;
 }
 
 }  // namespace span
@@ -688,9 +702,9 @@ extern "C" int pb_decode_span_smem(const PbDecodeSpanArgs* a, int* n_stages, int
   if (a->I > vin) vin = a->I;
   if ((G + 2) * a->D > vin) vin = (G + 2) * a->D;
   vin = (vin + 63) & ~63;
-  const size_t fixed = static_cast<size_t>(vin) * 2 + 4 * kMaxGroupRows * kConsumerWarps * 4 + (16 * kPage + 64) * 4 + 256 * 4 + 32 * 4 + 2 * kMaxStages * 8 + 1024;
+  const size_t fixed = static_cast<size_t>(vin) * 2 + (16 * kPage + 64) * 4 + 256 * 4 + 32 * 4 + 2 * kMaxStages * 8 + 1024;
   const size_t budget = 227 * 1024;
-  if (fixed + 2 * kStageBytes > budget) return -1;
+  if (fixed + 4 * kStageBytes > budget) return -1;
   int ns = static_cast<int>((budget - fixed) / kStageBytes);
   if (ns > kMaxStages) ns = kMaxStages;
   *n_stages = ns; *vin_elems = vin;
@@ -723,10 +737,10 @@ extern "C" int pb_decode_span(const PbDecodeSpanArgs* a, void* stream) {
   for (int r = 0; r < a->R; ++r) { p.oproj_push[r] = static_cast<uint2*>(a->oproj_push[r]); p.mlp_push[r] = static_cast<uint2*>(a->mlp_push[r]); }
   p.oproj_in = static_cast<const uint2*>(a->oproj_in); p.mlp_in = static_cast<const uint2*>(a->mlp_in);
   p.epoch = static_cast<const uint64_t*>(a->epoch); p.error_flag = static_cast<int*>(a->error_flag);
-  if (!make_geom(p.g_qkv, (a->Hq + 2 * a->Hkv) * a->D, a->H, 2, "decode_span: QKV geometry") ||
-      !make_geom(p.g_o, a->H, a->Hq * a->D, 2, "decode_span: O-projection geometry") ||
-      !make_geom(p.g_gu, a->I, a->H, 4, "decode_span: gate/up geometry") ||
-      !make_geom(p.g_down, a->H, a->I, 2, "decode_span: down-projection geometry"))
+  if (!make_geom(p.g_qkv, (a->Hq + 2 * a->Hkv) * a->D, a->H, false, "decode_span: QKV geometry") ||
+      !make_geom(p.g_o, a->H, a->Hq * a->D, false, "decode_span: O-projection geometry") ||
+      !make_geom(p.g_gu, a->I, a->H, true, "decode_span: gate/up geometry") ||
+      !make_geom(p.g_down, a->H, a->I, false, "decode_span: down-projection geometry"))
     return PB_ERR_UNSUPPORTED;
   int ns = 0, vin = 0;
   const int smem = pb_decode_span_smem(a, &ns, &vin);
