@@ -36,9 +36,11 @@ namespace span {
 
 constexpr int kStageBytes = 16 * 1024;   // one ring slot: one weight row (or R short rows, or one K chunk of a long row), or one K / V page
 constexpr int kMaxStages = 12;
-constexpr int kConsumerWarps = 8;
+constexpr int kConsumerWarps = 8;                       // warps 0-7: everything (gathers, norms, attention, projections)
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kThreads = kConsumerThreads + 32;
+constexpr int kGemvWarps = 11;                          // warps 0-10 take projection tasks; warps 8-10 do nothing else
+constexpr int kGemvThreads = kGemvWarps * 32;
+constexpr int kThreads = kGemvThreads + 32;             // warp 11: the producer. 12 warps x 168 registers fill the register file
 constexpr int kMaxRanks = 8;
 constexpr int kMaxStageRows = 8;
 constexpr int kPage = 64;
@@ -105,13 +107,14 @@ struct Params {
 // Diagnostics (PETALS_B200_SPAN_DEBUG): bit 0 = treat every polled unit as ready, bit 1 = skip the math. Results are garbage; the
 // two switches separate the cost of streaming, of computing and of waiting (tools/span_probe.py).
 __constant__ int c_debug = 0;
-#define SPAN_STAMP(slot) do { if (p.timing != nullptr && bid == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x == 0 || threadIdx.x == kConsumerThreads)) \
+#define SPAN_STAMP(slot) do { if (p.timing != nullptr && bid == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x == 0 || threadIdx.x == kGemvThreads)) \
     p.timing[static_cast<size_t>(l) * 24 + (slot)] = globaltimer_ns(); } while (0)
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------
 PB_DEVICE float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 PB_DEVICE float silu_f(float x) { return x / (1.f + __expf(-x)); }
 PB_DEVICE void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory"); }
+PB_DEVICE void gemv_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kGemvThreads) : "memory"); }   // main + helper warps
 
 PB_DEVICE uint2 ld_ll(const uint2* p) {
   uint2 v;
@@ -251,7 +254,7 @@ PB_DEVICE void consume_proj_r(const Params& p, const Ring& ring, uint32_t base, 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nt = tasks_of_cta(g, bid, grid);
   constexpr int NACC = (R >= 2) ? R : 2;   // outputs per task
-  for (int j = warp; j < nt; j += kConsumerWarps) {
+  for (int j = warp; j < nt; j += kGemvWarps) {
     const size_t t = static_cast<size_t>(bid) + static_cast<size_t>(j) * grid;
     uint32_t st = base + static_cast<uint32_t>(j) * g.S;
     float v[NACC], u[NACC];
@@ -273,8 +276,10 @@ PB_DEVICE void consume_proj_r(const Params& p, const Ring& ring, uint32_t base, 
           float acc[1] = {0.f};
           dot_rows<1>(sm, vin + static_cast<size_t>(c) * g.kc, g.kc, lane, acc);
           // rows of a task: plain n, n+1; dual g_i, u_i, g_{i+1}, u_{i+1}
-          if (EPI == 2) { if (row & 1) u[row >> 1] += acc[0]; else v[row >> 1] += acc[0]; }
-          else v[row] += acc[0];
+          const int o = (EPI == 2) ? row >> 1 : row;          // 0 or 1 (static indices below: the sums stay in registers)
+          const bool up = (EPI == 2) && (row & 1);
+          if (up) { if (o) u[1] += acc[0]; else u[0] += acc[0]; }
+          else    { if (o) v[1] += acc[0]; else v[0] += acc[0]; }
         }
       }
       __syncwarp();
@@ -302,6 +307,7 @@ PB_DEVICE void consume_proj_r(const Params& p, const Ring& ring, uint32_t base, 
 template <int EPI>
 PB_DEVICE void consume_proj(const Params& p, const Ring& ring, uint32_t& base, const Geom& g, const __nv_bfloat16* vin, uint2* const* push,
                             uint2* local_out, uint32_t tag, int bid, int grid) {
+  gemv_sync();   // the activation vector is complete: the helper warps may start
   switch (g.R) {
     case 1: consume_proj_r<EPI, 1>(p, ring, base, g, vin, push, local_out, tag, bid, grid); break;
     case 2: consume_proj_r<EPI, 2>(p, ring, base, g, vin, push, local_out, tag, bid, grid); break;
@@ -309,7 +315,7 @@ PB_DEVICE void consume_proj(const Params& p, const Ring& ring, uint32_t& base, c
     default: consume_proj_r<EPI, 8>(p, ring, base, g, vin, push, local_out, tag, bid, grid); break;
   }
   base += static_cast<uint32_t>(tasks_of_cta(g, bid, grid)) * g.S;
-  consumer_sync();   // the activation vector (and the next phase's gathers) belong to the whole CTA again
+  gemv_sync();   // every warp is done with the activation vector: it belongs to the main warps again
 }
 
 // Wait for 16 bytes (two LL units) to carry `tag`; `v` holds the first attempt.
@@ -575,7 +581,7 @@ PB_DEVICE void combine_heads(const Params& p, int pos, uint32_t tag_attp, uint32
   }
 }
 
-__global__ void __maxnreg__(224) decode_span_kernel(const __grid_constant__ Params p) {
+__global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_constant__ Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int bid = blockIdx.x, grid = gridDim.x;
@@ -601,7 +607,7 @@ __global__ void __maxnreg__(224) decode_span_kernel(const __grid_constant__ Para
   const uint32_t tag0 = static_cast<uint32_t>(*p.epoch) * kTagStride + 1u;  // fixed stride: spans of different lengths may share the buffers
   uint32_t base = 0;   // first ring stage of the current phase (same arithmetic in the producer and in every consumer warp)
 
-  if (warp == kConsumerWarps) {
+  if (warp == kGemvWarps) {
     // =============================== PRODUCER ===============================
     if ((tid & 31) == 0) {
       const uint64_t pol = policy_evict_first();
@@ -617,7 +623,23 @@ __global__ void __maxnreg__(224) decode_span_kernel(const __grid_constant__ Para
     return;
   }
 
-  // =============================== CONSUMERS ===============================
+  if (warp >= kConsumerWarps) {
+    // =============================== HELPER WARPS: projection tasks only ===============================
+    const int nch = pos / kPage + 1;
+    const int units = p.Hkv * nch;
+    const uint32_t kv_stages = 2u * static_cast<uint32_t>(units > bid ? (units - bid + grid - 1) / grid : 0);
+    for (int l = 0; l < p.n_layers; ++l) {
+      const uint32_t tg = tag0 + static_cast<uint32_t>(l) * T_PER_LAYER;
+      consume_proj<0>(p, ring, base, p.g_qkv, vin, nullptr, p.qkv_ll, tg + T_QKV, bid, grid);
+      base += kv_stages;   // the attention units' K / V pages are consumed by the main warps
+      consume_proj<1>(p, ring, base, p.g_o, vin, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid);
+      consume_proj<2>(p, ring, base, p.g_gu, vin, nullptr, p.act_ll, tg + T_ACT, bid, grid);
+      consume_proj<1>(p, ring, base, p.g_down, vin, p.mlp_push, nullptr, tg + T_MLP, bid, grid);
+    }
+    return;
+  }
+
+  // =============================== MAIN CONSUMER WARPS ===============================
   // slice of the residual stream this CTA owns in the all-reduce tails (pairs of elements)
   const int half_h = p.H >> 1;
   const int ppc = (half_h + grid - 1) / grid;

@@ -96,6 +96,25 @@ __global__ void swiglu_kernel(const uint4* __restrict__ g, const uint4* __restri
   }
 }
 
+// GELU (tanh or erf form) on its own: what a fused GEMV/GEMM epilogue applies, for paths that add a low-rank term before it
+__global__ void gelu_kernel(const uint4* __restrict__ x, uint4* __restrict__ o, long nvec, int erf_form) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long>(gridDim.x) * blockDim.x) {
+    const uint4 a = __ldg(x + i);
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+    uint32_t ow[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v[2] = {bf16_lo(aw[j]), bf16_hi(aw[j])};
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        v[h] = erf_form ? 0.5f * v[h] * (1.f + erff(v[h] * 0.7071067811865475f))
+                        : 0.5f * v[h] * (1.f + tanhf(0.7978845608028654f * (v[h] + 0.044715f * v[h] * v[h] * v[h])));
+      ow[j] = pack_bf16(v[0], v[1]);
+    }
+    o[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  }
+}
+
 __global__ void add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ o, long nvec) {
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < nvec; i += static_cast<long>(gridDim.x) * blockDim.x) {
     const uint4 x = __ldg(a + i), y = __ldg(b + i);
@@ -213,6 +232,13 @@ extern "C" int pb_swiglu(const void* gate, const void* up, void* out, long n, vo
   if (n == 0) return PB_OK;
   swiglu_kernel<<<grid_for(n >> 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(gate), static_cast<const uint4*>(up), static_cast<uint4*>(out), n >> 3);
+  return pb_check_launch("elementwise");
+}
+
+extern "C" int pb_gelu(const void* x, void* out, long n, int erf_form, void* stream) {
+  if (n & 7) return PB_ERR_SHAPE;
+  if (n == 0) return PB_OK;
+  gelu_kernel<<<grid_for(n >> 3), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<uint4*>(out), n >> 3, erf_form);
   return pb_check_launch("elementwise");
 }
 

@@ -83,6 +83,7 @@ int pb_embedding(const void* table, const void* ids /*int64*/, void* out, int n_
 int pb_argmax(const void* logits, int is_fp32, void* out_ids, int rows, int vocab, void* stream);
 int pb_add_prompts(void* hidden /*[B,T,H]*/, const void* prompts /*[Bp,P,H]*/, int B, int T, int H,
                    int Bp, int P, const void* pos_ptr, void* stream);
+int pb_gelu(const void* x, void* out, long n, int erf_form, void* stream);
 int pb_bump_epoch(void* epoch, void* stream);
 int pb_advance_pos(void* pos, int delta, void* stream);
 

@@ -341,6 +341,17 @@ def swiglu(gate: torch.Tensor, up: torch.Tensor, out: Optional[torch.Tensor] = N
     return out
 
 
+def activation(x: torch.Tensor, act: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The stand-alone form of a fused epilogue activation (``ACT_GELU_TANH`` / ``ACT_GELU_ERF``; ``ACT_NONE`` copies)."""
+    out = torch.empty_like(x) if out is None else out
+    if act == ACT_NONE:
+        return out.copy_(x)
+    if act not in (ACT_GELU_TANH, ACT_GELU_ERF):
+        raise ValueError(f"activation {act} has no stand-alone kernel")
+    check(native.lib().pb_gelu(ptr(_bf16c(x, "x")), ptr(out), x.numel(), int(act == ACT_GELU_ERF), stream_ptr()), "gelu")
+    return out
+
+
 def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     if out is None:
         out = torch.empty_like(a)

@@ -154,6 +154,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.pb_norm.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, cf, ci, vp]
     lib.pb_swiglu.argtypes = [vp, vp, vp, cl, vp]
     lib.pb_add.argtypes = [vp, vp, vp, cl, vp]
+    lib.pb_gelu.argtypes = [vp, vp, cl, ci, vp]
+    lib.pb_gelu.restype = ci
     lib.pb_embedding.argtypes = [vp, vp, vp, ci, ci, vp]
     lib.pb_argmax.argtypes = [vp, ci, vp, ci, ci, vp]
     lib.pb_add_prompts.argtypes = [vp, vp, ci, ci, ci, ci, ci, vp, vp]

@@ -106,7 +106,13 @@ class StageEngine:
         # opt-in (PETALS_B200_LORA_ENGINE=1): requests with an active LoRA adapter run on the kernels against per-adapter merged copies
         # of the targeted projections (utils/peft.py:MergedAdapterBlock) instead of falling back to the PyTorch executor. Each adapter
         # has its own weight views and its own captured graphs; activation buffers are shared. Not combined with FP8 weights.
-        self.lora_on_engine = os.environ.get("PETALS_B200_LORA_ENGINE", "0") != "0" and not fp8
+        # PETALS_B200_LORA_ENGINE: "lowrank" (default) = base projection + x.A^T.B^T.scale as two extra skinny launches per adapted projection,
+        # no weight copies (reference semantics: utils/peft.py:173-209); "merged" = per-adapter merged copies of the targeted projections;
+        # "0" = adapter requests run on the PyTorch executor.
+        mode = os.environ.get("PETALS_B200_LORA_ENGINE", "lowrank").lower()
+        self.lora_mode = {"1": "merged", "merged": "merged", "lowrank": "lowrank"}.get(mode)
+        self.lora_on_engine = self.lora_mode is not None and not fp8
+        self._lora_tables: Dict[tuple, Optional[Tuple[torch.Tensor, torch.Tensor]]] = {}
         self._adapter: Optional[str] = None
         self._adapter_state: Dict[Optional[str], tuple] = {}
         # scratch one-layer pool for cache-less forward passes
@@ -144,15 +150,66 @@ class StageEngine:
             raise RuntimeError("this engine does not serve adapters (PETALS_B200_LORA_ENGINE=1 enables merged-weight serving)")
         self._adapter_state[self._adapter] = (self.blocks, self._graphs)
         if name not in self._adapter_state:
-            from petals_b200.utils.peft import MergedAdapterBlock
-
             base = self._adapter_state[None][0] if None in self._adapter_state else self.blocks
-            with torch.inference_mode(False):
-                views = [MergedAdapterBlock(b, name) for b in base]
-            logger.info(f"adapter {name}: merged copies of the targeted projections take {sum(v.merged_bytes for v in views) / 2**20:.0f} MiB")
-            self._adapter_state[name] = (views, {})
+            if self.lora_mode == "merged":
+                from petals_b200.utils.peft import MergedAdapterBlock
+
+                with torch.inference_mode(False):
+                    views = [MergedAdapterBlock(b, name) for b in base]
+                logger.info(f"adapter {name}: merged copies of the targeted projections take {sum(v.merged_bytes for v in views) / 2**20:.0f} MiB")
+                self._adapter_state[name] = (views, {})
+            else:
+                for b in base:
+                    if name not in getattr(b, "lora_adapters", {}):
+                        raise KeyError(f"Adapter {name!r} is not loaded on this server (available: {sorted(getattr(b, 'lora_adapters', {}))})")
+                self._adapter_state[name] = (base, {})  # same weights, own graph cache: the low-rank factors ride next to the base GEMVs
         self.blocks, self._graphs = self._adapter_state[name]
         self._adapter = name
+
+    def _lora(self, slot: int, name: str) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+        """Low-rank factors of the active adapter for projection ``name`` of block ``slot``: ``(A [r, in], B [out, r])`` with every pair on
+        that projection stacked along r (a pair on q_proj only touches the q rows of the fused QKV: its B is zero elsewhere), the
+        scale folded into B, r padded to a multiple of 64 with zeros (tile-aligned for both kernels). None: nothing to add."""
+        if self._adapter is None or self.lora_mode != "lowrank":
+            return None
+        key = (self._adapter, slot, name)
+        if key not in self._lora_tables:
+            entries = getattr(self.blocks[slot], "lora_adapters", {}).get(self._adapter, {}).get(name)
+            if not entries:
+                self._lora_tables[key] = None
+            else:
+                w = getattr(self.blocks[slot], name)
+                r_tot = sum(A.shape[0] for A, _, _, _ in entries)
+                r_pad = (r_tot + 63) // 64 * 64
+                with torch.inference_mode(False):
+                    A_cat = torch.zeros(r_pad, w.shape[1], dtype=self.dtype, device=self.device)
+                    B_cat = torch.zeros(w.shape[0], r_pad, dtype=torch.float32, device=self.device)
+                    r0 = 0
+                    for A, Bm, scale, rows in entries:
+                        r = A.shape[0]
+                        A_cat[r0:r0 + r] = A.to(self.device, self.dtype)
+                        B_cat[(slice(None) if rows is None else rows), r0:r0 + r] = Bm.to(self.device, torch.float32) * float(scale)
+                        r0 += r
+                    self._lora_tables[key] = (A_cat, B_cat.to(self.dtype).contiguous())
+        return self._lora_tables[key]
+
+    def _lora_add_decode(self, slot: int, name: str, x: torch.Tensor, y: torch.Tensor, **prologue) -> None:
+        """y += (prologue(x) A^T) B^T for decode shapes: two skinny weight-streaming launches, the second accumulates into y."""
+        ab = self._lora(slot, name)
+        if ab is None:
+            return
+        t = Fn.linear_decode(x, ab[0], out=self._buf("lora_t", x.shape[0], ab[0].shape[0]), **prologue)
+        Fn.linear_decode(t, ab[1], residual=y, out=y)
+
+    def _lora_add_prefill(self, slot: int, name: str, xn: torch.Tensor, y: torch.Tensor) -> None:
+        ab = self._lora(slot, name)
+        if ab is None:
+            return
+        t = Fn.gemm(xn, ab[0], out=self._buf("lora_t_p", xn.shape[0], ab[0].shape[0]))
+        Fn.gemm(t, ab[1], residual=y, out=y)
+
+    def _has_lora(self, slot: int, *names: str) -> bool:
+        return any(self._lora(slot, n) is not None for n in names)
 
     # ---- buffers ---------------------------------------------------------------------------------------
     def _w(self, slot: int, name: str) -> Optional[torch.Tensor]:
@@ -256,7 +313,7 @@ class StageEngine:
         s, w = self.spec, self.blocks[slot]
         M = B * T
         eps = s.norm_eps
-        if self.fuse_rope and self.fp8 is None and w._p("bqkv") is None and not s.qkv_interleaved:
+        if self.fuse_rope and self.fp8 is None and w._p("bqkv") is None and not s.qkv_interleaved and not self._has_lora(slot, "wqkv"):
             # QKV projection whose epilogue rotates q/k and appends k/v to the cache pages: no RoPE launch, no qkv round trip
             Fn.linear_decode(x, w.wqkv, norm_weight=w.ln1_w, norm_bias=w._p("ln1_b"), norm_kind=self.norm_kind, eps=eps,
                              error_flag=self.err_flag.data_ptr(),
@@ -266,8 +323,10 @@ class StageEngine:
         else:
             qkv = self._lin_decode(slot, "wqkv", x, bias=w._p("bqkv"), norm_weight=w.ln1_w, norm_bias=w._p("ln1_b"), norm_kind=self.norm_kind,
                                    eps=eps, out=self._buf("qkv", M, s.qkv_dim))
+            self._lora_add_decode(slot, "wqkv", x, qkv, norm_weight=w.ln1_w, norm_bias=w._p("ln1_b"), norm_kind=self.norm_kind, eps=eps)
         attn = self._attention(qkv, slot, B, T, table, pos_ptr, pools, splits, "")
         h1 = self._lin_decode(slot, "wo", attn, bias=w._p("bo"), residual=x, out=out)
+        self._lora_add_decode(slot, "wo", attn, h1)
         if s.mlp == "moe":
             # router + the k chosen experts' GEMVs + combine: sync-free, so the whole block stays graph-capturable
             return Fn.moe_decode(h1, w.ln2_w, w.router, w.we_gate, w.we_up, w.we_down, top_k=s.top_k, eps=eps, out=x, bufs=self._moe_bufs)
@@ -275,15 +334,31 @@ class StageEngine:
             mlp_in, ln_w, ln_b = x, (w.ln2_w if s.dual_ln else w.ln1_w), (w._p("ln2_b") if s.dual_ln else w._p("ln1_b"))
         else:
             mlp_in, ln_w, ln_b = h1, w.ln2_w, w._p("ln2_b")
-        if s.mlp == "swiglu":
-            act = self._lin_decode(slot, "w_gate", mlp_in, "w_up", act=Fn.ACT_SWIGLU, norm_weight=ln_w, norm_bias=ln_b,
-                                   norm_kind=self.norm_kind, eps=eps, out=self._buf("act", M, s.intermediate_size))
+        norm_kw = dict(norm_weight=ln_w, norm_bias=ln_b, norm_kind=self.norm_kind, eps=eps)
+        if s.mlp == "swiglu" and self._has_lora(slot, "w_gate", "w_up"):
+            # the low-rank terms enter before the activation: gate and up separately, then the SwiGLU kernel
+            g = self._lin_decode(slot, "w_gate", mlp_in, out=self._buf("lora_g", M, s.intermediate_size), **norm_kw)
+            u = self._lin_decode(slot, "w_up", mlp_in, out=self._buf("lora_u", M, s.intermediate_size), **norm_kw)
+            self._lora_add_decode(slot, "w_gate", mlp_in, g, **norm_kw)
+            self._lora_add_decode(slot, "w_up", mlp_in, u, **norm_kw)
+            act = Fn.swiglu(g, u, out=self._buf("act", M, s.intermediate_size))
+        elif s.mlp == "swiglu":
+            act = self._lin_decode(slot, "w_gate", mlp_in, "w_up", act=Fn.ACT_SWIGLU, out=self._buf("act", M, s.intermediate_size), **norm_kw)
+        elif self._has_lora(slot, "w_up"):
+            pre = self._lin_decode(slot, "w_up", mlp_in, bias=w._p("b_up"), out=self._buf("lora_u", M, s.intermediate_size), **norm_kw)
+            self._lora_add_decode(slot, "w_up", mlp_in, pre, **norm_kw)
+            act = Fn.activation(pre, self.act, out=self._buf("act", M, s.intermediate_size))
         else:
-            act = self._lin_decode(slot, "w_up", mlp_in, bias=w._p("b_up"), act=self.act, norm_weight=ln_w, norm_bias=ln_b,
-                                   norm_kind=self.norm_kind, eps=eps, out=self._buf("act", M, s.intermediate_size))
+            act = self._lin_decode(slot, "w_up", mlp_in, bias=w._p("b_up"), act=self.act, out=self._buf("act", M, s.intermediate_size), **norm_kw)
         # down projection + residual; write into x's buffer (x is dead for sequential blocks, and for
         # parallel blocks h1 already contains x + attn). With `hop`, the same epilogue also stores the rows into the
         # next stage's landing zone over NVLink and publishes its flag: the stage hop costs no extra kernel.
+        if self._has_lora(slot, "w_down"):
+            y = self._lin_decode(slot, "w_down", act, bias=w._p("b_down"), residual=h1, out=x)
+            self._lora_add_decode(slot, "w_down", act, y)
+            if hop is not None:
+                hop[0].send(y, hop[2], hop[1])
+            return y
         return self._lin_decode(slot, "w_down", act, bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop))
 
     def _block_prefill(self, x: torch.Tensor, slot: int, B: int, T: int, table, pos_ptr, pools, hop: Optional[tuple] = None) -> torch.Tensor:
@@ -293,8 +368,10 @@ class StageEngine:
         eps = s.norm_eps
         xn = Fn.norm(x, w.ln1_w, w._p("ln1_b"), kind=self.norm_kind, eps=eps, out=self._buf("xn_p", M, s.hidden_size))
         qkv = Fn.gemm(xn, self._w(slot, "wqkv"), bias=w._p("bqkv"), out=self._buf("qkv_p", M, s.qkv_dim))
+        self._lora_add_prefill(slot, "wqkv", xn, qkv)
         attn = self._attention(qkv, slot, B, T, table, pos_ptr, pools, 1, "_p")
         h1 = Fn.gemm(attn, self._w(slot, "wo"), bias=w._p("bo"), residual=x, out=self._buf("h1_p", M, s.hidden_size))
+        self._lora_add_prefill(slot, "wo", attn, h1)
         if s.mlp == "moe":
             return self._moe_prefill(h1, w, x)
         if s.parallel_attn:
@@ -302,10 +379,26 @@ class StageEngine:
         else:
             xn2 = Fn.norm(h1, w.ln2_w, w._p("ln2_b"), kind=self.norm_kind, eps=eps, out=xn)
         act_buf = self._buf("act_p", M, s.intermediate_size)
-        if s.mlp == "swiglu":
+        if s.mlp == "swiglu" and self._has_lora(slot, "w_gate", "w_up"):
+            g = Fn.gemm(xn2, self._w(slot, "w_gate"), out=self._buf("lora_g_p", M, s.intermediate_size))
+            u = Fn.gemm(xn2, self._w(slot, "w_up"), out=self._buf("lora_u_p", M, s.intermediate_size))
+            self._lora_add_prefill(slot, "w_gate", xn2, g)
+            self._lora_add_prefill(slot, "w_up", xn2, u)
+            act = Fn.swiglu(g, u, out=act_buf)
+        elif s.mlp == "swiglu":
             act = Fn.gemm(xn2, self._w(slot, "w_gate"), b2=self._w(slot, "w_up"), act=Fn.ACT_SWIGLU, out=act_buf)
+        elif self._has_lora(slot, "w_up"):
+            pre = Fn.gemm(xn2, self._w(slot, "w_up"), bias=w._p("b_up"), out=self._buf("lora_u_p", M, s.intermediate_size))
+            self._lora_add_prefill(slot, "w_up", xn2, pre)
+            act = Fn.activation(pre, self.act, out=act_buf)
         else:
             act = Fn.gemm(xn2, self._w(slot, "w_up"), bias=w._p("b_up"), act=self.act, out=act_buf)
+        if self._has_lora(slot, "w_down"):
+            y = Fn.gemm(act, self._w(slot, "w_down"), bias=w._p("b_down"), residual=h1, out=x)
+            self._lora_add_prefill(slot, "w_down", act, y)
+            if hop is not None:
+                hop[0].send(y, hop[2], hop[1])
+            return y
         return Fn.gemm(act, self._w(slot, "w_down"), bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop, gemm=True))
 
     def _moe_prefill(self, h1: torch.Tensor, w: GenericBlock, out: torch.Tensor) -> torch.Tensor:
@@ -353,7 +446,7 @@ class StageEngine:
 
     def _chain_ok(self, M: int, lo: int, hi: int, prompts) -> bool:
         s = self.spec
-        return (self.use_chain and self.fuse_rope and M <= 4 and self.fp8 is None and prompts is None and s.mlp in ("swiglu", "gelu")
+        return (self.use_chain and self._adapter is None and self.fuse_rope and M <= 4 and self.fp8 is None and prompts is None and s.mlp in ("swiglu", "gelu")
                 and not s.parallel_attn and not s.qkv_interleaved and not s.post_ln_residual
                 and all(self.blocks[i]._p("bqkv") is None for i in range(lo, hi)))
 
@@ -395,7 +488,8 @@ class StageEngine:
     def _run_span(self, x: torch.Tensor, B: int, T: int, lo: int, hi: int, table, pos_ptr, pools_of, prompts, decode: bool, splits: int,
                   hop: Optional[tuple] = None) -> torch.Tensor:
         M = B * T
-        if decode and M == 1 and self.use_span_kernel and prompts is None and hop is None and hi > lo and pools_of == self.cache.layer_pools:
+        if (decode and M == 1 and self.use_span_kernel and prompts is None and hop is None and hi > lo and pools_of == self.cache.layer_pools
+                and (self._adapter is None or self.lora_mode == "merged")):
             out = self._buf("h_alt", M, self.spec.hidden_size)
             return Fn.decode_span(self._span_kernel_plan(), x, out, table, pos_ptr, self.cos, self.sin, lo=lo, hi=hi)
         if decode and self._chain_ok(M, lo, hi, prompts) and (hop is None or self.spec.mlp != "moe"):
@@ -566,9 +660,9 @@ class StageEngine:
         """Block layouts whose backward runs on the kernels end to end (Llama-style: RMSNorm, SwiGLU, rotary GQA, no biases).
         Other families are differentiated by autograd over the oracle block (server/backend.py)."""
         s = self.spec
-        return (self.fp8 is None and s.norm == "rms" and s.mlp == "swiglu" and s.rotary and not s.qkv_interleaved and not s.parallel_attn
-                and not s.post_ln_residual and not s.alibi and not s.sliding_window and not (s.qkv_bias or s.out_bias or s.mlp_bias)
-                and s.head_dim in (64, 128) and s.hidden_size % 64 == 0 and s.intermediate_size % 64 == 0 and s.qkv_dim % 64 == 0
+        return (self.fp8 is None and self._adapter is None and s.norm == "rms" and s.mlp == "swiglu" and s.rotary and not s.qkv_interleaved
+                and not s.parallel_attn and not s.post_ln_residual and not s.alibi and not s.sliding_window
+                and not (s.qkv_bias or s.out_bias or s.mlp_bias) and s.head_dim in (64, 128) and s.hidden_size % 64 == 0 and s.intermediate_size % 64 == 0 and s.qkv_dim % 64 == 0
                 and all(b._p("bqkv") is None for b in self.blocks))
 
     def _forward_saving(self, x: torch.Tensor, slot: int, nb: int, T: int, table: torch.Tensor, zero_ptr: int) -> Tuple[torch.Tensor, dict]:

@@ -30,6 +30,14 @@ MODEL_PRESETS = {
     "mixtral-8x7b": dict(model_type="mixtral", vocab_size=32000, hidden_size=4096, intermediate_size=14336, num_hidden_layers=32,
                          num_attention_heads=32, num_key_value_heads=8, num_local_experts=8, num_experts_per_tok=2, rms_norm_eps=1e-5,
                          rope_theta=1e6, max_position_embeddings=32768),
+    # Falcon layouts (reference GPU test: tests/test_optimized_layers.py:187-224): 7B-style = multi-query + parallel attention + one
+    # LayerNorm; 40B-style = new decoder architecture (grouped KV, two parallel LayerNorms, interleaved fused QKV); RW = ALiBi, sequential
+    "falcon-tiny-7b": dict(model_type="falcon", vocab_size=4096, hidden_size=1024, num_hidden_layers=3, num_attention_heads=16, multi_query=True,
+                           parallel_attn=True, new_decoder_architecture=False, alibi=False, bias=False, layer_norm_epsilon=1e-5),
+    "falcon-tiny-40b": dict(model_type="falcon", vocab_size=4096, hidden_size=1024, num_hidden_layers=3, num_attention_heads=8, num_kv_heads=2,
+                            new_decoder_architecture=True, parallel_attn=True, alibi=False, bias=False, layer_norm_epsilon=1e-5),
+    "falcon-tiny-rw": dict(model_type="falcon", vocab_size=4096, hidden_size=1024, num_hidden_layers=3, num_attention_heads=16, multi_query=False,
+                           parallel_attn=False, new_decoder_architecture=False, alibi=True, bias=True, layer_norm_epsilon=1e-5),
     "bloom-560m": dict(model_type="bloom", vocab_size=250880, hidden_size=1024, n_layer=24, n_head=16, layer_norm_epsilon=1e-5),
 }
 

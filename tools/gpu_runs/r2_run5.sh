@@ -1,0 +1,21 @@
+#!/bin/bash
+# Round 2, call 5: span kernel v2 with 11 projection warps; LoRA low-rank path; Falcon on the engine; full GPU suite.
+mkdir -p gpurun_out
+S=gpurun_out/r2_5_summary.txt; : > $S
+timeout 600 python -m pytest tests/test_decode_span_gpu.py -q --timeout=150 > gpurun_out/r2_5_span_tests.log 2>&1; echo "span tests exit=$?" | tee -a $S
+tail -4 gpurun_out/r2_5_span_tests.log | cut -c1-250 | tee -a $S
+for shape in 70b-tp8 70b 8b; do
+  for dbg in 0 3; do
+    PETALS_B200_SPAN_DEBUG=$dbg timeout 300 python tools/span_probe.py --shape $shape 2>&1 | grep '^{' | tee -a $S
+  done
+done
+timeout 900 python -m pytest tests -q -m gpu --timeout=200 > gpurun_out/r2_5_pytest.log 2>&1; echo "pytest -m gpu exit=$?" | tee -a $S
+grep -E "passed|failed|FAILED|ERROR" gpurun_out/r2_5_pytest.log | tail -12 | cut -c1-250 | tee -a $S
+run() { name=$1; shift
+  timeout 600 python bench.py --steps 24 --warmup 4 --skip-fp8 "$@" > gpurun_out/r2_5_$name.log 2>&1; echo "$name exit=$?" | tee -a $S
+  grep '^{' gpurun_out/r2_5_$name.log | python -c "import sys,json; [print({k:d[k] for k in ('value','ms_per_step','gpu_launches') if k in d}, d.get('e2e',{}).get('value'), d.get('roofline',{}).get('frac_of_measured_hbm'), (d.get('prefill') or {}).get('tokens_per_s')) for d in map(json.loads, sys.stdin)]" | tee -a $S
+  grep -iE "error|Traceback" gpurun_out/r2_5_$name.log | head -3 | cut -c1-300 | tee -a $S
+}
+run tp8emu_span --tp-emulate 8 --skip-prefill
+run 70b_span --skip-prefill
+run 8b_span --model llama-3-8b --skip-prefill
