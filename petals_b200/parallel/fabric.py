@@ -30,98 +30,111 @@ logger = get_logger(__name__)
 _fabric: Optional["Fabric"] = None
 
 
+KINDS = {"x_in": 0, "y_ret": 1}
+
+
 class Fabric:
-    def __init__(self, hidden_size: int, max_tokens: int = 8192, group=None, extra_bytes: int = (256 << 20) + (1 << 20)):
-        self.hidden_size, self.max_tokens = hidden_size, max_tokens
-        zone = max_tokens * hidden_size * 2
-        self.heap = SymmetricHeap(2 * zone + extra_bytes, group=group)
+    """Landing rings in the symmetric heap. Every rank owns, per kind ("x_in": input of its span, "y_ret": results returned to a
+    client on this rank), ``n_slots`` landing slots of ``max_tokens x hidden`` bf16 plus, per slot, a data flag (incremented by the
+    producer's release after its stores) and an acknowledgement flag ON THE PRODUCER (incremented by the consumer when the slot
+    may be overwritten). All counters are monotonic and per slot, so transfers through different slots are independent: a
+    producer can have up to ``n_slots`` chunks in flight towards the same consumer (chunked prefill / micro-batches in a
+    pipeline), and nothing is ever reset."""
+
+    def __init__(self, hidden_size: int, max_tokens: int = 8192, group=None, extra_bytes: int = (256 << 20) + (1 << 20), n_slots: int = 4):
+        self.hidden_size, self.max_tokens, self.n_slots = hidden_size, max_tokens, n_slots
+        self.zone_bytes = max_tokens * hidden_size * 2
+        self.heap = SymmetricHeap(2 * n_slots * self.zone_bytes + extra_bytes, group=group)
         self.rank, self.world, self.device = self.heap.rank, self.heap.world, self.heap.device
-        self.off_x_in = self.heap.alloc(zone)
-        self.off_y_ret = self.heap.alloc(zone)
-        self.off_flags = self.heap.alloc(64)
-        self.x_in = self.heap.tensor(self.off_x_in, (max_tokens, hidden_size), torch.bfloat16)
-        self.y_ret = self.heap.tensor(self.off_y_ret, (max_tokens, hidden_size), torch.bfloat16)
-        # device-resident counts of consumed transfers (one per landing zone) + producer-side election counter
-        self.in_epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self.ret_epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.off_zones = self.heap.alloc(2 * n_slots * self.zone_bytes)
+        self.off_flags = self.heap.alloc(2 * 2 * n_slots * 8 + 64)  # [data | ack][kind][slot] u64
+        self._zone_views = {}
+        # device-resident counters: transfers consumed per (kind, slot) and pushes issued per (kind, slot)
+        self.consumed = torch.zeros(2, n_slots, dtype=torch.int64, device=self.device)
+        self.pushed = torch.zeros(2, n_slots, dtype=torch.int64, device=self.device)
         self.done_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._flag_src = torch.zeros(16, dtype=torch.uint8, device=self.device)
         self._scratch_off = self.heap.alloc(64)
-        # back-pressure: a producer may not overwrite a landing zone before the consumer copied the previous transfer out.
-        # Every consumer acknowledges to the producer's ack flag; the pushing kernel's prologue waits for
-        # ack >= number of pushes issued so far (the flag starts at 1, so the first push never waits).
-        self.push_epoch = torch.zeros(1, dtype=torch.int64, device=self.device)
-        self.heap.tensor(self.off_flags + 16, (1,), torch.int64).fill_(1)
+        # back-pressure: the pushing kernel's prologue waits for ack >= number of pushes issued through this slot so far; the
+        # acknowledgement flags start at 1, so the first push through a slot never waits
+        self.heap.tensor(self.off_flags + 2 * n_slots * 8, (2 * n_slots,), torch.int64).fill_(1)
         torch.cuda.synchronize(self.device)
         host_barrier(group)
 
     # ---- addresses ---------------------------------------------------------------------------------------------
-    def x_in_addr(self, rank: int) -> int:
-        return self.heap.addr(rank, self.off_x_in)
+    def _zone_off(self, kind: str, slot: int) -> int:
+        return self.off_zones + (KINDS[kind] * self.n_slots + slot % self.n_slots) * self.zone_bytes
 
-    def y_ret_addr(self, rank: int) -> int:
-        return self.heap.addr(rank, self.off_y_ret)
+    def _data_flag_off(self, kind: str, slot: int) -> int:
+        return self.off_flags + (KINDS[kind] * self.n_slots + slot % self.n_slots) * 8
 
-    def in_flag_addr(self, rank: int) -> int:
-        return self.heap.addr(rank, self.off_flags)
+    def _ack_flag_off(self, kind: str, slot: int) -> int:
+        return self.off_flags + (2 * self.n_slots + KINDS[kind] * self.n_slots + slot % self.n_slots) * 8
 
-    def ret_flag_addr(self, rank: int) -> int:
-        return self.heap.addr(rank, self.off_flags + 8)
+    def zone(self, kind: str, rank: int, slot: int = 0):
+        """(data address, data-flag address) of landing slot ``slot`` of ``kind`` on ``rank``."""
+        if kind not in KINDS:
+            raise ValueError(kind)
+        return self.heap.addr(rank, self._zone_off(kind, slot)), self.heap.addr(rank, self._data_flag_off(kind, slot))
 
-    def ack_flag_addr(self, rank: int) -> int:
-        return self.heap.addr(rank, self.off_flags + 16)
+    def ack_flag_addr(self, rank: int, kind: str = "x_in", slot: int = 0) -> int:
+        """Where the consumer of a transfer acknowledges: on the PRODUCER ``rank``, per (kind, slot) of the consumer's ring."""
+        return self.heap.addr(rank, self._ack_flag_off(kind, slot))
 
-    def begin_push(self) -> dict:
-        """Call right before launching a kernel whose epilogue pushes into a peer's landing zone: returns the prologue
-        wait arguments that implement the back-pressure described above."""
-        native.check(native.lib().pb_bump_epoch(self.push_epoch.data_ptr(), native.stream_ptr()), "bump_epoch")
-        return dict(wait_flag=self.ack_flag_addr(self.rank), wait_per_epoch=1, epoch=self.push_epoch.data_ptr(), error_flag=self.err.data_ptr())
+    def view(self, kind: str, slot: int = 0) -> torch.Tensor:
+        """This rank's landing slot as a [max_tokens, hidden] tensor (no copy)."""
+        key = (kind, slot % self.n_slots)
+        if key not in self._zone_views:
+            self._zone_views[key] = self.heap.tensor(self._zone_off(kind, slot), (self.max_tokens, self.hidden_size), torch.bfloat16)
+        return self._zone_views[key]
 
-    def take(self, M: int, kind: str, src_rank: int, out: torch.Tensor) -> torch.Tensor:
-        """Consume the next transfer into this rank's ``kind`` zone: wait, copy the rows out, acknowledge to ``src_rank``."""
-        self.wait(kind)
-        buf = self.y_ret if kind == "y_ret" else self.x_in
-        out.copy_(buf[:M])
-        self._signal(self.ack_flag_addr(src_rank), src_rank)
+    def begin_push(self, kind: str = "x_in", slot: int = 0) -> dict:
+        """Call right before launching a kernel whose epilogue pushes into a peer's landing slot: returns the prologue wait
+        arguments that implement the back-pressure described above."""
+        counter = self.pushed[KINDS[kind], slot % self.n_slots]
+        native.check(native.lib().pb_bump_epoch(counter.data_ptr(), native.stream_ptr()), "bump_epoch")
+        return dict(wait_flag=self.ack_flag_addr(self.rank, kind, slot), wait_per_epoch=1, epoch=counter.data_ptr(), error_flag=self.err.data_ptr())
+
+    def wait(self, kind: str = "y_ret", slot: int = 0) -> None:
+        """Enqueue a wait for the next transfer into this rank's landing slot (advances the slot's consumed count)."""
+        counter = self.consumed[KINDS[kind], slot % self.n_slots]
+        _, flag = self.zone(kind, self.rank, slot)
+        lib = native.lib()
+        native.check(lib.pb_bump_epoch(counter.data_ptr(), native.stream_ptr()), "bump_epoch")
+        native.check(lib.pb_wait_flag(flag, counter.data_ptr(), 1, 0, self.err.data_ptr(), native.stream_ptr()), "wait_flag")
+
+    def acknowledge(self, kind: str, src_rank: int, slot: int = 0) -> None:
+        """Tell ``src_rank`` that landing slot ``slot`` may be overwritten (stream ordered: after everything that read it)."""
+        self._signal(self.ack_flag_addr(src_rank, kind, slot), src_rank)
+
+    def take(self, M: int, kind: str, src_rank: int, out: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        """Consume the next transfer into slot ``slot``: wait, copy the rows out, acknowledge to ``src_rank``."""
+        self.wait(kind, slot)
+        out.copy_(self.view(kind, slot)[:M])
+        self.acknowledge(kind, src_rank, slot)
         return out
 
     def _signal(self, flag_addr: int, rank: int) -> None:
         scratch = ptr_array([self.heap.addr(rank, self._scratch_off)])
         native.check(native.lib().pb_push_rows(self._flag_src.data_ptr(), scratch, ptr_array([flag_addr]), 1, 16, native.stream_ptr()), "fabric signal")
 
-    def zone(self, kind: str, rank: int):
-        """(data address, flag address) of a landing zone on ``rank``."""
-        if kind == "x_in":
-            return self.x_in_addr(rank), self.in_flag_addr(rank)
-        if kind == "y_ret":
-            return self.y_ret_addr(rank), self.ret_flag_addr(rank)
-        raise ValueError(kind)
-
     # ---- host-issued transfers (client -> first stage; anything not produced by a fused epilogue) ---------------------
-    def send(self, rows: torch.Tensor, rank: int, kind: str = "x_in") -> None:
-        """Copy ``rows`` [M, H] into a landing zone of ``rank`` and publish it (stream ordered)."""
+    def send(self, rows: torch.Tensor, rank: int, kind: str = "x_in", slot: int = 0) -> None:
+        """Copy ``rows`` [M, H] into a landing slot of ``rank`` and publish it (stream ordered)."""
         M = rows.shape[0]
         if M > self.max_tokens:
             raise ValueError(f"{M} rows exceed the fabric landing zone ({self.max_tokens})")
-        data, flag = self.zone(kind, rank)
+        data, flag = self.zone(kind, rank, slot)
         dst = tensor_from_ptr(data, (M, self.hidden_size), torch.bfloat16, self.device)
-        kw = self.begin_push()  # honour back-pressure like the fused pushes do
+        kw = self.begin_push(kind, slot)  # honour back-pressure like the fused pushes do
         native.check(native.lib().pb_wait_flag(kw["wait_flag"], kw["epoch"], 1, 0, kw["error_flag"], native.stream_ptr()), "wait_flag")
         dst.copy_(rows.reshape(M, self.hidden_size).to(torch.bfloat16))  # P2P memcpy over NVLink
         self._signal(flag, rank)
 
-    def wait(self, kind: str = "y_ret") -> None:
-        """Enqueue a wait for the next transfer into this rank's zone (advances the zone's epoch)."""
-        epoch = self.ret_epoch if kind == "y_ret" else self.in_epoch
-        _, flag = self.zone(kind, self.rank)
-        lib = native.lib()
-        native.check(lib.pb_bump_epoch(epoch.data_ptr(), native.stream_ptr()), "bump_epoch")
-        native.check(lib.pb_wait_flag(flag, epoch.data_ptr(), 1, 0, self.err.data_ptr(), native.stream_ptr()), "wait_flag")
-
-    def recv(self, M: int, kind: str, src_rank: int) -> torch.Tensor:
+    def recv(self, M: int, kind: str, src_rank: int, slot: int = 0) -> torch.Tensor:
         out = torch.empty(M, self.hidden_size, dtype=torch.bfloat16, device=self.device)
-        return self.take(M, kind, src_rank, out)
+        return self.take(M, kind, src_rank, out, slot)
 
     def check_errors(self) -> None:
         if int(self.err.item()):
@@ -134,21 +147,22 @@ class Fabric:
 
 class HostFabric:
     """The same protocol over POSIX shared memory, for CPU processes (gloo): lets the multi-process plumbing tests exercise
-    the fabric code paths of the client and the handlers (landing zones, flags, acknowledgements) without GPUs."""
+    the fabric code paths of the client and the handlers (landing rings, per-slot flags, acknowledgements) without GPUs."""
 
-    def __init__(self, hidden_size: int, max_tokens: int = 1024, group=None, dtype: torch.dtype = torch.float32):
+    def __init__(self, hidden_size: int, max_tokens: int = 1024, group=None, dtype: torch.dtype = torch.float32, n_slots: int = 4):
         import time
         from multiprocessing import shared_memory
 
         import numpy as np
 
-        self.hidden_size, self.max_tokens, self.dtype = hidden_size, max_tokens, dtype
+        self.hidden_size, self.max_tokens, self.dtype, self.n_slots = hidden_size, max_tokens, dtype, n_slots
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.device = torch.device("cpu")
         self._time, self._np = time, np
         itemsize = torch.empty(0, dtype=dtype).element_size()
         self._zone_bytes = max_tokens * hidden_size * itemsize
-        per_rank = 2 * self._zone_bytes + 64
+        self._flag_bytes = 2 * 2 * n_slots * 8
+        per_rank = 2 * n_slots * self._zone_bytes + self._flag_bytes
         names = [None]
         if self.rank == 0:
             self._shm = shared_memory.SharedMemory(create=True, size=per_rank * self.world)
@@ -160,19 +174,23 @@ class HostFabric:
 
             self._shm = attach_shared_memory(names[0])
         self._per_rank = per_rank
-        self._consumed = {"x_in": 0, "y_ret": 0}
-        self._pushes = 0
-        for r in range(self.world):
-            self._flags(r)[2] = 1  # ack flags start at 1 (first push never waits)
+        self._consumed = np.zeros((2, n_slots), dtype=np.int64)
+        self._pushed = np.zeros((2, n_slots), dtype=np.int64)
+        if self.rank == 0:
+            for r in range(self.world):
+                self._flags(r)[2 * n_slots:] = 1  # acknowledgement flags start at 1 (the first push through a slot never waits)
         host_barrier(group)
 
     def _flags(self, rank: int):
-        off = rank * self._per_rank + 2 * self._zone_bytes
-        return self._np.ndarray((8,), dtype=self._np.uint64, buffer=self._shm.buf, offset=off)
+        """u64 [data flags: kind x slot | ack flags: kind x slot] of ``rank``."""
+        off = rank * self._per_rank + 2 * self.n_slots * self._zone_bytes
+        return self._np.ndarray((4 * self.n_slots,), dtype=self._np.uint64, buffer=self._shm.buf, offset=off)
 
-    def _zone(self, kind: str, rank: int, rows: int) -> torch.Tensor:
-        off = rank * self._per_rank + (0 if kind == "x_in" else self._zone_bytes)
-        itemsize = torch.empty(0, dtype=self.dtype).element_size()
+    def _idx(self, kind: str, slot: int) -> int:
+        return KINDS[kind] * self.n_slots + slot % self.n_slots
+
+    def _zone(self, kind: str, rank: int, rows: int, slot: int) -> torch.Tensor:
+        off = rank * self._per_rank + self._idx(kind, slot) * self._zone_bytes
         flat = torch.frombuffer(self._shm.buf, dtype=self.dtype, count=rows * self.hidden_size, offset=off)
         return flat.view(rows, self.hidden_size)
 
@@ -183,24 +201,26 @@ class HostFabric:
                 raise TimeoutError(f"rank {self.rank}: timed out waiting for {what}")
             self._time.sleep(0)
 
-    def send(self, rows: torch.Tensor, rank: int, kind: str = "x_in") -> None:
+    def send(self, rows: torch.Tensor, rank: int, kind: str = "x_in", slot: int = 0) -> None:
         M = rows.shape[0]
         if M > self.max_tokens:
             raise ValueError(f"{M} rows exceed the fabric landing zone ({self.max_tokens})")
-        self._pushes += 1
-        self._spin(self.rank, 2, self._pushes, "the consumer's acknowledgement")
-        self._zone(kind, rank, M).copy_(rows.reshape(M, self.hidden_size).to(self.dtype))
-        self._flags(rank)[0 if kind == "x_in" else 1] += 1
+        i = self._idx(kind, slot)
+        self._pushed[KINDS[kind], slot % self.n_slots] += 1
+        self._spin(self.rank, 2 * self.n_slots + i, int(self._pushed[KINDS[kind], slot % self.n_slots]), "the consumer's acknowledgement")
+        self._zone(kind, rank, M, slot).copy_(rows.reshape(M, self.hidden_size).to(self.dtype))
+        self._flags(rank)[i] += 1
 
-    def take(self, M: int, kind: str, src_rank: int, out: torch.Tensor) -> torch.Tensor:
-        self._consumed[kind] += 1
-        self._spin(self.rank, 0 if kind == "x_in" else 1, self._consumed[kind], f"a transfer into {kind}")
-        out.copy_(self._zone(kind, self.rank, M))
-        self._flags(src_rank)[2] += 1
+    def take(self, M: int, kind: str, src_rank: int, out: torch.Tensor, slot: int = 0) -> torch.Tensor:
+        i = self._idx(kind, slot)
+        self._consumed[KINDS[kind], slot % self.n_slots] += 1
+        self._spin(self.rank, i, int(self._consumed[KINDS[kind], slot % self.n_slots]), f"a transfer into {kind}[{slot}]")
+        out.copy_(self._zone(kind, self.rank, M, slot))
+        self._flags(src_rank)[2 * self.n_slots + i] += 1
         return out
 
-    def recv(self, M: int, kind: str, src_rank: int) -> torch.Tensor:
-        return self.take(M, kind, src_rank, torch.empty(M, self.hidden_size, dtype=self.dtype))
+    def recv(self, M: int, kind: str, src_rank: int, slot: int = 0) -> torch.Tensor:
+        return self.take(M, kind, src_rank, torch.empty(M, self.hidden_size, dtype=self.dtype), slot)
 
     def check_errors(self) -> None:
         pass
@@ -217,15 +237,15 @@ class HostFabric:
             pass
 
 
-def init_fabric(hidden_size: int, max_tokens: int = 8192, group=None, host_dtype: torch.dtype = torch.float32):
+def init_fabric(hidden_size: int, max_tokens: int = 8192, group=None, host_dtype: torch.dtype = torch.float32, n_slots: int = 4):
     """Collective over ``group``. Returns None when there is nothing to connect (single process)."""
     global _fabric
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
         return None
     if torch.cuda.is_available():
-        _fabric = Fabric(hidden_size, max_tokens, group)
+        _fabric = Fabric(hidden_size, max_tokens, group, n_slots=n_slots)
     else:
-        _fabric = HostFabric(hidden_size, min(max_tokens, 1024), group, host_dtype)
+        _fabric = HostFabric(hidden_size, min(max_tokens, 1024), group, host_dtype, n_slots=n_slots)
     return _fabric
 
 

@@ -174,11 +174,11 @@ class Stage:
                     return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi), take_from=take_from, push_to=push_to)
                 return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi))
         if take_from is not None:  # executors without fused hops still honour the fabric protocol (host-issued copies)
-            fabric, src_rank, B, T = take_from
-            hidden = fabric.recv(B * T, "x_in", src_rank).view(B, T, -1)
+            fabric, src_rank, B, T = take_from[:4]
+            hidden = fabric.recv(B * T, "x_in", src_rank, *take_from[4:5]).view(B, T, -1)
         out = self._oracle_inference(session, hidden, prompts, hypo_ids, lo, hi)
         if push_to is not None:
-            push_to[0].send(out.reshape(-1, out.shape[-1]), push_to[2], push_to[1])
+            push_to[0].send(out.reshape(-1, out.shape[-1]), push_to[2], push_to[1], *push_to[3:4])
             return out[:, :0]
         return out
 

@@ -159,13 +159,16 @@ class InferenceStream:
             fb, ft, src = int(fin["B"]), int(fin["T"]), int(fin["src_rank"])
             if fb < 1 or ft < 1 or fb * ft > fabric.max_tokens or not 0 <= src < getattr(fabric, "world", src + 1):
                 raise ValueError(f"fabric_in describes {fb} x {ft} rows from rank {src}: outside this stage's landing zone ({fabric.max_tokens} rows)")
-            take_from = (fabric, src, fb, ft)
+            slot_in = int(fin.get("slot", 0))
+            if not 0 <= slot_in < getattr(fabric, "n_slots", 1):
+                raise ValueError(f"fabric_in names landing slot {slot_in}; this stage's ring has {getattr(fabric, 'n_slots', 1)}")
+            take_from = (fabric, src, fb, ft, slot_in)
             hidden = torch.empty(int(fin["B"]), int(fin["T"]), self.handler.stage.spec.hidden_size, dtype=self.handler.stage.dtype,
                                  device=self.handler.stage.device)  # shape carrier only
         if fout is not None:
             if fabric is None:
                 raise RuntimeError("this stage has no NVLink fabric but the request asks to push its output")
-            push_to = (fabric, str(fout["kind"]), int(fout["rank"]))
+            push_to = (fabric, str(fout["kind"]), int(fout["rank"]), int(fout.get("slot", 0)) % max(1, getattr(fabric, "n_slots", 1)))
         if hidden.dim() != 3 or not hidden.is_floating_point():
             raise ValueError(f"hidden states must be a floating-point tensor [batch, seq, hidden], got {tuple(hidden.shape)} {hidden.dtype}")
         if hidden.shape[2] != self.handler.stage.spec.hidden_size:  # kernels index by the model's hidden size: never trust the wire

@@ -297,9 +297,10 @@ class StageEngine:
         """Epilogue/prologue arguments that turn the span's last kernel into the fused stage hop (see parallel/fabric.py)."""
         if hop is None:
             return {}
-        fabric, kind, rank = hop
-        data, flag = fabric.zone(kind, rank)
-        kw = fabric.begin_push()
+        fabric, kind, rank = hop[:3]
+        slot = hop[3] if len(hop) > 3 else 0
+        data, flag = fabric.zone(kind, rank, slot)
+        kw = fabric.begin_push(kind, slot)
         kw.update(push_out=[data], done_counter=fabric.done_counter.data_ptr())
         if gemm:
             kw["push_done_flag"] = [flag]
@@ -357,7 +358,7 @@ class StageEngine:
             y = self._lin_decode(slot, "w_down", act, bias=w._p("b_down"), residual=h1, out=x)
             self._lora_add_decode(slot, "w_down", act, y)
             if hop is not None:
-                hop[0].send(y, hop[2], hop[1])
+                hop[0].send(y, hop[2], hop[1], *hop[3:4])
             return y
         return self._lin_decode(slot, "w_down", act, bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop))
 
@@ -397,7 +398,7 @@ class StageEngine:
             y = Fn.gemm(act, self._w(slot, "w_down"), bias=w._p("b_down"), residual=h1, out=x)
             self._lora_add_prefill(slot, "w_down", act, y)
             if hop is not None:
-                hop[0].send(y, hop[2], hop[1])
+                hop[0].send(y, hop[2], hop[1], *hop[3:4])
             return y
         return Fn.gemm(act, self._w(slot, "w_down"), bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop, gemm=True))
 
@@ -507,7 +508,7 @@ class StageEngine:
             else:
                 cur = self._block_prefill(cur, slot, B, T, table, pos_ptr, pools_of(slot), fused_hop)
         if hop is not None and (self.spec.mlp == "moe" or (decode and self.fp8 is not None)):  # no fused epilogue here yet: host-issued NVLink copy
-            hop[0].send(cur, hop[2], hop[1])
+            hop[0].send(cur, hop[2], hop[1], *hop[3:4])
         return cur
 
     def inference_step(self, session: SessionCache, hidden: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None,
@@ -515,15 +516,15 @@ class StageEngine:
                        take_from: Optional[tuple] = None, push_to: Optional[tuple] = None) -> torch.Tensor:
         """One rpc_inference step through blocks [lo, hi) of this stage (reference: backend.py:111-144).
 
-        ``take_from = (fabric, src_rank, B, T)``: the input was pushed into this rank's landing zone by ``src_rank``'s last
-        kernel (``hidden`` is then only a shape carrier). ``push_to = (fabric, kind, rank)``: the span's last kernel stores
-        its output into that rank's landing zone; the returned tensor is then empty."""
+        ``take_from = (fabric, src_rank, B, T[, slot])``: the input was pushed into landing slot ``slot`` of this rank by
+        ``src_rank``'s last kernel (``hidden`` is then only a shape carrier). ``push_to = (fabric, kind, rank[, slot])``: the span's
+        last kernel stores its output into that landing slot of ``rank``; the returned tensor is then empty."""
         lo, hi = block_range or (0, self.n_blocks)
         if take_from is not None:
-            fabric, src_rank, B, T = take_from
+            fabric, src_rank, B, T = take_from[:4]
             H = self.spec.hidden_size
             staged = self._buf("x_taken", B * T, H)
-            fabric.take(B * T, "x_in", src_rank, staged)
+            fabric.take(B * T, "x_in", src_rank, staged, *take_from[4:5])
             hidden = staged.view(B, T, H)
         B, T, H = hidden.shape
         if hypo_ids is not None and not is_dummy(hypo_ids):
@@ -562,7 +563,7 @@ class StageEngine:
         pools_of = self.cache.layer_pools
         decode = M <= self.max_decode_rows
         if decode and self.use_cuda_graphs and prompts is None:
-            key = (B, T, lo, hi) if hop is None else (B, T, lo, hi, hop[1], hop[2])
+            key = (B, T, lo, hi) if hop is None else (B, T, lo, hi) + tuple(hop[1:])
             g = self._graphs.get(key)
             if g is None:
                 g = self._capture(B, T, lo, hi, table, hop)
@@ -616,7 +617,7 @@ class StageEngine:
         native.add_launches(-launches)  # captured, not executed
         self.pos_static.copy_(saved_pos)  # capture does not execute, but keep the invariant explicit
         g = dict(graph=graph, x=x, out=out, launches=launches)
-        self._graphs[(B, T, lo, hi) if hop is None else (B, T, lo, hi, hop[1], hop[2])] = g
+        self._graphs[(B, T, lo, hi) if hop is None else (B, T, lo, hi) + tuple(hop[1:])] = g
         logger.debug(f"captured decode graph B={B} T={T} blocks [{lo},{hi}) splits={splits}")
         return g
 
