@@ -38,6 +38,7 @@ class ClientConfig:
     allowed_servers: Optional[Sequence[str]] = None  # only route through these peer ids ...
     blocked_servers: Optional[Sequence[str]] = None  # ... and never through these
     use_server_to_server: bool = True  # let stage i hand its output to stage i+1 directly (fused NVLink hop / rpc_push)
+    pipeline_chunk_tokens: int = 512  # a step of >= 2x this many tokens over >= 2 stages is ingested as a wavefront of chunks (0: never)
     show_route: Union[str, bool] = "inference"  # log the chosen chain: for inference sessions only, always (True) or never (False)
     max_pinged: int = 3  # how many candidate first-hop servers are pinged when a route is planned
     ping_timeout: float = 2

@@ -15,6 +15,10 @@ Design here (one NVLink box, one process per GPU):
 * when every hop of the chain rides the NVLink fabric (``parallel/fabric.py``) and every stream is primed, the wave is
   **dispatched to all stages at once** (:meth:`_fabric_wave`): stage *i*'s first kernel spins on its landing-zone flag and
   stage *i-1*'s last kernel fills it, so the hops are ordered on the devices, not by one client round trip per hop;
+* a long step (prompt ingestion) over several stages is cut into chunks along the sequence and run as a **wavefront**
+  (:meth:`_pipelined_wave`, client/pipeline.py): chunk *c* enters stage *s+1* while chunk *c+1* enters stage *s* — the stages'
+  KV sessions make the causal attention of later chunks see the earlier ones, so S stages ingest a prompt concurrently instead
+  of one after the other. Over the fabric the chunks travel through the landing RINGS (one slot per chunk in flight);
 * activations that only ever lived in landing zones are unknown to the client; such a chain is rebuilt from the first
   stage's log as a whole.
 """
@@ -109,7 +113,7 @@ class StageStream:
         self.cursor = position
         self.log.truncate(position)
 
-    def _request(self, step_id: str, deliver_to: Optional[dict]) -> Dict[str, Any]:
+    def _request(self, step_id: str, deliver_to: Optional[dict]) -> Dict[str, Any]:  # noqa: D401
         meta: Dict[str, Any] = {"step_id": step_id}
         if self.primed:
             meta["start_from_position"] = self.cursor  # a no-op unless the session was rolled back
@@ -152,8 +156,8 @@ class StageStream:
         return result
 
     def feed_landed(self, shape: Tuple[int, int, int], src_rank: int, prompts: torch.Tensor, hypo_ids: torch.Tensor, *, step_id: str,
-                    n_new: int, deliver_to: Optional[dict] = None) -> None:
-        """Run one step whose input ``src_rank`` stored (or is about to store) into this stage's landing zone."""
+                    n_new: int, deliver_to: Optional[dict] = None, slot: int = 0) -> None:
+        """Run one step whose input ``src_rank`` stored (or is about to store) into landing slot ``slot`` of this stage."""
         if self.closed:
             raise RuntimeError("this stage stream is closed")
         B, L, _ = shape
@@ -162,7 +166,7 @@ class StageStream:
         self.log.forget()
         self.no_history = True
         meta = self._request(step_id, deliver_to)
-        meta["fabric_in"] = {"src_rank": src_rank, "B": B, "T": L}
+        meta["fabric_in"] = {"src_rank": src_rank, "B": B, "T": L, "slot": slot}
         self.stream.step(torch.empty(0), prompts, hypo_ids, metadata=meta)
         self.primed, self.cursor = True, self.cursor + n_new
 
@@ -382,6 +386,68 @@ class InferenceSession:
         B, L, H = shape
         return fabric.recv(B * L, "y_ret", chain[-1].fabric_rank).view(B, L, H)
 
+    def _pipelined_wave(self, fabric, x: torch.Tensor, prompts, hypo_ids, n_new: int) -> Optional[torch.Tensor]:
+        """Chunked prompt ingestion as a wavefront over the chain. Returns None when the step does not qualify (short step, one
+        stage, deep prompts / beam reordering in play, chain not in step); raises when a stage fails (the caller rebuilds)."""
+        from petals_b200.client.pipeline import run_wave
+
+        chain, config = self._chain, self._manager.config
+        chunk = int(getattr(config, "pipeline_chunk_tokens", 0) or 0)
+        B = x.shape[0]
+        if (chunk <= 0 or len(chain) < 2 or n_new < 2 * chunk or not is_dummy(prompts) or not is_dummy(hypo_ids)
+                or chain[0].span.start != 0 or chain[-1].span.end != self.num_blocks
+                or any(s.closed or s.cursor != self._position for s in chain) or (self._position > 0 and any(not s.primed for s in chain))):
+            return None
+        if fabric is not None:
+            chunk = max(1, min(chunk, fabric.max_tokens // max(B, 1)))
+        bounds = [(t0, min(n_new, t0 + chunk)) for t0 in range(0, n_new, chunk)]
+        n_slots = getattr(fabric, "n_slots", 1) if fabric is not None else 1
+        step_id = str(uuid.uuid4())
+        H = x.shape[2]
+
+        class Chunk:  # one item of the wavefront
+            def __init__(self, index: int, t0: int, t1: int):
+                self.index, self.t0, self.t1 = index, t0, t1
+                self.x: Any = None  # tensor, or (src_rank, shape) when the activations sit in the next landing slot
+                self.error: Optional[BaseException] = None
+                self.detached = False
+
+        items = [Chunk(i, a, b) for i, (a, b) in enumerate(bounds)]
+        for it in items:
+            it.x = x[:, x.shape[1] - n_new + it.t0: x.shape[1] - n_new + it.t1]
+
+        def stage_work(i: int):
+            stage = chain[i]
+
+            def work(it: "Chunk") -> None:
+                n = it.t1 - it.t0
+                shape = (B, n, H)
+                target = self._landing(fabric, i, shape)
+                if target is not None:
+                    target = dict(target, slot=it.index % n_slots)
+                sid = f"{step_id}:{it.index}"
+                if isinstance(it.x, tuple):  # landed in this stage's ring by the previous stage
+                    stage.feed_landed(shape, it.x[0], DUMMY, DUMMY_INT64, step_id=sid, n_new=n, deliver_to=target, slot=it.index % n_slots)
+                    result = shape
+                else:
+                    result = stage.feed(it.x, DUMMY, DUMMY_INT64, step_id=sid, n_new=n, deliver_to=target)
+                it.x = (stage.fabric_rank, shape) if target is not None else result
+                self._manager.on_request_success(stage.span.peer_id)
+            return work
+
+        def collect(it: "Chunk") -> None:  # last lane: bring the chunk's result home (frees the y_ret slot for a later chunk)
+            if isinstance(it.x, tuple):
+                n = it.t1 - it.t0
+                it.x = fabric.recv(B * n, "y_ret", it.x[0], it.index % n_slots).view(B, n, H)
+
+        run_wave(items, [stage_work(i) for i in range(len(chain))] + [collect], threaded=True)
+        failed = [it for it in items if it.error is not None]
+        if failed:
+            for stage in chain:  # some stages are chunks ahead of others: the chain is rebuilt from the first stage's log
+                stage.no_history = True
+            raise failed[0].error
+        return torch.cat([it.x.to(x.device, x.dtype) for it in items], dim=1)
+
     def _run_wave(self, step_inputs: torch.Tensor, prompts, hypo_ids, n_new: int) -> torch.Tensor:
         from petals_b200.parallel.fabric import get_fabric
 
@@ -400,7 +466,11 @@ class InferenceSession:
             try:
                 if try_all_at_once and idx == 0:
                     try_all_at_once = False
+                    if not self._chain:
+                        self._reroute(0, 0, False)  # first step of the session: route the whole model now
                     done = self._fabric_wave(fabric, x, prompts, hypo_ids, n_new, step_id)
+                    if done is None and self._chain:
+                        done = self._pipelined_wave(fabric, x, prompts, hypo_ids, n_new)
                     if done is not None:
                         return done
                 if idx >= len(self._chain) or failures > 0:

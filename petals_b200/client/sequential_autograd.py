@@ -21,14 +21,13 @@ This module implements that as an explicit **wavefront schedule** (all-forward, 
 """
 from __future__ import annotations
 
-import queue
-import threading
 import time
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
 import torch
 
+from petals_b200.client.pipeline import run_wave as _run_wave
 from petals_b200.client.remote_forward_backward import run_remote_backward, run_remote_forward
 from petals_b200.client.routing import RemoteSequenceManager, maybe_log_traceback
 from petals_b200.data_structures import RemoteSpanInfo
@@ -142,62 +141,7 @@ def backward_hops(manager: RemoteSequenceManager, mb: MicroBatch) -> None:
             mb.hops.extend(redo.hops)  # same blocks, new stages; the activations entering them were recomputed
 
 
-# ---- the wavefront --------------------------------------------------------------------------------------------------
-class _Lane(threading.Thread):
-    """Worker of one stage of the route. Pulls micro-batches in arrival order — which is micro-batch order, since the previous
-    lane emits them in order — runs ``work`` on each and passes it on."""
-
-    _STOP = object()
-
-    def __init__(self, name: str, work, downstream: Optional["_Lane"], finished: "queue.Queue"):
-        super().__init__(name=name, daemon=True)
-        self.inbox: "queue.Queue" = queue.Queue()
-        self.work, self.downstream, self.finished = work, downstream, finished
-
-    def run(self) -> None:
-        while True:
-            mb = self.inbox.get()
-            if mb is _Lane._STOP:
-                if self.downstream is not None:
-                    self.downstream.inbox.put(_Lane._STOP)
-                return
-            if not mb.detached and mb.error is None:
-                try:
-                    self.work(mb)
-                except BaseException as e:  # noqa: BLE001 - recorded on the micro-batch, re-raised by the caller
-                    mb.error = e
-            (self.downstream.inbox if self.downstream is not None else self.finished).put(mb)
-
-
-def _run_wave(micro_batches: Sequence[MicroBatch], stage_work: Sequence, threaded: bool) -> None:
-    """Push every micro-batch through ``stage_work[0], stage_work[1], ...`` in wavefront order."""
-    if not threaded or len(stage_work) * len(micro_batches) == 1:
-        # same (stage, micro-batch) order a pipeline would produce, on this thread: diagonal by diagonal
-        S, M = len(stage_work), len(micro_batches)
-        for diag in range(S + M - 1):
-            for s in range(max(0, diag - M + 1), min(S, diag + 1)):
-                mb = micro_batches[diag - s]
-                if not mb.detached and mb.error is None:
-                    try:
-                        stage_work[s](mb)
-                    except BaseException as e:  # noqa: BLE001
-                        mb.error = e
-        return
-    finished: "queue.Queue" = queue.Queue()
-    lanes: List[_Lane] = []
-    for s in reversed(range(len(stage_work))):
-        lanes.insert(0, _Lane(f"petals-lane-{s}", stage_work[s], lanes[0] if lanes else None, finished))
-    for lane in lanes:
-        lane.start()
-    for mb in micro_batches:
-        lanes[0].inbox.put(mb)
-    lanes[0].inbox.put(_Lane._STOP)
-    for _ in micro_batches:
-        finished.get()
-    for lane in lanes:
-        lane.join()
-
-
+# ---- the wavefront (client/pipeline.py) ------------------------------------------------------------------------------------
 def pipelined_forward(manager: RemoteSequenceManager, micro_batches: Sequence[MicroBatch], start: int, end: int) -> None:
     """All micro-batches through blocks [start, end); fills ``mb.x`` (outputs) and ``mb.hops`` (the tape)."""
     try:

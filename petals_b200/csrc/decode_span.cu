@@ -163,6 +163,20 @@ PB_DEVICE uint2 poll_ll2(const uint2* p, uint32_t tag, int* error_flag) {
   return make_uint2(v.x, v.z);
 }
 
+// mbarrier wait with context: on expiry prints WHO waits for WHAT (role, ring stage, parity) once per warp and traps.
+PB_DEVICE void span_wait(uint64_t* bar, uint32_t parity, char what, uint32_t stage, int aux) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = globaltimer_ns();
+  unsigned spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xff) == 0 && globaltimer_ns() - t0 > 3000000000ull) {  // 3 s
+      if ((threadIdx.x & 31) == 0)
+        printf("decode_span stuck: block %d warp %d waits %c stage %u parity %u aux %d\n", blockIdx.x, threadIdx.x >> 5, what, stage, parity, aux);
+      __trap();
+    }
+  }
+}
+
 struct Ring {
   uint8_t* base;    // n slots of kStageBytes
   uint64_t* full;   // [n]
@@ -197,7 +211,7 @@ PB_DEVICE void produce_proj(const Ring& ring, uint32_t& base, const Geom& g, con
         const size_t out = t * g.outs + (g.dual ? row >> 1 : row);
         src = (g.dual && (row & 1) ? w2 : w) + out * g.K + static_cast<size_t>(c) * g.kc;
       }
-      mbar_wait(ring.empty_bar(st), ring.parity(st) ^ 1u);
+      span_wait(ring.empty_bar(st), ring.parity(st) ^ 1u, 'E', st, g.S);
       mbar_expect_tx(ring.full_bar(st), bytes);
       bulk_load_hint(ring.slot(st), src, bytes, ring.full_bar(st), policy);
     }
@@ -215,10 +229,10 @@ PB_DEVICE void produce_kv(const Params& p, const Ring& ring, uint32_t& base, con
     int pg = c < p.max_pages ? p.block_table[c] : 0;
     pg = min(max(pg, 0), p.num_pages - 1);
     const size_t off = (static_cast<size_t>(pg) * p.Hkv + hk) * kPage * p.D;
-    mbar_wait(ring.empty_bar(st), ring.parity(st) ^ 1u);
+    span_wait(ring.empty_bar(st), ring.parity(st) ^ 1u, 'K', st, u);
     mbar_expect_tx(ring.full_bar(st), bytes);
     bulk_load_1d(ring.slot(st), L.k_pool + off, bytes, ring.full_bar(st));
-    mbar_wait(ring.empty_bar(st + 1), ring.parity(st + 1) ^ 1u);
+    span_wait(ring.empty_bar(st + 1), ring.parity(st + 1) ^ 1u, 'V', st + 1, u);
     mbar_expect_tx(ring.full_bar(st + 1), bytes);
     bulk_load_1d(ring.slot(st + 1), L.v_pool + off, bytes, ring.full_bar(st + 1));
   }
@@ -261,7 +275,7 @@ PB_DEVICE void consume_proj_r(const Params& p, const Ring& ring, uint32_t base, 
 #pragma unroll
     for (int i = 0; i < NACC; ++i) v[i] = u[i] = 0.f;
     for (int s_ = 0; s_ < g.S; ++s_, ++st) {
-      mbar_wait(ring.full_bar(st), ring.parity(st));
+      span_wait(ring.full_bar(st), ring.parity(st), 'F', st, EPI * 100 + s_);
       const __nv_bfloat16* sm = reinterpret_cast<const __nv_bfloat16*>(ring.slot(st));
       if (!(c_debug & 2)) {
         if constexpr (R >= 2) {
@@ -451,8 +465,8 @@ PB_DEVICE void consume_attention(const Params& p, const Ring& ring, uint32_t& ba
     }
     const uint32_t st = base;   // K page in stage st, V page in stage st + 1; every warp reads both
     base += 2;
-    mbar_wait(ring.full_bar(st), ring.parity(st));
-    mbar_wait(ring.full_bar(st + 1), ring.parity(st + 1));
+    span_wait(ring.full_bar(st), ring.parity(st), 'k', st, u);
+    span_wait(ring.full_bar(st + 1), ring.parity(st + 1), 'v', st + 1, u);
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(ring.slot(st));
     __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(ring.slot(st + 1));
     const int key0 = c * kPage;

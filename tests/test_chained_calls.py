@@ -66,3 +66,27 @@ def test_chain_inference_matches_local_blocks_with_explicit_kv(world, first, las
     # the cached token-by-token run equals one cache-less pass over the whole sequence
     with torch.no_grad():
         assert torch.allclose(torch.cat(got, 1), _local_chain(local, first, last, tokens), rtol=0, atol=1e-4)
+
+
+def test_long_prompt_is_ingested_as_a_wavefront_of_chunks():
+    """A long step over several stages is cut into chunks that travel through the stages as a wavefront (client/pipeline.py); the
+    stages' KV sessions make it exactly the unchunked computation, and the session continues normally afterwards."""
+    import torch
+
+    from petals_b200.utils.auto_config import AutoDistributedModelForCausalLM
+    from tests.utils import checkpoint, swarm_of
+
+    path = checkpoint("llama")
+    with swarm_of(path, ["0:1", "1:3", "3:4"]) as (swarm, _servers):
+        plain = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=swarm, pipeline_chunk_tokens=0)
+        piped = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=swarm, pipeline_chunk_tokens=8)
+        ids = torch.randint(0, plain.config.vocab_size, (2, 45))
+        outs = {}
+        for name, m in (("plain", plain), ("piped", piped)):
+            with torch.inference_mode(), m.inference_session(max_length=64) as sess:
+                a = m(ids[:, :37]).logits          # 37 tokens -> chunks of 8, 8, 8, 8, 5 through 3 stages
+                b = m(ids[:, 37:38]).logits        # ordinary single-token step on the same caches
+                c = m(ids[:, 38:]).logits          # 7 tokens: below 2 x chunk, not pipelined
+                outs[name] = torch.cat([a, b, c], 1)
+                assert [s.cursor for s in sess._server_sessions] == [45, 45, 45]
+        assert (outs["plain"] - outs["piped"]).abs().max().item() < 1e-4 * outs["plain"].abs().max().item() + 1e-5

@@ -28,8 +28,10 @@ def main():
     ap.add_argument("--shape", default="70b-tp8")
     ap.add_argument("--pos", type=int, default=130)
     ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--layers", type=int, default=0, help="override the number of blocks (0: the shape's default)")
     args = ap.parse_args()
     H, Hq, Hkv, D, I, L = SHAPES[args.shape]
+    L = args.layers or L
     dev = torch.device("cuda:0")
     g = torch.Generator(device=dev).manual_seed(0)
     rnd = lambda *s: (torch.randn(*s, device=dev, generator=g) * 0.02).to(torch.bfloat16)
