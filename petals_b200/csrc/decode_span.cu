@@ -181,11 +181,32 @@ struct Ring {
   uint8_t* base;    // n slots of kStageBytes
   uint64_t* full;   // [n]
   uint64_t* empty;  // [n]
+  volatile uint32_t* armed;  // [n]: 1 + the ring period (stage / n) the slot's full barrier is currently armed for
   int n;
   PB_DEVICE uint8_t* slot(uint32_t stage) const { return base + static_cast<size_t>(stage % n) * kStageBytes; }
   PB_DEVICE uint64_t* full_bar(uint32_t stage) const { return &full[stage % n]; }
   PB_DEVICE uint64_t* empty_bar(uint32_t stage) const { return &empty[stage % n]; }
   PB_DEVICE uint32_t parity(uint32_t stage) const { return (stage / n) & 1u; }
+  // Producer: the slot is free and about to be armed for `stage`.
+  PB_DEVICE void arm(uint32_t stage) const { armed[stage % n] = stage / n + 1u; }
+  // Consumer: wait for `stage`'s data. mbarrier phases are only told apart by parity, and a warp that owns tasks several ring
+  // periods apart may get here long before the producer: first wait until the slot is armed for THIS period (then the parity
+  // wait is at most one phase ahead of the barrier, which is what the parity protocol requires).
+  PB_DEVICE void wait_full(uint32_t stage, char what, int aux) const {
+    const uint32_t want = stage / n + 1u;
+    if (armed[stage % n] != want) {
+      const uint64_t t0 = globaltimer_ns();
+      unsigned spins = 0;
+      while (armed[stage % n] != want) {
+        if ((++spins & 0x3ff) == 0 && globaltimer_ns() - t0 > 3000000000ull) {
+          if ((threadIdx.x & 31) == 0)
+            printf("decode_span stuck: block %d warp %d waits arm of stage %u (%c, aux %d), slot armed for %u\n", blockIdx.x, threadIdx.x >> 5, stage, what, aux, armed[stage % n]);
+          __trap();
+        }
+      }
+    }
+    span_wait(full_bar(stage), parity(stage), what, stage, aux);
+  }
 };
 // Stages are numbered 0, 1, 2, ... in the order the producer issues them; stage i lives in slot i % n. Producer and consumers
 // derive the same numbers from the geometry (nothing is communicated): `base` = first stage of the current phase.
@@ -213,6 +234,7 @@ PB_DEVICE void produce_proj(const Ring& ring, uint32_t& base, const Geom& g, con
       }
       span_wait(ring.empty_bar(st), ring.parity(st) ^ 1u, 'E', st, g.S);
       mbar_expect_tx(ring.full_bar(st), bytes);
+      ring.arm(st);
       bulk_load_hint(ring.slot(st), src, bytes, ring.full_bar(st), policy);
     }
   }
@@ -231,9 +253,11 @@ PB_DEVICE void produce_kv(const Params& p, const Ring& ring, uint32_t& base, con
     const size_t off = (static_cast<size_t>(pg) * p.Hkv + hk) * kPage * p.D;
     span_wait(ring.empty_bar(st), ring.parity(st) ^ 1u, 'K', st, u);
     mbar_expect_tx(ring.full_bar(st), bytes);
+    ring.arm(st);
     bulk_load_1d(ring.slot(st), L.k_pool + off, bytes, ring.full_bar(st));
     span_wait(ring.empty_bar(st + 1), ring.parity(st + 1) ^ 1u, 'V', st + 1, u);
     mbar_expect_tx(ring.full_bar(st + 1), bytes);
+    ring.arm(st + 1);
     bulk_load_1d(ring.slot(st + 1), L.v_pool + off, bytes, ring.full_bar(st + 1));
   }
   base = st;
@@ -275,7 +299,7 @@ PB_DEVICE void consume_proj_r(const Params& p, const Ring& ring, uint32_t base, 
 #pragma unroll
     for (int i = 0; i < NACC; ++i) v[i] = u[i] = 0.f;
     for (int s_ = 0; s_ < g.S; ++s_, ++st) {
-      span_wait(ring.full_bar(st), ring.parity(st), 'F', st, EPI * 100 + s_);
+      ring.wait_full(st, 'F', EPI * 100 + s_);
       const __nv_bfloat16* sm = reinterpret_cast<const __nv_bfloat16*>(ring.slot(st));
       if (!(c_debug & 2)) {
         if constexpr (R >= 2) {
@@ -465,8 +489,8 @@ PB_DEVICE void consume_attention(const Params& p, const Ring& ring, uint32_t& ba
     }
     const uint32_t st = base;   // K page in stage st, V page in stage st + 1; every warp reads both
     base += 2;
-    span_wait(ring.full_bar(st), ring.parity(st), 'k', st, u);
-    span_wait(ring.full_bar(st + 1), ring.parity(st + 1), 'v', st + 1, u);
+    ring.wait_full(st, 'k', u);
+    ring.wait_full(st + 1, 'v', u);
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(ring.slot(st));
     __nv_bfloat16* Vs = reinterpret_cast<__nv_bfloat16*>(ring.slot(st + 1));
     const int key0 = c * kPage;
@@ -609,10 +633,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
   float* res = reinterpret_cast<float*>(q);                             q += 256 * sizeof(float);
   float* red = reinterpret_cast<float*>(q);                             q += 32 * sizeof(float);
   ring.full = reinterpret_cast<uint64_t*>(q);                           q += kMaxStages * 8;
-  ring.empty = reinterpret_cast<uint64_t*>(q);
+  ring.empty = reinterpret_cast<uint64_t*>(q);                          q += kMaxStages * 8;
+  ring.armed = reinterpret_cast<volatile uint32_t*>(q);
 
   if (tid == 0) {
-    for (int i = 0; i < p.n_stages; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], 1); }
+    for (int i = 0; i < p.n_stages; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], 1); ring.armed[i] = 0u; }
     mbar_fence_init();
   }
   __syncthreads();
@@ -738,7 +763,7 @@ extern "C" int pb_decode_span_smem(const PbDecodeSpanArgs* a, int* n_stages, int
   if (a->I > vin) vin = a->I;
   if ((G + 2) * a->D > vin) vin = (G + 2) * a->D;
   vin = (vin + 63) & ~63;
-  const size_t fixed = static_cast<size_t>(vin) * 2 + (16 * kPage + 64) * 4 + 256 * 4 + 32 * 4 + 2 * kMaxStages * 8 + 1024;
+  const size_t fixed = static_cast<size_t>(vin) * 2 + (16 * kPage + 64) * 4 + 256 * 4 + 32 * 4 + 2 * kMaxStages * 8 + kMaxStages * 4 + 1024;
   const size_t budget = 227 * 1024;
   if (fixed + 4 * kStageBytes > budget) return -1;
   int ns = static_cast<int>((budget - fixed) / kStageBytes);
