@@ -285,75 +285,102 @@ PB_DEVICE void dot_rows(const __nv_bfloat16* st, const __nv_bfloat16* x, int kc,
   }
 }
 
+// Shared bookkeeping of the tasks in flight: task j of this CTA uses slot j % kTaskSlots. Every stage of a task is computed by
+// whichever warp owns that STAGE (stage i of the phase -> warp i % 11), deposits its partial sums here, and the warp that
+// deposits last finishes the task. `gen` makes a slot's reuse wait for the previous occupant's finisher.
+constexpr int kTaskSlots = 16;
+constexpr int kPartFloats = 32;   // >= stages per task x rows per stage
+struct TaskBoard {
+  float* part;               // [kTaskSlots][kPartFloats]
+  unsigned int* cnt;         // [kTaskSlots] deposits so far
+  volatile unsigned int* gen;  // [kTaskSlots] occupants finished so far
+};
+
 // EPI: 0 = QKV (pairs -> qkv_ll), 1 = row-parallel push (pairs -> R peers), 2 = gate/up (SwiGLU -> act_ll)
 template <int EPI, int R>
-PB_DEVICE void consume_proj_r(const Params& p, const Ring& ring, uint32_t base, const Geom& g, const __nv_bfloat16* vin, uint2* const* push,
-                              uint2* local_out, uint32_t tag, int bid, int grid) {
+PB_DEVICE void consume_proj_r(const Params& p, const Ring& ring, const TaskBoard& tb, uint32_t base, const Geom& g, const __nv_bfloat16* vin,
+                              uint2* const* push, uint2* local_out, uint32_t tag, int bid, int grid) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nt = tasks_of_cta(g, bid, grid);
-  constexpr int NACC = (R >= 2) ? R : 2;   // outputs per task
-  for (int j = warp; j < nt; j += kGemvWarps) {
+  const int S = g.S, total = nt * S;
+  constexpr int NOUT = (R >= 2) ? R : 2;   // outputs per task
+  for (int i = warp; i < total; i += kGemvWarps) {   // one ring stage at a time, whatever task it belongs to
+    const int j = i / S, s_ = i - j * S;
+    const uint32_t st = base + static_cast<uint32_t>(i);
+    ring.wait_full(st, 'F', EPI * 100 + s_);
+    const __nv_bfloat16* sm = reinterpret_cast<const __nv_bfloat16*>(ring.slot(st));
+    float acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.f;
+    if (!(c_debug & 2)) {
+      if constexpr (R >= 2) dot_rows<R>(sm, vin, g.kc, lane, acc);
+      else dot_rows<1>(sm, vin + static_cast<size_t>(s_ % g.nkc) * g.kc, g.kc, lane, acc);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(ring.empty_bar(st));   // this warp was the stage's only reader: the slot may be refilled
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+    // ---- deposit; the last depositor of the task finishes it ----
+    const int slot = j % kTaskSlots;
+    const unsigned int my_gen = static_cast<unsigned int>(j / kTaskSlots);
+    float* part = tb.part + slot * kPartFloats;
+    if (lane == 0) {
+      unsigned spins = 0;
+      while (tb.gen[slot] != my_gen) { if (++spins > (1u << 26)) { if (p.error_flag != nullptr) atomicExch(p.error_flag, 3); break; } }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < R; ++r) if (lane == r) part[s_ * R + r] = acc[r];
+    __threadfence_block();
+    __syncwarp();
+    unsigned int old = 0;
+    if (lane == 0) old = atomicAdd(&tb.cnt[slot], 1u);
+    old = __shfl_sync(0xffffffffu, old, 0);
+    if (old != static_cast<unsigned int>(S - 1)) continue;
+    __threadfence_block();
     const size_t t = static_cast<size_t>(bid) + static_cast<size_t>(j) * grid;
-    uint32_t st = base + static_cast<uint32_t>(j) * g.S;
-    float v[NACC], u[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) v[i] = u[i] = 0.f;
-    for (int s_ = 0; s_ < g.S; ++s_, ++st) {
-      ring.wait_full(st, 'F', EPI * 100 + s_);
-      const __nv_bfloat16* sm = reinterpret_cast<const __nv_bfloat16*>(ring.slot(st));
-      if (!(c_debug & 2)) {
-        if constexpr (R >= 2) {
-          float acc[R];
-#pragma unroll
-          for (int i = 0; i < R; ++i) acc[i] = 0.f;
-          dot_rows<R>(sm, vin, g.kc, lane, acc);
-#pragma unroll
-          for (int i = 0; i < R; ++i) { if (EPI == 2 && s_ == 1) u[i] = acc[i]; else v[i] = acc[i]; }
+    const size_t n0 = t * NOUT;
+    if (lane < NOUT / 2) {
+      float v0, v1;
+      if constexpr (R >= 2) {
+        v0 = part[2 * lane]; v1 = part[2 * lane + 1];
+        if (EPI == 2) {   // stage 0: gate rows, stage 1: up rows
+          const float u0 = part[R + 2 * lane], u1 = part[R + 2 * lane + 1];
+          v0 = rbf(silu_f(rbf(v0))) * rbf(u0); v1 = rbf(silu_f(rbf(v1))) * rbf(u1);   // HF: bf16(silu(bf16 gate)) * bf16 up
+        }
+      } else {
+        // rows of the task in stage order, nkc chunk partials each: plain n, n+1; gate/up g_i, u_i, g_{i+1}, u_{i+1}
+        auto row_sum = [&](int row) { float a = 0.f; for (int c = 0; c < g.nkc; ++c) a += part[row * g.nkc + c]; return a; };
+        if (EPI == 2) {
+          v0 = rbf(silu_f(rbf(row_sum(0)))) * rbf(row_sum(1));
+          v1 = rbf(silu_f(rbf(row_sum(2)))) * rbf(row_sum(3));
         } else {
-          const int row = s_ / g.nkc, c = s_ - row * g.nkc;
-          float acc[1] = {0.f};
-          dot_rows<1>(sm, vin + static_cast<size_t>(c) * g.kc, g.kc, lane, acc);
-          // rows of a task: plain n, n+1; dual g_i, u_i, g_{i+1}, u_{i+1}
-          const int o = (EPI == 2) ? row >> 1 : row;          // 0 or 1 (static indices below: the sums stay in registers)
-          const bool up = (EPI == 2) && (row & 1);
-          if (up) { if (o) u[1] += acc[0]; else u[0] += acc[0]; }
-          else    { if (o) v[1] += acc[0]; else v[0] += acc[0]; }
+          v0 = row_sum(0); v1 = row_sum(1);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(ring.empty_bar(st));   // this warp was the stage's only reader
+      const uint32_t packed = pack_bf16(v0, v1);
+      const size_t unit = (n0 >> 1) + lane;
+      if (EPI == 1) { for (int r = 0; r < p.R; ++r) st_ll(push[r] + unit, packed, tag); }
+      else st_ll(local_out + unit, packed, tag);
     }
-    // ---- finish the task: all lanes get all sums, lane i publishes output pair i ----
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) { v[i] = warp_sum(v[i]); if (EPI == 2) u[i] = warp_sum(u[i]); }
-    if (EPI == 2) {
-#pragma unroll
-      for (int i = 0; i < NACC; ++i) v[i] = rbf(silu_f(rbf(v[i]))) * rbf(u[i]);   // HF: bf16(silu(bf16 gate)) * bf16 up
-    }
-    const size_t n0 = t * NACC;
-#pragma unroll
-    for (int i = 0; i < NACC; i += 2) {
-      if (lane == (i >> 1)) {
-        const uint32_t packed = pack_bf16(v[i], v[i + 1]);
-        if (EPI == 1) { for (int r = 0; r < p.R; ++r) st_ll(push[r] + ((n0 + i) >> 1), packed, tag); }
-        else st_ll(local_out + ((n0 + i) >> 1), packed, tag);
-      }
-    }
+    __syncwarp();
+    if (lane == 0) { tb.cnt[slot] = 0u; __threadfence_block(); tb.gen[slot] = my_gen + 1u; }
   }
 }
 
 template <int EPI>
-PB_DEVICE void consume_proj(const Params& p, const Ring& ring, uint32_t& base, const Geom& g, const __nv_bfloat16* vin, uint2* const* push,
-                            uint2* local_out, uint32_t tag, int bid, int grid) {
-  gemv_sync();   // the activation vector is complete: the helper warps may start
+PB_DEVICE void consume_proj(const Params& p, const Ring& ring, const TaskBoard& tb, uint32_t& base, const Geom& g, const __nv_bfloat16* vin,
+                            uint2* const* push, uint2* local_out, uint32_t tag, int bid, int grid) {
+  gemv_sync();   // the activation vector is complete (and the task board is clean): every projection warp may start
   switch (g.R) {
-    case 1: consume_proj_r<EPI, 1>(p, ring, base, g, vin, push, local_out, tag, bid, grid); break;
-    case 2: consume_proj_r<EPI, 2>(p, ring, base, g, vin, push, local_out, tag, bid, grid); break;
-    case 4: consume_proj_r<EPI, 4>(p, ring, base, g, vin, push, local_out, tag, bid, grid); break;
-    default: consume_proj_r<EPI, 8>(p, ring, base, g, vin, push, local_out, tag, bid, grid); break;
+    case 1: consume_proj_r<EPI, 1>(p, ring, tb, base, g, vin, push, local_out, tag, bid, grid); break;
+    case 2: consume_proj_r<EPI, 2>(p, ring, tb, base, g, vin, push, local_out, tag, bid, grid); break;
+    case 4: consume_proj_r<EPI, 4>(p, ring, tb, base, g, vin, push, local_out, tag, bid, grid); break;
+    default: consume_proj_r<EPI, 8>(p, ring, tb, base, g, vin, push, local_out, tag, bid, grid); break;
   }
   base += static_cast<uint32_t>(tasks_of_cta(g, bid, grid)) * g.S;
   gemv_sync();   // every warp is done with the activation vector: it belongs to the main warps again
+  if (threadIdx.x < kTaskSlots) { tb.cnt[threadIdx.x] = 0u; tb.gen[threadIdx.x] = 0u; }   // ordered before the next phase by its first gemv_sync
 }
 
 // Wait for 16 bytes (two LL units) to carry `tag`; `v` holds the first attempt.
@@ -634,10 +661,15 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
   float* red = reinterpret_cast<float*>(q);                             q += 32 * sizeof(float);
   ring.full = reinterpret_cast<uint64_t*>(q);                           q += kMaxStages * 8;
   ring.empty = reinterpret_cast<uint64_t*>(q);                          q += kMaxStages * 8;
-  ring.armed = reinterpret_cast<volatile uint32_t*>(q);
+  ring.armed = reinterpret_cast<volatile uint32_t*>(q);                 q += kMaxStages * 4;
+  TaskBoard tb;
+  tb.part = reinterpret_cast<float*>(q);                                q += kTaskSlots * kPartFloats * 4;
+  tb.cnt = reinterpret_cast<unsigned int*>(q);                          q += kTaskSlots * 4;
+  tb.gen = reinterpret_cast<volatile unsigned int*>(q);
 
   if (tid == 0) {
     for (int i = 0; i < p.n_stages; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], 1); ring.armed[i] = 0u; }
+    for (int i = 0; i < kTaskSlots; ++i) { tb.cnt[i] = 0u; tb.gen[i] = 0u; }
     mbar_fence_init();
   }
   __syncthreads();
@@ -669,11 +701,11 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
     const uint32_t kv_stages = 2u * static_cast<uint32_t>(units > bid ? (units - bid + grid - 1) / grid : 0);
     for (int l = 0; l < p.n_layers; ++l) {
       const uint32_t tg = tag0 + static_cast<uint32_t>(l) * T_PER_LAYER;
-      consume_proj<0>(p, ring, base, p.g_qkv, vin, nullptr, p.qkv_ll, tg + T_QKV, bid, grid);
+      consume_proj<0>(p, ring, tb, base, p.g_qkv, vin, nullptr, p.qkv_ll, tg + T_QKV, bid, grid);
       base += kv_stages;   // the attention units' K / V pages are consumed by the main warps
-      consume_proj<1>(p, ring, base, p.g_o, vin, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid);
-      consume_proj<2>(p, ring, base, p.g_gu, vin, nullptr, p.act_ll, tg + T_ACT, bid, grid);
-      consume_proj<1>(p, ring, base, p.g_down, vin, p.mlp_push, nullptr, tg + T_MLP, bid, grid);
+      consume_proj<1>(p, ring, tb, base, p.g_o, vin, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid);
+      consume_proj<2>(p, ring, tb, base, p.g_gu, vin, nullptr, p.act_ll, tg + T_ACT, bid, grid);
+      consume_proj<1>(p, ring, tb, base, p.g_down, vin, p.mlp_push, nullptr, tg + T_MLP, bid, grid);
     }
     return;
   }
@@ -701,7 +733,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
     // ---- P1: norm + QKV ----
     SPAN_STAMP(0);
     rmsnorm_inplace(vin, L.ln1, p.H, p.eps, red);                                                   SPAN_STAMP(1);
-    consume_proj<0>(p, ring, base, p.g_qkv, vin, nullptr, p.qkv_ll, tg + T_QKV, bid, grid);    SPAN_STAMP(2);
+    consume_proj<0>(p, ring, tb, base, p.g_qkv, vin, nullptr, p.qkv_ll, tg + T_QKV, bid, grid);    SPAN_STAMP(2);
     // ---- P2: attention of the new token ----
     consume_attention(p, ring, base, L, pos, vin, scr, tg + T_QKV, tg + T_ATTP, bid, grid);         SPAN_STAMP(3);
     combine_heads(p, pos, tg + T_ATTP, tg + T_ATTN, bid, grid);                                     SPAN_STAMP(4);
@@ -709,17 +741,17 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
     consumer_sync();
     gather_ll(p.attn_ll, vin, p.Hq * p.D, tg + T_ATTN, p.error_flag);
     consumer_sync();                                                                                 SPAN_STAMP(5);
-    consume_proj<1>(p, ring, base, p.g_o, vin, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid); SPAN_STAMP(6);
+    consume_proj<1>(p, ring, tb, base, p.g_o, vin, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid); SPAN_STAMP(6);
     // ---- all-reduce tail + norm + gate/up ----
     reduce_slice(p, p.oproj_in, res, p0, p1, tg + T_OPROJ, tg + T_X1, p.x_ll, nullptr);            SPAN_STAMP(7);
     gather_ll(p.x_ll, vin, p.H, tg + T_X1, p.error_flag);
     consumer_sync();
     rmsnorm_inplace(vin, L.ln2, p.H, p.eps, red);                                                   SPAN_STAMP(8);
-    consume_proj<2>(p, ring, base, p.g_gu, vin, nullptr, p.act_ll, tg + T_ACT, bid, grid);    SPAN_STAMP(9);
+    consume_proj<2>(p, ring, tb, base, p.g_gu, vin, nullptr, p.act_ll, tg + T_ACT, bid, grid);    SPAN_STAMP(9);
     // ---- P5: down projection, partials pushed to every rank ----
     gather_ll(p.act_ll, vin, p.I, tg + T_ACT, p.error_flag);
     consumer_sync();                                                                                 SPAN_STAMP(10);
-    consume_proj<1>(p, ring, base, p.g_down, vin, p.mlp_push, nullptr, tg + T_MLP, bid, grid); SPAN_STAMP(11);
+    consume_proj<1>(p, ring, tb, base, p.g_down, vin, p.mlp_push, nullptr, tg + T_MLP, bid, grid); SPAN_STAMP(11);
     // ---- all-reduce tail: next block's input, or the span output ----
     const bool last = (l + 1 == p.n_layers);
     reduce_slice(p, p.mlp_in, res, p0, p1, tg + T_MLP, tg + T_X2, p.x_ll, last ? p.x_out : nullptr);
@@ -747,6 +779,7 @@ static bool make_geom(Geom& g, int N, int K, bool dual, const char* what) {
     g.R = 1; g.nkc = nkc; g.kc = K / nkc; g.outs = 2; g.S = (dual ? 4 : 2) * nkc;
   }
   g.ntasks = N / g.outs;
+  if (g.S * g.R > kPartFloats) { pb_set_error(what); return false; }   // the task board holds S x R partial sums per task
   return g.ntasks * g.outs == N;
 }
 
@@ -763,7 +796,7 @@ extern "C" int pb_decode_span_smem(const PbDecodeSpanArgs* a, int* n_stages, int
   if (a->I > vin) vin = a->I;
   if ((G + 2) * a->D > vin) vin = (G + 2) * a->D;
   vin = (vin + 63) & ~63;
-  const size_t fixed = static_cast<size_t>(vin) * 2 + (16 * kPage + 64) * 4 + 256 * 4 + 32 * 4 + 2 * kMaxStages * 8 + kMaxStages * 4 + 1024;
+  const size_t fixed = static_cast<size_t>(vin) * 2 + (16 * kPage + 64) * 4 + 256 * 4 + 32 * 4 + 2 * kMaxStages * 8 + kMaxStages * 4 + 16 * 32 * 4 + 2 * 16 * 4 + 1024;
   const size_t budget = 227 * 1024;
   if (fixed + 4 * kStageBytes > budget) return -1;
   int ns = static_cast<int>((budget - fixed) / kStageBytes);
