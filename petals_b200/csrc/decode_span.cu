@@ -101,6 +101,7 @@ struct Params {
   Geom g_qkv, g_o, g_gu, g_down;
   int n_stages;
   int vin_elems;  // bf16 elements of the activation vector buffer
+  int pf_window;   // ring stages the producer asks L2 to prefetch beyond the ring while the ring is full (0: off)
   unsigned long long* timing;  // optional [n_layers][24] %globaltimer stamps of CTA 0 (consumer slots 0-12, producer slots 16-20)
 };
 
@@ -214,53 +215,103 @@ struct Ring {
 PB_DEVICE int tasks_of_cta(const Geom& g, int bid, int grid) { return g.ntasks > bid ? (g.ntasks - bid + grid - 1) / grid : 0; }
 
 // ---- producer ------------------------------------------------------------------------------------------------------------
-PB_DEVICE void produce_proj(const Ring& ring, uint32_t& base, const Geom& g, const __nv_bfloat16* w, const __nv_bfloat16* w2, int bid, int grid,
-                            uint64_t policy) {
-  const int nt = tasks_of_cta(g, bid, grid);
-  const uint32_t bytes = static_cast<uint32_t>(g.R) * g.kc * 2u;
-  uint32_t st = base;
-  for (int j = 0; j < nt; ++j) {
-    const size_t t = static_cast<size_t>(bid) + static_cast<size_t>(j) * grid;
-    for (int s_ = 0; s_ < g.S; ++s_, ++st) {
-      // which rows / chunk is stage s_ of a task?  R >= 2: [gate rows][up rows], one stage each.  R == 1: row-major over
-      // (row, chunk) with rows ordered g_i, u_i, g_{i+1}, u_{i+1} (dual) or n, n+1 (plain)
-      const __nv_bfloat16* src;
-      if (g.R >= 2) {
-        src = (g.dual && s_ == 1 ? w2 : w) + t * g.outs * g.K;
-      } else {
-        const int row = s_ / g.nkc, c = s_ - row * g.nkc;
-        const size_t out = t * g.outs + (g.dual ? row >> 1 : row);
-        src = (g.dual && (row & 1) ? w2 : w) + out * g.K + static_cast<size_t>(c) * g.kc;
-      }
-      span_wait(ring.empty_bar(st), ring.parity(st) ^ 1u, 'E', st, g.S);
-      mbar_expect_tx(ring.full_bar(st), bytes);
-      ring.arm(st);
-      bulk_load_hint(ring.slot(st), src, bytes, ring.full_bar(st), policy);
-    }
-  }
-  base = st;
-}
+// The sequence of ring stages of this CTA for the whole launch, as an iterator: blocks x {QKV rows, K/V pages of the attention
+// units, O rows, gate/up rows, down rows}. The producer walks it twice: the LOAD cursor fills ring slots; the PREFETCH cursor
+// runs ahead of it and, whenever the ring is full (the consumers are busy with a phase hand-off, the attention, a norm), asks
+// the L2 to fetch the stages that come next (cp.async.bulk.prefetch.L2). HBM then keeps streaming through the phases that do
+// not consume weights, and the ring refills from L2 when the consumers come back.
+struct StageIter {
+  int l, ph, j, s_;        // block, phase (0 QKV, 1 K/V pages, 2 O, 3 gate/up, 4 down), task (or unit) of this CTA, stage in task
+  PB_DEVICE bool valid(const Params& p) const { return l < p.n_layers; }
+};
+struct StageDesc { const void* src; uint32_t bytes; bool weights; };
 
-PB_DEVICE void produce_kv(const Params& p, const Ring& ring, uint32_t& base, const Layer& L, int pos, int bid, int grid) {
-  const int nch = pos / kPage + 1;
-  const int units = p.Hkv * nch;
-  const uint32_t bytes = static_cast<uint32_t>(kPage) * p.D * 2u;
-  uint32_t st = base;
-  for (int u = bid; u < units; u += grid, st += 2) {
+PB_DEVICE const Geom& geom_of(const Params& p, int ph) { return ph == 0 ? p.g_qkv : ph == 2 ? p.g_o : ph == 3 ? p.g_gu : p.g_down; }
+
+// Skip exhausted phases / blocks so that `it` points at an existing stage (or past the end).
+PB_DEVICE void settle_iter(const Params& p, StageIter& it, int kv_units, int bid, int grid) {
+  while (it.l < p.n_layers) {
+    const int n = it.ph == 1 ? kv_units : tasks_of_cta(geom_of(p, it.ph), bid, grid);
+    if (it.j < n) return;
+    it.j = 0; it.s_ = 0;
+    if (++it.ph == 5) { it.ph = 0; ++it.l; }
+  }
+}
+PB_DEVICE void advance_iter(const Params& p, StageIter& it, int kv_units, int bid, int grid) {
+  const int S = it.ph == 1 ? 2 : geom_of(p, it.ph).S;
+  if (++it.s_ == S) { it.s_ = 0; ++it.j; }
+  settle_iter(p, it, kv_units, bid, grid);
+}
+PB_DEVICE StageDesc describe(const Params& p, const StageIter& it, int pos, int bid, int grid) {
+  const Layer& L = p.layers[it.l];
+  StageDesc d;
+  if (it.ph == 1) {   // K page (s_ == 0) / V page (s_ == 1) of attention unit u = bid + j * grid
+    const int nch = pos / kPage + 1;
+    const int u = bid + it.j * grid;
     const int hk = u / nch, c = u - hk * nch;
     int pg = c < p.max_pages ? p.block_table[c] : 0;
     pg = min(max(pg, 0), p.num_pages - 1);
     const size_t off = (static_cast<size_t>(pg) * p.Hkv + hk) * kPage * p.D;
-    span_wait(ring.empty_bar(st), ring.parity(st) ^ 1u, 'K', st, u);
-    mbar_expect_tx(ring.full_bar(st), bytes);
-    ring.arm(st);
-    bulk_load_1d(ring.slot(st), L.k_pool + off, bytes, ring.full_bar(st));
-    span_wait(ring.empty_bar(st + 1), ring.parity(st + 1) ^ 1u, 'V', st + 1, u);
-    mbar_expect_tx(ring.full_bar(st + 1), bytes);
-    ring.arm(st + 1);
-    bulk_load_1d(ring.slot(st + 1), L.v_pool + off, bytes, ring.full_bar(st + 1));
+    d.src = (it.s_ == 0 ? L.k_pool : L.v_pool) + off;
+    d.bytes = static_cast<uint32_t>(kPage) * p.D * 2u;
+    d.weights = false;
+    return d;
   }
-  base = st;
+  const Geom& g = geom_of(p, it.ph);
+  const __nv_bfloat16* w = it.ph == 0 ? L.wqkv : it.ph == 2 ? L.wo : it.ph == 3 ? L.wgate : L.wdown;
+  const __nv_bfloat16* w2 = it.ph == 3 ? L.wup : nullptr;
+  const size_t t = static_cast<size_t>(bid) + static_cast<size_t>(it.j) * grid;
+  // which rows / chunk is stage s_ of a task?  R >= 2: [gate rows][up rows], one stage each.  R == 1: row-major over
+  // (row, chunk) with rows ordered g_i, u_i, g_{i+1}, u_{i+1} (dual) or n, n+1 (plain)
+  if (g.R >= 2) {
+    d.src = (g.dual && it.s_ == 1 ? w2 : w) + t * g.outs * g.K;
+  } else {
+    const int row = it.s_ / g.nkc, c = it.s_ - row * g.nkc;
+    const size_t out = t * g.outs + (g.dual ? row >> 1 : row);
+    d.src = (g.dual && (row & 1) ? w2 : w) + out * g.K + static_cast<size_t>(c) * g.kc;
+  }
+  d.bytes = static_cast<uint32_t>(g.R) * g.kc * 2u;
+  d.weights = true;
+  return d;
+}
+
+PB_DEVICE void l2_prefetch_bulk(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+PB_DEVICE void produce_all(const Params& p, const Ring& ring, int pos, int bid, int grid) {
+  const uint64_t policy = policy_evict_first();
+  const int nch = pos / kPage + 1, units = p.Hkv * nch;
+  const int kv_units = units > bid ? (units - bid + grid - 1) / grid : 0;
+  StageIter ld{0, 0, 0, 0}, pf{0, 0, 0, 0};
+  settle_iter(p, ld, kv_units, bid, grid);
+  settle_iter(p, pf, kv_units, bid, grid);
+  uint32_t st = 0, pf_st = 0;
+  const uint32_t window = static_cast<uint32_t>(p.pf_window);
+  int last_l = -1;
+  while (ld.valid(p)) {
+    if (p.timing != nullptr && bid == 0 && ld.l != last_l) { if (last_l >= 0) p.timing[static_cast<size_t>(last_l) * 24 + 20] = globaltimer_ns(); last_l = ld.l; }
+    if (window > 0 && !mbar_try_wait(ring.empty_bar(st), ring.parity(st) ^ 1u)) {
+      // the ring is full: spend the wait asking L2 for what comes after it
+      const uint32_t lo = st + static_cast<uint32_t>(ring.n), hi = lo + window;
+      while (pf_st < hi && pf.valid(p)) {
+        if (pf_st >= lo) {
+          const StageDesc d = describe(p, pf, pos, bid, grid);
+          if (d.weights) l2_prefetch_bulk(d.src, d.bytes);
+        }
+        advance_iter(p, pf, kv_units, bid, grid);
+        ++pf_st;
+      }
+    }
+    const StageDesc d = describe(p, ld, pos, bid, grid);
+    span_wait(ring.empty_bar(st), ring.parity(st) ^ 1u, 'E', st, ld.ph);
+    mbar_expect_tx(ring.full_bar(st), d.bytes);
+    ring.arm(st);
+    if (d.weights) bulk_load_hint(ring.slot(st), d.src, d.bytes, ring.full_bar(st), policy);
+    else bulk_load_1d(ring.slot(st), d.src, d.bytes, ring.full_bar(st));
+    advance_iter(p, ld, kv_units, bid, grid);
+    ++st;
+  }
 }
 
 // ---- consumer: projections. Every warp works alone: it owns whole tasks (task j of this CTA -> warp j % 8), waits for its own
@@ -395,7 +446,7 @@ PB_DEVICE void settle2(uint4& v, const uint4* q, uint32_t tag, int* err) {
 // Gather an LL-tagged bf16 vector of n elements (n/2 units, n % 4 == 0, 16-byte aligned) into shared memory. Every thread first
 // issues a batch of independent 16-byte loads and only then looks at the tags: once the data is there a gather costs about one
 // L2 round trip, not one per unit.
-PB_DEVICE void gather_ll(const uint2* src, __nv_bfloat16* dst, int n, uint32_t tag, int* err) {
+PB_DEVICE void gather_ll(const uint2* src, __nv_bfloat16* dst, int n, uint32_t tag, int* err, float* sumsq = nullptr) {
   constexpr int U = 4;
   const uint4* s4 = reinterpret_cast<const uint4*>(src);
   uint2* d2 = reinterpret_cast<uint2*>(dst);
@@ -413,20 +464,29 @@ PB_DEVICE void gather_ll(const uint2* src, __nv_bfloat16* dst, int n, uint32_t t
       if (i < n16) {
         settle2(v[j], s4 + i, tag, err);
         d2[i] = make_uint2(v[j].x, v[j].z);
+        if (sumsq != nullptr) {   // the RMS statistic of the vector, while its elements pass through registers anyway
+          const float a = bf16_lo(v[j].x), b = bf16_hi(v[j].x), c = bf16_lo(v[j].z), d = bf16_hi(v[j].z);
+          *sumsq += a * a + b * b + c * c + d * d;
+        }
       }
     }
   }
 }
 
 // vin holds a bf16 vector x[H] (already complete in shared memory): RMS-normalise it in place with weight g (HF rounding).
-PB_DEVICE void rmsnorm_inplace(__nv_bfloat16* vin, const __nv_bfloat16* gw, int H, float eps, float* red) {
+// `ss_in` < 0: compute the sum of squares here; otherwise it is this thread's share of it (collected by gather_ll).
+PB_DEVICE void rmsnorm_inplace(__nv_bfloat16* vin, const __nv_bfloat16* gw, int H, float eps, float* red, float ss_in = -1.f) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float ss = 0.f;
-  for (int i = tid * 8; i < H; i += kConsumerThreads * 8) {
-    const uint4 v = *reinterpret_cast<const uint4*>(vin + i);
-    const float f0 = bf16_lo(v.x), f1 = bf16_hi(v.x), f2 = bf16_lo(v.y), f3 = bf16_hi(v.y);
-    const float f4 = bf16_lo(v.z), f5 = bf16_hi(v.z), f6 = bf16_lo(v.w), f7 = bf16_hi(v.w);
-    ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + f4 * f4 + f5 * f5 + f6 * f6 + f7 * f7;
+  if (ss_in >= 0.f) {
+    ss = ss_in;
+  } else {
+    for (int i = tid * 8; i < H; i += kConsumerThreads * 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(vin + i);
+      const float f0 = bf16_lo(v.x), f1 = bf16_hi(v.x), f2 = bf16_lo(v.y), f3 = bf16_hi(v.y);
+      const float f4 = bf16_lo(v.z), f5 = bf16_hi(v.z), f6 = bf16_lo(v.w), f7 = bf16_hi(v.w);
+      ss += f0 * f0 + f1 * f1 + f2 * f2 + f3 * f3 + f4 * f4 + f5 * f5 + f6 * f6 + f7 * f7;
+    }
   }
   ss = warp_sum(ss);
   if (lane == 0) red[warp] = ss;
@@ -619,25 +679,32 @@ PB_DEVICE void combine_heads(const Params& p, int pos, uint32_t tag_attp, uint32
       }
       __syncwarp();
     }
-    // pass 2: plain (L2) loads, fully pipelined. lane handles dims [lane*per, lane*per + per)
+    // pass 2: plain (L2) loads, four chunks' worth in flight before any of them is used. lane handles dims [lane*per, +per)
     const int per = D >> 5;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     float M = -INFINITY, Lsum = 0.f;
-    for (int c = 0; c < nch; ++c) {
-      const uint2* u = base + static_cast<size_t>(c) * (D + 2);
-      const float m = __uint_as_float(ld_ll(u + D).x);
-      const float l = __uint_as_float(ld_ll(u + D + 1).x);
-      const float Mn = fmaxf(M, m);
-      const float a = exp2f(M - Mn), b = exp2f(m - Mn);
-      Lsum = Lsum * a + l * b;
+    for (int c0 = 0; c0 < nch; c0 += 4) {
+      float mm[4], ll[4], oo[4][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        if (j < per) {
-          const float o = __uint_as_float(ld_ll(u + lane * per + j).x);
-          acc[j] = acc[j] * a + o * b;
+      for (int q = 0; q < 4; ++q) {
+        const int c = min(c0 + q, nch - 1);
+        const uint2* u = base + static_cast<size_t>(c) * (D + 2);
+        mm[q] = __uint_as_float(ld_ll(u + D).x);
+        ll[q] = __uint_as_float(ld_ll(u + D + 1).x);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oo[q][j] = j < per ? __uint_as_float(ld_ll(u + lane * per + j).x) : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (c0 + q < nch) {
+          const float Mn = fmaxf(M, mm[q]);
+          const float a = exp2f(M - Mn), b = exp2f(mm[q] - Mn);
+          Lsum = Lsum * a + ll[q] * b;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[j] = acc[j] * a + oo[q][j] * b;
+          M = Mn;
         }
       }
-      M = Mn;
     }
     const float inv = 1.f / Lsum;
     uint2* dst = p.attn_ll + ((static_cast<size_t>(h) * D + lane * per) >> 1);
@@ -680,17 +747,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
 
   if (warp == kGemvWarps) {
     // =============================== PRODUCER ===============================
-    if ((tid & 31) == 0) {
-      const uint64_t pol = policy_evict_first();
-      for (int l = 0; l < p.n_layers; ++l) {
-        const Layer& L = p.layers[l];
-        produce_proj(ring, base, p.g_qkv, L.wqkv, nullptr, bid, grid, pol);   SPAN_STAMP(16);
-        produce_kv(p, ring, base, L, pos, bid, grid);                          SPAN_STAMP(17);
-        produce_proj(ring, base, p.g_o, L.wo, nullptr, bid, grid, pol);        SPAN_STAMP(18);
-        produce_proj(ring, base, p.g_gu, L.wgate, L.wup, bid, grid, pol);      SPAN_STAMP(19);
-        produce_proj(ring, base, p.g_down, L.wdown, nullptr, bid, grid, pol);  SPAN_STAMP(20);
-      }
-    }
+    if ((tid & 31) == 0) produce_all(p, ring, pos, bid, grid);
     return;
   }
 
@@ -727,12 +784,13 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
     *reinterpret_cast<uint4*>(vin + i) = __ldcg(reinterpret_cast<const uint4*>(p.x_in + i));
   consumer_sync();
 
+  float ss_carry = -1.f;   // this thread's share of sum(x^2) of the vector in `vin`, when the gather already computed it
   for (int l = 0; l < p.n_layers; ++l) {
     const Layer& L = p.layers[l];
     const uint32_t tg = tag0 + static_cast<uint32_t>(l) * T_PER_LAYER;
     // ---- P1: norm + QKV ----
     SPAN_STAMP(0);
-    rmsnorm_inplace(vin, L.ln1, p.H, p.eps, red);                                                   SPAN_STAMP(1);
+    rmsnorm_inplace(vin, L.ln1, p.H, p.eps, red, ss_carry);                                                   SPAN_STAMP(1);
     consume_proj<0>(p, ring, tb, base, p.g_qkv, vin, nullptr, p.qkv_ll, tg + T_QKV, bid, grid);    SPAN_STAMP(2);
     // ---- P2: attention of the new token ----
     consume_attention(p, ring, base, L, pos, vin, scr, tg + T_QKV, tg + T_ATTP, bid, grid);         SPAN_STAMP(3);
@@ -744,9 +802,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
     consume_proj<1>(p, ring, tb, base, p.g_o, vin, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid); SPAN_STAMP(6);
     // ---- all-reduce tail + norm + gate/up ----
     reduce_slice(p, p.oproj_in, res, p0, p1, tg + T_OPROJ, tg + T_X1, p.x_ll, nullptr);            SPAN_STAMP(7);
-    gather_ll(p.x_ll, vin, p.H, tg + T_X1, p.error_flag);
+    float ss1 = 0.f;
+    gather_ll(p.x_ll, vin, p.H, tg + T_X1, p.error_flag, &ss1);
     consumer_sync();
-    rmsnorm_inplace(vin, L.ln2, p.H, p.eps, red);                                                   SPAN_STAMP(8);
+    rmsnorm_inplace(vin, L.ln2, p.H, p.eps, red, ss1);                                                   SPAN_STAMP(8);
     consume_proj<2>(p, ring, tb, base, p.g_gu, vin, nullptr, p.act_ll, tg + T_ACT, bid, grid);    SPAN_STAMP(9);
     // ---- P5: down projection, partials pushed to every rank ----
     gather_ll(p.act_ll, vin, p.I, tg + T_ACT, p.error_flag);
@@ -756,7 +815,8 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
     const bool last = (l + 1 == p.n_layers);
     reduce_slice(p, p.mlp_in, res, p0, p1, tg + T_MLP, tg + T_X2, p.x_ll, last ? p.x_out : nullptr);
     if (!last) {
-      gather_ll(p.x_ll, vin, p.H, tg + T_X2, p.error_flag);
+      ss_carry = 0.f;
+      gather_ll(p.x_ll, vin, p.H, tg + T_X2, p.error_flag, &ss_carry);
       consumer_sync();
     }
     SPAN_STAMP(12);
@@ -841,6 +901,10 @@ extern "C" int pb_decode_span(const PbDecodeSpanArgs* a, void* stream) {
   if (smem < 0) { pb_set_error("decode_span: activation vector does not fit beside the weight ring"); return PB_ERR_UNSUPPORTED; }
   p.n_stages = ns; p.vin_elems = vin;
   p.timing = static_cast<unsigned long long*>(a->timing);
+  {
+    static const int env_pf = [] { const char* e = getenv("PETALS_B200_SPAN_PF"); return e ? atoi(e) : 32; }();
+    p.pf_window = env_pf < 0 ? 0 : env_pf;
+  }
   {
     static int cur_debug = 0;
     static const int env_debug = [] { const char* e = getenv("PETALS_B200_SPAN_DEBUG"); return e ? atoi(e) : 0; }();

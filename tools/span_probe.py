@@ -64,7 +64,7 @@ def main():
     c = [int(v) for v in t[mid, :13]]
     names = ["norm1", "qkv", "attn units", "combine", "gather attn", "o-proj", "reduce1", "gather+norm2", "gate/up", "gather act", "down", "reduce2+gather"]
     phases = {n: round((c[i + 1] - c[i]) / 1e3, 2) for i, n in enumerate(names)}
-    prod = {f"p{j}": round((int(t[mid, 16 + j]) - c[0]) / 1e3, 2) for j in range(5)}
+    prod = {"all_issued": round((int(t[mid, 20]) - c[0]) / 1e3, 2)}
     print(json.dumps({"shape": args.shape, "debug": int(os.environ.get("PETALS_B200_SPAN_DEBUG", "0")), "ms_per_step": round(ms, 3),
                       "us_per_layer": round(1e3 * ms / L, 1), "GBps": round(nbytes / ms / 1e6, 1), "frac_hbm": round(nbytes / ms / 1e6 / peaks["hbm_gbs"], 3),
                       "layer_us": round((int(t[mid + 1, 0]) - c[0]) / 1e3, 2), "consumer_phase_us": phases,
