@@ -38,9 +38,9 @@ constexpr int kStageBytes = 16 * 1024;   // one ring slot: one weight row (or R 
 constexpr int kMaxStages = 12;
 constexpr int kConsumerWarps = 8;                       // warps 0-7: everything (gathers, norms, attention, projections)
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kGemvWarps = 11;                          // warps 0-10 take projection tasks; warps 8-10 do nothing else
+constexpr int kGemvWarps = 10;                          // warps 0-9 take projection tasks; warps 8-9 do nothing else
 constexpr int kGemvThreads = kGemvWarps * 32;
-constexpr int kThreads = kGemvThreads + 32;             // warp 11: the producer. 12 warps x 168 registers fill the register file
+constexpr int kThreads = kGemvThreads + 64;             // warp 10: the L2 prefetcher, warp 11: the loader. 12 warps x 168 registers
 constexpr int kMaxRanks = 8;
 constexpr int kMaxStageRows = 8;
 constexpr int kPage = 64;
@@ -108,7 +108,7 @@ struct Params {
 // Diagnostics (PETALS_B200_SPAN_DEBUG): bit 0 = treat every polled unit as ready, bit 1 = skip the math. Results are garbage; the
 // two switches separate the cost of streaming, of computing and of waiting (tools/span_probe.py).
 __constant__ int c_debug = 0;
-#define SPAN_STAMP(slot) do { if (p.timing != nullptr && bid == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x == 0 || threadIdx.x == kGemvThreads)) \
+#define SPAN_STAMP(slot) do { if (p.timing != nullptr && bid == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x == 0 || threadIdx.x == kGemvThreads + 32)) \
     p.timing[static_cast<size_t>(l) * 24 + (slot)] = globaltimer_ns(); } while (0)
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------
@@ -215,104 +215,84 @@ struct Ring {
 PB_DEVICE int tasks_of_cta(const Geom& g, int bid, int grid) { return g.ntasks > bid ? (g.ntasks - bid + grid - 1) / grid : 0; }
 
 // ---- producer ------------------------------------------------------------------------------------------------------------
-// The sequence of ring stages of this CTA for the whole launch, as an iterator: blocks x {QKV rows, K/V pages of the attention
-// units, O rows, gate/up rows, down rows}. The producer walks it twice: the LOAD cursor fills ring slots; the PREFETCH cursor
-// runs ahead of it and, whenever the ring is full (the consumers are busy with a phase hand-off, the attention, a norm), asks
-// the L2 to fetch the stages that come next (cp.async.bulk.prefetch.L2). HBM then keeps streaming through the phases that do
-// not consume weights, and the ring refills from L2 when the consumers come back.
-struct StageIter {
-  int l, ph, j, s_;        // block, phase (0 QKV, 1 K/V pages, 2 O, 3 gate/up, 4 down), task (or unit) of this CTA, stage in task
-  PB_DEVICE bool valid(const Params& p) const { return l < p.n_layers; }
-};
-struct StageDesc { const void* src; uint32_t bytes; bool weights; };
-
-PB_DEVICE const Geom& geom_of(const Params& p, int ph) { return ph == 0 ? p.g_qkv : ph == 2 ? p.g_o : ph == 3 ? p.g_gu : p.g_down; }
-
-// Skip exhausted phases / blocks so that `it` points at an existing stage (or past the end).
-PB_DEVICE void settle_iter(const Params& p, StageIter& it, int kv_units, int bid, int grid) {
-  while (it.l < p.n_layers) {
-    const int n = it.ph == 1 ? kv_units : tasks_of_cta(geom_of(p, it.ph), bid, grid);
-    if (it.j < n) return;
-    it.j = 0; it.s_ = 0;
-    if (++it.ph == 5) { it.ph = 0; ++it.l; }
+// `walk_stages` enumerates the ring stages of this CTA for the whole launch, in order: blocks x {QKV rows, K/V pages of the
+// attention units, O rows, gate/up rows, down rows}, and calls f(stage number, source, bytes, is_weight) for each. Two lanes
+// walk it: the LOADER fills ring slots; the PREFETCHER (another warp) runs ahead of the loader by up to `pf_window` stages beyond
+// the ring and asks the L2 for them (cp.async.bulk.prefetch.L2), so HBM keeps streaming while the consumers are busy with a
+// phase hand-off / the attention / a norm and the ring is full; the ring then refills from L2.
+template <typename F>
+PB_DEVICE void walk_proj(uint32_t& st, const Geom& g, const __nv_bfloat16* w, const __nv_bfloat16* w2, int bid, int grid, F& f) {
+  const int nt = tasks_of_cta(g, bid, grid);
+  const uint32_t bytes = static_cast<uint32_t>(g.R) * g.kc * 2u;
+  for (int j = 0; j < nt; ++j) {
+    const size_t t = static_cast<size_t>(bid) + static_cast<size_t>(j) * grid;
+    if (g.R >= 2) {   // [gate rows][up rows], one stage each
+      f(st++, w + t * g.outs * g.K, bytes, true);
+      if (g.dual) f(st++, w2 + t * g.outs * g.K, bytes, true);
+    } else {          // row-major over (row, chunk); rows ordered g_i, u_i, g_{i+1}, u_{i+1} (dual) or n, n+1 (plain)
+      const int rows = g.dual ? 4 : 2;
+      for (int row = 0; row < rows; ++row) {
+        const size_t out = t * 2 + (g.dual ? row >> 1 : row);
+        const __nv_bfloat16* src = (g.dual && (row & 1) ? w2 : w) + out * g.K;
+        for (int c = 0; c < g.nkc; ++c) f(st++, src + static_cast<size_t>(c) * g.kc, bytes, true);
+      }
+    }
   }
 }
-PB_DEVICE void advance_iter(const Params& p, StageIter& it, int kv_units, int bid, int grid) {
-  const int S = it.ph == 1 ? 2 : geom_of(p, it.ph).S;
-  if (++it.s_ == S) { it.s_ = 0; ++it.j; }
-  settle_iter(p, it, kv_units, bid, grid);
-}
-PB_DEVICE StageDesc describe(const Params& p, const StageIter& it, int pos, int bid, int grid) {
-  const Layer& L = p.layers[it.l];
-  StageDesc d;
-  if (it.ph == 1) {   // K page (s_ == 0) / V page (s_ == 1) of attention unit u = bid + j * grid
-    const int nch = pos / kPage + 1;
-    const int u = bid + it.j * grid;
-    const int hk = u / nch, c = u - hk * nch;
-    int pg = c < p.max_pages ? p.block_table[c] : 0;
-    pg = min(max(pg, 0), p.num_pages - 1);
-    const size_t off = (static_cast<size_t>(pg) * p.Hkv + hk) * kPage * p.D;
-    d.src = (it.s_ == 0 ? L.k_pool : L.v_pool) + off;
-    d.bytes = static_cast<uint32_t>(kPage) * p.D * 2u;
-    d.weights = false;
-    return d;
+
+template <typename F>
+PB_DEVICE void walk_stages(const Params& p, int pos, int bid, int grid, F& f) {
+  const int nch = pos / kPage + 1, units = p.Hkv * nch;
+  const uint32_t page_bytes = static_cast<uint32_t>(kPage) * p.D * 2u;
+  uint32_t st = 0;
+  for (int l = 0; l < p.n_layers; ++l) {
+    const Layer& L = p.layers[l];
+    walk_proj(st, p.g_qkv, L.wqkv, nullptr, bid, grid, f);
+    for (int u = bid; u < units; u += grid) {
+      const int hk = u / nch, c = u - hk * nch;
+      int pg = c < p.max_pages ? p.block_table[c] : 0;
+      pg = min(max(pg, 0), p.num_pages - 1);
+      const size_t off = (static_cast<size_t>(pg) * p.Hkv + hk) * kPage * p.D;
+      f(st++, L.k_pool + off, page_bytes, false);
+      f(st++, L.v_pool + off, page_bytes, false);
+    }
+    walk_proj(st, p.g_o, L.wo, nullptr, bid, grid, f);
+    walk_proj(st, p.g_gu, L.wgate, L.wup, bid, grid, f);
+    walk_proj(st, p.g_down, L.wdown, nullptr, bid, grid, f);
   }
-  const Geom& g = geom_of(p, it.ph);
-  const __nv_bfloat16* w = it.ph == 0 ? L.wqkv : it.ph == 2 ? L.wo : it.ph == 3 ? L.wgate : L.wdown;
-  const __nv_bfloat16* w2 = it.ph == 3 ? L.wup : nullptr;
-  const size_t t = static_cast<size_t>(bid) + static_cast<size_t>(it.j) * grid;
-  // which rows / chunk is stage s_ of a task?  R >= 2: [gate rows][up rows], one stage each.  R == 1: row-major over
-  // (row, chunk) with rows ordered g_i, u_i, g_{i+1}, u_{i+1} (dual) or n, n+1 (plain)
-  if (g.R >= 2) {
-    d.src = (g.dual && it.s_ == 1 ? w2 : w) + t * g.outs * g.K;
-  } else {
-    const int row = it.s_ / g.nkc, c = it.s_ - row * g.nkc;
-    const size_t out = t * g.outs + (g.dual ? row >> 1 : row);
-    d.src = (g.dual && (row & 1) ? w2 : w) + out * g.K + static_cast<size_t>(c) * g.kc;
-  }
-  d.bytes = static_cast<uint32_t>(g.R) * g.kc * 2u;
-  d.weights = true;
-  return d;
 }
 
 PB_DEVICE void l2_prefetch_bulk(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
-PB_DEVICE void produce_all(const Params& p, const Ring& ring, int pos, int bid, int grid) {
-  const uint64_t policy = policy_evict_first();
-  const int nch = pos / kPage + 1, units = p.Hkv * nch;
-  const int kv_units = units > bid ? (units - bid + grid - 1) / grid : 0;
-  StageIter ld{0, 0, 0, 0}, pf{0, 0, 0, 0};
-  settle_iter(p, ld, kv_units, bid, grid);
-  settle_iter(p, pf, kv_units, bid, grid);
-  uint32_t st = 0, pf_st = 0;
-  const uint32_t window = static_cast<uint32_t>(p.pf_window);
-  int last_l = -1;
-  while (ld.valid(p)) {
-    if (p.timing != nullptr && bid == 0 && ld.l != last_l) { if (last_l >= 0) p.timing[static_cast<size_t>(last_l) * 24 + 20] = globaltimer_ns(); last_l = ld.l; }
-    if (window > 0 && !mbar_try_wait(ring.empty_bar(st), ring.parity(st) ^ 1u)) {
-      // the ring is full: spend the wait asking L2 for what comes after it
-      const uint32_t lo = st + static_cast<uint32_t>(ring.n), hi = lo + window;
-      while (pf_st < hi && pf.valid(p)) {
-        if (pf_st >= lo) {
-          const StageDesc d = describe(p, pf, pos, bid, grid);
-          if (d.weights) l2_prefetch_bulk(d.src, d.bytes);
-        }
-        advance_iter(p, pf, kv_units, bid, grid);
-        ++pf_st;
-      }
-    }
-    const StageDesc d = describe(p, ld, pos, bid, grid);
-    span_wait(ring.empty_bar(st), ring.parity(st) ^ 1u, 'E', st, ld.ph);
-    mbar_expect_tx(ring.full_bar(st), d.bytes);
+struct Loader {
+  const Ring& ring; uint64_t policy; volatile uint32_t* progress;
+  PB_DEVICE void operator()(uint32_t st, const void* src, uint32_t bytes, bool weights) {
+    span_wait(ring.empty_bar(st), ring.parity(st) ^ 1u, 'E', st, 0);
+    mbar_expect_tx(ring.full_bar(st), bytes);
     ring.arm(st);
-    if (d.weights) bulk_load_hint(ring.slot(st), d.src, d.bytes, ring.full_bar(st), policy);
-    else bulk_load_1d(ring.slot(st), d.src, d.bytes, ring.full_bar(st));
-    advance_iter(p, ld, kv_units, bid, grid);
-    ++st;
+    if (weights) bulk_load_hint(ring.slot(st), src, bytes, ring.full_bar(st), policy);
+    else bulk_load_1d(ring.slot(st), src, bytes, ring.full_bar(st));
+    *progress = st + 1u;   // stages issued so far (the prefetcher paces itself on this)
   }
-}
+};
+struct Prefetcher {
+  const Ring& ring; uint32_t window; volatile uint32_t* progress; int* error_flag;
+  PB_DEVICE void operator()(uint32_t st, const void* src, uint32_t bytes, bool weights) {
+    if (!weights) return;
+    // stay inside (issued + ring, issued + ring + window]: never behind the loader (pointless), never too far ahead (L2 capacity)
+    uint32_t issued = *progress;
+    if (st < issued + static_cast<uint32_t>(ring.n)) return;
+    unsigned spins = 0;
+    while (st >= issued + static_cast<uint32_t>(ring.n) + window) {
+      __nanosleep(200);
+      issued = *progress;
+      if (++spins > (1u << 24)) return;   // the step is broken; the loader's watchdog reports it
+    }
+    l2_prefetch_bulk(src, bytes);
+  }
+};
 
 // ---- consumer: projections. Every warp works alone: it owns whole tasks (task j of this CTA -> warp j % 8), waits for its own
 // stages, reduces inside the warp and publishes its outputs. No block-wide barrier inside a projection: eight independent
@@ -729,6 +709,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
   ring.full = reinterpret_cast<uint64_t*>(q);                           q += kMaxStages * 8;
   ring.empty = reinterpret_cast<uint64_t*>(q);                          q += kMaxStages * 8;
   ring.armed = reinterpret_cast<volatile uint32_t*>(q);                 q += kMaxStages * 4;
+  volatile uint32_t* progress = reinterpret_cast<volatile uint32_t*>(q);   q += 16;   // stages the loader has issued
   TaskBoard tb;
   tb.part = reinterpret_cast<float*>(q);                                q += kTaskSlots * kPartFloats * 4;
   tb.cnt = reinterpret_cast<unsigned int*>(q);                          q += kTaskSlots * 4;
@@ -737,6 +718,7 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
   if (tid == 0) {
     for (int i = 0; i < p.n_stages; ++i) { mbar_init(&ring.full[i], 1); mbar_init(&ring.empty[i], 1); ring.armed[i] = 0u; }
     for (int i = 0; i < kTaskSlots; ++i) { tb.cnt[i] = 0u; tb.gen[i] = 0u; }
+    *progress = 0u;
     mbar_fence_init();
   }
   __syncthreads();
@@ -745,9 +727,17 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
   const uint32_t tag0 = static_cast<uint32_t>(*p.epoch) * kTagStride + 1u;  // fixed stride: spans of different lengths may share the buffers
   uint32_t base = 0;   // first ring stage of the current phase (same arithmetic in the producer and in every consumer warp)
 
-  if (warp == kGemvWarps) {
-    // =============================== PRODUCER ===============================
-    if ((tid & 31) == 0) produce_all(p, ring, pos, bid, grid);
+  if (warp >= kGemvWarps) {
+    // =============================== PRODUCER (loader lane + L2 prefetcher lane) ===============================
+    if ((tid & 31) == 0) {
+      if (warp == kGemvWarps + 1) {
+        Loader f{ring, policy_evict_first(), progress};
+        walk_stages(p, pos, bid, grid, f);
+      } else if (p.pf_window > 0) {
+        Prefetcher f{ring, static_cast<uint32_t>(p.pf_window), progress, p.error_flag};
+        walk_stages(p, pos, bid, grid, f);
+      }
+    }
     return;
   }
 
@@ -856,7 +846,7 @@ extern "C" int pb_decode_span_smem(const PbDecodeSpanArgs* a, int* n_stages, int
   if (a->I > vin) vin = a->I;
   if ((G + 2) * a->D > vin) vin = (G + 2) * a->D;
   vin = (vin + 63) & ~63;
-  const size_t fixed = static_cast<size_t>(vin) * 2 + (16 * kPage + 64) * 4 + 256 * 4 + 32 * 4 + 2 * kMaxStages * 8 + kMaxStages * 4 + 16 * 32 * 4 + 2 * 16 * 4 + 1024;
+  const size_t fixed = static_cast<size_t>(vin) * 2 + (16 * kPage + 64) * 4 + 256 * 4 + 32 * 4 + 2 * kMaxStages * 8 + kMaxStages * 4 + 16 + 16 * 32 * 4 + 2 * 16 * 4 + 1024;
   const size_t budget = 227 * 1024;
   if (fixed + 4 * kStageBytes > budget) return -1;
   int ns = static_cast<int>((budget - fixed) / kStageBytes);
