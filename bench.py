@@ -52,6 +52,8 @@ def main() -> None:
     ap.add_argument("--tp-emulate", type=int, default=0, help="DIAGNOSTIC (not a benchmark result): run the compute of ONE rank of a "
                     "tensor-parallel group of this size on one GPU (heads, KV heads and FFN columns divided), to measure the fixed per-layer costs")
     ap.add_argument("--skip-fp8", action="store_true", help="do not append the block-scaled FP8 decode measurement")
+    ap.add_argument("--skip-pipeline", action="store_true", help="N > 1: do not append the pipeline-parallel record (same model as N stages)")
+    ap.add_argument("--pp-chunk-tokens", type=int, default=256, help="positions per chunk of the pipelined prompt ingestion (pipeline record)")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

@@ -67,6 +67,7 @@ def run_multi_gpu(args) -> None:
         dist.all_gather_object(gathered, (ms, pms))
         host_barrier()
         heap.close()
+        _pipeline_appendix(args, engine, cache)
         dist.destroy_process_group()
         return
 
@@ -151,8 +152,32 @@ def run_multi_gpu(args) -> None:
     container.shutdown()
     host_barrier()
     heap.close()
+    result["pipeline"] = _pipeline_appendix(args, engine, cache)
     print(json.dumps(result))
     dist.destroy_process_group()
+
+
+def _pipeline_appendix(args, engine, cache) -> dict:
+    """The same model as N pipeline stages (BASELINE.json configs #2/#3), measured in the same job after the tensor-parallel run has
+    released its shards: every rank must call this (collective). A failure here never costs the headline line."""
+    if getattr(args, "skip_pipeline", False):
+        return {"skipped": True}
+    try:
+        import gc
+
+        engine.shards.clear()
+        engine._graphs.clear()
+        engine._span_plan = None
+        cache.pool = None
+        gc.collect()
+        torch.cuda.empty_cache()
+        return pipeline_record(args)
+    except Exception as e:  # noqa: BLE001
+        try:
+            host_barrier()
+        except Exception:  # noqa: BLE001
+            pass
+        return {"error": repr(e)[:300]}
 
 
 def follower_loop_with_marks(engine, cache, ring, consumer: int) -> dict:
@@ -196,8 +221,15 @@ def follower_loop_with_marks(engine, cache, ring, consumer: int) -> dict:
     return marks
 
 
-def run_pipeline(args) -> None:
-    """N pipeline stages (one per GPU) joined by the fused NVLink stage hop; single stream through the public client API."""
+def pipeline_record(args, *, with_decode: bool = True) -> dict:
+    """N pipeline stages (one per GPU, equal spans) joined by the NVLink landing rings; the public client API on rank 0.
+    Collective over the initialised process group; returns the record on rank 0 and {} elsewhere.
+
+    * decode: single stream, one token per step; every hop is the producing stage's last kernel storing into the next stage's
+      landing slot (no tensor in any RPC);
+    * prompt ingestion: [prefill_batch, prefill_seq] tokens through an inference session; the client cuts the step into chunks of
+      ``pipeline_chunk_tokens`` positions and runs them as a wavefront over the stages (client/inference_session.py), the
+      chunks travel through the landing rings. Ideal bubble fraction (S - 1) / (M + S - 1) for M chunks over S stages."""
     import tempfile
 
     from petals_b200.ops import native
@@ -208,16 +240,15 @@ def run_pipeline(args) -> None:
     from petals_b200.utils.peaks import NVLINK_PEER_GBS, measured_peaks
     from petals_b200.utils.random_model import MODEL_PRESETS, launch_random_stage, random_client_model, write_config_only
 
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=dev)
-    native.lib()
+    rank, world = dist.get_rank(), dist.get_world_size()
+    dev = torch.device("cuda", torch.cuda.current_device())
     path = write_config_only(args.model)
     config = AutoDistributedConfig.from_pretrained(path)
     n_layers = MODEL_PRESETS[args.model]["num_hidden_layers"]
-    fabric = init_fabric(config.hidden_size, max_tokens=4096)
+    PB, PT = args.prefill_batch, args.prefill_seq
+    chunk = int(getattr(args, "pp_chunk_tokens", 256))
+    do_prefill = not args.skip_prefill
+    fabric = init_fabric(config.hidden_size, max_tokens=max(PB * chunk, 64), n_slots=4)
     probe = fabric.heap.alloc(8)
     peer_gbs = measure_peer_bandwidth(fabric.heap, 0, 1)
     hop_us = measure_hop_latency(fabric.heap, probe, 0, 1)
@@ -226,48 +257,93 @@ def run_pipeline(args) -> None:
     swarm = FileSwarm(dirs[0])
     bounds = [round(i * n_layers / world) for i in range(world + 1)]
     t0 = time.time()
-    stage = launch_random_stage(path, range(bounds[rank], bounds[rank + 1]), swarm, dev, peer_id=f"stage{rank}", attn_cache_tokens=args.seq_len + 256,
-                                inference_max_length=args.seq_len, max_batch_size=1 << 20)
+    cache_tokens = (max(args.seq_len, PB * PT) if do_prefill else args.seq_len) + 256
+    stage = launch_random_stage(path, range(bounds[rank], bounds[rank + 1]), swarm, dev, peer_id=f"stage{rank}", attn_cache_tokens=cache_tokens,
+                                inference_max_length=max(args.seq_len, PT), max_batch_size=1 << 20)
     torch.cuda.synchronize()
     host_barrier()
     build_s = time.time() - t0
     K, W = args.steps, max(args.warmup, 3)
+    record: dict = {}
     if rank == 0:
-        model = random_client_model(path, swarm, dev)
+        model = random_client_model(path, swarm, dev, pipeline_chunk_tokens=chunk)
         vocab = model.config.vocab_size
-        prompt = torch.randint(0, vocab, (1, args.prompt_len), device=dev)
-        with torch.inference_mode(), model.inference_session(max_length=args.seq_len) as sess:
-            prime_session(model, sess, prompt, W)
-            sampler = ClockSampler(local_rank)
-            sampler.start()
-            # rank 0 waits for the last stage's result every step: its device time IS the max over ranks
-            ms, launches = device_timed_decode(model, sess, K)
-            clocks = sampler.stop()
-            e2e_s, h2d, d2h = e2e_decode(model, sess, K, dev)
-            over_fabric = [s.no_history for s in sess._server_sessions]
+        record = {"parallelism": f"pp{world} ({world} stages x {n_layers // world} blocks, NVLink landing rings)", "build_s": round(build_s, 1),
+                  "stage_hop": {"peer_store_GBps": None if peer_gbs is None else round(peer_gbs, 1),
+                                "frac_of_measured_peer_copy": None if peer_gbs is None else round(peer_gbs / NVLINK_PEER_GBS, 3),
+                                "flag_latency_us": None if hop_us is None else round(hop_us, 2), "hop_payload_bytes": config.hidden_size * 2,
+                                "hops_per_token": world, "reference_hop_model_ms": 18.0}}
+        if with_decode:
+            prompt = torch.randint(0, vocab, (1, args.prompt_len), device=dev)
+            with torch.inference_mode(), model.inference_session(max_length=args.seq_len) as sess:
+                prime_session(model, sess, prompt, W)
+                sampler = ClockSampler(dev.index)
+                sampler.start()
+                # rank 0 waits for the last stage's result every step: its device time IS the max over ranks
+                ms, launches = device_timed_decode(model, sess, K)
+                record["clocks"] = sampler.stop()
+                e2e_s, h2d, d2h = e2e_decode(model, sess, K, dev)
+                record["inputs_over_fabric"] = [s.no_history for s in sess._server_sessions]
+            record["decode"] = {"tokens_per_s": round(K / (ms / 1e3), 3), "ms_per_step": round(ms / K, 4), "gpu_launches_rank0": launches,
+                                "e2e_tokens_per_s": round(K / e2e_s, 3), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        if do_prefill:
+            try:
+                ids = torch.randint(0, vocab, (PB, PT), device=dev)
+                times = []
+                for it in range(1 + args.prefill_steps):
+                    with torch.inference_mode(), model.inference_session(max_length=PT) as sess:
+                        torch.cuda.synchronize()
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record()
+                        model.model(input_ids=ids)
+                        b.record()
+                        torch.cuda.synchronize()
+                        if it > 0:
+                            times.append(a.elapsed_time(b))
+                pms = sum(times) / len(times)
+                spec_ = config.block_spec()
+                flops = 2.0 * spec_.num_params() * n_layers * PB * PT + 4.0 * n_layers * PB * PT * PT * spec_.num_heads * spec_.head_dim / 2
+                pk = measured_peaks()
+                M = (PT + chunk - 1) // chunk
+                record["prefill"] = {"tokens_per_s": round(PB * PT / (pms / 1e3), 1), "ms_per_step": round(pms, 2), "batch": PB, "seq_len": PT,
+                                     "chunk_tokens": chunk, "chunks": M, "stages": world, "ideal_bubble_fraction": round((world - 1) / (M + world - 1), 3),
+                                     "TFLOPs_total": round(flops / pms / 1e9, 1),
+                                     "frac_of_measured_bf16_sustained_per_gpu": round(flops / pms / 1e9 / world / pk["bf16_tflops_sustained"], 3),
+                                     "path": "chunked prompt ingestion as a wavefront over the stages; chunks travel through the landing rings (fused GEMM-epilogue push)"}
+            except Exception as e:  # noqa: BLE001 - the decode number stands on its own
+                record["prefill"] = {"error": repr(e)[:300]}
         fabric.check_errors()
-        value = K / (ms / 1e3)
-        peaks = measured_peaks()
-        spec = config.block_spec()
-        result = {
-            "metric": metric_name(args.model),
-            "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3), "dtype": "bf16",
-            "data": "synthetic token ids; random-init weights of the named architecture",
-            "config": {"model": args.model, "global_batch": 1, "seq_len": args.seq_len,
-                       "parallelism": f"pp{world} ({world} stages x {n_layers // world} blocks, fused GEMV-epilogue NVLink stage hop)",
-                       "l2": "each step streams every stage's full weight span (>> 126 MB L2): inputs larger than L2", "build_s": round(build_s, 1),
-                       "inputs_over_fabric": over_fabric},
-            "clocks": clocks, "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches,
-            "stage_hop": {"peer_store_GBps": None if peer_gbs is None else round(peer_gbs, 1),
-                          "frac_of_measured_peer_copy": None if peer_gbs is None else round(peer_gbs / NVLINK_PEER_GBS, 3),
-                          "flag_latency_us": None if hop_us is None else round(hop_us, 2), "hop_payload_bytes": spec.hidden_size * 2,
-                          "hops_per_token": world, "reference_hop_model_ms": 18.0},
-        }
-        print(json.dumps(result))
     host_barrier()
     stage.shutdown()
     host_barrier()
     fabric.close()
+    return record
+
+
+def run_pipeline(args) -> None:
+    """``bench.py --parallelism ppN``: the pipeline layout as the headline line."""
+    from petals_b200.ops import native
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=dev)
+    native.lib()
+    rec = pipeline_record(args)
+    if rank == 0:
+        d = rec.get("decode", {})
+        value = d.get("tokens_per_s", 0.0)
+        result = {
+            "metric": metric_name(args.model), "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": d.get("ms_per_step"), "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3),
+            "dtype": "bf16", "data": "synthetic token ids; random-init weights of the named architecture",
+            "config": {"model": args.model, "global_batch": 1, "seq_len": args.seq_len, "parallelism": rec.get("parallelism"),
+                       "l2": "each step streams every stage's full weight span (>> 126 MB L2): inputs larger than L2", "build_s": rec.get("build_s"),
+                       "inputs_over_fabric": rec.get("inputs_over_fabric")},
+            "clocks": rec.get("clocks"),
+            "e2e": {"value": d.get("e2e_tokens_per_s"), "unit": "tokens/s", "h2d_bytes_per_step": d.get("h2d_bytes_per_step"), "d2h_bytes_per_step": d.get("d2h_bytes_per_step")},
+            "gpu_launches": d.get("gpu_launches_rank0"), "prefill": rec.get("prefill"), "stage_hop": rec.get("stage_hop"),
+        }
+        print(json.dumps(result))
     dist.destroy_process_group()
