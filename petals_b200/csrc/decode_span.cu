@@ -38,9 +38,9 @@ constexpr int kStageBytes = 16 * 1024;   // one ring slot: one weight row (or R 
 constexpr int kMaxStages = 12;
 constexpr int kConsumerWarps = 8;                       // warps 0-7: everything (gathers, norms, attention, projections)
 constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kGemvWarps = 10;                          // warps 0-9 take projection tasks; warps 8-9 do nothing else
+constexpr int kGemvWarps = 11;                          // warps 0-10 take projection tasks; warps 8-10 do nothing else
 constexpr int kGemvThreads = kGemvWarps * 32;
-constexpr int kThreads = kGemvThreads + 64;             // warp 10: the L2 prefetcher, warp 11: the loader. 12 warps x 168 registers
+constexpr int kThreads = kGemvThreads + 32;             // warp 11: the loader. 12 warps x 168 registers fill the register file
 constexpr int kMaxRanks = 8;
 constexpr int kMaxStageRows = 8;
 constexpr int kPage = 64;
@@ -96,19 +96,26 @@ struct Params {
   uint2* mlp_push[kMaxRanks];
   const uint2* oproj_in;         // local [R][H/2]
   const uint2* mlp_in;
+  // NVSwitch multicast (NVLS) variants, when the heap has a multicast mapping:
+  //   *_mc_push: multicast address of slot [rank] — ONE multimem.st replaces the R peer stores of a partial;
+  //   *_mc_sum : with `nvls_reduce`, every rank keeps its partial in slot [0] of its OWN heap and the slice owners read the
+  //              switch-side sum of all ranks' copies (multimem.ld_reduce: payloads as bf16x2 adds, validity as the sum of tags).
+  uint2* oproj_mc_push; uint2* mlp_mc_push;
+  const uint2* oproj_mc_sum; const uint2* mlp_mc_sum;
+  int nvls_reduce;
+  int n_push;       // unicast push targets of a partial: R, or 1 (our own slot [0]) with nvls_reduce
   const uint64_t* epoch;
   int* error_flag;
   Geom g_qkv, g_o, g_gu, g_down;
   int n_stages;
   int vin_elems;  // bf16 elements of the activation vector buffer
-  int pf_window;   // ring stages the producer asks L2 to prefetch beyond the ring while the ring is full (0: off)
   unsigned long long* timing;  // optional [n_layers][24] %globaltimer stamps of CTA 0 (consumer slots 0-12, producer slots 16-20)
 };
 
 // Diagnostics (PETALS_B200_SPAN_DEBUG): bit 0 = treat every polled unit as ready, bit 1 = skip the math. Results are garbage; the
 // two switches separate the cost of streaming, of computing and of waiting (tools/span_probe.py).
 __constant__ int c_debug = 0;
-#define SPAN_STAMP(slot) do { if (p.timing != nullptr && bid == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x == 0 || threadIdx.x == kGemvThreads + 32)) \
+#define SPAN_STAMP(slot) do { if (p.timing != nullptr && bid == 0 && (threadIdx.x & 31) == 0 && (threadIdx.x == 0 || threadIdx.x == kGemvThreads)) \
     p.timing[static_cast<size_t>(l) * 24 + (slot)] = globaltimer_ns(); } while (0)
 
 // ---- small helpers ---------------------------------------------------------------------------------------------------
@@ -123,6 +130,23 @@ PB_DEVICE uint2 ld_ll(const uint2* p) {
   return v;
 }
 PB_DEVICE void st_ll(uint2* p, uint32_t data, uint32_t tag) { st_relaxed_sys_v2(p, data, tag); }
+// One store through the NVSwitch multicast mapping: lands at the same offset of every rank's heap (SASS: a plain STG — the
+// replication is a property of the multicast address).
+PB_DEVICE void st_ll_mc(uint2* mc, uint32_t data, uint32_t tag) {
+  const unsigned long long v = (static_cast<unsigned long long>(tag) << 32) | data;
+  asm volatile("multimem.st.relaxed.sys.global.b64 [%0], %1;" ::"l"(mc), "l"(v) : "memory");
+}
+// Switch-side reductions over all ranks' copies of one LL unit (SASS: LDGMC.ADD).
+PB_DEVICE uint32_t ld_reduce_tag(const uint2* mc) {
+  uint32_t t;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.u32 %0, [%1];" : "=r"(t) : "l"(reinterpret_cast<const uint32_t*>(mc) + 1) : "memory");
+  return t;
+}
+PB_DEVICE uint32_t ld_reduce_payload(const uint2* mc) {
+  uint32_t v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.bf16x2 %0, [%1];" : "=r"(v) : "l"(mc) : "memory");
+  return v;
+}
 
 PB_DEVICE void bulk_load_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -216,10 +240,9 @@ PB_DEVICE int tasks_of_cta(const Geom& g, int bid, int grid) { return g.ntasks >
 
 // ---- producer ------------------------------------------------------------------------------------------------------------
 // `walk_stages` enumerates the ring stages of this CTA for the whole launch, in order: blocks x {QKV rows, K/V pages of the
-// attention units, O rows, gate/up rows, down rows}, and calls f(stage number, source, bytes, is_weight) for each. Two lanes
-// walk it: the LOADER fills ring slots; the PREFETCHER (another warp) runs ahead of the loader by up to `pf_window` stages beyond
-// the ring and asks the L2 for them (cp.async.bulk.prefetch.L2), so HBM keeps streaming while the consumers are busy with a
-// phase hand-off / the attention / a norm and the ring is full; the ring then refills from L2.
+// attention units, O rows, gate/up rows, down rows}, and calls f(stage number, source, bytes, is_weight) for each.
+// (Measured dead end, profiles/r2_span_probe.txt: a second lane walking ahead of the loader with cp.async.bulk.prefetch.L2
+// while the ring is full — meant to keep HBM busy through the non-weight phases — made every shape 10-70 % slower.)
 template <typename F>
 PB_DEVICE void walk_proj(uint32_t& st, const Geom& g, const __nv_bfloat16* w, const __nv_bfloat16* w2, int bid, int grid, F& f) {
   const int nt = tasks_of_cta(g, bid, grid);
@@ -262,10 +285,6 @@ PB_DEVICE void walk_stages(const Params& p, int pos, int bid, int grid, F& f) {
   }
 }
 
-PB_DEVICE void l2_prefetch_bulk(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
-
 struct Loader {
   const Ring& ring; uint64_t policy; volatile uint32_t* progress;
   PB_DEVICE void operator()(uint32_t st, const void* src, uint32_t bytes, bool weights) {
@@ -277,23 +296,6 @@ struct Loader {
     *progress = st + 1u;   // stages issued so far (the prefetcher paces itself on this)
   }
 };
-struct Prefetcher {
-  const Ring& ring; uint32_t window; volatile uint32_t* progress; int* error_flag;
-  PB_DEVICE void operator()(uint32_t st, const void* src, uint32_t bytes, bool weights) {
-    if (!weights) return;
-    // stay inside (issued + ring, issued + ring + window]: never behind the loader (pointless), never too far ahead (L2 capacity)
-    uint32_t issued = *progress;
-    if (st < issued + static_cast<uint32_t>(ring.n)) return;
-    unsigned spins = 0;
-    while (st >= issued + static_cast<uint32_t>(ring.n) + window) {
-      __nanosleep(200);
-      issued = *progress;
-      if (++spins > (1u << 24)) return;   // the step is broken; the loader's watchdog reports it
-    }
-    l2_prefetch_bulk(src, bytes);
-  }
-};
-
 // ---- consumer: projections. Every warp works alone: it owns whole tasks (task j of this CTA -> warp j % 8), waits for its own
 // stages, reduces inside the warp and publishes its outputs. No block-wide barrier inside a projection: eight independent
 // latency chains per SM instead of one.
@@ -391,8 +393,12 @@ PB_DEVICE void consume_proj_r(const Params& p, const Ring& ring, const TaskBoard
       }
       const uint32_t packed = pack_bf16(v0, v1);
       const size_t unit = (n0 >> 1) + lane;
-      if (EPI == 1) { for (int r = 0; r < p.R; ++r) st_ll(push[r] + unit, packed, tag); }
-      else st_ll(local_out + unit, packed, tag);
+      if (EPI == 1) {
+        if (local_out != nullptr) st_ll_mc(local_out + unit, packed, tag);       // NVLS: one store, replicated by the switch
+        else for (int r = 0; r < p.n_push; ++r) st_ll(push[r] + unit, packed, tag);   // unicast peer stores (only our own slot with nvls_reduce)
+      } else {
+        st_ll(local_out + unit, packed, tag);
+      }
     }
     __syncwarp();
     if (lane == 0) { tb.cnt[slot] = 0u; __threadfence_block(); tb.gen[slot] = my_gen + 1u; }
@@ -489,10 +495,26 @@ PB_DEVICE void rmsnorm_inplace(__nv_bfloat16* vin, const __nv_bfloat16* gw, int 
 
 // All-reduce tail: this CTA owns pairs [p0, p1) of the residual stream. Sum the R partials (rank order) + residual, keep the new
 // residual, publish it to x_ll (or, for the span output, to x_out).
-PB_DEVICE void reduce_slice(const Params& p, const uint2* parts_in, float* res, int p0, int p1, uint32_t tag_in, uint32_t tag_out,
+PB_DEVICE void reduce_slice(const Params& p, const uint2* parts_in, const uint2* mc_sum, float* res, int p0, int p1, uint32_t tag_in, uint32_t tag_out,
                             uint2* x_ll, __nv_bfloat16* x_out) {
   const int tid = threadIdx.x;
   const int half_h = p.H >> 1;
+  if (mc_sum != nullptr) {
+    // NVLS all-reduce tail: the switch sums the R ranks' units. All R tags equal tag_in  <=>  their sum is R * tag_in (stale tags are
+    // smaller), and a unit is one atomic 8-byte store, so the payload sum read after that is complete.
+    const uint32_t want = tag_in * static_cast<uint32_t>(p.R);
+    for (int i = p0 + tid; i < p1; i += kConsumerThreads) {
+      unsigned long long t0 = 0;
+      for (unsigned spins = 1; ld_reduce_tag(mc_sum + i) != want; ++spins)
+        if (give_up(spins, t0, p.error_flag)) break;
+      const uint32_t sum = ld_reduce_payload(mc_sum + i);
+      const uint32_t packed = pack_bf16(res[2 * (i - p0)] + bf16_lo(sum), res[2 * (i - p0) + 1] + bf16_hi(sum));
+      res[2 * (i - p0)] = bf16_lo(packed); res[2 * (i - p0) + 1] = bf16_hi(packed);
+      if (x_out != nullptr) reinterpret_cast<uint32_t*>(x_out)[i] = packed;
+      else st_ll(x_ll + i, packed, tag_out);
+    }
+    return;
+  }
   for (int i = p0 + tid; i < p1; i += kConsumerThreads) {
     uint2 v[kMaxRanks];
 #pragma unroll
@@ -514,6 +536,20 @@ PB_DEVICE void reduce_slice(const Params& p, const uint2* parts_in, float* res, 
   }
 }
 
+PB_DEVICE void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+PB_DEVICE void ldsm_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+PB_DEVICE void ldsm_x2_t(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+PB_DEVICE void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
 // ---- consumer: attention units ---------------------------------------------------------------------------------------------
 // Shared scratch: qs[G][D] fp32-free bf16 rotated q, knew[D], vnew[D], S[G][64], m/l.
 PB_DEVICE void consume_attention(const Params& p, const Ring& ring, uint32_t& base, const Layer& L, int pos, __nv_bfloat16* vin, float* scr,
@@ -522,10 +558,11 @@ PB_DEVICE void consume_attention(const Params& p, const Ring& ring, uint32_t& ba
   const int D = p.D, G = p.Hq / p.Hkv, half_d = D >> 1;
   const int nch = pos / kPage + 1;
   const int units = p.Hkv * nch;
-  // vin layout here: q[G*D] | knew[D] | vnew[D]  (bf16)
+  // vin layout here: q[16][D] (rows >= G are zero) | knew[D] | vnew[D] | P[16][64]   (bf16)
   __nv_bfloat16* qs = vin;
-  __nv_bfloat16* knew = vin + G * D;
+  __nv_bfloat16* knew = vin + 16 * D;
   __nv_bfloat16* vnew = knew + D;
+  __nv_bfloat16* Pb = vnew + D;
   float* S = scr;                 // [G][64]
   float* ml = scr + 16 * kPage;   // [G][2]
   int loaded_hk = -1;
@@ -535,6 +572,8 @@ PB_DEVICE void consume_attention(const Params& p, const Ring& ring, uint32_t& ba
     if (hk != loaded_hk) {
       // fetch this kv head's query group and the new k / v from the tagged buffer (wide, batched polls), then rotate q and k
       consumer_sync();
+      for (int e = tid; e < (16 - G) * D / 8; e += kConsumerThreads)   // zero the padding rows of the 16-row MMA tile
+        reinterpret_cast<uint4*>(qs + G * D)[e] = make_uint4(0u, 0u, 0u, 0u);
       gather_ll(p.qkv_ll + ((static_cast<size_t>(hk) * G * D) >> 1), qs, G * D, tag_qkv, p.error_flag);
       gather_ll(p.qkv_ll + ((static_cast<size_t>(p.Hq + hk) * D) >> 1), knew, D, tag_qkv, p.error_flag);
       gather_ll(p.qkv_ll + ((static_cast<size_t>(p.Hq + p.Hkv + hk) * D) >> 1), vnew, D, tag_qkv, p.error_flag);
@@ -579,52 +618,61 @@ PB_DEVICE void consume_attention(const Params& p, const Ring& ring, uint32_t& ba
       }
       consumer_sync();
     }
-    // ---- scores: thread -> key = tid % 64, heads g = tid / 64 + 4 j ----
+    // ---- scores on the tensor cores: S[16 heads x 64 keys] = Q K^T, warp w -> keys 8w .. 8w+7 ----
     if (c_debug & 2) { consumer_sync(); if (tid == 0) { mbar_arrive(ring.empty_bar(st)); mbar_arrive(ring.empty_bar(st + 1)); } continue; }
-    const int key = tid & (kPage - 1);
-    const int nchunk16 = D >> 3;  // 16-byte chunks per row
-    for (int g = tid >> 6; g < G; g += kConsumerThreads / kPage) {
-      float s = 0.f;
-      const __nv_bfloat16* kr = Ks + key * D;
-      const __nv_bfloat16* qr = qs + g * D;
-      for (int cc = 0; cc < nchunk16; ++cc) {
-        const int ch = (cc + lane) & (nchunk16 - 1);  // rotate the chunk order per lane: bank-conflict-free row reads
-        const uint4 kv = *reinterpret_cast<const uint4*>(kr + ch * 8);
-        const uint4 qv = *reinterpret_cast<const uint4*>(qr + ch * 8);
-        s = fmaf(bf16_lo(kv.x), bf16_lo(qv.x), s); s = fmaf(bf16_hi(kv.x), bf16_hi(qv.x), s);
-        s = fmaf(bf16_lo(kv.y), bf16_lo(qv.y), s); s = fmaf(bf16_hi(kv.y), bf16_hi(qv.y), s);
-        s = fmaf(bf16_lo(kv.z), bf16_lo(qv.z), s); s = fmaf(bf16_hi(kv.z), bf16_hi(qv.z), s);
-        s = fmaf(bf16_lo(kv.w), bf16_lo(qv.w), s); s = fmaf(bf16_hi(kv.w), bf16_hi(qv.w), s);
+    {
+      float sc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t q_addr = smem_u32(qs) + static_cast<uint32_t>(((lane & 15) * D + (lane >> 4) * 8) * 2);
+      const uint32_t k_addr = smem_u32(Ks) + static_cast<uint32_t>(((8 * warp + (lane & 7)) * D + ((lane >> 3) & 1) * 8) * 2);
+      for (int kk = 0; kk < D / 16; ++kk) {
+        uint32_t a0, a1, a2, a3, b0, b1;
+        ldsm_x4(q_addr + kk * 32, a0, a1, a2, a3);
+        ldsm_x2(k_addr + kk * 32, b0, b1);
+        mma16816(sc, a0, a1, a2, a3, b0, b1);
       }
-      S[g * kPage + key] = (key0 + key <= pos) ? s * p.scale_log2 : -INFINITY;
+      // accumulator layout: rows (heads) lane/4 and lane/4 + 8, columns (keys) 8w + 2 (lane%4) + {0, 1}
+      const int kcol = 8 * warp + 2 * (lane & 3);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int g = (lane >> 2) + (e >> 1) * 8, key = kcol + (e & 1);
+        if (g < G) S[g * kPage + key] = (key0 + key <= pos) ? sc[e] * p.scale_log2 : -INFINITY;
+      }
     }
     consumer_sync();
-    // ---- softmax statistics: warp w -> heads w, w + 8 ----
-    for (int g = warp; g < G; g += kConsumerWarps) {
-      const float s0 = S[g * kPage + lane], s1 = S[g * kPage + lane + 32];
-      const float m = warp_max(fmaxf(s0, s1));  // the chunk always holds at least one valid key
-      const float p0 = exp2f(s0 - m), p1 = exp2f(s1 - m);
-      S[g * kPage + lane] = p0; S[g * kPage + lane + 32] = p1;
-      const float l = warp_sum(p0 + p1);
-      if (lane == 0) { ml[2 * g] = m; ml[2 * g + 1] = l; }
+    // ---- softmax statistics: warp w -> heads w, w + 8; probabilities as the bf16 A operand of P V ----
+    for (int g = warp; g < 16; g += kConsumerWarps) {
+      float p0 = 0.f, p1 = 0.f;
+      if (g < G) {
+        const float s0 = S[g * kPage + lane], s1 = S[g * kPage + lane + 32];
+        const float m = warp_max(fmaxf(s0, s1));  // the chunk always holds at least one valid key
+        p0 = exp2f(s0 - m); p1 = exp2f(s1 - m);
+        const float l = warp_sum(p0 + p1);
+        if (lane == 0) { ml[2 * g] = m; ml[2 * g + 1] = l; }
+      }
+      Pb[g * kPage + lane] = __float2bfloat16_rn(p0);
+      Pb[g * kPage + lane + 32] = __float2bfloat16_rn(p1);
     }
     consumer_sync();
-    // ---- o[g][d pair] = sum_key P[g][key] V[key][d pair]; publish {o, m, l} ----
-    const int dpairs = D >> 1;
-    for (int e = tid; e < G * dpairs; e += kConsumerThreads) {
-      const int g = e / dpairs, dp = e - g * dpairs;
-      float o0 = 0.f, o1 = 0.f;
-      const float* pr = S + g * kPage;
-      const uint32_t* vcol = reinterpret_cast<const uint32_t*>(Vs) + dp;
-#pragma unroll 8
-      for (int k = 0; k < kPage; ++k) {
-        const uint32_t vv = vcol[k * dpairs];
-        const float pk = pr[k];
-        o0 = fmaf(pk, bf16_lo(vv), o0); o1 = fmaf(pk, bf16_hi(vv), o1);
+    // ---- O[16 heads x D] = P V on the tensor cores: warp w -> dims [w D/8, (w+1) D/8); publish {o, m, l} ----
+    {
+      const int dper = D / kConsumerWarps;   // 16 (D = 128) or 8 (D = 64) output dims per warp
+      const uint32_t p_addr = smem_u32(Pb) + static_cast<uint32_t>(((lane & 15) * kPage + (lane >> 4) * 8) * 2);
+      for (int d0 = warp * dper; d0 < (warp + 1) * dper; d0 += 8) {
+        float oc[4] = {0.f, 0.f, 0.f, 0.f};
+        const uint32_t v_addr = smem_u32(Vs) + static_cast<uint32_t>(((lane & 15) * D + d0) * 2);
+#pragma unroll
+        for (int ks = 0; ks < kPage / 16; ++ks) {
+          uint32_t a0, a1, a2, a3, b0, b1;
+          ldsm_x4(p_addr + ks * 32, a0, a1, a2, a3);
+          ldsm_x2_t(v_addr + ks * 16 * D * 2, b0, b1);
+          mma16816(oc, a0, a1, a2, a3, b0, b1);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int g = (lane >> 2) + (e >> 1) * 8, d = d0 + 2 * (lane & 3) + (e & 1);
+          if (g < G) st_ll(p.attp_ll + (static_cast<size_t>(hk * G + g) * p.max_chunks + c) * (D + 2) + d, __float_as_uint(oc[e]), tag_attp);
+        }
       }
-      uint2* dst = p.attp_ll + (static_cast<size_t>(hk * G + g) * p.max_chunks + c) * (D + 2);
-      st_ll(dst + 2 * dp, __float_as_uint(o0), tag_attp);
-      st_ll(dst + 2 * dp + 1, __float_as_uint(o1), tag_attp);
     }
     if (tid < 2 * G) {
       const int g = tid >> 1;
@@ -728,15 +776,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
   uint32_t base = 0;   // first ring stage of the current phase (same arithmetic in the producer and in every consumer warp)
 
   if (warp >= kGemvWarps) {
-    // =============================== PRODUCER (loader lane + L2 prefetcher lane) ===============================
+    // =============================== PRODUCER: one lane feeds the ring for the whole launch ===============================
     if ((tid & 31) == 0) {
-      if (warp == kGemvWarps + 1) {
-        Loader f{ring, policy_evict_first(), progress};
-        walk_stages(p, pos, bid, grid, f);
-      } else if (p.pf_window > 0) {
-        Prefetcher f{ring, static_cast<uint32_t>(p.pf_window), progress, p.error_flag};
-        walk_stages(p, pos, bid, grid, f);
-      }
+      Loader f{ring, policy_evict_first(), progress};
+      walk_stages(p, pos, bid, grid, f);
     }
     return;
   }
@@ -750,9 +793,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
       const uint32_t tg = tag0 + static_cast<uint32_t>(l) * T_PER_LAYER;
       consume_proj<0>(p, ring, tb, base, p.g_qkv, vin, nullptr, p.qkv_ll, tg + T_QKV, bid, grid);
       base += kv_stages;   // the attention units' K / V pages are consumed by the main warps
-      consume_proj<1>(p, ring, tb, base, p.g_o, vin, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid);
+      consume_proj<1>(p, ring, tb, base, p.g_o, vin, p.oproj_push, p.oproj_mc_push, tg + T_OPROJ, bid, grid);
       consume_proj<2>(p, ring, tb, base, p.g_gu, vin, nullptr, p.act_ll, tg + T_ACT, bid, grid);
-      consume_proj<1>(p, ring, tb, base, p.g_down, vin, p.mlp_push, nullptr, tg + T_MLP, bid, grid);
+      consume_proj<1>(p, ring, tb, base, p.g_down, vin, p.mlp_push, p.mlp_mc_push, tg + T_MLP, bid, grid);
     }
     return;
   }
@@ -789,9 +832,9 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
     consumer_sync();
     gather_ll(p.attn_ll, vin, p.Hq * p.D, tg + T_ATTN, p.error_flag);
     consumer_sync();                                                                                 SPAN_STAMP(5);
-    consume_proj<1>(p, ring, tb, base, p.g_o, vin, p.oproj_push, nullptr, tg + T_OPROJ, bid, grid); SPAN_STAMP(6);
+    consume_proj<1>(p, ring, tb, base, p.g_o, vin, p.oproj_push, p.oproj_mc_push, tg + T_OPROJ, bid, grid); SPAN_STAMP(6);
     // ---- all-reduce tail + norm + gate/up ----
-    reduce_slice(p, p.oproj_in, res, p0, p1, tg + T_OPROJ, tg + T_X1, p.x_ll, nullptr);            SPAN_STAMP(7);
+    reduce_slice(p, p.oproj_in, p.oproj_mc_sum, res, p0, p1, tg + T_OPROJ, tg + T_X1, p.x_ll, nullptr);            SPAN_STAMP(7);
     float ss1 = 0.f;
     gather_ll(p.x_ll, vin, p.H, tg + T_X1, p.error_flag, &ss1);
     consumer_sync();
@@ -800,10 +843,10 @@ __global__ void __launch_bounds__(kThreads, 1) decode_span_kernel(const __grid_c
     // ---- P5: down projection, partials pushed to every rank ----
     gather_ll(p.act_ll, vin, p.I, tg + T_ACT, p.error_flag);
     consumer_sync();                                                                                 SPAN_STAMP(10);
-    consume_proj<1>(p, ring, tb, base, p.g_down, vin, p.mlp_push, nullptr, tg + T_MLP, bid, grid); SPAN_STAMP(11);
+    consume_proj<1>(p, ring, tb, base, p.g_down, vin, p.mlp_push, p.mlp_mc_push, tg + T_MLP, bid, grid); SPAN_STAMP(11);
     // ---- all-reduce tail: next block's input, or the span output ----
     const bool last = (l + 1 == p.n_layers);
-    reduce_slice(p, p.mlp_in, res, p0, p1, tg + T_MLP, tg + T_X2, p.x_ll, last ? p.x_out : nullptr);
+    reduce_slice(p, p.mlp_in, p.mlp_mc_sum, res, p0, p1, tg + T_MLP, tg + T_X2, p.x_ll, last ? p.x_out : nullptr);
     if (!last) {
       ss_carry = 0.f;
       gather_ll(p.x_ll, vin, p.H, tg + T_X2, p.error_flag, &ss_carry);
@@ -844,7 +887,8 @@ extern "C" int pb_decode_span_smem(const PbDecodeSpanArgs* a, int* n_stages, int
   int vin = a->H;
   if (a->Hq * a->D > vin) vin = a->Hq * a->D;
   if (a->I > vin) vin = a->I;
-  if ((G + 2) * a->D > vin) vin = (G + 2) * a->D;
+  (void)G;
+  if (18 * a->D + 16 * kPage > vin) vin = 18 * a->D + 16 * kPage;   // attention staging: q[16][D], new k, new v, P[16][64]
   vin = (vin + 63) & ~63;
   const size_t fixed = static_cast<size_t>(vin) * 2 + (16 * kPage + 64) * 4 + 256 * 4 + 32 * 4 + 2 * kMaxStages * 8 + kMaxStages * 4 + 16 + 16 * 32 * 4 + 2 * 16 * 4 + 1024;
   const size_t budget = 227 * 1024;
@@ -880,6 +924,10 @@ extern "C" int pb_decode_span(const PbDecodeSpanArgs* a, void* stream) {
   p.R = a->R; p.rank = a->rank;
   for (int r = 0; r < a->R; ++r) { p.oproj_push[r] = static_cast<uint2*>(a->oproj_push[r]); p.mlp_push[r] = static_cast<uint2*>(a->mlp_push[r]); }
   p.oproj_in = static_cast<const uint2*>(a->oproj_in); p.mlp_in = static_cast<const uint2*>(a->mlp_in);
+  p.oproj_mc_push = static_cast<uint2*>(a->oproj_mc_push); p.mlp_mc_push = static_cast<uint2*>(a->mlp_mc_push);
+  p.oproj_mc_sum = static_cast<const uint2*>(a->oproj_mc_sum); p.mlp_mc_sum = static_cast<const uint2*>(a->mlp_mc_sum);
+  p.nvls_reduce = a->nvls_reduce;
+  p.n_push = a->nvls_reduce ? 1 : a->R;
   p.epoch = static_cast<const uint64_t*>(a->epoch); p.error_flag = static_cast<int*>(a->error_flag);
   if (!make_geom(p.g_qkv, (a->Hq + 2 * a->Hkv) * a->D, a->H, false, "decode_span: QKV geometry") ||
       !make_geom(p.g_o, a->H, a->Hq * a->D, false, "decode_span: O-projection geometry") ||
@@ -891,10 +939,6 @@ extern "C" int pb_decode_span(const PbDecodeSpanArgs* a, void* stream) {
   if (smem < 0) { pb_set_error("decode_span: activation vector does not fit beside the weight ring"); return PB_ERR_UNSUPPORTED; }
   p.n_stages = ns; p.vin_elems = vin;
   p.timing = static_cast<unsigned long long*>(a->timing);
-  {
-    static const int env_pf = [] { const char* e = getenv("PETALS_B200_SPAN_PF"); return e ? atoi(e) : 32; }();
-    p.pf_window = env_pf < 0 ? 0 : env_pf;
-  }
   {
     static int cur_debug = 0;
     static const int env_debug = [] { const char* e = getenv("PETALS_B200_SPAN_DEBUG"); return e ? atoi(e) : 0; }();

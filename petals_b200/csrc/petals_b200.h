@@ -105,6 +105,10 @@ typedef struct {
   int num_sms;
   int prepare_only;        // 1: validate the shapes and set the kernel's shared-memory attribute, launch nothing
   void* timing;            // optional uint64 [n_layers][24]: %globaltimer stamps of CTA 0 at every phase boundary (diagnostics)
+  // NVSwitch multicast (all NULL / 0 without a multicast mapping of the heap):
+  void* oproj_mc_push; void* mlp_mc_push;            // multicast address of slot [rank]: one multimem.st instead of R peer stores
+  const void* oproj_mc_sum; const void* mlp_mc_sum;  // multicast address of slot [0]: owners multimem.ld_reduce the R partials (nvls_reduce)
+  int nvls_reduce;
 } PbDecodeSpanArgs;
 int pb_decode_span(const PbDecodeSpanArgs* a, void* stream);
 int pb_decode_span_smem(const PbDecodeSpanArgs* a, int* n_stages, int* vin_elems);

@@ -600,7 +600,12 @@ class DecodeSpanPlan:
 
     def __init__(self, layers: Sequence[dict], *, H: int, Hq: int, Hkv: int, D: int, I: int, eps: float, attn_scale: float, max_chunks: int,
                  device, R: int = 1, rank: int = 0, oproj: Optional[tuple] = None, mlp: Optional[tuple] = None, epoch: Optional[torch.Tensor] = None,
-                 error_flag: Optional[torch.Tensor] = None):
+                 error_flag: Optional[torch.Tensor] = None, nvls: Optional[dict] = None):
+        """``nvls`` (NVSwitch multicast, tensor parallel only): ``{"mode": "st" | "reduce", "oproj": addr, "mlp": addr}`` with the
+        multicast addresses of slot [rank] ("st": one ``multimem.st`` instead of R peer stores) or of slot [0] ("reduce": partials
+        stay in the own heap, the slice owners ``multimem.ld_reduce`` them; ``oproj`` / ``mlp`` push lists then hold only this rank's
+        slot [0])."""
+        self.nvls = nvls or {}
         self.device = torch.device(device)
         self.H, self.Hq, self.Hkv, self.D, self.I, self.eps, self.attn_scale = H, Hq, Hkv, D, I, eps, attn_scale
         self.R, self.rank, self.max_chunks = R, rank, max_chunks
@@ -619,7 +624,7 @@ class DecodeSpanPlan:
                 mlp = ([self._mlp.data_ptr()], self._mlp.data_ptr())
         self.oproj_push, self.oproj_in = oproj
         self.mlp_push, self.mlp_in = mlp
-        assert len(self.oproj_push) == R and len(self.mlp_push) == R
+        assert len(self.oproj_push) in (1, R) and len(self.mlp_push) in (1, R)
         self.num_pages = layers[0]["k_pool"].shape[0]
         # validate the shapes and set the kernel attribute now (not under a stream capture, not inside a timed step)
         dummy = torch.zeros(1, H, dtype=torch.bfloat16, device=self.device)
@@ -643,9 +648,13 @@ class DecodeSpanPlan:
                                                             self.x_ll.data_ptr(), self.act_ll.data_ptr())
         a.max_chunks = min(self.max_chunks, block_table.shape[1])
         a.R, a.rank = self.R, self.rank
-        for r in range(self.R):
+        for r in range(len(self.oproj_push)):
             a.oproj_push[r], a.mlp_push[r] = self.oproj_push[r], self.mlp_push[r]
         a.oproj_in, a.mlp_in = self.oproj_in, self.mlp_in
+        if self.nvls.get("mode") == "st":
+            a.oproj_mc_push, a.mlp_mc_push = self.nvls["oproj"], self.nvls["mlp"]
+        elif self.nvls.get("mode") == "reduce":
+            a.oproj_mc_sum, a.mlp_mc_sum, a.nvls_reduce = self.nvls["oproj"], self.nvls["mlp"], 1
         a.epoch, a.error_flag = self.epoch.data_ptr(), self.err.data_ptr()
         a.num_sms = native.sm_count(self.device.index)
         a.timing = ptr(getattr(self, "timing", None))

@@ -96,6 +96,7 @@ class DecodeSpanArgs(C.Structure):
         ("oproj_push", C.c_void_p * PB_MAX_PEERS), ("mlp_push", C.c_void_p * PB_MAX_PEERS),
         ("oproj_in", C.c_void_p), ("mlp_in", C.c_void_p),
         ("epoch", C.c_void_p), ("error_flag", C.c_void_p), ("num_sms", C.c_int), ("prepare_only", C.c_int), ("timing", C.c_void_p),
+        ("oproj_mc_push", C.c_void_p), ("mlp_mc_push", C.c_void_p), ("oproj_mc_sum", C.c_void_p), ("mlp_mc_sum", C.c_void_p), ("nvls_reduce", C.c_int),
     ]
 
 

@@ -52,6 +52,34 @@ def tensor_from_ptr(ptr: int, shape: Sequence[int], dtype: torch.dtype, device) 
 
 
 class SymmetricHeap:
+    """``multicast_ptr`` (0 when unavailable): an NVSwitch multicast mapping of the same heap — a ``multimem.st`` to
+    ``multicast_ptr + off`` lands at offset ``off`` of EVERY rank's heap in one store (NVLS), a ``multimem.ld_reduce`` reads the
+    switch-side sum of all ranks' copies. The CUDA VMM / multicast-object / file-descriptor plumbing is torch's symmetric-memory
+    allocator (``torch.distributed._symmetric_memory``); when it cannot be set up (no NVSwitch, old driver, CPU build) the heap
+    is a plain ``cudaMalloc`` exported with CUDA IPC and ``multicast_ptr`` stays 0."""
+
+    def _try_symm_mem(self, group) -> bool:
+        import os
+
+        if os.environ.get("PETALS_B200_SYMM_MEM", "1") == "0":
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+
+            with torch.cuda.device(self.device):
+                buf = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+                hdl = symm_mem.rendezvous(buf, group if group is not None else dist.group.WORLD)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            if len(ptrs) != self.world or not all(ptrs):
+                return False
+            self._symm_buf, self._symm_hdl = buf, hdl  # keep the mapping alive
+            self.ptrs, self.local_ptr = ptrs, ptrs[self.rank]
+            self.multicast_ptr = int(getattr(hdl, "multicast_ptr", 0) or 0)
+            return True
+        except Exception as e:  # noqa: BLE001 - any failure means: use the IPC heap
+            logger.info(f"rank {dist.get_rank(group)}: symmetric-memory allocator unavailable ({type(e).__name__}: {str(e)[:120]}); using CUDA IPC")
+            return False
+
     def __init__(self, nbytes: int, group: Optional[dist.ProcessGroup] = None, device: Optional[torch.device] = None):
         self.group = group
         self.rank = dist.get_rank(group)
@@ -59,6 +87,24 @@ class SymmetricHeap:
         self.device = device or torch.device("cuda", torch.cuda.current_device())
         self.nbytes = (nbytes + 4095) // 4096 * 4096
         self._lib = native.lib()
+        self.multicast_ptr = 0
+        self._symm_buf = self._symm_hdl = None
+        # every rank must take the same branch: agree on the outcome
+        ok = torch.tensor([1 if self._try_symm_mem(group) else 0])
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if int(ok.item()) == 1:
+            mc = torch.tensor([1 if self.multicast_ptr else 0])
+            dist.all_reduce(mc, op=dist.ReduceOp.MIN, group=group)
+            if int(mc.item()) == 0:
+                self.multicast_ptr = 0
+            self._top = 0
+            self.tensor(0, (self.nbytes,), torch.uint8).zero_()
+            torch.cuda.synchronize(self.device)
+            host_barrier(group)
+            logger.info(f"rank {self.rank}: symmetric heap of {self.nbytes >> 20} MiB mapped on {self.world} ranks (VMM, multicast {'on' if self.multicast_ptr else 'off'})")
+            return
+        self._symm_buf = self._symm_hdl = None
+        self.multicast_ptr = 0
         base = C.c_void_p()
         with torch.cuda.device(self.device):
             native.check(self._lib.pb_ipc_malloc(C.byref(base), self.nbytes), "ipc_malloc", 0)
@@ -98,6 +144,10 @@ class SymmetricHeap:
     def addr(self, rank: int, off: int) -> int:
         return self.ptrs[rank] + off
 
+    def mc_addr(self, off: int) -> int:
+        """Multicast address of offset ``off`` (0 when the heap has no multicast mapping)."""
+        return self.multicast_ptr + off if self.multicast_ptr else 0
+
     def tensor(self, off: int, shape: Sequence[int], dtype: torch.dtype) -> torch.Tensor:
         return tensor_from_ptr(self.local_ptr + off, shape, dtype, self.device)
 
@@ -107,6 +157,10 @@ class SymmetricHeap:
         host_barrier(self.group)
 
     def close(self) -> None:
+        if self._symm_hdl is not None:  # released with the tensor / handle
+            self._symm_hdl = self._symm_buf = None
+            self.local_ptr = 0
+            return
         for r, p in enumerate(self.ptrs):
             if r != self.rank and p:
                 self._lib.pb_ipc_close_handle(p)

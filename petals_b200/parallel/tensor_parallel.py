@@ -320,12 +320,26 @@ class TPDecodeEngine:
                 k_pool, v_pool = self.cache.layer_pools(l)
                 layers.append(dict(wqkv=w["wqkv"], wo=w["wo"], w_gate=w["w_gate"], w_up=w["w_up"], w_down=w["w_down"], ln1_w=w["ln1_w"],
                                    ln2_w=w["ln2_w"], k_pool=k_pool, v_pool=v_pool))
+            # PETALS_B200_SPAN_NVLS: "0" = unicast peer stores; "st" = one multimem.st per partial (NVSwitch replicates it into every
+            # rank's slot); "reduce" = partials stay local, the slice owners multimem.ld_reduce them (in-switch sum). Needs the
+            # heap's multicast mapping (parallel/symmetric.py); without it every mode degrades to unicast.
+            mode = os.environ.get("PETALS_B200_SPAN_NVLS", "st").lower()
+            mc = getattr(self.heap, "multicast_ptr", 0)
+            nvls = None
             push = lambda off: [self.heap.addr(r, off + me * self.span_slot_bytes) for r in range(R)]
+            push_attn, push_mlp = push(self.off_span_attn), push(self.off_span_mlp)
+            if mc and R > 1 and mode == "st":
+                nvls = dict(mode="st", oproj=self.heap.mc_addr(self.off_span_attn + me * self.span_slot_bytes),
+                            mlp=self.heap.mc_addr(self.off_span_mlp + me * self.span_slot_bytes))
+            elif mc and R > 1 and mode == "reduce":
+                nvls = dict(mode="reduce", oproj=self.heap.mc_addr(self.off_span_attn), mlp=self.heap.mc_addr(self.off_span_mlp))
+                push_attn, push_mlp = [self.heap.addr(me, self.off_span_attn)], [self.heap.addr(me, self.off_span_mlp)]
+            self.span_nvls_mode = nvls["mode"] if nvls else "unicast"
             self._span_plan = Fn.DecodeSpanPlan(
                 layers, H=s.hidden_size, Hq=ls.num_heads, Hkv=ls.num_kv_heads, D=ls.head_dim, I=ls.intermediate_size, eps=s.norm_eps,
                 attn_scale=s.attn_scale, max_chunks=self.max_pages, device=self.device, R=R, rank=me,
-                oproj=(push(self.off_span_attn), self.heap.addr(me, self.off_span_attn)),
-                mlp=(push(self.off_span_mlp), self.heap.addr(me, self.off_span_mlp)), epoch=self.epoch, error_flag=self.err)
+                oproj=(push_attn, self.heap.addr(me, self.off_span_attn)), mlp=(push_mlp, self.heap.addr(me, self.off_span_mlp)),
+                epoch=self.epoch, error_flag=self.err, nvls=nvls)
         return self._span_plan
 
     # ---- sequence-parallel prefill ---------------------------------------------------------------------------------------

@@ -5,7 +5,7 @@ S=gpurun_out/r2_7_summary.txt; : > $S
 timeout 600 python -m pytest tests/test_decode_span_gpu.py -q --timeout=150 > gpurun_out/r2_7_span_tests.log 2>&1; echo "span tests exit=$?" | tee -a $S
 tail -3 gpurun_out/r2_7_span_tests.log | cut -c1-250 | tee -a $S
 for shape in 70b-tp8 70b 8b; do
-  for pf in 0 16 32 64; do
+  for pf in 0; do
     echo "PF=$pf" | tee -a $S
     PETALS_B200_SPAN_PF=$pf timeout 300 python tools/span_probe.py --shape $shape 2>&1 | grep '^{' | tee -a $S
   done
