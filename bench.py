@@ -185,7 +185,7 @@ def bench_prefill(model, args, peaks, spec, n_layers) -> dict:
         end.record()
         torch.cuda.synchronize()
     ms = start.elapsed_time(end) / args.prefill_steps
-    flops = 2.0 * spec.num_params() * n_layers * B * T + 4.0 * n_layers * B * T * T * spec.num_heads * spec.head_dim / 2
+    flops = 2.0 * spec.active_params() * n_layers * B * T + 4.0 * n_layers * B * T * T * spec.num_heads * spec.head_dim / 2
     return {"tokens_per_s": round(B * T / (ms / 1e3), 1), "ms_per_step": round(ms, 2), "batch": B, "seq_len": T,
             "TFLOPs": round(flops / ms / 1e9, 1), "frac_of_measured_bf16_sustained": round(flops / ms / 1e9 / peaks["bf16_tflops_sustained"], 3)}
 

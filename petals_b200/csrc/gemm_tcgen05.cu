@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "petals_b200.h"
 
+#include <atomic>
 #include <mutex>
 
 namespace pb {
@@ -53,6 +54,13 @@ struct GemmParams {
   uint64_t wait_per_epoch;
   const uint64_t* epoch;
   int* error_flag;
+  // Grouped (ragged-M) mode for sparse MoE layers: the M dimension is a concatenation of per-expert row groups and every group
+  // multiplies its own weight matrix (the experts' weights are stacked along N: expert e owns rows [e * grp_n, (e+1) * grp_n) of B).
+  // `grp` is a DEVICE table built by moe_plan_kernel — {n_mtiles, expert[], first row[], valid rows[]} — so the host never learns
+  // (or waits for) the routing: the persistent CTAs read the tile count when they start.
+  const int* grp;
+  int grp_cap;   // capacity of each table array
+  int grp_n;     // B rows per expert
 };
 
 PB_DEVICE float gelu_tanh_f(float x) {
@@ -98,7 +106,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   uint8_t* push_stage = reinterpret_cast<uint8_t*>(tmem_slot) + 64;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_blocks = (p.M + BM - 1) / BM;
+  const bool grouped = p.grp != nullptr;
+  const int m_blocks = grouped ? min(p.grp[0], p.grp_cap) : (p.M + BM - 1) / BM;
+  const int* g_expert = p.grp + 1;
+  const int* g_row0 = g_expert + p.grp_cap;
+  const int* g_rows = g_row0 + p.grp_cap;
   const int n_blocks = (p.N + OUT_BN - 1) / OUT_BN;
   const int num_tiles = m_blocks * n_blocks;
   const int num_kb = (p.K + BK - 1) / BK;
@@ -139,18 +151,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         int m_blk, n_blk;
         tile_coords(tile, m_blocks, n_blocks, m_blk, n_blk);
+        const int a_row = grouped ? g_row0[m_blk] : m_blk * BM;
+        const int b_row = grouped ? g_expert[m_blk] * p.grp_n : 0;   // this group's expert: its slab of the stacked weights
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
           uint8_t* sb = sa + A_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
           if (!B_MN) {
             if (!DUAL) {
-              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN);
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, b_row + n_blk * BN);
             } else {
-              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * OUT_BN);
-              tma_load_2d(sb + B_BYTES / 2, &tmap_b2, &full_bar[stage], kb * BK, n_blk * OUT_BN);
+              tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, b_row + n_blk * OUT_BN);
+              tma_load_2d(sb + B_BYTES / 2, &tmap_b2, &full_bar[stage], kb * BK, b_row + n_blk * OUT_BN);
             }
           } else {
             // MN-major: BN/64 boxes of [64 k-rows x 64 n-elements], 8 KB each
@@ -204,8 +218,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aphase);
       tc_fence_after();
-      const int row = m_blk * BM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const int tile_row0 = grouped ? g_row0[m_blk] : m_blk * BM;
+      const int row = tile_row0 + quarter * 32 + lane;
+      const bool row_ok = grouped ? (quarter * 32 + lane) < g_rows[m_blk] : row < p.M;   // grouped: rows past the group's end belong to the next expert
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
       for (int c = 0; c < OUT_BN; c += 32) {
@@ -328,8 +343,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int rr = 8 * i + (lane >> 2), piece = lane & 3;
-            const int grow = m_blk * BM + quarter * 32 + rr;
-            if (grow < p.M) {
+            const int grow = tile_row0 + quarter * 32 + rr;
+            if (grouped ? (quarter * 32 + rr) < g_rows[m_blk] : grow < p.M) {
               const uint4 val = *reinterpret_cast<const uint4*>(sbase + rr * 80 + piece * 16);
               if (p.push_rows_per_owner > 0) {
                 const int owner = grow / p.push_rows_per_owner;
@@ -431,12 +446,13 @@ static int launch_gemm(const PbGemmArgs* a, cudaStream_t stream) {
   const int lda = a->lda > 0 ? a->lda : a->K;
   CUtensorMap ta, tb, tb2;
   if (!make_tmap_2d(&ta, a->a, a->M, a->K, lda, BM, BK)) return PB_ERR_DRIVER;
+  const uint64_t b_rows = a->grp != nullptr ? static_cast<uint64_t>(a->grp_experts) * a->N : a->N;   // grouped: experts stacked along N
   if (!B_MN) {
     const int ldb = a->ldb > 0 ? a->ldb : a->K;
     const uint32_t box_rows = DUAL ? BN / 2 : BN;
-    if (!make_tmap_2d(&tb, a->b, a->N, a->K, ldb, box_rows, BK)) return PB_ERR_DRIVER;
+    if (!make_tmap_2d(&tb, a->b, b_rows, a->K, ldb, box_rows, BK)) return PB_ERR_DRIVER;
     if (DUAL) {
-      if (!make_tmap_2d(&tb2, a->b2, a->N, a->K, ldb, box_rows, BK)) return PB_ERR_DRIVER;
+      if (!make_tmap_2d(&tb2, a->b2, b_rows, a->K, ldb, box_rows, BK)) return PB_ERR_DRIVER;
     } else {
       tb2 = tb;
     }
@@ -467,17 +483,22 @@ static int launch_gemm(const PbGemmArgs* a, cudaStream_t stream) {
   p.wait_per_epoch = a->wait_per_epoch;
   p.epoch = static_cast<const uint64_t*>(a->epoch);
   p.error_flag = static_cast<int*>(a->error_flag);
+  p.grp = static_cast<const int*>(a->grp); p.grp_cap = a->grp_cap; p.grp_n = a->N;
 
   auto kern = gemm_tcgen05_kernel<BN, B_MN, DUAL, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // once per (instantiation, device): function attributes are per device, and several stage threads may get here at once
+  static std::atomic<uint64_t> attr_done{0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  if (!(attr_done.load(std::memory_order_acquire) & bit)) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)) != cudaSuccess)
       return PB_ERR_CUDA;
-    attr_set = true;
+    attr_done.fetch_or(bit, std::memory_order_release);
   }
   const int sms = a->num_sms > 0 ? a->num_sms : 148;
   const int m_blocks = (a->M + BM - 1) / BM, n_blocks = (a->N + OUT_BN - 1) / OUT_BN;
-  const int tiles = m_blocks * n_blocks;
+  const int tiles = (a->grp != nullptr ? a->grp_cap : m_blocks) * n_blocks;   // grouped: the real count lives on the device; size the grid for the cap
   const int grid = tiles < sms ? tiles : sms;
   kern<<<grid, kGemmThreads, smem, stream>>>(ta, tb, tb2, p);
   return pb_check_launch("gemm_tcgen05");
@@ -498,6 +519,7 @@ extern "C" int pb_gemm_bf16(const PbGemmArgs* a, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const bool dual = a->act == 1;
   if (dual && (a->b2 == nullptr || a->b_mn_major)) return PB_ERR_SHAPE;
+  if (a->grp != nullptr && (a->b_mn_major || a->n_push > 0 || a->grp_cap <= 0 || a->grp_experts <= 0)) return PB_ERR_SHAPE;
   int bn = a->block_n;
   if (bn == 0) {
     // Enough tiles to fill the machine with the widest accumulator that still does so.

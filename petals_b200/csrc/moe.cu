@@ -156,6 +156,62 @@ __global__ void moe_combine_kernel(const __nv_bfloat16* __restrict__ y, const fl
 
 using namespace pb;
 
+// ---- prefill-sized MoE without a host round trip --------------------------------------------------------------------------
+// The reference loops over the experts in Python with boolean masks and index_add (HF MixtralSparseMoeBlock, wrapped at
+// src/petals/models/mixtral/block.py:13-19): one host synchronisation per layer to learn the group sizes. Here the routing stays
+// on the device: moe_plan_kernel turns topi[M*k] into (a) the destination row of every (token, expert) pair in expert-major order
+// and (b) the tile table of the grouped tcgen05 GEMM (gemm_tcgen05.cu, `grp`): for every expert its row range cut into 128-row tiles.
+// One CTA; E <= 64 experts.
+__global__ void __launch_bounds__(1024) moe_plan_kernel(const int* __restrict__ topi, int pairs, int E, int* __restrict__ pos, int* __restrict__ table,
+                                                        int cap) {
+  __shared__ int cnt[64], off[64], cur[64];
+  const int tid = threadIdx.x;
+  if (tid < 64) { cnt[tid] = 0; cur[tid] = 0; }
+  __syncthreads();
+  for (int p = tid; p < pairs; p += blockDim.x) {
+    const int e = topi[p];
+    if (e >= 0 && e < E) atomicAdd(&cnt[e], 1);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int acc = 0, nt = 0;
+    int* t_e = table + 1; int* t_row0 = t_e + cap; int* t_rows = t_row0 + cap;
+    for (int e = 0; e < E; ++e) {
+      off[e] = acc;
+      for (int r = 0; r < cnt[e] && nt < cap; r += 128, ++nt) { t_e[nt] = e; t_row0[nt] = acc + r; t_rows[nt] = min(128, cnt[e] - r); }
+      acc += cnt[e];
+    }
+    table[0] = nt;
+  }
+  __syncthreads();
+  for (int p = tid; p < pairs; p += blockDim.x) {
+    const int e = topi[p];
+    pos[p] = (e >= 0 && e < E) ? off[e] + atomicAdd(&cur[e], 1) : 0;
+  }
+}
+
+// gathered[pos[p]] = x[p / topk]   (one CTA per pair, 16-byte vectors)
+__global__ void moe_gather_kernel(const uint4* __restrict__ x, const int* __restrict__ pos, uint4* __restrict__ out, int vec_per_row, int topk) {
+  const int p = blockIdx.x;
+  const uint4* src = x + static_cast<size_t>(p / topk) * vec_per_row;
+  uint4* dst = out + static_cast<size_t>(pos[p]) * vec_per_row;
+  for (int i = threadIdx.x; i < vec_per_row; i += blockDim.x) dst[i] = src[i];
+}
+
+// out[m] = residual[m] + sum_j topw[m, j] * y[pos[m * topk + j]]   (HF rounding as in moe_combine_kernel)
+__global__ void moe_combine_pos_kernel(const __nv_bfloat16* __restrict__ y, const float* __restrict__ topw, const int* __restrict__ pos,
+                                       const __nv_bfloat16* __restrict__ residual, __nv_bfloat16* __restrict__ out, int H, int topk) {
+  const int m = blockIdx.x;
+  for (int k = threadIdx.x; k < H; k += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < topk; ++j) {
+      const int p = m * topk + j;
+      acc = rbf16(acc + rbf16(__bfloat162float(y[static_cast<size_t>(pos[p]) * H + k]) * topw[p]));
+    }
+    out[static_cast<size_t>(m) * H + k] = __float2bfloat16_rn(__bfloat162float(residual[static_cast<size_t>(m) * H + k]) + acc);
+  }
+}
+
 extern "C" int pb_moe_router(const void* h, const void* norm_w, const void* router, void* xn_out, void* topi, void* topw, int M, int H, int E,
                              int topk, float eps, void* stream) {
   if (M == 0) return PB_OK;
@@ -196,4 +252,24 @@ extern "C" int pb_moe_combine(const void* y, const void* topw, const void* resid
   moe_combine_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const float*>(topw),
                                                                       static_cast<const __nv_bfloat16*>(residual), static_cast<__nv_bfloat16*>(out), H, topk);
   return pb_check_launch("moe_combine");
+}
+
+extern "C" int pb_moe_plan(const void* topi, int pairs, int E, void* pos, void* table, int cap, void* stream) {
+  if (E > 64 || E <= 0 || cap <= 0) return PB_ERR_UNSUPPORTED;
+  if (pairs == 0) return PB_OK;
+  moe_plan_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const int*>(topi), pairs, E, static_cast<int*>(pos), static_cast<int*>(table), cap);
+  return pb_check_launch("moe_plan");
+}
+extern "C" int pb_moe_gather(const void* x, const void* pos, void* out, int pairs, int H, int topk, void* stream) {
+  if (H % 8 != 0) return PB_ERR_SHAPE;
+  if (pairs == 0) return PB_OK;
+  moe_gather_kernel<<<pairs, 128, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const uint4*>(x), static_cast<const int*>(pos), static_cast<uint4*>(out), H / 8, topk);
+  return pb_check_launch("moe_gather");
+}
+extern "C" int pb_moe_combine_pos(const void* y, const void* topw, const void* pos, const void* residual, void* out, int M, int H, int topk, void* stream) {
+  if (M == 0) return PB_OK;
+  moe_combine_pos_kernel<<<M, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(y), static_cast<const float*>(topw),
+                                                                           static_cast<const int*>(pos), static_cast<const __nv_bfloat16*>(residual),
+                                                                           static_cast<__nv_bfloat16*>(out), H, topk);
+  return pb_check_launch("moe_combine_pos");
 }

@@ -68,6 +68,9 @@ typedef struct {
   int num_sms; int block_n;   // 0 = auto
   void* push_done_flag[PB_MAX_PEERS]; void* done_counter;  // once-per-launch completion flag (last CTA)
   int push_rows_per_owner;    // > 0: reduce-scatter routing of output rows to their owner rank (see gemm_tcgen05.cu)
+  // grouped (ragged-M) mode for sparse MoE: `grp` = device table from pb_moe_plan {n_mtiles, expert[cap], row0[cap], rows[cap]};
+  // B holds grp_experts matrices of N rows each, stacked along N; M is the total number of (token, expert) rows
+  const void* grp; int grp_cap; int grp_experts;
 } PbGemmArgs;
 int pb_gemm_bf16(const PbGemmArgs* a, void* stream);
 
@@ -193,6 +196,11 @@ int pb_moe_router(const void* h, const void* norm_w, const void* router, void* x
 int pb_moe_gemv(const void* x, const void* w_all, const void* w2_all, const void* topi, void* out, int pairs, int N, int K,
                 long expert_stride, int x_row_div, int num_sms, void* stream);
 int pb_moe_combine(const void* y, const void* topw, const void* residual, void* out, int M, int H, int topk, void* stream);
+
+// prefill-sized MoE without host synchronisation: routing plan (destination rows + grouped-GEMM tile table), gather, combine
+int pb_moe_plan(const void* topi, int pairs, int E, void* pos, void* table, int cap, void* stream);
+int pb_moe_gather(const void* x, const void* pos, void* out, int pairs, int H, int topk, void* stream);
+int pb_moe_combine_pos(const void* y, const void* topw, const void* pos, const void* residual, void* out, int M, int H, int topk, void* stream);
 
 // ---- KV cache utilities -----------------------------------------------------------------------------
 int pb_kv_copy_pages(void* pool, const void* src_pages, const void* dst_pages, int n, long page_elems,

@@ -258,7 +258,7 @@ def gemm(
     wait_flag: Optional[int] = None, wait_per_epoch: int = 0, epoch: Optional[int] = None,
     push_out: Sequence[int] = (), push_flag: Sequence[int] = (), error_flag: Optional[int] = None,
     store_local: bool = True, push_done_flag: Sequence[int] = (), done_counter: Optional[int] = None,
-    push_rows_per_owner: int = 0,
+    push_rows_per_owner: int = 0, grp: Optional[torch.Tensor] = None, grp_cap: int = 0, grp_experts: int = 0,
 ) -> torch.Tensor:
     """``out[M,N] = epilogue(a[M,K] @ op(b))`` on the tcgen05 tensor cores. See csrc/gemm_tcgen05.cu.
 
@@ -267,9 +267,14 @@ def gemm(
     a2 = _bf16c(a_, "a").reshape(-1, a_.shape[-1])
     b = _bf16c(b, "b")
     M, K = a2.shape
-    N = b.shape[1] if b_mn_major else b.shape[0]
-    if (b.shape[0] if b_mn_major else b.shape[1]) != K:
-        raise ValueError(f"b shape {tuple(b.shape)} incompatible with K={K}")
+    if grp is not None:  # grouped: b is [E, N, K] (experts stacked along N), rows of `a` are grouped by expert (see moe_prefill)
+        if b.dim() != 3 or b_mn_major or b.shape[0] != grp_experts or b.shape[2] != K:
+            raise ValueError(f"grouped GEMM needs b [E, N, K]; got {tuple(b.shape)} for E={grp_experts}, K={K}")
+        N = b.shape[1]
+    else:
+        N = b.shape[1] if b_mn_major else b.shape[0]
+        if (b.shape[0] if b_mn_major else b.shape[1]) != K:
+            raise ValueError(f"b shape {tuple(b.shape)} incompatible with K={K}")
     if out is None and store_local:
         out = torch.empty(*a_.shape[:-1], N, dtype=torch.float32 if out_fp32 else torch.bfloat16, device=a_.device)
     g = GemmArgs()
@@ -289,6 +294,7 @@ def gemm(
     g.wait_flag, g.wait_per_epoch, g.epoch, g.error_flag = wait_flag, wait_per_epoch, epoch, error_flag
     g.num_sms = native.sm_count(a_.device.index)
     g.block_n = block_n
+    g.grp, g.grp_cap, g.grp_experts = ptr(grp), grp_cap, grp_experts
     check(native.lib().pb_gemm_bf16(C.byref(g), stream_ptr()), "gemm_bf16")
     return out
 
@@ -587,6 +593,42 @@ def moe_decode(h: torch.Tensor, norm_w: torch.Tensor, router: torch.Tensor, we_g
     check(lib.pb_moe_gemv(ptr(xn), ptr(we_gate), ptr(we_up), ptr(topi), ptr(act), M * top_k, I, H, I * H, top_k, sms, st), "moe_gemv(gate/up)")
     check(lib.pb_moe_gemv(ptr(act), ptr(we_down), None, ptr(topi), ptr(y), M * top_k, H, I, H * I, 1, sms, st), "moe_gemv(down)")
     check(lib.pb_moe_combine(ptr(y), ptr(topw), ptr(h), ptr(out), M, H, top_k, st), "moe_combine")
+    return out
+
+
+def moe_prefill(h: torch.Tensor, norm_w: torch.Tensor, router: torch.Tensor, we_gate: torch.Tensor, we_up: torch.Tensor, we_down: torch.Tensor,
+                *, top_k: int, eps: float, out: torch.Tensor, bufs: Optional[dict] = None) -> torch.Tensor:
+    """out = h + MoE(RMSNorm(h)) for any number of rows, with NO host synchronisation: router kernel -> routing plan on the device
+    (destination row of every (token, expert) pair in expert-major order + the tile table of the grouped GEMM) -> gather -> grouped
+    tcgen05 GEMM gate/up with the SwiGLU epilogue -> grouped GEMM down -> weighted combine + residual. Reference (a Python loop over
+    the experts with masks and index_add): HF MixtralSparseMoeBlock wrapped at src/petals/models/mixtral/block.py:13-19."""
+    M, H = h.shape
+    E, I, _ = we_gate.shape
+    pairs = M * top_k
+    cap = pairs // 128 + E + 1  # 128-row tiles over all groups, at most one ragged tail per expert
+    bufs = bufs if bufs is not None else {}
+
+    def buf(name, n, dtype):  # grow-only
+        t = bufs.get(name)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            with torch.inference_mode(False):
+                t = torch.empty(n, dtype=dtype, device=h.device)
+            bufs[name] = t
+        return t[:n]
+
+    xn = buf("moep_xn", M * H, torch.bfloat16).view(M, H)
+    topi, topw = buf("moep_topi", pairs, torch.int32), buf("moep_topw", pairs, torch.float32)
+    pos, table = buf("moep_pos", pairs, torch.int32), buf("moep_table", 1 + 3 * cap, torch.int32)
+    gathered = buf("moep_gathered", pairs * H, torch.bfloat16).view(pairs, H)
+    act = buf("moep_act", pairs * I, torch.bfloat16).view(pairs, I)
+    y = buf("moep_y", pairs * H, torch.bfloat16).view(pairs, H)
+    lib, st = native.lib(), stream_ptr()
+    check(lib.pb_moe_router(ptr(h), ptr(norm_w), ptr(router), ptr(xn), ptr(topi), ptr(topw), M, H, E, top_k, eps, st), "moe_router")
+    check(lib.pb_moe_plan(ptr(topi), pairs, E, ptr(pos), ptr(table), cap, st), "moe_plan")
+    check(lib.pb_moe_gather(ptr(xn), ptr(pos), ptr(gathered), pairs, H, top_k, st), "moe_gather")
+    gemm(gathered, we_gate, b2=we_up, act=ACT_SWIGLU, out=act, grp=table, grp_cap=cap, grp_experts=E)
+    gemm(act, we_down, out=y, grp=table, grp_cap=cap, grp_experts=E)
+    check(lib.pb_moe_combine_pos(ptr(y), ptr(topw), ptr(pos), ptr(h), ptr(out), M, H, top_k, st), "moe_combine_pos")
     return out
 
 

@@ -68,6 +68,7 @@ class GemmArgs(C.Structure):
         ("wait_flag", C.c_void_p), ("wait_per_epoch", C.c_uint64), ("epoch", C.c_void_p), ("error_flag", C.c_void_p),
         ("num_sms", C.c_int), ("block_n", C.c_int),
         ("push_done_flag", C.c_void_p * PB_MAX_PEERS), ("done_counter", C.c_void_p), ("push_rows_per_owner", C.c_int),
+        ("grp", C.c_void_p), ("grp_cap", C.c_int), ("grp_experts", C.c_int),
     ]
 
 
@@ -193,7 +194,10 @@ def _declare(lib: C.CDLL) -> None:
     lib.pb_moe_router.argtypes = [vp, vp, vp, vp, vp, vp, ci, ci, ci, ci, cf, vp]
     lib.pb_moe_gemv.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, cl, ci, ci, vp]
     lib.pb_moe_combine.argtypes = [vp, vp, vp, vp, ci, ci, ci, vp]
-    for name in ("pb_moe_router", "pb_moe_gemv", "pb_moe_combine"):
+    lib.pb_moe_plan.argtypes = [vp, ci, ci, vp, vp, ci, vp]
+    lib.pb_moe_gather.argtypes = [vp, vp, vp, ci, ci, ci, vp]
+    lib.pb_moe_combine_pos.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
+    for name in ("pb_moe_router", "pb_moe_gemv", "pb_moe_combine", "pb_moe_plan", "pb_moe_gather", "pb_moe_combine_pos"):
         getattr(lib, name).restype = ci
     lib.pb_last_error.argtypes = []
     lib.pb_last_error.restype = C.c_char_p

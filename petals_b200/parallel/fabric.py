@@ -6,7 +6,11 @@ Here each worker process owns a *landing zone* in a CUDA-IPC symmetric heap:
 
 * ``x_in``  — where the previous stage's **last kernel** (down-projection GEMV or tcgen05 GEMM + residual) stores its
   output tiles directly over NVLink (``push_out`` epilogue), followed by one release-increment of ``in_flag``;
-* ``y_ret`` — the same for the last stage returning the final hidden states to the client's GPU.
+* ``y_ret`` — the same for the last stage returning the final hidden states to the client's GPU (and, in training, for the first
+  stage returning the gradient of the span input);
+* ``g_in``  — the gradient hop: the **last kernel of stage i+1's backward** (the RMSNorm backward of its first block, which adds
+  the residual gradient) stores dL/d(hidden) straight into stage i's landing slot, so ``rpc_backward`` between stages carries no
+  tensor bytes either (``server/stage_engine.py:backward``).
 
 The consuming stage's **first kernel** waits on the flag (``ld.acquire.sys``) — so the hop costs one NVLink store stream
 overlapped with the producer's math plus a flag latency, and the control RPC between processes carries *no tensor
@@ -30,12 +34,13 @@ logger = get_logger(__name__)
 _fabric: Optional["Fabric"] = None
 
 
-KINDS = {"x_in": 0, "y_ret": 1}
+KINDS = {"x_in": 0, "y_ret": 1, "g_in": 2}
+NK = len(KINDS)
 
 
 class Fabric:
     """Landing rings in the symmetric heap. Every rank owns, per kind ("x_in": input of its span, "y_ret": results returned to a
-    client on this rank), ``n_slots`` landing slots of ``max_tokens x hidden`` bf16 plus, per slot, a data flag (incremented by the
+    client on this rank, "g_in": gradient of its span's output), ``n_slots`` landing slots of ``max_tokens x hidden`` bf16 plus, per slot, a data flag (incremented by the
     producer's release after its stores) and an acknowledgement flag ON THE PRODUCER (incremented by the consumer when the slot
     may be overwritten). All counters are monotonic and per slot, so transfers through different slots are independent: a
     producer can have up to ``n_slots`` chunks in flight towards the same consumer (chunked prefill / micro-batches in a
@@ -44,21 +49,21 @@ class Fabric:
     def __init__(self, hidden_size: int, max_tokens: int = 8192, group=None, extra_bytes: int = (256 << 20) + (1 << 20), n_slots: int = 4):
         self.hidden_size, self.max_tokens, self.n_slots = hidden_size, max_tokens, n_slots
         self.zone_bytes = max_tokens * hidden_size * 2
-        self.heap = SymmetricHeap(2 * n_slots * self.zone_bytes + extra_bytes, group=group)
+        self.heap = SymmetricHeap(NK * n_slots * self.zone_bytes + extra_bytes, group=group)
         self.rank, self.world, self.device = self.heap.rank, self.heap.world, self.heap.device
-        self.off_zones = self.heap.alloc(2 * n_slots * self.zone_bytes)
-        self.off_flags = self.heap.alloc(2 * 2 * n_slots * 8 + 64)  # [data | ack][kind][slot] u64
+        self.off_zones = self.heap.alloc(NK * n_slots * self.zone_bytes)
+        self.off_flags = self.heap.alloc(2 * NK * n_slots * 8 + 64)  # [data | ack][kind][slot] u64
         self._zone_views = {}
         # device-resident counters: transfers consumed per (kind, slot) and pushes issued per (kind, slot)
-        self.consumed = torch.zeros(2, n_slots, dtype=torch.int64, device=self.device)
-        self.pushed = torch.zeros(2, n_slots, dtype=torch.int64, device=self.device)
+        self.consumed = torch.zeros(NK, n_slots, dtype=torch.int64, device=self.device)
+        self.pushed = torch.zeros(NK, n_slots, dtype=torch.int64, device=self.device)
         self.done_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._flag_src = torch.zeros(16, dtype=torch.uint8, device=self.device)
         self._scratch_off = self.heap.alloc(64)
         # back-pressure: the pushing kernel's prologue waits for ack >= number of pushes issued through this slot so far; the
         # acknowledgement flags start at 1, so the first push through a slot never waits
-        self.heap.tensor(self.off_flags + 2 * n_slots * 8, (2 * n_slots,), torch.int64).fill_(1)
+        self.heap.tensor(self.off_flags + NK * n_slots * 8, (NK * n_slots,), torch.int64).fill_(1)
         torch.cuda.synchronize(self.device)
         host_barrier(group)
 
@@ -70,7 +75,7 @@ class Fabric:
         return self.off_flags + (KINDS[kind] * self.n_slots + slot % self.n_slots) * 8
 
     def _ack_flag_off(self, kind: str, slot: int) -> int:
-        return self.off_flags + (2 * self.n_slots + KINDS[kind] * self.n_slots + slot % self.n_slots) * 8
+        return self.off_flags + (NK * self.n_slots + KINDS[kind] * self.n_slots + slot % self.n_slots) * 8
 
     def zone(self, kind: str, rank: int, slot: int = 0):
         """(data address, data-flag address) of landing slot ``slot`` of ``kind`` on ``rank``."""
@@ -114,6 +119,27 @@ class Fabric:
         out.copy_(self.view(kind, slot)[:M])
         self.acknowledge(kind, src_rank, slot)
         return out
+
+    # ---- zero-copy halves of a transfer: the consumer reads the landing slot in place, the producer's kernel writes into the peer's ----
+    def landing(self, M: int, kind: str, slot: int = 0) -> torch.Tensor:
+        """Wait (on the stream) for the next transfer into slot ``slot`` and return its rows IN PLACE. The caller acknowledges
+        (:meth:`acknowledge`) once the last kernel that reads them has been enqueued."""
+        self.wait(kind, slot)
+        return self.view(kind, slot)[:M]
+
+    def open_push(self, M: int, rank: int, kind: str, slot: int = 0) -> torch.Tensor:
+        """Rows [M, H] of landing slot ``slot`` on ``rank`` as a tensor a kernel can store into (peer memory over NVLink); the
+        back-pressure wait is enqueued first. Follow the producing kernel with :meth:`publish`."""
+        if M > self.max_tokens:
+            raise ValueError(f"{M} rows exceed the fabric landing zone ({self.max_tokens})")
+        data, _ = self.zone(kind, rank, slot)
+        kw = self.begin_push(kind, slot)
+        native.check(native.lib().pb_wait_flag(kw["wait_flag"], kw["epoch"], 1, 0, kw["error_flag"], native.stream_ptr()), "wait_flag")
+        return tensor_from_ptr(data, (M, self.hidden_size), torch.bfloat16, self.device)
+
+    def publish(self, rank: int, kind: str, slot: int = 0) -> None:
+        """Release-increment the data flag of the slot :meth:`open_push` handed out (stream ordered after the stores)."""
+        self._signal(self.zone(kind, rank, slot)[1], rank)
 
     def _signal(self, flag_addr: int, rank: int) -> None:
         scratch = ptr_array([self.heap.addr(rank, self._scratch_off)])
@@ -161,8 +187,8 @@ class HostFabric:
         self._time, self._np = time, np
         itemsize = torch.empty(0, dtype=dtype).element_size()
         self._zone_bytes = max_tokens * hidden_size * itemsize
-        self._flag_bytes = 2 * 2 * n_slots * 8
-        per_rank = 2 * n_slots * self._zone_bytes + self._flag_bytes
+        self._flag_bytes = 2 * NK * n_slots * 8
+        per_rank = NK * n_slots * self._zone_bytes + self._flag_bytes
         names = [None]
         if self.rank == 0:
             self._shm = shared_memory.SharedMemory(create=True, size=per_rank * self.world)
@@ -174,17 +200,18 @@ class HostFabric:
 
             self._shm = attach_shared_memory(names[0])
         self._per_rank = per_rank
-        self._consumed = np.zeros((2, n_slots), dtype=np.int64)
-        self._pushed = np.zeros((2, n_slots), dtype=np.int64)
+        self._consumed = np.zeros((NK, n_slots), dtype=np.int64)
+        self._pushed = np.zeros((NK, n_slots), dtype=np.int64)
+        self._open = {}
         if self.rank == 0:
             for r in range(self.world):
-                self._flags(r)[2 * n_slots:] = 1  # acknowledgement flags start at 1 (the first push through a slot never waits)
+                self._flags(r)[NK * n_slots:] = 1  # acknowledgement flags start at 1 (the first push through a slot never waits)
         host_barrier(group)
 
     def _flags(self, rank: int):
         """u64 [data flags: kind x slot | ack flags: kind x slot] of ``rank``."""
-        off = rank * self._per_rank + 2 * self.n_slots * self._zone_bytes
-        return self._np.ndarray((4 * self.n_slots,), dtype=self._np.uint64, buffer=self._shm.buf, offset=off)
+        off = rank * self._per_rank + NK * self.n_slots * self._zone_bytes
+        return self._np.ndarray((2 * NK * self.n_slots,), dtype=self._np.uint64, buffer=self._shm.buf, offset=off)
 
     def _idx(self, kind: str, slot: int) -> int:
         return KINDS[kind] * self.n_slots + slot % self.n_slots
@@ -207,7 +234,7 @@ class HostFabric:
             raise ValueError(f"{M} rows exceed the fabric landing zone ({self.max_tokens})")
         i = self._idx(kind, slot)
         self._pushed[KINDS[kind], slot % self.n_slots] += 1
-        self._spin(self.rank, 2 * self.n_slots + i, int(self._pushed[KINDS[kind], slot % self.n_slots]), "the consumer's acknowledgement")
+        self._spin(self.rank, NK * self.n_slots + i, int(self._pushed[KINDS[kind], slot % self.n_slots]), "the consumer's acknowledgement")
         self._zone(kind, rank, M, slot).copy_(rows.reshape(M, self.hidden_size).to(self.dtype))
         self._flags(rank)[i] += 1
 
@@ -216,8 +243,28 @@ class HostFabric:
         self._consumed[KINDS[kind], slot % self.n_slots] += 1
         self._spin(self.rank, i, int(self._consumed[KINDS[kind], slot % self.n_slots]), f"a transfer into {kind}[{slot}]")
         out.copy_(self._zone(kind, self.rank, M, slot))
-        self._flags(src_rank)[2 * self.n_slots + i] += 1
+        self._flags(src_rank)[NK * self.n_slots + i] += 1
         return out
+
+    def landing(self, M: int, kind: str, slot: int = 0) -> torch.Tensor:
+        i = self._idx(kind, slot)
+        self._consumed[KINDS[kind], slot % self.n_slots] += 1
+        self._spin(self.rank, i, int(self._consumed[KINDS[kind], slot % self.n_slots]), f"a transfer into {kind}[{slot}]")
+        return self._zone(kind, self.rank, M, slot)
+
+    def acknowledge(self, kind: str, src_rank: int, slot: int = 0) -> None:
+        self._flags(src_rank)[NK * self.n_slots + self._idx(kind, slot)] += 1
+
+    def open_push(self, M: int, rank: int, kind: str, slot: int = 0) -> torch.Tensor:
+        if M > self.max_tokens:
+            raise ValueError(f"{M} rows exceed the fabric landing zone ({self.max_tokens})")
+        i = self._idx(kind, slot)
+        self._pushed[KINDS[kind], slot % self.n_slots] += 1
+        self._spin(self.rank, NK * self.n_slots + i, int(self._pushed[KINDS[kind], slot % self.n_slots]), "the consumer's acknowledgement")
+        return self._zone(kind, rank, M, slot)
+
+    def publish(self, rank: int, kind: str, slot: int = 0) -> None:
+        self._flags(rank)[self._idx(kind, slot)] += 1
 
     def recv(self, M: int, kind: str, src_rank: int, slot: int = 0) -> torch.Tensor:
         return self.take(M, kind, src_rank, torch.empty(M, self.hidden_size, dtype=self.dtype), slot)

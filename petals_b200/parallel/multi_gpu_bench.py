@@ -117,7 +117,7 @@ def run_multi_gpu(args) -> None:
     if do_prefill and prefill is None:
         pms = max(float(x[1]) for x in gathered) / args.prefill_steps
         spec_ = config.block_spec()
-        flops = 2.0 * spec_.num_params() * n_layers * PB * PT + 4.0 * n_layers * PB * PT * PT * spec_.num_heads * spec_.head_dim / 2
+        flops = 2.0 * spec_.active_params() * n_layers * PB * PT + 4.0 * n_layers * PB * PT * PT * spec_.num_heads * spec_.head_dim / 2
         pk = measured_peaks()
         prefill = {"tokens_per_s": round(PB * PT / (pms / 1e3), 1), "ms_per_step": round(pms, 2), "batch": PB, "seq_len": PT,
                    "TFLOPs_total": round(flops / pms / 1e9, 1), "frac_of_measured_bf16_sustained_per_gpu": round(flops / pms / 1e9 / world / pk["bf16_tflops_sustained"], 3),
@@ -257,7 +257,7 @@ def pipeline_record(args, *, with_decode: bool = True) -> dict:
     swarm = FileSwarm(dirs[0])
     bounds = [round(i * n_layers / world) for i in range(world + 1)]
     t0 = time.time()
-    cache_tokens = (max(args.seq_len, PB * PT) if do_prefill else args.seq_len) + 256
+    cache_tokens = (max(args.seq_len, PB * (PT + 128)) if do_prefill else args.seq_len) + 256  # sessions round every row up to whole pages
     stage = launch_random_stage(path, range(bounds[rank], bounds[rank + 1]), swarm, dev, peer_id=f"stage{rank}", attn_cache_tokens=cache_tokens,
                                 inference_max_length=max(args.seq_len, PT), max_batch_size=1 << 20)
     torch.cuda.synchronize()
@@ -302,7 +302,7 @@ def pipeline_record(args, *, with_decode: bool = True) -> dict:
                             times.append(a.elapsed_time(b))
                 pms = sum(times) / len(times)
                 spec_ = config.block_spec()
-                flops = 2.0 * spec_.num_params() * n_layers * PB * PT + 4.0 * n_layers * PB * PT * PT * spec_.num_heads * spec_.head_dim / 2
+                flops = 2.0 * spec_.active_params() * n_layers * PB * PT + 4.0 * n_layers * PB * PT * PT * spec_.num_heads * spec_.head_dim / 2
                 pk = measured_peaks()
                 M = (PT + chunk - 1) // chunk
                 record["prefill"] = {"tokens_per_s": round(PB * PT / (pms / 1e3), 1), "ms_per_step": round(pms, 2), "batch": PB, "seq_len": PT,

@@ -143,7 +143,7 @@ class TPDecodeEngine:
         self.off_span_attn = heap.alloc(R * self.span_slot_bytes, align=4096)
         self.off_span_mlp = heap.alloc(R * self.span_slot_bytes, align=4096)
         ls_ = self.ls
-        self.use_span_kernel = (os.environ.get("PETALS_B200_SPAN_KERNEL", "1") != "0" and spec.norm == "rms" and spec.mlp == "swiglu" and spec.rotary
+        self.use_span_kernel = (os.environ.get("PETALS_B200_SPAN_KERNEL", "1") != "0" and self.use_ll and spec.norm == "rms" and spec.mlp == "swiglu" and spec.rotary
                                 and not spec.sliding_window
                                 and Fn.decode_span_supported(H=H, Hq=ls_.num_heads, Hkv=ls_.num_kv_heads, D=ls_.head_dim, I=ls_.intermediate_size))
         self._span_plan: Optional[Fn.DecodeSpanPlan] = None
@@ -164,6 +164,10 @@ class TPDecodeEngine:
         dev = self.device
         self.epoch = torch.zeros(1, dtype=torch.int64, device=dev)
         self.epoch_p = torch.zeros(1, dtype=torch.int64, device=dev)  # prefill steps count their own epochs (own flag set)
+        # Counter flags target `epoch * sources`, so every step that bumps an epoch must also feed every flag waiting on it. The span
+        # kernel feeds only the step-input flag (its partial sums travel as tagged LL units), so the multi-launch path counts the steps
+        # of the flag that only IT feeds (last block's MLP partials -> final reduce) in an epoch of its own.
+        self.epoch_f = torch.zeros(1, dtype=torch.int64, device=dev) if self.use_span_kernel else self.epoch
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self.done_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         self.fuse_rope = os.environ.get("PETALS_B200_FUSE_ROPE", "1") != "0"
@@ -223,6 +227,9 @@ class TPDecodeEngine:
                            in_flag=self.flag(me, 0), in_per_epoch=1, bump_epoch=False)
             native.check(native.lib().pb_advance_pos(pos_ptr, T, native.stream_ptr()), "advance_pos")
             return self.out[:M]
+        ep_f = self.epoch_f.data_ptr()
+        if ep_f != ep:
+            native.check(native.lib().pb_bump_epoch(ep_f, native.stream_ptr()), "bump_epoch")
         h = [self._buf("h_a", M, H), self._buf("h_b", M, H)]
         cur = self.x_in[:M]  # residual stream entering layer 0 (pushed by the leader)
         nxt = 0
@@ -306,7 +313,7 @@ class TPDecodeEngine:
                     launch(kw)
         if final_reduce:
             parts = ptr_array(mlp_parts)
-            native.check(native.lib().pb_reduce_parts(cur.data_ptr(), parts, R, self.flag_mlp(me, self.n_blocks - 1), R, ep, self.out.data_ptr(),
+            native.check(native.lib().pb_reduce_parts(cur.data_ptr(), parts, R, self.flag_mlp(me, self.n_blocks - 1), R, ep_f, self.out.data_ptr(),
                                                       M * H * 2, err, native.stream_ptr()), "reduce_parts")
         native.check(native.lib().pb_advance_pos(pos_ptr, T, native.stream_ptr()), "advance_pos")
         self._last_residual, self._last_parts = cur, mlp_parts

@@ -12,7 +12,9 @@ w.r.t. the span input and the deep prompts; weights are frozen (reference backen
 from __future__ import annotations
 
 import os
-
+import threading
+import time
+from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -49,6 +51,10 @@ class Stage:
                                       use_cuda_graphs=use_cuda_graphs, fp8=fp8)
         self.fp8 = fp8 and self.engine is not None
         self.active_adapter: Optional[str] = None
+        # training over the NVLink fabric: the span input of a forward micro-batch stays here until its backward arrives (the client
+        # never sees intermediate activations on that path, so it cannot send them back like the reference's client does)
+        self._stash: "OrderedDict[str, Tuple[torch.Tensor, float]]" = OrderedDict()
+        self._stash_lock = threading.Lock()
 
     def __len__(self) -> int:
         return len(self.blocks)
@@ -82,18 +88,50 @@ class Stage:
         return max(1, self.max_chunk_size_bytes // per_token)
 
     # ---- public span ops -----------------------------------------------------------------------------------
-    def forward(self, hidden: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None, lo: int = 0, hi: Optional[int] = None) -> torch.Tensor:
+    STASH_ENTRIES, STASH_TTL = 64, 600.0
+
+    def stash_put(self, key: str, hidden: torch.Tensor) -> None:
+        now = time.monotonic()
+        with self._stash_lock:
+            self._stash[key] = (hidden, now)
+            self._stash.move_to_end(key)
+            while len(self._stash) > self.STASH_ENTRIES or (self._stash and now - next(iter(self._stash.values()))[1] > self.STASH_TTL):
+                self._stash.popitem(last=False)
+
+    def stash_pop(self, key: str) -> torch.Tensor:
+        with self._stash_lock:
+            item = self._stash.pop(key, None)
+        if item is None:
+            raise KeyError(f"no activations are stashed under {key!r} (expired, evicted, or this stage never ran that forward)")
+        return item[0]
+
+    def forward(self, hidden: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None, lo: int = 0, hi: Optional[int] = None,
+                take_from: Optional[tuple] = None, push_to: Optional[tuple] = None, stash: Optional[str] = None) -> torch.Tensor:
+        """``take_from = (fabric, src_rank, B, T[, slot])``: the input sits in this rank's "x_in" landing slot; ``push_to = (fabric, kind,
+        rank[, slot])``: the output goes to that landing slot (fused into the span's last GEMM when it can be) and the return value is
+        empty; ``stash``: keep the span input under that key for the matching :meth:`backward` (forward/backward hops of training,
+        parallel/fabric.py)."""
         hi = len(self.blocks) if hi is None else hi
+        if take_from is not None:
+            fabric, src_rank, B, T = take_from[:4]
+            hidden = fabric.recv(B * T, "x_in", src_rank, *take_from[4:5]).view(B, T, -1)  # a fresh tensor: it doubles as the stash copy
         hidden = hidden.to(self.device)
+        if stash is not None:
+            self.stash_put(stash, hidden if take_from is not None else hidden.clone())
         prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device).contiguous() for p in prompts]
-        if self.engine is not None and self._lora_free():  # stages are stateless: forward never records autograd state
+        if self.engine is not None and self._lora_free() and not (push_to is not None and getattr(self.engine, "whole_span_only", False)):
             with nvtx_range(f"stage[{self.start_block + lo}:{self.start_block + hi}].forward"):
-                return self.engine.forward(hidden, prompts, (lo, hi))
+                if push_to is None:
+                    return self.engine.forward(hidden, prompts, (lo, hi))
+                return self.engine.forward(hidden, prompts, (lo, hi), hop=push_to)[:, :0]
         h = hidden.to(self.dtype)
         with torch.no_grad():
             for i in range(lo, hi):
                 h = self._add_prompt(h, prompts[i - lo] if prompts is not None else None)
                 h = self.blocks[i].forward_cached(h, None, None, 0)
+        if push_to is not None:
+            push_to[0].send(h.reshape(-1, h.shape[-1]), push_to[2], push_to[1], *push_to[3:4])
+            return h[:, :0]
         return h
 
     def _materialize(self, slot: int) -> None:
@@ -113,10 +151,36 @@ class Stage:
                 p = getattr(self.blocks[slot], name)
                 p.data = torch.empty(0, dtype=p.dtype, device=p.device)
 
-    def backward(self, hidden: torch.Tensor, grad_out: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None,
-                 lo: int = 0, hi: Optional[int] = None) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
-        """Returns (grad wrt span input, [grad wrt each block's prompt or None])."""
+    def backward(self, hidden: Optional[torch.Tensor], grad_out: Optional[torch.Tensor], prompts: Optional[Sequence[torch.Tensor]] = None,
+                 lo: int = 0, hi: Optional[int] = None, stash: Optional[str] = None, grad_from: Optional[tuple] = None,
+                 push_to: Optional[tuple] = None) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
+        """Returns (grad wrt span input, [grad wrt each block's prompt or None]). Over the fabric: ``stash`` names the span input kept by
+        :meth:`forward`; ``grad_from = (fabric, src_rank, B, T[, slot])`` says dL/d(output) sits in this rank's "g_in" landing slot (read
+        in place by the kernels); with ``push_to = (fabric, kind, rank[, slot])`` the gradient of the span input is stored into that
+        landing slot by the last backward kernel and the returned gradient is empty."""
         hi = len(self.blocks) if hi is None else hi
+        if stash is not None:
+            hidden = self.stash_pop(stash)
+        grad_ack = None
+        if grad_from is not None:
+            fabric, src_rank, B, T = grad_from[:4]
+            slot = grad_from[4] if len(grad_from) > 4 else 0
+            grad_out = fabric.landing(B * T, "g_in", slot).view(B, T, -1)
+            grad_ack = (fabric, "g_in", src_rank, slot)
+        if tuple(hidden.shape) != tuple(grad_out.shape):
+            raise ValueError(f"inputs {tuple(hidden.shape)} and grad_outputs {tuple(grad_out.shape)} must have the same shape")
+        engine_hops = (self.engine is not None and self._lora_free() and not getattr(self.engine, "whole_span_only", False)
+                       and getattr(self.engine, "backward_supported", lambda: False)() and os.environ.get("PETALS_B200_ENGINE_BACKWARD", "1") != "0")
+        if (grad_ack is not None or push_to is not None) and not engine_hops:
+            # executors without the fused hops honour the protocol with host-issued copies around the plain call
+            if grad_ack is not None:
+                grad_out = grad_out.clone()
+                fabric.acknowledge(*grad_ack[1:])
+            g, gp = self.backward(hidden, grad_out, prompts, lo, hi)
+            if push_to is not None:
+                push_to[0].send(g.reshape(-1, g.shape[-1]), push_to[2], push_to[1], *push_to[3:4])
+                g = g[:, :0]
+            return g, gp
         if getattr(self.engine, "whole_span_only", False):
             # a tensor-parallel stage: the weights exist only as per-rank shards, so the whole worker group runs the recompute
             if not hasattr(self.engine, "backward"):
@@ -130,7 +194,8 @@ class Stage:
             # the whole backward on the kernels: dgrad GEMMs (tcgen05, untransposed weights), flash-attention backward, norm / SwiGLU /
             # RoPE backward kernels (server/stage_engine.py:backward)
             with torch.no_grad():
-                return self.engine.backward(hidden, grad, prompts, (lo, hi))
+                g, gp = self.engine.backward(hidden, grad, prompts, (lo, hi), grad_hop=push_to, grad_ack=grad_ack)
+                return (g if push_to is None else hidden[:, :0]), gp
         # pass 1 (no grad): remember every block's input
         inputs = []
         h = hidden

@@ -403,34 +403,10 @@ class StageEngine:
         return Fn.gemm(act, self._w(slot, "w_down"), bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop, gemm=True))
 
     def _moe_prefill(self, h1: torch.Tensor, w: GenericBlock, out: torch.Tensor) -> torch.Tensor:
-        """out = h1 + MoE(RMSNorm(h1)) for many tokens: tokens are grouped by expert (one host sync for the group sizes) and every
-        expert runs two tcgen05 GEMMs (gate/up fused with SwiGLU, then down) on its own tokens only."""
+        """out = h1 + MoE(RMSNorm(h1)) for many tokens, entirely on the device: the routing plan (expert-major row order + the tile
+        table of the grouped tcgen05 GEMM) is built by a kernel, so no group size ever travels to the host (ops/functional.py)."""
         s = self.spec
-        M, H = h1.shape
-        xn = Fn.norm(h1, w.ln2_w, None, kind=self.norm_kind, eps=s.norm_eps, out=self._buf("xn_p", M, H))
-        logits = torch.nn.functional.linear(xn, w.router)  # [M, E]: tiny
-        probs = torch.softmax(logits.float(), dim=-1)
-        topw, topi = torch.topk(probs, s.top_k, dim=-1)
-        topw = (topw / topw.sum(-1, keepdim=True)).to(torch.bfloat16)
-        flat_e = topi.reshape(-1)
-        order = torch.argsort(flat_e, stable=True)
-        counts = torch.bincount(flat_e, minlength=s.num_experts).tolist()  # the only host sync of the block
-        tok_of = (order // s.top_k)
-        gathered = xn.index_select(0, tok_of)  # [M*k, H] grouped by expert
-        y = torch.empty(M * s.top_k, H, dtype=torch.bfloat16, device=h1.device)
-        start = 0
-        for e, n in enumerate(counts):
-            if n == 0:
-                continue
-            xe = gathered[start:start + n]
-            he = Fn.gemm(xe, w.we_gate[e], b2=w.we_up[e], act=Fn.ACT_SWIGLU)
-            Fn.gemm(he, w.we_down[e], out=y[start:start + n])
-            start += n
-        wsorted = topw.reshape(-1).index_select(0, order)
-        acc = torch.zeros(M, H, dtype=torch.bfloat16, device=h1.device)
-        acc.index_add_(0, tok_of, y * wsorted[:, None])
-        torch.add(h1, acc, out=out)
-        return out
+        return Fn.moe_prefill(h1, w.ln2_w, w.router, w.we_gate, w.we_up, w.we_down, top_k=s.top_k, eps=s.norm_eps, out=out, bufs=self._moe_bufs)
 
     # ---- span execution ------------------------------------------------------------------------------------
     def _sync_session(self, session: SessionCache, B: int) -> torch.Tensor:
@@ -623,7 +599,9 @@ class StageEngine:
 
     # ---- cache-less forward (rpc_forward / training forward) ----------------------------------------------------
     def forward(self, hidden: torch.Tensor, prompts: Optional[Sequence[torch.Tensor]] = None,
-                block_range: Optional[Tuple[int, int]] = None) -> torch.Tensor:
+                block_range: Optional[Tuple[int, int]] = None, hop: Optional[tuple] = None) -> torch.Tensor:
+        """``hop = (fabric, kind, rank[, slot])``: the span output is also stored into that landing slot — by the epilogue of the
+        span's last GEMM when the batch is one group (the forward micro-batch hop of training), by a peer copy otherwise."""
         lo, hi = block_range or (0, self.n_blocks)
         B, T, H = hidden.shape
         if T == 0 or B == 0:
@@ -651,8 +629,11 @@ class StageEngine:
                 pr = [p if is_dummy(p) or p.shape[0] == 1 else p[b0:b1] for p in prompts]
             scratch = lambda slot: (self._scratch_pool[0], self._scratch_pool[1])
             decode = nb * T <= self.max_decode_rows
-            y = self._run_span(x, nb, T, lo, hi, table, zero.data_ptr(), scratch, pr, decode, 1)
+            fused = hop if (hop is not None and nb == B and hi > lo) else None
+            y = self._run_span(x, nb, T, lo, hi, table, zero.data_ptr(), scratch, pr, decode, 1, fused)
             out[b0:b1] = y.view(nb, T, H)
+        if hop is not None and not (rows_per_group >= B and hi > lo):
+            hop[0].send(out.view(B * T, H), hop[2], hop[1], *hop[3:4])
         self._active = None  # the static table/pos were not touched, but be conservative
         return out
 
@@ -689,9 +670,10 @@ class StageEngine:
         act = Fn.swiglu(sv["g"], sv["u"], out=self._buf("bw_act_p", M, s.intermediate_size))
         return Fn.gemm(act, w.w_down, residual=sv["h1"]), sv
 
-    def _backward_block(self, dy: torch.Tensor, sv: dict, slot: int, nb: int, T: int, table: torch.Tensor) -> torch.Tensor:
+    def _backward_block(self, dy: torch.Tensor, sv: dict, slot: int, nb: int, T: int, table: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """dL/d(block input) from dL/d(block output): dgrad GEMMs on the untransposed weights (tcgen05, MN-major B), SwiGLU / RMSNorm /
-        RoPE backward kernels, flash-attention backward."""
+        RoPE backward kernels, flash-attention backward. ``out``: where the block's last kernel stores the result (the previous stage's
+        landing slot when this is the gradient hop)."""
         s, w = self.spec, self.blocks[slot]
         M = nb * T
         d_act = Fn.gemm(dy, w.w_down, b_mn_major=True, out=self._buf("bw_act_p", M, s.intermediate_size))
@@ -705,13 +687,19 @@ class StageEngine:
         d_qkv = Fn.qkv_grad_merge(dq, dk, dv, self.cos, self.sin, T=T, Hq=s.num_heads, Hkv=s.num_kv_heads, D=s.head_dim,
                                   out=self._buf("bw_qkv_p", M, s.qkv_dim))
         d_xn1 = Fn.gemm(d_qkv, w.wqkv, b_mn_major=True, out=d_xn2)
-        return Fn.rmsnorm_bwd(d_xn1, sv["x"], w.ln1_w, s.norm_eps, d_res=d_h1)
+        return Fn.rmsnorm_bwd(d_xn1, sv["x"], w.ln1_w, s.norm_eps, d_res=d_h1, out=out)
 
     def backward(self, hidden: torch.Tensor, grad_out: torch.Tensor, prompts: Optional[Sequence[Optional[torch.Tensor]]] = None,
-                 block_range: Optional[Tuple[int, int]] = None) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
+                 block_range: Optional[Tuple[int, int]] = None, grad_hop: Optional[tuple] = None,
+                 grad_ack: Optional[tuple] = None) -> Tuple[torch.Tensor, List[Optional[torch.Tensor]]]:
         """``rpc_backward`` of blocks [lo, hi) on the kernels (reference: src/petals/server/block_functions.py:84-141). One forward that
         saves the per-block intermediates, then the blocks' backward in reverse order — or, when the saved tensors of the whole
-        span would not fit the budget, the reference's schedule: remember the block inputs, recompute one block at a time."""
+        span would not fit the budget, the reference's schedule: remember the block inputs, recompute one block at a time.
+
+        The gradient hop (parallel/fabric.py, kind "g_in"): ``grad_out`` may be the rows of this rank's landing slot, read in place —
+        ``grad_ack = (fabric, kind, src_rank, slot)`` acknowledges the slot once the last kernel reading it is enqueued; with
+        ``grad_hop = (fabric, kind, rank[, slot])`` the last kernel of the first block's backward (RMSNorm backward + residual gradient)
+        stores dL/d(span input) straight into the previous stage's landing slot and the returned tensor is empty."""
         lo, hi = block_range or (0, self.n_blocks)
         B, T, H = hidden.shape
         grad_prompts: List[Optional[torch.Tensor]] = [None] * (hi - lo)
@@ -719,13 +707,18 @@ class StageEngine:
             return grad_out, grad_prompts
         hidden, grad_out = hidden.to(self.dtype), grad_out.to(self.dtype)
         s = self.spec
+        if hi <= lo:
+            grad_hop = self._finish_grad_hop(grad_out.reshape(B * T, H), grad_hop, grad_ack)
+            return (grad_out if grad_hop is None else grad_out.new_empty(0)), grad_prompts
         pages_per_seq = (T + PAGE - 1) // PAGE
         per_token = 2 * (3 * s.hidden_size + 2 * s.num_heads * s.head_dim + 2 * s.num_kv_heads * s.head_dim + 2 * s.intermediate_size)
         budget = float(os.environ.get("PETALS_B200_BWD_SAVE_GB", "16")) * 2 ** 30
         if pages_per_seq > self._scratch_pages:
             raise ValueError(f"sequence of {T} tokens exceeds max_chunk_tokens={self.max_chunk_tokens} for a backward pass")
         rows_per_group = max(1, min(B, self._scratch_pages // pages_per_seq))
-        grad_in = torch.empty_like(hidden)
+        first_prompt = prompts is not None and prompts[0] is not None and not is_dummy(prompts[0])
+        fused_hop = grad_hop is not None and rows_per_group >= B and not first_prompt  # the prompt gradient is sliced from d: keep it local
+        grad_in = torch.empty_like(hidden) if not fused_hop else None
         zero = torch.zeros(1, dtype=torch.int32, device=self.device)
         for b0 in range(0, B, rows_per_group):
             b1 = min(B, b0 + rows_per_group)
@@ -752,7 +745,15 @@ class StageEngine:
                 sv = saves.pop()
                 if not keep_all:
                     _, sv = self._forward_saving(sv, slot, nb, T, table, zero.data_ptr())
-                d = self._backward_block(d, sv, slot, nb, T, table)
+                dst = None
+                if fused_hop and slot == lo:
+                    dst = grad_hop[0].open_push(M, grad_hop[2], grad_hop[1], *grad_hop[3:4])
+                d = self._backward_block(d, sv, slot, nb, T, table, out=dst)
+                if slot == hi - 1 and b1 == B and grad_ack is not None:  # the landing slot holding grad_out has been read for the last time
+                    grad_ack[0].acknowledge(*grad_ack[1:])
+                    grad_ack = None
+                if dst is not None:
+                    grad_hop[0].publish(grad_hop[2], grad_hop[1], *grad_hop[3:4])
                 p = pr[slot - lo]
                 if p is not None:
                     gp = d.view(nb, T, H)[:, : p.shape[1]]
@@ -763,9 +764,24 @@ class StageEngine:
                         if grad_prompts[slot - lo] is None:
                             grad_prompts[slot - lo] = torch.zeros(B, p.shape[1], H, dtype=self.dtype, device=self.device)
                         grad_prompts[slot - lo][b0:b1] = gp
-            grad_in[b0:b1] = d.view(nb, T, H)
+            if grad_in is not None:
+                grad_in[b0:b1] = d.view(nb, T, H)
         self._active = None
+        if fused_hop:
+            return hidden.new_empty(0), grad_prompts
+        if grad_hop is not None:
+            self._finish_grad_hop(grad_in.view(B * T, H), grad_hop, None)
+            return hidden.new_empty(0), grad_prompts
         return grad_in, grad_prompts
+
+    @staticmethod
+    def _finish_grad_hop(rows: torch.Tensor, grad_hop: Optional[tuple], grad_ack: Optional[tuple]) -> Optional[tuple]:
+        """The unfused tail of a gradient hop: a peer copy of finished rows, then the acknowledgement of the slot they came from."""
+        if grad_hop is not None:
+            grad_hop[0].send(rows, grad_hop[2], grad_hop[1], *grad_hop[3:4])
+        if grad_ack is not None:
+            grad_ack[0].acknowledge(*grad_ack[1:])
+        return grad_hop
 
     def check_errors(self) -> None:
         code = int(self.err_flag.item())

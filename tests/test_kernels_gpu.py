@@ -291,6 +291,39 @@ def test_moe_decode(M):
     _close(out, want, 3e-2, 3e-2, "moe decode")
 
 
+@pytest.mark.parametrize("M,skew", [(9, False), (200, False), (777, False), (300, True)])
+def test_moe_prefill_grouped_gemm(M, skew):
+    """Any number of rows through the sync-free MoE path: device-built routing plan, gather, grouped tcgen05 GEMMs (ragged 128-row
+    tiles, some experts empty when the router is skewed), weighted combine. Compared with the oracle block's expert loop."""
+    from petals_b200.models.block_oracle import GenericBlock
+    from petals_b200.models.spec import BlockSpec
+
+    torch.manual_seed(23)
+    spec = BlockSpec(family="mixtral", hidden_size=1024, num_heads=8, num_kv_heads=2, head_dim=128, intermediate_size=1408, mlp="moe",
+                     num_experts=8, top_k=2, norm_eps=1e-5)
+    blk = GenericBlock(spec, dtype=torch.bfloat16, device=DEV, init_std=0.03)
+    blk.ln2_w.data = (1 + 0.1 * torch.randn(1024, device=DEV)).to(torch.bfloat16)
+    if skew:  # experts 0..2 take (almost) everything: five groups are empty, three span several tiles
+        blk.router.data[3:] = 0
+        blk.router.data[:3] *= 4
+    h = _rand(M, 1024)
+    out = torch.empty_like(h)
+    bufs = {}
+    Fn.moe_prefill(h, blk.ln2_w, blk.router, blk.we_gate, blk.we_up, blk.we_down, top_k=2, eps=1e-5, out=out, bufs=bufs)
+    want = h + blk.mlp(Fn.norm_ref(h, blk.ln2_w, None, Fn.NORM_RMS, 1e-5).view(1, M, 1024)).view(M, 1024)
+    _close(out, want, 3e-2, 3e-2, "moe prefill")
+    # the plan itself: positions are a permutation of the pairs, grouped by expert in ascending order
+    pairs = M * 2
+    pos, topi = bufs["moep_pos"][:pairs].long().cpu(), bufs["moep_topi"][:pairs].long().cpu()
+    assert sorted(pos.tolist()) == list(range(pairs))
+    by_pos = torch.empty(pairs, dtype=torch.long)
+    by_pos[pos] = topi
+    assert torch.equal(by_pos, by_pos.sort().values)
+    again = torch.empty_like(h)  # buffers are reused (grow-only): a second, smaller call must not see stale state
+    Fn.moe_prefill(h[: M // 2 + 1], blk.ln2_w, blk.router, blk.we_gate, blk.we_up, blk.we_down, top_k=2, eps=1e-5, out=again[: M // 2 + 1], bufs=bufs)
+    _close(again[: M // 2 + 1], want[: M // 2 + 1], 3e-2, 3e-2, "moe prefill (reused buffers)")
+
+
 # ---- sequence-parallel prefill primitives, in loopback: the "peers" are local buffers (same kernels, same flag protocol) ----
 def test_gemm_reduce_scatter_routing_loopback():
     """Row-parallel GEMM whose epilogue routes row r only to owner r // rows_per_owner (at local row r % rows_per_owner) and

@@ -136,7 +136,7 @@ def test_engine_adapter_switching_keeps_separate_graph_caches():
     from petals_b200.server.stage_engine import StageEngine
 
     base_blocks, base_graphs = [object(), object()], {("g", 0): "base-graph"}
-    eng = types.SimpleNamespace(lora_on_engine=True, _adapter=None, _adapter_state={}, blocks=base_blocks, _graphs=base_graphs)
+    eng = types.SimpleNamespace(lora_on_engine=True, lora_mode="merged", _adapter=None, _adapter_state={}, blocks=base_blocks, _graphs=base_graphs)
     made = []
 
     class FakeView:
@@ -166,6 +166,15 @@ def test_engine_adapter_switching_keeps_separate_graph_caches():
             StageEngine.use_adapter(eng, "b")
     finally:
         peft.MergedAdapterBlock = real
+    # low-rank mode: the adapter shares the base weight views, owns its graph cache, and an unknown name is refused
+    blocks = [types.SimpleNamespace(lora_adapters={"a": {}}), types.SimpleNamespace(lora_adapters={"a": {}})]
+    eng = types.SimpleNamespace(lora_on_engine=True, lora_mode="lowrank", _adapter=None, _adapter_state={}, blocks=blocks, _graphs={"k": "base"})
+    StageEngine.use_adapter(eng, "a")
+    assert eng.blocks is blocks and eng._graphs == {} and eng._adapter == "a"
+    with pytest.raises(KeyError):
+        StageEngine.use_adapter(eng, "missing")
+    StageEngine.use_adapter(eng, None)
+    assert eng._graphs == {"k": "base"}
 
 
 def test_adapter_for_another_model_is_refused_at_load_time(tmp_path):
