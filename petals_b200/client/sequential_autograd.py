@@ -15,13 +15,21 @@ This module implements that as an explicit **wavefront schedule** (all-forward, 
 * a stage that fails takes its micro-batch off the wavefront: :func:`finish_forward_alone` / :func:`backward_hops` complete it
   with back-off and fresh routes (for a backward hop that means recomputing the lost span's forward on the replacement
   first), while the other micro-batches keep flowing through the healthy lanes.
+* when every stage of the route sits on the NVLink fabric (``parallel/fabric.py``), micro-batches and their gradients **hop from
+  stage to stage through the landing rings** (:class:`FabricPlan`): stage *i* stores its output into stage *i+1*'s ``x_in`` slot from
+  the epilogue of its last GEMM and keeps its own input ("stash"); in the backward wave the last kernel of stage *i+1*'s backward
+  stores dL/dx into stage *i*'s ``g_in`` slot. The RPCs of such a pass carry no activations, and because a stage only *enqueues* its
+  kernels before answering, the lanes dispatch a micro-batch to all stages almost at once: the order is kept on the devices by the
+  landing flags. A failure on that path re-runs the micro-batch on the tensor-carrying path from the activations the client holds.
 * the backward wave runs its lanes on worker threads too, except when an in-process stage would have to call the autograd
   engine for CUDA tensors from a foreign thread while this thread blocks the device's autograd worker; then the same wave
   order is executed inline.
 """
 from __future__ import annotations
 
+import os
 import time
+import uuid
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence, Tuple
 
@@ -42,7 +50,9 @@ MAX_TOKENS_IN_BATCH = 1024
 class Hop:
     """One span executed for one micro-batch: the tape entry the backward needs."""
     span: RemoteSpanInfo
-    entered: torch.Tensor  # activations that went into span.start
+    entered: Optional[torch.Tensor]  # activations that went into span.start (None: they stayed on the stage, see ``stash``)
+    stash: Optional[str] = None  # key under which the stage keeps its input (fabric passes)
+    stage: int = -1  # position in the FabricPlan
 
 
 @dataclass
@@ -54,6 +64,11 @@ class MicroBatch:
     grad_prompts: List[torch.Tensor] = field(default_factory=list)  # per executed span, in backward order
     error: Optional[BaseException] = None
     detached: bool = False  # left the wavefront (a stage failed): completed on its own
+    x0: Optional[torch.Tensor] = None  # what entered the pass (forward input / output gradient): the restart point of a fabric pass
+    landed: bool = False  # x currently sits in the next stage's landing slot, not here
+    key: str = ""
+    fwd_input: Optional[torch.Tensor] = None  # the forward input, kept for fabric passes (the stages hold everything else)
+    plan: Optional[object] = None  # the FabricPlan this micro-batch's tape was recorded on
 
     def prompts_for(self, span: RemoteSpanInfo) -> torch.Tensor:
         return DUMMY if is_dummy(self.prompts) else self.prompts[span.start: span.end]
@@ -70,6 +85,98 @@ class Route:
 
     def __len__(self) -> int:
         return len(self.spans)
+
+
+class FabricPlan:
+    """A route whose stages all sit on the NVLink fabric of this process: who pushes into whose landing ring.
+
+    Forward of micro-batch m (ring slot m mod n_slots): the client hands x to stage 0 with the RPC (same process or Unix socket),
+    stage i stores its output into ``x_in[slot]`` of stage i+1, the last stage into ``y_ret[slot]`` of this rank (or answers with
+    the tensor when it shares this rank's GPU). Backward: the client stores dL/dy into ``g_in[slot]`` of the last stage, stage i
+    stores dL/dx into ``g_in[slot]`` of stage i-1, stage 0 answers with the tensor. Every stage keeps its own input between the two
+    calls (``stash``). One producer per (consumer, kind, slot) at any time, as the ring protocol requires."""
+
+    hops_done = {"forward": 0, "backward": 0}  # process-wide counters (self-tests check that this path really ran)
+
+    def __init__(self, fabric, spans: Sequence[RemoteSpanInfo], ranks: Sequence[int]):
+        self.fabric, self.spans, self.ranks = fabric, list(spans), list(ranks)
+
+    @classmethod
+    def probe(cls, manager: RemoteSequenceManager, route: Optional[Route], shape: Tuple[int, int, int]) -> Optional["FabricPlan"]:
+        if route is None or len(route) < 2 or os.environ.get("PETALS_B200_FABRIC_TRAINING", "1") == "0":
+            return None
+        from petals_b200.parallel.fabric import get_fabric
+
+        fabric = get_fabric()
+        B, T, H = shape
+        if fabric is None or H != fabric.hidden_size or B * T > fabric.max_tokens or B * T == 0:
+            return None
+        ranks = []
+        for span in route.spans:
+            try:
+                rank = manager.connect(span.peer_id).rpc_info().get("fabric_rank")
+            except Exception:  # noqa: BLE001 - an unreachable stage: the tensor-carrying path deals with it
+                return None
+            if rank is None or (ranks and rank == ranks[-1]):
+                return None
+            ranks.append(int(rank))
+        return cls(fabric, route.spans, ranks)
+
+    def slot(self, mb: "MicroBatch") -> int:
+        return mb.index % max(1, getattr(self.fabric, "n_slots", 1))
+
+    def forward_hop(self, manager: RemoteSequenceManager, mb: "MicroBatch", i: int) -> None:
+        span, last = self.spans[i], i == len(self.spans) - 1
+        uids = manager.block_uids[span.start: span.end]
+        meta = dict(manager.get_request_metadata("rpc_forward", None, *uids))
+        B, T, H = mb.x0.shape
+        slot, key = self.slot(mb), f"{mb.key}:{i}"
+        meta["stash"] = key
+        if i > 0:
+            meta["fabric_in"] = {"src_rank": self.ranks[i - 1], "B": B, "T": T, "slot": slot}
+        returns = last and self.ranks[i] == self.fabric.rank  # a last stage on this rank's GPU answers with the tensor
+        if not returns:
+            meta["fabric_out"] = ({"kind": "y_ret", "rank": self.fabric.rank, "slot": slot} if last
+                                  else {"kind": "x_in", "rank": self.ranks[i + 1], "slot": slot})
+        p = mb.prompts_for(span)
+        out = manager.connect(span.peer_id).rpc_forward(list(uids), mb.x.detach() if i == 0 else torch.empty(0), None if is_dummy(p) else p, metadata=meta)
+        mb.hops.append(Hop(span, None, stash=key, stage=i))
+        if returns:
+            mb.x, mb.landed = out, False
+        elif last:
+            mb.x, mb.landed = self.fabric.recv(B * T, "y_ret", self.ranks[i], slot).view(B, T, H), False
+        else:
+            mb.landed = True
+        FabricPlan.hops_done["forward"] += 1
+        manager.on_request_success(span.peer_id)
+
+    def backward_hop(self, manager: RemoteSequenceManager, mb: "MicroBatch", hop: Hop) -> None:
+        i, span = hop.stage, hop.span
+        last = i == len(self.spans) - 1
+        uids = manager.block_uids[span.start: span.end]
+        meta = dict(manager.get_request_metadata("rpc_backward", None, *uids))
+        B, T, H = mb.x0.shape
+        slot = self.slot(mb)
+        meta["stash"] = hop.stash
+        grad = torch.empty(0)
+        if last and self.ranks[i] == self.fabric.rank:
+            grad = mb.x.detach()
+        else:
+            if last:  # dL/dy is here: store it into the last stage's gradient slot
+                self.fabric.send(mb.x.detach().reshape(B * T, H), self.ranks[i], "g_in", slot)
+            meta["fabric_in"] = {"src_rank": self.fabric.rank if last else self.ranks[i + 1], "B": B, "T": T, "slot": slot}
+        if i > 0:
+            meta["fabric_out"] = {"kind": "g_in", "rank": self.ranks[i - 1], "slot": slot}
+        p = mb.prompts_for(span)
+        grads = manager.connect(span.peer_id).rpc_backward(list(uids), torch.empty(0), grad, None if is_dummy(p) else p, metadata=meta)
+        if i == 0:
+            mb.x, mb.landed = grads[0], False
+        else:
+            mb.landed = True
+        if len(grads) > 1:
+            mb.grad_prompts.append(grads[1])
+        FabricPlan.hops_done["backward"] += 1
+        manager.on_request_success(span.peer_id)
 
 
 # ---- single hops ---------------------------------------------------------------------------------------------------
@@ -161,7 +268,26 @@ def pipelined_forward(manager: RemoteSequenceManager, micro_batches: Sequence[Mi
                 finish_forward_alone(manager, mb, span.start, end, failures=1)
         return work
 
-    if route is not None:
+    def fabric_work(plan: FabricPlan, i: int):
+        def work(mb: MicroBatch) -> None:
+            try:
+                plan.forward_hop(manager, mb, i)
+            except Exception as e:  # noqa: BLE001 - activations in flight are lost with the hop: restart this micro-batch with tensors
+                manager.on_request_failure(plan.spans[i].peer_id)
+                mb.detached, mb.landed, mb.x, mb.hops = True, False, mb.x0, []
+                _give_up_or_wait(manager, 1, f"fabric forward of micro-batch {mb.index} via {plan.spans[i]}", e)
+                finish_forward_alone(manager, mb, start, end, failures=1)
+        return work
+
+    for mb in micro_batches:
+        mb.x0, mb.fwd_input, mb.key = mb.x, mb.x, uuid.uuid4().hex
+    plan = FabricPlan.probe(manager, route, tuple(micro_batches[0].x.shape)) if micro_batches else None
+    if plan is not None and all(tuple(mb.x.shape[1:]) == tuple(micro_batches[0].x.shape[1:]) and mb.x.shape[0] <= micro_batches[0].x.shape[0]
+                                for mb in micro_batches):
+        _run_wave(micro_batches, [fabric_work(plan, i) for i in range(len(plan.spans))], threaded=len(micro_batches) > 1)
+        for mb in micro_batches:
+            mb.plan = plan if (mb.error is None and all(h.stash is not None for h in mb.hops)) else None
+    elif route is not None:
         _run_wave(micro_batches, [stage_work(s) for s in route.spans], threaded=len(micro_batches) > 1)
     else:
         _run_wave(micro_batches, [lambda mb: finish_forward_alone(manager, mb, start, end)], threaded=len(micro_batches) > 1)
@@ -186,6 +312,20 @@ def _autograd_needs_this_thread(manager: RemoteSequenceManager, micro_batches: S
             except Exception:  # noqa: BLE001 - an unreachable peer is handled (and replaced) by the hop itself
                 continue
     return False
+
+
+def _redo_with_tensors(manager: RemoteSequenceManager, mb: MicroBatch, plan: Optional[FabricPlan], backward: bool = True) -> None:
+    """A fabric pass lost this micro-batch's activations or gradients: recompute its forward on the tensor-carrying path from the
+    input the client still holds, and (``backward``) walk the new tape with the output gradient the client still holds."""
+    g0 = mb.x0
+    redo = MicroBatch(mb.index, mb.fwd_input, mb.prompts)
+    start = min(h.span.start for h in mb.hops) if (mb.hops and plan is None) else (plan.spans[0].start if plan is not None else 0)
+    end = plan.spans[-1].end if plan is not None else max(h.span.end for h in mb.hops)
+    finish_forward_alone(manager, redo, start, end)
+    mb.hops, mb.grad_prompts, mb.landed, mb.detached = redo.hops, [], False, True
+    mb.x = g0
+    if backward:
+        backward_hops(manager, mb)
 
 
 def pipelined_backward(manager: RemoteSequenceManager, micro_batches: Sequence[MicroBatch]) -> None:
@@ -215,6 +355,30 @@ def pipelined_backward(manager: RemoteSequenceManager, micro_batches: Sequence[M
                     backward_hops(manager, mb)
                     return
 
+    for mb in micro_batches:
+        mb.x0 = mb.x
+    plans = {id(getattr(mb, "plan", None)) for mb in micro_batches}
+    plan = getattr(micro_batches[0], "plan", None) if micro_batches and len(plans) == 1 else None
+    if plan is not None and same_shape and depth == len(plan.spans):
+        def pop_fabric(mb: MicroBatch) -> None:
+            hop = mb.hops.pop()
+            try:
+                plan.backward_hop(manager, mb, hop)
+            except Exception as e:  # noqa: BLE001 - gradients in flight are lost with the hop: redo this micro-batch with tensors
+                manager.on_request_failure(hop.span.peer_id)
+                _give_up_or_wait(manager, 1, f"fabric backward of micro-batch {mb.index} via {hop.span}", e)
+                _redo_with_tensors(manager, mb, plan)
+
+        _run_wave(micro_batches, [pop_fabric] * depth, threaded=len(micro_batches) > 1)
+        for mb in micro_batches:
+            if mb.error is not None:
+                raise mb.error
+        return
+    for mb in micro_batches:
+        if any(h.entered is None for h in mb.hops):  # a fabric tape without its plan (mixed pass): rebuild it with tensors
+            _redo_with_tensors(manager, mb, None, backward=False)
+    depth = max((len(mb.hops) for mb in micro_batches), default=0)
+    same_shape = all(len(mb.hops) == depth for mb in micro_batches)
     threaded = len(micro_batches) > 1 and not _autograd_needs_this_thread(manager, micro_batches)
     if same_shape and depth > 0:
         _run_wave(micro_batches, [pop_one] * depth, threaded=threaded)

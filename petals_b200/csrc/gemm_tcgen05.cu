@@ -431,6 +431,18 @@ static bool make_tmap_2d(CUtensorMap* m, const void* base, uint64_t rows, uint64
   return r == CUDA_SUCCESS;
 }
 
+// 2-D byte tensor (FP8 payloads) with the same 128B swizzle: one box row = box_cols bytes (gemm_mxfp8.cu)
+bool make_tmap_2d_u8(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // exported to the other translation units that build TMA descriptors (attention_tc.cu)
 bool make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
   return make_tmap_2d(m, base, rows, cols, ld, box_rows, box_cols);

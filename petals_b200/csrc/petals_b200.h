@@ -202,6 +202,27 @@ int pb_moe_plan(const void* topi, int pairs, int E, void* pos, void* table, int 
 int pb_moe_gather(const void* x, const void* pos, void* out, int pairs, int H, int topk, void* stream);
 int pb_moe_combine_pos(const void* y, const void* topw, const void* pos, const void* residual, void* out, int M, int H, int topk, void* stream);
 
+// ---- block-scaled FP8 GEMM (gemm_mxfp8.cu): both operands MXFP8 (E4M3 payload + UE8M0 scale per 32 values along K) -------------
+// Scale arrays use the tensor cores' block layout: [K / 128][ceil(rows / 128)][512 B], scale of (row r, K slice c) of a block at
+// (r % 32) * 16 + (r / 32) * 4 + c  (ops/quant.py:pack_scales; pb_quant_mxfp8 writes it for activations).
+typedef struct {
+  const void* a_q;   // [M, K] e4m3
+  const void* a_sf;
+  const void* b_q;   // [N, K] e4m3 (nn.Linear weight layout)
+  const void* b_sf;
+  const void* b2_q;  // act == 1: second weight (up_proj); the epilogue emits silu(a b^T) * (a b2^T)
+  const void* b2_sf;
+  const void* residual;  // bf16 [M, N] or null
+  void* out;             // bf16 [M, N]
+  int M, N, K;
+  int ldo, ldres;        // 0 = N
+  int act;               // 0 none, 1 SwiGLU
+  int num_sms;
+} PbGemmFp8Args;
+int pb_gemm_mxfp8(const PbGemmFp8Args* args, void* stream);
+// x bf16 [M, K] -> q e4m3 [M, K] + scales in the block layout; with norm_w: quantises RMSNorm(x) * norm_w (HF rounding) instead.
+int pb_quant_mxfp8(const void* x, const void* norm_w, float eps, void* q, void* sf, int M, int K, void* stream);
+
 // ---- KV cache utilities -----------------------------------------------------------------------------
 int pb_kv_copy_pages(void* pool, const void* src_pages, const void* dst_pages, int n, long page_elems,
                      long layer_stride_elems, int n_layer_slabs, void* stream);

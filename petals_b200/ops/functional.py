@@ -596,6 +596,40 @@ def moe_decode(h: torch.Tensor, norm_w: torch.Tensor, router: torch.Tensor, we_g
     return out
 
 
+def quant_mxfp8(x: torch.Tensor, norm_weight: Optional[torch.Tensor] = None, eps: float = 0.0, *, q: Optional[torch.Tensor] = None,
+                sf: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Rows of ``x`` [M, K] (bf16; with ``norm_weight``: RMSNorm(x) * weight first) -> MXFP8: E4M3 payload [M, K] (uint8 storage) and the
+    UE8M0 scales in the tensor cores' block layout (ops/quant.py:pack_scales)."""
+    x = _bf16c(x, "x")
+    M, K = x.shape
+    if q is None:
+        q = torch.empty(M, K, dtype=torch.uint8, device=x.device)
+    if sf is None:
+        sf = torch.zeros((K // 128) * ((M + 127) // 128) * 512, dtype=torch.uint8, device=x.device)
+    check(native.lib().pb_quant_mxfp8(ptr(x), ptr(_bf16c(norm_weight, "norm_weight")), eps, ptr(q), ptr(sf), M, K, stream_ptr()), "quant_mxfp8")
+    return q, sf
+
+
+def gemm_mxfp8(a_q: torch.Tensor, a_sf: torch.Tensor, b_q: torch.Tensor, b_sf: torch.Tensor, *, b2_q: Optional[torch.Tensor] = None,
+               b2_sf: Optional[torch.Tensor] = None, residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out = [residual +] A B^T`` with both operands MXFP8 and packed scales (``tcgen05.mma.kind::mxf8f6f4.block_scale``); with ``b2``
+    the epilogue emits ``silu(A B^T) * (A B2^T)``. A [M, K], B [N, K] (nn.Linear layout), out bf16 [M, N]."""
+    M, K = a_q.shape
+    N = b_q.shape[0]
+    if b_q.shape[1] != K or K % 128:
+        raise ValueError(f"gemm_mxfp8: A {tuple(a_q.shape)} x B {tuple(b_q.shape)} (K must match and be a multiple of 128)")
+    if out is None:
+        out = torch.empty(M, N, dtype=torch.bfloat16, device=a_q.device)
+    g = native.GemmFp8Args()
+    g.a_q, g.a_sf, g.b_q, g.b_sf, g.b2_q, g.b2_sf = ptr(a_q), ptr(a_sf), ptr(b_q), ptr(b_sf), ptr(b2_q), ptr(b2_sf)
+    g.residual, g.out = ptr(_bf16c(residual, "residual")), ptr(out)
+    g.M, g.N, g.K, g.ldo, g.ldres = M, N, K, out.stride(0), (residual.stride(0) if residual is not None else 0)
+    g.act = 1 if b2_q is not None else 0
+    g.num_sms = native.sm_count(a_q.device.index)
+    check(native.lib().pb_gemm_mxfp8(C.byref(g), stream_ptr()), "gemm_mxfp8")
+    return out
+
+
 def moe_prefill(h: torch.Tensor, norm_w: torch.Tensor, router: torch.Tensor, we_gate: torch.Tensor, we_up: torch.Tensor, we_down: torch.Tensor,
                 *, top_k: int, eps: float, out: torch.Tensor, bufs: Optional[dict] = None) -> torch.Tensor:
     """out = h + MoE(RMSNorm(h)) for any number of rows, with NO host synchronisation: router kernel -> routing plan on the device

@@ -57,6 +57,14 @@ class LinearFp8Args(C.Structure):
     ]
 
 
+class GemmFp8Args(C.Structure):
+    _fields_ = [
+        ("a_q", C.c_void_p), ("a_sf", C.c_void_p), ("b_q", C.c_void_p), ("b_sf", C.c_void_p), ("b2_q", C.c_void_p), ("b2_sf", C.c_void_p),
+        ("residual", C.c_void_p), ("out", C.c_void_p),
+        ("M", C.c_int), ("N", C.c_int), ("K", C.c_int), ("ldo", C.c_int), ("ldres", C.c_int), ("act", C.c_int), ("num_sms", C.c_int),
+    ]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [
         ("a", C.c_void_p), ("b", C.c_void_p), ("b2", C.c_void_p),
@@ -199,6 +207,9 @@ def _declare(lib: C.CDLL) -> None:
     lib.pb_moe_combine_pos.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
     for name in ("pb_moe_router", "pb_moe_gemv", "pb_moe_combine", "pb_moe_plan", "pb_moe_gather", "pb_moe_combine_pos"):
         getattr(lib, name).restype = ci
+    lib.pb_gemm_mxfp8.argtypes = [C.POINTER(GemmFp8Args), vp]
+    lib.pb_quant_mxfp8.argtypes = [vp, vp, C.c_float, vp, vp, ci, ci, vp]
+    lib.pb_gemm_mxfp8.restype = lib.pb_quant_mxfp8.restype = ci
     lib.pb_last_error.argtypes = []
     lib.pb_last_error.restype = C.c_char_p
     for name in ("pb_linear_decode", "pb_gemm_bf16", "pb_gemm_tiles", "pb_norm", "pb_swiglu", "pb_add", "pb_embedding",

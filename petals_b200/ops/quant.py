@@ -35,6 +35,26 @@ def dequantize_mxfp8(q: torch.Tensor, e: torch.Tensor, dtype: torch.dtype = torc
     return (q.float().view(N, K // BLOCK, BLOCK) * scale[..., None]).view(N, K).to(dtype)
 
 
+def pack_scales(e: torch.Tensor) -> torch.Tensor:
+    """Scale exponents [rows, K/32] -> the block layout the tensor cores read (csrc/gemm_mxfp8.cu): ``[K/128][ceil(rows/128)][512]``
+    bytes, the scale of (row r, K slice c) of a block at ``(r % 32) * 16 + (r // 32) * 4 + c``. Rows are padded with exponent 0."""
+    rows, kb32 = e.shape
+    if kb32 % 4:
+        raise ValueError(f"K={kb32 * BLOCK} must be a multiple of 128")
+    blocks = (rows + 127) // 128
+    padded = torch.zeros(blocks * 128, kb32, dtype=torch.uint8, device=e.device)
+    padded[:rows] = e
+    # [block, r1 (4), r0 (32), kb128, c (4)] -> [kb128, block, r0, r1, c]
+    return padded.view(blocks, 4, 32, kb32 // 4, 4).permute(3, 0, 2, 1, 4).contiguous().view(-1)
+
+
+def unpack_scales(packed: torch.Tensor, rows: int, K: int) -> torch.Tensor:
+    """Inverse of :func:`pack_scales` (tests)."""
+    blocks, kb128 = (rows + 127) // 128, K // 128
+    e = packed.view(kb128, blocks, 32, 4, 4).permute(1, 3, 2, 0, 4).contiguous().view(blocks * 128, kb128 * 4)
+    return e[:rows]
+
+
 def fake_quantize_mxfp8(w: torch.Tensor) -> torch.Tensor:
     """Round-trip through MXFP8 (what an oracle block must hold to match the fp8 engine bit-for-bit in weights)."""
     if w.dim() == 3:

@@ -40,18 +40,25 @@ def _check_activations(name: str, t: torch.Tensor, handler) -> None:
 
 
 def run_rpc_forward(hidden_states: torch.Tensor, prompts: Optional[torch.Tensor], *, backends: Sequence, handler,
-                    active_adapter: Optional[str] = None, points: float = 0.0) -> torch.Tensor:
+                    active_adapter: Optional[str] = None, points: float = 0.0, take_from: Optional[tuple] = None,
+                    push_to: Optional[tuple] = None, stash: Optional[str] = None) -> torch.Tensor:
+    """``take_from`` / ``push_to`` / ``stash``: the forward micro-batch hop over the NVLink fabric (server/backend.py:Stage.forward);
+    ``hidden_states`` is then only a shape carrier (a meta tensor)."""
     _check_activations("hidden_states", hidden_states, handler)
     B, T, H = hidden_states.shape
     block_prompts = _split_prompts(prompts, len(backends), B, H)
     lo, hi = backends[0].slot, backends[-1].slot + 1
     priority = handler.prioritizer.prioritize(hidden_states, points=points / max(len(backends), 1), type="forward")
-    fut = handler.forward_pool.submit_task(hidden_states, block_prompts, lo, hi, active_adapter, priority=priority, size=B * T)
+    hops = {k: v for k, v in (("take_from", take_from), ("push_to", push_to), ("stash", stash)) if v is not None}
+    fut = handler.forward_pool.submit_task(hidden_states, block_prompts, lo, hi, active_adapter, *([hops] if hops else []), priority=priority, size=B * T)
     return fut.result(timeout=handler.request_timeout)
 
 
 def run_rpc_backward(inputs: torch.Tensor, grad_outputs: torch.Tensor, prompts: Optional[torch.Tensor], *, backends: Sequence,
-                     handler, active_adapter: Optional[str] = None, points: float = 0.0) -> List[torch.Tensor]:
+                     handler, active_adapter: Optional[str] = None, points: float = 0.0, grad_from: Optional[tuple] = None,
+                     push_to: Optional[tuple] = None, stash: Optional[str] = None) -> List[torch.Tensor]:
+    """``grad_from`` / ``push_to`` / ``stash``: the gradient hop over the NVLink fabric (server/backend.py:Stage.backward); ``inputs`` /
+    ``grad_outputs`` are then shape carriers (meta tensors)."""
     _check_activations("inputs", inputs, handler)
     _check_activations("grad_outputs", grad_outputs, handler)
     if inputs.shape != grad_outputs.shape:
@@ -60,7 +67,8 @@ def run_rpc_backward(inputs: torch.Tensor, grad_outputs: torch.Tensor, prompts: 
     block_prompts = _split_prompts(prompts, len(backends), B, H)
     lo, hi = backends[0].slot, backends[-1].slot + 1
     priority = handler.prioritizer.prioritize(inputs, grad_outputs, points=points / max(len(backends), 1), type="backward")
-    fut = handler.backward_pool.submit_task(inputs, grad_outputs, block_prompts, lo, hi, active_adapter, priority=priority, size=B * T)
+    hops = {k: v for k, v in (("grad_from", grad_from), ("push_to", push_to), ("stash", stash)) if v is not None}
+    fut = handler.backward_pool.submit_task(inputs, grad_outputs, block_prompts, lo, hi, active_adapter, *([hops] if hops else []), priority=priority, size=B * T)
     grad_inputs, grad_prompts = fut.result(timeout=handler.request_timeout)
     out = [grad_inputs]
     if block_prompts is not None:

@@ -46,6 +46,35 @@ CACHE_TOKENS_AVAILABLE = "cache_tokens_available"  # rpc_info key (reference: ha
 logger = get_logger(__name__)
 
 
+def fabric_endpoints(metadata: Dict[str, Any]) -> Tuple[Optional[tuple], Optional[tuple]]:
+    """Validated ``(take_from, push_to)`` of a request that rides the NVLink fabric (parallel/fabric.py): ``fabric_in = {B, T, src_rank,
+    slot}`` says the tensor argument already sits in a landing slot of this rank, ``fabric_out = {kind, rank, slot}`` asks for the result to
+    be stored into a landing slot of ``rank``. Never trust the wire: sizes and slots index device memory."""
+    from petals_b200.parallel.fabric import KINDS, get_fabric
+
+    fin, fout = metadata.get("fabric_in"), metadata.get("fabric_out")
+    if fin is None and fout is None:
+        return None, None
+    fabric = get_fabric()
+    if fabric is None:
+        raise RuntimeError("this stage has no NVLink fabric but the request names landing slots")
+    n_slots, world = getattr(fabric, "n_slots", 1), getattr(fabric, "world", None)
+    take_from = push_to = None
+    if fin is not None:
+        fb, ft, src, slot = int(fin["B"]), int(fin["T"]), int(fin["src_rank"]), int(fin.get("slot", 0))
+        if fb < 1 or ft < 1 or fb * ft > fabric.max_tokens or src < 0 or (world is not None and src >= world):
+            raise ValueError(f"fabric_in describes {fb} x {ft} rows from rank {src}: outside this stage's landing zone ({fabric.max_tokens} rows)")
+        if not 0 <= slot < n_slots:
+            raise ValueError(f"fabric_in names landing slot {slot}; this stage's ring has {n_slots}")
+        take_from = (fabric, src, fb, ft, slot)
+    if fout is not None:
+        kind, rank = str(fout["kind"]), int(fout["rank"])
+        if kind not in KINDS or rank < 0 or (world is not None and rank >= world):
+            raise ValueError(f"fabric_out names landing zone {kind!r} of rank {rank}")
+        push_to = (fabric, kind, rank, int(fout.get("slot", 0)) % max(1, n_slots))
+    return take_from, push_to
+
+
 class InferenceStream:
     """Server side of one ``rpc_inference`` stream: a KV session + step loop state."""
 
@@ -148,27 +177,10 @@ class InferenceStream:
                 hypo_ids = pushed[2] if len(pushed) > 2 else hypo_ids
         # NVLink fabric (parallel/fabric.py): the input may already sit in this rank's landing zone, and/or the output
         # may have to be stored straight into the next stage's (or the client's) landing zone by the span's last kernel
-        from petals_b200.parallel.fabric import get_fabric
-
-        fabric = get_fabric()
-        fin, fout = metadata.get("fabric_in"), metadata.get("fabric_out")
-        take_from = push_to = None
-        if fin is not None:
-            if fabric is None:
-                raise RuntimeError("this stage has no NVLink fabric but the request says its input was pushed")
-            fb, ft, src = int(fin["B"]), int(fin["T"]), int(fin["src_rank"])
-            if fb < 1 or ft < 1 or fb * ft > fabric.max_tokens or not 0 <= src < getattr(fabric, "world", src + 1):
-                raise ValueError(f"fabric_in describes {fb} x {ft} rows from rank {src}: outside this stage's landing zone ({fabric.max_tokens} rows)")
-            slot_in = int(fin.get("slot", 0))
-            if not 0 <= slot_in < getattr(fabric, "n_slots", 1):
-                raise ValueError(f"fabric_in names landing slot {slot_in}; this stage's ring has {getattr(fabric, 'n_slots', 1)}")
-            take_from = (fabric, src, fb, ft, slot_in)
-            hidden = torch.empty(int(fin["B"]), int(fin["T"]), self.handler.stage.spec.hidden_size, dtype=self.handler.stage.dtype,
+        take_from, push_to = fabric_endpoints(metadata)
+        if take_from is not None:
+            hidden = torch.empty(take_from[2], take_from[3], self.handler.stage.spec.hidden_size, dtype=self.handler.stage.dtype,
                                  device=self.handler.stage.device)  # shape carrier only
-        if fout is not None:
-            if fabric is None:
-                raise RuntimeError("this stage has no NVLink fabric but the request asks to push its output")
-            push_to = (fabric, str(fout["kind"]), int(fout["rank"]), int(fout.get("slot", 0)) % max(1, getattr(fabric, "n_slots", 1)))
         if hidden.dim() != 3 or not hidden.is_floating_point():
             raise ValueError(f"hidden states must be a floating-point tensor [batch, seq, hidden], got {tuple(hidden.shape)} {hidden.dtype}")
         if hidden.shape[2] != self.handler.stage.spec.hidden_size:  # kernels index by the model's hidden size: never trust the wire
@@ -307,8 +319,11 @@ class TransformerConnectionHandler:
         metadata = metadata or {}
         self.check_adapter(metadata.get("active_adapter"))
         backends = [self.module_backends[u] for u in uids]
+        take_from, push_to = fabric_endpoints(metadata)
+        if take_from is not None:  # the micro-batch already sits in this rank's landing slot: `hidden` is a shape carrier
+            hidden = torch.empty(take_from[2], take_from[3], self.stage.spec.hidden_size, dtype=self.stage.dtype, device="meta")
         return run_rpc_forward(hidden, prompts, backends=backends, handler=self, active_adapter=metadata.get("active_adapter"),
-                               points=float(metadata.get("points", 0)))
+                               points=float(metadata.get("points", 0)), take_from=take_from, push_to=push_to, stash=self._stash_key(metadata))
 
     def rpc_backward(self, uids, inputs: torch.Tensor, grad_outputs: torch.Tensor, prompts: Optional[torch.Tensor] = None,
                      metadata: Optional[Dict[str, Any]] = None) -> List[torch.Tensor]:
@@ -328,8 +343,25 @@ class TransformerConnectionHandler:
         metadata = metadata or {}
         self.check_adapter(metadata.get("active_adapter"))
         backends = [self.module_backends[u] for u in uids]
+        grad_from, push_to = fabric_endpoints(metadata)
+        stash = self._stash_key(metadata)
+        if grad_from is not None:
+            grad_outputs = torch.empty(grad_from[2], grad_from[3], self.stage.spec.hidden_size, dtype=self.stage.dtype, device="meta")
+        if stash is not None:  # the span input stayed on this stage since the forward (see Stage.stash_put)
+            inputs = torch.empty(tuple(grad_outputs.shape), dtype=self.stage.dtype, device="meta")
         return run_rpc_backward(inputs, grad_outputs, prompts, backends=backends, handler=self,
-                                active_adapter=metadata.get("active_adapter"), points=float(metadata.get("points", 0)))
+                                active_adapter=metadata.get("active_adapter"), points=float(metadata.get("points", 0)),
+                                grad_from=grad_from, push_to=push_to, stash=stash)
+
+    @staticmethod
+    def _stash_key(metadata: Dict[str, Any]) -> Optional[str]:
+        key = metadata.get("stash")
+        if key is None:
+            return None
+        key = str(key)
+        if not 0 < len(key) <= 128:
+            raise ValueError("stash keys are 1..128 characters")
+        return key
 
     def rpc_push(self, uids, *tensors: torch.Tensor, metadata: Optional[Dict[str, Any]] = None) -> None:
         metadata = metadata or {}

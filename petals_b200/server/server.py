@@ -361,13 +361,13 @@ class ModuleContainer:
             backends[uid] = TransformerBackend(uid, block, stage=stage, slot=slot, max_batch_size=max_batch_size, runtime=runtime)
         inference_pool = merge_inference_pools_inplace(backends, stage, runtime, max_batch_size)
 
-        def span_forward(hidden, prompts, lo, hi, active_adapter):
+        def span_forward(hidden, prompts, lo, hi, active_adapter, hops=None):
             stage.use_adapter(active_adapter)
-            return stage.forward(hidden, prompts, lo, hi)
+            return stage.forward(hidden, prompts, lo, hi, **(hops or {}))
 
-        def span_backward(hidden, grad, prompts, lo, hi, active_adapter):
+        def span_backward(hidden, grad, prompts, lo, hi, active_adapter, hops=None):
             stage.use_adapter(active_adapter)
-            return stage.backward(hidden, grad, prompts, lo, hi)
+            return stage.backward(hidden, grad, prompts, lo, hi, **(hops or {}))
 
         forward_pool = PrioritizedTaskPool(span_forward, max_batch_size, "span_forward", runtime)
         backward_pool = PrioritizedTaskPool(span_backward, max_batch_size, "span_backward", runtime, in_caller_thread=True)

@@ -9,9 +9,16 @@ from tests.utils import checkpoint
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_fabric_protocol_two_processes():
+import pytest
+
+
+@pytest.mark.parametrize("stages", [2, 4])
+def test_fabric_protocol_between_processes(stages):
+    """Inference steps (landing zones, rollback) and a training pass (micro-batches hop forward through the x_in rings, gradients hop
+    back through the g_in rings, every stage stashes its input) over the shared-memory twin of the NVLink fabric; with 4 stages the
+    middle ones both take from and push into rings."""
     path = checkpoint("llama")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29741",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={stages}", "--master-addr", "127.0.0.1", "--master-port", str(29741 + stages),
            os.path.join(ROOT, "tools", "pp_selftest_cpu.py"), path]
     env = dict(os.environ, PYTHONPATH=ROOT, CUDA_VISIBLE_DEVICES="")
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
@@ -19,3 +26,4 @@ def test_fabric_protocol_two_processes():
     assert proc.returncode == 0 and lines, proc.stdout[-3000:] + proc.stderr[-3000:]
     report = json.loads(lines[-1])
     assert report["pp_selftest_cpu"] == "ok", report
+    assert report["training_fabric_hops"] == {"forward": 3 * stages, "backward": 3 * stages}, report

@@ -64,6 +64,44 @@ def main():
         ok = err < 0.05 and agree > 0.9 and all(used_fabric[1:]) and len(peers) == world
         report = {"pp_selftest": "ok" if ok else "FAILED", "world": world, "rel_err": round(err, 5), "argmax_agreement": round(agree, 4),
                   "stages": peers, "inputs_over_fabric": used_fabric, "generated": out[0, 8:].tolist()}
+        # training over the fabric (BASELINE config #5): 3 micro-batches hop forward through the x_in rings (GEMM-epilogue pushes), the
+        # gradients hop back through the g_in rings (stored by the last kernel of each stage's backward), every stage stashes its
+        # input; compared with fp32 autograd through the oracle blocks, deep prompts included
+        import copy
+
+        import petals_b200.client.sequential_autograd as sa
+
+        sa.MAX_TOKENS_IN_BATCH = 2 * 48
+        H = config.hidden_size
+        blocks32 = [copy.deepcopy(b).float() for b in blocks]
+        rel = lambda a, b: ((a.float() - b).abs().mean() / (b.abs().mean() + 1e-9)).item()
+        t_err, hops = {}, {}
+        for tag, use_prompts in (("prompts", True), ("plain", False)):  # without prompts the gradient hop is the fused one (last kernel stores to the peer)
+            torch.manual_seed(1)
+            x = (0.7 * torch.randn(6, 48, H, device=dev)).to(torch.bfloat16).requires_grad_(True)
+            prompts = (0.1 * torch.randn(n_layers, 1, 4, H, device=dev)).to(torch.bfloat16).requires_grad_(True) if use_prompts else None
+            before = dict(sa.FabricPlan.hops_done)
+            y = model.model.layers(x, prompts=prompts)
+            w = (0.1 * torch.randn_like(y)).float()
+            (y.float() * w).sum().backward()
+            hops[tag] = {k: sa.FabricPlan.hops_done[k] - before[k] for k in before}
+            fabric.check_errors()
+            x2 = x.detach().float().requires_grad_(True)
+            p2 = prompts.detach().float().requires_grad_(True) if use_prompts else None
+            h = x2
+            for i, b32 in enumerate(blocks32):
+                if use_prompts:
+                    h = torch.cat([h[:, :4] + p2[i], h[:, 4:]], 1)
+                h = b32.forward_cached(h, None, None, 0)
+            (h * w).sum().backward()
+            t_err[tag] = {"y": rel(y, h.detach()), "grad_x": rel(x.grad, x2.grad)}
+            if use_prompts:
+                t_err[tag]["grad_prompts"] = rel(prompts.grad, p2.grad)
+        t_ok = (max(v for e in t_err.values() for v in e.values()) < 2e-2
+                and all(h_ == {"forward": 3 * world, "backward": 3 * world} for h_ in hops.values()))
+        ok = ok and t_ok
+        t_err = {k: {kk: round(vv, 5) for kk, vv in v.items()} for k, v in t_err.items()}
+        report.update(pp_selftest="ok" if ok else "FAILED", training_rel_err=t_err, training_fabric_hops=hops)
     host_barrier()
     stage.shutdown()
     fabric.check_errors()

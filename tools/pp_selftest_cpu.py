@@ -55,6 +55,31 @@ def main():
         parts = [(a - ref[:, :7]).abs().max().item(), (b_ - ref[:, 7:8]).abs().max().item(), (c - ref[:, 8:]).abs().max().item()]
         ok = err < 1e-3 and all(used[1:]) and len(peers) == world
         report = {"pp_selftest_cpu": "ok" if ok else "FAILED", "max_err": err, "stages": peers, "inputs_over_fabric": used, "part_errs": parts}
+        # training over the fabric: micro-batches hop forward through x_in rings, gradients hop back through g_in rings, every stage
+        # stashes its input; compared with local autograd through the same blocks (deep prompts included)
+        from petals_b200.client.sequential_autograd import FabricPlan
+        import petals_b200.client.sequential_autograd as sa
+
+        sa.MAX_TOKENS_IN_BATCH = 24  # 3 micro-batches of 2 sequences
+        torch.manual_seed(1)
+        x = torch.randn(6, 12, config.hidden_size, requires_grad=True)
+        prompts = (0.1 * torch.randn(n, 1, 3, config.hidden_size)).requires_grad_(True)
+        before = dict(FabricPlan.hops_done)
+        y = model.model.layers(x, prompts=prompts)
+        w = torch.randn_like(y)
+        (y * w).sum().backward()
+        hops = {k: FabricPlan.hops_done[k] - before[k] for k in before}
+        x2, p2 = x.detach().clone().requires_grad_(True), prompts.detach().clone().requires_grad_(True)
+        h = x2
+        for i in range(n):
+            blk = load_pretrained_block(path, i, torch_dtype=torch.float32)
+            h = torch.cat([h[:, :3] + p2[i], h[:, 3:]], 1)
+            h = blk(h)[0]
+        (h * w).sum().backward()
+        t_err = {"y": (y - h).abs().max().item(), "grad_x": (x.grad - x2.grad).abs().max().item(), "grad_prompts": (prompts.grad - p2.grad).abs().max().item()}
+        t_ok = max(t_err.values()) < 1e-3 and hops == {"forward": 3 * world, "backward": 3 * world}
+        ok = ok and t_ok
+        report.update(pp_selftest_cpu="ok" if ok else "FAILED", training_err=t_err, training_fabric_hops=hops)
     host_barrier()
     server.shutdown()
     host_barrier()
