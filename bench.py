@@ -52,6 +52,7 @@ def main() -> None:
     ap.add_argument("--tp-emulate", type=int, default=0, help="DIAGNOSTIC (not a benchmark result): run the compute of ONE rank of a "
                     "tensor-parallel group of this size on one GPU (heads, KV heads and FFN columns divided), to measure the fixed per-layer costs")
     ap.add_argument("--skip-fp8", action="store_true", help="do not append the block-scaled FP8 decode measurement")
+    ap.add_argument("--skip-selftests", action="store_true", help="N > 1: do not run the TP / pipeline numerics self-tests before the timed runs")
     ap.add_argument("--skip-pipeline", action="store_true", help="N > 1: do not append the pipeline-parallel record (same model as N stages)")
     ap.add_argument("--pp-chunk-tokens", type=int, default=256, help="positions per chunk of the pipelined prompt ingestion (pipeline record)")
     args = ap.parse_args()
@@ -161,8 +162,18 @@ def bench_fp8_decode(args, path, n_layers, swarm, dev, K, W, spec, vocab, peaks)
             ms, _ = device_timed_decode(model, sess, K)
         value = K / (ms / 1e3)
         weight_bytes = spec.active_params() * n_layers * (1 + 1 / 32) + vocab * spec.hidden_size * 2
-        return {"tokens_per_s": round(value, 3), "ms_per_step": round(ms / K, 4), "weight_bytes_per_token": int(weight_bytes),
-                "frac_of_measured_hbm": round(weight_bytes * value / 1e9 / peaks["hbm_gbs"], 3), "format": "E4M3 + UE8M0 scale per 32 (MXFP8)"}
+        rec = {"tokens_per_s": round(value, 3), "ms_per_step": round(ms / K, 4), "weight_bytes_per_token": int(weight_bytes),
+               "frac_of_measured_hbm": round(weight_bytes * value / 1e9 / peaks["hbm_gbs"], 3), "format": "E4M3 + UE8M0 scale per 32 (MXFP8)"}
+        if not args.skip_prefill:
+            # prompt ingestion with BOTH operands in MXFP8 on the block-scaled tensor-core path (csrc/gemm_mxfp8.cu)
+            try:
+                pf = bench_prefill(model, args, peaks, spec, n_layers)
+                pf["path"] = ("tcgen05.mma kind::mxf8f6f4.block_scale, activations quantised per 32 values (fused with the RMSNorm)"
+                              if getattr(stage.stage.engine, "fp8_w8a8", False) else "weights dequantised per projection, bf16 tcgen05 GEMM")
+                rec["prefill"] = pf
+            except Exception as e:  # noqa: BLE001
+                rec["prefill"] = {"error": repr(e)[:200]}
+        return rec
     finally:
         stage.shutdown()
 

@@ -21,6 +21,27 @@ from petals_b200.utils.bench_common import (BASELINE_TOKENS_PER_S, ClockSampler,
                                             prime_session)
 
 
+def run_selftests(args, dev, which=("tp", "pp")) -> dict:
+    """The numerics self-tests of the multi-GPU paths (parallel/selftests.py: tiny model, public client API, compared with the oracle
+    blocks / fp32 autograd), run inside the benchmark job so that every multi-GPU number comes with proof that the engine producing it
+    computes the right thing on this box. Collective; the reports land on rank 0. ``--skip-selftests`` turns them off."""
+    if getattr(args, "skip_selftests", False):
+        return {"skipped": True}
+    from petals_b200.parallel import selftests
+
+    out = {}
+    for name in which:
+        try:
+            out[name] = getattr(selftests, f"{name}_selftest")(dev)
+        except Exception as e:  # noqa: BLE001 - reported (and fatal for the run) on rank 0
+            out[name] = {f"{name}_selftest": "FAILED", "error": repr(e)[:300]}
+    return out
+
+
+def _selftests_ok(reports: dict) -> bool:
+    return bool(reports.get("skipped")) or all(r.get(f"{k}_selftest") == "ok" for k, r in reports.items())
+
+
 def run_multi_gpu(args) -> None:
     if str(args.parallelism).startswith("pp"):
         return run_pipeline(args)
@@ -42,6 +63,7 @@ def run_multi_gpu(args) -> None:
     dev = torch.device("cuda", local_rank)
     dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=dev)
     native.lib()
+    selftests = run_selftests(args, dev, ("tp",) if getattr(args, "skip_pipeline", False) else ("tp", "pp"))
     path = write_config_only(args.model)
     config = AutoDistributedConfig.from_pretrained(path)
     n_layers = MODEL_PRESETS[args.model]["num_hidden_layers"]
@@ -153,8 +175,13 @@ def run_multi_gpu(args) -> None:
     host_barrier()
     heap.close()
     result["pipeline"] = _pipeline_appendix(args, engine, cache)
+    result["selftests"] = selftests
+    if not _selftests_ok(selftests):
+        result["invalid"] = "a numerics self-test of the multi-GPU engine failed on this box: the numbers above are not to be trusted"
     print(json.dumps(result))
     dist.destroy_process_group()
+    if "invalid" in result:
+        raise SystemExit(1)
 
 
 def _pipeline_appendix(args, engine, cache) -> dict:
@@ -330,6 +357,7 @@ def run_pipeline(args) -> None:
     dev = torch.device("cuda", local_rank)
     dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=dev)
     native.lib()
+    selftests = run_selftests(args, dev, ("pp",))
     rec = pipeline_record(args)
     if rank == 0:
         d = rec.get("decode", {})
@@ -343,7 +371,12 @@ def run_pipeline(args) -> None:
                        "inputs_over_fabric": rec.get("inputs_over_fabric")},
             "clocks": rec.get("clocks"),
             "e2e": {"value": d.get("e2e_tokens_per_s"), "unit": "tokens/s", "h2d_bytes_per_step": d.get("h2d_bytes_per_step"), "d2h_bytes_per_step": d.get("d2h_bytes_per_step")},
-            "gpu_launches": d.get("gpu_launches_rank0"), "prefill": rec.get("prefill"), "stage_hop": rec.get("stage_hop"),
+            "gpu_launches": d.get("gpu_launches_rank0"), "prefill": rec.get("prefill"), "stage_hop": rec.get("stage_hop"), "selftests": selftests,
         }
+        if not _selftests_ok(selftests):
+            result["invalid"] = "the numerics self-test of the pipeline fabric failed on this box: the numbers above are not to be trusted"
         print(json.dumps(result))
+        if "invalid" in result:
+            dist.destroy_process_group()
+            raise SystemExit(1)
     dist.destroy_process_group()

@@ -52,14 +52,19 @@ class StageEngine:
                  max_chunk_tokens: int = 8192, use_cuda_graphs: bool = True, fp8: bool = False, free_bf16: bool = True):
         self.spec, self.blocks, self.cache = spec, list(blocks), cache
         # Block-scaled FP8 serving (--quant_type fp8): projections are kept as E4M3 payload + UE8M0 scales (ops/quant.py).
-        # Decode streams the 1-byte weights directly (csrc/linear_decode_fp8.cu); prefill dequantises one projection at a
-        # time into a bf16 scratch and runs the tcgen05 GEMM on it.
+        # Decode streams the 1-byte weights directly (csrc/linear_decode_fp8.cu). Prefill quantises the activations to MXFP8 too
+        # (fused with the RMSNorm in front of the projection) and multiplies on the block-scaled tensor-core path
+        # (csrc/gemm_mxfp8.cu: tcgen05.mma kind::mxf8f6f4.block_scale, twice the bf16 rate); layouts that path does not cover
+        # (or PETALS_B200_FP8_PREFILL=dequant) dequantise one projection at a time into a bf16 scratch for the bf16 GEMM.
         self.fp8: Optional[List[Dict[str, Tuple[torch.Tensor, torch.Tensor]]]] = None
+        self.fp8_sf: Optional[List[Dict[str, torch.Tensor]]] = None  # weight scales in the tensor cores' block layout
         self.max_decode_rows = MAX_DECODE_ROWS
         if fp8:
             from petals_b200.ops.quant import quantize_mxfp8
 
-            self.fp8 = []
+            from petals_b200.ops.quant import pack_scales
+
+            self.fp8, self.fp8_sf = [], []
             self.max_decode_rows = 4
             for block in self.blocks:
                 entry = {}
@@ -71,6 +76,11 @@ class StageEngine:
                     if free_bf16:
                         p.data = torch.empty(0, dtype=p.dtype, device=p.device)
                 self.fp8.append(entry)
+                self.fp8_sf.append({n: pack_scales(e) for n, (q, e) in entry.items() if q.shape[1] % 128 == 0})
+            s_ = spec
+            self.fp8_w8a8 = (os.environ.get("PETALS_B200_FP8_PREFILL", "w8a8").lower() != "dequant" and torch.device(device).type == "cuda"
+                             and s_.norm == "rms" and s_.mlp == "swiglu" and not s_.parallel_attn and not (s_.qkv_bias or s_.out_bias or s_.mlp_bias)
+                             and all(set(sf) >= set(self.FP8_NAMES) for sf in self.fp8_sf))
         self.device = torch.device(device)
         self.n_blocks = len(self.blocks)
         self.max_chunk_tokens = max_chunk_tokens
@@ -362,11 +372,38 @@ class StageEngine:
             return y
         return self._lin_decode(slot, "w_down", act, bias=w._p("b_down"), residual=h1, out=x, **self._push_kwargs(hop))
 
+    def _quant_rows(self, x: torch.Tensor, norm_w: Optional[torch.Tensor], tag: str) -> Tuple[torch.Tensor, torch.Tensor]:
+        """MXFP8 copy of the rows of ``x`` (RMSNorm(x) * norm_w when a weight is given) in grow-only scratch buffers."""
+        M, K = x.shape
+        q = self._buf(f"q8{tag}_p", M, K, torch.uint8)
+        sf = self._buf(f"sf8{tag}_p", ((M + 127) // 128) * (K // 128), 512, torch.uint8)
+        return Fn.quant_mxfp8(x, norm_w, self.spec.norm_eps, q=q, sf=sf)
+
+    def _block_prefill_fp8(self, x: torch.Tensor, slot: int, B: int, T: int, table, pos_ptr, pools, hop: Optional[tuple] = None) -> torch.Tensor:
+        """The prefill block with every projection on the block-scaled FP8 tensor-core path: activations are quantised per 32 values
+        along K right where they are produced (norm outputs: fused with the norm), weights are the stage's MXFP8 payloads."""
+        s, w, f, sf = self.spec, self.blocks[slot], self.fp8[slot], self.fp8_sf[slot]
+        M = B * T
+        aq, asf = self._quant_rows(x, w.ln1_w, "h")
+        qkv = Fn.gemm_mxfp8(aq, asf, f["wqkv"][0], sf["wqkv"], out=self._buf("qkv_p", M, s.qkv_dim))
+        attn = self._attention(qkv, slot, B, T, table, pos_ptr, pools, 1, "_p")
+        aq, asf = self._quant_rows(attn, None, "a")
+        h1 = Fn.gemm_mxfp8(aq, asf, f["wo"][0], sf["wo"], residual=x, out=self._buf("h1_p", M, s.hidden_size))
+        aq, asf = self._quant_rows(h1, w.ln2_w, "h")
+        act = Fn.gemm_mxfp8(aq, asf, f["w_gate"][0], sf["w_gate"], b2_q=f["w_up"][0], b2_sf=sf["w_up"], out=self._buf("act_p", M, s.intermediate_size))
+        aq, asf = self._quant_rows(act, None, "i")
+        y = Fn.gemm_mxfp8(aq, asf, f["w_down"][0], sf["w_down"], residual=h1, out=x)
+        if hop is not None:
+            hop[0].send(y, hop[2], hop[1], *hop[3:4])
+        return y
+
     def _block_prefill(self, x: torch.Tensor, slot: int, B: int, T: int, table, pos_ptr, pools, hop: Optional[tuple] = None) -> torch.Tensor:
         """x: [M, H] (overwritten with the block output)."""
         s, w = self.spec, self.blocks[slot]
         M = B * T
         eps = s.norm_eps
+        if self.fp8 is not None and self.fp8_w8a8:
+            return self._block_prefill_fp8(x, slot, B, T, table, pos_ptr, pools, hop)
         xn = Fn.norm(x, w.ln1_w, w._p("ln1_b"), kind=self.norm_kind, eps=eps, out=self._buf("xn_p", M, s.hidden_size))
         qkv = Fn.gemm(xn, self._w(slot, "wqkv"), bias=w._p("bqkv"), out=self._buf("qkv_p", M, s.qkv_dim))
         self._lora_add_prefill(slot, "wqkv", xn, qkv)

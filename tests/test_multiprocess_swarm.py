@@ -34,7 +34,7 @@ def test_two_server_processes(family, compression, atol, tmp_path):
              _spawn(["petals.cli.run_server", path, "--block_indices", "2:4", "--peer_id", "stage1", "--attn_cache_tokens", "2048",
                      "--max_chunk_size_bytes", "1024", *common], logs[1])]  # tiny chunk size => chunked prefill is exercised
     try:
-        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[rendezvous], max_retries=40, min_backoff=0.5, max_backoff=1.0)
+        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[rendezvous], max_retries=150, min_backoff=0.5, max_backoff=1.0)
         config = AutoDistributedConfig.from_pretrained(path)
         ids = torch.randint(0, config.vocab_size, (1, 7), generator=torch.Generator().manual_seed(0))
         with torch.inference_mode():

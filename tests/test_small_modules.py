@@ -173,3 +173,19 @@ def test_safetensors_reader_refuses_inconsistent_files(tmp_path):
         assert torch.equal(f.get_tensor("a"), torch.arange(12, dtype=torch.float32).reshape(3, 4))
         with pytest.raises(IOError, match="unsupported dtype"):
             f.get_tensor("z")
+
+
+def test_mxfp8_scale_block_layout_round_trip():
+    """ops/quant.py:pack_scales lays the UE8M0 exponents out the way tcgen05.cp copies them into tensor memory (csrc/gemm_mxfp8.cu):
+    [K/128][rows/128][512 B], scale of (row r, K slice c) at (r % 32) * 16 + (r // 32) * 4 + c; unpack_scales inverts it."""
+    import torch
+
+    from petals_b200.ops.quant import pack_scales, unpack_scales
+
+    e = torch.randint(1, 255, (300, 8), dtype=torch.uint8)
+    p = pack_scales(e)
+    assert p.numel() == 2 * 3 * 512 and torch.equal(unpack_scales(p, 300, 256), e)
+    for r, j in [(0, 0), (33, 1), (127, 7), (128, 4), (299, 3)]:
+        off = ((j // 4) * 3 + r // 128) * 512 + (r % 128 % 32) * 16 + (r % 128 // 32) * 4 + j % 4
+        assert p[off] == e[r, j]
+    assert int(p.view(2, 3, 32, 4, 4)[:, 2, 12:, 1].sum()) == 0  # rows 300..383 are padding

@@ -150,7 +150,7 @@ def test_run_dht_registry_and_two_server_processes_over_tcp(tmp_path):
         for i, span in enumerate(["0:2", "2:4"]):
             logs.append(open(tmp_path / f"server{i}.log", "w"))
             procs.append(_spawn(["petals.cli.run_server", path, "--block_indices", span, "--peer_id", f"stage{i}", *common], logs[-1]))
-        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[maddr], max_retries=40, min_backoff=0.5, max_backoff=1.0)
+        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[maddr], max_retries=150, min_backoff=0.5, max_backoff=1.0)
         config = AutoDistributedConfig.from_pretrained(path)
         ids = torch.randint(0, config.vocab_size, (1, 6), generator=torch.Generator().manual_seed(0))
         with torch.inference_mode():
@@ -193,7 +193,7 @@ def test_failover_when_a_server_process_is_killed_mid_session(tmp_path):
         for name, span in spans.items():
             logs.append(open(tmp_path / f"{name}.log", "w"))
             procs[name] = _spawn(["petals.cli.run_server", path, "--block_indices", span, "--peer_id", name, *common], logs[-1])
-        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[maddr], max_retries=40, min_backoff=0.3, max_backoff=1.0,
+        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[maddr], max_retries=150, min_backoff=0.3, max_backoff=1.0,
                                                                 update_period=1.0)
         config = AutoDistributedConfig.from_pretrained(path)
         manager = model.model.layers.sequence_manager

@@ -191,6 +191,43 @@ def bench_gemv_fp8(results, peaks):
             del qs, q2s
 
 
+def bench_gemm_fp8(results, peaks):
+    """Block-scaled MXFP8 GEMM (tcgen05.mma kind::mxf8f6f4.block_scale) on the 70B prefill shapes, the bf16 tcgen05 GEMM alongside;
+    the activation quantiser (what the fp8 path pays extra per projection) is timed separately."""
+    from petals_b200.ops.quant import pack_scales, quantize_mxfp8
+
+    shapes = [("70b.qkv", 8192, 10240, 8192, False), ("70b.o", 8192, 8192, 8192, False), ("70b.gate_up", 8192, 28672, 8192, True),
+              ("70b.down", 8192, 8192, 28672, False), ("sq4096", 4096, 4096, 4096, False)]
+    for name, M, N, K, dual in shapes:
+        nbuf = 2
+        A = [torch.randn(M, K, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
+        W = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * K ** -0.5 for _ in range(nbuf * (2 if dual else 1))]
+        Aq = [Fn.quant_mxfp8(a) for a in A]
+        Wq = [(lambda qe: (qe[0].view(torch.uint8), pack_scales(qe[1])))(quantize_mxfp8(w)) for w in W]
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+
+        def mk(i):
+            if dual:
+                return lambda: Fn.gemm_mxfp8(Aq[i][0], Aq[i][1], Wq[2 * i][0], Wq[2 * i][1], b2_q=Wq[2 * i + 1][0], b2_sf=Wq[2 * i + 1][1], out=out)
+            return lambda: Fn.gemm_mxfp8(Aq[i][0], Aq[i][1], Wq[i][0], Wq[i][1], out=out)
+
+        def mk16(i):
+            if dual:
+                return lambda: Fn.gemm(A[i], W[2 * i], b2=W[2 * i + 1], act=Fn.ACT_SWIGLU, out=out)
+            return lambda: Fn.gemm(A[i], W[i], out=out)
+
+        ms = time_fn([mk(i) for i in range(nbuf)], iters=10)
+        ms16 = time_fn([mk16(i) for i in range(nbuf)], iters=10)
+        qms = time_fn([(lambda i=i: Fn.quant_mxfp8(A[i], q=Aq[i][0], sf=Aq[i][1])) for i in range(nbuf)], iters=10)
+        flops = 2.0 * M * N * K * (2 if dual else 1)
+        row = dict(kernel="gemm_mxfp8", shape=name, M=M, N=N, K=K, ms=ms, TFLOPs=flops / ms / 1e9, bf16_ms=ms16, bf16_TFLOPs=flops / ms16 / 1e9,
+                   quant_ms=qms, quant_GBps=M * K * 3 / qms / 1e6, speedup_vs_bf16=ms16 / ms, speedup_incl_quant=ms16 / (ms + qms))
+        results.append(row)
+        print(f"gemm_mxfp8 {name:12s} {M}x{N}x{K} {ms:8.3f} ms {row['TFLOPs']:7.0f} TFLOP/s | bf16 tcgen05 {ms16:8.3f} ms {row['bf16_TFLOPs']:7.0f} | "
+              f"quantise A {qms:6.3f} ms | x{row['speedup_vs_bf16']:.2f} (x{row['speedup_incl_quant']:.2f} with the quantiser)", flush=True)
+        del A, W, Aq, Wq
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default="")
@@ -207,6 +244,8 @@ def main():
         bench_gemv(results, peaks)
     if args.only in ("", "gemm"):
         bench_gemm(results, peaks)
+    if args.only in ("", "gemm_fp8"):
+        bench_gemm_fp8(results, peaks)
     os.makedirs("gpurun_out", exist_ok=True)
     with open(f"gpurun_out/kernel_bench{('_' + args.only) if args.only else ''}.json", "w") as f:
         json.dump(dict(peaks=peaks, results=results), f, indent=1)
