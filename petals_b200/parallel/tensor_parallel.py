@@ -330,7 +330,9 @@ class TPDecodeEngine:
             # PETALS_B200_SPAN_NVLS: "0" = unicast peer stores; "st" = one multimem.st per partial (NVSwitch replicates it into every
             # rank's slot); "reduce" = partials stay local, the slice owners multimem.ld_reduce them (in-switch sum). Needs the
             # heap's multicast mapping (parallel/symmetric.py); without it every mode degrades to unicast.
-            mode = os.environ.get("PETALS_B200_SPAN_NVLS", "st").lower()
+            # Default = what measured fastest on B200 boxes (profiles/r2_2gpu_selftests_and_bench.txt, r2_8gpu_bench_selftests_pipeline.txt):
+            # 2 ranks: multimem.st 13.47 ms/token vs 13.59 unicast; 8 ranks: unicast 6.89 vs 7.06 for multimem.st.
+            mode = os.environ.get("PETALS_B200_SPAN_NVLS", "st" if R <= 2 else "0").lower()
             mc = getattr(self.heap, "multicast_ptr", 0)
             nvls = None
             push = lambda off: [self.heap.addr(r, off + me * self.span_slot_bytes) for r in range(R)]
