@@ -28,18 +28,22 @@ __global__ void __launch_bounds__(256) moe_router_kernel(const __nv_bfloat16* __
   __shared__ float logits[64];
   const int m = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const __nv_bfloat16* x = h + static_cast<size_t>(m) * H;
-  float ss = 0.f;
-  for (int k = tid; k < H; k += blockDim.x) { const float f = __bfloat162float(x[k]); ss += f * f; }
-  ss = warp_sum(ss);
-  if (lane == 0) red[warp] = ss;
-  __syncthreads();
-  float tot = lane < nw ? red[lane] : 0.f;
-  tot = warp_sum(tot);
-  const float rstd = rsqrtf(tot / H + eps);
-  for (int k = tid; k < H; k += blockDim.x) {
-    const __nv_bfloat16 v = __float2bfloat16_rn(rbf16(__bfloat162float(x[k]) * rstd) * __bfloat162float(norm_w[k]));
-    xs[k] = v;
-    xn_out[static_cast<size_t>(m) * H + k] = v;
+  if (norm_w != nullptr) {
+    float ss = 0.f;
+    for (int k = tid; k < H; k += blockDim.x) { const float f = __bfloat162float(x[k]); ss += f * f; }
+    ss = warp_sum(ss);
+    if (lane == 0) red[warp] = ss;
+    __syncthreads();
+    float tot = lane < nw ? red[lane] : 0.f;
+    tot = warp_sum(tot);
+    const float rstd = rsqrtf(tot / H + eps);
+    for (int k = tid; k < H; k += blockDim.x) {
+      const __nv_bfloat16 v = __float2bfloat16_rn(rbf16(__bfloat162float(x[k]) * rstd) * __bfloat162float(norm_w[k]));
+      xs[k] = v;
+      xn_out[static_cast<size_t>(m) * H + k] = v;
+    }
+  } else {  // the rows are normalised already (tensor-parallel prefill: the all-gather delivers norm outputs)
+    for (int k = tid; k < H; k += blockDim.x) xs[k] = x[k];
   }
   __syncthreads();
   for (int e = warp; e < E; e += nw) {
@@ -148,7 +152,7 @@ __global__ void moe_combine_kernel(const __nv_bfloat16* __restrict__ y, const fl
       const int p = m * topk + j;
       acc = rbf16(acc + rbf16(__bfloat162float(y[static_cast<size_t>(p) * H + k]) * topw[p]));
     }
-    out[static_cast<size_t>(m) * H + k] = __float2bfloat16_rn(__bfloat162float(residual[static_cast<size_t>(m) * H + k]) + acc);
+    out[static_cast<size_t>(m) * H + k] = __float2bfloat16_rn((residual != nullptr ? __bfloat162float(residual[static_cast<size_t>(m) * H + k]) : 0.f) + acc);
   }
 }
 
@@ -208,7 +212,7 @@ __global__ void moe_combine_pos_kernel(const __nv_bfloat16* __restrict__ y, cons
       const int p = m * topk + j;
       acc = rbf16(acc + rbf16(__bfloat162float(y[static_cast<size_t>(pos[p]) * H + k]) * topw[p]));
     }
-    out[static_cast<size_t>(m) * H + k] = __float2bfloat16_rn(__bfloat162float(residual[static_cast<size_t>(m) * H + k]) + acc);
+    out[static_cast<size_t>(m) * H + k] = __float2bfloat16_rn((residual != nullptr ? __bfloat162float(residual[static_cast<size_t>(m) * H + k]) : 0.f) + acc);
   }
 }
 

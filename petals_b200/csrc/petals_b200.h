@@ -223,6 +223,11 @@ int pb_gemm_mxfp8(const PbGemmFp8Args* args, void* stream);
 // x bf16 [M, K] -> q e4m3 [M, K] + scales in the block layout; with norm_w: quantises RMSNorm(x) * norm_w (HF rounding) instead.
 int pb_quant_mxfp8(const void* x, const void* norm_w, float eps, void* q, void* sf, int M, int K, void* stream);
 
+// ---- stand-alone halves of the LL all-reduce (ll_collectives.cu): tag = *epoch * mul + add -----------------------------------
+int pb_ll_reduce(const void* x, void* const* parts, int R, const void* epoch, unsigned mul, unsigned add, void* out, long n_values,
+                 void* error_flag, void* stream);
+int pb_ll_push(const void* x, void* const* dst, int R, const void* epoch, unsigned mul, unsigned add, long n_values, void* stream);
+
 // ---- KV cache utilities -----------------------------------------------------------------------------
 int pb_kv_copy_pages(void* pool, const void* src_pages, const void* dst_pages, int n, long page_elems,
                      long layer_stride_elems, int n_layer_slabs, void* stream);

@@ -567,8 +567,9 @@ def attention_ref(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, *, pos0: in
 # sparse MoE (decode)
 # ----------------------------------------------------------------------------------------------------
 def moe_decode(h: torch.Tensor, norm_w: torch.Tensor, router: torch.Tensor, we_gate: torch.Tensor, we_up: torch.Tensor, we_down: torch.Tensor,
-               *, top_k: int, eps: float, out: torch.Tensor, bufs: Optional[dict] = None) -> torch.Tensor:
-    """out = h + MoE(RMSNorm(h)) for M <= 8 rows without any host synchronisation (csrc/moe.cu)."""
+               *, top_k: int, eps: float, out: torch.Tensor, bufs: Optional[dict] = None, add_residual: bool = True) -> torch.Tensor:
+    """out = h + MoE(RMSNorm(h)) for M <= 8 rows without any host synchronisation (csrc/moe.cu). ``add_residual=False``: out = MoE(...)
+    alone — a tensor-parallel rank's partial sum over its slice of every expert's FFN columns (the residual joins in the all-reduce)."""
     M, H = h.shape
     E, I, _ = we_gate.shape
     bufs = bufs if bufs is not None else {}
@@ -592,8 +593,22 @@ def moe_decode(h: torch.Tensor, norm_w: torch.Tensor, router: torch.Tensor, we_g
     check(lib.pb_moe_router(ptr(h), ptr(norm_w), ptr(router), ptr(xn), ptr(topi), ptr(topw), M, H, E, top_k, eps, st), "moe_router")
     check(lib.pb_moe_gemv(ptr(xn), ptr(we_gate), ptr(we_up), ptr(topi), ptr(act), M * top_k, I, H, I * H, top_k, sms, st), "moe_gemv(gate/up)")
     check(lib.pb_moe_gemv(ptr(act), ptr(we_down), None, ptr(topi), ptr(y), M * top_k, H, I, H * I, 1, sms, st), "moe_gemv(down)")
-    check(lib.pb_moe_combine(ptr(y), ptr(topw), ptr(h), ptr(out), M, H, top_k, st), "moe_combine")
+    check(lib.pb_moe_combine(ptr(y), ptr(topw), ptr(h) if add_residual else None, ptr(out), M, H, top_k, st), "moe_combine")
     return out
+
+
+def ll_reduce(x: torch.Tensor, parts: Sequence[int], tag: Tuple[int, int], epoch: int, out: torch.Tensor, error_flag: int = 0) -> torch.Tensor:
+    """``out = x + sum_r parts[r]`` where every part is a buffer of LL {2 x bf16, tag} units (addresses) written by ``ll_push`` /
+    a GEMV epilogue of source rank r; tag = epoch * tag[0] + tag[1] (csrc/ll_collectives.cu)."""
+    arr = (C.c_void_p * len(parts))(*parts)
+    check(native.lib().pb_ll_reduce(ptr(x), arr, len(parts), epoch, tag[0], tag[1], ptr(out), x.numel(), error_flag or None, stream_ptr()), "ll_reduce")
+    return out
+
+
+def ll_push(x: torch.Tensor, dst: Sequence[int], tag: Tuple[int, int], epoch: int) -> None:
+    """Store ``x`` as LL units into ``dst`` (one address per destination rank: this rank's slot over there)."""
+    arr = (C.c_void_p * len(dst))(*dst)
+    check(native.lib().pb_ll_push(ptr(x), arr, len(dst), epoch, tag[0], tag[1], x.numel(), stream_ptr()), "ll_push")
 
 
 def quant_mxfp8(x: torch.Tensor, norm_weight: Optional[torch.Tensor] = None, eps: float = 0.0, *, q: Optional[torch.Tensor] = None,
@@ -631,8 +646,9 @@ def gemm_mxfp8(a_q: torch.Tensor, a_sf: torch.Tensor, b_q: torch.Tensor, b_sf: t
 
 
 def moe_prefill(h: torch.Tensor, norm_w: torch.Tensor, router: torch.Tensor, we_gate: torch.Tensor, we_up: torch.Tensor, we_down: torch.Tensor,
-                *, top_k: int, eps: float, out: torch.Tensor, bufs: Optional[dict] = None) -> torch.Tensor:
-    """out = h + MoE(RMSNorm(h)) for any number of rows, with NO host synchronisation: router kernel -> routing plan on the device
+                *, top_k: int, eps: float, out: torch.Tensor, bufs: Optional[dict] = None, add_residual: bool = True) -> torch.Tensor:
+    """out = h + MoE(RMSNorm(h)) for any number of rows (``norm_w=None``: ``h`` is normalised already; ``add_residual=False``: the MoE
+    term alone — both for tensor-parallel ranks, which hold a slice of every expert's FFN columns), with NO host synchronisation: router kernel -> routing plan on the device
     (destination row of every (token, expert) pair in expert-major order + the tile table of the grouped GEMM) -> gather -> grouped
     tcgen05 GEMM gate/up with the SwiGLU epilogue -> grouped GEMM down -> weighted combine + residual. Reference (a Python loop over
     the experts with masks and index_add): HF MixtralSparseMoeBlock wrapped at src/petals/models/mixtral/block.py:13-19."""
@@ -650,19 +666,19 @@ def moe_prefill(h: torch.Tensor, norm_w: torch.Tensor, router: torch.Tensor, we_
             bufs[name] = t
         return t[:n]
 
-    xn = buf("moep_xn", M * H, torch.bfloat16).view(M, H)
+    xn = buf("moep_xn", M * H, torch.bfloat16).view(M, H) if norm_w is not None else _bf16c(h, "h")
     topi, topw = buf("moep_topi", pairs, torch.int32), buf("moep_topw", pairs, torch.float32)
     pos, table = buf("moep_pos", pairs, torch.int32), buf("moep_table", 1 + 3 * cap, torch.int32)
     gathered = buf("moep_gathered", pairs * H, torch.bfloat16).view(pairs, H)
     act = buf("moep_act", pairs * I, torch.bfloat16).view(pairs, I)
     y = buf("moep_y", pairs * H, torch.bfloat16).view(pairs, H)
     lib, st = native.lib(), stream_ptr()
-    check(lib.pb_moe_router(ptr(h), ptr(norm_w), ptr(router), ptr(xn), ptr(topi), ptr(topw), M, H, E, top_k, eps, st), "moe_router")
+    check(lib.pb_moe_router(ptr(h), ptr(norm_w), ptr(router), ptr(xn) if norm_w is not None else None, ptr(topi), ptr(topw), M, H, E, top_k, eps, st), "moe_router")
     check(lib.pb_moe_plan(ptr(topi), pairs, E, ptr(pos), ptr(table), cap, st), "moe_plan")
     check(lib.pb_moe_gather(ptr(xn), ptr(pos), ptr(gathered), pairs, H, top_k, st), "moe_gather")
     gemm(gathered, we_gate, b2=we_up, act=ACT_SWIGLU, out=act, grp=table, grp_cap=cap, grp_experts=E)
     gemm(act, we_down, out=y, grp=table, grp_cap=cap, grp_experts=E)
-    check(lib.pb_moe_combine_pos(ptr(y), ptr(topw), ptr(pos), ptr(h), ptr(out), M, H, top_k, st), "moe_combine_pos")
+    check(lib.pb_moe_combine_pos(ptr(y), ptr(topw), ptr(pos), ptr(h) if add_residual else None, ptr(out), M, H, top_k, st), "moe_combine_pos")
     return out
 
 

@@ -32,6 +32,9 @@ def run_selftests(args, dev, which=("tp", "pp")) -> dict:
     out = {}
     for name in which:
         try:
+            if name == "tp" and str(getattr(args, "model", "")).startswith("mixtral"):
+                out[name] = selftests.tp_selftest(dev, "mixtral-tiny")
+                continue
             out[name] = getattr(selftests, f"{name}_selftest")(dev)
         except Exception as e:  # noqa: BLE001 - reported (and fatal for the run) on rank 0
             out[name] = {f"{name}_selftest": "FAILED", "error": repr(e)[:300]}
@@ -150,7 +153,7 @@ def run_multi_gpu(args) -> None:
     value = K / (ms / 1e3)
     peaks = measured_peaks()
     spec = config.block_spec()
-    weight_bytes_rank = (spec.num_params() * n_layers) * 2 / world + vocab * spec.hidden_size * 2  # LM head is replicated on rank 0
+    weight_bytes_rank = (spec.active_params() * n_layers) * 2 / world + vocab * spec.hidden_size * 2  # LM head is replicated on rank 0
     hop_bytes = spec.hidden_size * 2
     result = {
         "metric": metric_name(args.model),

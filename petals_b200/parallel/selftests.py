@@ -9,11 +9,12 @@ import torch
 import torch.distributed as dist
 
 
-def tp_selftest(dev: torch.device) -> dict:
+def tp_selftest(dev: torch.device, preset: str = "llama-tiny") -> dict:
     """Collective over the default process group (>= 2 ranks, one GPU each). Every rank builds the SAME random tiny-Llama blocks, keeps
     its shard, and the group runs a multi-step session (prompt ingestion, single-token steps, a rollback, a long chunked prompt)
     through the public client API on rank 0; the result is compared with the oracle blocks evaluated on rank 0. Returns the report on
-    rank 0 (``{"tp_selftest": "ok" | "FAILED", ...}``) and ``{}`` elsewhere."""
+    rank 0 (``{"tp_selftest": "ok" | "FAILED", ...}``) and ``{}`` elsewhere. ``preset="mixtral-tiny"``: sparse-MoE blocks, every expert's
+    FFN columns split over the ranks, router replicated (BASELINE config #4 is this layout on Mixtral-8x7B)."""
     from petals_b200.data_structures import ModelInfo, ServerInfo, ServerState
     from petals_b200.parallel.swarm import Swarm
     from petals_b200.parallel.symmetric import host_barrier, measure_hop_latency, measure_peer_bandwidth
@@ -29,7 +30,7 @@ def tp_selftest(dev: torch.device) -> dict:
     if os.environ.get("TP_SELFTEST_HIDDEN"):  # e.g. 2048: wide enough for the split-K decode path of small QKV shards
         h = int(os.environ["TP_SELFTEST_HIDDEN"])
         overrides.update(hidden_size=h, intermediate_size=2 * h, head_dim=128 if h >= 1024 else 64)
-    path = write_config_only("llama-tiny", overrides)
+    path = write_config_only(preset, overrides)
     config = AutoDistributedConfig.from_pretrained(path)
     n = config.num_hidden_layers
     blocks = random_blocks(config, range(n), dev, seed=3)  # identical on every rank (seeded)
@@ -86,7 +87,7 @@ def tp_selftest(dev: torch.device) -> dict:
         host_barrier()
         heap.close()
     ok = err < 0.05 and agree > 0.9 and err2 < 0.05 and agree2 > 0.9
-    return {"tp_selftest": "ok" if ok else "FAILED", "world": world, "rel_err": round(err, 5), "argmax_agreement": round(agree, 4),
+    return {"tp_selftest": "ok" if ok else "FAILED", "model": preset, "world": world, "rel_err": round(err, 5), "argmax_agreement": round(agree, 4),
                       "prefill_rel_err": round(err2, 5), "prefill_argmax_agreement": round(agree2, 4),
                       "generated": out[0, 8:].tolist(), "peer_store_GBps": bw, "flag_latency_us": lat}
 

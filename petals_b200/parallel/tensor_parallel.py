@@ -38,8 +38,11 @@ MAX_ROWS = 8
 
 def tp_supported(spec: BlockSpec, world: int) -> bool:
     """Layouts the NVLink engine shards itself. Everything else (biases on the projections, ALiBi, fused interleaved QKV, parallel
-    attention, MoE) is split by the generic path (parallel/tp_generic.py) — `shard_block` below carries no bias tensors."""
-    return (spec.mlp in ("swiglu", "gelu") and not spec.parallel_attn and not spec.qkv_interleaved and not spec.post_ln_residual
+    attention) is split by the generic path (parallel/tp_generic.py) — `shard_block` below carries no bias tensors. Sparse-MoE blocks
+    (Mixtral) are sharded along every expert's FFN dimension with the router replicated."""
+    if spec.mlp == "moe" and not (spec.norm == "rms" and 0 < spec.num_experts <= 64 and 0 < spec.top_k <= 8):
+        return False
+    return (spec.mlp in ("swiglu", "gelu", "moe") and not spec.parallel_attn and not spec.qkv_interleaved and not spec.post_ln_residual
             and not (spec.qkv_bias or spec.out_bias or spec.mlp_bias) and not spec.alibi
             and spec.num_kv_heads % world == 0 and spec.num_heads % world == 0 and spec.intermediate_size % (2 * world) == 0
             and spec.head_dim in (64, 128))
@@ -61,10 +64,13 @@ def shard_block(block: GenericBlock, spec: BlockSpec, rank: int, world: int, dev
         "wqkv": torch.cat([w[q0 + rank * hq * D: q0 + (rank + 1) * hq * D], w[k0 + rank * hkv * D: k0 + (rank + 1) * hkv * D],
                            w[v0 + rank * hkv * D: v0 + (rank + 1) * hkv * D]], 0),
         "wo": block.wo[:, rank * hq * D: (rank + 1) * hq * D],
-        "w_down": block.w_down[:, rank * I: (rank + 1) * I],
-        "w_up": block.w_up[rank * I: (rank + 1) * I],
         "ln1_w": block.ln1_w, "ln2_w": block.ln2_w,
     }
+    if spec.mlp == "moe":  # every rank holds 1/world of EVERY expert's FFN columns; the router is replicated
+        out.update(router=block.router, we_gate=block.we_gate[:, rank * I: (rank + 1) * I], we_up=block.we_up[:, rank * I: (rank + 1) * I],
+                   we_down=block.we_down[:, :, rank * I: (rank + 1) * I])
+    else:
+        out.update(w_down=block.w_down[:, rank * I: (rank + 1) * I], w_up=block.w_up[rank * I: (rank + 1) * I])
     if spec.mlp == "swiglu":
         out["w_gate"] = block.w_gate[rank * I: (rank + 1) * I]
     for name in ("ln1_b", "ln2_b"):
@@ -82,9 +88,16 @@ def random_shard(spec: BlockSpec, rank: int, world: int, layer: int, device, see
     def rnd(*shape):
         return (torch.randn(*shape, device=device, dtype=torch.float32, generator=g) * std).to(torch.bfloat16)
 
-    out = {"wqkv": rnd(ls.qkv_dim, H), "wo": rnd(H, ls.num_heads * ls.head_dim), "w_up": rnd(ls.intermediate_size, H),
-           "w_down": rnd(H, ls.intermediate_size), "ln1_w": torch.ones(H, device=device, dtype=torch.bfloat16),
+    out = {"wqkv": rnd(ls.qkv_dim, H), "wo": rnd(H, ls.num_heads * ls.head_dim), "ln1_w": torch.ones(H, device=device, dtype=torch.bfloat16),
            "ln2_w": torch.ones(H, device=device, dtype=torch.bfloat16)}
+    if spec.mlp == "moe":
+        E, I = spec.num_experts, ls.intermediate_size
+        # the router must be IDENTICAL on every rank: its own generator, seeded without the rank
+        gr = torch.Generator(device=device).manual_seed(seed * 1000003 + layer * 64 + 63)
+        out.update(router=(torch.randn(E, H, device=device, dtype=torch.float32, generator=gr) * std).to(torch.bfloat16),
+                   we_gate=rnd(E, I, H), we_up=rnd(E, I, H), we_down=rnd(E, H, I))
+    else:
+        out.update(w_up=rnd(ls.intermediate_size, H), w_down=rnd(H, ls.intermediate_size))
     if spec.mlp == "swiglu":
         out["w_gate"] = rnd(ls.intermediate_size, H)
     if spec.norm == "layer":
@@ -174,6 +187,7 @@ class TPDecodeEngine:
         self.use_chain = os.environ.get("PETALS_B200_CHAIN", "0") != "0"
         self._chain_bar = torch.zeros(max(1, len(self.shards)), 64, dtype=torch.int32, device=dev)  # grid-barrier words per block
         self._split_ctr = torch.zeros(1024, dtype=torch.int32, device=dev)  # split-KV arrival counters (self-resetting)
+        self._moe_bufs: Dict[object, torch.Tensor] = {}  # sparse-MoE scratch (ops/functional.py: moe_decode / moe_prefill)
         self.pos_static = torch.zeros(1, dtype=torch.int32, device=dev)
         self.max_pages = cache.max_pages_per_seq
         self._tables: Dict[int, torch.Tensor] = {}
@@ -288,6 +302,29 @@ class TPDecodeEngine:
             else:
                 k2 = dict(x=attn, w=w["wo"], store_local=False, push_out=[self.parts(self.off_parts_attn, r, me) for r in range(R)],
                           push_flag=[self.flag_attn(r, l) for r in range(R)], done_counter=ctr, error_flag=err)
+            if s.mlp == "moe":
+                # sparse MoE: no single GEMV consumes / produces the all-reduced vectors, so the two halves of the LL all-reduce run as
+                # their own small kernels (csrc/ll_collectives.cu) around the device-routed expert GEMVs (csrc/moe.cu). Every rank sums
+                # the partials in the same order -> bit-identical h1 -> identical routing on every rank.
+                launch(k2)
+                h1 = h[nxt]
+                if ll:
+                    Fn.ll_reduce(cur, ll_attn_in, (L, l), ep, h1, err)
+                else:
+                    native.check(native.lib().pb_reduce_parts(cur.data_ptr(), ptr_array(attn_parts), R, self.flag_attn(me, l), R, ep, h1.data_ptr(),
+                                                              M * H * 2, err, native.stream_ptr()), "reduce_parts")
+                cur, nxt = h1, nxt ^ 1
+                part = Fn.moe_decode(cur, w["ln2_w"], w["router"], w["we_gate"], w["we_up"], w["we_down"], top_k=s.top_k, eps=eps,
+                                     out=self._buf("moe_part", M, H), bufs=self._moe_bufs, add_residual=False)
+                if ll and l + 1 < L:
+                    Fn.ll_push(part, ll_mlp_out, (L, l), ep)
+                else:
+                    native.check(native.lib().pb_push_rows(part.data_ptr(), ptr_array([self.parts(self.off_parts_mlp, r, me) for r in range(R)]),
+                                                           ptr_array([self.flag_mlp(r, l) for r in range(R)]), R, M * H * 2, native.stream_ptr()), "push_rows")
+                if l + 1 < L:
+                    kw1, cur, nxt = k1_kwargs(l + 1, cur, nxt)
+                    launch(kw1)
+                continue
             # K3: [all-reduce tail of attention] + norm + column-parallel gate/up (+SwiGLU)
             k3 = dict(x=cur, norm_weight=w["ln2_w"], norm_bias=w.get("ln2_b"), norm_kind=self.norm_kind, eps=eps, out=act, epoch=ep, x_out=h[nxt],
                       error_flag=err)
@@ -403,13 +440,27 @@ class TPDecodeEngine:
             Fn.norm_reduce_gather(x_res, x_res, parts=my_parts, norm_weight=w["ln2_w"], norm_bias=w.get("ln2_b"), norm_kind=self.norm_kind,
                                   gather_out=gather_xn, gather_flag=[self._p_layer_flag(r, l, 2) for r in range(R)],
                                   wait_flag=self._p_layer_flag(me, l, 1), wait_per_epoch=R, **common)
+            if s.mlp == "moe":
+                # every rank routes ALL rows (replicated router on the gathered norm outputs) through its slice of every expert: device-built
+                # routing plan + grouped tcgen05 GEMMs (ops/functional.py:moe_prefill); the partial rows then go to their owners' slots
+                native.check(native.lib().pb_wait_flag(self._p_layer_flag(me, l, 2), ep, R, 0, err, native.stream_ptr()), "wait_flag")
+                part = Fn.moe_prefill(xn, None, w["router"], w["we_gate"], w["we_up"], w["we_down"], top_k=s.top_k, eps=eps,
+                                      out=self._buf("p_moe_part", M, H), bufs=self._moe_bufs, add_residual=False)
+                for r in range(R):
+                    rows = max(0, min(mo, M - r * mo))
+                    Fn.norm_reduce_gather(part[r * mo: r * mo + rows] if rows else part[:0], None, rows=rows, H=H, norm_kind=Fn.NORM_NONE,
+                                          gather_out=[push_parts[r]], gather_flag=[self._p_layer_flag(r, l, 3)], done_counter=ctr, error_flag=err,
+                                          device_index=dev)
             kw = dict(out=act, wait_flag=self._p_layer_flag(me, l, 2), wait_per_epoch=R, epoch=ep, error_flag=err)
-            if s.mlp == "swiglu":
+            if s.mlp == "moe":
+                pass
+            elif s.mlp == "swiglu":
                 Fn.gemm(xn, w["w_gate"], b2=w["w_up"], act=Fn.ACT_SWIGLU, **kw)
             else:
                 Fn.gemm(xn, w["w_up"], act=self.act, **kw)
-            Fn.gemm(act, w["w_down"], store_local=False, push_out=push_parts, push_rows_per_owner=mo,
-                    push_done_flag=[self._p_layer_flag(r, l, 3) for r in range(R)], done_counter=ctr, error_flag=err)
+            if s.mlp != "moe":
+                Fn.gemm(act, w["w_down"], store_local=False, push_out=push_parts, push_rows_per_owner=mo,
+                        push_done_flag=[self._p_layer_flag(r, l, 3) for r in range(R)], done_counter=ctr, error_flag=err)
             if l + 1 < L:
                 wn = self.shards[l + 1]
                 Fn.norm_reduce_gather(x_res, x_res, parts=my_parts, norm_weight=wn["ln1_w"], norm_bias=wn.get("ln1_b"), norm_kind=self.norm_kind,
@@ -494,6 +545,11 @@ class TPDecodeEngine:
             self._buf("po", splits * M * ls.num_heads, ls.head_dim, torch.float32), self._buf("pl", splits, M * ls.num_heads, torch.float32)
         scratch = torch.zeros(M, H, dtype=torch.bfloat16, device=self.device)
         Fn.linear_decode(attn, w["wo"], out=scratch)
+        if s.mlp == "moe":
+            Fn.moe_decode(x, w["ln2_w"], w["router"], w["we_gate"], w["we_up"], w["we_down"], top_k=s.top_k, eps=s.norm_eps,
+                          out=self._buf("moe_part", M, H), bufs=self._moe_bufs, add_residual=False)
+            torch.cuda.synchronize(self.device)
+            return
         if s.mlp == "swiglu":
             Fn.linear_decode(x, w["w_gate"], w2=w["w_up"], act=Fn.ACT_SWIGLU, norm_weight=w["ln2_w"], norm_kind=self.norm_kind, eps=s.norm_eps,
                              out=act, parts=[scratch], x_out=self._buf("h_b", M, H))

@@ -17,7 +17,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=dev)
-    report = tp_selftest(dev)
+    report = tp_selftest(dev, os.environ.get("TP_SELFTEST_MODEL", "llama-tiny"))
     if report:
         print(json.dumps(report))
     dist.destroy_process_group()
