@@ -43,7 +43,7 @@ def main() -> None:
     ap.add_argument("--model", default="llama-3-70b")
     ap.add_argument("--seq-len", type=int, default=2048, help="session max_length (reference benchmark default)")
     ap.add_argument("--prompt-len", type=int, default=128)
-    ap.add_argument("--parallelism", default="auto", help="auto | ppN | tpN")
+    ap.add_argument("--parallelism", default="auto", help="auto | ppN | tpN | ppSxtpT (S pipeline stages of T-way tensor-parallel groups, S*T = --gpus)")
     ap.add_argument("--prefill-seq", type=int, default=4096)
     ap.add_argument("--prefill-batch", type=int, default=8)
     ap.add_argument("--prefill-steps", type=int, default=2)

@@ -202,6 +202,9 @@ int pb_moe_plan(const void* topi, int pairs, int E, void* pos, void* table, int 
 int pb_moe_gather(const void* x, const void* pos, void* out, int pairs, int H, int topk, void* stream);
 int pb_moe_combine_pos(const void* y, const void* topw, const void* pos, const void* residual, void* out, int M, int H, int topk, void* stream);
 
+// 2-CTA variant (gemm_tcgen05_2cta.cu): plain K-major GEMMs with optional SwiGLU / residual; PB_ERR_UNSUPPORTED for anything else
+int pb_gemm_bf16_2cta(const PbGemmArgs* args, void* stream);
+
 // ---- block-scaled FP8 GEMM (gemm_mxfp8.cu): both operands MXFP8 (E4M3 payload + UE8M0 scale per 32 values along K) -------------
 // Scale arrays use the tensor cores' block layout: [K / 128][ceil(rows / 128)][512 B], scale of (row r, K slice c) of a block at
 // (r % 32) * 16 + (r / 32) * 4 + c  (ops/quant.py:pack_scales; pb_quant_mxfp8 writes it for activations).

@@ -295,8 +295,22 @@ def gemm(
     g.num_sms = native.sm_count(a_.device.index)
     g.block_n = block_n
     g.grp, g.grp_cap, g.grp_experts = ptr(grp), grp_cap, grp_experts
+    if (_GEMM_2CTA and M >= 1024 and N >= 1024 and block_n == 0 and not b_mn_major and not push_out and not wait_flag and grp is None
+            and bias is None and bias2 is None and not out_fp32 and act in (ACT_NONE, ACT_SWIGLU)):
+        # large plain GEMMs: one 256 x 256 tile per SM pair (csrc/gemm_tcgen05_2cta.cu): each SM stages only half of the weight tile
+        check(native.lib().pb_gemm_bf16_2cta(C.byref(g), stream_ptr()), "gemm_bf16_2cta")
+        return out
     check(native.lib().pb_gemm_bf16(C.byref(g), stream_ptr()), "gemm_bf16")
     return out
+
+
+_GEMM_2CTA = os.environ.get("PETALS_B200_GEMM_2CTA", "0") != "0"
+
+
+def set_gemm_2cta(on: bool) -> None:
+    """Route large plain GEMMs to the 2-CTA (cta_group::2) kernel (tests and tools/kernel_bench.py flip it)."""
+    global _GEMM_2CTA
+    _GEMM_2CTA = bool(on)
 
 
 # ----------------------------------------------------------------------------------------------------

@@ -207,6 +207,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.pb_moe_combine_pos.argtypes = [vp, vp, vp, vp, vp, ci, ci, ci, vp]
     for name in ("pb_moe_router", "pb_moe_gemv", "pb_moe_combine", "pb_moe_plan", "pb_moe_gather", "pb_moe_combine_pos"):
         getattr(lib, name).restype = ci
+    lib.pb_gemm_bf16_2cta.argtypes = [C.POINTER(GemmArgs), vp]
+    lib.pb_gemm_bf16_2cta.restype = ci
     lib.pb_ll_reduce.argtypes = [vp, vpp, ci, vp, C.c_uint, C.c_uint, vp, cl, vp, vp]
     lib.pb_ll_push.argtypes = [vp, vpp, ci, vp, C.c_uint, C.c_uint, cl, vp]
     lib.pb_ll_reduce.restype = lib.pb_ll_push.restype = ci

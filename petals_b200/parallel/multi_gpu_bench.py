@@ -45,7 +45,150 @@ def _selftests_ok(reports: dict) -> bool:
     return bool(reports.get("skipped")) or all(r.get(f"{k}_selftest") == "ok" for k, r in reports.items())
 
 
+def run_pp_tp(args, n_stages: int, tp: int) -> None:
+    """``bench.py --parallelism pp<S>xtp<T>`` (S * T = N GPUs): a pipeline of S stages, each stage a tensor-parallel group of T GPUs —
+    BASELINE.json config #4 names this layout for Mixtral-8x7B (4 stages x TP 2). Ranks [gT, (g+1)T) form group g and serve blocks
+    [bounds[g], bounds[g+1]); the group's first rank is its leader (stage process: handler, KV bookkeeping, command ring to the
+    followers), the client runs on rank 0. Inside a group everything is the tensor-parallel engine (NVLink LL all-reduces, sequence-
+    parallel prefill); between stages the activations of one token (hidden_size x 2 bytes) travel with the stage-to-stage RPC."""
+    import tempfile
+
+    from petals_b200.data_structures import ModelInfo, ServerInfo, ServerState
+    from petals_b200.ops import native
+    from petals_b200.parallel.swarm import FileSwarm
+    from petals_b200.parallel.tp_worker import TPLeaderEngine, build_tp_engine, follower_loop, make_ring
+    from petals_b200.server.backend import Stage
+    from petals_b200.server.server import ModuleContainer
+    from petals_b200.utils.auto_config import AutoDistributedConfig
+    from petals_b200.utils.peaks import measured_peaks
+    from petals_b200.utils.random_model import MODEL_PRESETS, random_client_model, write_config_only
+    import petals_b200
+
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    if n_stages * tp != world:
+        raise SystemExit(f"--parallelism pp{n_stages}xtp{tp} needs {n_stages * tp} GPUs, the job has {world}")
+    os.environ.setdefault("PETALS_B200_SYMM_MEM", "0")  # heaps of sub-groups: plain CUDA IPC (pairs do not need the multicast mapping)
+    local_rank = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=dev)
+    native.lib()
+    groups = [dist.new_group(list(range(g * tp, (g + 1) * tp)), backend="cpu:gloo,cuda:nccl") for g in range(n_stages)]  # collective: every rank, every group
+    g, grank = rank // tp, rank % tp
+    group = groups[g]
+    path = write_config_only(args.model)
+    config = AutoDistributedConfig.from_pretrained(path)
+    n_layers = MODEL_PRESETS[args.model]["num_hidden_layers"]
+    bounds = [round(i * n_layers / n_stages) for i in range(n_stages + 1)]
+    n_mine = bounds[g + 1] - bounds[g]
+    do_prefill = not args.skip_prefill
+    PB, PT = args.prefill_batch, args.prefill_seq
+    max_len = max(args.seq_len, PT) if do_prefill else args.seq_len
+    t0 = time.time()
+    engine, cache, heap = build_tp_engine(config, n_mine, group=group, seed=g + 1, attn_cache_tokens=(max(args.seq_len, PB * PT) if do_prefill else args.seq_len) + 512,
+                                          inference_max_length=max_len, max_prefill_rows=args.tp_prefill_rows)
+    ring = make_ring(group)
+    dirs = [tempfile.mkdtemp(prefix="pb200-pptp-") if rank == 0 else None]
+    dist.broadcast_object_list(dirs, src=0)
+    build_s = time.time() - t0
+    if grank != 0:
+        follower_loop(engine, cache, ring, grank - 1)
+        host_barrier()
+        heap.close()
+        dist.destroy_process_group()
+        return
+    swarm = FileSwarm(dirs[0])
+    leader = TPLeaderEngine(engine, ring)
+    stage = Stage(config, [torch.nn.Identity() for _ in range(n_mine)], bounds[g], device=dev, memory_cache=cache, torch_dtype=torch.bfloat16, engine=leader)
+    info = ServerInfo(state=ServerState.JOINING, throughput=1.0, version=petals_b200.__version__, torch_dtype="bfloat16", quant_type="none", using_relay=False)
+    container = ModuleContainer.from_stage(dht=swarm, dht_prefix=config.dht_prefix, block_config=config, stage=stage, server_info=info,
+                                           model_info=ModelInfo(num_blocks=n_layers, repository=path), peer_id=f"stage{g}-tp{tp}", inference_max_length=max_len)
+    result = None
+    if rank == 0:
+        K, W = args.steps, max(args.warmup, 3)
+        peaks = measured_peaks()
+        model = random_client_model(path, swarm, dev, max_retries=60, min_backoff=0.5, max_backoff=1.0)
+        model.model.layers.sequence_manager.update(wait=True)
+        vocab = model.config.vocab_size
+        spec = config.block_spec()
+        prompt = torch.randint(0, vocab, (1, args.prompt_len), device=dev)
+        with torch.inference_mode(), model.inference_session(max_length=args.seq_len) as sess:
+            prime_session(model, sess, prompt, W)
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            ms, launches = device_timed_decode(model, sess, K)
+            clocks = sampler.stop()
+            e2e_s, h2d, d2h = e2e_decode(model, sess, K, dev)
+            stages_used = [s_.span.peer_id for s_ in sess._server_sessions]
+        engine.check_errors()
+        value = K / (ms / 1e3)
+        prefill = None
+        if do_prefill:
+            try:
+                ids = torch.randint(0, vocab, (PB, PT), device=dev)
+                with torch.inference_mode():
+                    model.model(input_ids=ids)
+                    torch.cuda.synchronize()
+                    ps, pe = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ps.record()
+                    for _ in range(args.prefill_steps):
+                        model.model(input_ids=ids)
+                    pe.record()
+                    torch.cuda.synchronize()
+                pms = ps.elapsed_time(pe) / args.prefill_steps
+                flops = 2.0 * spec.active_params() * n_layers * PB * PT + 4.0 * n_layers * PB * PT * PT * spec.num_heads * spec.head_dim / 2
+                prefill = {"tokens_per_s": round(PB * PT / (pms / 1e3), 1), "ms_per_step": round(pms, 2), "batch": PB, "seq_len": PT,
+                           "TFLOPs_total": round(flops / pms / 1e9, 1),
+                           "path": "micro-batches of <= 1024 tokens as a wavefront over the stages (client/sequential_autograd.py); sequence-parallel tcgen05 GEMMs inside a stage"}
+            except Exception as e:  # noqa: BLE001
+                prefill = {"error": repr(e)[:300]}
+        weight_bytes_rank = (spec.active_params() * n_layers) * 2 / world
+        result = {
+            "metric": metric_name(args.model), "value": round(value, 3), "unit": "tokens/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": round(value / BASELINE_TOKENS_PER_S, 3),
+            "dtype": "bf16", "data": "synthetic token ids; random-init weights of the named architecture",
+            "config": {"model": args.model, "global_batch": 1, "seq_len": args.seq_len, "parallelism": f"pp{n_stages}xtp{tp}",
+                       "layout": f"{n_stages} pipeline stages x tensor-parallel groups of {tp} GPUs; blocks per stage {[bounds[i + 1] - bounds[i] for i in range(n_stages)]}",
+                       "stages": stages_used, "build_s": round(build_s, 1),
+                       "l2": "each step streams every rank's full weight shard (>> 126 MB L2): inputs larger than L2",
+                       "timing": "CUDA events on rank 0 (client + leader of the first stage), which receives every token from the last stage before the next step starts"},
+            "clocks": clocks,
+            "e2e": {"value": round(K / e2e_s, 3), "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "model.generate(max_new_tokens=1, session=sess) per step; token in from pinned host memory, token out to the host"},
+            "gpu_launches": launches, "prefill": prefill,
+            "roofline": {"weight_bytes_per_token_per_rank": int(weight_bytes_rank), "note": "single stream: one stage (T ranks) works at a time",
+                         "frac_of_measured_hbm_while_active": round(weight_bytes_rank * n_stages * value / 1e9 / peaks["hbm_gbs"], 3)},
+        }
+    host_barrier_leaders(n_stages, tp)
+    leader.shutdown()
+    container.shutdown()
+    host_barrier()
+    heap.close()
+    if result is not None:
+        print(json.dumps(result))
+    dist.destroy_process_group()
+
+
+def host_barrier_leaders(n_stages: int, tp: int) -> None:
+    """Leaders wait here until the client (rank 0) is done with every stage; followers are parked in their command loops and reach
+    the world barrier only after their leader's shutdown, so this is a file-free rendezvous over the store: a tiny all-gather among
+    the leaders would need its own group created collectively — the TCP store of the default group is enough."""
+    store = dist.distributed_c10d._get_default_store()
+    store.add("pb200_pptp_leaders_done", 1)
+    import time as _t
+
+    deadline = _t.time() + 3600
+    while int(store.add("pb200_pptp_leaders_done", 0)) < n_stages:
+        if _t.time() > deadline:
+            raise TimeoutError("leaders of the other stages never finished")
+        _t.sleep(0.05)
+
+
 def run_multi_gpu(args) -> None:
+    par = str(args.parallelism)
+    if par.startswith("pp") and "xtp" in par:
+        s_, t_ = par[2:].split("xtp")
+        return run_pp_tp(args, int(s_), int(t_))
     if str(args.parallelism).startswith("pp"):
         return run_pipeline(args)
     from petals_b200.data_structures import ModelInfo, ServerInfo, ServerState

@@ -230,7 +230,7 @@ def make_ring(group=None, n_followers: Optional[int] = None) -> CommandRing:
     if rank == 0:
         ring = CommandRing(None, create=True, n_consumers=(world - 1) if n_followers is None else n_followers)
         names[0] = ring.name
-    dist.broadcast_object_list(names, src=0, group=group)
+    dist.broadcast_object_list(names, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
     if rank != 0:
         ring = CommandRing(names[0], create=False)
     host_barrier(group)

@@ -84,6 +84,26 @@ def test_gemm_plain(M, N, K):
     _close(got, Fn.linear_ref(a, b), 2e-2, 2e-2, f"gemm {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("M,N,K", [(1024, 1024, 512), (1100, 2048 + 64, 1024), (4096, 8192, 1024), (2048, 1280, 8192)])
+def test_gemm_2cta_matches_the_1cta_kernel(M, N, K):
+    """csrc/gemm_tcgen05_2cta.cu (tcgen05.mma.cta_group::2: one 256 x 256 tile per SM pair): same products and the same fp32
+    accumulation order per output as the 1-CTA kernel, so the results must agree to the bf16 rounding of the output — plain, with the
+    residual epilogue, and with the SwiGLU epilogue (gate rows staged by the even CTA, up rows by the odd one). Ragged M and N tails."""
+    torch.manual_seed(55)
+    a, b, b2, res = _rand(M, K), _rand(N, K, scale=K ** -0.5), _rand(N, K, scale=K ** -0.5), _rand(M, N)
+    try:
+        Fn.set_gemm_2cta(False)
+        want = [Fn.gemm(a, b), Fn.gemm(a, b, residual=res), Fn.gemm(a, b, b2=b2, act=Fn.ACT_SWIGLU)]
+        Fn.set_gemm_2cta(True)
+        got = [Fn.gemm(a, b), Fn.gemm(a, b, residual=res), Fn.gemm(a, b, b2=b2, act=Fn.ACT_SWIGLU)]
+    finally:
+        Fn.set_gemm_2cta(False)
+    _close(got[0], Fn.linear_ref(a, b), 2e-2, 2e-2, f"2cta gemm {M}x{N}x{K}")
+    for g, w, what in zip(got, want, ("plain", "residual", "swiglu")):
+        assert (g.float() - w.float()).abs().max().item() <= 2e-2 * w.float().abs().max().item(), what
+        assert (g.float() - w.float()).abs().mean().item() <= 2e-3 * w.float().abs().mean().item() + 1e-6, what
+
+
 @pytest.mark.parametrize("bn", [64, 128, 256])
 def test_gemm_block_n(bn):
     torch.manual_seed(6)

@@ -191,6 +191,41 @@ def bench_gemv_fp8(results, peaks):
             del qs, q2s
 
 
+def bench_gemm_2cta(results, peaks):
+    """1-CTA vs 2-CTA (cta_group::2) tcgen05 GEMM vs cuBLAS on the 70B prefill shapes."""
+    shapes = [("70b.qkv", 8192, 10240, 8192, {}), ("70b.o", 8192, 8192, 8192, dict(residual=True)), ("70b.gate_up", 8192, 28672, 8192, dict(dual=True)),
+              ("70b.down", 8192, 8192, 28672, dict(residual=True)), ("8b.qkv", 8192, 6144, 4096, {}), ("sq4096", 4096, 4096, 4096, {})]
+    for name, M, N, K, opt in shapes:
+        nbuf = 2
+        As = [torch.randn(M, K, device="cuda", dtype=torch.bfloat16) for _ in range(nbuf)]
+        Bs = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * K ** -0.5 for _ in range(nbuf)]
+        B2 = [torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * K ** -0.5 for _ in range(nbuf)] if opt.get("dual") else None
+        res = torch.randn(M, N, device="cuda", dtype=torch.bfloat16) if opt.get("residual") else None
+        out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+
+        def mk(i):
+            kw = dict(out=out)
+            if opt.get("dual"):
+                kw.update(b2=B2[i], act=Fn.ACT_SWIGLU)
+            if res is not None:
+                kw.update(residual=res)
+            return lambda: Fn.gemm(As[i], Bs[i], **kw)
+
+        flops = 2.0 * M * N * K * (2 if opt.get("dual") else 1)
+        ms = {}
+        for on in (False, True):
+            Fn.set_gemm_2cta(on)
+            ms[on] = time_fn([mk(i) for i in range(nbuf)], iters=10)
+        Fn.set_gemm_2cta(False)
+        ref_ms = time_fn([(lambda i=i: torch.matmul(As[i], Bs[i].T)) for i in range(nbuf)], iters=10) * (2 if opt.get("dual") else 1)
+        row = dict(kernel="gemm_tcgen05_2cta", shape=name, M=M, N=N, K=K, ms_1cta=ms[False], ms_2cta=ms[True], TFLOPs_1cta=flops / ms[False] / 1e9,
+                   TFLOPs_2cta=flops / ms[True] / 1e9, cublas_TFLOPs=flops / ref_ms / 1e9)
+        results.append(row)
+        print(f"gemm2 {name:12s} {M}x{N}x{K}  1-CTA {ms[False]:7.3f} ms {row['TFLOPs_1cta']:6.0f} TFLOP/s | 2-CTA {ms[True]:7.3f} ms {row['TFLOPs_2cta']:6.0f} TFLOP/s | "
+              f"cuBLAS {row['cublas_TFLOPs']:6.0f} | 2-CTA / cuBLAS {row['TFLOPs_2cta'] / row['cublas_TFLOPs']:.2f}", flush=True)
+        del As, Bs, B2
+
+
 def bench_gemm_fp8(results, peaks):
     """Block-scaled MXFP8 GEMM (tcgen05.mma kind::mxf8f6f4.block_scale) on the 70B prefill shapes, the bf16 tcgen05 GEMM alongside;
     the activation quantiser (what the fp8 path pays extra per projection) is timed separately."""
@@ -244,6 +279,8 @@ def main():
         bench_gemv(results, peaks)
     if args.only in ("", "gemm"):
         bench_gemm(results, peaks)
+    if args.only in ("", "gemm_2cta"):
+        bench_gemm_2cta(results, peaks)
     if args.only in ("", "gemm_fp8"):
         bench_gemm_fp8(results, peaks)
     os.makedirs("gpurun_out", exist_ok=True)

@@ -3,7 +3,8 @@
 
 For every selected kernel: `profiles/sass/<name>.sass` = its instruction stream (addresses + mnemonics + operands, encodings
 stripped) and one line in `profiles/sass/INDEX.md` with the register count and the counts of the mnemonics that matter
-(UTC*MMA = tcgen05.mma, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG/UBLKCP = TMA, HMMA = mma.sync, MULTIMEM, SYNCS = mbarrier,
+(UTC*MMA = tcgen05.mma (UTCQMMA = block-scaled FP8), UTCCP = tcgen05.cp, LDTM/STTM = tcgen05.ld/st, UTMALDG/UTMASTG/UBLKCP = TMA, UCGABAR = cluster
+barrier, HMMA = mma.sync, LDGMC = multimem.ld_reduce (multimem.st lowers to a plain STG on the multicast address), SYNCS = mbarrier,
 ACQBULK/PREEXIT = programmatic dependent launch). Runs on the CPU-only box: `python tools/sass_listing.py`."""
 import collections
 import os
@@ -19,11 +20,12 @@ SELECT = {
     "gemm_tcgen05.o": ["gemm_tcgen05_kernelILi256ELb0ELb0", "gemm_tcgen05_kernelILi256ELb1ELb0"], "attention_tc.o": ["attn_fwd_tc_kernelILi128"], "attention.o": ["attn_fwd_kernelILi128"],
     "attention_bwd.o": ["attn_bwd_dq_kernelILi128", "attn_bwd_dkdv_kernelILi128"], "decode_span.o": ["decode_span_kernel"],
     "linear_decode.o": ["linear_decode_kernelILi1ELb1ELb1ELb0ELb0", "linear_decode_kernelILi1ELb0ELb1ELb1ELb0"],
-    "linear_decode_fp8.o": ["linear_decode_fp8"], "linear_decode_mma.o": ["linear_decode_mma"], "moe.o": ["moe_gemv", "moe_router"],
-    "seq_parallel.o": ["norm_reduce_gather"], "train_kernels.o": ["rmsnorm_bwd_kernelILi4", "swiglu_bwd"], "gemm_fp8.o": ["gemm_mxfp8"],
+    "linear_decode_fp8.o": ["linear_decode_fp8"], "linear_decode_mma.o": ["linear_decode_mma"], "moe.o": ["moe_gemv", "moe_router", "moe_plan"],
+    "seq_parallel.o": ["norm_reduce_gather"], "train_kernels.o": ["rmsnorm_bwd_kernelILi4", "swiglu_bwd"], "gemm_mxfp8.o": ["gemm_mxfp8_kernelILb0", "gemm_mxfp8_kernelILb1", "quant_mxfp8"],
+    "gemm_tcgen05_2cta.o": ["gemm_2cta_kernelILb0"], "ll_collectives.o": ["ll_reduce", "ll_push"],
     "elementwise.o": ["norm_kernel"], "rope_kv.o": ["rope_kv_kernel"], "ipc.o": ["push_rows"],
 }
-KEY = ["UTCHMMA", "UTCQMMA", "UTCOMMA", "UTCMXQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCCP", "UTCBAR", "HMMA", "MULTIMEM", "SYNCS", "LDGSTS",
+KEY = ["UTCHMMA", "UTCQMMA", "UTCOMMA", "UTCMXQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTCCP", "UTCBAR", "UCGABAR_ARV", "HMMA", "MULTIMEM", "LDGMC", "SYNCS", "LDGSTS",
        "ACQBULK", "PREEXIT", "LDG", "STG", "LDS", "STS", "FFMA", "BAR"]
 
 
