@@ -28,3 +28,23 @@ def test_defaults_follow_the_timing_rules():
     assert 'add_argument("--gpus", type=int, default=1)' in src
     assert 'add_argument("--warmup", type=int, default=4)' in src and "args.warmup < 3" in src
     assert callable(bench.main) and callable(bench.reference_arm)
+
+
+def test_a_failed_selftest_invalidates_a_multi_gpu_line():
+    """parallel/multi_gpu_bench.py: every multi-GPU bench job runs the TP / pipeline numerics self-tests first; a report that is not
+    "ok" (or a self-test that raised) marks the JSON line invalid and fails the run; --skip-selftests is the only way around."""
+    from petals_b200.parallel.multi_gpu_bench import _selftests_ok
+
+    assert _selftests_ok({"skipped": True})
+    assert _selftests_ok({"tp": {"tp_selftest": "ok"}, "pp": {"pp_selftest": "ok", "world": 8}})
+    assert not _selftests_ok({"tp": {"tp_selftest": "ok"}, "pp": {"pp_selftest": "FAILED"}})
+    assert not _selftests_ok({"tp": {"tp_selftest": "FAILED", "error": "RuntimeError(...)"}})
+    assert not _selftests_ok({"tp": {}})  # a rank-0 report must exist
+
+
+def test_bench_accepts_the_pipeline_of_tp_groups_layout():
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--help"], capture_output=True, text=True, cwd=ROOT).stdout
+    assert "ppSxtpT" in out and "--skip-selftests" in out and "--skip-pipeline" in out

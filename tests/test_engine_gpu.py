@@ -20,7 +20,7 @@ def _oracle_logits(model, stage, ids):
     return model.lm_head(model.model.final_norm(h))
 
 
-@pytest.mark.parametrize("preset,overrides", [
+PRESETS = [
     ("llama-tiny", {}),
     ("llama-tiny", dict(num_attention_heads=16, num_key_value_heads=16, hidden_size=1024)),  # MHA, D=64
     ("bloom-560m", dict(n_layer=3, vocab_size=4096)),
@@ -28,7 +28,10 @@ def _oracle_logits(model, stage, ids):
     ("falcon-tiny-7b", {}),   # multi-query, parallel attention, one LayerNorm (reference GPU test: tests/test_optimized_layers.py:187-224)
     ("falcon-tiny-40b", {}),  # new decoder architecture: grouped KV with interleaved fused QKV, two parallel LayerNorms
     ("falcon-tiny-rw", {}),   # ALiBi, sequential blocks, biases, per-head interleaved QKV
-])
+]
+
+
+@pytest.mark.parametrize("preset,overrides", PRESETS)
 def test_session_matches_oracle(preset, overrides, tmp_path):
     path = write_config_only(preset, overrides, str(tmp_path / "m"))
     swarm = Swarm(f"t-{preset}-{len(overrides)}")
