@@ -36,6 +36,7 @@ extern "C" int pb_set_error(const char* msg);
 namespace pb {
 
 bool make_tmap_2d_u8(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols);
+bool make_tmap_sf_blocks(CUtensorMap* m, const void* base, uint64_t blocks, uint32_t box_rows);
 
 namespace f8 {
 
@@ -101,6 +102,64 @@ PB_DEVICE void tile_coords(int tile, int m_blocks, int n_blocks, int& m_blk, int
   const int r = tile - g * per_group;
   m_blk = first_m + r % gsize;
   n_blk = r / gsize;
+}
+
+// One warp's share of a finished accumulator tile: 32 rows (this lane = one row) x OUT_BN columns, 32 columns at a time.
+template <bool DUAL>
+PB_DEVICE void epilogue_rows(const Params& p, uint32_t taddr, int row, bool row_ok, int n_blk) {
+  constexpr int OUT_BN = DUAL ? BN / 2 : BN;
+#pragma unroll 1
+  for (int c = 0; c < OUT_BN; c += 32) {
+    const int col0 = n_blk * OUT_BN + c;
+    if (col0 >= p.N) break;  // warp-uniform
+    uint32_t r[32];
+    float v[32];
+    tmem_ld_32x32(taddr + c, r);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+    if (DUAL) {
+      uint32_t r2[32];
+      tmem_ld_32x32(taddr + OUT_BN + c, r2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = round_bf16(silu_f(round_bf16(v[i]))) * round_bf16(__uint_as_float(r2[i]));
+    }
+    if (row_ok) {
+      const bool full = col0 + 32 <= p.N;
+      if (p.residual != nullptr) {
+        const __nv_bfloat16* rp = p.residual + static_cast<size_t>(row) * p.ldres + col0;
+        if (full) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(rp + q * 8);
+            const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              v[q * 8 + 2 * j] = round_bf16(v[q * 8 + 2 * j]) + bf16_lo(w[j]);
+              v[q * 8 + 2 * j + 1] = round_bf16(v[q * 8 + 2 * j + 1]) + bf16_hi(w[j]);
+            }
+          }
+        } else {
+          for (int i = 0; i < 32 && col0 + i < p.N; ++i) v[i] = round_bf16(v[i]) + __bfloat162float(rp[i]);
+        }
+      }
+      __nv_bfloat16* op = p.out + static_cast<size_t>(row) * p.ldo + col0;
+      if (full) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 pk;
+          pk.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+          pk.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+          pk.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+          pk.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+          reinterpret_cast<uint4*>(op)[q] = pk;
+        }
+      } else {
+        for (int i = 0; i < 32 && col0 + i < p.N; ++i) op[i] = __float2bfloat16_rn(v[i]);
+      }
+    }
+  }
 }
 
 // DUAL: the B tile is 128 rows of `b` (gate) + 128 rows of `b2` (up); the epilogue emits silu(gate) * up, 128 columns per tile.
@@ -219,58 +278,7 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int row = m_blk * BM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < OUT_BN; c += 32) {
-        const int col0 = n_blk * OUT_BN + c;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        float v[32];
-        tmem_ld_32x32(taddr + c, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-        if (DUAL) {
-          uint32_t r2[32];
-          tmem_ld_32x32(taddr + OUT_BN + c, r2);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = round_bf16(silu_f(round_bf16(v[i]))) * round_bf16(__uint_as_float(r2[i]));
-        }
-        if (row_ok) {
-          const bool full = col0 + 32 <= p.N;
-          if (p.residual != nullptr) {
-            const __nv_bfloat16* rp = p.residual + static_cast<size_t>(row) * p.ldres + col0;
-            if (full) {
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const uint4 rv = *reinterpret_cast<const uint4*>(rp + q * 8);
-                const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  v[q * 8 + 2 * j] = round_bf16(v[q * 8 + 2 * j]) + bf16_lo(w[j]);
-                  v[q * 8 + 2 * j + 1] = round_bf16(v[q * 8 + 2 * j + 1]) + bf16_hi(w[j]);
-                }
-              }
-            } else {
-              for (int i = 0; i < 32 && col0 + i < p.N; ++i) v[i] = round_bf16(v[i]) + __bfloat162float(rp[i]);
-            }
-          }
-          __nv_bfloat16* op = p.out + static_cast<size_t>(row) * p.ldo + col0;
-          if (full) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 pk;
-              pk.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
-              pk.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
-              pk.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
-              pk.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
-              reinterpret_cast<uint4*>(op)[q] = pk;
-            }
-          } else {
-            for (int i = 0; i < 32 && col0 + i < p.N; ++i) op[i] = __float2bfloat16_rn(v[i]);
-          }
-        }
-      }
+      epilogue_rows<DUAL>(p, taddr, row, row_ok, n_blk);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tmem_empty);
@@ -284,6 +292,181 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
+
+// ---- 2-CTA variant: one 256 x 256 tile per SM pair (tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale) -----------------------------
+// Same idea as gemm_tcgen05_2cta.cu: each CTA stages its own 128 rows of A and HALF of the B tile, so the operand stream per SM drops
+// from 48 KB to 32 KB per K block — this kernel is L2 -> SM bound at the FP8 math rate. Scale factors: each SM's tensor core needs the
+// scales of its own 128 A rows and of ALL 256 B rows, so both CTAs load the same two B blocks; `tcgen05.cp.cta_group::2` copies each
+// CTA's shared-memory blocks into that CTA's tensor memory. All loads are tensor-map TMA with `.cta_group::2` (completion bytes counted on
+// the leader's barrier); the scale array is addressed as [blocks, 128] 32-bit words.
+namespace pair {
+
+constexpr int STAGES = 6;
+constexpr int A2_BYTES = BM * BK, B2_BYTES = (BN / 2) * BK, STAGE2_BYTES = A2_BYTES + B2_BYTES;   // 16 KB + 16 KB
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+
+PB_DEVICE uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+PB_DEVICE void cluster_sync() { asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+PB_DEVICE void tma_pair(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1)
+      : "memory");
+}
+PB_DEVICE void tc_cp_sf_pair(uint32_t tmem_dst, uint64_t desc) {
+  asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(tmem_dst), "l"(desc) : "memory");
+}
+PB_DEVICE void tc_mma_mxf8_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate, uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+PB_DEVICE void tc_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+PB_DEVICE void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+
+template <bool DUAL>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_mxfp8_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b2,
+                       const __grid_constant__ CUtensorMap tmap_sfa, const __grid_constant__ CUtensorMap tmap_sfb, const __grid_constant__ CUtensorMap tmap_sfb2,
+                       const Params p) {
+  constexpr int OUT_BN = DUAL ? BN / 2 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sf_smem = smem + STAGES * STAGE2_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sf_smem + STAGES * SF_STAGE);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = cta == 0;
+  const int m_pairs = (p.M + 2 * BM - 1) / (2 * BM);
+  const int n_blocks = (p.N + OUT_BN - 1) / OUT_BN;
+  const int num_tiles = m_pairs * n_blocks;
+  const int num_kb = p.K / BK;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmap_a); prefetch_tmap(&tmap_b); prefetch_tmap(&tmap_sfa); prefetch_tmap(&tmap_sfb);
+    if (DUAL) { prefetch_tmap(&tmap_b2); prefetch_tmap(&tmap_sfb2); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 8);   // 4 epilogue warps x 2 CTAs, on the leader's copy
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        const int m_pair = tile % m_pairs, n_blk = tile / m_pairs;   // M fastest: the 74 concurrent pairs share few weight tiles
+        const int m_blk = m_pair * 2 + static_cast<int>(cta);        // this CTA's 128-row block of A
+        const int nb0 = DUAL ? n_blk : 2 * n_blk;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE2_BYTES;
+          uint8_t* sb = sa + A2_BYTES;
+          uint8_t* ss = sf_smem + stage * SF_STAGE;
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * (STAGE2_BYTES + SF_STAGE));
+          tma_pair(sa, &tmap_a, &full_bar[stage], kb * BK, m_blk * BM);
+          if (!DUAL) {
+            tma_pair(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN + static_cast<int>(cta) * (BN / 2));
+          } else {
+            tma_pair(sb, leader ? &tmap_b : &tmap_b2, &full_bar[stage], kb * BK, n_blk * OUT_BN);
+          }
+          tma_pair(ss, &tmap_sfa, &full_bar[stage], 0, kb * p.sfa_blocks + m_blk);
+          if (!DUAL) {
+            tma_pair(ss + SF_BLOCK, &tmap_sfb, &full_bar[stage], 0, kb * p.sfb_blocks + nb0);   // box of 2 blocks (the 2nd is zero-filled / unused past the end)
+          } else {
+            tma_pair(ss + SF_BLOCK, &tmap_sfb, &full_bar[stage], 0, kb * p.sfb_blocks + nb0);
+            tma_pair(ss + 2 * SF_BLOCK, &tmap_sfb2, &full_bar[stage], 0, kb * p.sfb_blocks + nb0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
+        mbar_wait(tmem_empty, (it & 1) ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE2_BYTES);
+          const uint32_t sb = sa + A2_BYTES;
+          const uint32_t ss = smem_u32(sf_smem + stage * SF_STAGE);
+          tc_cp_sf_pair(tmem_base + SFA_COL, sf_desc(ss));
+          tc_cp_sf_pair(tmem_base + SFB_COL, sf_desc(ss + SF_BLOCK));
+          tc_cp_sf_pair(tmem_base + SFB_COL + 4, sf_desc(ss + 2 * SF_BLOCK));
+#pragma unroll
+          for (int k = 0; k < BK / 32; ++k)
+            tc_mma_mxf8_pair(tmem_base, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc_mxf8(2 * BM, BN, k, k), (kb | k) != 0 ? 1u : 0u,
+                             tmem_base + SFA_COL, tmem_base + SFB_COL);
+          tc_commit_pair(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit_pair(tmem_full);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
+      const int m_pair = tile % m_pairs, n_blk = tile / m_pairs;
+      mbar_wait(tmem_full, it & 1);
+      tc_fence_after();
+      const int row = (m_pair * 2 + static_cast<int>(cta)) * BM + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+      epilogue_rows<DUAL>(p, taddr, row, row < p.M, n_blk);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tmem_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace pair
 
 // ---- activation quantisation (optionally fused with the RMSNorm in front of the projection) ---------------------------
 // One warp per row. Pass 1 (only with a norm weight): sum of squares. Pass 2: 8 values per lane, 4 lanes per 32-value group:
@@ -381,6 +564,40 @@ static int launch(const PbGemmFp8Args* a, cudaStream_t stream) {
   return pb_check_launch("gemm_mxfp8");
 }
 
+template <bool DUAL>
+static int launch_pair(const PbGemmFp8Args* a, cudaStream_t stream) {
+  constexpr int OUT_BN = DUAL ? BN / 2 : BN;
+  CUtensorMap ta, tb, tb2, tsa, tsb, tsb2;
+  if (!make_tmap_2d_u8(&ta, a->a_q, a->M, a->K, a->K, BM, BK)) return PB_ERR_CUDA;
+  if (!make_tmap_2d_u8(&tb, a->b_q, a->N, a->K, a->K, BN / 2, BK)) return PB_ERR_CUDA;
+  tb2 = tb;
+  if (DUAL && !make_tmap_2d_u8(&tb2, a->b2_q, a->N, a->K, a->K, BN / 2, BK)) return PB_ERR_CUDA;
+  const int kb = a->K / BK, sfa_blocks = (a->M + 127) / 128, sfb_blocks = (a->N + 127) / 128;
+  if (!make_tmap_sf_blocks(&tsa, a->a_sf, static_cast<uint64_t>(kb) * sfa_blocks, 1)) return PB_ERR_CUDA;
+  if (!make_tmap_sf_blocks(&tsb, a->b_sf, static_cast<uint64_t>(kb) * sfb_blocks, DUAL ? 1 : 2)) return PB_ERR_CUDA;
+  tsb2 = tsb;
+  if (DUAL && !make_tmap_sf_blocks(&tsb2, a->b2_sf, static_cast<uint64_t>(kb) * sfb_blocks, 1)) return PB_ERR_CUDA;
+  Params p{};
+  p.residual = static_cast<const __nv_bfloat16*>(a->residual); p.out = static_cast<__nv_bfloat16*>(a->out);
+  p.M = a->M; p.N = a->N; p.K = a->K; p.ldo = a->ldo > 0 ? a->ldo : a->N; p.ldres = a->ldres > 0 ? a->ldres : a->N;
+  p.sfa_blocks = sfa_blocks; p.sfb_blocks = sfb_blocks;
+  const int smem = pair::STAGES * (pair::STAGE2_BYTES + SF_STAGE) + 1024 + 256;
+  auto kern = pair::gemm_mxfp8_2cta_kernel<DUAL>;
+  static std::atomic<bool> attr_done[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_done[dev & 63].load()) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return pb_check_launch("gemm_mxfp8_2cta attr");
+    attr_done[dev & 63].store(true);
+  }
+  const int tiles = ((a->M + 2 * BM - 1) / (2 * BM)) * ((a->N + OUT_BN - 1) / OUT_BN);
+  const int sms = a->num_sms > 0 ? a->num_sms : 148;
+  int clusters = sms / 2;
+  if (tiles < clusters) clusters = tiles;
+  kern<<<2 * clusters, kThreads, smem, stream>>>(ta, tb, tb2, tsa, tsb, tsb2, p);
+  return pb_check_launch("gemm_mxfp8_2cta");
+}
+
 }  // namespace f8
 }  // namespace pb
 
@@ -395,6 +612,18 @@ extern "C" int pb_gemm_mxfp8(const PbGemmFp8Args* a, void* stream) {
   }
   if (a->act != 0) { pb_set_error("gemm_mxfp8: only act 0 (none) and 1 (SwiGLU) are fused"); return PB_ERR_UNSUPPORTED; }
   return f8::launch<false>(a, static_cast<cudaStream_t>(stream));
+}
+
+// 2-CTA variant of pb_gemm_mxfp8 (same arguments): one 256 x 256 tile per SM pair.
+extern "C" int pb_gemm_mxfp8_2cta(const PbGemmFp8Args* a, void* stream) {
+  if (a == nullptr || a->M <= 0 || a->N <= 0 || a->K <= 0 || a->K % f8::BK != 0) { pb_set_error("gemm_mxfp8_2cta: K must be a positive multiple of 128"); return PB_ERR_SHAPE; }
+  if (a->a_q == nullptr || a->a_sf == nullptr || a->b_q == nullptr || a->b_sf == nullptr || a->out == nullptr) return PB_ERR_SHAPE;
+  if (a->act == 1) {
+    if (a->b2_q == nullptr || a->b2_sf == nullptr) return PB_ERR_SHAPE;
+    return f8::launch_pair<true>(a, static_cast<cudaStream_t>(stream));
+  }
+  if (a->act != 0) return PB_ERR_UNSUPPORTED;
+  return f8::launch_pair<false>(a, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int pb_quant_mxfp8(const void* x, const void* norm_w, float eps, void* q, void* sf, int M, int K, void* stream) {

@@ -443,6 +443,18 @@ bool make_tmap_2d_u8(CUtensorMap* m, const void* base, uint64_t rows, uint64_t c
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// scale-factor blocks (gemm_mxfp8.cu, 2-CTA variant): the packed scale array as [blocks, 128] 32-bit words, no swizzle, box = `box_rows` blocks
+bool make_tmap_sf_blocks(CUtensorMap* m, const void* base, uint64_t blocks, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return false;
+  cuuint64_t gdim[2] = {128, blocks};
+  cuuint64_t gstride[1] = {512};
+  cuuint32_t box[2] = {128, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // exported to the other translation units that build TMA descriptors (attention_tc.cu)
 bool make_tmap_2d_bf16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows, uint32_t box_cols) {
   return make_tmap_2d(m, base, rows, cols, ld, box_rows, box_cols);

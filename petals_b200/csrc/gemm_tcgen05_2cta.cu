@@ -47,6 +47,11 @@ struct Params {
   __nv_bfloat16* out;
   int M, N, K;
   int ldo, ldres;
+  // optional prologue wait (sequence-parallel prefill: the A rows are all-gathered by peers, flag = epoch * per_epoch when they landed)
+  const uint64_t* wait_flag;
+  uint64_t wait_per_epoch;
+  const uint64_t* epoch;
+  int* error_flag;
 };
 
 PB_DEVICE uint32_t cluster_ctarank() {
@@ -152,6 +157,10 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   if (warp == 0) {
     // =============================== producer (both CTAs) ===============================
     if (lane == 0) {
+      if (p.wait_flag != nullptr) {
+        if (!spin_wait_ge(p.wait_flag, *p.epoch * p.wait_per_epoch) && p.error_flag != nullptr) atomicExch(p.error_flag, 1);
+        asm volatile("fence.proxy.async;" ::: "memory");
+      }
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
@@ -293,6 +302,8 @@ static int launch(const PbGemmArgs* a, cudaStream_t stream) {
   Params p{};
   p.residual = static_cast<const __nv_bfloat16*>(a->residual); p.out = static_cast<__nv_bfloat16*>(a->out);
   p.M = a->M; p.N = a->N; p.K = a->K; p.ldo = a->ldo > 0 ? a->ldo : a->N; p.ldres = a->ldres > 0 ? a->ldres : a->N;
+  p.wait_flag = static_cast<const uint64_t*>(a->wait_flag); p.wait_per_epoch = a->wait_per_epoch; p.epoch = static_cast<const uint64_t*>(a->epoch);
+  p.error_flag = static_cast<int*>(a->error_flag);
   const int smem = STAGES * STAGE_BYTES + 1024 + 256;
   auto kern = gemm_2cta_kernel<DUAL>;
   static std::atomic<bool> attr_done[64];
@@ -318,7 +329,7 @@ using namespace pb;
 // Same argument block as pb_gemm_bf16; refuses (PB_ERR_UNSUPPORTED) what only the 1-CTA kernel does.
 extern "C" int pb_gemm_bf16_2cta(const PbGemmArgs* a, void* stream) {
   if (a == nullptr || a->M <= 0 || a->N <= 0 || a->K <= 0 || (a->K & 7) || (a->N & 7)) return PB_ERR_SHAPE;
-  if (a->b_mn_major || a->n_push > 0 || a->wait_flag != nullptr || a->grp != nullptr || a->bias != nullptr || a->bias2 != nullptr || a->out_fp32 ||
+  if (a->b_mn_major || a->n_push > 0 || (a->wait_flag != nullptr && a->epoch == nullptr) || a->grp != nullptr || a->bias != nullptr || a->bias2 != nullptr || a->out_fp32 ||
       a->accumulate || a->out == nullptr || (a->act != 0 && a->act != 1)) {
     pb_set_error("gemm_2cta: plain K-major GEMM (optional SwiGLU / residual) only");
     return PB_ERR_UNSUPPORTED;

@@ -223,6 +223,7 @@ typedef struct {
   int num_sms;
 } PbGemmFp8Args;
 int pb_gemm_mxfp8(const PbGemmFp8Args* args, void* stream);
+int pb_gemm_mxfp8_2cta(const PbGemmFp8Args* args, void* stream);   // cta_group::2: one 256 x 256 tile per SM pair
 // x bf16 [M, K] -> q e4m3 [M, K] + scales in the block layout; with norm_w: quantises RMSNorm(x) * norm_w (HF rounding) instead.
 int pb_quant_mxfp8(const void* x, const void* norm_w, float eps, void* q, void* sf, int M, int K, void* stream);
 

@@ -295,7 +295,7 @@ def gemm(
     g.num_sms = native.sm_count(a_.device.index)
     g.block_n = block_n
     g.grp, g.grp_cap, g.grp_experts = ptr(grp), grp_cap, grp_experts
-    if (_GEMM_2CTA and M >= 1024 and N >= 1024 and block_n == 0 and not b_mn_major and not push_out and not wait_flag and grp is None
+    if (_GEMM_2CTA and M >= 1024 and N >= 1024 and block_n == 0 and not b_mn_major and not push_out and grp is None
             and bias is None and bias2 is None and not out_fp32 and act in (ACT_NONE, ACT_SWIGLU)):
         # large plain GEMMs: one 256 x 256 tile per SM pair (csrc/gemm_tcgen05_2cta.cu): each SM stages only half of the weight tile
         check(native.lib().pb_gemm_bf16_2cta(C.byref(g), stream_ptr()), "gemm_bf16_2cta")
@@ -655,7 +655,10 @@ def gemm_mxfp8(a_q: torch.Tensor, a_sf: torch.Tensor, b_q: torch.Tensor, b_sf: t
     g.M, g.N, g.K, g.ldo, g.ldres = M, N, K, out.stride(0), (residual.stride(0) if residual is not None else 0)
     g.act = 1 if b2_q is not None else 0
     g.num_sms = native.sm_count(a_q.device.index)
-    check(native.lib().pb_gemm_mxfp8(C.byref(g), stream_ptr()), "gemm_mxfp8")
+    if _GEMM_2CTA and M >= 1024 and N >= 1024:
+        check(native.lib().pb_gemm_mxfp8_2cta(C.byref(g), stream_ptr()), "gemm_mxfp8_2cta")
+    else:
+        check(native.lib().pb_gemm_mxfp8(C.byref(g), stream_ptr()), "gemm_mxfp8")
     return out
 
 

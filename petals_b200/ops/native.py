@@ -214,7 +214,8 @@ def _declare(lib: C.CDLL) -> None:
     lib.pb_ll_reduce.restype = lib.pb_ll_push.restype = ci
     lib.pb_gemm_mxfp8.argtypes = [C.POINTER(GemmFp8Args), vp]
     lib.pb_quant_mxfp8.argtypes = [vp, vp, C.c_float, vp, vp, ci, ci, vp]
-    lib.pb_gemm_mxfp8.restype = lib.pb_quant_mxfp8.restype = ci
+    lib.pb_gemm_mxfp8_2cta.argtypes = [C.POINTER(GemmFp8Args), vp]
+    lib.pb_gemm_mxfp8.restype = lib.pb_quant_mxfp8.restype = lib.pb_gemm_mxfp8_2cta.restype = ci
     lib.pb_last_error.argtypes = []
     lib.pb_last_error.restype = C.c_char_p
     for name in ("pb_linear_decode", "pb_gemm_bf16", "pb_gemm_tiles", "pb_norm", "pb_swiglu", "pb_add", "pb_embedding",

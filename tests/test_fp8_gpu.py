@@ -124,3 +124,34 @@ def test_block_scaled_gemm_swiglu_epilogue():
     ref = (torch.nn.functional.silu(g.float()).to(torch.bfloat16).float() * u.float())
     out = Fn.gemm_mxfp8(aq, asf, gq.view(torch.uint8), pack_scales(ge), b2_q=uq.view(torch.uint8), b2_sf=pack_scales(ue)).float()
     assert (out - ref).abs().mean().item() < 1e-2 * ref.abs().mean().item() + 1e-4
+
+
+@pytest.mark.parametrize("M,N,K", [(1024, 1024, 512), (1100, 2048 + 128, 1024), (4096, 4096, 4096)])
+def test_block_scaled_gemm_2cta_matches_the_1cta_kernel(M, N, K):
+    """The cta_group::2 variant (one 256 x 256 tile per SM pair, each SM stages half of the weight tile, scale factors of all 256 weight rows
+    in both SMs' tensor memory) against the 1-CTA kernel: plain, residual and SwiGLU epilogues, ragged M / N tails."""
+    from petals_b200.ops import functional as Fn
+    from petals_b200.ops.quant import pack_scales, quantize_mxfp8
+
+    torch.manual_seed(6)
+    a = (torch.randn(M, K, device=DEV) * (0.2 + torch.rand(M, 1, device=DEV))).to(torch.bfloat16)
+    ws = [(torch.randn(N, K, device=DEV) * 0.05 * (0.2 + torch.rand(N, 1, device=DEV))).to(torch.bfloat16) for _ in range(2)]
+    res = torch.randn(M, N, device=DEV).to(torch.bfloat16)
+    aq, asf = Fn.quant_mxfp8(a)
+    (q1, e1), (q2, e2) = [quantize_mxfp8(w) for w in ws]
+    q1, q2, s1, s2 = q1.view(torch.uint8), q2.view(torch.uint8), pack_scales(e1), pack_scales(e2)
+
+    def run():
+        return [Fn.gemm_mxfp8(aq, asf, q1, s1).float(), Fn.gemm_mxfp8(aq, asf, q1, s1, residual=res).float(),
+                Fn.gemm_mxfp8(aq, asf, q1, s1, b2_q=q2, b2_sf=s2).float()]
+
+    try:
+        Fn.set_gemm_2cta(False)
+        want = run()
+        Fn.set_gemm_2cta(True)
+        got = run()
+    finally:
+        Fn.set_gemm_2cta(False)
+    for g, w, what in zip(got, want, ("plain", "residual", "swiglu")):
+        assert (g - w).abs().max().item() <= 2e-2 * w.abs().max().item(), what
+        assert (g - w).abs().mean().item() <= 2e-3 * w.abs().mean().item() + 1e-6, what

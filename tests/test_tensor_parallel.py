@@ -54,6 +54,23 @@ def test_tp_block_matches_dense(world):
     assert torch.allclose(dense_k[:, :prefix], kc[:, :prefix], atol=1e-5)
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_tp_moe_block_matches_dense(world):
+    """Sparse-MoE blocks in the engine's split (parallel/tensor_parallel.py:shard_block): every rank holds 1/world of EVERY expert's FFN
+    columns and the whole router; the ranks' partial MoE outputs sum to the dense block's output."""
+    path = checkpoint("mixtral", hidden_size=256, intermediate_size=256, num_attention_heads=4, num_key_value_heads=4)  # head_dim 64
+    config = AutoDistributedConfig.from_pretrained(path)
+    spec = config.block_spec()
+    assert tp_supported(spec, world)
+    block = load_pretrained_block(path, 0, torch_dtype=torch.float32)
+    shards = shard_oracle_blocks(block, spec, world)
+    assert all(torch.equal(s.router, block.router) for s in shards)
+    assert sum(s.we_gate.numel() + s.we_up.numel() + s.we_down.numel() for s in shards) == block.we_gate.numel() + block.we_up.numel() + block.we_down.numel()
+    torch.manual_seed(0)
+    x = torch.randn(2, 9, spec.hidden_size)
+    assert torch.allclose(tp_oracle_forward(shards, x), block.forward_cached(x, None, None, 0), atol=2e-5)
+
+
 def test_tp_support_matrix():
     llama = AutoDistributedConfig.from_pretrained(checkpoint("llama", hidden_size=512, intermediate_size=1024, num_attention_heads=8, num_key_value_heads=4)).block_spec()
     assert tp_supported(llama, 2) and tp_supported(llama, 4) and not tp_supported(llama, 8) and not tp_supported(llama, 3)
