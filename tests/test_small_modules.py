@@ -189,3 +189,58 @@ def test_mxfp8_scale_block_layout_round_trip():
         off = ((j // 4) * 3 + r // 128) * 512 + (r % 128 % 32) * 16 + (r % 128 // 32) * 4 + j % 4
         assert p[off] == e[r, j]
     assert int(p.view(2, 3, 32, 4, 4)[:, 2, 12:, 1].sum()) == 0  # rows 300..383 are padding
+
+
+def test_fabric_request_metadata_is_validated_before_it_indexes_device_memory(monkeypatch):
+    """server/handler.py:fabric_endpoints — landing-slot coordinates come from the wire: sizes, ranks, slots and kinds are checked against
+    the fabric of this process before any kernel sees them; without a fabric such a request is refused."""
+    import types
+
+    import pytest
+
+    import petals_b200.parallel.fabric as fabric_mod
+    from petals_b200.server.handler import fabric_endpoints
+
+    assert fabric_endpoints({}) == (None, None)
+    monkeypatch.setattr(fabric_mod, "_fabric", None)
+    with pytest.raises(RuntimeError):
+        fabric_endpoints({"fabric_in": {"B": 1, "T": 1, "src_rank": 0}})
+    fab = types.SimpleNamespace(max_tokens=64, n_slots=4, world=4, rank=1, hidden_size=8)
+    monkeypatch.setattr(fabric_mod, "_fabric", fab)
+    take, push = fabric_endpoints({"fabric_in": {"B": 2, "T": 16, "src_rank": 0, "slot": 3}, "fabric_out": {"kind": "g_in", "rank": 2, "slot": 5}})
+    assert take == (fab, 0, 2, 16, 3) and push == (fab, "g_in", 2, 1)  # the output slot wraps around the ring
+    for bad in ({"B": 0, "T": 4, "src_rank": 0}, {"B": 2, "T": 64, "src_rank": 0}, {"B": 1, "T": 1, "src_rank": 4}, {"B": 1, "T": 1, "src_rank": -1},
+                {"B": 1, "T": 1, "src_rank": 0, "slot": 4}, {"B": 1, "T": 1, "src_rank": 0, "slot": -1}):
+        with pytest.raises(ValueError):
+            fabric_endpoints({"fabric_in": bad})
+    for bad in ({"kind": "weights", "rank": 0}, {"kind": "x_in", "rank": 4}, {"kind": "x_in", "rank": -1}):
+        with pytest.raises(ValueError):
+            fabric_endpoints({"fabric_out": bad})
+
+
+def test_stage_activation_stash_is_bounded_and_single_use():
+    """server/backend.py:Stage.stash_put / stash_pop — the span inputs a stage keeps between a fabric forward and its backward: at most
+    STASH_ENTRIES micro-batches, expired entries dropped, an entry can be consumed once, unknown keys are an error (not silence)."""
+    import collections
+    import threading
+    import time
+
+    import pytest
+    import torch
+
+    from petals_b200.server.backend import Stage
+
+    st = Stage.__new__(Stage)
+    st._stash, st._stash_lock = collections.OrderedDict(), threading.Lock()
+    for i in range(Stage.STASH_ENTRIES + 5):
+        st.stash_put(f"k{i}", torch.full((1,), float(i)))
+    assert len(st._stash) == Stage.STASH_ENTRIES and "k0" not in st._stash and "k5" in st._stash
+    assert st.stash_pop("k7").item() == 7.0
+    with pytest.raises(KeyError):
+        st.stash_pop("k7")
+    with pytest.raises(KeyError):
+        st.stash_pop("k0")
+    st._stash["old"] = (torch.zeros(1), time.monotonic() - Stage.STASH_TTL - 1)
+    st._stash.move_to_end("old", last=False)
+    st.stash_put("fresh", torch.zeros(1))
+    assert "old" not in st._stash and "fresh" in st._stash
