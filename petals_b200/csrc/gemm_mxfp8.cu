@@ -583,16 +583,24 @@ static int launch_pair(const PbGemmFp8Args* a, cudaStream_t stream) {
   p.sfa_blocks = sfa_blocks; p.sfb_blocks = sfb_blocks;
   const int smem = pair::STAGES * (pair::STAGE2_BYTES + SF_STAGE) + 1024 + 256;
   auto kern = pair::gemm_mxfp8_2cta_kernel<DUAL>;
-  static std::atomic<bool> attr_done[64];
+  static std::atomic<int> max_clusters[64];   // 0 = not asked yet
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!attr_done[dev & 63].load()) {
+  const int sms = a->num_sms > 0 ? a->num_sms : 148;
+  if (max_clusters[dev & 63].load() == 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return pb_check_launch("gemm_mxfp8_2cta attr");
-    attr_done[dev & 63].store(true);
+    cudaLaunchConfig_t cfg = {};   // persistent grid = the co-resident pairs, not more
+    cfg.gridDim = dim3(sms / 2 * 2); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = sms / 2; }
+    max_clusters[dev & 63].store(n < sms / 2 ? n : sms / 2);
   }
   const int tiles = ((a->M + 2 * BM - 1) / (2 * BM)) * ((a->N + OUT_BN - 1) / OUT_BN);
-  const int sms = a->num_sms > 0 ? a->num_sms : 148;
-  int clusters = sms / 2;
+  int clusters = max_clusters[dev & 63].load();
   if (tiles < clusters) clusters = tiles;
   kern<<<2 * clusters, kThreads, smem, stream>>>(ta, tb, tb2, tsa, tsb, tsb2, p);
   return pb_check_launch("gemm_mxfp8_2cta");

@@ -306,16 +306,25 @@ static int launch(const PbGemmArgs* a, cudaStream_t stream) {
   p.error_flag = static_cast<int*>(a->error_flag);
   const int smem = STAGES * STAGE_BYTES + 1024 + 256;
   auto kern = gemm_2cta_kernel<DUAL>;
-  static std::atomic<bool> attr_done[64];
+  static std::atomic<int> max_clusters[64];   // 0 = not asked yet
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!attr_done[dev & 63].load()) {
+  const int sms = a->num_sms > 0 ? a->num_sms : 148;
+  if (max_clusters[dev & 63].load() == 0) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return pb_check_launch("gemm_2cta attr");
-    attr_done[dev & 63].store(true);
+    // a persistent grid must not exceed what is co-resident: a pair that waits for a free TPC would start its tiles when the others finish
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sms / 2 * 2); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = sms / 2; }
+    max_clusters[dev & 63].store(n < sms / 2 ? n : sms / 2);
   }
   const int tiles = ((a->M + 2 * BM - 1) / (2 * BM)) * ((a->N + OUT_BN - 1) / OUT_BN);
-  const int sms = a->num_sms > 0 ? a->num_sms : 148;
-  int clusters = sms / 2;
+  int clusters = max_clusters[dev & 63].load();
   if (tiles < clusters) clusters = tiles;
   kern<<<2 * clusters, kThreads, smem, stream>>>(ta, tb, tb2, p);
   return pb_check_launch("gemm_2cta");

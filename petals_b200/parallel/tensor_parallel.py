@@ -451,14 +451,12 @@ class TPDecodeEngine:
                     Fn.norm_reduce_gather(part[r * mo: r * mo + rows] if rows else part[:0], None, rows=rows, H=H, norm_kind=Fn.NORM_NONE,
                                           gather_out=[push_parts[r]], gather_flag=[self._p_layer_flag(r, l, 3)], done_counter=ctr, error_flag=err,
                                           device_index=dev)
-            kw = dict(out=act, wait_flag=self._p_layer_flag(me, l, 2), wait_per_epoch=R, epoch=ep, error_flag=err)
-            if s.mlp == "moe":
-                pass
-            elif s.mlp == "swiglu":
-                Fn.gemm(xn, w["w_gate"], b2=w["w_up"], act=Fn.ACT_SWIGLU, **kw)
             else:
-                Fn.gemm(xn, w["w_up"], act=self.act, **kw)
-            if s.mlp != "moe":
+                kw = dict(out=act, wait_flag=self._p_layer_flag(me, l, 2), wait_per_epoch=R, epoch=ep, error_flag=err)
+                if s.mlp == "swiglu":
+                    Fn.gemm(xn, w["w_gate"], b2=w["w_up"], act=Fn.ACT_SWIGLU, **kw)
+                else:
+                    Fn.gemm(xn, w["w_up"], act=self.act, **kw)
                 Fn.gemm(act, w["w_down"], store_local=False, push_out=push_parts, push_rows_per_owner=mo,
                         push_done_flag=[self._p_layer_flag(r, l, 3) for r in range(R)], done_counter=ctr, error_flag=err)
             if l + 1 < L:

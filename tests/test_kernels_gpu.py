@@ -720,3 +720,30 @@ def test_swiglu_and_rope_backward_match_autograd():
     (ref_q,) = torch.autograd.grad(rot(xq), xq, dq.float().view(B, T, Hq, D))
     _close(merged[:, :, :Hq], ref_q, 2e-2, 3e-2, "rope^T dq")
     _close(merged[:, :, Hq + Hkv:], dv.float().view(B, T, Hkv, D), 1e-2, 1e-2, "dv passthrough")
+
+
+def test_ll_collectives_loopback():
+    """csrc/ll_collectives.cu in loop-back (the "peers" are local buffers): ll_push writes {2 x bf16, tag} units, ll_reduce polls them and
+    adds them to the residual in source order with one rounding — the stand-alone halves of the all-reduce around a sparse-MoE block."""
+    torch.manual_seed(31)
+    M, H, R = 3, 1024, 4
+    epoch = torch.full((1,), 7, dtype=torch.int64, device=DEV)
+    x = _rand(M, H)
+    parts = [_rand(M, H) for _ in range(R)]
+    slots = [torch.zeros(M * H // 2, 2, dtype=torch.int32, device=DEV) for _ in range(R)]
+    for r in range(R):
+        Fn.ll_push(parts[r], [slots[r].data_ptr()], (5, 2), epoch.data_ptr())
+    tags = torch.stack([s[:, 1] for s in slots])
+    assert (tags == 7 * 5 + 2).all()
+    out = torch.empty_like(x)
+    err = torch.zeros(1, dtype=torch.int32, device=DEV)
+    Fn.ll_reduce(x, [s.data_ptr() for s in slots], (5, 2), epoch.data_ptr(), out, err.data_ptr())
+    want = (x.float() + sum(p.float() for p in parts)).to(torch.bfloat16)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    assert (out.float() - want.float()).abs().max().item() <= 2 ** -6 * want.float().abs().max().item()  # summation order may differ from torch's by one rounding
+    # one push to several destinations at once
+    more = [torch.zeros(M * H // 2, 2, dtype=torch.int32, device=DEV) for _ in range(3)]
+    Fn.ll_push(parts[0], [m.data_ptr() for m in more], (5, 3), epoch.data_ptr())
+    assert all(torch.equal(m, more[0]) for m in more) and (more[0][:, 1] == 7 * 5 + 3).all()
+    assert torch.equal(more[0][:, 0].contiguous().view(torch.bfloat16).view(M, H), parts[0])

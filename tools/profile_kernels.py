@@ -20,6 +20,23 @@ elif which == "gemm_plain":
     w = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16) * 0.01
     for _ in range(4):
         Fn.gemm(a, w)
+elif which == "gemm_2cta":  # the same gate/up GEMM on the cta_group::2 kernel
+    Fn.set_gemm_2cta(True)
+    a = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+    wg = torch.randn(28672, 8192, device="cuda", dtype=torch.bfloat16) * 0.01
+    wu = torch.randn(28672, 8192, device="cuda", dtype=torch.bfloat16) * 0.01
+    for _ in range(4):
+        Fn.gemm(a, wg, b2=wu, act=Fn.ACT_SWIGLU)
+elif which in ("gemm_mxfp8", "gemm_mxfp8_2cta"):  # block-scaled FP8 down projection (K = 28672), 8192 tokens
+    from petals_b200.ops.quant import pack_scales, quantize_mxfp8
+
+    Fn.set_gemm_2cta(which.endswith("2cta"))
+    a = torch.randn(8192, 28672, device="cuda", dtype=torch.bfloat16)
+    q, e = quantize_mxfp8(torch.randn(8192, 28672, device="cuda", dtype=torch.bfloat16) * 0.01)
+    aq, asf = Fn.quant_mxfp8(a)
+    wq, wsf = q.view(torch.uint8), pack_scales(e)
+    for _ in range(4):
+        Fn.gemm_mxfp8(aq, asf, wq, wsf)
 elif which == "gemv":  # decode gate/up with fused RMSNorm + SwiGLU, 1 token
     x = torch.randn(1, 8192, device="cuda", dtype=torch.bfloat16)
     g = torch.ones(8192, device="cuda", dtype=torch.bfloat16)
