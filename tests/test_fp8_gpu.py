@@ -7,6 +7,9 @@ from petals_b200.utils.convert_block import QuantType
 from petals_b200.utils.random_model import launch_random_stage, random_client_model, write_config_only
 
 pytestmark = pytest.mark.gpu
+# tests of kernels that have not had their first hardware run yet are opt-in (a trap in one of them would poison the CUDA context of the whole
+# session); the run scripts under tools/gpu_runs set the variable, and the gate is removed once the kernel has passed on a B200
+UNVALIDATED = pytest.mark.skipif(__import__("os").environ.get("PETALS_B200_RUN_UNVALIDATED") != "1", reason="first hardware run pending (PETALS_B200_RUN_UNVALIDATED=1)")
 DEV = "cuda:0"
 
 
@@ -126,6 +129,7 @@ def test_block_scaled_gemm_swiglu_epilogue():
     assert (out - ref).abs().mean().item() < 1e-2 * ref.abs().mean().item() + 1e-4
 
 
+@UNVALIDATED
 @pytest.mark.parametrize("M,N,K", [(1024, 1024, 512), (1100, 2048 + 128, 1024), (4096, 4096, 4096)])
 def test_block_scaled_gemm_2cta_matches_the_1cta_kernel(M, N, K):
     """The cta_group::2 variant (one 256 x 256 tile per SM pair, each SM stages half of the weight tile, scale factors of all 256 weight rows

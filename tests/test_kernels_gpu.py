@@ -7,6 +7,9 @@ import torch
 from petals_b200.ops import functional as Fn
 
 pytestmark = pytest.mark.gpu
+# tests of kernels that have not had their first hardware run yet are opt-in (a trap in one of them would poison the CUDA context of the whole
+# session); the run scripts under tools/gpu_runs set the variable, and the gate is removed once the kernel has passed on a B200
+UNVALIDATED = pytest.mark.skipif(__import__("os").environ.get("PETALS_B200_RUN_UNVALIDATED") != "1", reason="first hardware run pending (PETALS_B200_RUN_UNVALIDATED=1)")
 DEV = "cuda"
 
 
@@ -84,6 +87,7 @@ def test_gemm_plain(M, N, K):
     _close(got, Fn.linear_ref(a, b), 2e-2, 2e-2, f"gemm {M}x{N}x{K}")
 
 
+@UNVALIDATED
 @pytest.mark.parametrize("M,N,K", [(1024, 1024, 512), (1100, 2048 + 64, 1024), (4096, 8192, 1024), (2048, 1280, 8192)])
 def test_gemm_2cta_matches_the_1cta_kernel(M, N, K):
     """csrc/gemm_tcgen05_2cta.cu (tcgen05.mma.cta_group::2: one 256 x 256 tile per SM pair): same products and the same fp32
@@ -722,6 +726,7 @@ def test_swiglu_and_rope_backward_match_autograd():
     _close(merged[:, :, Hq + Hkv:], dv.float().view(B, T, Hkv, D), 1e-2, 1e-2, "dv passthrough")
 
 
+@UNVALIDATED
 def test_ll_collectives_loopback():
     """csrc/ll_collectives.cu in loop-back (the "peers" are local buffers): ll_push writes {2 x bf16, tag} units, ll_reduce polls them and
     adds them to the residual in source order with one rounding — the stand-alone halves of the all-reduce around a sparse-MoE block."""
