@@ -304,13 +304,19 @@ def gemm(
     return out
 
 
-_GEMM_2CTA = os.environ.get("PETALS_B200_GEMM_2CTA", "0") != "0"
+# Measured on B200 (profiles/r2_gemm_2cta.txt): the bf16 pair kernel is 4-8 % faster on the 70B shapes and 12-19 % on smaller ones (default on);
+# the block-scaled FP8 pair kernel is not faster than its 1-CTA twin (that kernel is bound by per-stage issue overhead, not operand traffic),
+# so it stays opt-in (PETALS_B200_FP8_2CTA=1).
+_GEMM_2CTA = os.environ.get("PETALS_B200_GEMM_2CTA", "1") != "0"
+_FP8_2CTA = os.environ.get("PETALS_B200_FP8_2CTA", "0") != "0"
 
 
-def set_gemm_2cta(on: bool) -> None:
-    """Route large plain GEMMs to the 2-CTA (cta_group::2) kernel (tests and tools/kernel_bench.py flip it)."""
-    global _GEMM_2CTA
+def set_gemm_2cta(on: bool, fp8: Optional[bool] = None) -> None:
+    """Route large plain GEMMs to the 2-CTA (cta_group::2) kernels (tests and tools/kernel_bench.py flip it). ``fp8``: the block-scaled
+    FP8 pair kernel, which has its own switch (default: follow ``on``)."""
+    global _GEMM_2CTA, _FP8_2CTA
     _GEMM_2CTA = bool(on)
+    _FP8_2CTA = bool(on if fp8 is None else fp8)
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -655,7 +661,7 @@ def gemm_mxfp8(a_q: torch.Tensor, a_sf: torch.Tensor, b_q: torch.Tensor, b_sf: t
     g.M, g.N, g.K, g.ldo, g.ldres = M, N, K, out.stride(0), (residual.stride(0) if residual is not None else 0)
     g.act = 1 if b2_q is not None else 0
     g.num_sms = native.sm_count(a_q.device.index)
-    if _GEMM_2CTA and M >= 1024 and N >= 1024:
+    if _FP8_2CTA and M >= 1024 and N >= 1024:
         check(native.lib().pb_gemm_mxfp8_2cta(C.byref(g), stream_ptr()), "gemm_mxfp8_2cta")
     else:
         check(native.lib().pb_gemm_mxfp8(C.byref(g), stream_ptr()), "gemm_mxfp8")

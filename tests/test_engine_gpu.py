@@ -52,9 +52,18 @@ def test_session_matches_oracle(preset, overrides, tmp_path):
                 d = model(ids[:, 35:38]).logits  # 3-token step (B*T = 6 rows: decode kernels)
                 e = model(ids[:, 38:]).logits
             sess = torch.cat([a, b, c, d, e], 1).float()
+        # Bounds set from measurements on B200 (tools/engine_error_stats.py, profiles/r2_engine_error_stats.txt), in units of mean |logit|:
+        # dense families: mean 0.6-1.0 %, 99.9th percentile 3-5 %, worst element 5-12 %. Sparse MoE: a routing decision that flips at a
+        # near-tie changes a whole row (mean 3.5 %, worst element > 100 %), so those are bounded on the mean and row-wise.
         scale = ref.abs().mean().item()
-        assert (full - ref).abs().mean().item() < 0.05 * scale + 1e-3
-        assert (sess - ref).abs().mean().item() < 0.05 * scale + 1e-3
+        for name, got in (("forward", full), ("session", sess)):
+            err = (got - ref).abs() / scale
+            if preset == "mixtral-tiny":
+                assert err.mean().item() < 0.06, (name, err.mean().item())
+                assert (err.amax(-1) < 0.25).float().mean().item() > 0.8, name  # rows without a flipped routing decision are tight
+            else:
+                p999 = err.flatten().kthvalue(int(err.numel() * 0.999)).values.item()
+                assert err.mean().item() < 0.02 and p999 < 0.10 and err.max().item() < 0.25, (name, err.mean().item(), p999, err.max().item())
         assert (sess.argmax(-1) == ref.argmax(-1)).float().mean().item() > 0.9
     finally:
         stage.shutdown()

@@ -7,9 +7,6 @@ from petals_b200.utils.convert_block import QuantType
 from petals_b200.utils.random_model import launch_random_stage, random_client_model, write_config_only
 
 pytestmark = pytest.mark.gpu
-# tests of kernels that have not had their first hardware run yet are opt-in (a trap in one of them would poison the CUDA context of the whole
-# session); the run scripts under tools/gpu_runs set the variable, and the gate is removed once the kernel has passed on a B200
-UNVALIDATED = pytest.mark.skipif(__import__("os").environ.get("PETALS_B200_RUN_UNVALIDATED") != "1", reason="first hardware run pending (PETALS_B200_RUN_UNVALIDATED=1)")
 DEV = "cuda:0"
 
 
@@ -129,7 +126,6 @@ def test_block_scaled_gemm_swiglu_epilogue():
     assert (out - ref).abs().mean().item() < 1e-2 * ref.abs().mean().item() + 1e-4
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("M,N,K", [(1024, 1024, 512), (1100, 2048 + 128, 1024), (4096, 4096, 4096)])
 def test_block_scaled_gemm_2cta_matches_the_1cta_kernel(M, N, K):
     """The cta_group::2 variant (one 256 x 256 tile per SM pair, each SM stages half of the weight tile, scale factors of all 256 weight rows
@@ -150,12 +146,12 @@ def test_block_scaled_gemm_2cta_matches_the_1cta_kernel(M, N, K):
                 Fn.gemm_mxfp8(aq, asf, q1, s1, b2_q=q2, b2_sf=s2).float()]
 
     try:
-        Fn.set_gemm_2cta(False)
+        Fn.set_gemm_2cta(True, fp8=False)
         want = run()
-        Fn.set_gemm_2cta(True)
+        Fn.set_gemm_2cta(True, fp8=True)
         got = run()
     finally:
-        Fn.set_gemm_2cta(False)
+        Fn.set_gemm_2cta(True, fp8=False)  # the defaults
     for g, w, what in zip(got, want, ("plain", "residual", "swiglu")):
         assert (g - w).abs().max().item() <= 2e-2 * w.abs().max().item(), what
         assert (g - w).abs().mean().item() <= 2e-3 * w.abs().mean().item() + 1e-6, what

@@ -7,9 +7,6 @@ import torch
 from petals_b200.ops import functional as Fn
 
 pytestmark = pytest.mark.gpu
-# tests of kernels that have not had their first hardware run yet are opt-in (a trap in one of them would poison the CUDA context of the whole
-# session); the run scripts under tools/gpu_runs set the variable, and the gate is removed once the kernel has passed on a B200
-UNVALIDATED = pytest.mark.skipif(__import__("os").environ.get("PETALS_B200_RUN_UNVALIDATED") != "1", reason="first hardware run pending (PETALS_B200_RUN_UNVALIDATED=1)")
 DEV = "cuda"
 
 
@@ -87,7 +84,6 @@ def test_gemm_plain(M, N, K):
     _close(got, Fn.linear_ref(a, b), 2e-2, 2e-2, f"gemm {M}x{N}x{K}")
 
 
-@UNVALIDATED
 @pytest.mark.parametrize("M,N,K", [(1024, 1024, 512), (1100, 2048 + 64, 1024), (4096, 8192, 1024), (2048, 1280, 8192)])
 def test_gemm_2cta_matches_the_1cta_kernel(M, N, K):
     """csrc/gemm_tcgen05_2cta.cu (tcgen05.mma.cta_group::2: one 256 x 256 tile per SM pair): same products and the same fp32
@@ -101,8 +97,12 @@ def test_gemm_2cta_matches_the_1cta_kernel(M, N, K):
         Fn.set_gemm_2cta(True)
         got = [Fn.gemm(a, b), Fn.gemm(a, b, residual=res), Fn.gemm(a, b, b2=b2, act=Fn.ACT_SWIGLU)]
     finally:
-        Fn.set_gemm_2cta(False)
+        Fn.set_gemm_2cta(True, fp8=False)  # the defaults
     _close(got[0], Fn.linear_ref(a, b), 2e-2, 2e-2, f"2cta gemm {M}x{N}x{K}")
+    # the flag-wait prologue (sequence-parallel prefill: the A rows are gathered by peers) with an already satisfied flag
+    epoch, flag, err = torch.full((1,), 3, dtype=torch.int64, device=DEV), torch.full((1,), 6, dtype=torch.int64, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
+    waited = Fn.gemm(a, b, wait_flag=flag.data_ptr(), wait_per_epoch=2, epoch=epoch.data_ptr(), error_flag=err.data_ptr())
+    assert torch.equal(waited, got[0]) and int(err.item()) == 0
     for g, w, what in zip(got, want, ("plain", "residual", "swiglu")):
         assert (g.float() - w.float()).abs().max().item() <= 2e-2 * w.float().abs().max().item(), what
         assert (g.float() - w.float()).abs().mean().item() <= 2e-3 * w.float().abs().mean().item() + 1e-6, what
@@ -726,7 +726,6 @@ def test_swiglu_and_rope_backward_match_autograd():
     _close(merged[:, :, Hq + Hkv:], dv.float().view(B, T, Hkv, D), 1e-2, 1e-2, "dv passthrough")
 
 
-@UNVALIDATED
 def test_ll_collectives_loopback():
     """csrc/ll_collectives.cu in loop-back (the "peers" are local buffers): ll_push writes {2 x bf16, tag} units, ll_reduce polls them and
     adds them to the residual in source order with one rounding — the stand-alone halves of the all-reduce around a sparse-MoE block."""

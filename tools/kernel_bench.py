@@ -216,7 +216,7 @@ def bench_gemm_2cta(results, peaks):
         for on in (False, True):
             Fn.set_gemm_2cta(on)
             ms[on] = time_fn([mk(i) for i in range(nbuf)], iters=10)
-        Fn.set_gemm_2cta(False)
+        Fn.set_gemm_2cta(True, fp8=False)
         ref_ms = time_fn([(lambda i=i: torch.matmul(As[i], Bs[i].T)) for i in range(nbuf)], iters=10) * (2 if opt.get("dual") else 1)
         row = dict(kernel="gemm_tcgen05_2cta", shape=name, M=M, N=N, K=K, ms_1cta=ms[False], ms_2cta=ms[True], TFLOPs_1cta=flops / ms[False] / 1e9,
                    TFLOPs_2cta=flops / ms[True] / 1e9, cublas_TFLOPs=flops / ref_ms / 1e9)
