@@ -16,6 +16,9 @@ from the definitions, with torch ops only:
 * ``QUANTILE_8BIT``  – 256 buckets with (sampled) quantile borders; codebook = bucket means.
 * ``BLOCKWISE_8BIT`` – blocks of 4096 values scaled by their absmax, signed 8-bit code on a quadratic grid
                         (dense near zero, where hidden states live).
+* ``MXFP8``          – not a hivemind codec: the block-scaled FP8 format of ``ops/quant.py`` (E4M3 payload, one UE8M0 power-of-two
+                        scale per 32 values along the last dimension) — the format Blackwell tensor cores consume and the fp8 stages
+                        quantise their activations to anyway; 1.03 bytes/value, no code book, error bounded per 32-value group.
 
 ``encode`` returns ``(meta, [flat uint8 tensors])`` and ``decode`` inverts it; both are exact inverses for ``NONE`` and
 lossy within the bounds tested in tests/test_compression.py otherwise.
@@ -36,6 +39,7 @@ class CompressionType(IntEnum):
     QUANTILE_8BIT = 3
     UNIFORM_8BIT = 4
     BLOCKWISE_8BIT = 5
+    MXFP8 = 6  # beyond the reference's enum: block-scaled FP8 (ops/quant.py)
 
 
 CodecSpec = Union[None, str, int, CompressionType]
@@ -163,6 +167,15 @@ def encode(t: torch.Tensor, compression: CodecSpec = None) -> Tuple[Dict[str, An
         idx, book = _bucket_encode(flat, borders)
         return meta, [_raw(idx), _raw(book)]
 
+    if codec == CompressionType.MXFP8:
+        from petals_b200.ops.quant import BLOCK, quantize_mxfp8
+
+        n = flat.numel()
+        rows = torch.nn.functional.pad(flat, (0, (-n) % BLOCK)).reshape(-1, BLOCK)  # groups of 32 consecutive values (rows of hidden states are multiples of 32)
+        q, e = quantize_mxfp8(rows)
+        meta["n"] = n
+        return meta, [_raw(q.view(torch.uint8).reshape(-1)[:n]), _raw(e.reshape(-1))]
+
     if codec == CompressionType.BLOCKWISE_8BIT:
         n = flat.numel()
         pad = (-n) % _BLOCK
@@ -200,6 +213,19 @@ def decode(meta: Dict[str, Any], blobs: Sequence[torch.Tensor], dtype: torch.dty
         idx = _from_raw(blobs[0], torch.uint8, [numel]).long()
         book = _from_raw(blobs[1], torch.float32, [_N_BUCKETS])
         return book[idx].reshape(list(shape)).to(dtype)
+
+    if codec == CompressionType.MXFP8:
+        from petals_b200.ops.quant import BLOCK, dequantize_mxfp8
+
+        n = int(meta["n"])
+        if n != numel:
+            raise WireFormatError(f"MXFP8: {n} values announced for {numel} elements")
+        groups = (n + BLOCK - 1) // BLOCK
+        q = torch.zeros(groups * BLOCK, dtype=torch.uint8)
+        q[:n] = _from_raw(blobs[0], torch.uint8, [n])
+        e = _from_raw(blobs[1], torch.uint8, [groups, 1])
+        vals = dequantize_mxfp8(q.view(torch.float8_e4m3fn).view(groups, BLOCK), e, torch.float32).reshape(-1)[:n]
+        return vals.reshape(list(shape)).to(dtype)
 
     if codec == CompressionType.BLOCKWISE_8BIT:
         n = int(meta["n"])

@@ -43,7 +43,8 @@ def test_none_is_exact(dtype):
 # every outlier into their end buckets (beyond ±6σ / the last 1/256 quantile), so they are only meant for — and
 # checked on — outlier-free tensors; the per-row and per-block codecs must cope with the outlier feature.
 _GLOBAL_CODEBOOK = ("UNIFORM_8BIT", "QUANTILE_8BIT")
-_RMS_BOUND = {"FLOAT16": 1e-3, "MEANSTD_16BIT": 2e-3, "UNIFORM_8BIT": 0.03, "QUANTILE_8BIT": 0.05, "BLOCKWISE_8BIT": 0.03}
+_RMS_BOUND = {"FLOAT16": 1e-3, "MEANSTD_16BIT": 2e-3, "UNIFORM_8BIT": 0.03, "QUANTILE_8BIT": 0.05, "BLOCKWISE_8BIT": 0.03,
+              "MXFP8": 0.04}  # E4M3 has 3 mantissa bits: <= 6.25 % per value, ~2.5-3 % RMS; a power-of-two scale per 32 values keeps outliers local
 
 
 @pytest.mark.parametrize("codec", sorted(_RMS_BOUND))
@@ -64,6 +65,20 @@ def test_codecs_restore_dtype_and_handle_odd_sizes(codec):
         y = roundtrip(x, codec)
         assert y.dtype == torch.bfloat16 and y.shape == x.shape
         assert torch.isfinite(y.float()).all()
+
+
+def test_mxfp8_codec_is_the_tensor_core_format():
+    """The MXFP8 wire codec is ops/quant.py's format (E4M3 payload + one UE8M0 exponent per 32 values): what an fp8 stage would feed its
+    block-scaled GEMM, so a receiver could consume the payload without a dequantise / requantise round trip."""
+    from petals_b200.ops.quant import dequantize_mxfp8, quantize_mxfp8
+    from petals_b200.utils.compression import encode
+
+    x = _hidden(shape=(4, 256), dtype=torch.float32, seed=5)
+    meta, blobs = encode(x, "MXFP8")
+    q, e = quantize_mxfp8(x.reshape(-1, 32))
+    assert meta["codec"] == "MXFP8" and torch.equal(blobs[0], q.view(torch.uint8).reshape(-1)) and torch.equal(blobs[1], e.reshape(-1))
+    assert torch.equal(roundtrip(x, "MXFP8"), dequantize_mxfp8(q, e, torch.float32).reshape(4, 256))
+    assert abs(compressed_nbytes(x, "MXFP8") / x.numel() - (1 + 1 / 32)) < 1e-6
 
 
 def test_float16_clamps_instead_of_overflowing():
