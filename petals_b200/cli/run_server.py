@@ -55,7 +55,7 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--no_auto_relay", action="store_false", dest="use_auto_relay")
     p.add_argument("--daemon_startup_timeout", type=float, default=60)
     p.add_argument("--compression", type=str, default="NONE", help="wire codec for the hidden states this server returns over the socket transport: NONE, FLOAT16, MEANSTD_16BIT, "
-                        "QUANTILE_8BIT, UNIFORM_8BIT or BLOCKWISE_8BIT (clients can override per request with output_compression; "
+                        "QUANTILE_8BIT, UNIFORM_8BIT, BLOCKWISE_8BIT or MXFP8 (clients can override per request with output_compression; "
                         "NVLink stage hops are never compressed)")
     p.add_argument("--num_handlers", type=int, default=8)
     p.add_argument("--prefetch_batches", type=int, default=1)

@@ -338,6 +338,19 @@ PB_DEVICE void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
 }
 
+// groups of 4 tile pairs (1024 rows) along M, N fastest inside a group: the ~74 concurrent pairs share 4 row blocks of A and ~18 weight
+// tiles, whatever K is (an M-fastest order would re-stream all of A every wave once A no longer fits in L2)
+PB_DEVICE void pair_coords(int tile, int m_pairs, int n_blocks, int& m_pair, int& n_blk) {
+  constexpr int kGroup = 4;
+  const int per_group = kGroup * n_blocks;
+  const int g = tile / per_group;
+  const int first_m = g * kGroup;
+  const int gsize = min(kGroup, m_pairs - first_m);
+  const int r = tile - g * per_group;
+  m_pair = first_m + r % gsize;
+  n_blk = r / gsize;
+}
+
 template <bool DUAL>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_mxfp8_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b2,
@@ -388,7 +401,8 @@ gemm_mxfp8_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
-        const int m_pair = tile % m_pairs, n_blk = tile / m_pairs;   // M fastest: the 74 concurrent pairs share few weight tiles
+        int m_pair, n_blk;
+        pair_coords(tile, m_pairs, n_blocks, m_pair, n_blk);
         const int m_blk = m_pair * 2 + static_cast<int>(cta);        // this CTA's 128-row block of A
         const int nb0 = DUAL ? n_blk : 2 * n_blk;
         for (int kb = 0; kb < num_kb; ++kb) {
@@ -445,7 +459,8 @@ gemm_mxfp8_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const int quarter = warp & 3;
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
-      const int m_pair = tile % m_pairs, n_blk = tile / m_pairs;
+      int m_pair, n_blk;
+      pair_coords(tile, m_pairs, n_blocks, m_pair, n_blk);
       mbar_wait(tmem_full, it & 1);
       tc_fence_after();
       const int row = (m_pair * 2 + static_cast<int>(cta)) * BM + quarter * 32 + lane;

@@ -12,3 +12,5 @@ grep '^{' gpurun_out/r2_19_bench.log | python -c "import sys,json; [print({k:d[k
 timeout 600 python benchmarks/benchmark_training.py --model llama-3-8b --n_steps 8 --warmup_steps 3 --batch_size 8 --seq_len 128 > gpurun_out/r2_19_training.log 2>&1; echo "training bench exit=$?" | tee -a $S
 grep -iE "tokens/s|tok/s|forward|backward" gpurun_out/r2_19_training.log | tail -6 | cut -c1-300 | tee -a $S
 bash tools/gpu_runs/r2_run18_ncu.sh > /dev/null 2>&1; cat gpurun_out/r2_18_summary.txt | cut -c1-200 | tee -a $S
+PETALS_B200_FP8_2CTA=1 timeout 600 python tools/kernel_bench.py --only gemm_fp8 > gpurun_out/r2_19_kernel_bench_fp8_2cta.log 2>&1; echo "fp8 2cta (grouped raster) kernel bench exit=$?" | tee -a $S
+grep "gemm_mxfp8" gpurun_out/r2_19_kernel_bench_fp8_2cta.log | cut -c1-300 | tee -a $S
