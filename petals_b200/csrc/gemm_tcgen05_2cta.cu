@@ -36,7 +36,7 @@ constexpr int BM = 128;        // rows per CTA (256 per pair)
 constexpr int BN = 256;        // accumulator columns (MMA N); each CTA stages BN / 2 weight rows
 constexpr int BK = 64;
 constexpr int kThreads = 192;
-constexpr int kGroupM = 4;     // tile pairs per rasterisation group along M (4 x 256 rows)
+constexpr int kGroupM = 4;     // default tile pairs per rasterisation group along M (PETALS_B200_GEMM_GROUP_M overrides: measured in profiles/)
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STAGES = 6;
 constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -47,6 +47,7 @@ struct Params {
   __nv_bfloat16* out;
   int M, N, K;
   int ldo, ldres;
+  int group_m;   // tile pairs per rasterisation group along M: the concurrent pairs cover group_m x 256 rows of A and (pairs / group_m) weight tiles
   // optional prologue wait (sequence-parallel prefill: the A rows are all-gathered by peers, flag = epoch * per_epoch when they landed)
   const uint64_t* wait_flag;
   uint64_t wait_per_epoch;
@@ -98,11 +99,11 @@ PB_DEVICE void mbar_arrive_leader(uint64_t* bar) {
 PB_DEVICE float silu_f(float x) { return x / (1.f + __expf(-x)); }
 PB_DEVICE float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
-PB_DEVICE void tile_coords(int tile, int m_pairs, int n_blocks, int& m_pair, int& n_blk) {
-  const int per_group = kGroupM * n_blocks;
+PB_DEVICE void tile_coords(int tile, int m_pairs, int n_blocks, int group_m, int& m_pair, int& n_blk) {
+  const int per_group = group_m * n_blocks;
   const int g = tile / per_group;
-  const int first_m = g * kGroupM;
-  const int gsize = min(kGroupM, m_pairs - first_m);
+  const int first_m = g * group_m;
+  const int gsize = min(group_m, m_pairs - first_m);
   const int r = tile - g * per_group;
   m_pair = first_m + r % gsize;
   n_blk = r / gsize;
@@ -165,7 +166,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       uint32_t phase = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
         int m_pair, n_blk;
-        tile_coords(tile, m_pairs, n_blocks, m_pair, n_blk);
+        tile_coords(tile, m_pairs, n_blocks, p.group_m, m_pair, n_blk);
         const int a_row = m_pair * 2 * BM + static_cast<int>(cta) * BM;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -215,7 +216,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     int it = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += n_clusters, ++it) {
       int m_pair, n_blk;
-      tile_coords(tile, m_pairs, n_blocks, m_pair, n_blk);
+      tile_coords(tile, m_pairs, n_blocks, p.group_m, m_pair, n_blk);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_full[as], aphase);
@@ -302,6 +303,8 @@ static int launch(const PbGemmArgs* a, cudaStream_t stream) {
   Params p{};
   p.residual = static_cast<const __nv_bfloat16*>(a->residual); p.out = static_cast<__nv_bfloat16*>(a->out);
   p.M = a->M; p.N = a->N; p.K = a->K; p.ldo = a->ldo > 0 ? a->ldo : a->N; p.ldres = a->ldres > 0 ? a->ldres : a->N;
+  static const int env_group = [] { const char* e = getenv("PETALS_B200_GEMM_GROUP_M"); const int v = e ? atoi(e) : 0; return v > 0 ? v : kGroupM; }();
+  p.group_m = env_group;
   p.wait_flag = static_cast<const uint64_t*>(a->wait_flag); p.wait_per_epoch = a->wait_per_epoch; p.epoch = static_cast<const uint64_t*>(a->epoch);
   p.error_flag = static_cast<int*>(a->error_flag);
   const int smem = STAGES * STAGE_BYTES + 1024 + 256;

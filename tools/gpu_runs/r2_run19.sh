@@ -14,3 +14,7 @@ grep -iE "tokens/s|tok/s|forward|backward" gpurun_out/r2_19_training.log | tail 
 bash tools/gpu_runs/r2_run18_ncu.sh > /dev/null 2>&1; cat gpurun_out/r2_18_summary.txt | cut -c1-200 | tee -a $S
 PETALS_B200_FP8_2CTA=1 timeout 600 python tools/kernel_bench.py --only gemm_fp8 > gpurun_out/r2_19_kernel_bench_fp8_2cta.log 2>&1; echo "fp8 2cta (grouped raster) kernel bench exit=$?" | tee -a $S
 grep "gemm_mxfp8" gpurun_out/r2_19_kernel_bench_fp8_2cta.log | cut -c1-300 | tee -a $S
+for g in 2 8 16; do
+  PETALS_B200_GEMM_GROUP_M=$g timeout 300 python tools/kernel_bench.py --only gemm_2cta > gpurun_out/r2_19_kb_group$g.log 2>&1; echo "2cta group_m=$g exit=$?" | tee -a $S
+  grep "gemm2" gpurun_out/r2_19_kb_group$g.log | cut -c1-130 | tee -a $S
+done
