@@ -109,7 +109,9 @@ PB_DEVICE void tile_coords(int tile, int m_pairs, int n_blocks, int group_m, int
   n_blk = r / gsize;
 }
 
-template <bool DUAL>
+// B_MN: B is the [K, N] row-major view of the weight (the dgrad dX = dY . W on the untransposed nn.Linear weight): each CTA stages its
+// 128-wide half of the N extent as two 64-column boxes per K block and the MMA reads B MN-major.
+template <bool DUAL, bool B_MN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_b2,
                  const Params p) {
@@ -174,7 +176,11 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint8_t* sb = sa + A_BYTES;
           if (leader) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
           tma_load_2d_pair(sa, &tmap_a, &full_bar[stage], kb * BK, a_row);
-          if (!DUAL) {
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 2 / 64; ++j)   // [64 k-rows x 64 n-columns] boxes, 8 KB each
+              tma_load_2d_pair(sb + j * 8192, &tmap_b, &full_bar[stage], n_blk * BN + static_cast<int>(cta) * (BN / 2) + j * 64, kb * BK);
+          } else if (!DUAL) {
             tma_load_2d_pair(sb, &tmap_b, &full_bar[stage], kb * BK, n_blk * BN + static_cast<int>(cta) * (BN / 2));
           } else {  // leader: gate rows, peer: up rows of the same output columns
             tma_load_2d_pair(sb, leader ? &tmap_b : &tmap_b2, &full_bar[stage], kb * BK, n_blk * OUT_BN);
@@ -186,7 +192,7 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else if (warp == 1) {
     // =============================== MMA issuer (leader CTA only) =================================
     if (leader && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, 0);
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN, 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
@@ -203,7 +209,8 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            tc_mma_f16_pair(d_tmem, umma_desc_k_sw128(sa + k * 32), umma_desc_k_sw128(sb + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_f16_pair(d_tmem, umma_desc_k_sw128(sa + k * 32), B_MN ? umma_desc_mn_sw128(sb + k * 2048, 8192) : umma_desc_k_sw128(sb + k * 32), idesc,
+                            (kb | k) != 0 ? 1u : 0u);
           tc_commit_pair(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -291,13 +298,17 @@ gemm_2cta_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-template <bool DUAL>
+template <bool DUAL, bool B_MN>
 static int launch(const PbGemmArgs* a, cudaStream_t stream) {
   constexpr int OUT_BN = DUAL ? BN / 2 : BN;
   const int lda = a->lda > 0 ? a->lda : a->K, ldb = a->ldb > 0 ? a->ldb : a->K;
   CUtensorMap ta, tb, tb2;
   if (!make_tmap_2d_bf16(&ta, a->a, a->M, a->K, lda, BM, BK)) return PB_ERR_DRIVER;
-  if (!make_tmap_2d_bf16(&tb, a->b, a->N, a->K, ldb, BN / 2, BK)) return PB_ERR_DRIVER;
+  if (B_MN) {  // B is [K, N] row-major: box = 64 k-rows x 64 n-columns
+    if (!make_tmap_2d_bf16(&tb, a->b, a->K, a->N, a->ldb > 0 ? a->ldb : a->N, BK, 64)) return PB_ERR_DRIVER;
+  } else if (!make_tmap_2d_bf16(&tb, a->b, a->N, a->K, ldb, BN / 2, BK)) {
+    return PB_ERR_DRIVER;
+  }
   tb2 = tb;
   if (DUAL && !make_tmap_2d_bf16(&tb2, a->b2, a->N, a->K, ldb, BN / 2, BK)) return PB_ERR_DRIVER;
   Params p{};
@@ -308,7 +319,7 @@ static int launch(const PbGemmArgs* a, cudaStream_t stream) {
   p.wait_flag = static_cast<const uint64_t*>(a->wait_flag); p.wait_per_epoch = a->wait_per_epoch; p.epoch = static_cast<const uint64_t*>(a->epoch);
   p.error_flag = static_cast<int*>(a->error_flag);
   const int smem = STAGES * STAGE_BYTES + 1024 + 256;
-  auto kern = gemm_2cta_kernel<DUAL>;
+  auto kern = gemm_2cta_kernel<DUAL, B_MN>;
   static std::atomic<int> max_clusters[64];   // 0 = not asked yet
   int dev = 0;
   cudaGetDevice(&dev);
@@ -341,14 +352,15 @@ using namespace pb;
 // Same argument block as pb_gemm_bf16; refuses (PB_ERR_UNSUPPORTED) what only the 1-CTA kernel does.
 extern "C" int pb_gemm_bf16_2cta(const PbGemmArgs* a, void* stream) {
   if (a == nullptr || a->M <= 0 || a->N <= 0 || a->K <= 0 || (a->K & 7) || (a->N & 7)) return PB_ERR_SHAPE;
-  if (a->b_mn_major || a->n_push > 0 || (a->wait_flag != nullptr && a->epoch == nullptr) || a->grp != nullptr || a->bias != nullptr || a->bias2 != nullptr || a->out_fp32 ||
+  if ((a->b_mn_major && a->act != 0) || a->n_push > 0 || (a->wait_flag != nullptr && a->epoch == nullptr) || a->grp != nullptr || a->bias != nullptr || a->bias2 != nullptr || a->out_fp32 ||
       a->accumulate || a->out == nullptr || (a->act != 0 && a->act != 1)) {
     pb_set_error("gemm_2cta: plain K-major GEMM (optional SwiGLU / residual) only");
     return PB_ERR_UNSUPPORTED;
   }
   if (a->act == 1) {
     if (a->b2 == nullptr) return PB_ERR_SHAPE;
-    return g2::launch<true>(a, static_cast<cudaStream_t>(stream));
+    return g2::launch<true, false>(a, static_cast<cudaStream_t>(stream));
   }
-  return g2::launch<false>(a, static_cast<cudaStream_t>(stream));
+  if (a->b_mn_major) return g2::launch<false, true>(a, static_cast<cudaStream_t>(stream));
+  return g2::launch<false, false>(a, static_cast<cudaStream_t>(stream));
 }

@@ -295,8 +295,8 @@ def gemm(
     g.num_sms = native.sm_count(a_.device.index)
     g.block_n = block_n
     g.grp, g.grp_cap, g.grp_experts = ptr(grp), grp_cap, grp_experts
-    if (_GEMM_2CTA and M >= 1024 and N >= 1024 and block_n == 0 and not b_mn_major and not push_out and grp is None
-            and bias is None and bias2 is None and not out_fp32 and act in (ACT_NONE, ACT_SWIGLU)):
+    if (_GEMM_2CTA and M >= 1024 and N >= 1024 and block_n == 0 and not push_out and grp is None and bias is None and bias2 is None and not out_fp32
+            and (act == ACT_NONE or (act == ACT_SWIGLU and not b_mn_major)) and (not b_mn_major or (_GEMM_2CTA_MN and N % 64 == 0))):
         # large plain GEMMs: one 256 x 256 tile per SM pair (csrc/gemm_tcgen05_2cta.cu): each SM stages only half of the weight tile
         check(native.lib().pb_gemm_bf16_2cta(C.byref(g), stream_ptr()), "gemm_bf16_2cta")
         return out
@@ -309,14 +309,16 @@ def gemm(
 # so it stays opt-in (PETALS_B200_FP8_2CTA=1).
 _GEMM_2CTA = os.environ.get("PETALS_B200_GEMM_2CTA", "1") != "0"
 _FP8_2CTA = os.environ.get("PETALS_B200_FP8_2CTA", "0") != "0"
+_GEMM_2CTA_MN = os.environ.get("PETALS_B200_GEMM_2CTA_MN", "0") != "0"  # MN-major B (dgrad) on the pair kernel: on after its first hardware pass
 
 
-def set_gemm_2cta(on: bool, fp8: Optional[bool] = None) -> None:
+def set_gemm_2cta(on: bool, fp8: Optional[bool] = None, mn: Optional[bool] = None) -> None:
     """Route large plain GEMMs to the 2-CTA (cta_group::2) kernels (tests and tools/kernel_bench.py flip it). ``fp8``: the block-scaled
-    FP8 pair kernel, which has its own switch (default: follow ``on``)."""
-    global _GEMM_2CTA, _FP8_2CTA
+    FP8 pair kernel, ``mn``: MN-major B (dgrad) on the pair kernel — both have their own switches (default: follow ``on``)."""
+    global _GEMM_2CTA, _FP8_2CTA, _GEMM_2CTA_MN
     _GEMM_2CTA = bool(on)
     _FP8_2CTA = bool(on if fp8 is None else fp8)
+    _GEMM_2CTA_MN = bool(on if mn is None else mn)
 
 
 # ----------------------------------------------------------------------------------------------------

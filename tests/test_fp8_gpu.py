@@ -7,6 +7,7 @@ from petals_b200.utils.convert_block import QuantType
 from petals_b200.utils.random_model import launch_random_stage, random_client_model, write_config_only
 
 pytestmark = pytest.mark.gpu
+_MN_DEFAULT = __import__("os").environ.get("PETALS_B200_GEMM_2CTA_MN", "0") != "0"
 DEV = "cuda:0"
 
 
@@ -146,12 +147,12 @@ def test_block_scaled_gemm_2cta_matches_the_1cta_kernel(M, N, K):
                 Fn.gemm_mxfp8(aq, asf, q1, s1, b2_q=q2, b2_sf=s2).float()]
 
     try:
-        Fn.set_gemm_2cta(True, fp8=False)
+        Fn.set_gemm_2cta(True, fp8=False, mn=_MN_DEFAULT)
         want = run()
         Fn.set_gemm_2cta(True, fp8=True)
         got = run()
     finally:
-        Fn.set_gemm_2cta(True, fp8=False)  # the defaults
+        Fn.set_gemm_2cta(True, fp8=False, mn=_MN_DEFAULT)  # the defaults
     for g, w, what in zip(got, want, ("plain", "residual", "swiglu")):
         assert (g - w).abs().max().item() <= 2e-2 * w.abs().max().item(), what
         assert (g - w).abs().mean().item() <= 2e-3 * w.abs().mean().item() + 1e-6, what

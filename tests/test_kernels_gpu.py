@@ -7,6 +7,7 @@ import torch
 from petals_b200.ops import functional as Fn
 
 pytestmark = pytest.mark.gpu
+_MN_DEFAULT = __import__("os").environ.get("PETALS_B200_GEMM_2CTA_MN", "0") != "0"
 DEV = "cuda"
 
 
@@ -91,21 +92,29 @@ def test_gemm_2cta_matches_the_1cta_kernel(M, N, K):
     residual epilogue, and with the SwiGLU epilogue (gate rows staged by the even CTA, up rows by the odd one). Ragged M and N tails."""
     torch.manual_seed(55)
     a, b, b2, res = _rand(M, K), _rand(N, K, scale=K ** -0.5), _rand(N, K, scale=K ** -0.5), _rand(M, N)
+    bt = b.t().contiguous()  # [K, N]: the dgrad view of a weight (B consumed MN-major)
+
+    mn = _MN_DEFAULT or __import__("os").environ.get("PETALS_B200_RUN_UNVALIDATED") == "1"  # MN-major B on the pair kernel: first hardware pass pending
+
+    def run():
+        return [Fn.gemm(a, b), Fn.gemm(a, b, residual=res), Fn.gemm(a, b, b2=b2, act=Fn.ACT_SWIGLU), Fn.gemm(a, bt, b_mn_major=True)]
+
     try:
         Fn.set_gemm_2cta(False)
-        want = [Fn.gemm(a, b), Fn.gemm(a, b, residual=res), Fn.gemm(a, b, b2=b2, act=Fn.ACT_SWIGLU)]
-        Fn.set_gemm_2cta(True)
-        got = [Fn.gemm(a, b), Fn.gemm(a, b, residual=res), Fn.gemm(a, b, b2=b2, act=Fn.ACT_SWIGLU)]
+        want = run()
+        Fn.set_gemm_2cta(True, mn=mn)
+        got = run()
     finally:
-        Fn.set_gemm_2cta(True, fp8=False)  # the defaults
+        Fn.set_gemm_2cta(True, fp8=False, mn=_MN_DEFAULT)  # the defaults
     _close(got[0], Fn.linear_ref(a, b), 2e-2, 2e-2, f"2cta gemm {M}x{N}x{K}")
     # the flag-wait prologue (sequence-parallel prefill: the A rows are gathered by peers) with an already satisfied flag
     epoch, flag, err = torch.full((1,), 3, dtype=torch.int64, device=DEV), torch.full((1,), 6, dtype=torch.int64, device=DEV), torch.zeros(1, dtype=torch.int32, device=DEV)
     waited = Fn.gemm(a, b, wait_flag=flag.data_ptr(), wait_per_epoch=2, epoch=epoch.data_ptr(), error_flag=err.data_ptr())
     assert torch.equal(waited, got[0]) and int(err.item()) == 0
-    for g, w, what in zip(got, want, ("plain", "residual", "swiglu")):
+    for g, w, what in zip(got, want, ("plain", "residual", "swiglu", "MN-major B")):
         assert (g.float() - w.float()).abs().max().item() <= 2e-2 * w.float().abs().max().item(), what
         assert (g.float() - w.float()).abs().mean().item() <= 2e-3 * w.float().abs().mean().item() + 1e-6, what
+    assert (got[3].float() - got[0].float()).abs().max().item() <= 2e-2 * got[0].float().abs().max().item()  # a . (b^T)^T == a . b^T
 
 
 @pytest.mark.parametrize("bn", [64, 128, 256])

@@ -3,6 +3,7 @@
 # default now) — then the ncu captures of the round's new kernels.
 mkdir -p gpurun_out
 S=gpurun_out/r2_19_summary.txt; : > $S
+PETALS_B200_RUN_UNVALIDATED=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -q --timeout=120 -x -k "2cta" > gpurun_out/r2_19_mn_test.log 2>&1; echo "2cta incl. MN-major exit=$?" | tee -a $S; tail -3 gpurun_out/r2_19_mn_test.log | cut -c1-300 | tee -a $S
 timeout 1500 python -m pytest tests -m gpu -q --timeout=300 -x > gpurun_out/r2_19_gpu_suite.log 2>&1; echo "gpu suite exit=$?" | tee -a $S
 tail -6 gpurun_out/r2_19_gpu_suite.log | cut -c1-300 | tee -a $S
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_19_smoke.log 2>&1; echo "smoke exit=$?" | tee -a $S
@@ -18,3 +19,5 @@ for g in 2 8 16; do
   PETALS_B200_GEMM_GROUP_M=$g timeout 300 python tools/kernel_bench.py --only gemm_2cta > gpurun_out/r2_19_kb_group$g.log 2>&1; echo "2cta group_m=$g exit=$?" | tee -a $S
   grep "gemm2" gpurun_out/r2_19_kb_group$g.log | cut -c1-130 | tee -a $S
 done
+PETALS_B200_GEMM_2CTA_MN=1 timeout 600 python benchmarks/benchmark_training.py --model llama-3-8b --n_steps 8 --warmup_steps 3 --batch_size 8 --seq_len 128 > gpurun_out/r2_19_training_mn.log 2>&1; echo "training bench (MN dgrad on the pair kernel) exit=$?" | tee -a $S
+grep -iE "tokens/s|tok/s|forward|backward" gpurun_out/r2_19_training_mn.log | tail -6 | cut -c1-300 | tee -a $S

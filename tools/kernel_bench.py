@@ -18,6 +18,9 @@ from petals_b200.ops import functional as Fn  # noqa: E402
 from petals_b200.utils.peaks import measured_peaks  # noqa: E402
 
 
+_MN_DEFAULT = os.environ.get("PETALS_B200_GEMM_2CTA_MN", "0") != "0"
+
+
 def time_fn(fns, iters=20, warmup=3):
     """fns: list of callables rotated round-robin (distinct buffers => cold L2). Returns ms per call."""
     for i in range(warmup):
@@ -216,7 +219,7 @@ def bench_gemm_2cta(results, peaks):
         for on in (False, True):
             Fn.set_gemm_2cta(on)
             ms[on] = time_fn([mk(i) for i in range(nbuf)], iters=10)
-        Fn.set_gemm_2cta(True, fp8=False)
+        Fn.set_gemm_2cta(True, fp8=False, mn=_MN_DEFAULT)
         ref_ms = time_fn([(lambda i=i: torch.matmul(As[i], Bs[i].T)) for i in range(nbuf)], iters=10) * (2 if opt.get("dual") else 1)
         row = dict(kernel="gemm_tcgen05_2cta", shape=name, M=M, N=N, K=K, ms_1cta=ms[False], ms_2cta=ms[True], TFLOPs_1cta=flops / ms[False] / 1e9,
                    TFLOPs_2cta=flops / ms[True] / 1e9, cublas_TFLOPs=flops / ref_ms / 1e9)
