@@ -163,7 +163,7 @@ PB_DEVICE void epilogue_rows(const Params& p, uint32_t taddr, int row, bool row_
 }
 
 // DUAL: the B tile is 128 rows of `b` (gate) + 128 rows of `b2` (up); the epilogue emits silu(gate) * up, 128 columns per tile.
-template <bool DUAL, int STAGES>
+template <bool DUAL, int STAGES, bool SFPIPE>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                   const __grid_constant__ CUtensorMap tmap_b2, const Params p) {
@@ -238,30 +238,46 @@ gemm_mxfp8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     }
   } else if (warp == 1) {
     // =============================== MMA issuer =================================
+    // The K blocks of all this CTA's tiles form one stream g = 0, 1, 2, ...: ring stage g % STAGES, scale columns of parity g & 1.
+    // SFPIPE: the scale factors of block g + 1 are copied into the OTHER column set before the MMAs of block g are issued, so the
+    // copy can overlap those MMAs instead of sitting between two MMA groups.
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+      const long total = static_cast<long>(my_tiles) * num_kb;
+      auto sf_cols = [&](long g) { return tmem_base + SFA_COL + (SFPIPE ? static_cast<uint32_t>(g & 1) * 16u : 0u); };
+      auto copy_scales = [&](long g) {
+        const int s_ = static_cast<int>(g % STAGES);
+        mbar_wait(&full_bar[s_], static_cast<uint32_t>((g / STAGES) & 1));
+        tc_fence_after();
+        const uint32_t ss = smem_u32(sf_smem + s_ * SF_STAGE);
+        const uint32_t c = sf_cols(g);
+        tc_cp_sf(c, sf_desc(ss));
+        tc_cp_sf(c + 4, sf_desc(ss + SF_BLOCK));
+        tc_cp_sf(c + 8, sf_desc(ss + 2 * SF_BLOCK));
+      };
+      long g = 0;
+      if (SFPIPE && total > 0) copy_scales(0);
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         mbar_wait(tmem_empty, (it & 1) ^ 1);
         tc_fence_after();
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          if (SFPIPE) {
+            if (g + 1 < total) copy_scales(g + 1);
+          } else {
+            copy_scales(g);
+          }
+          const int stage = static_cast<int>(g % STAGES);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint32_t sb = sa + A_BYTES;
-          const uint32_t ss = smem_u32(sf_smem + stage * SF_STAGE);
-          tc_cp_sf(tmem_base + SFA_COL, sf_desc(ss));
-          tc_cp_sf(tmem_base + SFB_COL, sf_desc(ss + SF_BLOCK));
-          tc_cp_sf(tmem_base + SFB_COL + 4, sf_desc(ss + 2 * SF_BLOCK));
+          const uint32_t c = sf_cols(g);
 #pragma unroll
           for (int k = 0; k < BK / 32; ++k) {
             const uint64_t adesc = umma_desc_k_sw128(sa + k * 32);
             const uint64_t bdesc = umma_desc_k_sw128(sb + k * 32);
-            tc_mma_mxf8(tmem_base, adesc, bdesc, idesc_mxf8(BM, BN, k, k), (kb | k) != 0 ? 1u : 0u, tmem_base + SFA_COL, tmem_base + SFB_COL);
+            tc_mma_mxf8(tmem_base, adesc, bdesc, idesc_mxf8(BM, BN, k, k), (kb | k) != 0 ? 1u : 0u, c, c + 4);
           }
           tc_commit(&empty_bar[stage]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(tmem_full);
       }
@@ -564,7 +580,8 @@ static int launch(const PbGemmFp8Args* a, cudaStream_t stream) {
   p.M = a->M; p.N = a->N; p.K = a->K; p.ldo = a->ldo > 0 ? a->ldo : a->N; p.ldres = a->ldres > 0 ? a->ldres : a->N;
   p.sfa_blocks = (a->M + 127) / 128; p.sfb_blocks = (a->N + 127) / 128;
   const int smem = STAGES * (STAGE_BYTES + SF_STAGE) + 1024 + 256;
-  auto kern = gemm_mxfp8_kernel<DUAL, STAGES>;
+  static const bool sfpipe = [] { const char* e = getenv("PETALS_B200_FP8_SFPIPE"); return e == nullptr || atoi(e) != 0; }();
+  auto kern = sfpipe ? gemm_mxfp8_kernel<DUAL, STAGES, true> : gemm_mxfp8_kernel<DUAL, STAGES, false>;
   static std::atomic<bool> attr_done[64];
   int dev = 0;
   cudaGetDevice(&dev);

@@ -36,7 +36,7 @@ constexpr int BM = 128;        // rows per CTA (256 per pair)
 constexpr int BN = 256;        // accumulator columns (MMA N); each CTA stages BN / 2 weight rows
 constexpr int BK = 64;
 constexpr int kThreads = 192;
-constexpr int kGroupM = 4;     // default tile pairs per rasterisation group along M (PETALS_B200_GEMM_GROUP_M overrides: measured in profiles/)
+constexpr int kGroupM = 8;     // default tile pairs per rasterisation group along M (PETALS_B200_GEMM_GROUP_M overrides: measured in profiles/)
 constexpr int A_BYTES = BM * BK * 2, B_BYTES = (BN / 2) * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int STAGES = 6;
 constexpr uint32_t TMEM_COLS = 2 * BN;
