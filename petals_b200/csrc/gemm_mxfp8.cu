@@ -580,7 +580,8 @@ static int launch(const PbGemmFp8Args* a, cudaStream_t stream) {
   p.M = a->M; p.N = a->N; p.K = a->K; p.ldo = a->ldo > 0 ? a->ldo : a->N; p.ldres = a->ldres > 0 ? a->ldres : a->N;
   p.sfa_blocks = (a->M + 127) / 128; p.sfb_blocks = (a->N + 127) / 128;
   const int smem = STAGES * (STAGE_BYTES + SF_STAGE) + 1024 + 256;
-  static const bool sfpipe = [] { const char* e = getenv("PETALS_B200_FP8_SFPIPE"); return e == nullptr || atoi(e) != 0; }();
+  // measured (profiles/r2_fp8_sfpipe_mn_group8.txt): copying one block ahead is 7-14 % SLOWER than copying right before the MMAs -> off
+  static const bool sfpipe = [] { const char* e = getenv("PETALS_B200_FP8_SFPIPE"); return e != nullptr && atoi(e) != 0; }();
   auto kern = sfpipe ? gemm_mxfp8_kernel<DUAL, STAGES, true> : gemm_mxfp8_kernel<DUAL, STAGES, false>;
   static std::atomic<bool> attr_done[64];
   int dev = 0;

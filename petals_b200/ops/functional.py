@@ -309,7 +309,7 @@ def gemm(
 # so it stays opt-in (PETALS_B200_FP8_2CTA=1).
 _GEMM_2CTA = os.environ.get("PETALS_B200_GEMM_2CTA", "1") != "0"
 _FP8_2CTA = os.environ.get("PETALS_B200_FP8_2CTA", "0") != "0"
-_GEMM_2CTA_MN = os.environ.get("PETALS_B200_GEMM_2CTA_MN", "0") != "0"  # MN-major B (dgrad) on the pair kernel: on after its first hardware pass
+_GEMM_2CTA_MN = os.environ.get("PETALS_B200_GEMM_2CTA_MN", "1") != "0"  # MN-major B (the dgrad of rpc_backward) on the pair kernel
 
 
 def set_gemm_2cta(on: bool, fp8: Optional[bool] = None, mn: Optional[bool] = None) -> None:

@@ -7,7 +7,7 @@ from petals_b200.utils.convert_block import QuantType
 from petals_b200.utils.random_model import launch_random_stage, random_client_model, write_config_only
 
 pytestmark = pytest.mark.gpu
-_MN_DEFAULT = __import__("os").environ.get("PETALS_B200_GEMM_2CTA_MN", "0") != "0"
+_MN_DEFAULT = __import__("os").environ.get("PETALS_B200_GEMM_2CTA_MN", "1") != "0"
 DEV = "cuda:0"
 
 

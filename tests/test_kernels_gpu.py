@@ -7,7 +7,7 @@ import torch
 from petals_b200.ops import functional as Fn
 
 pytestmark = pytest.mark.gpu
-_MN_DEFAULT = __import__("os").environ.get("PETALS_B200_GEMM_2CTA_MN", "0") != "0"
+_MN_DEFAULT = __import__("os").environ.get("PETALS_B200_GEMM_2CTA_MN", "1") != "0"
 DEV = "cuda"
 
 
@@ -94,15 +94,13 @@ def test_gemm_2cta_matches_the_1cta_kernel(M, N, K):
     a, b, b2, res = _rand(M, K), _rand(N, K, scale=K ** -0.5), _rand(N, K, scale=K ** -0.5), _rand(M, N)
     bt = b.t().contiguous()  # [K, N]: the dgrad view of a weight (B consumed MN-major)
 
-    mn = _MN_DEFAULT or __import__("os").environ.get("PETALS_B200_RUN_UNVALIDATED") == "1"  # MN-major B on the pair kernel: first hardware pass pending
-
     def run():
         return [Fn.gemm(a, b), Fn.gemm(a, b, residual=res), Fn.gemm(a, b, b2=b2, act=Fn.ACT_SWIGLU), Fn.gemm(a, bt, b_mn_major=True)]
 
     try:
         Fn.set_gemm_2cta(False)
         want = run()
-        Fn.set_gemm_2cta(True, mn=mn)
+        Fn.set_gemm_2cta(True)
         got = run()
     finally:
         Fn.set_gemm_2cta(True, fp8=False, mn=_MN_DEFAULT)  # the defaults

@@ -18,7 +18,7 @@ from petals_b200.ops import functional as Fn  # noqa: E402
 from petals_b200.utils.peaks import measured_peaks  # noqa: E402
 
 
-_MN_DEFAULT = os.environ.get("PETALS_B200_GEMM_2CTA_MN", "0") != "0"
+_MN_DEFAULT = os.environ.get("PETALS_B200_GEMM_2CTA_MN", "1") != "0"
 
 
 def time_fn(fns, iters=20, warmup=3):
