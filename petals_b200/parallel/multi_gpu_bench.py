@@ -74,6 +74,7 @@ def run_pp_tp(args, n_stages: int, tp: int) -> None:
     dist.init_process_group(backend="cpu:gloo,cuda:nccl", device_id=dev)
     native.lib()
     groups = [dist.new_group(list(range(g * tp, (g + 1) * tp)), backend="cpu:gloo,cuda:nccl") for g in range(n_stages)]  # collective: every rank, every group
+    leaders_group = dist.new_group([i * tp for i in range(n_stages)], backend="cpu:gloo,cuda:nccl")
     g, grank = rank // tp, rank % tp
     group = groups[g]
     path = write_config_only(args.model)
@@ -97,6 +98,11 @@ def run_pp_tp(args, n_stages: int, tp: int) -> None:
         heap.close()
         dist.destroy_process_group()
         return
+    # the leaders share an NVLink fabric of their own (landing rings, parallel/fabric.py): the hidden state of a token hops from the last
+    # kernel's output of stage g to stage g + 1 as a peer copy + flag, and the client issues a step to all four leaders at once
+    from petals_b200.parallel.fabric import init_fabric
+
+    fabric = init_fabric(config.hidden_size, max_tokens=max(PB * 256, 1024), group=leaders_group, n_slots=4) if os.environ.get("PETALS_B200_PPTP_FABRIC", "1") != "0" else None
     swarm = FileSwarm(dirs[0])
     leader = TPLeaderEngine(engine, ring)
     stage = Stage(config, [torch.nn.Identity() for _ in range(n_mine)], bounds[g], device=dev, memory_cache=cache, torch_dtype=torch.bfloat16, engine=leader)
@@ -120,6 +126,7 @@ def run_pp_tp(args, n_stages: int, tp: int) -> None:
             clocks = sampler.stop()
             e2e_s, h2d, d2h = e2e_decode(model, sess, K, dev)
             stages_used = [s_.span.peer_id for s_ in sess._server_sessions]
+            over_fabric = [s_.no_history for s_ in sess._server_sessions]
         engine.check_errors()
         value = K / (ms / 1e3)
         prefill = None
@@ -149,7 +156,7 @@ def run_pp_tp(args, n_stages: int, tp: int) -> None:
             "dtype": "bf16", "data": "synthetic token ids; random-init weights of the named architecture",
             "config": {"model": args.model, "global_batch": 1, "seq_len": args.seq_len, "parallelism": f"pp{n_stages}xtp{tp}",
                        "layout": f"{n_stages} pipeline stages x tensor-parallel groups of {tp} GPUs; blocks per stage {[bounds[i + 1] - bounds[i] for i in range(n_stages)]}",
-                       "stages": stages_used, "build_s": round(build_s, 1),
+                       "stages": stages_used, "inputs_over_fabric": over_fabric, "build_s": round(build_s, 1),
                        "l2": "each step streams every rank's full weight shard (>> 126 MB L2): inputs larger than L2",
                        "timing": "CUDA events on rank 0 (client + leader of the first stage), which receives every token from the last stage before the next step starts"},
             "clocks": clocks,
@@ -162,6 +169,9 @@ def run_pp_tp(args, n_stages: int, tp: int) -> None:
     host_barrier_leaders(n_stages, tp)
     leader.shutdown()
     container.shutdown()
+    if fabric is not None:
+        fabric.check_errors()
+        fabric.close()
     host_barrier()
     heap.close()
     if result is not None:

@@ -119,11 +119,15 @@ class Stage:
         if stash is not None:
             self.stash_put(stash, hidden if take_from is not None else hidden.clone())
         prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device).contiguous() for p in prompts]
-        if self.engine is not None and self._lora_free() and not (push_to is not None and getattr(self.engine, "whole_span_only", False)):
+        if self.engine is not None and self._lora_free():
             with nvtx_range(f"stage[{self.start_block + lo}:{self.start_block + hi}].forward"):
                 if push_to is None:
                     return self.engine.forward(hidden, prompts, (lo, hi))
-                return self.engine.forward(hidden, prompts, (lo, hi), hop=push_to)[:, :0]
+                if not getattr(self.engine, "whole_span_only", False):
+                    return self.engine.forward(hidden, prompts, (lo, hi), hop=push_to)[:, :0]
+                out = self.engine.forward(hidden, prompts, (lo, hi))  # a tensor-parallel leader has no fused hop: host-issued peer copy
+                push_to[0].send(out.reshape(-1, out.shape[-1]), push_to[2], push_to[1], *push_to[3:4])
+                return out[:, :0]
         h = hidden.to(self.dtype)
         with torch.no_grad():
             for i in range(lo, hi):
@@ -235,9 +239,17 @@ class Stage:
         prompts = None if prompts is None else [None if is_dummy(p) else p.to(self.device).contiguous() for p in prompts]
         if self.engine is not None and self._lora_free():
             with nvtx_range(f"stage[{self.start_block + lo}:{self.start_block + hi}].inference_step"):
-                if take_from is not None or push_to is not None:
+                fused_hops = not getattr(self.engine, "whole_span_only", False)  # a tensor-parallel leader has no fused hop: host-issued copies
+                if (take_from is not None or push_to is not None) and fused_hops:
                     return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi), take_from=take_from, push_to=push_to)
-                return self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi))
+                if take_from is not None:
+                    fabric, src_rank, B, T = take_from[:4]
+                    hidden = fabric.recv(B * T, "x_in", src_rank, *take_from[4:5]).view(B, T, -1)
+                out = self.engine.inference_step(session, hidden, prompts, hypo_ids, (lo, hi))
+                if push_to is not None:
+                    push_to[0].send(out.reshape(-1, out.shape[-1]), push_to[2], push_to[1], *push_to[3:4])
+                    return out[:, :0]
+                return out
         if take_from is not None:  # executors without fused hops still honour the fabric protocol (host-issued copies)
             fabric, src_rank, B, T = take_from[:4]
             hidden = fabric.recv(B * T, "x_in", src_rank, *take_from[4:5]).view(B, T, -1)
