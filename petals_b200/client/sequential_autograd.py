@@ -44,6 +44,7 @@ from petals_b200.utils.misc import DUMMY, is_dummy
 
 logger = get_logger(__name__)
 MAX_TOKENS_IN_BATCH = 1024
+FABRIC_COOL_DOWN = 60.0  # seconds without fabric passes after a failed hop (the stages drain what they can; rings of a dead peer time out)
 
 
 @dataclass
@@ -104,6 +105,8 @@ class FabricPlan:
     @classmethod
     def probe(cls, manager: RemoteSequenceManager, route: Optional[Route], shape: Tuple[int, int, int]) -> Optional["FabricPlan"]:
         if route is None or len(route) < 2 or os.environ.get("PETALS_B200_FABRIC_TRAINING", "1") == "0":
+            return None
+        if time.monotonic() < getattr(manager, "fabric_broken_until", 0.0):  # a hop failed recently: rings may be out of step, carry tensors
             return None
         from petals_b200.parallel.fabric import get_fabric
 
@@ -273,6 +276,7 @@ def pipelined_forward(manager: RemoteSequenceManager, micro_batches: Sequence[Mi
             try:
                 plan.forward_hop(manager, mb, i)
             except Exception as e:  # noqa: BLE001 - activations in flight are lost with the hop: restart this micro-batch with tensors
+                manager.fabric_broken_until = time.monotonic() + FABRIC_COOL_DOWN
                 manager.on_request_failure(plan.spans[i].peer_id)
                 mb.detached, mb.landed, mb.x, mb.hops = True, False, mb.x0, []
                 _give_up_or_wait(manager, 1, f"fabric forward of micro-batch {mb.index} via {plan.spans[i]}", e)
@@ -365,6 +369,7 @@ def pipelined_backward(manager: RemoteSequenceManager, micro_batches: Sequence[M
             try:
                 plan.backward_hop(manager, mb, hop)
             except Exception as e:  # noqa: BLE001 - gradients in flight are lost with the hop: redo this micro-batch with tensors
+                manager.fabric_broken_until = time.monotonic() + FABRIC_COOL_DOWN
                 manager.on_request_failure(hop.span.peer_id)
                 _give_up_or_wait(manager, 1, f"fabric backward of micro-batch {mb.index} via {hop.span}", e)
                 _redo_with_tensors(manager, mb, plan)

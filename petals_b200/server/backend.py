@@ -163,14 +163,19 @@ class Stage:
         in place by the kernels); with ``push_to = (fabric, kind, rank[, slot])`` the gradient of the span input is stored into that
         landing slot by the last backward kernel and the returned gradient is empty."""
         hi = len(self.blocks) if hi is None else hi
-        if stash is not None:
-            hidden = self.stash_pop(stash)
         grad_ack = None
-        if grad_from is not None:
+        if grad_from is not None:  # first of all: the ring protocol counts transfers, a request that fails later must still consume its slot
             fabric, src_rank, B, T = grad_from[:4]
             slot = grad_from[4] if len(grad_from) > 4 else 0
             grad_out = fabric.landing(B * T, "g_in", slot).view(B, T, -1)
             grad_ack = (fabric, "g_in", src_rank, slot)
+        if stash is not None:
+            try:
+                hidden = self.stash_pop(stash)
+            except KeyError:
+                if grad_ack is not None:
+                    grad_ack[0].acknowledge(*grad_ack[1:])
+                raise
         if tuple(hidden.shape) != tuple(grad_out.shape):
             raise ValueError(f"inputs {tuple(hidden.shape)} and grad_outputs {tuple(grad_out.shape)} must have the same shape")
         engine_hops = (self.engine is not None and self._lora_free() and not getattr(self.engine, "whole_span_only", False)

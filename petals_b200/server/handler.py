@@ -75,6 +75,24 @@ def fabric_endpoints(metadata: Dict[str, Any]) -> Tuple[Optional[tuple], Optiona
     return take_from, push_to
 
 
+def drain_landing(take_from: Optional[tuple], kind: str, device) -> None:
+    """A request that announced a transfer into a landing slot of this rank failed BEFORE the stage consumed it. The ring protocol counts
+    transfers (parallel/fabric.py), so the slot must still be consumed and acknowledged once — otherwise the producer's next push
+    through that slot waits for an acknowledgement that never comes. Best effort: the wait is enqueued like a normal take (device
+    watchdog / host time-out apply when the producer never delivered)."""
+    if take_from is None:
+        return
+    fabric, src_rank, B, T = take_from[:4]
+    try:
+        if torch.device(device).type == "cuda":
+            with torch.cuda.device(device):
+                fabric.recv(B * T, kind, src_rank, *take_from[4:5])
+        else:
+            fabric.recv(B * T, kind, src_rank, *take_from[4:5])
+    except Exception as e:  # noqa: BLE001
+        logger.warning(f"could not drain landing slot {kind}{list(take_from[4:5])} after a failed request: {e!r}")
+
+
 class InferenceStream:
     """Server side of one ``rpc_inference`` stream: a KV session + step loop state."""
 
@@ -153,6 +171,16 @@ class InferenceStream:
     def _step(self, hidden: torch.Tensor, prompts: Optional[torch.Tensor] = None, hypo_ids: Optional[torch.Tensor] = None,
               metadata: Optional[Dict[str, Any]] = None) -> torch.Tensor:
         metadata = metadata or {}
+        take_from, push_to = fabric_endpoints(metadata)
+        state = {"taken": take_from is None}
+        try:
+            return self._step_guarded(hidden, prompts, hypo_ids, metadata, take_from, push_to, state)
+        except BaseException:
+            if not state["taken"]:
+                drain_landing(take_from, "x_in", self.handler.stage.device)
+            raise
+
+    def _step_guarded(self, hidden, prompts, hypo_ids, metadata, take_from, push_to, state) -> torch.Tensor:
         maybe_fail("rpc_inference", self.handler.peer_id)
         if self.closed:
             raise RuntimeError("inference session is closed")
@@ -177,7 +205,6 @@ class InferenceStream:
                 hypo_ids = pushed[2] if len(pushed) > 2 else hypo_ids
         # NVLink fabric (parallel/fabric.py): the input may already sit in this rank's landing zone, and/or the output
         # may have to be stored straight into the next stage's (or the client's) landing zone by the span's last kernel
-        take_from, push_to = fabric_endpoints(metadata)
         if take_from is not None:
             hidden = torch.empty(take_from[2], take_from[3], self.handler.stage.spec.hidden_size, dtype=self.handler.stage.dtype,
                                  device=self.handler.stage.device)  # shape carrier only
@@ -215,6 +242,7 @@ class InferenceStream:
         h = self.handler
         whole_span = getattr(h.stage.engine, "whole_span_only", False)  # tensor-parallel groups step their span as one unit
         if B * T <= MAX_SHORT_INFERENCE_TOKENS or n == 1 or take_from is not None or push_to is not None or whole_span:
+            state["taken"] = True  # from here on the stage consumes the landing slot itself (first thing it does)
             fut = h.inference_pool.submit_task(hidden, hypo_ids, cache, self.lo, self.hi, block_prompts, self.active_adapter, take_from, push_to,
                                                priority=priority, size=B * T)
             out = fut.result(timeout=h.step_timeout)
@@ -314,16 +342,24 @@ class TransformerConnectionHandler:
         return out
 
     def _rpc_forward(self, uids, hidden: torch.Tensor, prompts: Optional[torch.Tensor] = None, metadata: Optional[Dict[str, Any]] = None) -> torch.Tensor:
-        maybe_fail("rpc_forward", self.peer_id)
-        uids = self._check_uids(uids)
         metadata = metadata or {}
-        self.check_adapter(metadata.get("active_adapter"))
-        backends = [self.module_backends[u] for u in uids]
         take_from, push_to = fabric_endpoints(metadata)
-        if take_from is not None:  # the micro-batch already sits in this rank's landing slot: `hidden` is a shape carrier
-            hidden = torch.empty(take_from[2], take_from[3], self.stage.spec.hidden_size, dtype=self.stage.dtype, device="meta")
-        return run_rpc_forward(hidden, prompts, backends=backends, handler=self, active_adapter=metadata.get("active_adapter"),
-                               points=float(metadata.get("points", 0)), take_from=take_from, push_to=push_to, stash=self._stash_key(metadata))
+        state = {"taken": take_from is None}
+        try:
+            maybe_fail("rpc_forward", self.peer_id)
+            uids = self._check_uids(uids)
+            self.check_adapter(metadata.get("active_adapter"))
+            backends = [self.module_backends[u] for u in uids]
+            if take_from is not None:  # the micro-batch already sits in this rank's landing slot: `hidden` is a shape carrier
+                hidden = torch.empty(take_from[2], take_from[3], self.stage.spec.hidden_size, dtype=self.stage.dtype, device="meta")
+            stash = self._stash_key(metadata)
+            state["taken"] = True  # Stage.forward consumes the slot before anything else
+            return run_rpc_forward(hidden, prompts, backends=backends, handler=self, active_adapter=metadata.get("active_adapter"),
+                                   points=float(metadata.get("points", 0)), take_from=take_from, push_to=push_to, stash=stash)
+        except BaseException:
+            if not state["taken"]:
+                drain_landing(take_from, "x_in", self.stage.device)
+            raise
 
     def rpc_backward(self, uids, inputs: torch.Tensor, grad_outputs: torch.Tensor, prompts: Optional[torch.Tensor] = None,
                      metadata: Optional[Dict[str, Any]] = None) -> List[torch.Tensor]:
@@ -338,20 +374,29 @@ class TransformerConnectionHandler:
 
     def _rpc_backward(self, uids, inputs: torch.Tensor, grad_outputs: torch.Tensor, prompts: Optional[torch.Tensor] = None,
                       metadata: Optional[Dict[str, Any]] = None) -> List[torch.Tensor]:
-        maybe_fail("rpc_backward", self.peer_id)
-        uids = self._check_uids(uids)
         metadata = metadata or {}
-        self.check_adapter(metadata.get("active_adapter"))
-        backends = [self.module_backends[u] for u in uids]
         grad_from, push_to = fabric_endpoints(metadata)
-        stash = self._stash_key(metadata)
-        if grad_from is not None:
-            grad_outputs = torch.empty(grad_from[2], grad_from[3], self.stage.spec.hidden_size, dtype=self.stage.dtype, device="meta")
-        if stash is not None:  # the span input stayed on this stage since the forward (see Stage.stash_put)
-            inputs = torch.empty(tuple(grad_outputs.shape), dtype=self.stage.dtype, device="meta")
-        return run_rpc_backward(inputs, grad_outputs, prompts, backends=backends, handler=self,
-                                active_adapter=metadata.get("active_adapter"), points=float(metadata.get("points", 0)),
-                                grad_from=grad_from, push_to=push_to, stash=stash)
+        state = {"taken": grad_from is None}
+        try:
+            maybe_fail("rpc_backward", self.peer_id)
+            uids = self._check_uids(uids)
+            self.check_adapter(metadata.get("active_adapter"))
+            backends = [self.module_backends[u] for u in uids]
+            stash = self._stash_key(metadata)
+            if grad_from is not None:
+                grad_outputs = torch.empty(grad_from[2], grad_from[3], self.stage.spec.hidden_size, dtype=self.stage.dtype, device="meta")
+            if stash is not None:  # the span input stayed on this stage since the forward (see Stage.stash_put)
+                inputs = torch.empty(tuple(grad_outputs.shape), dtype=self.stage.dtype, device="meta")
+                if stash not in self.stage._stash:
+                    raise KeyError(f"no activations are stashed under {stash!r} (expired, evicted, or this stage never ran that forward)")
+            state["taken"] = True  # Stage.backward reads (and acknowledges) the gradient slot itself
+            return run_rpc_backward(inputs, grad_outputs, prompts, backends=backends, handler=self,
+                                    active_adapter=metadata.get("active_adapter"), points=float(metadata.get("points", 0)),
+                                    grad_from=grad_from, push_to=push_to, stash=stash)
+        except BaseException:
+            if not state["taken"]:
+                drain_landing(grad_from, "g_in", self.stage.device)
+            raise
 
     @staticmethod
     def _stash_key(metadata: Dict[str, Any]) -> Optional[str]:

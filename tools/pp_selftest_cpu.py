@@ -80,6 +80,31 @@ def main():
         t_ok = max(t_err.values()) < 1e-3 and hops == {"forward": 3 * world, "backward": 3 * world}
         ok = ok and t_ok
         report.update(pp_selftest_cpu="ok" if ok else "FAILED", training_err=t_err, training_fabric_hops=hops)
+        if os.environ.get("PP_SELFTEST_FAULT") == "1":
+            # PETALS_B200_FAULTS makes the LAST stage refuse its 4th rpc_forward (= micro-batch 0 of the next pass) after the previous stage
+            # has already pushed into its landing slot: the stage must drain that slot, the client must finish the micro-batch on the
+            # tensor-carrying path, pause fabric passes, and the rings must still be in step afterwards
+            import time
+
+            def one_pass():
+                xa, pa = x.detach().clone().requires_grad_(True), prompts.detach().clone().requires_grad_(True)
+                before = dict(FabricPlan.hops_done)
+                t0 = time.monotonic()
+                ya = model.model.layers(xa, prompts=pa)
+                (ya * w).sum().backward()
+                err = max((ya - h).abs().max().item(), (xa.grad - x2.grad).abs().max().item(), (pa.grad - p2.grad).abs().max().item())
+                return err, {k: FabricPlan.hops_done[k] - before[k] for k in before}, time.monotonic() - t0
+
+            manager = model.model.layers.sequence_manager
+            faulted = one_pass()      # fault injected at the last stage: one micro-batch redone with tensors
+            cooling = one_pass()      # inside the cool-down: no fabric hops at all
+            manager.fabric_broken_until = 0.0
+            healed = one_pass()       # fabric again: only works if the refused transfer was drained
+            f_ok = (max(faulted[0], cooling[0], healed[0]) < 1e-3 and faulted[1]["forward"] < 3 * world and cooling[1] == {"forward": 0, "backward": 0}
+                    and healed[1] == {"forward": 3 * world, "backward": 3 * world} and healed[2] < 20)
+            ok = ok and f_ok
+            report.update(pp_selftest_cpu="ok" if ok else "FAILED",
+                          fault_passes={"faulted": faulted[1], "cooling": cooling[1], "healed": healed[1], "max_err": max(faulted[0], cooling[0], healed[0]), "healed_s": round(healed[2], 2)})
     host_barrier()
     server.shutdown()
     host_barrier()
