@@ -322,8 +322,8 @@ class InferenceSession:
     def _landing(self, fabric, idx: int, shape: Tuple[int, int, int]) -> Optional[dict]:
         """Where stage ``idx`` should store its output: the next stage's landing zone, this process's (last stage), or None =
         return it with the RPC."""
-        if fabric is None:
-            return None
+        if fabric is None or time.monotonic() < getattr(self._manager, "fabric_broken_until", 0.0):
+            return None  # no fabric, or a hop failed recently (the rings may be out of step until the stages have drained them)
         here = self._chain[idx]
         rows = shape[0] * shape[1]
         if here.fabric_rank is None or rows == 0 or rows > min(fabric.max_tokens, 4096) or shape[2] != fabric.hidden_size:
@@ -382,6 +382,7 @@ class InferenceSession:
         if errors:
             for stage in chain:  # landing-zone contents are unknown now: the whole chain is rebuilt from the first stage's log
                 stage.no_history = True
+            self._manager.fabric_broken_until = time.monotonic() + 60.0  # tensors travel with the RPCs for a while
             raise errors[0][1]
         B, L, H = shape
         return fabric.recv(B * L, "y_ret", chain[-1].fabric_rank).view(B, L, H)
