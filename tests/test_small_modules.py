@@ -244,3 +244,48 @@ def test_stage_activation_stash_is_bounded_and_single_use():
     st._stash.move_to_end("old", last=False)
     st.stash_put("fresh", torch.zeros(1))
     assert "old" not in st._stash and "fresh" in st._stash
+
+
+def test_failed_fabric_request_drains_its_landing_slot(monkeypatch):
+    """server/handler.py: rpc_forward / rpc_backward that fail before the stage consumed the announced transfer (fault injection, unknown
+    adapter, missing stash) still take + acknowledge the landing slot exactly once; requests that fail later do not drain twice."""
+    import types
+
+    import pytest
+    import torch
+
+    import petals_b200.parallel.fabric as fabric_mod
+    import petals_b200.server.handler as handler_mod
+
+    drained = []
+
+    class FakeFabric:
+        max_tokens, n_slots, world, rank, hidden_size = 64, 4, 2, 1, 8
+
+        def recv(self, rows, kind, src, slot=0):
+            drained.append((rows, kind, src, slot))
+            return torch.zeros(rows, 8)
+
+    fab = FakeFabric()
+    monkeypatch.setattr(fabric_mod, "_fabric", fab)
+    stage = types.SimpleNamespace(device=torch.device("cpu"), dtype=torch.float32, spec=types.SimpleNamespace(hidden_size=8), _stash={})
+    h = types.SimpleNamespace(peer_id="s1", stage=stage, module_backends={}, _check_uids=lambda uids: (_ for _ in ()).throw(ValueError("unknown uid")),
+                              check_adapter=lambda a: None, _stash_key=handler_mod.TransformerConnectionHandler._stash_key)
+    meta = {"fabric_in": {"B": 2, "T": 3, "src_rank": 0, "slot": 2}}
+    with pytest.raises(ValueError):
+        handler_mod.TransformerConnectionHandler._rpc_forward(h, ["x"], torch.empty(0), None, dict(meta))
+    assert drained == [(6, "x_in", 0, 2)]
+    with pytest.raises(ValueError):
+        handler_mod.TransformerConnectionHandler._rpc_backward(h, ["x"], torch.empty(0), torch.empty(0), None, dict(meta))
+    assert drained[-1] == (6, "g_in", 0, 2) and len(drained) == 2
+    # a backward whose stash is gone: refused before the stage runs, gradient slot drained
+    h._check_uids = lambda uids: list(uids)
+    h.module_backends = {"x": object()}
+    with pytest.raises(KeyError):
+        handler_mod.TransformerConnectionHandler._rpc_backward(h, ["x"], torch.empty(0), torch.empty(0), None, dict(meta, stash="gone"))
+    assert len(drained) == 3
+    # no fabric metadata: nothing to drain
+    h._check_uids = lambda uids: (_ for _ in ()).throw(ValueError("unknown uid"))
+    with pytest.raises(ValueError):
+        handler_mod.TransformerConnectionHandler._rpc_forward(h, ["x"], torch.zeros(1, 1, 8), None, {})
+    assert len(drained) == 3
