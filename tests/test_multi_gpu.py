@@ -23,13 +23,30 @@ def test_tp2_matches_oracle():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
+def test_tp2_sparse_moe_matches_oracle():
+    """Mixtral blocks in the tensor-parallel engine: every expert's FFN columns split over the pair, replicated router, stand-alone LL
+    all-reduce halves around the device-routed expert GEMVs (decode) and grouped-GEMM prefill with owner scatter (validated on 2 and 8
+    B200s: profiles/r2_bench_mixtral_8x7b_tp8.json `selftests`)."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29733",
+           os.path.join(ROOT, "tools", "tp_selftest.py")]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, TP_SELFTEST_MODEL="mixtral-tiny"))
+    lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
+    assert proc.returncode == 0 and lines, proc.stdout[-2000:] + proc.stderr[-2000:]
+    report = json.loads(lines[-1])
+    assert report["tp_selftest"] == "ok" and report["model"] == "mixtral-tiny"
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_pp2_fused_stage_hop_matches_oracle():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1", "--master-port", "29732",
            os.path.join(ROOT, "tools", "pp_selftest.py")]
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     lines = [l for l in proc.stdout.splitlines() if l.startswith("{")]
     assert proc.returncode == 0 and lines, proc.stdout[-2000:] + proc.stderr[-2000:]
-    assert json.loads(lines[-1])["pp_selftest"] == "ok"
+    report = json.loads(lines[-1])
+    assert report["pp_selftest"] == "ok"
+    # training over the fabric: every forward micro-batch and every gradient hopped through the landing rings, with and without deep prompts
+    assert all(h == {"forward": 6, "backward": 6} for h in report["training_fabric_hops"].values()), report
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
