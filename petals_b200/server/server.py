@@ -219,6 +219,9 @@ class Server:
                 self.module_container.ready.wait()
                 if not self.skip_reachability_check:
                     validate_direct_reachability(self.dht, self.peer_id)
+                from petals_b200.utils.version import validate_version
+
+                validate_version(self.dht, self.module_uids)  # newer peers in the swarm?
                 while not self.stop.is_set():
                     timeout = random.random() * 2 * self.mean_balance_check_period
                     if self.stop.wait(timeout):

@@ -289,3 +289,28 @@ def test_failed_fabric_request_drains_its_landing_slot(monkeypatch):
     with pytest.raises(ValueError):
         handler_mod.TransformerConnectionHandler._rpc_forward(h, ["x"], torch.zeros(1, 1, 8), None, {})
     assert len(drained) == 3
+
+
+def test_version_check_looks_at_the_peers_of_the_swarm():
+    """utils/version.py: offline there is no package index to ask for updates, but the peers of the swarm announce their versions —
+    a process warns (and returns the version) when peers serving the same blocks run a newer release; malformed versions sort lowest."""
+    import time
+
+    import petals_b200
+    from petals_b200.data_structures import ServerInfo, ServerState, make_uid
+    from petals_b200.parallel.swarm import Swarm
+    from petals_b200.utils.dht import declare_active_modules
+    from petals_b200.utils.version import newest_version, parse_version, validate_version
+
+    assert parse_version("2.3.0.dev2") == (2, 3, 0) and parse_version("v10.1") == (10, 1) and parse_version("garbage") == () and parse_version(None) == ()
+    assert newest_version(["1.9.9", None, "1.10.0", "x"]) == "1.10.0" and newest_version([]) is None
+    swarm = Swarm("t-version")
+    uids = [make_uid("m", i) for i in range(2)]
+    mine = parse_version(petals_b200.__version__)
+    newer = ".".join(str(p) for p in (mine[0] + 1,) + tuple(mine[1:])) if mine else "999.0"
+    assert validate_version() is None and validate_version(swarm, uids) is None  # nobody else around
+    info = ServerInfo(state=ServerState.ONLINE, throughput=1.0, version=petals_b200.__version__)
+    declare_active_modules(swarm, uids, info, time.time() + 60, peer_id="same")
+    assert validate_version(swarm, uids) is None
+    declare_active_modules(swarm, uids[:1], ServerInfo(state=ServerState.ONLINE, throughput=1.0, version=newer), time.time() + 60, peer_id="newer")
+    assert validate_version(swarm, uids) == newer
