@@ -8,7 +8,6 @@ from __future__ import annotations
 import argparse
 import os
 import signal
-import sys
 
 import torch
 import yaml

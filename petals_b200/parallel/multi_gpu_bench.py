@@ -365,8 +365,6 @@ def _pipeline_appendix(args, engine, cache) -> dict:
 
 def follower_loop_with_marks(engine, cache, ring, consumer: int) -> dict:
     """follower_loop + CUDA-event marks so that every rank times the same K steps on its own device."""
-    from petals_b200.server.memory_cache import SessionCache
-
     sessions = {}
     marks = {}
     while True:

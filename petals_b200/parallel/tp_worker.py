@@ -16,7 +16,6 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 import torch.distributed as dist
 
-from petals_b200.ops.functional import PAGE
 from petals_b200.parallel.control import CommandRing
 from petals_b200.parallel.symmetric import SymmetricHeap, host_barrier
 from petals_b200.parallel.tensor_parallel import MAX_ROWS, TPDecodeEngine, local_spec

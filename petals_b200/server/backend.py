@@ -19,7 +19,6 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 
-from petals_b200.data_structures import make_uid
 from petals_b200.models.block_oracle import GenericBlock
 from petals_b200.server.memory_cache import MemoryCache, SessionCache
 from petals_b200.server.task_pool import PrioritizedTaskPool, Runtime

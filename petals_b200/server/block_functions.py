@@ -11,7 +11,7 @@ from typing import List, Optional, Sequence
 
 import torch
 
-from petals_b200.utils.misc import DUMMY, is_dummy
+from petals_b200.utils.misc import is_dummy
 
 # Steps with at most this many tokens run the whole span as one atomic runtime task (reference :26).
 MAX_SHORT_INFERENCE_TOKENS = 128

@@ -29,17 +29,16 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple
 import torch
 
 import petals_b200
-from petals_b200.data_structures import CHAIN_DELIMITER, ModuleUID, split_uids
+from petals_b200.data_structures import ModuleUID, split_uids
 from petals_b200.server.backend import Stage, TransformerBackend
 from petals_b200.server.block_functions import MAX_SHORT_INFERENCE_TOKENS, run_rpc_backward, run_rpc_forward
-from petals_b200.server.memory_cache import AllocationFailed, SessionCache
+from petals_b200.server.memory_cache import SessionCache
 from petals_b200.server.task_pool import PrioritizedTaskPool
 from petals_b200.server.task_prioritizer import DummyTaskPrioritizer, TaskPrioritizerBase
 from petals_b200.utils.logging import get_logger
 from petals_b200.utils.metrics import ServerMetrics
 from petals_b200.utils.fault_injection import maybe_fail
-from petals_b200.utils.misc import DUMMY, is_dummy
-from petals_b200.utils.tracing import nvtx_range
+from petals_b200.utils.misc import is_dummy
 
 CACHE_TOKENS_AVAILABLE = "cache_tokens_available"  # rpc_info key (reference: handler.py:52)
 

@@ -26,7 +26,7 @@ lossy within the bounds tested in tests/test_compression.py otherwise.
 from __future__ import annotations
 
 from enum import IntEnum
-from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
+from typing import Any, Dict, List, Sequence, Tuple, Union
 
 import torch
 

@@ -14,7 +14,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     from petals_b200.parallel.symmetric import host_barrier
     from petals_b200.parallel.fabric import init_fabric
-    from petals_b200.parallel.swarm import FileSwarm
     from petals_b200.server.from_pretrained import load_pretrained_block
     from petals_b200.server.server import Server
     from petals_b200.utils.auto_config import AutoDistributedConfig, AutoDistributedModelForCausalLM
