@@ -86,7 +86,10 @@ def tp_selftest(dev: torch.device, preset: str = "llama-tiny") -> dict:
         container.shutdown()
         host_barrier()
         heap.close()
-    ok = err < 0.05 and agree > 0.9 and err2 < 0.05 and agree2 > 0.9
+    # Bounds with head-room over what B200 boxes measured (profiles/): dense 0.9-1.0 % at 2-8 ranks; sparse MoE 0.8 % on decode steps and
+    # 3.7-4.3 % on the chunked prompt (a routing decision that flips at a near-tie changes a whole row), arg-max agreement 92-97 % there
+    moe = config.block_spec().mlp == "moe"
+    ok = err < 0.05 and agree > 0.9 and err2 < (0.08 if moe else 0.05) and agree2 > (0.85 if moe else 0.9)
     return {"tp_selftest": "ok" if ok else "FAILED", "model": preset, "world": world, "rel_err": round(err, 5), "argmax_agreement": round(agree, 4),
                       "prefill_rel_err": round(err2, 5), "prefill_argmax_agreement": round(agree2, 4),
                       "generated": out[0, 8:].tolist(), "peer_store_GBps": bw, "flag_latency_us": lat}
@@ -181,7 +184,8 @@ def pp_selftest(dev: torch.device) -> dict:
                 t_err[tag] = {"y": rel(y, h.detach()), "grad_x": rel(x.grad, x2.grad)}
                 if use_prompts:
                     t_err[tag]["grad_prompts"] = rel(prompts.grad, p2.grad)
-            t_ok = (max(v for e in t_err.values() for v in e.values()) < 2e-2
+            # bf16 rounding accumulates with depth (2 blocks per stage): 0.7 % at 2 stages, 1.5 % at 8 on B200 boxes — 2 % per 8 blocks
+        t_ok = (max(v for e in t_err.values() for v in e.values()) < 2e-2 * max(1.0, n_layers / 8)
                     and all(h_ == {"forward": 3 * world, "backward": 3 * world} for h_ in hops.values()))
             ok = ok and t_ok
             t_err = {k: {kk: round(vv, 5) for kk, vv in v.items()} for k, v in t_err.items()}
