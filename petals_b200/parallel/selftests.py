@@ -185,7 +185,7 @@ def pp_selftest(dev: torch.device) -> dict:
                 if use_prompts:
                     t_err[tag]["grad_prompts"] = rel(prompts.grad, p2.grad)
             # bf16 rounding accumulates with depth (2 blocks per stage): 0.7 % at 2 stages, 1.5 % at 8 on B200 boxes — 2 % per 8 blocks
-        t_ok = (max(v for e in t_err.values() for v in e.values()) < 2e-2 * max(1.0, n_layers / 8)
+            t_ok = (max(v for e in t_err.values() for v in e.values()) < 2e-2 * max(1.0, n_layers / 8)
                     and all(h_ == {"forward": 3 * world, "backward": 3 * world} for h_ in hops.values()))
             ok = ok and t_ok
             t_err = {k: {kk: round(vv, 5) for kk, vv in v.items()} for k, v in t_err.items()}
