@@ -50,7 +50,8 @@ def run_pp_tp(args, n_stages: int, tp: int) -> None:
     BASELINE.json config #4 names this layout for Mixtral-8x7B (4 stages x TP 2). Ranks [gT, (g+1)T) form group g and serve blocks
     [bounds[g], bounds[g+1]); the group's first rank is its leader (stage process: handler, KV bookkeeping, command ring to the
     followers), the client runs on rank 0. Inside a group everything is the tensor-parallel engine (NVLink LL all-reduces, sequence-
-    parallel prefill); between stages the activations of one token (hidden_size x 2 bytes) travel with the stage-to-stage RPC."""
+    parallel prefill); between stages the hidden states hop through an NVLink fabric the LEADERS share (landing rings, one peer copy +
+    flag per hop; PETALS_B200_PPTP_FABRIC=0: with the stage-to-stage RPCs instead)."""
     import tempfile
 
     from petals_b200.data_structures import ModelInfo, ServerInfo, ServerState
