@@ -314,3 +314,47 @@ def test_version_check_looks_at_the_peers_of_the_swarm():
     assert validate_version(swarm, uids) is None
     declare_active_modules(swarm, uids[:1], ServerInfo(state=ServerState.ONLINE, throughput=1.0, version=newer), time.time() + 60, peer_id="newer")
     assert validate_version(swarm, uids) == newer
+
+
+def test_stages_without_fused_hops_use_host_issued_fabric_copies():
+    """server/backend.py: a tensor-parallel leader (``whole_span_only`` engine) has no epilogue that stores into a peer's landing slot, so
+    Stage.inference_step / Stage.forward take the input with a fabric receive and deliver the output with a fabric send around the plain
+    engine call — the protocol the fused engines implement inside their kernels."""
+    import collections
+    import threading
+
+    import torch
+
+    from petals_b200.server.backend import Stage
+
+    log = []
+
+    class FakeFabric:
+        def recv(self, rows, kind, src, slot=0):
+            log.append(("recv", rows, kind, src, slot))
+            return torch.full((rows, 4), 2.0)
+
+        def send(self, rows, rank, kind, slot=0):
+            log.append(("send", tuple(rows.shape), rank, kind, slot, float(rows.sum())))
+
+    class LeaderEngine:
+        whole_span_only = True
+
+        def inference_step(self, session, hidden, prompts, hypo_ids, block_range):
+            return hidden + 1
+
+        def forward(self, hidden, prompts, block_range):
+            return hidden * 3
+
+    st = Stage.__new__(Stage)
+    st.engine, st.blocks, st.device, st.dtype, st.start_block, st.active_adapter = LeaderEngine(), [None, None], torch.device("cpu"), torch.float32, 0, None
+    st._stash, st._stash_lock = collections.OrderedDict(), threading.Lock()
+    fab = FakeFabric()
+    out = st.inference_step(None, torch.empty(1, 2, 4), None, None, 0, 2, take_from=(fab, 0, 1, 2, 3), push_to=(fab, "x_in", 2, 1))
+    assert out.shape == (1, 0, 4) and log == [("recv", 2, "x_in", 0, 3), ("send", (2, 4), 2, "x_in", 1, 24.0)]
+    log.clear()
+    out = st.forward(torch.empty(1, 2, 4), None, 0, 2, take_from=(fab, 1, 1, 2, 0), push_to=(fab, "y_ret", 0, 2), stash="k")
+    assert out.shape == (1, 0, 4) and log == [("recv", 2, "x_in", 1, 0), ("send", (2, 4), 0, "y_ret", 2, 48.0)]
+    assert torch.equal(st.stash_pop("k"), torch.full((1, 2, 4), 2.0))  # the stage kept its input for the backward
+    log.clear()
+    assert torch.equal(st.inference_step(None, torch.ones(1, 1, 4), None, None, 0, 2), torch.full((1, 1, 4), 2.0)) and not log  # no fabric: plain call
