@@ -66,3 +66,50 @@ def test_sample_up_to_is_an_ordered_subset_of_the_right_size(population, k):
     assert len(chosen) == min(len(population), max(k, 0)) and len(set(chosen)) == len(chosen)
     positions = [population.index(c) for c in chosen]
     assert positions == sorted(positions)
+
+
+@given(st.integers(1, 5), st.integers(1, 7), st.sets(st.tuples(st.integers(0, 4), st.integers(0, 6)), max_size=6), st.booleans())
+@settings(max_examples=40, deadline=None)
+def test_wavefront_keeps_item_order_on_every_stage_and_skips_failed_items(n_stages, n_items, failures, threaded):
+    """client/pipeline.py:run_wave — whatever fails where: every stage sees the items it processes in item order, an item visits the
+    stages in stage order, an item whose work raised is skipped by all later stages and carries the error, nothing is lost or duplicated."""
+    import threading
+
+    from petals_b200.client.pipeline import run_wave
+
+    class Item:
+        def __init__(self, index):
+            self.index, self.error, self.detached, self.visited = index, None, False, []
+
+    items = [Item(i) for i in range(n_items)]
+    seen = [[] for _ in range(n_stages)]
+    lock = threading.Lock()
+
+    def stage_work(s):
+        def work(it):
+            with lock:
+                seen[s].append(it.index)
+            it.visited.append(s)
+            if (s, it.index) in failures:
+                raise RuntimeError(f"stage {s} refuses item {it.index}")
+        return work
+
+    run_wave(items, [stage_work(s) for s in range(n_stages)], threaded=threaded)
+    for s in range(n_stages):
+        assert seen[s] == sorted(seen[s]) and len(set(seen[s])) == len(seen[s])  # item order, no duplicates
+    for it in items:
+        first_fail = min((s for s in range(n_stages) if (s, it.index) in failures), default=None)
+        expect = list(range(n_stages)) if first_fail is None else list(range(first_fail + 1))
+        assert it.visited == expect and (it.error is None) == (first_fail is None)
+
+
+@given(st.integers(1, 300), st.integers(1, 6))
+@settings(max_examples=30, deadline=None)
+def test_mxfp8_scale_layout_round_trips_for_any_shape(rows, kblocks128):
+    from petals_b200.ops.quant import pack_scales, unpack_scales
+
+    K = 128 * kblocks128
+    e = torch.randint(0, 256, (rows, K // 32), dtype=torch.uint8)
+    packed = pack_scales(e)
+    assert packed.numel() == kblocks128 * ((rows + 127) // 128) * 512
+    assert torch.equal(unpack_scales(packed, rows, K), e)
