@@ -53,6 +53,11 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--public_ip", type=str, default=None, help="multi-box swarms: shorthand for --announce_maddrs /ip4/<ip>/tcp/0")
     p.add_argument("--no_auto_relay", action="store_false", dest="use_auto_relay")
     p.add_argument("--daemon_startup_timeout", type=float, default=60)
+    p.add_argument("--fabric_address", type=str, default=None, help="HOST:PORT where the stage processes of this NVLink box rendezvous to form a "
+                        "landing-ring fabric: between members, hidden states / micro-batches / gradients hop GPU to GPU instead of travelling with the RPCs")
+    p.add_argument("--fabric_rank", type=int, default=None, help="this process's index among the fabric members (0 .. fabric_world - 1)")
+    p.add_argument("--fabric_world", type=int, default=None, help="number of stage processes forming the fabric (all must start; joining is collective)")
+    p.add_argument("--fabric_max_tokens", type=int, default=8192, help="rows (batch x positions) one landing slot holds; larger steps travel with the RPCs")
     p.add_argument("--compression", type=str, default="NONE", help="wire codec for the hidden states this server returns over the socket transport: NONE, FLOAT16, MEANSTD_16BIT, "
                         "QUANTILE_8BIT, UNIFORM_8BIT, BLOCKWISE_8BIT or MXFP8 (clients can override per request with output_compression; "
                         "NVLink stage hops are never compressed)")

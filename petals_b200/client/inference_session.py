@@ -79,6 +79,7 @@ class StageStream:
         self.closed = False
         self.successor: Optional["StageStream"] = None
         self.fabric_rank: Optional[int] = None  # rank of the stage in the NVLink fabric (None: tensors travel with the RPC)
+        self.fabric_info: Optional[dict] = None  # what the stage announced about that fabric: id, rank, max_tokens, hidden_size, n_slots
         self.no_history = False  # some input arrived over the fabric: the client cannot replay this stream
 
     @classmethod
@@ -89,13 +90,20 @@ class StageStream:
         request.update(max_length=max_length, session_id=session_id, alloc_timeout=float(alloc_timeout))
         stub = manager.connect(span.peer_id)
         self = cls(manager.config, span, uids, stub.rpc_inference(list(uids), request), max_length=max_length, session_id=session_id)
-        from petals_b200.parallel.fabric import get_fabric
-
-        if get_fabric() is not None and manager.config.use_server_to_server:
+        if manager.config.use_server_to_server:
+            # which NVLink fabric (if any) the stage sits on: two stages announcing the same fabric id hop through each other's landing
+            # rings whether or not this client is a member of that fabric
             try:
-                self.fabric_rank = stub.rpc_info().get("fabric_rank")
+                info = stub.rpc_info()
+                self.fabric_info = info.get("fabric")
+                self.fabric_rank = self.fabric_info["rank"] if self.fabric_info else info.get("fabric_rank")
+                if self.fabric_info is None and self.fabric_rank is not None:  # older stage: rank only; usable when this process is a member
+                    from petals_b200.parallel.fabric import fabric_info, get_fabric
+
+                    mine = fabric_info(get_fabric())
+                    self.fabric_info = dict(mine, rank=self.fabric_rank) if mine else None
             except Exception:  # noqa: BLE001 - a stage that cannot tell simply gets its tensors with the RPC
-                self.fabric_rank = None
+                self.fabric_info, self.fabric_rank = None, None
         return self
 
     # the attributes below keep older call sites (tests, tools) readable
@@ -156,8 +164,9 @@ class StageStream:
         return result
 
     def feed_landed(self, shape: Tuple[int, int, int], src_rank: int, prompts: torch.Tensor, hypo_ids: torch.Tensor, *, step_id: str,
-                    n_new: int, deliver_to: Optional[dict] = None, slot: int = 0) -> None:
-        """Run one step whose input ``src_rank`` stored (or is about to store) into landing slot ``slot`` of this stage."""
+                    n_new: int, deliver_to: Optional[dict] = None, slot: int = 0):
+        """Run one step whose input ``src_rank`` stored (or is about to store) into landing slot ``slot`` of this stage. Returns the
+        stage's output, or only its shape when the output went to a landing zone (``deliver_to``)."""
         if self.closed:
             raise RuntimeError("this stage stream is closed")
         B, L, _ = shape
@@ -167,8 +176,9 @@ class StageStream:
         self.no_history = True
         meta = self._request(step_id, deliver_to)
         meta["fabric_in"] = {"src_rank": src_rank, "B": B, "T": L, "slot": slot}
-        self.stream.step(torch.empty(0), prompts, hypo_ids, metadata=meta)
+        result = self.stream.step(torch.empty(0), prompts, hypo_ids, metadata=meta)
         self.primed, self.cursor = True, self.cursor + n_new
+        return tuple(shape) if deliver_to is not None else result
 
     def close(self) -> None:
         if not self.closed:
@@ -322,18 +332,20 @@ class InferenceSession:
     def _landing(self, fabric, idx: int, shape: Tuple[int, int, int]) -> Optional[dict]:
         """Where stage ``idx`` should store its output: the next stage's landing zone, this process's (last stage), or None =
         return it with the RPC."""
-        if fabric is None or time.monotonic() < getattr(self._manager, "fabric_broken_until", 0.0):
-            return None  # no fabric, or a hop failed recently (the rings may be out of step until the stages have drained them)
-        here = self._chain[idx]
+        if time.monotonic() < getattr(self._manager, "fabric_broken_until", 0.0):
+            return None  # a hop failed recently (the rings may be out of step until the stages have drained them)
+        here = self._chain[idx].fabric_info
         rows = shape[0] * shape[1]
-        if here.fabric_rank is None or rows == 0 or rows > min(fabric.max_tokens, 4096) or shape[2] != fabric.hidden_size:
+        if here is None or rows == 0 or rows > min(here["max_tokens"], 4096) or shape[2] != here["hidden_size"]:
             return None
         if idx + 1 < len(self._chain):
-            there = self._chain[idx + 1]
-            if there.fabric_rank is None or there.fabric_rank == here.fabric_rank:
-                return None
-            return {"kind": "x_in", "rank": there.fabric_rank}
-        if here.span.end == self.num_blocks and here.fabric_rank != fabric.rank:
+            there = self._chain[idx + 1].fabric_info
+            if there is None or there.get("id") != here.get("id") or there["rank"] == here["rank"]:
+                return None  # not on the same fabric (or the same GPU): the tensor travels with the RPCs
+            return {"kind": "x_in", "rank": there["rank"]}
+        # the last stage can only return through a landing ring when THIS process is a member of the same fabric
+        if (fabric is not None and getattr(fabric, "fabric_id", None) == here.get("id") and self._chain[idx].span.end == self.num_blocks
+                and here["rank"] != fabric.rank):
             return {"kind": "y_ret", "rank": fabric.rank}
         return None
 
@@ -356,13 +368,15 @@ class InferenceSession:
         """Steady state of a chain that lives entirely on the NVLink fabric: issue this step to ALL stages at once. Returns
         None when the chain does not qualify (the caller then walks it stage by stage)."""
         chain = self._chain
-        if (fabric is None or len(chain) < 2 or chain[0].span.start != 0 or chain[-1].span.end != self.num_blocks
+        if (len(chain) < 2 or chain[0].span.start != 0 or chain[-1].span.end != self.num_blocks
                 or any(not s.primed or s.closed or s.cursor != self._position for s in chain)):
             return None
         shape = tuple(x.shape)
         targets = [self._landing(fabric, i, shape) for i in range(len(chain))]
-        if any(t is None for t in targets):
-            return None
+        if any(t is None for t in targets[:-1]):
+            return None  # some hop between stages does not ride a fabric
+        # targets[-1] is None when this process is not a member of the stages' fabric (or shares the last stage's GPU): the last stage
+        # then answers with the tensor
 
         def span_prompts(stage: StageStream):
             return DUMMY if is_dummy(prompts) else prompts[stage.span.start: stage.span.end]
@@ -371,10 +385,10 @@ class InferenceSession:
         for i in range(1, len(chain)):
             jobs.append(_dispatch.submit(chain[i].feed_landed, shape, chain[i - 1].fabric_rank, span_prompts(chain[i]), hypo_ids,
                                          step_id=step_id, n_new=n_new, deliver_to=targets[i]))
-        errors = []
+        errors, last = [], None
         for stage, job in zip(chain, jobs):
             try:
-                job.result()
+                last = job.result()
                 self._manager.on_request_success(stage.span.peer_id)
             except Exception as e:  # noqa: BLE001
                 self._manager.on_request_failure(stage.span.peer_id)
@@ -384,6 +398,8 @@ class InferenceSession:
                 stage.no_history = True
             self._manager.fabric_broken_until = time.monotonic() + 60.0  # tensors travel with the RPCs for a while
             raise errors[0][1]
+        if targets[-1] is None:
+            return last
         B, L, H = shape
         return fabric.recv(B * L, "y_ret", chain[-1].fabric_rank).view(B, L, H)
 
@@ -399,10 +415,11 @@ class InferenceSession:
                 or chain[0].span.start != 0 or chain[-1].span.end != self.num_blocks
                 or any(s.closed or s.cursor != self._position for s in chain) or (self._position > 0 and any(not s.primed for s in chain))):
             return None
-        if fabric is not None:
-            chunk = max(1, min(chunk, fabric.max_tokens // max(B, 1)))
+        infos = [s.fabric_info for s in chain if s.fabric_info is not None]
+        if infos:  # chunks must fit the smallest landing slot on the way; one ring slot per chunk in flight
+            chunk = max(1, min(chunk, min(i["max_tokens"] for i in infos) // max(B, 1)))
         bounds = [(t0, min(n_new, t0 + chunk)) for t0 in range(0, n_new, chunk)]
-        n_slots = getattr(fabric, "n_slots", 1) if fabric is not None else 1
+        n_slots = min((i.get("n_slots", 1) for i in infos), default=1)
         step_id = str(uuid.uuid4())
         H = x.shape[2]
 
@@ -428,8 +445,7 @@ class InferenceSession:
                     target = dict(target, slot=it.index % n_slots)
                 sid = f"{step_id}:{it.index}"
                 if isinstance(it.x, tuple):  # landed in this stage's ring by the previous stage
-                    stage.feed_landed(shape, it.x[0], DUMMY, DUMMY_INT64, step_id=sid, n_new=n, deliver_to=target, slot=it.index % n_slots)
-                    result = shape
+                    result = stage.feed_landed(shape, it.x[0], DUMMY, DUMMY_INT64, step_id=sid, n_new=n, deliver_to=target, slot=it.index % n_slots)
                 else:
                     result = stage.feed(it.x, DUMMY, DUMMY_INT64, step_id=sid, n_new=n, deliver_to=target)
                 it.x = (stage.fabric_rank, shape) if target is not None else result
@@ -488,8 +504,7 @@ class InferenceSession:
                 shape = landed[1] if landed is not None else tuple(x.shape)
                 deliver_to = self._landing(fabric, idx, shape)
                 if landed is not None:
-                    stage.feed_landed(shape, landed[0], span_prompts, hypo_ids, step_id=step_id, n_new=n_new, deliver_to=deliver_to)
-                    result = shape
+                    result = stage.feed_landed(shape, landed[0], span_prompts, hypo_ids, step_id=step_id, n_new=n_new, deliver_to=deliver_to)
                 else:
                     result = stage.feed(x, span_prompts, hypo_ids, step_id=step_id, n_new=n_new, deliver_to=deliver_to)
                 if deliver_to is not None:

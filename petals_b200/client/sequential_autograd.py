@@ -99,8 +99,11 @@ class FabricPlan:
 
     hops_done = {"forward": 0, "backward": 0}  # process-wide counters (self-tests check that this path really ran)
 
-    def __init__(self, fabric, spans: Sequence[RemoteSpanInfo], ranks: Sequence[int]):
+    def __init__(self, fabric, spans: Sequence[RemoteSpanInfo], ranks: Sequence[int], n_slots: Optional[int] = None):
+        # ``fabric``: this process's own membership of the stages' fabric, or None — the stages then still hop among themselves and the
+        # two ends of a pass (output of the last stage, gradient into the last stage) travel with the RPCs
         self.fabric, self.spans, self.ranks = fabric, list(spans), list(ranks)
+        self.n_slots = max(1, n_slots if n_slots is not None else getattr(fabric, "n_slots", 1))
 
     @classmethod
     def probe(cls, manager: RemoteSequenceManager, route: Optional[Route], shape: Tuple[int, int, int]) -> Optional["FabricPlan"]:
@@ -108,25 +111,30 @@ class FabricPlan:
             return None
         if time.monotonic() < getattr(manager, "fabric_broken_until", 0.0):  # a hop failed recently: rings may be out of step, carry tensors
             return None
-        from petals_b200.parallel.fabric import get_fabric
+        from petals_b200.parallel.fabric import fabric_info, get_fabric
 
         fabric = get_fabric()
+        mine = fabric_info(fabric)
         B, T, H = shape
-        if fabric is None or H != fabric.hidden_size or B * T > fabric.max_tokens or B * T == 0:
-            return None
-        ranks = []
+        infos = []
         for span in route.spans:
             try:
-                rank = manager.connect(span.peer_id).rpc_info().get("fabric_rank")
+                announced = manager.connect(span.peer_id).rpc_info()
             except Exception:  # noqa: BLE001 - an unreachable stage: the tensor-carrying path deals with it
                 return None
-            if rank is None or (ranks and rank == ranks[-1]):
-                return None
-            ranks.append(int(rank))
-        return cls(fabric, route.spans, ranks)
+            info = announced.get("fabric")
+            if info is None and announced.get("fabric_rank") is not None and mine is not None:  # older stage: rank only
+                info = dict(mine, rank=announced["fabric_rank"])
+            if info is None or (infos and (info.get("id") != infos[-1].get("id") or info["rank"] == infos[-1]["rank"])):
+                return None  # some pair of neighbours does not share a fabric (or shares a GPU)
+            infos.append(info)
+        if H != infos[0]["hidden_size"] or B * T == 0 or B * T > min(i["max_tokens"] for i in infos):
+            return None
+        member = mine is not None and mine.get("id") == infos[0].get("id")
+        return cls(fabric if member else None, route.spans, [int(i["rank"]) for i in infos], n_slots=min(i.get("n_slots", 1) for i in infos))
 
     def slot(self, mb: "MicroBatch") -> int:
-        return mb.index % max(1, getattr(self.fabric, "n_slots", 1))
+        return mb.index % self.n_slots
 
     def forward_hop(self, manager: RemoteSequenceManager, mb: "MicroBatch", i: int) -> None:
         span, last = self.spans[i], i == len(self.spans) - 1
@@ -137,7 +145,7 @@ class FabricPlan:
         meta["stash"] = key
         if i > 0:
             meta["fabric_in"] = {"src_rank": self.ranks[i - 1], "B": B, "T": T, "slot": slot}
-        returns = last and self.ranks[i] == self.fabric.rank  # a last stage on this rank's GPU answers with the tensor
+        returns = last and (self.fabric is None or self.ranks[i] == self.fabric.rank)  # not a member / same GPU: the tensor comes with the answer
         if not returns:
             meta["fabric_out"] = ({"kind": "y_ret", "rank": self.fabric.rank, "slot": slot} if last
                                   else {"kind": "x_in", "rank": self.ranks[i + 1], "slot": slot})
@@ -162,7 +170,7 @@ class FabricPlan:
         slot = self.slot(mb)
         meta["stash"] = hop.stash
         grad = torch.empty(0)
-        if last and self.ranks[i] == self.fabric.rank:
+        if last and (self.fabric is None or self.ranks[i] == self.fabric.rank):
             grad = mb.x.detach()
         else:
             if last:  # dL/dy is here: store it into the last stage's gradient slot

@@ -293,7 +293,23 @@ def init_fabric(hidden_size: int, max_tokens: int = 8192, group=None, host_dtype
         _fabric = Fabric(hidden_size, max_tokens, group, n_slots=n_slots)
     else:
         _fabric = HostFabric(hidden_size, min(max_tokens, 1024), group, host_dtype, n_slots=n_slots)
+    # one identity per fabric: clients learn from `rpc_info` which stages can reach each other's landing rings (two stages hop over NVLink
+    # only if they announce the same id), whether or not the client itself is a member
+    import uuid
+
+    ident = [uuid.uuid4().hex if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    _fabric.fabric_id = ident[0]
     return _fabric
+
+
+def fabric_info(fabric=None) -> Optional[dict]:
+    """What a stage announces about its fabric membership (``rpc_info()["fabric"]``)."""
+    fabric = fabric if fabric is not None else _fabric
+    if fabric is None:
+        return None
+    return {"id": getattr(fabric, "fabric_id", None), "rank": fabric.rank, "world": fabric.world, "max_tokens": fabric.max_tokens,
+            "hidden_size": fabric.hidden_size, "n_slots": getattr(fabric, "n_slots", 1)}
 
 
 def get_fabric() -> Optional[Fabric]:

@@ -453,7 +453,13 @@ class TransformerConnectionHandler:
             outputs_schema=dict(hidden_size=spec.hidden_size),
             inference_schema=dict(args=("hidden_states", "prompts", "hypo_ids"), hidden_size=spec.hidden_size),
             device=str(self.stage.device), engine="sm_100a" if self.stage.engine is not None else "oracle", metrics=self.metrics.snapshot(),
-            fabric_rank=self._fabric_rank())
+            fabric_rank=self._fabric_rank(), fabric=self._fabric_info())
+
+    @staticmethod
+    def _fabric_info() -> Optional[dict]:
+        from petals_b200.parallel.fabric import fabric_info
+
+        return fabric_info()
 
     @staticmethod
     def _fabric_rank() -> Optional[int]:

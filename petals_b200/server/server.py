@@ -68,7 +68,8 @@ class Server:
                  use_auto_relay: bool = True, adapters: Sequence[str] = (), peer_id: Optional[str] = None,
                  use_cuda_graphs: bool = True, force_oracle: bool = False, host_maddrs: Optional[Sequence[str]] = None,
                  announce_maddrs: Optional[Sequence[str]] = None, public_ip: Optional[str] = None, metrics_port: Optional[int] = None,
-                 **kwargs):
+                 fabric_address: Optional[str] = None, fabric_rank: Optional[int] = None, fabric_world: Optional[int] = None,
+                 fabric_max_tokens: int = 8192, **kwargs):
         if kwargs:
             logger.debug(f"ignoring networking options that have no meaning on one box: {sorted(kwargs)}")
         self.converted_model_name_or_path = converted_model_name_or_path
@@ -129,6 +130,8 @@ class Server:
         if len(self.tensor_parallel_devices) > 1:
             check_device_balance(self.tensor_parallel_devices)
         self.quant_type = resolve_quant_type(quant_type) if quant_type is not None else QuantType.NONE
+        self._owns_process_group = False
+        self.fabric = self._join_fabric(fabric_address, fabric_rank, fabric_world, fabric_max_tokens)
 
         spec = self.block_config.block_spec()
         is_multiquery_attn = spec.num_kv_heads < spec.num_heads
@@ -271,6 +274,38 @@ class Server:
         module_infos = get_remote_module_infos(self.dht, self.module_uids, latest=True)
         return block_selection.should_choose_other_blocks(self.peer_id, module_infos, self.balance_quality)
 
+    def _join_fabric(self, address: Optional[str], rank: Optional[int], world: Optional[int], max_tokens: int):
+        """``--fabric_address HOST:PORT --fabric_rank R --fabric_world N``: the N stage processes of one NVLink box form a landing-ring
+        fabric (parallel/fabric.py) — between them hidden states, training micro-batches and gradients hop GPU to GPU instead of
+        travelling with the RPCs, for any client (a client needs no membership; it learns from ``rpc_info`` which stages share a
+        fabric). Collective: returns when all N processes have joined. Without the flags, under ``torchrun`` (RANK / WORLD_SIZE /
+        MASTER_ADDR / MASTER_PORT in the environment) the same happens with the launcher's values when ``PETALS_B200_FABRIC=env``."""
+        import torch.distributed as dist
+
+        from petals_b200.parallel.fabric import get_fabric, init_fabric
+
+        if address is None and os.environ.get("PETALS_B200_FABRIC", "") == "env" and "RANK" in os.environ and "WORLD_SIZE" in os.environ:
+            address = f"{os.environ.get('MASTER_ADDR', '127.0.0.1')}:{os.environ.get('MASTER_PORT', '29500')}"
+            rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+        if address is None:
+            return get_fabric()  # possibly created by the embedding process (benchmarks, self-tests)
+        if rank is None or world is None or not 0 <= rank < world or world < 2:
+            raise ValueError("--fabric_address needs --fabric_rank R and --fabric_world N with 0 <= R < N and N >= 2")
+        if len(self.tensor_parallel_devices) > 1:
+            raise ValueError("a tensor-parallel server owns its own process group: it cannot also join a box fabric (use one GPU per fabric member)")
+        if get_fabric() is not None:
+            return get_fabric()
+        if not dist.is_initialized():
+            cuda = self.device.type == "cuda"
+            if cuda:
+                torch.cuda.set_device(self.device)
+            dist.init_process_group(backend="cpu:gloo,cuda:nccl" if cuda else "gloo", init_method=f"tcp://{address}", rank=rank, world_size=world,
+                                    **({"device_id": self.device} if cuda else {}))
+            self._owns_process_group = True
+        fabric = init_fabric(self.block_config.hidden_size, max_tokens=max_tokens, host_dtype=self.torch_dtype if self.device.type == "cpu" else torch.float32)
+        logger.info(f"Joined the NVLink fabric {getattr(fabric, 'fabric_id', '?')[:8]} as member {rank} of {world} ({max_tokens} rows per landing slot)")
+        return fabric
+
     def shutdown(self, timeout: Optional[float] = 5) -> None:
         self.stop.set()
         if self.metrics_server is not None:
@@ -281,6 +316,20 @@ class Server:
         if self.module_container is not None:
             self.module_container.shutdown()
             self.module_container = None
+        if self._owns_process_group:
+            import torch.distributed as dist
+
+            import petals_b200.parallel.fabric as fabric_mod
+
+            try:
+                if self.fabric is not None:
+                    self.fabric.close()
+                fabric_mod._fabric = None
+                if dist.is_initialized():
+                    dist.destroy_process_group()
+            except Exception as e:  # noqa: BLE001 - peers may already be gone
+                logger.debug(f"leaving the fabric: {e!r}")
+            self._owns_process_group = False
 
 
 class ModuleContainer:

@@ -68,3 +68,65 @@ def test_two_server_processes(family, compression, atol, tmp_path):
                 p.kill()
         for f in logs:
             f.close()
+
+
+def test_run_server_processes_join_a_fabric_and_serve_a_client_outside_it(tmp_path):
+    """`run_server --fabric_address/--fabric_rank/--fabric_world`: two independently started stage processes form a landing-ring fabric
+    (the shared-memory twin on CPU); a client that is NOT a member learns from `rpc_info` that the stages share a fabric, so hidden
+    states, training micro-batches and gradients hop stage to stage through the rings and only the two ends travel with the RPCs."""
+    import socket
+
+    path = checkpoint("llama")
+    rendezvous = str(tmp_path / "swarm")
+    subprocess.run([sys.executable, "-m", "petals.cli.run_dht", "--rendezvous", rendezvous, "--once"], check=True, cwd=ROOT, env=dict(os.environ, PYTHONPATH=ROOT))
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    logs = [open(tmp_path / f"server{i}.log", "w") for i in range(2)]
+    common = ["--initial_peers", rendezvous, "--torch_dtype", "float32", "--device", "cpu", "--throughput", "1", "--update_period", "1",
+              "--fabric_address", f"127.0.0.1:{port}", "--fabric_world", "2", "--fabric_max_tokens", "256"]
+    procs = [_spawn(["petals.cli.run_server", path, "--block_indices", "0:2", "--peer_id", "stage0", "--fabric_rank", "0", *common], logs[0]),
+             _spawn(["petals.cli.run_server", path, "--block_indices", "2:4", "--peer_id", "stage1", "--fabric_rank", "1", *common], logs[1])]
+    try:
+        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[rendezvous], max_retries=150, min_backoff=0.5, max_backoff=1.0)
+        config = AutoDistributedConfig.from_pretrained(path)
+        ids = torch.randint(0, config.vocab_size, (2, 9), generator=torch.Generator().manual_seed(0))
+        blocks = list(local_blocks(path, config.num_hidden_layers))
+        with torch.inference_mode():
+            h = model.model.embed(ids)
+            for b in blocks:
+                h = b(h)[0]
+            ref = model.lm_head(model.model.final_norm(h))
+            with model.inference_session(max_length=16) as sess:
+                a = model(ids[:, :6]).logits
+                b_ = model(ids[:, 6:7]).logits
+                c = model(ids[:, 7:]).logits
+                over_fabric = [s.no_history for s in sess._server_sessions]
+                same_fabric = len({s.fabric_info["id"] for s in sess._server_sessions}) == 1
+            assert all(p.poll() is None for p in procs), "a server process died"
+        assert torch.allclose(torch.cat([a, b_, c], 1), ref, atol=1e-3)
+        assert over_fabric == [False, True] and same_fabric  # the second stage never got a tensor from the client
+        # training: forward micro-batches and gradients hop between the stages, the ends travel with the RPCs
+        from petals_b200.client.sequential_autograd import FabricPlan
+
+        x = torch.randn(2, 9, config.hidden_size, requires_grad=True)
+        before = dict(FabricPlan.hops_done)
+        y = model.model.layers(x)
+        y.sum().backward()
+        assert {k: FabricPlan.hops_done[k] - before[k] for k in before} == {"forward": 2, "backward": 2}
+        x2 = x.detach().clone().requires_grad_(True)
+        h = x2
+        for b in blocks:
+            h = b(h)[0]
+        h.sum().backward()
+        assert torch.allclose(y, h, atol=1e-4) and torch.allclose(x.grad, x2.grad, atol=1e-3)
+    finally:
+        for p in procs:
+            p.terminate()
+        for p in procs:
+            try:
+                p.wait(timeout=10)
+            except subprocess.TimeoutExpired:
+                p.kill()
+        for log in logs:
+            log.close()
