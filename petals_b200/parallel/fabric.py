@@ -303,6 +303,43 @@ def init_fabric(hidden_size: int, max_tokens: int = 8192, group=None, host_dtype
     return _fabric
 
 
+def join_fabric(address: str, rank: int, world: int, hidden_size: int, *, device=None, max_tokens: int = 8192,
+                host_dtype: torch.dtype = torch.float32, n_slots: int = 4):
+    """Rendezvous of independently started processes of one NVLink box (stage servers: ``run_server --fabric_address ...``; a co-located
+    client: ``from_pretrained(..., fabric_address=...)``) into one landing-ring fabric. Collective over the ``world`` processes that call
+    it with the same ``address`` ("host:port"); initialises ``torch.distributed`` for them if the process has not done so itself.
+    Returns ``(fabric, owns_process_group)``."""
+    if rank is None or world is None or not 0 <= rank < world or world < 2:
+        raise ValueError("a fabric needs fabric_rank R and fabric_world N with 0 <= R < N and N >= 2")
+    if _fabric is not None:
+        return _fabric, False
+    owns = False
+    if not dist.is_initialized():
+        device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        cuda = device.type == "cuda"
+        if cuda:
+            torch.cuda.set_device(device)
+        dist.init_process_group(backend="cpu:gloo,cuda:nccl" if cuda else "gloo", init_method=f"tcp://{address}", rank=rank, world_size=world,
+                                **({"device_id": device} if cuda else {}))
+        owns = True
+    fabric = init_fabric(hidden_size, max_tokens=max_tokens, host_dtype=host_dtype, n_slots=n_slots)
+    logger.info(f"Joined the NVLink fabric {str(getattr(fabric, 'fabric_id', '?'))[:8]} as member {rank} of {world} ({fabric.max_tokens} rows per landing slot)")
+    return fabric, owns
+
+
+def leave_fabric(owns_process_group: bool) -> None:
+    """Undo :func:`join_fabric` (best effort: peers may already be gone)."""
+    global _fabric
+    try:
+        if _fabric is not None:
+            _fabric.close()
+        _fabric = None
+        if owns_process_group and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception as e:  # noqa: BLE001
+        logger.debug(f"leaving the fabric: {e!r}")
+
+
 def fabric_info(fabric=None) -> Optional[dict]:
     """What a stage announces about its fabric membership (``rpc_info()["fabric"]``)."""
     fabric = fabric if fabric is not None else _fabric

@@ -280,9 +280,7 @@ class Server:
         travelling with the RPCs, for any client (a client needs no membership; it learns from ``rpc_info`` which stages share a
         fabric). Collective: returns when all N processes have joined. Without the flags, under ``torchrun`` (RANK / WORLD_SIZE /
         MASTER_ADDR / MASTER_PORT in the environment) the same happens with the launcher's values when ``PETALS_B200_FABRIC=env``."""
-        import torch.distributed as dist
-
-        from petals_b200.parallel.fabric import get_fabric, init_fabric
+        from petals_b200.parallel.fabric import get_fabric, join_fabric
 
         if address is None and os.environ.get("PETALS_B200_FABRIC", "") == "env" and "RANK" in os.environ and "WORLD_SIZE" in os.environ:
             address = f"{os.environ.get('MASTER_ADDR', '127.0.0.1')}:{os.environ.get('MASTER_PORT', '29500')}"
@@ -293,17 +291,8 @@ class Server:
             raise ValueError("--fabric_address needs --fabric_rank R and --fabric_world N with 0 <= R < N and N >= 2")
         if len(self.tensor_parallel_devices) > 1:
             raise ValueError("a tensor-parallel server owns its own process group: it cannot also join a box fabric (use one GPU per fabric member)")
-        if get_fabric() is not None:
-            return get_fabric()
-        if not dist.is_initialized():
-            cuda = self.device.type == "cuda"
-            if cuda:
-                torch.cuda.set_device(self.device)
-            dist.init_process_group(backend="cpu:gloo,cuda:nccl" if cuda else "gloo", init_method=f"tcp://{address}", rank=rank, world_size=world,
-                                    **({"device_id": self.device} if cuda else {}))
-            self._owns_process_group = True
-        fabric = init_fabric(self.block_config.hidden_size, max_tokens=max_tokens, host_dtype=self.torch_dtype if self.device.type == "cpu" else torch.float32)
-        logger.info(f"Joined the NVLink fabric {getattr(fabric, 'fabric_id', '?')[:8]} as member {rank} of {world} ({max_tokens} rows per landing slot)")
+        fabric, self._owns_process_group = join_fabric(address, rank, world, self.block_config.hidden_size, device=self.device, max_tokens=max_tokens,
+                                                       host_dtype=self.torch_dtype if self.device.type == "cpu" else torch.float32)
         return fabric
 
     def shutdown(self, timeout: Optional[float] = 5) -> None:
@@ -317,18 +306,9 @@ class Server:
             self.module_container.shutdown()
             self.module_container = None
         if self._owns_process_group:
-            import torch.distributed as dist
+            from petals_b200.parallel.fabric import leave_fabric
 
-            import petals_b200.parallel.fabric as fabric_mod
-
-            try:
-                if self.fabric is not None:
-                    self.fabric.close()
-                fabric_mod._fabric = None
-                if dist.is_initialized():
-                    dist.destroy_process_group()
-            except Exception as e:  # noqa: BLE001 - peers may already be gone
-                logger.debug(f"leaving the fabric: {e!r}")
+            leave_fabric(True)
             self._owns_process_group = False
 
 

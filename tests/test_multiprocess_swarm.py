@@ -70,7 +70,8 @@ def test_two_server_processes(family, compression, atol, tmp_path):
             f.close()
 
 
-def test_run_server_processes_join_a_fabric_and_serve_a_client_outside_it(tmp_path):
+@pytest.mark.parametrize("member_client", [False, True])
+def test_run_server_processes_join_a_fabric_and_serve_a_client_outside_it(member_client, tmp_path):
     """`run_server --fabric_address/--fabric_rank/--fabric_world`: two independently started stage processes form a landing-ring fabric
     (the shared-memory twin on CPU); a client that is NOT a member learns from `rpc_info` that the stages share a fabric, so hidden
     states, training micro-batches and gradients hop stage to stage through the rings and only the two ends travel with the RPCs."""
@@ -84,11 +85,14 @@ def test_run_server_processes_join_a_fabric_and_serve_a_client_outside_it(tmp_pa
         port = s.getsockname()[1]
     logs = [open(tmp_path / f"server{i}.log", "w") for i in range(2)]
     common = ["--initial_peers", rendezvous, "--torch_dtype", "float32", "--device", "cpu", "--throughput", "1", "--update_period", "1",
-              "--fabric_address", f"127.0.0.1:{port}", "--fabric_world", "2", "--fabric_max_tokens", "256"]
+              "--fabric_address", f"127.0.0.1:{port}", "--fabric_world", "3" if member_client else "2", "--fabric_max_tokens", "256"]
     procs = [_spawn(["petals.cli.run_server", path, "--block_indices", "0:2", "--peer_id", "stage0", "--fabric_rank", "0", *common], logs[0]),
              _spawn(["petals.cli.run_server", path, "--block_indices", "2:4", "--peer_id", "stage1", "--fabric_rank", "1", *common], logs[1])]
     try:
-        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[rendezvous], max_retries=150, min_backoff=0.5, max_backoff=1.0)
+        # member_client: this process joins the fabric as its third member (from_pretrained(..., fabric_address=...)): the last stage then
+        # returns through the client's own landing ring and the client stores the output gradient into the last stage's ring
+        extra = dict(fabric_address=f"127.0.0.1:{port}", fabric_rank=2, fabric_world=3, fabric_max_tokens=256) if member_client else {}
+        model = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[rendezvous], max_retries=150, min_backoff=0.5, max_backoff=1.0, **extra)
         config = AutoDistributedConfig.from_pretrained(path)
         ids = torch.randint(0, config.vocab_size, (2, 9), generator=torch.Generator().manual_seed(0))
         blocks = list(local_blocks(path, config.num_hidden_layers))
@@ -130,3 +134,7 @@ def test_run_server_processes_join_a_fabric_and_serve_a_client_outside_it(tmp_pa
                 p.kill()
         for log in logs:
             log.close()
+        if member_client:
+            from petals_b200.parallel.fabric import leave_fabric
+
+            leave_fabric(True)
