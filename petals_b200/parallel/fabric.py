@@ -17,8 +17,12 @@ overlapped with the producer's math plus a flag latency, and the control RPC bet
 bytes* (only "your input is in your landing zone"). Flags are monotonic; every consumer keeps a device-resident count
 of consumed transfers (the "epoch" passed to the kernels), so nothing is ever reset and CUDA graphs stay valid.
 
-Created once per process by :func:`init_fabric` after ``torch.distributed`` is initialised; absent (``get_fabric()`` is
-None) in single-process / CPU runs, where stages exchange tensors by reference or over the Unix-socket transport."""
+Created once per process: by :func:`join_fabric` when independently started processes of a box rendezvous (``run_server
+--fabric_address HOST:PORT --fabric_rank R --fabric_world N``, ``from_pretrained(..., fabric_address=...)`` for a co-located client), or by
+:func:`init_fabric` inside a job that is already one ``torch.distributed`` world (benchmarks, self-tests). Stages announce their membership
+(:func:`fabric_info`) in ``rpc_info``; clients route hops by those announcements and need no membership themselves. Absent
+(``get_fabric()`` is None) otherwise: stages then exchange tensors by reference or over the socket transport. On CPU the same protocol
+runs over POSIX shared memory (:class:`HostFabric`)."""
 from __future__ import annotations
 
 from typing import Optional
