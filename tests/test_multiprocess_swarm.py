@@ -110,6 +110,29 @@ def test_run_server_processes_join_a_fabric_and_serve_a_client_outside_it(member
             assert all(p.poll() is None for p in procs), "a server process died"
         assert torch.allclose(torch.cat([a, b_, c], 1), ref, atol=1e-3)
         assert over_fabric == [False, True] and same_fabric  # the second stage never got a tensor from the client
+        # a long prompt is cut into chunks that travel as a wavefront through the landing RINGS (one slot per chunk in flight)
+        chunky = AutoDistributedModelForCausalLM.from_pretrained(path, initial_peers=[rendezvous], max_retries=150, min_backoff=0.5, max_backoff=1.0,
+                                                                 pipeline_chunk_tokens=2)
+        chunky.load_state_dict(model.state_dict())
+        from petals_b200.client.inference_session import InferenceSession
+
+        waves, original = [], InferenceSession._pipelined_wave
+
+        def counting(self, *a, **k):
+            out = original(self, *a, **k)
+            waves.append(out is not None)
+            return out
+
+        InferenceSession._pipelined_wave = counting
+        try:
+            with torch.inference_mode(), chunky.inference_session(max_length=16) as sess:
+                d = chunky(ids[:, :8]).logits  # 4 chunks of 2 positions over 2 stages
+                e = chunky(ids[:, 8:]).logits
+                assert [s.no_history for s in sess._server_sessions] == [False, True]
+        finally:
+            InferenceSession._pipelined_wave = original
+        assert waves and waves[0], "the long prompt was not ingested as a wavefront of chunks"
+        assert torch.allclose(torch.cat([d, e], 1), ref, atol=1e-3)
         # training: forward micro-batches and gradients hop between the stages, the ends travel with the RPCs
         from petals_b200.client.sequential_autograd import FabricPlan
 
