@@ -293,6 +293,12 @@ def init_fabric(hidden_size: int, max_tokens: int = 8192, group=None, host_dtype
     global _fabric
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) < 2:
         return None
+    # the landing rings live at the same offsets of every member's heap: every member must size them identically
+    mine = (int(hidden_size), int(max_tokens), int(n_slots), bool(torch.cuda.is_available()))
+    everyone = [None] * dist.get_world_size(group)
+    dist.all_gather_object(everyone, mine, group=group)
+    if any(other != mine for other in everyone):
+        raise ValueError(f"the members of a fabric must agree on (hidden_size, max_tokens, n_slots, cuda): {everyone}")
     if torch.cuda.is_available():
         _fabric = Fabric(hidden_size, max_tokens, group, n_slots=n_slots)
     else:
